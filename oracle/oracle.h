@@ -1,0 +1,81 @@
+/*
+ * oracle.h — TEST INFRASTRUCTURE ONLY (CPU restatement of the reference algorithms).
+ *
+ * Plain-C restatements of the five FFmpeg DSP hot paths, written from the reference's behaviour
+ * (each function cites the reference file:line it follows).  They are the checker for the CUDA path:
+ * only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may load liboracle.so.
+ * The product (ffmpeg_b200/, libb200dsp.so) never links or calls anything declared here.
+ *
+ * Parity pinning: every function below is checked bit-for-bit (tx: bit-for-bit too, same float op order)
+ * against the unmodified reference compiled in oracle/_ref (tests/test_oracle_vs_ref.py, run wherever
+ * oracle/_ref/libffref.so exists) and against the committed fixtures in tests/golden/ (generated from
+ * oracle/_ref by scripts/gen_golden.py).
+ */
+#ifndef B200_ORACLE_H
+#define B200_ORACLE_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ swscale: yuv420p -> rgb24 */
+/* flag values identical to libswscale/swscale.h:88-118 */
+#define ORC_SWS_FAST_BILINEAR 0x1
+#define ORC_SWS_BILINEAR      0x2
+#define ORC_SWS_BICUBIC       0x4
+#define ORC_SWS_POINT         0x10
+#define ORC_SWS_AREA          0x20
+#define ORC_SWS_BICUBLIN      0x40
+#define ORC_SWS_FULL_CHR_H_INT 0x2000
+#define ORC_SWS_ACCURATE_RND  0x40000
+#define ORC_SWS_BITEXACT      0x80000
+
+typedef struct OrcSws OrcSws;
+
+OrcSws *orc_sws_open(int srcW, int srcH, int dstW, int dstH, int flags);
+void    orc_sws_close(OrcSws *s);
+/* inv_table = 4 coefficients as ff_yuv2rgb_coeffs rows; contrast/saturation 16.16 */
+int     orc_sws_set_colorspace(OrcSws *s, const int inv_table[4], int srcRange,
+                               int brightness, int contrast, int saturation);
+/* whole-frame conversion; returns number of output lines or <0 */
+int     orc_sws_scale(OrcSws *s, const uint8_t *y, int ys, const uint8_t *u, int us,
+                      const uint8_t *v, int vs, uint8_t *dst, int ds);
+/* 16 ints, same layout as ffref_sws_info */
+int     orc_sws_info(const OrcSws *s, int *out);
+/* which: 0 hLum 1 hChr 2 vLum 3 vChr; returns n entries copied */
+int     orc_sws_get_filter(const OrcSws *s, int which, int16_t *filter, int32_t *pos, int cap);
+/* the bare horizontal FIR */
+void    orc_hscale8to15(int16_t *dst, int dstW, const uint8_t *src, const int16_t *filter,
+                        const int32_t *filterPos, int filterSize);
+
+/* ------------------------------------------------------------------ idctdsp (simple_idct 8 bit) */
+void orc_idct(int16_t *block);                                            /* in place */
+void orc_idct_put(uint8_t *dest, ptrdiff_t line_size, int16_t *block);
+void orc_idct_add(uint8_t *dest, ptrdiff_t line_size, int16_t *block);
+void orc_idct_batch(int kind, int16_t *blocks, int nblocks, uint8_t *dest, ptrdiff_t line_size,
+                    const int64_t *dest_off);
+void orc_pixels_clamped(int kind, const int16_t *block, uint8_t *pixels, ptrdiff_t line_size);
+
+/* ------------------------------------------------------------------ me_cmp */
+/* fn: 0 sad, 1 sse, 2 pix_abs[idx>>2][idx&3]; idx for sad/sse: 0=16 wide,1=8,2=4 (sse only) */
+int  orc_me_cmp(int fn, int idx, const uint8_t *blk1, const uint8_t *blk2, ptrdiff_t stride, int h);
+void orc_esa_frame(const uint8_t *cur, const uint8_t *ref, int linesize, int width, int height,
+                   int mb_size, int search_param, int mb_row0, int mb_row1, int32_t *out_mv, uint64_t *out_cost);
+
+/* ------------------------------------------------------------------ h264qpel / hpeldsp (8 bit) */
+void orc_h264qpel(int avg, int size_idx, int pos, uint8_t *dst, const uint8_t *src, ptrdiff_t stride);
+int  orc_hpel(int tab, int size_idx, int xy, uint8_t *block, const uint8_t *pixels, ptrdiff_t line_size, int h);
+
+/* ------------------------------------------------------------------ tx (float FFT / MDCT, power-of-two) */
+typedef struct OrcTx OrcTx;
+OrcTx *orc_tx_open(int type /*0 FFT, 1 MDCT*/, int inv, int len, float scale, unsigned flags);
+void   orc_tx_close(OrcTx *t);
+void   orc_tx_run(OrcTx *t, void *out, void *in, ptrdiff_t stride, int count, ptrdiff_t out_step, ptrdiff_t in_step);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

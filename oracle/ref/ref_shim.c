@@ -1,0 +1,305 @@
+/*
+ * ref_shim.c — TEST INFRASTRUCTURE ONLY.
+ *
+ * Flat C ABI over the UNMODIFIED reference (FFmpeg) C implementation of the five DSP hot paths,
+ * linked from the reference sources where they lie (see Makefile in this directory).  It is used
+ *   - by tests/ to validate the oracle restatement (oracle/*.c) and the CUDA path against the real thing,
+ *   - by scripts/gen_golden.py to produce tests/golden/ fixtures,
+ *   - by bench.py's cpu_baseline / --impl reference leg (kind "reference").
+ * Nothing in the product path (ffmpeg_b200/) may load this library.
+ *
+ * Every entry point only forwards to the reference's own table entry; no arithmetic lives here.
+ */
+#include <stdint.h>
+#include <stddef.h>
+#include <string.h>
+#include <stdlib.h>
+
+#include "config.h"
+#include "libavutil/mem.h"
+#include "libavutil/log.h"
+#include "libavutil/pixfmt.h"
+#include "libavutil/tx.h"
+#include "libavutil/cpu.h"
+#include "libswscale/swscale.h"
+#include "libswscale/swscale_internal.h"
+#include "libswscale/graph.h"
+#include "libavcodec/avcodec.h"
+#include "libavcodec/idctdsp.h"
+#include "libavcodec/me_cmp.h"
+#include "libavcodec/h264qpel.h"
+#include "libavcodec/hpeldsp.h"
+#include "libavfilter/motion_estimation.h"
+
+/* ---- link stubs: the new-API filter graph (sws_scale_frame) is not part of the legacy hot path ---- */
+int  ff_sws_pass_aligned_width(const SwsPass *pass, int width) { return width; }
+SwsGraph *ff_sws_graph_alloc(void) { return NULL; }
+void ff_sws_graph_free(SwsGraph **graph) { if (graph) *graph = NULL; }
+int  ff_sws_graph_reinit(SwsGraph *graph, SwsContext *ctx, const SwsFormat *dst, const SwsFormat *src) { return AVERROR(ENOSYS); }
+int  ff_sws_graph_run(SwsGraph *graph, const AVFrame *dst, const AVFrame *src) { return AVERROR(ENOSYS); }
+
+#define API __attribute__((visibility("default")))
+
+API int ffref_abi_version(void) { return 1; }
+API unsigned ffref_swscale_version(void) { return swscale_version(); }
+API int ffref_cpu_flags(void) { return av_get_cpu_flags(); }
+API void ffref_set_quiet(void) { av_log_set_level(AV_LOG_ERROR); }
+
+/* ------------------------------------------------------------------ swscale ------------------------------------- */
+
+/* Opaque handle = the reference SwsContext (legacy API: sws_getContext + sws_scale). */
+API void *ffref_sws_open(int srcW, int srcH, int dstW, int dstH, int flags, int threads)
+{
+    SwsContext *c = sws_alloc_context();
+    if (!c) return NULL;
+    c->src_w = srcW; c->src_h = srcH; c->dst_w = dstW; c->dst_h = dstH;
+    c->src_format = AV_PIX_FMT_YUV420P; c->dst_format = AV_PIX_FMT_RGB24;
+    c->flags = flags;
+    c->threads = threads;
+    if (sws_init_context(c, NULL, NULL) < 0) { sws_freeContext(c); return NULL; }
+    return c;
+}
+
+API void ffref_sws_close(void *h) { sws_freeContext((SwsContext *)h); }
+
+/* colorspace details pass-through (sws_setColorspaceDetails); table index = SWS_CS_* */
+API int ffref_sws_set_colorspace(void *h, int src_cs, int src_range, int dst_cs, int dst_range,
+                                 int brightness, int contrast, int saturation)
+{
+    return sws_setColorspaceDetails((SwsContext *)h, sws_getCoefficients(src_cs), src_range,
+                                    sws_getCoefficients(dst_cs), dst_range, brightness, contrast, saturation);
+}
+
+API int ffref_sws_scale(void *h, const uint8_t *y, int ys, const uint8_t *u, int us, const uint8_t *v, int vs,
+                        int srcSliceY, int srcSliceH, uint8_t *dst, int ds)
+{
+    const uint8_t *src[4] = { y, u, v, NULL };
+    int sstr[4] = { ys, us, vs, 0 };
+    uint8_t *d[4] = { dst, NULL, NULL, NULL };
+    int dstr[4] = { ds, 0, 0, 0 };
+    return sws_scale((SwsContext *)h, src, sstr, srcSliceY, srcSliceH, d, dstr);
+}
+
+/* Introspection of the initialised context, for checking the host-side filter generation. */
+API int ffref_sws_info(void *h, int *out /* 16 ints */)
+{
+    SwsInternal *c = sws_internal((SwsContext *)h);
+    out[0] = c->hLumFilterSize; out[1] = c->hChrFilterSize;
+    out[2] = c->vLumFilterSize; out[3] = c->vChrFilterSize;
+    out[4] = c->chrSrcW; out[5] = c->chrSrcH; out[6] = c->chrDstW; out[7] = c->chrDstH;
+    out[8] = c->convert_unscaled != NULL;
+    out[9] = c->chrSrcHSubSample; out[10] = c->chrSrcVSubSample;
+    out[11] = c->chrDstHSubSample; out[12] = c->chrDstVSubSample;
+    out[13] = c->opts.dst_w; out[14] = c->opts.dst_h; out[15] = c->needs_hcscale;
+    return 0;
+}
+
+/* which: 0 hLum 1 hChr 2 vLum 3 vChr.  Copies filter (n*size int16) and pos (n int32). Returns n. */
+API int ffref_sws_get_filter(void *h, int which, int16_t *filter, int32_t *pos, int cap)
+{
+    SwsInternal *c = sws_internal((SwsContext *)h);
+    const int16_t *f; const int32_t *p; int n, fs;
+    switch (which) {
+    case 0: f = c->hLumFilter; p = c->hLumFilterPos; n = c->opts.dst_w;    fs = c->hLumFilterSize; break;
+    case 1: f = c->hChrFilter; p = c->hChrFilterPos; n = c->chrDstW; fs = c->hChrFilterSize; break;
+    case 2: f = c->vLumFilter; p = c->vLumFilterPos; n = c->opts.dst_h;    fs = c->vLumFilterSize; break;
+    default:f = c->vChrFilter; p = c->vChrFilterPos; n = c->chrDstH; fs = c->vChrFilterSize; break;
+    }
+    if (!f || !p) return 0;
+    if (n > cap) n = cap;
+    if (filter) memcpy(filter, f, (size_t)n * fs * sizeof(int16_t));
+    if (pos)    memcpy(pos, p, (size_t)n * sizeof(int32_t));
+    return n;
+}
+
+/* LUTs: table_rV/gU/gV/bU are pointer tables into yuvTable; export them as byte offsets from yuvTable
+ * (gV is an int table), plus the yuvTable bytes themselves.  Returns the size of yuvTable copied. */
+API int ffref_sws_get_tables(void *h, int32_t *rV, int32_t *gU, int32_t *gV, int32_t *bU /* 256+2*512 each */,
+                             uint8_t *yuvtab, int cap)
+{
+    SwsInternal *c = sws_internal((SwsContext *)h);
+    int n = 256 + 2 * YUVRGB_TABLE_HEADROOM;
+    for (int i = 0; i < n; i++) {
+        rV[i] = (int32_t)((uint8_t *)c->table_rV[i] - (uint8_t *)c->yuvTable);
+        gU[i] = (int32_t)((uint8_t *)c->table_gU[i] - (uint8_t *)c->yuvTable);
+        gV[i] = c->table_gV[i];
+        bU[i] = (int32_t)((uint8_t *)c->table_bU[i] - (uint8_t *)c->yuvTable);
+    }
+    int sz = 1024 * 3 + 2 * YUVRGB_TABLE_LUMA_HEADROOM * 3; /* upper bound for 24bpp: see yuv2rgb.c */
+    if (sz > cap) sz = cap;
+    if (yuvtab && c->yuvTable) memcpy(yuvtab, c->yuvTable, sz);
+    return sz;
+}
+
+/* The reference's horizontal scaler kernel as installed in the context (hyScale / hcScale). */
+API void ffref_sws_hscale(void *h, int chroma, int16_t *dst, int dstW, const uint8_t *src,
+                          const int16_t *filter, const int32_t *filterPos, int filterSize)
+{
+    SwsInternal *c = sws_internal((SwsContext *)h);
+    (chroma ? c->hcScale : c->hyScale)(c, dst, dstW, src, filter, filterPos, filterSize);
+}
+
+/* ------------------------------------------------------------------ idctdsp ------------------------------------- */
+
+static IDCTDSPContext g_idsp; static int g_idsp_ok;
+static void idsp_init(void)
+{
+    if (g_idsp_ok) return;
+    AVCodecContext *avctx = av_mallocz(sizeof(*avctx));
+    avctx->idct_algo = FF_IDCT_SIMPLE;
+    avctx->bits_per_raw_sample = 8;
+    ff_idctdsp_init(&g_idsp, avctx);
+    av_free(avctx);
+    g_idsp_ok = 1;
+}
+
+API int ffref_idct_perm_type(uint8_t *perm64)
+{
+    idsp_init();
+    if (perm64) memcpy(perm64, g_idsp.idct_permutation, 64);
+    return g_idsp.perm_type;
+}
+
+/* kind: 0 = idct (in place), 1 = idct_put, 2 = idct_add.  blocks are clobbered like the reference does.
+ * dest_off[i] = byte offset of block i's top-left in dest. */
+API void ffref_idct_batch(int kind, int16_t *blocks, int nblocks, uint8_t *dest, ptrdiff_t line_size,
+                          const int64_t *dest_off)
+{
+    idsp_init();
+    for (int i = 0; i < nblocks; i++) {
+        int16_t *b = blocks + 64 * (size_t)i;
+        if (kind == 0)      g_idsp.idct(b);
+        else if (kind == 1) g_idsp.idct_put(dest + dest_off[i], line_size, b);
+        else                g_idsp.idct_add(dest + dest_off[i], line_size, b);
+    }
+}
+
+/* clamp helpers: kind 0 put_pixels_clamped, 1 put_signed_pixels_clamped, 2 add_pixels_clamped */
+API void ffref_pixels_clamped(int kind, const int16_t *block, uint8_t *pixels, ptrdiff_t line_size)
+{
+    idsp_init();
+    if (kind == 0) g_idsp.put_pixels_clamped(block, pixels, line_size);
+    else if (kind == 1) g_idsp.put_signed_pixels_clamped(block, pixels, line_size);
+    else g_idsp.add_pixels_clamped(block, pixels, line_size);
+}
+
+/* ------------------------------------------------------------------ me_cmp -------------------------------------- */
+
+static MECmpContext g_mecmp; static int g_mecmp_ok;
+static void mecmp_init(void)
+{
+    if (g_mecmp_ok) return;
+    AVCodecContext *avctx = av_mallocz(sizeof(*avctx));
+    avctx->flags |= AV_CODEC_FLAG_BITEXACT;
+    ff_me_cmp_init(&g_mecmp, avctx);
+    av_free(avctx);
+    g_mecmp_ok = 1;
+}
+
+/* fn: 0 sad[idx], 1 sse[idx], 2 pix_abs[idx>>2][idx&3] */
+API int ffref_me_cmp(int fn, int idx, const uint8_t *blk1, const uint8_t *blk2, ptrdiff_t stride, int h)
+{
+    mecmp_init();
+    me_cmp_func f = fn == 0 ? g_mecmp.sad[idx] : fn == 1 ? g_mecmp.sse[idx] : g_mecmp.pix_abs[idx >> 2][idx & 3];
+    if (!f) return -1;
+    return f(NULL, blk1, blk2, stride, h);
+}
+
+/* many calls in one go (for the CPU baseline): offsets into two frames */
+API void ffref_me_cmp_batch(int fn, int idx, const uint8_t *f1, const uint8_t *f2, ptrdiff_t stride, int h,
+                            const int64_t *off1, const int64_t *off2, int n, int32_t *out)
+{
+    mecmp_init();
+    me_cmp_func f = fn == 0 ? g_mecmp.sad[idx] : fn == 1 ? g_mecmp.sse[idx] : g_mecmp.pix_abs[idx >> 2][idx & 3];
+    for (int i = 0; i < n; i++) out[i] = f(NULL, f1 + off1[i], f2 + off2[i], stride, h);
+}
+
+/* Exhaustive search exactly as libavfilter/vf_mestimate.c drives ff_me_search_esa: for every mb of the frame
+ * (raster order) mv initialised to (x_mb,y_mb); rows [mb_row0, mb_row1) only (to split over threads).
+ * out_mv: 2 ints per mb, out_cost: 1 uint64 per mb, indexed by mb_y*b_width+mb_x. */
+API void ffref_esa_frame(const uint8_t *cur, const uint8_t *ref, int linesize, int width, int height,
+                         int mb_size, int search_param, int mb_row0, int mb_row1, int32_t *out_mv, uint64_t *out_cost)
+{
+    AVMotionEstContext me = { 0 };
+    int log2_mb = 0; while ((1 << log2_mb) < mb_size) log2_mb++;
+    int b_width = width >> log2_mb, b_height = height >> log2_mb;
+    ff_me_init_context(&me, mb_size, search_param, width, height,
+                       0, (b_width - 1) << log2_mb, 0, (b_height - 1) << log2_mb);
+    me.data_cur = (uint8_t *)cur; me.data_ref = (uint8_t *)ref; me.linesize = linesize;
+    if (mb_row1 > b_height) mb_row1 = b_height;
+    for (int mb_y = mb_row0; mb_y < mb_row1; mb_y++)
+        for (int mb_x = 0; mb_x < b_width; mb_x++) {
+            int x_mb = mb_x << log2_mb, y_mb = mb_y << log2_mb;
+            int mv[2] = { x_mb, y_mb };
+            uint64_t cost = ff_me_search_esa(&me, x_mb, y_mb, mv);
+            out_mv[2 * (mb_y * b_width + mb_x) + 0] = mv[0];
+            out_mv[2 * (mb_y * b_width + mb_x) + 1] = mv[1];
+            out_cost[mb_y * b_width + mb_x] = cost;
+        }
+}
+
+/* ------------------------------------------------------------------ h264qpel / hpeldsp -------------------------- */
+
+static H264QpelContext g_qpel; static HpelDSPContext g_hpel; static int g_pel_ok;
+static void pel_init(void)
+{
+    if (g_pel_ok) return;
+    ff_h264qpel_init(&g_qpel, 8);
+    ff_hpeldsp_init(&g_hpel, AV_CODEC_FLAG_BITEXACT);
+    g_pel_ok = 1;
+}
+
+/* avg: 0 put 1 avg; size_idx 0:16 1:8 2:4; pos = x + 4*y */
+API void ffref_h264qpel(int avg, int size_idx, int pos, uint8_t *dst, const uint8_t *src, ptrdiff_t stride)
+{
+    pel_init();
+    (avg ? g_qpel.avg_h264_qpel_pixels_tab : g_qpel.put_h264_qpel_pixels_tab)[size_idx][pos](dst, src, stride);
+}
+
+API void ffref_h264qpel_batch(int n, const uint8_t *op /* n: bit0 avg, bits1-2 size_idx, bits 3-6 pos */,
+                              uint8_t *dstbase, const int64_t *dst_off, const uint8_t *srcbase,
+                              const int64_t *src_off, ptrdiff_t stride)
+{
+    pel_init();
+    for (int i = 0; i < n; i++) {
+        int avg = op[i] & 1, sz = (op[i] >> 1) & 3, pos = (op[i] >> 3) & 15;
+        (avg ? g_qpel.avg_h264_qpel_pixels_tab : g_qpel.put_h264_qpel_pixels_tab)[sz][pos]
+            (dstbase + dst_off[i], srcbase + src_off[i], stride);
+    }
+}
+
+/* tab: 0 put 1 avg 2 put_no_rnd 3 avg_no_rnd; size_idx 0:16 1:8 2:4 3:2; xy = xhalf + 2*yhalf */
+API int ffref_hpel(int tab, int size_idx, int xy, uint8_t *block, const uint8_t *pixels, ptrdiff_t line_size, int h)
+{
+    pel_init();
+    op_pixels_func f = NULL;
+    if (tab == 0) f = g_hpel.put_pixels_tab[size_idx][xy];
+    else if (tab == 1) f = g_hpel.avg_pixels_tab[size_idx][xy];
+    else if (tab == 2) f = size_idx < 3 ? g_hpel.put_no_rnd_pixels_tab[size_idx][xy] : NULL;
+    else f = size_idx == 0 ? g_hpel.avg_no_rnd_pixels_tab[xy] : NULL;
+    if (!f) return -1;
+    f(block, pixels, line_size, h);
+    return 0;
+}
+
+/* ------------------------------------------------------------------ tx ------------------------------------------ */
+
+typedef struct { AVTXContext *ctx; av_tx_fn fn; } RefTx;
+
+/* type: AV_TX_FLOAT_FFT=0, AV_TX_FLOAT_MDCT=1 (tx.h enum order) */
+API void *ffref_tx_open(int type, int inv, int len, float scale, unsigned flags)
+{
+    RefTx *t = calloc(1, sizeof(*t));
+    if (!t) return NULL;
+    if (av_tx_init(&t->ctx, &t->fn, (enum AVTXType)type, inv, len, &scale, flags) < 0) { free(t); return NULL; }
+    return t;
+}
+API void ffref_tx_close(void *h) { RefTx *t = h; if (t) { av_tx_uninit(&t->ctx); free(t); } }
+
+/* count transforms; in/out advance by in_step/out_step BYTES per transform; stride is the av_tx_fn stride arg */
+API void ffref_tx_run(void *h, void *out, void *in, ptrdiff_t stride, int count, ptrdiff_t out_step, ptrdiff_t in_step)
+{
+    RefTx *t = h;
+    for (int i = 0; i < count; i++)
+        t->fn(t->ctx, (uint8_t *)out + i * out_step, (uint8_t *)in + i * in_step, stride);
+}

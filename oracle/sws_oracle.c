@@ -1,0 +1,515 @@
+/*
+ * sws_oracle.c — TEST INFRASTRUCTURE ONLY.  CPU restatement of libswscale's legacy yuv420p -> rgb24 path.
+ *
+ * Written from the behaviour of the reference (FFmpeg 8.0.git), not copied from it.  Follows:
+ *   context set-up .......... libswscale/utils.c:1137-1760 (ff_sws_init_single_context)
+ *   filter generation ....... libswscale/utils.c:197-612   (initFilter), :168-175 (get_local_pos)
+ *   horizontal FIR .......... libswscale/swscale.c:128-142 (hScale8To15_c)
+ *   line scheduling ......... libswscale/swscale.c:412-535 (ff_swscale), libswscale/vscale.c:109-171 (packed_vscale)
+ *   vertical FIR + writers .. libswscale/output.c:1789-1939 (yuv2rgb_{X,2,1}_c_template), :1663-1713 (yuv2rgb_write)
+ *                             libswscale/output.c:1998-2330 (full-chroma variants, yuv2rgb_write_full)
+ *   LUT construction ........ libswscale/yuv2rgb.c:680-703 (fill_table, fill_gv_table), :717-914 (24 bpp case)
+ *   unscaled converter ...... libswscale/yuv2rgb.c:68-236 (YUV420FUNC/PUTRGB24), gate swscale_unscaled.c:2426-2431
+ *
+ * The reference schedules lines through a ring buffer; here whole horizontally-scaled planes are kept, which
+ * yields the same bytes because every output line depends only on its own taps (rgb24 has no dither state).
+ * filterAlign is 1 (generic C build of the reference: no MMX/NEON/AltiVec alignment padding, utils.c:1675-1710).
+ */
+#include "oracle.h"
+#include <stdlib.h>
+#include <string.h>
+#include <errno.h>
+
+#define HEADROOM      512   /* YUVRGB_TABLE_HEADROOM       swscale_internal.h */
+#define LUMA_HEADROOM 512   /* YUVRGB_TABLE_LUMA_HEADROOM  swscale_internal.h */
+#define NTAB          (256 + 2 * HEADROOM)
+#define YTAB_SIZE     (1024 + 2 * LUMA_HEADROOM)
+
+struct OrcSws {
+    int srcW, srcH, dstW, dstH, flags;
+    int chrSrcW, chrSrcH, chrDstW, chrDstH;
+    int chrDstHSub;            /* 1: one chroma sample per two output pixels, 0: full chroma */
+    int unscaled_lut;          /* 1: reference would install yuv2rgb_c_24_rgb as convert_unscaled */
+    int16_t *hLum, *hChr, *vLum, *vChr;
+    int32_t *hLumPos, *hChrPos, *vLumPos, *vChrPos;
+    int hLumSize, hChrSize, vLumSize, vChrSize;
+    /* yuv->rgb */
+    uint8_t ytab[YTAB_SIZE];
+    int offR[NTAB], offGU[NTAB], offGV[NTAB], offB[NTAB];
+    int y_offset, y_coeff, v2r, v2g, u2g, u2b;   /* int16 values for the full-chroma writer */
+};
+
+static int64_t i64abs(int64_t a) { return a < 0 ? -a : a; }
+static int ilog2(unsigned v) { int n = 0; v |= 1; while (v >>= 1) n++; return n; }
+static int clip_u8(int a) { return a < 0 ? 0 : a > 255 ? 255 : a; }
+static int64_t rounded_div(int64_t a, int64_t b) { return a >= 0 ? (a + (b >> 1)) / b : (a - (b >> 1)) / b; }
+static int ceil_rshift(int a, int b) { return -((-a) >> b); }
+
+/* utils.c:168-175 */
+static int local_pos(int chr_subsample, int pos)
+{
+    if (pos == -1 || pos <= -513)
+        pos = (128 << chr_subsample) - 128;
+    pos += 128;
+    return pos >> chr_subsample;
+}
+
+/* utils.c:197-612 with srcFilter = dstFilter = NULL, param = defaults, filterAlign = 1 */
+static int make_filter(int16_t **outFilter, int32_t **outPos, int *outSize, int xInc, int srcW, int dstW,
+                       int one, int scaler, int flags, int srcPos, int dstPos)
+{
+    const int64_t fone = 1LL << (54 - (ilog2(srcW / dstW) < 8 ? ilog2(srcW / dstW) : 8));
+    int32_t *pos = calloc((size_t)dstW + 3, sizeof(*pos));
+    int64_t *f = NULL;
+    int fs, i, j;
+    if (!pos) return -ENOMEM;
+
+    if (abs(xInc - 0x10000) < 10 && srcPos == dstPos) {            /* :221-231 identity */
+        fs = 1;
+        f = calloc(dstW, sizeof(*f));
+        for (i = 0; i < dstW; i++) { f[i] = fone; pos[i] = i; }
+    } else if (scaler == ORC_SWS_POINT) {                          /* :232-246 */
+        int64_t x = ((dstPos * (int64_t)xInc) >> 8) - ((srcPos * 0x8000LL) >> 7);
+        fs = 1;
+        f = calloc(dstW, sizeof(*f));
+        for (i = 0; i < dstW; i++) {
+            pos[i] = (int)((x - ((int64_t)(fs - 1) << 15) + (1 << 15)) >> 16);
+            f[i] = fone;
+            x += xInc;
+        }
+    } else if ((xInc <= (1 << 16) && scaler == ORC_SWS_AREA) || scaler == ORC_SWS_FAST_BILINEAR) {   /* :247-271 */
+        int64_t x = ((dstPos * (int64_t)xInc) >> 8) - ((srcPos * 0x8000LL) >> 7);
+        fs = 2;
+        f = calloc((size_t)dstW * fs, sizeof(*f));
+        for (i = 0; i < dstW; i++) {
+            int xx = (int)((x - ((int64_t)(fs - 1) << 15) + (1 << 15)) >> 16);
+            pos[i] = xx;
+            for (j = 0; j < fs; j++) {
+                int64_t coeff = fone - i64abs((int64_t)xx * (1 << 16) - x) * (fone >> 16);
+                f[i * fs + j] = coeff < 0 ? 0 : coeff;
+                xx++;
+            }
+            x += xInc;
+        }
+    } else {                                                       /* :272-383 */
+        int sizeFactor = scaler == ORC_SWS_BICUBIC ? 4 : scaler == ORC_SWS_BILINEAR ? 2 :
+                         scaler == ORC_SWS_AREA ? 1 : -1;
+        int64_t x;
+        if (sizeFactor < 0) { free(pos); return -ENOSYS; }        /* float-kernel scalers not restated */
+        if (xInc <= 1 << 16) fs = 1 + sizeFactor;
+        else                 fs = 1 + (int)(((int64_t)sizeFactor * srcW + dstW - 1) / dstW);
+        if (fs > srcW - 2) fs = srcW - 2;
+        if (fs < 1) fs = 1;
+        f = calloc((size_t)dstW * fs, sizeof(*f));
+        x = ((dstPos * (int64_t)xInc) >> 7) - ((srcPos * 0x10000LL) >> 7);
+        for (i = 0; i < dstW; i++) {
+            int xx = (int)((x - (fs - 2) * (1LL << 16)) / (1 << 17));
+            pos[i] = xx;
+            for (j = 0; j < fs; j++) {
+                int64_t d = i64abs(((int64_t)xx * (1 << 17)) - x) << 13;
+                int64_t coeff;
+                if (xInc > 1 << 16)
+                    d = d * dstW / srcW;
+                if (scaler == ORC_SWS_BICUBIC) {                   /* B = 0, C = 0.6 in 8.24 */
+                    int64_t B = 0;
+                    int64_t C = (int64_t)(0.6 * (1 << 24));
+                    if (d >= 1LL << 31) {
+                        coeff = 0;
+                    } else {
+                        int64_t dd  = (d * d) >> 30;
+                        int64_t ddd = (dd * d) >> 30;
+                        if (d < 1LL << 30)
+                            coeff = (12 * (1 << 24) - 9 * B - 6 * C) * ddd +
+                                    (-18 * (1 << 24) + 12 * B + 6 * C) * dd +
+                                    (6 * (1 << 24) - 2 * B) * (1LL << 30);
+                        else
+                            coeff = (-B - 6 * C) * ddd + (6 * B + 30 * C) * dd +
+                                    (-12 * B - 48 * C) * d + (8 * B + 24 * C) * (1LL << 30);
+                    }
+                    coeff /= (1LL << 54) / fone;
+                } else if (scaler == ORC_SWS_AREA) {
+                    int64_t d2 = d - (1 << 29);
+                    if (d2 * xInc < -(1LL << (29 + 16)))      coeff = 1LL << (30 + 16);
+                    else if (d2 * xInc < (1LL << (29 + 16)))  coeff = -d2 * xInc + (1LL << (29 + 16));
+                    else                                      coeff = 0;
+                    coeff *= fone >> (30 + 16);
+                } else {                                           /* bilinear */
+                    coeff = (1 << 30) - d;
+                    if (coeff < 0) coeff = 0;
+                    coeff *= fone >> 30;
+                }
+                f[i * fs + j] = coeff;
+                xx++;
+            }
+            x += 2LL * xInc;
+        }
+    }
+
+    /* size reduction, utils.c:417-457: strip near-zero taps left, count them right */
+    int minSize = 0;
+    for (i = dstW - 1; i >= 0; i--) {
+        int min = fs;
+        int64_t cut = 0;
+        for (j = 0; j < fs; j++) {
+            int k;
+            cut += i64abs(f[i * fs]);
+            if ((double)cut > 0.002 * (double)fone) break;
+            if (i < dstW - 1 && pos[i] >= pos[i + 1]) break;
+            for (k = 1; k < fs; k++) f[i * fs + k - 1] = f[i * fs + k];
+            f[i * fs + k - 1] = 0;
+            pos[i]++;
+        }
+        cut = 0;
+        for (j = fs - 1; j > 0; j--) {
+            cut += i64abs(f[i * fs + j]);
+            if ((double)cut > 0.002 * (double)fone) break;
+            min--;
+        }
+        if (min > minSize) minSize = min;
+    }
+    int nfs = minSize;                                             /* filterAlign == 1 */
+    if (nfs >= 256) { free(f); free(pos); return -ENOSYS; }        /* reference would cascade (:491-495) */
+    int64_t *g = calloc((size_t)dstW * nfs, sizeof(*g));
+    for (i = 0; i < dstW; i++)
+        for (j = 0; j < nfs; j++)
+            g[i * nfs + j] = j >= fs ? 0 : f[i * fs + j];
+    free(f);
+
+    /* border folding, utils.c:519-560 */
+    for (i = 0; i < dstW; i++) {
+        if (pos[i] < 0) {
+            for (j = 1; j < nfs; j++) {
+                int left = j + pos[i] > 0 ? j + pos[i] : 0;
+                g[i * nfs + left] += g[i * nfs + j];
+                g[i * nfs + j] = 0;
+            }
+            pos[i] = 0;
+        }
+        if (pos[i] + nfs > srcW) {
+            int shift = pos[i] + (nfs - srcW < 0 ? nfs - srcW : 0);
+            int64_t acc = 0;
+            for (j = nfs - 1; j >= 0; j--)
+                if (pos[i] + j >= srcW) { acc += g[i * nfs + j]; g[i * nfs + j] = 0; }
+            for (j = nfs - 1; j >= 0; j--)
+                g[i * nfs + j] = j < shift ? 0 : g[i * nfs + j - shift];
+            pos[i] -= shift;
+            g[i * nfs + srcW - 1 - pos[i]] += acc;
+        }
+    }
+
+    /* error-diffused normalisation to `one`, utils.c:568-588 */
+    int16_t *out = calloc((size_t)(dstW + 3) * nfs, sizeof(*out));
+    for (i = 0; i < dstW; i++) {
+        int64_t error = 0, sum = 0;
+        for (j = 0; j < nfs; j++) sum += g[i * nfs + j];
+        sum = (sum + one / 2) / one;
+        if (!sum) sum = 1;
+        for (j = 0; j < nfs; j++) {
+            int64_t v = g[i * nfs + j] + error;
+            int iv = (int)rounded_div(v, sum);
+            out[i * nfs + j] = (int16_t)iv;
+            error = v - iv * sum;
+        }
+    }
+    free(g);
+    pos[dstW] = pos[dstW + 1] = pos[dstW + 2] = pos[dstW - 1];
+    for (i = 0; i < nfs; i++) {
+        int k = (dstW - 1) * nfs + i;
+        out[k + nfs] = out[k + 2 * nfs] = out[k + 3 * nfs] = out[k];
+    }
+    *outFilter = out; *outPos = pos; *outSize = nfs;
+    return 0;
+}
+
+/* yuv2rgb.c:717-914 (bpp 24), fill_table :680-692, fill_gv_table :694-703 */
+int orc_sws_set_colorspace(OrcSws *s, const int inv_table[4], int fullRange,
+                           int brightness, int contrast, int saturation)
+{
+    const int yoffs = (fullRange ? 384 : 326) + LUMA_HEADROOM;
+    int64_t crv = inv_table[0], cbu = inv_table[1], cgu = -inv_table[2], cgv = -inv_table[3];
+    int64_t cy = 1 << 16, oy = 0, yb;
+    int i;
+    if (!fullRange) {
+        cy = (cy * 255) / 219;
+        oy = 16 << 16;
+    } else {
+        crv = (crv * 224) / 255; cbu = (cbu * 224) / 255;
+        cgu = (cgu * 224) / 255; cgv = (cgv * 224) / 255;
+    }
+    cy  = (cy * contrast) >> 16;
+    crv = (crv * contrast * saturation) >> 32;
+    cbu = (cbu * contrast * saturation) >> 32;
+    cgu = (cgu * contrast * saturation) >> 32;
+    cgv = (cgv * contrast * saturation) >> 32;
+    oy -= 256LL * brightness;
+
+#define R16(f) ({ int64_t f_ = (f); int r_ = (int)((f_ + (1 << 15)) >> 16); \
+                  (int16_t)(uint16_t)(r_ < -0x7FFF ? 0x8000 : r_ > 0x7FFF ? 0x7FFF : r_); })
+    s->y_coeff  = R16(cy  * (1 << 13));
+    s->y_offset = R16(oy  * (1 <<  9));
+    s->v2r      = R16(crv * (1 << 13));
+    s->v2g      = R16(cgv * (1 << 13));
+    s->u2g      = R16(cgu * (1 << 13));
+    s->u2b      = R16(cbu * (1 << 13));
+#undef R16
+
+    int64_t cyd = cy > 1 ? cy : 1;
+    crv = ((crv * (1 << 16)) + 0x8000) / cyd;
+    cbu = ((cbu * (1 << 16)) + 0x8000) / cyd;
+    cgu = ((cgu * (1 << 16)) + 0x8000) / cyd;
+    cgv = ((cgv * (1 << 16)) + 0x8000) / cyd;
+
+    yb = -(384 << 16) - LUMA_HEADROOM * cy - oy;
+    for (i = 0; i < YTAB_SIZE; i++) {
+        s->ytab[i] = (uint8_t)clip_u8((int)((yb + 0x8000) >> 16));
+        yb += cy;
+    }
+    for (i = 0; i < NTAB; i++) {
+        int64_t c8 = clip_u8(i - HEADROOM);
+        s->offR[i]  = (int)(yoffs - (crv >> 9) + ((c8 * crv) >> 16));
+        s->offGU[i] = (int)(yoffs - (cgu >> 9) + ((c8 * cgu) >> 16));
+        s->offB[i]  = (int)(yoffs - (cbu >> 9) + ((c8 * cbu) >> 16));
+        s->offGV[i] = (int)(-(cgv >> 9) + ((c8 * cgv) >> 16));
+    }
+    return 0;
+}
+
+static const int default_coeffs[4] = { 104597, 132201, 25675, 53279 };  /* yuv2rgb.c:47-59 row SWS_CS_DEFAULT */
+
+OrcSws *orc_sws_open(int srcW, int srcH, int dstW, int dstH, int flags)
+{
+    if (srcW < 1 || srcH < 1 || dstW < 1 || dstH < 1) return NULL;
+    OrcSws *s = calloc(1, sizeof(*s));
+    if (!s) return NULL;
+    int algo = flags & 0x7FF;
+    if (!algo) { algo = ORC_SWS_BICUBIC; flags |= algo; }           /* utils.c:1209-1217 */
+    else if (algo & (algo - 1)) goto fail;
+    if (algo == ORC_SWS_FAST_BILINEAR) goto fail;                  /* hyscale_fast path not restated */
+    if (dstW & 1) flags |= ORC_SWS_FULL_CHR_H_INT;                 /* utils.c:1271-1276 */
+    s->srcW = srcW; s->srcH = srcH; s->dstW = dstW; s->dstH = dstH; s->flags = flags;
+    s->chrDstHSub = (flags & ORC_SWS_FULL_CHR_H_INT) ? 0 : 1;      /* utils.c:1359-1360 */
+    s->chrSrcW = ceil_rshift(srcW, 1); s->chrSrcH = ceil_rshift(srcH, 1);
+    s->chrDstW = ceil_rshift(dstW, s->chrDstHSub); s->chrDstH = dstH;
+    orc_sws_set_colorspace(s, default_coeffs, 0, 0, 1 << 16, 1 << 16);
+
+    /* swscale_unscaled.c:2426-2431 through utils.c:1623-1637 */
+    if (srcW == dstW && srcH == dstH && !(flags & ORC_SWS_ACCURATE_RND) && !(dstH & 1)) {
+        s->unscaled_lut = 1;
+        return s;
+    }
+    int lum_scaler = algo == ORC_SWS_BICUBLIN ? ORC_SWS_BICUBIC : algo;
+    int chr_scaler = algo == ORC_SWS_BICUBLIN ? ORC_SWS_BILINEAR : algo;
+    int64_t lumXInc = (((int64_t)srcW << 16) + (dstW >> 1)) / dstW;
+    int64_t lumYInc = (((int64_t)srcH << 16) + (dstH >> 1)) / dstH;
+    int64_t chrXInc = (((int64_t)s->chrSrcW << 16) + (s->chrDstW >> 1)) / s->chrDstW;
+    int64_t chrYInc = (((int64_t)s->chrSrcH << 16) + (s->chrDstH >> 1)) / s->chrDstH;
+    if (make_filter(&s->hLum, &s->hLumPos, &s->hLumSize, (int)lumXInc, srcW, dstW, 1 << 14, lum_scaler, flags,
+                    local_pos(0, 0), local_pos(0, 0)) < 0) goto fail;
+    if (make_filter(&s->hChr, &s->hChrPos, &s->hChrSize, (int)chrXInc, s->chrSrcW, s->chrDstW, 1 << 14, chr_scaler, flags,
+                    local_pos(1, -513), local_pos(s->chrDstHSub, -513)) < 0) goto fail;
+    if (make_filter(&s->vLum, &s->vLumPos, &s->vLumSize, (int)lumYInc, srcH, dstH, 1 << 12, lum_scaler, flags,
+                    local_pos(0, 0), local_pos(0, 0)) < 0) goto fail;
+    if (make_filter(&s->vChr, &s->vChrPos, &s->vChrSize, (int)chrYInc, s->chrSrcH, s->chrDstH, 1 << 12, chr_scaler, flags,
+                    local_pos(1, -513), local_pos(0, -513)) < 0) goto fail;
+    return s;
+fail:
+    orc_sws_close(s);
+    return NULL;
+}
+
+void orc_sws_close(OrcSws *s)
+{
+    if (!s) return;
+    free(s->hLum); free(s->hChr); free(s->vLum); free(s->vChr);
+    free(s->hLumPos); free(s->hChrPos); free(s->vLumPos); free(s->vChrPos);
+    free(s);
+}
+
+int orc_sws_info(const OrcSws *s, int *out)
+{
+    out[0] = s->hLumSize; out[1] = s->hChrSize; out[2] = s->vLumSize; out[3] = s->vChrSize;
+    out[4] = s->chrSrcW; out[5] = s->chrSrcH; out[6] = s->chrDstW; out[7] = s->chrDstH;
+    out[8] = s->unscaled_lut; out[9] = 1; out[10] = 1; out[11] = s->chrDstHSub; out[12] = 0;
+    out[13] = s->dstW; out[14] = s->dstH; out[15] = 0;
+    return 0;
+}
+
+int orc_sws_get_filter(const OrcSws *s, int which, int16_t *filter, int32_t *pos, int cap)
+{
+    const int16_t *f; const int32_t *p; int n, fs;
+    switch (which) {
+    case 0: f = s->hLum; p = s->hLumPos; n = s->dstW;    fs = s->hLumSize; break;
+    case 1: f = s->hChr; p = s->hChrPos; n = s->chrDstW; fs = s->hChrSize; break;
+    case 2: f = s->vLum; p = s->vLumPos; n = s->dstH;    fs = s->vLumSize; break;
+    default:f = s->vChr; p = s->vChrPos; n = s->chrDstH; fs = s->vChrSize; break;
+    }
+    if (!f) return 0;
+    if (n > cap) n = cap;
+    if (filter) memcpy(filter, f, (size_t)n * fs * sizeof(int16_t));
+    if (pos) memcpy(pos, p, (size_t)n * sizeof(int32_t));
+    return n;
+}
+
+/* swscale.c:128-142 */
+void orc_hscale8to15(int16_t *dst, int dstW, const uint8_t *src, const int16_t *filter,
+                     const int32_t *filterPos, int filterSize)
+{
+    for (int i = 0; i < dstW; i++) {
+        int val = 0;
+        for (int j = 0; j < filterSize; j++)
+            val += (int)src[filterPos[i] + j] * filter[filterSize * i + j];
+        val >>= 7;
+        dst[i] = (int16_t)(val < 32767 ? val : 32767);
+    }
+}
+
+/* yuv2rgb_write, rgb24 branch (output.c:1697-1713): one chroma pair -> LUT bases, two lumas -> 6 bytes */
+static void put_pair(const OrcSws *s, uint8_t *d, int Y1, int Y2, int U, int V)
+{
+    const uint8_t *r = s->ytab + s->offR[V + HEADROOM];
+    const uint8_t *g = s->ytab + s->offGU[U + HEADROOM] + s->offGV[V + HEADROOM];
+    const uint8_t *b = s->ytab + s->offB[U + HEADROOM];
+    d[0] = r[Y1]; d[1] = g[Y1]; d[2] = b[Y1];
+    d[3] = r[Y2]; d[4] = g[Y2]; d[5] = b[Y2];
+}
+
+/* yuv2rgb_write_full, rgb24 (output.c:1998-2030) */
+static void put_full(const OrcSws *s, uint8_t *d, int Y, int U, int V)
+{
+    unsigned y = (unsigned)(Y - s->y_offset) * (unsigned)s->y_coeff + (1U << 21);
+    int R = (int)(y + (unsigned)V * (unsigned)s->v2r);
+    int G = (int)(y + (unsigned)V * (unsigned)s->v2g + (unsigned)U * (unsigned)s->u2g);
+    int B = (int)(y + (unsigned)U * (unsigned)s->u2b);
+    if ((R | G | B) & 0xC0000000) {
+#define CLIP30(a) (((a) & ~((1 << 30) - 1)) ? ((~(a)) >> 31 & ((1 << 30) - 1)) : (a))
+        R = CLIP30(R); G = CLIP30(G); B = CLIP30(B);
+#undef CLIP30
+    }
+    d[0] = (uint8_t)(R >> 22); d[1] = (uint8_t)(G >> 22); d[2] = (uint8_t)(B >> 22);
+}
+
+/* unscaled LUT converter yuv2rgb_c_24_rgb (yuv2rgb.c:137-236,530): chroma (x>>1, y>>1), no interpolation;
+ * per line-pair it covers (dstW>>3)*8 + (dstW&4) + (dstW&2) pixels, an odd last column is never written. */
+static void convert_unscaled(const OrcSws *s, const uint8_t *y, int ys, const uint8_t *u, int us,
+                             const uint8_t *v, int vs, uint8_t *dst, int ds)
+{
+    int wpix = ((s->dstW >> 3) << 3) + (s->dstW & 4) + (s->dstW & 2);
+    for (int row = 0; row < s->srcH; row++) {
+        const uint8_t *py = y + (ptrdiff_t)row * ys;
+        const uint8_t *pu = u + (ptrdiff_t)(row >> 1) * us;
+        const uint8_t *pv = v + (ptrdiff_t)(row >> 1) * vs;
+        uint8_t *d = dst + (ptrdiff_t)row * ds;
+        for (int i = 0; i < wpix / 2; i++)
+            put_pair(s, d + 6 * i, py[2 * i], py[2 * i + 1], pu[i], pv[i]);
+    }
+}
+
+int orc_sws_scale(OrcSws *s, const uint8_t *y, int ys, const uint8_t *u, int us,
+                  const uint8_t *v, int vs, uint8_t *dst, int ds)
+{
+    if (s->unscaled_lut) {
+        convert_unscaled(s, y, ys, u, us, v, vs, dst, ds);
+        return s->srcH;
+    }
+    const int dstW = s->dstW, cW = s->chrDstW;
+    int16_t *L = malloc((size_t)s->srcH * dstW * sizeof(int16_t));
+    int16_t *CU = malloc((size_t)s->chrSrcH * cW * sizeof(int16_t));
+    int16_t *CV = malloc((size_t)s->chrSrcH * cW * sizeof(int16_t));
+    if (!L || !CU || !CV) { free(L); free(CU); free(CV); return -ENOMEM; }
+    for (int r = 0; r < s->srcH; r++)
+        orc_hscale8to15(L + (size_t)r * dstW, dstW, y + (ptrdiff_t)r * ys, s->hLum, s->hLumPos, s->hLumSize);
+    for (int r = 0; r < s->chrSrcH; r++) {
+        orc_hscale8to15(CU + (size_t)r * cW, cW, u + (ptrdiff_t)r * us, s->hChr, s->hChrPos, s->hChrSize);
+        orc_hscale8to15(CV + (size_t)r * cW, cW, v + (ptrdiff_t)r * vs, s->hChr, s->hChrPos, s->hChrSize);
+    }
+    const int lfs = s->vLumSize, cfs = s->vChrSize, full = !s->chrDstHSub;
+#define LROW(k) (L  + (size_t)((k) < 0 ? 0 : (k) >= s->srcH    ? s->srcH    - 1 : (k)) * dstW)
+#define UROW(k) (CU + (size_t)((k) < 0 ? 0 : (k) >= s->chrSrcH ? s->chrSrcH - 1 : (k)) * cW)
+#define VROW(k) (CV + (size_t)((k) < 0 ? 0 : (k) >= s->chrSrcH ? s->chrSrcH - 1 : (k)) * cW)
+    for (int dy = 0; dy < s->dstH; dy++) {
+        /* packed_vscale, vscale.c:109-171 */
+        const int16_t *lf = s->vLum + dy * lfs, *cf = s->vChr + dy * cfs;
+        int firstLum = s->vLumPos[dy] > 1 - lfs ? s->vLumPos[dy] : 1 - lfs;
+        int firstChr = s->vChrPos[dy] > 1 - cfs ? s->vChrPos[dy] : 1 - cfs;
+        uint8_t *d = dst + (ptrdiff_t)dy * ds;
+        int mode;   /* 1: _1 writer, 2: _2 writer, 0: _X writer */
+        int uvalpha = 0, yalpha = 0;
+        if (lfs == 1 && cfs == 1) mode = 1;
+        else if (lfs == 1 && cfs == 2 && (uint16_t)cf[0] + (uint16_t)cf[1] == 4096 && (uint16_t)cf[1] <= 4096U) {
+            mode = 1; uvalpha = (uint16_t)cf[1];
+        } else if (lfs == 2 && cfs == 2 &&
+                   (uint16_t)lf[0] + (uint16_t)lf[1] == 4096 && (uint16_t)lf[1] <= 4096U &&
+                   (uint16_t)cf[0] + (uint16_t)cf[1] == 4096 && (uint16_t)cf[1] <= 4096U) {
+            mode = 2; yalpha = (uint16_t)lf[1]; uvalpha = (uint16_t)cf[1];
+        } else mode = 0;
+
+        if (!full) {
+            for (int i = 0; i < (dstW + 1) >> 1; i++) {
+                int Y1, Y2, U, V;
+                if (mode == 1) {                                   /* output.c:1883-1939 */
+                    const int16_t *b0 = LROW(firstLum);
+                    Y1 = (b0[2 * i] + 64) >> 7; Y2 = (b0[2 * i + 1] + 64) >> 7;
+                    if (!uvalpha) {
+                        U = (UROW(firstChr)[i] + 64) >> 7; V = (VROW(firstChr)[i] + 64) >> 7;
+                    } else {
+                        int a1 = 4096 - uvalpha;
+                        U = (UROW(firstChr)[i] * a1 + UROW(firstChr + 1)[i] * uvalpha + (128 << 11)) >> 19;
+                        V = (VROW(firstChr)[i] * a1 + VROW(firstChr + 1)[i] * uvalpha + (128 << 11)) >> 19;
+                    }
+                } else if (mode == 2) {                            /* output.c:1843-1880 */
+                    int ya1 = 4096 - yalpha, ua1 = 4096 - uvalpha;
+                    const int16_t *b0 = LROW(firstLum), *b1 = LROW(firstLum + 1);
+                    Y1 = (b0[2 * i] * ya1 + b1[2 * i] * yalpha) >> 19;
+                    Y2 = (b0[2 * i + 1] * ya1 + b1[2 * i + 1] * yalpha) >> 19;
+                    U = (UROW(firstChr)[i] * ua1 + UROW(firstChr + 1)[i] * uvalpha) >> 19;
+                    V = (VROW(firstChr)[i] * ua1 + VROW(firstChr + 1)[i] * uvalpha) >> 19;
+                } else {                                           /* output.c:1789-1840 */
+                    unsigned a1 = 1 << 18, a2 = 1 << 18, au = 1 << 18, av = 1 << 18;
+                    for (int j = 0; j < lfs; j++) {
+                        a1 += (unsigned)(LROW(firstLum + j)[2 * i]     * (unsigned)(int)lf[j]);
+                        a2 += (unsigned)(LROW(firstLum + j)[2 * i + 1] * (unsigned)(int)lf[j]);
+                    }
+                    for (int j = 0; j < cfs; j++) {
+                        au += (unsigned)(UROW(firstChr + j)[i] * (unsigned)(int)cf[j]);
+                        av += (unsigned)(VROW(firstChr + j)[i] * (unsigned)(int)cf[j]);
+                    }
+                    Y1 = (int)a1 >> 19; Y2 = (int)a2 >> 19; U = (int)au >> 19; V = (int)av >> 19;
+                }
+                put_pair(s, d + 6 * i, Y1, Y2, U, V);
+            }
+        } else {
+            for (int i = 0; i < dstW; i++) {
+                int Y, U, V;
+                if (mode == 1) {                                   /* output.c:2257-2310 */
+                    Y = LROW(firstLum)[i] * 4;
+                    if (!uvalpha) {
+                        U = (UROW(firstChr)[i] - (128 << 7)) * 4; V = (VROW(firstChr)[i] - (128 << 7)) * 4;
+                    } else {
+                        int a1 = 4096 - uvalpha;
+                        U = (UROW(firstChr)[i] * a1 + UROW(firstChr + 1)[i] * uvalpha - (128 << 19)) >> 10;
+                        V = (VROW(firstChr)[i] * a1 + VROW(firstChr + 1)[i] * uvalpha - (128 << 19)) >> 10;
+                    }
+                } else if (mode == 2) {                            /* output.c:2211-2254 */
+                    int ya1 = 4096 - yalpha, ua1 = 4096 - uvalpha;
+                    Y = (LROW(firstLum)[i] * ya1 + LROW(firstLum + 1)[i] * yalpha) >> 10;
+                    U = (UROW(firstChr)[i] * ua1 + UROW(firstChr + 1)[i] * uvalpha - (128 << 19)) >> 10;
+                    V = (VROW(firstChr)[i] * ua1 + VROW(firstChr + 1)[i] * uvalpha - (128 << 19)) >> 10;
+                } else {                                           /* output.c:2161-2208 */
+                    unsigned ay = 1 << 9, au = (1 << 9) - (128 << 19), av = (1 << 9) - (128 << 19);
+                    for (int j = 0; j < lfs; j++) ay += (unsigned)(LROW(firstLum + j)[i] * (unsigned)(int)lf[j]);
+                    for (int j = 0; j < cfs; j++) {
+                        au += (unsigned)(UROW(firstChr + j)[i] * (unsigned)(int)cf[j]);
+                        av += (unsigned)(VROW(firstChr + j)[i] * (unsigned)(int)cf[j]);
+                    }
+                    Y = (int)ay >> 10; U = (int)au >> 10; V = (int)av >> 10;
+                }
+                put_full(s, d + 3 * i, Y, U, V);
+            }
+        }
+    }
+#undef LROW
+#undef UROW
+#undef VROW
+    free(L); free(CU); free(CV);
+    return s->dstH;
+}

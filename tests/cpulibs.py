@@ -1,0 +1,157 @@
+"""ctypes loaders for the two CPU checkers (test infrastructure only):
+   - oracle/liboracle.so      : our plain-C restatement (travels, always built by __graft_entry__.build())
+   - oracle/_ref/libffref.so  : the unmodified reference compiled by oracle/ref/Makefile (present when built here)
+"""
+import ctypes as C
+import os
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_SO = os.path.join(ROOT, "oracle", "liboracle.so")
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libffref.so")
+
+SWS_FAST_BILINEAR, SWS_BILINEAR, SWS_BICUBIC, SWS_POINT, SWS_AREA, SWS_BICUBLIN = 1, 2, 4, 0x10, 0x20, 0x40
+SWS_FULL_CHR_H_INT, SWS_ACCURATE_RND, SWS_BITEXACT = 0x2000, 0x40000, 0x80000
+
+u8p = C.POINTER(C.c_uint8)
+i16p = C.POINTER(C.c_int16)
+i32p = C.POINTER(C.c_int32)
+i64p = C.POINTER(C.c_int64)
+u64p = C.POINTER(C.c_uint64)
+
+
+def ptr(a, t=u8p):
+    return a.ctypes.data_as(t)
+
+
+_oracle = None
+_ref = None
+
+
+def oracle():
+    global _oracle
+    if _oracle is None:
+        L = C.CDLL(ORACLE_SO)
+        L.orc_sws_open.restype = C.c_void_p
+        L.orc_sws_open.argtypes = [C.c_int] * 5
+        L.orc_sws_close.argtypes = [C.c_void_p]
+        L.orc_sws_set_colorspace.argtypes = [C.c_void_p, i32p, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.orc_sws_scale.argtypes = [C.c_void_p, u8p, C.c_int, u8p, C.c_int, u8p, C.c_int, u8p, C.c_int]
+        L.orc_sws_info.argtypes = [C.c_void_p, i32p]
+        L.orc_sws_get_filter.argtypes = [C.c_void_p, C.c_int, i16p, i32p, C.c_int]
+        L.orc_hscale8to15.argtypes = [i16p, C.c_int, u8p, i16p, i32p, C.c_int]
+        if hasattr(L, "orc_idct_batch"):
+            L.orc_idct_batch.argtypes = [C.c_int, i16p, C.c_int, u8p, C.c_ssize_t, i64p]
+            L.orc_pixels_clamped.argtypes = [C.c_int, i16p, u8p, C.c_ssize_t]
+        if hasattr(L, "orc_me_cmp"):
+            L.orc_me_cmp.argtypes = [C.c_int, C.c_int, u8p, u8p, C.c_ssize_t, C.c_int]
+            L.orc_esa_frame.argtypes = [u8p, u8p] + [C.c_int] * 7 + [i32p, u64p]
+        if hasattr(L, "orc_h264qpel"):
+            L.orc_h264qpel.argtypes = [C.c_int, C.c_int, C.c_int, u8p, u8p, C.c_ssize_t]
+            L.orc_hpel.argtypes = [C.c_int, C.c_int, C.c_int, u8p, u8p, C.c_ssize_t, C.c_int]
+        if hasattr(L, "orc_tx_open"):
+            L.orc_tx_open.restype = C.c_void_p
+            L.orc_tx_open.argtypes = [C.c_int, C.c_int, C.c_int, C.c_float, C.c_uint]
+            L.orc_tx_close.argtypes = [C.c_void_p]
+            L.orc_tx_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_ssize_t, C.c_int, C.c_ssize_t, C.c_ssize_t]
+        _oracle = L
+    return _oracle
+
+
+def have_ref():
+    return os.path.exists(REF_SO)
+
+
+def ref():
+    global _ref
+    if _ref is None:
+        L = C.CDLL(REF_SO)
+        L.ffref_set_quiet()
+        L.ffref_sws_open.restype = C.c_void_p
+        L.ffref_sws_open.argtypes = [C.c_int] * 6
+        L.ffref_sws_close.argtypes = [C.c_void_p]
+        L.ffref_sws_set_colorspace.argtypes = [C.c_void_p] + [C.c_int] * 7
+        L.ffref_sws_scale.argtypes = [C.c_void_p, u8p, C.c_int, u8p, C.c_int, u8p, C.c_int, C.c_int, C.c_int, u8p, C.c_int]
+        L.ffref_sws_info.argtypes = [C.c_void_p, i32p]
+        L.ffref_sws_get_filter.argtypes = [C.c_void_p, C.c_int, i16p, i32p, C.c_int]
+        L.ffref_sws_hscale.argtypes = [C.c_void_p, C.c_int, i16p, C.c_int, u8p, i16p, i32p, C.c_int]
+        L.ffref_idct_perm_type.argtypes = [u8p]
+        L.ffref_idct_batch.argtypes = [C.c_int, i16p, C.c_int, u8p, C.c_ssize_t, i64p]
+        L.ffref_pixels_clamped.argtypes = [C.c_int, i16p, u8p, C.c_ssize_t]
+        L.ffref_me_cmp.argtypes = [C.c_int, C.c_int, u8p, u8p, C.c_ssize_t, C.c_int]
+        L.ffref_me_cmp_batch.argtypes = [C.c_int, C.c_int, u8p, u8p, C.c_ssize_t, C.c_int, i64p, i64p, C.c_int, i32p]
+        L.ffref_esa_frame.argtypes = [u8p, u8p] + [C.c_int] * 7 + [i32p, u64p]
+        L.ffref_h264qpel.argtypes = [C.c_int, C.c_int, C.c_int, u8p, u8p, C.c_ssize_t]
+        L.ffref_h264qpel_batch.argtypes = [C.c_int, u8p, u8p, i64p, u8p, i64p, C.c_ssize_t]
+        L.ffref_hpel.argtypes = [C.c_int, C.c_int, C.c_int, u8p, u8p, C.c_ssize_t, C.c_int]
+        L.ffref_tx_open.restype = C.c_void_p
+        L.ffref_tx_open.argtypes = [C.c_int, C.c_int, C.c_int, C.c_float, C.c_uint]
+        L.ffref_tx_close.argtypes = [C.c_void_p]
+        L.ffref_tx_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_ssize_t, C.c_int, C.c_ssize_t, C.c_ssize_t]
+        _ref = L
+    return _ref
+
+
+# ---------------------------------------------------------------- swscale helpers
+def yuv_frame(w, h, seed, kind="random", pad=0):
+    """Synthetic yuv420p frame; returns (y,u,v) 2-D uint8 arrays (rows padded by `pad` bytes)."""
+    rng = np.random.default_rng(seed)
+    cw, ch = (w + 1) // 2, (h + 1) // 2
+    if kind == "random":
+        y = rng.integers(0, 256, (h, w + pad), dtype=np.uint8)
+        u = rng.integers(0, 256, (ch, cw + pad), dtype=np.uint8)
+        v = rng.integers(0, 256, (ch, cw + pad), dtype=np.uint8)
+    elif kind == "limited":
+        y = rng.integers(16, 236, (h, w + pad), dtype=np.uint8)
+        u = rng.integers(16, 241, (ch, cw + pad), dtype=np.uint8)
+        v = rng.integers(16, 241, (ch, cw + pad), dtype=np.uint8)
+    else:  # smooth
+        yy, xx = np.mgrid[0:h, 0:w + pad]
+        y = ((np.sin(xx / 17.0) + np.cos(yy / 11.0)) * 60 + 128).astype(np.uint8)
+        yy, xx = np.mgrid[0:ch, 0:cw + pad]
+        u = ((np.sin(xx / 9.0 + 1) * np.cos(yy / 13.0)) * 100 + 128).astype(np.uint8)
+        v = ((np.cos(xx / 7.0) * np.sin(yy / 5.0 + 2)) * 100 + 128).astype(np.uint8)
+    return np.ascontiguousarray(y), np.ascontiguousarray(u), np.ascontiguousarray(v)
+
+
+def _sws_run(lib, pre, w, h, dw, dh, flags, y, u, v, dst_pad=0, threads=1, colorspace=None):
+    if pre == "ffref":
+        ctx = lib.ffref_sws_open(w, h, dw, dh, flags, threads)
+    else:
+        ctx = lib.orc_sws_open(w, h, dw, dh, flags)
+    if not ctx:
+        return None
+    try:
+        if colorspace is not None:
+            if pre == "ffref":
+                lib.ffref_sws_set_colorspace(ctx, *colorspace)
+            else:
+                tab = np.array(COEFFS[colorspace[0]], dtype=np.int32)
+                lib.orc_sws_set_colorspace(ctx, ptr(tab, i32p), colorspace[1], colorspace[4], colorspace[5], colorspace[6])
+        ds = dw * 3 + dst_pad
+        dst = np.full((dh, ds), 0xA5, dtype=np.uint8)
+        if pre == "ffref":
+            n = lib.ffref_sws_scale(ctx, ptr(y), y.strides[0], ptr(u), u.strides[0], ptr(v), v.strides[0], 0, h, ptr(dst), ds)
+        else:
+            n = lib.orc_sws_scale(ctx, ptr(y), y.strides[0], ptr(u), u.strides[0], ptr(v), v.strides[0], ptr(dst), ds)
+        assert n == dh, n
+        return dst
+    finally:
+        (lib.ffref_sws_close if pre == "ffref" else lib.orc_sws_close)(ctx)
+
+
+COEFFS = {  # libswscale/yuv2rgb.c:47-59, indexed by SWS_CS_*
+    0: (104597, 132201, 25675, 53279), 1: (117489, 138438, 13975, 34925), 2: (104597, 132201, 25675, 53279),
+    3: (104597, 132201, 25675, 53279), 4: (104448, 132798, 24759, 53109), 5: (104597, 132201, 25675, 53279),
+    6: (104597, 132201, 25675, 53279), 7: (117579, 136230, 16907, 35559), 9: (110013, 140363, 12277, 42626),
+    10: (110013, 140363, 12277, 42626),
+}
+
+
+def ref_sws(w, h, dw, dh, flags, y, u, v, **kw):
+    return _sws_run(ref(), "ffref", w, h, dw, dh, flags, y, u, v, **kw)
+
+
+def orc_sws(w, h, dw, dh, flags, y, u, v, **kw):
+    kw.pop("threads", None)
+    return _sws_run(oracle(), "orc", w, h, dw, dh, flags, y, u, v, **kw)
