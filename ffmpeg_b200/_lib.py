@@ -1,0 +1,95 @@
+"""ctypes binding of libb200dsp.so (the C ABI declared in include/b200dsp.h).
+
+The library is built in-tree by `__graft_entry__.build()` (ffmpeg_b200/csrc/Makefile, nvcc, sm_100a only).
+There is no fallback: if the shared object is missing, or no CUDA device is usable, everything here raises.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libb200dsp.so")
+
+u8p = C.POINTER(C.c_uint8)
+i16p = C.POINTER(C.c_int16)
+i32p = C.POINTER(C.c_int32)
+i64p = C.POINTER(C.c_int64)
+vp = C.c_void_p
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+class IDCTDSPContext(C.Structure):
+    """Same member order as IDCTDSPContext, libavcodec/idctdsp.h:43-91."""
+    _fields_ = [
+        ("put_pixels_clamped", C.CFUNCTYPE(None, i16p, u8p, C.c_ssize_t)),
+        ("put_signed_pixels_clamped", C.CFUNCTYPE(None, i16p, u8p, C.c_ssize_t)),
+        ("add_pixels_clamped", C.CFUNCTYPE(None, i16p, u8p, C.c_ssize_t)),
+        ("idct", C.CFUNCTYPE(None, i16p)),
+        ("idct_put", C.CFUNCTYPE(None, u8p, C.c_ssize_t, i16p)),
+        ("idct_add", C.CFUNCTYPE(None, u8p, C.c_ssize_t, i16p)),
+        ("idct_permutation", C.c_uint8 * 64),
+        ("perm_type", C.c_int),
+        ("mpeg4_studio_profile", C.c_int),
+    ]
+
+
+# name -> (restype, argtypes): every symbol include/b200dsp.h declares
+PROTOTYPES = {
+    "b200_abi_version": (C.c_int, []),
+    "b200_last_error": (C.c_char_p, []),
+    "b200_device_open": (C.c_int, [C.POINTER(vp), C.c_int, vp]),
+    "b200_device_close": (None, [vp]),
+    "b200_device_sync": (C.c_int, [vp]),
+    "b200_device_ordinal": (C.c_int, [vp]),
+    "b200_device_stream": (vp, [vp]),
+    "b200_device_sm_count": (C.c_int, [vp]),
+    "b200_set_default_device": (C.c_int, [vp]),
+    "b200_malloc_device": (vp, [vp, C.c_size_t]),
+    "b200_free_device": (None, [vp, vp]),
+    "b200_malloc_host": (vp, [C.c_size_t]),
+    "b200_free_host": (None, [vp]),
+    "b200_memcpy_h2d": (C.c_int, [vp, vp, vp, C.c_size_t]),
+    "b200_memcpy_d2h": (C.c_int, [vp, vp, vp, C.c_size_t]),
+    "b200_launch_count": (C.c_uint64, []),
+    "b200_sws_getContext": (vp, [vp] + [C.c_int] * 7),
+    "b200_sws_freeContext": (None, [vp]),
+    "b200_sws_setColorspaceDetails": (C.c_int, [vp, i32p, C.c_int, i32p, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "b200_sws_scale": (C.c_int, [vp, C.POINTER(vp), i32p, C.c_int, C.c_int, C.POINTER(vp), i32p]),
+    "b200_sws_func": (C.c_int, [vp, C.POINTER(vp), i32p, C.c_int, C.c_int, C.POINTER(vp), i32p]),
+    "b200_sws_scale_batch_device": (C.c_int, [vp, C.POINTER(vp), i32p, i64p, vp, C.c_int, C.c_int64, C.c_int]),
+    "b200_sws_scale_batch_host": (C.c_int, [vp, C.POINTER(vp), i32p, i64p, vp, C.c_int, C.c_int64, C.c_int]),
+    "b200_sws_info": (C.c_int, [vp, i32p]),
+    "b200_sws_get_filter": (C.c_int, [vp, C.c_int, i16p, i32p, C.c_int]),
+    "b200_sws_plan_probe": (C.c_int, [C.c_int] * 6 + [i16p, i32p, C.c_int, i32p]),
+    "b200_idctdsp_init": (C.c_int, [C.POINTER(IDCTDSPContext), C.c_int, C.c_int, C.c_int]),
+    "b200_idct_batch_device": (C.c_int, [vp, C.c_int, vp, C.c_int64, vp, vp, vp, C.c_int]),
+    "b200_idct_mb420_device": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.POINTER(vp), i32p, i64p]),
+    "b200_idct_mb420_host": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.POINTER(vp), i32p, i64p]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load libb200dsp.so (once).  Raises B200Error when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise B200Error(f"{SO_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                            "(nvcc, sm_100a).  There is no CPU fallback.")
+        L = C.CDLL(SO_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(L, name)            # AttributeError here = header/library mismatch
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(ret, what):
+    if ret is None or (isinstance(ret, int) and ret < 0):
+        msg = lib().b200_last_error()
+        raise B200Error(f"{what} failed ({ret}): {msg.decode() if msg else ''}")
+    return ret

@@ -1,0 +1,314 @@
+// sws_plan.cpp — host-side set-up of the swscale replacement: chroma geometry, scaler tap tables and the
+// yuv->rgb constants.  This is cold code that must agree bit-for-bit with what the reference computes in
+//   ff_sws_init_single_context  libswscale/utils.c:1137-1760
+//   initFilter                  libswscale/utils.c:197-612  (filterAlign = 1: the generic-C layout; the reference's
+//                               x86/NEON builds only append zero taps, utils.c:1675-1710, which cannot change results
+//                               under SWS_BITEXACT)
+//   ff_yuv2rgb_c_init_tables    libswscale/yuv2rgb.c:717-914
+//   packed_vscale               libswscale/vscale.c:144-169 (writer choice per output line)
+// The device kernels consume the tables produced here; nothing below touches the GPU.
+#include "sws_plan.h"
+#include "b200dsp.h"
+#include <cstdlib>
+#include <cmath>
+#include <algorithm>
+#include <limits>
+
+namespace {
+
+using i64 = int64_t;
+
+inline int floor_log2(unsigned v) { int n = 0; v |= 1; while (v >>= 1) ++n; return n; }
+inline i64 iabs64(i64 v) { return v < 0 ? -v : v; }
+inline int clip_byte(i64 v) { return v < 0 ? 0 : v > 255 ? 255 : (int)v; }
+inline int chroma_shift_up(int v, int sh) { return -((-v) >> sh); }          // AV_CEIL_RSHIFT
+
+// get_local_pos, utils.c:168-175
+inline int sample_origin(int subsample, int pos)
+{
+    if (pos == -1 || pos <= -513) pos = (128 << subsample) - 128;
+    return (pos + 128) >> subsample;
+}
+
+enum Kernel { K_POINT, K_LINEAR2, K_CUBIC, K_TRIANGLE, K_BOX };
+
+// One row of raw (un-normalised, 64-bit) taps per output sample.
+struct RawTaps {
+    std::vector<i64> w;
+    std::vector<int32_t> first;
+    int taps = 0;
+};
+
+// The weight of a source sample at distance d (Q30 after the <<13) from the output sample centre.
+i64 cubic_weight(i64 d)
+{
+    // Mitchell-Netravali with B = 0, C = 0.6 in Q24 (the reference's SWS_PARAM_DEFAULT), utils.c:312-332
+    const i64 B = 0, C = (i64)(0.6 * (1 << 24));
+    if (d >= (i64)1 << 31) return 0;
+    const i64 dd = (d * d) >> 30, ddd = (dd * d) >> 30;
+    if (d < (i64)1 << 30)
+        return (12 * (1 << 24) - 9 * B - 6 * C) * ddd + (-18 * (1 << 24) + 12 * B + 6 * C) * dd +
+               (6 * (1 << 24) - 2 * B) * ((i64)1 << 30);
+    return (-B - 6 * C) * ddd + (6 * B + 30 * C) * dd + (-12 * B - 48 * C) * d + (8 * B + 24 * C) * ((i64)1 << 30);
+}
+
+int raw_taps(RawTaps &r, int scaler, int inc, int srcN, int dstN, int srcOrg, int dstOrg, i64 unit)
+{
+    r.first.assign((size_t)dstN + 3, 0);
+    if (std::abs(inc - 0x10000) < 10 && srcOrg == dstOrg) {                      // utils.c:221-231
+        r.taps = 1;
+        r.w.assign(dstN, unit);
+        for (int i = 0; i < dstN; i++) r.first[i] = i;
+        return 0;
+    }
+    if (scaler == B200_SWS_POINT) {                                              // utils.c:232-246
+        r.taps = 1;
+        r.w.assign(dstN, unit);
+        i64 x = ((dstOrg * (i64)inc) >> 8) - ((srcOrg * 0x8000LL) >> 7);
+        for (int i = 0; i < dstN; i++, x += inc) r.first[i] = (int32_t)((x + (1 << 15)) >> 16);
+        return 0;
+    }
+    if ((inc <= (1 << 16) && scaler == B200_SWS_AREA) || scaler == B200_SWS_FAST_BILINEAR) {   // utils.c:247-271
+        r.taps = 2;
+        r.w.assign((size_t)dstN * 2, 0);
+        i64 x = ((dstOrg * (i64)inc) >> 8) - ((srcOrg * 0x8000LL) >> 7);
+        for (int i = 0; i < dstN; i++, x += inc) {
+            int s = (int)((x - (1 << 15) + (1 << 15)) >> 16);
+            r.first[i] = s;
+            for (int j = 0; j < 2; j++, s++)
+                r.w[(size_t)i * 2 + j] = std::max<i64>(0, unit - iabs64((i64)s * (1 << 16) - x) * (unit >> 16));
+        }
+        return 0;
+    }
+    int support;                                                                 // scale_algorithms[], utils.c:183-195
+    switch (scaler) {
+    case B200_SWS_BICUBIC:  support = 4; break;
+    case B200_SWS_BILINEAR: support = 2; break;
+    case B200_SWS_AREA:     support = 1; break;
+    default: return B200_ENOSYS;                                                 // float kernels (gauss, sinc, ...) not built
+    }
+    int taps = inc <= (1 << 16) ? 1 + support : 1 + (int)(((i64)support * srcN + dstN - 1) / dstN);
+    taps = std::max(1, std::min(taps, srcN - 2));
+    r.taps = taps;
+    r.w.assign((size_t)dstN * taps, 0);
+    i64 x = ((dstOrg * (i64)inc) >> 7) - ((srcOrg * 0x10000LL) >> 7);
+    for (int i = 0; i < dstN; i++, x += 2LL * inc) {
+        int s = (int)((x - (taps - 2) * ((i64)1 << 16)) / (1 << 17));
+        r.first[i] = s;
+        for (int j = 0; j < taps; j++, s++) {
+            i64 d = iabs64((i64)s * (1 << 17) - x) << 13;
+            if (inc > (1 << 16)) d = d * dstN / srcN;
+            i64 w;
+            if (scaler == B200_SWS_BICUBIC) {
+                w = cubic_weight(d) / (((i64)1 << 54) / unit);
+            } else if (scaler == B200_SWS_AREA) {
+                const i64 d2 = d - (1 << 29);
+                if (d2 * inc < -((i64)1 << 45))      w = (i64)1 << 46;
+                else if (d2 * inc < ((i64)1 << 45))  w = -d2 * inc + ((i64)1 << 45);
+                else                                 w = 0;
+                w *= unit >> 46;
+            } else {
+                w = std::max<i64>(0, (1 << 30) - d) * (unit >> 30);
+            }
+            r.w[(size_t)i * taps + j] = w;
+        }
+    }
+    return 0;
+}
+
+int build_bank(SwsFilterBank &bank, int scaler, int inc, int srcN, int dstN, int one, int srcOrg, int dstOrg)
+{
+    const i64 unit = (i64)1 << (54 - std::min(floor_log2((unsigned)(srcN / dstN)), 8));
+    RawTaps r;
+    int ret = raw_taps(r, scaler, inc, srcN, dstN, srcOrg, dstOrg, unit);
+    if (ret < 0) return ret;
+    const int T = r.taps;
+    const double cutoff = 0.002 * (double)unit;                                  // SWS_MAX_REDUCE_CUTOFF, swscale.h:447
+
+    // 1. trim negligible taps: shift them out on the left, count them on the right (utils.c:417-457)
+    int keep = 0;
+    for (int i = dstN - 1; i >= 0; i--) {
+        i64 *w = &r.w[(size_t)i * T];
+        i64 mass = 0;
+        for (int j = 0; j < T; j++) {
+            mass += iabs64(w[0]);
+            if ((double)mass > cutoff) break;
+            if (i < dstN - 1 && r.first[i] >= r.first[i + 1]) break;             // keep positions monotonic
+            std::copy(w + 1, w + T, w);
+            w[T - 1] = 0;
+            r.first[i]++;
+        }
+        int need = T;
+        mass = 0;
+        for (int j = T - 1; j > 0; j--) {
+            mass += iabs64(w[j]);
+            if ((double)mass > cutoff) break;
+            need--;
+        }
+        keep = std::max(keep, need);
+    }
+    if (keep >= 256) return B200_ENOSYS;                                         // reference cascades contexts here (utils.c:491-495)
+
+    // 2. fold taps that fall outside [0, srcN) onto the border sample (utils.c:519-560)
+    std::vector<i64> g((size_t)dstN * keep);
+    for (int i = 0; i < dstN; i++) {
+        i64 *o = &g[(size_t)i * keep];
+        for (int j = 0; j < keep; j++) o[j] = j < T ? r.w[(size_t)i * T + j] : 0;
+        int &p = r.first[i];
+        if (p < 0) {
+            for (int j = 1; j < keep; j++) {
+                o[std::max(j + p, 0)] += o[j];
+                o[j] = 0;
+            }
+            p = 0;
+        }
+        if (p + keep > srcN) {
+            const int shift = p + std::min(keep - srcN, 0);
+            i64 spill = 0;
+            for (int j = keep - 1; j >= 0; j--)
+                if (p + j >= srcN) { spill += o[j]; o[j] = 0; }
+            for (int j = keep - 1; j >= 0; j--) o[j] = j < shift ? 0 : o[j - shift];
+            p -= shift;
+            o[srcN - 1 - p] += spill;
+        }
+    }
+
+    // 3. normalise every row to `one` with error feedback (utils.c:568-588)
+    bank.size = keep;
+    bank.n = dstN;
+    bank.coef.assign((size_t)dstN * keep, 0);
+    bank.pos.assign(r.first.begin(), r.first.begin() + dstN);
+    for (int i = 0; i < dstN; i++) {
+        const i64 *o = &g[(size_t)i * keep];
+        i64 sum = 0, carry = 0;
+        for (int j = 0; j < keep; j++) sum += o[j];
+        sum = (sum + one / 2) / one;
+        if (!sum) sum = 1;
+        for (int j = 0; j < keep; j++) {
+            const i64 v = o[j] + carry;
+            const int q = (int)(v >= 0 ? (v + (sum >> 1)) / sum : (v - (sum >> 1)) / sum);   // ROUNDED_DIV
+            bank.coef[(size_t)i * keep + j] = (int16_t)q;
+            carry = v - q * sum;
+        }
+    }
+    return 0;
+}
+
+inline int16_t round_q16(i64 f)                                                  // roundToInt16, yuv2rgb.c:705-715
+{
+    int r = (int)((f + (1 << 15)) >> 16);
+    if (r < -0x7FFF) return (int16_t)0x8000;
+    if (r > 0x7FFF) return 0x7FFF;
+    return (int16_t)r;
+}
+
+} // namespace
+
+bool SwsFilterBank::identity() const
+{
+    if (size != 1) return false;
+    for (int i = 0; i < n; i++)
+        if (pos[i] != i || coef[i] != (1 << 14)) return false;
+    return true;
+}
+
+int sws_plan_colorspace(SwsPlan &p, const int inv_table[4], int fullRange, int brightness, int contrast, int saturation)
+{
+    const int headroom = 512;                                                    // YUVRGB_TABLE_LUMA_HEADROOM
+    const int yoffs = (fullRange ? 384 : 326) + headroom;
+    i64 crv = inv_table[0], cbu = inv_table[1], cgu = -(i64)inv_table[2], cgv = -(i64)inv_table[3];
+    i64 cy = 1 << 16, oy = 0;
+    if (!fullRange) { cy = (cy * 255) / 219; oy = 16 << 16; }
+    else { crv = (crv * 224) / 255; cbu = (cbu * 224) / 255; cgu = (cgu * 224) / 255; cgv = (cgv * 224) / 255; }
+    cy  = (cy * contrast) >> 16;
+    crv = (crv * contrast * saturation) >> 32;
+    cbu = (cbu * contrast * saturation) >> 32;
+    cgu = (cgu * contrast * saturation) >> 32;
+    cgv = (cgv * contrast * saturation) >> 32;
+    oy -= 256LL * brightness;
+
+    SwsColorConst &c = p.color;
+    c.y_coeff = round_q16(cy * (1 << 13));
+    c.y_offset = round_q16(oy * (1 << 9));
+    c.v2r = round_q16(crv * (1 << 13));
+    c.v2g = round_q16(cgv * (1 << 13));
+    c.u2g = round_q16(cgu * (1 << 13));
+    c.u2b = round_q16(cbu * (1 << 13));
+
+    const i64 den = std::max<i64>(cy, 1);
+    crv = ((crv * (1 << 16)) + 0x8000) / den;
+    cbu = ((cbu * (1 << 16)) + 0x8000) / den;
+    cgu = ((cgu * (1 << 16)) + 0x8000) / den;
+    cgv = ((cgv * (1 << 16)) + 0x8000) / den;
+
+    const i64 yb0 = -((i64)384 << 16) - headroom * cy - oy + 0x8000;
+    const i64 baseR = yoffs - (crv >> 9), baseB = yoffs - (cbu >> 9), baseG = yoffs - (cgu >> 9) - (cgv >> 9);
+    // the kernels evaluate the tables in 32-bit arithmetic: refuse settings that would overflow there
+    const i64 lim = std::numeric_limits<int32_t>::max();
+    const i64 worst_idx = 4096;                                                  // |table index + luma| bound with margin
+    if (cy <= 0 || iabs64(yb0) + worst_idx * cy >= lim ||
+        255 * iabs64(crv) >= lim || 255 * iabs64(cbu) >= lim || 255 * iabs64(cgu) >= lim || 255 * iabs64(cgv) >= lim ||
+        iabs64(baseR) > 2048 || iabs64(baseG) > 2048 || iabs64(baseB) > 2048)
+        return B200_ENOSYS;
+    c.cy = (int)cy; c.yb0 = (int)yb0;
+    c.baseR = (int)baseR; c.baseG = (int)baseG; c.baseB = (int)baseB;
+    c.crv = (int)crv; c.cgu = (int)cgu; c.cgv = (int)cgv; c.cbu = (int)cbu;
+    return 0;
+}
+
+int sws_plan_build(SwsPlan &p, int srcW, int srcH, int dstW, int dstH, int flags)
+{
+    if (srcW < 1 || srcH < 1 || dstW < 1 || dstH < 1) return B200_EINVAL;
+    int algo = flags & 0x7FF;                                                    // scaler bits, utils.c:1196-1222
+    if (!algo) { algo = B200_SWS_BICUBIC; flags |= algo; }
+    else if (algo & (algo - 1)) return B200_EINVAL;
+    if (algo == B200_SWS_FAST_BILINEAR) return B200_ENOSYS;                      // hyscale_fast path (hscale_fast_bilinear.c) not built
+    if (dstW & 1) flags |= B200_SWS_FULL_CHR_H_INT;                              // utils.c:1271-1276
+    p.srcW = srcW; p.srcH = srcH; p.dstW = dstW; p.dstH = dstH; p.flags = flags;
+    p.chrDstHSub = (flags & B200_SWS_FULL_CHR_H_INT) ? 0 : 1;                    // utils.c:1359-1360
+    p.chrSrcW = chroma_shift_up(srcW, 1);
+    p.chrSrcH = chroma_shift_up(srcH, 1);
+    p.chrDstW = chroma_shift_up(dstW, p.chrDstHSub);
+    p.chrDstH = dstH;                                                            // rgb24 has no vertical chroma subsampling
+    static const int bt601[4] = { 104597, 132201, 25675, 53279 };                // ff_yuv2rgb_coeffs[SWS_CS_DEFAULT], yuv2rgb.c:47-59
+    int ret = sws_plan_colorspace(p, bt601, 0, 0, 1 << 16, 1 << 16);
+    if (ret < 0) return ret;
+
+    // unscaled special converter gate: swscale_unscaled.c:2426-2431 reached from utils.c:1623-1637
+    p.unscaled_lut = srcW == dstW && srcH == dstH && !(flags & B200_SWS_ACCURATE_RND) && !(dstH & 1);
+    if (p.unscaled_lut) return 0;
+
+    const int lumScaler = algo == B200_SWS_BICUBLIN ? B200_SWS_BICUBIC : algo;
+    const int chrScaler = algo == B200_SWS_BICUBLIN ? B200_SWS_BILINEAR : algo;
+    const i64 lumXInc = (((i64)srcW << 16) + (dstW >> 1)) / dstW;                // utils.c:1250-1251,1425-1426
+    const i64 lumYInc = (((i64)srcH << 16) + (dstH >> 1)) / dstH;
+    const i64 chrXInc = (((i64)p.chrSrcW << 16) + (p.chrDstW >> 1)) / p.chrDstW;
+    const i64 chrYInc = (((i64)p.chrSrcH << 16) + (p.chrDstH >> 1)) / p.chrDstH;
+    if (lumXInc < 10 || lumYInc < 10 || chrXInc < 10 || chrYInc < 10 ||
+        lumXInc > INT32_MAX || lumYInc > INT32_MAX || chrXInc > INT32_MAX || chrYInc > INT32_MAX)
+        return B200_ENOSYS;
+    if ((ret = build_bank(p.hLum, lumScaler, (int)lumXInc, srcW, dstW, 1 << 14, sample_origin(0, 0), sample_origin(0, 0))) < 0) return ret;
+    if ((ret = build_bank(p.hChr, chrScaler, (int)chrXInc, p.chrSrcW, p.chrDstW, 1 << 14,
+                          sample_origin(1, -513), sample_origin(p.chrDstHSub, -513))) < 0) return ret;
+    if ((ret = build_bank(p.vLum, lumScaler, (int)lumYInc, srcH, dstH, 1 << 12, sample_origin(0, 0), sample_origin(0, 0))) < 0) return ret;
+    if ((ret = build_bank(p.vChr, chrScaler, (int)chrYInc, p.chrSrcH, p.chrDstH, 1 << 12,
+                          sample_origin(1, -513), sample_origin(0, -513))) < 0) return ret;
+
+    // writer per output line, as packed_vscale decides it (vscale.c:144-169); coefficients are read as uint16 there
+    p.rowMode.assign((size_t)dstH * 4, 0);
+    const int L = p.vLum.size, C = p.vChr.size;
+    for (int y = 0; y < dstH; y++) {
+        const uint16_t *lf = (const uint16_t *)&p.vLum.coef[(size_t)y * L];
+        const uint16_t *cf = (const uint16_t *)&p.vChr.coef[(size_t)y * C];
+        int mode = 0, ya = 0, ua = 0;
+        if (L == 1 && C == 1) mode = 1;
+        else if (L == 1 && C == 2 && cf[0] + cf[1] == 4096 && cf[1] <= 4096) { mode = 1; ua = cf[1]; }
+        else if (L == 2 && C == 2 && lf[0] + lf[1] == 4096 && lf[1] <= 4096 && cf[0] + cf[1] == 4096 && cf[1] <= 4096) {
+            mode = 2; ya = lf[1]; ua = cf[1];
+        }
+        p.rowMode[(size_t)y * 4 + 0] = mode;
+        p.rowMode[(size_t)y * 4 + 1] = ya;
+        p.rowMode[(size_t)y * 4 + 2] = ua;
+    }
+    return 0;
+}

@@ -1,0 +1,38 @@
+// sws_plan.h — host-side plan of one yuv420p -> rgb24 conversion (what SwsInternal holds after sws_init_context)
+#pragma once
+#include <vector>
+#include <cstdint>
+
+struct SwsFilterBank {            // one of hLum / hChr / vLum / vChr (SwsInternal fields, swscale_internal.h:437-448)
+    std::vector<int16_t> coef;    // n * size, normalised to 1<<14 (horizontal) or 1<<12 (vertical)
+    std::vector<int32_t> pos;     // n first-tap positions
+    int size = 0;
+    int n = 0;
+    bool identity() const;        // size 1, pos[i] == i, coef == 1<<14  (unscaled horizontal pass)
+};
+
+// Closed form of the reference's yuv->rgb look-up tables (libswscale/yuv2rgb.c:717-914, 24 bpp case):
+//   y_table[k] = clip_u8((yb0 + k*cy) >> 16)   with the +0x8000 rounding folded into yb0
+//   r = y_table[baseR + ((clip_u8(V)*crv) >> 16) + Y]  etc.   (fill_table / fill_gv_table, yuv2rgb.c:680-703)
+struct SwsColorConst {
+    int cy, yb0;
+    int baseR, baseG, baseB;      // baseG = yoffs - (cgu>>9) - (cgv>>9)
+    int crv, cgu, cgv, cbu;
+    // full-chroma writer (yuv2rgb_write_full, output.c:1998-2030)
+    int y_offset, y_coeff, v2r, v2g, u2g, u2b;
+};
+
+struct SwsPlan {
+    int srcW = 0, srcH = 0, dstW = 0, dstH = 0, flags = 0;
+    int chrSrcW = 0, chrSrcH = 0, chrDstW = 0, chrDstH = 0;
+    int chrDstHSub = 1;
+    bool unscaled_lut = false;    // reference installs yuv2rgb_c_24_rgb as convert_unscaled
+    SwsFilterBank hLum, hChr, vLum, vChr;
+    SwsColorConst color{};
+    // per output line: writer selected by packed_vscale (vscale.c:144-169): 0 = _X, 1 = _1, 2 = _2, plus alphas
+    std::vector<int32_t> rowMode;  // dstH * 4: mode, yalpha, uvalpha, pad
+};
+
+// returns 0 or a negative B200_E* code
+int sws_plan_build(SwsPlan &p, int srcW, int srcH, int dstW, int dstH, int flags);
+int sws_plan_colorspace(SwsPlan &p, const int inv_table[4], int fullRange, int brightness, int contrast, int saturation);

@@ -1,0 +1,102 @@
+"""Host-side mirror of the libswscale interface for the accelerated path (yuv420p -> rgb24).
+
+Names and argument meaning follow libswscale/swscale.h: sws_getContext (:utils.c:1919), sws_setColorspaceDetails
+(utils.c:849), sws_scale (swscale.c:1626), sws_freeContext.  Arrays are numpy (host) for sws_scale / scale_batch_host
+and torch CUDA tensors or raw device pointers for scale_batch_device.  Everything goes through the C ABI.
+"""
+import ctypes as C
+import numpy as np
+from ._lib import lib, check, vp, i16p, i32p, i64p, B200Error
+
+AV_PIX_FMT_YUV420P, AV_PIX_FMT_RGB24 = 0, 2
+SWS_FAST_BILINEAR, SWS_BILINEAR, SWS_BICUBIC, SWS_POINT, SWS_AREA, SWS_BICUBLIN = 1, 2, 4, 0x10, 0x20, 0x40
+SWS_FULL_CHR_H_INT, SWS_ACCURATE_RND, SWS_BITEXACT = 0x2000, 0x40000, 0x80000
+# libswscale/yuv2rgb.c:47-59 (sws_getCoefficients)
+SWS_CS_ITU709, SWS_CS_FCC, SWS_CS_ITU601, SWS_CS_SMPTE240M, SWS_CS_DEFAULT, SWS_CS_BT2020 = 1, 4, 5, 7, 5, 9
+_COEFFS = {0: (104597, 132201, 25675, 53279), 1: (117489, 138438, 13975, 34925), 4: (104448, 132798, 24759, 53109),
+           7: (117579, 136230, 16907, 35559), 9: (110013, 140363, 12277, 42626)}
+
+
+def sws_getCoefficients(colorspace):
+    return _COEFFS.get(colorspace, _COEFFS[0])
+
+
+def _dptr(x):
+    return int(x.data_ptr()) if hasattr(x, "data_ptr") else int(x)
+
+
+class SwsContext:
+    def __init__(self, device, srcW, srcH, srcFormat, dstW, dstH, dstFormat, flags):
+        self.device = device
+        self.srcW, self.srcH, self.dstW, self.dstH, self.flags = srcW, srcH, dstW, dstH, flags
+        h = lib().b200_sws_getContext(device.handle, srcW, srcH, srcFormat, dstW, dstH, dstFormat, flags)
+        if not h:
+            raise B200Error("sws_getContext failed: " + lib().b200_last_error().decode())
+        self._h = vp(h)
+
+    def setColorspaceDetails(self, inv_table, srcRange, table, dstRange, brightness, contrast, saturation):
+        it = (C.c_int32 * 4)(*inv_table)
+        tb = (C.c_int32 * 4)(*table)
+        return check(lib().b200_sws_setColorspaceDetails(self._h, it, srcRange, tb, dstRange, brightness, contrast, saturation),
+                     "sws_setColorspaceDetails")
+
+    def info(self):
+        o = (C.c_int32 * 16)()
+        check(lib().b200_sws_info(self._h, o), "b200_sws_info")
+        return list(o)
+
+    def get_filter(self, which):
+        info = self.info()
+        size = info[which]
+        n = [self.dstW, info[6], self.dstH, info[7]][which]
+        if size == 0:
+            return None, None, 0
+        f = np.zeros(n * size, np.int16)
+        p = np.zeros(n, np.int32)
+        check(lib().b200_sws_get_filter(self._h, which, f.ctypes.data_as(i16p), p.ctypes.data_as(i32p), n), "get_filter")
+        return f.reshape(n, size), p, size
+
+    def scale(self, src, srcStride, srcSliceY, srcSliceH, dst, dstStride):
+        """sws_scale(): src = [y,u,v] numpy uint8 arrays (or ints = host addresses), dst = [rgb]. Returns lines."""
+        sp = (vp * 4)(*[a.ctypes.data if hasattr(a, "ctypes") else int(a) for a in src] + [0] * (4 - len(src)))
+        ss = (C.c_int32 * 4)(*list(srcStride) + [0] * (4 - len(srcStride)))
+        dp = (vp * 4)(*[a.ctypes.data if hasattr(a, "ctypes") else int(a) for a in dst] + [0] * (4 - len(dst)))
+        dsr = (C.c_int32 * 4)(*list(dstStride) + [0] * (4 - len(dstStride)))
+        return check(lib().b200_sws_scale(self._h, sp, ss, srcSliceY, srcSliceH, dp, dsr), "sws_scale")
+
+    def convert(self, y, u, v, dst_pad=0):
+        """Convenience: whole frame from 2-D uint8 arrays, returns (dstH, dstW*3+pad) array."""
+        ds = self.dstW * 3 + dst_pad
+        out = np.full((self.dstH, ds), 0xA5, np.uint8)
+        n = self.scale([y, u, v], [y.strides[0], u.strides[0], v.strides[0]], 0, self.srcH, [out], [ds])
+        assert n == self.dstH
+        return out
+
+    def _batch(self, fn, src, srcStride, srcFrameStride, dst, dstStride, dstFrameStride, nframes, what):
+        sp = (vp * 3)(*[_dptr(a) for a in src])
+        ss = (C.c_int32 * 3)(*srcStride)
+        fs = (C.c_int64 * 3)(*srcFrameStride)
+        return check(fn(self._h, sp, ss, fs, vp(_dptr(dst)), dstStride, dstFrameStride, nframes), what)
+
+    def scale_batch_device(self, src, srcStride, srcFrameStride, dst, dstStride, dstFrameStride, nframes):
+        return self._batch(lib().b200_sws_scale_batch_device, src, srcStride, srcFrameStride, dst, dstStride,
+                           dstFrameStride, nframes, "sws_scale_batch_device")
+
+    def scale_batch_host(self, src, srcStride, srcFrameStride, dst, dstStride, dstFrameStride, nframes):
+        return self._batch(lib().b200_sws_scale_batch_host, src, srcStride, srcFrameStride, dst, dstStride,
+                           dstFrameStride, nframes, "sws_scale_batch_host")
+
+    def free(self):
+        if self._h:
+            lib().b200_sws_freeContext(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def sws_getContext(device, srcW, srcH, srcFormat, dstW, dstH, dstFormat, flags):
+    return SwsContext(device, srcW, srcH, srcFormat, dstW, dstH, dstFormat, flags)

@@ -1,0 +1,116 @@
+/*
+ * idct_oracle.c — TEST INFRASTRUCTURE ONLY.  CPU restatement of libavcodec's 8-bit "simple" IDCT.
+ *
+ * Follows (behaviour, not text):
+ *   libavcodec/simple_idct_template.c:48-61   constants W1..W7 (W4 = 16383), ROW_SHIFT 11, COL_SHIFT 20, DC_SHIFT 3
+ *   libavcodec/simple_idct_template.c:114-206 idctRowCondDC: rows whose AC terms are all zero become (row[0]*8)&0xffff,
+ *                                             other rows use the rounded butterfly; results are stored back as int16
+ *   libavcodec/simple_idct_template.c:209-327 IDCT_COLS + idctSparseCol{,Put,Add}
+ *   libavcodec/simple_idct_template.c:329-368 ff_simple_idct_{put,add,}_int16_8bit
+ *   libavcodec/idctdsp.c:73-165               put / put_signed / add _pixels_clamped
+ * The zero-tests inside the reference's column pass only skip additions of zero, so they are dropped here.
+ * All arithmetic is unsigned 32-bit (wrap-around) exactly like the reference's SUINT.
+ */
+#include "oracle.h"
+
+enum { W1 = 22725, W2 = 21407, W3 = 19266, W4 = 16383, W5 = 12873, W6 = 8867, W7 = 4520 };
+
+static uint8_t clip8(int a) { return (uint8_t)(a < 0 ? 0 : a > 255 ? 255 : a); }
+
+static void row_pass(int16_t *r)
+{
+    if (!(r[1] | r[2] | r[3] | r[4] | r[5] | r[6] | r[7])) {
+        int16_t dc = (int16_t)(uint16_t)(((unsigned)r[0] << 3) & 0xffff);
+        for (int i = 0; i < 8; i++) r[i] = dc;
+        return;
+    }
+    uint32_t a0 = (uint32_t)W4 * r[0] + (1u << 10), a1 = a0, a2 = a0, a3 = a0;
+    a0 += (uint32_t)W2 * r[2]; a1 += (uint32_t)W6 * r[2];
+    a2 -= (uint32_t)W6 * r[2]; a3 -= (uint32_t)W2 * r[2];
+    uint32_t b0 = (uint32_t)(W1 * r[1]) + (uint32_t)(W3 * r[3]);
+    uint32_t b1 = (uint32_t)(W3 * r[1]) - (uint32_t)(W7 * r[3]);
+    uint32_t b2 = (uint32_t)(W5 * r[1]) - (uint32_t)(W1 * r[3]);
+    uint32_t b3 = (uint32_t)(W7 * r[1]) - (uint32_t)(W5 * r[3]);
+    a0 += (uint32_t)W4 * r[4] + (uint32_t)W6 * r[6];
+    a1 += (uint32_t)-W4 * r[4] - (uint32_t)W2 * r[6];
+    a2 += (uint32_t)-W4 * r[4] + (uint32_t)W2 * r[6];
+    a3 += (uint32_t)W4 * r[4] - (uint32_t)W6 * r[6];
+    b0 += (uint32_t)(W5 * r[5]) + (uint32_t)(W7 * r[7]);
+    b1 += (uint32_t)(-W1 * r[5]) + (uint32_t)(-W5 * r[7]);
+    b2 += (uint32_t)(W7 * r[5]) + (uint32_t)(W3 * r[7]);
+    b3 += (uint32_t)(W3 * r[5]) + (uint32_t)(-W1 * r[7]);
+    r[0] = (int16_t)((int32_t)(a0 + b0) >> 11); r[7] = (int16_t)((int32_t)(a0 - b0) >> 11);
+    r[1] = (int16_t)((int32_t)(a1 + b1) >> 11); r[6] = (int16_t)((int32_t)(a1 - b1) >> 11);
+    r[2] = (int16_t)((int32_t)(a2 + b2) >> 11); r[5] = (int16_t)((int32_t)(a2 - b2) >> 11);
+    r[3] = (int16_t)((int32_t)(a3 + b3) >> 11); r[4] = (int16_t)((int32_t)(a3 - b3) >> 11);
+}
+
+static void col_pass(const int16_t *c, int out[8])
+{
+    uint32_t a0 = (uint32_t)W4 * (uint32_t)(c[0] + ((1 << 19) / W4)), a1 = a0, a2 = a0, a3 = a0;
+    a0 += (uint32_t)W2 * c[16]; a1 += (uint32_t)W6 * c[16];
+    a2 += (uint32_t)-W6 * c[16]; a3 += (uint32_t)-W2 * c[16];
+    uint32_t b0 = (uint32_t)(W1 * c[8]), b1 = (uint32_t)(W3 * c[8]), b2 = (uint32_t)(W5 * c[8]), b3 = (uint32_t)(W7 * c[8]);
+    b0 += (uint32_t)(W3 * c[24]); b1 += (uint32_t)(-W7 * c[24]); b2 += (uint32_t)(-W1 * c[24]); b3 += (uint32_t)(-W5 * c[24]);
+    a0 += (uint32_t)W4 * c[32]; a1 += (uint32_t)-W4 * c[32]; a2 += (uint32_t)-W4 * c[32]; a3 += (uint32_t)W4 * c[32];
+    b0 += (uint32_t)(W5 * c[40]); b1 += (uint32_t)(-W1 * c[40]); b2 += (uint32_t)(W7 * c[40]); b3 += (uint32_t)(W3 * c[40]);
+    a0 += (uint32_t)W6 * c[48]; a1 += (uint32_t)-W2 * c[48]; a2 += (uint32_t)W2 * c[48]; a3 += (uint32_t)-W6 * c[48];
+    b0 += (uint32_t)(W7 * c[56]); b1 += (uint32_t)(-W5 * c[56]); b2 += (uint32_t)(W3 * c[56]); b3 += (uint32_t)(-W1 * c[56]);
+    out[0] = (int32_t)(a0 + b0) >> 20; out[1] = (int32_t)(a1 + b1) >> 20;
+    out[2] = (int32_t)(a2 + b2) >> 20; out[3] = (int32_t)(a3 + b3) >> 20;
+    out[4] = (int32_t)(a3 - b3) >> 20; out[5] = (int32_t)(a2 - b2) >> 20;
+    out[6] = (int32_t)(a1 - b1) >> 20; out[7] = (int32_t)(a0 - b0) >> 20;
+}
+
+void orc_idct(int16_t *block)
+{
+    int o[8];
+    for (int i = 0; i < 8; i++) row_pass(block + 8 * i);
+    for (int i = 0; i < 8; i++) {
+        col_pass(block + i, o);
+        for (int k = 0; k < 8; k++) block[8 * k + i] = (int16_t)o[k];
+    }
+}
+
+void orc_idct_put(uint8_t *dest, ptrdiff_t ls, int16_t *block)
+{
+    int o[8];
+    for (int i = 0; i < 8; i++) row_pass(block + 8 * i);
+    for (int i = 0; i < 8; i++) {
+        col_pass(block + i, o);
+        for (int k = 0; k < 8; k++) dest[k * ls + i] = clip8(o[k]);
+    }
+}
+
+void orc_idct_add(uint8_t *dest, ptrdiff_t ls, int16_t *block)
+{
+    int o[8];
+    for (int i = 0; i < 8; i++) row_pass(block + 8 * i);
+    for (int i = 0; i < 8; i++) {
+        col_pass(block + i, o);
+        for (int k = 0; k < 8; k++) dest[k * ls + i] = clip8(dest[k * ls + i] + o[k]);
+    }
+}
+
+void orc_idct_batch(int kind, int16_t *blocks, int nblocks, uint8_t *dest, ptrdiff_t line_size, const int64_t *dest_off)
+{
+    for (int i = 0; i < nblocks; i++) {
+        int16_t *b = blocks + 64 * (size_t)i;
+        if (kind == 0)      orc_idct(b);
+        else if (kind == 1) orc_idct_put(dest + dest_off[i], line_size, b);
+        else                orc_idct_add(dest + dest_off[i], line_size, b);
+    }
+}
+
+/* idctdsp.c:73-165; kind 0 put, 1 put_signed, 2 add */
+void orc_pixels_clamped(int kind, const int16_t *block, uint8_t *pixels, ptrdiff_t ls)
+{
+    for (int i = 0; i < 8; i++)
+        for (int j = 0; j < 8; j++) {
+            int b = block[8 * i + j];
+            uint8_t *p = pixels + i * ls + j;
+            if (kind == 0)      *p = clip8(b);
+            else if (kind == 1) *p = b < -128 ? 0 : b > 127 ? 255 : (uint8_t)(b + 128);
+            else                *p = clip8(*p + b);
+        }
+}

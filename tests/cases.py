@@ -1,0 +1,67 @@
+"""Shared case lists and synthetic-input generators for the parity tests and scripts/gen_golden.py."""
+import numpy as np
+
+SWS_BILINEAR, SWS_BICUBIC, SWS_POINT, SWS_AREA, SWS_BICUBLIN = 2, 4, 0x10, 0x20, 0x40
+SWS_FULL_CHR_H_INT, SWS_ACCURATE_RND, SWS_BITEXACT = 0x2000, 0x40000, 0x80000
+FATE = SWS_BICUBIC | SWS_ACCURATE_RND | SWS_BITEXACT      # tests/fate-run.sh:262-265 sws_flags
+
+# (srcW, srcH, dstW, dstH, flags, input kind) — small: inputs and reference outputs are stored in tests/golden
+SWS_SMALL_CASES = [
+    (64, 48, 64, 48, FATE, "random"),            # same size, FATE flags: _X writer, 4-tap vertical chroma
+    (64, 48, 64, 48, SWS_BICUBIC, "random"),     # same size, plain bicubic: unscaled LUT converter
+    (64, 48, 128, 96, FATE, "smooth"),           # 2x up
+    (64, 48, 32, 24, FATE, "random"),            # 2x down
+    (64, 48, 37, 21, FATE, "random"),            # odd output width: full-chroma writer
+    (34, 18, 34, 18, SWS_BICUBIC, "random"),     # width % 16 != 0 on the LUT path (tails 2 wide)
+    (38, 20, 38, 20, FATE, "limited"),
+    (64, 48, 100, 60, SWS_BILINEAR, "random"),   # _2 writer
+    (64, 48, 64, 48, SWS_BILINEAR | SWS_ACCURATE_RND, "random"),  # _1 writer with uvalpha
+    (64, 48, 80, 33, SWS_POINT, "random"),
+    (64, 48, 40, 30, SWS_AREA, "random"),
+    (64, 48, 96, 72, SWS_AREA, "random"),
+    (64, 48, 90, 50, SWS_BICUBLIN, "smooth"),
+    (64, 48, 64, 48, FATE | SWS_FULL_CHR_H_INT, "random"),
+    (16, 16, 16, 16, FATE, "random"),
+    (8, 8, 8, 8, SWS_BICUBIC, "random"),
+    (2, 2, 2, 2, FATE, "random"),
+    (4, 4, 8, 8, FATE, "random"),
+    (64, 48, 64, 47, SWS_BICUBIC, "random"),     # odd height: no LUT converter even without accurate_rnd
+    (33, 17, 64, 40, FATE, "random"),            # odd source size
+]
+
+# larger: only sha256 of the reference output is stored (inputs regenerated from the seed, input hash checked too)
+SWS_HASH_CASES = [
+    (352, 288, 352, 288, FATE, "random"),        # the FATE filter-pixfmts geometry (vsynth1 is 352x288)
+    (352, 288, 352, 288, SWS_BICUBIC, "random"),
+    (352, 288, 200, 100, FATE, "smooth"),        # filter-pixfmts-scale geometry
+    (640, 360, 640, 360, FATE, "random"),        # BASELINE.json configs[0]
+    (640, 360, 640, 360, SWS_BICUBIC, "limited"),
+    (640, 360, 1280, 720, FATE, "random"),
+    (1920, 1080, 1280, 720, FATE, "random"),
+    (352, 288, 351, 288, FATE, "random"),
+    (720, 576, 1000, 563, SWS_BILINEAR | SWS_BITEXACT, "smooth"),
+]
+
+
+def idct_blocks(kind, n, seed=0):
+    """Coefficient blocks like the reference's tests generate them."""
+    rng = np.random.default_rng(seed)
+    if kind == "dense":      # tests/checkasm/idctdsp.c:40-48: rnd() % 0x201 - 0x100
+        return rng.integers(-256, 257, (n, 64)).astype(np.int16)
+    if kind == "wide":
+        return rng.integers(-2048, 2048, (n, 64)).astype(np.int16)
+    if kind == "extreme":
+        return rng.integers(-32768, 32768, (n, 64)).astype(np.int16)
+    b = np.zeros((n, 64), np.int16)
+    if kind == "sparse":     # libavcodec/tests/dct.c:144-150: 1..10 non-zero coefficients
+        for i in range(n):
+            k = int(rng.integers(1, 11))
+            b[i, rng.integers(0, 64, k)] = rng.integers(-1024, 1024, k)
+    elif kind == "dc63":     # libavcodec/tests/dct.c:151-154
+        b[:, 0] = rng.integers(-1024, 1024, n)
+        b[:, 63] = rng.integers(-3, 4, n)
+    elif kind == "dconly":
+        b[:, 0] = rng.integers(-2048, 2048, n)
+    else:
+        raise ValueError(kind)
+    return b

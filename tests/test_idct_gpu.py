@@ -1,0 +1,157 @@
+"""GPU tier: the CUDA IDCT path (through the C ABI) against the oracle and the golden fixtures."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import cpulibs as cl
+from cases import idct_blocks
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+KINDS = ("dense", "wide", "extreme", "sparse", "dc63", "dconly")
+
+
+def gpu_batch(device, op, blk, dest, off, ls):
+    import torch
+    from ffmpeg_b200 import idctdsp
+    st = torch.cuda.ExternalStream(device.stream)
+    with torch.cuda.stream(st):
+        db = torch.from_numpy(blk).cuda()
+        dd = torch.from_numpy(dest).cuda()
+        do = torch.from_numpy(off).cuda()
+        idctdsp.idct_batch_device(device, op, db, blk.shape[0], dd, do, None, ls)
+        device.sync()
+        return db.cpu().numpy(), dd.cpu().numpy()
+
+
+def test_golden(device):
+    g = np.load(os.path.join(G, "idct.npz"))
+    off = (np.arange(256) * 8).astype(np.int64)
+    for kind in KINDS:
+        for op in (0, 1, 2):
+            b, d = gpu_batch(device, op, g[f"{kind}_in"].copy(), g[f"{kind}_dest"].copy(), off, 256 * 8)
+            ref = g[f"{kind}_op{op}"]
+            got = b if op == 0 else d
+            assert np.array_equal(got, ref), (kind, op, int((got != ref).sum()))
+            if op != 0:
+                assert np.array_equal(b, g[f"{kind}_in"])      # coefficients untouched (documented difference)
+
+
+@pytest.mark.parametrize("n", [1, 3, 4, 31, 33, 1000, 48960])
+def test_vs_oracle_ragged_counts(device, n):
+    O = cl.oracle()
+    rng = np.random.default_rng(n)
+    off = (rng.permutation(n) * 8).astype(np.int64)            # scattered, non-monotonic destinations
+    for kind in KINDS:
+        for op in (0, 1, 2):
+            blk = idct_blocks(kind, n, seed=n + op)
+            dest = rng.integers(0, 256, (8, n * 8), dtype=np.uint8)
+            b2, d2 = blk.copy(), dest.copy()
+            O.orc_idct_batch(op, cl.ptr(b2, cl.i16p), n, cl.ptr(d2), n * 8, cl.ptr(off, cl.i64p))
+            b1, d1 = gpu_batch(device, op, blk.copy(), dest.copy(), off, n * 8)
+            if op == 0:
+                assert np.array_equal(b1, b2), (kind, n)
+            else:
+                assert np.array_equal(d1, d2), (kind, op, n)
+
+
+def test_empty_batch(device):
+    from ffmpeg_b200 import idctdsp
+    import torch
+    t = torch.zeros(64, dtype=torch.int16, device="cuda")
+    assert idctdsp.idct_batch_device(device, 0, t, 0) == 0
+
+
+def test_unaligned_dest(device):
+    """dest rows that are not 8-byte aligned take the byte path."""
+    O = cl.oracle()
+    n = 64
+    rng = np.random.default_rng(3)
+    off = (np.arange(n) * 8 + 3).astype(np.int64)
+    blk = idct_blocks("dense", n, 5)
+    dest = rng.integers(0, 256, (8, n * 8 + 8), dtype=np.uint8)
+    for op in (1, 2):
+        b2, d2 = blk.copy(), dest.copy()
+        O.orc_idct_batch(op, cl.ptr(b2, cl.i16p), n, cl.ptr(d2), n * 8 + 8, cl.ptr(off, cl.i64p))
+        _, d1 = gpu_batch(device, op, blk.copy(), dest.copy(), off, n * 8 + 8)
+        assert np.array_equal(d1, d2)
+
+
+def test_pointer_table_dropin(device):
+    """IDCTDSPContext filled by ff_idctdsp_init: per-block calls on HOST pointers, like checkasm drives the reference."""
+    from ffmpeg_b200 import idctdsp
+    from ffmpeg_b200._lib import u8p, i16p
+    O = cl.oracle()
+    c = idctdsp.ff_idctdsp_init(idctdsp.FF_IDCT_SIMPLE, 8, 0)
+    assert c.perm_type == 0 and list(c.idct_permutation) == list(range(64))
+    rng = np.random.default_rng(1)
+    for kind in ("dense", "sparse", "dconly"):
+        blk = idct_blocks(kind, 1, 3)[0]
+        dest = rng.integers(0, 256, (8, 24), dtype=np.uint8)
+        b1, b2, d1, d2 = blk.copy(), blk.copy(), dest.copy(), dest.copy()
+        c.idct_put(d1[:, 8:].ctypes.data_as(u8p), 24, b1.ctypes.data_as(i16p))
+        O.orc_idct_batch(1, cl.ptr(b2, cl.i16p), 1, d2[:, 8:].ctypes.data_as(cl.u8p), 24, cl.ptr(np.zeros(1, np.int64), cl.i64p))
+        assert np.array_equal(d1, d2)
+        b1, b2 = blk.copy(), blk.copy()
+        c.idct_add(d1[:, 8:].ctypes.data_as(u8p), 24, b1.ctypes.data_as(i16p))
+        O.orc_idct_batch(2, cl.ptr(b2, cl.i16p), 1, d2[:, 8:].ctypes.data_as(cl.u8p), 24, cl.ptr(np.zeros(1, np.int64), cl.i64p))
+        assert np.array_equal(d1, d2)
+        b1, b2 = blk.copy(), blk.copy()
+        c.idct(b1.ctypes.data_as(i16p))
+        O.orc_idct_batch(0, cl.ptr(b2, cl.i16p), 1, None, 0, None)
+        assert np.array_equal(b1, b2)
+        for k, fn in enumerate((c.put_pixels_clamped, c.put_signed_pixels_clamped, c.add_pixels_clamped)):
+            big = rng.integers(-600, 600, 64).astype(np.int16)
+            p1 = rng.integers(0, 256, (8, 16), dtype=np.uint8); p2 = p1.copy()
+            fn(big.ctypes.data_as(i16p), p1.ctypes.data_as(u8p), 16)
+            O.orc_pixels_clamped(k, cl.ptr(big, cl.i16p), cl.ptr(p2), 16)
+            assert np.array_equal(p1, p2), k
+    assert idctdsp.lib().b200_idctdsp_init(C.byref(c), 1, 8, 0) < 0      # FF_IDCT_INT: not implemented -> ENOSYS
+
+
+@pytest.mark.parametrize("op", [1, 2])
+def test_mb420_frames(device, op):
+    """Macroblock stream of BASELINE config 3 (1080p = 120x68 MBs x 6 blocks): device and host entry points vs oracle."""
+    import torch
+    from ffmpeg_b200 import idctdsp
+    O = cl.oracle()
+    mb_w, mb_h, nf = 120, 68, 3
+    nblk = mb_w * mb_h * 6 * nf
+    blk = np.concatenate([idct_blocks(k, nblk // 4 + 1, 17) for k in ("dense", "sparse", "dc63", "wide")])[:nblk]
+    blk = np.ascontiguousarray(blk[np.random.default_rng(2).permutation(nblk)])
+    W, H = mb_w * 16, mb_h * 16
+    ls = [W + 64, W // 2 + 32, W // 2 + 32]
+    rng = np.random.default_rng(4)
+    planes = [rng.integers(0, 256, (nf, H, ls[0]), dtype=np.uint8), rng.integers(0, 256, (nf, H // 2, ls[1]), dtype=np.uint8),
+              rng.integers(0, 256, (nf, H // 2, ls[2]), dtype=np.uint8)]
+    # oracle: per plane offset lists
+    ref = [p.copy() for p in planes]
+    b = np.arange(nblk)
+    f, r = b // (mb_w * mb_h * 6), b % (mb_w * mb_h * 6)
+    mb, k = r // 6, r % 6
+    mby, mbx = mb // mb_w, mb % mb_w
+    for pl in range(3):
+        sel = (k < 4) if pl == 0 else (k == 3 + pl)
+        if pl == 0:
+            off = f * H * ls[0] + (mby * 16 + (k >> 1) * 8) * ls[0] + mbx * 16 + (k & 1) * 8
+        else:
+            off = f * (H // 2) * ls[pl] + (mby * 8) * ls[pl] + mbx * 8
+        bs = np.ascontiguousarray(blk[sel])
+        O.orc_idct_batch(op, cl.ptr(bs, cl.i16p), int(sel.sum()), cl.ptr(ref[pl]), ls[pl], cl.ptr(np.ascontiguousarray(off[sel]).astype(np.int64), cl.i64p))
+    fs = [H * ls[0], (H // 2) * ls[1], (H // 2) * ls[2]]
+    st = torch.cuda.ExternalStream(device.stream)
+    with torch.cuda.stream(st):
+        db = torch.from_numpy(blk).cuda()
+        dp = [torch.from_numpy(p).cuda() for p in planes]
+        idctdsp.idct_mb420_device(device, op, db, mb_w, mb_h, nf, dp, ls, fs)
+        device.sync()
+        for pl in range(3):
+            got = dp[pl].cpu().numpy()
+            assert np.array_equal(got, ref[pl]), (pl, int((got != ref[pl]).sum()))
+    hp = [p.copy() for p in planes]
+    idctdsp.idct_mb420_host(device, op, blk, mb_w, mb_h, nf, hp, ls, fs)
+    for pl in range(3):
+        # the host entry point only writes the picture area (W x H), padding columns stay untouched
+        assert np.array_equal(hp[pl], ref[pl]), pl

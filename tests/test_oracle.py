@@ -1,0 +1,110 @@
+"""CPU tier: pin the oracle (oracle/liboracle.so) against
+   (a) the committed golden fixtures produced by the unmodified reference (scripts/gen_golden.py), always;
+   (b) the reference itself (oracle/_ref/libffref.so) on fresh random inputs, wherever that library exists."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+import cpulibs as cl
+from cases import SWS_SMALL_CASES, SWS_HASH_CASES, FATE, idct_blocks
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+needs_ref = pytest.mark.skipif(not cl.have_ref(), reason="oracle/_ref not built (no /root/reference here)")
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def test_sws_oracle_vs_golden_small():
+    g = np.load(os.path.join(G, "sws_small.npz"))
+    for i, (w, h, dw, dh, fl, kind) in enumerate(SWS_SMALL_CASES):
+        out = cl.orc_sws(w, h, dw, dh, fl, g[f"c{i}_y"], g[f"c{i}_u"], g[f"c{i}_v"])
+        assert out is not None
+        assert np.array_equal(out, g[f"c{i}_rgb"]), (i, w, h, dw, dh, hex(fl))
+
+
+def test_sws_oracle_vs_golden_hashes():
+    for line in open(os.path.join(G, "sws_hashes.txt")):
+        i, w, h, dw, dh, fl, kind, hin, hout = line.split()
+        i, w, h, dw, dh, fl = map(int, (i, w, h, dw, dh, fl))
+        y, u, v = cl.yuv_frame(w, h, 200 + i, kind)
+        assert sha(np.concatenate([y.ravel(), u.ravel(), v.ravel()])) == hin, "input generator drifted"
+        out = cl.orc_sws(w, h, dw, dh, fl, y, u, v)
+        assert sha(out) == hout, (i, w, h, dw, dh, hex(fl))
+
+
+def test_sws_oracle_colorspace_golden():
+    g = np.load(os.path.join(G, "sws_colorspace.npz"))
+    y, u, v = g["y"], g["u"], g["v"]
+    css = [(1, 0, 1, 0, 0, 1 << 16, 1 << 16), (5, 1, 5, 1, 0, 1 << 16, 1 << 16),
+           (9, 0, 9, 0, 3000, 70000, 80000), (7, 1, 7, 0, -2000, 60000, 50000)]
+    for j, cs in enumerate(css):
+        for k, fl in enumerate([FATE, cl.SWS_BICUBIC]):
+            assert np.array_equal(cl.orc_sws(64, 48, 64, 48, fl, y, u, v, colorspace=cs), g[f"cs{j}_{k}"]), (j, k)
+            assert np.array_equal(cl.orc_sws(64, 48, 96, 80, fl, y, u, v, colorspace=cs), g[f"cs{j}_{k}_s"]), (j, k, "s")
+
+
+def test_idct_oracle_vs_golden():
+    g = np.load(os.path.join(G, "idct.npz"))
+    O = cl.oracle()
+    off = (np.arange(256) * 8).astype(np.int64)
+    for kind in ("dense", "wide", "extreme", "sparse", "dc63", "dconly"):
+        for op in (0, 1, 2):
+            b, de = g[f"{kind}_in"].copy(), g[f"{kind}_dest"].copy()
+            O.orc_idct_batch(op, cl.ptr(b, cl.i16p), 256, cl.ptr(de), 256 * 8, cl.ptr(off, cl.i64p))
+            assert np.array_equal(b if op == 0 else de, g[f"{kind}_op{op}"]), (kind, op)
+
+
+@needs_ref
+@pytest.mark.parametrize("case", [(352, 288, 352, 288, FATE), (352, 288, 352, 288, cl.SWS_BICUBIC),
+                                  (352, 288, 200, 100, FATE), (100, 50, 37, 21, FATE), (352, 288, 640, 360, cl.SWS_BILINEAR),
+                                  (350, 288, 350, 288, cl.SWS_BICUBIC), (352, 288, 300, 200, cl.SWS_BICUBLIN)])
+def test_sws_oracle_vs_reference_live(case):
+    w, h, dw, dh, fl = case
+    for seed, kind in ((1, "random"), (2, "smooth"), (3, "limited")):
+        y, u, v = cl.yuv_frame(w, h, seed, kind, pad=7)
+        a = cl.ref_sws(w, h, dw, dh, fl, y, u, v, dst_pad=5)
+        b = cl.orc_sws(w, h, dw, dh, fl, y, u, v, dst_pad=5)
+        assert np.array_equal(a, b)
+
+
+@needs_ref
+def test_idct_oracle_vs_reference_live():
+    R, O = cl.ref(), cl.oracle()
+    n = 4096
+    off = (np.arange(n) * 8).astype(np.int64)
+    for kind in ("dense", "wide", "extreme", "sparse", "dc63", "dconly"):
+        for op in (0, 1, 2):
+            blk = idct_blocks(kind, n, seed=op + 31)
+            d0 = np.random.default_rng(5).integers(0, 256, (8, n * 8), dtype=np.uint8)
+            b1, b2, d1, d2 = blk.copy(), blk.copy(), d0.copy(), d0.copy()
+            R.ffref_idct_batch(op, cl.ptr(b1, cl.i16p), n, cl.ptr(d1), n * 8, cl.ptr(off, cl.i64p))
+            O.orc_idct_batch(op, cl.ptr(b2, cl.i16p), n, cl.ptr(d2), n * 8, cl.ptr(off, cl.i64p))
+            assert np.array_equal(d1, d2) and (op != 0 or np.array_equal(b1, b2)), (kind, op)
+
+
+def test_host_filter_tables_match_oracle():
+    """The product's host-side filter generation (sws_plan.cpp) against the oracle's, no GPU involved."""
+    import ffmpeg_b200 as fb
+    L, O = fb.lib(), cl.oracle()
+    for (w, h, dw, dh, fl, _k) in SWS_SMALL_CASES + SWS_HASH_CASES + [(3840, 2160, 3840, 2160, FATE, ""), (3840, 2160, 1920, 1080, FATE, "")]:
+        ctx = O.orc_sws_open(w, h, dw, dh, fl)
+        assert ctx
+        oi = np.zeros(16, np.int32)
+        O.orc_sws_info(ctx, cl.ptr(oi, cl.i32p))
+        for which in range(4):
+            pi = np.zeros(16, np.int32)
+            assert L.b200_sws_plan_probe(w, h, dw, dh, fl, which, None, None, 0, cl.ptr(pi, cl.i32p)) >= 0
+            assert list(pi) == list(oi)
+            size, cnt = int(pi[which]), [dw, int(pi[6]), dh, int(pi[7])][which]
+            if size == 0:
+                continue
+            f1, p1 = np.zeros(cnt * size, np.int16), np.zeros(cnt, np.int32)
+            f2, p2 = f1.copy(), p1.copy()
+            L.b200_sws_plan_probe(w, h, dw, dh, fl, which, cl.ptr(f1, cl.i16p), cl.ptr(p1, cl.i32p), cnt, None)
+            O.orc_sws_get_filter(ctx, which, cl.ptr(f2, cl.i16p), cl.ptr(p2, cl.i32p), cnt)
+            assert np.array_equal(f1, f2) and np.array_equal(p1, p2), (w, h, dw, dh, hex(fl), which)
+        O.orc_sws_close(ctx)

