@@ -16,12 +16,14 @@
 #include <vector>
 #include <cstring>
 #include <new>
+#include <cstdlib>
 
 // ------------------------------------------------------------------------------------------------ device helpers
 struct SwsDevTables {            // device copies of the vertical banks and the per-line writer choice
     const int16_t *vLum; const int32_t *vLumPos; int vLumSize;
     const int16_t *vChr; const int32_t *vChrPos; int vChrSize;
     const int32_t *rowMode;
+    const int32_t *vLum2, *vChr2;     // vertical banks with tap pairs packed (lo16 = tap 2j, hi16 = tap 2j+1 or 0)
     const int16_t *hLum; const int32_t *hLumPos; int hLumSize;
     const int16_t *hChr; const int32_t *hChrPos; int hChrSize;
 };
@@ -34,7 +36,13 @@ struct SwsFrameArgs {
     int srcH, chrSrcH, dstW, dstH, chrDstW;
 };
 
-__device__ __forceinline__ int clamp_u8(int v) { return min(max(v, 0), 255); }
+
+__device__ __forceinline__ int clamp_u8(int v) { return __vimin_s32_relu(v, 255); }   // one VIMNMX.RELU
+
+__device__ __forceinline__ int dp2a_lo_su(int a, unsigned b, int c)   // c + a.h0*b.b0 + a.h1*b.b1 (s16 x u8)
+{ int d; asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+__device__ __forceinline__ int dp2a_hi_su(int a, unsigned b, int c)   // c + a.h0*b.b2 + a.h1*b.b3
+{ int d; asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
 
 // colour constants per chroma sample: A_c such that channel = clip_u8((A_c + Y*cy) >> 16)
 struct ChromaBase { int r, g, b; };
@@ -48,106 +56,87 @@ __device__ __forceinline__ ChromaBase chroma_base(const SwsColorConst &c, int U,
     return o;
 }
 
-// writes 2 pixels (6 bytes) worth of channels into out[0..5]
-__device__ __forceinline__ void pair_rgb(const SwsColorConst &c, const ChromaBase &cb, int Y1, int Y2, int *out)
+// Two pixels sharing one chroma sample -> three words holding (r0,g0) (b0,r1) (g1,b1) as clamped s16x2 (bytes 0 and 2).
+// (A + Y*cy) >> 16 is the high half of the 32-bit sum: PRMT picks the high halves, VIMNMX.S16x2.RELU clamps both to 0..255.
+__device__ __forceinline__ void pair_rgb_packed(int cy, const ChromaBase &cb, int Y0, int Y1, unsigned *m)
 {
-    const int t1 = Y1 * c.cy, t2 = Y2 * c.cy;
-    out[0] = clamp_u8((cb.r + t1) >> 16); out[1] = clamp_u8((cb.g + t1) >> 16); out[2] = clamp_u8((cb.b + t1) >> 16);
-    out[3] = clamp_u8((cb.r + t2) >> 16); out[4] = clamp_u8((cb.g + t2) >> 16); out[5] = clamp_u8((cb.b + t2) >> 16);
+    const int r0 = Y0 * cy + cb.r, g0 = Y0 * cy + cb.g, b0 = Y0 * cy + cb.b;
+    const int r1 = Y1 * cy + cb.r, g1 = Y1 * cy + cb.g, b1 = Y1 * cy + cb.b;
+    m[0] = __vimin_s16x2_relu(__byte_perm(r0, g0, 0x7632), 0x00ff00ffu);
+    m[1] = __vimin_s16x2_relu(__byte_perm(b0, r1, 0x7632), 0x00ff00ffu);
+    m[2] = __vimin_s16x2_relu(__byte_perm(g1, b1, 0x7632), 0x00ff00ffu);
 }
-
-__device__ __forceinline__ unsigned pack4(int a, int b, int c, int d)
+// 16 px = 8 pairs = 24 packed words -> 12 output words (48 bytes), stored as three 128-bit words
+__device__ __forceinline__ void store_packed48(uint8_t *dst, const unsigned *m)
 {
-    return (unsigned)a | ((unsigned)b << 8) | ((unsigned)c << 16) | ((unsigned)d << 24);
-}
-
-// store 16 px (48 channel values) starting at dst; vector path when `vec`, else byte stores of `npx` pixels
-__device__ __forceinline__ void store_px16(uint8_t *dst, const int *ch, bool vec, int npx)
-{
-    if (vec) {
-        uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+    uint4 *d4 = reinterpret_cast<uint4 *>(dst);
 #pragma unroll
-        for (int k = 0; k < 3; k++) {
-            uint4 v;
-            v.x = pack4(ch[16 * k + 0], ch[16 * k + 1], ch[16 * k + 2], ch[16 * k + 3]);
-            v.y = pack4(ch[16 * k + 4], ch[16 * k + 5], ch[16 * k + 6], ch[16 * k + 7]);
-            v.z = pack4(ch[16 * k + 8], ch[16 * k + 9], ch[16 * k + 10], ch[16 * k + 11]);
-            v.w = pack4(ch[16 * k + 12], ch[16 * k + 13], ch[16 * k + 14], ch[16 * k + 15]);
-            d4[k] = v;
-        }
-    } else {
-        for (int i = 0; i < npx * 3; i++) dst[i] = (uint8_t)ch[i];
+    for (int k = 0; k < 3; k++) {
+        uint4 v;
+        v.x = __byte_perm(m[8 * k + 0], m[8 * k + 1], 0x6420);
+        v.y = __byte_perm(m[8 * k + 2], m[8 * k + 3], 0x6420);
+        v.z = __byte_perm(m[8 * k + 4], m[8 * k + 5], 0x6420);
+        v.w = __byte_perm(m[8 * k + 6], m[8 * k + 7], 0x6420);
+        d4[k] = v;
+    }
+}
+__device__ __forceinline__ int byte_of(unsigned w, int k) { return (int)__byte_perm(w, 0, 0x4440 | k); }
+
+// scalar writer used by the slow (edge / unaligned / int16-source) kernels
+__device__ __forceinline__ void put_pair_bytes(uint8_t *d, const SwsColorConst &c, const ChromaBase &cb, int Y0, int Y1, bool second)
+{
+    const int t0 = Y0 * c.cy;
+    d[0] = (uint8_t)clamp_u8((cb.r + t0) >> 16); d[1] = (uint8_t)clamp_u8((cb.g + t0) >> 16); d[2] = (uint8_t)clamp_u8((cb.b + t0) >> 16);
+    if (second) {
+        const int t1 = Y1 * c.cy;
+        d[3] = (uint8_t)clamp_u8((cb.r + t1) >> 16); d[4] = (uint8_t)clamp_u8((cb.g + t1) >> 16); d[5] = (uint8_t)clamp_u8((cb.b + t1) >> 16);
     }
 }
 
-__device__ __forceinline__ void unpack16(const uint4 &q, int *o)
+// ------------------------------------------------------------------------------------------------ kernel: unscaled LUT path (fast)
+// yuv2rgb_c_24_rgb: chroma sample (x>>1, y>>1), no interpolation.  One thread = 16 px x 2 lines (one chroma line):
+// 2 x LDG.128 luma + 2 x LDG.64 chroma in, 6 x STG.128 out.  Grid: x over 16-px groups, y over line pairs, z over frames.
+__global__ void __launch_bounds__(128)
+sws_unscaled_kernel(SwsFrameArgs a, SwsColorConst c, int ngroups)
 {
-    const unsigned w[4] = { q.x, q.y, q.z, q.w };
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        o[4 * k + 0] = w[k] & 0xff; o[4 * k + 1] = (w[k] >> 8) & 0xff;
-        o[4 * k + 2] = (w[k] >> 16) & 0xff; o[4 * k + 3] = w[k] >> 24;
-    }
-}
-__device__ __forceinline__ void unpack8(const uint2 &q, int *o)
-{
-    o[0] = q.x & 0xff; o[1] = (q.x >> 8) & 0xff; o[2] = (q.x >> 16) & 0xff; o[3] = q.x >> 24;
-    o[4] = q.y & 0xff; o[5] = (q.y >> 8) & 0xff; o[6] = (q.y >> 16) & 0xff; o[7] = q.y >> 24;
-}
-
-// 16 consecutive u8 samples (or fewer at the right edge: missing ones read as 0)
-__device__ __forceinline__ void load_u8x16(const uint8_t *p, int avail, bool vec, int *o)
-{
-    if (vec && avail >= 16) {
-        unpack16(__ldg(reinterpret_cast<const uint4 *>(p)), o);
-    } else {
-#pragma unroll
-        for (int i = 0; i < 16; i++) o[i] = i < avail ? (int)__ldg(p + i) : 0;
-    }
-}
-__device__ __forceinline__ void load_u8x8(const uint8_t *p, int avail, bool vec, int *o)
-{
-    if (vec && avail >= 8) {
-        unpack8(__ldg(reinterpret_cast<const uint2 *>(p)), o);
-    } else {
-#pragma unroll
-        for (int i = 0; i < 8; i++) o[i] = i < avail ? (int)__ldg(p + i) : 0;
-    }
-}
-__device__ __forceinline__ void load_s16(const int16_t *p, int n, int avail, int *o)
-{
-    for (int i = 0; i < n; i++) o[i] = i < avail ? (int)__ldg(p + i) : 0;
-}
-
-// ------------------------------------------------------------------------------------------------ kernel: unscaled LUT path
-// One thread = 16 px x 2 lines (one chroma line).  Grid: x over 16-px groups, y over line pairs, z over frames.
-__global__ void __launch_bounds__(256)
-sws_unscaled_kernel(SwsFrameArgs a, SwsColorConst c, int wpix /* pixels the reference writes per line */, int vecOK)
-{
-    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    const int xg = blockIdx.x * blockDim.x + threadIdx.x;
+    if (xg >= ngroups) return;
     const int row = blockIdx.y * 2;
-    if (x0 >= wpix) return;
     const long long f = blockIdx.z;
-    const uint8_t *py = a.y + f * a.yfs + (long long)row * a.ys + x0;
-    const uint8_t *pu = a.u + f * a.ufs + (long long)(row >> 1) * a.us + (x0 >> 1);
-    const uint8_t *pv = a.v + f * a.vfs + (long long)(row >> 1) * a.vs + (x0 >> 1);
-    uint8_t *d0 = a.dst + f * a.dfs + (long long)row * a.ds + (long long)x0 * 3;
-    const int npx = min(16, wpix - x0);            // even by construction
-    const bool vec = vecOK && npx == 16;
-    int U[8], V[8], Y0[16], Y1[16];
-    load_u8x8(pu, npx >> 1, vec, U);
-    load_u8x8(pv, npx >> 1, vec, V);
-    load_u8x16(py, npx, vec, Y0);
-    load_u8x16(py + a.ys, npx, vec, Y1);
-    int ch0[48], ch1[48];
+    const uint8_t *py = a.y + f * a.yfs + (long long)row * a.ys + xg * 16;
+    const uint2 u = __ldg(reinterpret_cast<const uint2 *>(a.u + f * a.ufs + (long long)(row >> 1) * a.us + xg * 8));
+    const uint2 v = __ldg(reinterpret_cast<const uint2 *>(a.v + f * a.vfs + (long long)(row >> 1) * a.vs + xg * 8));
+    const uint4 y0 = __ldg(reinterpret_cast<const uint4 *>(py));
+    const uint4 y1 = __ldg(reinterpret_cast<const uint4 *>(py + a.ys));
+    const unsigned uw[2] = { u.x, u.y }, vw[2] = { v.x, v.y };
+    const unsigned y0w[4] = { y0.x, y0.y, y0.z, y0.w }, y1w[4] = { y1.x, y1.y, y1.z, y1.w };
+    unsigned m0[24], m1[24];
 #pragma unroll
     for (int i = 0; i < 8; i++) {
-        const ChromaBase cb = chroma_base(c, U[i], V[i]);
-        pair_rgb(c, cb, Y0[2 * i], Y0[2 * i + 1], ch0 + 6 * i);
-        pair_rgb(c, cb, Y1[2 * i], Y1[2 * i + 1], ch1 + 6 * i);
+        const ChromaBase cb = chroma_base(c, byte_of(uw[i >> 2], i & 3), byte_of(vw[i >> 2], i & 3));
+        const int w = i >> 1, k = (i & 1) * 2;
+        pair_rgb_packed(c.cy, cb, byte_of(y0w[w], k), byte_of(y0w[w], k + 1), m0 + 3 * i);
+        pair_rgb_packed(c.cy, cb, byte_of(y1w[w], k), byte_of(y1w[w], k + 1), m1 + 3 * i);
     }
-    store_px16(d0, ch0, vec, npx);
-    store_px16(d0 + a.ds, ch1, vec, npx);
+    uint8_t *d0 = a.dst + f * a.dfs + (long long)row * a.ds + (long long)xg * 48;
+    store_packed48(d0, m0);
+    store_packed48(d0 + a.ds, m1);
+}
+
+// slow variant: one thread = one pixel pair x 2 lines, any alignment; covers pairs [p0, p1)
+__global__ void __launch_bounds__(128)
+sws_unscaled_slow_kernel(SwsFrameArgs a, SwsColorConst c, int p0, int p1)
+{
+    const int p = p0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= p1) return;
+    const int row = blockIdx.y * 2;
+    const long long f = blockIdx.z;
+    const uint8_t *py = a.y + f * a.yfs + (long long)row * a.ys + 2 * p;
+    const int U = a.u[f * a.ufs + (long long)(row >> 1) * a.us + p], V = a.v[f * a.vfs + (long long)(row >> 1) * a.vs + p];
+    const ChromaBase cb = chroma_base(c, U, V);
+    uint8_t *d = a.dst + f * a.dfs + (long long)row * a.ds + (long long)p * 6;
+    put_pair_bytes(d, c, cb, py[0], py[1], true);
+    put_pair_bytes(d + a.ds, c, cb, py[a.ys], py[a.ys + 1], true);
 }
 
 // ------------------------------------------------------------------------------------------------ kernel: horizontal FIR
@@ -166,117 +155,153 @@ sws_hscale_kernel(const uint8_t *src, long long sstride, long long sfs, int16_t 
     dst[(long long)blockIdx.z * dfs + (long long)blockIdx.y * dstW + i] = (int16_t)min(acc, 32767);
 }
 
-// ------------------------------------------------------------------------------------------------ kernel: vertical FIR + rgb24 writer
-// SRC8: the horizontal pass is the identity, so taps are read straight from the u8 planes and widened (<<7) here,
-//       exactly what hScale8To15_c produces for coefficient 1<<14.  Otherwise taps come from int16 line planes.
+// ------------------------------------------------------------------------------------------------ kernel: vertical FIR + rgb24 (fast)
+// Same-size conversion with the reference's scaler flags (the FATE path): the horizontal pass is the identity, so the
+// vertical taps are read straight from the u8 planes.  Only the general `_X` writer (yuv2rgb_X_c_template,
+// output.c:1789-1840) is handled here; lines that the reference sends to the `_1`/`_2` writers go to the slow kernel.
+//   Y = (2^18 + sum_j (y_j << 7) * lf_j) >> 19  ==  (2^11 + sum_j y_j * lf_j) >> 12   (same for U, V)
+// which holds while the 32-bit sum does not wrap (the host checks sum |coef| per line).  Two taps are folded per
+// IDP.2A (s16 coefficient pair x u8 sample pair) after interleaving two source lines with PRMT.
+// LUMID: the luma bank is a single tap of 4096 on every line, so Y is the source byte itself.
 // One thread = 16 px of one output line.  Grid: x over 16-px groups, y over lines, z over frames.
-template <bool SRC8>
-__global__ void __launch_bounds__(256)
-sws_vscale_rgb24_kernel(SwsFrameArgs a, SwsDevTables t, SwsColorConst c, int vecOK)
+// chroma taps of two source lines folded into 8 accumulators (4 PRMT + 8 IDP.2A per plane)
+__device__ __forceinline__ void fold2(int k2, const uint2 &r0, const uint2 &r1, int *acc)
 {
-    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    unsigned lo = __byte_perm(r0.x, r1.x, 0x5140), hi = __byte_perm(r0.x, r1.x, 0x7362);
+    acc[0] = dp2a_lo_su(k2, lo, acc[0]); acc[1] = dp2a_hi_su(k2, lo, acc[1]); acc[2] = dp2a_lo_su(k2, hi, acc[2]); acc[3] = dp2a_hi_su(k2, hi, acc[3]);
+    lo = __byte_perm(r0.y, r1.y, 0x5140); hi = __byte_perm(r0.y, r1.y, 0x7362);
+    acc[4] = dp2a_lo_su(k2, lo, acc[4]); acc[5] = dp2a_hi_su(k2, lo, acc[5]); acc[6] = dp2a_lo_su(k2, hi, acc[6]); acc[7] = dp2a_hi_su(k2, hi, acc[7]);
+}
+
+// CFS4: the chroma bank has exactly 4 taps (bicubic 2x vertical chroma up-sampling, the BASELINE case): fully unrolled.
+// Line offsets are 32-bit (the host guarantees |stride| * lines < 2^31); coefficient pairs come pre-packed (t.vChr2/vLum2).
+template <bool LUMID, bool CFS4>
+__global__ void __launch_bounds__(128, 12)
+sws_vscale_rgb24_fast_kernel(SwsFrameArgs a, SwsDevTables t, SwsColorConst c, int ngroups)
+{
+    const int xg = blockIdx.x * blockDim.x + threadIdx.x;
+    if (xg >= ngroups) return;
     const int dy = blockIdx.y;
-    if (x0 >= a.dstW) return;
     const long long f = blockIdx.z;
-    const int npx = min(16, a.dstW - x0);          // dstW is even on this path
-    const int nch = (npx + 1) >> 1;
-    const bool vec = vecOK && npx == 16;
+    const int lfs = t.vLumSize, cfs = CFS4 ? 4 : t.vChrSize;
+    const int lp = (lfs + 1) >> 1, cp = (cfs + 1) >> 1;
+    const int firstLum = max(1 - lfs, __ldg(t.vLumPos + dy));
+    const int firstChr = max(1 - cfs, __ldg(t.vChrPos + dy));
+    const uint8_t *ub = a.u + f * a.ufs + xg * 8, *vb = a.v + f * a.vfs + xg * 8, *yb = a.y + f * a.yfs + xg * 16;
+    const int us = (int)a.us, vs = (int)a.vs, ys = (int)a.ys, chmax = a.chrSrcH - 1;
+
+    int aU[8], aV[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) aU[i] = aV[i] = 1 << 11;
+    if (CFS4) {
+        const int2 k = __ldg(reinterpret_cast<const int2 *>(t.vChr2 + 2 * dy));
+        const int l0 = min(max(firstChr, 0), chmax), l1 = min(max(firstChr + 1, 0), chmax);
+        const int l2 = min(max(firstChr + 2, 0), chmax), l3 = min(max(firstChr + 3, 0), chmax);
+        const uint2 u0 = __ldg(reinterpret_cast<const uint2 *>(ub + l0 * us)), u1 = __ldg(reinterpret_cast<const uint2 *>(ub + l1 * us));
+        const uint2 u2 = __ldg(reinterpret_cast<const uint2 *>(ub + l2 * us)), u3 = __ldg(reinterpret_cast<const uint2 *>(ub + l3 * us));
+        const uint2 v0 = __ldg(reinterpret_cast<const uint2 *>(vb + l0 * vs)), v1 = __ldg(reinterpret_cast<const uint2 *>(vb + l1 * vs));
+        const uint2 v2 = __ldg(reinterpret_cast<const uint2 *>(vb + l2 * vs)), v3 = __ldg(reinterpret_cast<const uint2 *>(vb + l3 * vs));
+        fold2(k.x, u0, u1, aU); fold2(k.y, u2, u3, aU);
+        fold2(k.x, v0, v1, aV); fold2(k.y, v2, v3, aV);
+    } else {
+        for (int j = 0; j < cp; j++) {
+            const int k2 = __ldg(t.vChr2 + (long long)dy * cp + j);
+            const int l0 = min(max(firstChr + 2 * j, 0), chmax), l1 = min(max(firstChr + 2 * j + 1, 0), chmax);
+            const uint2 u0 = __ldg(reinterpret_cast<const uint2 *>(ub + l0 * us)), u1 = __ldg(reinterpret_cast<const uint2 *>(ub + l1 * us));
+            const uint2 v0 = __ldg(reinterpret_cast<const uint2 *>(vb + l0 * vs)), v1 = __ldg(reinterpret_cast<const uint2 *>(vb + l1 * vs));
+            fold2(k2, u0, u1, aU);
+            fold2(k2, v0, v1, aV);
+        }
+    }
+
+    int Y[16];
+    if (LUMID) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4 *>(yb + min(max(firstLum, 0), a.srcH - 1) * ys));
+        const unsigned w[4] = { q.x, q.y, q.z, q.w };
+#pragma unroll
+        for (int i = 0; i < 16; i++) Y[i] = byte_of(w[i >> 2], i & 3);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; i++) Y[i] = 1 << 11;
+        for (int j = 0; j < lp; j++) {
+            const int k2 = __ldg(t.vLum2 + (long long)dy * lp + j);
+            const int l0 = min(max(firstLum + 2 * j, 0), a.srcH - 1), l1 = min(max(firstLum + 2 * j + 1, 0), a.srcH - 1);
+            const uint4 q0 = __ldg(reinterpret_cast<const uint4 *>(yb + l0 * ys)), q1 = __ldg(reinterpret_cast<const uint4 *>(yb + l1 * ys));
+            const uint2 a0 = make_uint2(q0.x, q0.y), a1 = make_uint2(q1.x, q1.y), b0 = make_uint2(q0.z, q0.w), b1 = make_uint2(q1.z, q1.w);
+            fold2(k2, a0, a1, Y);
+            fold2(k2, b0, b1, Y + 8);
+        }
+#pragma unroll
+        for (int i = 0; i < 16; i++) Y[i] >>= 12;
+    }
+
+    unsigned m[24];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const ChromaBase cb = chroma_base(c, aU[i] >> 12, aV[i] >> 12);
+        pair_rgb_packed(c.cy, cb, Y[2 * i], Y[2 * i + 1], m + 3 * i);
+    }
+    store_packed48(a.dst + f * a.dfs + (long long)dy * (int)a.ds + xg * 48, m);
+}
+
+// ------------------------------------------------------------------------------------------------ kernel: vertical FIR + rgb24 (slow, general)
+// All three writers (_X, _1, _2), u8 (identity horizontal pass) or int16 line-plane sources, any alignment.
+// One thread = one pixel pair of one output line; covers pairs [p0, p1).  Grid: x over pairs, y over lines, z over frames.
+template <bool SRC8>
+__global__ void __launch_bounds__(128)
+sws_vscale_rgb24_slow_kernel(SwsFrameArgs a, SwsDevTables t, SwsColorConst c, int p0, int p1)
+{
+    const int p = p0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= p1) return;
+    const int dy = blockIdx.y;
+    const long long f = blockIdx.z;
     const int lfs = t.vLumSize, cfs = t.vChrSize;
     const int16_t *lf = t.vLum + (long long)dy * lfs, *cf = t.vChr + (long long)dy * cfs;
     const int firstLum = max(1 - lfs, __ldg(t.vLumPos + dy));
     const int firstChr = max(1 - cfs, __ldg(t.vChrPos + dy));
     const int mode = __ldg(t.rowMode + 4 * dy), yalpha = __ldg(t.rowMode + 4 * dy + 1), uvalpha = __ldg(t.rowMode + 4 * dy + 2);
-    const uint8_t *ybase = a.y + f * a.yfs, *ubase = a.u + f * a.ufs, *vbase = a.v + f * a.vfs;
-
-    auto lum = [&](int line, int *o) {
+    const bool second = 2 * p + 1 < a.dstW;
+    auto lum = [&](int line, int x) -> int {
         line = min(max(line, 0), a.srcH - 1);
-        if (SRC8) {
-            load_u8x16(ybase + line * a.ys + x0, npx, vec, o);
-#pragma unroll
-            for (int i = 0; i < 16; i++) o[i] <<= 7;
-        } else {
-            load_s16(reinterpret_cast<const int16_t *>(ybase + line * a.ys) + x0, 16, npx, o);
-        }
+        const uint8_t *b = a.y + f * a.yfs + (long long)line * a.ys;
+        return SRC8 ? ((int)b[x] << 7) : (int)reinterpret_cast<const int16_t *>(b)[x];
     };
-    auto chr = [&](const uint8_t *base, long long stride, int line, int *o) {
+    auto chr = [&](const uint8_t *base, long long fs_, long long stride, int line) -> int {
         line = min(max(line, 0), a.chrSrcH - 1);
-        if (SRC8) {
-            load_u8x8(base + line * stride + (x0 >> 1), nch, vec, o);
-#pragma unroll
-            for (int i = 0; i < 8; i++) o[i] <<= 7;
-        } else {
-            load_s16(reinterpret_cast<const int16_t *>(base + line * stride) + (x0 >> 1), 8, nch, o);
-        }
+        const uint8_t *b = base + f * fs_ + (long long)line * stride;
+        return SRC8 ? ((int)b[p] << 7) : (int)reinterpret_cast<const int16_t *>(b)[p];
     };
-
-    int Y[16], U[8], V[8], s[16];
+    const int x0 = 2 * p, x1 = second ? 2 * p + 1 : 2 * p;
+    int Y0, Y1, U, V;
     if (mode == 1) {                                   // yuv2rgb_1_c_template, output.c:1883-1939
-        lum(firstLum, s);
-#pragma unroll
-        for (int i = 0; i < 16; i++) Y[i] = (s[i] + 64) >> 7;
+        Y0 = (lum(firstLum, x0) + 64) >> 7; Y1 = (lum(firstLum, x1) + 64) >> 7;
         if (!uvalpha) {
-            chr(ubase, a.us, firstChr, s);
-#pragma unroll
-            for (int i = 0; i < 8; i++) U[i] = (s[i] + 64) >> 7;
-            chr(vbase, a.vs, firstChr, s);
-#pragma unroll
-            for (int i = 0; i < 8; i++) V[i] = (s[i] + 64) >> 7;
+            U = (chr(a.u, a.ufs, a.us, firstChr) + 64) >> 7; V = (chr(a.v, a.vfs, a.vs, firstChr) + 64) >> 7;
         } else {
             const int a1 = 4096 - uvalpha;
-            int s1[8];
-            chr(ubase, a.us, firstChr, s); chr(ubase, a.us, firstChr + 1, s1);
-#pragma unroll
-            for (int i = 0; i < 8; i++) U[i] = (s[i] * a1 + s1[i] * uvalpha + (128 << 11)) >> 19;
-            chr(vbase, a.vs, firstChr, s); chr(vbase, a.vs, firstChr + 1, s1);
-#pragma unroll
-            for (int i = 0; i < 8; i++) V[i] = (s[i] * a1 + s1[i] * uvalpha + (128 << 11)) >> 19;
+            U = (chr(a.u, a.ufs, a.us, firstChr) * a1 + chr(a.u, a.ufs, a.us, firstChr + 1) * uvalpha + (128 << 11)) >> 19;
+            V = (chr(a.v, a.vfs, a.vs, firstChr) * a1 + chr(a.v, a.vfs, a.vs, firstChr + 1) * uvalpha + (128 << 11)) >> 19;
         }
     } else if (mode == 2) {                            // yuv2rgb_2_c_template, output.c:1843-1880
         const int ya1 = 4096 - yalpha, ua1 = 4096 - uvalpha;
-        int s1[16];
-        lum(firstLum, s); lum(firstLum + 1, s1);
-#pragma unroll
-        for (int i = 0; i < 16; i++) Y[i] = (s[i] * ya1 + s1[i] * yalpha) >> 19;
-        chr(ubase, a.us, firstChr, s); chr(ubase, a.us, firstChr + 1, s1);
-#pragma unroll
-        for (int i = 0; i < 8; i++) U[i] = (s[i] * ua1 + s1[i] * uvalpha) >> 19;
-        chr(vbase, a.vs, firstChr, s); chr(vbase, a.vs, firstChr + 1, s1);
-#pragma unroll
-        for (int i = 0; i < 8; i++) V[i] = (s[i] * ua1 + s1[i] * uvalpha) >> 19;
+        Y0 = (lum(firstLum, x0) * ya1 + lum(firstLum + 1, x0) * yalpha) >> 19;
+        Y1 = (lum(firstLum, x1) * ya1 + lum(firstLum + 1, x1) * yalpha) >> 19;
+        U = (chr(a.u, a.ufs, a.us, firstChr) * ua1 + chr(a.u, a.ufs, a.us, firstChr + 1) * uvalpha) >> 19;
+        V = (chr(a.v, a.vfs, a.vs, firstChr) * ua1 + chr(a.v, a.vfs, a.vs, firstChr + 1) * uvalpha) >> 19;
     } else {                                           // yuv2rgb_X_c_template, output.c:1789-1840 (unsigned wrap-around sums)
-        unsigned ay[16], au[8], av[8];
-#pragma unroll
-        for (int i = 0; i < 16; i++) ay[i] = 1u << 18;
-#pragma unroll
-        for (int i = 0; i < 8; i++) au[i] = av[i] = 1u << 18;
+        unsigned s0 = 1u << 18, s1 = 1u << 18, su = 1u << 18, sv = 1u << 18;
         for (int j = 0; j < lfs; j++) {
             const unsigned k = (unsigned)(int)__ldg(lf + j);
-            lum(firstLum + j, s);
-#pragma unroll
-            for (int i = 0; i < 16; i++) ay[i] += (unsigned)s[i] * k;
+            s0 += (unsigned)lum(firstLum + j, x0) * k; s1 += (unsigned)lum(firstLum + j, x1) * k;
         }
         for (int j = 0; j < cfs; j++) {
             const unsigned k = (unsigned)(int)__ldg(cf + j);
-            chr(ubase, a.us, firstChr + j, s);
-#pragma unroll
-            for (int i = 0; i < 8; i++) au[i] += (unsigned)s[i] * k;
-            chr(vbase, a.vs, firstChr + j, s);
-#pragma unroll
-            for (int i = 0; i < 8; i++) av[i] += (unsigned)s[i] * k;
+            su += (unsigned)chr(a.u, a.ufs, a.us, firstChr + j) * k; sv += (unsigned)chr(a.v, a.vfs, a.vs, firstChr + j) * k;
         }
-#pragma unroll
-        for (int i = 0; i < 16; i++) Y[i] = (int)ay[i] >> 19;
-#pragma unroll
-        for (int i = 0; i < 8; i++) { U[i] = (int)au[i] >> 19; V[i] = (int)av[i] >> 19; }
+        Y0 = (int)s0 >> 19; Y1 = (int)s1 >> 19; U = (int)su >> 19; V = (int)sv >> 19;
     }
-
-    int ch[48];
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-        const ChromaBase cb = chroma_base(c, U[i], V[i]);
-        pair_rgb(c, cb, Y[2 * i], Y[2 * i + 1], ch + 6 * i);
-    }
-    store_px16(a.dst + f * a.dfs + (long long)dy * a.ds + (long long)x0 * 3, ch, vec, npx);
+    const ChromaBase cb = chroma_base(c, U, V);
+    put_pair_bytes(a.dst + f * a.dfs + (long long)dy * a.ds + (long long)p * 6, c, cb, Y0, Y1, second);
 }
 
 // ------------------------------------------------------------------------------------------------ kernel: full-chroma writer
@@ -343,7 +368,9 @@ struct B200SwsContext {
     SwsPlan plan;
     void *tables = nullptr;          // one device allocation holding all banks
     SwsDevTables dt{};
-    bool h_identity = false;         // both horizontal banks are the identity -> SRC8 kernels
+    bool h_identity = false;         // both horizontal banks are the identity -> u8-source kernels
+    bool fast_x = false;             // every line uses the _X writer and no 32-bit sum can wrap -> vector kernel
+    bool lum_identity = false;       // vertical luma bank is a single tap of 4096 on every line
     // intermediate int16 line planes for the scaled path (grown on demand, per batch)
     void *mid = nullptr; size_t mid_bytes = 0;
 };
@@ -360,6 +387,20 @@ static int upload_tables(B200SwsContext *c)
     size_t o_vc = off;  off += al(p.vChr.coef.size() * 2);
     size_t o_vcp = off; off += al(p.vChr.pos.size() * 4);
     size_t o_rm = off;  off += al(p.rowMode.size() * 4);
+    auto pack_pairs = [](const SwsFilterBank &b) {
+        const int np = (b.size + 1) / 2;
+        std::vector<int32_t> o((size_t)b.n * np);
+        for (int i = 0; i < b.n; i++)
+            for (int j = 0; j < np; j++) {
+                const uint32_t lo = (uint16_t)b.coef[(size_t)i * b.size + 2 * j];
+                const uint32_t hi = 2 * j + 1 < b.size ? (uint16_t)b.coef[(size_t)i * b.size + 2 * j + 1] : 0;
+                o[(size_t)i * np + j] = (int32_t)(lo | (hi << 16));
+            }
+        return o;
+    };
+    const std::vector<int32_t> vl2 = pack_pairs(p.vLum), vc2 = pack_pairs(p.vChr);
+    size_t o_vl2 = off; off += al(vl2.size() * 4);
+    size_t o_vc2 = off; off += al(vc2.size() * 4);
     size_t o_hl = off;  off += al(p.hLum.coef.size() * 2);
     size_t o_hlp = off; off += al(p.hLum.pos.size() * 4);
     size_t o_hc = off;  off += al(p.hChr.coef.size() * 2);
@@ -370,6 +411,8 @@ static int upload_tables(B200SwsContext *c)
     memcpy(&host[o_vc], p.vChr.coef.data(), p.vChr.coef.size() * 2);
     memcpy(&host[o_vcp], p.vChr.pos.data(), p.vChr.pos.size() * 4);
     memcpy(&host[o_rm], p.rowMode.data(), p.rowMode.size() * 4);
+    memcpy(&host[o_vl2], vl2.data(), vl2.size() * 4);
+    memcpy(&host[o_vc2], vc2.data(), vc2.size() * 4);
     memcpy(&host[o_hl], p.hLum.coef.data(), p.hLum.coef.size() * 2);
     memcpy(&host[o_hlp], p.hLum.pos.data(), p.hLum.pos.size() * 4);
     memcpy(&host[o_hc], p.hChr.coef.data(), p.hChr.coef.size() * 2);
@@ -380,9 +423,20 @@ static int upload_tables(B200SwsContext *c)
     c->dt.vLum = (const int16_t *)(b + o_vl); c->dt.vLumPos = (const int32_t *)(b + o_vlp); c->dt.vLumSize = p.vLum.size;
     c->dt.vChr = (const int16_t *)(b + o_vc); c->dt.vChrPos = (const int32_t *)(b + o_vcp); c->dt.vChrSize = p.vChr.size;
     c->dt.rowMode = (const int32_t *)(b + o_rm);
+    c->dt.vLum2 = (const int32_t *)(b + o_vl2); c->dt.vChr2 = (const int32_t *)(b + o_vc2);
     c->dt.hLum = (const int16_t *)(b + o_hl); c->dt.hLumPos = (const int32_t *)(b + o_hlp); c->dt.hLumSize = p.hLum.size;
     c->dt.hChr = (const int16_t *)(b + o_hc); c->dt.hChrPos = (const int32_t *)(b + o_hcp); c->dt.hChrSize = p.hChr.size;
     c->h_identity = p.chrDstHSub == 1 && p.hLum.identity() && p.hChr.identity();
+    c->fast_x = c->h_identity;
+    c->lum_identity = p.vLum.size == 1;
+    for (int y = 0; y < p.dstH && c->fast_x; y++) {
+        if (p.rowMode[(size_t)y * 4] != 0) c->fast_x = false;
+        long long sl = 0, sc = 0;
+        for (int j = 0; j < p.vLum.size; j++) sl += std::abs((int)p.vLum.coef[(size_t)y * p.vLum.size + j]);
+        for (int j = 0; j < p.vChr.size; j++) sc += std::abs((int)p.vChr.coef[(size_t)y * p.vChr.size + j]);
+        if (sl > 60000 || sc > 60000) c->fast_x = false;         // (2^18 + 32640 * sum|coef|) must stay below 2^31
+        if (p.vLum.size != 1 || p.vLum.coef[y] != 4096) c->lum_identity = false;
+    }
     return 0;
 }
 
@@ -492,13 +546,37 @@ static int launch_batch(B200SwsContext *c, cudaStream_t stream, const uint8_t *c
         if (p.unscaled_lut) {
             const int wpix = ((p.dstW >> 3) << 3) + (p.dstW & 4) + (p.dstW & 2);
             if (wpix == 0) continue;
-            dim3 block(128), grid(b200_ceil_div(b200_ceil_div(wpix, 16), 128), p.dstH / 2, nf);
-            sws_unscaled_kernel<<<grid, block, 0, stream>>>(b, p.color, wpix, vecOK);
-            B200_LAUNCHED();
+            const int ngroups = vecOK ? wpix / 16 : 0;
+            if (ngroups) {
+                dim3 block(128), grid(b200_ceil_div(ngroups, 128), p.dstH / 2, nf);
+                sws_unscaled_kernel<<<grid, block, 0, stream>>>(b, p.color, ngroups);
+                B200_LAUNCHED();
+            }
+            const int p0 = ngroups * 8, p1 = wpix / 2;
+            if (p1 > p0) {
+                dim3 block(128), grid(b200_ceil_div(p1 - p0, 128), p.dstH / 2, nf);
+                sws_unscaled_slow_kernel<<<grid, block, 0, stream>>>(b, p.color, p0, p1);
+                B200_LAUNCHED();
+            }
         } else if (c->h_identity) {
-            dim3 block(128), grid(b200_ceil_div(b200_ceil_div(p.dstW, 16), 128), p.dstH, nf);
-            sws_vscale_rgb24_kernel<true><<<grid, block, 0, stream>>>(b, c->dt, p.color, vecOK);
-            B200_LAUNCHED();
+            auto fits32 = [](long long stride, long long lines) { return (stride < 0 ? -stride : stride) * (lines + 1) < (1LL << 31); };
+            const bool off32 = fits32(b.ys, p.srcH) && fits32(b.us, p.chrSrcH) && fits32(b.vs, p.chrSrcH) && fits32(b.ds, p.dstH);
+            const int ngroups = (vecOK && c->fast_x && off32) ? p.dstW / 16 : 0;
+            if (ngroups) {
+                dim3 block(128), grid(b200_ceil_div(ngroups, 128), p.dstH, nf);
+                const bool c4 = p.vChr.size == 4;
+                if (c->lum_identity && c4)  sws_vscale_rgb24_fast_kernel<true, true><<<grid, block, 0, stream>>>(b, c->dt, p.color, ngroups);
+                else if (c->lum_identity)   sws_vscale_rgb24_fast_kernel<true, false><<<grid, block, 0, stream>>>(b, c->dt, p.color, ngroups);
+                else if (c4)                sws_vscale_rgb24_fast_kernel<false, true><<<grid, block, 0, stream>>>(b, c->dt, p.color, ngroups);
+                else                        sws_vscale_rgb24_fast_kernel<false, false><<<grid, block, 0, stream>>>(b, c->dt, p.color, ngroups);
+                B200_LAUNCHED();
+            }
+            const int p0 = ngroups * 8, p1 = (p.dstW + 1) / 2;
+            if (p1 > p0) {
+                dim3 block(128), grid(b200_ceil_div(p1 - p0, 128), p.dstH, nf);
+                sws_vscale_rgb24_slow_kernel<true><<<grid, block, 0, stream>>>(b, c->dt, p.color, p0, p1);
+                B200_LAUNCHED();
+            }
         } else {
             // scaled path: horizontal pass into int16 line planes, then the vertical pass
             const size_t lumPlane = (size_t)p.srcH * p.dstW * 2, chrPlane = (size_t)p.chrSrcH * p.chrDstW * 2;
@@ -528,8 +606,9 @@ static int launch_batch(B200SwsContext *c, cudaStream_t stream, const uint8_t *c
             m.ys = (long long)p.dstW * 2; m.us = m.vs = (long long)p.chrDstW * 2;
             m.yfs = m.ufs = m.vfs = (long long)perFrame;
             if (p.chrDstHSub) {
-                dim3 block(128), grid(b200_ceil_div(b200_ceil_div(p.dstW, 16), 128), p.dstH, nf);
-                sws_vscale_rgb24_kernel<false><<<grid, block, 0, stream>>>(m, c->dt, p.color, aligned16(dst, ds, dfs));
+                const int np = (p.dstW + 1) / 2;
+                dim3 block(128), grid(b200_ceil_div(np, 128), p.dstH, nf);
+                sws_vscale_rgb24_slow_kernel<false><<<grid, block, 0, stream>>>(m, c->dt, p.color, 0, np);
             } else {
                 dim3 block(256), grid(b200_ceil_div(p.dstW, 256), p.dstH, nf);
                 sws_vscale_rgb24_full_kernel<<<grid, block, 0, stream>>>(m, c->dt, p.color);
