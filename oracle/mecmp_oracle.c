@@ -1,0 +1,92 @@
+/*
+ * mecmp_oracle.c — TEST INFRASTRUCTURE ONLY.  CPU restatement of libavcodec's me_cmp SAD/SSE and of the exhaustive
+ * search that drives it.
+ *
+ * Follows (behaviour, not text):
+ *   pix_abs16_c / pix_abs8_c ........ libavcodec/me_cmp.c:117-143, 272-290     sum |a-b| over w x h, one stride for both
+ *   pix_abs{16,8}_{x2,y2,xy2}_c ..... libavcodec/me_cmp.c:145-385             blk2 interpolated: avg2 = (a+b+1)>>1,
+ *                                                                             avg4 = (a+b+c+d+2)>>2 (:114-115)
+ *   sse16_c / sse8_c / sse4_c ....... libavcodec/me_cmp.c:37-103               sum (a-b)^2
+ *   table layout .................... libavcodec/me_cmp.c:961-1027             sad[0]=16 wide, sad[1]=8; sse[0..2]=16,8,4;
+ *                                                                             pix_abs[0=16,1=8][0 full,1 x2,2 y2,3 xy2]
+ *   ff_me_cmp_sad, ff_me_search_esa . libavfilter/motion_estimation.c:60-97   cost(0 mv) first, return at once if it is 0,
+ *                                                                             raster scan, strict '<' keeps the first minimum
+ *   frame driver .................... libavfilter/vf_mestimate.c:85-127       mv initialised to the block's own position,
+ *                                                                             window clipped to [0, (b_w-1)<<log2] etc.
+ */
+#include "oracle.h"
+#include <stdlib.h>
+
+static int sad_wh(const uint8_t *a, const uint8_t *b, ptrdiff_t stride, int w, int h, int mode)
+{
+    int s = 0;
+    for (int y = 0; y < h; y++, a += stride, b += stride)
+        for (int x = 0; x < w; x++) {
+            int p;
+            switch (mode) {
+            case 0:  p = b[x]; break;
+            case 1:  p = (b[x] + b[x + 1] + 1) >> 1; break;
+            case 2:  p = (b[x] + b[x + stride] + 1) >> 1; break;
+            default: p = (b[x] + b[x + 1] + b[x + stride] + b[x + stride + 1] + 2) >> 2; break;
+            }
+            s += abs(a[x] - p);
+        }
+    return s;
+}
+
+static int sse_wh(const uint8_t *a, const uint8_t *b, ptrdiff_t stride, int w, int h)
+{
+    int s = 0;
+    for (int y = 0; y < h; y++, a += stride, b += stride)
+        for (int x = 0; x < w; x++) {
+            int d = a[x] - b[x];
+            s += d * d;
+        }
+    return s;
+}
+
+int orc_me_cmp(int fn, int idx, const uint8_t *blk1, const uint8_t *blk2, ptrdiff_t stride, int h)
+{
+    if (fn == 0) return idx == 0 ? sad_wh(blk1, blk2, stride, 16, h, 0) : idx == 1 ? sad_wh(blk1, blk2, stride, 8, h, 0) : -1;
+    if (fn == 1) return idx <= 2 ? sse_wh(blk1, blk2, stride, 16 >> idx, h) : -1;
+    if (fn == 2) return idx < 8 ? sad_wh(blk1, blk2, stride, idx < 4 ? 16 : 8, h, idx & 3) : -1;
+    return -1;
+}
+
+void orc_esa_frame(const uint8_t *cur, const uint8_t *ref, int linesize, int width, int height,
+                   int mb_size, int search_param, int mb_row0, int mb_row1, int32_t *out_mv, uint64_t *out_cost)
+{
+    int log2_mb = 0;
+    while ((1 << log2_mb) < mb_size) log2_mb++;
+    const int b_w = width >> log2_mb, b_h = height >> log2_mb;
+    const int gx_max = (b_w - 1) << log2_mb, gy_max = (b_h - 1) << log2_mb;
+    if (mb_row1 > b_h) mb_row1 = b_h;
+    for (int by = mb_row0; by < mb_row1; by++)
+        for (int bx = 0; bx < b_w; bx++) {
+            const int x_mb = bx << log2_mb, y_mb = by << log2_mb;
+            const uint8_t *c = cur + (ptrdiff_t)y_mb * linesize + x_mb;
+            int best_x = x_mb, best_y = y_mb;
+            uint64_t best = 0;
+            for (int j = 0; j < mb_size; j++)
+                for (int i = 0; i < mb_size; i++)
+                    best += abs(ref[(ptrdiff_t)(y_mb + j) * linesize + x_mb + i] - c[(ptrdiff_t)j * linesize + i]);
+            if (best) {
+                const int x0 = x_mb - search_param > 0 ? x_mb - search_param : 0;
+                const int y0 = y_mb - search_param > 0 ? y_mb - search_param : 0;
+                const int x1 = x_mb + search_param < gx_max ? x_mb + search_param : gx_max;
+                const int y1 = y_mb + search_param < gy_max ? y_mb + search_param : gy_max;
+                for (int y = y0; y <= y1; y++)
+                    for (int x = x0; x <= x1; x++) {
+                        uint64_t cost = 0;
+                        const uint8_t *r = ref + (ptrdiff_t)y * linesize + x;
+                        for (int j = 0; j < mb_size; j++)
+                            for (int i = 0; i < mb_size; i++)
+                                cost += abs(r[(ptrdiff_t)j * linesize + i] - c[(ptrdiff_t)j * linesize + i]);
+                        if (cost < best) { best = cost; best_x = x; best_y = y; }
+                    }
+            }
+            out_mv[2 * (by * b_w + bx)] = best_x;
+            out_mv[2 * (by * b_w + bx) + 1] = best_y;
+            out_cost[by * b_w + bx] = best;
+        }
+}

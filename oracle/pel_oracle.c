@@ -1,0 +1,100 @@
+/*
+ * pel_oracle.c — TEST INFRASTRUCTURE ONLY.  CPU restatement of libavcodec's 8-bit H.264 quarter-pel and MPEG half-pel
+ * motion-compensation interpolators.
+ *
+ * Follows (behaviour, not text):
+ *   H264_LOWPASS h/v/hv .... libavcodec/h264qpel_template.c:77-305   taps (1,-5,20,20,-5,1); h and v: clip((t+16)>>5);
+ *                                                                    hv: unrounded 16-bit horizontal sums over size+5 rows,
+ *                                                                    then the vertical taps and clip((t+512)>>10)
+ *   H264_MC mc00..mc33 ..... libavcodec/h264qpel_template.c:313-456  which of {full, h-half, v-half, hv-half} each
+ *                                                                    quarter position averages ((a+b+1)>>1, pixelsN_l2)
+ *   put / avg ops .......... libavcodec/h264qpel_template.c:461-465  avg: dst = (dst + value + 1) >> 1
+ *   table index ............ libavcodec/h264qpel.c:50-104            [0:16,1:8,2:4][x + 4*y]
+ *   hpeldsp PIXOP2 ......... libavcodec/hpeldsp.c:38-325             x2/y2: (a+b+1)>>1 (rnd) or (a+b)>>1 (no_rnd);
+ *                                                                    xy2: (a+b+c+d+2)>>2 (rnd) or +1 (no_rnd);
+ *                                                                    avg tables: dst = (dst + value + 1) >> 1 (rnd_avg32, rnd_avg.h:31-39)
+ *   hpel table layout ...... libavcodec/hpeldsp.c:337-352            put[4 sizes 16,8,4,2], avg[4], put_no_rnd[2: 16,8], avg_no_rnd[16 only]
+ */
+#include "oracle.h"
+
+static int clip8(int v) { return v < 0 ? 0 : v > 255 ? 255 : v; }
+static int tap6(int a, int b, int c, int d, int e, int f) { return a - 5 * b + 20 * c + 20 * d - 5 * e + f; }
+
+/* the four sample planes at integer position (x,y) of the block: F full, H horizontal half (between x and x+1),
+ * V vertical half (between y and y+1), J centre */
+static int sF(const uint8_t *s, ptrdiff_t st, int x, int y) { return s[y * st + x]; }
+static int sH(const uint8_t *s, ptrdiff_t st, int x, int y)
+{
+    const uint8_t *p = s + y * st + x;
+    return clip8((tap6(p[-2], p[-1], p[0], p[1], p[2], p[3]) + 16) >> 5);
+}
+static int sV(const uint8_t *s, ptrdiff_t st, int x, int y)
+{
+    const uint8_t *p = s + y * st + x;
+    return clip8((tap6(p[-2 * st], p[-st], p[0], p[st], p[2 * st], p[3 * st]) + 16) >> 5);
+}
+static int hraw(const uint8_t *s, ptrdiff_t st, int x, int y)
+{
+    const uint8_t *p = s + y * st + x;
+    return tap6(p[-2], p[-1], p[0], p[1], p[2], p[3]);
+}
+static int sJ(const uint8_t *s, ptrdiff_t st, int x, int y)
+{
+    return clip8((tap6(hraw(s, st, x, y - 2), hraw(s, st, x, y - 1), hraw(s, st, x, y), hraw(s, st, x, y + 1),
+                       hraw(s, st, x, y + 2), hraw(s, st, x, y + 3)) + 512) >> 10);
+}
+
+void orc_h264qpel(int avg, int size_idx, int pos, uint8_t *dst, const uint8_t *src, ptrdiff_t stride)
+{
+    const int size = 16 >> size_idx, qx = pos & 3, qy = pos >> 2;
+    uint8_t out[16 * 16];
+    for (int y = 0; y < size; y++)
+        for (int x = 0; x < size; x++) {
+            int v;
+            if (qy == 0) {
+                v = qx == 0 ? sF(src, stride, x, y) : qx == 2 ? sH(src, stride, x, y)
+                  : (sF(src, stride, x + (qx == 3), y) + sH(src, stride, x, y) + 1) >> 1;
+            } else if (qx == 0) {
+                v = qy == 2 ? sV(src, stride, x, y) : (sF(src, stride, x, y + (qy == 3)) + sV(src, stride, x, y) + 1) >> 1;
+            } else if (qx == 2 && qy == 2) {
+                v = sJ(src, stride, x, y);
+            } else if (qx == 2) {                   /* mc21, mc23 */
+                v = (sH(src, stride, x, y + (qy == 3)) + sJ(src, stride, x, y) + 1) >> 1;
+            } else if (qy == 2) {                   /* mc12, mc32 */
+                v = (sV(src, stride, x + (qx == 3), y) + sJ(src, stride, x, y) + 1) >> 1;
+            } else {                                /* mc11, mc31, mc13, mc33 */
+                v = (sH(src, stride, x, y + (qy == 3)) + sV(src, stride, x + (qx == 3), y) + 1) >> 1;
+            }
+            out[y * 16 + x] = (uint8_t)v;
+        }
+    for (int y = 0; y < size; y++)
+        for (int x = 0; x < size; x++)
+            dst[y * stride + x] = avg ? (uint8_t)((dst[y * stride + x] + out[y * 16 + x] + 1) >> 1) : out[y * 16 + x];
+}
+
+int orc_hpel(int tab, int size_idx, int xy, uint8_t *block, const uint8_t *pixels, ptrdiff_t ls, int h)
+{
+    const int w = 16 >> size_idx, no_rnd = tab >= 2;
+    /* quirk kept from the reference: avg_pixels2_xy2 stores without averaging ("FIXME non put", hpeldsp.c:134-166) */
+    const int avg = (tab & 1) && !(size_idx == 3 && xy == 3);
+    if (tab == 2 && size_idx > 1) return -1;
+    if (tab == 3 && size_idx != 0) return -1;
+    uint8_t out[16 * 64];
+    if (h > 64) return -1;
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            const uint8_t *p = pixels + y * ls + x;
+            int v;
+            switch (xy) {
+            case 0:  v = p[0]; break;
+            case 1:  v = (p[0] + p[1] + 1 - no_rnd) >> 1; break;
+            case 2:  v = (p[0] + p[ls] + 1 - no_rnd) >> 1; break;
+            default: v = (p[0] + p[1] + p[ls] + p[ls + 1] + 2 - no_rnd) >> 2; break;
+            }
+            out[y * 16 + x] = (uint8_t)v;
+        }
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++)
+            block[y * ls + x] = avg ? (uint8_t)((block[y * ls + x] + out[y * 16 + x] + 1) >> 1) : out[y * 16 + x];
+    return 0;
+}
