@@ -35,6 +35,34 @@ class IDCTDSPContext(C.Structure):
     ]
 
 
+_CMP = C.CFUNCTYPE(C.c_int, C.c_void_p, u8p, u8p, C.c_ssize_t, C.c_int)
+
+
+class MECmpContext(C.Structure):
+    """Same member order as MECmpContext, libavcodec/me_cmp.h:53-77."""
+    _fields_ = [("sum_abs_dctelem", C.CFUNCTYPE(C.c_int, i16p))] + \
+        [(n, _CMP * 6) for n in ("sad", "sse", "hadamard8_diff", "dct_sad", "quant_psnr", "bit", "rd", "vsad", "vsse",
+                                 "nsse", "w53", "w97", "dct_max", "dct264_sad")] + \
+        [("pix_abs", (_CMP * 4) * 2), ("median_sad", _CMP * 6)]
+
+
+_QPEL = C.CFUNCTYPE(None, u8p, u8p, C.c_ssize_t)
+_HPEL = C.CFUNCTYPE(None, u8p, u8p, C.c_ssize_t, C.c_int)
+
+
+class H264QpelContext(C.Structure):
+    """libavcodec/h264qpel.h:27-30"""
+    _fields_ = [("put_h264_qpel_pixels_tab", (_QPEL * 16) * 3), ("avg_h264_qpel_pixels_tab", (_QPEL * 16) * 3)]
+
+
+class HpelDSPContext(C.Structure):
+    """libavcodec/hpeldsp.h:39-97"""
+    _fields_ = [("put_pixels_tab", (_HPEL * 4) * 4), ("avg_pixels_tab", (_HPEL * 4) * 4),
+                ("put_no_rnd_pixels_tab", (_HPEL * 4) * 3), ("avg_no_rnd_pixels_tab", _HPEL * 4)]
+
+
+TX_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_void_p, C.c_ssize_t)
+
 # name -> (restype, argtypes): every symbol include/b200dsp.h declares
 PROTOTYPES = {
     "b200_abi_version": (C.c_int, []),
@@ -67,6 +95,17 @@ PROTOTYPES = {
     "b200_idct_batch_device": (C.c_int, [vp, C.c_int, vp, C.c_int64, vp, vp, vp, C.c_int]),
     "b200_idct_mb420_device": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.POINTER(vp), i32p, i64p]),
     "b200_idct_mb420_host": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.POINTER(vp), i32p, i64p]),
+    "b200_me_cmp_init": (C.c_int, [C.POINTER(MECmpContext), C.c_int]),
+    "b200_me_cmp_batch_device": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, C.c_ssize_t, C.c_int, vp, vp, C.c_int64, vp]),
+    "b200_me_esa_device": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, vp, vp]),
+    "b200_h264qpel_init": (C.c_int, [C.POINTER(H264QpelContext), C.c_int]),
+    "b200_hpeldsp_init": (C.c_int, [C.POINTER(HpelDSPContext), C.c_int]),
+    "b200_h264qpel_batch_device": (C.c_int, [vp, C.c_int64, vp, vp, vp, vp, vp, C.c_ssize_t]),
+    "b200_hpel_batch_device": (C.c_int, [vp, C.c_int64, vp, vp, vp, vp, vp, vp, C.c_ssize_t]),
+    "b200_tx_init": (C.c_int, [C.POINTER(vp), C.POINTER(TX_FN), C.c_int, C.c_int, C.c_int, vp, C.c_uint64]),
+    "b200_tx_init_device": (C.c_int, [vp, C.POINTER(vp), C.POINTER(TX_FN), C.c_int, C.c_int, C.c_int, vp, C.c_uint64]),
+    "b200_tx_uninit": (None, [C.POINTER(vp)]),
+    "b200_tx_batch_device": (C.c_int, [vp, vp, vp, C.c_ssize_t, C.c_int64, C.c_ssize_t, C.c_ssize_t]),
 }
 
 _lib = None

@@ -1,0 +1,243 @@
+// mecmp.cu — libavcodec me_cmp SAD/SSE block compare and the exhaustive motion search on sm_100a (C ABI: "me_cmp").
+//
+// Reference semantics reproduced bit-for-bit (checker: oracle/mecmp_oracle.c):
+//   pix_abs16_c / pix_abs8_c, *_x2 / _y2 / _xy2   libavcodec/me_cmp.c:114-385
+//   sse16_c / sse8_c / sse4_c                     libavcodec/me_cmp.c:37-103
+//   ff_me_cmp_sad, ff_me_search_esa               libavfilter/motion_estimation.c:60-97 (driver vf_mestimate.c:85-127)
+//
+// ESA kernel: one CTA per macroblock.  The current block and the clipped search window of the reference frame are
+// staged in shared memory once (coalesced row reads); every thread then scores candidates with VABSDIFF4 (4 bytes per
+// instruction, unaligned candidate rows are re-assembled from two words with PRMT).  The winner is a 64-bit key
+// (cost, not-the-zero-vector, raster index) reduced with warp shuffles: strict '<' in raster order with the zero
+// vector tested first is exactly "smallest key".  This search is integer-ALU bound (about 2100 op/byte), not HBM bound.
+#include "common.h"
+#include <cstring>
+
+namespace {
+
+__device__ __forceinline__ int px_ref(const uint8_t *b, long long stride, int x, int mode)
+{
+    switch (mode) {
+    case 0:  return b[x];
+    case 1:  return (b[x] + b[x + 1] + 1) >> 1;
+    case 2:  return (b[x] + b[x + stride] + 1) >> 1;
+    default: return (b[x] + b[x + 1] + b[x + stride] + b[x + stride + 1] + 2) >> 2;
+    }
+}
+
+// one warp per comparison; lane = column (w <= 16 -> two rows per pass)
+__global__ void __launch_bounds__(256)
+me_cmp_kernel(int fn, int w, int mode, const uint8_t *f1, const uint8_t *f2, long long stride, int h,
+              const int64_t *off1, const int64_t *off2, long long n, int32_t *out)
+{
+    const long long i = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= n) return;
+    const int lane = threadIdx.x & 31;
+    const uint8_t *a = f1 + off1[i], *b = f2 + off2[i];
+    const int rows_per_pass = 32 / w, x = lane % w, r0 = lane / w;
+    int s = 0;
+    for (int y = r0; y < h; y += rows_per_pass) {
+        const int pa = a[y * stride + x];
+        const int pb = px_ref(b + y * stride, stride, x, mode);
+        const int d = pa - pb;
+        s += fn == B200_MECMP_SSE ? d * d : abs(d);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[i] = s;
+}
+
+// ---------------------------------------------------------------- exhaustive search
+constexpr int ESA_THREADS = 256;
+
+template <int MB>
+__global__ void __launch_bounds__(ESA_THREADS)
+esa_kernel(const uint8_t *cur, const uint8_t *ref, int linesize, long long frame_stride, int b_w, int b_h,
+           int search, int win_pitch /* words */, int32_t *out_mv, unsigned long long *out_cost)
+{
+    extern __shared__ unsigned smem[];
+    unsigned *scur = smem;                         // MB rows x MB/4 words
+    unsigned *swin = smem + MB * (MB / 4);         // window rows x win_pitch words
+    __shared__ unsigned long long best[ESA_THREADS / 32];
+
+    const int bx = blockIdx.x, by = blockIdx.y;
+    const long long f = blockIdx.z;
+    const int x_mb = bx * MB, y_mb = by * MB;
+    const int gx_max = (b_w - 1) * MB, gy_max = (b_h - 1) * MB;
+    const int x0 = max(x_mb - search, 0), y0 = max(y_mb - search, 0);
+    const int x1 = min(x_mb + search, gx_max), y1 = min(y_mb + search, gy_max);
+    const int nx = x1 - x0 + 1, ny = y1 - y0 + 1;
+    const int wrows = ny + MB - 1, wcols = nx + MB - 1;            // bytes of the window actually needed
+    const uint8_t *c = cur + f * frame_stride + (long long)y_mb * linesize + x_mb;
+    const uint8_t *r = ref + f * frame_stride + (long long)y0 * linesize + x0;
+
+    // stage: bytes are written individually into the word arrays (little endian), rows padded to win_pitch words
+    uint8_t *scur8 = reinterpret_cast<uint8_t *>(scur), *swin8 = reinterpret_cast<uint8_t *>(swin);
+    for (int i = threadIdx.x; i < MB * MB; i += ESA_THREADS) scur8[i] = c[(long long)(i / MB) * linesize + (i % MB)];
+    const int wpb = win_pitch * 4;
+    for (int i = threadIdx.x; i < wrows * wpb; i += ESA_THREADS) {
+        const int yy = i / wpb, xx = i - yy * wpb;
+        swin8[i] = xx < wcols ? r[(long long)yy * linesize + xx] : 0;
+    }
+    __syncthreads();
+
+    unsigned long long mine = ~0ull;
+    const int ncand = nx * ny;
+    for (int k = threadIdx.x; k < ncand; k += ESA_THREADS) {
+        const int cy = k / nx, cx = k - cy * nx;
+        const int wq = cx >> 2, sh = cx & 3;
+        const unsigned sel = 0x3210u + 0x1111u * sh;              // bytes sh..sh+3 of the pair (lo, hi)
+        unsigned sad = 0;
+#pragma unroll 4
+        for (int j = 0; j < MB; j++) {
+            const unsigned *row = swin + (cy + j) * win_pitch + wq;
+            unsigned lo = row[0];
+#pragma unroll
+            for (int q = 0; q < MB / 4; q++) {
+                const unsigned hi = row[q + 1];
+                sad = __vsadu4(__byte_perm(lo, hi, sel), scur[j * (MB / 4) + q]) + sad;
+                lo = hi;
+            }
+        }
+        const int ax = x0 + cx, ay = y0 + cy;
+        const unsigned notzero = (ax == x_mb && ay == y_mb) ? 0u : 1u;
+        const unsigned long long key = ((unsigned long long)sad << 32) | ((unsigned long long)notzero << 31) | (unsigned)k;
+        mine = key < mine ? key : mine;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, mine, o);
+        mine = other < mine ? other : mine;
+    }
+    if ((threadIdx.x & 31) == 0) best[threadIdx.x >> 5] = mine;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long m = best[0];
+        for (int i = 1; i < ESA_THREADS / 32; i++) m = best[i] < m ? best[i] : m;
+        const int k = (int)(m & 0x7fffffffu);
+        const int cy = k / nx, cx = k - cy * nx;
+        const long long o = (f * b_h + by) * b_w + bx;
+        out_mv[2 * o] = x0 + cx;
+        out_mv[2 * o + 1] = y0 + cy;
+        out_cost[o] = m >> 32;
+    }
+}
+
+template <int MB>
+int launch_esa(cudaStream_t st, const uint8_t *cur, const uint8_t *ref, int linesize, long long fs, int b_w, int b_h,
+               int nframes, int search, int32_t *mv, unsigned long long *cost)
+{
+    const int wcols = 2 * search + MB;                           // widest window in bytes
+    const int win_pitch = (wcols + 3) / 4 + 1;                   // +1 word: the PRMT pair read one past the last needed word
+    const size_t smem = ((size_t)MB * (MB / 4) + (size_t)(2 * search + MB) * win_pitch) * 4;
+    if (smem > 200 * 1024) return B200_ENOSYS;
+    if (smem > 48 * 1024)
+        B200_CUDA_OK(cudaFuncSetAttribute(esa_kernel<MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (int f0 = 0; f0 < nframes; f0 += 65535) {
+        const int nf = nframes - f0 < 65535 ? nframes - f0 : 65535;
+        dim3 grid(b_w, b_h, nf);
+        esa_kernel<MB><<<grid, ESA_THREADS, smem, st>>>(cur + (long long)f0 * fs, ref + (long long)f0 * fs, linesize, fs, b_w, b_h,
+                                                        search, win_pitch, mv + 2LL * f0 * b_w * b_h, cost + (long long)f0 * b_w * b_h);
+        B200_LAUNCHED();
+    }
+    B200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int decode(int fn, int idx, int *w, int *mode)
+{
+    *mode = 0;
+    if (fn == B200_MECMP_SAD) { if (idx < 0 || idx > 1) return B200_EINVAL; *w = 16 >> idx; return 0; }
+    if (fn == B200_MECMP_SSE) { if (idx < 0 || idx > 2) return B200_EINVAL; *w = 16 >> idx; return 0; }
+    if (fn == B200_MECMP_PIX_ABS) { if (idx < 0 || idx > 7) return B200_EINVAL; *w = idx < 4 ? 16 : 8; *mode = idx & 3; return 0; }
+    return B200_EINVAL;
+}
+
+} // namespace
+
+B200_API int b200_me_cmp_batch_device(B200Device *dev, int fn, int idx, const uint8_t *frame1, const uint8_t *frame2,
+                                      ptrdiff_t stride, int h, const int64_t *off1, const int64_t *off2, int64_t n, int32_t *out)
+{
+    if (!dev || !frame1 || !frame2 || !off1 || !off2 || !out || n < 0 || h < 0) return B200_EINVAL;
+    int w, mode;
+    int ret = decode(fn, idx, &w, &mode);
+    if (ret < 0) return ret;
+    if (n == 0) return 0;
+    B200_CUDA_OK(cudaSetDevice(dev->ordinal));
+    const long long blocks = (n + 7) / 8;
+    if (blocks > 0x7fffffffLL) return B200_EINVAL;
+    me_cmp_kernel<<<(unsigned)blocks, 256, 0, dev->stream>>>(fn, w, mode, frame1, frame2, stride, h, off1, off2, n, out);
+    B200_LAUNCHED();
+    B200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+B200_API int b200_me_esa_device(B200Device *dev, const uint8_t *cur, const uint8_t *ref, int linesize, int width, int height,
+                                int64_t frame_stride, int nframes, int mb_size, int search_param, int32_t *out_mv, uint64_t *out_cost)
+{
+    if (!dev || !cur || !ref || !out_mv || !out_cost || nframes < 0 || search_param < 0 || width <= 0 || height <= 0) return B200_EINVAL;
+    if (mb_size != 4 && mb_size != 8 && mb_size != 16) return B200_ENOSYS;
+    const int b_w = width / mb_size, b_h = height / mb_size;
+    if (b_w == 0 || b_h == 0) return B200_EINVAL;                 // vf_mestimate.c:93-94
+    if (b_h > 65535) return B200_ENOSYS;
+    if (nframes == 0) return 0;
+    B200_CUDA_OK(cudaSetDevice(dev->ordinal));
+    unsigned long long *cost = reinterpret_cast<unsigned long long *>(out_cost);
+    switch (mb_size) {
+    case 4:  return launch_esa<4>(dev->stream, cur, ref, linesize, frame_stride, b_w, b_h, nframes, search_param, out_mv, cost);
+    case 8:  return launch_esa<8>(dev->stream, cur, ref, linesize, frame_stride, b_w, b_h, nframes, search_param, out_mv, cost);
+    default: return launch_esa<16>(dev->stream, cur, ref, linesize, frame_stride, b_w, b_h, nframes, search_param, out_mv, cost);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ drop-in pointer table
+namespace {
+
+int host_cmp(int fn, int idx, const uint8_t *blk1, const uint8_t *blk2, ptrdiff_t stride, int h)
+{
+    auto fail = [](const char *what) { fprintf(stderr, "libb200dsp: me_cmp failed: %s (%s)\n", what, b200_last_error()); abort(); };
+    B200Device *dev = b200_default_device();
+    if (!dev) fail("no device");
+    int w, mode;
+    if (decode(fn, idx, &w, &mode) < 0) fail("bad index");
+    if (cudaSetDevice(dev->ordinal) != cudaSuccess) fail("cudaSetDevice");
+    const int cw = w + 1, ch = h + 1;                             // x2/y2/xy2 read one extra column / row of blk2
+    const size_t pitch = 32;
+    uint8_t *scr = (uint8_t *)b200_scratch(dev, 2 * pitch * (ch + 1) + 64);
+    if (!scr) fail("scratch");
+    uint8_t *d1 = scr, *d2 = scr + pitch * (ch + 1);
+    int64_t *offs = (int64_t *)(scr + 2 * pitch * (ch + 1));
+    int32_t *dout = (int32_t *)(offs + 2);
+    cudaStream_t st = dev->stream;
+    const size_t as = (size_t)(stride < 0 ? -stride : stride);
+    if (stride < 0) fail("negative stride");
+    if (cudaMemcpy2DAsync(d1, pitch, blk1, as, w, h, cudaMemcpyHostToDevice, st) != cudaSuccess) fail("h2d");
+    const int bw = mode & 1 ? cw : w, bh = mode & 2 ? ch : h;
+    if (cudaMemcpy2DAsync(d2, pitch, blk2, as, bw, bh, cudaMemcpyHostToDevice, st) != cudaSuccess) fail("h2d");
+    if (cudaMemsetAsync(offs, 0, 16, st) != cudaSuccess) fail("memset");
+    me_cmp_kernel<<<1, 32, 0, st>>>(fn, w, mode, d1, d2, (long long)pitch, h, offs, offs + 1, 1, dout);
+    B200_LAUNCHED();
+    int32_t res = 0;
+    if (cudaMemcpyAsync(&res, dout, 4, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) fail("d2h");
+    return res;
+}
+
+template <int FN, int IDX>
+int tab_fn(void *, const uint8_t *a, const uint8_t *b, ptrdiff_t stride, int h) { return host_cmp(FN, IDX, a, b, stride, h); }
+
+} // namespace
+
+B200_API int b200_me_cmp_init(B200MECmpContext *c, int codec_flags)
+{
+    (void)codec_flags;
+    if (!c) return B200_EINVAL;
+    if (!b200_default_device()) return B200_ENODEV;
+    memset(c, 0, sizeof(*c));
+    c->sad[0] = tab_fn<B200_MECMP_SAD, 0>; c->sad[1] = tab_fn<B200_MECMP_SAD, 1>;
+    c->sse[0] = tab_fn<B200_MECMP_SSE, 0>; c->sse[1] = tab_fn<B200_MECMP_SSE, 1>; c->sse[2] = tab_fn<B200_MECMP_SSE, 2>;
+    c->pix_abs[0][0] = tab_fn<B200_MECMP_PIX_ABS, 0>; c->pix_abs[0][1] = tab_fn<B200_MECMP_PIX_ABS, 1>;
+    c->pix_abs[0][2] = tab_fn<B200_MECMP_PIX_ABS, 2>; c->pix_abs[0][3] = tab_fn<B200_MECMP_PIX_ABS, 3>;
+    c->pix_abs[1][0] = tab_fn<B200_MECMP_PIX_ABS, 4>; c->pix_abs[1][1] = tab_fn<B200_MECMP_PIX_ABS, 5>;
+    c->pix_abs[1][2] = tab_fn<B200_MECMP_PIX_ABS, 6>; c->pix_abs[1][3] = tab_fn<B200_MECMP_PIX_ABS, 7>;
+    return 0;
+}

@@ -1,0 +1,371 @@
+// tx.cu — libavutil/tx float32 power-of-two FFT and MDCT on sm_100a: kernels + the C ABI (include/b200dsp.h, "tx").
+//
+// Reference semantics reproduced with the SAME float operation order, so results are bit-identical to the
+// *_float_c codelets (checker: oracle/tx_oracle.c; build uses --fmad=false so no product/sum is contracted):
+//   ff_tx_fft{2..131072}_ns, ff_tx_fft_sr_combine   libavutil/tx_template.c:562-722
+//   ff_tx_fft (permute + codelet)                   libavutil/tx_template.c:763-778
+//   ff_tx_mdct_fwd / ff_tx_mdct_inv                 libavutil/tx_template.c:1273-1342
+//   tables: ff_tx_init_tab_N (:65-77), ff_tx_mdct_gen_exp (:2107-2134), ff_tx_gen_ptwo_revtab (tx.c:125-154)
+//
+// The reference's recursion  fft(S) = fft(S/2) | fft(S/4) | fft(S/4) ; combine(S)  is flattened into levels: all
+// blocks of one size are independent, so a CTA keeps one transform in shared memory and sweeps S = 2, 4, ..., N with
+// one barrier per level.  The hard-coded base cases are instances of the same rule (fft4 = fft2 + butterflies,
+// fft8 = fft4 + 2 fft2 + combine, fft16 = fft8 + 2 fft4 + combine) except that for S <= 16 the j = 0 butterfly
+// skips the multiplication by (1, 0); that distinction is kept.
+// HBM traffic per transform is the algorithmic 8N in + 8N out (FFT) or 4*len in + 4*len out (iMDCT).
+#include "common.h"
+#include <vector>
+#include <cmath>
+#include <cstring>
+#include <new>
+
+namespace {
+
+struct TxDev {                 // device-side plan
+    int n;                     // complex FFT points
+    int nlevels;               // levels S = 2^1 .. 2^nlevels
+    const int *blk_off;        // block offsets, all levels concatenated
+    int lvl_start[18], lvl_cnt[18];
+    const float *tab;          // cosine tables, tab_off[k] = start of tab_{2^k}
+    int tab_off[18];
+    const int *scatter;        // FFT: z[scatter[g]] = src[g]
+    const int *sub_map;        // MDCT index map (doubled for the inverse)
+    const float2 *exp;         // MDCT twiddles
+    int len;                   // MDCT length (2n)
+};
+
+__device__ __forceinline__ void butterflies(float2 &a0, float2 &a1, float2 &a2, float2 &a3, float t1, float t2, float t5, float t6)
+{
+    const float r0 = a0.x, i0 = a0.y, r1 = a1.x, i1 = a1.y;
+    const float t3 = t5 - t1; t5 = t5 + t1;
+    a2.x = r0 - t5; a0.x = r0 + t5;
+    a3.y = i1 - t3; a1.y = i1 + t3;
+    const float t4 = t2 - t6; t6 = t2 + t6;
+    a3.x = r1 - t4; a1.x = r1 + t4;
+    a2.y = i0 - t6; a0.y = i0 + t6;
+}
+
+// all levels on the transform held in z[0..n)
+__device__ void fft_levels(const TxDev &p, float2 *z)
+{
+    for (int L = 1; L <= p.nlevels; L++) {
+        const int S = 1 << L;
+        const int *off = p.blk_off + p.lvl_start[L];
+        if (L == 1) {
+            for (int b = threadIdx.x; b < p.lvl_cnt[L]; b += blockDim.x) {
+                const int o = __ldg(off + b);
+                const float2 s0 = z[o], s1 = z[o + 1];
+                z[o] = make_float2(s0.x + s1.x, s0.y + s1.y);
+                z[o + 1] = make_float2(s0.x - s1.x, s0.y - s1.y);
+            }
+        } else {
+            const int lq = L - 2, q = 1 << lq;
+            const float *tab = p.tab + p.tab_off[L];
+            const int total = p.lvl_cnt[L] << lq;
+            for (int b = threadIdx.x; b < total; b += blockDim.x) {
+                const int o = __ldg(off + (b >> lq)), j = b & (q - 1);
+                float2 a0 = z[o + j], a1 = z[o + q + j], a2 = z[o + 2 * q + j], a3 = z[o + 3 * q + j];
+                if (S <= 16 && j == 0) {
+                    butterflies(a0, a1, a2, a3, a2.x, a2.y, a3.x, a3.y);
+                } else {
+                    const float wre = __ldg(tab + j), wim = __ldg(tab + q - j);
+                    const float t1 = a2.x * wre - a2.y * (-wim);
+                    const float t2 = a2.x * (-wim) + a2.y * wre;
+                    const float t5 = a3.x * wre - a3.y * wim;
+                    const float t6 = a3.x * wim + a3.y * wre;
+                    butterflies(a0, a1, a2, a3, t1, t2, t5, t6);
+                }
+                z[o + j] = a0; z[o + q + j] = a1; z[o + 2 * q + j] = a2; z[o + 3 * q + j] = a3;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// one CTA per transform; steps are in BYTES between consecutive transforms
+__global__ void __launch_bounds__(256)
+tx_fft_kernel(TxDev p, float2 *out, const float2 *in, long long out_step, long long in_step)
+{
+    extern __shared__ float2 z[];
+    const float2 *src = reinterpret_cast<const float2 *>(reinterpret_cast<const char *>(in) + blockIdx.x * in_step);
+    float2 *dst = reinterpret_cast<float2 *>(reinterpret_cast<char *>(out) + blockIdx.x * out_step);
+    for (int g = threadIdx.x; g < p.n; g += blockDim.x) z[__ldg(p.scatter + g)] = src[g];
+    __syncthreads();
+    fft_levels(p, z);
+    for (int i = threadIdx.x; i < p.n; i += blockDim.x) dst[i] = z[i];
+}
+
+// ff_tx_mdct_inv: len floats in (element k at in + k*stride floats), len floats out (contiguous)
+__global__ void __launch_bounds__(256)
+tx_mdct_inv_kernel(TxDev p, float *out, const float *in, long long stride, long long out_step, long long in_step)
+{
+    extern __shared__ float2 z[];
+    const float *src = reinterpret_cast<const float *>(reinterpret_cast<const char *>(in) + blockIdx.x * in_step);
+    float2 *dst = reinterpret_cast<float2 *>(reinterpret_cast<char *>(out) + blockIdx.x * out_step);
+    const int len2 = p.len >> 1, len4 = p.len >> 2;
+    const float *in1 = src, *in2 = src + (long long)(len2 * 2 - 1) * stride;
+    for (int i = threadIdx.x; i < len2; i += blockDim.x) {
+        const int k = __ldg(p.sub_map + i);
+        const float are = in2[-(long long)k * stride], aim = in1[(long long)k * stride];
+        const float2 e = __ldg(p.exp + i);
+        z[i] = make_float2(are * e.x - aim * e.y, are * e.y + aim * e.x);
+    }
+    __syncthreads();
+    fft_levels(p, z);
+    const float2 *e = p.exp + len2;
+    for (int i = threadIdx.x; i < len4; i += blockDim.x) {
+        const int i0 = len4 + i, i1 = len4 - i - 1;
+        const float2 z1 = z[i1], z0 = z[i0], e1 = __ldg(e + i1), e0 = __ldg(e + i0);
+        const float s1re = z1.y, s1im = z1.x, s0re = z0.y, s0im = z0.x;
+        float2 o1, o0;
+        o1.x = s1re * e1.y - s1im * e1.x;      // z[i1].re
+        o0.y = s1re * e1.x + s1im * e1.y;      // z[i0].im
+        o0.x = s0re * e0.y - s0im * e0.x;      // z[i0].re
+        o1.y = s0re * e0.x + s0im * e0.y;      // z[i1].im
+        z[i1] = o1; z[i0] = o0;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < len2; i += blockDim.x) dst[i] = z[i];
+}
+
+// ff_tx_mdct_fwd: 2*len floats in (contiguous), len floats out (element k at out + k*stride floats)
+__global__ void __launch_bounds__(256)
+tx_mdct_fwd_kernel(TxDev p, float *out, const float *in, long long stride, long long out_step, long long in_step)
+{
+    extern __shared__ float2 z[];
+    const float *src = reinterpret_cast<const float *>(reinterpret_cast<const char *>(in) + blockIdx.x * in_step);
+    float *dst = reinterpret_cast<float *>(reinterpret_cast<char *>(out) + blockIdx.x * out_step);
+    const int len2 = p.len >> 1, len4 = p.len >> 2, len3 = len2 * 3;
+    for (int i = threadIdx.x; i < len2; i += blockDim.x) {
+        const int k = 2 * i, idx = __ldg(p.sub_map + i);
+        float re, im;
+        if (k < len2) {
+            re = -src[len2 + k] + src[1 * len2 - 1 - k];
+            im = -src[len3 + k] + -src[1 * len3 - 1 - k];
+        } else {
+            re = -src[len2 + k] + -src[5 * len2 - 1 - k];
+            im = src[-len2 + k] + -src[1 * len3 - 1 - k];
+        }
+        const float2 e = __ldg(p.exp + i);
+        z[idx] = make_float2(re * e.y + im * e.x, re * e.x - im * e.y);     // (.re, .im) = (dim, dre) of the reference's CMUL
+    }
+    __syncthreads();
+    fft_levels(p, z);
+    for (int i = threadIdx.x; i < len4; i += blockDim.x) {
+        const int i0 = len4 + i, i1 = len4 - i - 1;
+        const float2 s1 = z[i1], s0 = z[i0], e1 = __ldg(p.exp + i1), e0 = __ldg(p.exp + i0);
+        dst[(2LL * i1 + 1) * stride] = s0.x * e0.y - s0.y * e0.x;
+        dst[(2LL * i0) * stride]     = s0.x * e0.x + s0.y * e0.y;
+        dst[(2LL * i0 + 1) * stride] = s1.x * e1.y - s1.y * e1.x;
+        dst[(2LL * i1) * stride]     = s1.x * e1.x + s1.y * e1.y;
+    }
+}
+
+int sr_perm(int i, int len, int inv)       // split_radix_permutation, tx.c:125-134
+{
+    len >>= 1;
+    if (len <= 1) return i & 1;
+    if (!(i & len)) return sr_perm(i, len, inv) * 2;
+    len >>= 1;
+    return sr_perm(i, len, inv) * 4 + 1 - 2 * (!(i & len) ^ inv);
+}
+
+void collect_blocks(std::vector<std::vector<int>> &lv, int L, int off)   // block of size 2^L at `off`
+{
+    if (L < 1) return;
+    lv[L].push_back(off);
+    const int S = 1 << L;
+    collect_blocks(lv, L - 1, off);
+    if (L >= 2) {
+        collect_blocks(lv, L - 2, off + S / 2);
+        collect_blocks(lv, L - 2, off + 3 * S / 4);
+    }
+}
+
+} // namespace
+
+struct B200TXContext {
+    B200Device *dev = nullptr;
+    int type = 0, inv = 0, len = 0;
+    TxDev d{};
+    void *blob = nullptr;
+    size_t smem = 0;
+};
+
+static int tx_build(B200TXContext *c, float scale)
+{
+    const int n = c->type == 0 ? c->len : c->len >> 1;
+    int k = 0;
+    while ((1 << k) < n) k++;
+    TxDev &d = c->d;
+    d.n = n; d.nlevels = k; d.len = c->len;
+    std::vector<std::vector<int>> lv(18);
+    collect_blocks(lv, k, 0);
+    std::vector<int> blk;
+    for (int L = 0; L < 18; L++) {
+        d.lvl_start[L] = (int)blk.size();
+        d.lvl_cnt[L] = (int)lv[L].size();
+        blk.insert(blk.end(), lv[L].begin(), lv[L].end());
+    }
+    std::vector<float> tab;
+    for (int L = 0; L < 18; L++) {
+        d.tab_off[L] = (int)tab.size();
+        if (L >= 3 && L <= k) {                                      // ff_tx_init_tab_N, tx_template.c:65-77
+            const int N = 1 << L;
+            const double freq = 2 * M_PI / N;
+            for (int i = 0; i < N / 4; i++) tab.push_back((float)cos(i * freq));
+            tab.push_back(0.0f);
+        } else if (L == 2) {                                         // never multiplied (S <= 16, j == 0 only) but keep indexing valid
+            tab.push_back(1.0f); tab.push_back(0.0f);
+        }
+    }
+    std::vector<int> gather(n), scatter(n), sub_map;
+    const bool mdct_scatter = c->type == 1 && !c->inv;               // ff_tx_mdct_init: map_dir = !inv ? SCATTER : GATHER
+    for (int i = 0; i < n; i++) {
+        const int p = n == 1 ? 0 : (-sr_perm(i, n, c->inv)) & (n - 1);
+        if (mdct_scatter) gather[p] = i; else gather[i] = p;
+    }
+    for (int i = 0; i < n; i++) scatter[gather[i]] = i;              // dst[i] = src[gather[i]]  <=>  dst[scatter[g]] = src[g]
+    std::vector<float2> ex;
+    if (c->type == 1) {                                              // ff_tx_mdct_gen_exp, tx_template.c:2107-2134
+        const int len4 = c->len >> 1;
+        const double sc = (double)scale;
+        const double theta = (sc < 0 ? len4 : 0) + 1.0 / 8.0;
+        const double amp = sqrt(fabs(sc));
+        std::vector<float2> full(len4);
+        for (int i = 0; i < len4; i++) {
+            const double alpha = M_PI_2 * (i + theta) / len4;
+            full[i] = make_float2((float)(cos(alpha) * amp), (float)(sin(alpha) * amp));
+        }
+        sub_map.resize(len4);
+        if (c->inv) {
+            ex.resize(2 * (size_t)len4);
+            for (int i = 0; i < len4; i++) { ex[len4 + i] = full[i]; ex[i] = full[gather[i]]; sub_map[i] = gather[i] << 1; }
+        } else {
+            ex = full;
+            for (int i = 0; i < len4; i++) sub_map[i] = gather[i];
+        }
+    }
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    size_t off = 0;
+    const size_t o_blk = off; off += al(blk.size() * 4);
+    const size_t o_tab = off; off += al(tab.size() * 4);
+    const size_t o_sc = off;  off += al(scatter.size() * 4);
+    const size_t o_sm = off;  off += al(sub_map.size() * 4 + 4);
+    const size_t o_ex = off;  off += al(ex.size() * 8 + 8);
+    std::vector<uint8_t> host(off, 0);
+    memcpy(&host[o_blk], blk.data(), blk.size() * 4);
+    memcpy(&host[o_tab], tab.data(), tab.size() * 4);
+    memcpy(&host[o_sc], scatter.data(), scatter.size() * 4);
+    if (!sub_map.empty()) memcpy(&host[o_sm], sub_map.data(), sub_map.size() * 4);
+    if (!ex.empty()) memcpy(&host[o_ex], ex.data(), ex.size() * 8);
+    B200_CUDA_OK(cudaMalloc(&c->blob, off));
+    B200_CUDA_OK(cudaMemcpy(c->blob, host.data(), off, cudaMemcpyHostToDevice));
+    uint8_t *b = (uint8_t *)c->blob;
+    d.blk_off = (const int *)(b + o_blk); d.tab = (const float *)(b + o_tab); d.scatter = (const int *)(b + o_sc);
+    d.sub_map = (const int *)(b + o_sm); d.exp = (const float2 *)(b + o_ex);
+    c->smem = (size_t)n * sizeof(float2);
+    if (c->smem > 48 * 1024) {
+        B200_CUDA_OK(cudaFuncSetAttribute(tx_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem));
+        B200_CUDA_OK(cudaFuncSetAttribute(tx_mdct_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem));
+        B200_CUDA_OK(cudaFuncSetAttribute(tx_mdct_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem));
+    }
+    return 0;
+}
+
+static int tx_launch(B200TXContext *c, cudaStream_t st, void *out, const void *in, ptrdiff_t stride, int64_t count,
+                     ptrdiff_t out_step, ptrdiff_t in_step)
+{
+    if (count <= 0) return 0;
+    const int threads = c->d.n >= 1024 ? 256 : c->d.n >= 256 ? 128 : 64;
+    for (int64_t c0 = 0; c0 < count; c0 += 0x7fffffff) {
+        const unsigned nb = (unsigned)(count - c0 < 0x7fffffff ? count - c0 : 0x7fffffff);
+        char *o = (char *)out + c0 * out_step;
+        const char *i = (const char *)in + c0 * in_step;
+        if (c->type == 0)
+            tx_fft_kernel<<<nb, threads, c->smem, st>>>(c->d, (float2 *)o, (const float2 *)i, out_step, in_step);
+        else if (c->inv)
+            tx_mdct_inv_kernel<<<nb, threads, c->smem, st>>>(c->d, (float *)o, (const float *)i, stride / 4, out_step, in_step);
+        else
+            tx_mdct_fwd_kernel<<<nb, threads, c->smem, st>>>(c->d, (float *)o, (const float *)i, stride / 4, out_step, in_step);
+        B200_LAUNCHED();
+    }
+    B200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// av_tx_fn shaped entry: HOST pointers, one transform
+static void tx_host_fn(B200TXContext *c, void *out, void *in, ptrdiff_t stride)
+{
+    auto fail = [](const char *what) { fprintf(stderr, "libb200dsp: av_tx_fn failed: %s (%s)\n", what, b200_last_error()); abort(); };
+    B200Device *d = c->dev;
+    if (cudaSetDevice(d->ordinal) != cudaSuccess) fail("cudaSetDevice");
+    const size_t n = c->d.n, len = c->len;
+    size_t in_elems, out_elems;            // floats
+    if (c->type == 0) { in_elems = out_elems = 2 * n; }
+    else if (c->inv) { in_elems = len; out_elems = len; }
+    else { in_elems = 2 * len; out_elems = len; }
+    float *scr = (float *)b200_scratch(d, (in_elems + out_elems) * 4 + 512);
+    if (!scr) fail("scratch");
+    float *din = scr, *dout = scr + ((in_elems + 63) & ~(size_t)63);
+    cudaStream_t st = d->stream;
+    cudaError_t e;
+    const bool strided_in = c->type == 1 && c->inv && stride != 4;
+    const bool strided_out = c->type == 1 && !c->inv && stride != 4;
+    if (strided_in) e = cudaMemcpy2DAsync(din, 4, in, (size_t)stride, 4, in_elems, cudaMemcpyHostToDevice, st);
+    else e = cudaMemcpyAsync(din, in, in_elems * 4, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) fail("h2d");
+    if (tx_launch(c, st, dout, din, 4, 1, 0, 0) < 0) fail("launch");
+    if (strided_out) e = cudaMemcpy2DAsync(out, (size_t)stride, dout, 4, 4, out_elems, cudaMemcpyDeviceToHost, st);
+    else e = cudaMemcpyAsync(out, dout, out_elems * 4, cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) fail("d2h");
+}
+
+B200_API int b200_tx_init_device(B200Device *dev, B200TXContext **ctx, b200_tx_fn *tx, int type, int inv, int len,
+                                 const void *scale, uint64_t flags)
+{
+    if (!ctx || !len) return B200_EINVAL;                            // av_tx_init, tx.c:903-940
+    *ctx = nullptr;
+    if (!dev) return B200_ENODEV;
+    if (type != B200_TX_FLOAT_FFT && type != B200_TX_FLOAT_MDCT) return B200_ENOSYS;
+    if (flags & ~(uint64_t)B200_TX_UNALIGNED) return B200_ENOSYS;    // INPLACE / FULL_IMDCT / REAL_TO_* not implemented
+    if (len < 2 || (len & (len - 1))) return B200_ENOSYS;            // PFA (3/5/7/9/15 x 2^n) lengths not implemented
+    const int n = type == 0 ? len : len >> 1;
+    if (n < 1 || n > 16384) return B200_ENOSYS;                      // one transform must fit a CTA's shared memory
+    float sc = 1.0f;                                                 // default_scale_f
+    if (type == B200_TX_FLOAT_MDCT && scale) sc = *(const float *)scale;
+    B200TXContext *c = new (std::nothrow) B200TXContext();
+    if (!c) return B200_ENOMEM;
+    c->dev = dev; c->type = type; c->inv = !!inv; c->len = len;
+    if (cudaSetDevice(dev->ordinal) != cudaSuccess) { delete c; return B200_EEXTERNAL; }
+    int ret = tx_build(c, sc);
+    if (ret < 0) { if (c->blob) cudaFree(c->blob); delete c; return ret; }
+    *ctx = c;
+    if (tx) *tx = tx_host_fn;
+    return 0;
+}
+
+B200_API int b200_tx_init(B200TXContext **ctx, b200_tx_fn *tx, int type, int inv, int len, const void *scale, uint64_t flags)
+{
+    return b200_tx_init_device(b200_default_device(), ctx, tx, type, inv, len, scale, flags);
+}
+
+B200_API void b200_tx_uninit(B200TXContext **ctx)
+{
+    if (!ctx || !*ctx) return;
+    B200TXContext *c = *ctx;
+    cudaSetDevice(c->dev->ordinal);
+    cudaStreamSynchronize(c->dev->stream);
+    if (c->blob) cudaFree(c->blob);
+    delete c;
+    *ctx = nullptr;
+}
+
+B200_API int b200_tx_batch_device(B200TXContext *c, void *out, const void *in, ptrdiff_t stride, int64_t count,
+                                  ptrdiff_t out_step, ptrdiff_t in_step)
+{
+    if (!c || !out || !in || count < 0) return B200_EINVAL;
+    if (c->type == 1 && (stride & 3)) return B200_EINVAL;
+    B200_CUDA_OK(cudaSetDevice(c->dev->ordinal));
+    return tx_launch(c, c->dev->stream, out, in, c->type == 1 ? stride : 8, count, out_step, in_step);
+}

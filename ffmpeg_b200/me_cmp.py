@@ -1,0 +1,27 @@
+"""Host-side mirror of libavcodec's me_cmp interface (MECmpContext as filled by ff_me_cmp_init, libavcodec/me_cmp.c:961-1027)
+and of the exhaustive search libavfilter drives it with (libavfilter/motion_estimation.c:78-97)."""
+import ctypes as C
+from ._lib import lib, check, vp, MECmpContext
+
+SAD, SSE, PIX_ABS = 0, 1, 2
+AV_CODEC_FLAG_BITEXACT = 1 << 23
+
+
+def _dptr(x):
+    return int(x.data_ptr()) if hasattr(x, "data_ptr") else int(x)
+
+
+def ff_me_cmp_init(codec_flags=AV_CODEC_FLAG_BITEXACT):
+    c = MECmpContext()
+    check(lib().b200_me_cmp_init(C.byref(c), codec_flags), "ff_me_cmp_init")
+    return c
+
+
+def me_cmp_batch_device(device, fn, idx, frame1, frame2, stride, h, off1, off2, n, out):
+    return check(lib().b200_me_cmp_batch_device(device.handle, fn, idx, vp(_dptr(frame1)), vp(_dptr(frame2)), stride, h,
+                                                vp(_dptr(off1)), vp(_dptr(off2)), n, vp(_dptr(out))), "me_cmp_batch_device")
+
+
+def me_esa_device(device, cur, ref, linesize, width, height, frame_stride, nframes, mb_size, search_param, out_mv, out_cost):
+    return check(lib().b200_me_esa_device(device.handle, vp(_dptr(cur)), vp(_dptr(ref)), linesize, width, height, frame_stride,
+                                          nframes, mb_size, search_param, vp(_dptr(out_mv)), vp(_dptr(out_cost))), "me_esa_device")

@@ -1,0 +1,38 @@
+"""Host-side mirror of libavcodec's h264qpel / hpeldsp interfaces (H264QpelContext from ff_h264qpel_init,
+libavcodec/h264qpel.c:50-120; HpelDSPContext from ff_hpeldsp_init, libavcodec/hpeldsp.c:337-352) and the batched entry points."""
+import ctypes as C
+from ._lib import lib, check, vp, H264QpelContext, HpelDSPContext
+
+
+def _dptr(x):
+    return int(x.data_ptr()) if hasattr(x, "data_ptr") else int(x)
+
+
+def ff_h264qpel_init(bit_depth=8):
+    c = H264QpelContext()
+    check(lib().b200_h264qpel_init(C.byref(c), bit_depth), "ff_h264qpel_init")
+    return c
+
+
+def ff_hpeldsp_init(flags=0):
+    c = HpelDSPContext()
+    check(lib().b200_hpeldsp_init(C.byref(c), flags), "ff_hpeldsp_init")
+    return c
+
+
+def qpel_op(avg, size_idx, pos):
+    return (avg & 1) | (size_idx << 1) | (pos << 3)
+
+
+def hpel_op(tab, size_idx, xy):
+    return tab | (size_idx << 2) | (xy << 4)
+
+
+def h264qpel_batch_device(device, n, op, dst, dst_off, src, src_off, stride):
+    return check(lib().b200_h264qpel_batch_device(device.handle, n, vp(_dptr(op)), vp(_dptr(dst)), vp(_dptr(dst_off)),
+                                                  vp(_dptr(src)), vp(_dptr(src_off)), stride), "h264qpel_batch_device")
+
+
+def hpel_batch_device(device, n, op, h, dst, dst_off, src, src_off, stride):
+    return check(lib().b200_hpel_batch_device(device.handle, n, vp(_dptr(op)), vp(_dptr(h)), vp(_dptr(dst)), vp(_dptr(dst_off)),
+                                              vp(_dptr(src)), vp(_dptr(src_off)), stride), "hpel_batch_device")

@@ -1,0 +1,45 @@
+"""Host-side mirror of libavutil/tx's public interface (av_tx_init / av_tx_fn / av_tx_uninit, libavutil/tx.h:151,202-208)
+for AV_TX_FLOAT_FFT and AV_TX_FLOAT_MDCT, plus the batched device entry point."""
+import ctypes as C
+from ._lib import lib, check, vp, TX_FN
+
+AV_TX_FLOAT_FFT, AV_TX_FLOAT_MDCT = 0, 1
+
+
+def _dptr(x):
+    return int(x.data_ptr()) if hasattr(x, "data_ptr") else int(x)
+
+
+class AVTXContext:
+    def __init__(self, type, inv, len, scale=None, flags=0, device=None):
+        self._h = vp()
+        self._fn = TX_FN()
+        sc = C.byref(C.c_float(scale)) if scale is not None else None
+        if device is None:
+            ret = lib().b200_tx_init(C.byref(self._h), C.byref(self._fn), type, inv, len, sc, flags)
+        else:
+            ret = lib().b200_tx_init_device(device.handle, C.byref(self._h), C.byref(self._fn), type, inv, len, sc, flags)
+        check(ret, "av_tx_init")
+        self.type, self.inv, self.len = type, inv, len
+
+    def fn(self, out, inp, stride):
+        """av_tx_fn on HOST numpy arrays."""
+        self._fn(self._h, out.ctypes.data, inp.ctypes.data, stride)
+
+    def batch_device(self, out, inp, stride, count, out_step, in_step):
+        return check(lib().b200_tx_batch_device(self._h, vp(_dptr(out)), vp(_dptr(inp)), stride, count, out_step, in_step),
+                     "tx_batch_device")
+
+    def uninit(self):
+        if self._h:
+            lib().b200_tx_uninit(C.byref(self._h))
+
+    def __del__(self):
+        try:
+            self.uninit()
+        except Exception:
+            pass
+
+
+def av_tx_init(type, inv, len, scale=None, flags=0, device=None):
+    return AVTXContext(type, inv, len, scale, flags, device)

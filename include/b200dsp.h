@@ -156,6 +156,97 @@ int  b200_idct_mb420_device(B200Device *dev, int kind, const int16_t *blocks, in
 int  b200_idct_mb420_host(B200Device *dev, int kind, const int16_t *blocks, int mb_w, int mb_h, int nframes,
                           uint8_t *const planes[3], const int linesize[3], const int64_t frame_stride[3]);
 
+/* ------------------------------------------------------------------------------------------------ me_cmp
+ * Replaces MECmpContext (libavcodec/me_cmp.h:53-77) as filled by ff_me_cmp_init (libavcodec/me_cmp.c:961-1027) for the
+ * SAD / SSE entries: sad[0..1] = pix_abs16_c / pix_abs8_c, sse[0..2] = sse16_c / sse8_c / sse4_c,
+ * pix_abs[0..1][0..3] = full / x2 / y2 / xy2 (me_cmp.c:37-385).  Entries this library does not implement stay NULL.
+ * me_cmp_func (me_cmp.h:47-51): the first argument (MPVEncContext *) is unused by these functions and may be NULL. */
+typedef int (*b200_me_cmp_func)(void *c, const uint8_t *blk1, const uint8_t *blk2, ptrdiff_t stride, int h);
+typedef struct B200MECmpContext {
+    int (*sum_abs_dctelem)(const int16_t *block);
+    b200_me_cmp_func sad[6];
+    b200_me_cmp_func sse[6];
+    b200_me_cmp_func hadamard8_diff[6];
+    b200_me_cmp_func dct_sad[6];
+    b200_me_cmp_func quant_psnr[6];
+    b200_me_cmp_func bit[6];
+    b200_me_cmp_func rd[6];
+    b200_me_cmp_func vsad[6];
+    b200_me_cmp_func vsse[6];
+    b200_me_cmp_func nsse[6];
+    b200_me_cmp_func w53[6];
+    b200_me_cmp_func w97[6];
+    b200_me_cmp_func dct_max[6];
+    b200_me_cmp_func dct264_sad[6];
+    b200_me_cmp_func pix_abs[2][4];
+    b200_me_cmp_func median_sad[6];
+} B200MECmpContext;
+/* like ff_me_cmp_init(c, avctx); avctx->flags passed explicitly (only AV_CODEC_FLAG_BITEXACT matters upstream) */
+int  b200_me_cmp_init(B200MECmpContext *c, int codec_flags);
+
+#define B200_MECMP_SAD     0   /* idx 0: 16 wide, 1: 8 wide */
+#define B200_MECMP_SSE     1   /* idx 0: 16, 1: 8, 2: 4 wide */
+#define B200_MECMP_PIX_ABS 2   /* idx = 4*size(0:16,1:8) + (0 full, 1 x2, 2 y2, 3 xy2) */
+/* batched, DEVICE pointers: out[i] = fn(frame1 + off1[i], frame2 + off2[i], stride, h) */
+int  b200_me_cmp_batch_device(B200Device *dev, int fn, int idx, const uint8_t *frame1, const uint8_t *frame2,
+                              ptrdiff_t stride, int h, const int64_t *off1, const int64_t *off2, int64_t n, int32_t *out);
+/* exhaustive search over whole frames, DEVICE pointers: ff_me_search_esa (libavfilter/motion_estimation.c:78-97) driven
+ * like vf_mestimate.c:85-127 — for every mb_size x mb_size block of every frame pair: cost of the zero vector first,
+ * raster scan of the +-search_param window clipped to the frame, strict '<' (first minimum in raster order wins, the
+ * zero vector wins ties against everything).  mb_size in {4, 8, 16}.  out_mv: 2 ints (absolute x, y of the best match)
+ * per block in raster order per frame; out_cost: its SAD. */
+int  b200_me_esa_device(B200Device *dev, const uint8_t *cur, const uint8_t *ref, int linesize, int width, int height,
+                        int64_t frame_stride, int nframes, int mb_size, int search_param, int32_t *out_mv, uint64_t *out_cost);
+
+/* ------------------------------------------------------------------------------------------------ h264qpel / hpeldsp
+ * Replaces H264QpelContext (libavcodec/h264qpel.h:27-30) as filled by ff_h264qpel_init(c, 8) (libavcodec/h264qpel.c:50-120)
+ * and HpelDSPContext (libavcodec/hpeldsp.h:39-97) as filled by ff_hpeldsp_init (libavcodec/hpeldsp.c:337-352), 8 bit.
+ * qpel_mc_func (libavcodec/qpeldsp.h:65-67), op_pixels_func (libavcodec/hpeldsp.h:39-41). */
+typedef void (*b200_qpel_mc_func)(uint8_t *dst, const uint8_t *src, ptrdiff_t stride);
+typedef void (*b200_op_pixels_func)(uint8_t *block, const uint8_t *pixels, ptrdiff_t line_size, int h);
+typedef struct B200H264QpelContext {
+    b200_qpel_mc_func put_h264_qpel_pixels_tab[3][16];     /* [0:16x16, 1:8x8, 2:4x4][x + 4*y] */
+    b200_qpel_mc_func avg_h264_qpel_pixels_tab[3][16];
+} B200H264QpelContext;
+typedef struct B200HpelDSPContext {
+    b200_op_pixels_func put_pixels_tab[4][4];              /* [0:16, 1:8, 2:4, 3:2 wide][xhalf + 2*yhalf] */
+    b200_op_pixels_func avg_pixels_tab[4][4];
+    b200_op_pixels_func put_no_rnd_pixels_tab[3][4];       /* only [0..1] filled, like the reference */
+    b200_op_pixels_func avg_no_rnd_pixels_tab[4];
+} B200HpelDSPContext;
+int  b200_h264qpel_init(B200H264QpelContext *c, int bit_depth);    /* bit_depth must be 8, else B200_ENOSYS */
+int  b200_hpeldsp_init(B200HpelDSPContext *c, int flags);
+
+/* batched motion compensation, DEVICE pointers: operation i interpolates the block at src + src_off[i] into
+ * dst + dst_off[i] (same stride for both, like the reference's single stride argument).
+ * qpel op byte: bit0 avg, bits1-2 size index (0:16,1:8,2:4), bits3-6 position x+4*y.
+ * hpel op byte: bits0-1 table (0 put, 1 avg, 2 put_no_rnd, 3 avg_no_rnd), bits2-3 size index (0:16,1:8,2:4,3:2),
+ * bits4-5 xy; h[i] = block height. Destination blocks of one call must not overlap each other. */
+int  b200_h264qpel_batch_device(B200Device *dev, int64_t n, const uint8_t *op, uint8_t *dst, const int64_t *dst_off,
+                                const uint8_t *src, const int64_t *src_off, ptrdiff_t stride);
+int  b200_hpel_batch_device(B200Device *dev, int64_t n, const uint8_t *op, const uint8_t *h, uint8_t *dst,
+                            const int64_t *dst_off, const uint8_t *src, const int64_t *src_off, ptrdiff_t stride);
+
+/* ------------------------------------------------------------------------------------------------ libavutil/tx
+ * Replaces av_tx_init / av_tx_uninit / av_tx_fn (libavutil/tx.h:151,202-208) for AV_TX_FLOAT_FFT and AV_TX_FLOAT_MDCT,
+ * power-of-two lengths, with the float operation order of the reference's C codelets (bit-identical results).
+ * Inside FFmpeg the plug point is a codelet list with prio FF_TX_PRIO_MAX (libavutil/tx_priv.h:168, tx.c:340-351). */
+#define B200_TX_FLOAT_FFT   0     /* AV_TX_FLOAT_FFT  */
+#define B200_TX_FLOAT_MDCT  1     /* AV_TX_FLOAT_MDCT */
+#define B200_TX_UNALIGNED   2     /* AV_TX_UNALIGNED (accepted, no effect) */
+typedef struct B200TXContext B200TXContext;
+typedef void (*b200_tx_fn)(B200TXContext *s, void *out, void *in, ptrdiff_t stride);   /* av_tx_fn: HOST pointers */
+/* like av_tx_init(); uses the process-wide default device.  scale: const float * (MDCT), ignored for FFT.
+ * Returns 0 or B200_ENOSYS (unsupported type / flags / length), B200_EINVAL, B200_ENODEV. */
+int  b200_tx_init(B200TXContext **ctx, b200_tx_fn *tx, int type, int inv, int len, const void *scale, uint64_t flags);
+int  b200_tx_init_device(B200Device *dev, B200TXContext **ctx, b200_tx_fn *tx, int type, int inv, int len,
+                         const void *scale, uint64_t flags);
+void b200_tx_uninit(B200TXContext **ctx);
+/* batched, DEVICE pointers: transform i reads in + i*in_step and writes out + i*out_step (bytes); `stride` as av_tx_fn
+ * (bytes between MDCT input samples for the inverse / output samples for the forward transform; unused for FFT). */
+int  b200_tx_batch_device(B200TXContext *ctx, void *out, const void *in, ptrdiff_t stride, int64_t count,
+                          ptrdiff_t out_step, ptrdiff_t in_step);
+
 #ifdef __cplusplus
 }
 #endif

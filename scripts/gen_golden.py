@@ -7,6 +7,7 @@ from /root/reference).  Run in the build container only; the fixtures travel to 
 Every fixture stores the inputs (or the seed + a sha256 of the inputs, for the larger cases) and the reference's
 outputs, so the tests need neither /root/reference nor oracle/_ref at run time.
 """
+import ctypes as C
 import hashlib
 import os
 import sys
@@ -68,10 +69,94 @@ def gen_idct():
     np.savez_compressed(os.path.join(OUT, "idct.npz"), **d)
 
 
+def gen_mecmp():
+    R = cl.ref()
+    rng = np.random.default_rng(21)
+    img1 = rng.integers(0, 256, (64, 64), dtype=np.uint8)          # tests/checkasm/motion.c:38-88: 64x64 random images
+    img2 = rng.integers(0, 256, (64, 64), dtype=np.uint8)
+    rows = []
+    for fn, idxs in ((0, (0, 1)), (1, (0, 1, 2)), (2, range(8))):
+        for idx in idxs:
+            for _ in range(12):
+                x1, y1, x2, y2 = (int(v) for v in rng.integers(0, 40, 4))
+                h = int(rng.choice([4, 8, 16]))
+                v = R.ffref_me_cmp(fn, idx, C.cast(img1.ctypes.data + y1 * 64 + x1, cl.u8p), C.cast(img2.ctypes.data + y2 * 64 + x2, cl.u8p), 64, h)
+                rows.append((fn, idx, x1, y1, x2, y2, h, v))
+    d = {"img1": img1, "img2": img2, "cases": np.array(rows, np.int32)}
+    # exhaustive search: shifted + noisy reference, a flat pair (all ties) and an identical pair (early exit)
+    W, H = 96, 64
+    cur = rng.integers(0, 256, (H, W), dtype=np.uint8)
+    ref_ = np.roll(cur, (2, -3), (0, 1)).copy()
+    ref_[::5, ::3] ^= 5
+    flat = np.full((H, W), 99, np.uint8)
+    d["esa_cur"], d["esa_ref"] = cur, ref_
+    for name, (a, b) in {"shift": (cur, ref_), "flat": (flat, flat), "same": (cur, cur)}.items():
+        for mb, sp in ((16, 7), (8, 4), (16, 32), (4, 3)):
+            bw, bh = W // mb, H // mb
+            mv = np.zeros((bh * bw, 2), np.int32)
+            cost = np.zeros(bh * bw, np.uint64)
+            R.ffref_esa_frame(cl.ptr(a), cl.ptr(b), W, W, H, mb, sp, 0, bh, cl.ptr(mv, cl.i32p), cl.ptr(cost, cl.u64p))
+            d[f"esa_{name}_{mb}_{sp}_mv"], d[f"esa_{name}_{mb}_{sp}_cost"] = mv, cost
+    np.savez_compressed(os.path.join(OUT, "mecmp.npz"), **d)
+
+
+def gen_pel():
+    R = cl.ref()
+    rng = np.random.default_rng(22)
+    src = rng.integers(0, 256, (40, 48), dtype=np.uint8)
+    dst0 = rng.integers(0, 256, (40, 48), dtype=np.uint8)
+    d = {"src": src, "dst0": dst0}
+    ps = C.cast(src.ctypes.data + 8 * 48 + 8, cl.u8p)
+    for avg in (0, 1):
+        for sz in (0, 1, 2):
+            for pos in range(16):
+                o = dst0.copy()
+                R.ffref_h264qpel(avg, sz, pos, C.cast(o.ctypes.data + 8 * 48 + 8, cl.u8p), ps, 48)
+                d[f"q_{avg}_{sz}_{pos}"] = o[8:24, 8:24].copy()
+    for tab in range(4):
+        for sz in range(4):
+            for xy in range(4):
+                for h in ((8, 16) if sz < 2 else (2, 8)):
+                    o = dst0.copy()
+                    if R.ffref_hpel(tab, sz, xy, C.cast(o.ctypes.data + 8 * 48 + 8, cl.u8p), ps, 48, h) == 0:
+                        d[f"h_{tab}_{sz}_{xy}_{h}"] = o[8:24, 8:24].copy()
+    np.savez_compressed(os.path.join(OUT, "pel.npz"), **d)
+
+
+def gen_tx():
+    R = cl.ref()
+    rng = np.random.default_rng(23)
+    d = {}
+
+    def run(typ, inv, n, scale, x, out_floats):
+        h = R.ffref_tx_open(typ, inv, n, scale, 0)
+        assert h
+        out = np.zeros((x.shape[0], out_floats), np.float32)
+        R.ffref_tx_run(h, out.ctypes.data, x.ctypes.data, 8 if typ == 0 else 4, x.shape[0], out.strides[0], x.strides[0])
+        R.ffref_tx_close(h)
+        return out
+    for n in (2, 4, 8, 16, 32, 64, 256, 1024, 2048):            # tests/checkasm/av_tx.c:38-40 power-of-two lengths + BASELINE sizes
+        x = rng.random((2, 2 * n), dtype=np.float32)            # in[i] = rnd()/UINT_MAX like checkasm (av_tx.c:33-41)
+        d[f"fft_in_{n}"] = x
+        for inv in (0, 1):
+            d[f"fft_{n}_{inv}"] = run(0, inv, n, 1.0, x, 2 * n)
+    for n in (8, 16, 64, 256, 1024, 2048):
+        x = rng.random((2, n), dtype=np.float32)
+        x2 = rng.random((2, 2 * n), dtype=np.float32)
+        d[f"imdct_in_{n}"], d[f"mdct_in_{n}"] = x, x2
+        for j, sc in enumerate((1.0 / n, -1.0, 1.0)):
+            d[f"imdct_{n}_{j}"] = run(1, 1, n, sc, x, n)
+            d[f"mdct_{n}_{j}"] = run(1, 0, n, sc, x2, n)
+    np.savez_compressed(os.path.join(OUT, "tx.npz"), **d)
+
+
 if __name__ == "__main__":
     assert cl.have_ref(), "build oracle/_ref first: make -C oracle/ref"
     os.makedirs(OUT, exist_ok=True)
     gen_sws()
     gen_idct()
+    gen_mecmp()
+    gen_pel()
+    gen_tx()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -1,0 +1,312 @@
+"""GPU tier: me_cmp / ESA, h264qpel / hpeldsp and float tx CUDA paths (through the C ABI) against the oracle and the
+golden fixtures generated from the unmodified reference."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import cpulibs as cl
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def on_stream(device):
+    import torch
+    return torch.cuda.stream(torch.cuda.ExternalStream(device.stream))
+
+
+# ---------------------------------------------------------------------------------------------- me_cmp
+def test_mecmp_pointer_table_golden(device):
+    """MECmpContext entries called like checkasm motion.c does (NULL context, random offsets, h in {4,8,16})."""
+    from ffmpeg_b200 import me_cmp
+    from ffmpeg_b200._lib import u8p
+    g = np.load(os.path.join(G, "mecmp.npz"))
+    c = me_cmp.ff_me_cmp_init()
+    img1, img2 = g["img1"], g["img2"]
+    assert not c.hadamard8_diff[0] and not c.sad[2]            # entries not implemented stay NULL
+    for fn, idx, x1, y1, x2, y2, h, v in g["cases"]:
+        f = c.sad[idx] if fn == 0 else c.sse[idx] if fn == 1 else c.pix_abs[idx >> 2][idx & 3]
+        got = f(None, C.cast(img1.ctypes.data + int(y1) * 64 + int(x1), u8p), C.cast(img2.ctypes.data + int(y2) * 64 + int(x2), u8p), 64, int(h))
+        assert got == v, (fn, idx, h)
+
+
+def test_mecmp_batch_vs_oracle(device):
+    import torch
+    from ffmpeg_b200 import me_cmp
+    O = cl.oracle()
+    rng = np.random.default_rng(5)
+    W, H, n = 256, 128, 3000
+    f1 = rng.integers(0, 256, (H, W), dtype=np.uint8)
+    f2 = rng.integers(0, 256, (H, W), dtype=np.uint8)
+    xs1, ys1, xs2, ys2 = (rng.integers(0, d - 20, n) for d in (W, H, W, H))
+    off1 = (ys1 * W + xs1).astype(np.int64)
+    off2 = (ys2 * W + xs2).astype(np.int64)
+    with on_stream(device):
+        d1, d2 = torch.from_numpy(f1).cuda(), torch.from_numpy(f2).cuda()
+        o1, o2 = torch.from_numpy(off1).cuda(), torch.from_numpy(off2).cuda()
+        out = torch.zeros(n, dtype=torch.int32, device="cuda")
+        for fn, idxs in ((0, (0, 1)), (1, (0, 1, 2)), (2, range(8))):
+            for idx in idxs:
+                for h in (4, 8, 16):
+                    me_cmp.me_cmp_batch_device(device, fn, idx, d1, d2, W, h, o1, o2, n, out)
+                    device.sync()
+                    got = out.cpu().numpy()
+                    exp = np.array([O.orc_me_cmp(fn, idx, C.cast(f1.ctypes.data + int(a), cl.u8p), C.cast(f2.ctypes.data + int(b), cl.u8p), W, h)
+                                    for a, b in zip(off1[:400], off2[:400])])
+                    assert np.array_equal(got[:400], exp), (fn, idx, h)
+
+
+def gpu_esa(device, cur, ref_, mb, sp):
+    import torch
+    from ffmpeg_b200 import me_cmp
+    nf, H, W = cur.shape
+    bw, bh = W // mb, H // mb
+    with on_stream(device):
+        dc, dr = torch.from_numpy(cur).cuda(), torch.from_numpy(ref_).cuda()
+        mv = torch.zeros((nf, bh * bw, 2), dtype=torch.int32, device="cuda")
+        cost = torch.zeros((nf, bh * bw), dtype=torch.int64, device="cuda")
+        me_cmp.me_esa_device(device, dc, dr, W, W, H, W * H, nf, mb, sp, mv, cost)
+        device.sync()
+        return mv.cpu().numpy(), cost.cpu().numpy().astype(np.uint64)
+
+
+def test_esa_golden(device):
+    g = np.load(os.path.join(G, "mecmp.npz"))
+    W, H = 96, 64
+    cur, ref_ = g["esa_cur"], g["esa_ref"]
+    flat = np.full((H, W), 99, np.uint8)
+    for name, (a, b) in {"shift": (cur, ref_), "flat": (flat, flat), "same": (cur, cur)}.items():
+        for mb, sp in ((16, 7), (8, 4), (16, 32), (4, 3)):
+            mv, cost = gpu_esa(device, a[None], b[None], mb, sp)
+            assert np.array_equal(mv[0], g[f"esa_{name}_{mb}_{sp}_mv"]), (name, mb, sp)
+            assert np.array_equal(cost[0], g[f"esa_{name}_{mb}_{sp}_cost"]), (name, mb, sp)
+
+
+def test_esa_vs_oracle_multi_frame(device):
+    """720p-sized frame pairs, +-32 window (BASELINE config 4 geometry at a size the oracle finishes in seconds is too
+    slow; use 320x192 for the oracle and check 4K through the minimum-cost property)."""
+    O = cl.oracle()
+    rng = np.random.default_rng(9)
+    nf, W, H, mb, sp = 2, 320, 192, 16, 32
+    cur = rng.integers(0, 256, (nf, H, W), dtype=np.uint8)
+    ref_ = np.stack([np.roll(cur[i], (5 - 9 * i, -7 + 3 * i), (0, 1)) for i in range(nf)])
+    ref_ = (ref_.astype(np.int16) + rng.integers(-2, 3, ref_.shape)).clip(0, 255).astype(np.uint8)
+    mv, cost = gpu_esa(device, cur, ref_, mb, sp)
+    bw, bh = W // mb, H // mb
+    for i in range(nf):
+        emv, ec = np.zeros((bh * bw, 2), np.int32), np.zeros(bh * bw, np.uint64)
+        O.orc_esa_frame(cl.ptr(cur[i]), cl.ptr(ref_[i]), W, W, H, mb, sp, 0, bh, cl.ptr(emv, cl.i32p), cl.ptr(ec, cl.u64p))
+        assert np.array_equal(mv[i], emv) and np.array_equal(cost[i], ec), i
+
+
+def test_esa_4k_property(device):
+    """Full-size 4K pair: the returned cost must equal the SAD at the returned vector and be <= the zero-vector SAD and
+    the SAD at a few probe vectors (size-independent property; the oracle would need minutes here)."""
+    rng = np.random.default_rng(10)
+    W, H, mb, sp = 3840, 2160, 16, 32
+    cur = rng.integers(0, 256, (1, H, W), dtype=np.uint8)
+    ref_ = np.roll(cur, (0, 11, -6), (0, 1, 2)).copy()
+    mv, cost = gpu_esa(device, cur, ref_, mb, sp)
+    bw = W // mb
+    for b in rng.integers(0, mv.shape[1], 200):
+        by, bx = divmod(int(b), bw)
+        x_mb, y_mb = bx * mb, by * mb
+        blk = cur[0, y_mb:y_mb + mb, x_mb:x_mb + mb].astype(np.int32)
+        x, y = mv[0, b]
+        sad = lambda xx, yy: int(np.abs(ref_[0, yy:yy + mb, xx:xx + mb].astype(np.int32) - blk).sum())
+        assert sad(x, y) == int(cost[0, b])
+        assert int(cost[0, b]) <= sad(x_mb, y_mb)
+        if 32 <= y_mb <= H - 48 and 32 <= x_mb <= W - 48:
+            assert int(cost[0, b]) == 0 and (x, y) == (x_mb - 6, y_mb + 11)        # the true shift is found exactly
+
+
+# ---------------------------------------------------------------------------------------------- qpel / hpel
+def test_pel_pointer_tables_golden(device):
+    from ffmpeg_b200 import pel
+    from ffmpeg_b200._lib import u8p
+    g = np.load(os.path.join(G, "pel.npz"))
+    q, hp = pel.ff_h264qpel_init(8), pel.ff_hpeldsp_init(0)
+    src, dst0 = g["src"], g["dst0"]
+    ps = C.cast(src.ctypes.data + 8 * 48 + 8, u8p)
+    for key in g.files:
+        if key in ("src", "dst0"):
+            continue
+        o = dst0.copy()
+        po = C.cast(o.ctypes.data + 8 * 48 + 8, u8p)
+        parts = [int(v) for v in key.split("_")[1:]]
+        if key[0] == "q":
+            (q.avg_h264_qpel_pixels_tab if parts[0] else q.put_h264_qpel_pixels_tab)[parts[1]][parts[2]](po, ps, 48)
+        else:
+            tab = [hp.put_pixels_tab, hp.avg_pixels_tab, hp.put_no_rnd_pixels_tab, None][parts[0]]
+            f = hp.avg_no_rnd_pixels_tab[parts[2]] if parts[0] == 3 else tab[parts[1]][parts[2]]
+            f(po, ps, 48, parts[3])
+        assert np.array_equal(o[8:24, 8:24], g[key]), key
+        assert np.array_equal(o[:8], dst0[:8]) and np.array_equal(o[24:], dst0[24:]) and np.array_equal(o[:, :8], dst0[:, :8]), key
+    assert not hp.put_no_rnd_pixels_tab[2][0]                  # sizes the reference leaves empty stay NULL
+
+
+def test_qpel_batch_vs_oracle(device):
+    """A macroblock-stream like BASELINE config 3: random quarter-pel positions, put/avg and sizes over a frame."""
+    import torch
+    from ffmpeg_b200 import pel
+    O = cl.oracle()
+    rng = np.random.default_rng(12)
+    W, H = 640, 368
+    ref_ = rng.integers(0, 256, (H, W), dtype=np.uint8)
+    dst0 = rng.integers(0, 256, (H, W), dtype=np.uint8)
+    ops, doffs, soffs = [], [], []
+    for by in range(1, H // 16 - 1):
+        for bx in range(1, W // 16 - 1):
+            size_idx = int(rng.integers(0, 3))
+            op = pel.qpel_op(int(rng.integers(0, 2)), size_idx, int(rng.integers(0, 16)))
+            dx, dy = (int(v) for v in rng.integers(-10, 11, 2))
+            ops.append(op); doffs.append(by * 16 * W + bx * 16); soffs.append((by * 16 + dy) * W + bx * 16 + dx)
+    n = len(ops)
+    ops_a, do_a, so_a = np.array(ops, np.uint8), np.array(doffs, np.int64), np.array(soffs, np.int64)
+    exp = dst0.copy()
+    for op, do, so in zip(ops, doffs, soffs):
+        O.orc_h264qpel(op & 1, (op >> 1) & 3, (op >> 3) & 15, C.cast(exp.ctypes.data + do, cl.u8p), C.cast(ref_.ctypes.data + so, cl.u8p), W)
+    with on_stream(device):
+        d_ops, d_do, d_so = torch.from_numpy(ops_a).cuda(), torch.from_numpy(do_a).cuda(), torch.from_numpy(so_a).cuda()
+        d_dst, d_src = torch.from_numpy(dst0).cuda(), torch.from_numpy(ref_).cuda()
+        pel.h264qpel_batch_device(device, n, d_ops, d_dst, d_do, d_src, d_so, W)
+        device.sync()
+        got = d_dst.cpu().numpy()
+    assert np.array_equal(got, exp), int((got != exp).sum())
+
+
+def test_hpel_batch_vs_oracle(device):
+    import torch
+    from ffmpeg_b200 import pel
+    O = cl.oracle()
+    rng = np.random.default_rng(13)
+    W, H = 320, 192
+    ref_ = rng.integers(0, 256, (H, W), dtype=np.uint8)
+    dst0 = rng.integers(0, 256, (H, W), dtype=np.uint8)
+    ops, hs, doffs, soffs = [], [], [], []
+    for by in range(1, H // 16 - 1):
+        for bx in range(1, W // 16 - 1):
+            tab = int(rng.integers(0, 4))
+            sidx = 0 if tab == 3 else int(rng.integers(0, 2)) if tab == 2 else int(rng.integers(0, 4))
+            h = int(rng.choice([4, 8, 16] if sidx < 2 else [2, 4, 8]))
+            ops.append(pel.hpel_op(tab, sidx, int(rng.integers(0, 4)))); hs.append(h)
+            dx, dy = (int(v) for v in rng.integers(-8, 9, 2))
+            doffs.append(by * 16 * W + bx * 16); soffs.append((by * 16 + dy) * W + bx * 16 + dx)
+    exp = dst0.copy()
+    for op, h, do, so in zip(ops, hs, doffs, soffs):
+        assert O.orc_hpel(op & 3, (op >> 2) & 3, (op >> 4) & 3, C.cast(exp.ctypes.data + do, cl.u8p), C.cast(ref_.ctypes.data + so, cl.u8p), W, h) == 0
+    with on_stream(device):
+        t = lambda a, dt: torch.from_numpy(np.array(a, dt)).cuda()
+        d_dst, d_src = torch.from_numpy(dst0).cuda(), torch.from_numpy(ref_).cuda()
+        pel.hpel_batch_device(device, len(ops), t(ops, np.uint8), t(hs, np.uint8), d_dst, t(doffs, np.int64), d_src, t(soffs, np.int64), W)
+        device.sync()
+        got = d_dst.cpu().numpy()
+    assert np.array_equal(got, exp), int((got != exp).sum())
+
+
+# ---------------------------------------------------------------------------------------------- tx
+def ulp_diff(a, b):
+    ai, bi = a.view(np.int32).astype(np.int64), b.view(np.int32).astype(np.int64)
+    ai = np.where(ai < 0, -(ai & 0x7fffffff), ai)
+    bi = np.where(bi < 0, -(bi & 0x7fffffff), bi)
+    return np.abs(ai - bi).max()
+
+
+def test_tx_host_fn_golden(device):
+    """av_tx_fn on host buffers: north_star bar is 1 ULP against the reference's *_float_c; we expect 0."""
+    from ffmpeg_b200 import tx
+    g = np.load(os.path.join(G, "tx.npz"))
+    for n in (2, 4, 8, 16, 32, 64, 256, 1024, 2048):
+        for inv in (0, 1):
+            c = tx.av_tx_init(tx.AV_TX_FLOAT_FFT, inv, n)
+            x = g[f"fft_in_{n}"]
+            out = np.zeros_like(x)
+            for r in range(x.shape[0]):
+                c.fn(out[r], x[r].copy(), 8)
+            assert ulp_diff(out, g[f"fft_{n}_{inv}"]) <= 1, (n, inv)
+            assert np.array_equal(out, g[f"fft_{n}_{inv}"]), (n, inv)
+            c.uninit()
+    for n in (8, 16, 64, 256, 1024, 2048):
+        for j, sc in enumerate((1.0 / n, -1.0, 1.0)):
+            c = tx.av_tx_init(tx.AV_TX_FLOAT_MDCT, 1, n, scale=sc)
+            x = g[f"imdct_in_{n}"]
+            out = np.zeros((x.shape[0], n), np.float32)
+            for r in range(x.shape[0]):
+                c.fn(out[r], x[r].copy(), 4)
+            assert np.array_equal(out, g[f"imdct_{n}_{j}"]), (n, j)
+            c.uninit()
+            c = tx.av_tx_init(tx.AV_TX_FLOAT_MDCT, 0, n, scale=sc)
+            x = g[f"mdct_in_{n}"]
+            out = np.zeros((x.shape[0], n), np.float32)
+            for r in range(x.shape[0]):
+                c.fn(out[r], x[r].copy(), 4)
+            assert np.array_equal(out, g[f"mdct_{n}_{j}"]), (n, j)
+            c.uninit()
+
+
+@pytest.mark.parametrize("n", [512, 1024, 2048, 4096])
+def test_tx_batch_vs_oracle(device, n):
+    import torch
+    from ffmpeg_b200 import tx
+    O = cl.oracle()
+    rng = np.random.default_rng(n)
+    cnt = 300
+
+    def orc(typ, inv, scale, x, of):
+        h = O.orc_tx_open(typ, inv, n, scale, 0)
+        out = np.zeros((x.shape[0], of), np.float32)
+        O.orc_tx_run(h, out.ctypes.data, x.ctypes.data, 8 if typ == 0 else 4, x.shape[0], out.strides[0], x.strides[0])
+        O.orc_tx_close(h)
+        return out
+    with on_stream(device):
+        x = rng.random((cnt, 2 * n), dtype=np.float32)
+        dx = torch.from_numpy(x).cuda()
+        for inv in (0, 1):
+            c = tx.av_tx_init(tx.AV_TX_FLOAT_FFT, inv, n, device=device)
+            do = torch.zeros_like(dx)
+            c.batch_device(do, dx, 8, cnt, 8 * n, 8 * n)
+            device.sync()
+            assert np.array_equal(do.cpu().numpy(), orc(0, inv, 1.0, x, 2 * n)), ("fft", inv)
+            c.uninit()
+        xi = np.ascontiguousarray(x[:, :n])
+        c = tx.av_tx_init(tx.AV_TX_FLOAT_MDCT, 1, n, scale=1.0 / n, device=device)
+        di, do = torch.from_numpy(xi).cuda(), torch.zeros((cnt, n), dtype=torch.float32, device="cuda")
+        c.batch_device(do, di, 4, cnt, 4 * n, 4 * n)
+        device.sync()
+        assert np.array_equal(do.cpu().numpy(), orc(1, 1, 1.0 / n, xi, n)), "imdct"
+        c.uninit()
+        c = tx.av_tx_init(tx.AV_TX_FLOAT_MDCT, 0, n, scale=-1.0, device=device)
+        do = torch.zeros((cnt, n), dtype=torch.float32, device="cuda")
+        c.batch_device(do, dx, 4, cnt, 4 * n, 8 * n)
+        device.sync()
+        assert np.array_equal(do.cpu().numpy(), orc(1, 0, -1.0, x, n)), "mdct"
+        c.uninit()
+
+
+def test_tx_linearity_1m_batch(device):
+    """BASELINE config 5 size (a large batch of len-1024 transforms): FFT(a) + FFT(b) ~= FFT(a + b) and Parseval,
+    size-independent properties at a size the oracle cannot cover; plus unsupported configurations are refused loudly."""
+    import torch
+    import ffmpeg_b200 as fb
+    from ffmpeg_b200 import tx
+    n, cnt = 1024, 200_000
+    with on_stream(device):
+        a = torch.rand((cnt, 2 * n), device="cuda")
+        b = torch.rand((cnt, 2 * n), device="cuda")
+        c = tx.av_tx_init(tx.AV_TX_FLOAT_FFT, 0, n, device=device)
+        fa, fb_, fab = torch.empty_like(a), torch.empty_like(a), torch.empty_like(a)
+        c.batch_device(fa, a, 8, cnt, 8 * n, 8 * n)
+        c.batch_device(fb_, b, 8, cnt, 8 * n, 8 * n)
+        c.batch_device(fab, a + b, 8, cnt, 8 * n, 8 * n)
+        device.sync()
+        assert float((fa + fb_ - fab).abs().max()) < 2e-2
+        e_t = (a[:1000].double() ** 2).sum(1)
+        e_f = (fa[:1000].double() ** 2).sum(1) / n
+        assert float(((e_t - e_f).abs() / e_t).max()) < 1e-5
+        c.uninit()
+    with pytest.raises(fb.B200Error):
+        tx.av_tx_init(tx.AV_TX_FLOAT_FFT, 0, 960, device=device)            # PFA length: not implemented
+    with pytest.raises(fb.B200Error):
+        tx.av_tx_init(5, 0, 1024, device=device)                            # other transform types

@@ -1,0 +1,109 @@
+"""CPU tier: pin the me_cmp / h264qpel / hpeldsp / tx oracles against the golden fixtures (always) and the compiled
+reference (where oracle/_ref exists)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import cpulibs as cl
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+needs_ref = pytest.mark.skipif(not cl.have_ref(), reason="oracle/_ref not built (no /root/reference here)")
+
+
+def test_mecmp_oracle_golden():
+    g = np.load(os.path.join(G, "mecmp.npz"))
+    O = cl.oracle()
+    img1, img2 = g["img1"], g["img2"]
+    for fn, idx, x1, y1, x2, y2, h, v in g["cases"]:
+        got = O.orc_me_cmp(int(fn), int(idx), C.cast(img1.ctypes.data + int(y1) * 64 + int(x1), cl.u8p),
+                           C.cast(img2.ctypes.data + int(y2) * 64 + int(x2), cl.u8p), 64, int(h))
+        assert got == v, (fn, idx, h)
+    W, H = 96, 64
+    cur, ref_ = g["esa_cur"], g["esa_ref"]
+    flat = np.full((H, W), 99, np.uint8)
+    for name, (a, b) in {"shift": (cur, ref_), "flat": (flat, flat), "same": (cur, cur)}.items():
+        for mb, sp in ((16, 7), (8, 4), (16, 32), (4, 3)):
+            bw, bh = W // mb, H // mb
+            mv, cost = np.zeros((bh * bw, 2), np.int32), np.zeros(bh * bw, np.uint64)
+            O.orc_esa_frame(cl.ptr(a), cl.ptr(b), W, W, H, mb, sp, 0, bh, cl.ptr(mv, cl.i32p), cl.ptr(cost, cl.u64p))
+            assert np.array_equal(mv, g[f"esa_{name}_{mb}_{sp}_mv"]) and np.array_equal(cost, g[f"esa_{name}_{mb}_{sp}_cost"]), (name, mb, sp)
+
+
+def test_pel_oracle_golden():
+    g = np.load(os.path.join(G, "pel.npz"))
+    O = cl.oracle()
+    src, dst0 = g["src"], g["dst0"]
+    ps = C.cast(src.ctypes.data + 8 * 48 + 8, cl.u8p)
+    n = 0
+    for key in g.files:
+        if key[0] not in "qh" or key in ("src", "dst0"):
+            continue
+        o = dst0.copy()
+        po = C.cast(o.ctypes.data + 8 * 48 + 8, cl.u8p)
+        parts = [int(v) for v in key.split("_")[1:]]
+        if key[0] == "q":
+            O.orc_h264qpel(parts[0], parts[1], parts[2], po, ps, 48)
+        else:
+            assert O.orc_hpel(parts[0], parts[1], parts[2], po, ps, 48, parts[3]) == 0
+        assert np.array_equal(o[8:24, 8:24], g[key]), key
+        assert np.array_equal(o[:8], dst0[:8]) and np.array_equal(o[24:], dst0[24:]), key      # guard rows untouched
+        n += 1
+    assert n > 150
+
+
+def _tx(L, pre, typ, inv, n, scale, x, out_floats):
+    h = getattr(L, pre + "_tx_open")(typ, inv, n, scale, 0)
+    assert h
+    out = np.zeros((x.shape[0], out_floats), np.float32)
+    getattr(L, pre + "_tx_run")(h, out.ctypes.data, x.ctypes.data, 8 if typ == 0 else 4, x.shape[0], out.strides[0], x.strides[0])
+    getattr(L, pre + "_tx_close")(h)
+    return out
+
+
+def test_tx_oracle_golden_bitexact():
+    g = np.load(os.path.join(G, "tx.npz"))
+    O = cl.oracle()
+    for n in (2, 4, 8, 16, 32, 64, 256, 1024, 2048):
+        for inv in (0, 1):
+            got = _tx(O, "orc", 0, inv, n, 1.0, g[f"fft_in_{n}"], 2 * n)
+            assert np.array_equal(got.view(np.uint32), g[f"fft_{n}_{inv}"].view(np.uint32)), (n, inv)
+    for n in (8, 16, 64, 256, 1024, 2048):
+        for j, sc in enumerate((1.0 / n, -1.0, 1.0)):
+            assert np.array_equal(_tx(O, "orc", 1, 1, n, sc, g[f"imdct_in_{n}"], n).view(np.uint32), g[f"imdct_{n}_{j}"].view(np.uint32)), (n, j)
+            assert np.array_equal(_tx(O, "orc", 1, 0, n, sc, g[f"mdct_in_{n}"], n).view(np.uint32), g[f"mdct_{n}_{j}"].view(np.uint32)), (n, j)
+
+
+def test_tx_oracle_is_a_dft():
+    """Independent sanity check of the oracle itself: against numpy's double-precision FFT (eps like checkasm av_tx.c:27)."""
+    O = cl.oracle()
+    rng = np.random.default_rng(1)
+    for n in (16, 1024, 2048):
+        x = rng.random((1, 2 * n), dtype=np.float32)
+        z = x[0, 0::2].astype(np.float64) + 1j * x[0, 1::2].astype(np.float64)
+        got = _tx(O, "orc", 0, 0, n, 1.0, x, 2 * n)[0]
+        ref = np.fft.fft(z)
+        assert np.abs(got[0::2] - ref.real).max() < 5e-4 * n and np.abs(got[1::2] - ref.imag).max() < 5e-4 * n
+
+
+@needs_ref
+def test_more_oracles_vs_reference_live():
+    R, O = cl.ref(), cl.oracle()
+    rng = np.random.default_rng(77)
+    img1 = rng.integers(0, 256, (80, 96), dtype=np.uint8)
+    img2 = rng.integers(0, 256, (80, 96), dtype=np.uint8)
+    for _ in range(100):
+        x1, y1, x2, y2 = (int(v) for v in rng.integers(0, 60, 4))
+        h = int(rng.choice([4, 8, 16]))
+        for fn, idxs in ((0, (0, 1)), (1, (0, 1, 2)), (2, range(8))):
+            for idx in idxs:
+                p1 = C.cast(img1.ctypes.data + y1 * 96 + x1, cl.u8p)
+                p2 = C.cast(img2.ctypes.data + y2 * 96 + x2, cl.u8p)
+                assert R.ffref_me_cmp(fn, idx, p1, p2, 96, h) == O.orc_me_cmp(fn, idx, p1, p2, 96, h)
+    for n in (32, 128, 512, 4096):
+        x = rng.random((3, 2 * n), dtype=np.float32)
+        for inv in (0, 1):
+            assert np.array_equal(_tx(R, "ffref", 0, inv, n, 1.0, x, 2 * n).view(np.uint32), _tx(O, "orc", 0, inv, n, 1.0, x, 2 * n).view(np.uint32))
+        assert np.array_equal(_tx(R, "ffref", 1, 1, n, 1.0 / n, x[:, :n], n).view(np.uint32), _tx(O, "orc", 1, 1, n, 1.0 / n, x[:, :n], n).view(np.uint32))
+        assert np.array_equal(_tx(R, "ffref", 1, 0, n, -1.0, x, n).view(np.uint32), _tx(O, "orc", 1, 0, n, -1.0, x, n).view(np.uint32))
