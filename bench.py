@@ -56,38 +56,44 @@ def ncu_traffic(kernel_key):
     return None
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed regions (B200_PROFILING.md recipe): one streaming
+    `nvidia-smi -lms 100` process, started before the first timed region and stopped after the last."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        super().__init__(daemon=True)
         self.index = index
-        self.rows = []
-        self.stop_flag = threading.Event()
+        self.proc = None
 
-    def run(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        while not self.stop_flag.is_set():
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        rows = []
+        if self.proc:
+            self.proc.terminate()
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                out, _ = self.proc.communicate(timeout=5)
             except Exception:
-                pass
-            self.stop_flag.wait(0.2)
-
-    def summary(self):
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+                self.proc.kill()
+                out = ""
+            rows = [[x.strip() for x in ln.split(",")] for ln in out.splitlines() if ln.strip()]
+        sm = sorted(int(r[0]) for r in rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in rows if len(r) > 1 and r[1].isdigit()]
+        pw = [float(r[2]) for r in rows if len(r) > 2 and r[2].replace(".", "", 1).isdigit()]
         reasons = set()
-        for r in self.rows:
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+        for r in rows:
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.rows)}
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(rows)}
 
 
 # ------------------------------------------------------------------------------------------------ CPU arms
@@ -117,16 +123,16 @@ def cpu_sws_fps(flags, seconds_budget=12.0, threads=None):
         else:
             lib.orc_sws_scale(ctxs[i], cl.ptr(y), W4K, cl.ptr(u), W4K // 2, cl.ptr(v), W4K // 2, cl.ptr(out[i]), W4K * 3)
 
-    t0 = time.perf_counter()
-    one(0)                                       # warm-up + per-frame cost estimate
-    per = time.perf_counter() - t0
-    reps = max(1, min(64, int(seconds_budget / max(per, 1e-3))))
+    one(0)                                       # warm-up
     counts = [0] * threads
+    deadline = time.perf_counter() + seconds_budget
 
     def worker(i):
-        for _ in range(reps):
+        while True:
             one(i)
             counts[i] += 1
+            if time.perf_counter() >= deadline:
+                break
 
     ts = [threading.Thread(target=worker, args=(i,)) for i in range(threads)]
     t0 = time.perf_counter()
@@ -139,7 +145,7 @@ def cpu_sws_fps(flags, seconds_budget=12.0, threads=None):
         (lib.ffref_sws_close if pre == "ffref" else lib.orc_sws_close)(c)
     frames = sum(counts)
     return frames / dt, {"kind": kind, "cores": threads,
-                         "sample": f"{frames} 4K frames ({reps} per thread x {threads} threads), {dt:.1f} s"}
+                         "sample": f"{frames} 4K frames on {threads} threads, {dt:.1f} s"}
 
 
 def cpu_idct_bps(seconds_budget=4.0, threads=None):
@@ -159,14 +165,16 @@ def cpu_idct_bps(seconds_budget=4.0, threads=None):
         b[:] = blk0                                 # the reference clobbers the coefficients
         fn(1, cl.ptr(b, cl.i16p), n, cl.ptr(d), n * 8, cl.ptr(off, cl.i64p))
 
-    t0 = time.perf_counter()
     one(0)
-    per = time.perf_counter() - t0
-    reps = max(1, min(200, int(seconds_budget / max(per, 1e-4))))
+    counts = [0] * threads
+    deadline = time.perf_counter() + seconds_budget
 
     def worker(i):
-        for _ in range(reps):
+        while True:
             one(i)
+            counts[i] += 1
+            if time.perf_counter() >= deadline:
+                break
 
     ts = [threading.Thread(target=worker, args=(i,)) for i in range(threads)]
     t0 = time.perf_counter()
@@ -175,7 +183,7 @@ def cpu_idct_bps(seconds_budget=4.0, threads=None):
     for t in ts:
         t.join()
     dt = time.perf_counter() - t0
-    return n * reps * threads / dt, {"kind": kind, "cores": threads, "sample": f"{reps * threads} x {n} blocks, {dt:.1f} s"}
+    return n * sum(counts) / dt, {"kind": kind, "cores": threads, "sample": f"{sum(counts)} x {n} blocks on {threads} threads, {dt:.1f} s"}
 
 
 def run_reference(args, rank, world):
@@ -207,6 +215,95 @@ def run_reference(args, rank, world):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
+def extra_paths(args, dev, stream, g, world, barrier, reduce_max, peak):
+    """The other rows of SURVEY.md 8(d): ESA motion search, H.264 qpel MC and float FFT / iMDCT, each on a bounded batch."""
+    import torch
+    from ffmpeg_b200 import me_cmp, pel, tx
+    out = {}
+    steps = max(2, min(args.steps, 5))
+
+    def timed(call):
+        with torch.cuda.stream(stream):
+            for _ in range(2):
+                call()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for _ in range(steps):
+                call()
+            e1.record(stream)
+        barrier()
+        return reduce_max(e0.elapsed_time(e1)) / steps
+
+    # --- config 4: SAD full search 16x16, +-32, 4K luma pairs (integer-ALU bound; bytes are 16.6 MB per pair)
+    npairs = 4
+    with torch.cuda.stream(stream):
+        cur = torch.randint(0, 256, (npairs, H4K, W4K), dtype=torch.uint8, device="cuda", generator=g)
+        ref = torch.roll(cur, shifts=(7, -13), dims=(1, 2)).contiguous()
+        nmb = (W4K // 16) * (H4K // 16)
+        mv = torch.zeros((npairs, nmb, 2), dtype=torch.int32, device="cuda")
+        cost = torch.zeros((npairs, nmb), dtype=torch.int64, device="cuda")
+    ms = timed(lambda: me_cmp.me_esa_device(dev, cur, ref, W4K, W4K, H4K, W4K * H4K, npairs, 16, 32, mv, cost))
+    absdiff = 32400.0 * 4225 * 256                   # per pair (interior blocks; border windows are clipped, so this is an upper bound)
+    out["me_esa"] = {"value": world * npairs / (ms / 1e3), "unit": "4K frame pairs/s", "ms_per_step": ms,
+                     "config": f"SAD full search 16x16 +-32, {npairs} 4K pairs per step",
+                     "roofline": {"bound": "integer alu", "achieved": absdiff * npairs / (ms / 1e3) / 1e12, "unit": "T abs-diff/s",
+                                  "hbm_GBps": 2 * W4K * H4K * npairs / (ms / 1e3) / 1e9, "hbm_frac": 2 * W4K * H4K * npairs / (ms / 1e3) / 1e9 / peak}}
+    del cur, ref, mv, cost
+
+    # --- config 3 (MC half): H.264 qpel 16x16, random quarter-pel vectors within +-16 px, random put/avg, 1080p frames
+    nfr, W, H, apron = 64, 1920, 1088, 32
+    PW, PH = W + 2 * apron, H + 2 * apron
+    with torch.cuda.stream(stream):
+        refp = torch.randint(0, 256, (nfr, PH, PW), dtype=torch.uint8, device="cuda", generator=g)
+        dstp = torch.randint(0, 256, (nfr, PH, PW), dtype=torch.uint8, device="cuda", generator=g)
+        fidx = torch.arange(nfr, device="cuda").view(-1, 1, 1)
+        by = torch.arange(H // 16, device="cuda").view(1, -1, 1)
+        bx = torch.arange(W // 16, device="cuda").view(1, 1, -1)
+        base = fidx * (PH * PW) + (by * 16 + apron) * PW + bx * 16 + apron
+        dx = torch.randint(-16, 17, base.shape, device="cuda", generator=g)
+        dy = torch.randint(-16, 17, base.shape, device="cuda", generator=g)
+        doff = base.reshape(-1).to(torch.int64).contiguous()
+        soff = (base + dy * PW + dx).reshape(-1).to(torch.int64).contiguous()
+        ops = (torch.randint(0, 2, (doff.numel(),), device="cuda", generator=g) |
+               (torch.randint(0, 16, (doff.numel(),), device="cuda", generator=g) << 3)).to(torch.uint8)
+    nops = doff.numel()
+    ms = timed(lambda: pel.h264qpel_batch_device(dev, nops, ops, dstp, doff, refp, soff, PW))
+    qbytes = 441 + 256 + 128                         # 21x21 reference window + 16x16 out (+ dst read for the avg half)
+    out["h264qpel"] = {"value": world * nops / (ms / 1e3), "unit": "16x16 blocks/s", "ms_per_step": ms,
+                       "config": f"{nfr} 1080p frames x 8160 MBs, random qpel position and put/avg",
+                       "roofline": {"bound": "hbm", "achieved": qbytes * nops / (ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                                    "frac": qbytes * nops / (ms / 1e3) / 1e9 / peak, "bytes_per_block": qbytes}}
+    del refp, dstp, doff, soff, ops
+
+    # --- config 5: float FFT and iMDCT, len 1024 and 2048
+    txr = {}
+    for n in (1024, 2048):
+        cnt = (1 << 18) if n == 1024 else (1 << 17)
+        with torch.cuda.stream(stream):
+            x = torch.rand((cnt, 2 * n), device="cuda", generator=g)
+            y = torch.empty_like(x)
+        c = tx.av_tx_init(tx.AV_TX_FLOAT_FFT, 0, n, device=dev)
+        ms = timed(lambda: c.batch_device(y, x, 8, cnt, 8 * n, 8 * n))
+        c.uninit()
+        b = 16 * n
+        txr[f"fft{n}"] = {"value": world * cnt / (ms / 1e3), "unit": "transforms/s", "ms_per_step": ms, "batch": cnt,
+                          "roofline": {"bound": "hbm", "achieved": b * cnt / (ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                                       "frac": b * cnt / (ms / 1e3) / 1e9 / peak, "bytes_per_transform": b}}
+        c = tx.av_tx_init(tx.AV_TX_FLOAT_MDCT, 1, n, scale=1.0 / n, device=dev)
+        ms = timed(lambda: c.batch_device(y, x, 4, cnt, 4 * n, 4 * n))
+        c.uninit()
+        b = 8 * n
+        txr[f"imdct{n}"] = {"value": world * cnt / (ms / 1e3), "unit": "transforms/s", "ms_per_step": ms, "batch": cnt,
+                            "roofline": {"bound": "hbm", "achieved": b * cnt / (ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                                         "frac": b * cnt / (ms / 1e3) / 1e9 / peak, "bytes_per_transform": b}}
+        del x, y
+    out["tx"] = txr
+    return out
+
+
+
 def run_b200(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -250,9 +347,6 @@ def run_b200(args, rank, world, local_rank):
             for _ in range(warmup):
                 call()
         barrier()
-        sampler = ClockSampler(local_rank) if sample_clocks else None
-        if sampler:
-            sampler.start()
         l0 = fb.launch_count()
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -265,23 +359,22 @@ def run_b200(args, rank, world, local_rank):
             e1.record(stream)
         barrier()
         launches = fb.launch_count() - l0
-        if sampler:
-            sampler.stop_flag.set()
-            sampler.join()
         total_ms = reduce_max(e0.elapsed_time(e1))
         kern_ms = sum(a.elapsed_time(b) for a, b in evs) / steps
         ctx.free()
-        return total_ms, kern_ms, launches, (sampler.summary() if sampler else None)
+        return total_ms, kern_ms, launches
 
     # headline: FATE flags (full h/v pipeline semantics; same-size -> fused vertical+convert kernel)
-    total_ms, kern_ms, launches, clocks = timed_sws(FLAGS_FATE, args.steps, args.warmup, True)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    total_ms, kern_ms, launches = timed_sws(FLAGS_FATE, args.steps, args.warmup, True)
     fps = world * BATCH * args.steps / (total_ms / 1e3)
     ach = FRAME_BYTES * BATCH / (kern_ms / 1e3) / 1e9
     roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src,
             "kernel": "sws_vscale_rgb24_kernel<true>", "bytes_per_launch": FRAME_BYTES * BATCH,
             "launch_ms": kern_ms, "traffic": ncu_traffic("sws_vscale_rgb24_kernel")}
     # variant: flags=bicubic only (the reference takes its unscaled LUT converter; different, cheaper arithmetic)
-    t2, k2, _, _ = timed_sws(SWS_BICUBIC, max(3, args.steps // 2), args.warmup, False)
+    t2, k2, _ = timed_sws(SWS_BICUBIC, max(3, args.steps // 2), args.warmup, False)
     fps2 = world * BATCH * max(3, args.steps // 2) / (t2 / 1e3)
     ach2 = FRAME_BYTES * BATCH / (k2 / 1e3) / 1e9
     results["variant_flags_bicubic"] = {"value": fps2, "unit": "frames/s", "roofline": {
@@ -319,6 +412,24 @@ def run_b200(args, rank, world, local_rank):
                                    "kernel": f"idct8x8_kernel<{name},mb420>", "bytes_per_block": bpb,
                                    "traffic": ncu_traffic(f"idct8x8_{name}")}}
     del blocks, planes
+    results.update(extra_paths(args, dev, stream, g, world, barrier, reduce_max, peak))
+    clocks = sampler.stop()
+
+    # ---- mux boundary (N > 1 only): gather a slice of every rank's output on rank 0 over NCCL/NVLink, timed separately
+    mux = None
+    if world > 1:
+        from ffmpeg_b200.sharding import gather_to_mux
+        gf = 32
+        torch.cuda.synchronize()
+        gather_to_mux(OUT[:2], dst=0)                       # warm-up (communicator set-up)
+        barrier()
+        t0 = time.perf_counter()
+        got = gather_to_mux(OUT[:gf], dst=0)
+        torch.cuda.synchronize()
+        dt = reduce_max(time.perf_counter() - t0)
+        mux = {"frames_per_rank": gf, "ms": dt * 1e3, "GBps_into_rank0": (world - 1) * gf * FRAME_BYTES_OUT / dt / 1e9,
+               "note": "optional collect of finished rgb24 frames at the muxing rank; not part of `value`"}
+        del got
 
     # ---- e2e: the C-ABI host entry point with pinned host buffers (H2D + kernels + D2H inside the timed region)
     e2e = None
@@ -368,7 +479,7 @@ def run_b200(args, rank, world, local_rank):
                        "l2": "inputs (3.2 GB) and outputs (6.4 GB) per step exceed L2 (126 MB): no flush needed",
                        "sharding": "frames of the batch are independent; each rank converts its own batch, no collective on the data path"},
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "idct": idct, **results,
+            "idct": idct, "mux_gather": mux, **results,
         }
         print(json.dumps(line), flush=True)
     dev.close()

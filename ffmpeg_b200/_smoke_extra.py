@@ -1,0 +1,54 @@
+"""smoke() checks for the paths added after the first slice: ESA motion search, H.264 qpel MC, float FFT / iMDCT —
+one small call each, bit-compared with the oracle (tests/cpulibs.py loads it; this module is only used by smoke())."""
+import ctypes as C
+import numpy as np
+
+
+def run(dev):
+    import torch
+    import cpulibs as cl
+    from ffmpeg_b200 import me_cmp, pel, tx
+    O = cl.oracle()
+    rng = np.random.default_rng(3)
+    st = torch.cuda.ExternalStream(dev.stream)
+    with torch.cuda.stream(st):
+        # exhaustive search on one 160x96 pair
+        W, H, mb, sp = 160, 96, 16, 16
+        cur = rng.integers(0, 256, (H, W), dtype=np.uint8)
+        ref = np.roll(cur, (3, -4), (0, 1)).copy()
+        bw, bh = W // mb, H // mb
+        emv, ec = np.zeros((bh * bw, 2), np.int32), np.zeros(bh * bw, np.uint64)
+        O.orc_esa_frame(cl.ptr(cur), cl.ptr(ref), W, W, H, mb, sp, 0, bh, cl.ptr(emv, cl.i32p), cl.ptr(ec, cl.u64p))
+        mv = torch.zeros((bh * bw, 2), dtype=torch.int32, device="cuda")
+        cost = torch.zeros(bh * bw, dtype=torch.int64, device="cuda")
+        me_cmp.me_esa_device(dev, torch.from_numpy(cur).cuda(), torch.from_numpy(ref).cuda(), W, W, H, W * H, 1, mb, sp, mv, cost)
+        dev.sync()
+        assert np.array_equal(mv.cpu().numpy(), emv) and np.array_equal(cost.cpu().numpy().astype(np.uint64), ec), "esa mismatch"
+        # qpel: all 16 positions, put and avg, on one 16x16 block each
+        src = rng.integers(0, 256, (64, 64 * 32), dtype=np.uint8)
+        dst = rng.integers(0, 256, (64, 64 * 32), dtype=np.uint8)
+        ops = np.array([pel.qpel_op(a, 0, p) for a in (0, 1) for p in range(16)], np.uint8)
+        offs = np.array([16 * src.shape[1] + 24 + 64 * i for i in range(32)], np.int64)
+        exp = dst.copy()
+        for o, off in zip(ops, offs):
+            O.orc_h264qpel(int(o) & 1, 0, int(o) >> 3, C.cast(exp.ctypes.data + int(off), cl.u8p), C.cast(src.ctypes.data + int(off), cl.u8p), src.shape[1])
+        d_dst = torch.from_numpy(dst).cuda()
+        d_off = torch.from_numpy(offs).cuda()
+        pel.h264qpel_batch_device(dev, 32, torch.from_numpy(ops).cuda(), d_dst, d_off, torch.from_numpy(src).cuda(), d_off, src.shape[1])
+        dev.sync()
+        assert np.array_equal(d_dst.cpu().numpy(), exp), "qpel mismatch"
+        # tx: FFT-1024 and iMDCT-1024, 4 transforms each
+        n = 1024
+        x = rng.random((4, 2 * n), dtype=np.float32)
+        for typ, inv, scale, inw, outw, stride in ((0, 0, 1.0, 2 * n, 2 * n, 8), (1, 1, 1.0 / n, n, n, 4)):
+            h = O.orc_tx_open(typ, inv, n, scale, 0)
+            xi = np.ascontiguousarray(x[:, :inw])
+            e = np.zeros((4, outw), np.float32)
+            O.orc_tx_run(h, e.ctypes.data, xi.ctypes.data, stride, 4, e.strides[0], xi.strides[0])
+            O.orc_tx_close(h)
+            c = tx.av_tx_init(typ, inv, n, scale=scale if typ else None, device=dev)
+            do = torch.zeros((4, outw), dtype=torch.float32, device="cuda")
+            c.batch_device(do, torch.from_numpy(xi).cuda(), stride, 4, 4 * outw, 4 * inw)
+            dev.sync()
+            assert np.array_equal(do.cpu().numpy(), e), "tx mismatch"
+            c.uninit()
