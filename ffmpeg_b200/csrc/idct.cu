@@ -189,6 +189,248 @@ idct8x8_kernel(const int16_t *blocks, int16_t *blocks_out, long long nblocks,
     }
 }
 
+// ================================================================================================ thread-per-block kernels
+// One thread owns one 8x8 block: no shuffles, no transposes — the row pass leaves 64 ints in registers and the column
+// pass reads them by column.  Coalescing is recovered through shared memory:
+//   in : the CTA's coefficient blocks are one contiguous byte range; it is copied with 16-byte cp.async (LDGSTS) into
+//        shared memory with the 16-byte row slots of block b XOR-swizzled by (b & 7), so that lane t reading row j of
+//        its own block (slot j ^ (t & 7)) is bank-conflict free;
+//   out: (macroblock stream) each 8-macroblock segment of a macroblock row owns a 16 x 128 luma tile and two 8 x 64
+//        chroma tiles in shared memory; threads drop their 8-byte rows there and the tile goes out as full 16-byte
+//        chunks of whole rows (128-byte lines).  For `add` the tile is first filled from the destination the same way.
+// HBM traffic stays the algorithmic 128 B in + 64 B out (+ 64 B) per block.
+
+__device__ __forceinline__ int sx_lo(unsigned v) { return (int)__byte_perm(v, 0, 0x9910); }   // sign-extend low half (1 PRMT)
+__device__ __forceinline__ int sx_hi(unsigned v) { return (int)v >> 16; }
+// Row pass with every constant pre-multiplied by 32: only bits 11..26 of the reference's 32-bit row sums survive the
+// ">> 11, store as int16" step, and those are bits 16..31 of (32 * sum) mod 2^32 — so (int)sum32 >> 16 IS the
+// sign-extended int16 the reference stores (one shift instead of shift + wrap).
+// simple_idct_template.c:114-206 on packed input, 8 sign-extended int16 results
+__device__ __forceinline__ void row_pass_i(const uint4 &in, int *o)
+{
+    constexpr unsigned X1 = 32u * W1, X2 = 32u * W2, X3 = 32u * W3, X4 = 32u * W4, X5 = 32u * W5, X6 = 32u * W6, X7 = 32u * W7;
+    const int r0 = sx_lo(in.x), r1 = sx_hi(in.x), r2 = sx_lo(in.y), r3 = sx_hi(in.y);
+    const int r4 = sx_lo(in.z), r5 = sx_hi(in.z), r6 = sx_lo(in.w), r7 = sx_hi(in.w);
+    if (((in.x >> 16) | in.y | in.z | in.w) == 0) {
+        const int dc = (int)(short)(((unsigned)r0 << 3) & 0xffff);
+#pragma unroll
+        for (int i = 0; i < 8; i++) o[i] = dc;
+        return;
+    }
+    const unsigned p = X4 * (unsigned)(r0 + r4) + (32u << 10), q = X4 * (unsigned)(r0 - r4) + (32u << 10);
+    const unsigned s = X2 * (unsigned)r2 + X6 * (unsigned)r6, d = X6 * (unsigned)r2 - X2 * (unsigned)r6;
+    const unsigned a0 = p + s, a3 = p - s, a1 = q + d, a2 = q - d;
+    const unsigned b0 = X1 * (unsigned)r1 + X3 * (unsigned)r3 + X5 * (unsigned)r5 + X7 * (unsigned)r7;
+    const unsigned b1 = X3 * (unsigned)r1 - X7 * (unsigned)r3 - X1 * (unsigned)r5 - X5 * (unsigned)r7;
+    const unsigned b2 = X5 * (unsigned)r1 - X1 * (unsigned)r3 + X7 * (unsigned)r5 + X3 * (unsigned)r7;
+    const unsigned b3 = X7 * (unsigned)r1 - X5 * (unsigned)r3 + X3 * (unsigned)r5 - X1 * (unsigned)r7;
+    o[0] = (int)(a0 + b0) >> 16; o[7] = (int)(a0 - b0) >> 16;
+    o[1] = (int)(a1 + b1) >> 16; o[6] = (int)(a1 - b1) >> 16;
+    o[2] = (int)(a2 + b2) >> 16; o[5] = (int)(a2 - b2) >> 16;
+    o[3] = (int)(a3 + b3) >> 16; o[4] = (int)(a3 - b3) >> 16;
+}
+
+// IDCT_COLS (simple_idct_template.c:209-257): eight inputs of one column -> eight results (already >> 20)
+__device__ __forceinline__ void col_pass_i(int c0, int c1, int c2, int c3, int c4, int c5, int c6, int c7, int *o)
+{
+    const unsigned rnd = (unsigned)W4 * (unsigned)((1 << 19) / W4);
+    const unsigned p = (unsigned)W4 * (unsigned)(c0 + c4) + rnd, q = (unsigned)W4 * (unsigned)(c0 - c4) + rnd;
+    const unsigned s = (unsigned)W2 * (unsigned)c2 + (unsigned)W6 * (unsigned)c6, d = (unsigned)W6 * (unsigned)c2 - (unsigned)W2 * (unsigned)c6;
+    const unsigned a0 = p + s, a3 = p - s, a1 = q + d, a2 = q - d;
+    const unsigned b0 = (unsigned)W1 * (unsigned)c1 + (unsigned)W3 * (unsigned)c3 + (unsigned)W5 * (unsigned)c5 + (unsigned)W7 * (unsigned)c7;
+    const unsigned b1 = (unsigned)W3 * (unsigned)c1 - (unsigned)W7 * (unsigned)c3 - (unsigned)W1 * (unsigned)c5 - (unsigned)W5 * (unsigned)c7;
+    const unsigned b2 = (unsigned)W5 * (unsigned)c1 - (unsigned)W1 * (unsigned)c3 + (unsigned)W7 * (unsigned)c5 + (unsigned)W3 * (unsigned)c7;
+    const unsigned b3 = (unsigned)W7 * (unsigned)c1 - (unsigned)W5 * (unsigned)c3 + (unsigned)W3 * (unsigned)c5 - (unsigned)W1 * (unsigned)c7;
+    o[0] = (int)(a0 + b0) >> 20; o[7] = (int)(a0 - b0) >> 20;
+    o[1] = (int)(a1 + b1) >> 20; o[6] = (int)(a1 - b1) >> 20;
+    o[2] = (int)(a2 + b2) >> 20; o[5] = (int)(a2 - b2) >> 20;
+    o[3] = (int)(a3 + b3) >> 20; o[4] = (int)(a3 - b3) >> 20;
+}
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
+{
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// Full 8x8 inverse transform of the block whose swizzled rows start at `rows` (8 x uint4), lane swizzle key `key`.
+// Result: for KIND == B200_IDCT the int16 block (packed, 8 x uint4 via outp); else 8 rows of clipped bytes (two words
+// each) with `dest_rows` (8 x uint2 of existing pixels) added first when KIND == B200_IDCT_ADD.
+template <int KIND>
+__device__ __forceinline__ void idct_block(const uint4 *rows, int key, const uint2 *dest_rows, uint2 *out_rows, uint4 *out_coef)
+{
+    int R[8][8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) row_pass_i(rows[j ^ key], R[j]);
+    unsigned P[8][4];                                  // per output row: four s16x2 pairs (clamped for put/add)
+#pragma unroll
+    for (int c = 0; c < 8; c += 2) {
+        int oa[8], ob[8];
+        col_pass_i(R[0][c], R[1][c], R[2][c], R[3][c], R[4][c], R[5][c], R[6][c], R[7][c], oa);
+        col_pass_i(R[0][c + 1], R[1][c + 1], R[2][c + 1], R[3][c + 1], R[4][c + 1], R[5][c + 1], R[6][c + 1], R[7][c + 1], ob);
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            if (KIND == B200_IDCT_ADD) {
+                const unsigned w = c < 4 ? dest_rows[k].x : dest_rows[k].y;
+                oa[k] += (int)__byte_perm(w, 0, 0x4440 | (c & 3));
+                ob[k] += (int)__byte_perm(w, 0, 0x4440 | ((c + 1) & 3));
+            }
+            const unsigned pr = __byte_perm((unsigned)oa[k], (unsigned)ob[k], 0x5410);     // (lo16(a), lo16(b))
+            P[k][c >> 1] = KIND == B200_IDCT ? pr : __vimin_s16x2_relu(pr, 0x00ff00ffu);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        if (KIND == B200_IDCT) {
+            out_coef[k] = make_uint4(P[k][0], P[k][1], P[k][2], P[k][3]);
+        } else {
+            out_rows[k] = make_uint2(__byte_perm(P[k][0], P[k][1], 0x6420), __byte_perm(P[k][2], P[k][3], 0x6420));
+        }
+    }
+}
+
+constexpr int TPB_GEN = 128;        // blocks (= threads) per CTA, generic kernel
+
+// generic destinations: dest + dest_off[b], rows stored straight to global memory (8-byte stores when aligned)
+template <int KIND>
+__global__ void __launch_bounds__(TPB_GEN)
+idct_tpb_kernel(const int16_t *blocks, int16_t *blocks_out, long long nblocks, uint8_t *dest,
+                const int64_t *__restrict__ dest_off, const int32_t *__restrict__ line_size, int uniform_ls)
+{
+    __shared__ uint4 sin[TPB_GEN * 8];
+    const long long b0 = (long long)blockIdx.x * TPB_GEN;
+    const int nb = (int)min((long long)TPB_GEN, nblocks - b0);
+    const uint4 *g = reinterpret_cast<const uint4 *>(blocks) + b0 * 8;
+    for (int i = threadIdx.x; i < nb * 8; i += TPB_GEN) {
+        const int b = i >> 3, r = i & 7;
+        cp_async16(&sin[b * 8 + (r ^ (b & 7))], g + i);
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    const int t = threadIdx.x;
+    const bool live = t < nb;
+    uint2 drows[8], orows[8];
+    uint4 ocoef[8];
+    uint8_t *d = nullptr;
+    long long ls = 0;
+    if (live && KIND != B200_IDCT) {
+        ls = line_size ? __ldg(line_size + b0 + t) : uniform_ls;
+        d = dest + __ldg(dest_off + b0 + t);
+    }
+    const bool al8 = ((reinterpret_cast<uintptr_t>(d) | (unsigned long long)ls) & 7) == 0;
+    if (live && KIND == B200_IDCT_ADD) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const uint8_t *p = d + k * ls;
+            if (al8) drows[k] = *reinterpret_cast<const uint2 *>(p);
+            else {
+                drows[k].x = p[0] | (p[1] << 8) | (p[2] << 16) | ((unsigned)p[3] << 24);
+                drows[k].y = p[4] | (p[5] << 8) | (p[6] << 16) | ((unsigned)p[7] << 24);
+            }
+        }
+    }
+    if (live) idct_block<KIND>(&sin[t * 8], t & 7, drows, orows, ocoef);
+    if (KIND == B200_IDCT) {
+        __syncthreads();                                   // everybody has consumed its input rows
+        if (live) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) sin[t * 8 + (k ^ (t & 7))] = ocoef[k];
+        }
+        __syncthreads();
+        uint4 *go = reinterpret_cast<uint4 *>(blocks_out) + b0 * 8;
+        for (int i = threadIdx.x; i < nb * 8; i += TPB_GEN) {
+            const int b = i >> 3, r = i & 7;
+            go[i] = sin[b * 8 + (r ^ (b & 7))];
+        }
+    } else if (live) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            uint8_t *p = d + k * ls;
+            if (al8) *reinterpret_cast<uint2 *>(p) = orows[k];
+            else {
+#pragma unroll
+                for (int i = 0; i < 4; i++) { p[i] = (uint8_t)(orows[k].x >> (8 * i)); p[4 + i] = (uint8_t)(orows[k].y >> (8 * i)); }
+            }
+        }
+    }
+}
+
+// 4:2:0 macroblock stream.  blockDim.x = 48 * SEGS; segment = 8 consecutive macroblocks of one macroblock row.
+// Grid: x over groups of SEGS segments of a row, y over macroblock rows, z over frames.
+constexpr int MAX_SEGS = 6;
+template <int KIND>
+__global__ void __launch_bounds__(48 * MAX_SEGS)
+idct_mb420_kernel(const int16_t *blocks, Mb420Geom g, int segs_per_cta)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint4 *sin = reinterpret_cast<uint4 *>(smem_raw);                                     // segs * 48 * 8 uint4
+    unsigned char *tiles = smem_raw + (size_t)segs_per_cta * 48 * 128;                    // segs * 3072 B
+    const int t = threadIdx.x, seg = t / 48, w = t - seg * 48;
+    const int mby = blockIdx.y;
+    const long long f = blockIdx.z;
+    const int sx = blockIdx.x * segs_per_cta + seg;                                       // segment index within the row
+    const int mbx0 = sx * 8;
+    const int nmb = min(8, g.mb_w - mbx0);                                                // <= 0: segment beyond the row
+    uint4 *my_in = sin + seg * 48 * 8;
+    unsigned char *tile = tiles + seg * 3072;                                             // luma 16x128, U 8x64, V 8x64
+    const int ls0 = g.linesize[0], ls1 = g.linesize[1], ls2 = g.linesize[2];
+    uint8_t *py = g.plane[0] + f * g.frame_stride[0] + (long long)(mby * 16) * ls0 + mbx0 * 16;
+    uint8_t *pu = g.plane[1] + f * g.frame_stride[1] + (long long)(mby * 8) * ls1 + mbx0 * 8;
+    uint8_t *pv = g.plane[2] + f * g.frame_stride[2] + (long long)(mby * 8) * ls2 + mbx0 * 8;
+    if (nmb > 0) {
+        const long long blk0 = (((f * g.mb_h + mby) * g.mb_w) + mbx0) * 6;
+        const uint4 *gsrc = reinterpret_cast<const uint4 *>(blocks) + blk0 * 8;
+        for (int i = w; i < nmb * 48; i += 48) {
+            const int b = i >> 3, r = i & 7;
+            cp_async16(&my_in[b * 8 + (r ^ (b & 7))], gsrc + i);
+        }
+        if (KIND == B200_IDCT_ADD) {                                                      // stage the destination tile
+            for (int i = w; i < 128; i += 48) {                                           // luma: 16 rows x 8 chunks of 16 B
+                const int row = i >> 3, ch = i & 7;
+                if (ch < nmb) cp_async16(tile + row * 128 + ch * 16, py + (long long)row * ls0 + ch * 16);
+            }
+            for (int i = w; i < 64; i += 48) {                                            // chroma: 8 rows x 8 chunks of 8 B each plane
+                const int row = i >> 3, ch = i & 7;
+                if (ch < nmb) {
+                    *reinterpret_cast<uint2 *>(tile + 2048 + row * 64 + ch * 8) = *reinterpret_cast<const uint2 *>(pu + (long long)row * ls1 + ch * 8);
+                    *reinterpret_cast<uint2 *>(tile + 2560 + row * 64 + ch * 8) = *reinterpret_cast<const uint2 *>(pv + (long long)row * ls2 + ch * 8);
+                }
+            }
+        }
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    const int m = w / 6, k = w - m * 6;                                                   // macroblock in segment, block in macroblock
+    if (m < nmb) {
+        unsigned char *trow; int tp;
+        if (k < 4) { trow = tile + ((k >> 1) * 8) * 128 + m * 16 + (k & 1) * 8; tp = 128; }
+        else       { trow = tile + (k == 4 ? 2048 : 2560) + m * 8; tp = 64; }
+        uint2 drows[8], orows[8];
+        if (KIND == B200_IDCT_ADD) {
+#pragma unroll
+            for (int r = 0; r < 8; r++) drows[r] = *reinterpret_cast<const uint2 *>(trow + r * tp);
+        }
+        idct_block<KIND>(&my_in[w * 8], w & 7, drows, orows, nullptr);
+#pragma unroll
+        for (int r = 0; r < 8; r++) *reinterpret_cast<uint2 *>(trow + r * tp) = orows[r];
+    }
+    __syncthreads();
+    if (nmb > 0) {
+        for (int i = w; i < 128; i += 48) {
+            const int row = i >> 3, ch = i & 7;
+            if (ch < nmb) *reinterpret_cast<uint4 *>(py + (long long)row * ls0 + ch * 16) = *reinterpret_cast<const uint4 *>(tile + row * 128 + ch * 16);
+        }
+        for (int i = w; i < 64; i += 48) {
+            const int row = i >> 3, ch = i & 7;
+            if (ch < nmb) {
+                *reinterpret_cast<uint2 *>(pu + (long long)row * ls1 + ch * 8) = *reinterpret_cast<const uint2 *>(tile + 2048 + row * 64 + ch * 8);
+                *reinterpret_cast<uint2 *>(pv + (long long)row * ls2 + ch * 8) = *reinterpret_cast<const uint2 *>(tile + 2560 + row * 64 + ch * 8);
+            }
+        }
+    }
+}
+
 // clamp helpers on one block (drop-in level only): kind 0 put, 1 put_signed, 2 add
 __global__ void pixels_clamped_kernel(int kind, const int16_t *block, uint8_t *pix /* packed 8x8 */)
 {
@@ -213,15 +455,66 @@ int launch_idct(cudaStream_t st, const int16_t *blocks, int16_t *out, long long 
     return 0;
 }
 
-int dispatch(cudaStream_t st, int kind, bool mb420, const int16_t *blocks, int16_t *out, long long n, uint8_t *dest,
-             const int64_t *off, const int32_t *ls, int uls, const Mb420Geom &g)
+template <int KIND>
+int launch_tpb(cudaStream_t st, const int16_t *blocks, int16_t *out, long long nblocks, uint8_t *dest,
+               const int64_t *dest_off, const int32_t *line_size, int uls)
 {
+    if (nblocks <= 0) return 0;
+    const long long ctas = (nblocks + TPB_GEN - 1) / TPB_GEN;
+    if (ctas > 0x7fffffffLL) return B200_EINVAL;
+    idct_tpb_kernel<KIND><<<(unsigned)ctas, TPB_GEN, 0, st>>>(blocks, out, nblocks, dest, dest_off, line_size, uls);
+    B200_LAUNCHED();
+    B200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// macroblock stream through the tiled kernel when planes/strides allow 16-byte (luma) and 8-byte (chroma) chunks
+template <int KIND>
+int launch_mb420(cudaStream_t st, const int16_t *blocks, const Mb420Geom &g, int nframes, bool *handled)
+{
+    *handled = false;
+    const bool ok = (((uintptr_t)g.plane[0] | (uintptr_t)g.linesize[0] | (uintptr_t)g.frame_stride[0]) & 15) == 0 &&
+                    (((uintptr_t)g.plane[1] | (uintptr_t)g.linesize[1] | (uintptr_t)g.frame_stride[1] |
+                      (uintptr_t)g.plane[2] | (uintptr_t)g.linesize[2] | (uintptr_t)g.frame_stride[2]) & 7) == 0 &&
+                    g.mb_h <= 65535 && g.linesize[0] > 0 && g.linesize[1] > 0 && g.linesize[2] > 0;
+    if (!ok) return 0;
+    const int segs_row = (g.mb_w + 7) / 8;
+    int best = 4, waste = 1 << 30;
+    for (int s = 3; s <= MAX_SEGS; s++) {                     // pick the CTA width that wastes the fewest idle segments
+        const int wst = ((segs_row + s - 1) / s) * s - segs_row;
+        if (wst < waste || (wst == waste && s > best)) { waste = wst; best = s; }
+    }
+    const size_t smem = (size_t)best * (48 * 128 + 3072);
+    B200_CUDA_OK(cudaFuncSetAttribute(idct_mb420_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (int f0 = 0; f0 < nframes; f0 += 65535) {
+        const int nf = nframes - f0 < 65535 ? nframes - f0 : 65535;
+        Mb420Geom gg = g;
+        for (int i = 0; i < 3; i++) gg.plane[i] += (long long)f0 * g.frame_stride[i];
+        dim3 grid((segs_row + best - 1) / best, g.mb_h, nf);
+        idct_mb420_kernel<KIND><<<grid, 48 * best, smem, st>>>(blocks + (long long)f0 * g.mb_w * g.mb_h * 6 * 64, gg, best);
+        B200_LAUNCHED();
+    }
+    B200_CUDA_OK(cudaGetLastError());
+    *handled = true;
+    return 0;
+}
+
+int dispatch(cudaStream_t st, int kind, bool mb420, const int16_t *blocks, int16_t *out, long long n, uint8_t *dest,
+             const int64_t *off, const int32_t *ls, int uls, const Mb420Geom &g, int nframes = 0)
+{
+    if (mb420) {
+        bool handled = false;
+        int ret = kind == B200_IDCT_PUT ? launch_mb420<B200_IDCT_PUT>(st, blocks, g, nframes, &handled)
+                                        : launch_mb420<B200_IDCT_ADD>(st, blocks, g, nframes, &handled);
+        if (ret < 0 || handled) return ret;
+        // unaligned planes: the warp-cooperative kernel computes the implied destinations itself
+        return kind == B200_IDCT_PUT ? launch_idct<B200_IDCT_PUT, true>(st, blocks, out, n, dest, off, ls, uls, g)
+                                     : launch_idct<B200_IDCT_ADD, true>(st, blocks, out, n, dest, off, ls, uls, g);
+    }
     switch (kind) {
-    case B200_IDCT:     return launch_idct<B200_IDCT, false>(st, blocks, out, n, dest, off, ls, uls, g);
-    case B200_IDCT_PUT: return mb420 ? launch_idct<B200_IDCT_PUT, true>(st, blocks, out, n, dest, off, ls, uls, g)
-                                     : launch_idct<B200_IDCT_PUT, false>(st, blocks, out, n, dest, off, ls, uls, g);
-    case B200_IDCT_ADD: return mb420 ? launch_idct<B200_IDCT_ADD, true>(st, blocks, out, n, dest, off, ls, uls, g)
-                                     : launch_idct<B200_IDCT_ADD, false>(st, blocks, out, n, dest, off, ls, uls, g);
+    case B200_IDCT:     return launch_tpb<B200_IDCT>(st, blocks, out, n, dest, off, ls, uls);
+    case B200_IDCT_PUT: return launch_tpb<B200_IDCT_PUT>(st, blocks, out, n, dest, off, ls, uls);
+    case B200_IDCT_ADD: return launch_tpb<B200_IDCT_ADD>(st, blocks, out, n, dest, off, ls, uls);
     }
     return B200_EINVAL;
 }
@@ -250,7 +543,7 @@ B200_API int b200_idct_mb420_device(B200Device *dev, int kind, const int16_t *bl
     g.mb_w = mb_w; g.mb_h = mb_h;
     for (int i = 0; i < 3; i++) { g.plane[i] = planes[i]; g.linesize[i] = linesize[i]; g.frame_stride[i] = frame_stride[i]; }
     const long long n = (long long)mb_w * mb_h * 6 * nframes;
-    return dispatch(dev->stream, kind, true, blocks, nullptr, n, nullptr, nullptr, nullptr, 0, g);
+    return dispatch(dev->stream, kind, true, blocks, nullptr, n, nullptr, nullptr, nullptr, 0, g, nframes);
 }
 
 B200_API int b200_idct_mb420_host(B200Device *dev, int kind, const int16_t *blocks, int mb_w, int mb_h, int nframes,
@@ -288,7 +581,7 @@ B200_API int b200_idct_mb420_host(B200Device *dev, int kind, const int16_t *bloc
         Mb420Geom g{};
         g.mb_w = mb_w; g.mb_h = mb_h;
         for (int i = 0; i < 3; i++) { g.plane[i] = pbase + off[i]; g.linesize[i] = (int)pitch[i]; g.frame_stride[i] = (long long)frameBytes; }
-        int ret = dispatch(st, kind, true, (const int16_t *)cbase, nullptr, (long long)mb_w * mb_h * 6 * nf, nullptr, nullptr, nullptr, 0, g);
+        int ret = dispatch(st, kind, true, (const int16_t *)cbase, nullptr, (long long)mb_w * mb_h * 6 * nf, nullptr, nullptr, nullptr, 0, g, nf);
         if (ret < 0) return ret;
         for (int f = 0; f < nf; f++)
             for (int i = 0; i < 3; i++)

@@ -112,6 +112,47 @@ def test_pointer_table_dropin(device):
 
 
 @pytest.mark.parametrize("op", [1, 2])
+@pytest.mark.parametrize("geom", [(120, 68, 64, 32), (45, 3, 3, 1), (7, 2, 0, 0), (8, 1, 16, 8)])
+def test_mb420_geometries(device, op, geom):
+    """Partial segments (mb_w % 8 != 0), odd line sizes (falls back to the warp-cooperative kernel) and tiny frames."""
+    import torch
+    from ffmpeg_b200 import idctdsp
+    O = cl.oracle()
+    mb_w, mb_h, padl, padc = geom
+    nf = 2
+    nblk = mb_w * mb_h * 6 * nf
+    blk = idct_blocks("dense", nblk, 23)
+    W, H = mb_w * 16, mb_h * 16
+    ls = [W + padl, W // 2 + padc, W // 2 + padc]
+    rng = np.random.default_rng(6)
+    planes = [rng.integers(0, 256, (nf, H, ls[0]), dtype=np.uint8), rng.integers(0, 256, (nf, H // 2, ls[1]), dtype=np.uint8),
+              rng.integers(0, 256, (nf, H // 2, ls[2]), dtype=np.uint8)]
+    ref = [p.copy() for p in planes]
+    b = np.arange(nblk)
+    f, r = b // (mb_w * mb_h * 6), b % (mb_w * mb_h * 6)
+    mb, k = r // 6, r % 6
+    mby, mbx = mb // mb_w, mb % mb_w
+    for pl in range(3):
+        sel = (k < 4) if pl == 0 else (k == 3 + pl)
+        if pl == 0:
+            off = f * H * ls[0] + (mby * 16 + (k >> 1) * 8) * ls[0] + mbx * 16 + (k & 1) * 8
+        else:
+            off = f * (H // 2) * ls[pl] + (mby * 8) * ls[pl] + mbx * 8
+        bs = np.ascontiguousarray(blk[sel])
+        O.orc_idct_batch(op, cl.ptr(bs, cl.i16p), int(sel.sum()), cl.ptr(ref[pl]), ls[pl], cl.ptr(np.ascontiguousarray(off[sel]).astype(np.int64), cl.i64p))
+    fs = [H * ls[0], (H // 2) * ls[1], (H // 2) * ls[2]]
+    st = torch.cuda.ExternalStream(device.stream)
+    with torch.cuda.stream(st):
+        db = torch.from_numpy(blk).cuda()
+        dp = [torch.from_numpy(p).cuda() for p in planes]
+        idctdsp.idct_mb420_device(device, op, db, mb_w, mb_h, nf, dp, ls, fs)
+        device.sync()
+        for pl in range(3):
+            got = dp[pl].cpu().numpy()
+            assert np.array_equal(got, ref[pl]), (pl, int((got != ref[pl]).sum()))
+
+
+@pytest.mark.parametrize("op", [1, 2])
 def test_mb420_frames(device, op):
     """Macroblock stream of BASELINE config 3 (1080p = 120x68 MBs x 6 blocks): device and host entry points vs oracle."""
     import torch
