@@ -200,7 +200,14 @@ idct8x8_kernel(const int16_t *blocks, int16_t *blocks_out, long long nblocks,
 //        chunks of whole rows (128-byte lines).  For `add` the tile is first filled from the destination the same way.
 // HBM traffic stays the algorithmic 128 B in + 64 B out (+ 64 B) per block.
 
-__device__ __forceinline__ int sx_lo(unsigned v) { return (int)__byte_perm(v, 0, 0x9910); }   // sign-extend low half (1 PRMT)
+// sign-extend the low half in one PRMT: selector nibble 9 = "replicate the sign of byte 1".  __byte_perm() masks the
+// selector to 3 bits per nibble, so the sign-replicate mode needs the PTX instruction itself.
+__device__ __forceinline__ int sx_lo(unsigned v)
+{
+    int d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(v), "r"(0u), "r"(0x9910u));
+    return d;
+}
 __device__ __forceinline__ int sx_hi(unsigned v) { return (int)v >> 16; }
 // Row pass with every constant pre-multiplied by 32: only bits 11..26 of the reference's 32-bit row sums survive the
 // ">> 11, store as int16" step, and those are bits 16..31 of (32 * sum) mod 2^32 — so (int)sum32 >> 16 IS the
