@@ -237,6 +237,28 @@ __device__ __forceinline__ void row_pass_i(const uint4 &in, int *o)
     o[3] = (int)(a3 + b3) >> 16; o[4] = (int)(a3 - b3) >> 16;
 }
 
+// same, results left packed as four (int16, int16) words: the high halves of the x32 sums are picked by PRMT
+__device__ __forceinline__ void row_pass_packed(const uint4 &in, unsigned *o)
+{
+    constexpr unsigned X1 = 32u * W1, X2 = 32u * W2, X3 = 32u * W3, X4 = 32u * W4, X5 = 32u * W5, X6 = 32u * W6, X7 = 32u * W7;
+    if (((in.x >> 16) | in.y | in.z | in.w) == 0) {
+        const unsigned dc = ((in.x & 0xffffu) << 3) & 0xffffu;
+        o[0] = o[1] = o[2] = o[3] = dc | (dc << 16);
+        return;
+    }
+    const int r0 = sx_lo(in.x), r1 = sx_hi(in.x), r2 = sx_lo(in.y), r3 = sx_hi(in.y);
+    const int r4 = sx_lo(in.z), r5 = sx_hi(in.z), r6 = sx_lo(in.w), r7 = sx_hi(in.w);
+    const unsigned p = X4 * (unsigned)(r0 + r4) + (32u << 10), q = X4 * (unsigned)(r0 - r4) + (32u << 10);
+    const unsigned s = X2 * (unsigned)r2 + X6 * (unsigned)r6, d = X6 * (unsigned)r2 - X2 * (unsigned)r6;
+    const unsigned a0 = p + s, a3 = p - s, a1 = q + d, a2 = q - d;
+    const unsigned b0 = X1 * (unsigned)r1 + X3 * (unsigned)r3 + X5 * (unsigned)r5 + X7 * (unsigned)r7;
+    const unsigned b1 = X3 * (unsigned)r1 - X7 * (unsigned)r3 - X1 * (unsigned)r5 - X5 * (unsigned)r7;
+    const unsigned b2 = X5 * (unsigned)r1 - X1 * (unsigned)r3 + X7 * (unsigned)r5 + X3 * (unsigned)r7;
+    const unsigned b3 = X7 * (unsigned)r1 - X5 * (unsigned)r3 + X3 * (unsigned)r5 - X1 * (unsigned)r7;
+    o[0] = __byte_perm(a0 + b0, a1 + b1, 0x7632); o[1] = __byte_perm(a2 + b2, a3 + b3, 0x7632);
+    o[2] = __byte_perm(a3 - b3, a2 - b2, 0x7632); o[3] = __byte_perm(a1 - b1, a0 - b0, 0x7632);
+}
+
 // IDCT_COLS (simple_idct_template.c:209-257): eight inputs of one column -> eight results (already >> 20)
 __device__ __forceinline__ void col_pass_i(int c0, int c1, int c2, int c3, int c4, int c5, int c6, int c7, int *o)
 {
@@ -365,9 +387,15 @@ idct_tpb_kernel(const int16_t *blocks, int16_t *blocks_out, long long nblocks, u
 
 // 4:2:0 macroblock stream.  blockDim.x = 48 * SEGS; segment = 8 consecutive macroblocks of one macroblock row.
 // Grid: x over groups of SEGS segments of a row, y over macroblock rows, z over frames.
+// Registers are kept low (4 CTAs per SM) by holding the row-pass result packed (32 words) and by sending every clamped
+// pixel pair straight to the shared-memory tile (2-byte stores; for `add` the same 2 bytes are read first).
+// Luma tile rows 8..15 are stored with their 64-byte halves swapped so that blocks Y0/Y2 (and Y1/Y3) of one
+// macroblock, which sit 8 rows = 1024 B apart, do not share banks.
 constexpr int MAX_SEGS = 6;
+__device__ __forceinline__ int luma_swz(int row) { return (row & 8) << 3; }               // 0 or 64
+
 template <int KIND>
-__global__ void __launch_bounds__(48 * MAX_SEGS)
+__global__ void __launch_bounds__(48 * MAX_SEGS, 4)
 idct_mb420_kernel(const int16_t *blocks, Mb420Geom g, int segs_per_cta)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -395,7 +423,7 @@ idct_mb420_kernel(const int16_t *blocks, Mb420Geom g, int segs_per_cta)
         if (KIND == B200_IDCT_ADD) {                                                      // stage the destination tile
             for (int i = w; i < 128; i += 48) {                                           // luma: 16 rows x 8 chunks of 16 B
                 const int row = i >> 3, ch = i & 7;
-                if (ch < nmb) cp_async16(tile + row * 128 + ch * 16, py + (long long)row * ls0 + ch * 16);
+                if (ch < nmb) cp_async16(tile + row * 128 + ((ch * 16) ^ luma_swz(row)), py + (long long)row * ls0 + ch * 16);
             }
             for (int i = w; i < 64; i += 48) {                                            // chroma: 8 rows x 8 chunks of 8 B each plane
                 const int row = i >> 3, ch = i & 7;
@@ -411,22 +439,39 @@ idct_mb420_kernel(const int16_t *blocks, Mb420Geom g, int segs_per_cta)
     const int m = w / 6, k = w - m * 6;                                                   // macroblock in segment, block in macroblock
     if (m < nmb) {
         unsigned char *trow; int tp;
-        if (k < 4) { trow = tile + ((k >> 1) * 8) * 128 + m * 16 + (k & 1) * 8; tp = 128; }
+        if (k < 4) { trow = tile + ((k >> 1) * 8) * 128 + ((m * 16 + (k & 1) * 8) ^ ((k >> 1) * 64)); tp = 128; }
         else       { trow = tile + (k == 4 ? 2048 : 2560) + m * 8; tp = 64; }
-        uint2 drows[8], orows[8];
-        if (KIND == B200_IDCT_ADD) {
+        const uint4 *rows = &my_in[w * 8];
+        const int key = w & 7;
+        unsigned R2[8][4];
 #pragma unroll
-            for (int r = 0; r < 8; r++) drows[r] = *reinterpret_cast<const uint2 *>(trow + r * tp);
+        for (int j = 0; j < 8; j++) row_pass_packed(rows[j ^ key], R2[j]);
+#pragma unroll
+        for (int cp = 0; cp < 4; cp++) {
+            int oa[8], ob[8];
+            col_pass_i(sx_lo(R2[0][cp]), sx_lo(R2[1][cp]), sx_lo(R2[2][cp]), sx_lo(R2[3][cp]),
+                       sx_lo(R2[4][cp]), sx_lo(R2[5][cp]), sx_lo(R2[6][cp]), sx_lo(R2[7][cp]), oa);
+            col_pass_i(sx_hi(R2[0][cp]), sx_hi(R2[1][cp]), sx_hi(R2[2][cp]), sx_hi(R2[3][cp]),
+                       sx_hi(R2[4][cp]), sx_hi(R2[5][cp]), sx_hi(R2[6][cp]), sx_hi(R2[7][cp]), ob);
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                unsigned short *px = reinterpret_cast<unsigned short *>(trow + r * tp + 2 * cp);
+                if (KIND == B200_IDCT_ADD) {
+                    const unsigned dd = *px;
+                    oa[r] += (int)(dd & 0xff);
+                    ob[r] += (int)(dd >> 8);
+                }
+                const unsigned cl = __vimin_s16x2_relu(__byte_perm((unsigned)oa[r], (unsigned)ob[r], 0x5410), 0x00ff00ffu);
+                *px = (unsigned short)__byte_perm(cl, 0, 0x4420);
+            }
         }
-        idct_block<KIND>(&my_in[w * 8], w & 7, drows, orows, nullptr);
-#pragma unroll
-        for (int r = 0; r < 8; r++) *reinterpret_cast<uint2 *>(trow + r * tp) = orows[r];
     }
     __syncthreads();
     if (nmb > 0) {
         for (int i = w; i < 128; i += 48) {
             const int row = i >> 3, ch = i & 7;
-            if (ch < nmb) *reinterpret_cast<uint4 *>(py + (long long)row * ls0 + ch * 16) = *reinterpret_cast<const uint4 *>(tile + row * 128 + ch * 16);
+            if (ch < nmb) *reinterpret_cast<uint4 *>(py + (long long)row * ls0 + ch * 16) =
+                              *reinterpret_cast<const uint4 *>(tile + row * 128 + ((ch * 16) ^ luma_swz(row)));
         }
         for (int i = w; i < 64; i += 48) {
             const int row = i >> 3, ch = i & 7;
