@@ -416,9 +416,13 @@ idct_mb420_kernel(const int16_t *blocks, Mb420Geom g, int segs_per_cta)
     if (nmb > 0) {
         const long long blk0 = (((f * g.mb_h + mby) * g.mb_w) + mbx0) * 6;
         const uint4 *gsrc = reinterpret_cast<const uint4 *>(blocks) + blk0 * 8;
-        for (int i = w; i < nmb * 48; i += 48) {
-            const int b = i >> 3, r = i & 7;
-            cp_async16(&my_in[b * 8 + (r ^ (b & 7))], gsrc + i);
+        {
+            const int r = w & 7, nb = nmb * 6;
+#pragma unroll
+            for (int it = 0; it < 8; it++) {                                              // i = w + 48*it: block (w>>3) + 6*it, row w&7
+                const int b = (w >> 3) + 6 * it;
+                if (b < nb) cp_async16(&my_in[b * 8 + (r ^ (b & 7))], gsrc + b * 8 + r);
+            }
         }
         if (KIND == B200_IDCT_ADD) {                                                      // stage the destination tile
             for (int i = w; i < 128; i += 48) {                                           // luma: 16 rows x 8 chunks of 16 B
@@ -447,22 +451,28 @@ idct_mb420_kernel(const int16_t *blocks, Mb420Geom g, int segs_per_cta)
 #pragma unroll
         for (int j = 0; j < 8; j++) row_pass_packed(rows[j ^ key], R2[j]);
 #pragma unroll
-        for (int cp = 0; cp < 4; cp++) {
-            int oa[8], ob[8];
-            col_pass_i(sx_lo(R2[0][cp]), sx_lo(R2[1][cp]), sx_lo(R2[2][cp]), sx_lo(R2[3][cp]),
-                       sx_lo(R2[4][cp]), sx_lo(R2[5][cp]), sx_lo(R2[6][cp]), sx_lo(R2[7][cp]), oa);
-            col_pass_i(sx_hi(R2[0][cp]), sx_hi(R2[1][cp]), sx_hi(R2[2][cp]), sx_hi(R2[3][cp]),
-                       sx_hi(R2[4][cp]), sx_hi(R2[5][cp]), sx_hi(R2[6][cp]), sx_hi(R2[7][cp]), ob);
+        for (int half = 0; half < 2; half++) {             // four columns (one 32-bit tile word per row) at a time
+            int o0[8], o1[8], o2[8], o3[8];
+            const int c0 = 2 * half, c1 = 2 * half + 1;
+            col_pass_i(sx_lo(R2[0][c0]), sx_lo(R2[1][c0]), sx_lo(R2[2][c0]), sx_lo(R2[3][c0]),
+                       sx_lo(R2[4][c0]), sx_lo(R2[5][c0]), sx_lo(R2[6][c0]), sx_lo(R2[7][c0]), o0);
+            col_pass_i(sx_hi(R2[0][c0]), sx_hi(R2[1][c0]), sx_hi(R2[2][c0]), sx_hi(R2[3][c0]),
+                       sx_hi(R2[4][c0]), sx_hi(R2[5][c0]), sx_hi(R2[6][c0]), sx_hi(R2[7][c0]), o1);
+            col_pass_i(sx_lo(R2[0][c1]), sx_lo(R2[1][c1]), sx_lo(R2[2][c1]), sx_lo(R2[3][c1]),
+                       sx_lo(R2[4][c1]), sx_lo(R2[5][c1]), sx_lo(R2[6][c1]), sx_lo(R2[7][c1]), o2);
+            col_pass_i(sx_hi(R2[0][c1]), sx_hi(R2[1][c1]), sx_hi(R2[2][c1]), sx_hi(R2[3][c1]),
+                       sx_hi(R2[4][c1]), sx_hi(R2[5][c1]), sx_hi(R2[6][c1]), sx_hi(R2[7][c1]), o3);
 #pragma unroll
             for (int r = 0; r < 8; r++) {
-                unsigned short *px = reinterpret_cast<unsigned short *>(trow + r * tp + 2 * cp);
+                unsigned *px = reinterpret_cast<unsigned *>(trow + r * tp + 4 * half);
                 if (KIND == B200_IDCT_ADD) {
                     const unsigned dd = *px;
-                    oa[r] += (int)(dd & 0xff);
-                    ob[r] += (int)(dd >> 8);
+                    o0[r] += (int)__byte_perm(dd, 0, 0x4440); o1[r] += (int)__byte_perm(dd, 0, 0x4441);
+                    o2[r] += (int)__byte_perm(dd, 0, 0x4442); o3[r] += (int)(dd >> 24);
                 }
-                const unsigned cl = __vimin_s16x2_relu(__byte_perm((unsigned)oa[r], (unsigned)ob[r], 0x5410), 0x00ff00ffu);
-                *px = (unsigned short)__byte_perm(cl, 0, 0x4420);
+                const unsigned lo = __vimin_s16x2_relu(__byte_perm((unsigned)o0[r], (unsigned)o1[r], 0x5410), 0x00ff00ffu);
+                const unsigned hi = __vimin_s16x2_relu(__byte_perm((unsigned)o2[r], (unsigned)o3[r], 0x5410), 0x00ff00ffu);
+                *px = __byte_perm(lo, hi, 0x6420);
             }
         }
     }

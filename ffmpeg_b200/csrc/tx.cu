@@ -28,7 +28,10 @@ struct TxDev {                 // device-side plan
     int lvl_start[18], lvl_cnt[18];
     const float *tab;          // cosine tables, tab_off[k] = start of tab_{2^k}
     int tab_off[18];
+    const int *leaf16; int n_leaf16;   // offsets of the size-16 blocks (done in registers)
+    const int *leaf8;  int n_leaf8;    // offsets of size-8 blocks that are not part of a size-16 block
     const int *scatter;        // FFT: z[scatter[g]] = src[g]
+    const int *imap;           // inverse MDCT: z[imap[m]] gets the pair (in[len-1-2m], in[2m])
     const int *sub_map;        // MDCT index map (doubled for the inverse)
     const float2 *exp;         // MDCT twiddles
     int len;                   // MDCT length (2n)
@@ -45,18 +48,80 @@ __device__ __forceinline__ void butterflies(float2 &a0, float2 &a1, float2 &a2, 
     a2.y = i0 - t6; a0.y = i0 + t6;
 }
 
-// all levels on the transform held in z[0..n)
+// shared-memory index with one pad element per 16 (kills the bank conflicts of the bit-reversal-like scatter)
+__device__ __forceinline__ int PAD(int i) { return i + (i >> 4); }
+
+__device__ __forceinline__ void fft2r(float2 &a, float2 &b)
+{
+    const float2 s0 = a, s1 = b;
+    a = make_float2(s0.x + s1.x, s0.y + s1.y);
+    b = make_float2(s0.x - s1.x, s0.y - s1.y);
+}
+__device__ __forceinline__ void bfly_nomul(float2 &a0, float2 &a1, float2 &a2, float2 &a3) { butterflies(a0, a1, a2, a3, a2.x, a2.y, a3.x, a3.y); }
+__device__ __forceinline__ void bfly_mul(float2 &a0, float2 &a1, float2 &a2, float2 &a3, float wre, float wim)
+{
+    const float t1 = a2.x * wre - a2.y * (-wim);
+    const float t2 = a2.x * (-wim) + a2.y * wre;
+    const float t5 = a3.x * wre - a3.y * wim;
+    const float t6 = a3.x * wim + a3.y * wre;
+    butterflies(a0, a1, a2, a3, t1, t2, t5, t6);
+}
+// ff_tx_fft8_ns on v[0..7] (tx_template.c:660-679), c8 = tab_8[1]
+__device__ __forceinline__ void leaf_fft8(float2 *v, float c8)
+{
+    fft2r(v[0], v[1]); fft2r(v[4], v[5]); fft2r(v[6], v[7]);
+    bfly_nomul(v[0], v[1], v[2], v[3]);
+    bfly_nomul(v[0], v[2], v[4], v[6]);
+    bfly_mul(v[1], v[3], v[5], v[7], c8, c8);
+}
+// ff_tx_fft16_ns on v[0..15] (tx_template.c:681-704)
+__device__ __forceinline__ void leaf_fft16(float2 *v, float c8, float c1, float c2, float c3)
+{
+    leaf_fft8(v, c8);
+    fft2r(v[8], v[9]);   bfly_nomul(v[8], v[9], v[10], v[11]);
+    fft2r(v[12], v[13]); bfly_nomul(v[12], v[13], v[14], v[15]);
+    bfly_nomul(v[0], v[4], v[8], v[12]);
+    bfly_mul(v[2], v[6], v[10], v[14], c2, c2);
+    bfly_mul(v[1], v[5], v[9], v[13], c1, c3);
+    bfly_mul(v[3], v[7], v[11], v[15], c3, c1);
+}
+
+// all levels on the transform held in z[PAD(0..n))
 __device__ void fft_levels(const TxDev &p, float2 *z)
 {
-    for (int L = 1; L <= p.nlevels; L++) {
+    int first = 1;
+    if (p.nlevels >= 5) {                                  // sizes 2..16 in registers, one thread per leaf block
+        const float c8 = __ldg(p.tab + p.tab_off[3] + 1);
+        const float *t16 = p.tab + p.tab_off[4];
+        const float c1 = __ldg(t16 + 1), c2 = __ldg(t16 + 2), c3 = __ldg(t16 + 3);
+        for (int b = threadIdx.x; b < p.n_leaf16 + p.n_leaf8; b += blockDim.x) {
+            float2 v[16];
+            if (b < p.n_leaf16) {
+                const int o = __ldg(p.leaf16 + b);
+#pragma unroll
+                for (int i = 0; i < 16; i++) v[i] = z[PAD(o) + i];            // o is a multiple of 16: one pad run
+                leaf_fft16(v, c8, c1, c2, c3);
+#pragma unroll
+                for (int i = 0; i < 16; i++) z[PAD(o) + i] = v[i];
+            } else {
+                const int o = __ldg(p.leaf8 + b - p.n_leaf16);                // multiple of 8
+#pragma unroll
+                for (int i = 0; i < 8; i++) v[i] = z[PAD(o) + i];
+                leaf_fft8(v, c8);
+#pragma unroll
+                for (int i = 0; i < 8; i++) z[PAD(o) + i] = v[i];
+            }
+        }
+        __syncthreads();
+        first = 5;
+    }
+    for (int L = first; L <= p.nlevels; L++) {
         const int S = 1 << L;
         const int *off = p.blk_off + p.lvl_start[L];
         if (L == 1) {
             for (int b = threadIdx.x; b < p.lvl_cnt[L]; b += blockDim.x) {
                 const int o = __ldg(off + b);
-                const float2 s0 = z[o], s1 = z[o + 1];
-                z[o] = make_float2(s0.x + s1.x, s0.y + s1.y);
-                z[o + 1] = make_float2(s0.x - s1.x, s0.y - s1.y);
+                fft2r(z[PAD(o)], z[PAD(o + 1)]);
             }
         } else {
             const int lq = L - 2, q = 1 << lq;
@@ -64,18 +129,11 @@ __device__ void fft_levels(const TxDev &p, float2 *z)
             const int total = p.lvl_cnt[L] << lq;
             for (int b = threadIdx.x; b < total; b += blockDim.x) {
                 const int o = __ldg(off + (b >> lq)), j = b & (q - 1);
-                float2 a0 = z[o + j], a1 = z[o + q + j], a2 = z[o + 2 * q + j], a3 = z[o + 3 * q + j];
-                if (S <= 16 && j == 0) {
-                    butterflies(a0, a1, a2, a3, a2.x, a2.y, a3.x, a3.y);
-                } else {
-                    const float wre = __ldg(tab + j), wim = __ldg(tab + q - j);
-                    const float t1 = a2.x * wre - a2.y * (-wim);
-                    const float t2 = a2.x * (-wim) + a2.y * wre;
-                    const float t5 = a3.x * wre - a3.y * wim;
-                    const float t6 = a3.x * wim + a3.y * wre;
-                    butterflies(a0, a1, a2, a3, t1, t2, t5, t6);
-                }
-                z[o + j] = a0; z[o + q + j] = a1; z[o + 2 * q + j] = a2; z[o + 3 * q + j] = a3;
+                const int i0 = PAD(o + j), i1 = PAD(o + q + j), i2 = PAD(o + 2 * q + j), i3 = PAD(o + 3 * q + j);
+                float2 a0 = z[i0], a1 = z[i1], a2 = z[i2], a3 = z[i3];
+                if (S <= 16 && j == 0) bfly_nomul(a0, a1, a2, a3);
+                else bfly_mul(a0, a1, a2, a3, __ldg(tab + j), __ldg(tab + q - j));
+                z[i0] = a0; z[i1] = a1; z[i2] = a2; z[i3] = a3;
             }
         }
         __syncthreads();
@@ -89,10 +147,10 @@ tx_fft_kernel(TxDev p, float2 *out, const float2 *in, long long out_step, long l
     extern __shared__ float2 z[];
     const float2 *src = reinterpret_cast<const float2 *>(reinterpret_cast<const char *>(in) + blockIdx.x * in_step);
     float2 *dst = reinterpret_cast<float2 *>(reinterpret_cast<char *>(out) + blockIdx.x * out_step);
-    for (int g = threadIdx.x; g < p.n; g += blockDim.x) z[__ldg(p.scatter + g)] = src[g];
+    for (int g = threadIdx.x; g < p.n; g += blockDim.x) z[PAD(__ldg(p.scatter + g))] = src[g];
     __syncthreads();
     fft_levels(p, z);
-    for (int i = threadIdx.x; i < p.n; i += blockDim.x) dst[i] = z[i];
+    for (int i = threadIdx.x; i < p.n; i += blockDim.x) dst[i] = z[PAD(i)];
 }
 
 // ff_tx_mdct_inv: len floats in (element k at in + k*stride floats), len floats out (contiguous)
@@ -104,28 +162,27 @@ tx_mdct_inv_kernel(TxDev p, float *out, const float *in, long long stride, long 
     float2 *dst = reinterpret_cast<float2 *>(reinterpret_cast<char *>(out) + blockIdx.x * out_step);
     const int len2 = p.len >> 1, len4 = p.len >> 2;
     const float *in1 = src, *in2 = src + (long long)(len2 * 2 - 1) * stride;
-    for (int i = threadIdx.x; i < len2; i += blockDim.x) {
-        const int k = __ldg(p.sub_map + i);
-        const float are = in2[-(long long)k * stride], aim = in1[(long long)k * stride];
-        const float2 e = __ldg(p.exp + i);
-        z[i] = make_float2(are * e.x - aim * e.y, are * e.y + aim * e.x);
+    const float2 *e = p.exp + len2;                         // twiddles in natural order
+    for (int m = threadIdx.x; m < len2; m += blockDim.x) {  // source order (coalesced reads), scattered into z
+        const float are = in2[-(long long)(2 * m) * stride], aim = in1[(long long)(2 * m) * stride];
+        const float2 w = __ldg(e + m);
+        z[PAD(__ldg(p.imap + m))] = make_float2(are * w.x - aim * w.y, are * w.y + aim * w.x);
     }
     __syncthreads();
     fft_levels(p, z);
-    const float2 *e = p.exp + len2;
     for (int i = threadIdx.x; i < len4; i += blockDim.x) {
         const int i0 = len4 + i, i1 = len4 - i - 1;
-        const float2 z1 = z[i1], z0 = z[i0], e1 = __ldg(e + i1), e0 = __ldg(e + i0);
+        const float2 z1 = z[PAD(i1)], z0 = z[PAD(i0)], e1 = __ldg(e + i1), e0 = __ldg(e + i0);
         const float s1re = z1.y, s1im = z1.x, s0re = z0.y, s0im = z0.x;
         float2 o1, o0;
         o1.x = s1re * e1.y - s1im * e1.x;      // z[i1].re
         o0.y = s1re * e1.x + s1im * e1.y;      // z[i0].im
         o0.x = s0re * e0.y - s0im * e0.x;      // z[i0].re
         o1.y = s0re * e0.x + s0im * e0.y;      // z[i1].im
-        z[i1] = o1; z[i0] = o0;
+        z[PAD(i1)] = o1; z[PAD(i0)] = o0;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < len2; i += blockDim.x) dst[i] = z[i];
+    for (int i = threadIdx.x; i < len2; i += blockDim.x) dst[i] = z[PAD(i)];
 }
 
 // ff_tx_mdct_fwd: 2*len floats in (contiguous), len floats out (element k at out + k*stride floats)
@@ -147,13 +204,13 @@ tx_mdct_fwd_kernel(TxDev p, float *out, const float *in, long long stride, long 
             im = src[-len2 + k] + -src[1 * len3 - 1 - k];
         }
         const float2 e = __ldg(p.exp + i);
-        z[idx] = make_float2(re * e.y + im * e.x, re * e.x - im * e.y);     // (.re, .im) = (dim, dre) of the reference's CMUL
+        z[PAD(idx)] = make_float2(re * e.y + im * e.x, re * e.x - im * e.y); // (.re, .im) = (dim, dre) of the reference's CMUL
     }
     __syncthreads();
     fft_levels(p, z);
     for (int i = threadIdx.x; i < len4; i += blockDim.x) {
         const int i0 = len4 + i, i1 = len4 - i - 1;
-        const float2 s1 = z[i1], s0 = z[i0], e1 = __ldg(p.exp + i1), e0 = __ldg(p.exp + i0);
+        const float2 s1 = z[PAD(i1)], s0 = z[PAD(i0)], e1 = __ldg(p.exp + i1), e0 = __ldg(p.exp + i0);
         dst[(2LL * i1 + 1) * stride] = s0.x * e0.y - s0.y * e0.x;
         dst[(2LL * i0) * stride]     = s0.x * e0.x + s0.y * e0.y;
         dst[(2LL * i0 + 1) * stride] = s1.x * e1.y - s1.y * e1.x;
@@ -201,6 +258,12 @@ static int tx_build(B200TXContext *c, float scale)
     d.n = n; d.nlevels = k; d.len = c->len;
     std::vector<std::vector<int>> lv(18);
     collect_blocks(lv, k, 0);
+    std::vector<int> leaf16 = lv[4], leaf8;
+    for (int o : lv[3]) {                                            // size-8 blocks that are quarter blocks of a size-32 block
+        bool inside16 = false;
+        for (int o16 : lv[4]) if (o >= o16 && o < o16 + 16) { inside16 = true; break; }
+        if (!inside16) leaf8.push_back(o);
+    }
     std::vector<int> blk;
     for (int L = 0; L < 18; L++) {
         d.lvl_start[L] = (int)blk.size();
@@ -253,18 +316,30 @@ static int tx_build(B200TXContext *c, float scale)
     const size_t o_sc = off;  off += al(scatter.size() * 4);
     const size_t o_sm = off;  off += al(sub_map.size() * 4 + 4);
     const size_t o_ex = off;  off += al(ex.size() * 8 + 8);
+    std::vector<int> imap(sub_map.size() + 1, 0);
+    if (c->type == 1 && c->inv)
+        for (size_t i = 0; i < sub_map.size(); i++) imap[sub_map[i] >> 1] = (int)i;
+    const size_t o_im = off;  off += al(imap.size() * 4);
+    const size_t o_l16 = off; off += al(leaf16.size() * 4 + 4);
+    const size_t o_l8 = off;  off += al(leaf8.size() * 4 + 4);
     std::vector<uint8_t> host(off, 0);
     memcpy(&host[o_blk], blk.data(), blk.size() * 4);
     memcpy(&host[o_tab], tab.data(), tab.size() * 4);
     memcpy(&host[o_sc], scatter.data(), scatter.size() * 4);
     if (!sub_map.empty()) memcpy(&host[o_sm], sub_map.data(), sub_map.size() * 4);
     if (!ex.empty()) memcpy(&host[o_ex], ex.data(), ex.size() * 8);
+    memcpy(&host[o_im], imap.data(), imap.size() * 4);
+    if (!leaf16.empty()) memcpy(&host[o_l16], leaf16.data(), leaf16.size() * 4);
+    if (!leaf8.empty()) memcpy(&host[o_l8], leaf8.data(), leaf8.size() * 4);
     B200_CUDA_OK(cudaMalloc(&c->blob, off));
     B200_CUDA_OK(cudaMemcpy(c->blob, host.data(), off, cudaMemcpyHostToDevice));
     uint8_t *b = (uint8_t *)c->blob;
     d.blk_off = (const int *)(b + o_blk); d.tab = (const float *)(b + o_tab); d.scatter = (const int *)(b + o_sc);
     d.sub_map = (const int *)(b + o_sm); d.exp = (const float2 *)(b + o_ex);
-    c->smem = (size_t)n * sizeof(float2);
+    d.imap = (const int *)(b + o_im);
+    d.leaf16 = (const int *)(b + o_l16); d.n_leaf16 = (int)leaf16.size();
+    d.leaf8 = (const int *)(b + o_l8); d.n_leaf8 = (int)leaf8.size();
+    c->smem = (size_t)(n + (n >> 4) + 1) * sizeof(float2);
     if (c->smem > 48 * 1024) {
         B200_CUDA_OK(cudaFuncSetAttribute(tx_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem));
         B200_CUDA_OK(cudaFuncSetAttribute(tx_mdct_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem));

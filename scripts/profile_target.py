@@ -47,5 +47,41 @@ with torch.cuda.stream(stream):
                 idctdsp.idct_mb420_device(dev, kind, blk, mbw, mbh, fr, pl, [mbw * 16, mbw * 8, mbw * 8],
                                           [mbw * 16 * mbh * 16, mbw * 8 * mbh * 8, mbw * 8 * mbh * 8])
             dev.sync()
+    if what in ("tx", "all"):
+        from ffmpeg_b200 import tx
+        n, cnt = 1024, 1 << 16
+        x = torch.rand((cnt, 2 * n), device="cuda"); y = torch.empty_like(x)
+        c = tx.av_tx_init(0, 0, n, device=dev)
+        for _ in range(3):
+            c.batch_device(y, x, 8, cnt, 8 * n, 8 * n)
+        dev.sync(); c.uninit()
+        c = tx.av_tx_init(1, 1, n, scale=1.0 / n, device=dev)
+        for _ in range(3):
+            c.batch_device(y, x, 4, cnt, 4 * n, 4 * n)
+        dev.sync(); c.uninit()
+    if what in ("qpel", "all"):
+        from ffmpeg_b200 import pel
+        nfr, Wd, Hd, ap = 16, 1920, 1088, 32
+        PW, PH = Wd + 2 * ap, Hd + 2 * ap
+        refp = torch.randint(0, 256, (nfr, PH, PW), dtype=torch.uint8, device="cuda")
+        dstp = torch.randint(0, 256, (nfr, PH, PW), dtype=torch.uint8, device="cuda")
+        fi = torch.arange(nfr, device="cuda").view(-1, 1, 1)
+        by = torch.arange(Hd // 16, device="cuda").view(1, -1, 1); bx = torch.arange(Wd // 16, device="cuda").view(1, 1, -1)
+        base = fi * (PH * PW) + (by * 16 + ap) * PW + bx * 16 + ap
+        dx = torch.randint(-16, 17, base.shape, device="cuda"); dy = torch.randint(-16, 17, base.shape, device="cuda")
+        doff = base.reshape(-1).to(torch.int64).contiguous(); soff = (base + dy * PW + dx).reshape(-1).to(torch.int64).contiguous()
+        ops = (torch.randint(0, 2, (doff.numel(),), device="cuda") | (torch.randint(0, 16, (doff.numel(),), device="cuda") << 3)).to(torch.uint8)
+        for _ in range(3):
+            pel.h264qpel_batch_device(dev, doff.numel(), ops, dstp, doff, refp, soff, PW)
+        dev.sync()
+    if what in ("esa", "all"):
+        from ffmpeg_b200 import me_cmp
+        cur = torch.randint(0, 256, (1, H, W), dtype=torch.uint8, device="cuda")
+        ref = torch.roll(cur, shifts=(7, -13), dims=(1, 2)).contiguous()
+        nmb = (W // 16) * (H // 16)
+        mv = torch.zeros((1, nmb, 2), dtype=torch.int32, device="cuda"); cost = torch.zeros((1, nmb), dtype=torch.int64, device="cuda")
+        for _ in range(2):
+            me_cmp.me_esa_device(dev, cur, ref, W, W, H, W * H, 1, 16, 32, mv, cost)
+        dev.sync()
 dev.close()
 print("done", fb.launch_count())
