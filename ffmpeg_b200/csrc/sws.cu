@@ -175,16 +175,13 @@ __device__ __forceinline__ void fold2(int k2, const uint2 &r0, const uint2 &r1, 
 
 // CFS4: the chroma bank has exactly 4 taps (bicubic 2x vertical chroma up-sampling, the BASELINE case): fully unrolled.
 // Line offsets are 32-bit (the host guarantees |stride| * lines < 2^31); coefficient pairs come pre-packed (t.vChr2/vLum2).
-// A CTA covers `rows_per_cta` whole output lines (rows_per_cta * ngroups threads, chosen by the host so that the
-// thread count is a multiple of 32 whenever possible: 4K has 240 groups per line, 2 lines = 480 threads = 15 full warps).
 template <bool LUMID, bool CFS4>
-__global__ void __launch_bounds__(512, 3)
-sws_vscale_rgb24_fast_kernel(SwsFrameArgs a, SwsDevTables t, SwsColorConst c, int ngroups, int rows_per_cta, unsigned div_magic)
+__global__ void __launch_bounds__(128, 12)
+sws_vscale_rgb24_fast_kernel(SwsFrameArgs a, SwsDevTables t, SwsColorConst c, int ngroups)
 {
-    const int r = (int)__umulhi((unsigned)threadIdx.x, div_magic);       // threadIdx.x / ngroups (host-verified magic)
-    const int xg = threadIdx.x - r * ngroups;
-    const int dy = blockIdx.y * rows_per_cta + r;
-    if (r >= rows_per_cta || dy >= a.dstH) return;
+    const int xg = blockIdx.x * blockDim.x + threadIdx.x;
+    if (xg >= ngroups) return;
+    const int dy = blockIdx.y;
     const long long f = blockIdx.z;
     const int lfs = t.vLumSize, cfs = CFS4 ? 4 : t.vChrSize;
     const int lp = (lfs + 1) >> 1, cp = (cfs + 1) >> 1;
@@ -564,28 +561,15 @@ static int launch_batch(B200SwsContext *c, cudaStream_t stream, const uint8_t *c
         } else if (c->h_identity) {
             auto fits32 = [](long long stride, long long lines) { return (stride < 0 ? -stride : stride) * (lines + 1) < (1LL << 31); };
             const bool off32 = fits32(b.ys, p.srcH) && fits32(b.us, p.chrSrcH) && fits32(b.vs, p.chrSrcH) && fits32(b.ds, p.dstH);
-            int ngroups = (vecOK && c->fast_x && off32) ? p.dstW / 16 : 0;
-            if (ngroups > 512) ngroups = 0;                  // wider than 8192 px: the general kernel handles the whole line
+            const int ngroups = (vecOK && c->fast_x && off32) ? p.dstW / 16 : 0;
             if (ngroups) {
-                // lines per CTA: fill warps completely when possible (few idle lanes otherwise), at most 512 threads
-                int R = 1, bestWaste = 1 << 30;
-                for (int r = 1; r <= 8 && r * ngroups <= 512; r++) {
-                    const int thr = r * ngroups, waste = ((thr + 31) / 32 * 32 - thr) * 64 / thr;     // idle lanes per 64 useful
-                    if (waste < bestWaste) { bestWaste = waste; R = r; }
-                }
-                const unsigned magic = (unsigned)((0x100000000ULL + (unsigned)ngroups - 1) / (unsigned)ngroups);
-                for (int tt = 0; tt < 1024; tt++)            // the magic is exact for every thread index (d <= 512, t < 1024)
-                    if ((int)(((unsigned long long)tt * magic) >> 32) != tt / ngroups) return B200_EEXTERNAL;
-                {
-                    const int threads = ((R * ngroups + 31) / 32) * 32;
-                    dim3 block(threads), grid(1, b200_ceil_div(p.dstH, R), nf);
-                    const bool c4 = p.vChr.size == 4;
-                    if (c->lum_identity && c4)  sws_vscale_rgb24_fast_kernel<true, true><<<grid, block, 0, stream>>>(b, c->dt, p.color, ngroups, R, magic);
-                    else if (c->lum_identity)   sws_vscale_rgb24_fast_kernel<true, false><<<grid, block, 0, stream>>>(b, c->dt, p.color, ngroups, R, magic);
-                    else if (c4)                sws_vscale_rgb24_fast_kernel<false, true><<<grid, block, 0, stream>>>(b, c->dt, p.color, ngroups, R, magic);
-                    else                        sws_vscale_rgb24_fast_kernel<false, false><<<grid, block, 0, stream>>>(b, c->dt, p.color, ngroups, R, magic);
-                    B200_LAUNCHED();
-                }
+                dim3 block(128), grid(b200_ceil_div(ngroups, 128), p.dstH, nf);
+                const bool c4 = p.vChr.size == 4;
+                if (c->lum_identity && c4)  sws_vscale_rgb24_fast_kernel<true, true><<<grid, block, 0, stream>>>(b, c->dt, p.color, ngroups);
+                else if (c->lum_identity)   sws_vscale_rgb24_fast_kernel<true, false><<<grid, block, 0, stream>>>(b, c->dt, p.color, ngroups);
+                else if (c4)                sws_vscale_rgb24_fast_kernel<false, true><<<grid, block, 0, stream>>>(b, c->dt, p.color, ngroups);
+                else                        sws_vscale_rgb24_fast_kernel<false, false><<<grid, block, 0, stream>>>(b, c->dt, p.color, ngroups);
+                B200_LAUNCHED();
             }
             const int p0 = ngroups * 8, p1 = (p.dstW + 1) / 2;
             if (p1 > p0) {
