@@ -16,14 +16,45 @@ namespace {
 __device__ __forceinline__ int clip8(int v) { return __vimin_s32_relu(v, 255); }
 __device__ __forceinline__ int tap6(int a, int b, int c, int d, int e, int f) { return a - 5 * b + 20 * c + 20 * d - 5 * e + f; }
 
-constexpr int QW = 24;                 // window pitch (bytes): 16 + 5 -> 21, padded
+constexpr int QW = 32;                 // window pitch in bytes; block pixel (0,0) sits at column 8 of window row 2
+constexpr int QX = 8;                  // so that every 8-pixel segment of a row starts 8-byte aligned in shared memory
 constexpr int WARPS = 4;
 
-struct QpelSmem {
-    uint8_t win[21 * QW];              // source rows -2 .. size+2, columns -2 .. size+2
-    short hraw[21 * 16];               // unrounded horizontal sums for rows -2 .. size+2
+struct __align__(16) QpelSmem {
+    uint8_t win[21 * QW];              // source rows -2 .. size+2; source column x is at byte QX + x (x = -2 .. size+2)
+    short hraw[21 * 16];               // unrounded horizontal 6-tap sums for the same rows, block columns 0 .. 15
 };
 
+// 16 consecutive bytes of a window row starting at 4-aligned byte offset `o`, unpacked
+__device__ __forceinline__ void row16(const uint8_t *row, int o, int *b)
+{
+    const unsigned *w = reinterpret_cast<const unsigned *>(row + o);
+    const unsigned w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        b[i] = (int)__byte_perm(w0, 0, 0x4440 | i); b[4 + i] = (int)__byte_perm(w1, 0, 0x4440 | i);
+        b[8 + i] = (int)__byte_perm(w2, 0, 0x4440 | i); b[12 + i] = (int)__byte_perm(w3, 0, 0x4440 | i);
+    }
+}
+// 8 bytes starting at byte offset QX + x0 + dx (dx = 0 or 1) of a window row
+__device__ __forceinline__ void row8(const uint8_t *row, int x0, int dx, int *b)
+{
+    const unsigned *w = reinterpret_cast<const unsigned *>(row + QX + x0);
+    unsigned w0 = w[0], w1 = w[1];
+    if (dx) { const unsigned w2 = w[2]; w0 = __funnelshift_r(w0, w1, 8); w1 = __funnelshift_r(w1, w2, 8); }
+#pragma unroll
+    for (int i = 0; i < 4; i++) { b[i] = (int)__byte_perm(w0, 0, 0x4440 | i); b[4 + i] = (int)__byte_perm(w1, 0, 0x4440 | i); }
+}
+// unrounded horizontal 6-tap sums for block columns x0 .. x0+7 of window row `row`
+__device__ __forceinline__ void hsum8(const uint8_t *row, int x0, int *o)
+{
+    int b[16];
+    row16(row, QX + x0 - 4, b);                          // bytes of source columns x0-4 .. x0+11; taps need x0-2 .. x0+10
+#pragma unroll
+    for (int i = 0; i < 8; i++) o[i] = tap6(b[i + 2], b[i + 3], b[i + 4], b[i + 5], b[i + 6], b[i + 7]);
+}
+
+// One warp per operation.  Lane l works on one 8-pixel (4 for size 4) row segment: row l>>1, half l&1 for 16x16.
 __global__ void __launch_bounds__(32 * WARPS)
 qpel_kernel(long long n, const uint8_t *op, uint8_t *dst, const int64_t *dst_off, const uint8_t *src,
             const int64_t *src_off, long long stride)
@@ -40,35 +71,94 @@ qpel_kernel(long long n, const uint8_t *op, uint8_t *dst, const int64_t *dst_off
     const int wdim = size + 5;
     for (int k = lane; k < wdim * wdim; k += 32) {
         const int r = k / wdim, c = k - r * wdim;
-        s.win[r * QW + c] = __ldg(sp + (long long)(r - 2) * stride + (c - 2));
+        s.win[r * QW + QX - 2 + c] = __ldg(sp + (long long)(r - 2) * stride + (c - 2));
     }
     __syncwarp();
-    const bool need_j = (qx == 2 && qy != 0) || (qy == 2 && qx != 0);      // positions built from the centre sample
+    const int npx = size < 8 ? size : 8, segs = size >> 3 ? size >> 3 : 1;       // segments per row
+    const bool need_j = (qx == 2 && qy != 0) || (qy == 2 && qx != 0);             // positions built from the centre sample
     if (need_j) {
-        for (int k = lane; k < wdim * size; k += 32) {
-            const int r = k / size, c = k - r * size;
-            const uint8_t *p = &s.win[r * QW + c];                             // taps at columns c-2 .. c+3 of the block
-            s.hraw[r * 16 + c] = (short)tap6(p[0], p[1], p[2], p[3], p[4], p[5]);
+        for (int k = lane; k < wdim * segs; k += 32) {
+            const int r = k / segs, x0 = (k - r * segs) * 8;
+            int h[8];
+            hsum8(&s.win[r * QW], x0, h);
+            uint4 pk;
+            pk.x = (unsigned)(h[0] & 0xffff) | ((unsigned)h[1] << 16); pk.y = (unsigned)(h[2] & 0xffff) | ((unsigned)h[3] << 16);
+            pk.z = (unsigned)(h[4] & 0xffff) | ((unsigned)h[5] << 16); pk.w = (unsigned)(h[6] & 0xffff) | ((unsigned)h[7] << 16);
+            *reinterpret_cast<uint4 *>(&s.hraw[r * 16 + x0]) = pk;
         }
         __syncwarp();
     }
-    auto F = [&](int x, int y) { return (int)s.win[(y + 2) * QW + x + 2]; };
-    auto H = [&](int x, int y) { const uint8_t *p = &s.win[(y + 2) * QW + x]; return clip8((tap6(p[0], p[1], p[2], p[3], p[4], p[5]) + 16) >> 5); };
-    auto V = [&](int x, int y) { const uint8_t *p = &s.win[y * QW + x + 2];
-        return clip8((tap6(p[0], p[QW], p[2 * QW], p[3 * QW], p[4 * QW], p[5 * QW]) + 16) >> 5); };
-    auto J = [&](int x, int y) { const short *p = &s.hraw[y * 16 + x];
-        return clip8((tap6(p[0], p[16], p[32], p[48], p[64], p[80]) + 512) >> 10); };
-    for (int k = lane; k < size * size; k += 32) {
-        const int y = k / size, x = k - y * size;
-        int v;
-        if (qy == 0)            v = qx == 0 ? F(x, y) : qx == 2 ? H(x, y) : (F(x + (qx == 3), y) + H(x, y) + 1) >> 1;
-        else if (qx == 0)       v = qy == 2 ? V(x, y) : (F(x, y + (qy == 3)) + V(x, y) + 1) >> 1;
-        else if (qx == 2 && qy == 2) v = J(x, y);
-        else if (qx == 2)       v = (H(x, y + (qy == 3)) + J(x, y) + 1) >> 1;
-        else if (qy == 2)       v = (V(x + (qx == 3), y) + J(x, y) + 1) >> 1;
-        else                    v = (H(x, y + (qy == 3)) + V(x + (qx == 3), y) + 1) >> 1;
-        uint8_t *d = dp + (long long)y * stride + x;
-        *d = (uint8_t)(avg ? (*d + v + 1) >> 1 : v);
+    if (lane < size * segs) {
+        const int y = lane / segs, x0 = (lane - y * segs) * 8;
+        int v[8];
+        // the one or two samples each quarter position averages (h264qpel_template.c:313-456): F full-pel, H horizontal
+        // half, V vertical half, J centre.  acc collects them; two samples -> (a + b + 1) >> 1.
+        const bool useF = (qy == 0 && qx != 2) || (qx == 0 && (qy & 1));
+        const bool useH = qx != 0 && qy != 2;
+        const bool useV = qy != 0 && qx != 2;
+        int acc[8], t[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) acc[k] = 0;
+        int count = 0;
+        if (useF) {
+            row8(&s.win[(y + 2 + (qy == 3)) * QW], x0, qx == 3, t);
+#pragma unroll
+            for (int k = 0; k < 8; k++) acc[k] += t[k];
+            count++;
+        }
+        if (useH) {
+            hsum8(&s.win[(y + 2 + (qy == 3)) * QW], x0, t);
+#pragma unroll
+            for (int k = 0; k < 8; k++) acc[k] += clip8((t[k] + 16) >> 5);
+            count++;
+        }
+        if (useV) {
+            int r0[8], r1[8], r2[8], r3[8], r4[8], r5[8];
+            const int dx = qx == 3;
+            row8(&s.win[(y + 0) * QW], x0, dx, r0); row8(&s.win[(y + 1) * QW], x0, dx, r1); row8(&s.win[(y + 2) * QW], x0, dx, r2);
+            row8(&s.win[(y + 3) * QW], x0, dx, r3); row8(&s.win[(y + 4) * QW], x0, dx, r4); row8(&s.win[(y + 5) * QW], x0, dx, r5);
+#pragma unroll
+            for (int k = 0; k < 8; k++) acc[k] += clip8((tap6(r0[k], r1[k], r2[k], r3[k], r4[k], r5[k]) + 16) >> 5);
+            count++;
+        }
+        if (need_j) {
+            int j6[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) j6[k] = 512;
+            const int coef[6] = { 1, -5, 20, 20, -5, 1 };
+#pragma unroll
+            for (int j = 0; j < 6; j++) {
+                const uint4 pk = *reinterpret_cast<const uint4 *>(&s.hraw[(y + j) * 16 + x0]);
+                const unsigned w[4] = { pk.x, pk.y, pk.z, pk.w };
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    j6[2 * k] += coef[j] * (int)(short)(w[k] & 0xffff);
+                    j6[2 * k + 1] += coef[j] * ((int)w[k] >> 16);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) acc[k] += clip8(j6[k] >> 10);
+            count++;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = count == 2 ? (acc[k] + 1) >> 1 : acc[k];
+        uint8_t *d = dp + (long long)y * stride + x0;
+        if (npx == 8 && ((reinterpret_cast<uintptr_t>(d)) & 7) == 0) {
+            if (avg) {
+                const uint2 pv = *reinterpret_cast<const uint2 *>(d);
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    v[k] = (v[k] + (int)__byte_perm(pv.x, 0, 0x4440 | k) + 1) >> 1;
+                    v[4 + k] = (v[4 + k] + (int)__byte_perm(pv.y, 0, 0x4440 | k) + 1) >> 1;
+                }
+            }
+            uint2 ov;
+            ov.x = (unsigned)v[0] | ((unsigned)v[1] << 8) | ((unsigned)v[2] << 16) | ((unsigned)v[3] << 24);
+            ov.y = (unsigned)v[4] | ((unsigned)v[5] << 8) | ((unsigned)v[6] << 16) | ((unsigned)v[7] << 24);
+            *reinterpret_cast<uint2 *>(d) = ov;
+        } else {
+            for (int k = 0; k < npx; k++) d[k] = (uint8_t)(avg ? (d[k] + v[k] + 1) >> 1 : v[k]);
+        }
     }
 }
 
