@@ -81,28 +81,40 @@ esa_kernel(const uint8_t *cur, const uint8_t *ref, int linesize, long long frame
     }
     __syncthreads();
 
+    // Four horizontally adjacent candidates per thread and pass: they share the window words of every row (5 loads for
+    // 4 x 16 pixels) and the current-block words; candidate s is re-aligned with PRMT (s = 0 needs none).
     unsigned long long mine = ~0ull;
-    const int ncand = nx * ny;
-    for (int k = threadIdx.x; k < ncand; k += ESA_THREADS) {
-        const int cy = k / nx, cx = k - cy * nx;
-        const int wq = cx >> 2, sh = cx & 3;
-        const unsigned sel = 0x3210u + 0x1111u * sh;              // bytes sh..sh+3 of the pair (lo, hi)
-        unsigned sad = 0;
-#pragma unroll 4
+    const int ngx = (nx + 3) >> 2, ngroups = ngx * ny;
+    for (int g = threadIdx.x; g < ngroups; g += ESA_THREADS) {
+        const int cy = g / ngx, gx = g - cy * ngx;
+        const int cx0 = gx * 4, wq = gx;
+        unsigned sad0 = 0, sad1 = 0, sad2 = 0, sad3 = 0;
+#pragma unroll 2
         for (int j = 0; j < MB; j++) {
             const unsigned *row = swin + (cy + j) * win_pitch + wq;
+            const unsigned *crow = scur + j * (MB / 4);
             unsigned lo = row[0];
 #pragma unroll
             for (int q = 0; q < MB / 4; q++) {
-                const unsigned hi = row[q + 1];
-                sad = __vsadu4(__byte_perm(lo, hi, sel), scur[j * (MB / 4) + q]) + sad;
+                const unsigned hi = row[q + 1], cw = crow[q];
+                sad0 = __vsadu4(lo, cw) + sad0;
+                sad1 = __vsadu4(__byte_perm(lo, hi, 0x4321), cw) + sad1;
+                sad2 = __vsadu4(__byte_perm(lo, hi, 0x5432), cw) + sad2;
+                sad3 = __vsadu4(__byte_perm(lo, hi, 0x6543), cw) + sad3;
                 lo = hi;
             }
         }
-        const int ax = x0 + cx, ay = y0 + cy;
-        const unsigned notzero = (ax == x_mb && ay == y_mb) ? 0u : 1u;
-        const unsigned long long key = ((unsigned long long)sad << 32) | ((unsigned long long)notzero << 31) | (unsigned)k;
-        mine = key < mine ? key : mine;
+        const unsigned sads[4] = { sad0, sad1, sad2, sad3 };
+#pragma unroll
+        for (int sft = 0; sft < 4; sft++) {
+            const int cx = cx0 + sft;
+            if (cx < nx) {
+                const int ax = x0 + cx, ay = y0 + cy;
+                const unsigned notzero = (ax == x_mb && ay == y_mb) ? 0u : 1u;
+                const unsigned long long key = ((unsigned long long)sads[sft] << 32) | ((unsigned long long)notzero << 31) | (unsigned)(cy * nx + cx);
+                mine = key < mine ? key : mine;
+            }
+        }
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) {
