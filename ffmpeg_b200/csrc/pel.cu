@@ -69,27 +69,9 @@ qpel_kernel(long long n, const uint8_t *op, uint8_t *dst, const int64_t *dst_off
     const uint8_t *sp = src + src_off[i];
     uint8_t *dp = dst + dst_off[i];
     const int wdim = size + 5;
-    // Stage the window: lane r copies source row r-2.  Only the aligned words that contain at least one needed byte
-    // (columns -2 .. size+2) are loaded, so nothing outside the caller's rows is ever touched; the words are then
-    // re-aligned with funnel shifts so that block column 0 lands on byte QX of the shared-memory row.
-    if (lane < wdim) {
-        const uint8_t *first = sp + (long long)(lane - 2) * stride - 2;            // column -2
-        const unsigned sh = (unsigned)(reinterpret_cast<uintptr_t>(first) & 3);
-        const unsigned *base = reinterpret_cast<const unsigned *>(first - sh);
-        const int nw = (int)((sh + wdim + 3) >> 2);                                // <= 6
-        unsigned LL[8];
-        LL[0] = 0;
-#pragma unroll
-        for (int k = 0; k < 6; k++) LL[k + 1] = k < nw ? __ldg(base + k) : 0u;
-        LL[7] = 0;
-        // window byte p (p = 4 .. 27) holds source column p - QX; loaded byte offset of column x is sh + x + 2
-        const unsigned tt = sh + 2, i0 = tt >> 2, fs = (tt & 3) * 8;
-        unsigned *wrow = reinterpret_cast<unsigned *>(&s.win[lane * QW]);
-#pragma unroll
-        for (int j = 1; j <= 6; j++) {
-            const unsigned lo = i0 ? LL[j] : LL[j - 1], hi = i0 ? LL[j + 1] : LL[j];
-            wrow[j] = __funnelshift_r(lo, hi, fs);
-        }
+    for (int k = lane; k < wdim * wdim; k += 32) {          // byte loads: measured faster than per-row word loads + funnel shifts
+        const int r = k / wdim, c = k - r * wdim;
+        s.win[r * QW + QX - 2 + c] = __ldg(sp + (long long)(r - 2) * stride + (c - 2));
     }
     __syncwarp();
     const int npx = size < 8 ? size : 8, segs = size >> 3 ? size >> 3 : 1;       // segments per row
