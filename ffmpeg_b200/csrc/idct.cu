@@ -276,10 +276,12 @@ __device__ __forceinline__ void col_pass_i(int c0, int c1, int c2, int c3, int c
     o[3] = (int)(a3 + b3) >> 20; o[4] = (int)(a3 - b3) >> 20;
 }
 
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
+// 16-byte LDGSTS to a 32-bit shared-window address (convert the base pointer ONCE with smem_addr(): doing the
+// generic->shared conversion per copy costs three extra instructions each)
+__device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(unsigned smem_dst, const void *gsrc)
 {
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
@@ -331,9 +333,10 @@ idct_tpb_kernel(const int16_t *blocks, int16_t *blocks_out, long long nblocks, u
     const long long b0 = (long long)blockIdx.x * TPB_GEN;
     const int nb = (int)min((long long)TPB_GEN, nblocks - b0);
     const uint4 *g = reinterpret_cast<const uint4 *>(blocks) + b0 * 8;
+    const unsigned s_in = smem_addr(sin);
     for (int i = threadIdx.x; i < nb * 8; i += TPB_GEN) {
         const int b = i >> 3, r = i & 7;
-        cp_async16(&sin[b * 8 + (r ^ (b & 7))], g + i);
+        cp_async16(s_in + (unsigned)(b * 8 + (r ^ (b & 7))) * 16u, g + i);
     }
     cp_async_wait_all();
     __syncthreads();
@@ -417,17 +420,19 @@ idct_mb420_kernel(const int16_t *blocks, Mb420Geom g, int segs_per_cta)
         const long long blk0 = (((f * g.mb_h + mby) * g.mb_w) + mbx0) * 6;
         const uint4 *gsrc = reinterpret_cast<const uint4 *>(blocks) + blk0 * 8;
         {
-            const int r = w & 7, nb = nmb * 6;
+            const int r = w & 7, nb = nmb * 6, b0 = w >> 3;
+            const unsigned s_in = smem_addr(my_in);
+            const uint4 *gp = gsrc + b0 * 8 + r;
 #pragma unroll
-            for (int it = 0; it < 8; it++) {                                              // i = w + 48*it: block (w>>3) + 6*it, row w&7
-                const int b = (w >> 3) + 6 * it;
-                if (b < nb) cp_async16(&my_in[b * 8 + (r ^ (b & 7))], gsrc + b * 8 + r);
+            for (int it = 0; it < 8; it++) {                                              // i = w + 48*it: block b0 + 6*it, row w&7
+                const int b = b0 + 6 * it;
+                if (b < nb) cp_async16(s_in + (unsigned)(b * 8 + (r ^ (b & 7))) * 16u, gp + it * 48);
             }
         }
         if (KIND == B200_IDCT_ADD) {                                                      // stage the destination tile
             for (int i = w; i < 128; i += 48) {                                           // luma: 16 rows x 8 chunks of 16 B
                 const int row = i >> 3, ch = i & 7;
-                if (ch < nmb) cp_async16(tile + row * 128 + ((ch * 16) ^ luma_swz(row)), py + (long long)row * ls0 + ch * 16);
+                if (ch < nmb) cp_async16(smem_addr(tile) + (unsigned)(row * 128 + ((ch * 16) ^ luma_swz(row))), py + (long long)row * ls0 + ch * 16);
             }
             for (int i = w; i < 64; i += 48) {                                            // chroma: 8 rows x 8 chunks of 8 B each plane
                 const int row = i >> 3, ch = i & 7;

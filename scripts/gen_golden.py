@@ -150,6 +150,29 @@ def gen_tx():
     np.savez_compressed(os.path.join(OUT, "tx.npz"), **d)
 
 
+def gen_vsynth1():
+    """Frame 0 of FATE's vsynth1 (tests/videogen.c -> tests/vsynth1/00.pgm, a pgmyuv file: Y plane, then rows of U|V),
+    converted by the reference with the FATE flags: the exact picture filter-pixfmts-{null,copy,...} hash for rgb24
+    (tests/ref/fate/filter-pixfmts-null:93) before it is wrapped in NUT."""
+    import subprocess, tempfile
+    vg = os.path.join(ROOT, "oracle", "_ref", "videogen")
+    with tempfile.TemporaryDirectory() as td:
+        subprocess.run([vg, td + "/"], check=True)
+        raw = open(os.path.join(td, "00.pgm"), "rb").read()
+    hdr, rest = raw.split(b"\n255\n", 1)
+    assert hdr.split()[0] == b"P5" and hdr.split()[1:] == [b"352", b"432"], hdr
+    a = np.frombuffer(rest, np.uint8).reshape(432, 352)
+    y = np.ascontiguousarray(a[:288])
+    u = np.ascontiguousarray(a[288:, :176])
+    v = np.ascontiguousarray(a[288:, 176:])
+    FATE = cl.SWS_BICUBIC | cl.SWS_ACCURATE_RND | cl.SWS_BITEXACT
+    d = {"y": y, "u": u, "v": v}
+    d["rgb_same"] = cl.ref_sws(352, 288, 352, 288, FATE, y, u, v)
+    d["rgb_200x100"] = cl.ref_sws(352, 288, 200, 100, FATE, y, u, v)          # filter-pixfmts-scale geometry
+    d["rgb_lut"] = cl.ref_sws(352, 288, 352, 288, cl.SWS_BICUBIC, y, u, v)
+    np.savez_compressed(os.path.join(OUT, "vsynth1_f0.npz"), **d)
+
+
 if __name__ == "__main__":
     assert cl.have_ref(), "build oracle/_ref first: make -C oracle/ref"
     os.makedirs(OUT, exist_ok=True)
@@ -158,5 +181,6 @@ if __name__ == "__main__":
     gen_mecmp()
     gen_pel()
     gen_tx()
+    gen_vsynth1()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -108,3 +108,12 @@ def test_host_filter_tables_match_oracle():
             O.orc_sws_get_filter(ctx, which, cl.ptr(f2, cl.i16p), cl.ptr(p2, cl.i32p), cnt)
             assert np.array_equal(f1, f2) and np.array_equal(p1, p2), (w, h, dw, dh, hex(fl), which)
         O.orc_sws_close(ctx)
+
+
+def test_sws_oracle_vsynth1_frame0():
+    """The FATE picture itself (vsynth1 frame 0, tests/videogen.c) converted by the reference with FATE's sws flags."""
+    g = np.load(os.path.join(G, "vsynth1_f0.npz"))
+    y, u, v = g["y"], g["u"], g["v"]
+    assert np.array_equal(cl.orc_sws(352, 288, 352, 288, FATE, y, u, v), g["rgb_same"])
+    assert np.array_equal(cl.orc_sws(352, 288, 200, 100, FATE, y, u, v), g["rgb_200x100"])
+    assert np.array_equal(cl.orc_sws(352, 288, 352, 288, cl.SWS_BICUBIC, y, u, v), g["rgb_lut"])

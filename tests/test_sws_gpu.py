@@ -134,3 +134,12 @@ def test_batch_device_and_host_4k(device, fl):
     # checksum of checksums over the whole batch: each frame differs from its neighbours
     assert len({sha(got[i]) for i in range(n)}) == n
     ctx.free()
+
+
+def test_vsynth1_frame0(device):
+    """FATE's own test picture (vsynth1 frame 0) through the CUDA path, against the reference's output fixtures."""
+    g = np.load(os.path.join(G, "vsynth1_f0.npz"))
+    y, u, v = g["y"], g["u"], g["v"]
+    assert np.array_equal(gpu_sws(device, 352, 288, 352, 288, FATE, y, u, v), g["rgb_same"])
+    assert np.array_equal(gpu_sws(device, 352, 288, 200, 100, FATE, y, u, v), g["rgb_200x100"])
+    assert np.array_equal(gpu_sws(device, 352, 288, 352, 288, cl.SWS_BICUBIC, y, u, v), g["rgb_lut"])
