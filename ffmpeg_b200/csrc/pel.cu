@@ -69,9 +69,21 @@ qpel_kernel(long long n, const uint8_t *op, uint8_t *dst, const int64_t *dst_off
     const uint8_t *sp = src + src_off[i];
     uint8_t *dp = dst + dst_off[i];
     const int wdim = size + 5;
-    for (int k = lane; k < wdim * wdim; k += 32) {          // byte loads: measured faster than per-row word loads + funnel shifts
-        const int r = k / wdim, c = k - r * wdim;
-        s.win[r * QW + QX - 2 + c] = __ldg(sp + (long long)(r - 2) * stride + (c - 2));
+    {   // byte loads, all issued before the first shared-memory store (14 independent loads in flight per lane)
+        uint8_t px[14];
+        const int total = wdim * wdim;
+#pragma unroll
+        for (int it = 0; it < 14; it++) {
+            const int k = lane + 32 * it;
+            const int r = k / wdim, c = k - r * wdim;
+            px[it] = k < total ? __ldg(sp + (long long)(r - 2) * stride + (c - 2)) : (uint8_t)0;
+        }
+#pragma unroll
+        for (int it = 0; it < 14; it++) {
+            const int k = lane + 32 * it;
+            const int r = k / wdim, c = k - r * wdim;
+            if (k < total) s.win[r * QW + QX - 2 + c] = px[it];
+        }
     }
     __syncwarp();
     const int npx = size < 8 ? size : 8, segs = size >> 3 ? size >> 3 : 1;       // segments per row

@@ -1,0 +1,81 @@
+#!/usr/bin/env python
+"""Time one path quickly on the GPU box: python scripts/quick_bench.py qpel|idct|sws|lut|tx|esa [reps]"""
+import os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import ffmpeg_b200 as fb
+from ffmpeg_b200 import swscale as sw, idctdsp, pel, tx, me_cmp
+
+what = sys.argv[1]
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+stream = torch.cuda.Stream()
+dev = fb.Device(0, stream=stream.cuda_stream)
+g = torch.Generator(device="cuda"); g.manual_seed(1)
+
+
+def timed(call, n_units, unit, bytes_per_unit=None):
+    with torch.cuda.stream(stream):
+        for _ in range(3):
+            call()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            call()
+        e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    line = f"{what}: {n_units / ms / 1e6:.3f} G{unit}/s  ({ms:.3f} ms)"
+    if bytes_per_unit:
+        line += f"  {n_units * bytes_per_unit / ms / 1e6:.0f} GB/s = {n_units * bytes_per_unit / ms / 1e6 / 6571.9:.3f} of peak"
+    print(line)
+
+
+with torch.cuda.stream(stream):
+    if what == "qpel":
+        nfr, W, H, ap = 64, 1920, 1088, 32
+        PW, PH = W + 2 * ap, H + 2 * ap
+        refp = torch.randint(0, 256, (nfr, PH, PW), dtype=torch.uint8, device="cuda", generator=g)
+        dstp = torch.randint(0, 256, (nfr, PH, PW), dtype=torch.uint8, device="cuda", generator=g)
+        fi = torch.arange(nfr, device="cuda").view(-1, 1, 1)
+        by = torch.arange(H // 16, device="cuda").view(1, -1, 1); bx = torch.arange(W // 16, device="cuda").view(1, 1, -1)
+        base = fi * (PH * PW) + (by * 16 + ap) * PW + bx * 16 + ap
+        dx = torch.randint(-16, 17, base.shape, device="cuda", generator=g); dy = torch.randint(-16, 17, base.shape, device="cuda", generator=g)
+        doff = base.reshape(-1).to(torch.int64).contiguous(); soff = (base + dy * PW + dx).reshape(-1).to(torch.int64).contiguous()
+        ops = (torch.randint(0, 2, (doff.numel(),), device="cuda", generator=g) | (torch.randint(0, 16, (doff.numel(),), device="cuda", generator=g) << 3)).to(torch.uint8)
+        n = doff.numel()
+        timed(lambda: pel.h264qpel_batch_device(dev, n, ops, dstp, doff, refp, soff, PW), n, "blocks", 825)
+    elif what == "idct":
+        mbw, mbh, fr = 120, 68, 256
+        n = mbw * mbh * 6 * fr
+        blk = torch.randint(-256, 257, (n, 64), dtype=torch.int16, device="cuda", generator=g)
+        pl = [torch.zeros((fr, mbh * 16, mbw * 16), dtype=torch.uint8, device="cuda"), torch.zeros((fr, mbh * 8, mbw * 8), dtype=torch.uint8, device="cuda"),
+              torch.zeros((fr, mbh * 8, mbw * 8), dtype=torch.uint8, device="cuda")]
+        for kind, name, b in ((1, "put", 192), (2, "add", 256)):
+            what = "idct_" + name
+            timed(lambda: idctdsp.idct_mb420_device(dev, kind, blk, mbw, mbh, fr, pl, [mbw * 16, mbw * 8, mbw * 8],
+                                                    [mbw * 16 * mbh * 16, mbw * 8 * mbh * 8, mbw * 8 * mbh * 8]), n, "blocks", b)
+    elif what in ("sws", "lut"):
+        W, H, nf = 3840, 2160, 128
+        Y = torch.randint(0, 256, (nf, H, W), dtype=torch.uint8, device="cuda", generator=g)
+        U = torch.randint(0, 256, (nf, H // 2, W // 2), dtype=torch.uint8, device="cuda", generator=g)
+        V = torch.randint(0, 256, (nf, H // 2, W // 2), dtype=torch.uint8, device="cuda", generator=g)
+        O = torch.empty((nf, H, W * 3), dtype=torch.uint8, device="cuda")
+        c = sw.sws_getContext(dev, W, H, 0, W, H, 2, (4 | 0x40000 | 0x80000) if what == "sws" else 4)
+        timed(lambda: c.scale_batch_device([Y, U, V], [W, W // 2, W // 2], [W * H, W * H // 4, W * H // 4], O, W * 3, W * H * 3, nf), nf, "frames", 37324800)
+    elif what == "tx":
+        for n in (1024, 2048):
+            cnt = 1 << 17
+            x = torch.rand((cnt, 2 * n), device="cuda", generator=g); y = torch.empty_like(x)
+            c = tx.av_tx_init(0, 0, n, device=dev); what = f"fft{n}"
+            timed(lambda: c.batch_device(y, x, 8, cnt, 8 * n, 8 * n), cnt, "tx", 16 * n); c.uninit()
+            c = tx.av_tx_init(1, 1, n, scale=1.0 / n, device=dev); what = f"imdct{n}"
+            timed(lambda: c.batch_device(y, x, 4, cnt, 4 * n, 4 * n), cnt, "tx", 8 * n); c.uninit()
+    elif what == "esa":
+        W, H, npairs = 3840, 2160, 4
+        cur = torch.randint(0, 256, (npairs, H, W), dtype=torch.uint8, device="cuda", generator=g)
+        ref = torch.roll(cur, shifts=(7, -13), dims=(1, 2)).contiguous()
+        nmb = (W // 16) * (H // 16)
+        mv = torch.zeros((npairs, nmb, 2), dtype=torch.int32, device="cuda"); cost = torch.zeros((npairs, nmb), dtype=torch.int64, device="cuda")
+        timed(lambda: me_cmp.me_esa_device(dev, cur, ref, W, W, H, W * H, npairs, 16, 32, mv, cost), npairs, "pairs")
+dev.close()
