@@ -69,20 +69,27 @@ qpel_kernel(long long n, const uint8_t *op, uint8_t *dst, const int64_t *dst_off
     const uint8_t *sp = src + src_off[i];
     uint8_t *dp = dst + dst_off[i];
     const int wdim = size + 5;
-    {   // byte loads, all issued before the first shared-memory store (14 independent loads in flight per lane)
-        uint8_t px[14];
-        const int total = wdim * wdim;
+    // Stage the window with 32-bit loads: 7 lanes per source row (4 rows per pass, 6 passes for 21 rows), so one load
+    // instruction touches at most 4 rows (few L1 wavefronts).  Lane j of a row holds LL[j]: LL[0] = 0, LL[1..6] = the
+    // aligned words that contain at least one needed byte (columns -2 .. size+2; nothing else is ever read), LL[7] = 0.
+    // Window word jj (bytes 4jj .. 4jj+3 of the shared row, block column 0 at byte QX) = funnel(LL[jj-1+i0], LL[jj+i0]).
+    {
+        const int q7 = lane / 7, j = lane - q7 * 7;
 #pragma unroll
-        for (int it = 0; it < 14; it++) {
-            const int k = lane + 32 * it;
-            const int r = k / wdim, c = k - r * wdim;
-            px[it] = k < total ? __ldg(sp + (long long)(r - 2) * stride + (c - 2)) : (uint8_t)0;
-        }
-#pragma unroll
-        for (int it = 0; it < 14; it++) {
-            const int k = lane + 32 * it;
-            const int r = k / wdim, c = k - r * wdim;
-            if (k < total) s.win[r * QW + QX - 2 + c] = px[it];
+        for (int it = 0; it < 6; it++) {
+            const int r = 4 * it + q7;
+            const bool rowok = lane < 28 && r < wdim;
+            const uint8_t *first = sp + (long long)(r - 2) * stride - 2;                 // column -2 of this row
+            const unsigned sh = (unsigned)(reinterpret_cast<uintptr_t>(first) & 3);
+            const int nw = (int)((sh + wdim + 3) >> 2);
+            unsigned v = 0;
+            if (rowok && j >= 1 && j - 1 < nw) v = __ldg(reinterpret_cast<const unsigned *>(first - sh) + (j - 1));
+            const unsigned nxt = __shfl_down_sync(0xffffffffu, v, 1);
+            const unsigned hi = j == 6 ? 0u : nxt;
+            const unsigned tt = sh + 2, i0 = tt >> 2, fs = (tt & 3) * 8;
+            const int jj = j + 1 - (int)i0;
+            if (rowok && jj >= 1 && jj <= 6)
+                reinterpret_cast<unsigned *>(&s.win[r * QW])[jj] = __funnelshift_r(v, hi, fs);
         }
     }
     __syncwarp();
