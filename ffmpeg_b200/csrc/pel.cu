@@ -75,21 +75,26 @@ qpel_kernel(long long n, const uint8_t *op, uint8_t *dst, const int64_t *dst_off
     // Window word jj (bytes 4jj .. 4jj+3 of the shared row, block column 0 at byte QX) = funnel(LL[jj-1+i0], LL[jj+i0]).
     {
         const int q7 = lane / 7, j = lane - q7 * 7;
+        unsigned v[6], shv[6];
 #pragma unroll
-        for (int it = 0; it < 6; it++) {
+        for (int it = 0; it < 6; it++) {                                                 // all loads first: 6 in flight per lane
             const int r = 4 * it + q7;
-            const bool rowok = lane < 28 && r < wdim;
             const uint8_t *first = sp + (long long)(r - 2) * stride - 2;                 // column -2 of this row
             const unsigned sh = (unsigned)(reinterpret_cast<uintptr_t>(first) & 3);
             const int nw = (int)((sh + wdim + 3) >> 2);
-            unsigned v = 0;
-            if (rowok && j >= 1 && j - 1 < nw) v = __ldg(reinterpret_cast<const unsigned *>(first - sh) + (j - 1));
-            const unsigned nxt = __shfl_down_sync(0xffffffffu, v, 1);
+            shv[it] = sh;
+            v[it] = 0;
+            if (lane < 28 && r < wdim && j >= 1 && j - 1 < nw) v[it] = __ldg(reinterpret_cast<const unsigned *>(first - sh) + (j - 1));
+        }
+#pragma unroll
+        for (int it = 0; it < 6; it++) {
+            const int r = 4 * it + q7;
+            const unsigned nxt = __shfl_down_sync(0xffffffffu, v[it], 1);
             const unsigned hi = j == 6 ? 0u : nxt;
-            const unsigned tt = sh + 2, i0 = tt >> 2, fs = (tt & 3) * 8;
+            const unsigned tt = shv[it] + 2, i0 = tt >> 2, fs = (tt & 3) * 8;
             const int jj = j + 1 - (int)i0;
-            if (rowok && jj >= 1 && jj <= 6)
-                reinterpret_cast<unsigned *>(&s.win[r * QW])[jj] = __funnelshift_r(v, hi, fs);
+            if (lane < 28 && r < wdim && jj >= 1 && jj <= 6)
+                reinterpret_cast<unsigned *>(&s.win[r * QW])[jj] = __funnelshift_r(v[it], hi, fs);
         }
     }
     __syncwarp();
