@@ -54,135 +54,170 @@ __device__ __forceinline__ void hsum8(const uint8_t *row, int x0, int *o)
     for (int i = 0; i < 8; i++) o[i] = tap6(b[i + 2], b[i + 3], b[i + 4], b[i + 5], b[i + 6], b[i + 7]);
 }
 
-// One warp per operation.  Lane l works on one 8-pixel (4 for size 4) row segment: row l>>1, half l&1 for 16x16.
+// The kernel is latency-bound if every operation waits for its descriptor, then its window, then (avg) its
+// destination.  Each warp therefore walks QK consecutive operations and software-pipelines them: while operation t is
+// computed, the window words of t+1 are already in flight into registers, the descriptor of t+2 is being fetched, and
+// the destination row of t (avg) was requested before the shared-memory staging started.
+constexpr int QK = 8;
+
+struct QMeta { int o; long long soff, doff; };
+__device__ __forceinline__ QMeta load_meta(const uint8_t *op, const int64_t *src_off, const int64_t *dst_off, long long i, long long n)
+{
+    QMeta m; m.o = -1; m.soff = 0; m.doff = 0;
+    if (i < n) { m.o = __ldg(op + i); m.soff = __ldg(src_off + i); m.doff = __ldg(dst_off + i); }
+    return m;
+}
+struct QWin { unsigned v[6]; unsigned sh[6]; };
+// window words of one operation into registers: 7 lanes per source row, 4 rows per pass (see stage_window)
+__device__ __forceinline__ void load_window(QWin &w, const uint8_t *sp, long long stride, int wdim, int lane, bool valid)
+{
+    const int q7 = lane / 7, j = lane - q7 * 7;
+#pragma unroll
+    for (int it = 0; it < 6; it++) {
+        const int r = 4 * it + q7;
+        const uint8_t *first = sp + (long long)(r - 2) * stride - 2;                     // column -2 of this row
+        const unsigned sh = (unsigned)(reinterpret_cast<uintptr_t>(first) & 3);
+        const int nw = (int)((sh + wdim + 3) >> 2);
+        w.sh[it] = sh;
+        w.v[it] = 0;
+        if (valid && lane < 28 && r < wdim && j >= 1 && j - 1 < nw) w.v[it] = __ldg(reinterpret_cast<const unsigned *>(first - sh) + (j - 1));
+    }
+}
+// Lane j of a row holds LL[j]: LL[0] = 0, LL[1..6] = the aligned words that contain at least one needed byte (columns
+// -2 .. size+2; nothing else is ever read), LL[7] = 0.  Window word jj (bytes 4jj .. 4jj+3 of the shared row, block
+// column 0 at byte QX) = funnel(LL[jj-1+i0], LL[jj+i0]) with i0, shift from the row's address alignment.
+__device__ __forceinline__ void stage_window(QpelSmem &s, const QWin &w, int wdim, int lane)
+{
+    const int q7 = lane / 7, j = lane - q7 * 7;
+#pragma unroll
+    for (int it = 0; it < 6; it++) {
+        const int r = 4 * it + q7;
+        const unsigned nxt = __shfl_down_sync(0xffffffffu, w.v[it], 1);
+        const unsigned hi = j == 6 ? 0u : nxt;
+        const unsigned tt = w.sh[it] + 2, i0 = tt >> 2, fs = (tt & 3) * 8;
+        const int jj = j + 1 - (int)i0;
+        if (lane < 28 && r < wdim && jj >= 1 && jj <= 6)
+            reinterpret_cast<unsigned *>(&s.win[r * QW])[jj] = __funnelshift_r(w.v[it], hi, fs);
+    }
+}
+
+// Lane l works on one 8-pixel (4 for size 4) row segment: row l>>1, half l&1 for 16x16.
 __global__ void __launch_bounds__(32 * WARPS)
 qpel_kernel(long long n, const uint8_t *op, uint8_t *dst, const int64_t *dst_off, const uint8_t *src,
             const int64_t *src_off, long long stride)
 {
     __shared__ QpelSmem sm[WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long i = (long long)blockIdx.x * WARPS + warp;
-    if (i >= n) return;
+    const long long first_op = ((long long)blockIdx.x * WARPS + warp) * QK;
+    if (first_op >= n) return;
     QpelSmem &s = sm[warp];
-    const int o = op[i];
-    const int avg = o & 1, size = 16 >> ((o >> 1) & 3), qx = (o >> 3) & 3, qy = (o >> 5) & 3;
-    const uint8_t *sp = src + src_off[i];
-    uint8_t *dp = dst + dst_off[i];
-    const int wdim = size + 5;
-    // Stage the window with 32-bit loads: 7 lanes per source row (4 rows per pass, 6 passes for 21 rows), so one load
-    // instruction touches at most 4 rows (few L1 wavefronts).  Lane j of a row holds LL[j]: LL[0] = 0, LL[1..6] = the
-    // aligned words that contain at least one needed byte (columns -2 .. size+2; nothing else is ever read), LL[7] = 0.
-    // Window word jj (bytes 4jj .. 4jj+3 of the shared row, block column 0 at byte QX) = funnel(LL[jj-1+i0], LL[jj+i0]).
-    {
-        const int q7 = lane / 7, j = lane - q7 * 7;
-        unsigned v[6], shv[6];
-#pragma unroll
-        for (int it = 0; it < 6; it++) {                                                 // all loads first: 6 in flight per lane
-            const int r = 4 * it + q7;
-            const uint8_t *first = sp + (long long)(r - 2) * stride - 2;                 // column -2 of this row
-            const unsigned sh = (unsigned)(reinterpret_cast<uintptr_t>(first) & 3);
-            const int nw = (int)((sh + wdim + 3) >> 2);
-            shv[it] = sh;
-            v[it] = 0;
-            if (lane < 28 && r < wdim && j >= 1 && j - 1 < nw) v[it] = __ldg(reinterpret_cast<const unsigned *>(first - sh) + (j - 1));
-        }
-#pragma unroll
-        for (int it = 0; it < 6; it++) {
-            const int r = 4 * it + q7;
-            const unsigned nxt = __shfl_down_sync(0xffffffffu, v[it], 1);
-            const unsigned hi = j == 6 ? 0u : nxt;
-            const unsigned tt = shv[it] + 2, i0 = tt >> 2, fs = (tt & 3) * 8;
-            const int jj = j + 1 - (int)i0;
-            if (lane < 28 && r < wdim && jj >= 1 && jj <= 6)
-                reinterpret_cast<unsigned *>(&s.win[r * QW])[jj] = __funnelshift_r(v[it], hi, fs);
-        }
-    }
-    __syncwarp();
-    const int npx = size < 8 ? size : 8, segs = size >> 3 ? size >> 3 : 1;       // segments per row
-    const bool need_j = (qx == 2 && qy != 0) || (qy == 2 && qx != 0);             // positions built from the centre sample
-    if (need_j) {
-        for (int k = lane; k < wdim * segs; k += 32) {
-            const int r = k / segs, x0 = (k - r * segs) * 8;
-            int h[8];
-            hsum8(&s.win[r * QW], x0, h);
-            uint4 pk;
-            pk.x = (unsigned)(h[0] & 0xffff) | ((unsigned)h[1] << 16); pk.y = (unsigned)(h[2] & 0xffff) | ((unsigned)h[3] << 16);
-            pk.z = (unsigned)(h[4] & 0xffff) | ((unsigned)h[5] << 16); pk.w = (unsigned)(h[6] & 0xffff) | ((unsigned)h[7] << 16);
-            *reinterpret_cast<uint4 *>(&s.hraw[r * 16 + x0]) = pk;
-        }
-        __syncwarp();
-    }
-    if (lane < size * segs) {
+    QMeta m0 = load_meta(op, src_off, dst_off, first_op, n);
+    QMeta m1 = load_meta(op, src_off, dst_off, first_op + 1, n);
+    QWin w0, w1;
+    load_window(w0, src + m0.soff, stride, (16 >> ((m0.o >> 1) & 3)) + 5, lane, m0.o >= 0);
+    for (int t = 0; t < QK; t++) {
+        if (m0.o < 0) break;                                                             // past the end (warp-uniform)
+        const QMeta m2 = load_meta(op, src_off, dst_off, first_op + t + 2, (t + 2 < QK) ? n : 0);
+        const bool next_ok = t + 1 < QK && m1.o >= 0;
+        load_window(w1, src + m1.soff, stride, (16 >> ((m1.o >> 1) & 3)) + 5, lane, next_ok);
+
+        const int o = m0.o;
+        const int avg = o & 1, size = 16 >> ((o >> 1) & 3), qx = (o >> 3) & 3, qy = (o >> 5) & 3;
+        uint8_t *dp = dst + m0.doff;
+        const int wdim = size + 5;
+        const int npx = size < 8 ? size : 8, segs = size >> 3 ? size >> 3 : 1;           // segments per row
+        const bool mine = lane < size * segs;
         const int y = lane / segs, x0 = (lane - y * segs) * 8;
-        int v[8];
-        // the one or two samples each quarter position averages (h264qpel_template.c:313-456): F full-pel, H horizontal
-        // half, V vertical half, J centre.  acc collects them; two samples -> (a + b + 1) >> 1.
-        const bool useF = (qy == 0 && qx != 2) || (qx == 0 && (qy & 1));
-        const bool useH = qx != 0 && qy != 2;
-        const bool useV = qy != 0 && qx != 2;
-        int acc[8], t[8];
-#pragma unroll
-        for (int k = 0; k < 8; k++) acc[k] = 0;
-        int count = 0;
-        if (useF) {
-            row8(&s.win[(y + 2 + (qy == 3)) * QW], x0, qx == 3, t);
-#pragma unroll
-            for (int k = 0; k < 8; k++) acc[k] += t[k];
-            count++;
-        }
-        if (useH) {
-            hsum8(&s.win[(y + 2 + (qy == 3)) * QW], x0, t);
-#pragma unroll
-            for (int k = 0; k < 8; k++) acc[k] += clip8((t[k] + 16) >> 5);
-            count++;
-        }
-        if (useV) {
-            int r0[8], r1[8], r2[8], r3[8], r4[8], r5[8];
-            const int dx = qx == 3;
-            row8(&s.win[(y + 0) * QW], x0, dx, r0); row8(&s.win[(y + 1) * QW], x0, dx, r1); row8(&s.win[(y + 2) * QW], x0, dx, r2);
-            row8(&s.win[(y + 3) * QW], x0, dx, r3); row8(&s.win[(y + 4) * QW], x0, dx, r4); row8(&s.win[(y + 5) * QW], x0, dx, r5);
-#pragma unroll
-            for (int k = 0; k < 8; k++) acc[k] += clip8((tap6(r0[k], r1[k], r2[k], r3[k], r4[k], r5[k]) + 16) >> 5);
-            count++;
-        }
-        if (need_j) {
-            int j6[8];
-#pragma unroll
-            for (int k = 0; k < 8; k++) j6[k] = 512;
-            const int coef[6] = { 1, -5, 20, 20, -5, 1 };
-#pragma unroll
-            for (int j = 0; j < 6; j++) {
-                const uint4 pk = *reinterpret_cast<const uint4 *>(&s.hraw[(y + j) * 16 + x0]);
-                const unsigned w[4] = { pk.x, pk.y, pk.z, pk.w };
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    j6[2 * k] += coef[j] * (int)(short)(w[k] & 0xffff);
-                    j6[2 * k + 1] += coef[j] * ((int)w[k] >> 16);
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < 8; k++) acc[k] += clip8(j6[k] >> 10);
-            count++;
-        }
-#pragma unroll
-        for (int k = 0; k < 8; k++) v[k] = count == 2 ? (acc[k] + 1) >> 1 : acc[k];
         uint8_t *d = dp + (long long)y * stride + x0;
-        if (npx == 8 && ((reinterpret_cast<uintptr_t>(d)) & 7) == 0) {
-            if (avg) {
-                const uint2 pv = *reinterpret_cast<const uint2 *>(d);
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    v[k] = (v[k] + (int)__byte_perm(pv.x, 0, 0x4440 | k) + 1) >> 1;
-                    v[4 + k] = (v[4 + k] + (int)__byte_perm(pv.y, 0, 0x4440 | k) + 1) >> 1;
-                }
+        const bool vec = npx == 8 && ((reinterpret_cast<uintptr_t>(d)) & 7) == 0;
+        uint2 pv = make_uint2(0, 0);
+        if (mine && avg && vec) pv = *reinterpret_cast<const uint2 *>(d);                // destination row requested early
+
+        stage_window(s, w0, wdim, lane);
+        __syncwarp();
+        const bool need_j = (qx == 2 && qy != 0) || (qy == 2 && qx != 0);                // positions built from the centre sample
+        if (need_j) {
+            for (int k = lane; k < wdim * segs; k += 32) {
+                const int r = k / segs, xx = (k - r * segs) * 8;
+                int h[8];
+                hsum8(&s.win[r * QW], xx, h);
+                uint4 pk;
+                pk.x = (unsigned)(h[0] & 0xffff) | ((unsigned)h[1] << 16); pk.y = (unsigned)(h[2] & 0xffff) | ((unsigned)h[3] << 16);
+                pk.z = (unsigned)(h[4] & 0xffff) | ((unsigned)h[5] << 16); pk.w = (unsigned)(h[6] & 0xffff) | ((unsigned)h[7] << 16);
+                *reinterpret_cast<uint4 *>(&s.hraw[r * 16 + xx]) = pk;
             }
-            uint2 ov;
-            ov.x = (unsigned)v[0] | ((unsigned)v[1] << 8) | ((unsigned)v[2] << 16) | ((unsigned)v[3] << 24);
-            ov.y = (unsigned)v[4] | ((unsigned)v[5] << 8) | ((unsigned)v[6] << 16) | ((unsigned)v[7] << 24);
-            *reinterpret_cast<uint2 *>(d) = ov;
-        } else {
-            for (int k = 0; k < npx; k++) d[k] = (uint8_t)(avg ? (d[k] + v[k] + 1) >> 1 : v[k]);
+            __syncwarp();
         }
+        if (mine) {
+            // the one or two samples each quarter position averages (h264qpel_template.c:313-456): F full-pel, H horizontal
+            // half, V vertical half, J centre.  acc collects them; two samples -> (a + b + 1) >> 1.
+            const bool useF = (qy == 0 && qx != 2) || (qx == 0 && (qy & 1));
+            const bool useH = qx != 0 && qy != 2;
+            const bool useV = qy != 0 && qx != 2;
+            int acc[8], tt[8], v[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) acc[k] = 0;
+            int count = 0;
+            if (useF) {
+                row8(&s.win[(y + 2 + (qy == 3)) * QW], x0, qx == 3, tt);
+#pragma unroll
+                for (int k = 0; k < 8; k++) acc[k] += tt[k];
+                count++;
+            }
+            if (useH) {
+                hsum8(&s.win[(y + 2 + (qy == 3)) * QW], x0, tt);
+#pragma unroll
+                for (int k = 0; k < 8; k++) acc[k] += clip8((tt[k] + 16) >> 5);
+                count++;
+            }
+            if (useV) {
+                int r0[8], r1[8], r2[8], r3[8], r4[8], r5[8];
+                const int dx = qx == 3;
+                row8(&s.win[(y + 0) * QW], x0, dx, r0); row8(&s.win[(y + 1) * QW], x0, dx, r1); row8(&s.win[(y + 2) * QW], x0, dx, r2);
+                row8(&s.win[(y + 3) * QW], x0, dx, r3); row8(&s.win[(y + 4) * QW], x0, dx, r4); row8(&s.win[(y + 5) * QW], x0, dx, r5);
+#pragma unroll
+                for (int k = 0; k < 8; k++) acc[k] += clip8((tap6(r0[k], r1[k], r2[k], r3[k], r4[k], r5[k]) + 16) >> 5);
+                count++;
+            }
+            if (need_j) {
+                int j6[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) j6[k] = 512;
+                const int coef[6] = { 1, -5, 20, 20, -5, 1 };
+#pragma unroll
+                for (int j = 0; j < 6; j++) {
+                    const uint4 pk = *reinterpret_cast<const uint4 *>(&s.hraw[(y + j) * 16 + x0]);
+                    const unsigned ww[4] = { pk.x, pk.y, pk.z, pk.w };
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        j6[2 * k] += coef[j] * (int)(short)(ww[k] & 0xffff);
+                        j6[2 * k + 1] += coef[j] * ((int)ww[k] >> 16);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 8; k++) acc[k] += clip8(j6[k] >> 10);
+                count++;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[k] = count == 2 ? (acc[k] + 1) >> 1 : acc[k];
+            if (vec) {
+                if (avg) {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        v[k] = (v[k] + (int)__byte_perm(pv.x, 0, 0x4440 | k) + 1) >> 1;
+                        v[4 + k] = (v[4 + k] + (int)__byte_perm(pv.y, 0, 0x4440 | k) + 1) >> 1;
+                    }
+                }
+                uint2 ov;
+                ov.x = (unsigned)v[0] | ((unsigned)v[1] << 8) | ((unsigned)v[2] << 16) | ((unsigned)v[3] << 24);
+                ov.y = (unsigned)v[4] | ((unsigned)v[5] << 8) | ((unsigned)v[6] << 16) | ((unsigned)v[7] << 24);
+                *reinterpret_cast<uint2 *>(d) = ov;
+            } else {
+                for (int k = 0; k < npx; k++) d[k] = (uint8_t)(avg ? (d[k] + v[k] + 1) >> 1 : v[k]);
+            }
+        }
+        __syncwarp();                                                                    // shared window is reused by the next operation
+        m0 = m1; m1 = m2; w0 = w1;
     }
 }
 
@@ -306,7 +341,7 @@ B200_API int b200_h264qpel_batch_device(B200Device *dev, int64_t n, const uint8_
     if (!dev || n < 0 || !op || !dst || !dst_off || !src || !src_off) return B200_EINVAL;
     if (n == 0) return 0;
     B200_CUDA_OK(cudaSetDevice(dev->ordinal));
-    const long long blocks = (n + WARPS - 1) / WARPS;
+    const long long blocks = (n + WARPS * QK - 1) / (WARPS * QK);
     if (blocks > 0x7fffffffLL) return B200_EINVAL;
     qpel_kernel<<<(unsigned)blocks, 32 * WARPS, 0, dev->stream>>>(n, op, dst, dst_off, src, src_off, stride);
     B200_LAUNCHED();
