@@ -30,6 +30,9 @@ struct TxDev {                 // device-side plan
     int tab_off[18];
     const int *leaf16; int n_leaf16;   // offsets of the size-16 blocks (done in registers)
     const int *leaf8;  int n_leaf8;    // offsets of size-8 blocks that are not part of a size-16 block
+    const int *bfd;            // levels >= 5: padded index of the first element of every butterfly, all levels concatenated
+    const float2 *tw2;         // levels >= 5: (tab_S[j], tab_S[S/4 - j]) pairs
+    int bfd_start[18], tw2_start[18];
     const int *scatter;        // FFT: z[scatter[g]] = src[g]
     const int *imap;           // inverse MDCT: z[imap[m]] gets the pair (in[len-1-2m], in[2m])
     const int *sub_map;        // MDCT index map (doubled for the inverse)
@@ -118,6 +121,24 @@ __device__ void fft_levels(const TxDev &p, float2 *z)
     for (int L = first; L <= p.nlevels; L++) {
         const int S = 1 << L;
         const int *off = p.blk_off + p.lvl_start[L];
+        if (L >= 5) {
+            // one table word per butterfly (padded index of a0) and one float2 per twiddle pair; the other three elements
+            // sit at fixed padded distances: k*q + (k*q >> 4) for q >= 16, and 8 / 17 / 25 for q == 8
+            const int lq = L - 2, q = 1 << lq;
+            const int d1 = q == 8 ? 8 : q + (q >> 4), d2 = q == 8 ? 17 : 2 * q + (q >> 3), d3 = q == 8 ? 25 : 3 * q + ((3 * q) >> 4);
+            const int *bd = p.bfd + p.bfd_start[L];
+            const float2 *tw = p.tw2 + p.tw2_start[L];
+            const int total = p.lvl_cnt[L] << lq;
+            for (int b = threadIdx.x; b < total; b += blockDim.x) {
+                const int i0 = __ldg(bd + b);
+                const float2 w = __ldg(tw + (b & (q - 1)));
+                float2 a0 = z[i0], a1 = z[i0 + d1], a2 = z[i0 + d2], a3 = z[i0 + d3];
+                bfly_mul(a0, a1, a2, a3, w.x, w.y);
+                z[i0] = a0; z[i0 + d1] = a1; z[i0 + d2] = a2; z[i0 + d3] = a3;
+            }
+            __syncthreads();
+            continue;
+        }
         if (L == 1) {
             for (int b = threadIdx.x; b < p.lvl_cnt[L]; b += blockDim.x) {
                 const int o = __ldg(off + b);
@@ -316,6 +337,21 @@ static int tx_build(B200TXContext *c, float scale)
     const size_t o_sc = off;  off += al(scatter.size() * 4);
     const size_t o_sm = off;  off += al(sub_map.size() * 4 + 4);
     const size_t o_ex = off;  off += al(ex.size() * 8 + 8);
+    std::vector<int> bfd;
+    std::vector<float2> tw2;
+    for (int L = 0; L < 18; L++) {
+        d.bfd_start[L] = (int)bfd.size();
+        d.tw2_start[L] = (int)tw2.size();
+        if (L >= 5 && L <= k) {
+            const int q = 1 << (L - 2);
+            for (int o : lv[L])
+                for (int j = 0; j < q; j++) bfd.push_back((o + j) + ((o + j) >> 4));
+            const float *tb = &tab[d.tab_off[L]];
+            for (int j = 0; j < q; j++) tw2.push_back(make_float2(tb[j], tb[q - j]));
+        }
+    }
+    const size_t o_bfd = off; off += al(bfd.size() * 4 + 4);
+    const size_t o_tw2 = off; off += al(tw2.size() * 8 + 8);
     std::vector<int> imap(sub_map.size() + 1, 0);
     if (c->type == 1 && c->inv)
         for (size_t i = 0; i < sub_map.size(); i++) imap[sub_map[i] >> 1] = (int)i;
@@ -328,6 +364,8 @@ static int tx_build(B200TXContext *c, float scale)
     memcpy(&host[o_sc], scatter.data(), scatter.size() * 4);
     if (!sub_map.empty()) memcpy(&host[o_sm], sub_map.data(), sub_map.size() * 4);
     if (!ex.empty()) memcpy(&host[o_ex], ex.data(), ex.size() * 8);
+    if (!bfd.empty()) memcpy(&host[o_bfd], bfd.data(), bfd.size() * 4);
+    if (!tw2.empty()) memcpy(&host[o_tw2], tw2.data(), tw2.size() * 8);
     memcpy(&host[o_im], imap.data(), imap.size() * 4);
     if (!leaf16.empty()) memcpy(&host[o_l16], leaf16.data(), leaf16.size() * 4);
     if (!leaf8.empty()) memcpy(&host[o_l8], leaf8.data(), leaf8.size() * 4);
@@ -337,6 +375,7 @@ static int tx_build(B200TXContext *c, float scale)
     d.blk_off = (const int *)(b + o_blk); d.tab = (const float *)(b + o_tab); d.scatter = (const int *)(b + o_sc);
     d.sub_map = (const int *)(b + o_sm); d.exp = (const float2 *)(b + o_ex);
     d.imap = (const int *)(b + o_im);
+    d.bfd = (const int *)(b + o_bfd); d.tw2 = (const float2 *)(b + o_tw2);
     d.leaf16 = (const int *)(b + o_l16); d.n_leaf16 = (int)leaf16.size();
     d.leaf8 = (const int *)(b + o_l8); d.n_leaf8 = (int)leaf8.size();
     c->smem = (size_t)(n + (n >> 4) + 1) * sizeof(float2);
