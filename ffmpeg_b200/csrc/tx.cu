@@ -89,30 +89,36 @@ __device__ __forceinline__ void leaf_fft16(float2 *v, float c8, float c1, float 
     bfly_mul(v[3], v[7], v[11], v[15], c3, c1);
 }
 
-// all levels on the transform held in z[PAD(0..n))
-__device__ void fft_levels(const TxDev &p, float2 *z)
+// All levels on TB transforms held in z[k*zs + PAD(0..n)), k < TB.  A CTA works on TB transforms at once so that the
+// per-butterfly table word and twiddle pair are fetched once for TB butterflies and every barrier covers TB times
+// more work (the loads of the TB inputs are also all in flight together).
+template <int TB>
+__device__ void fft_levels(const TxDev &p, float2 *z, int zs)
 {
     int first = 1;
     if (p.nlevels >= 5) {                                  // sizes 2..16 in registers, one thread per leaf block
         const float c8 = __ldg(p.tab + p.tab_off[3] + 1);
         const float *t16 = p.tab + p.tab_off[4];
         const float c1 = __ldg(t16 + 1), c2 = __ldg(t16 + 2), c3 = __ldg(t16 + 3);
-        for (int b = threadIdx.x; b < p.n_leaf16 + p.n_leaf8; b += blockDim.x) {
+        const int nleaf = p.n_leaf16 + p.n_leaf8;
+        for (int bb = threadIdx.x; bb < nleaf * TB; bb += blockDim.x) {
+            const int k = bb / nleaf, b = bb - k * nleaf;
+            float2 *zk = z + k * zs;
             float2 v[16];
             if (b < p.n_leaf16) {
                 const int o = __ldg(p.leaf16 + b);
 #pragma unroll
-                for (int i = 0; i < 16; i++) v[i] = z[PAD(o) + i];            // o is a multiple of 16: one pad run
+                for (int i = 0; i < 16; i++) v[i] = zk[PAD(o) + i];           // o is a multiple of 16: one pad run
                 leaf_fft16(v, c8, c1, c2, c3);
 #pragma unroll
-                for (int i = 0; i < 16; i++) z[PAD(o) + i] = v[i];
+                for (int i = 0; i < 16; i++) zk[PAD(o) + i] = v[i];
             } else {
                 const int o = __ldg(p.leaf8 + b - p.n_leaf16);                // multiple of 8
 #pragma unroll
-                for (int i = 0; i < 8; i++) v[i] = z[PAD(o) + i];
+                for (int i = 0; i < 8; i++) v[i] = zk[PAD(o) + i];
                 leaf_fft8(v, c8);
 #pragma unroll
-                for (int i = 0; i < 8; i++) z[PAD(o) + i] = v[i];
+                for (int i = 0; i < 8; i++) zk[PAD(o) + i] = v[i];
             }
         }
         __syncthreads();
@@ -132,110 +138,155 @@ __device__ void fft_levels(const TxDev &p, float2 *z)
             for (int b = threadIdx.x; b < total; b += blockDim.x) {
                 const int i0 = __ldg(bd + b);
                 const float2 w = __ldg(tw + (b & (q - 1)));
-                float2 a0 = z[i0], a1 = z[i0 + d1], a2 = z[i0 + d2], a3 = z[i0 + d3];
-                bfly_mul(a0, a1, a2, a3, w.x, w.y);
-                z[i0] = a0; z[i0 + d1] = a1; z[i0 + d2] = a2; z[i0 + d3] = a3;
+#pragma unroll
+                for (int k = 0; k < TB; k++) {
+                    float2 *zk = z + k * zs + i0;
+                    float2 a0 = zk[0], a1 = zk[d1], a2 = zk[d2], a3 = zk[d3];
+                    bfly_mul(a0, a1, a2, a3, w.x, w.y);
+                    zk[0] = a0; zk[d1] = a1; zk[d2] = a2; zk[d3] = a3;
+                }
             }
             __syncthreads();
             continue;
         }
-        if (L == 1) {
-            for (int b = threadIdx.x; b < p.lvl_cnt[L]; b += blockDim.x) {
-                const int o = __ldg(off + b);
-                fft2r(z[PAD(o)], z[PAD(o + 1)]);
-            }
-        } else {
-            const int lq = L - 2, q = 1 << lq;
-            const float *tab = p.tab + p.tab_off[L];
-            const int total = p.lvl_cnt[L] << lq;
-            for (int b = threadIdx.x; b < total; b += blockDim.x) {
-                const int o = __ldg(off + (b >> lq)), j = b & (q - 1);
-                const int i0 = PAD(o + j), i1 = PAD(o + q + j), i2 = PAD(o + 2 * q + j), i3 = PAD(o + 3 * q + j);
-                float2 a0 = z[i0], a1 = z[i1], a2 = z[i2], a3 = z[i3];
-                if (S <= 16 && j == 0) bfly_nomul(a0, a1, a2, a3);
-                else bfly_mul(a0, a1, a2, a3, __ldg(tab + j), __ldg(tab + q - j));
-                z[i0] = a0; z[i1] = a1; z[i2] = a2; z[i3] = a3;
+        for (int k = 0; k < TB; k++) {
+            float2 *zk = z + k * zs;
+            if (L == 1) {
+                for (int b = threadIdx.x; b < p.lvl_cnt[L]; b += blockDim.x) {
+                    const int o = __ldg(off + b);
+                    fft2r(zk[PAD(o)], zk[PAD(o + 1)]);
+                }
+            } else {
+                const int lq = L - 2, q = 1 << lq;
+                const float *tab = p.tab + p.tab_off[L];
+                const int total = p.lvl_cnt[L] << lq;
+                for (int b = threadIdx.x; b < total; b += blockDim.x) {
+                    const int o = __ldg(off + (b >> lq)), j = b & (q - 1);
+                    const int i0 = PAD(o + j), i1 = PAD(o + q + j), i2 = PAD(o + 2 * q + j), i3 = PAD(o + 3 * q + j);
+                    float2 a0 = zk[i0], a1 = zk[i1], a2 = zk[i2], a3 = zk[i3];
+                    if (S <= 16 && j == 0) bfly_nomul(a0, a1, a2, a3);
+                    else bfly_mul(a0, a1, a2, a3, __ldg(tab + j), __ldg(tab + q - j));
+                    zk[i0] = a0; zk[i1] = a1; zk[i2] = a2; zk[i3] = a3;
+                }
             }
         }
         __syncthreads();
     }
 }
 
-// one CTA per transform; steps are in BYTES between consecutive transforms
+// TB transforms per CTA; steps are in BYTES between consecutive transforms
+template <int TB>
 __global__ void __launch_bounds__(256)
-tx_fft_kernel(TxDev p, float2 *out, const float2 *in, long long out_step, long long in_step)
+tx_fft_kernel(TxDev p, float2 *out, const float2 *in, long long out_step, long long in_step, long long count)
 {
     extern __shared__ float2 z[];
-    const float2 *src = reinterpret_cast<const float2 *>(reinterpret_cast<const char *>(in) + blockIdx.x * in_step);
-    float2 *dst = reinterpret_cast<float2 *>(reinterpret_cast<char *>(out) + blockIdx.x * out_step);
-    for (int g = threadIdx.x; g < p.n; g += blockDim.x) z[PAD(__ldg(p.scatter + g))] = src[g];
+    const int zs = p.n + (p.n >> 4) + 1;
+    const long long t0 = (long long)blockIdx.x * TB;
+#pragma unroll
+    for (int k = 0; k < TB; k++) {
+        if (t0 + k >= count) break;
+        const float2 *src = reinterpret_cast<const float2 *>(reinterpret_cast<const char *>(in) + (t0 + k) * in_step);
+        for (int g = threadIdx.x; g < p.n; g += blockDim.x) z[k * zs + PAD(__ldg(p.scatter + g))] = src[g];
+    }
     __syncthreads();
-    fft_levels(p, z);
-    for (int i = threadIdx.x; i < p.n; i += blockDim.x) dst[i] = z[PAD(i)];
+    fft_levels<TB>(p, z, zs);
+#pragma unroll
+    for (int k = 0; k < TB; k++) {
+        if (t0 + k >= count) break;
+        float2 *dst = reinterpret_cast<float2 *>(reinterpret_cast<char *>(out) + (t0 + k) * out_step);
+        for (int i = threadIdx.x; i < p.n; i += blockDim.x) dst[i] = z[k * zs + PAD(i)];
+    }
 }
 
 // ff_tx_mdct_inv: len floats in (element k at in + k*stride floats), len floats out (contiguous)
+template <int TB>
 __global__ void __launch_bounds__(256)
-tx_mdct_inv_kernel(TxDev p, float *out, const float *in, long long stride, long long out_step, long long in_step)
+tx_mdct_inv_kernel(TxDev p, float *out, const float *in, long long stride, long long out_step, long long in_step, long long count)
 {
     extern __shared__ float2 z[];
-    const float *src = reinterpret_cast<const float *>(reinterpret_cast<const char *>(in) + blockIdx.x * in_step);
-    float2 *dst = reinterpret_cast<float2 *>(reinterpret_cast<char *>(out) + blockIdx.x * out_step);
+    const int zs = p.n + (p.n >> 4) + 1;
+    const long long t0 = (long long)blockIdx.x * TB;
     const int len2 = p.len >> 1, len4 = p.len >> 2;
-    const float *in1 = src, *in2 = src + (long long)(len2 * 2 - 1) * stride;
     const float2 *e = p.exp + len2;                         // twiddles in natural order
-    for (int m = threadIdx.x; m < len2; m += blockDim.x) {  // source order (coalesced reads), scattered into z
-        const float are = in2[-(long long)(2 * m) * stride], aim = in1[(long long)(2 * m) * stride];
-        const float2 w = __ldg(e + m);
-        z[PAD(__ldg(p.imap + m))] = make_float2(are * w.x - aim * w.y, are * w.y + aim * w.x);
+#pragma unroll
+    for (int k = 0; k < TB; k++) {
+        if (t0 + k >= count) break;
+        const float *src = reinterpret_cast<const float *>(reinterpret_cast<const char *>(in) + (t0 + k) * in_step);
+        const float *in1 = src, *in2 = src + (long long)(len2 * 2 - 1) * stride;
+        for (int m = threadIdx.x; m < len2; m += blockDim.x) {  // source order (coalesced reads), scattered into z
+            const float are = in2[-(long long)(2 * m) * stride], aim = in1[(long long)(2 * m) * stride];
+            const float2 w = __ldg(e + m);
+            z[k * zs + PAD(__ldg(p.imap + m))] = make_float2(are * w.x - aim * w.y, are * w.y + aim * w.x);
+        }
     }
     __syncthreads();
-    fft_levels(p, z);
-    for (int i = threadIdx.x; i < len4; i += blockDim.x) {
-        const int i0 = len4 + i, i1 = len4 - i - 1;
-        const float2 z1 = z[PAD(i1)], z0 = z[PAD(i0)], e1 = __ldg(e + i1), e0 = __ldg(e + i0);
-        const float s1re = z1.y, s1im = z1.x, s0re = z0.y, s0im = z0.x;
-        float2 o1, o0;
-        o1.x = s1re * e1.y - s1im * e1.x;      // z[i1].re
-        o0.y = s1re * e1.x + s1im * e1.y;      // z[i0].im
-        o0.x = s0re * e0.y - s0im * e0.x;      // z[i0].re
-        o1.y = s0re * e0.x + s0im * e0.y;      // z[i1].im
-        z[PAD(i1)] = o1; z[PAD(i0)] = o0;
+    fft_levels<TB>(p, z, zs);
+#pragma unroll
+    for (int k = 0; k < TB; k++) {
+        float2 *zk = z + k * zs;
+        for (int i = threadIdx.x; i < len4; i += blockDim.x) {
+            const int i0 = len4 + i, i1 = len4 - i - 1;
+            const float2 z1 = zk[PAD(i1)], z0 = zk[PAD(i0)], e1 = __ldg(e + i1), e0 = __ldg(e + i0);
+            const float s1re = z1.y, s1im = z1.x, s0re = z0.y, s0im = z0.x;
+            float2 o1, o0;
+            o1.x = s1re * e1.y - s1im * e1.x;      // z[i1].re
+            o0.y = s1re * e1.x + s1im * e1.y;      // z[i0].im
+            o0.x = s0re * e0.y - s0im * e0.x;      // z[i0].re
+            o1.y = s0re * e0.x + s0im * e0.y;      // z[i1].im
+            zk[PAD(i1)] = o1; zk[PAD(i0)] = o0;
+        }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < len2; i += blockDim.x) dst[i] = z[PAD(i)];
+#pragma unroll
+    for (int k = 0; k < TB; k++) {
+        if (t0 + k >= count) break;
+        float2 *dst = reinterpret_cast<float2 *>(reinterpret_cast<char *>(out) + (t0 + k) * out_step);
+        for (int i = threadIdx.x; i < len2; i += blockDim.x) dst[i] = z[k * zs + PAD(i)];
+    }
 }
 
 // ff_tx_mdct_fwd: 2*len floats in (contiguous), len floats out (element k at out + k*stride floats)
+template <int TB>
 __global__ void __launch_bounds__(256)
-tx_mdct_fwd_kernel(TxDev p, float *out, const float *in, long long stride, long long out_step, long long in_step)
+tx_mdct_fwd_kernel(TxDev p, float *out, const float *in, long long stride, long long out_step, long long in_step, long long count)
 {
     extern __shared__ float2 z[];
-    const float *src = reinterpret_cast<const float *>(reinterpret_cast<const char *>(in) + blockIdx.x * in_step);
-    float *dst = reinterpret_cast<float *>(reinterpret_cast<char *>(out) + blockIdx.x * out_step);
+    const int zs = p.n + (p.n >> 4) + 1;
+    const long long t0 = (long long)blockIdx.x * TB;
     const int len2 = p.len >> 1, len4 = p.len >> 2, len3 = len2 * 3;
-    for (int i = threadIdx.x; i < len2; i += blockDim.x) {
-        const int k = 2 * i, idx = __ldg(p.sub_map + i);
-        float re, im;
-        if (k < len2) {
-            re = -src[len2 + k] + src[1 * len2 - 1 - k];
-            im = -src[len3 + k] + -src[1 * len3 - 1 - k];
-        } else {
-            re = -src[len2 + k] + -src[5 * len2 - 1 - k];
-            im = src[-len2 + k] + -src[1 * len3 - 1 - k];
+#pragma unroll
+    for (int k = 0; k < TB; k++) {
+        if (t0 + k >= count) break;
+        const float *src = reinterpret_cast<const float *>(reinterpret_cast<const char *>(in) + (t0 + k) * in_step);
+        for (int i = threadIdx.x; i < len2; i += blockDim.x) {
+            const int kk = 2 * i, idx = __ldg(p.sub_map + i);
+            float re, im;
+            if (kk < len2) {
+                re = -src[len2 + kk] + src[1 * len2 - 1 - kk];
+                im = -src[len3 + kk] + -src[1 * len3 - 1 - kk];
+            } else {
+                re = -src[len2 + kk] + -src[5 * len2 - 1 - kk];
+                im = src[-len2 + kk] + -src[1 * len3 - 1 - kk];
+            }
+            const float2 ee = __ldg(p.exp + i);
+            z[k * zs + PAD(idx)] = make_float2(re * ee.y + im * ee.x, re * ee.x - im * ee.y); // (.re, .im) = (dim, dre) of the reference's CMUL
         }
-        const float2 e = __ldg(p.exp + i);
-        z[PAD(idx)] = make_float2(re * e.y + im * e.x, re * e.x - im * e.y); // (.re, .im) = (dim, dre) of the reference's CMUL
     }
     __syncthreads();
-    fft_levels(p, z);
-    for (int i = threadIdx.x; i < len4; i += blockDim.x) {
-        const int i0 = len4 + i, i1 = len4 - i - 1;
-        const float2 s1 = z[PAD(i1)], s0 = z[PAD(i0)], e1 = __ldg(p.exp + i1), e0 = __ldg(p.exp + i0);
-        dst[(2LL * i1 + 1) * stride] = s0.x * e0.y - s0.y * e0.x;
-        dst[(2LL * i0) * stride]     = s0.x * e0.x + s0.y * e0.y;
-        dst[(2LL * i0 + 1) * stride] = s1.x * e1.y - s1.y * e1.x;
-        dst[(2LL * i1) * stride]     = s1.x * e1.x + s1.y * e1.y;
+    fft_levels<TB>(p, z, zs);
+#pragma unroll
+    for (int k = 0; k < TB; k++) {
+        if (t0 + k >= count) break;
+        float *dst = reinterpret_cast<float *>(reinterpret_cast<char *>(out) + (t0 + k) * out_step);
+        const float2 *zk = z + k * zs;
+        for (int i = threadIdx.x; i < len4; i += blockDim.x) {
+            const int i0 = len4 + i, i1 = len4 - i - 1;
+            const float2 s1 = zk[PAD(i1)], s0 = zk[PAD(i0)], e1 = __ldg(p.exp + i1), e0 = __ldg(p.exp + i0);
+            dst[(2LL * i1 + 1) * stride] = s0.x * e0.y - s0.y * e0.x;
+            dst[(2LL * i0) * stride]     = s0.x * e0.x + s0.y * e0.y;
+            dst[(2LL * i0 + 1) * stride] = s1.x * e1.y - s1.y * e1.x;
+            dst[(2LL * i1) * stride]     = s1.x * e1.x + s1.y * e1.y;
+        }
     }
 }
 
@@ -268,6 +319,7 @@ struct B200TXContext {
     TxDev d{};
     void *blob = nullptr;
     size_t smem = 0;
+    int tb = 1;
 };
 
 static int tx_build(B200TXContext *c, float scale)
@@ -378,11 +430,12 @@ static int tx_build(B200TXContext *c, float scale)
     d.bfd = (const int *)(b + o_bfd); d.tw2 = (const float2 *)(b + o_tw2);
     d.leaf16 = (const int *)(b + o_l16); d.n_leaf16 = (int)leaf16.size();
     d.leaf8 = (const int *)(b + o_l8); d.n_leaf8 = (int)leaf8.size();
-    c->smem = (size_t)(n + (n >> 4) + 1) * sizeof(float2);
+    c->tb = n <= 1024 ? 4 : n <= 2048 ? 2 : 1;                     // transforms per CTA (about 35 KB of shared memory up to n = 2048)
+    c->smem = (size_t)c->tb * (n + (n >> 4) + 1) * sizeof(float2);
     if (c->smem > 48 * 1024) {
-        B200_CUDA_OK(cudaFuncSetAttribute(tx_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem));
-        B200_CUDA_OK(cudaFuncSetAttribute(tx_mdct_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem));
-        B200_CUDA_OK(cudaFuncSetAttribute(tx_mdct_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem));
+        B200_CUDA_OK(cudaFuncSetAttribute(tx_fft_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem));
+        B200_CUDA_OK(cudaFuncSetAttribute(tx_mdct_inv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem));
+        B200_CUDA_OK(cudaFuncSetAttribute(tx_mdct_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem));
     }
     return 0;
 }
@@ -391,17 +444,21 @@ static int tx_launch(B200TXContext *c, cudaStream_t st, void *out, const void *i
                      ptrdiff_t out_step, ptrdiff_t in_step)
 {
     if (count <= 0) return 0;
-    const int threads = c->d.n >= 1024 ? 256 : c->d.n >= 256 ? 128 : 64;
-    for (int64_t c0 = 0; c0 < count; c0 += 0x7fffffff) {
-        const unsigned nb = (unsigned)(count - c0 < 0x7fffffff ? count - c0 : 0x7fffffff);
+    const int threads = c->d.n * c->tb >= 1024 ? 256 : c->d.n * c->tb >= 256 ? 128 : 64;
+    const long long per = 0x7fffffffLL / 4 * c->tb;              // transforms per launch (grid.x limit)
+    for (int64_t c0 = 0; c0 < count; c0 += per) {
+        const long long cnt = count - c0 < per ? count - c0 : per;
+        const unsigned nb = (unsigned)((cnt + c->tb - 1) / c->tb);
         char *o = (char *)out + c0 * out_step;
         const char *i = (const char *)in + c0 * in_step;
-        if (c->type == 0)
-            tx_fft_kernel<<<nb, threads, c->smem, st>>>(c->d, (float2 *)o, (const float2 *)i, out_step, in_step);
-        else if (c->inv)
-            tx_mdct_inv_kernel<<<nb, threads, c->smem, st>>>(c->d, (float *)o, (const float *)i, stride / 4, out_step, in_step);
-        else
-            tx_mdct_fwd_kernel<<<nb, threads, c->smem, st>>>(c->d, (float *)o, (const float *)i, stride / 4, out_step, in_step);
+#define TX_LAUNCH(TB)                                                                                                          \
+        do {                                                                                                                   \
+            if (c->type == 0)   tx_fft_kernel<TB><<<nb, threads, c->smem, st>>>(c->d, (float2 *)o, (const float2 *)i, out_step, in_step, cnt); \
+            else if (c->inv)    tx_mdct_inv_kernel<TB><<<nb, threads, c->smem, st>>>(c->d, (float *)o, (const float *)i, stride / 4, out_step, in_step, cnt); \
+            else                tx_mdct_fwd_kernel<TB><<<nb, threads, c->smem, st>>>(c->d, (float *)o, (const float *)i, stride / 4, out_step, in_step, cnt); \
+        } while (0)
+        if (c->tb == 4) TX_LAUNCH(4); else if (c->tb == 2) TX_LAUNCH(2); else TX_LAUNCH(1);
+#undef TX_LAUNCH
         B200_LAUNCHED();
     }
     B200_CUDA_OK(cudaGetLastError());
