@@ -1,5 +1,6 @@
 """smoke() checks for the paths added after the first slice: ESA motion search, H.264 qpel MC, float FFT / iMDCT —
-one small call each, bit-compared with the oracle (tests/cpulibs.py loads it; this module is only used by smoke())."""
+one small call each, bit-compared with the oracle.  Lives under tests/ because it loads the checker; only
+__graft_entry__.smoke() imports it."""
 import ctypes as C
 import numpy as np
 
