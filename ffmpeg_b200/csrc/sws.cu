@@ -17,6 +17,7 @@
 #include <cstring>
 #include <new>
 #include <cstdlib>
+#include <algorithm>
 
 // ------------------------------------------------------------------------------------------------ device helpers
 struct SwsDevTables {            // device copies of the vertical banks and the per-line writer choice
@@ -34,6 +35,7 @@ struct SwsFrameArgs {
     long long yfs, ufs, vfs;          // frame strides in bytes
     uint8_t *dst; long long ds, dfs;
     int srcH, chrSrcH, dstW, dstH, chrDstW;
+    int y0;                           // first output line of this launch (slice calls), 0 for whole frames
 };
 
 
@@ -101,7 +103,7 @@ sws_unscaled_kernel(SwsFrameArgs a, SwsColorConst c, int ngroups)
 {
     const int xg = blockIdx.x * blockDim.x + threadIdx.x;
     if (xg >= ngroups) return;
-    const int row = blockIdx.y * 2;
+    const int row = blockIdx.y * 2 + a.y0;
     const long long f = blockIdx.z;
     const uint8_t *py = a.y + f * a.yfs + (long long)row * a.ys + xg * 16;
     const uint2 u = __ldg(reinterpret_cast<const uint2 *>(a.u + f * a.ufs + (long long)(row >> 1) * a.us + xg * 8));
@@ -129,7 +131,7 @@ sws_unscaled_slow_kernel(SwsFrameArgs a, SwsColorConst c, int p0, int p1)
 {
     const int p = p0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= p1) return;
-    const int row = blockIdx.y * 2;
+    const int row = blockIdx.y * 2 + a.y0;
     const long long f = blockIdx.z;
     const uint8_t *py = a.y + f * a.yfs + (long long)row * a.ys + 2 * p;
     const int U = a.u[f * a.ufs + (long long)(row >> 1) * a.us + p], V = a.v[f * a.vfs + (long long)(row >> 1) * a.vs + p];
@@ -143,16 +145,17 @@ sws_unscaled_slow_kernel(SwsFrameArgs a, SwsColorConst c, int p0, int p1)
 // dst[i] = min((sum_j src[pos[i]+j] * coef[i*fs+j]) >> 7, 32767); one thread per output sample, grid y = lines, z = frames.
 __global__ void __launch_bounds__(256)
 sws_hscale_kernel(const uint8_t *src, long long sstride, long long sfs, int16_t *dst, int dstW, long long dfs,
-                  const int16_t *coef, const int32_t *pos, int fs)
+                  const int16_t *coef, const int32_t *pos, int fs, int line0)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= dstW) return;
-    const uint8_t *s = src + (long long)blockIdx.z * sfs + (long long)blockIdx.y * sstride + __ldg(pos + i);
+    const int line = blockIdx.y + line0;
+    const uint8_t *s = src + (long long)blockIdx.z * sfs + (long long)line * sstride + __ldg(pos + i);
     const int16_t *k = coef + (long long)i * fs;
     int acc = 0;
     for (int j = 0; j < fs; j++) acc += (int)__ldg(s + j) * (int)__ldg(k + j);
     acc >>= 7;
-    dst[(long long)blockIdx.z * dfs + (long long)blockIdx.y * dstW + i] = (int16_t)min(acc, 32767);
+    dst[(long long)blockIdx.z * dfs + (long long)line * dstW + i] = (int16_t)min(acc, 32767);
 }
 
 // ------------------------------------------------------------------------------------------------ kernel: vertical FIR + rgb24 (fast)
@@ -181,7 +184,7 @@ sws_vscale_rgb24_fast_kernel(SwsFrameArgs a, SwsDevTables t, SwsColorConst c, in
 {
     const int xg = blockIdx.x * blockDim.x + threadIdx.x;
     if (xg >= ngroups) return;
-    const int dy = blockIdx.y;
+    const int dy = blockIdx.y + a.y0;
     const long long f = blockIdx.z;
     const int lfs = t.vLumSize, cfs = CFS4 ? 4 : t.vChrSize;
     const int lp = (lfs + 1) >> 1, cp = (cfs + 1) >> 1;
@@ -253,7 +256,7 @@ sws_vscale_rgb24_slow_kernel(SwsFrameArgs a, SwsDevTables t, SwsColorConst c, in
 {
     const int p = p0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= p1) return;
-    const int dy = blockIdx.y;
+    const int dy = blockIdx.y + a.y0;
     const long long f = blockIdx.z;
     const int lfs = t.vLumSize, cfs = t.vChrSize;
     const int16_t *lf = t.vLum + (long long)dy * lfs, *cf = t.vChr + (long long)dy * cfs;
@@ -310,7 +313,7 @@ __global__ void __launch_bounds__(256)
 sws_vscale_rgb24_full_kernel(SwsFrameArgs a, SwsDevTables t, SwsColorConst c)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int dy = blockIdx.y;
+    const int dy = blockIdx.y + a.y0;
     if (x >= a.dstW) return;
     const long long f = blockIdx.z;
     const int lfs = t.vLumSize, cfs = t.vChrSize;
@@ -373,6 +376,11 @@ struct B200SwsContext {
     bool lum_identity = false;       // vertical luma bank is a single tap of 4096 on every line
     // intermediate int16 line planes for the scaled path (grown on demand, per batch)
     void *mid = nullptr; size_t mid_bytes = 0;
+    // slice calls (sws_scale with srcSliceH < srcH): device copies of the source planes and of the picture being built,
+    // plus the next output line (SwsInternal.dstY, swscale.c:297,551)
+    void *slice_buf = nullptr;
+    int next_dst_y = 0;
+    bool slice_open = false;
 };
 
 static int upload_tables(B200SwsContext *c)
@@ -465,6 +473,7 @@ B200_API void b200_sws_freeContext(B200SwsContext *c)
     cudaStreamSynchronize(c->dev->stream);
     if (c->tables) cudaFree(c->tables);
     if (c->mid) cudaFree(c->mid);
+    if (c->slice_buf) cudaFree(c->slice_buf);
     delete c;
 }
 
@@ -526,17 +535,26 @@ static bool aligned8(const void *p, long long stride, long long fstride)
 }
 
 // enqueue the conversion of nframes frames on `stream`
+// Which lines a launch covers.  Whole frames: everything.  Slice calls: the output lines that became computable and the
+// source lines that were just uploaded (only those need the horizontal pass).
+struct SwsRows { int dy0, ndy, ly0, nly, cy0, ncy; };
+
 static int launch_batch(B200SwsContext *c, cudaStream_t stream, const uint8_t *const src[3], const long long sstr[3],
-                        const long long sfs[3], uint8_t *dst, long long ds, long long dfs, int nframes)
+                        const long long sfs[3], uint8_t *dst, long long ds, long long dfs, int nframes,
+                        const SwsRows *rows = nullptr)
 {
     const SwsPlan &p = c->plan;
     if (nframes <= 0) return 0;
+    const SwsRows full = { 0, p.dstH, 0, p.srcH, 0, p.chrSrcH };
+    const SwsRows R = rows ? *rows : full;
+    if (R.ndy <= 0 && R.nly <= 0 && R.ncy <= 0) return 0;
     SwsFrameArgs a{};
     a.y = src[0]; a.u = src[1]; a.v = src[2];
     a.ys = sstr[0]; a.us = sstr[1]; a.vs = sstr[2];
     a.yfs = sfs[0]; a.ufs = sfs[1]; a.vfs = sfs[2];
     a.dst = dst; a.ds = ds; a.dfs = dfs;
     a.srcH = p.srcH; a.chrSrcH = p.chrSrcH; a.dstW = p.dstW; a.dstH = p.dstH; a.chrDstW = p.chrDstW;
+    a.y0 = R.dy0;
     const int vecSrc = aligned16(src[0], sstr[0], sfs[0]) && aligned8(src[1], sstr[1], sfs[1]) && aligned8(src[2], sstr[2], sfs[2]);
     const int vecOK = vecSrc && aligned16(dst, ds, dfs);
     for (int f0 = 0; f0 < nframes; f0 += 65535) {            // gridDim.z limit
@@ -545,25 +563,25 @@ static int launch_batch(B200SwsContext *c, cudaStream_t stream, const uint8_t *c
         b.y += (long long)f0 * a.yfs; b.u += (long long)f0 * a.ufs; b.v += (long long)f0 * a.vfs; b.dst += (long long)f0 * a.dfs;
         if (p.unscaled_lut) {
             const int wpix = ((p.dstW >> 3) << 3) + (p.dstW & 4) + (p.dstW & 2);
-            if (wpix == 0) continue;
+            if (wpix == 0 || R.ndy < 2) continue;
             const int ngroups = vecOK ? wpix / 16 : 0;
             if (ngroups) {
-                dim3 block(128), grid(b200_ceil_div(ngroups, 128), p.dstH / 2, nf);
+                dim3 block(128), grid(b200_ceil_div(ngroups, 128), R.ndy / 2, nf);
                 sws_unscaled_kernel<<<grid, block, 0, stream>>>(b, p.color, ngroups);
                 B200_LAUNCHED();
             }
             const int p0 = ngroups * 8, p1 = wpix / 2;
             if (p1 > p0) {
-                dim3 block(128), grid(b200_ceil_div(p1 - p0, 128), p.dstH / 2, nf);
+                dim3 block(128), grid(b200_ceil_div(p1 - p0, 128), R.ndy / 2, nf);
                 sws_unscaled_slow_kernel<<<grid, block, 0, stream>>>(b, p.color, p0, p1);
                 B200_LAUNCHED();
             }
         } else if (c->h_identity) {
             auto fits32 = [](long long stride, long long lines) { return (stride < 0 ? -stride : stride) * (lines + 1) < (1LL << 31); };
             const bool off32 = fits32(b.ys, p.srcH) && fits32(b.us, p.chrSrcH) && fits32(b.vs, p.chrSrcH) && fits32(b.ds, p.dstH);
-            const int ngroups = (vecOK && c->fast_x && off32) ? p.dstW / 16 : 0;
+            const int ngroups = (vecOK && c->fast_x && off32 && R.ndy > 0) ? p.dstW / 16 : 0;
             if (ngroups) {
-                dim3 block(128), grid(b200_ceil_div(ngroups, 128), p.dstH, nf);
+                dim3 block(128), grid(b200_ceil_div(ngroups, 128), R.ndy, nf);
                 const bool c4 = p.vChr.size == 4;
                 if (c->lum_identity && c4)  sws_vscale_rgb24_fast_kernel<true, true><<<grid, block, 0, stream>>>(b, c->dt, p.color, ngroups);
                 else if (c->lum_identity)   sws_vscale_rgb24_fast_kernel<true, false><<<grid, block, 0, stream>>>(b, c->dt, p.color, ngroups);
@@ -572,8 +590,8 @@ static int launch_batch(B200SwsContext *c, cudaStream_t stream, const uint8_t *c
                 B200_LAUNCHED();
             }
             const int p0 = ngroups * 8, p1 = (p.dstW + 1) / 2;
-            if (p1 > p0) {
-                dim3 block(128), grid(b200_ceil_div(p1 - p0, 128), p.dstH, nf);
+            if (p1 > p0 && R.ndy > 0) {
+                dim3 block(128), grid(b200_ceil_div(p1 - p0, 128), R.ndy, nf);
                 sws_vscale_rgb24_slow_kernel<true><<<grid, block, 0, stream>>>(b, c->dt, p.color, p0, p1);
                 B200_LAUNCHED();
             }
@@ -591,27 +609,31 @@ static int launch_batch(B200SwsContext *c, cudaStream_t stream, const uint8_t *c
             int16_t *mU = (int16_t *)((uint8_t *)c->mid + lumPlane);
             int16_t *mV = (int16_t *)((uint8_t *)c->mid + lumPlane + chrPlane);
             const long long mfs = (long long)(perFrame / 2);
-            {
-                dim3 block(256), grid(b200_ceil_div(p.dstW, 256), p.srcH, nf);
-                sws_hscale_kernel<<<grid, block, 0, stream>>>(b.y, b.ys, b.yfs, mY, p.dstW, mfs, c->dt.hLum, c->dt.hLumPos, c->dt.hLumSize);
-                B200_LAUNCHED();
-                dim3 gridc(b200_ceil_div(p.chrDstW, 256), p.chrSrcH, nf);
-                sws_hscale_kernel<<<gridc, block, 0, stream>>>(b.u, b.us, b.ufs, mU, p.chrDstW, mfs, c->dt.hChr, c->dt.hChrPos, c->dt.hChrSize);
-                B200_LAUNCHED();
-                sws_hscale_kernel<<<gridc, block, 0, stream>>>(b.v, b.vs, b.vfs, mV, p.chrDstW, mfs, c->dt.hChr, c->dt.hChrPos, c->dt.hChrSize);
+            dim3 block(256);
+            if (R.nly > 0) {
+                dim3 grid(b200_ceil_div(p.dstW, 256), R.nly, nf);
+                sws_hscale_kernel<<<grid, block, 0, stream>>>(b.y, b.ys, b.yfs, mY, p.dstW, mfs, c->dt.hLum, c->dt.hLumPos, c->dt.hLumSize, R.ly0);
                 B200_LAUNCHED();
             }
+            if (R.ncy > 0) {
+                dim3 gridc(b200_ceil_div(p.chrDstW, 256), R.ncy, nf);
+                sws_hscale_kernel<<<gridc, block, 0, stream>>>(b.u, b.us, b.ufs, mU, p.chrDstW, mfs, c->dt.hChr, c->dt.hChrPos, c->dt.hChrSize, R.cy0);
+                B200_LAUNCHED();
+                sws_hscale_kernel<<<gridc, block, 0, stream>>>(b.v, b.vs, b.vfs, mV, p.chrDstW, mfs, c->dt.hChr, c->dt.hChrPos, c->dt.hChrSize, R.cy0);
+                B200_LAUNCHED();
+            }
+            if (R.ndy <= 0) continue;
             SwsFrameArgs m = b;
             m.y = (const uint8_t *)mY; m.u = (const uint8_t *)mU; m.v = (const uint8_t *)mV;
             m.ys = (long long)p.dstW * 2; m.us = m.vs = (long long)p.chrDstW * 2;
             m.yfs = m.ufs = m.vfs = (long long)perFrame;
             if (p.chrDstHSub) {
                 const int np = (p.dstW + 1) / 2;
-                dim3 block(128), grid(b200_ceil_div(np, 128), p.dstH, nf);
-                sws_vscale_rgb24_slow_kernel<false><<<grid, block, 0, stream>>>(m, c->dt, p.color, 0, np);
+                dim3 block2(128), grid(b200_ceil_div(np, 128), R.ndy, nf);
+                sws_vscale_rgb24_slow_kernel<false><<<grid, block2, 0, stream>>>(m, c->dt, p.color, 0, np);
             } else {
-                dim3 block(256), grid(b200_ceil_div(p.dstW, 256), p.dstH, nf);
-                sws_vscale_rgb24_full_kernel<<<grid, block, 0, stream>>>(m, c->dt, p.color);
+                dim3 block2(256), grid(b200_ceil_div(p.dstW, 256), R.ndy, nf);
+                sws_vscale_rgb24_full_kernel<<<grid, block2, 0, stream>>>(m, c->dt, p.color);
             }
             B200_LAUNCHED();
         }
@@ -698,15 +720,75 @@ B200_API int b200_sws_scale_batch_host(B200SwsContext *c, const uint8_t *const s
     return 0;
 }
 
+// sws_scale() called with a horizontal band of the source (top-down slices, like slice-threaded decoders feed it).
+// Mirrors scale_internal() (swscale.c:1022-1200) and the line scheduling of ff_swscale() (swscale.c:412-535): the band
+// is uploaded into a device copy of the source picture, the horizontal pass runs on the new lines only, and every
+// output line whose vertical taps are now complete is produced and copied back.  Returns the number of lines written.
+static int sws_scale_slice(B200SwsContext *c, const uint8_t *const srcSlice[], const int srcStride[],
+                           int srcSliceY, int srcSliceH, uint8_t *const dst[], const int dstStride[])
+{
+    const SwsPlan &p = c->plan;
+    // parameter checks of scale_internal (macro_height_src = 2 for yuv420p)
+    if ((srcSliceY & 1) || ((srcSliceH & 1) && srcSliceY + srcSliceH != p.srcH) || srcSliceY + srcSliceH > p.srcH ||
+        srcSliceY < 0 || srcSliceH < 0) {
+        b200_set_error("Slice parameters %d, %d are invalid", srcSliceY, srcSliceH);
+        return B200_EINVAL;
+    }
+    if (srcSliceH == 0) return 0;
+    if (srcStride[0] < 0 || srcStride[1] < 0 || srcStride[2] < 0 || dstStride[0] < 0) return B200_ENOSYS;
+    if (!c->slice_open && srcSliceY != 0) {
+        // "Slices start in the middle!" unless it is a bottom-up sequence, which is not implemented here
+        b200_set_error("slices must start at line 0 (bottom-up slice order is not implemented)");
+        return srcSliceY + srcSliceH == p.srcH ? B200_ENOSYS : B200_EINVAL;
+    }
+    B200Device *d = c->dev;
+    B200_CUDA_OK(cudaSetDevice(d->ordinal));
+    const PackedLayout L = packed_layout(p);
+    cudaStream_t st = d->stream;
+    if (!c->slice_buf) B200_CUDA_OK(cudaMalloc(&c->slice_buf, L.srcBytes + L.dstBytes));
+    uint8_t *sb = (uint8_t *)c->slice_buf, *db = sb + L.srcBytes;
+    if (srcSliceY == 0) { c->next_dst_y = 0; c->slice_open = true; }
+    const int chrY = srcSliceY >> 1, chrH = -((-srcSliceH) >> 1);                       // AV_CEIL_RSHIFT
+    B200_CUDA_OK(cudaMemcpy2DAsync(sb + L.yOff + (size_t)srcSliceY * L.yPitch, L.yPitch, srcSlice[0], (size_t)srcStride[0], p.srcW, srcSliceH, cudaMemcpyHostToDevice, st));
+    B200_CUDA_OK(cudaMemcpy2DAsync(sb + L.uOff + (size_t)chrY * L.cPitch, L.cPitch, srcSlice[1], (size_t)srcStride[1], p.chrSrcW, chrH, cudaMemcpyHostToDevice, st));
+    B200_CUDA_OK(cudaMemcpy2DAsync(sb + L.vOff + (size_t)chrY * L.cPitch, L.cPitch, srcSlice[2], (size_t)srcStride[2], p.chrSrcW, chrH, cudaMemcpyHostToDevice, st));
+    const uint8_t *sp[3] = { sb + L.yOff, sb + L.uOff, sb + L.vOff };
+    const long long ss[3] = { (long long)L.yPitch, (long long)L.cPitch, (long long)L.cPitch };
+    const long long fs[3] = { 0, 0, 0 };
+    int y0, y1;
+    if (p.unscaled_lut) {                                   // convert_unscaled handles exactly the band it is given
+        y0 = srcSliceY; y1 = srcSliceY + (srcSliceH & ~1);
+    } else {
+        y0 = c->next_dst_y;
+        const int avail_l = srcSliceY + srcSliceH, avail_c = -((-(srcSliceY + srcSliceH)) >> 1);
+        for (y1 = y0; y1 < p.dstH; y1++) {                  // "enough_lines", swscale.c:463-465
+            const int firstLum = std::max(1 - p.vLum.size, p.vLum.pos[y1]);
+            const int firstChr = std::max(1 - p.vChr.size, p.vChr.pos[y1]);
+            const int lastLum = std::min(p.srcH, firstLum + p.vLum.size) - 1;
+            const int lastChr = std::min(p.chrSrcH, firstChr + p.vChr.size) - 1;
+            if (!(lastLum < avail_l && lastChr < avail_c)) break;
+        }
+        c->next_dst_y = y1;
+    }
+    const SwsRows R = { y0, y1 - y0, srcSliceY, srcSliceH, chrY, chrH };
+    int ret = launch_batch(c, st, sp, ss, fs, db, (long long)L.dPitch, 0, 1, &R);
+    if (ret < 0) return ret;
+    if (y1 > y0)
+        B200_CUDA_OK(cudaMemcpy2DAsync(dst[0] + (long long)y0 * dstStride[0], (size_t)dstStride[0], db + (size_t)y0 * L.dPitch, L.dPitch,
+                                       (size_t)p.dstW * 3, y1 - y0, cudaMemcpyDeviceToHost, st));
+    B200_CUDA_OK(cudaStreamSynchronize(st));
+    if (srcSliceY + srcSliceH == p.srcH) c->slice_open = false;
+    return p.unscaled_lut ? srcSliceH : y1 - y0;
+}
+
 B200_API int b200_sws_scale(B200SwsContext *c, const uint8_t *const srcSlice[], const int srcStride[],
                             int srcSliceY, int srcSliceH, uint8_t *const dst[], const int dstStride[])
 {
     if (!c || !srcSlice || !srcStride || !dst || !dstStride) return B200_EINVAL;
     const SwsPlan &p = c->plan;
-    if (srcSliceY != 0 || srcSliceH != p.srcH) {
-        b200_set_error("b200_sws_scale: only whole-frame calls are implemented (slice %d+%d of %d)", srcSliceY, srcSliceH, p.srcH);
-        return B200_ENOSYS;
-    }
+    if (srcSliceY != 0 || srcSliceH != p.srcH)
+        return sws_scale_slice(c, srcSlice, srcStride, srcSliceY, srcSliceH, dst, dstStride);
+    c->slice_open = false;
     B200Device *d = c->dev;
     B200_CUDA_OK(cudaSetDevice(d->ordinal));
     const PackedLayout L = packed_layout(p);

@@ -173,6 +173,27 @@ def gen_vsynth1():
     np.savez_compressed(os.path.join(OUT, "vsynth1_f0.npz"), **d)
 
 
+def gen_sws_slices():
+    """sws_scale() fed with top-down bands: the reference's per-call return values (lines written) and final picture."""
+    R = cl.ref()
+    FATE = cl.SWS_BICUBIC | cl.SWS_ACCURATE_RND | cl.SWS_BITEXACT
+    d = {}
+    y, u, v = cl.yuv_frame(64, 48, 400, "random")
+    d["y"], d["u"], d["v"] = y, u, v
+    from cases import SWS_SLICE_CASES
+    for ci, (dw, dh, fl, bands) in enumerate(SWS_SLICE_CASES):
+        ctx = R.ffref_sws_open(64, 48, dw, dh, fl, 1)
+        out = np.full((dh, dw * 3), 0xA5, np.uint8)
+        rets = []
+        for (sy, sh) in bands:
+            rets.append(R.ffref_sws_scale(ctx, C.cast(y.ctypes.data + sy * 64, cl.u8p), 64, C.cast(u.ctypes.data + (sy // 2) * 32, cl.u8p), 32,
+                                          C.cast(v.ctypes.data + (sy // 2) * 32, cl.u8p), 32, sy, sh, cl.ptr(out), dw * 3))
+        R.ffref_sws_close(ctx)
+        d[f"s{ci}_rets"] = np.array(rets, np.int32)
+        d[f"s{ci}_rgb"] = out
+    np.savez_compressed(os.path.join(OUT, "sws_slices.npz"), **d)
+
+
 if __name__ == "__main__":
     assert cl.have_ref(), "build oracle/_ref first: make -C oracle/ref"
     os.makedirs(OUT, exist_ok=True)
@@ -182,5 +203,6 @@ if __name__ == "__main__":
     gen_pel()
     gen_tx()
     gen_vsynth1()
+    gen_sws_slices()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -65,3 +65,15 @@ def idct_blocks(kind, n, seed=0):
     else:
         raise ValueError(kind)
     return b
+
+
+# (dstW, dstH, flags, [(srcSliceY, srcSliceH), ...]) on a 64x48 source: sws_scale() called band by band
+SWS_SLICE_CASES = [
+    (64, 48, FATE, [(0, 16), (16, 16), (32, 16)]),
+    (64, 48, FATE, [(0, 2), (2, 46)]),
+    (64, 48, SWS_BICUBIC, [(0, 16), (16, 32)]),                    # unscaled LUT converter
+    (100, 60, SWS_BILINEAR, [(0, 8), (8, 8), (16, 8), (24, 24)]),
+    (32, 24, FATE, [(0, 24), (24, 24)]),
+    (37, 21, FATE, [(0, 10), (10, 20), (30, 18)]),                  # odd width: full-chroma writer
+    (64, 96, FATE, [(0, 4), (4, 4), (8, 40)]),
+]

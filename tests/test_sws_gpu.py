@@ -94,14 +94,34 @@ def test_bottom_up_strides(device):
     ctx.free()
 
 
-def test_slice_calls_rejected(device):
+def test_slice_calls_match_reference(device):
+    """sws_scale() band by band: per-call return values and the final picture equal the reference's (fixtures)."""
+    from ffmpeg_b200 import swscale as sw
+    from cases import SWS_SLICE_CASES
+    g = np.load(os.path.join(G, "sws_slices.npz"))
+    y, u, v = g["y"], g["u"], g["v"]
+    for ci, (dw, dh, fl, bands) in enumerate(SWS_SLICE_CASES):
+        ctx = sw.sws_getContext(device, 64, 48, 0, dw, dh, 2, fl)
+        out = np.full((dh, dw * 3), 0xA5, np.uint8)
+        rets = []
+        for rep in range(2):                                        # the context is reusable for the next frame
+            rets = [ctx.scale([y.ctypes.data + sy * 64, u.ctypes.data + (sy // 2) * 32, v.ctypes.data + (sy // 2) * 32],
+                              [64, 32, 32], sy, sh, [out], [dw * 3]) for (sy, sh) in bands]
+        assert rets == list(g[f"s{ci}_rets"]), (ci, rets, list(g[f"s{ci}_rets"]))
+        assert np.array_equal(out, g[f"s{ci}_rgb"]), ci
+        ctx.free()
+
+
+def test_bad_slices_rejected(device):
     from ffmpeg_b200 import swscale as sw
     import ffmpeg_b200 as fb
     ctx = sw.sws_getContext(device, 64, 48, 0, 64, 48, 2, FATE)
     y, u, v = cl.yuv_frame(64, 48, 1)
     out = np.zeros((48, 192), np.uint8)
     with pytest.raises(fb.B200Error):
-        ctx.scale([y, u, v], [64, 32, 32], 0, 16, [out], [192])
+        ctx.scale([y, u, v], [64, 32, 32], 1, 16, [out], [192])     # odd start line: "Slice parameters invalid"
+    with pytest.raises(fb.B200Error):
+        ctx.scale([y, u, v], [64, 32, 32], 16, 16, [out], [192])    # "Slices start in the middle!"
     ctx.free()
     with pytest.raises(fb.B200Error):
         sw.sws_getContext(device, 64, 48, 0, 64, 48, 2, cl.SWS_BICUBIC | cl.SWS_BILINEAR)   # two scalers: EINVAL like the reference
