@@ -277,6 +277,32 @@ def extra_paths(args, dev, stream, g, world, barrier, reduce_max, peak):
                                     "frac": qbytes * nops / (ms / 1e3) / 1e9 / peak, "bytes_per_block": qbytes}}
     del refp, dstp, doff, soff, ops
 
+    # --- widening row: the chroma half of the same stream, h264chroma mc8 8x8 on the two 960x544 chroma planes
+    CW, CH, capron = W // 2, H // 2, 16
+    CPW, CPH = CW + 2 * capron, CH + 2 * capron
+    with torch.cuda.stream(stream):
+        refc = torch.randint(0, 256, (2 * nfr, CPH, CPW), dtype=torch.uint8, device="cuda", generator=g)
+        dstc = torch.randint(0, 256, (2 * nfr, CPH, CPW), dtype=torch.uint8, device="cuda", generator=g)
+        fidx = torch.arange(2 * nfr, device="cuda").view(-1, 1, 1)
+        by = torch.arange(CH // 8, device="cuda").view(1, -1, 1)
+        bx = torch.arange(CW // 8, device="cuda").view(1, 1, -1)
+        base = fidx * (CPH * CPW) + (by * 8 + capron) * CPW + bx * 8 + capron
+        dx = torch.randint(-8, 9, base.shape, device="cuda", generator=g)
+        dy = torch.randint(-8, 9, base.shape, device="cuda", generator=g)
+        doff = base.reshape(-1).to(torch.int64).contiguous()
+        soff = (base + dy * CPW + dx).reshape(-1).to(torch.int64).contiguous()
+        ops = torch.randint(0, 2, (doff.numel(),), device="cuda", generator=g).to(torch.uint8)
+        hs = torch.full((doff.numel(),), 8, dtype=torch.uint8, device="cuda")
+        xys = torch.randint(0, 64, (doff.numel(),), device="cuda", generator=g).to(torch.uint8)
+    nops = doff.numel()
+    ms = timed(lambda: pel.h264chroma_batch_device(dev, nops, ops, hs, xys, dstc, doff, refc, soff, CPW))
+    cbytes = 81 + 64 + 32                            # 9x9 reference window + 8x8 out (+ dst read for the avg half)
+    out["h264chroma"] = {"value": world * nops / (ms / 1e3), "unit": "8x8 blocks/s", "ms_per_step": ms,
+                         "config": f"{2 * nfr} 960x544 chroma planes x 8160 blocks, random eighth-pel phase and put/avg",
+                         "roofline": {"bound": "hbm", "achieved": cbytes * nops / (ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                                      "frac": cbytes * nops / (ms / 1e3) / 1e9 / peak, "bytes_per_block": cbytes}}
+    del refc, dstc, doff, soff, ops, hs, xys
+
     # --- config 5: float FFT and iMDCT, len 1024 and 2048
     txr = {}
     for n in (1024, 2048):

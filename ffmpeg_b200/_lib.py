@@ -61,6 +61,23 @@ class HpelDSPContext(C.Structure):
                 ("put_no_rnd_pixels_tab", (_HPEL * 4) * 3), ("avg_no_rnd_pixels_tab", _HPEL * 4)]
 
 
+_CHROMA = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_ssize_t, C.c_int, C.c_int, C.c_int)
+
+
+class H264ChromaContext(C.Structure):
+    """libavcodec/h264chroma.h:26-31"""
+    _fields_ = [("put_h264_chroma_pixels_tab", _CHROMA * 4), ("avg_h264_chroma_pixels_tab", _CHROMA * 4)]
+
+
+_EDGE = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_ssize_t, C.c_ssize_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int)
+_PREFETCH = C.CFUNCTYPE(None, C.c_void_p, C.c_ssize_t, C.c_int)
+
+
+class VideoDSPContext(C.Structure):
+    """libavcodec/videodsp.h:32-69"""
+    _fields_ = [("emulated_edge_mc", _EDGE), ("prefetch", _PREFETCH)]
+
+
 TX_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_void_p, C.c_ssize_t)
 
 # name -> (restype, argtypes): every symbol include/b200dsp.h declares
@@ -102,6 +119,10 @@ PROTOTYPES = {
     "b200_hpeldsp_init": (C.c_int, [C.POINTER(HpelDSPContext), C.c_int]),
     "b200_h264qpel_batch_device": (C.c_int, [vp, C.c_int64, vp, vp, vp, vp, vp, C.c_ssize_t]),
     "b200_hpel_batch_device": (C.c_int, [vp, C.c_int64, vp, vp, vp, vp, vp, vp, C.c_ssize_t]),
+    "b200_videodsp_init": (C.c_int, [C.POINTER(VideoDSPContext), C.c_int]),
+    "b200_emulated_edge_mc_batch_device": (C.c_int, [vp, C.c_int64, vp, vp, C.c_ssize_t, vp, vp, C.c_ssize_t, vp, C.c_int, C.c_int]),
+    "b200_h264chroma_init": (C.c_int, [C.POINTER(H264ChromaContext), C.c_int]),
+    "b200_h264chroma_batch_device": (C.c_int, [vp, C.c_int64, vp, vp, vp, vp, vp, vp, vp, C.c_ssize_t]),
     "b200_tx_init": (C.c_int, [C.POINTER(vp), C.POINTER(TX_FN), C.c_int, C.c_int, C.c_int, vp, C.c_uint64]),
     "b200_tx_init_device": (C.c_int, [vp, C.POINTER(vp), C.POINTER(TX_FN), C.c_int, C.c_int, C.c_int, vp, C.c_uint64]),
     "b200_tx_uninit": (None, [C.POINTER(vp)]),

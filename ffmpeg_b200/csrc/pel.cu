@@ -1,4 +1,4 @@
-// pel.cu — libavcodec h264qpel (8 bit) and hpeldsp motion-compensation interpolation on sm_100a (C ABI: "h264qpel / hpeldsp").
+// pel.cu — libavcodec h264qpel (8 bit), h264chroma (8 bit) and hpeldsp motion-compensation interpolation on sm_100a (C ABI: "h264qpel / hpeldsp").
 //
 // Reference semantics reproduced bit-for-bit (checker: oracle/pel_oracle.c):
 //   H264_LOWPASS / H264_MC / op_put, op_avg   libavcodec/h264qpel_template.c:77-465
@@ -9,6 +9,7 @@
 // unrounded horizontal 6-tap sums once (size+5 rows of int16), and then every lane produces its pixels from shared
 // memory.  The 6-tap is never recomputed per output pixel and the reference block is read from HBM exactly once.
 #include "common.h"
+#include <algorithm>
 #include <cstring>
 
 namespace {
@@ -250,36 +251,109 @@ hpel_kernel(long long n, const uint8_t *op, const uint8_t *hh, uint8_t *dst, con
     }
 }
 
+// h264chroma: bilinear eighth-pel (h264chroma_template.c:27-176).  16 lanes per operation, a lane owns up to 4 consecutive
+// pixels of one row; the x == 0 / y == 0 cases skip the right column / lower row like the reference's D == 0 branches.
+constexpr int CH_LANES = 16;
+__global__ void __launch_bounds__(32 * WARPS)
+chroma_kernel(long long n, const uint8_t *op, const uint8_t *hh, const uint8_t *xy, uint8_t *dst, const int64_t *dst_off,
+              const uint8_t *src, const int64_t *src_off, long long stride)
+{
+    const long long i = ((long long)blockIdx.x * (32 * WARPS) + threadIdx.x) / CH_LANES;
+    if (i >= n) return;
+    const int sub = threadIdx.x & (CH_LANES - 1);
+    const int o = op[i], h = hh[i], fx = xy[i] & 7, fy = (xy[i] >> 3) & 7;
+    const int avg = o & 1, w = 8 >> ((o >> 1) & 3);
+    const int A = (8 - fx) * (8 - fy), B = fx * (8 - fy), C = (8 - fx) * fy, D = fx * fy;
+    const int segs = w > 4 ? 2 : 1, npx = w < 4 ? w : 4;
+    const uint8_t *sp = src + src_off[i];
+    uint8_t *dp = dst + dst_off[i];
+    for (int y = sub / segs; y < h; y += CH_LANES / segs) {
+        const int x0 = (sub % segs) * 4;
+        const uint8_t *p = sp + (long long)y * stride + x0;
+        int t[5], b[5];
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            const bool in = k < npx || (k == npx && fx);                       // right neighbour only when B or D is non-zero
+            t[k] = in ? __ldg(p + k) : 0;
+            b[k] = (in && fy) ? __ldg(p + stride + k) : 0;                     // lower row only when C or D is non-zero
+        }
+        uint8_t *d = dp + (long long)y * stride + x0;
+        uint32_t pack = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int v = (A * t[k] + B * t[k + 1] + C * b[k] + D * b[k + 1] + 32) >> 6;
+            pack |= (uint32_t)v << (8 * k);
+        }
+        if (npx == 4 && ((uintptr_t)d & 3) == 0) {
+            uint32_t *d4 = (uint32_t *)d;
+            *d4 = avg ? __vavgu4(*d4, pack) : pack;
+        } else {
+            for (int k = 0; k < npx; k++) {
+                const int v = (pack >> (8 * k)) & 255;
+                d[k] = (uint8_t)(avg ? (d[k] + v + 1) >> 1 : v);
+            }
+        }
+    }
+}
+
+// emulated_edge_mc (videodsp_template.c:24-101) as a clamped gather: one warp per window, lanes across columns.
+// geom[4*i..] = block_w, block_h, src_x, src_y; origin[i] = offset of that picture's sample (0, 0) from `src`.
+__global__ void __launch_bounds__(32 * WARPS)
+edge_kernel(long long n, uint8_t *buf, const int64_t *buf_off, long long buf_ls, const uint8_t *src, const int64_t *origin,
+            long long src_ls, const int32_t *geom, int w, int h)
+{
+    const long long i = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5);
+    if (i >= n) return;
+    const int lane = threadIdx.x & 31;
+    const int4 gm = __ldg((const int4 *)geom + i);
+    const int bw = gm.x, bh = gm.y, sx = gm.z, sy = gm.w;
+    const uint8_t *pic = src + origin[i];
+    uint8_t *out = buf + buf_off[i];
+    for (int x = lane; x < bw; x += 32) {
+        const int px = min(max(sx + x, 0), w - 1);
+        for (int y = 0; y < bh; y++) {
+            const int py = min(max(sy + y, 0), h - 1);
+            out[(long long)y * buf_ls + x] = __ldg(pic + (long long)py * src_ls + px);
+        }
+    }
+}
+
 void die(const char *what)
 {
     fprintf(stderr, "libb200dsp: motion compensation failed: %s (%s)\n", what, b200_last_error());
     abort();
 }
 
-// one block through the device for the drop-in tables; `pad` = rows/cols read around the block
-void host_op(bool qpel, int o, int h, int w, uint8_t *dst, const uint8_t *src, ptrdiff_t stride)
+enum HostKind { HOST_QPEL, HOST_HPEL, HOST_CHROMA };
+
+// one block through the device for the drop-in tables.  Only the source rectangle the reference function itself reads is
+// copied from the caller's buffer (bx/ax columns left/right, by/ay rows above/below the block).
+void host_op(HostKind kind, int o, int h, int w, uint8_t *dst, const uint8_t *src, ptrdiff_t stride,
+             int bx, int ax, int by, int ay, int fxy = 0)
 {
     B200Device *dev = b200_default_device();
     if (!dev) die("no device");
     if (stride < 0) die("negative stride");
     if (cudaSetDevice(dev->ordinal) != cudaSuccess) die("cudaSetDevice");
-    const int before = qpel ? 2 : 0, after = qpel ? 3 : 1;
-    const int sw = w + before + after, sh = h + before + after;
+    const int before = kind == HOST_QPEL ? 2 : 0, after = kind == HOST_QPEL ? 3 : 1;   // the window the kernels may touch
+    const int sh = h + before + after;
     const size_t pitch = 32;
     uint8_t *scr = (uint8_t *)b200_scratch(dev, pitch * (sh + h) + 256);
     if (!scr) die("scratch");
     uint8_t *dsrc = scr, *ddst = scr + pitch * sh;
     uint8_t *meta = scr + pitch * (sh + h);           // op, h, offsets
     cudaStream_t st = dev->stream;
-    if (cudaMemcpy2DAsync(dsrc, pitch, src - before * stride - before, (size_t)stride, sw, sh, cudaMemcpyHostToDevice, st) != cudaSuccess) die("h2d src");
+    if (cudaMemcpy2DAsync(dsrc + (before - by) * pitch + (before - bx), pitch, src - by * stride - bx, (size_t)stride,
+                          w + bx + ax, h + by + ay, cudaMemcpyHostToDevice, st) != cudaSuccess) die("h2d src");
     if (cudaMemcpy2DAsync(ddst, pitch, dst, (size_t)stride, w, h, cudaMemcpyHostToDevice, st) != cudaSuccess) die("h2d dst");
-    struct { int64_t doff, soff; uint8_t op, h; } m = { 0, (int64_t)(before * pitch + before), (uint8_t)o, (uint8_t)h };
+    struct { int64_t doff, soff; uint8_t op, h, xy; } m = { 0, (int64_t)(before * pitch + before), (uint8_t)o, (uint8_t)h, (uint8_t)fxy };
     if (cudaMemcpyAsync(meta, &m, sizeof(m), cudaMemcpyHostToDevice, st) != cudaSuccess) die("h2d meta");
     const int64_t *doff = (const int64_t *)meta, *soff = doff + 1;
-    const uint8_t *dop = meta + 16, *dh = meta + 17;
+    const uint8_t *dop = meta + 16, *dh = meta + 17, *dxy = meta + 18;
     // dst and src live in one buffer with the same pitch, like the reference's single stride
-    if (qpel) qpel_kernel<<<1, 32 * WARPS, 0, st>>>(1, dop, ddst, doff, dsrc, soff, (long long)pitch);
-    else      hpel_kernel<<<1, 32 * WARPS, 0, st>>>(1, dop, dh, ddst, doff, dsrc, soff, (long long)pitch);
+    if (kind == HOST_QPEL)      qpel_kernel<<<1, 32 * WARPS, 0, st>>>(1, dop, ddst, doff, dsrc, soff, (long long)pitch);
+    else if (kind == HOST_HPEL) hpel_kernel<<<1, 32 * WARPS, 0, st>>>(1, dop, dh, ddst, doff, dsrc, soff, (long long)pitch);
+    else                        chroma_kernel<<<1, 32 * WARPS, 0, st>>>(1, dop, dh, dxy, ddst, doff, dsrc, soff, (long long)pitch);
     B200_LAUNCHED();
     if (cudaMemcpy2DAsync(dst, (size_t)stride, ddst, pitch, w, h, cudaMemcpyDeviceToHost, st) != cudaSuccess) die("d2h");
     if (cudaStreamSynchronize(st) != cudaSuccess) die("sync");
@@ -288,12 +362,19 @@ void host_op(bool qpel, int o, int h, int w, uint8_t *dst, const uint8_t *src, p
 template <int AVG, int SIDX, int POS>
 void qpel_tab(uint8_t *dst, const uint8_t *src, ptrdiff_t stride)
 {
-    host_op(true, AVG | (SIDX << 1) | (POS << 3), 16 >> SIDX, 16 >> SIDX, dst, src, stride);
+    constexpr int X = POS & 3, Y = POS >> 2;           // h264qpel_template.c: mc{x}{y} filters horizontally iff x, vertically iff y
+    host_op(HOST_QPEL, AVG | (SIDX << 1) | (POS << 3), 16 >> SIDX, 16 >> SIDX, dst, src, stride, X ? 2 : 0, X ? 3 : 0, Y ? 2 : 0, Y ? 3 : 0);
 }
 template <int TAB, int SIDX, int XY>
 void hpel_tab(uint8_t *block, const uint8_t *pixels, ptrdiff_t line_size, int h)
 {
-    host_op(false, TAB | (SIDX << 2) | (XY << 4), h, 16 >> SIDX, block, pixels, line_size);
+    host_op(HOST_HPEL, TAB | (SIDX << 2) | (XY << 4), h, 16 >> SIDX, block, pixels, line_size, 0, XY & 1, 0, XY >> 1);
+}
+template <int AVG, int IDX>
+void chroma_tab(uint8_t *dst, const uint8_t *src, ptrdiff_t stride, int h, int x, int y)
+{
+    if ((unsigned)x > 7 || (unsigned)y > 7) die("h264chroma: x, y must be in 0..7");     // av_assert2 in the reference
+    host_op(HOST_CHROMA, AVG | (IDX << 1), h, 8 >> IDX, dst, src, stride, 0, x ? 1 : 0, 0, y ? 1 : 0, x | (y << 3));
 }
 
 template <int AVG, int SIDX>
@@ -332,6 +413,92 @@ B200_API int b200_hpeldsp_init(B200HpelDSPContext *c, int flags)
     fill_hpel<1, 0>(c->avg_pixels_tab[0]); fill_hpel<1, 1>(c->avg_pixels_tab[1]); fill_hpel<1, 2>(c->avg_pixels_tab[2]); fill_hpel<1, 3>(c->avg_pixels_tab[3]);
     fill_hpel<2, 0>(c->put_no_rnd_pixels_tab[0]); fill_hpel<2, 1>(c->put_no_rnd_pixels_tab[1]);
     fill_hpel<3, 0>(c->avg_no_rnd_pixels_tab);
+    return 0;
+}
+
+namespace {
+void edge_tab(uint8_t *buf, const uint8_t *src, ptrdiff_t buf_linesize, ptrdiff_t src_linesize, int block_w, int block_h,
+              int src_x, int src_y, int w, int h)
+{
+    if (!w || !h) return;                                          // videodsp_template.c:33-34
+    if (block_w <= 0 || block_h <= 0) return;
+    B200Device *dev = b200_default_device();
+    if (!dev) die("no device");
+    if (buf_linesize < 0 || src_linesize < 0) die("negative linesize");
+    if (cudaSetDevice(dev->ordinal) != cudaSuccess) die("cudaSetDevice");
+    // the part of the picture the window can reach after clamping
+    const int x0 = std::min(std::max(src_x, 0), w - 1), x1 = std::min(std::max(src_x + block_w - 1, 0), w - 1);
+    const int y0 = std::min(std::max(src_y, 0), h - 1), y1 = std::min(std::max(src_y + block_h - 1, 0), h - 1);
+    const size_t rw = (size_t)(x1 - x0 + 1), rh = (size_t)(y1 - y0 + 1);
+    const size_t rp = (rw + 15) & ~(size_t)15, bp = ((size_t)block_w + 15) & ~(size_t)15;
+    uint8_t *scr = (uint8_t *)b200_scratch(dev, rp * rh + bp * block_h + 256);
+    if (!scr) die("scratch");
+    uint8_t *drect = scr, *dbuf = scr + rp * rh, *meta = dbuf + bp * block_h;
+    meta += (16 - ((uintptr_t)meta & 15)) & 15;
+    cudaStream_t st = dev->stream;
+    const uint8_t *pic = src - (ptrdiff_t)src_y * src_linesize - src_x;
+    if (cudaMemcpy2DAsync(drect, rp, pic + (ptrdiff_t)y0 * src_linesize + x0, (size_t)src_linesize, rw, rh, cudaMemcpyHostToDevice, st) != cudaSuccess) die("h2d");
+    struct { int32_t g[4]; int64_t boff, origin; } m = { { block_w, block_h, src_x, src_y }, 0, -((int64_t)y0 * (int64_t)rp + x0) };
+    if (cudaMemcpyAsync(meta, &m, sizeof(m), cudaMemcpyHostToDevice, st) != cudaSuccess) die("h2d meta");
+    edge_kernel<<<1, 32 * WARPS, 0, st>>>(1, dbuf, (const int64_t *)(meta + 16), (long long)bp, drect, (const int64_t *)(meta + 24),
+                                          (long long)rp, (const int32_t *)meta, w, h);
+    B200_LAUNCHED();
+    if (cudaMemcpy2DAsync(buf, (size_t)buf_linesize, dbuf, bp, (size_t)block_w, (size_t)block_h, cudaMemcpyDeviceToHost, st) != cudaSuccess) die("d2h");
+    if (cudaStreamSynchronize(st) != cudaSuccess) die("sync");
+}
+void prefetch_nop(const uint8_t *, ptrdiff_t, int) {}
+} // namespace
+
+B200_API int b200_videodsp_init(B200VideoDSPContext *c, int bpc)
+{
+    if (!c) return B200_EINVAL;
+    if (bpc > 8) return B200_ENOSYS;                               // videodsp.c:41-45 installs the 16 bit template above 8
+    if (!b200_default_device()) return B200_ENODEV;
+    c->emulated_edge_mc = edge_tab;
+    c->prefetch = prefetch_nop;                                    // videodsp.c:34-36: the C prefetch is an empty function
+    return 0;
+}
+
+B200_API int b200_emulated_edge_mc_batch_device(B200Device *dev, int64_t n, uint8_t *buf, const int64_t *buf_off,
+                                                ptrdiff_t buf_linesize, const uint8_t *src, const int64_t *origin,
+                                                ptrdiff_t src_linesize, const int32_t *geom, int w, int h)
+{
+    if (!dev || n < 0 || !buf || !buf_off || !src || !origin || !geom || w < 0 || h < 0) return B200_EINVAL;
+    if (((uintptr_t)geom & 15) != 0) return B200_EINVAL;
+    if (n == 0 || !w || !h) return 0;
+    B200_CUDA_OK(cudaSetDevice(dev->ordinal));
+    const long long blocks = (n + WARPS - 1) / WARPS;
+    if (blocks > 0x7fffffffLL) return B200_EINVAL;
+    edge_kernel<<<(unsigned)blocks, 32 * WARPS, 0, dev->stream>>>(n, buf, buf_off, buf_linesize, src, origin, src_linesize, geom, w, h);
+    B200_LAUNCHED();
+    B200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+B200_API int b200_h264chroma_init(B200H264ChromaContext *c, int bit_depth)
+{
+    if (!c) return B200_EINVAL;
+    if (bit_depth != 8) return B200_ENOSYS;                        // h264chroma.c:46-50 installs the 16 bit template above 8
+    if (!b200_default_device()) return B200_ENODEV;
+    memset(c, 0, sizeof(*c));                                      // entry [3] stays NULL like the reference's
+    c->put_h264_chroma_pixels_tab[0] = chroma_tab<0, 0>; c->put_h264_chroma_pixels_tab[1] = chroma_tab<0, 1>; c->put_h264_chroma_pixels_tab[2] = chroma_tab<0, 2>;
+    c->avg_h264_chroma_pixels_tab[0] = chroma_tab<1, 0>; c->avg_h264_chroma_pixels_tab[1] = chroma_tab<1, 1>; c->avg_h264_chroma_pixels_tab[2] = chroma_tab<1, 2>;
+    return 0;
+}
+
+B200_API int b200_h264chroma_batch_device(B200Device *dev, int64_t n, const uint8_t *op, const uint8_t *h, const uint8_t *xy,
+                                          uint8_t *dst, const int64_t *dst_off, const uint8_t *src, const int64_t *src_off,
+                                          ptrdiff_t stride)
+{
+    if (!dev || n < 0 || !op || !h || !xy || !dst || !dst_off || !src || !src_off) return B200_EINVAL;
+    if (n == 0) return 0;
+    B200_CUDA_OK(cudaSetDevice(dev->ordinal));
+    const int per_cta = 32 * WARPS / CH_LANES;
+    const long long blocks = (n + per_cta - 1) / per_cta;
+    if (blocks > 0x7fffffffLL) return B200_EINVAL;
+    chroma_kernel<<<(unsigned)blocks, 32 * WARPS, 0, dev->stream>>>(n, op, h, xy, dst, dst_off, src, src_off, stride);
+    B200_LAUNCHED();
+    B200_CUDA_OK(cudaGetLastError());
     return 0;
 }
 

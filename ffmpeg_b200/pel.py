@@ -1,7 +1,8 @@
-"""Host-side mirror of libavcodec's h264qpel / hpeldsp interfaces (H264QpelContext from ff_h264qpel_init,
-libavcodec/h264qpel.c:50-120; HpelDSPContext from ff_hpeldsp_init, libavcodec/hpeldsp.c:337-352) and the batched entry points."""
+"""Host-side mirror of libavcodec's h264qpel / h264chroma / hpeldsp interfaces (H264QpelContext from ff_h264qpel_init,
+libavcodec/h264qpel.c:50-120; H264ChromaContext from ff_h264chroma_init, libavcodec/h264chroma.c:36-65; HpelDSPContext from
+ff_hpeldsp_init, libavcodec/hpeldsp.c:337-352) and the batched entry points."""
 import ctypes as C
-from ._lib import lib, check, vp, H264QpelContext, HpelDSPContext
+from ._lib import lib, check, vp, H264QpelContext, HpelDSPContext, H264ChromaContext, VideoDSPContext
 
 
 def _dptr(x):
@@ -20,6 +21,23 @@ def ff_hpeldsp_init(flags=0):
     return c
 
 
+def ff_h264chroma_init(bit_depth=8):
+    c = H264ChromaContext()
+    check(lib().b200_h264chroma_init(C.byref(c), bit_depth), "ff_h264chroma_init")
+    return c
+
+
+def ff_videodsp_init(bpc=8):
+    """VideoDSPContext from ff_videodsp_init (libavcodec/videodsp.c:32-62): emulated_edge_mc + prefetch."""
+    c = VideoDSPContext()
+    check(lib().b200_videodsp_init(C.byref(c), bpc), "ff_videodsp_init")
+    return c
+
+
+def chroma_op(avg, idx):
+    return (avg & 1) | (idx << 1)
+
+
 def qpel_op(avg, size_idx, pos):
     return (avg & 1) | (size_idx << 1) | (pos << 3)
 
@@ -36,3 +54,16 @@ def h264qpel_batch_device(device, n, op, dst, dst_off, src, src_off, stride):
 def hpel_batch_device(device, n, op, h, dst, dst_off, src, src_off, stride):
     return check(lib().b200_hpel_batch_device(device.handle, n, vp(_dptr(op)), vp(_dptr(h)), vp(_dptr(dst)), vp(_dptr(dst_off)),
                                               vp(_dptr(src)), vp(_dptr(src_off)), stride), "hpel_batch_device")
+
+
+def h264chroma_batch_device(device, n, op, h, xy, dst, dst_off, src, src_off, stride):
+    return check(lib().b200_h264chroma_batch_device(device.handle, n, vp(_dptr(op)), vp(_dptr(h)), vp(_dptr(xy)), vp(_dptr(dst)),
+                                                    vp(_dptr(dst_off)), vp(_dptr(src)), vp(_dptr(src_off)), stride),
+                 "h264chroma_batch_device")
+
+
+def emulated_edge_mc_batch_device(device, n, buf, buf_off, buf_linesize, src, origin, src_linesize, geom, w, h):
+    """geom: int32 [n, 4] = block_w, block_h, src_x, src_y; origin: int64 offset of each window's picture sample (0, 0)."""
+    return check(lib().b200_emulated_edge_mc_batch_device(device.handle, n, vp(_dptr(buf)), vp(_dptr(buf_off)), buf_linesize,
+                                                          vp(_dptr(src)), vp(_dptr(origin)), src_linesize, vp(_dptr(geom)), w, h),
+                 "emulated_edge_mc_batch_device")

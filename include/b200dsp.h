@@ -222,11 +222,44 @@ int  b200_hpeldsp_init(B200HpelDSPContext *c, int flags);
  * dst + dst_off[i] (same stride for both, like the reference's single stride argument).
  * qpel op byte: bit0 avg, bits1-2 size index (0:16,1:8,2:4), bits3-6 position x+4*y.
  * hpel op byte: bits0-1 table (0 put, 1 avg, 2 put_no_rnd, 3 avg_no_rnd), bits2-3 size index (0:16,1:8,2:4,3:2),
- * bits4-5 xy; h[i] = block height. Destination blocks of one call must not overlap each other. */
+ * bits4-5 xy; h[i] = block height. Destination blocks of one call must not overlap each other.
+ * The qpel kernel may load the whole (size+5)^2 window of an operation whatever its position (unused taps never reach the
+ * result): keep the planes edge-padded by 3 pixels / rows, as H.264 reference frames are (h264_mb.c mc_dir_part). */
 int  b200_h264qpel_batch_device(B200Device *dev, int64_t n, const uint8_t *op, uint8_t *dst, const int64_t *dst_off,
                                 const uint8_t *src, const int64_t *src_off, ptrdiff_t stride);
 int  b200_hpel_batch_device(B200Device *dev, int64_t n, const uint8_t *op, const uint8_t *h, uint8_t *dst,
                             const int64_t *dst_off, const uint8_t *src, const int64_t *src_off, ptrdiff_t stride);
+
+/* h264chroma: replaces H264ChromaContext (libavcodec/h264chroma.h:26-31) as filled by ff_h264chroma_init(c, 8)
+ * (libavcodec/h264chroma.c:36-65): h264_chroma_mc_func (h264chroma.h:24), bilinear eighth-pel, x, y in 0..7. */
+typedef void (*b200_h264_chroma_mc_func)(uint8_t *dst, const uint8_t *src, ptrdiff_t srcStride, int h, int x, int y);
+typedef struct B200H264ChromaContext {
+    b200_h264_chroma_mc_func put_h264_chroma_pixels_tab[4];   /* [0: 8 wide, 1: 4, 2: 2]; [3] is NULL like the reference's */
+    b200_h264_chroma_mc_func avg_h264_chroma_pixels_tab[4];
+} B200H264ChromaContext;
+int  b200_h264chroma_init(B200H264ChromaContext *c, int bit_depth);   /* bit_depth must be 8, else B200_ENOSYS */
+/* batched, DEVICE pointers.  op byte: bit0 avg, bits1-2 width index (0:8,1:4,2:2); h[i] = rows; xy[i] = x | y << 3.
+ * Like the reference, x == 0 never reads the column right of the block and y == 0 never reads the row below it. */
+int  b200_h264chroma_batch_device(B200Device *dev, int64_t n, const uint8_t *op, const uint8_t *h, const uint8_t *xy,
+                                  uint8_t *dst, const int64_t *dst_off, const uint8_t *src, const int64_t *src_off,
+                                  ptrdiff_t stride);
+
+/* videodsp: replaces VideoDSPContext (libavcodec/videodsp.h:32-69) as filled by ff_videodsp_init(ctx, 8)
+ * (libavcodec/videodsp.c:32-62): emulated_edge_mc copies a block_w x block_h window whose top-left sample is picture
+ * position (src_x, src_y) (src points AT that sample, inside or outside the picture) and replicates the border samples of
+ * the w x h picture for everything outside it (videodsp_template.c:24-101).  prefetch is the reference's empty function. */
+typedef struct B200VideoDSPContext {
+    void (*emulated_edge_mc)(uint8_t *dst, const uint8_t *src, ptrdiff_t dst_linesize, ptrdiff_t src_linesize,
+                             int block_w, int block_h, int src_x, int src_y, int w, int h);
+    void (*prefetch)(const uint8_t *buf, ptrdiff_t stride, int h);
+} B200VideoDSPContext;
+int  b200_videodsp_init(B200VideoDSPContext *c, int bpc);             /* bpc must be <= 8, else B200_ENOSYS */
+/* batched, DEVICE pointers: window i = geom[4i..4i+3] = {block_w, block_h, src_x, src_y} of the picture whose sample (0, 0)
+ * is src + origin[i] (so one call can span many frames of equal w x h and linesize), written to buf + buf_off[i].
+ * geom must be 16-byte aligned.  w == 0 or h == 0 writes nothing, like the reference. */
+int  b200_emulated_edge_mc_batch_device(B200Device *dev, int64_t n, uint8_t *buf, const int64_t *buf_off,
+                                        ptrdiff_t buf_linesize, const uint8_t *src, const int64_t *origin,
+                                        ptrdiff_t src_linesize, const int32_t *geom, int w, int h);
 
 /* ------------------------------------------------------------------------------------------------ libavutil/tx
  * Replaces av_tx_init / av_tx_uninit / av_tx_fn (libavutil/tx.h:151,202-208) for AV_TX_FLOAT_FFT and AV_TX_FLOAT_MDCT,

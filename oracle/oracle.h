@@ -68,6 +68,9 @@ void orc_esa_frame(const uint8_t *cur, const uint8_t *ref, int linesize, int wid
 /* ------------------------------------------------------------------ h264qpel / hpeldsp (8 bit) */
 void orc_h264qpel(int avg, int size_idx, int pos, uint8_t *dst, const uint8_t *src, ptrdiff_t stride);
 int  orc_hpel(int tab, int size_idx, int xy, uint8_t *block, const uint8_t *pixels, ptrdiff_t line_size, int h);
+void orc_emulated_edge_mc(uint8_t *buf, const uint8_t *src, ptrdiff_t buf_linesize, ptrdiff_t src_linesize,
+                          int block_w, int block_h, int src_x, int src_y, int w, int h);
+int  orc_h264chroma(int avg, int idx, uint8_t *dst, const uint8_t *src, ptrdiff_t stride, int h, int x, int y);
 
 /* ------------------------------------------------------------------ tx (float FFT / MDCT, power-of-two) */
 typedef struct OrcTx OrcTx;

@@ -14,6 +14,14 @@
  *                                                                    xy2: (a+b+c+d+2)>>2 (rnd) or +1 (no_rnd);
  *                                                                    avg tables: dst = (dst + value + 1) >> 1 (rnd_avg32, rnd_avg.h:31-39)
  *   hpel table layout ...... libavcodec/hpeldsp.c:337-352            put[4 sizes 16,8,4,2], avg[4], put_no_rnd[2: 16,8], avg_no_rnd[16 only]
+ *   h264chroma ............. libavcodec/h264chroma_template.c:27-176  bilinear eighth-pel: (A*p00 + B*p01 + C*p10 + D*p11 + 32) >> 6 with
+ *                                                                    A=(8-x)(8-y), B=x(8-y), C=(8-x)y, D=xy; the reference's D==0 / B+C==0
+ *                                                                    branches are the same value but skip the unused row / column reads;
+ *                                                                    table libavcodec/h264chroma.c:36-44: [0]=8 wide, [1]=4, [2]=2
+ *   emulated_edge_mc ....... libavcodec/videodsp_template.c:24-101   block_w x block_h window whose top-left sample is picture position
+ *                                                                    (src_x, src_y); samples outside the w x h picture replicate the
+ *                                                                    nearest border sample (the reference clamps the window so at least
+ *                                                                    one row and column is inside, then copies and smears the edges)
  */
 #include "oracle.h"
 
@@ -97,4 +105,39 @@ int orc_hpel(int tab, int size_idx, int xy, uint8_t *block, const uint8_t *pixel
         for (int x = 0; x < w; x++)
             block[y * ls + x] = avg ? (uint8_t)((block[y * ls + x] + out[y * 16 + x] + 1) >> 1) : out[y * 16 + x];
     return 0;
+}
+
+int orc_h264chroma(int avg, int idx, uint8_t *dst, const uint8_t *src, ptrdiff_t stride, int h, int x, int y)
+{
+    if (idx < 0 || idx > 2 || x < 0 || x > 7 || y < 0 || y > 7) return -1;
+    const int w = 8 >> idx;
+    const int A = (8 - x) * (8 - y), B = x * (8 - y), C = (8 - x) * y, D = x * y;
+    for (int i = 0; i < h; i++)
+        for (int j = 0; j < w; j++) {
+            const uint8_t *p = src + i * stride + j;
+            int v = A * p[0];
+            if (B) v += B * p[1];                 /* only touch the neighbours the reference touches */
+            if (C) v += C * p[stride];
+            if (D) v += D * p[stride + 1];
+            v = (v + 32) >> 6;
+            uint8_t *d = dst + i * stride + j;
+            *d = (uint8_t)(avg ? (*d + v + 1) >> 1 : v);
+        }
+    return 0;
+}
+
+void orc_emulated_edge_mc(uint8_t *buf, const uint8_t *src, ptrdiff_t buf_linesize, ptrdiff_t src_linesize,
+                          int block_w, int block_h, int src_x, int src_y, int w, int h)
+{
+    if (!w || !h) return;
+    const uint8_t *origin = src - (ptrdiff_t)src_y * src_linesize - src_x;       /* picture sample (0, 0) */
+    for (int y = 0; y < block_h; y++) {
+        int py = src_y + y;
+        py = py < 0 ? 0 : py > h - 1 ? h - 1 : py;
+        for (int x = 0; x < block_w; x++) {
+            int px = src_x + x;
+            px = px < 0 ? 0 : px > w - 1 ? w - 1 : px;
+            buf[y * buf_linesize + x] = origin[py * src_linesize + px];
+        }
+    }
 }

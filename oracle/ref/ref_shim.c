@@ -29,6 +29,8 @@
 #include "libavcodec/me_cmp.h"
 #include "libavcodec/h264qpel.h"
 #include "libavcodec/hpeldsp.h"
+#include "libavcodec/h264chroma.h"
+#include "libavcodec/videodsp.h"
 #include "libavfilter/motion_estimation.h"
 
 /* ---- link stubs: the new-API filter graph (sws_scale_frame) is not part of the legacy hot path ---- */
@@ -280,6 +282,25 @@ API int ffref_hpel(int tab, int size_idx, int xy, uint8_t *block, const uint8_t 
     if (!f) return -1;
     f(block, pixels, line_size, h);
     return 0;
+}
+
+/* avg: 0 put 1 avg; idx 0: 8 wide, 1: 4 wide, 2: 2 wide; x, y in 0..7 (eighth-pel) */
+API int ffref_h264chroma(int avg, int idx, uint8_t *dst, const uint8_t *src, ptrdiff_t stride, int h, int x, int y)
+{
+    static H264ChromaContext c; static int ok;
+    if (!ok) { ff_h264chroma_init(&c, 8); ok = 1; }
+    h264_chroma_mc_func f = (avg ? c.avg_h264_chroma_pixels_tab : c.put_h264_chroma_pixels_tab)[idx];
+    if (!f) return -1;
+    f(dst, src, stride, h, x, y);
+    return 0;
+}
+
+API void ffref_emulated_edge_mc(uint8_t *buf, const uint8_t *src, ptrdiff_t buf_linesize, ptrdiff_t src_linesize,
+                                int block_w, int block_h, int src_x, int src_y, int w, int h)
+{
+    static VideoDSPContext c; static int ok;
+    if (!ok) { ff_videodsp_init(&c, 8); ok = 1; }
+    c.emulated_edge_mc(buf, src, buf_linesize, src_linesize, block_w, block_h, src_x, src_y, w, h);
 }
 
 /* ------------------------------------------------------------------ tx ------------------------------------------ */

@@ -100,6 +100,40 @@ def gen_mecmp():
     np.savez_compressed(os.path.join(OUT, "mecmp.npz"), **d)
 
 
+def gen_chroma():
+    """h264chroma put/avg, all three widths, every (x, y) eighth-pel phase, h in {2,4,8,16} per width."""
+    R = cl.ref()
+    rng = np.random.default_rng(23)
+    src = rng.integers(0, 256, (40, 48), dtype=np.uint8)
+    dst0 = rng.integers(0, 256, (40, 48), dtype=np.uint8)
+    d = {"src": src, "dst0": dst0}
+    ps = C.cast(src.ctypes.data + 8 * 48 + 8, cl.u8p)
+    for avg in (0, 1):
+        for idx in (0, 1, 2):
+            for h in ((4, 8, 16), (2, 4, 8), (2, 4))[idx]:
+                outs = []
+                for xy in range(64):
+                    o = dst0.copy()
+                    assert R.ffref_h264chroma(avg, idx, C.cast(o.ctypes.data + 8 * 48 + 8, cl.u8p), ps, 48, h, xy & 7, xy >> 3) == 0
+                    assert np.array_equal(o[:8], dst0[:8]) and np.array_equal(o[8 + h:], dst0[8 + h:])
+                    outs.append(o[8:24, 8:16].copy())
+                d[f"c_{avg}_{idx}_{h}"] = np.stack(outs)
+    np.savez_compressed(os.path.join(OUT, "chroma.npz"), **d)
+
+
+def gen_edge():
+    from cases import EDGE_PIC, EDGE_CASES
+    R = cl.ref()
+    W, H, LS = EDGE_PIC
+    pic = np.random.default_rng(24).integers(0, 256, (H, LS), dtype=np.uint8)
+    d = {"pic": pic}
+    for i, (bw, bh, sx, sy) in enumerate(EDGE_CASES):
+        b = np.full((24, 32), 0x5A, np.uint8)
+        R.ffref_emulated_edge_mc(cl.ptr(b), pic.ctypes.data + sy * LS + sx, 32, LS, bw, bh, sx, sy, W, H)
+        d[f"e{i}"] = b
+    np.savez_compressed(os.path.join(OUT, "edge.npz"), **d)
+
+
 def gen_pel():
     R = cl.ref()
     rng = np.random.default_rng(22)
@@ -201,6 +235,8 @@ if __name__ == "__main__":
     gen_idct()
     gen_mecmp()
     gen_pel()
+    gen_chroma()
+    gen_edge()
     gen_tx()
     gen_vsynth1()
     gen_sws_slices()

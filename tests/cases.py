@@ -77,3 +77,12 @@ SWS_SLICE_CASES = [
     (37, 21, FATE, [(0, 10), (10, 20), (30, 18)]),                  # odd width: full-chroma writer
     (64, 96, FATE, [(0, 4), (4, 4), (8, 40)]),
 ]
+
+
+# emulated_edge_mc fixture: picture 37 x 29 (linesize 48); (block_w, block_h, src_x, src_y) — inside, each edge, each corner,
+# fully outside on every side (the reference's src_y >= h / <= -block_h / src_x >= w / <= -block_w clamps), 1-wide windows
+EDGE_PIC = (37, 29, 48)
+EDGE_CASES = [(9, 9, 5, 5), (21, 21, -3, 4), (21, 21, 30, 4), (21, 21, 8, -2), (21, 21, 8, 20), (21, 21, -5, -5), (21, 21, 25, 15),
+              (9, 9, -3, 25), (9, 9, 33, -4), (17, 9, -17, 3), (17, 9, -40, 3), (17, 9, 37, 3), (17, 9, 90, 3), (9, 17, 3, -17),
+              (9, 17, 3, -50), (9, 17, 3, 29), (9, 17, 3, 77), (23, 23, -60, -60), (23, 23, 60, 60), (1, 1, -1, -1), (1, 5, 36, 27),
+              (5, 1, 36, 28), (23, 23, -10, -10), (4, 4, 0, 0), (4, 4, 33, 25), (2, 13, 36, -6)]

@@ -49,6 +49,11 @@ def oracle():
         if hasattr(L, "orc_h264qpel"):
             L.orc_h264qpel.argtypes = [C.c_int, C.c_int, C.c_int, u8p, u8p, C.c_ssize_t]
             L.orc_hpel.argtypes = [C.c_int, C.c_int, C.c_int, u8p, u8p, C.c_ssize_t, C.c_int]
+        if hasattr(L, "orc_emulated_edge_mc"):
+            L.orc_emulated_edge_mc.argtypes = [u8p, C.c_void_p, C.c_ssize_t, C.c_ssize_t] + [C.c_int] * 6
+            L.orc_emulated_edge_mc.restype = None
+        if hasattr(L, "orc_h264chroma"):
+            L.orc_h264chroma.argtypes = [C.c_int, C.c_int, u8p, u8p, C.c_ssize_t, C.c_int, C.c_int, C.c_int]
         if hasattr(L, "orc_tx_open"):
             L.orc_tx_open.restype = C.c_void_p
             L.orc_tx_open.argtypes = [C.c_int, C.c_int, C.c_int, C.c_float, C.c_uint]
@@ -84,6 +89,11 @@ def ref():
         L.ffref_h264qpel.argtypes = [C.c_int, C.c_int, C.c_int, u8p, u8p, C.c_ssize_t]
         L.ffref_h264qpel_batch.argtypes = [C.c_int, u8p, u8p, i64p, u8p, i64p, C.c_ssize_t]
         L.ffref_hpel.argtypes = [C.c_int, C.c_int, C.c_int, u8p, u8p, C.c_ssize_t, C.c_int]
+        if hasattr(L, "ffref_emulated_edge_mc"):
+            L.ffref_emulated_edge_mc.argtypes = [u8p, C.c_void_p, C.c_ssize_t, C.c_ssize_t] + [C.c_int] * 6
+            L.ffref_emulated_edge_mc.restype = None
+        if hasattr(L, "ffref_h264chroma"):
+            L.ffref_h264chroma.argtypes = [C.c_int, C.c_int, u8p, u8p, C.c_ssize_t, C.c_int, C.c_int, C.c_int]
         L.ffref_tx_open.restype = C.c_void_p
         L.ffref_tx_open.argtypes = [C.c_int, C.c_int, C.c_int, C.c_float, C.c_uint]
         L.ffref_tx_close.argtypes = [C.c_void_p]

@@ -38,6 +38,21 @@ def run(dev):
         pel.h264qpel_batch_device(dev, 32, torch.from_numpy(ops).cuda(), d_dst, d_off, torch.from_numpy(src).cuda(), d_off, src.shape[1])
         dev.sync()
         assert np.array_equal(d_dst.cpu().numpy(), exp), "qpel mismatch"
+        # h264chroma: all 64 phases, put and avg, 8x8
+        ops = np.array([pel.chroma_op(a, 0) for a in (0, 1) for p in range(64)], np.uint8)
+        xys = np.array([p for a in (0, 1) for p in range(64)], np.uint8)
+        src, dst = src[:, :64 * 128 // 4], dst[:, :64 * 128 // 4]
+        src, dst = np.ascontiguousarray(np.tile(src, (1, 4))), np.ascontiguousarray(np.tile(dst, (1, 4)))
+        offs = np.array([16 * src.shape[1] + 24 + 64 * i for i in range(128)], np.int64)
+        exp = dst.copy()
+        for o, xy, off in zip(ops, xys, offs):
+            O.orc_h264chroma(int(o) & 1, 0, C.cast(exp.ctypes.data + int(off), cl.u8p), C.cast(src.ctypes.data + int(off), cl.u8p), src.shape[1], 8, int(xy) & 7, int(xy) >> 3)
+        d_dst = torch.from_numpy(dst).cuda()
+        d_off = torch.from_numpy(offs).cuda()
+        pel.h264chroma_batch_device(dev, 128, torch.from_numpy(ops).cuda(), torch.full((128,), 8, dtype=torch.uint8, device="cuda"),
+                                    torch.from_numpy(xys).cuda(), d_dst, d_off, torch.from_numpy(src).cuda(), d_off, src.shape[1])
+        dev.sync()
+        assert np.array_equal(d_dst.cpu().numpy(), exp), "h264chroma mismatch"
         # tx: FFT-1024 and iMDCT-1024, 4 transforms each
         n = 1024
         x = rng.random((4, 2 * n), dtype=np.float32)

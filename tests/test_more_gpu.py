@@ -206,6 +206,135 @@ def test_hpel_batch_vs_oracle(device):
     assert np.array_equal(got, exp), int((got != exp).sum())
 
 
+def test_h264chroma_pointer_table_golden(device):
+    """H264ChromaContext drop-in (host pointers): every phase / width / height of chroma.npz, guard pixels untouched."""
+    from ffmpeg_b200 import pel
+    from ffmpeg_b200._lib import u8p
+    g = np.load(os.path.join(G, "chroma.npz"))
+    c = pel.ff_h264chroma_init(8)
+    assert not c.put_h264_chroma_pixels_tab[3] and not c.avg_h264_chroma_pixels_tab[3]
+    src, dst0 = g["src"], g["dst0"]
+    ps = C.cast(src.ctypes.data + 8 * 48 + 8, u8p)
+    for key in g.files:
+        if key[0] != "c":
+            continue
+        avg, idx, h = (int(v) for v in key.split("_")[1:])
+        f = (c.avg_h264_chroma_pixels_tab if avg else c.put_h264_chroma_pixels_tab)[idx]
+        for xy in range(0, 64, 3 if h != 8 else 1):
+            o = dst0.copy()
+            f(C.cast(o.ctypes.data + 8 * 48 + 8, u8p), ps, 48, h, xy & 7, xy >> 3)
+            assert np.array_equal(o[8:24, 8:16], g[key][xy]), (key, xy)
+            assert np.array_equal(o[:8], dst0[:8]) and np.array_equal(o[8 + h:], dst0[8 + h:]) and np.array_equal(o[:, 16:], dst0[:, 16:]), key
+    with pytest.raises(Exception):
+        pel.ff_h264chroma_init(10)
+
+
+def test_h264chroma_batch_vs_oracle(device):
+    """Chroma half of a 4:2:0 macroblock stream: random eighth-pel phases, widths, heights, unaligned offsets."""
+    import torch
+    from ffmpeg_b200 import pel
+    O = cl.oracle()
+    rng = np.random.default_rng(14)
+    W, H = 336, 208
+    ref_ = rng.integers(0, 256, (H, W), dtype=np.uint8)
+    dst0 = rng.integers(0, 256, (H, W), dtype=np.uint8)
+    ops, hs, xys, doffs, soffs = [], [], [], [], []
+    for by in range(1, H // 16 - 1):
+        for bx in range(1, W // 16 - 1):
+            idx = int(rng.integers(0, 3))
+            ops.append(pel.chroma_op(int(rng.integers(0, 2)), idx))
+            hs.append(int(rng.choice(((4, 8, 16), (2, 4, 8), (2, 4))[idx])))
+            xys.append(int(rng.integers(0, 64)))
+            dx, dy, jx = int(rng.integers(-8, 9)), int(rng.integers(-8, 9)), int(rng.integers(0, 8))
+            doffs.append(by * 16 * W + bx * 16 + jx); soffs.append((by * 16 + dy) * W + bx * 16 + dx)
+    exp = dst0.copy()
+    for op, h, xy, do, so in zip(ops, hs, xys, doffs, soffs):
+        assert O.orc_h264chroma(op & 1, op >> 1, C.cast(exp.ctypes.data + do, cl.u8p), C.cast(ref_.ctypes.data + so, cl.u8p), W, h, xy & 7, xy >> 3) == 0
+    with on_stream(device):
+        t = lambda a, dt: torch.from_numpy(np.array(a, dt)).cuda()
+        d_dst, d_src = torch.from_numpy(dst0).cuda(), torch.from_numpy(ref_).cuda()
+        pel.h264chroma_batch_device(device, len(ops), t(ops, np.uint8), t(hs, np.uint8), t(xys, np.uint8), d_dst, t(doffs, np.int64),
+                                    d_src, t(soffs, np.int64), W)
+        device.sync()
+        got = d_dst.cpu().numpy()
+    assert np.array_equal(got, exp), int((got != exp).sum())
+
+
+def test_h264chroma_no_reads_past_block_when_phase_zero(device):
+    """x == 0 / y == 0 must not touch the column right of / the row below the block (h264chroma_template.c D == 0 branches):
+    blocks that end exactly at the end of the device allocation, checked under the allocation's own bounds."""
+    import torch
+    from ffmpeg_b200 import pel
+    O = cl.oracle()
+    rng = np.random.default_rng(15)
+    W = 64
+    for (x, y) in ((0, 0), (0, 5), (3, 0)):
+        rows = 8 + (1 if y else 0)
+        src = rng.integers(0, 256, rows * W, dtype=np.uint8)
+        if x == 0:
+            src = src[: (rows - 1) * W + 56 + 8]                   # block is the last 8 columns of the buffer: nothing after it
+        dst0 = rng.integers(0, 256, 8 * W, dtype=np.uint8)
+        so = 56 if x == 0 else 40
+        exp = dst0.copy()
+        pad = np.concatenate([src, np.zeros(2 * W, np.uint8)])
+        assert O.orc_h264chroma(0, 0, cl.ptr(exp), C.cast(pad.ctypes.data + so, cl.u8p), W, 8, x, y) == 0
+        with on_stream(device):
+            t = lambda a, dt: torch.from_numpy(np.array(a, dt)).cuda()
+            d_dst, d_src = torch.from_numpy(dst0).cuda(), torch.from_numpy(src).cuda()
+            pel.h264chroma_batch_device(device, 1, t([0], np.uint8), t([8], np.uint8), t([x | y << 3], np.uint8), d_dst, t([0], np.int64),
+                                        d_src, t([so], np.int64), W)
+            device.sync()
+            assert np.array_equal(d_dst.cpu().numpy(), exp), (x, y)
+
+
+def test_emulated_edge_mc_pointer_table_golden(device):
+    from cases import EDGE_PIC, EDGE_CASES
+    from ffmpeg_b200 import pel
+    g = np.load(os.path.join(G, "edge.npz"))
+    v = pel.ff_videodsp_init(8)
+    W, H, LS = EDGE_PIC
+    pic = g["pic"]
+    for i, (bw, bh, sx, sy) in enumerate(EDGE_CASES):
+        b = np.full((24, 32), 0x5A, np.uint8)
+        v.emulated_edge_mc(b.ctypes.data, pic.ctypes.data + sy * LS + sx, 32, LS, bw, bh, sx, sy, W, H)
+        assert np.array_equal(b, g[f"e{i}"]), (i, bw, bh, sx, sy)
+    b = np.full((24, 32), 0x5A, np.uint8)
+    v.emulated_edge_mc(b.ctypes.data, pic.ctypes.data, 32, LS, 8, 8, 0, 0, 0, H)
+    assert (b == 0x5A).all()
+    v.prefetch(pic.ctypes.data, LS, 4)
+    with pytest.raises(Exception):
+        pel.ff_videodsp_init(10)
+
+
+def test_emulated_edge_mc_batch_vs_oracle(device):
+    """Windows hanging over every border of several frames in one call (the mc_dir_part case: 21x21 luma, 9x9 chroma)."""
+    import torch
+    from ffmpeg_b200 import pel
+    O = cl.oracle()
+    rng = np.random.default_rng(16)
+    NF, W, H, LS = 3, 100, 60, 112
+    pics = rng.integers(0, 256, (NF, H, LS), dtype=np.uint8)
+    n = 600
+    geom = np.zeros((n, 4), np.int32)
+    geom[:, 0] = rng.choice([9, 21, 5, 16], n); geom[:, 1] = rng.choice([9, 21, 5, 16], n)
+    geom[:, 2] = rng.integers(-30, W + 10, n); geom[:, 3] = rng.integers(-30, H + 10, n)
+    fr = rng.integers(0, NF, n)
+    origin = (fr * H * LS).astype(np.int64)
+    BLS = 32
+    boff = (np.arange(n) * 24 * BLS).astype(np.int64)
+    exp = np.full((n * 24, BLS), 0x33, np.uint8)
+    for i in range(n):
+        bw, bh, sx, sy = (int(v) for v in geom[i])
+        O.orc_emulated_edge_mc(C.cast(exp.ctypes.data + int(boff[i]), cl.u8p), pics[fr[i]].ctypes.data + sy * LS + sx, BLS, LS, bw, bh, sx, sy, W, H)
+    with on_stream(device):
+        d_buf = torch.full((n * 24, BLS), 0x33, dtype=torch.uint8, device="cuda")
+        pel.emulated_edge_mc_batch_device(device, n, d_buf, torch.from_numpy(boff).cuda(), BLS, torch.from_numpy(pics).cuda(),
+                                          torch.from_numpy(origin).cuda(), LS, torch.from_numpy(geom).cuda(), W, H)
+        device.sync()
+        got = d_buf.cpu().numpy()
+    assert np.array_equal(got, exp), int((got != exp).sum())
+
+
 # ---------------------------------------------------------------------------------------------- tx
 def ulp_diff(a, b):
     ai, bi = a.view(np.int32).astype(np.int64), b.view(np.int32).astype(np.int64)

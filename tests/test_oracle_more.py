@@ -31,6 +31,81 @@ def test_mecmp_oracle_golden():
             assert np.array_equal(mv, g[f"esa_{name}_{mb}_{sp}_mv"]) and np.array_equal(cost, g[f"esa_{name}_{mb}_{sp}_cost"]), (name, mb, sp)
 
 
+def test_h264chroma_oracle_golden():
+    """All 64 eighth-pel phases x put/avg x widths 8/4/2 x heights against the reference's outputs (chroma.npz)."""
+    g = np.load(os.path.join(G, "chroma.npz"))
+    O = cl.oracle()
+    src, dst0 = g["src"], g["dst0"]
+    ps = C.cast(src.ctypes.data + 8 * 48 + 8, cl.u8p)
+    n = 0
+    for key in g.files:
+        if key[0] != "c":
+            continue
+        avg, idx, h = (int(v) for v in key.split("_")[1:])
+        for xy in range(64):
+            o = dst0.copy()
+            assert O.orc_h264chroma(avg, idx, C.cast(o.ctypes.data + 8 * 48 + 8, cl.u8p), ps, 48, h, xy & 7, xy >> 3) == 0
+            assert np.array_equal(o[8:24, 8:16], g[key][xy]), (key, xy)
+            assert np.array_equal(o[:8], dst0[:8]) and np.array_equal(o[8 + h:], dst0[8 + h:]) and np.array_equal(o[:, 16:], dst0[:, 16:]), key
+            n += 1
+    assert n == 2 * 8 * 64
+    assert O.orc_h264chroma(0, 3, cl.ptr(dst0.copy()), ps, 48, 8, 0, 0) < 0          # table entry [3] does not exist
+
+
+def test_h264chroma_oracle_vs_ref():
+    if not cl.have_ref():
+        import pytest
+        pytest.skip("oracle/_ref not built")
+    R, O = cl.ref(), cl.oracle()
+    rng = np.random.default_rng(5)
+    for it in range(400):
+        src = rng.integers(0, 256, (40, 48), dtype=np.uint8)
+        if it % 7 == 0:
+            src[:] = rng.choice([0, 255], src.shape)
+        d1 = rng.integers(0, 256, (40, 48), dtype=np.uint8)
+        d2 = d1.copy()
+        avg, idx, x, y = int(rng.integers(0, 2)), int(rng.integers(0, 3)), int(rng.integers(0, 8)), int(rng.integers(0, 8))
+        h = int(rng.choice([2, 4, 8, 16]))
+        ps = C.cast(src.ctypes.data + 8 * 48 + 8, cl.u8p)
+        assert R.ffref_h264chroma(avg, idx, C.cast(d1.ctypes.data + 8 * 48 + 8, cl.u8p), ps, 48, h, x, y) == 0
+        assert O.orc_h264chroma(avg, idx, C.cast(d2.ctypes.data + 8 * 48 + 8, cl.u8p), ps, 48, h, x, y) == 0
+        assert np.array_equal(d1, d2), (avg, idx, x, y, h)
+
+
+def test_emulated_edge_mc_oracle_golden():
+    from cases import EDGE_PIC, EDGE_CASES
+    g = np.load(os.path.join(G, "edge.npz"))
+    O = cl.oracle()
+    W, H, LS = EDGE_PIC
+    pic = g["pic"]
+    for i, (bw, bh, sx, sy) in enumerate(EDGE_CASES):
+        b = np.full((24, 32), 0x5A, np.uint8)
+        O.orc_emulated_edge_mc(cl.ptr(b), pic.ctypes.data + sy * LS + sx, 32, LS, bw, bh, sx, sy, W, H)
+        assert np.array_equal(b, g[f"e{i}"]), (i, bw, bh, sx, sy)
+    b = np.full((24, 32), 0x5A, np.uint8)
+    O.orc_emulated_edge_mc(cl.ptr(b), pic.ctypes.data, 32, LS, 8, 8, 0, 0, 0, H)       # w == 0: nothing written
+    assert (b == 0x5A).all()
+
+
+def test_emulated_edge_mc_oracle_vs_ref():
+    if not cl.have_ref():
+        import pytest
+        pytest.skip("oracle/_ref not built")
+    R, O = cl.ref(), cl.oracle()
+    rng = np.random.default_rng(6)
+    W, H, LS = 37, 29, 48
+    pic = rng.integers(0, 256, (H, LS), dtype=np.uint8)
+    for it in range(3000):
+        bw, bh = int(rng.integers(1, 24)), int(rng.integers(1, 24))
+        sx, sy = int(rng.integers(-40, W + 40)), int(rng.integers(-40, H + 40))
+        b1 = np.full((24, 32), 7, np.uint8)
+        b2 = b1.copy()
+        src = pic.ctypes.data + sy * LS + sx
+        R.ffref_emulated_edge_mc(cl.ptr(b1), src, 32, LS, bw, bh, sx, sy, W, H)
+        O.orc_emulated_edge_mc(cl.ptr(b2), src, 32, LS, bw, bh, sx, sy, W, H)
+        assert np.array_equal(b1, b2), (bw, bh, sx, sy)
+
+
 def test_pel_oracle_golden():
     g = np.load(os.path.join(G, "pel.npz"))
     O = cl.oracle()
