@@ -1,4 +1,4 @@
-// sws.cu — libswscale yuv420p -> rgb24 on sm_100a: kernels + the C ABI (include/b200dsp.h, "libswscale" section).
+// sws.cu — libswscale yuv420p -> packed 8-bit RGB (rgb24, bgr24, rgba, bgra, argb, abgr) on sm_100a: kernels + the C ABI (include/b200dsp.h, "libswscale" section).
 //
 // Reference semantics reproduced bit-for-bit (see oracle/sws_oracle.c for the CPU restatement used as checker):
 //   unscaled LUT converter  yuv2rgb_c_24_rgb          libswscale/yuv2rgb.c:137-236,530   -> sws_unscaled_kernel
@@ -36,6 +36,7 @@ struct SwsFrameArgs {
     uint8_t *dst; long long ds, dfs;
     int srcH, chrSrcH, dstW, dstH, chrDstW;
     int y0;                           // first output line of this launch (slice calls), 0 for whole frames
+    int bpp, ro, go, bo, ao;          // output pixel: bytes and channel byte positions (scalar writers; ao < 0: no alpha)
 };
 
 
@@ -68,6 +69,39 @@ __device__ __forceinline__ void pair_rgb_packed(int cy, const ChromaBase &cb, in
     m[1] = __vimin_s16x2_relu(__byte_perm(b0, r1, 0x7632), 0x00ff00ffu);
     m[2] = __vimin_s16x2_relu(__byte_perm(g1, b1, 0x7632), 0x00ff00ffu);
 }
+// 32-bit outputs: one pixel -> one word.  (r,g) and (b,255) are clamped as s16x2, then one PRMT orders the four bytes.
+template <int KIND>
+__device__ __forceinline__ void pair_rgb32(int cy, const ChromaBase &cb, int Y0, int Y1, unsigned *m)
+{
+    constexpr unsigned SEL = KIND == SWS_OUT_RGBA ? 0x6420 : KIND == SWS_OUT_BGRA ? 0x6024 : KIND == SWS_OUT_ARGB ? 0x4206 : 0x0246;
+    const int r0 = Y0 * cy + cb.r, g0 = Y0 * cy + cb.g, b0 = Y0 * cy + cb.b;
+    const int r1 = Y1 * cy + cb.r, g1 = Y1 * cy + cb.g, b1 = Y1 * cy + cb.b;
+    const unsigned p0 = __vimin_s16x2_relu(__byte_perm(r0, g0, 0x7632), 0x00ff00ffu), q0 = __vimin_s16x2_relu(__byte_perm(b0, 0xffu, 0x5432), 0x00ff00ffu);
+    const unsigned p1 = __vimin_s16x2_relu(__byte_perm(r1, g1, 0x7632), 0x00ff00ffu), q1 = __vimin_s16x2_relu(__byte_perm(b1, 0xffu, 0x5432), 0x00ff00ffu);
+    m[0] = __byte_perm(p0, q0, SEL);
+    m[1] = __byte_perm(p1, q1, SEL);
+}
+// words one pixel pair occupies in the per-thread staging array
+template <int KIND> struct OutWords { static constexpr int per_pair = KIND <= SWS_OUT_BGR24 ? 3 : 2, bpp = KIND <= SWS_OUT_BGR24 ? 3 : 4; };
+template <int KIND>
+__device__ __forceinline__ void pair_out(int cy, ChromaBase cb, int Y0, int Y1, unsigned *m)
+{
+    if (KIND == SWS_OUT_RGB24) pair_rgb_packed(cy, cb, Y0, Y1, m);
+    else if (KIND == SWS_OUT_BGR24) { const int t = cb.r; cb.r = cb.b; cb.b = t; pair_rgb_packed(cy, cb, Y0, Y1, m); }
+    else pair_rgb32<KIND>(cy, cb, Y0, Y1, m);
+}
+__device__ __forceinline__ void store_packed48(uint8_t *dst, const unsigned *m);
+// 16 px of one line: 48 bytes (three 128-bit stores) or 64 bytes (four)
+template <int KIND>
+__device__ __forceinline__ void store_out(uint8_t *dst, const unsigned *m)
+{
+    if (KIND <= SWS_OUT_BGR24) store_packed48(dst, m);
+    else {
+        uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+#pragma unroll
+        for (int k = 0; k < 4; k++) d4[k] = make_uint4(m[4 * k], m[4 * k + 1], m[4 * k + 2], m[4 * k + 3]);
+    }
+}
 // 16 px = 8 pairs = 24 packed words -> 12 output words (48 bytes), stored as three 128-bit words
 __device__ __forceinline__ void store_packed48(uint8_t *dst, const unsigned *m)
 {
@@ -85,22 +119,27 @@ __device__ __forceinline__ void store_packed48(uint8_t *dst, const unsigned *m)
 __device__ __forceinline__ int byte_of(unsigned w, int k) { return (int)__byte_perm(w, 0, 0x4440 | k); }
 
 // scalar writer used by the slow (edge / unaligned / int16-source) kernels
-__device__ __forceinline__ void put_pair_bytes(uint8_t *d, const SwsColorConst &c, const ChromaBase &cb, int Y0, int Y1, bool second)
+__device__ __forceinline__ void put_pair_bytes(uint8_t *d, const SwsFrameArgs &a, const SwsColorConst &c, const ChromaBase &cb, int Y0, int Y1, bool second)
 {
     const int t0 = Y0 * c.cy;
-    d[0] = (uint8_t)clamp_u8((cb.r + t0) >> 16); d[1] = (uint8_t)clamp_u8((cb.g + t0) >> 16); d[2] = (uint8_t)clamp_u8((cb.b + t0) >> 16);
+    d[a.ro] = (uint8_t)clamp_u8((cb.r + t0) >> 16); d[a.go] = (uint8_t)clamp_u8((cb.g + t0) >> 16); d[a.bo] = (uint8_t)clamp_u8((cb.b + t0) >> 16);
+    if (a.ao >= 0) d[a.ao] = 255;
     if (second) {
         const int t1 = Y1 * c.cy;
-        d[3] = (uint8_t)clamp_u8((cb.r + t1) >> 16); d[4] = (uint8_t)clamp_u8((cb.g + t1) >> 16); d[5] = (uint8_t)clamp_u8((cb.b + t1) >> 16);
+        d += a.bpp;
+        d[a.ro] = (uint8_t)clamp_u8((cb.r + t1) >> 16); d[a.go] = (uint8_t)clamp_u8((cb.g + t1) >> 16); d[a.bo] = (uint8_t)clamp_u8((cb.b + t1) >> 16);
+        if (a.ao >= 0) d[a.ao] = 255;
     }
 }
 
 // ------------------------------------------------------------------------------------------------ kernel: unscaled LUT path (fast)
 // yuv2rgb_c_24_rgb: chroma sample (x>>1, y>>1), no interpolation.  One thread = 16 px x 2 lines (one chroma line):
 // 2 x LDG.128 luma + 2 x LDG.64 chroma in, 6 x STG.128 out.  Grid: x over 16-px groups, y over line pairs, z over frames.
+template <int KIND>
 __global__ void __launch_bounds__(128)
 sws_unscaled_kernel(SwsFrameArgs a, SwsColorConst c, int ngroups)
 {
+    constexpr int PW = OutWords<KIND>::per_pair;
     const int xg = blockIdx.x * blockDim.x + threadIdx.x;
     if (xg >= ngroups) return;
     const int row = blockIdx.y * 2 + a.y0;
@@ -112,17 +151,17 @@ sws_unscaled_kernel(SwsFrameArgs a, SwsColorConst c, int ngroups)
     const uint4 y1 = __ldg(reinterpret_cast<const uint4 *>(py + a.ys));
     const unsigned uw[2] = { u.x, u.y }, vw[2] = { v.x, v.y };
     const unsigned y0w[4] = { y0.x, y0.y, y0.z, y0.w }, y1w[4] = { y1.x, y1.y, y1.z, y1.w };
-    unsigned m0[24], m1[24];
+    unsigned m0[8 * PW], m1[8 * PW];
 #pragma unroll
     for (int i = 0; i < 8; i++) {
         const ChromaBase cb = chroma_base(c, byte_of(uw[i >> 2], i & 3), byte_of(vw[i >> 2], i & 3));
         const int w = i >> 1, k = (i & 1) * 2;
-        pair_rgb_packed(c.cy, cb, byte_of(y0w[w], k), byte_of(y0w[w], k + 1), m0 + 3 * i);
-        pair_rgb_packed(c.cy, cb, byte_of(y1w[w], k), byte_of(y1w[w], k + 1), m1 + 3 * i);
+        pair_out<KIND>(c.cy, cb, byte_of(y0w[w], k), byte_of(y0w[w], k + 1), m0 + PW * i);
+        pair_out<KIND>(c.cy, cb, byte_of(y1w[w], k), byte_of(y1w[w], k + 1), m1 + PW * i);
     }
-    uint8_t *d0 = a.dst + f * a.dfs + (long long)row * a.ds + (long long)xg * 48;
-    store_packed48(d0, m0);
-    store_packed48(d0 + a.ds, m1);
+    uint8_t *d0 = a.dst + f * a.dfs + (long long)row * a.ds + (long long)xg * (16 * OutWords<KIND>::bpp);
+    store_out<KIND>(d0, m0);
+    store_out<KIND>(d0 + a.ds, m1);
 }
 
 // slow variant: one thread = one pixel pair x 2 lines, any alignment; covers pairs [p0, p1)
@@ -136,9 +175,9 @@ sws_unscaled_slow_kernel(SwsFrameArgs a, SwsColorConst c, int p0, int p1)
     const uint8_t *py = a.y + f * a.yfs + (long long)row * a.ys + 2 * p;
     const int U = a.u[f * a.ufs + (long long)(row >> 1) * a.us + p], V = a.v[f * a.vfs + (long long)(row >> 1) * a.vs + p];
     const ChromaBase cb = chroma_base(c, U, V);
-    uint8_t *d = a.dst + f * a.dfs + (long long)row * a.ds + (long long)p * 6;
-    put_pair_bytes(d, c, cb, py[0], py[1], true);
-    put_pair_bytes(d + a.ds, c, cb, py[a.ys], py[a.ys + 1], true);
+    uint8_t *d = a.dst + f * a.dfs + (long long)row * a.ds + (long long)p * (2 * a.bpp);
+    put_pair_bytes(d, a, c, cb, py[0], py[1], true);
+    put_pair_bytes(d + a.ds, a, c, cb, py[a.ys], py[a.ys + 1], true);
 }
 
 // ------------------------------------------------------------------------------------------------ kernel: horizontal FIR
@@ -178,10 +217,11 @@ __device__ __forceinline__ void fold2(int k2, const uint2 &r0, const uint2 &r1, 
 
 // CFS4: the chroma bank has exactly 4 taps (bicubic 2x vertical chroma up-sampling, the BASELINE case): fully unrolled.
 // Line offsets are 32-bit (the host guarantees |stride| * lines < 2^31); coefficient pairs come pre-packed (t.vChr2/vLum2).
-template <bool LUMID, bool CFS4>
-__global__ void __launch_bounds__(128, 12)
+template <bool LUMID, bool CFS4, int KIND>
+__global__ void __launch_bounds__(128, LUMID ? (KIND <= SWS_OUT_BGR24 ? 12 : 10) : 8)
 sws_vscale_rgb24_fast_kernel(SwsFrameArgs a, SwsDevTables t, SwsColorConst c, int ngroups)
 {
+    constexpr int PW = OutWords<KIND>::per_pair;
     const int xg = blockIdx.x * blockDim.x + threadIdx.x;
     if (xg >= ngroups) return;
     const int dy = blockIdx.y + a.y0;
@@ -238,13 +278,13 @@ sws_vscale_rgb24_fast_kernel(SwsFrameArgs a, SwsDevTables t, SwsColorConst c, in
         for (int i = 0; i < 16; i++) Y[i] >>= 12;
     }
 
-    unsigned m[24];
+    unsigned m[8 * PW];
 #pragma unroll
     for (int i = 0; i < 8; i++) {
         const ChromaBase cb = chroma_base(c, aU[i] >> 12, aV[i] >> 12);
-        pair_rgb_packed(c.cy, cb, Y[2 * i], Y[2 * i + 1], m + 3 * i);
+        pair_out<KIND>(c.cy, cb, Y[2 * i], Y[2 * i + 1], m + PW * i);
     }
-    store_packed48(a.dst + f * a.dfs + (long long)dy * (int)a.ds + xg * 48, m);
+    store_out<KIND>(a.dst + f * a.dfs + (long long)dy * (int)a.ds + xg * (16 * OutWords<KIND>::bpp), m);
 }
 
 // ------------------------------------------------------------------------------------------------ kernel: vertical FIR + rgb24 (slow, general)
@@ -304,7 +344,7 @@ sws_vscale_rgb24_slow_kernel(SwsFrameArgs a, SwsDevTables t, SwsColorConst c, in
         Y0 = (int)s0 >> 19; Y1 = (int)s1 >> 19; U = (int)su >> 19; V = (int)sv >> 19;
     }
     const ChromaBase cb = chroma_base(c, U, V);
-    put_pair_bytes(a.dst + f * a.dfs + (long long)dy * a.ds + (long long)p * 6, c, cb, Y0, Y1, second);
+    put_pair_bytes(a.dst + f * a.dfs + (long long)dy * a.ds + (long long)p * (2 * a.bpp), a, c, cb, Y0, Y1, second);
 }
 
 // ------------------------------------------------------------------------------------------------ kernel: full-chroma writer
@@ -361,8 +401,9 @@ sws_vscale_rgb24_full_kernel(SwsFrameArgs a, SwsDevTables t, SwsColorConst c)
         G = (G & 0xC0000000) ? ((~G) >> 31 & 0x3FFFFFFF) : G;
         B = (B & 0xC0000000) ? ((~B) >> 31 & 0x3FFFFFFF) : B;
     }
-    uint8_t *d = a.dst + f * a.dfs + (long long)dy * a.ds + (long long)x * 3;
-    d[0] = (uint8_t)(R >> 22); d[1] = (uint8_t)(G >> 22); d[2] = (uint8_t)(B >> 22);
+    uint8_t *d = a.dst + f * a.dfs + (long long)dy * a.ds + (long long)x * a.bpp;
+    d[a.ro] = (uint8_t)(R >> 22); d[a.go] = (uint8_t)(G >> 22); d[a.bo] = (uint8_t)(B >> 22);
+    if (a.ao >= 0) d[a.ao] = 255;
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -452,13 +493,15 @@ B200_API B200SwsContext *b200_sws_getContext(B200Device *dev, int srcW, int srcH
                                              int dstW, int dstH, int dstFormat, int flags)
 {
     if (!dev) { b200_set_error("b200_sws_getContext: no device"); return nullptr; }
-    if (srcFormat != B200_PIX_FMT_YUV420P || dstFormat != B200_PIX_FMT_RGB24) {
-        b200_set_error("b200_sws_getContext: only yuv420p -> rgb24 is implemented");
+    SwsOutFmt out;
+    if (srcFormat != B200_PIX_FMT_YUV420P || !sws_out_format(dstFormat, out)) {
+        b200_set_error("b200_sws_getContext: only yuv420p -> rgb24 / bgr24 / rgba / bgra / argb / abgr is implemented");
         return nullptr;
     }
     B200SwsContext *c = new (std::nothrow) B200SwsContext();
     if (!c) return nullptr;
     c->dev = dev;
+    c->plan.out = out;
     int ret = sws_plan_build(c->plan, srcW, srcH, dstW, dstH, flags);
     if (ret < 0) { b200_set_error("b200_sws_getContext: unsupported configuration (%d)", ret); delete c; return nullptr; }
     cudaSetDevice(dev->ordinal);
@@ -534,6 +577,16 @@ static bool aligned8(const void *p, long long stride, long long fstride)
     return (((uintptr_t)p) & 7) == 0 && (stride & 7) == 0 && (fstride & 7) == 0;
 }
 
+template <int KIND>
+static void launch_vscale_fast(bool lumid, bool c4, dim3 grid, dim3 block, cudaStream_t stream, const SwsFrameArgs &b,
+                               const SwsDevTables &dt, const SwsColorConst &col, int ngroups)
+{
+    if (lumid && c4)  sws_vscale_rgb24_fast_kernel<true, true, KIND><<<grid, block, 0, stream>>>(b, dt, col, ngroups);
+    else if (lumid)   sws_vscale_rgb24_fast_kernel<true, false, KIND><<<grid, block, 0, stream>>>(b, dt, col, ngroups);
+    else if (c4)      sws_vscale_rgb24_fast_kernel<false, true, KIND><<<grid, block, 0, stream>>>(b, dt, col, ngroups);
+    else              sws_vscale_rgb24_fast_kernel<false, false, KIND><<<grid, block, 0, stream>>>(b, dt, col, ngroups);
+}
+
 // enqueue the conversion of nframes frames on `stream`
 // Which lines a launch covers.  Whole frames: everything.  Slice calls: the output lines that became computable and the
 // source lines that were just uploaded (only those need the horizontal pass).
@@ -555,6 +608,7 @@ static int launch_batch(B200SwsContext *c, cudaStream_t stream, const uint8_t *c
     a.dst = dst; a.ds = ds; a.dfs = dfs;
     a.srcH = p.srcH; a.chrSrcH = p.chrSrcH; a.dstW = p.dstW; a.dstH = p.dstH; a.chrDstW = p.chrDstW;
     a.y0 = R.dy0;
+    a.bpp = p.out.bpp; a.ro = p.out.ro; a.go = p.out.go; a.bo = p.out.bo; a.ao = p.out.ao;
     const int vecSrc = aligned16(src[0], sstr[0], sfs[0]) && aligned8(src[1], sstr[1], sfs[1]) && aligned8(src[2], sstr[2], sfs[2]);
     const int vecOK = vecSrc && aligned16(dst, ds, dfs);
     for (int f0 = 0; f0 < nframes; f0 += 65535) {            // gridDim.z limit
@@ -567,7 +621,14 @@ static int launch_batch(B200SwsContext *c, cudaStream_t stream, const uint8_t *c
             const int ngroups = vecOK ? wpix / 16 : 0;
             if (ngroups) {
                 dim3 block(128), grid(b200_ceil_div(ngroups, 128), R.ndy / 2, nf);
-                sws_unscaled_kernel<<<grid, block, 0, stream>>>(b, p.color, ngroups);
+                switch (p.out.kind) {
+                case SWS_OUT_RGB24: sws_unscaled_kernel<SWS_OUT_RGB24><<<grid, block, 0, stream>>>(b, p.color, ngroups); break;
+                case SWS_OUT_BGR24: sws_unscaled_kernel<SWS_OUT_BGR24><<<grid, block, 0, stream>>>(b, p.color, ngroups); break;
+                case SWS_OUT_RGBA:  sws_unscaled_kernel<SWS_OUT_RGBA><<<grid, block, 0, stream>>>(b, p.color, ngroups); break;
+                case SWS_OUT_BGRA:  sws_unscaled_kernel<SWS_OUT_BGRA><<<grid, block, 0, stream>>>(b, p.color, ngroups); break;
+                case SWS_OUT_ARGB:  sws_unscaled_kernel<SWS_OUT_ARGB><<<grid, block, 0, stream>>>(b, p.color, ngroups); break;
+                default:            sws_unscaled_kernel<SWS_OUT_ABGR><<<grid, block, 0, stream>>>(b, p.color, ngroups); break;
+                }
                 B200_LAUNCHED();
             }
             const int p0 = ngroups * 8, p1 = wpix / 2;
@@ -583,10 +644,14 @@ static int launch_batch(B200SwsContext *c, cudaStream_t stream, const uint8_t *c
             if (ngroups) {
                 dim3 block(128), grid(b200_ceil_div(ngroups, 128), R.ndy, nf);
                 const bool c4 = p.vChr.size == 4;
-                if (c->lum_identity && c4)  sws_vscale_rgb24_fast_kernel<true, true><<<grid, block, 0, stream>>>(b, c->dt, p.color, ngroups);
-                else if (c->lum_identity)   sws_vscale_rgb24_fast_kernel<true, false><<<grid, block, 0, stream>>>(b, c->dt, p.color, ngroups);
-                else if (c4)                sws_vscale_rgb24_fast_kernel<false, true><<<grid, block, 0, stream>>>(b, c->dt, p.color, ngroups);
-                else                        sws_vscale_rgb24_fast_kernel<false, false><<<grid, block, 0, stream>>>(b, c->dt, p.color, ngroups);
+                switch (p.out.kind) {
+                case SWS_OUT_RGB24: launch_vscale_fast<SWS_OUT_RGB24>(c->lum_identity, c4, grid, block, stream, b, c->dt, p.color, ngroups); break;
+                case SWS_OUT_BGR24: launch_vscale_fast<SWS_OUT_BGR24>(c->lum_identity, c4, grid, block, stream, b, c->dt, p.color, ngroups); break;
+                case SWS_OUT_RGBA:  launch_vscale_fast<SWS_OUT_RGBA>(c->lum_identity, c4, grid, block, stream, b, c->dt, p.color, ngroups); break;
+                case SWS_OUT_BGRA:  launch_vscale_fast<SWS_OUT_BGRA>(c->lum_identity, c4, grid, block, stream, b, c->dt, p.color, ngroups); break;
+                case SWS_OUT_ARGB:  launch_vscale_fast<SWS_OUT_ARGB>(c->lum_identity, c4, grid, block, stream, b, c->dt, p.color, ngroups); break;
+                default:            launch_vscale_fast<SWS_OUT_ABGR>(c->lum_identity, c4, grid, block, stream, b, c->dt, p.color, ngroups); break;
+                }
                 B200_LAUNCHED();
             }
             const int p0 = ngroups * 8, p1 = (p.dstW + 1) / 2;
@@ -662,7 +727,7 @@ static PackedLayout packed_layout(const SwsPlan &p)
     PackedLayout L;
     L.yPitch = ((size_t)p.srcW + 255) & ~(size_t)255;
     L.cPitch = ((size_t)p.chrSrcW + 255) & ~(size_t)255;
-    L.dPitch = ((size_t)p.dstW * 3 + 255) & ~(size_t)255;
+    L.dPitch = ((size_t)p.dstW * p.out.bpp + 255) & ~(size_t)255;
     L.yOff = 0; L.uOff = L.yPitch * p.srcH; L.vOff = L.uOff + L.cPitch * p.chrSrcH;
     L.srcBytes = L.vOff + L.cPitch * p.chrSrcH;
     L.dstBytes = L.dPitch * p.dstH;
@@ -713,7 +778,7 @@ B200_API int b200_sws_scale_batch_host(B200SwsContext *c, const uint8_t *const s
         if (ret < 0) return ret;
         for (int f = 0; f < nf; f++)
             B200_CUDA_OK(cudaMemcpy2DAsync(dst + (int64_t)(f0 + f) * dstFrameStride, (size_t)dstStride,
-                                           dbase + (size_t)f * L.dstBytes, L.dPitch, (size_t)p.dstW * 3, p.dstH,
+                                           dbase + (size_t)f * L.dstBytes, L.dPitch, (size_t)p.dstW * p.out.bpp, p.dstH,
                                            cudaMemcpyDeviceToHost, st));
     }
     for (int i = 0; i < K; i++) B200_CUDA_OK(cudaStreamSynchronize(d->pipe[i]));
@@ -775,7 +840,7 @@ static int sws_scale_slice(B200SwsContext *c, const uint8_t *const srcSlice[], c
     if (ret < 0) return ret;
     if (y1 > y0)
         B200_CUDA_OK(cudaMemcpy2DAsync(dst[0] + (long long)y0 * dstStride[0], (size_t)dstStride[0], db + (size_t)y0 * L.dPitch, L.dPitch,
-                                       (size_t)p.dstW * 3, y1 - y0, cudaMemcpyDeviceToHost, st));
+                                       (size_t)p.dstW * p.out.bpp, y1 - y0, cudaMemcpyDeviceToHost, st));
     B200_CUDA_OK(cudaStreamSynchronize(st));
     if (srcSliceY + srcSliceH == p.srcH) c->slice_open = false;
     return p.unscaled_lut ? srcSliceH : y1 - y0;
@@ -816,9 +881,9 @@ B200_API int b200_sws_scale(B200SwsContext *c, const uint8_t *const srcSlice[], 
     if (dsl < 0) {
         // flip while copying back: row r of the device picture goes to dst[0] + r*dsl
         for (int r = 0; r < p.dstH; r++)
-            B200_CUDA_OK(cudaMemcpyAsync(dst[0] + (long long)r * dsl, dd + (size_t)r * L.dPitch, (size_t)p.dstW * 3, cudaMemcpyDeviceToHost, st));
+            B200_CUDA_OK(cudaMemcpyAsync(dst[0] + (long long)r * dsl, dd + (size_t)r * L.dPitch, (size_t)p.dstW * p.out.bpp, cudaMemcpyDeviceToHost, st));
     } else {
-        B200_CUDA_OK(cudaMemcpy2DAsync(dst[0], (size_t)dabs, dd, L.dPitch, (size_t)p.dstW * 3, p.dstH, cudaMemcpyDeviceToHost, st));
+        B200_CUDA_OK(cudaMemcpy2DAsync(dst[0], (size_t)dabs, dd, L.dPitch, (size_t)p.dstW * p.out.bpp, p.dstH, cudaMemcpyDeviceToHost, st));
     }
     B200_CUDA_OK(cudaStreamSynchronize(st));
     return p.dstH;

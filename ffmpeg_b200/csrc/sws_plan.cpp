@@ -256,6 +256,19 @@ int sws_plan_colorspace(SwsPlan &p, const int inv_table[4], int fullRange, int b
     return 0;
 }
 
+bool sws_out_format(int f, SwsOutFmt &o)
+{
+    switch (f) {
+    case B200_PIX_FMT_RGB24: o = { SWS_OUT_RGB24, 3, 0, 1, 2, -1 }; return true;
+    case B200_PIX_FMT_BGR24: o = { SWS_OUT_BGR24, 3, 2, 1, 0, -1 }; return true;
+    case B200_PIX_FMT_RGBA:  o = { SWS_OUT_RGBA,  4, 0, 1, 2, 3 };  return true;
+    case B200_PIX_FMT_BGRA:  o = { SWS_OUT_BGRA,  4, 2, 1, 0, 3 };  return true;
+    case B200_PIX_FMT_ARGB:  o = { SWS_OUT_ARGB,  4, 1, 2, 3, 0 };  return true;
+    case B200_PIX_FMT_ABGR:  o = { SWS_OUT_ABGR,  4, 3, 2, 1, 0 };  return true;
+    }
+    return false;
+}
+
 int sws_plan_build(SwsPlan &p, int srcW, int srcH, int dstW, int dstH, int flags)
 {
     if (srcW < 1 || srcH < 1 || dstW < 1 || dstH < 1) return B200_EINVAL;

@@ -1,4 +1,4 @@
-// sws_plan.h — host-side plan of one yuv420p -> rgb24 conversion (what SwsInternal holds after sws_init_context)
+// sws_plan.h — host-side plan of one yuv420p -> packed 8-bit RGB conversion (what SwsInternal holds after sws_init_context)
 #pragma once
 #include <vector>
 #include <cstdint>
@@ -22,8 +22,15 @@ struct SwsColorConst {
     int y_offset, y_coeff, v2r, v2g, u2g, u2b;
 };
 
+// Packed 8-bit RGB outputs: bytes per pixel and the byte position of each channel (ao < 0: no alpha byte).
+// 32-bit formats carry alpha = 255 (yuv2rgb.c:947-960 adds 255 << abase to the ramp; output.c:2066-2095 stores 255).
+enum SwsOutKind { SWS_OUT_RGB24, SWS_OUT_BGR24, SWS_OUT_RGBA, SWS_OUT_BGRA, SWS_OUT_ARGB, SWS_OUT_ABGR };
+struct SwsOutFmt { int kind, bpp, ro, go, bo, ao; };
+bool sws_out_format(int av_pix_fmt, SwsOutFmt &o);
+
 struct SwsPlan {
     int srcW = 0, srcH = 0, dstW = 0, dstH = 0, flags = 0;
+    SwsOutFmt out{ SWS_OUT_RGB24, 3, 0, 1, 2, -1 };
     int chrSrcW = 0, chrSrcH = 0, chrDstW = 0, chrDstH = 0;
     int chrDstHSub = 1;
     bool unscaled_lut = false;    // reference installs yuv2rgb_c_24_rgb as convert_unscaled

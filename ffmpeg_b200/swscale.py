@@ -1,4 +1,4 @@
-"""Host-side mirror of the libswscale interface for the accelerated path (yuv420p -> rgb24).
+"""Host-side mirror of the libswscale interface for the accelerated path (yuv420p -> rgb24 / bgr24 / rgba / bgra / argb / abgr).
 
 Names and argument meaning follow libswscale/swscale.h: sws_getContext (:utils.c:1919), sws_setColorspaceDetails
 (utils.c:849), sws_scale (swscale.c:1626), sws_freeContext.  Arrays are numpy (host) for sws_scale / scale_batch_host
@@ -8,7 +8,8 @@ import ctypes as C
 import numpy as np
 from ._lib import lib, check, vp, i16p, i32p, i64p, B200Error
 
-AV_PIX_FMT_YUV420P, AV_PIX_FMT_RGB24 = 0, 2
+AV_PIX_FMT_YUV420P, AV_PIX_FMT_RGB24, AV_PIX_FMT_BGR24 = 0, 2, 3                       # libavutil/pixfmt.h
+AV_PIX_FMT_ARGB, AV_PIX_FMT_RGBA, AV_PIX_FMT_ABGR, AV_PIX_FMT_BGRA = 25, 26, 27, 28
 SWS_FAST_BILINEAR, SWS_BILINEAR, SWS_BICUBIC, SWS_POINT, SWS_AREA, SWS_BICUBLIN = 1, 2, 4, 0x10, 0x20, 0x40
 SWS_FULL_CHR_H_INT, SWS_ACCURATE_RND, SWS_BITEXACT = 0x2000, 0x40000, 0x80000
 # libswscale/yuv2rgb.c:47-59 (sws_getCoefficients)
@@ -29,6 +30,8 @@ class SwsContext:
     def __init__(self, device, srcW, srcH, srcFormat, dstW, dstH, dstFormat, flags):
         self.device = device
         self.srcW, self.srcH, self.dstW, self.dstH, self.flags = srcW, srcH, dstW, dstH, flags
+        self.dstFormat = dstFormat
+        self.bpp = 3 if dstFormat in (AV_PIX_FMT_RGB24, AV_PIX_FMT_BGR24) else 4
         h = lib().b200_sws_getContext(device.handle, srcW, srcH, srcFormat, dstW, dstH, dstFormat, flags)
         if not h:
             raise B200Error("sws_getContext failed: " + lib().b200_last_error().decode())
@@ -65,8 +68,8 @@ class SwsContext:
         return check(lib().b200_sws_scale(self._h, sp, ss, srcSliceY, srcSliceH, dp, dsr), "sws_scale")
 
     def convert(self, y, u, v, dst_pad=0):
-        """Convenience: whole frame from 2-D uint8 arrays, returns (dstH, dstW*3+pad) array."""
-        ds = self.dstW * 3 + dst_pad
+        """Convenience: whole frame from 2-D uint8 arrays, returns (dstH, dstW*bpp+pad) array."""
+        ds = self.dstW * self.bpp + dst_pad
         out = np.full((self.dstH, ds), 0xA5, np.uint8)
         n = self.scale([y, u, v], [y.strides[0], u.strides[0], v.strides[0]], 0, self.srcH, [out], [ds])
         assert n == self.dstH

@@ -69,6 +69,11 @@ uint64_t b200_launch_count(void);
  * C path (the one FATE pins with accurate_rnd+bitexact, and yuv2rgb_c_24_rgb without accurate_rnd).  */
 #define B200_PIX_FMT_YUV420P 0     /* AV_PIX_FMT_YUV420P, libavutil/pixfmt.h */
 #define B200_PIX_FMT_RGB24   2     /* AV_PIX_FMT_RGB24 */
+#define B200_PIX_FMT_BGR24   3     /* AV_PIX_FMT_BGR24 */
+#define B200_PIX_FMT_ARGB    25    /* AV_PIX_FMT_ARGB  (alpha byte = 255, the source has no alpha plane) */
+#define B200_PIX_FMT_RGBA    26    /* AV_PIX_FMT_RGBA  */
+#define B200_PIX_FMT_ABGR    27    /* AV_PIX_FMT_ABGR  */
+#define B200_PIX_FMT_BGRA    28    /* AV_PIX_FMT_BGRA  */
 
 #define B200_SWS_FAST_BILINEAR 0x1
 #define B200_SWS_BILINEAR      0x2

@@ -29,7 +29,8 @@ struct OrcSws {
     int srcW, srcH, dstW, dstH, flags;
     int chrSrcW, chrSrcH, chrDstW, chrDstH;
     int chrDstHSub;            /* 1: one chroma sample per two output pixels, 0: full chroma */
-    int unscaled_lut;          /* 1: reference would install yuv2rgb_c_24_rgb as convert_unscaled */
+    int unscaled_lut;          /* 1: reference would install yuv2rgb_c_24_rgb / _24_bgr / _32 as convert_unscaled */
+    int bpp, ro, go, bo, ao;   /* bytes per pixel and byte positions of R, G, B, A (ao < 0: no alpha byte) */
     int16_t *hLum, *hChr, *vLum, *vChr;
     int32_t *hLumPos, *hChrPos, *vLumPos, *vChrPos;
     int hLumSize, hChrSize, vLumSize, vChrSize;
@@ -278,9 +279,33 @@ static const int default_coeffs[4] = { 104597, 132201, 25675, 53279 };  /* yuv2r
 
 OrcSws *orc_sws_open(int srcW, int srcH, int dstW, int dstH, int flags)
 {
+    return orc_sws_open_fmt(srcW, srcH, dstW, dstH, ORC_PIX_FMT_RGB24, flags);
+}
+
+/* Byte order of the packed 8-bit RGB outputs.  The 32-bit formats carry alpha = 255 for a source without alpha: the
+ * reference adds 255 << abase to every luma-ramp entry (yuv2rgb.c:947-960) and yuv2rgb_write_full stores 255
+ * (output.c:2066-2095).  R, G and B are the same values as for rgb24: the 32 bpp ramp is the 24 bpp one shifted
+ * (yuv2rgb.c:901-914 vs :947-966), and yuv2rgb_write sums r[Y] + g[Y] + b[Y] (output.c:1676-1695). */
+static int set_format(OrcSws *s, int fmt)
+{
+    switch (fmt) {
+    case ORC_PIX_FMT_RGB24: s->bpp = 3; s->ro = 0; s->go = 1; s->bo = 2; s->ao = -1; break;
+    case ORC_PIX_FMT_BGR24: s->bpp = 3; s->ro = 2; s->go = 1; s->bo = 0; s->ao = -1; break;
+    case ORC_PIX_FMT_RGBA:  s->bpp = 4; s->ro = 0; s->go = 1; s->bo = 2; s->ao = 3;  break;
+    case ORC_PIX_FMT_BGRA:  s->bpp = 4; s->ro = 2; s->go = 1; s->bo = 0; s->ao = 3;  break;
+    case ORC_PIX_FMT_ARGB:  s->bpp = 4; s->ro = 1; s->go = 2; s->bo = 3; s->ao = 0;  break;
+    case ORC_PIX_FMT_ABGR:  s->bpp = 4; s->ro = 3; s->go = 2; s->bo = 1; s->ao = 0;  break;
+    default: return -1;
+    }
+    return 0;
+}
+
+OrcSws *orc_sws_open_fmt(int srcW, int srcH, int dstW, int dstH, int dstFormat, int flags)
+{
     if (srcW < 1 || srcH < 1 || dstW < 1 || dstH < 1) return NULL;
     OrcSws *s = calloc(1, sizeof(*s));
     if (!s) return NULL;
+    if (set_format(s, dstFormat) < 0) { free(s); return NULL; }
     int algo = flags & 0x7FF;
     if (!algo) { algo = ORC_SWS_BICUBIC; flags |= algo; }           /* utils.c:1209-1217 */
     else if (algo & (algo - 1)) goto fail;
@@ -363,17 +388,19 @@ void orc_hscale8to15(int16_t *dst, int dstW, const uint8_t *src, const int16_t *
     }
 }
 
-/* yuv2rgb_write, rgb24 branch (output.c:1697-1713): one chroma pair -> LUT bases, two lumas -> 6 bytes */
+/* yuv2rgb_write, 24 and 32 bpp branches (output.c:1676-1713): one chroma pair -> LUT bases, two lumas -> two pixels */
 static void put_pair(const OrcSws *s, uint8_t *d, int Y1, int Y2, int U, int V)
 {
     const uint8_t *r = s->ytab + s->offR[V + HEADROOM];
     const uint8_t *g = s->ytab + s->offGU[U + HEADROOM] + s->offGV[V + HEADROOM];
     const uint8_t *b = s->ytab + s->offB[U + HEADROOM];
-    d[0] = r[Y1]; d[1] = g[Y1]; d[2] = b[Y1];
-    d[3] = r[Y2]; d[4] = g[Y2]; d[5] = b[Y2];
+    uint8_t *e = d + s->bpp;
+    d[s->ro] = r[Y1]; d[s->go] = g[Y1]; d[s->bo] = b[Y1];
+    e[s->ro] = r[Y2]; e[s->go] = g[Y2]; e[s->bo] = b[Y2];
+    if (s->ao >= 0) d[s->ao] = e[s->ao] = 255;
 }
 
-/* yuv2rgb_write_full, rgb24 (output.c:1998-2030) */
+/* yuv2rgb_write_full (output.c:1998-2095) */
 static void put_full(const OrcSws *s, uint8_t *d, int Y, int U, int V)
 {
     unsigned y = (unsigned)(Y - s->y_offset) * (unsigned)s->y_coeff + (1U << 21);
@@ -385,7 +412,8 @@ static void put_full(const OrcSws *s, uint8_t *d, int Y, int U, int V)
         R = CLIP30(R); G = CLIP30(G); B = CLIP30(B);
 #undef CLIP30
     }
-    d[0] = (uint8_t)(R >> 22); d[1] = (uint8_t)(G >> 22); d[2] = (uint8_t)(B >> 22);
+    d[s->ro] = (uint8_t)(R >> 22); d[s->go] = (uint8_t)(G >> 22); d[s->bo] = (uint8_t)(B >> 22);
+    if (s->ao >= 0) d[s->ao] = 255;
 }
 
 /* unscaled LUT converter yuv2rgb_c_24_rgb (yuv2rgb.c:137-236,530): chroma (x>>1, y>>1), no interpolation;
@@ -400,7 +428,7 @@ static void convert_unscaled(const OrcSws *s, const uint8_t *y, int ys, const ui
         const uint8_t *pv = v + (ptrdiff_t)(row >> 1) * vs;
         uint8_t *d = dst + (ptrdiff_t)row * ds;
         for (int i = 0; i < wpix / 2; i++)
-            put_pair(s, d + 6 * i, py[2 * i], py[2 * i + 1], pu[i], pv[i]);
+            put_pair(s, d + 2 * s->bpp * i, py[2 * i], py[2 * i + 1], pu[i], pv[i]);
     }
 }
 
@@ -475,7 +503,7 @@ int orc_sws_scale(OrcSws *s, const uint8_t *y, int ys, const uint8_t *u, int us,
                     }
                     Y1 = (int)a1 >> 19; Y2 = (int)a2 >> 19; U = (int)au >> 19; V = (int)av >> 19;
                 }
-                put_pair(s, d + 6 * i, Y1, Y2, U, V);
+                put_pair(s, d + 2 * s->bpp * i, Y1, Y2, U, V);
             }
         } else {
             for (int i = 0; i < dstW; i++) {
@@ -503,7 +531,7 @@ int orc_sws_scale(OrcSws *s, const uint8_t *y, int ys, const uint8_t *u, int us,
                     }
                     Y = (int)ay >> 10; U = (int)au >> 10; V = (int)av >> 10;
                 }
-                put_full(s, d + 3 * i, Y, U, V);
+                put_full(s, d + s->bpp * i, Y, U, V);
             }
         }
     }

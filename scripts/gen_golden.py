@@ -52,6 +52,21 @@ def gen_sws():
     np.savez_compressed(os.path.join(OUT, "sws_colorspace.npz"), **d)
 
 
+def gen_sws_formats():
+    """bgr24 / rgba / bgra / argb / abgr outputs of the reference for SWS_FORMAT_CASES, as sha256 lines."""
+    from cases import SWS_FORMAT_CASES
+    lines = []
+    for name, fmt in cl.PACKED_RGB_FORMATS.items():
+        if name == "rgb24":
+            continue
+        for i, (w, h, dw, dh, fl, kind) in enumerate(SWS_FORMAT_CASES):
+            y, u, v = cl.yuv_frame(w, h, 500 + i, kind)
+            out = cl.ref_sws(w, h, dw, dh, fl, y, u, v, fmt=fmt)
+            assert out is not None and out.shape == (dh, dw * cl.fmt_bpp(fmt))
+            lines.append(f"{name} {i} {w} {h} {dw} {dh} {fl} {kind} {sha(out)}")
+    open(os.path.join(OUT, "sws_format_hashes.txt"), "w").write("\n".join(lines) + "\n")
+
+
 def gen_idct():
     R = cl.ref()
     d = {}
@@ -232,6 +247,7 @@ if __name__ == "__main__":
     assert cl.have_ref(), "build oracle/_ref first: make -C oracle/ref"
     os.makedirs(OUT, exist_ok=True)
     gen_sws()
+    gen_sws_formats()
     gen_idct()
     gen_mecmp()
     gen_pel()

@@ -86,3 +86,12 @@ EDGE_CASES = [(9, 9, 5, 5), (21, 21, -3, 4), (21, 21, 30, 4), (21, 21, 8, -2), (
               (9, 9, -3, 25), (9, 9, 33, -4), (17, 9, -17, 3), (17, 9, -40, 3), (17, 9, 37, 3), (17, 9, 90, 3), (9, 17, 3, -17),
               (9, 17, 3, -50), (9, 17, 3, 29), (9, 17, 3, 77), (23, 23, -60, -60), (23, 23, 60, 60), (1, 1, -1, -1), (1, 5, 36, 27),
               (5, 1, 36, 28), (23, 23, -10, -10), (4, 4, 0, 0), (4, 4, 33, 25), (2, 13, 36, -6)]
+
+
+# other packed RGB writers of the same pipeline: (w, h, dw, dh, flags, input kind) run for every format of
+# cpulibs.PACKED_RGB_FORMATS except rgb24 — the _X writer same-size (FATE flags), the unscaled LUT converter, a rescale
+# through the int16 line planes, full chroma (odd width forces it), widths that leave scalar tails, and a vector-width case
+SWS_FORMAT_CASES = [(64, 48, 64, 48, FATE, "random"), (64, 48, 64, 48, SWS_BICUBIC, "random"), (64, 48, 100, 70, FATE, "limited"),
+                    (64, 48, 33, 21, SWS_BILINEAR, "random"), (38, 22, 38, 22, SWS_BICUBIC, "random"), (70, 30, 70, 30, FATE, "smooth"),
+                    (64, 48, 64, 48, FATE | SWS_FULL_CHR_H_INT, "random"), (352, 288, 352, 288, FATE, "random"),
+                    (352, 288, 352, 288, SWS_BICUBIC, "limited"), (352, 288, 200, 100, FATE, "random")]

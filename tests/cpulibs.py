@@ -34,6 +34,8 @@ def oracle():
         L = C.CDLL(ORACLE_SO)
         L.orc_sws_open.restype = C.c_void_p
         L.orc_sws_open.argtypes = [C.c_int] * 5
+        L.orc_sws_open_fmt.restype = C.c_void_p
+        L.orc_sws_open_fmt.argtypes = [C.c_int] * 6
         L.orc_sws_close.argtypes = [C.c_void_p]
         L.orc_sws_set_colorspace.argtypes = [C.c_void_p, i32p, C.c_int, C.c_int, C.c_int, C.c_int]
         L.orc_sws_scale.argtypes = [C.c_void_p, u8p, C.c_int, u8p, C.c_int, u8p, C.c_int, u8p, C.c_int]
@@ -74,6 +76,8 @@ def ref():
         L.ffref_set_quiet()
         L.ffref_sws_open.restype = C.c_void_p
         L.ffref_sws_open.argtypes = [C.c_int] * 6
+        L.ffref_sws_open_fmt.restype = C.c_void_p
+        L.ffref_sws_open_fmt.argtypes = [C.c_int] * 7
         L.ffref_sws_close.argtypes = [C.c_void_p]
         L.ffref_sws_set_colorspace.argtypes = [C.c_void_p] + [C.c_int] * 7
         L.ffref_sws_scale.argtypes = [C.c_void_p, u8p, C.c_int, u8p, C.c_int, u8p, C.c_int, C.c_int, C.c_int, u8p, C.c_int]
@@ -124,11 +128,20 @@ def yuv_frame(w, h, seed, kind="random", pad=0):
     return np.ascontiguousarray(y), np.ascontiguousarray(u), np.ascontiguousarray(v)
 
 
-def _sws_run(lib, pre, w, h, dw, dh, flags, y, u, v, dst_pad=0, threads=1, colorspace=None):
+PIX_FMT_RGB24, PIX_FMT_BGR24, PIX_FMT_ARGB, PIX_FMT_RGBA, PIX_FMT_ABGR, PIX_FMT_BGRA = 2, 3, 25, 26, 27, 28   # libavutil/pixfmt.h
+PACKED_RGB_FORMATS = {"rgb24": PIX_FMT_RGB24, "bgr24": PIX_FMT_BGR24, "argb": PIX_FMT_ARGB, "rgba": PIX_FMT_RGBA,
+                      "abgr": PIX_FMT_ABGR, "bgra": PIX_FMT_BGRA}
+
+
+def fmt_bpp(fmt):
+    return 3 if fmt in (PIX_FMT_RGB24, PIX_FMT_BGR24) else 4
+
+
+def _sws_run(lib, pre, w, h, dw, dh, flags, y, u, v, dst_pad=0, threads=1, colorspace=None, fmt=PIX_FMT_RGB24):
     if pre == "ffref":
-        ctx = lib.ffref_sws_open(w, h, dw, dh, flags, threads)
+        ctx = lib.ffref_sws_open_fmt(w, h, dw, dh, fmt, flags, threads)
     else:
-        ctx = lib.orc_sws_open(w, h, dw, dh, flags)
+        ctx = lib.orc_sws_open_fmt(w, h, dw, dh, fmt, flags)
     if not ctx:
         return None
     try:
@@ -138,7 +151,7 @@ def _sws_run(lib, pre, w, h, dw, dh, flags, y, u, v, dst_pad=0, threads=1, color
             else:
                 tab = np.array(COEFFS[colorspace[0]], dtype=np.int32)
                 lib.orc_sws_set_colorspace(ctx, ptr(tab, i32p), colorspace[1], colorspace[4], colorspace[5], colorspace[6])
-        ds = dw * 3 + dst_pad
+        ds = dw * fmt_bpp(fmt) + dst_pad
         dst = np.full((dh, ds), 0xA5, dtype=np.uint8)
         if pre == "ffref":
             n = lib.ffref_sws_scale(ctx, ptr(y), y.strides[0], ptr(u), u.strides[0], ptr(v), v.strides[0], 0, h, ptr(dst), ds)

@@ -36,6 +36,31 @@ def test_sws_oracle_vs_golden_hashes():
         assert sha(out) == hout, (i, w, h, dw, dh, hex(fl))
 
 
+def test_sws_oracle_other_formats_golden_hashes():
+    """bgr24 / rgba / bgra / argb / abgr writers against the reference's outputs (sws_format_hashes.txt)."""
+    n = 0
+    for line in open(os.path.join(G, "sws_format_hashes.txt")):
+        name, i, w, h, dw, dh, fl, kind, hout = line.split()
+        i, w, h, dw, dh, fl = map(int, (i, w, h, dw, dh, fl))
+        y, u, v = cl.yuv_frame(w, h, 500 + i, kind)
+        out = cl.orc_sws(w, h, dw, dh, fl, y, u, v, fmt=cl.PACKED_RGB_FORMATS[name])
+        assert sha(out) == hout, (name, i, w, h, dw, dh, hex(fl))
+        n += 1
+    assert n == 50
+
+
+def test_sws_oracle_formats_are_byte_permutations_of_rgb24():
+    """Size-independent property: every format carries the rgb24 values, reordered, plus alpha 255."""
+    y, u, v = cl.yuv_frame(96, 64, 9, "random")
+    for (dw, dh, fl) in ((96, 64, FATE), (96, 64, cl.SWS_BICUBIC), (50, 40, FATE), (97, 64, FATE)):
+        base = cl.orc_sws(96, 64, dw, dh, fl, y, u, v).reshape(dh, dw, 3)
+        for name, order in (("bgr24", "bgr"), ("rgba", "rgba"), ("bgra", "bgra"), ("argb", "argb"), ("abgr", "abgr")):
+            out = cl.orc_sws(96, 64, dw, dh, fl, y, u, v, fmt=cl.PACKED_RGB_FORMATS[name]).reshape(dh, dw, len(order))
+            for k, ch in enumerate(order):
+                exp = 255 if ch == "a" else base[:, :, "rgb".index(ch)]
+                assert np.array_equal(out[:, :, k], np.broadcast_to(exp, (dh, dw))), (name, ch, dw, dh, hex(fl))
+
+
 def test_sws_oracle_colorspace_golden():
     g = np.load(os.path.join(G, "sws_colorspace.npz"))
     y, u, v = g["y"], g["u"], g["v"]

@@ -17,9 +17,9 @@ def sha(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
 
-def gpu_sws(device, w, h, dw, dh, fl, y, u, v, dst_pad=0, colorspace=None):
+def gpu_sws(device, w, h, dw, dh, fl, y, u, v, dst_pad=0, colorspace=None, fmt=cl.PIX_FMT_RGB24):
     from ffmpeg_b200 import swscale as sw
-    ctx = sw.sws_getContext(device, w, h, sw.AV_PIX_FMT_YUV420P, dw, dh, sw.AV_PIX_FMT_RGB24, fl)
+    ctx = sw.sws_getContext(device, w, h, sw.AV_PIX_FMT_YUV420P, dw, dh, fmt, fl)
     try:
         if colorspace is not None:
             ctx.setColorspaceDetails(cl.COEFFS[colorspace[0]], colorspace[1], cl.COEFFS[colorspace[2]], colorspace[3],
@@ -74,6 +74,61 @@ def test_vs_oracle_padded_strides(device, case):
         a = cl.orc_sws(w, h, dw, dh, fl, y, u, v, dst_pad=dpad)
         b = gpu_sws(device, w, h, dw, dh, fl, y, u, v, dst_pad=dpad)
         assert np.array_equal(a, b), (case, seed, int((a != b).sum()))
+
+
+def test_other_formats_golden_hashes(device):
+    """bgr24 / rgba / bgra / argb / abgr against the reference's outputs (sws_format_hashes.txt)."""
+    n = 0
+    for line in open(os.path.join(G, "sws_format_hashes.txt")):
+        name, i, w, h, dw, dh, fl, kind, hout = line.split()
+        i, w, h, dw, dh, fl = map(int, (i, w, h, dw, dh, fl))
+        y, u, v = cl.yuv_frame(w, h, 500 + i, kind)
+        out = gpu_sws(device, w, h, dw, dh, fl, y, u, v, fmt=cl.PACKED_RGB_FORMATS[name])
+        assert sha(out) == hout, (name, i, w, h, dw, dh, hex(fl))
+        n += 1
+    assert n == 50
+
+
+@pytest.mark.parametrize("name", ["bgr24", "rgba", "bgra", "argb", "abgr"])
+def test_other_formats_vs_oracle(device, name):
+    """Vector and scalar kernels of every writer: aligned and odd strides, 4K same-size (FATE flags and LUT), a rescale."""
+    fmt = cl.PACKED_RGB_FORMATS[name]
+    for (w, h, dw, dh, fl) in ((640, 360, 640, 360, FATE), (640, 360, 640, 360, cl.SWS_BICUBIC), (346, 286, 346, 286, FATE),
+                               (352, 288, 300, 200, cl.SWS_BICUBLIN), (351, 288, 351, 288, FATE),
+                               (3840, 2160, 3840, 2160, FATE), (3840, 2160, 3840, 2160, cl.SWS_BICUBIC)):
+        for seed, kind, pad, dpad in ((1, "random", 0, 0), (2, "limited", 7, 5)):
+            if w >= 3840 and (seed == 2 or name in ("argb", "abgr")):
+                continue
+            y, u, v = cl.yuv_frame(w, h, seed, kind, pad=pad)
+            a = cl.orc_sws(w, h, dw, dh, fl, y, u, v, dst_pad=dpad, fmt=fmt)
+            b = gpu_sws(device, w, h, dw, dh, fl, y, u, v, dst_pad=dpad, fmt=fmt)
+            assert np.array_equal(a, b), (name, w, h, dw, dh, hex(fl), seed, int((a != b).sum()))
+
+
+def test_other_formats_slices_and_batch(device):
+    """bgra through the slice entry and the batched device entry: same bytes as the whole-frame call."""
+    import torch
+    from ffmpeg_b200 import swscale as sw
+    w, h = 128, 96
+    y, u, v = cl.yuv_frame(w, h, 77, "random")
+    for fl in (FATE, cl.SWS_BICUBIC):
+        ref = cl.orc_sws(w, h, w, h, fl, y, u, v, fmt=cl.PIX_FMT_BGRA)
+        ctx = sw.sws_getContext(device, w, h, 0, w, h, sw.AV_PIX_FMT_BGRA, fl)
+        out = np.full((h, w * 4), 0xA5, np.uint8)
+        total = 0
+        for sy in range(0, h, 32):
+            total += ctx.scale([y[sy:], u[sy // 2:], v[sy // 2:]], [w, w // 2, w // 2], sy, 32, [out], [w * 4])
+        assert total == h and np.array_equal(out, ref), hex(fl)
+        with torch.cuda.stream(torch.cuda.ExternalStream(device.stream)):
+            dy, du, dv = (torch.from_numpy(np.stack([a, a])).cuda() for a in (y, u, v))
+            dout = torch.zeros((2, h, w * 4), dtype=torch.uint8, device="cuda")
+            ctx.scale_batch_device([dy, du, dv], [w, w // 2, w // 2], [w * h, w * h // 4, w * h // 4], dout, w * 4, w * h * 4, 2)
+            device.sync()
+            got = dout.cpu().numpy()
+        assert np.array_equal(got[0], ref) and np.array_equal(got[1], ref), hex(fl)
+        ctx.free()
+    with pytest.raises(Exception):
+        sw.sws_getContext(device, 64, 48, 0, 64, 48, 4, FATE)           # AV_PIX_FMT_YUV422P as destination: not this path
 
 
 def test_bottom_up_strides(device):
