@@ -366,9 +366,10 @@ def run_b200(args, rank, world, local_rank):
     sstr = [W4K, W4K // 2, W4K // 2]
     sfs = [W4K * H4K, W4K * H4K // 4, W4K * H4K // 4]
 
-    def timed_sws(flags, steps, warmup, sample_clocks):
-        ctx = sw.sws_getContext(dev, W4K, H4K, sw.AV_PIX_FMT_YUV420P, W4K, H4K, sw.AV_PIX_FMT_RGB24, flags)
-        call = lambda: ctx.scale_batch_device([Y, U, V], sstr, sfs, OUT, W4K * 3, W4K * H4K * 3, BATCH)
+    def timed_sws(flags, steps, warmup, sample_clocks, fmt=sw.AV_PIX_FMT_RGB24, out=None):
+        ctx = sw.sws_getContext(dev, W4K, H4K, sw.AV_PIX_FMT_YUV420P, W4K, H4K, fmt, flags)
+        out = OUT if out is None else out
+        call = lambda: ctx.scale_batch_device([Y, U, V], sstr, sfs, out, W4K * ctx.bpp, W4K * H4K * ctx.bpp, BATCH)
         with torch.cuda.stream(stream):
             for _ in range(warmup):
                 call()
@@ -406,6 +407,15 @@ def run_b200(args, rank, world, local_rank):
     results["variant_flags_bicubic"] = {"value": fps2, "unit": "frames/s", "roofline": {
         "bound": "hbm", "achieved": ach2, "peak": peak, "unit": "GB/s", "frac": ach2 / peak, "kernel": "sws_unscaled_kernel",
         "launch_ms": k2, "traffic": ncu_traffic("sws_unscaled_kernel")}}
+    # variant: rgba output, FATE flags; 4 bytes per pixel out
+    with torch.cuda.stream(stream):
+        OUT4 = torch.empty((BATCH, H4K, W4K * 4), dtype=torch.uint8, device="cuda")
+    t3, k3, _ = timed_sws(FLAGS_FATE, max(3, args.steps // 2), args.warmup, False, sw.AV_PIX_FMT_RGBA, OUT4)
+    bytes4 = (W4K * H4K * 3 // 2 + W4K * H4K * 4) * BATCH
+    results["variant_rgba"] = {"value": world * BATCH * max(3, args.steps // 2) / (t3 / 1e3), "unit": "frames/s", "roofline": {
+        "bound": "hbm", "achieved": bytes4 / (k3 / 1e3) / 1e9, "peak": peak, "unit": "GB/s", "frac": bytes4 / (k3 / 1e3) / 1e9 / peak,
+        "kernel": "sws_vscale_rgb24_fast_kernel<true,true,RGBA>", "launch_ms": k3, "bytes_per_frame": bytes4 // BATCH}}
+    del OUT4
 
     # ---- IDCT put on the 1080p macroblock stream (configs[2]): 256 frames x 48 960 blocks per step
     nblk = MB_W * MB_H * 6 * IDCT_FRAMES

@@ -15,7 +15,6 @@
 namespace {
 
 __device__ __forceinline__ int clip8(int v) { return __vimin_s32_relu(v, 255); }
-__device__ __forceinline__ int tap6(int a, int b, int c, int d, int e, int f) { return a - 5 * b + 20 * c + 20 * d - 5 * e + f; }
 
 constexpr int QW = 32;                 // window pitch in bytes; block pixel (0,0) sits at column 8 of window row 2
 constexpr int QX = 8;                  // so that every 8-pixel segment of a row starts 8-byte aligned in shared memory
@@ -26,33 +25,66 @@ struct __align__(16) QpelSmem {
     short hraw[21 * 16];               // unrounded horizontal 6-tap sums for the same rows, block columns 0 .. 15
 };
 
-// 16 consecutive bytes of a window row starting at 4-aligned byte offset `o`, unpacked
-__device__ __forceinline__ void row16(const uint8_t *row, int o, int *b)
-{
-    const unsigned *w = reinterpret_cast<const unsigned *>(row + o);
-    const unsigned w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        b[i] = (int)__byte_perm(w0, 0, 0x4440 | i); b[4 + i] = (int)__byte_perm(w1, 0, 0x4440 | i);
-        b[8 + i] = (int)__byte_perm(w2, 0, 0x4440 | i); b[12 + i] = (int)__byte_perm(w3, 0, 0x4440 | i);
-    }
-}
-// 8 bytes starting at byte offset QX + x0 + dx (dx = 0 or 1) of a window row
-__device__ __forceinline__ void row8(const uint8_t *row, int x0, int dx, int *b)
+// ---- packed arithmetic helpers --------------------------------------------------------------------------------------
+// The 6-tap (1,-5,20,20,-5,1) is evaluated with the integer dot-product instructions: IDP.4A for the horizontal filter
+// (u8 pixels x s8 taps, 4 taps per instruction), IDP.2A for the vertical ones (two rows interleaved by PRMT, s16 tap pair
+// x u8 pixels for V; s16 sums x s8 tap pair for the centre sample).  Every component of a quarter-pel position ends up as
+// two packed u8x4 words, so the (a + b + 1) >> 1 combinations are byte-SIMD averages.
+__device__ __forceinline__ int dp4a_us(unsigned a, int b, int c)      // c + sum_k a.u8[k] * b.s8[k]
+{ int d; asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+__device__ __forceinline__ int dp2a_lo_su(int a, unsigned b, int c)   // c + a.s16[0]*b.u8[0] + a.s16[1]*b.u8[1]
+{ int d; asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+__device__ __forceinline__ int dp2a_hi_su(int a, unsigned b, int c)   // c + a.s16[0]*b.u8[2] + a.s16[1]*b.u8[3]
+{ int d; asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+__device__ __forceinline__ int dp2a_lo_ss(unsigned a, int b, int c)   // c + a.s16[0]*b.s8[0] + a.s16[1]*b.s8[1]
+{ int d; asm("dp2a.lo.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+
+constexpr int TAP4_A = 0x1414FB01;     // s8 (1, -5, 20, 20)
+constexpr int TAP4_B = 0x000001FB;     // s8 (-5, 1, 0, 0)
+__host__ __device__ constexpr int tap2_16(int j) { return j == 0 ? (int)0xFFFB0001 : j == 1 ? 0x00140014 : 0x0001FFFB; }   // s16 pairs (1,-5) (20,20) (-5,1)
+__host__ __device__ constexpr int tap2_8(int j)  { return j == 0 ? 0x0000FB01 : j == 1 ? 0x00001414 : 0x000001FB; }        // s8 pairs, same taps
+
+// 8 packed bytes of a window row: block columns x0+dx .. x0+dx+7 (dx = 0 or 1)
+__device__ __forceinline__ uint2 row8p(const uint8_t *row, int x0, int dx)
 {
     const unsigned *w = reinterpret_cast<const unsigned *>(row + QX + x0);
     unsigned w0 = w[0], w1 = w[1];
     if (dx) { const unsigned w2 = w[2]; w0 = __funnelshift_r(w0, w1, 8); w1 = __funnelshift_r(w1, w2, 8); }
-#pragma unroll
-    for (int i = 0; i < 4; i++) { b[i] = (int)__byte_perm(w0, 0, 0x4440 | i); b[4 + i] = (int)__byte_perm(w1, 0, 0x4440 | i); }
+    return make_uint2(w0, w1);
 }
-// unrounded horizontal 6-tap sums for block columns x0 .. x0+7 of window row `row`
-__device__ __forceinline__ void hsum8(const uint8_t *row, int x0, int *o)
+// unrounded horizontal 6-tap sums (+ init) for block columns x0 .. x0+7 of window row `row`
+__device__ __forceinline__ void hsum8(const uint8_t *row, int x0, int init, int *o)
 {
-    int b[16];
-    row16(row, QX + x0 - 4, b);                          // bytes of source columns x0-4 .. x0+11; taps need x0-2 .. x0+10
+    const unsigned *w = reinterpret_cast<const unsigned *>(row + QX + x0 - 4);     // A[0] = columns x0-4 .. x0-1
+    const unsigned A[5] = { w[0], w[1], w[2], w[3], w[4] };
+    unsigned S[12];                                                                  // S[i] = columns x0-2+i .. x0+1+i
 #pragma unroll
-    for (int i = 0; i < 8; i++) o[i] = tap6(b[i + 2], b[i + 3], b[i + 4], b[i + 5], b[i + 6], b[i + 7]);
+    for (int i = 0; i < 12; i++) {
+        const int b = 2 + i;
+        S[i] = (b & 3) ? __funnelshift_r(A[b >> 2], A[(b >> 2) + 1], (b & 3) * 8) : A[b >> 2];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) o[i] = dp4a_us(S[i + 4], TAP4_B, dp4a_us(S[i], TAP4_A, init));
+}
+// one vertical tap pair over two rows of 8 packed pixels
+__device__ __forceinline__ void vfold(int k2, const uint2 &r0, const uint2 &r1, int *acc)
+{
+    unsigned lo = __byte_perm(r0.x, r1.x, 0x5140), hi = __byte_perm(r0.x, r1.x, 0x7362);
+    acc[0] = dp2a_lo_su(k2, lo, acc[0]); acc[1] = dp2a_hi_su(k2, lo, acc[1]); acc[2] = dp2a_lo_su(k2, hi, acc[2]); acc[3] = dp2a_hi_su(k2, hi, acc[3]);
+    lo = __byte_perm(r0.y, r1.y, 0x5140); hi = __byte_perm(r0.y, r1.y, 0x7362);
+    acc[4] = dp2a_lo_su(k2, lo, acc[4]); acc[5] = dp2a_hi_su(k2, lo, acc[5]); acc[6] = dp2a_lo_su(k2, hi, acc[6]); acc[7] = dp2a_hi_su(k2, hi, acc[7]);
+}
+// clip8(v[k] >> SH) for 8 values -> two packed words
+template <int SH>
+__device__ __forceinline__ uint2 clip_pack8(const int *v)
+{
+    unsigned c[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) c[k] = (unsigned)clip8(v[k] >> SH);
+    uint2 o;
+    o.x = __byte_perm(__byte_perm(c[0], c[1], 0x1140), __byte_perm(c[2], c[3], 0x1140), 0x5410);
+    o.y = __byte_perm(__byte_perm(c[4], c[5], 0x1140), __byte_perm(c[6], c[7], 0x1140), 0x5410);
+    return o;
 }
 
 // The kernel is latency-bound if every operation waits for its descriptor, then its window, then (avg) its
@@ -141,10 +173,10 @@ qpel_kernel(long long n, const uint8_t *op, uint8_t *dst, const int64_t *dst_off
             for (int k = lane; k < wdim * segs; k += 32) {
                 const int r = k / segs, xx = (k - r * segs) * 8;
                 int h[8];
-                hsum8(&s.win[r * QW], xx, h);
+                hsum8(&s.win[r * QW], xx, 0, h);
                 uint4 pk;
-                pk.x = (unsigned)(h[0] & 0xffff) | ((unsigned)h[1] << 16); pk.y = (unsigned)(h[2] & 0xffff) | ((unsigned)h[3] << 16);
-                pk.z = (unsigned)(h[4] & 0xffff) | ((unsigned)h[5] << 16); pk.w = (unsigned)(h[6] & 0xffff) | ((unsigned)h[7] << 16);
+                pk.x = __byte_perm(h[0], h[1], 0x5410); pk.y = __byte_perm(h[2], h[3], 0x5410);
+                pk.z = __byte_perm(h[4], h[5], 0x5410); pk.w = __byte_perm(h[6], h[7], 0x5410);
                 *reinterpret_cast<uint4 *>(&s.hraw[r * 16 + xx]) = pk;
             }
             __syncwarp();
@@ -155,66 +187,53 @@ qpel_kernel(long long n, const uint8_t *op, uint8_t *dst, const int64_t *dst_off
             const bool useF = (qy == 0 && qx != 2) || (qx == 0 && (qy & 1));
             const bool useH = qx != 0 && qy != 2;
             const bool useV = qy != 0 && qx != 2;
-            int acc[8], tt[8], v[8];
-#pragma unroll
-            for (int k = 0; k < 8; k++) acc[k] = 0;
-            int count = 0;
-            if (useF) {
-                row8(&s.win[(y + 2 + (qy == 3)) * QW], x0, qx == 3, tt);
-#pragma unroll
-                for (int k = 0; k < 8; k++) acc[k] += tt[k];
-                count++;
-            }
+            uint2 res = make_uint2(0, 0);
+            bool have = false;
+            auto add = [&](const uint2 &c) {
+                if (have) { res.x = __vavgu4(res.x, c.x); res.y = __vavgu4(res.y, c.y); }
+                else { res = c; have = true; }
+            };
+            if (useF) add(row8p(&s.win[(y + 2 + (qy == 3)) * QW], x0, qx == 3));
             if (useH) {
-                hsum8(&s.win[(y + 2 + (qy == 3)) * QW], x0, tt);
-#pragma unroll
-                for (int k = 0; k < 8; k++) acc[k] += clip8((tt[k] + 16) >> 5);
-                count++;
+                int h[8];
+                hsum8(&s.win[(y + 2 + (qy == 3)) * QW], x0, 16, h);
+                add(clip_pack8<5>(h));
             }
             if (useV) {
-                int r0[8], r1[8], r2[8], r3[8], r4[8], r5[8];
                 const int dx = qx == 3;
-                row8(&s.win[(y + 0) * QW], x0, dx, r0); row8(&s.win[(y + 1) * QW], x0, dx, r1); row8(&s.win[(y + 2) * QW], x0, dx, r2);
-                row8(&s.win[(y + 3) * QW], x0, dx, r3); row8(&s.win[(y + 4) * QW], x0, dx, r4); row8(&s.win[(y + 5) * QW], x0, dx, r5);
+                int a8[8];
 #pragma unroll
-                for (int k = 0; k < 8; k++) acc[k] += clip8((tap6(r0[k], r1[k], r2[k], r3[k], r4[k], r5[k]) + 16) >> 5);
-                count++;
+                for (int k = 0; k < 8; k++) a8[k] = 16;
+#pragma unroll
+                for (int j = 0; j < 3; j++)
+                    vfold(tap2_16(j), row8p(&s.win[(y + 2 * j) * QW], x0, dx), row8p(&s.win[(y + 2 * j + 1) * QW], x0, dx), a8);
+                add(clip_pack8<5>(a8));
             }
             if (need_j) {
                 int j6[8];
 #pragma unroll
                 for (int k = 0; k < 8; k++) j6[k] = 512;
-                const int coef[6] = { 1, -5, 20, 20, -5, 1 };
 #pragma unroll
-                for (int j = 0; j < 6; j++) {
-                    const uint4 pk = *reinterpret_cast<const uint4 *>(&s.hraw[(y + j) * 16 + x0]);
-                    const unsigned ww[4] = { pk.x, pk.y, pk.z, pk.w };
+                for (int j = 0; j < 3; j++) {
+                    const uint4 pa = *reinterpret_cast<const uint4 *>(&s.hraw[(y + 2 * j) * 16 + x0]);
+                    const uint4 pb = *reinterpret_cast<const uint4 *>(&s.hraw[(y + 2 * j + 1) * 16 + x0]);
+                    const unsigned wa[4] = { pa.x, pa.y, pa.z, pa.w }, wb[4] = { pb.x, pb.y, pb.z, pb.w };
 #pragma unroll
                     for (int k = 0; k < 4; k++) {
-                        j6[2 * k] += coef[j] * (int)(short)(ww[k] & 0xffff);
-                        j6[2 * k + 1] += coef[j] * ((int)ww[k] >> 16);
+                        j6[2 * k]     = dp2a_lo_ss(__byte_perm(wa[k], wb[k], 0x5410), tap2_8(j), j6[2 * k]);
+                        j6[2 * k + 1] = dp2a_lo_ss(__byte_perm(wa[k], wb[k], 0x7632), tap2_8(j), j6[2 * k + 1]);
                     }
                 }
-#pragma unroll
-                for (int k = 0; k < 8; k++) acc[k] += clip8(j6[k] >> 10);
-                count++;
+                add(clip_pack8<10>(j6));
             }
-#pragma unroll
-            for (int k = 0; k < 8; k++) v[k] = count == 2 ? (acc[k] + 1) >> 1 : acc[k];
             if (vec) {
-                if (avg) {
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        v[k] = (v[k] + (int)__byte_perm(pv.x, 0, 0x4440 | k) + 1) >> 1;
-                        v[4 + k] = (v[4 + k] + (int)__byte_perm(pv.y, 0, 0x4440 | k) + 1) >> 1;
-                    }
-                }
-                uint2 ov;
-                ov.x = (unsigned)v[0] | ((unsigned)v[1] << 8) | ((unsigned)v[2] << 16) | ((unsigned)v[3] << 24);
-                ov.y = (unsigned)v[4] | ((unsigned)v[5] << 8) | ((unsigned)v[6] << 16) | ((unsigned)v[7] << 24);
-                *reinterpret_cast<uint2 *>(d) = ov;
+                if (avg) { res.x = __vavgu4(res.x, pv.x); res.y = __vavgu4(res.y, pv.y); }
+                *reinterpret_cast<uint2 *>(d) = res;
             } else {
-                for (int k = 0; k < npx; k++) d[k] = (uint8_t)(avg ? (d[k] + v[k] + 1) >> 1 : v[k]);
+                for (int k = 0; k < npx; k++) {
+                    const int v = (int)__byte_perm(k < 4 ? res.x : res.y, 0, 0x4440 | (k & 3));
+                    d[k] = (uint8_t)(avg ? (d[k] + v + 1) >> 1 : v);
+                }
             }
         }
         __syncwarp();                                                                    // shared window is reused by the next operation
@@ -251,46 +270,80 @@ hpel_kernel(long long n, const uint8_t *op, const uint8_t *hh, uint8_t *dst, con
     }
 }
 
-// h264chroma: bilinear eighth-pel (h264chroma_template.c:27-176).  16 lanes per operation, a lane owns up to 4 consecutive
-// pixels of one row; the x == 0 / y == 0 cases skip the right column / lower row like the reference's D == 0 branches.
-constexpr int CH_LANES = 16;
+// h264chroma: bilinear eighth-pel (h264chroma_template.c:27-176).  8 lanes per operation, lane r owns row r (and r+8 of a
+// 16-row block).  A row is fetched as the one or two aligned 8-byte words that hold bytes the reference itself reads (x == 0
+// never touches the column right of the block, y == 0 never the row below it) and normalised to block column 0 with funnel
+// shifts; the row below comes from the next lane by shuffle.  (A*t0 + B*t1 + C*b0 + D*b1 + 32) >> 6 is evaluated with
+// coefficients scaled by 4, so that the result is byte 1 of the sum: two IDP.2A per pixel and no shifts.
+constexpr int CH_LANES = 8;
+struct ChRow { unsigned r0, r1, r2; };
+__device__ __forceinline__ ChRow chroma_row(const uint8_t *p, int nbytes, bool on)
+{
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const unsigned sh = (unsigned)(a & 7);
+    const uint2 *q = reinterpret_cast<const uint2 *>(a & ~(uintptr_t)7);
+    uint2 v0 = make_uint2(0, 0), v1 = make_uint2(0, 0);
+    if (on) {
+        v0 = __ldg(q);
+        if (sh + nbytes > 8) v1 = __ldg(q + 1);
+    }
+    const bool up = sh & 4;
+    const unsigned t0 = up ? v0.y : v0.x, t1 = up ? v1.x : v0.y, t2 = up ? v1.y : v1.x, t3 = up ? 0u : v1.y;
+    const unsigned fs = (sh & 3) * 8;
+    ChRow o;
+    o.r0 = __funnelshift_r(t0, t1, fs); o.r1 = __funnelshift_r(t1, t2, fs); o.r2 = __funnelshift_r(t2, t3, fs);
+    return o;
+}
 __global__ void __launch_bounds__(32 * WARPS)
 chroma_kernel(long long n, const uint8_t *op, const uint8_t *hh, const uint8_t *xy, uint8_t *dst, const int64_t *dst_off,
               const uint8_t *src, const int64_t *src_off, long long stride)
 {
-    const long long i = ((long long)blockIdx.x * (32 * WARPS) + threadIdx.x) / CH_LANES;
-    if (i >= n) return;
+    const long long gi = ((long long)blockIdx.x * (32 * WARPS) + threadIdx.x) / CH_LANES;
+    const bool valid = gi < n;
+    const long long i = valid ? gi : n - 1;                       // every lane stays in the shuffles
     const int sub = threadIdx.x & (CH_LANES - 1);
-    const int o = op[i], h = hh[i], fx = xy[i] & 7, fy = (xy[i] >> 3) & 7;
+    const int o = __ldg(op + i), h = __ldg(hh + i), pq = __ldg(xy + i), fx = pq & 7, fy = (pq >> 3) & 7;
     const int avg = o & 1, w = 8 >> ((o >> 1) & 3);
-    const int A = (8 - fx) * (8 - fy), B = fx * (8 - fy), C = (8 - fx) * fy, D = fx * fy;
-    const int segs = w > 4 ? 2 : 1, npx = w < 4 ? w : 4;
-    const uint8_t *sp = src + src_off[i];
-    uint8_t *dp = dst + dst_off[i];
-    for (int y = sub / segs; y < h; y += CH_LANES / segs) {
-        const int x0 = (sub % segs) * 4;
-        const uint8_t *p = sp + (long long)y * stride + x0;
-        int t[5], b[5];
-#pragma unroll
-        for (int k = 0; k < 5; k++) {
-            const bool in = k < npx || (k == npx && fx);                       // right neighbour only when B or D is non-zero
-            t[k] = in ? __ldg(p + k) : 0;
-            b[k] = (in && fy) ? __ldg(p + stride + k) : 0;                     // lower row only when C or D is non-zero
-        }
-        uint8_t *d = dp + (long long)y * stride + x0;
-        uint32_t pack = 0;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int v = (A * t[k] + B * t[k + 1] + C * b[k] + D * b[k + 1] + 32) >> 6;
-            pack |= (uint32_t)v << (8 * k);
-        }
-        if (npx == 4 && ((uintptr_t)d & 3) == 0) {
-            uint32_t *d4 = (uint32_t *)d;
-            *d4 = avg ? __vavgu4(*d4, pack) : pack;
+    const int kab = 4 * ((8 - fx) * (8 - fy)) | (4 * (fx * (8 - fy))) << 16;      // s16 pairs (4A, 4B) and (4C, 4D)
+    const int kcd = 4 * ((8 - fx) * fy) | (4 * (fx * fy)) << 16;
+    const uint8_t *sp = src + __ldg(src_off + i);
+    uint8_t *dp = dst + __ldg(dst_off + i);
+    const int nbytes = w + (fx != 0);
+    const int hmax = __reduce_max_sync(0xffffffffu, valid ? h : 0);   // the four operations of a warp may differ in height
+    for (int y0 = 0; y0 < hmax; y0 += CH_LANES) {
+        const int y = y0 + sub;
+        const bool mine = valid && y < h;
+        const uint8_t *rowp = sp + (long long)y * stride;
+        const ChRow t = chroma_row(rowp, nbytes, mine);
+        ChRow b;
+        b.r0 = __shfl_down_sync(0xffffffffu, t.r0, 1, CH_LANES); b.r1 = __shfl_down_sync(0xffffffffu, t.r1, 1, CH_LANES);
+        b.r2 = __shfl_down_sync(0xffffffffu, t.r2, 1, CH_LANES);
+        const bool last = sub == CH_LANES - 1 || y == h - 1;          // the row below is not held by the next lane
+        if (last) b = chroma_row(rowp + stride, nbytes, mine && fy != 0);
+        if (!mine) continue;
+        const unsigned ta = __funnelshift_r(t.r0, t.r1, 8), tb = __funnelshift_r(t.r1, t.r2, 8);
+        const unsigned ba = __funnelshift_r(b.r0, b.r1, 8), bb = __funnelshift_r(b.r1, b.r2, 8);
+        int v[8];
+        v[0] = dp2a_lo_su(kcd, b.r0, dp2a_lo_su(kab, t.r0, 128)); v[1] = dp2a_lo_su(kcd, ba, dp2a_lo_su(kab, ta, 128));
+        v[2] = dp2a_hi_su(kcd, b.r0, dp2a_hi_su(kab, t.r0, 128)); v[3] = dp2a_hi_su(kcd, ba, dp2a_hi_su(kab, ta, 128));
+        v[4] = dp2a_lo_su(kcd, b.r1, dp2a_lo_su(kab, t.r1, 128)); v[5] = dp2a_lo_su(kcd, bb, dp2a_lo_su(kab, tb, 128));
+        v[6] = dp2a_hi_su(kcd, b.r1, dp2a_hi_su(kab, t.r1, 128)); v[7] = dp2a_hi_su(kcd, bb, dp2a_hi_su(kab, tb, 128));
+        unsigned w0 = __byte_perm(__byte_perm(v[0], v[1], 0x5151), __byte_perm(v[2], v[3], 0x5151), 0x5410);
+        unsigned w1 = __byte_perm(__byte_perm(v[4], v[5], 0x5151), __byte_perm(v[6], v[7], 0x5151), 0x5410);
+        uint8_t *d = dp + (long long)y * stride;
+        const unsigned al = (unsigned)(reinterpret_cast<uintptr_t>(d) & 7);
+        if (w == 8 && al == 0) {
+            uint2 *d8 = reinterpret_cast<uint2 *>(d);
+            if (avg) { const uint2 pv = *d8; w0 = __vavgu4(pv.x, w0); w1 = __vavgu4(pv.y, w1); }
+            *d8 = make_uint2(w0, w1);
+        } else if (w >= 4 && (al & 3) == 0) {
+            unsigned *d4 = reinterpret_cast<unsigned *>(d);
+            d4[0] = avg ? __vavgu4(d4[0], w0) : w0;
+            if (w == 8) d4[1] = avg ? __vavgu4(d4[1], w1) : w1;
         } else {
-            for (int k = 0; k < npx; k++) {
-                const int v = (pack >> (8 * k)) & 255;
-                d[k] = (uint8_t)(avg ? (d[k] + v + 1) >> 1 : v);
+            for (int k = 0; k < w; k++) {
+                const int px = (int)__byte_perm(k < 4 ? w0 : w1, 0, 0x4440 | (k & 3));
+                d[k] = (uint8_t)(avg ? (d[k] + px + 1) >> 1 : px);
             }
         }
     }

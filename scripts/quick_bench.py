@@ -45,6 +45,21 @@ with torch.cuda.stream(stream):
         ops = (torch.randint(0, 2, (doff.numel(),), device="cuda", generator=g) | (torch.randint(0, 16, (doff.numel(),), device="cuda", generator=g) << 3)).to(torch.uint8)
         n = doff.numel()
         timed(lambda: pel.h264qpel_batch_device(dev, n, ops, dstp, doff, refp, soff, PW), n, "blocks", 825)
+    elif what == "chroma":
+        nfr, W, H, ap = 128, 960, 544, 16
+        PW, PH = W + 2 * ap, H + 2 * ap
+        refp = torch.randint(0, 256, (nfr, PH, PW), dtype=torch.uint8, device="cuda", generator=g)
+        dstp = torch.randint(0, 256, (nfr, PH, PW), dtype=torch.uint8, device="cuda", generator=g)
+        fi = torch.arange(nfr, device="cuda").view(-1, 1, 1)
+        by = torch.arange(H // 8, device="cuda").view(1, -1, 1); bx = torch.arange(W // 8, device="cuda").view(1, 1, -1)
+        base = fi * (PH * PW) + (by * 8 + ap) * PW + bx * 8 + ap
+        dx = torch.randint(-8, 9, base.shape, device="cuda", generator=g); dy = torch.randint(-8, 9, base.shape, device="cuda", generator=g)
+        doff = base.reshape(-1).to(torch.int64).contiguous(); soff = (base + dy * PW + dx).reshape(-1).to(torch.int64).contiguous()
+        n = doff.numel()
+        ops = torch.randint(0, 2, (n,), device="cuda", generator=g).to(torch.uint8)
+        hs = torch.full((n,), 8, dtype=torch.uint8, device="cuda")
+        xys = torch.randint(0, 64, (n,), device="cuda", generator=g).to(torch.uint8)
+        timed(lambda: pel.h264chroma_batch_device(dev, n, ops, hs, xys, dstp, doff, refp, soff, PW), n, "blocks", 177)
     elif what == "idct":
         mbw, mbh, fr = 120, 68, 256
         n = mbw * mbh * 6 * fr
