@@ -16,13 +16,15 @@ namespace {
 
 __device__ __forceinline__ int clip8(int v) { return __vimin_s32_relu(v, 255); }
 
-constexpr int QW = 32;                 // window pitch in bytes; block pixel (0,0) sits at column 8 of window row 2
+constexpr int QW = 48;                 // window pitch in bytes (12 words: the 8-byte row segments of a half-warp fall in 16 distinct
+                                       // bank pairs); only bytes 0..31 are used, block pixel (0,0) sits at byte 8 of window row 2
 constexpr int QX = 8;                  // so that every 8-pixel segment of a row starts 8-byte aligned in shared memory
 constexpr int WARPS = 4;
 
 struct __align__(16) QpelSmem {
     uint8_t win[21 * QW];              // source rows -2 .. size+2; source column x is at byte QX + x (x = -2 .. size+2)
     short hraw[21 * 16];               // unrounded horizontal 6-tap sums for the same rows, block columns 0 .. 15
+    unsigned raw[12 * 32];             // scratch of stage_window: word k of lane l at raw[k * 32 + l] (conflict-free both ways)
 };
 
 // ---- packed arithmetic helpers --------------------------------------------------------------------------------------
@@ -100,38 +102,41 @@ __device__ __forceinline__ QMeta load_meta(const uint8_t *op, const int64_t *src
     if (i < n) { m.o = __ldg(op + i); m.soff = __ldg(src_off + i); m.doff = __ldg(dst_off + i); }
     return m;
 }
-struct QWin { unsigned v[6]; unsigned sh[6]; };
-// window words of one operation into registers: 7 lanes per source row, 4 rows per pass (see stage_window)
+struct QWin { uint4 v[3]; unsigned sh; };
+// Window row `lane` (source row lane-2, columns -2 .. size+2) into registers: the one to three aligned 16-byte words that
+// contain at least one needed byte (nothing else is ever read), plus the byte offset of column -2 inside the first.
 __device__ __forceinline__ void load_window(QWin &w, const uint8_t *sp, long long stride, int wdim, int lane, bool valid)
 {
-    const int q7 = lane / 7, j = lane - q7 * 7;
-#pragma unroll
-    for (int it = 0; it < 6; it++) {
-        const int r = 4 * it + q7;
-        const uint8_t *first = sp + (long long)(r - 2) * stride - 2;                     // column -2 of this row
-        const unsigned sh = (unsigned)(reinterpret_cast<uintptr_t>(first) & 3);
-        const int nw = (int)((sh + wdim + 3) >> 2);
-        w.sh[it] = sh;
-        w.v[it] = 0;
-        if (valid && lane < 28 && r < wdim && j >= 1 && j - 1 < nw) w.v[it] = __ldg(reinterpret_cast<const unsigned *>(first - sh) + (j - 1));
+    const uintptr_t first = reinterpret_cast<uintptr_t>(sp + (long long)(lane - 2) * stride - 2);
+    const uint4 *q = reinterpret_cast<const uint4 *>(first & ~(uintptr_t)15);
+    w.sh = (unsigned)(first & 15);
+    const int nv = (int)((w.sh + wdim + 15) >> 4);
+    w.v[0] = w.v[1] = w.v[2] = make_uint4(0, 0, 0, 0);
+    if (valid && lane < wdim) {
+        w.v[0] = __ldg(q);
+        if (nv > 1) w.v[1] = __ldg(q + 1);
+        if (nv > 2) w.v[2] = __ldg(q + 2);
     }
 }
-// Lane j of a row holds LL[j]: LL[0] = 0, LL[1..6] = the aligned words that contain at least one needed byte (columns
-// -2 .. size+2; nothing else is ever read), LL[7] = 0.  Window word jj (bytes 4jj .. 4jj+3 of the shared row, block
-// column 0 at byte QX) = funnel(LL[jj-1+i0], LL[jj+i0]) with i0, shift from the row's address alignment.
+// Each lane re-aligns its own row: raw words go through a private column of shared memory (a register array cannot be
+// indexed by the run-time word shift), come back as 7 words at the shifted position and are funnel-shifted so that block
+// column 0 sits at byte QX of the window row.  No cross-lane traffic, so no barrier between the two steps.
 __device__ __forceinline__ void stage_window(QpelSmem &s, const QWin &w, int wdim, int lane)
 {
-    const int q7 = lane / 7, j = lane - q7 * 7;
+    if (lane >= wdim) return;
+    unsigned *raw = &s.raw[lane];
 #pragma unroll
-    for (int it = 0; it < 6; it++) {
-        const int r = 4 * it + q7;
-        const unsigned nxt = __shfl_down_sync(0xffffffffu, w.v[it], 1);
-        const unsigned hi = j == 6 ? 0u : nxt;
-        const unsigned tt = w.sh[it] + 2, i0 = tt >> 2, fs = (tt & 3) * 8;
-        const int jj = j + 1 - (int)i0;
-        if (lane < 28 && r < wdim && jj >= 1 && jj <= 6)
-            reinterpret_cast<unsigned *>(&s.win[r * QW])[jj] = __funnelshift_r(w.v[it], hi, fs);
+    for (int k = 0; k < 3; k++) {
+        raw[(4 * k + 0) * 32] = w.v[k].x; raw[(4 * k + 1) * 32] = w.v[k].y; raw[(4 * k + 2) * 32] = w.v[k].z; raw[(4 * k + 3) * 32] = w.v[k].w;
     }
+    const int ws = (int)((w.sh + 2) >> 2) - 1;                   // window word j = raw bytes sh + 4j - 6 .. sh + 4j - 3
+    const unsigned fs = ((w.sh + 2) & 3) * 8;
+    unsigned x[7];
+#pragma unroll
+    for (int i = 0; i < 7; i++) x[i] = raw[max(ws + i, 0) * 32];   // ws + i <= 9; index -1 only feeds columns -4, -3 (unused)
+    uint4 *row = reinterpret_cast<uint4 *>(&s.win[lane * QW]);
+    row[0] = make_uint4(0u, __funnelshift_r(x[0], x[1], fs), __funnelshift_r(x[1], x[2], fs), __funnelshift_r(x[2], x[3], fs));
+    row[1] = make_uint4(__funnelshift_r(x[3], x[4], fs), __funnelshift_r(x[4], x[5], fs), __funnelshift_r(x[5], x[6], fs), 0u);
 }
 
 // Lane l works on one 8-pixel (4 for size 4) row segment: row l>>1, half l&1 for 16x16.

@@ -61,7 +61,7 @@ with torch.cuda.stream(stream):
         dev.sync(); c.uninit()
     if what in ("qpel", "all"):
         from ffmpeg_b200 import pel
-        nfr, Wd, Hd, ap = 16, 1920, 1088, 32
+        nfr, Wd, Hd, ap = max(16, nf), 1920, 1088, 32
         PW, PH = Wd + 2 * ap, Hd + 2 * ap
         refp = torch.randint(0, 256, (nfr, PH, PW), dtype=torch.uint8, device="cuda")
         dstp = torch.randint(0, 256, (nfr, PH, PW), dtype=torch.uint8, device="cuda")
