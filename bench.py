@@ -398,7 +398,7 @@ def run_b200(args, rank, world, local_rank):
     fps = world * BATCH * args.steps / (total_ms / 1e3)
     ach = FRAME_BYTES * BATCH / (kern_ms / 1e3) / 1e9
     roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src,
-            "kernel": "sws_vscale_rgb24_kernel<true>", "bytes_per_launch": FRAME_BYTES * BATCH,
+            "kernel": "sws_vscale_rgb24_fast_kernel<LUMID=true,CFS4=true,RGB24>", "bytes_per_launch": FRAME_BYTES * BATCH,
             "launch_ms": kern_ms, "traffic": ncu_traffic("sws_vscale_rgb24_kernel")}
     # variant: flags=bicubic only (the reference takes its unscaled LUT converter; different, cheaper arithmetic)
     t2, k2, _ = timed_sws(SWS_BICUBIC, max(3, args.steps // 2), args.warmup, False)
@@ -445,7 +445,7 @@ def run_b200(args, rank, world, local_rank):
         a = bpb * nblk / (ms / args.steps / 1e3) / 1e9
         idct[name] = {"value": bps, "unit": "blocks/s", "ms_per_step": ms / args.steps,
                       "roofline": {"bound": "hbm", "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak,
-                                   "kernel": f"idct8x8_kernel<{name},mb420>", "bytes_per_block": bpb,
+                                   "kernel": f"idct_mb420_kernel<{name}>", "bytes_per_block": bpb,
                                    "traffic": ncu_traffic(f"idct8x8_{name}")}}
     del blocks, planes
     results.update(extra_paths(args, dev, stream, g, world, barrier, reduce_max, peak))

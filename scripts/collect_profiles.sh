@@ -12,5 +12,6 @@ ncu --set full --clock-control none --import-source on -k regex:"idct_mb420" -s 
 ncu --set full --clock-control none --import-source on -k regex:"idct_mb420" -s 7 -c 1 -o gpurun_out/r01_idct_add python scripts/profile_target.py idct 32 > gpurun_out/p4.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"tx_fft" -s 1 -c 1 -o gpurun_out/r01_tx_fft python scripts/profile_target.py tx 8 > gpurun_out/p5.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"qpel_" -s 1 -c 1 -o gpurun_out/r01_qpel python scripts/profile_target.py qpel 8 > gpurun_out/p6.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"chroma_" -s 1 -c 1 -o gpurun_out/r01_chroma python scripts/profile_target.py chroma 8 > gpurun_out/p8.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"esa_" -s 1 -c 1 -o gpurun_out/r01_esa python scripts/profile_target.py esa 8 > gpurun_out/p7.log 2>&1
 ls -la gpurun_out

@@ -28,10 +28,11 @@ def raw(rep):
 lines = [f"# ncu summaries, {tag} (one launch each, `ncu --set full --clock-control none`, scripts/collect_profiles.sh)", ""]
 traffic = {}
 names = {"sws_fate": "sws_vscale_rgb24_kernel", "sws_lut": "sws_unscaled_kernel", "idct_put": "idct8x8_put", "idct_add": "idct8x8_add",
-         "tx_fft": "tx_fft_kernel", "qpel": "qpel_kernel", "esa": "esa_kernel"}
+         "tx_fft": "tx_fft_kernel", "qpel": "qpel_kernel", "chroma": "chroma_kernel", "esa": "esa_kernel"}
 work = {"sws_fate": ("32 x 4K frames", 32 * 37324800), "sws_lut": ("32 x 4K frames", 32 * 37324800),
         "idct_put": ("32 x 48960 blocks", 32 * 48960 * 192), "idct_add": ("32 x 48960 blocks", 32 * 48960 * 256),
-        "tx_fft": ("65536 x FFT-1024", 65536 * 16384), "qpel": ("16 x 8160 16x16 blocks", None), "esa": ("1 4K pair", None)}
+        "tx_fft": ("65536 x FFT-1024", 65536 * 16384), "qpel": ("16 x 8160 16x16 blocks", 16 * 8160 * 825), "chroma": ("32 x 8160 8x8 blocks", 32 * 8160 * 177),
+        "esa": ("1 4K pair", None)}
 for key in names:
     rep = os.path.join(G, f"{tag}_{key}.ncu-rep")
     if not os.path.exists(rep):

@@ -74,6 +74,24 @@ with torch.cuda.stream(stream):
         for _ in range(3):
             pel.h264qpel_batch_device(dev, doff.numel(), ops, dstp, doff, refp, soff, PW)
         dev.sync()
+    if what in ("chroma", "all"):
+        from ffmpeg_b200 import pel
+        nfr, Wd, Hd, ap = 32, 960, 544, 16
+        PW, PH = Wd + 2 * ap, Hd + 2 * ap
+        refp = torch.randint(0, 256, (nfr, PH, PW), dtype=torch.uint8, device="cuda")
+        dstp = torch.randint(0, 256, (nfr, PH, PW), dtype=torch.uint8, device="cuda")
+        fi = torch.arange(nfr, device="cuda").view(-1, 1, 1)
+        by = torch.arange(Hd // 8, device="cuda").view(1, -1, 1); bx = torch.arange(Wd // 8, device="cuda").view(1, 1, -1)
+        base = fi * (PH * PW) + (by * 8 + ap) * PW + bx * 8 + ap
+        dx = torch.randint(-8, 9, base.shape, device="cuda"); dy = torch.randint(-8, 9, base.shape, device="cuda")
+        doff = base.reshape(-1).to(torch.int64).contiguous(); soff = (base + dy * PW + dx).reshape(-1).to(torch.int64).contiguous()
+        n = doff.numel()
+        ops = torch.randint(0, 2, (n,), device="cuda").to(torch.uint8)
+        hs = torch.full((n,), 8, dtype=torch.uint8, device="cuda")
+        xys = torch.randint(0, 64, (n,), device="cuda").to(torch.uint8)
+        for _ in range(3):
+            pel.h264chroma_batch_device(dev, n, ops, hs, xys, dstp, doff, refp, soff, PW)
+        dev.sync()
     if what in ("esa", "all"):
         from ffmpeg_b200 import me_cmp
         cur = torch.randint(0, 256, (1, H, W), dtype=torch.uint8, device="cuda")
