@@ -209,6 +209,36 @@ __device__ __forceinline__ int sx_lo(unsigned v)
     return d;
 }
 __device__ __forceinline__ int sx_hi(unsigned v) { return (int)v >> 16; }
+// The 8-point butterfly shared by both passes (simple_idct_template.c:157-199 rows, :209-257 columns), all sums mod 2^32
+// like the reference's unsigned arithmetic.  Every output sum is ONE multiply-add chain that starts from the even part
+// (a_i + b_i accumulated in place) and its mirror output is 2*a_i - (a_i + b_i): 22 multiply-adds + 8 adds per
+// transform instead of 22 + 14, and the adds that remain are the only work left for the ALU pipe.
+//   e[0..7] = a0+b0, a1+b1, a2+b2, a3+b3, a3-b3, a2-b2, a1-b1, a0-b0   (before the final shift)
+// mad.lo through inline PTX so that the compiler cannot re-associate the chains back into separate sums
+__device__ __forceinline__ unsigned mad(unsigned k, unsigned x, unsigned acc)
+{
+    unsigned d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(x), "r"(k), "r"(acc));
+    return d;
+}
+template <unsigned K1, unsigned K2, unsigned K3, unsigned K4, unsigned K5, unsigned K6, unsigned K7>
+__device__ __forceinline__ void odd_even_sums(int c0, int c1, int c2, int c3, int c4, int c5, int c6, int c7, unsigned rnd, unsigned *e)
+{
+    const unsigned u1 = (unsigned)c1, u2 = (unsigned)c2, u3 = (unsigned)c3, u5 = (unsigned)c5, u6 = (unsigned)c6, u7 = (unsigned)c7;
+    const unsigned p = mad(K4, (unsigned)(c0 + c4), rnd), q = mad(K4, (unsigned)(c0 - c4), rnd);
+    const unsigned a0 = mad(K2, u2, mad(K6, u6, p)), a3 = 2u * p - a0;
+    const unsigned a1 = mad(K6, u2, mad(0u - K2, u6, q)), a2 = 2u * q - a1;
+    e[0] = mad(K1, u1, mad(K3, u3, mad(K5, u5, mad(K7, u7, a0))));
+    e[1] = mad(K3, u1, mad(0u - K7, u3, mad(0u - K1, u5, mad(0u - K5, u7, a1))));
+    e[2] = mad(K5, u1, mad(0u - K1, u3, mad(K7, u5, mad(K3, u7, a2))));
+    e[3] = mad(K7, u1, mad(0u - K5, u3, mad(K3, u5, mad(0u - K1, u7, a3))));
+    e[7] = 2u * a0 - e[0]; e[6] = 2u * a1 - e[1]; e[5] = 2u * a2 - e[2]; e[4] = 2u * a3 - e[3];
+}
+__device__ __forceinline__ void col_sums(int c0, int c1, int c2, int c3, int c4, int c5, int c6, int c7, unsigned *e)
+{
+    odd_even_sums<W1, W2, W3, W4, W5, W6, W7>(c0, c1, c2, c3, c4, c5, c6, c7, (unsigned)W4 * (unsigned)((1 << 19) / W4), e);
+}
+
 // Row pass with every constant pre-multiplied by 32: only bits 11..26 of the reference's 32-bit row sums survive the
 // ">> 11, store as int16" step, and those are bits 16..31 of (32 * sum) mod 2^32 — so (int)sum32 >> 16 IS the
 // sign-extended int16 the reference stores (one shift instead of shift + wrap).
@@ -224,17 +254,10 @@ __device__ __forceinline__ void row_pass_i(const uint4 &in, int *o)
         for (int i = 0; i < 8; i++) o[i] = dc;
         return;
     }
-    const unsigned p = X4 * (unsigned)(r0 + r4) + (32u << 10), q = X4 * (unsigned)(r0 - r4) + (32u << 10);
-    const unsigned s = X2 * (unsigned)r2 + X6 * (unsigned)r6, d = X6 * (unsigned)r2 - X2 * (unsigned)r6;
-    const unsigned a0 = p + s, a3 = p - s, a1 = q + d, a2 = q - d;
-    const unsigned b0 = X1 * (unsigned)r1 + X3 * (unsigned)r3 + X5 * (unsigned)r5 + X7 * (unsigned)r7;
-    const unsigned b1 = X3 * (unsigned)r1 - X7 * (unsigned)r3 - X1 * (unsigned)r5 - X5 * (unsigned)r7;
-    const unsigned b2 = X5 * (unsigned)r1 - X1 * (unsigned)r3 + X7 * (unsigned)r5 + X3 * (unsigned)r7;
-    const unsigned b3 = X7 * (unsigned)r1 - X5 * (unsigned)r3 + X3 * (unsigned)r5 - X1 * (unsigned)r7;
-    o[0] = (int)(a0 + b0) >> 16; o[7] = (int)(a0 - b0) >> 16;
-    o[1] = (int)(a1 + b1) >> 16; o[6] = (int)(a1 - b1) >> 16;
-    o[2] = (int)(a2 + b2) >> 16; o[5] = (int)(a2 - b2) >> 16;
-    o[3] = (int)(a3 + b3) >> 16; o[4] = (int)(a3 - b3) >> 16;
+    unsigned e[8];
+    odd_even_sums<X1, X2, X3, X4, X5, X6, X7>(r0, r1, r2, r3, r4, r5, r6, r7, 32u << 10, e);
+#pragma unroll
+    for (int i = 0; i < 8; i++) o[i] = (int)e[i] >> 16;
 }
 
 // same, results left packed as four (int16, int16) words: the high halves of the x32 sums are picked by PRMT
@@ -248,32 +271,19 @@ __device__ __forceinline__ void row_pass_packed(const uint4 &in, unsigned *o)
     }
     const int r0 = sx_lo(in.x), r1 = sx_hi(in.x), r2 = sx_lo(in.y), r3 = sx_hi(in.y);
     const int r4 = sx_lo(in.z), r5 = sx_hi(in.z), r6 = sx_lo(in.w), r7 = sx_hi(in.w);
-    const unsigned p = X4 * (unsigned)(r0 + r4) + (32u << 10), q = X4 * (unsigned)(r0 - r4) + (32u << 10);
-    const unsigned s = X2 * (unsigned)r2 + X6 * (unsigned)r6, d = X6 * (unsigned)r2 - X2 * (unsigned)r6;
-    const unsigned a0 = p + s, a3 = p - s, a1 = q + d, a2 = q - d;
-    const unsigned b0 = X1 * (unsigned)r1 + X3 * (unsigned)r3 + X5 * (unsigned)r5 + X7 * (unsigned)r7;
-    const unsigned b1 = X3 * (unsigned)r1 - X7 * (unsigned)r3 - X1 * (unsigned)r5 - X5 * (unsigned)r7;
-    const unsigned b2 = X5 * (unsigned)r1 - X1 * (unsigned)r3 + X7 * (unsigned)r5 + X3 * (unsigned)r7;
-    const unsigned b3 = X7 * (unsigned)r1 - X5 * (unsigned)r3 + X3 * (unsigned)r5 - X1 * (unsigned)r7;
-    o[0] = __byte_perm(a0 + b0, a1 + b1, 0x7632); o[1] = __byte_perm(a2 + b2, a3 + b3, 0x7632);
-    o[2] = __byte_perm(a3 - b3, a2 - b2, 0x7632); o[3] = __byte_perm(a1 - b1, a0 - b0, 0x7632);
+    unsigned e[8];
+    odd_even_sums<X1, X2, X3, X4, X5, X6, X7>(r0, r1, r2, r3, r4, r5, r6, r7, 32u << 10, e);
+    o[0] = __byte_perm(e[0], e[1], 0x7632); o[1] = __byte_perm(e[2], e[3], 0x7632);
+    o[2] = __byte_perm(e[4], e[5], 0x7632); o[3] = __byte_perm(e[6], e[7], 0x7632);
 }
 
 // IDCT_COLS (simple_idct_template.c:209-257): eight inputs of one column -> eight results (already >> 20)
 __device__ __forceinline__ void col_pass_i(int c0, int c1, int c2, int c3, int c4, int c5, int c6, int c7, int *o)
 {
-    const unsigned rnd = (unsigned)W4 * (unsigned)((1 << 19) / W4);
-    const unsigned p = (unsigned)W4 * (unsigned)(c0 + c4) + rnd, q = (unsigned)W4 * (unsigned)(c0 - c4) + rnd;
-    const unsigned s = (unsigned)W2 * (unsigned)c2 + (unsigned)W6 * (unsigned)c6, d = (unsigned)W6 * (unsigned)c2 - (unsigned)W2 * (unsigned)c6;
-    const unsigned a0 = p + s, a3 = p - s, a1 = q + d, a2 = q - d;
-    const unsigned b0 = (unsigned)W1 * (unsigned)c1 + (unsigned)W3 * (unsigned)c3 + (unsigned)W5 * (unsigned)c5 + (unsigned)W7 * (unsigned)c7;
-    const unsigned b1 = (unsigned)W3 * (unsigned)c1 - (unsigned)W7 * (unsigned)c3 - (unsigned)W1 * (unsigned)c5 - (unsigned)W5 * (unsigned)c7;
-    const unsigned b2 = (unsigned)W5 * (unsigned)c1 - (unsigned)W1 * (unsigned)c3 + (unsigned)W7 * (unsigned)c5 + (unsigned)W3 * (unsigned)c7;
-    const unsigned b3 = (unsigned)W7 * (unsigned)c1 - (unsigned)W5 * (unsigned)c3 + (unsigned)W3 * (unsigned)c5 - (unsigned)W1 * (unsigned)c7;
-    o[0] = (int)(a0 + b0) >> 20; o[7] = (int)(a0 - b0) >> 20;
-    o[1] = (int)(a1 + b1) >> 20; o[6] = (int)(a1 - b1) >> 20;
-    o[2] = (int)(a2 + b2) >> 20; o[5] = (int)(a2 - b2) >> 20;
-    o[3] = (int)(a3 + b3) >> 20; o[4] = (int)(a3 - b3) >> 20;
+    unsigned e[8];
+    col_sums(c0, c1, c2, c3, c4, c5, c6, c7, e);
+#pragma unroll
+    for (int i = 0; i < 8; i++) o[i] = (int)e[i] >> 20;
 }
 
 // 16-byte LDGSTS to a 32-bit shared-window address (convert the base pointer ONCE with smem_addr(): doing the
@@ -457,27 +467,33 @@ idct_mb420_kernel(const int16_t *blocks, Mb420Geom g, int segs_per_cta)
         for (int j = 0; j < 8; j++) row_pass_packed(rows[j ^ key], R2[j]);
 #pragma unroll
         for (int half = 0; half < 2; half++) {             // four columns (one 32-bit tile word per row) at a time
-            int o0[8], o1[8], o2[8], o3[8];
+            unsigned e0[8], e1[8], e2[8], e3[8];             // column sums before the >> 20 (rows in the order 0,1,2,3,4,5,6,7)
             const int c0 = 2 * half, c1 = 2 * half + 1;
-            col_pass_i(sx_lo(R2[0][c0]), sx_lo(R2[1][c0]), sx_lo(R2[2][c0]), sx_lo(R2[3][c0]),
-                       sx_lo(R2[4][c0]), sx_lo(R2[5][c0]), sx_lo(R2[6][c0]), sx_lo(R2[7][c0]), o0);
-            col_pass_i(sx_hi(R2[0][c0]), sx_hi(R2[1][c0]), sx_hi(R2[2][c0]), sx_hi(R2[3][c0]),
-                       sx_hi(R2[4][c0]), sx_hi(R2[5][c0]), sx_hi(R2[6][c0]), sx_hi(R2[7][c0]), o1);
-            col_pass_i(sx_lo(R2[0][c1]), sx_lo(R2[1][c1]), sx_lo(R2[2][c1]), sx_lo(R2[3][c1]),
-                       sx_lo(R2[4][c1]), sx_lo(R2[5][c1]), sx_lo(R2[6][c1]), sx_lo(R2[7][c1]), o2);
-            col_pass_i(sx_hi(R2[0][c1]), sx_hi(R2[1][c1]), sx_hi(R2[2][c1]), sx_hi(R2[3][c1]),
-                       sx_hi(R2[4][c1]), sx_hi(R2[5][c1]), sx_hi(R2[6][c1]), sx_hi(R2[7][c1]), o3);
+            col_sums(sx_lo(R2[0][c0]), sx_lo(R2[1][c0]), sx_lo(R2[2][c0]), sx_lo(R2[3][c0]),
+                     sx_lo(R2[4][c0]), sx_lo(R2[5][c0]), sx_lo(R2[6][c0]), sx_lo(R2[7][c0]), e0);
+            col_sums(sx_hi(R2[0][c0]), sx_hi(R2[1][c0]), sx_hi(R2[2][c0]), sx_hi(R2[3][c0]),
+                     sx_hi(R2[4][c0]), sx_hi(R2[5][c0]), sx_hi(R2[6][c0]), sx_hi(R2[7][c0]), e1);
+            col_sums(sx_lo(R2[0][c1]), sx_lo(R2[1][c1]), sx_lo(R2[2][c1]), sx_lo(R2[3][c1]),
+                     sx_lo(R2[4][c1]), sx_lo(R2[5][c1]), sx_lo(R2[6][c1]), sx_lo(R2[7][c1]), e2);
+            col_sums(sx_hi(R2[0][c1]), sx_hi(R2[1][c1]), sx_hi(R2[2][c1]), sx_hi(R2[3][c1]),
+                     sx_hi(R2[4][c1]), sx_hi(R2[5][c1]), sx_hi(R2[6][c1]), sx_hi(R2[7][c1]), e3);
 #pragma unroll
             for (int r = 0; r < 8; r++) {
                 unsigned *px = reinterpret_cast<unsigned *>(trow + r * tp + 4 * half);
                 if (KIND == B200_IDCT_ADD) {
                     const unsigned dd = *px;
-                    o0[r] += (int)__byte_perm(dd, 0, 0x4440); o1[r] += (int)__byte_perm(dd, 0, 0x4441);
-                    o2[r] += (int)__byte_perm(dd, 0, 0x4442); o3[r] += (int)(dd >> 24);
+                    const int o0 = ((int)e0[r] >> 20) + (int)__byte_perm(dd, 0, 0x4440), o1 = ((int)e1[r] >> 20) + (int)__byte_perm(dd, 0, 0x4441);
+                    const int o2 = ((int)e2[r] >> 20) + (int)__byte_perm(dd, 0, 0x4442), o3 = ((int)e3[r] >> 20) + (int)(dd >> 24);
+                    const unsigned lo = __vimin_s16x2_relu(__byte_perm((unsigned)o0, (unsigned)o1, 0x5410), 0x00ff00ffu);
+                    const unsigned hi = __vimin_s16x2_relu(__byte_perm((unsigned)o2, (unsigned)o3, 0x5410), 0x00ff00ffu);
+                    *px = __byte_perm(lo, hi, 0x6420);
+                } else {
+                    // clip_u8(sum >> 20) == clamp(sum >> 16, 0, 4095) >> 4: take the high halves (PRMT), clamp both as s16x2,
+                    // shift the pair once; bytes 0 and 2 of the shifted pair are the pixels
+                    const unsigned lo = __vimin_s16x2_relu(__byte_perm(e0[r], e1[r], 0x7632), 0x0fff0fffu) >> 4;
+                    const unsigned hi = __vimin_s16x2_relu(__byte_perm(e2[r], e3[r], 0x7632), 0x0fff0fffu) >> 4;
+                    *px = __byte_perm(lo, hi, 0x6420);
                 }
-                const unsigned lo = __vimin_s16x2_relu(__byte_perm((unsigned)o0[r], (unsigned)o1[r], 0x5410), 0x00ff00ffu);
-                const unsigned hi = __vimin_s16x2_relu(__byte_perm((unsigned)o2[r], (unsigned)o3[r], 0x5410), 0x00ff00ffu);
-                *px = __byte_perm(lo, hi, 0x6420);
             }
         }
     }
