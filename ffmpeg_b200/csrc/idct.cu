@@ -430,14 +430,17 @@ idct_mb420_kernel(const int16_t *blocks, Mb420Geom g, int segs_per_cta)
         const long long blk0 = (((f * g.mb_h + mby) * g.mb_w) + mbx0) * 6;
         const uint4 *gsrc = reinterpret_cast<const uint4 *>(blocks) + blk0 * 8;
         {
+            // chunk i = w + 48*it of the segment: block b = b0 + 6*it, row r = w & 7, swizzled slot r ^ (b & 7).
+            // (b & 7) = (b0 + 2k) & 7 with k = (3*it) & 3, so four slot offsets cover all eight copies.
             const int r = w & 7, nb = nmb * 6, b0 = w >> 3;
-            const unsigned s_in = smem_addr(my_in);
+            const unsigned s_in = smem_addr(my_in) + (unsigned)b0 * 128u;
             const uint4 *gp = gsrc + b0 * 8 + r;
+            unsigned slot[4];
 #pragma unroll
-            for (int it = 0; it < 8; it++) {                                              // i = w + 48*it: block b0 + 6*it, row w&7
-                const int b = b0 + 6 * it;
-                if (b < nb) cp_async16(s_in + (unsigned)(b * 8 + (r ^ (b & 7))) * 16u, gp + it * 48);
-            }
+            for (int k = 0; k < 4; k++) slot[k] = (unsigned)(r ^ ((b0 + 2 * k) & 7)) * 16u;
+#pragma unroll
+            for (int it = 0; it < 8; it++)
+                if (b0 + 6 * it < nb) cp_async16(s_in + (unsigned)it * 768u + slot[(3 * it) & 3], gp + it * 48);
         }
         if (KIND == B200_IDCT_ADD) {                                                      // stage the destination tile
             for (int i = w; i < 128; i += 48) {                                           // luma: 16 rows x 8 chunks of 16 B
