@@ -104,6 +104,7 @@ PROTOTYPES = {
     "b200_sws_scale": (C.c_int, [vp, C.POINTER(vp), i32p, C.c_int, C.c_int, C.POINTER(vp), i32p]),
     "b200_sws_func": (C.c_int, [vp, C.POINTER(vp), i32p, C.c_int, C.c_int, C.POINTER(vp), i32p]),
     "b200_sws_scale_batch_device": (C.c_int, [vp, C.POINTER(vp), i32p, i64p, vp, C.c_int, C.c_int64, C.c_int]),
+    "b200_sws_scale_batch_device_planar": (C.c_int, [vp, C.POINTER(vp), C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(vp), C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.c_int]),
     "b200_sws_scale_batch_host": (C.c_int, [vp, C.POINTER(vp), i32p, i64p, vp, C.c_int, C.c_int64, C.c_int]),
     "b200_sws_info": (C.c_int, [vp, i32p]),
     "b200_sws_get_filter": (C.c_int, [vp, C.c_int, i16p, i32p, C.c_int]),

@@ -406,6 +406,46 @@ sws_vscale_rgb24_full_kernel(SwsFrameArgs a, SwsDevTables t, SwsColorConst c)
     if (a.ao >= 0) d[a.ao] = 255;
 }
 
+// ------------------------------------------------------------------------------------------------ kernels: planar destination
+// yuv2planeX_8_c / yuv2plane1_8_c (output.c:468-493) with the flat dither of the 8-bit path (sws_pb_64, swscale.c:385-387):
+//   fs > 1: clip_u8(((64 << 12) + sum_j line[first+j][x] * coef[j]) >> 19)      fs == 1: clip_u8((line[first][x] + 64) >> 7)
+// One thread per output sample of one plane; lines outside the plane replicate the border line like the reference's ring.
+__global__ void __launch_bounds__(256)
+sws_vscale_planar_kernel(const int16_t *src, int sls, long long sfs, int nlines, uint8_t *dst, long long ds, long long dfs,
+                         int w, const int16_t *coef, const int32_t *pos, int fs, int line0)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= w) return;
+    const int dy = blockIdx.y + line0;
+    const long long f = blockIdx.z;
+    const int16_t *p = reinterpret_cast<const int16_t *>(reinterpret_cast<const char *>(src) + f * sfs) + x;
+    const int first = max(1 - fs, __ldg(pos + dy));
+    int val;
+    if (fs == 1) {
+        val = ((int)__ldg(p + (long long)min(max(first, 0), nlines - 1) * sls) + 64) >> 7;
+    } else {
+        unsigned acc = 64u << 12;
+        const int16_t *k = coef + (long long)dy * fs;
+        for (int j = 0; j < fs; j++)
+            acc += (unsigned)((int)__ldg(p + (long long)min(max(first + j, 0), nlines - 1) * sls) * (int)__ldg(k + j));
+        val = (int)acc >> 19;
+    }
+    dst[f * dfs + (long long)dy * ds + x] = (uint8_t)clamp_u8(val);
+}
+
+// planarCopyWrapper (swscale_unscaled.c:2220-2333, 8-bit planes): row copies, 16 bytes per thread when everything is aligned
+__global__ void __launch_bounds__(256)
+sws_plane_copy_kernel(const uint8_t *src, long long ss, long long sfs, uint8_t *dst, long long ds, long long dfs, int w, int vec)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint8_t *s = src + blockIdx.z * sfs + (long long)blockIdx.y * ss;
+    uint8_t *d = dst + blockIdx.z * dfs + (long long)blockIdx.y * ds;
+    if (vec) {
+        if (i * 16 + 16 <= w) reinterpret_cast<uint4 *>(d)[i] = __ldg(reinterpret_cast<const uint4 *>(s) + i);
+        else for (int k = i * 16; k < w; k++) d[k] = s[k];
+    } else if (i < w) d[i] = s[i];
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 struct B200SwsContext {
     B200Device *dev = nullptr;
@@ -428,7 +468,7 @@ static int upload_tables(B200SwsContext *c)
 {
     const SwsPlan &p = c->plan;
     if (c->tables) { cudaFree(c->tables); c->tables = nullptr; }
-    if (p.unscaled_lut) return 0;
+    if (p.unscaled_lut || p.planar_copy) return 0;
     auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
     size_t off = 0;
     size_t o_vl = off;  off += al(p.vLum.coef.size() * 2);
@@ -476,7 +516,7 @@ static int upload_tables(B200SwsContext *c)
     c->dt.hLum = (const int16_t *)(b + o_hl); c->dt.hLumPos = (const int32_t *)(b + o_hlp); c->dt.hLumSize = p.hLum.size;
     c->dt.hChr = (const int16_t *)(b + o_hc); c->dt.hChrPos = (const int32_t *)(b + o_hcp); c->dt.hChrSize = p.hChr.size;
     c->h_identity = p.chrDstHSub == 1 && p.hLum.identity() && p.hChr.identity();
-    c->fast_x = c->h_identity;
+    c->fast_x = c->h_identity && !p.planar;
     c->lum_identity = p.vLum.size == 1;
     for (int y = 0; y < p.dstH && c->fast_x; y++) {
         if (p.rowMode[(size_t)y * 4] != 0) c->fast_x = false;
@@ -495,7 +535,7 @@ B200_API B200SwsContext *b200_sws_getContext(B200Device *dev, int srcW, int srcH
     if (!dev) { b200_set_error("b200_sws_getContext: no device"); return nullptr; }
     SwsOutFmt out;
     if (srcFormat != B200_PIX_FMT_YUV420P || !sws_out_format(dstFormat, out)) {
-        b200_set_error("b200_sws_getContext: only yuv420p -> rgb24 / bgr24 / rgba / bgra / argb / abgr is implemented");
+        b200_set_error("b200_sws_getContext: only yuv420p -> rgb24 / bgr24 / rgba / bgra / argb / abgr / yuv420p is implemented");
         return nullptr;
     }
     B200SwsContext *c = new (std::nothrow) B200SwsContext();
@@ -712,10 +752,111 @@ B200_API int b200_sws_scale_batch_device(B200SwsContext *c, const uint8_t *const
                                          int64_t dstFrameStride, int nframes)
 {
     if (!c || !src || !srcStride || !srcFrameStride || !dst) return B200_EINVAL;
+    if (c->plan.planar) return B200_EINVAL;                   // three destination planes: b200_sws_scale_batch_device_planar
     B200_CUDA_OK(cudaSetDevice(c->dev->ordinal));
     const long long ss[3] = { srcStride[0], srcStride[1], srcStride[2] };
     const long long fs[3] = { srcFrameStride[0], srcFrameStride[1], srcFrameStride[2] };
     return launch_batch(c, c->dev->stream, src, ss, fs, dst, dstStride, dstFrameStride, nframes);
+}
+
+// yuv420p -> yuv420p: horizontal pass of the three planes into int16 line planes, then one vertical pass per plane
+static int launch_planar(B200SwsContext *c, cudaStream_t stream, const uint8_t *const src[3], const long long sstr[3],
+                         const long long sfs[3], uint8_t *const dst[3], const long long dstr[3], const long long dfs[3], int nframes)
+{
+    const SwsPlan &p = c->plan;
+    if (nframes <= 0) return 0;
+    const int sw[3] = { p.srcW, p.chrSrcW, p.chrSrcW }, sh[3] = { p.srcH, p.chrSrcH, p.chrSrcH };
+    const int dw[3] = { p.dstW, p.chrDstW, p.chrDstW }, dh[3] = { p.dstH, p.chrDstH, p.chrDstH };
+    for (int f0 = 0; f0 < nframes; f0 += 65535) {
+        const int nf = nframes - f0 < 65535 ? nframes - f0 : 65535;
+        if (p.planar_copy) {
+            for (int pl = 0; pl < 3; pl++) {
+                const uint8_t *s = src[pl] + (long long)f0 * sfs[pl];
+                uint8_t *d = dst[pl] + (long long)f0 * dfs[pl];
+                const int vec = aligned16(s, sstr[pl], sfs[pl]) && aligned16(d, dstr[pl], dfs[pl]);
+                dim3 block(256), grid(b200_ceil_div(vec ? b200_ceil_div(sw[pl], 16) : sw[pl], 256), sh[pl], nf);
+                sws_plane_copy_kernel<<<grid, block, 0, stream>>>(s, sstr[pl], sfs[pl], d, dstr[pl], dfs[pl], sw[pl], vec);
+                B200_LAUNCHED();
+            }
+            continue;
+        }
+        const size_t plane[3] = { (size_t)p.srcH * p.dstW * 2, (size_t)p.chrSrcH * p.chrDstW * 2, (size_t)p.chrSrcH * p.chrDstW * 2 };
+        const size_t perFrame = ((plane[0] + plane[1] + plane[2]) + 255) & ~(size_t)255;
+        const size_t need = perFrame * nf;
+        if (c->mid_bytes < need) {
+            if (c->mid) { cudaStreamSynchronize(stream); cudaFree(c->mid); c->mid = nullptr; c->mid_bytes = 0; }
+            B200_CUDA_OK(cudaMalloc(&c->mid, need));
+            c->mid_bytes = need;
+        }
+        int16_t *m[3] = { (int16_t *)c->mid, (int16_t *)((uint8_t *)c->mid + plane[0]), (int16_t *)((uint8_t *)c->mid + plane[0] + plane[1]) };
+        const int16_t *hc[3] = { c->dt.hLum, c->dt.hChr, c->dt.hChr };
+        const int32_t *hp[3] = { c->dt.hLumPos, c->dt.hChrPos, c->dt.hChrPos };
+        const int hs[3] = { c->dt.hLumSize, c->dt.hChrSize, c->dt.hChrSize };
+        const int16_t *vc[3] = { c->dt.vLum, c->dt.vChr, c->dt.vChr };
+        const int32_t *vp[3] = { c->dt.vLumPos, c->dt.vChrPos, c->dt.vChrPos };
+        const int vs[3] = { c->dt.vLumSize, c->dt.vChrSize, c->dt.vChrSize };
+        for (int pl = 0; pl < 3; pl++) {
+            dim3 block(256), gh(b200_ceil_div(dw[pl], 256), sh[pl], nf), gv(b200_ceil_div(dw[pl], 256), dh[pl], nf);
+            sws_hscale_kernel<<<gh, block, 0, stream>>>(src[pl] + (long long)f0 * sfs[pl], sstr[pl], sfs[pl], m[pl], dw[pl],
+                                                        (long long)(perFrame / 2), hc[pl], hp[pl], hs[pl], 0);
+            B200_LAUNCHED();
+            sws_vscale_planar_kernel<<<gv, block, 0, stream>>>(m[pl], dw[pl], (long long)perFrame, sh[pl], dst[pl] + (long long)f0 * dfs[pl],
+                                                               dstr[pl], dfs[pl], dw[pl], vc[pl], vp[pl], vs[pl], 0);
+            B200_LAUNCHED();
+        }
+    }
+    B200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+B200_API int b200_sws_scale_batch_device_planar(B200SwsContext *c, const uint8_t *const src[3], const int srcStride[3],
+                                                const int64_t srcFrameStride[3], uint8_t *const dst[3], const int dstStride[3],
+                                                const int64_t dstFrameStride[3], int nframes)
+{
+    if (!c || !src || !srcStride || !srcFrameStride || !dst || !dstStride || !dstFrameStride) return B200_EINVAL;
+    if (!c->plan.planar) return B200_EINVAL;
+    for (int i = 0; i < 3; i++) if (!src[i] || !dst[i] || srcStride[i] < 0 || dstStride[i] < 0) return B200_EINVAL;
+    B200_CUDA_OK(cudaSetDevice(c->dev->ordinal));
+    const long long ss[3] = { srcStride[0], srcStride[1], srcStride[2] };
+    const long long fs[3] = { srcFrameStride[0], srcFrameStride[1], srcFrameStride[2] };
+    const long long ds[3] = { dstStride[0], dstStride[1], dstStride[2] };
+    const long long df[3] = { dstFrameStride[0], dstFrameStride[1], dstFrameStride[2] };
+    return launch_planar(c, c->dev->stream, src, ss, fs, dst, ds, df, nframes);
+}
+
+// sws_scale() with a yuv420p destination: whole frames, host pointers
+static int sws_scale_planar_host(B200SwsContext *c, const uint8_t *const srcSlice[], const int srcStride[],
+                                 int srcSliceY, int srcSliceH, uint8_t *const dst[], const int dstStride[])
+{
+    const SwsPlan &p = c->plan;
+    if (srcSliceY != 0 || srcSliceH != p.srcH) {
+        b200_set_error("yuv420p destination: only whole-frame calls are implemented");
+        return B200_ENOSYS;
+    }
+    for (int i = 0; i < 3; i++)
+        if (!srcSlice[i] || !dst[i] || srcStride[i] < 0 || dstStride[i] < 0) return srcSlice[i] && dst[i] ? B200_ENOSYS : B200_EINVAL;
+    B200Device *d = c->dev;
+    B200_CUDA_OK(cudaSetDevice(d->ordinal));
+    const int sw[3] = { p.srcW, p.chrSrcW, p.chrSrcW }, sh[3] = { p.srcH, p.chrSrcH, p.chrSrcH };
+    const int dw[3] = { p.dstW, p.chrDstW, p.chrDstW }, dh[3] = { p.dstH, p.chrDstH, p.chrDstH };
+    size_t spitch[3], dpitch[3], soff[3], doff[3], total = 0;
+    for (int i = 0; i < 3; i++) { spitch[i] = ((size_t)sw[i] + 255) & ~(size_t)255; soff[i] = total; total += spitch[i] * sh[i]; }
+    for (int i = 0; i < 3; i++) { dpitch[i] = ((size_t)dw[i] + 255) & ~(size_t)255; doff[i] = total; total += dpitch[i] * dh[i]; }
+    uint8_t *scr = (uint8_t *)b200_scratch(d, total);
+    if (!scr) return B200_ENOMEM;
+    cudaStream_t st = d->stream;
+    const uint8_t *sp[3]; uint8_t *dp[3]; long long ss[3], ds[3];
+    const long long zero[3] = { 0, 0, 0 };
+    for (int i = 0; i < 3; i++) {
+        B200_CUDA_OK(cudaMemcpy2DAsync(scr + soff[i], spitch[i], srcSlice[i], (size_t)srcStride[i], sw[i], sh[i], cudaMemcpyHostToDevice, st));
+        sp[i] = scr + soff[i]; dp[i] = scr + doff[i]; ss[i] = (long long)spitch[i]; ds[i] = (long long)dpitch[i];
+    }
+    int ret = launch_planar(c, st, sp, ss, zero, dp, ds, zero, 1);
+    if (ret < 0) return ret;
+    for (int i = 0; i < 3; i++)
+        B200_CUDA_OK(cudaMemcpy2DAsync(dst[i], (size_t)dstStride[i], dp[i], dpitch[i], dw[i], dh[i], cudaMemcpyDeviceToHost, st));
+    B200_CUDA_OK(cudaStreamSynchronize(st));
+    return p.dstH;
 }
 
 // device-side packed layout used by the host-pointer entry points
@@ -739,6 +880,7 @@ B200_API int b200_sws_scale_batch_host(B200SwsContext *c, const uint8_t *const s
                                        int64_t dstFrameStride, int nframes)
 {
     if (!c || !src || !srcStride || !srcFrameStride || !dst || nframes < 0) return B200_EINVAL;
+    if (c->plan.planar) return B200_EINVAL;
     B200Device *d = c->dev;
     B200_CUDA_OK(cudaSetDevice(d->ordinal));
     const SwsPlan &p = c->plan;
@@ -851,6 +993,7 @@ B200_API int b200_sws_scale(B200SwsContext *c, const uint8_t *const srcSlice[], 
 {
     if (!c || !srcSlice || !srcStride || !dst || !dstStride) return B200_EINVAL;
     const SwsPlan &p = c->plan;
+    if (p.planar) return sws_scale_planar_host(c, srcSlice, srcStride, srcSliceY, srcSliceH, dst, dstStride);
     if (srcSliceY != 0 || srcSliceH != p.srcH)
         return sws_scale_slice(c, srcSlice, srcStride, srcSliceY, srcSliceH, dst, dstStride);
     c->slice_open = false;

@@ -265,6 +265,7 @@ bool sws_out_format(int f, SwsOutFmt &o)
     case B200_PIX_FMT_BGRA:  o = { SWS_OUT_BGRA,  4, 2, 1, 0, 3 };  return true;
     case B200_PIX_FMT_ARGB:  o = { SWS_OUT_ARGB,  4, 1, 2, 3, 0 };  return true;
     case B200_PIX_FMT_ABGR:  o = { SWS_OUT_ABGR,  4, 3, 2, 1, 0 };  return true;
+    case B200_PIX_FMT_YUV420P: o = { SWS_OUT_YUV420P, 1, 0, 0, 0, -1 }; return true;
     }
     return false;
 }
@@ -276,19 +277,23 @@ int sws_plan_build(SwsPlan &p, int srcW, int srcH, int dstW, int dstH, int flags
     if (!algo) { algo = B200_SWS_BICUBIC; flags |= algo; }
     else if (algo & (algo - 1)) return B200_EINVAL;
     if (algo == B200_SWS_FAST_BILINEAR) return B200_ENOSYS;                      // hyscale_fast path (hscale_fast_bilinear.c) not built
-    if (dstW & 1) flags |= B200_SWS_FULL_CHR_H_INT;                              // utils.c:1271-1276
+    p.planar = p.out.kind == SWS_OUT_YUV420P;
+    if (!p.planar && (dstW & 1)) flags |= B200_SWS_FULL_CHR_H_INT;               // utils.c:1271-1276 (RGB destinations only)
     p.srcW = srcW; p.srcH = srcH; p.dstW = dstW; p.dstH = dstH; p.flags = flags;
-    p.chrDstHSub = (flags & B200_SWS_FULL_CHR_H_INT) ? 0 : 1;                    // utils.c:1359-1360
+    p.chrDstHSub = (!p.planar && (flags & B200_SWS_FULL_CHR_H_INT)) ? 0 : 1;     // utils.c:1359-1360
+    const int chrDstVSub = p.planar ? 1 : 0;                                     // av_pix_fmt_get_chroma_sub_sample(dstFormat), utils.c:1266
     p.chrSrcW = chroma_shift_up(srcW, 1);
     p.chrSrcH = chroma_shift_up(srcH, 1);
     p.chrDstW = chroma_shift_up(dstW, p.chrDstHSub);
-    p.chrDstH = dstH;                                                            // rgb24 has no vertical chroma subsampling
+    p.chrDstH = chroma_shift_up(dstH, chrDstVSub);                               // packed RGB has no vertical chroma subsampling
     static const int bt601[4] = { 104597, 132201, 25675, 53279 };                // ff_yuv2rgb_coeffs[SWS_CS_DEFAULT], yuv2rgb.c:47-59
     int ret = sws_plan_colorspace(p, bt601, 0, 0, 1 << 16, 1 << 16);
     if (ret < 0) return ret;
 
     // unscaled special converter gate: swscale_unscaled.c:2426-2431 reached from utils.c:1623-1637
-    p.unscaled_lut = srcW == dstW && srcH == dstH && !(flags & B200_SWS_ACCURATE_RND) && !(dstH & 1);
+    p.planar_copy = p.planar && srcW == dstW && srcH == dstH;
+    if (p.planar_copy) return 0;
+    p.unscaled_lut = !p.planar && srcW == dstW && srcH == dstH && !(flags & B200_SWS_ACCURATE_RND) && !(dstH & 1);
     if (p.unscaled_lut) return 0;
 
     const int lumScaler = algo == B200_SWS_BICUBLIN ? B200_SWS_BICUBIC : algo;
@@ -305,7 +310,8 @@ int sws_plan_build(SwsPlan &p, int srcW, int srcH, int dstW, int dstH, int flags
                           sample_origin(1, -513), sample_origin(p.chrDstHSub, -513))) < 0) return ret;
     if ((ret = build_bank(p.vLum, lumScaler, (int)lumYInc, srcH, dstH, 1 << 12, sample_origin(0, 0), sample_origin(0, 0))) < 0) return ret;
     if ((ret = build_bank(p.vChr, chrScaler, (int)chrYInc, p.chrSrcH, p.chrDstH, 1 << 12,
-                          sample_origin(1, -513), sample_origin(0, -513))) < 0) return ret;
+                          sample_origin(1, -513), sample_origin(chrDstVSub, -513))) < 0) return ret;
+    if (p.planar) return 0;
 
     // writer per output line, as packed_vscale decides it (vscale.c:144-169); coefficients are read as uint16 there
     p.rowMode.assign((size_t)dstH * 4, 0);

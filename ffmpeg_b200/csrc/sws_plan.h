@@ -24,7 +24,8 @@ struct SwsColorConst {
 
 // Packed 8-bit RGB outputs: bytes per pixel and the byte position of each channel (ao < 0: no alpha byte).
 // 32-bit formats carry alpha = 255 (yuv2rgb.c:947-960 adds 255 << abase to the ramp; output.c:2066-2095 stores 255).
-enum SwsOutKind { SWS_OUT_RGB24, SWS_OUT_BGR24, SWS_OUT_RGBA, SWS_OUT_BGRA, SWS_OUT_ARGB, SWS_OUT_ABGR };
+enum SwsOutKind { SWS_OUT_RGB24, SWS_OUT_BGR24, SWS_OUT_RGBA, SWS_OUT_BGRA, SWS_OUT_ARGB, SWS_OUT_ABGR,
+                  SWS_OUT_YUV420P /* planar destination: three planes, bpp = 1 */ };
 struct SwsOutFmt { int kind, bpp, ro, go, bo, ao; };
 bool sws_out_format(int av_pix_fmt, SwsOutFmt &o);
 
@@ -34,6 +35,8 @@ struct SwsPlan {
     int chrSrcW = 0, chrSrcH = 0, chrDstW = 0, chrDstH = 0;
     int chrDstHSub = 1;
     bool unscaled_lut = false;    // reference installs yuv2rgb_c_24_rgb as convert_unscaled
+    bool planar = false;          // destination yuv420p (yuv2planeX / yuv2plane1 writers, vscale.c:34-107)
+    bool planar_copy = false;     // same size yuv420p -> yuv420p: planarCopyWrapper (swscale_unscaled.c:2220,2675-2693)
     SwsFilterBank hLum, hChr, vLum, vChr;
     SwsColorConst color{};
     // per output line: writer selected by packed_vscale (vscale.c:144-169): 0 = _X, 1 = _1, 2 = _2, plus alphas

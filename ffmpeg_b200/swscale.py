@@ -1,4 +1,4 @@
-"""Host-side mirror of the libswscale interface for the accelerated path (yuv420p -> rgb24 / bgr24 / rgba / bgra / argb / abgr).
+"""Host-side mirror of the libswscale interface for the accelerated path (yuv420p -> rgb24 / bgr24 / rgba / bgra / argb / abgr / yuv420p).
 
 Names and argument meaning follow libswscale/swscale.h: sws_getContext (:utils.c:1919), sws_setColorspaceDetails
 (utils.c:849), sws_scale (swscale.c:1626), sws_freeContext.  Arrays are numpy (host) for sws_scale / scale_batch_host
@@ -31,7 +31,8 @@ class SwsContext:
         self.device = device
         self.srcW, self.srcH, self.dstW, self.dstH, self.flags = srcW, srcH, dstW, dstH, flags
         self.dstFormat = dstFormat
-        self.bpp = 3 if dstFormat in (AV_PIX_FMT_RGB24, AV_PIX_FMT_BGR24) else 4
+        self.planar = dstFormat == AV_PIX_FMT_YUV420P
+        self.bpp = 1 if self.planar else 3 if dstFormat in (AV_PIX_FMT_RGB24, AV_PIX_FMT_BGR24) else 4
         h = lib().b200_sws_getContext(device.handle, srcW, srcH, srcFormat, dstW, dstH, dstFormat, flags)
         if not h:
             raise B200Error("sws_getContext failed: " + lib().b200_last_error().decode())
@@ -74,6 +75,26 @@ class SwsContext:
         n = self.scale([y, u, v], [y.strides[0], u.strides[0], v.strides[0]], 0, self.srcH, [out], [ds])
         assert n == self.dstH
         return out
+
+    def convert_planar(self, y, u, v, dst_pad=0):
+        """yuv420p destination: whole frame, returns (Y, U, V) arrays."""
+        cw, ch = (self.dstW + 1) // 2, (self.dstH + 1) // 2
+        dy = np.full((self.dstH, self.dstW + dst_pad), 0xA5, np.uint8)
+        du = np.full((ch, cw + dst_pad), 0xA5, np.uint8)
+        dv = np.full((ch, cw + dst_pad), 0xA5, np.uint8)
+        n = self.scale([y, u, v], [y.strides[0], u.strides[0], v.strides[0]], 0, self.srcH, [dy, du, dv],
+                       [dy.strides[0], du.strides[0], dv.strides[0]])
+        assert n == self.dstH
+        return dy, du, dv
+
+    def scale_batch_device_planar(self, src, srcStride, srcFrameStride, dst, dstStride, dstFrameStride, nframes):
+        sp = (vp * 3)(*[_dptr(a) for a in src])
+        ss = (C.c_int32 * 3)(*srcStride)
+        fs = (C.c_int64 * 3)(*srcFrameStride)
+        dp = (vp * 3)(*[_dptr(a) for a in dst])
+        ds = (C.c_int32 * 3)(*dstStride)
+        df = (C.c_int64 * 3)(*dstFrameStride)
+        return check(lib().b200_sws_scale_batch_device_planar(self._h, sp, ss, fs, dp, ds, df, nframes), "sws_scale_batch_device_planar")
 
     def _batch(self, fn, src, srcStride, srcFrameStride, dst, dstStride, dstFrameStride, nframes, what):
         sp = (vp * 3)(*[_dptr(a) for a in src])

@@ -60,7 +60,8 @@ int   b200_memcpy_d2h(B200Device *dev, void *dst_host, const void *src_dev, size
 uint64_t b200_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------ libswscale
- * Replaces the legacy scaler for AV_PIX_FMT_YUV420P -> AV_PIX_FMT_RGB24:
+ * Replaces the legacy scaler for AV_PIX_FMT_YUV420P -> packed 8-bit RGB (rgb24, bgr24, rgba, bgra, argb, abgr) and
+ * AV_PIX_FMT_YUV420P -> AV_PIX_FMT_YUV420P (scaling):
  *   sws_getContext / sws_init_context ....... libswscale/utils.c:1919,1884 (ff_sws_init_single_context :1137)
  *   sws_setColorspaceDetails ................ libswscale/utils.c:849
  *   sws_scale ............................... libswscale/swscale.h:583, swscale.c:1626
@@ -107,6 +108,13 @@ int  b200_sws_func(void *c, const uint8_t *const src[], const int srcStride[], i
 int  b200_sws_scale_batch_device(B200SwsContext *c, const uint8_t *const src[3], const int srcStride[3],
                                  const int64_t srcFrameStride[3], uint8_t *dst, int dstStride,
                                  int64_t dstFrameStride, int nframes);
+/* yuv420p -> yuv420p (context created with dstFormat = B200_PIX_FMT_YUV420P; the reference's yuv2planeX_8_c / yuv2plane1_8_c
+ * writers, libswscale/output.c:468-493, and planarCopyWrapper at same size): three destination planes.
+ * b200_sws_scale() takes them as dst[0..2] / dstStride[0..2] like the reference; the single-plane batch entry points
+ * return B200_EINVAL for such a context and this one returns B200_EINVAL for a packed-RGB context. */
+int  b200_sws_scale_batch_device_planar(B200SwsContext *c, const uint8_t *const src[3], const int srcStride[3],
+                                        const int64_t srcFrameStride[3], uint8_t *const dst[3], const int dstStride[3],
+                                        const int64_t dstFrameStride[3], int nframes);
 /* batched, HOST pointers (pinned memory recommended): chunks of frames are copied in, converted and copied back
  * on rotating streams so that H2D, kernels and D2H overlap.  Synchronous: returns when dst is complete. */
 int  b200_sws_scale_batch_host(B200SwsContext *c, const uint8_t *const src[3], const int srcStride[3],

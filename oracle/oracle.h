@@ -36,6 +36,7 @@ extern "C" {
 typedef struct OrcSws OrcSws;
 
 /* AVPixelFormat values, libavutil/pixfmt.h */
+#define ORC_PIX_FMT_YUV420P 0
 #define ORC_PIX_FMT_RGB24 2
 #define ORC_PIX_FMT_BGR24 3
 #define ORC_PIX_FMT_ARGB  25
@@ -51,6 +52,9 @@ int     orc_sws_set_colorspace(OrcSws *s, const int inv_table[4], int srcRange,
 /* whole-frame conversion; returns number of output lines or <0 */
 int     orc_sws_scale(OrcSws *s, const uint8_t *y, int ys, const uint8_t *u, int us,
                       const uint8_t *v, int vs, uint8_t *dst, int ds);
+/* planar destination (context opened with ORC_PIX_FMT_YUV420P) */
+int     orc_sws_scale_planar(OrcSws *s, const uint8_t *y, int ys, const uint8_t *u, int us, const uint8_t *v, int vs,
+                             uint8_t *dy, int dys, uint8_t *du, int dus, uint8_t *dv, int dvs);
 /* 16 ints, same layout as ffref_sws_info */
 int     orc_sws_info(const OrcSws *s, int *out);
 /* which: 0 hLum 1 hChr 2 vLum 3 vChr; returns n entries copied */

@@ -89,6 +89,17 @@ API int ffref_sws_scale(void *h, const uint8_t *y, int ys, const uint8_t *u, int
     return sws_scale((SwsContext *)h, src, sstr, srcSliceY, srcSliceH, d, dstr);
 }
 
+/* planar destination (yuv420p -> yuv420p scaling): three destination planes */
+API int ffref_sws_scale_planar(void *h, const uint8_t *y, int ys, const uint8_t *u, int us, const uint8_t *v, int vs,
+                               int srcSliceY, int srcSliceH, uint8_t *dy, int dys, uint8_t *du, int dus, uint8_t *dv, int dvs)
+{
+    const uint8_t *src[4] = { y, u, v, NULL };
+    int sstr[4] = { ys, us, vs, 0 };
+    uint8_t *d[4] = { dy, du, dv, NULL };
+    int dstr[4] = { dys, dus, dvs, 0 };
+    return sws_scale((SwsContext *)h, src, sstr, srcSliceY, srcSliceH, d, dstr);
+}
+
 /* Introspection of the initialised context, for checking the host-side filter generation. */
 API int ffref_sws_info(void *h, int *out /* 16 ints */)
 {

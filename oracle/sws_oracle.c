@@ -31,6 +31,7 @@ struct OrcSws {
     int chrDstHSub;            /* 1: one chroma sample per two output pixels, 0: full chroma */
     int unscaled_lut;          /* 1: reference would install yuv2rgb_c_24_rgb / _24_bgr / _32 as convert_unscaled */
     int bpp, ro, go, bo, ao;   /* bytes per pixel and byte positions of R, G, B, A (ao < 0: no alpha byte) */
+    int planar;                /* 1: destination is yuv420p (three planes), 0: packed RGB */
     int16_t *hLum, *hChr, *vLum, *vChr;
     int32_t *hLumPos, *hChrPos, *vLumPos, *vChrPos;
     int hLumSize, hChrSize, vLumSize, vChrSize;
@@ -288,7 +289,9 @@ OrcSws *orc_sws_open(int srcW, int srcH, int dstW, int dstH, int flags)
  * (yuv2rgb.c:901-914 vs :947-966), and yuv2rgb_write sums r[Y] + g[Y] + b[Y] (output.c:1676-1695). */
 static int set_format(OrcSws *s, int fmt)
 {
+    s->planar = 0;
     switch (fmt) {
+    case ORC_PIX_FMT_YUV420P: s->planar = 1; s->bpp = 1; s->ro = s->go = s->bo = 0; s->ao = -1; break;
     case ORC_PIX_FMT_RGB24: s->bpp = 3; s->ro = 0; s->go = 1; s->bo = 2; s->ao = -1; break;
     case ORC_PIX_FMT_BGR24: s->bpp = 3; s->ro = 2; s->go = 1; s->bo = 0; s->ao = -1; break;
     case ORC_PIX_FMT_RGBA:  s->bpp = 4; s->ro = 0; s->go = 1; s->bo = 2; s->ao = 3;  break;
@@ -310,15 +313,20 @@ OrcSws *orc_sws_open_fmt(int srcW, int srcH, int dstW, int dstH, int dstFormat, 
     if (!algo) { algo = ORC_SWS_BICUBIC; flags |= algo; }           /* utils.c:1209-1217 */
     else if (algo & (algo - 1)) goto fail;
     if (algo == ORC_SWS_FAST_BILINEAR) goto fail;                  /* hyscale_fast path not restated */
-    if (dstW & 1) flags |= ORC_SWS_FULL_CHR_H_INT;                 /* utils.c:1271-1276 */
+    if (!s->planar && (dstW & 1)) flags |= ORC_SWS_FULL_CHR_H_INT; /* utils.c:1271-1276 (RGB destinations only) */
     s->srcW = srcW; s->srcH = srcH; s->dstW = dstW; s->dstH = dstH; s->flags = flags;
-    s->chrDstHSub = (flags & ORC_SWS_FULL_CHR_H_INT) ? 0 : 1;      /* utils.c:1359-1360 */
+    s->chrDstHSub = (!s->planar && (flags & ORC_SWS_FULL_CHR_H_INT)) ? 0 : 1;      /* utils.c:1359-1360 */
+    const int chrDstVSub = s->planar ? 1 : 0;                      /* av_pix_fmt_get_chroma_sub_sample(dstFormat), utils.c:1266 */
     s->chrSrcW = ceil_rshift(srcW, 1); s->chrSrcH = ceil_rshift(srcH, 1);
-    s->chrDstW = ceil_rshift(dstW, s->chrDstHSub); s->chrDstH = dstH;
+    s->chrDstW = ceil_rshift(dstW, s->chrDstHSub); s->chrDstH = ceil_rshift(dstH, chrDstVSub);
     orc_sws_set_colorspace(s, default_coeffs, 0, 0, 1 << 16, 1 << 16);
 
+    if (s->planar && srcW == dstW && srcH == dstH) {               /* planarCopyWrapper, swscale_unscaled.c:2675-2693 */
+        s->unscaled_lut = 2;
+        return s;
+    }
     /* swscale_unscaled.c:2426-2431 through utils.c:1623-1637 */
-    if (srcW == dstW && srcH == dstH && !(flags & ORC_SWS_ACCURATE_RND) && !(dstH & 1)) {
+    if (!s->planar && srcW == dstW && srcH == dstH && !(flags & ORC_SWS_ACCURATE_RND) && !(dstH & 1)) {
         s->unscaled_lut = 1;
         return s;
     }
@@ -335,7 +343,7 @@ OrcSws *orc_sws_open_fmt(int srcW, int srcH, int dstW, int dstH, int dstFormat, 
     if (make_filter(&s->vLum, &s->vLumPos, &s->vLumSize, (int)lumYInc, srcH, dstH, 1 << 12, lum_scaler, flags,
                     local_pos(0, 0), local_pos(0, 0)) < 0) goto fail;
     if (make_filter(&s->vChr, &s->vChrPos, &s->vChrSize, (int)chrYInc, s->chrSrcH, s->chrDstH, 1 << 12, chr_scaler, flags,
-                    local_pos(1, -513), local_pos(0, -513)) < 0) goto fail;
+                    local_pos(1, -513), local_pos(chrDstVSub, -513)) < 0) goto fail;
     return s;
 fail:
     orc_sws_close(s);
@@ -432,9 +440,69 @@ static void convert_unscaled(const OrcSws *s, const uint8_t *y, int ys, const ui
     }
 }
 
+/* yuv2planeX_8_c / yuv2plane1_8_c (output.c:468-493) with the flat dither the 8-bit path uses (sws_pb_64, swscale.c:385-387):
+ * one output line of one plane from `fs` int16 source lines */
+static void vscale_plane_line(uint8_t *dst, int w, const int16_t *plane, int pw, int nlines, int first, const int16_t *f, int fs)
+{
+    for (int i = 0; i < w; i++) {
+        int val;
+        if (fs == 1) {
+            int k = first < 0 ? 0 : first >= nlines ? nlines - 1 : first;
+            val = (plane[(size_t)k * pw + i] + 64) >> 7;
+        } else {
+            val = 64 << 12;
+            for (int j = 0; j < fs; j++) {
+                int k = first + j;
+                k = k < 0 ? 0 : k >= nlines ? nlines - 1 : k;
+                val += plane[(size_t)k * pw + i] * f[j];
+            }
+            val >>= 19;
+        }
+        dst[i] = (uint8_t)clip_u8(val);
+    }
+}
+
+/* yuv420p -> yuv420p: horizontal pass per plane, then lum_planar_vscale / chr_planar_vscale (vscale.c:34-107) */
+int orc_sws_scale_planar(OrcSws *s, const uint8_t *y, int ys, const uint8_t *u, int us, const uint8_t *v, int vs,
+                         uint8_t *dy, int dys, uint8_t *du, int dus, uint8_t *dv, int dvs)
+{
+    if (!s->planar) return -EINVAL;
+    if (s->unscaled_lut == 2) {
+        for (int r = 0; r < s->srcH; r++) memcpy(dy + (ptrdiff_t)r * dys, y + (ptrdiff_t)r * ys, s->srcW);
+        for (int r = 0; r < s->chrSrcH; r++) {
+            memcpy(du + (ptrdiff_t)r * dus, u + (ptrdiff_t)r * us, s->chrSrcW);
+            memcpy(dv + (ptrdiff_t)r * dvs, v + (ptrdiff_t)r * vs, s->chrSrcW);
+        }
+        return s->srcH;
+    }
+    const int dstW = s->dstW, cW = s->chrDstW;
+    int16_t *L = malloc((size_t)s->srcH * dstW * sizeof(int16_t));
+    int16_t *CU = malloc((size_t)s->chrSrcH * cW * sizeof(int16_t));
+    int16_t *CV = malloc((size_t)s->chrSrcH * cW * sizeof(int16_t));
+    if (!L || !CU || !CV) { free(L); free(CU); free(CV); return -ENOMEM; }
+    for (int r = 0; r < s->srcH; r++)
+        orc_hscale8to15(L + (size_t)r * dstW, dstW, y + (ptrdiff_t)r * ys, s->hLum, s->hLumPos, s->hLumSize);
+    for (int r = 0; r < s->chrSrcH; r++) {
+        orc_hscale8to15(CU + (size_t)r * cW, cW, u + (ptrdiff_t)r * us, s->hChr, s->hChrPos, s->hChrSize);
+        orc_hscale8to15(CV + (size_t)r * cW, cW, v + (ptrdiff_t)r * vs, s->hChr, s->hChrPos, s->hChrSize);
+    }
+    for (int d = 0; d < s->dstH; d++) {
+        int first = s->vLumPos[d] > 1 - s->vLumSize ? s->vLumPos[d] : 1 - s->vLumSize;
+        vscale_plane_line(dy + (ptrdiff_t)d * dys, dstW, L, dstW, s->srcH, first, s->vLum + d * s->vLumSize, s->vLumSize);
+    }
+    for (int d = 0; d < s->chrDstH; d++) {
+        int first = s->vChrPos[d] > 1 - s->vChrSize ? s->vChrPos[d] : 1 - s->vChrSize;
+        vscale_plane_line(du + (ptrdiff_t)d * dus, cW, CU, cW, s->chrSrcH, first, s->vChr + d * s->vChrSize, s->vChrSize);
+        vscale_plane_line(dv + (ptrdiff_t)d * dvs, cW, CV, cW, s->chrSrcH, first, s->vChr + d * s->vChrSize, s->vChrSize);
+    }
+    free(L); free(CU); free(CV);
+    return s->dstH;
+}
+
 int orc_sws_scale(OrcSws *s, const uint8_t *y, int ys, const uint8_t *u, int us,
                   const uint8_t *v, int vs, uint8_t *dst, int ds)
 {
+    if (s->planar) return -EINVAL;
     if (s->unscaled_lut) {
         convert_unscaled(s, y, ys, u, us, v, vs, dst, ds);
         return s->srcH;

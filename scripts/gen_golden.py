@@ -67,6 +67,18 @@ def gen_sws_formats():
     open(os.path.join(OUT, "sws_format_hashes.txt"), "w").write("\n".join(lines) + "\n")
 
 
+def gen_sws_planar():
+    """yuv420p -> yuv420p outputs of the reference for SWS_PLANAR_CASES (sha256 of Y, U, V planes concatenated)."""
+    from cases import SWS_PLANAR_CASES
+    lines = []
+    for i, (w, h, dw, dh, fl, kind) in enumerate(SWS_PLANAR_CASES):
+        y, u, v = cl.yuv_frame(w, h, 600 + i, kind)
+        out = cl.ref_sws_planar(w, h, dw, dh, fl, y, u, v)
+        assert out is not None
+        lines.append(f"{i} {w} {h} {dw} {dh} {fl} {kind} {sha(np.concatenate([p.ravel() for p in out]))}")
+    open(os.path.join(OUT, "sws_planar_hashes.txt"), "w").write("\n".join(lines) + "\n")
+
+
 def gen_idct():
     R = cl.ref()
     d = {}
@@ -248,6 +260,7 @@ if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     gen_sws()
     gen_sws_formats()
+    gen_sws_planar()
     gen_idct()
     gen_mecmp()
     gen_pel()

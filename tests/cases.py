@@ -95,3 +95,11 @@ SWS_FORMAT_CASES = [(64, 48, 64, 48, FATE, "random"), (64, 48, 64, 48, SWS_BICUB
                     (64, 48, 33, 21, SWS_BILINEAR, "random"), (38, 22, 38, 22, SWS_BICUBIC, "random"), (70, 30, 70, 30, FATE, "smooth"),
                     (64, 48, 64, 48, FATE | SWS_FULL_CHR_H_INT, "random"), (352, 288, 352, 288, FATE, "random"),
                     (352, 288, 352, 288, SWS_BICUBIC, "limited"), (352, 288, 200, 100, FATE, "random")]
+
+
+# yuv420p -> yuv420p (yuv2planeX / yuv2plane1 writers, planarCopyWrapper): (w, h, dw, dh, flags, kind)
+SWS_PLANAR_CASES = [(64, 48, 64, 48, FATE, "random"), (64, 48, 100, 70, FATE, "random"), (64, 48, 33, 21, SWS_BILINEAR, "limited"),
+                    (66, 50, 40, 96, SWS_BICUBIC, "random"), (64, 48, 128, 96, SWS_BILINEAR, "smooth"), (64, 48, 64, 30, FATE, "random"),
+                    (64, 48, 32, 48, SWS_BICUBIC, "random"), (352, 288, 200, 100, FATE, "random"), (100, 50, 37, 21, FATE, "limited"),
+                    (64, 48, 64, 47, SWS_POINT, "random"), (64, 48, 31, 17, SWS_AREA, "random"), (352, 288, 640, 360, SWS_BICUBLIN, "random"),
+                    (63, 47, 80, 60, SWS_BICUBIC, "random"), (352, 288, 176, 144, FATE, "smooth")]

@@ -39,6 +39,7 @@ def oracle():
         L.orc_sws_close.argtypes = [C.c_void_p]
         L.orc_sws_set_colorspace.argtypes = [C.c_void_p, i32p, C.c_int, C.c_int, C.c_int, C.c_int]
         L.orc_sws_scale.argtypes = [C.c_void_p, u8p, C.c_int, u8p, C.c_int, u8p, C.c_int, u8p, C.c_int]
+        L.orc_sws_scale_planar.argtypes = [C.c_void_p, u8p, C.c_int, u8p, C.c_int, u8p, C.c_int, u8p, C.c_int, u8p, C.c_int, u8p, C.c_int]
         L.orc_sws_info.argtypes = [C.c_void_p, i32p]
         L.orc_sws_get_filter.argtypes = [C.c_void_p, C.c_int, i16p, i32p, C.c_int]
         L.orc_hscale8to15.argtypes = [i16p, C.c_int, u8p, i16p, i32p, C.c_int]
@@ -81,6 +82,8 @@ def ref():
         L.ffref_sws_close.argtypes = [C.c_void_p]
         L.ffref_sws_set_colorspace.argtypes = [C.c_void_p] + [C.c_int] * 7
         L.ffref_sws_scale.argtypes = [C.c_void_p, u8p, C.c_int, u8p, C.c_int, u8p, C.c_int, C.c_int, C.c_int, u8p, C.c_int]
+        L.ffref_sws_scale_planar.argtypes = [C.c_void_p, u8p, C.c_int, u8p, C.c_int, u8p, C.c_int, C.c_int, C.c_int,
+                                             u8p, C.c_int, u8p, C.c_int, u8p, C.c_int]
         L.ffref_sws_info.argtypes = [C.c_void_p, i32p]
         L.ffref_sws_get_filter.argtypes = [C.c_void_p, C.c_int, i16p, i32p, C.c_int]
         L.ffref_sws_hscale.argtypes = [C.c_void_p, C.c_int, i16p, C.c_int, u8p, i16p, i32p, C.c_int]
@@ -161,6 +164,43 @@ def _sws_run(lib, pre, w, h, dw, dh, flags, y, u, v, dst_pad=0, threads=1, color
         return dst
     finally:
         (lib.ffref_sws_close if pre == "ffref" else lib.orc_sws_close)(ctx)
+
+
+PIX_FMT_YUV420P = 0
+
+
+def _sws_run_planar(lib, pre, w, h, dw, dh, flags, y, u, v, dst_pad=0, threads=1):
+    """yuv420p -> yuv420p; returns (Y, U, V) destination planes (pad bytes stay 0xA5)."""
+    if pre == "ffref":
+        ctx = lib.ffref_sws_open_fmt(w, h, dw, dh, PIX_FMT_YUV420P, flags, threads)
+    else:
+        ctx = lib.orc_sws_open_fmt(w, h, dw, dh, PIX_FMT_YUV420P, flags)
+    if not ctx:
+        return None
+    try:
+        cw, ch = (dw + 1) // 2, (dh + 1) // 2
+        dy = np.full((dh, dw + dst_pad), 0xA5, np.uint8)
+        du = np.full((ch, cw + dst_pad), 0xA5, np.uint8)
+        dv = np.full((ch, cw + dst_pad), 0xA5, np.uint8)
+        if pre == "ffref":
+            n = lib.ffref_sws_scale_planar(ctx, ptr(y), y.strides[0], ptr(u), u.strides[0], ptr(v), v.strides[0], 0, h,
+                                           ptr(dy), dy.strides[0], ptr(du), du.strides[0], ptr(dv), dv.strides[0])
+        else:
+            n = lib.orc_sws_scale_planar(ctx, ptr(y), y.strides[0], ptr(u), u.strides[0], ptr(v), v.strides[0],
+                                         ptr(dy), dy.strides[0], ptr(du), du.strides[0], ptr(dv), dv.strides[0])
+        assert n == dh, n
+        return dy, du, dv
+    finally:
+        (lib.ffref_sws_close if pre == "ffref" else lib.orc_sws_close)(ctx)
+
+
+def ref_sws_planar(w, h, dw, dh, flags, y, u, v, **kw):
+    return _sws_run_planar(ref(), "ffref", w, h, dw, dh, flags, y, u, v, **kw)
+
+
+def orc_sws_planar(w, h, dw, dh, flags, y, u, v, **kw):
+    kw.pop("threads", None)
+    return _sws_run_planar(oracle(), "orc", w, h, dw, dh, flags, y, u, v, **kw)
 
 
 COEFFS = {  # libswscale/yuv2rgb.c:47-59, indexed by SWS_CS_*

@@ -61,6 +61,33 @@ def test_sws_oracle_formats_are_byte_permutations_of_rgb24():
                 assert np.array_equal(out[:, :, k], np.broadcast_to(exp, (dh, dw))), (name, ch, dw, dh, hex(fl))
 
 
+def test_sws_oracle_planar_golden_hashes():
+    """yuv420p -> yuv420p scaling (yuv2planeX / yuv2plane1 / plane copy) against the reference's outputs."""
+    n = 0
+    for line in open(os.path.join(G, "sws_planar_hashes.txt")):
+        i, w, h, dw, dh, fl, kind, hout = line.split()
+        i, w, h, dw, dh, fl = map(int, (i, w, h, dw, dh, fl))
+        y, u, v = cl.yuv_frame(w, h, 600 + i, kind)
+        out = cl.orc_sws_planar(w, h, dw, dh, fl, y, u, v)
+        assert sha(np.concatenate([p.ravel() for p in out])) == hout, (i, w, h, dw, dh, hex(fl))
+        n += 1
+    assert n == 14
+
+
+def test_sws_oracle_planar_vs_ref():
+    if not cl.have_ref():
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(8)
+    for it in range(25):
+        w, h = int(rng.integers(8, 120)), int(rng.integers(8, 90))
+        dw, dh = int(rng.integers(8, 160)), int(rng.integers(8, 120))
+        fl = int(rng.choice([FATE, cl.SWS_BICUBIC, cl.SWS_BILINEAR, cl.SWS_POINT, cl.SWS_AREA, cl.SWS_BICUBLIN]))
+        y, u, v = cl.yuv_frame(w, h, 700 + it, "random", pad=int(rng.integers(0, 9)))
+        a = cl.ref_sws_planar(w, h, dw, dh, fl, y, u, v, dst_pad=3)
+        b = cl.orc_sws_planar(w, h, dw, dh, fl, y, u, v, dst_pad=3)
+        assert all(np.array_equal(p, q) for p, q in zip(a, b)), (w, h, dw, dh, hex(fl))
+
+
 def test_sws_oracle_colorspace_golden():
     g = np.load(os.path.join(G, "sws_colorspace.npz"))
     y, u, v = g["y"], g["u"], g["v"]

@@ -131,6 +131,73 @@ def test_other_formats_slices_and_batch(device):
         sw.sws_getContext(device, 64, 48, 0, 64, 48, 4, FATE)           # AV_PIX_FMT_YUV422P as destination: not this path
 
 
+def gpu_sws_planar(device, w, h, dw, dh, fl, y, u, v, dst_pad=0):
+    from ffmpeg_b200 import swscale as sw
+    ctx = sw.sws_getContext(device, w, h, sw.AV_PIX_FMT_YUV420P, dw, dh, sw.AV_PIX_FMT_YUV420P, fl)
+    try:
+        return ctx.convert_planar(y, u, v, dst_pad=dst_pad)
+    finally:
+        ctx.free()
+
+
+def test_planar_golden_hashes(device):
+    """yuv420p -> yuv420p scaling against the reference's outputs (sws_planar_hashes.txt)."""
+    n = 0
+    for line in open(os.path.join(G, "sws_planar_hashes.txt")):
+        i, w, h, dw, dh, fl, kind, hout = line.split()
+        i, w, h, dw, dh, fl = map(int, (i, w, h, dw, dh, fl))
+        y, u, v = cl.yuv_frame(w, h, 600 + i, kind)
+        out = gpu_sws_planar(device, w, h, dw, dh, fl, y, u, v)
+        assert sha(np.concatenate([p.ravel() for p in out])) == hout, (i, w, h, dw, dh, hex(fl))
+        n += 1
+    assert n == 14
+
+
+@pytest.mark.parametrize("case", [(640, 360, 1280, 720, FATE), (1920, 1080, 1280, 720, cl.SWS_BICUBIC), (3840, 2160, 1920, 1080, FATE),
+                                  (351, 287, 351, 287, cl.SWS_BICUBIC), (640, 360, 641, 361, cl.SWS_BILINEAR)])
+def test_planar_vs_oracle(device, case):
+    w, h, dw, dh, fl = case
+    for seed, kind, pad, dpad in ((1, "random", 0, 0), (2, "limited", 5, 3)):
+        y, u, v = cl.yuv_frame(w, h, seed, kind, pad=pad)
+        a = cl.orc_sws_planar(w, h, dw, dh, fl, y, u, v, dst_pad=dpad)
+        b = gpu_sws_planar(device, w, h, dw, dh, fl, y, u, v, dst_pad=dpad)
+        for pa, pb, name in zip(a, b, "YUV"):
+            assert np.array_equal(pa, pb), (case, seed, name, int((pa != pb).sum()))
+
+
+def test_planar_batch_device_and_errors(device):
+    import torch
+    import ffmpeg_b200 as fb
+    from ffmpeg_b200 import swscale as sw
+    w, h, dw, dh, n = 320, 180, 480, 270, 3
+    frames = [cl.yuv_frame(w, h, 90 + i, "random") for i in range(n)]
+    Y, U, V = (np.stack([f[k] for f in frames]) for k in range(3))
+    ctx = sw.sws_getContext(device, w, h, 0, dw, dh, sw.AV_PIX_FMT_YUV420P, FATE)
+    cw, ch, cdw, cdh = w // 2, h // 2, dw // 2, dh // 2
+    with torch.cuda.stream(torch.cuda.ExternalStream(device.stream)):
+        dY, dU, dV = torch.from_numpy(Y).cuda(), torch.from_numpy(U).cuda(), torch.from_numpy(V).cuda()
+        oY = torch.zeros((n, dh, dw), dtype=torch.uint8, device="cuda")
+        oU = torch.zeros((n, cdh, cdw), dtype=torch.uint8, device="cuda")
+        oV = torch.zeros((n, cdh, cdw), dtype=torch.uint8, device="cuda")
+        ctx.scale_batch_device_planar([dY, dU, dV], [w, cw, cw], [w * h, cw * ch, cw * ch], [oY, oU, oV], [dw, cdw, cdw],
+                                      [dw * dh, cdw * cdh, cdw * cdh], n)
+        with pytest.raises(fb.B200Error):                      # single-plane entry point on a planar context
+            ctx.scale_batch_device([dY, dU, dV], [w, cw, cw], [w * h, cw * ch, cw * ch], oY, dw, dw * dh, n)
+        device.sync()
+        got = [t.cpu().numpy() for t in (oY, oU, oV)]
+    for i in range(n):
+        ref = cl.orc_sws_planar(w, h, dw, dh, FATE, *frames[i])
+        for k in range(3):
+            assert np.array_equal(got[k][i], ref[k]), (i, k)
+    with pytest.raises(fb.B200Error):                          # slices are not implemented for the planar destination
+        ctx.scale([Y[0], U[0], V[0]], [w, cw, cw], 0, 16, [np.zeros((dh, dw), np.uint8)] * 3, [dw, cdw, cdw])
+    ctx.free()
+    rgb = sw.sws_getContext(device, w, h, 0, dw, dh, sw.AV_PIX_FMT_RGB24, FATE)
+    with pytest.raises(fb.B200Error):
+        rgb.scale_batch_device_planar([0, 0, 0], [w, cw, cw], [0, 0, 0], [0, 0, 0], [dw, cdw, cdw], [0, 0, 0], 1)
+    rgb.free()
+
+
 def test_bottom_up_strides(device):
     """Negative strides (bottom-up pictures) are legal for sws_scale (libswscale/swscale.c:1141-1159)."""
     from ffmpeg_b200 import swscale as sw
