@@ -196,3 +196,47 @@ def test_mb420_frames(device, op):
     for pl in range(3):
         # the host entry point only writes the picture area (W x H), padding columns stay untouched
         assert np.array_equal(hp[pl], ref[pl]), pl
+
+
+@pytest.mark.parametrize("op", [1, 2])
+def test_mb420_full_batch_properties(device, op):
+    """BASELINE config 3 batch size (256 x 1080p frames = 12.5 M blocks per call): 4 distinct frames of coefficients repeated
+    64 times into identical destination pictures must give 64 identical groups of pictures, and the first group equals the
+    oracle bit for bit (put: the result does not depend on the old destination; add: it does, so destinations repeat too)."""
+    import torch
+    from ffmpeg_b200 import idctdsp
+    O = cl.oracle()
+    mb_w, mb_h, nd, reps = 120, 68, 4, 64
+    per = mb_w * mb_h * 6
+    nblk = per * nd
+    blk = np.concatenate([idct_blocks(k, nblk // 4 + 1, 23) for k in ("dense", "sparse", "wide", "dc63")])[:nblk]
+    blk = np.ascontiguousarray(blk[np.random.default_rng(6).permutation(nblk)])
+    W, H = mb_w * 16, mb_h * 16
+    ls = [W, W // 2, W // 2]
+    rng = np.random.default_rng(7)
+    planes = [rng.integers(0, 256, (nd, H, ls[0]), dtype=np.uint8), rng.integers(0, 256, (nd, H // 2, ls[1]), dtype=np.uint8),
+              rng.integers(0, 256, (nd, H // 2, ls[2]), dtype=np.uint8)]
+    ref = [p.copy() for p in planes]
+    b = np.arange(nblk)
+    f, r = b // per, b % per
+    mb, k = r // 6, r % 6
+    mby, mbx = mb // mb_w, mb % mb_w
+    for pl in range(3):
+        sel = (k < 4) if pl == 0 else (k == 3 + pl)
+        if pl == 0:
+            off = f * H * ls[0] + (mby * 16 + (k >> 1) * 8) * ls[0] + mbx * 16 + (k & 1) * 8
+        else:
+            off = f * (H // 2) * ls[pl] + (mby * 8) * ls[pl] + mbx * 8
+        bs = np.ascontiguousarray(blk[sel])
+        O.orc_idct_batch(op, cl.ptr(bs, cl.i16p), int(sel.sum()), cl.ptr(ref[pl]), ls[pl], cl.ptr(np.ascontiguousarray(off[sel]).astype(np.int64), cl.i64p))
+    fs = [H * ls[0], (H // 2) * ls[1], (H // 2) * ls[2]]
+    with torch.cuda.stream(torch.cuda.ExternalStream(device.stream)):
+        db = torch.from_numpy(blk).cuda().repeat(reps, 1)
+        dp = [torch.from_numpy(p).cuda().repeat(reps, 1, 1) for p in planes]
+        idctdsp.idct_mb420_device(device, op, db, mb_w, mb_h, nd * reps, dp, ls, fs)
+        device.sync()
+        for pl in range(3):
+            base = dp[pl][:nd]
+            for rr in range(1, reps):
+                assert torch.equal(dp[pl][rr * nd:(rr + 1) * nd], base), (pl, rr)
+            assert np.array_equal(base.cpu().numpy(), ref[pl]), pl

@@ -278,6 +278,32 @@ def test_batch_device_and_host_4k(device, fl):
     ctx.free()
 
 
+def test_full_batch_256_properties(device):
+    """BASELINE config 2 at its full size (256 x 4K frames, 9.6 GB per call): the batch holds 8 distinct frames repeated 32
+    times, so every output must equal the output of the same frame elsewhere in the batch (frames are independent, no
+    state leaks across the batch), and two of the distinct frames are checked against the oracle bit for bit."""
+    import torch
+    from ffmpeg_b200 import swscale as sw
+    w, h, n, nd = 3840, 2160, 256, 8
+    frames = [cl.yuv_frame(w, h, 900 + i, "random" if i % 2 else "limited") for i in range(nd)]
+    ctx = sw.sws_getContext(device, w, h, 0, w, h, sw.AV_PIX_FMT_RGB24, FATE)
+    with torch.cuda.stream(torch.cuda.ExternalStream(device.stream)):
+        dY, dU, dV = (torch.from_numpy(np.stack([f[k] for f in frames])).cuda().repeat(n // nd, 1, 1) for k in range(3))
+        out = torch.empty((n, h, w * 3), dtype=torch.uint8, device="cuda")
+        ctx.scale_batch_device([dY, dU, dV], [w, w // 2, w // 2], [w * h, w * h // 4, w * h // 4], out, w * 3, w * h * 3, n)
+        device.sync()
+        base = out[:nd]
+        for r in range(1, n // nd):
+            assert torch.equal(out[r * nd:(r + 1) * nd], base), r
+        # checksum of checksums: the 8 distinct frames give 8 distinct pictures
+        sums = [int(base[i].to(torch.int64).sum().item()) for i in range(nd)]
+        assert len(set(sums)) == nd
+        got = {i: base[i].cpu().numpy() for i in (0, nd - 1)}
+    for i, g in got.items():
+        assert np.array_equal(g, cl.orc_sws(w, h, w, h, FATE, *frames[i])), i
+    ctx.free()
+
+
 def test_vsynth1_frame0(device):
     """FATE's own test picture (vsynth1 frame 0) through the CUDA path, against the reference's output fixtures."""
     g = np.load(os.path.join(G, "vsynth1_f0.npz"))
