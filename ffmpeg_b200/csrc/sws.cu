@@ -885,11 +885,13 @@ B200_API int b200_sws_scale_batch_host(B200SwsContext *c, const uint8_t *const s
     B200_CUDA_OK(cudaSetDevice(d->ordinal));
     const SwsPlan &p = c->plan;
     const PackedLayout L = packed_layout(p);
-    // chunk so that the 3 in-flight chunks stay within ~1.5 GB of scratch, and kernels stay large enough
+    // Chunks of at most 8 frames: the device-to-host copies are the bottleneck of this entry point (PCIe), and they can
+    // only start once the first chunk has been uploaded and converted, so short chunks keep the pipeline fill short;
+    // the three in-flight chunks stay within ~0.8 GB of scratch at 4K.
     const size_t perFrame = L.srcBytes + L.dstBytes;
-    int chunk = (int)((size_t)512 << 20) / (int)(perFrame ? perFrame : 1);
+    int chunk = (int)((size_t)256 << 20) / (int)(perFrame ? perFrame : 1);
     if (chunk < 1) chunk = 1;
-    if (chunk > 32) chunk = 32;
+    if (chunk > 8) chunk = 8;
     if (chunk > nframes) chunk = nframes > 0 ? nframes : 1;
     const int K = B200Device::kPipe;
     uint8_t *scr = (uint8_t *)b200_scratch(d, perFrame * chunk * K);
@@ -903,25 +905,28 @@ B200_API int b200_sws_scale_batch_host(B200SwsContext *c, const uint8_t *const s
         cudaStream_t st = d->pipe[slot];
         uint8_t *sbase = scr + (size_t)slot * perFrame * chunk;
         uint8_t *dbase = sbase + L.srcBytes * chunk;
-        for (int f = 0; f < nf; f++)
-            for (int pl = 0; pl < 3; pl++) {
+        for (int pl = 0; pl < 3; pl++) {
+            if (srcStride[pl] < 0) return B200_ENOSYS;                    // bottom-up pictures: use b200_sws_scale()
+            for (int f = 0; f < nf; f++) {
                 const uint8_t *hp = src[pl] + (int64_t)(f0 + f) * srcFrameStride[pl];
-                long long hs = srcStride[pl];
                 uint8_t *dp = sbase + (size_t)f * L.srcBytes + poff[pl];
-                if (hs < 0) {                                           // bottom-up picture: copy from the lowest address, flip on the device side
-                    return B200_ENOSYS;
-                }
-                B200_CUDA_OK(cudaMemcpy2DAsync(dp, pitch[pl], hp, (size_t)hs, wbytes[pl], rows[pl], cudaMemcpyHostToDevice, st));
+                B200_CUDA_OK(cudaMemcpy2DAsync(dp, pitch[pl], hp, (size_t)srcStride[pl], wbytes[pl], rows[pl], cudaMemcpyHostToDevice, st));
             }
+        }
         const uint8_t *sp[3] = { sbase + L.yOff, sbase + L.uOff, sbase + L.vOff };
         const long long ss[3] = { (long long)L.yPitch, (long long)L.cPitch, (long long)L.cPitch };
         const long long fs[3] = { (long long)L.srcBytes, (long long)L.srcBytes, (long long)L.srcBytes };
         int ret = launch_batch(c, st, sp, ss, fs, dbase, (long long)L.dPitch, (long long)L.dstBytes, nf);
         if (ret < 0) return ret;
-        for (int f = 0; f < nf; f++)
-            B200_CUDA_OK(cudaMemcpy2DAsync(dst + (int64_t)(f0 + f) * dstFrameStride, (size_t)dstStride,
-                                           dbase + (size_t)f * L.dstBytes, L.dPitch, (size_t)p.dstW * p.out.bpp, p.dstH,
-                                           cudaMemcpyDeviceToHost, st));
+        const size_t rowBytes = (size_t)p.dstW * p.out.bpp;
+        if ((size_t)dstStride == rowBytes && L.dPitch == rowBytes && dstFrameStride == (int64_t)(rowBytes * p.dstH)) {
+            // contiguous on both sides: the whole chunk comes back as one linear copy
+            B200_CUDA_OK(cudaMemcpyAsync(dst + (int64_t)f0 * dstFrameStride, dbase, L.dstBytes * nf, cudaMemcpyDeviceToHost, st));
+        } else {
+            for (int f = 0; f < nf; f++)
+                B200_CUDA_OK(cudaMemcpy2DAsync(dst + (int64_t)(f0 + f) * dstFrameStride, (size_t)dstStride,
+                                               dbase + (size_t)f * L.dstBytes, L.dPitch, rowBytes, p.dstH, cudaMemcpyDeviceToHost, st));
+        }
     }
     for (int i = 0; i < K; i++) B200_CUDA_OK(cudaStreamSynchronize(d->pipe[i]));
     return 0;

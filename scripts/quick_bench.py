@@ -60,6 +60,28 @@ with torch.cuda.stream(stream):
         hs = torch.full((n,), 8, dtype=torch.uint8, device="cuda")
         xys = torch.randint(0, 64, (n,), device="cuda", generator=g).to(torch.uint8)
         timed(lambda: pel.h264chroma_batch_device(dev, n, ops, hs, xys, dstp, doff, refp, soff, PW), n, "blocks", 177)
+    elif what == "e2e":
+        import time
+        W, H, B = 3840, 2160, 256
+        hY = torch.randint(0, 256, (B, H, W), dtype=torch.uint8).pin_memory()
+        hU = torch.randint(0, 256, (B, H // 2, W // 2), dtype=torch.uint8).pin_memory()
+        hV = torch.randint(0, 256, (B, H // 2, W // 2), dtype=torch.uint8).pin_memory()
+        hO = torch.empty((B, H, W * 3), dtype=torch.uint8).pin_memory()
+        ctx = sw.sws_getContext(dev, W, H, 0, W, H, 2, 4 | 0x40000 | 0x80000)
+        call = lambda: ctx.scale_batch_host([hY.data_ptr(), hU.data_ptr(), hV.data_ptr()], [W, W // 2, W // 2],
+                                            [W * H, W * H // 4, W * H // 4], hO.data_ptr(), W * 3, W * H * 3, B)
+        call()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            call()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / reps
+        print(f"e2e: {B / dt:.1f} frames/s  ({dt * 1e3:.1f} ms per 256-frame step, D2H {B * W * H * 3 / dt / 1e9:.1f} GB/s, H2D {B * W * H * 1.5 / dt / 1e9:.1f} GB/s)")
+        dY, dU, dV = hY[:2].cuda(), hU[:2].cuda(), hV[:2].cuda()
+        o = torch.empty((2, H, W * 3), dtype=torch.uint8, device="cuda")
+        ctx.scale_batch_device([dY, dU, dV], [W, W // 2, W // 2], [W * H, W * H // 4, W * H // 4], o, W * 3, W * H * 3, 2)
+        dev.sync()
+        print("matches device path:", bool(torch.equal(o.cpu(), hO[:2])))
     elif what == "idct":
         mbw, mbh, fr = 120, 68, 256
         n = mbw * mbh * 6 * fr
