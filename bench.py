@@ -218,7 +218,7 @@ def run_reference(args, rank, world):
 def extra_paths(args, dev, stream, g, world, barrier, reduce_max, peak):
     """The other rows of SURVEY.md 8(d): ESA motion search, H.264 qpel MC and float FFT / iMDCT, each on a bounded batch."""
     import torch
-    from ffmpeg_b200 import me_cmp, pel, tx
+    from ffmpeg_b200 import me_cmp, pel, tx, idctdsp
     out = {}
     steps = max(2, min(args.steps, 5))
 
@@ -302,6 +302,37 @@ def extra_paths(args, dev, stream, g, world, barrier, reduce_max, peak):
                          "roofline": {"bound": "hbm", "achieved": cbytes * nops / (ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
                                       "frac": cbytes * nops / (ms / 1e3) / 1e9 / peak, "bytes_per_block": cbytes}}
     del refc, dstc, doff, soff, ops, hs, xys
+
+    # --- widening row: H.264 residual add, 4x4 and 8x8 transforms over 1080p luma planes
+    hn = 32
+    with torch.cuda.stream(stream):
+        planes_h = torch.randint(0, 256, (hn, H, W), dtype=torch.uint8, device="cuda", generator=g)
+    h264r = {}
+    for kind, N, nm in ((0, 4, "idct4_add"), (1, 8, "idct8_add")):
+        nb = hn * (H // N) * (W // N)
+        with torch.cuda.stream(stream):
+            coef = torch.randint(-600, 601, (nb, N * N), dtype=torch.int16, device="cuda", generator=g)
+            keep = coef.clone()
+            bi = torch.arange(nb, device="cuda", dtype=torch.int64)
+            per = (H // N) * (W // N)
+            fr, r = bi // per, bi % per
+            hdoff = (fr * (H * W) + (r // (W // N)) * (N * W) + (r % (W // N)) * N).contiguous()
+            hboff = (bi * (N * N)).contiguous()
+
+        def h264_call():
+            coef.copy_(keep)                         # the transform clears its coefficients, like the reference
+            idctdsp.h264_idct_batch_device(dev, kind, nb, coef, hboff, planes_h, hdoff, W)
+        ms_all = timed(h264_call)
+        ms_copy = timed(lambda: coef.copy_(keep))
+        ms = max(ms_all - ms_copy, 1e-3)
+        bpb = 2 * N * N * 2 + 2 * N * N                # coefficients read + cleared, pixels read + written
+        h264r[nm] = {"value": world * nb / (ms / 1e3), "unit": "blocks/s", "ms_per_step": ms, "blocks": nb,
+                     "roofline": {"bound": "hbm", "achieved": bpb * nb / (ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                                  "frac": bpb * nb / (ms / 1e3) / 1e9 / peak, "bytes_per_block": bpb},
+                     "note": "time of the coefficient refill copy subtracted"}
+        del coef, keep, hdoff, hboff
+    out["h264_idct"] = h264r
+    del planes_h
 
     # --- config 5: float FFT and iMDCT, len 1024 and 2048
     txr = {}

@@ -61,6 +61,14 @@ class HpelDSPContext(C.Structure):
                 ("put_no_rnd_pixels_tab", (_HPEL * 4) * 3), ("avg_no_rnd_pixels_tab", _HPEL * 4)]
 
 
+_H264IDCT = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_ssize_t)
+
+
+class H264IDCTContext(C.Structure):
+    """the IDCT members of H264DSPContext, libavcodec/h264dsp.h:81-88"""
+    _fields_ = [("idct_add", _H264IDCT), ("idct8_add", _H264IDCT), ("idct_dc_add", _H264IDCT), ("idct8_dc_add", _H264IDCT)]
+
+
 _CHROMA = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_ssize_t, C.c_int, C.c_int, C.c_int)
 
 
@@ -120,6 +128,8 @@ PROTOTYPES = {
     "b200_hpeldsp_init": (C.c_int, [C.POINTER(HpelDSPContext), C.c_int]),
     "b200_h264qpel_batch_device": (C.c_int, [vp, C.c_int64, vp, vp, vp, vp, vp, C.c_ssize_t]),
     "b200_hpel_batch_device": (C.c_int, [vp, C.c_int64, vp, vp, vp, vp, vp, vp, C.c_ssize_t]),
+    "b200_h264_idct_init": (C.c_int, [C.POINTER(H264IDCTContext), C.c_int, C.c_int]),
+    "b200_h264_idct_batch_device": (C.c_int, [vp, C.c_int, C.c_int64, vp, vp, vp, vp, C.c_ssize_t]),
     "b200_videodsp_init": (C.c_int, [C.POINTER(VideoDSPContext), C.c_int]),
     "b200_emulated_edge_mc_batch_device": (C.c_int, [vp, C.c_int64, vp, vp, C.c_ssize_t, vp, vp, C.c_ssize_t, vp, C.c_int, C.c_int]),
     "b200_h264chroma_init": (C.c_int, [C.POINTER(H264ChromaContext), C.c_int]),

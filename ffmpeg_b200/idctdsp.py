@@ -44,3 +44,20 @@ def idct_mb420_device(device, kind, blocks, mb_w, mb_h, nframes, planes, linesiz
 def idct_mb420_host(device, kind, blocks, mb_w, mb_h, nframes, planes, linesize, frame_stride):
     return _mb420(lib().b200_idct_mb420_host, device, kind, blocks, mb_w, mb_h, nframes, planes, linesize, frame_stride,
                   "idct_mb420_host")
+
+
+# ---------------------------------------------------------------------------------------------- H.264 residual transforms
+H264_IDCT4, H264_IDCT8, H264_IDCT4_DC, H264_IDCT8_DC = 0, 1, 2, 3
+
+
+def ff_h264dsp_idct_init(bit_depth=8, chroma_format_idc=1):
+    """The IDCT members of H264DSPContext as ff_h264dsp_init installs them (libavcodec/h264dsp.c:66-139)."""
+    from ._lib import H264IDCTContext
+    c = H264IDCTContext()
+    check(lib().b200_h264_idct_init(C.byref(c), bit_depth, chroma_format_idc), "ff_h264dsp_init (idct)")
+    return c
+
+
+def h264_idct_batch_device(device, kind, n, blocks, blk_off, dst, dst_off, stride):
+    return check(lib().b200_h264_idct_batch_device(device.handle, kind, n, vp(_dptr(blocks)), vp(_dptr(blk_off)), vp(_dptr(dst)),
+                                                   vp(_dptr(dst_off)), stride), "h264_idct_batch_device")

@@ -170,6 +170,28 @@ int  b200_idct_mb420_device(B200Device *dev, int kind, const int16_t *blocks, in
 int  b200_idct_mb420_host(B200Device *dev, int kind, const int16_t *blocks, int mb_w, int mb_h, int nframes,
                           uint8_t *const planes[3], const int linesize[3], const int64_t frame_stride[3]);
 
+/* H.264 residual transforms, 8 bit: the IDCT members of H264DSPContext (libavcodec/h264dsp.h:81-88) as installed by
+ * ff_h264dsp_init(c, 8, chroma_format_idc) (libavcodec/h264dsp.c:66-139): ff_h264_idct_add_8_c, ff_h264_idct8_add_8_c,
+ * ff_h264_idct_dc_add_8_c, ff_h264_idct8_dc_add_8_c (libavcodec/h264idct_template.c:33-181).  The add16/add8/add4 wrappers
+ * of the reference only dispatch to these four per 4x4/8x8 block and keep working on top of them. */
+typedef void (*b200_h264_idct_fn)(uint8_t *dst, int16_t *block, ptrdiff_t stride);   /* block is cleared, like the reference */
+typedef struct B200H264IDCTContext {
+    b200_h264_idct_fn idct_add;        /* 4x4, dst 4-aligned */
+    b200_h264_idct_fn idct8_add;       /* 8x8, dst 8-aligned */
+    b200_h264_idct_fn idct_dc_add;     /* 4x4, only block[0] is read (and cleared) */
+    b200_h264_idct_fn idct8_dc_add;
+} B200H264IDCTContext;
+int  b200_h264_idct_init(B200H264IDCTContext *c, int bit_depth, int chroma_format_idc);   /* bit_depth must be 8 */
+#define B200_H264_IDCT4    0
+#define B200_H264_IDCT8    1
+#define B200_H264_IDCT4_DC 2
+#define B200_H264_IDCT8_DC 3
+/* batched, DEVICE pointers, one kind per call: block i = blocks + blk_off[i] (int16 elements, 16-byte aligned blocks of
+ * 16 or 64 coefficients; DC kinds touch block[0] only) is transformed, added to the 4x4 / 8x8 pixels at dst + dst_off[i]
+ * and cleared.  dst + dst_off[i] and stride must be 4-aligned (8 for the 8x8 kinds), as the reference requires. */
+int  b200_h264_idct_batch_device(B200Device *dev, int kind, int64_t n, int16_t *blocks, const int64_t *blk_off,
+                                 uint8_t *dst, const int64_t *dst_off, ptrdiff_t stride);
+
 /* ------------------------------------------------------------------------------------------------ me_cmp
  * Replaces MECmpContext (libavcodec/me_cmp.h:53-77) as filled by ff_me_cmp_init (libavcodec/me_cmp.c:961-1027) for the
  * SAD / SSE entries: sad[0..1] = pix_abs16_c / pix_abs8_c, sse[0..2] = sse16_c / sse8_c / sse4_c,

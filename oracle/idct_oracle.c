@@ -114,3 +114,77 @@ void orc_pixels_clamped(int kind, const int16_t *block, uint8_t *pixels, ptrdiff
             else                *p = clip8(*p + b);
         }
 }
+
+#include <string.h>
+static int clip_u8_i(int a) { return a < 0 ? 0 : a > 255 ? 255 : a; }
+
+/* ------------------------------------------------------------------ H.264 residual transforms (8 bit)
+ * libavcodec/h264idct_template.c:33-70 (ff_h264_idct_add), :72-145 (ff_h264_idct8_add), :147-181 (the two DC-only adds).
+ * Intermediate results go back into the int16 block (dctcoef), sums are formed mod 2^32 (SUINT), every function leaves
+ * the coefficients it consumed zeroed.  kind 0: 4x4, 1: 8x8, 2: 4x4 DC only, 3: 8x8 DC only. */
+static void h264_idct4_add(uint8_t *dst, int16_t *b, ptrdiff_t stride)
+{
+    b[0] += 1 << 5;
+    for (int i = 0; i < 4; i++) {
+        const unsigned z0 = b[i] + (unsigned)b[i + 8], z1 = b[i] - (unsigned)b[i + 8];
+        const unsigned z2 = (b[i + 4] >> 1) - (unsigned)b[i + 12], z3 = b[i + 4] + (unsigned)(b[i + 12] >> 1);
+        b[i] = (int16_t)(z0 + z3); b[i + 4] = (int16_t)(z1 + z2); b[i + 8] = (int16_t)(z1 - z2); b[i + 12] = (int16_t)(z0 - z3);
+    }
+    for (int i = 0; i < 4; i++) {
+        const unsigned z0 = b[4 * i] + (unsigned)b[2 + 4 * i], z1 = b[4 * i] - (unsigned)b[2 + 4 * i];
+        const unsigned z2 = (b[1 + 4 * i] >> 1) - (unsigned)b[3 + 4 * i], z3 = b[1 + 4 * i] + (unsigned)(b[3 + 4 * i] >> 1);
+        dst[i + 0 * stride] = (uint8_t)clip_u8_i(dst[i + 0 * stride] + ((int)(z0 + z3) >> 6));
+        dst[i + 1 * stride] = (uint8_t)clip_u8_i(dst[i + 1 * stride] + ((int)(z1 + z2) >> 6));
+        dst[i + 2 * stride] = (uint8_t)clip_u8_i(dst[i + 2 * stride] + ((int)(z1 - z2) >> 6));
+        dst[i + 3 * stride] = (uint8_t)clip_u8_i(dst[i + 3 * stride] + ((int)(z0 - z3) >> 6));
+    }
+    memset(b, 0, 16 * sizeof(int16_t));
+}
+
+/* one 8-point pass of ff_h264_idct8_add on in[0..7] (already sign-extended int16 values) -> out[0..7], sums mod 2^32 */
+static void h264_idct8_1d(const int *in, unsigned *out)
+{
+    const unsigned a0 = in[0] + (unsigned)in[4], a2 = in[0] - (unsigned)in[4];
+    const unsigned a4 = (in[2] >> 1) - (unsigned)in[6], a6 = (in[6] >> 1) + (unsigned)in[2];
+    const unsigned b0 = a0 + a6, b2 = a2 + a4, b4 = a2 - a4, b6 = a0 - a6;
+    const int a1 = (int)(-(unsigned)in[3] + (unsigned)in[5] - (unsigned)in[7] - (unsigned)(in[7] >> 1));
+    const int a3 = (int)((unsigned)in[1] + (unsigned)in[7] - (unsigned)in[3] - (unsigned)(in[3] >> 1));
+    const int a5 = (int)(-(unsigned)in[1] + (unsigned)in[7] + (unsigned)in[5] + (unsigned)(in[5] >> 1));
+    const int a7 = (int)((unsigned)in[3] + (unsigned)in[5] + (unsigned)in[1] + (unsigned)(in[1] >> 1));
+    const unsigned b1 = (unsigned)(a7 >> 2) + (unsigned)a1, b3 = (unsigned)a3 + (unsigned)(a5 >> 2);
+    const unsigned b5 = (unsigned)(a3 >> 2) - (unsigned)a5, b7 = (unsigned)a7 - (unsigned)(a1 >> 2);
+    out[0] = b0 + b7; out[7] = b0 - b7; out[1] = b2 + b5; out[6] = b2 - b5;
+    out[2] = b4 + b3; out[5] = b4 - b3; out[3] = b6 + b1; out[4] = b6 - b1;
+}
+
+static void h264_idct8_add(uint8_t *dst, int16_t *b, ptrdiff_t stride)
+{
+    b[0] += 32;
+    for (int i = 0; i < 8; i++) {
+        int in[8]; unsigned out[8];
+        for (int k = 0; k < 8; k++) in[k] = b[i + 8 * k];
+        h264_idct8_1d(in, out);
+        for (int k = 0; k < 8; k++) b[i + 8 * k] = (int16_t)out[k];
+    }
+    for (int i = 0; i < 8; i++) {
+        int in[8]; unsigned out[8];
+        for (int k = 0; k < 8; k++) in[k] = b[k + 8 * i];
+        h264_idct8_1d(in, out);
+        for (int k = 0; k < 8; k++) dst[i + k * stride] = (uint8_t)clip_u8_i(dst[i + k * stride] + ((int)out[k] >> 6));
+    }
+    memset(b, 0, 64 * sizeof(int16_t));
+}
+
+int orc_h264_idct(int kind, uint8_t *dst, int16_t *block, ptrdiff_t stride)
+{
+    if (kind == 0) { h264_idct4_add(dst, block, stride); return 0; }
+    if (kind == 1) { h264_idct8_add(dst, block, stride); return 0; }
+    if (kind == 2 || kind == 3) {
+        const int n = kind == 2 ? 4 : 8, dc = (block[0] + 32) >> 6;
+        block[0] = 0;
+        for (int j = 0; j < n; j++)
+            for (int i = 0; i < n; i++) dst[j * stride + i] = (uint8_t)clip_u8_i(dst[j * stride + i] + dc);
+        return 0;
+    }
+    return -1;
+}

@@ -69,6 +69,8 @@ void orc_idct_put(uint8_t *dest, ptrdiff_t line_size, int16_t *block);
 void orc_idct_add(uint8_t *dest, ptrdiff_t line_size, int16_t *block);
 void orc_idct_batch(int kind, int16_t *blocks, int nblocks, uint8_t *dest, ptrdiff_t line_size,
                     const int64_t *dest_off);
+/* H.264 residual add, 8 bit: kind 0 idct_add (4x4), 1 idct8_add, 2 idct_dc_add, 3 idct8_dc_add; clears the coefficients */
+int  orc_h264_idct(int kind, uint8_t *dst, int16_t *block, ptrdiff_t stride);
 void orc_pixels_clamped(int kind, const int16_t *block, uint8_t *pixels, ptrdiff_t line_size);
 
 /* ------------------------------------------------------------------ me_cmp */

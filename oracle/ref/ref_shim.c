@@ -31,6 +31,7 @@
 #include "libavcodec/hpeldsp.h"
 #include "libavcodec/h264chroma.h"
 #include "libavcodec/videodsp.h"
+#include "libavcodec/h264dsp.h"
 #include "libavfilter/motion_estimation.h"
 
 /* ---- link stubs: the new-API filter graph (sws_scale_frame) is not part of the legacy hot path ---- */
@@ -319,6 +320,20 @@ API void ffref_emulated_edge_mc(uint8_t *buf, const uint8_t *src, ptrdiff_t buf_
     static VideoDSPContext c; static int ok;
     if (!ok) { ff_videodsp_init(&c, 8); ok = 1; }
     c.emulated_edge_mc(buf, src, buf_linesize, src_linesize, block_w, block_h, src_x, src_y, w, h);
+}
+
+/* kind 0: idct_add (4x4), 1: idct8_add, 2: idct_dc_add, 3: idct8_dc_add; block is cleared like the reference does */
+API int ffref_h264_idct(int kind, uint8_t *dst, int16_t *block, ptrdiff_t stride)
+{
+    static H264DSPContext c; static int ok;
+    if (!ok) { ff_h264dsp_init(&c, 8, 1); ok = 1; }
+    switch (kind) {
+    case 0: c.idct_add(dst, block, stride); return 0;
+    case 1: c.idct8_add(dst, block, stride); return 0;
+    case 2: c.idct_dc_add(dst, block, stride); return 0;
+    case 3: c.idct8_dc_add(dst, block, stride); return 0;
+    }
+    return -1;
 }
 
 /* ------------------------------------------------------------------ tx ------------------------------------------ */

@@ -96,6 +96,41 @@ def gen_idct():
     np.savez_compressed(os.path.join(OUT, "idct.npz"), **d)
 
 
+def h264_blocks(kind, n, seed):
+    """coefficient blocks for the H.264 transforms: dequantised-residual-like, full-range, sparse and saturating ones"""
+    rng = np.random.default_rng(seed)
+    nc = 16 if kind in (0, 2) else 64
+    b = np.zeros((n, nc), np.int16)
+    for i in range(n):
+        m = i % 4
+        if m == 0:
+            b[i] = rng.integers(-512, 513, nc)
+        elif m == 1:
+            b[i] = rng.integers(-32768, 32768, nc)
+        elif m == 2:
+            k = rng.integers(0, nc, 3)
+            b[i, k] = rng.integers(-2000, 2001, 3)
+        else:
+            b[i] = rng.integers(0, 2, nc) * rng.choice([-32768, 32767], nc)
+    if kind >= 2:
+        b[:, 1:] = 0
+    return b
+
+
+def gen_h264idct():
+    R = cl.ref()
+    d = {}
+    for kind in range(4):
+        n, N = 64, 4 if kind in (0, 2) else 8
+        blk = h264_blocks(kind, n, 30 + kind)
+        dst0 = np.random.default_rng(40 + kind).integers(0, 256, (N, n * 8), dtype=np.uint8)
+        out, b2 = dst0.copy(), blk.copy()
+        for i in range(n):
+            R.ffref_h264_idct(kind, C.cast(out.ctypes.data + 8 * i, cl.u8p), C.cast(b2.ctypes.data + i * b2.strides[0], cl.i16p), n * 8)
+        d[f"k{kind}_in"], d[f"k{kind}_dst"], d[f"k{kind}_out"], d[f"k{kind}_blk_after"] = blk, dst0, out, b2
+    np.savez_compressed(os.path.join(OUT, "h264idct.npz"), **d)
+
+
 def gen_mecmp():
     R = cl.ref()
     rng = np.random.default_rng(21)
@@ -262,6 +297,7 @@ if __name__ == "__main__":
     gen_sws_formats()
     gen_sws_planar()
     gen_idct()
+    gen_h264idct()
     gen_mecmp()
     gen_pel()
     gen_chroma()

@@ -46,6 +46,8 @@ def oracle():
         if hasattr(L, "orc_idct_batch"):
             L.orc_idct_batch.argtypes = [C.c_int, i16p, C.c_int, u8p, C.c_ssize_t, i64p]
             L.orc_pixels_clamped.argtypes = [C.c_int, i16p, u8p, C.c_ssize_t]
+        if hasattr(L, "orc_h264_idct"):
+            L.orc_h264_idct.argtypes = [C.c_int, u8p, i16p, C.c_ssize_t]
         if hasattr(L, "orc_me_cmp"):
             L.orc_me_cmp.argtypes = [C.c_int, C.c_int, u8p, u8p, C.c_ssize_t, C.c_int]
             L.orc_esa_frame.argtypes = [u8p, u8p] + [C.c_int] * 7 + [i32p, u64p]
@@ -90,6 +92,8 @@ def ref():
         L.ffref_idct_perm_type.argtypes = [u8p]
         L.ffref_idct_batch.argtypes = [C.c_int, i16p, C.c_int, u8p, C.c_ssize_t, i64p]
         L.ffref_pixels_clamped.argtypes = [C.c_int, i16p, u8p, C.c_ssize_t]
+        if hasattr(L, "ffref_h264_idct"):
+            L.ffref_h264_idct.argtypes = [C.c_int, u8p, i16p, C.c_ssize_t]
         L.ffref_me_cmp.argtypes = [C.c_int, C.c_int, u8p, u8p, C.c_ssize_t, C.c_int]
         L.ffref_me_cmp_batch.argtypes = [C.c_int, C.c_int, u8p, u8p, C.c_ssize_t, C.c_int, i64p, i64p, C.c_int, i32p]
         L.ffref_esa_frame.argtypes = [u8p, u8p] + [C.c_int] * 7 + [i32p, u64p]

@@ -53,6 +53,20 @@ def run(dev):
                                     torch.from_numpy(xys).cuda(), d_dst, d_off, torch.from_numpy(src).cuda(), d_off, src.shape[1])
         dev.sync()
         assert np.array_equal(d_dst.cpu().numpy(), exp), "h264chroma mismatch"
+        # H.264 residual add: 4x4 and 8x8 transforms, 64 blocks each
+        from ffmpeg_b200 import idctdsp
+        for kind, N in ((0, 4), (1, 8)):
+            nb = 64
+            coef = rng.integers(-600, 601, (nb, N * N)).astype(np.int16)
+            pix = rng.integers(0, 256, (N, nb * 8), dtype=np.uint8)
+            e_pix, e_coef = pix.copy(), coef.copy()
+            for i in range(nb):
+                O.orc_h264_idct(kind, C.cast(e_pix.ctypes.data + 8 * i, cl.u8p), C.cast(e_coef.ctypes.data + i * e_coef.strides[0], cl.i16p), nb * 8)
+            d_coef, d_pix = torch.from_numpy(coef).cuda(), torch.from_numpy(pix).cuda()
+            idctdsp.h264_idct_batch_device(dev, kind, nb, d_coef, torch.arange(nb, dtype=torch.int64, device="cuda") * (N * N), d_pix,
+                                           torch.arange(nb, dtype=torch.int64, device="cuda") * 8, nb * 8)
+            dev.sync()
+            assert np.array_equal(d_pix.cpu().numpy(), e_pix) and np.array_equal(d_coef.cpu().numpy(), e_coef), "h264 idct mismatch"
         # tx: FFT-1024 and iMDCT-1024, 4 transforms each
         n = 1024
         x = rng.random((4, 2 * n), dtype=np.float32)

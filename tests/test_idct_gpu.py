@@ -240,3 +240,53 @@ def test_mb420_full_batch_properties(device, op):
             for rr in range(1, reps):
                 assert torch.equal(dp[pl][rr * nd:(rr + 1) * nd], base), (pl, rr)
             assert np.array_equal(base.cpu().numpy(), ref[pl]), pl
+
+
+# ---------------------------------------------------------------------------------------------- H.264 residual transforms
+def test_h264_idct_pointer_table_golden(device):
+    from ffmpeg_b200 import idctdsp
+    g = np.load(os.path.join(G, "h264idct.npz"))
+    t = idctdsp.ff_h264dsp_idct_init(8, 1)
+    fns = [t.idct_add, t.idct8_add, t.idct_dc_add, t.idct8_dc_add]
+    for kind in range(4):
+        blk, out = g[f"k{kind}_in"].copy(), g[f"k{kind}_dst"].copy()
+        n = blk.shape[0]
+        for i in range(0, n, 3):
+            fns[kind](out.ctypes.data + 8 * i, blk.ctypes.data + i * blk.strides[0], n * 8)
+            N = 4 if kind in (0, 2) else 8
+            assert np.array_equal(out[:, 8 * i:8 * i + N], g[f"k{kind}_out"][:, 8 * i:8 * i + N]), (kind, i)
+            assert np.array_equal(blk[i], g[f"k{kind}_blk_after"][i]), (kind, i)
+    with pytest.raises(Exception):
+        idctdsp.ff_h264dsp_idct_init(10, 1)
+
+
+@pytest.mark.parametrize("kind", [0, 1, 2, 3])
+def test_h264_idct_batch_vs_oracle(device, kind):
+    """A picture worth of residual blocks of one kind, in raster order over a 640x368 plane, checked against the oracle;
+    the coefficient buffer must come back cleared exactly like the reference leaves it."""
+    import torch
+    from ffmpeg_b200 import idctdsp
+    O = cl.oracle()
+    N, nc = (4, 16) if kind in (0, 2) else (8, 64)
+    W, H = 640, 368
+    rng = np.random.default_rng(50 + kind)
+    nb = (W // N) * (H // N)
+    blk = np.zeros((nb, 64), np.int16)                          # blocks spaced 64 coefficients apart (16-byte aligned starts)
+    vals = rng.integers(-700, 701, (nb, nc)).astype(np.int16)
+    vals[::5] = rng.integers(-32768, 32768, (len(vals[::5]), nc))
+    if kind >= 2:
+        vals[:, 1:] = 0
+    blk[:, :nc] = vals
+    dst0 = rng.integers(0, 256, (H, W), dtype=np.uint8)
+    by, bx = np.divmod(np.arange(nb), W // N)
+    doff = (by * N * W + bx * N).astype(np.int64)
+    boff = (np.arange(nb) * 64).astype(np.int64)
+    exp, eb = dst0.copy(), blk.copy()
+    for i in range(nb):
+        O.orc_h264_idct(kind, C.cast(exp.ctypes.data + int(doff[i]), cl.u8p), C.cast(eb.ctypes.data + i * 128, cl.i16p), W)
+    with torch.cuda.stream(torch.cuda.ExternalStream(device.stream)):
+        db, dd = torch.from_numpy(blk).cuda(), torch.from_numpy(dst0).cuda()
+        idctdsp.h264_idct_batch_device(device, kind, nb, db, torch.from_numpy(boff).cuda(), dd, torch.from_numpy(doff).cuda(), W)
+        device.sync()
+        assert np.array_equal(dd.cpu().numpy(), exp), kind
+        assert np.array_equal(db.cpu().numpy(), eb), kind

@@ -106,6 +106,39 @@ def test_emulated_edge_mc_oracle_vs_ref():
         assert np.array_equal(b1, b2), (bw, bh, sx, sy)
 
 
+def test_h264_idct_oracle_golden():
+    """ff_h264_idct_add / idct8_add / dc adds: oracle against the reference's outputs, incl. the cleared coefficients."""
+    g = np.load(os.path.join(G, "h264idct.npz"))
+    O = cl.oracle()
+    for kind in range(4):
+        blk, out = g[f"k{kind}_in"].copy(), g[f"k{kind}_dst"].copy()
+        n = blk.shape[0]
+        for i in range(n):
+            assert O.orc_h264_idct(kind, C.cast(out.ctypes.data + 8 * i, cl.u8p), C.cast(blk.ctypes.data + i * blk.strides[0], cl.i16p), n * 8) == 0
+        assert np.array_equal(out, g[f"k{kind}_out"]), kind
+        assert np.array_equal(blk, g[f"k{kind}_blk_after"]), kind
+    assert O.orc_h264_idct(4, cl.ptr(np.zeros(64, np.uint8)), cl.ptr(np.zeros(64, np.int16), cl.i16p), 8) < 0
+
+
+def test_h264_idct_oracle_vs_ref():
+    if not cl.have_ref():
+        import pytest
+        pytest.skip("oracle/_ref not built")
+    R, O = cl.ref(), cl.oracle()
+    rng = np.random.default_rng(9)
+    for it in range(3000):
+        kind = int(rng.integers(0, 4))
+        n = 16 if kind in (0, 2) else 64
+        blk = (rng.integers(-32768, 32768, n) if it % 2 else rng.integers(-600, 601, n)).astype(np.int16)
+        if kind >= 2:
+            blk[1:] = 0
+        d1 = rng.integers(0, 256, (12, 24), dtype=np.uint8)
+        d2, b1, b2 = d1.copy(), blk.copy(), blk.copy()
+        R.ffref_h264_idct(kind, C.cast(d1.ctypes.data + 2 * 24 + 8, cl.u8p), cl.ptr(b1, cl.i16p), 24)
+        O.orc_h264_idct(kind, C.cast(d2.ctypes.data + 2 * 24 + 8, cl.u8p), cl.ptr(b2, cl.i16p), 24)
+        assert np.array_equal(d1, d2) and np.array_equal(b1, b2), (kind, it)
+
+
 def test_pel_oracle_golden():
     g = np.load(os.path.join(G, "pel.npz"))
     O = cl.oracle()
