@@ -438,6 +438,38 @@ def run_b200(args, rank, world, local_rank):
     results["variant_flags_bicubic"] = {"value": fps2, "unit": "frames/s", "roofline": {
         "bound": "hbm", "achieved": ach2, "peak": peak, "unit": "GB/s", "frac": ach2 / peak, "kernel": "sws_unscaled_kernel",
         "launch_ms": k2, "traffic": ncu_traffic("sws_unscaled_kernel")}}
+    # variant: the scaler proper, 4K -> 1080p with FATE flags (horizontal pass -> int16 lines -> vertical pass), yuv420p and rgb24 out
+    NS = 32
+    sc = {}
+    for fmt, nm in ((sw.AV_PIX_FMT_YUV420P, "yuv420p"), (sw.AV_PIX_FMT_RGB24, "rgb24")):
+        ctx = sw.sws_getContext(dev, W4K, H4K, sw.AV_PIX_FMT_YUV420P, 1920, 1080, fmt, FLAGS_FATE)
+        with torch.cuda.stream(stream):
+            if fmt == sw.AV_PIX_FMT_YUV420P:
+                oy = torch.empty((NS, 1080, 1920), dtype=torch.uint8, device="cuda")
+                ou = torch.empty((NS, 540, 960), dtype=torch.uint8, device="cuda")
+                ov = torch.empty_like(ou)
+                call = lambda: ctx.scale_batch_device_planar([Y, U, V], sstr, sfs, [oy, ou, ov], [1920, 960, 960],
+                                                             [1920 * 1080, 960 * 540, 960 * 540], NS)
+                obytes = 1920 * 1080 * 3 // 2
+            else:
+                o3 = torch.empty((NS, 1080, 1920 * 3), dtype=torch.uint8, device="cuda")
+                call = lambda: ctx.scale_batch_device([Y, U, V], sstr, sfs, o3, 1920 * 3, 1920 * 1080 * 3, NS)
+                obytes = 1920 * 1080 * 3
+            for _ in range(3):
+                call()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(5):
+                call()
+            e1.record(stream)
+        barrier()
+        msc = reduce_max(e0.elapsed_time(e1)) / 5
+        ab = (FRAME_BYTES_IN + obytes) * NS
+        sc[nm] = {"value": world * NS / (msc / 1e3), "unit": "frames/s", "ms_per_step": msc, "frames": NS,
+                  "roofline": {"bound": "hbm", "achieved": ab / (msc / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                               "frac": ab / (msc / 1e3) / 1e9 / peak, "note": "not HBM-bound as built: two passes through int16 line planes"}}
+        ctx.free()
+    results["variant_scale_4k_to_1080p"] = sc
     # variant: rgba output, FATE flags; 4 bytes per pixel out
     with torch.cuda.stream(stream):
         OUT4 = torch.empty((BATCH, H4K, W4K * 4), dtype=torch.uint8, device="cuda")

@@ -2,7 +2,7 @@
 //
 // Reference semantics reproduced bit-for-bit (see oracle/sws_oracle.c for the CPU restatement used as checker):
 //   unscaled LUT converter  yuv2rgb_c_24_rgb          libswscale/yuv2rgb.c:137-236,530   -> sws_unscaled_kernel
-//   horizontal FIR          hScale8To15_c             libswscale/swscale.c:128-142       -> sws_hscale_kernel
+//   horizontal FIR          hScale8To15_c             libswscale/swscale.c:128-142       -> sws_hscale_kernel (IDP.2A)
 //   vertical FIR + writers  yuv2rgb24_{X,2,1}_c       libswscale/output.c:1789-1939      -> sws_vscale_rgb24_kernel
 //   full-chroma writers     yuv2rgb24_full_{X,2,1}_c  libswscale/output.c:2161-2310      -> sws_vscale_rgb24_full_kernel
 // The reference's pointer LUTs (table_rV/gU/gV/bU into a clipped luma ramp) are evaluated in closed form, which is
@@ -27,6 +27,7 @@ struct SwsDevTables {            // device copies of the vertical banks and the 
     const int32_t *vLum2, *vChr2;     // vertical banks with tap pairs packed (lo16 = tap 2j, hi16 = tap 2j+1 or 0)
     const int16_t *hLum; const int32_t *hLumPos; int hLumSize;
     const int16_t *hChr; const int32_t *hChrPos; int hChrSize;
+    const int32_t *hLum2, *hChr2;     // horizontal banks, tap pairs packed the same way
 };
 
 struct SwsFrameArgs {
@@ -182,19 +183,30 @@ sws_unscaled_slow_kernel(SwsFrameArgs a, SwsColorConst c, int p0, int p1)
 
 // ------------------------------------------------------------------------------------------------ kernel: horizontal FIR
 // dst[i] = min((sum_j src[pos[i]+j] * coef[i*fs+j]) >> 7, 32767); one thread per output sample, grid y = lines, z = frames.
+// The source window is fetched as aligned 32-bit words (only words that hold a needed byte), shifted to tap 0 with a funnel
+// shift, and each word feeds two IDP.2A (s16 tap pair x u8 sample pair); coef2 holds the taps packed in pairs.
 __global__ void __launch_bounds__(256)
 sws_hscale_kernel(const uint8_t *src, long long sstride, long long sfs, int16_t *dst, int dstW, long long dfs,
-                  const int16_t *coef, const int32_t *pos, int fs, int line0)
+                     const int32_t *coef2, const int32_t *pos, int fs, int line0)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= dstW) return;
     const int line = blockIdx.y + line0;
     const uint8_t *s = src + (long long)blockIdx.z * sfs + (long long)line * sstride + __ldg(pos + i);
-    const int16_t *k = coef + (long long)i * fs;
+    const unsigned sh = (unsigned)(reinterpret_cast<uintptr_t>(s) & 3);
+    const unsigned *w = reinterpret_cast<const unsigned *>(s - sh);
+    const int need = (int)sh + fs, np = (fs + 1) >> 1;
+    const int32_t *k = coef2 + (long long)i * np;
+    unsigned prev = __ldg(w);
     int acc = 0;
-    for (int j = 0; j < fs; j++) acc += (int)__ldg(s + j) * (int)__ldg(k + j);
-    acc >>= 7;
-    dst[(long long)blockIdx.z * dfs + (long long)line * dstW + i] = (int16_t)min(acc, 32767);
+    for (int q = 0; q * 4 < fs; q++) {                       // window word q = taps 4q .. 4q+3
+        const unsigned next = ((q + 1) * 4 < need) ? __ldg(w + q + 1) : 0u;
+        const unsigned win = __funnelshift_r(prev, next, sh * 8);
+        prev = next;
+        acc = dp2a_lo_su(__ldg(k + 2 * q), win, acc);
+        if (2 * q + 1 < np) acc = dp2a_hi_su(__ldg(k + 2 * q + 1), win, acc);
+    }
+    dst[(long long)blockIdx.z * dfs + (long long)line * dstW + i] = (int16_t)min(acc >> 7, 32767);
 }
 
 // ------------------------------------------------------------------------------------------------ kernel: vertical FIR + rgb24 (fast)
@@ -433,6 +445,38 @@ sws_vscale_planar_kernel(const int16_t *src, int sls, long long sfs, int nlines,
     dst[f * dfs + (long long)dy * ds + x] = (uint8_t)clamp_u8(val);
 }
 
+// four adjacent samples per thread: 64-bit loads of the int16 lines, one 32-bit store (w % 4 == 0, 4-aligned destination)
+__global__ void __launch_bounds__(256)
+sws_vscale_planar4_kernel(const int16_t *src, int sls, long long sfs, int nlines, uint8_t *dst, long long ds, long long dfs,
+                          int w, const int16_t *coef, const int32_t *pos, int fs, int line0)
+{
+    const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (x >= w) return;
+    const int dy = blockIdx.y + line0;
+    const long long f = blockIdx.z;
+    const int16_t *p = reinterpret_cast<const int16_t *>(reinterpret_cast<const char *>(src) + f * sfs) + x;
+    const int first = max(1 - fs, __ldg(pos + dy));
+    int v0, v1, v2, v3;
+    if (fs == 1) {
+        const uint2 q = __ldg(reinterpret_cast<const uint2 *>(p + (long long)min(max(first, 0), nlines - 1) * sls));
+        v0 = ((int)(short)(q.x & 0xffff) + 64) >> 7; v1 = (((int)q.x >> 16) + 64) >> 7;
+        v2 = ((int)(short)(q.y & 0xffff) + 64) >> 7; v3 = (((int)q.y >> 16) + 64) >> 7;
+    } else {
+        unsigned a0 = 64u << 12, a1 = a0, a2 = a0, a3 = a0;
+        const int16_t *k = coef + (long long)dy * fs;
+        for (int j = 0; j < fs; j++) {
+            const uint2 q = __ldg(reinterpret_cast<const uint2 *>(p + (long long)min(max(first + j, 0), nlines - 1) * sls));
+            const int c = (int)__ldg(k + j);
+            a0 += (unsigned)((int)(short)(q.x & 0xffff) * c); a1 += (unsigned)(((int)q.x >> 16) * c);
+            a2 += (unsigned)((int)(short)(q.y & 0xffff) * c); a3 += (unsigned)(((int)q.y >> 16) * c);
+        }
+        v0 = (int)a0 >> 19; v1 = (int)a1 >> 19; v2 = (int)a2 >> 19; v3 = (int)a3 >> 19;
+    }
+    const unsigned lo = __vimin_s16x2_relu(__byte_perm((unsigned)v0, (unsigned)v1, 0x5410), 0x00ff00ffu);
+    const unsigned hi = __vimin_s16x2_relu(__byte_perm((unsigned)v2, (unsigned)v3, 0x5410), 0x00ff00ffu);
+    *reinterpret_cast<unsigned *>(dst + f * dfs + (long long)dy * ds + x) = __byte_perm(lo, hi, 0x6420);
+}
+
 // planarCopyWrapper (swscale_unscaled.c:2220-2333, 8-bit planes): row copies, 16 bytes per thread when everything is aligned
 __global__ void __launch_bounds__(256)
 sws_plane_copy_kernel(const uint8_t *src, long long ss, long long sfs, uint8_t *dst, long long ds, long long dfs, int w, int vec)
@@ -490,6 +534,9 @@ static int upload_tables(B200SwsContext *c)
     const std::vector<int32_t> vl2 = pack_pairs(p.vLum), vc2 = pack_pairs(p.vChr);
     size_t o_vl2 = off; off += al(vl2.size() * 4);
     size_t o_vc2 = off; off += al(vc2.size() * 4);
+    const std::vector<int32_t> hl2 = pack_pairs(p.hLum), hc2 = pack_pairs(p.hChr);
+    size_t o_hl2 = off; off += al(hl2.size() * 4);
+    size_t o_hc2 = off; off += al(hc2.size() * 4);
     size_t o_hl = off;  off += al(p.hLum.coef.size() * 2);
     size_t o_hlp = off; off += al(p.hLum.pos.size() * 4);
     size_t o_hc = off;  off += al(p.hChr.coef.size() * 2);
@@ -502,6 +549,8 @@ static int upload_tables(B200SwsContext *c)
     memcpy(&host[o_rm], p.rowMode.data(), p.rowMode.size() * 4);
     memcpy(&host[o_vl2], vl2.data(), vl2.size() * 4);
     memcpy(&host[o_vc2], vc2.data(), vc2.size() * 4);
+    memcpy(&host[o_hl2], hl2.data(), hl2.size() * 4);
+    memcpy(&host[o_hc2], hc2.data(), hc2.size() * 4);
     memcpy(&host[o_hl], p.hLum.coef.data(), p.hLum.coef.size() * 2);
     memcpy(&host[o_hlp], p.hLum.pos.data(), p.hLum.pos.size() * 4);
     memcpy(&host[o_hc], p.hChr.coef.data(), p.hChr.coef.size() * 2);
@@ -513,6 +562,7 @@ static int upload_tables(B200SwsContext *c)
     c->dt.vChr = (const int16_t *)(b + o_vc); c->dt.vChrPos = (const int32_t *)(b + o_vcp); c->dt.vChrSize = p.vChr.size;
     c->dt.rowMode = (const int32_t *)(b + o_rm);
     c->dt.vLum2 = (const int32_t *)(b + o_vl2); c->dt.vChr2 = (const int32_t *)(b + o_vc2);
+    c->dt.hLum2 = (const int32_t *)(b + o_hl2); c->dt.hChr2 = (const int32_t *)(b + o_hc2);
     c->dt.hLum = (const int16_t *)(b + o_hl); c->dt.hLumPos = (const int32_t *)(b + o_hlp); c->dt.hLumSize = p.hLum.size;
     c->dt.hChr = (const int16_t *)(b + o_hc); c->dt.hChrPos = (const int32_t *)(b + o_hcp); c->dt.hChrSize = p.hChr.size;
     c->h_identity = p.chrDstHSub == 1 && p.hLum.identity() && p.hChr.identity();
@@ -717,14 +767,14 @@ static int launch_batch(B200SwsContext *c, cudaStream_t stream, const uint8_t *c
             dim3 block(256);
             if (R.nly > 0) {
                 dim3 grid(b200_ceil_div(p.dstW, 256), R.nly, nf);
-                sws_hscale_kernel<<<grid, block, 0, stream>>>(b.y, b.ys, b.yfs, mY, p.dstW, mfs, c->dt.hLum, c->dt.hLumPos, c->dt.hLumSize, R.ly0);
+                sws_hscale_kernel<<<grid, block, 0, stream>>>(b.y, b.ys, b.yfs, mY, p.dstW, mfs, c->dt.hLum2, c->dt.hLumPos, c->dt.hLumSize, R.ly0);
                 B200_LAUNCHED();
             }
             if (R.ncy > 0) {
                 dim3 gridc(b200_ceil_div(p.chrDstW, 256), R.ncy, nf);
-                sws_hscale_kernel<<<gridc, block, 0, stream>>>(b.u, b.us, b.ufs, mU, p.chrDstW, mfs, c->dt.hChr, c->dt.hChrPos, c->dt.hChrSize, R.cy0);
+                sws_hscale_kernel<<<gridc, block, 0, stream>>>(b.u, b.us, b.ufs, mU, p.chrDstW, mfs, c->dt.hChr2, c->dt.hChrPos, c->dt.hChrSize, R.cy0);
                 B200_LAUNCHED();
-                sws_hscale_kernel<<<gridc, block, 0, stream>>>(b.v, b.vs, b.vfs, mV, p.chrDstW, mfs, c->dt.hChr, c->dt.hChrPos, c->dt.hChrSize, R.cy0);
+                sws_hscale_kernel<<<gridc, block, 0, stream>>>(b.v, b.vs, b.vfs, mV, p.chrDstW, mfs, c->dt.hChr2, c->dt.hChrPos, c->dt.hChrSize, R.cy0);
                 B200_LAUNCHED();
             }
             if (R.ndy <= 0) continue;
@@ -789,7 +839,7 @@ static int launch_planar(B200SwsContext *c, cudaStream_t stream, const uint8_t *
             c->mid_bytes = need;
         }
         int16_t *m[3] = { (int16_t *)c->mid, (int16_t *)((uint8_t *)c->mid + plane[0]), (int16_t *)((uint8_t *)c->mid + plane[0] + plane[1]) };
-        const int16_t *hc[3] = { c->dt.hLum, c->dt.hChr, c->dt.hChr };
+        const int32_t *hc[3] = { c->dt.hLum2, c->dt.hChr2, c->dt.hChr2 };
         const int32_t *hp[3] = { c->dt.hLumPos, c->dt.hChrPos, c->dt.hChrPos };
         const int hs[3] = { c->dt.hLumSize, c->dt.hChrSize, c->dt.hChrSize };
         const int16_t *vc[3] = { c->dt.vLum, c->dt.vChr, c->dt.vChr };
@@ -798,10 +848,19 @@ static int launch_planar(B200SwsContext *c, cudaStream_t stream, const uint8_t *
         for (int pl = 0; pl < 3; pl++) {
             dim3 block(256), gh(b200_ceil_div(dw[pl], 256), sh[pl], nf), gv(b200_ceil_div(dw[pl], 256), dh[pl], nf);
             sws_hscale_kernel<<<gh, block, 0, stream>>>(src[pl] + (long long)f0 * sfs[pl], sstr[pl], sfs[pl], m[pl], dw[pl],
-                                                        (long long)(perFrame / 2), hc[pl], hp[pl], hs[pl], 0);
+                                                           (long long)(perFrame / 2), hc[pl], hp[pl], hs[pl], 0);
             B200_LAUNCHED();
-            sws_vscale_planar_kernel<<<gv, block, 0, stream>>>(m[pl], dw[pl], (long long)perFrame, sh[pl], dst[pl] + (long long)f0 * dfs[pl],
-                                                               dstr[pl], dfs[pl], dw[pl], vc[pl], vp[pl], vs[pl], 0);
+            uint8_t *dpl = dst[pl] + (long long)f0 * dfs[pl];
+            const bool v4 = dw[pl] % 4 == 0 && (plane[0] % 8 == 0) && (plane[1] % 8 == 0) &&
+                            (((uintptr_t)dpl | (uintptr_t)dstr[pl] | (uintptr_t)dfs[pl]) & 3) == 0;
+            if (v4) {
+                dim3 g4(b200_ceil_div(dw[pl] / 4, 256), dh[pl], nf);
+                sws_vscale_planar4_kernel<<<g4, block, 0, stream>>>(m[pl], dw[pl], (long long)perFrame, sh[pl], dpl, dstr[pl], dfs[pl],
+                                                                    dw[pl], vc[pl], vp[pl], vs[pl], 0);
+            } else {
+                sws_vscale_planar_kernel<<<gv, block, 0, stream>>>(m[pl], dw[pl], (long long)perFrame, sh[pl], dpl, dstr[pl], dfs[pl],
+                                                                   dw[pl], vc[pl], vp[pl], vs[pl], 0);
+            }
             B200_LAUNCHED();
         }
     }

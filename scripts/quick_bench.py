@@ -60,6 +60,27 @@ with torch.cuda.stream(stream):
         hs = torch.full((n,), 8, dtype=torch.uint8, device="cuda")
         xys = torch.randint(0, 64, (n,), device="cuda", generator=g).to(torch.uint8)
         timed(lambda: pel.h264chroma_batch_device(dev, n, ops, hs, xys, dstp, doff, refp, soff, PW), n, "blocks", 177)
+    elif what == "scale":
+        W, H, B = 3840, 2160, 32
+        Y = torch.randint(0, 256, (B, H, W), dtype=torch.uint8, device="cuda", generator=g)
+        U = torch.randint(0, 256, (B, H // 2, W // 2), dtype=torch.uint8, device="cuda", generator=g)
+        V = torch.randint(0, 256, (B, H // 2, W // 2), dtype=torch.uint8, device="cuda", generator=g)
+        FATE = 4 | 0x40000 | 0x80000
+        for (dw, dh, fmt, name) in ((1920, 1080, 0, "4k->1080p yuv420p"), (1920, 1080, 2, "4k->1080p rgb24"), (1280, 720, 0, "4k->720p yuv420p")):
+            what = "scale " + name
+            ctx = sw.sws_getContext(dev, W, H, 0, dw, dh, fmt, FATE)
+            if fmt == 0:
+                oY = torch.empty((B, dh, dw), dtype=torch.uint8, device="cuda")
+                oU = torch.empty((B, dh // 2, dw // 2), dtype=torch.uint8, device="cuda"); oV = torch.empty_like(oU)
+                call = lambda: ctx.scale_batch_device_planar([Y, U, V], [W, W // 2, W // 2], [W * H, W * H // 4, W * H // 4], [oY, oU, oV],
+                                                             [dw, dw // 2, dw // 2], [dw * dh, dw * dh // 4, dw * dh // 4], B)
+                ob = dw * dh * 3 // 2
+            else:
+                o = torch.empty((B, dh, dw * 3), dtype=torch.uint8, device="cuda")
+                call = lambda: ctx.scale_batch_device([Y, U, V], [W, W // 2, W // 2], [W * H, W * H // 4, W * H // 4], o, dw * 3, dw * dh * 3, B)
+                ob = dw * dh * 3
+            timed(call, B, "frames", W * H * 3 // 2 + ob)
+            ctx.free()
     elif what == "e2e":
         import time
         W, H, B = 3840, 2160, 256
