@@ -566,6 +566,8 @@ def run_b200(args, rank, world, local_rank):
     if rank == 0 and world == 1:
         v, info = cpu_sws_fps(FLAGS_FATE, seconds_budget=10.0)
         cpu = dict(info, value=v, unit="frames/s")
+        v1, info1 = cpu_sws_fps(FLAGS_FATE, seconds_budget=3.0, threads=1)     # one thread beside all threads
+        cpu["single_thread"] = {"value": v1, "unit": "frames/s", "sample": info1["sample"]}
         bv, binfo = cpu_idct_bps()
         idct["cpu_baseline"] = dict(binfo, value=bv, unit="blocks/s")
 
