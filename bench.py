@@ -348,6 +348,13 @@ def extra_paths(args, dev, stream, g, world, barrier, reduce_max, peak):
         txr[f"fft{n}"] = {"value": world * cnt / (ms / 1e3), "unit": "transforms/s", "ms_per_step": ms, "batch": cnt,
                           "roofline": {"bound": "hbm", "achieved": b * cnt / (ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
                                        "frac": b * cnt / (ms / 1e3) / 1e9 / peak, "bytes_per_transform": b}}
+        c = tx.av_tx_init(tx.AV_TX_FLOAT_RDFT, 0, n, scale=1.0, device=dev)      # r2c: n floats -> n/2+1 complex
+        ms = timed(lambda: c.batch_device(y, x, 4, cnt, 8 * n, 8 * n))
+        c.uninit()
+        b = 4 * n + 4 * (n + 2)
+        txr[f"rdft_r2c{n}"] = {"value": world * cnt / (ms / 1e3), "unit": "transforms/s", "ms_per_step": ms, "batch": cnt,
+                               "roofline": {"bound": "hbm", "achieved": b * cnt / (ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                                            "frac": b * cnt / (ms / 1e3) / 1e9 / peak, "bytes_per_transform": b}}
         c = tx.av_tx_init(tx.AV_TX_FLOAT_MDCT, 1, n, scale=1.0 / n, device=dev)
         ms = timed(lambda: c.batch_device(y, x, 4, cnt, 4 * n, 4 * n))
         c.uninit()

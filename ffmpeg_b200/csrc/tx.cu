@@ -37,7 +37,8 @@ struct TxDev {                 // device-side plan
     const int *imap;           // inverse MDCT: z[imap[m]] gets the pair (in[len-1-2m], in[2m])
     const int *sub_map;        // MDCT index map (doubled for the inverse)
     const float2 *exp;         // MDCT twiddles
-    int len;                   // MDCT length (2n)
+    int len;                   // MDCT / RDFT length (2n)
+    const float *rexp;         // RDFT: 8 factors, then tcos[len/4], tsin[len/4] (ff_tx_rdft_init, tx_template.c:1601-1653)
 };
 
 __device__ __forceinline__ void butterflies(float2 &a0, float2 &a1, float2 &a2, float2 &a3, float t1, float t2, float t5, float t6)
@@ -187,6 +188,117 @@ tx_fft_kernel(TxDev p, float2 *out, const float2 *in, long long out_step, long l
         if (t0 + k >= count) break;
         const float2 *src = reinterpret_cast<const float2 *>(reinterpret_cast<const char *>(in) + (t0 + k) * in_step);
         for (int g = threadIdx.x; g < p.n; g += blockDim.x) z[k * zs + PAD(__ldg(p.scatter + g))] = src[g];
+    }
+    __syncthreads();
+    fft_levels<TB>(p, z, zs);
+#pragma unroll
+    for (int k = 0; k < TB; k++) {
+        if (t0 + k >= count) break;
+        float2 *dst = reinterpret_cast<float2 *>(reinterpret_cast<char *>(out) + (t0 + k) * out_step);
+        for (int i = threadIdx.x; i < p.n; i += blockDim.x) dst[i] = z[k * zs + PAD(i)];
+    }
+}
+
+// ff_tx_rdft_r2c / ff_tx_rdft_c2r (DECL_RDFT, tx_template.c:1655-1724): the even/odd separation butterfly on the pair
+// (data[i], data[len2 - i]), 1 <= i < len4, and the two special elements 0 and len4.
+__device__ __forceinline__ void rdft_pair(const float *fact, float tc, float ts, float2 &a, float2 &b)
+{
+    const float t0re = fact[4] * (a.x + b.x), t0im = fact[5] * (a.y - b.y);
+    const float t1re = fact[6] * (a.y + b.y), t1im = fact[7] * (a.x - b.x);
+    const float t2re = t1re * tc - t1im * ts, t2im = t1re * ts + t1im * tc;
+    a = make_float2(t0re + t2re, t2im - t0im);
+    b = make_float2(t0re - t2re, t2im + t0im);
+}
+__device__ __forceinline__ void rdft_special(const float *fact, float2 &d0, float2 &dq)
+{
+    const float t0re = d0.x;
+    d0.x = t0re + d0.y; d0.y = t0re - d0.y;
+    d0.x = fact[0] * d0.x; d0.y = fact[1] * d0.y;
+    dq.x = fact[2] * dq.x; dq.y = fact[3] * dq.y;
+}
+
+// r2c: len floats in, len/2 + 1 complex out
+template <int TB>
+__global__ void __launch_bounds__(256)
+tx_rdft_r2c_kernel(TxDev p, float2 *out, const float2 *in, long long out_step, long long in_step, long long count)
+{
+    extern __shared__ float2 z[];
+    const int zs = p.n + (p.n >> 4) + 1;
+    const long long t0 = (long long)blockIdx.x * TB;
+    const int len2 = p.n, len4 = p.n >> 1;
+#pragma unroll
+    for (int k = 0; k < TB; k++) {
+        if (t0 + k >= count) break;
+        const float2 *src = reinterpret_cast<const float2 *>(reinterpret_cast<const char *>(in) + (t0 + k) * in_step);
+        for (int g = threadIdx.x; g < p.n; g += blockDim.x) z[k * zs + PAD(__ldg(p.scatter + g))] = src[g];
+    }
+    __syncthreads();
+    fft_levels<TB>(p, z, zs);
+    const float *fact = p.rexp, *tcos = fact + 8, *tsin = tcos + len4;
+#pragma unroll
+    for (int k = 0; k < TB; k++) {
+        float2 *zk = z + k * zs;
+        for (int i = threadIdx.x; i < max(len4, 1); i += blockDim.x) {
+            if (i == 0) {
+                float2 d0 = zk[PAD(0)], dq = zk[PAD(len4)];
+                rdft_special(fact, d0, dq);
+                if (len4 > 0) zk[PAD(len4)] = dq;
+                zk[PAD(0)] = d0;
+            } else {
+                float2 a = zk[PAD(i)], b = zk[PAD(len2 - i)];
+                rdft_pair(fact, __ldg(tcos + i), __ldg(tsin + i), a, b);
+                zk[PAD(i)] = a; zk[PAD(len2 - i)] = b;
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < TB; k++) {
+        if (t0 + k >= count) break;
+        float2 *dst = reinterpret_cast<float2 *>(reinterpret_cast<char *>(out) + (t0 + k) * out_step);
+        const float2 *zk = z + k * zs;
+        for (int i = threadIdx.x; i <= len2; i += blockDim.x) {
+            float2 v;
+            if (i == 0) v = make_float2(zk[PAD(0)].x, 0.0f);
+            else if (i == len2) v = make_float2(zk[PAD(0)].y, 0.0f);          // data[len2].re = data[0].im
+            else v = zk[PAD(i)];
+            dst[i] = v;
+        }
+    }
+}
+
+// c2r: len/2 + 1 complex in, len floats out.  The reference modifies its input in place before the inverse FFT; the
+// modified values are written to `wb` when it is not NULL (the host av_tx_fn path hands them back to the caller).
+template <int TB>
+__global__ void __launch_bounds__(256)
+tx_rdft_c2r_kernel(TxDev p, float2 *out, const float2 *in, float2 *wb, long long out_step, long long in_step, long long count)
+{
+    extern __shared__ float2 z[];
+    const int zs = p.n + (p.n >> 4) + 1;
+    const long long t0 = (long long)blockIdx.x * TB;
+    const int len2 = p.n, len4 = p.n >> 1;
+    const float *fact = p.rexp, *tcos = fact + 8, *tsin = tcos + len4;
+#pragma unroll
+    for (int k = 0; k < TB; k++) {
+        if (t0 + k >= count) break;
+        const float2 *src = reinterpret_cast<const float2 *>(reinterpret_cast<const char *>(in) + (t0 + k) * in_step);
+        float2 *w = wb ? reinterpret_cast<float2 *>(reinterpret_cast<char *>(wb) + (t0 + k) * in_step) : nullptr;
+        float2 *zk = z + k * zs;
+        for (int i = threadIdx.x; i < max(len4, 1); i += blockDim.x) {
+            if (i == 0) {
+                float2 d0 = src[0], dq = src[len4];
+                d0.y = src[len2].x;                                           // data[0].im = data[len2].re
+                rdft_special(fact, d0, dq);
+                zk[PAD(__ldg(p.scatter + 0))] = d0;
+                if (len4 > 0) zk[PAD(__ldg(p.scatter + len4))] = dq;
+                if (w) { w[0] = d0; if (len4 > 0) w[len4] = dq; }
+            } else {
+                float2 a = src[i], b = src[len2 - i];
+                rdft_pair(fact, __ldg(tcos + i), __ldg(tsin + i), a, b);
+                zk[PAD(__ldg(p.scatter + i))] = a; zk[PAD(__ldg(p.scatter + len2 - i))] = b;
+                if (w) { w[i] = a; w[len2 - i] = b; }
+            }
+        }
     }
     __syncthreads();
     fft_levels<TB>(p, z, zs);
@@ -404,6 +516,22 @@ static int tx_build(B200TXContext *c, float scale)
     }
     const size_t o_bfd = off; off += al(bfd.size() * 4 + 4);
     const size_t o_tw2 = off; off += al(tw2.size() * 8 + 8);
+    std::vector<float> rexp;
+    if (c->type == 6) {                                              // ff_tx_rdft_init, tx_template.c:1601-1653
+        const int len = c->len, len4 = len >> 2, inv = c->inv;
+        const double f = 2 * M_PI / len, m = inv ? 2 * (double)scale : (double)scale;
+        rexp.push_back((float)((inv ? 0.5 : 1.0) * m));
+        rexp.push_back((float)(inv ? 0.5 * m : 1.0 * m));
+        rexp.push_back((float)(m));
+        rexp.push_back((float)(-m));
+        rexp.push_back((float)((0.5 - 0.0) * m));
+        rexp.push_back((float)((0.0 - 0.5) * m));
+        rexp.push_back((float)((0.5 - inv) * m));
+        rexp.push_back((float)(-(0.5 - inv) * m));
+        for (int i = 0; i < len4; i++) rexp.push_back((float)cos(i * f));
+        for (int i = 0; i < len4; i++) rexp.push_back((float)cos(((len - i * 4) / 4.0) * f) * (inv ? 1 : -1));
+    }
+    const size_t o_rx = off; off += al(rexp.size() * 4 + 4);
     std::vector<int> imap(sub_map.size() + 1, 0);
     if (c->type == 1 && c->inv)
         for (size_t i = 0; i < sub_map.size(); i++) imap[sub_map[i] >> 1] = (int)i;
@@ -421,12 +549,14 @@ static int tx_build(B200TXContext *c, float scale)
     memcpy(&host[o_im], imap.data(), imap.size() * 4);
     if (!leaf16.empty()) memcpy(&host[o_l16], leaf16.data(), leaf16.size() * 4);
     if (!leaf8.empty()) memcpy(&host[o_l8], leaf8.data(), leaf8.size() * 4);
+    if (!rexp.empty()) memcpy(&host[o_rx], rexp.data(), rexp.size() * 4);
     B200_CUDA_OK(cudaMalloc(&c->blob, off));
     B200_CUDA_OK(cudaMemcpy(c->blob, host.data(), off, cudaMemcpyHostToDevice));
     uint8_t *b = (uint8_t *)c->blob;
     d.blk_off = (const int *)(b + o_blk); d.tab = (const float *)(b + o_tab); d.scatter = (const int *)(b + o_sc);
     d.sub_map = (const int *)(b + o_sm); d.exp = (const float2 *)(b + o_ex);
     d.imap = (const int *)(b + o_im);
+    d.rexp = (const float *)(b + o_rx);
     d.bfd = (const int *)(b + o_bfd); d.tw2 = (const float2 *)(b + o_tw2);
     d.leaf16 = (const int *)(b + o_l16); d.n_leaf16 = (int)leaf16.size();
     d.leaf8 = (const int *)(b + o_l8); d.n_leaf8 = (int)leaf8.size();
@@ -436,12 +566,14 @@ static int tx_build(B200TXContext *c, float scale)
         B200_CUDA_OK(cudaFuncSetAttribute(tx_fft_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem));
         B200_CUDA_OK(cudaFuncSetAttribute(tx_mdct_inv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem));
         B200_CUDA_OK(cudaFuncSetAttribute(tx_mdct_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem));
+        B200_CUDA_OK(cudaFuncSetAttribute(tx_rdft_r2c_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem));
+        B200_CUDA_OK(cudaFuncSetAttribute(tx_rdft_c2r_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem));
     }
     return 0;
 }
 
 static int tx_launch(B200TXContext *c, cudaStream_t st, void *out, const void *in, ptrdiff_t stride, int64_t count,
-                     ptrdiff_t out_step, ptrdiff_t in_step)
+                     ptrdiff_t out_step, ptrdiff_t in_step, void *c2r_writeback = nullptr)
 {
     if (count <= 0) return 0;
     const int threads = c->d.n * c->tb >= 1024 ? 256 : c->d.n * c->tb >= 256 ? 128 : 64;
@@ -454,6 +586,8 @@ static int tx_launch(B200TXContext *c, cudaStream_t st, void *out, const void *i
 #define TX_LAUNCH(TB)                                                                                                          \
         do {                                                                                                                   \
             if (c->type == 0)   tx_fft_kernel<TB><<<nb, threads, c->smem, st>>>(c->d, (float2 *)o, (const float2 *)i, out_step, in_step, cnt); \
+            else if (c->type == 6 && !c->inv) tx_rdft_r2c_kernel<TB><<<nb, threads, c->smem, st>>>(c->d, (float2 *)o, (const float2 *)i, out_step, in_step, cnt); \
+            else if (c->type == 6) tx_rdft_c2r_kernel<TB><<<nb, threads, c->smem, st>>>(c->d, (float2 *)o, (const float2 *)i, (float2 *)(c2r_writeback ? (char *)c2r_writeback + c0 * in_step : nullptr), out_step, in_step, cnt); \
             else if (c->inv)    tx_mdct_inv_kernel<TB><<<nb, threads, c->smem, st>>>(c->d, (float *)o, (const float *)i, stride / 4, out_step, in_step, cnt); \
             else                tx_mdct_fwd_kernel<TB><<<nb, threads, c->smem, st>>>(c->d, (float *)o, (const float *)i, stride / 4, out_step, in_step, cnt); \
         } while (0)
@@ -474,6 +608,7 @@ static void tx_host_fn(B200TXContext *c, void *out, void *in, ptrdiff_t stride)
     const size_t n = c->d.n, len = c->len;
     size_t in_elems, out_elems;            // floats
     if (c->type == 0) { in_elems = out_elems = 2 * n; }
+    else if (c->type == 6) { in_elems = c->inv ? len + 2 : len; out_elems = c->inv ? len : len + 2; }
     else if (c->inv) { in_elems = len; out_elems = len; }
     else { in_elems = 2 * len; out_elems = len; }
     float *scr = (float *)b200_scratch(d, (in_elems + out_elems) * 4 + 512);
@@ -486,7 +621,9 @@ static void tx_host_fn(B200TXContext *c, void *out, void *in, ptrdiff_t stride)
     if (strided_in) e = cudaMemcpy2DAsync(din, 4, in, (size_t)stride, 4, in_elems, cudaMemcpyHostToDevice, st);
     else e = cudaMemcpyAsync(din, in, in_elems * 4, cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) fail("h2d");
-    if (tx_launch(c, st, dout, din, 4, 1, 0, 0) < 0) fail("launch");
+    const bool clobbers = c->type == 6 && c->inv;                    // ff_tx_rdft_c2r rewrites its input (tx_template.c:1670-1696)
+    if (tx_launch(c, st, dout, din, 4, 1, 0, 0, clobbers ? din : nullptr) < 0) fail("launch");
+    if (clobbers && cudaMemcpyAsync(in, din, (in_elems - 2) * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) fail("d2h input");
     if (strided_out) e = cudaMemcpy2DAsync(out, (size_t)stride, dout, 4, 4, out_elems, cudaMemcpyDeviceToHost, st);
     else e = cudaMemcpyAsync(out, dout, out_elems * 4, cudaMemcpyDeviceToHost, st);
     if (e != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) fail("d2h");
@@ -498,13 +635,14 @@ B200_API int b200_tx_init_device(B200Device *dev, B200TXContext **ctx, b200_tx_f
     if (!ctx || !len) return B200_EINVAL;                            // av_tx_init, tx.c:903-940
     *ctx = nullptr;
     if (!dev) return B200_ENODEV;
-    if (type != B200_TX_FLOAT_FFT && type != B200_TX_FLOAT_MDCT) return B200_ENOSYS;
+    if (type != B200_TX_FLOAT_FFT && type != B200_TX_FLOAT_MDCT && type != B200_TX_FLOAT_RDFT) return B200_ENOSYS;
     if (flags & ~(uint64_t)B200_TX_UNALIGNED) return B200_ENOSYS;    // INPLACE / FULL_IMDCT / REAL_TO_* not implemented
     if (len < 2 || (len & (len - 1))) return B200_ENOSYS;            // PFA (3/5/7/9/15 x 2^n) lengths not implemented
+    if (type == B200_TX_FLOAT_RDFT && len < 4) return B200_ENOSYS;   // ff_tx_rdft_*_def: min_len 4
     const int n = type == 0 ? len : len >> 1;
     if (n < 1 || n > 16384) return B200_ENOSYS;                      // one transform must fit a CTA's shared memory
     float sc = 1.0f;                                                 // default_scale_f
-    if (type == B200_TX_FLOAT_MDCT && scale) sc = *(const float *)scale;
+    if (type != B200_TX_FLOAT_FFT && scale) sc = *(const float *)scale;
     B200TXContext *c = new (std::nothrow) B200TXContext();
     if (!c) return B200_ENOMEM;
     c->dev = dev; c->type = type; c->inv = !!inv; c->len = len;

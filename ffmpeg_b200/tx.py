@@ -1,9 +1,9 @@
 """Host-side mirror of libavutil/tx's public interface (av_tx_init / av_tx_fn / av_tx_uninit, libavutil/tx.h:151,202-208)
-for AV_TX_FLOAT_FFT and AV_TX_FLOAT_MDCT, plus the batched device entry point."""
+for AV_TX_FLOAT_FFT, AV_TX_FLOAT_MDCT and AV_TX_FLOAT_RDFT, plus the batched device entry point."""
 import ctypes as C
 from ._lib import lib, check, vp, TX_FN
 
-AV_TX_FLOAT_FFT, AV_TX_FLOAT_MDCT = 0, 1
+AV_TX_FLOAT_FFT, AV_TX_FLOAT_MDCT, AV_TX_FLOAT_RDFT = 0, 1, 6
 
 
 def _dptr(x):

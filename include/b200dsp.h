@@ -297,11 +297,17 @@ int  b200_emulated_edge_mc_batch_device(B200Device *dev, int64_t n, uint8_t *buf
                                         ptrdiff_t src_linesize, const int32_t *geom, int w, int h);
 
 /* ------------------------------------------------------------------------------------------------ libavutil/tx
- * Replaces av_tx_init / av_tx_uninit / av_tx_fn (libavutil/tx.h:151,202-208) for AV_TX_FLOAT_FFT and AV_TX_FLOAT_MDCT,
+ * Replaces av_tx_init / av_tx_uninit / av_tx_fn (libavutil/tx.h:151,202-208) for AV_TX_FLOAT_FFT, AV_TX_FLOAT_MDCT and
+ * AV_TX_FLOAT_RDFT,
  * power-of-two lengths, with the float operation order of the reference's C codelets (bit-identical results).
  * Inside FFmpeg the plug point is a codelet list with prio FF_TX_PRIO_MAX (libavutil/tx_priv.h:168, tx.c:340-351). */
 #define B200_TX_FLOAT_FFT   0     /* AV_TX_FLOAT_FFT  */
 #define B200_TX_FLOAT_MDCT  1     /* AV_TX_FLOAT_MDCT */
+#define B200_TX_FLOAT_RDFT  6     /* AV_TX_FLOAT_RDFT: forward = real-to-complex (len floats -> len/2+1 complex), inverse =
+                                   * complex-to-real; scale: const float *.  Like the reference's ff_tx_rdft_c2r
+                                   * (tx_template.c:1655-1724) the host av_tx_fn rewrites its input on the inverse; the
+                                   * batched device entry point leaves the input untouched.  AV_TX_REAL_TO_REAL /
+                                   * AV_TX_REAL_TO_IMAGINARY are not implemented. */
 #define B200_TX_UNALIGNED   2     /* AV_TX_UNALIGNED (accepted, no effect) */
 typedef struct B200TXContext B200TXContext;
 typedef void (*b200_tx_fn)(B200TXContext *s, void *out, void *in, ptrdiff_t stride);   /* av_tx_fn: HOST pointers */

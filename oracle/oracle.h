@@ -88,7 +88,7 @@ int  orc_h264chroma(int avg, int idx, uint8_t *dst, const uint8_t *src, ptrdiff_
 
 /* ------------------------------------------------------------------ tx (float FFT / MDCT, power-of-two) */
 typedef struct OrcTx OrcTx;
-OrcTx *orc_tx_open(int type /*0 FFT, 1 MDCT*/, int inv, int len, float scale, unsigned flags);
+OrcTx *orc_tx_open(int type /*0 FFT, 1 MDCT, 6 RDFT (r2c forward, c2r inverse)*/, int inv, int len, float scale, unsigned flags);
 void   orc_tx_close(OrcTx *t);
 void   orc_tx_run(OrcTx *t, void *out, void *in, ptrdiff_t stride, int count, ptrdiff_t out_step, ptrdiff_t in_step);
 

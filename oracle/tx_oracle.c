@@ -25,11 +25,12 @@
 typedef struct { float re, im; } cpx;
 
 struct OrcTx {
-    int type, inv, len;         /* len: FFT points, or MDCT len (len/2-point complex FFT inside) */
+    int type, inv, len;         /* type 0 FFT, 1 MDCT, 6 RDFT (AVTXType values); len: FFT points, or MDCT / RDFT len (len/2-point FFT inside) */
     int n;                      /* FFT size actually run */
     int *map;                   /* FFT permutation (gather for FFT / inverse MDCT, scatter for forward MDCT) */
     int *sub_map;               /* MDCT: map, doubled for the inverse */
     cpx *exp;                   /* MDCT twiddles */
+    float *rexp;                /* RDFT: 8 factors, then cos and sin-like tables of len/4 entries each */
     float *tab[18];             /* tab[k] = cosine table of size 2^k */
 };
 
@@ -141,7 +142,8 @@ static int ilog2i(int n) { int k = 0; while ((1 << k) < n) k++; return k; }
 
 OrcTx *orc_tx_open(int type, int inv, int len, float scale, unsigned flags)
 {
-    if (flags || (type != 0 && type != 1) || len < 2 || (len & (len - 1))) return NULL;
+    if (flags || (type != 0 && type != 1 && type != 6) || len < 2 || (len & (len - 1))) return NULL;
+    if (type == 6 && len < 4) return NULL;                     /* ff_tx_rdft_*_def: min_len 4 */
     OrcTx *t = calloc(1, sizeof(*t));
     t->type = type; t->inv = !!inv; t->len = len;
     t->n = type == 0 ? len : len >> 1;
@@ -175,6 +177,21 @@ OrcTx *orc_tx_open(int type, int inv, int len, float scale, unsigned flags)
         t->sub_map = malloc(sizeof(int) * len4);
         for (int i = 0; i < len4; i++) t->sub_map[i] = inv ? t->map[i] << 1 : t->map[i];
     }
+    if (type == 6) {                                           /* ff_tx_rdft_init, tx_template.c:1601-1653 */
+        const int len4 = len >> 2;
+        const double f = 2 * M_PI / len, m = inv ? 2 * (double)scale : (double)scale;
+        float *tab = t->rexp = malloc(sizeof(float) * (8 + 2 * len4));
+        *tab++ = (float)((inv ? 0.5 : 1.0) * m);
+        *tab++ = (float)(inv ? 0.5 * m : 1.0 * m);
+        *tab++ = (float)(m);
+        *tab++ = (float)(-m);
+        *tab++ = (float)((0.5 - 0.0) * m);
+        *tab++ = (float)((0.0 - 0.5) * m);
+        *tab++ = (float)((0.5 - inv) * m);
+        *tab++ = (float)(-(0.5 - inv) * m);
+        for (int i = 0; i < len4; i++) *tab++ = (float)cos(i * f);
+        for (int i = 0; i < len4; i++) *tab++ = (float)cos(((len - i * 4) / 4.0) * f) * (inv ? 1 : -1);
+    }
     return t;
 }
 
@@ -182,7 +199,7 @@ void orc_tx_close(OrcTx *t)
 {
     if (!t) return;
     for (int i = 0; i < 18; i++) free(t->tab[i]);
-    free(t->map); free(t->sub_map); free(t->exp); free(t);
+    free(t->map); free(t->sub_map); free(t->exp); free(t->rexp); free(t);
 }
 
 static void run_fft(OrcTx *t, cpx *dst, const cpx *src)
@@ -244,11 +261,58 @@ static void run_mdct_fwd(OrcTx *t, float *dst, const float *src, ptrdiff_t strid
     }
 }
 
+/* ff_tx_rdft_r2c / ff_tx_rdft_c2r (DECL_RDFT, tx_template.c:1655-1724): a len/2-point complex FFT plus the even/odd
+ * separation butterflies.  r2c: len floats in, len/2+1 complex out.  c2r: len/2+1 complex in (modified in place, like the
+ * reference does), len floats out. */
+static void rdft_butterflies(const OrcTx *t, cpx *data)
+{
+    const int len2 = t->len >> 1, len4 = t->len >> 2;
+    const float *fact = t->rexp, *tcos = fact + 8, *tsin = tcos + len4;
+    float t0re = data[0].re;
+    data[0].re = t0re + data[0].im;
+    data[0].im = t0re - data[0].im;
+    data[0].re = fact[0] * data[0].re;
+    data[0].im = fact[1] * data[0].im;
+    data[len4].re = fact[2] * data[len4].re;
+    data[len4].im = fact[3] * data[len4].im;
+    for (int i = 1; i < len4; i++) {
+        cpx a, b, c;
+        a.re = fact[4] * (data[i].re + data[len2 - i].re);
+        a.im = fact[5] * (data[i].im - data[len2 - i].im);
+        b.re = fact[6] * (data[i].im + data[len2 - i].im);
+        b.im = fact[7] * (data[i].re - data[len2 - i].re);
+        c.re = b.re * tcos[i] - b.im * tsin[i];
+        c.im = b.re * tsin[i] + b.im * tcos[i];
+        data[i].re = a.re + c.re;
+        data[i].im = c.im - a.im;
+        data[len2 - i].re = a.re - c.re;
+        data[len2 - i].im = c.im + a.im;
+    }
+}
+
+static void run_rdft(OrcTx *t, void *out, void *in)
+{
+    const int len2 = t->len >> 1;
+    if (!t->inv) {
+        cpx *data = out;
+        run_fft(t, data, in);
+        rdft_butterflies(t, data);
+        data[len2].re = data[0].im;
+        data[0].im = data[len2].im = 0;
+    } else {
+        cpx *data = in;
+        data[0].im = data[len2].re;
+        rdft_butterflies(t, data);
+        run_fft(t, out, data);
+    }
+}
+
 void orc_tx_run(OrcTx *t, void *out, void *in, ptrdiff_t stride, int count, ptrdiff_t out_step, ptrdiff_t in_step)
 {
     for (int c = 0; c < count; c++) {
         void *o = (uint8_t *)out + c * out_step, *i = (uint8_t *)in + c * in_step;
         if (t->type == 0) run_fft(t, o, i);
+        else if (t->type == 6) run_rdft(t, o, i);
         else if (t->inv) run_mdct_inv(t, o, i, stride / (ptrdiff_t)sizeof(float));
         else run_mdct_fwd(t, o, i, stride / (ptrdiff_t)sizeof(float));
     }

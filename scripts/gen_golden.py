@@ -244,6 +244,17 @@ def gen_tx():
             d[f"imdct_{n}_{j}"] = run(1, 1, n, sc, x, n)
             d[f"mdct_{n}_{j}"] = run(1, 0, n, sc, x2, n)
     np.savez_compressed(os.path.join(OUT, "tx.npz"), **d)
+    # AV_TX_FLOAT_RDFT: forward r2c (len floats -> len/2+1 complex) and inverse c2r; the inverse rewrites its input
+    d = {}
+    for n in (4, 8, 16, 64, 256, 1024, 2048, 4096):
+        for j, sc in enumerate((1.0, 1.0 / n)):
+            x = (rng.random((2, n), dtype=np.float32) * 2 - 1).astype(np.float32)
+            xc = (rng.random((2, n + 2), dtype=np.float32) * 2 - 1).astype(np.float32)
+            d[f"r2c_in_{n}_{j}"], d[f"c2r_in_{n}_{j}"] = x.copy(), xc.copy()
+            d[f"r2c_{n}_{j}"] = run(6, 0, n, sc, x, n + 2)
+            d[f"c2r_{n}_{j}"] = run(6, 1, n, sc, xc, n)
+            d[f"c2r_in_after_{n}_{j}"] = xc
+    np.savez_compressed(os.path.join(OUT, "tx_rdft.npz"), **d)
 
 
 def gen_vsynth1():

@@ -70,7 +70,7 @@ def run(dev):
         # tx: FFT-1024 and iMDCT-1024, 4 transforms each
         n = 1024
         x = rng.random((4, 2 * n), dtype=np.float32)
-        for typ, inv, scale, inw, outw, stride in ((0, 0, 1.0, 2 * n, 2 * n, 8), (1, 1, 1.0 / n, n, n, 4)):
+        for typ, inv, scale, inw, outw, stride in ((0, 0, 1.0, 2 * n, 2 * n, 8), (1, 1, 1.0 / n, n, n, 4), (6, 0, 1.0, n, n + 2, 4)):
             h = O.orc_tx_open(typ, inv, n, scale, 0)
             xi = np.ascontiguousarray(x[:, :inw])
             e = np.zeros((4, outw), np.float32)

@@ -414,6 +414,68 @@ def test_tx_batch_vs_oracle(device, n):
         c.uninit()
 
 
+def test_tx_rdft_host_fn_golden(device):
+    """AV_TX_FLOAT_RDFT through av_tx_fn on host buffers: bit-identical to the reference, and the inverse leaves the same
+    values in its input buffer as ff_tx_rdft_c2r does."""
+    from ffmpeg_b200 import tx
+    g = np.load(os.path.join(G, "tx_rdft.npz"))
+    for n in (4, 8, 16, 64, 256, 1024, 2048, 4096):
+        for j, sc in enumerate((1.0, 1.0 / n)):
+            c = tx.av_tx_init(tx.AV_TX_FLOAT_RDFT, 0, n, scale=sc)
+            x = g[f"r2c_in_{n}_{j}"].copy()
+            out = np.zeros((2, n + 2), np.float32)
+            for r in range(2):
+                c.fn(out[r], x[r], 4)
+            assert np.array_equal(out.view(np.uint32), g[f"r2c_{n}_{j}"].view(np.uint32)), ("r2c", n, j)
+            c.uninit()
+            c = tx.av_tx_init(tx.AV_TX_FLOAT_RDFT, 1, n, scale=sc)
+            xc = g[f"c2r_in_{n}_{j}"].copy()
+            out = np.zeros((2, n), np.float32)
+            for r in range(2):
+                c.fn(out[r], xc[r], 8)
+            assert np.array_equal(out.view(np.uint32), g[f"c2r_{n}_{j}"].view(np.uint32)), ("c2r", n, j)
+            assert np.array_equal(xc.view(np.uint32), g[f"c2r_in_after_{n}_{j}"].view(np.uint32)), ("c2r input", n, j)
+            c.uninit()
+    with pytest.raises(Exception):
+        tx.av_tx_init(tx.AV_TX_FLOAT_RDFT, 0, 2, scale=1.0)            # min_len 4
+    with pytest.raises(Exception):
+        tx.av_tx_init(tx.AV_TX_FLOAT_RDFT, 0, 96, scale=1.0)           # 3 x 2^n: PFA lengths are not implemented
+
+
+@pytest.mark.parametrize("n", [512, 2048, 8192])
+def test_tx_rdft_batch_vs_oracle(device, n):
+    import torch
+    from ffmpeg_b200 import tx
+    O = cl.oracle()
+    rng = np.random.default_rng(n + 1)
+    cnt = 203
+
+    def orc(inv, scale, x, of):
+        h = O.orc_tx_open(6, inv, n, scale, 0)
+        out = np.zeros((x.shape[0], of), np.float32)
+        O.orc_tx_run(h, out.ctypes.data, x.ctypes.data, 4, x.shape[0], out.strides[0], x.strides[0])
+        O.orc_tx_close(h)
+        return out
+    with on_stream(device):
+        x = (rng.random((cnt, n), dtype=np.float32) * 2 - 1).astype(np.float32)
+        c = tx.av_tx_init(tx.AV_TX_FLOAT_RDFT, 0, n, scale=1.0, device=device)
+        dx, do = torch.from_numpy(x).cuda(), torch.zeros((cnt, n + 2), dtype=torch.float32, device="cuda")
+        c.batch_device(do, dx, 4, cnt, 4 * (n + 2), 4 * n)
+        device.sync()
+        spec = do.cpu().numpy()
+        assert np.array_equal(spec.view(np.uint32), orc(0, 1.0, x.copy(), n + 2).view(np.uint32)), "r2c"
+        c.uninit()
+        c = tx.av_tx_init(tx.AV_TX_FLOAT_RDFT, 1, n, scale=1.0 / n, device=device)
+        di, do = torch.from_numpy(spec).cuda(), torch.zeros((cnt, n), dtype=torch.float32, device="cuda")
+        c.batch_device(do, di, 8, cnt, 4 * n, 4 * (n + 2))
+        device.sync()
+        back = do.cpu().numpy()
+        assert np.array_equal(di.cpu().numpy().view(np.uint32), spec.view(np.uint32)), "batched c2r must not touch its input"
+        assert np.array_equal(back.view(np.uint32), orc(1, 1.0 / n, spec.copy(), n).view(np.uint32)), "c2r"
+        assert np.abs(back - x).max() < 1e-4                      # r2c (scale 1) then c2r (scale 1/len) is the identity
+        c.uninit()
+
+
 def test_tx_linearity_1m_batch(device):
     """BASELINE config 5 size (a large batch of len-1024 transforms): FFT(a) + FFT(b) ~= FFT(a + b) and Parseval,
     size-independent properties at a size the oracle cannot cover; plus unsupported configurations are refused loudly."""

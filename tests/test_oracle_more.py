@@ -183,6 +183,35 @@ def test_tx_oracle_golden_bitexact():
             assert np.array_equal(_tx(O, "orc", 1, 0, n, sc, g[f"mdct_in_{n}"], n).view(np.uint32), g[f"mdct_{n}_{j}"].view(np.uint32)), (n, j)
 
 
+RDFT_SIZES = (4, 8, 16, 64, 256, 1024, 2048, 4096)
+
+
+def test_tx_rdft_oracle_golden_bitexact():
+    """AV_TX_FLOAT_RDFT r2c / c2r against the reference's outputs, including what c2r leaves in its input buffer."""
+    g = np.load(os.path.join(G, "tx_rdft.npz"))
+    O = cl.oracle()
+    for n in RDFT_SIZES:
+        for j, sc in enumerate((1.0, 1.0 / n)):
+            got = _tx(O, "orc", 6, 0, n, sc, g[f"r2c_in_{n}_{j}"].copy(), n + 2)
+            assert np.array_equal(got.view(np.uint32), g[f"r2c_{n}_{j}"].view(np.uint32)), (n, j)
+            xc = g[f"c2r_in_{n}_{j}"].copy()
+            got = _tx(O, "orc", 6, 1, n, sc, xc, n)
+            assert np.array_equal(got.view(np.uint32), g[f"c2r_{n}_{j}"].view(np.uint32)), (n, j)
+            assert np.array_equal(xc.view(np.uint32), g[f"c2r_in_after_{n}_{j}"].view(np.uint32)), (n, j)
+
+
+def test_tx_rdft_oracle_is_a_real_dft_and_round_trips():
+    O = cl.oracle()
+    rng = np.random.default_rng(3)
+    for n in (16, 1024):
+        x = (rng.random((1, n), dtype=np.float32) * 2 - 1).astype(np.float32)
+        spec = _tx(O, "orc", 6, 0, n, 1.0, x.copy(), n + 2)
+        ref = np.fft.rfft(x[0].astype(np.float64))
+        assert np.abs(spec[0, 0::2] - ref.real).max() < 5e-4 * n and np.abs(spec[0, 1::2] - ref.imag).max() < 5e-4 * n
+        back = _tx(O, "orc", 6, 1, n, 1.0 / n, spec.copy(), n)       # r2c(scale 1) then c2r(scale 1/len) is the identity
+        assert np.abs(back[0] - x[0]).max() < 1e-4
+
+
 def test_tx_oracle_is_a_dft():
     """Independent sanity check of the oracle itself: against numpy's double-precision FFT (eps like checkasm av_tx.c:27)."""
     O = cl.oracle()
@@ -214,4 +243,8 @@ def test_more_oracles_vs_reference_live():
         for inv in (0, 1):
             assert np.array_equal(_tx(R, "ffref", 0, inv, n, 1.0, x, 2 * n).view(np.uint32), _tx(O, "orc", 0, inv, n, 1.0, x, 2 * n).view(np.uint32))
         assert np.array_equal(_tx(R, "ffref", 1, 1, n, 1.0 / n, x[:, :n], n).view(np.uint32), _tx(O, "orc", 1, 1, n, 1.0 / n, x[:, :n], n).view(np.uint32))
+        xr = np.ascontiguousarray(x[:, :n])
+        assert np.array_equal(_tx(R, "ffref", 6, 0, n, 0.5, xr.copy(), n + 2).view(np.uint32), _tx(O, "orc", 6, 0, n, 0.5, xr.copy(), n + 2).view(np.uint32))
+        xc = np.ascontiguousarray(x[:, :n + 2])
+        assert np.array_equal(_tx(R, "ffref", 6, 1, n, 0.5, xc.copy(), n).view(np.uint32), _tx(O, "orc", 6, 1, n, 0.5, xc.copy(), n).view(np.uint32))
         assert np.array_equal(_tx(R, "ffref", 1, 0, n, -1.0, x, n).view(np.uint32), _tx(O, "orc", 1, 0, n, -1.0, x, n).view(np.uint32))
