@@ -209,6 +209,29 @@ sws_hscale_kernel(const uint8_t *src, long long sstride, long long sfs, int16_t 
     dst[(long long)blockIdx.z * dfs + (long long)line * dstW + i] = (int16_t)min(acc >> 7, 32767);
 }
 
+// SWS_FAST_BILINEAR horizontal pass (ff_hyscale_fast_c / ff_hcscale_fast_c, hscale_fast_bilinear.c:27-67): 16.16 stepping with
+// 7-bit blend weights; outputs whose left sample is the last source sample (or beyond) are src[srcW-1] * 128, which is what
+// the fix-up loop at the end of both reference functions leaves (so the sample right of the row end is never read).
+template <bool CHROMA>
+__global__ void __launch_bounds__(256)
+sws_hscale_fast_kernel(const uint8_t *src, long long sstride, long long sfs, int16_t *dst, int dstW, long long dfs,
+                       int srcW, int xInc, int line0)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= dstW) return;
+    const int line = blockIdx.y + line0;
+    const uint8_t *s = src + (long long)blockIdx.z * sfs + (long long)line * sstride;
+    const unsigned xpos = (unsigned)i * (unsigned)xInc;             // the reference accumulates in 32 bits
+    const unsigned xx = xpos >> 16, xalpha = (xpos & 0xFFFF) >> 9;
+    int v;
+    if ((((long long)i * xInc) >> 16) >= srcW - 1) v = (int)__ldg(s + srcW - 1) * 128;
+    else {
+        const int a = __ldg(s + xx), b = __ldg(s + xx + 1);
+        v = CHROMA ? a * (int)(xalpha ^ 127) + b * (int)xalpha : (a << 7) + (b - a) * (int)xalpha;
+    }
+    dst[(long long)blockIdx.z * dfs + (long long)line * dstW + i] = (int16_t)v;
+}
+
 // ------------------------------------------------------------------------------------------------ kernel: vertical FIR + rgb24 (fast)
 // Same-size conversion with the reference's scaler flags (the FATE path): the horizontal pass is the identity, so the
 // vertical taps are read straight from the u8 planes.  Only the general `_X` writer (yuv2rgb_X_c_template,
@@ -490,6 +513,19 @@ sws_plane_copy_kernel(const uint8_t *src, long long ss, long long sfs, uint8_t *
     } else if (i < w) d[i] = s[i];
 }
 
+// nv12 / nv21 source: plane 1 -> separate U and V planes (nvXXtoUV_c, input.c:921-948).  One thread per chroma sample pair.
+__global__ void __launch_bounds__(256)
+sws_nv_split_kernel(const uint8_t *uv, long long uvs, long long uvfs, uint8_t *u, uint8_t *v, long long pitch, long long fs,
+                    int cw, int row0)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cw) return;
+    const int r = blockIdx.y + row0;
+    const uint8_t *s = uv + blockIdx.z * uvfs + (long long)r * uvs + 2 * i;
+    const long long o = blockIdx.z * fs + (long long)r * pitch + i;
+    u[o] = __ldg(s); v[o] = __ldg(s + 1);
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 struct B200SwsContext {
     B200Device *dev = nullptr;
@@ -501,6 +537,8 @@ struct B200SwsContext {
     bool lum_identity = false;       // vertical luma bank is a single tap of 4096 on every line
     // intermediate int16 line planes for the scaled path (grown on demand, per batch)
     void *mid = nullptr; size_t mid_bytes = 0;
+    // de-interleaved chroma of an nv12 / nv21 source (persistent: slice calls keep earlier bands here)
+    void *nv_buf = nullptr; size_t nv_bytes = 0;
     // slice calls (sws_scale with srcSliceH < srcH): device copies of the source planes and of the picture being built,
     // plus the next output line (SwsInternal.dstY, swscale.c:297,551)
     void *slice_buf = nullptr;
@@ -565,7 +603,7 @@ static int upload_tables(B200SwsContext *c)
     c->dt.hLum2 = (const int32_t *)(b + o_hl2); c->dt.hChr2 = (const int32_t *)(b + o_hc2);
     c->dt.hLum = (const int16_t *)(b + o_hl); c->dt.hLumPos = (const int32_t *)(b + o_hlp); c->dt.hLumSize = p.hLum.size;
     c->dt.hChr = (const int16_t *)(b + o_hc); c->dt.hChrPos = (const int32_t *)(b + o_hcp); c->dt.hChrSize = p.hChr.size;
-    c->h_identity = p.chrDstHSub == 1 && p.hLum.identity() && p.hChr.identity();
+    c->h_identity = !p.fast_bilinear && p.chrDstHSub == 1 && p.hLum.identity() && p.hChr.identity();
     c->fast_x = c->h_identity && !p.planar;
     c->lum_identity = p.vLum.size == 1;
     for (int y = 0; y < p.dstH && c->fast_x; y++) {
@@ -584,7 +622,8 @@ B200_API B200SwsContext *b200_sws_getContext(B200Device *dev, int srcW, int srcH
 {
     if (!dev) { b200_set_error("b200_sws_getContext: no device"); return nullptr; }
     SwsOutFmt out;
-    if (srcFormat != B200_PIX_FMT_YUV420P || !sws_out_format(dstFormat, out)) {
+    const bool src_ok = srcFormat == B200_PIX_FMT_YUV420P || srcFormat == B200_PIX_FMT_NV12 || srcFormat == B200_PIX_FMT_NV21;
+    if (!src_ok || !sws_out_format(dstFormat, out)) {
         b200_set_error("b200_sws_getContext: only yuv420p -> rgb24 / bgr24 / rgba / bgra / argb / abgr / yuv420p is implemented");
         return nullptr;
     }
@@ -592,6 +631,7 @@ B200_API B200SwsContext *b200_sws_getContext(B200Device *dev, int srcW, int srcH
     if (!c) return nullptr;
     c->dev = dev;
     c->plan.out = out;
+    c->plan.src_nv = srcFormat == B200_PIX_FMT_NV12 ? 1 : srcFormat == B200_PIX_FMT_NV21 ? 2 : 0;
     int ret = sws_plan_build(c->plan, srcW, srcH, dstW, dstH, flags);
     if (ret < 0) { b200_set_error("b200_sws_getContext: unsupported configuration (%d)", ret); delete c; return nullptr; }
     cudaSetDevice(dev->ordinal);
@@ -606,6 +646,7 @@ B200_API void b200_sws_freeContext(B200SwsContext *c)
     cudaStreamSynchronize(c->dev->stream);
     if (c->tables) cudaFree(c->tables);
     if (c->mid) cudaFree(c->mid);
+    if (c->nv_buf) cudaFree(c->nv_buf);
     if (c->slice_buf) cudaFree(c->slice_buf);
     delete c;
 }
@@ -667,6 +708,39 @@ static bool aligned8(const void *p, long long stride, long long fstride)
     return (((uintptr_t)p) & 7) == 0 && (stride & 7) == 0 && (fstride & 7) == 0;
 }
 
+// nv12 / nv21: split plane 1 of `nframes` frames (chroma rows [row0, row0 + nrows)) into U and V planes and redirect the
+// plane pointers.  `scratch` (per-call) or the context's persistent buffer holds them: per frame U then V, pitch nv_pitch().
+static size_t nv_pitch(const SwsPlan &p) { return ((size_t)p.chrSrcW + 255) & ~(size_t)255; }
+static size_t nv_frame_bytes(const SwsPlan &p) { return 2 * nv_pitch(p) * p.chrSrcH; }
+static int nv_split(B200SwsContext *c, cudaStream_t stream, uint8_t *scratch, int nframes, int row0, int nrows,
+                    const uint8_t *s3[3], long long st3[3], long long fs3[3])
+{
+    const SwsPlan &p = c->plan;
+    const size_t pitch = nv_pitch(p), fb = nv_frame_bytes(p);
+    uint8_t *buf = scratch;
+    if (!buf) {
+        if (c->nv_bytes < fb * nframes) {
+            if (c->nv_buf) { cudaStreamSynchronize(stream); cudaFree(c->nv_buf); c->nv_buf = nullptr; c->nv_bytes = 0; }
+            B200_CUDA_OK(cudaMalloc(&c->nv_buf, fb * nframes));
+            c->nv_bytes = fb * nframes;
+        }
+        buf = (uint8_t *)c->nv_buf;
+    }
+    uint8_t *pu = buf, *pv = buf + pitch * p.chrSrcH;
+    if (p.src_nv == 2) { uint8_t *t = pu; pu = pv; pv = t; }               // nv21: first byte of a pair is V
+    for (int f0 = 0; f0 < nframes && nrows > 0; f0 += 65535) {
+        const int nf = nframes - f0 < 65535 ? nframes - f0 : 65535;
+        dim3 block(256), grid(b200_ceil_div(p.chrSrcW, 256), nrows, nf);
+        sws_nv_split_kernel<<<grid, block, 0, stream>>>(s3[1] + (long long)f0 * fs3[1], st3[1], fs3[1], pu + (size_t)f0 * fb, pv + (size_t)f0 * fb,
+                                                        (long long)pitch, (long long)fb, p.chrSrcW, row0);
+        B200_LAUNCHED();
+    }
+    s3[1] = buf; s3[2] = buf + pitch * p.chrSrcH;                          // [1] = U plane, [2] = V plane
+    st3[1] = st3[2] = (long long)pitch;
+    fs3[1] = fs3[2] = (long long)fb;
+    return 0;
+}
+
 template <int KIND>
 static void launch_vscale_fast(bool lumid, bool c4, dim3 grid, dim3 block, cudaStream_t stream, const SwsFrameArgs &b,
                                const SwsDevTables &dt, const SwsColorConst &col, int ngroups)
@@ -682,15 +756,21 @@ static void launch_vscale_fast(bool lumid, bool c4, dim3 grid, dim3 block, cudaS
 // source lines that were just uploaded (only those need the horizontal pass).
 struct SwsRows { int dy0, ndy, ly0, nly, cy0, ncy; };
 
-static int launch_batch(B200SwsContext *c, cudaStream_t stream, const uint8_t *const src[3], const long long sstr[3],
-                        const long long sfs[3], uint8_t *dst, long long ds, long long dfs, int nframes,
-                        const SwsRows *rows = nullptr)
+static int launch_batch(B200SwsContext *c, cudaStream_t stream, const uint8_t *const src_in[3], const long long sstr_in[3],
+                        const long long sfs_in[3], uint8_t *dst, long long ds, long long dfs, int nframes,
+                        const SwsRows *rows = nullptr, uint8_t *nv_scratch = nullptr)
 {
     const SwsPlan &p = c->plan;
     if (nframes <= 0) return 0;
     const SwsRows full = { 0, p.dstH, 0, p.srcH, 0, p.chrSrcH };
     const SwsRows R = rows ? *rows : full;
     if (R.ndy <= 0 && R.nly <= 0 && R.ncy <= 0) return 0;
+    const uint8_t *src[3] = { src_in[0], src_in[1], src_in[2] };
+    long long sstr[3] = { sstr_in[0], sstr_in[1], sstr_in[2] }, sfs[3] = { sfs_in[0], sfs_in[1], sfs_in[2] };
+    if (p.src_nv) {
+        int ret = nv_split(c, stream, nv_scratch, nframes, R.cy0, R.ncy, src, sstr, sfs);
+        if (ret < 0) return ret;
+    }
     SwsFrameArgs a{};
     a.y = src[0]; a.u = src[1]; a.v = src[2];
     a.ys = sstr[0]; a.us = sstr[1]; a.vs = sstr[2];
@@ -767,14 +847,17 @@ static int launch_batch(B200SwsContext *c, cudaStream_t stream, const uint8_t *c
             dim3 block(256);
             if (R.nly > 0) {
                 dim3 grid(b200_ceil_div(p.dstW, 256), R.nly, nf);
-                sws_hscale_kernel<<<grid, block, 0, stream>>>(b.y, b.ys, b.yfs, mY, p.dstW, mfs, c->dt.hLum2, c->dt.hLumPos, c->dt.hLumSize, R.ly0);
+                if (p.fast_bilinear) sws_hscale_fast_kernel<false><<<grid, block, 0, stream>>>(b.y, b.ys, b.yfs, mY, p.dstW, mfs, p.srcW, p.lumXInc, R.ly0);
+                else sws_hscale_kernel<<<grid, block, 0, stream>>>(b.y, b.ys, b.yfs, mY, p.dstW, mfs, c->dt.hLum2, c->dt.hLumPos, c->dt.hLumSize, R.ly0);
                 B200_LAUNCHED();
             }
             if (R.ncy > 0) {
                 dim3 gridc(b200_ceil_div(p.chrDstW, 256), R.ncy, nf);
-                sws_hscale_kernel<<<gridc, block, 0, stream>>>(b.u, b.us, b.ufs, mU, p.chrDstW, mfs, c->dt.hChr2, c->dt.hChrPos, c->dt.hChrSize, R.cy0);
+                if (p.fast_bilinear) sws_hscale_fast_kernel<true><<<gridc, block, 0, stream>>>(b.u, b.us, b.ufs, mU, p.chrDstW, mfs, p.chrSrcW, p.chrXInc, R.cy0);
+                else sws_hscale_kernel<<<gridc, block, 0, stream>>>(b.u, b.us, b.ufs, mU, p.chrDstW, mfs, c->dt.hChr2, c->dt.hChrPos, c->dt.hChrSize, R.cy0);
                 B200_LAUNCHED();
-                sws_hscale_kernel<<<gridc, block, 0, stream>>>(b.v, b.vs, b.vfs, mV, p.chrDstW, mfs, c->dt.hChr2, c->dt.hChrPos, c->dt.hChrSize, R.cy0);
+                if (p.fast_bilinear) sws_hscale_fast_kernel<true><<<gridc, block, 0, stream>>>(b.v, b.vs, b.vfs, mV, p.chrDstW, mfs, p.chrSrcW, p.chrXInc, R.cy0);
+                else sws_hscale_kernel<<<gridc, block, 0, stream>>>(b.v, b.vs, b.vfs, mV, p.chrDstW, mfs, c->dt.hChr2, c->dt.hChrPos, c->dt.hChrSize, R.cy0);
                 B200_LAUNCHED();
             }
             if (R.ndy <= 0) continue;
@@ -804,17 +887,24 @@ B200_API int b200_sws_scale_batch_device(B200SwsContext *c, const uint8_t *const
     if (!c || !src || !srcStride || !srcFrameStride || !dst) return B200_EINVAL;
     if (c->plan.planar) return B200_EINVAL;                   // three destination planes: b200_sws_scale_batch_device_planar
     B200_CUDA_OK(cudaSetDevice(c->dev->ordinal));
-    const long long ss[3] = { srcStride[0], srcStride[1], srcStride[2] };
-    const long long fs[3] = { srcFrameStride[0], srcFrameStride[1], srcFrameStride[2] };
+    const bool nv = c->plan.src_nv != 0;                      // nv12 / nv21: src[2] and its strides are not read
+    const long long ss[3] = { srcStride[0], srcStride[1], nv ? 0 : srcStride[2] };
+    const long long fs[3] = { srcFrameStride[0], srcFrameStride[1], nv ? 0 : srcFrameStride[2] };
     return launch_batch(c, c->dev->stream, src, ss, fs, dst, dstStride, dstFrameStride, nframes);
 }
 
 // yuv420p -> yuv420p: horizontal pass of the three planes into int16 line planes, then one vertical pass per plane
-static int launch_planar(B200SwsContext *c, cudaStream_t stream, const uint8_t *const src[3], const long long sstr[3],
-                         const long long sfs[3], uint8_t *const dst[3], const long long dstr[3], const long long dfs[3], int nframes)
+static int launch_planar(B200SwsContext *c, cudaStream_t stream, const uint8_t *const src_in[3], const long long sstr_in[3],
+                         const long long sfs_in[3], uint8_t *const dst[3], const long long dstr[3], const long long dfs[3], int nframes)
 {
     const SwsPlan &p = c->plan;
     if (nframes <= 0) return 0;
+    const uint8_t *src[3] = { src_in[0], src_in[1], src_in[2] };
+    long long sstr[3] = { sstr_in[0], sstr_in[1], sstr_in[2] }, sfs[3] = { sfs_in[0], sfs_in[1], sfs_in[2] };
+    if (p.src_nv) {
+        int ret = nv_split(c, stream, nullptr, nframes, 0, p.chrSrcH, src, sstr, sfs);
+        if (ret < 0) return ret;
+    }
     const int sw[3] = { p.srcW, p.chrSrcW, p.chrSrcW }, sh[3] = { p.srcH, p.chrSrcH, p.chrSrcH };
     const int dw[3] = { p.dstW, p.chrDstW, p.chrDstW }, dh[3] = { p.dstH, p.chrDstH, p.chrDstH };
     for (int f0 = 0; f0 < nframes; f0 += 65535) {
@@ -847,8 +937,15 @@ static int launch_planar(B200SwsContext *c, cudaStream_t stream, const uint8_t *
         const int vs[3] = { c->dt.vLumSize, c->dt.vChrSize, c->dt.vChrSize };
         for (int pl = 0; pl < 3; pl++) {
             dim3 block(256), gh(b200_ceil_div(dw[pl], 256), sh[pl], nf), gv(b200_ceil_div(dw[pl], 256), dh[pl], nf);
-            sws_hscale_kernel<<<gh, block, 0, stream>>>(src[pl] + (long long)f0 * sfs[pl], sstr[pl], sfs[pl], m[pl], dw[pl],
-                                                           (long long)(perFrame / 2), hc[pl], hp[pl], hs[pl], 0);
+            if (p.fast_bilinear && pl == 0)
+                sws_hscale_fast_kernel<false><<<gh, block, 0, stream>>>(src[pl] + (long long)f0 * sfs[pl], sstr[pl], sfs[pl], m[pl], dw[pl],
+                                                                        (long long)(perFrame / 2), sw[pl], p.lumXInc, 0);
+            else if (p.fast_bilinear)
+                sws_hscale_fast_kernel<true><<<gh, block, 0, stream>>>(src[pl] + (long long)f0 * sfs[pl], sstr[pl], sfs[pl], m[pl], dw[pl],
+                                                                       (long long)(perFrame / 2), sw[pl], p.chrXInc, 0);
+            else
+                sws_hscale_kernel<<<gh, block, 0, stream>>>(src[pl] + (long long)f0 * sfs[pl], sstr[pl], sfs[pl], m[pl], dw[pl],
+                                                            (long long)(perFrame / 2), hc[pl], hp[pl], hs[pl], 0);
             B200_LAUNCHED();
             uint8_t *dpl = dst[pl] + (long long)f0 * dfs[pl];
             const bool v4 = dw[pl] % 4 == 0 && (plane[0] % 8 == 0) && (plane[1] % 8 == 0) &&
@@ -874,10 +971,11 @@ B200_API int b200_sws_scale_batch_device_planar(B200SwsContext *c, const uint8_t
 {
     if (!c || !src || !srcStride || !srcFrameStride || !dst || !dstStride || !dstFrameStride) return B200_EINVAL;
     if (!c->plan.planar) return B200_EINVAL;
-    for (int i = 0; i < 3; i++) if (!src[i] || !dst[i] || srcStride[i] < 0 || dstStride[i] < 0) return B200_EINVAL;
+    const int nsp = c->plan.src_nv ? 2 : 3;
+    for (int i = 0; i < 3; i++) if ((i < nsp && (!src[i] || srcStride[i] < 0)) || !dst[i] || dstStride[i] < 0) return B200_EINVAL;
     B200_CUDA_OK(cudaSetDevice(c->dev->ordinal));
-    const long long ss[3] = { srcStride[0], srcStride[1], srcStride[2] };
-    const long long fs[3] = { srcFrameStride[0], srcFrameStride[1], srcFrameStride[2] };
+    const long long ss[3] = { srcStride[0], srcStride[1], nsp == 3 ? srcStride[2] : 0 };
+    const long long fs[3] = { srcFrameStride[0], srcFrameStride[1], nsp == 3 ? srcFrameStride[2] : 0 };
     const long long ds[3] = { dstStride[0], dstStride[1], dstStride[2] };
     const long long df[3] = { dstFrameStride[0], dstFrameStride[1], dstFrameStride[2] };
     return launch_planar(c, c->dev->stream, src, ss, fs, dst, ds, df, nframes);
@@ -892,11 +990,14 @@ static int sws_scale_planar_host(B200SwsContext *c, const uint8_t *const srcSlic
         b200_set_error("yuv420p destination: only whole-frame calls are implemented");
         return B200_ENOSYS;
     }
-    for (int i = 0; i < 3; i++)
-        if (!srcSlice[i] || !dst[i] || srcStride[i] < 0 || dstStride[i] < 0) return srcSlice[i] && dst[i] ? B200_ENOSYS : B200_EINVAL;
+    const int nsp = p.src_nv ? 2 : 3;                             // nv12 / nv21: plane 1 carries both chroma components
+    for (int i = 0; i < 3; i++) {
+        if (!dst[i] || (i < nsp && !srcSlice[i])) return B200_EINVAL;
+        if (dstStride[i] < 0 || (i < nsp && srcStride[i] < 0)) return B200_ENOSYS;
+    }
     B200Device *d = c->dev;
     B200_CUDA_OK(cudaSetDevice(d->ordinal));
-    const int sw[3] = { p.srcW, p.chrSrcW, p.chrSrcW }, sh[3] = { p.srcH, p.chrSrcH, p.chrSrcH };
+    const int sw[3] = { p.srcW, p.src_nv ? 2 * p.chrSrcW : p.chrSrcW, p.src_nv ? 0 : p.chrSrcW }, sh[3] = { p.srcH, p.chrSrcH, p.chrSrcH };
     const int dw[3] = { p.dstW, p.chrDstW, p.chrDstW }, dh[3] = { p.dstH, p.chrDstH, p.chrDstH };
     size_t spitch[3], dpitch[3], soff[3], doff[3], total = 0;
     for (int i = 0; i < 3; i++) { spitch[i] = ((size_t)sw[i] + 255) & ~(size_t)255; soff[i] = total; total += spitch[i] * sh[i]; }
@@ -907,7 +1008,8 @@ static int sws_scale_planar_host(B200SwsContext *c, const uint8_t *const srcSlic
     const uint8_t *sp[3]; uint8_t *dp[3]; long long ss[3], ds[3];
     const long long zero[3] = { 0, 0, 0 };
     for (int i = 0; i < 3; i++) {
-        B200_CUDA_OK(cudaMemcpy2DAsync(scr + soff[i], spitch[i], srcSlice[i], (size_t)srcStride[i], sw[i], sh[i], cudaMemcpyHostToDevice, st));
+        if (i < nsp)
+            B200_CUDA_OK(cudaMemcpy2DAsync(scr + soff[i], spitch[i], srcSlice[i], (size_t)srcStride[i], sw[i], sh[i], cudaMemcpyHostToDevice, st));
         sp[i] = scr + soff[i]; dp[i] = scr + doff[i]; ss[i] = (long long)spitch[i]; ds[i] = (long long)dpitch[i];
     }
     int ret = launch_planar(c, st, sp, ss, zero, dp, ds, zero, 1);
@@ -947,7 +1049,8 @@ B200_API int b200_sws_scale_batch_host(B200SwsContext *c, const uint8_t *const s
     // Chunks of at most 8 frames: the device-to-host copies are the bottleneck of this entry point (PCIe), and they can
     // only start once the first chunk has been uploaded and converted, so short chunks keep the pipeline fill short;
     // the three in-flight chunks stay within ~0.8 GB of scratch at 4K.
-    const size_t perFrame = L.srcBytes + L.dstBytes;
+    const size_t nvBytes = p.src_nv ? nv_frame_bytes(p) : 0;     // per-slot room for the de-interleaved chroma of nv12 / nv21
+    const size_t perFrame = L.srcBytes + L.dstBytes + nvBytes;
     int chunk = (int)((size_t)256 << 20) / (int)(perFrame ? perFrame : 1);
     if (chunk < 1) chunk = 1;
     if (chunk > 8) chunk = 8;
@@ -956,15 +1059,16 @@ B200_API int b200_sws_scale_batch_host(B200SwsContext *c, const uint8_t *const s
     uint8_t *scr = (uint8_t *)b200_scratch(d, perFrame * chunk * K);
     if (!scr) return B200_ENOMEM;
     B200_CUDA_OK(cudaStreamSynchronize(d->stream));
-    const int wbytes[3] = { p.srcW, p.chrSrcW, p.chrSrcW }, rows[3] = { p.srcH, p.chrSrcH, p.chrSrcH };
-    const size_t pitch[3] = { L.yPitch, L.cPitch, L.cPitch }, poff[3] = { L.yOff, L.uOff, L.vOff };
+    const int nsp = p.src_nv ? 2 : 3;
+    const int wbytes[3] = { p.srcW, p.src_nv ? 2 * p.chrSrcW : p.chrSrcW, p.chrSrcW }, rows[3] = { p.srcH, p.chrSrcH, p.chrSrcH };
+    const size_t pitch[3] = { L.yPitch, p.src_nv ? 2 * L.cPitch : L.cPitch, L.cPitch }, poff[3] = { L.yOff, L.uOff, L.vOff };
     int slot = 0;
     for (int f0 = 0; f0 < nframes; f0 += chunk, slot = (slot + 1) % K) {
         const int nf = nframes - f0 < chunk ? nframes - f0 : chunk;
         cudaStream_t st = d->pipe[slot];
         uint8_t *sbase = scr + (size_t)slot * perFrame * chunk;
         uint8_t *dbase = sbase + L.srcBytes * chunk;
-        for (int pl = 0; pl < 3; pl++) {
+        for (int pl = 0; pl < nsp; pl++) {
             if (srcStride[pl] < 0) return B200_ENOSYS;                    // bottom-up pictures: use b200_sws_scale()
             for (int f = 0; f < nf; f++) {
                 const uint8_t *hp = src[pl] + (int64_t)(f0 + f) * srcFrameStride[pl];
@@ -973,9 +1077,10 @@ B200_API int b200_sws_scale_batch_host(B200SwsContext *c, const uint8_t *const s
             }
         }
         const uint8_t *sp[3] = { sbase + L.yOff, sbase + L.uOff, sbase + L.vOff };
-        const long long ss[3] = { (long long)L.yPitch, (long long)L.cPitch, (long long)L.cPitch };
+        const long long ss[3] = { (long long)pitch[0], (long long)pitch[1], (long long)pitch[2] };
         const long long fs[3] = { (long long)L.srcBytes, (long long)L.srcBytes, (long long)L.srcBytes };
-        int ret = launch_batch(c, st, sp, ss, fs, dbase, (long long)L.dPitch, (long long)L.dstBytes, nf);
+        int ret = launch_batch(c, st, sp, ss, fs, dbase, (long long)L.dPitch, (long long)L.dstBytes, nf, nullptr,
+                               p.src_nv ? dbase + L.dstBytes * chunk : nullptr);
         if (ret < 0) return ret;
         const size_t rowBytes = (size_t)p.dstW * p.out.bpp;
         if ((size_t)dstStride == rowBytes && L.dPitch == rowBytes && dstFrameStride == (int64_t)(rowBytes * p.dstH)) {
@@ -1006,7 +1111,7 @@ static int sws_scale_slice(B200SwsContext *c, const uint8_t *const srcSlice[], c
         return B200_EINVAL;
     }
     if (srcSliceH == 0) return 0;
-    if (srcStride[0] < 0 || srcStride[1] < 0 || srcStride[2] < 0 || dstStride[0] < 0) return B200_ENOSYS;
+    if (srcStride[0] < 0 || srcStride[1] < 0 || (!p.src_nv && srcStride[2] < 0) || dstStride[0] < 0) return B200_ENOSYS;
     if (!c->slice_open && srcSliceY != 0) {
         // "Slices start in the middle!" unless it is a bottom-up sequence, which is not implemented here
         b200_set_error("slices must start at line 0 (bottom-up slice order is not implemented)");
@@ -1021,10 +1126,12 @@ static int sws_scale_slice(B200SwsContext *c, const uint8_t *const srcSlice[], c
     if (srcSliceY == 0) { c->next_dst_y = 0; c->slice_open = true; }
     const int chrY = srcSliceY >> 1, chrH = -((-srcSliceH) >> 1);                       // AV_CEIL_RSHIFT
     B200_CUDA_OK(cudaMemcpy2DAsync(sb + L.yOff + (size_t)srcSliceY * L.yPitch, L.yPitch, srcSlice[0], (size_t)srcStride[0], p.srcW, srcSliceH, cudaMemcpyHostToDevice, st));
-    B200_CUDA_OK(cudaMemcpy2DAsync(sb + L.uOff + (size_t)chrY * L.cPitch, L.cPitch, srcSlice[1], (size_t)srcStride[1], p.chrSrcW, chrH, cudaMemcpyHostToDevice, st));
-    B200_CUDA_OK(cudaMemcpy2DAsync(sb + L.vOff + (size_t)chrY * L.cPitch, L.cPitch, srcSlice[2], (size_t)srcStride[2], p.chrSrcW, chrH, cudaMemcpyHostToDevice, st));
+    const size_t cp1 = p.src_nv ? 2 * L.cPitch : L.cPitch;       // nv12 / nv21: plane 1 is twice as wide and holds both components
+    B200_CUDA_OK(cudaMemcpy2DAsync(sb + L.uOff + (size_t)chrY * cp1, cp1, srcSlice[1], (size_t)srcStride[1], p.src_nv ? 2 * p.chrSrcW : p.chrSrcW, chrH, cudaMemcpyHostToDevice, st));
+    if (!p.src_nv)
+        B200_CUDA_OK(cudaMemcpy2DAsync(sb + L.vOff + (size_t)chrY * L.cPitch, L.cPitch, srcSlice[2], (size_t)srcStride[2], p.chrSrcW, chrH, cudaMemcpyHostToDevice, st));
     const uint8_t *sp[3] = { sb + L.yOff, sb + L.uOff, sb + L.vOff };
-    const long long ss[3] = { (long long)L.yPitch, (long long)L.cPitch, (long long)L.cPitch };
+    const long long ss[3] = { (long long)L.yPitch, (long long)cp1, (long long)L.cPitch };
     const long long fs[3] = { 0, 0, 0 };
     int y0, y1;
     if (p.unscaled_lut) {                                   // convert_unscaled handles exactly the band it is given
@@ -1067,10 +1174,11 @@ B200_API int b200_sws_scale(B200SwsContext *c, const uint8_t *const srcSlice[], 
     uint8_t *scr = (uint8_t *)b200_scratch(d, L.srcBytes + L.dstBytes);
     if (!scr) return B200_ENOMEM;
     cudaStream_t st = d->stream;
-    const int wbytes[3] = { p.srcW, p.chrSrcW, p.chrSrcW }, rows[3] = { p.srcH, p.chrSrcH, p.chrSrcH };
-    const size_t pitch[3] = { L.yPitch, L.cPitch, L.cPitch }, poff[3] = { L.yOff, L.uOff, L.vOff };
-    const uint8_t *sp[3]; long long ss[3];
-    for (int pl = 0; pl < 3; pl++) {
+    const int nsp = p.src_nv ? 2 : 3;                             // nv12 / nv21: plane 1 carries both chroma components
+    const int wbytes[3] = { p.srcW, p.src_nv ? 2 * p.chrSrcW : p.chrSrcW, p.chrSrcW }, rows[3] = { p.srcH, p.chrSrcH, p.chrSrcH };
+    const size_t pitch[3] = { L.yPitch, p.src_nv ? 2 * L.cPitch : L.cPitch, L.cPitch }, poff[3] = { L.yOff, L.uOff, L.vOff };
+    const uint8_t *sp[3] = { nullptr, nullptr, nullptr }; long long ss[3] = { 0, 0, 0 };
+    for (int pl = 0; pl < nsp; pl++) {
         const long long hs = srcStride[pl];
         const long long habs = hs < 0 ? -hs : hs;
         // negative stride (bottom-up, swscale.c:1141-1159): copy from the lowest address, walk upwards on the device

@@ -276,7 +276,11 @@ int sws_plan_build(SwsPlan &p, int srcW, int srcH, int dstW, int dstH, int flags
     int algo = flags & 0x7FF;                                                    // scaler bits, utils.c:1196-1222
     if (!algo) { algo = B200_SWS_BICUBIC; flags |= algo; }
     else if (algo & (algo - 1)) return B200_EINVAL;
-    if (algo == B200_SWS_FAST_BILINEAR) return B200_ENOSYS;                      // hyscale_fast path (hscale_fast_bilinear.c) not built
+    if (algo == B200_SWS_FAST_BILINEAR && (srcW < 8 || dstW <= 8)) {             // utils.c:1224-1230
+        algo = B200_SWS_BILINEAR;
+        flags ^= B200_SWS_FAST_BILINEAR | algo;
+    }
+    p.fast_bilinear = algo == B200_SWS_FAST_BILINEAR;                            // swscale.c:676-681
     p.planar = p.out.kind == SWS_OUT_YUV420P;
     if (!p.planar && (dstW & 1)) flags |= B200_SWS_FULL_CHR_H_INT;               // utils.c:1271-1276 (RGB destinations only)
     p.srcW = srcW; p.srcH = srcH; p.dstW = dstW; p.dstH = dstH; p.flags = flags;
@@ -293,7 +297,8 @@ int sws_plan_build(SwsPlan &p, int srcW, int srcH, int dstW, int dstH, int flags
     // unscaled special converter gate: swscale_unscaled.c:2426-2431 reached from utils.c:1623-1637
     p.planar_copy = p.planar && srcW == dstW && srcH == dstH;
     if (p.planar_copy) return 0;
-    p.unscaled_lut = !p.planar && srcW == dstW && srcH == dstH && !(flags & B200_SWS_ACCURATE_RND) && !(dstH & 1);
+    // (only planar yuv420p / yuv422p sources have the LUT converter; nv12 / nv21 go through the scaler)
+    p.unscaled_lut = !p.planar && !p.src_nv && srcW == dstW && srcH == dstH && !(flags & B200_SWS_ACCURATE_RND) && !(dstH & 1);
     if (p.unscaled_lut) return 0;
 
     const int lumScaler = algo == B200_SWS_BICUBLIN ? B200_SWS_BICUBIC : algo;
@@ -305,6 +310,7 @@ int sws_plan_build(SwsPlan &p, int srcW, int srcH, int dstW, int dstH, int flags
     if (lumXInc < 10 || lumYInc < 10 || chrXInc < 10 || chrYInc < 10 ||
         lumXInc > INT32_MAX || lumYInc > INT32_MAX || chrXInc > INT32_MAX || chrYInc > INT32_MAX)
         return B200_ENOSYS;
+    p.lumXInc = (int)lumXInc; p.chrXInc = (int)chrXInc;
     if ((ret = build_bank(p.hLum, lumScaler, (int)lumXInc, srcW, dstW, 1 << 14, sample_origin(0, 0), sample_origin(0, 0))) < 0) return ret;
     if ((ret = build_bank(p.hChr, chrScaler, (int)chrXInc, p.chrSrcW, p.chrDstW, 1 << 14,
                           sample_origin(1, -513), sample_origin(p.chrDstHSub, -513))) < 0) return ret;

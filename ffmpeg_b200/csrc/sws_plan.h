@@ -35,6 +35,9 @@ struct SwsPlan {
     int chrSrcW = 0, chrSrcH = 0, chrDstW = 0, chrDstH = 0;
     int chrDstHSub = 1;
     bool unscaled_lut = false;    // reference installs yuv2rgb_c_24_rgb as convert_unscaled
+    int src_nv = 0;               // 0: yuv420p source; 1: nv12, 2: nv21 (plane 1 holds U,V / V,U interleaved; nvXXtoUV_c, input.c:921-948)
+    bool fast_bilinear = false;   // SWS_FAST_BILINEAR: horizontal pass = ff_hyscale_fast_c / ff_hcscale_fast_c (hscale_fast_bilinear.c:27-67)
+    int lumXInc = 0, chrXInc = 0; // 16.16 horizontal steps (utils.c:1250,1425)
     bool planar = false;          // destination yuv420p (yuv2planeX / yuv2plane1 writers, vscale.c:34-107)
     bool planar_copy = false;     // same size yuv420p -> yuv420p: planarCopyWrapper (swscale_unscaled.c:2220,2675-2693)
     SwsFilterBank hLum, hChr, vLum, vChr;

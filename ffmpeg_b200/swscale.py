@@ -10,6 +10,7 @@ from ._lib import lib, check, vp, i16p, i32p, i64p, B200Error
 
 AV_PIX_FMT_YUV420P, AV_PIX_FMT_RGB24, AV_PIX_FMT_BGR24 = 0, 2, 3                       # libavutil/pixfmt.h
 AV_PIX_FMT_ARGB, AV_PIX_FMT_RGBA, AV_PIX_FMT_ABGR, AV_PIX_FMT_BGRA = 25, 26, 27, 28
+AV_PIX_FMT_NV12, AV_PIX_FMT_NV21 = 23, 24                                                # source only: src[1] = interleaved chroma
 SWS_FAST_BILINEAR, SWS_BILINEAR, SWS_BICUBIC, SWS_POINT, SWS_AREA, SWS_BICUBLIN = 1, 2, 4, 0x10, 0x20, 0x40
 SWS_FULL_CHR_H_INT, SWS_ACCURATE_RND, SWS_BITEXACT = 0x2000, 0x40000, 0x80000
 # libswscale/yuv2rgb.c:47-59 (sws_getCoefficients)
@@ -30,7 +31,7 @@ class SwsContext:
     def __init__(self, device, srcW, srcH, srcFormat, dstW, dstH, dstFormat, flags):
         self.device = device
         self.srcW, self.srcH, self.dstW, self.dstH, self.flags = srcW, srcH, dstW, dstH, flags
-        self.dstFormat = dstFormat
+        self.srcFormat, self.dstFormat = srcFormat, dstFormat
         self.planar = dstFormat == AV_PIX_FMT_YUV420P
         self.bpp = 1 if self.planar else 3 if dstFormat in (AV_PIX_FMT_RGB24, AV_PIX_FMT_BGR24) else 4
         h = lib().b200_sws_getContext(device.handle, srcW, srcH, srcFormat, dstW, dstH, dstFormat, flags)
@@ -72,7 +73,7 @@ class SwsContext:
         """Convenience: whole frame from 2-D uint8 arrays, returns (dstH, dstW*bpp+pad) array."""
         ds = self.dstW * self.bpp + dst_pad
         out = np.full((self.dstH, ds), 0xA5, np.uint8)
-        n = self.scale([y, u, v], [y.strides[0], u.strides[0], v.strides[0]], 0, self.srcH, [out], [ds])
+        n = self.scale([y, u, v], [y.strides[0], u.strides[0], v.strides[0]], 0, self.srcH, [out], [ds])   # nv12: pass the UV plane as u (v unused)
         assert n == self.dstH
         return out
 
@@ -88,6 +89,7 @@ class SwsContext:
         return dy, du, dv
 
     def scale_batch_device_planar(self, src, srcStride, srcFrameStride, dst, dstStride, dstFrameStride, nframes):
+        src, srcStride, srcFrameStride = (list(src) + [0] * 3)[:3], (list(srcStride) + [0] * 3)[:3], (list(srcFrameStride) + [0] * 3)[:3]
         sp = (vp * 3)(*[_dptr(a) for a in src])
         ss = (C.c_int32 * 3)(*srcStride)
         fs = (C.c_int64 * 3)(*srcFrameStride)
@@ -97,6 +99,7 @@ class SwsContext:
         return check(lib().b200_sws_scale_batch_device_planar(self._h, sp, ss, fs, dp, ds, df, nframes), "sws_scale_batch_device_planar")
 
     def _batch(self, fn, src, srcStride, srcFrameStride, dst, dstStride, dstFrameStride, nframes, what):
+        src, srcStride, srcFrameStride = (list(src) + [0] * 3)[:3], (list(srcStride) + [0] * 3)[:3], (list(srcFrameStride) + [0] * 3)[:3]
         sp = (vp * 3)(*[_dptr(a) for a in src])
         ss = (C.c_int32 * 3)(*srcStride)
         fs = (C.c_int64 * 3)(*srcFrameStride)

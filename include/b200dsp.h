@@ -69,6 +69,8 @@ uint64_t b200_launch_count(void);
  * Flags keep the reference's values (libswscale/swscale.h:88-118).  Output is bit-identical to the reference's
  * C path (the one FATE pins with accurate_rnd+bitexact, and yuv2rgb_c_24_rgb without accurate_rnd).  */
 #define B200_PIX_FMT_YUV420P 0     /* AV_PIX_FMT_YUV420P, libavutil/pixfmt.h */
+#define B200_PIX_FMT_NV12    23    /* AV_PIX_FMT_NV12: source only; src[1] is the interleaved U,V plane, src[2] is ignored */
+#define B200_PIX_FMT_NV21    24    /* AV_PIX_FMT_NV21: same with V,U */
 #define B200_PIX_FMT_RGB24   2     /* AV_PIX_FMT_RGB24 */
 #define B200_PIX_FMT_BGR24   3     /* AV_PIX_FMT_BGR24 */
 #define B200_PIX_FMT_ARGB    25    /* AV_PIX_FMT_ARGB  (alpha byte = 255, the source has no alpha plane) */

@@ -38,13 +38,17 @@ typedef struct OrcSws OrcSws;
 /* AVPixelFormat values, libavutil/pixfmt.h */
 #define ORC_PIX_FMT_YUV420P 0
 #define ORC_PIX_FMT_RGB24 2
+#define ORC_PIX_FMT_NV12  23
+#define ORC_PIX_FMT_NV21  24
 #define ORC_PIX_FMT_BGR24 3
 #define ORC_PIX_FMT_ARGB  25
 #define ORC_PIX_FMT_RGBA  26
 #define ORC_PIX_FMT_ABGR  27
 #define ORC_PIX_FMT_BGRA  28
 OrcSws *orc_sws_open(int srcW, int srcH, int dstW, int dstH, int flags);                      /* rgb24 */
-OrcSws *orc_sws_open_fmt(int srcW, int srcH, int dstW, int dstH, int dstFormat, int flags);
+OrcSws *orc_sws_open_fmt(int srcW, int srcH, int dstW, int dstH, int dstFormat, int flags);                 /* yuv420p source */
+/* srcFormat yuv420p, nv12 or nv21: for the semi-planar sources the scale calls take the interleaved plane as `u` (`v` unused) */
+OrcSws *orc_sws_open_io(int srcFormat, int srcW, int srcH, int dstFormat, int dstW, int dstH, int flags);
 void    orc_sws_close(OrcSws *s);
 /* inv_table = 4 coefficients as ff_yuv2rgb_coeffs rows; contrast/saturation 16.16 */
 int     orc_sws_set_colorspace(OrcSws *s, const int inv_table[4], int srcRange,

@@ -57,13 +57,19 @@ API void *ffref_sws_open(int srcW, int srcH, int dstW, int dstH, int flags, int 
     return ffref_sws_open_fmt(srcW, srcH, dstW, dstH, AV_PIX_FMT_RGB24, flags, threads);
 }
 
-/* dstFormat: an AVPixelFormat value (packed 8-bit RGB family) */
+API void *ffref_sws_open_io(int srcFormat, int srcW, int srcH, int dstFormat, int dstW, int dstH, int flags, int threads);
+/* dstFormat: an AVPixelFormat value (packed 8-bit RGB family or yuv420p) */
 API void *ffref_sws_open_fmt(int srcW, int srcH, int dstW, int dstH, int dstFormat, int flags, int threads)
+{
+    return ffref_sws_open_io(AV_PIX_FMT_YUV420P, srcW, srcH, dstFormat, dstW, dstH, flags, threads);
+}
+
+API void *ffref_sws_open_io(int srcFormat, int srcW, int srcH, int dstFormat, int dstW, int dstH, int flags, int threads)
 {
     SwsContext *c = sws_alloc_context();
     if (!c) return NULL;
     c->src_w = srcW; c->src_h = srcH; c->dst_w = dstW; c->dst_h = dstH;
-    c->src_format = AV_PIX_FMT_YUV420P; c->dst_format = dstFormat;
+    c->src_format = srcFormat; c->dst_format = dstFormat;
     c->flags = flags;
     c->threads = threads;
     if (sws_init_context(c, NULL, NULL) < 0) { sws_freeContext(c); return NULL; }

@@ -32,6 +32,8 @@ struct OrcSws {
     int unscaled_lut;          /* 1: reference would install yuv2rgb_c_24_rgb / _24_bgr / _32 as convert_unscaled */
     int bpp, ro, go, bo, ao;   /* bytes per pixel and byte positions of R, G, B, A (ao < 0: no alpha byte) */
     int planar;                /* 1: destination is yuv420p (three planes), 0: packed RGB */
+    int src_nv;                /* 0: yuv420p source, 1: nv12 (U,V interleaved in plane 1), 2: nv21 (V,U) — nvXXtoUV_c, input.c:921-948 */
+    int fast_bilinear, lumXInc, chrXInc;   /* SWS_FAST_BILINEAR: the horizontal pass is ff_hyscale_fast_c / ff_hcscale_fast_c */
     int16_t *hLum, *hChr, *vLum, *vChr;
     int32_t *hLumPos, *hChrPos, *vLumPos, *vChrPos;
     int hLumSize, hChrSize, vLumSize, vChrSize;
@@ -305,14 +307,25 @@ static int set_format(OrcSws *s, int fmt)
 
 OrcSws *orc_sws_open_fmt(int srcW, int srcH, int dstW, int dstH, int dstFormat, int flags)
 {
+    return orc_sws_open_io(ORC_PIX_FMT_YUV420P, srcW, srcH, dstFormat, dstW, dstH, flags);
+}
+
+OrcSws *orc_sws_open_io(int srcFormat, int srcW, int srcH, int dstFormat, int dstW, int dstH, int flags)
+{
     if (srcW < 1 || srcH < 1 || dstW < 1 || dstH < 1) return NULL;
+    if (srcFormat != ORC_PIX_FMT_YUV420P && srcFormat != ORC_PIX_FMT_NV12 && srcFormat != ORC_PIX_FMT_NV21) return NULL;
     OrcSws *s = calloc(1, sizeof(*s));
     if (!s) return NULL;
     if (set_format(s, dstFormat) < 0) { free(s); return NULL; }
+    s->src_nv = srcFormat == ORC_PIX_FMT_NV12 ? 1 : srcFormat == ORC_PIX_FMT_NV21 ? 2 : 0;
     int algo = flags & 0x7FF;
     if (!algo) { algo = ORC_SWS_BICUBIC; flags |= algo; }           /* utils.c:1209-1217 */
     else if (algo & (algo - 1)) goto fail;
-    if (algo == ORC_SWS_FAST_BILINEAR) goto fail;                  /* hyscale_fast path not restated */
+    if (algo == ORC_SWS_FAST_BILINEAR && (srcW < 8 || dstW <= 8)) { /* utils.c:1224-1230 */
+        algo = ORC_SWS_BILINEAR;
+        flags ^= ORC_SWS_FAST_BILINEAR | algo;
+    }
+    s->fast_bilinear = algo == ORC_SWS_FAST_BILINEAR;              /* hyscale_fast / hcscale_fast, swscale.c:676-681 */
     if (!s->planar && (dstW & 1)) flags |= ORC_SWS_FULL_CHR_H_INT; /* utils.c:1271-1276 (RGB destinations only) */
     s->srcW = srcW; s->srcH = srcH; s->dstW = dstW; s->dstH = dstH; s->flags = flags;
     s->chrDstHSub = (!s->planar && (flags & ORC_SWS_FULL_CHR_H_INT)) ? 0 : 1;      /* utils.c:1359-1360 */
@@ -321,12 +334,14 @@ OrcSws *orc_sws_open_fmt(int srcW, int srcH, int dstW, int dstH, int dstFormat, 
     s->chrDstW = ceil_rshift(dstW, s->chrDstHSub); s->chrDstH = ceil_rshift(dstH, chrDstVSub);
     orc_sws_set_colorspace(s, default_coeffs, 0, 0, 1 << 16, 1 << 16);
 
-    if (s->planar && srcW == dstW && srcH == dstH) {               /* planarCopyWrapper, swscale_unscaled.c:2675-2693 */
+    if (s->planar && srcW == dstW && srcH == dstH) {               /* planarCopyWrapper (swscale_unscaled.c:2675-2693) or, for a
+                                                                    * semi-planar source, nv12ToPlanarWrapper (:167-188, :2415-2419):
+                                                                    * both are a luma copy plus a chroma copy / de-interleave */
         s->unscaled_lut = 2;
         return s;
     }
-    /* swscale_unscaled.c:2426-2431 through utils.c:1623-1637 */
-    if (!s->planar && srcW == dstW && srcH == dstH && !(flags & ORC_SWS_ACCURATE_RND) && !(dstH & 1)) {
+    /* swscale_unscaled.c:2426-2431 through utils.c:1623-1637: only planar yuv420p/422p sources have the LUT converter */
+    if (!s->planar && !s->src_nv && srcW == dstW && srcH == dstH && !(flags & ORC_SWS_ACCURATE_RND) && !(dstH & 1)) {
         s->unscaled_lut = 1;
         return s;
     }
@@ -336,6 +351,7 @@ OrcSws *orc_sws_open_fmt(int srcW, int srcH, int dstW, int dstH, int dstFormat, 
     int64_t lumYInc = (((int64_t)srcH << 16) + (dstH >> 1)) / dstH;
     int64_t chrXInc = (((int64_t)s->chrSrcW << 16) + (s->chrDstW >> 1)) / s->chrDstW;
     int64_t chrYInc = (((int64_t)s->chrSrcH << 16) + (s->chrDstH >> 1)) / s->chrDstH;
+    s->lumXInc = (int)lumXInc; s->chrXInc = (int)chrXInc;
     if (make_filter(&s->hLum, &s->hLumPos, &s->hLumSize, (int)lumXInc, srcW, dstW, 1 << 14, lum_scaler, flags,
                     local_pos(0, 0), local_pos(0, 0)) < 0) goto fail;
     if (make_filter(&s->hChr, &s->hChrPos, &s->hChrSize, (int)chrXInc, s->chrSrcW, s->chrDstW, 1 << 14, chr_scaler, flags,
@@ -394,6 +410,25 @@ void orc_hscale8to15(int16_t *dst, int dstW, const uint8_t *src, const int16_t *
         val >>= 7;
         dst[i] = (int16_t)(val < 32767 ? val : 32767);
     }
+}
+
+/* ff_hyscale_fast_c / ff_hcscale_fast_c (hscale_fast_bilinear.c:27-67): 16.16 stepping, 7-bit blend weights; every output
+ * whose left sample is the last source sample (or beyond) is src[srcW-1] * 128 (the fix-up loop at the end of both). */
+static void hscale_fast(int16_t *dst, int dstW, const uint8_t *src, int srcW, int xInc, int chroma)
+{
+    unsigned xpos = 0;
+    for (int i = 0; i < dstW; i++, xpos += (unsigned)xInc) {
+        const unsigned xx = xpos >> 16, xalpha = (xpos & 0xFFFF) >> 9;
+        if (((int64_t)i * xInc) >> 16 >= srcW - 1) dst[i] = (int16_t)(src[srcW - 1] * 128);
+        else if (chroma) dst[i] = (int16_t)(src[xx] * (xalpha ^ 127) + src[xx + 1] * xalpha);
+        else dst[i] = (int16_t)((src[xx] << 7) + (src[xx + 1] - src[xx]) * xalpha);
+    }
+}
+static void hpass(const OrcSws *s, int16_t *dst, int dstW, const uint8_t *src, int srcW, int chroma)
+{
+    if (s->fast_bilinear) hscale_fast(dst, dstW, src, srcW, chroma ? s->chrXInc : s->lumXInc, chroma);
+    else if (chroma) orc_hscale8to15(dst, dstW, src, s->hChr, s->hChrPos, s->hChrSize);
+    else orc_hscale8to15(dst, dstW, src, s->hLum, s->hLumPos, s->hLumSize);
 }
 
 /* yuv2rgb_write, 24 and 32 bpp branches (output.c:1676-1713): one chroma pair -> LUT bases, two lumas -> two pixels */
@@ -463,10 +498,35 @@ static void vscale_plane_line(uint8_t *dst, int w, const int16_t *plane, int pw,
 }
 
 /* yuv420p -> yuv420p: horizontal pass per plane, then lum_planar_vscale / chr_planar_vscale (vscale.c:34-107) */
+/* nvXXtoUV_c (input.c:921-948): plane 1 of an nv12 / nv21 picture split into U and V planes of chrSrcW x chrSrcH */
+static uint8_t *split_nv(const OrcSws *s, const uint8_t *uv, int uvs)
+{
+    uint8_t *t = malloc((size_t)2 * s->chrSrcW * s->chrSrcH);
+    if (!t) return NULL;
+    uint8_t *pu = t, *pv = t + (size_t)s->chrSrcW * s->chrSrcH;
+    if (s->src_nv == 2) { uint8_t *x = pu; pu = pv; pv = x; }
+    for (int r = 0; r < s->chrSrcH; r++)
+        for (int i = 0; i < s->chrSrcW; i++) {
+            pu[(size_t)r * s->chrSrcW + i] = uv[(ptrdiff_t)r * uvs + 2 * i];
+            pv[(size_t)r * s->chrSrcW + i] = uv[(ptrdiff_t)r * uvs + 2 * i + 1];
+        }
+    return t;
+}
+
 int orc_sws_scale_planar(OrcSws *s, const uint8_t *y, int ys, const uint8_t *u, int us, const uint8_t *v, int vs,
                          uint8_t *dy, int dys, uint8_t *du, int dus, uint8_t *dv, int dvs)
 {
     if (!s->planar) return -EINVAL;
+    if (s->src_nv) {
+        uint8_t *t = split_nv(s, u, us);
+        if (!t) return -ENOMEM;
+        const int nv = s->src_nv;
+        s->src_nv = 0;
+        int r = orc_sws_scale_planar(s, y, ys, t, s->chrSrcW, t + (size_t)s->chrSrcW * s->chrSrcH, s->chrSrcW, dy, dys, du, dus, dv, dvs);
+        s->src_nv = nv;
+        free(t);
+        return r;
+    }
     if (s->unscaled_lut == 2) {
         for (int r = 0; r < s->srcH; r++) memcpy(dy + (ptrdiff_t)r * dys, y + (ptrdiff_t)r * ys, s->srcW);
         for (int r = 0; r < s->chrSrcH; r++) {
@@ -481,10 +541,10 @@ int orc_sws_scale_planar(OrcSws *s, const uint8_t *y, int ys, const uint8_t *u, 
     int16_t *CV = malloc((size_t)s->chrSrcH * cW * sizeof(int16_t));
     if (!L || !CU || !CV) { free(L); free(CU); free(CV); return -ENOMEM; }
     for (int r = 0; r < s->srcH; r++)
-        orc_hscale8to15(L + (size_t)r * dstW, dstW, y + (ptrdiff_t)r * ys, s->hLum, s->hLumPos, s->hLumSize);
+        hpass(s, L + (size_t)r * dstW, dstW, y + (ptrdiff_t)r * ys, s->srcW, 0);
     for (int r = 0; r < s->chrSrcH; r++) {
-        orc_hscale8to15(CU + (size_t)r * cW, cW, u + (ptrdiff_t)r * us, s->hChr, s->hChrPos, s->hChrSize);
-        orc_hscale8to15(CV + (size_t)r * cW, cW, v + (ptrdiff_t)r * vs, s->hChr, s->hChrPos, s->hChrSize);
+        hpass(s, CU + (size_t)r * cW, cW, u + (ptrdiff_t)r * us, s->chrSrcW, 1);
+        hpass(s, CV + (size_t)r * cW, cW, v + (ptrdiff_t)r * vs, s->chrSrcW, 1);
     }
     for (int d = 0; d < s->dstH; d++) {
         int first = s->vLumPos[d] > 1 - s->vLumSize ? s->vLumPos[d] : 1 - s->vLumSize;
@@ -503,6 +563,16 @@ int orc_sws_scale(OrcSws *s, const uint8_t *y, int ys, const uint8_t *u, int us,
                   const uint8_t *v, int vs, uint8_t *dst, int ds)
 {
     if (s->planar) return -EINVAL;
+    if (s->src_nv) {
+        uint8_t *t = split_nv(s, u, us);
+        if (!t) return -ENOMEM;
+        const int nv = s->src_nv;
+        s->src_nv = 0;
+        int r = orc_sws_scale(s, y, ys, t, s->chrSrcW, t + (size_t)s->chrSrcW * s->chrSrcH, s->chrSrcW, dst, ds);
+        s->src_nv = nv;
+        free(t);
+        return r;
+    }
     if (s->unscaled_lut) {
         convert_unscaled(s, y, ys, u, us, v, vs, dst, ds);
         return s->srcH;
@@ -513,10 +583,10 @@ int orc_sws_scale(OrcSws *s, const uint8_t *y, int ys, const uint8_t *u, int us,
     int16_t *CV = malloc((size_t)s->chrSrcH * cW * sizeof(int16_t));
     if (!L || !CU || !CV) { free(L); free(CU); free(CV); return -ENOMEM; }
     for (int r = 0; r < s->srcH; r++)
-        orc_hscale8to15(L + (size_t)r * dstW, dstW, y + (ptrdiff_t)r * ys, s->hLum, s->hLumPos, s->hLumSize);
+        hpass(s, L + (size_t)r * dstW, dstW, y + (ptrdiff_t)r * ys, s->srcW, 0);
     for (int r = 0; r < s->chrSrcH; r++) {
-        orc_hscale8to15(CU + (size_t)r * cW, cW, u + (ptrdiff_t)r * us, s->hChr, s->hChrPos, s->hChrSize);
-        orc_hscale8to15(CV + (size_t)r * cW, cW, v + (ptrdiff_t)r * vs, s->hChr, s->hChrPos, s->hChrSize);
+        hpass(s, CU + (size_t)r * cW, cW, u + (ptrdiff_t)r * us, s->chrSrcW, 1);
+        hpass(s, CV + (size_t)r * cW, cW, v + (ptrdiff_t)r * vs, s->chrSrcW, 1);
     }
     const int lfs = s->vLumSize, cfs = s->vChrSize, full = !s->chrDstHSub;
 #define LROW(k) (L  + (size_t)((k) < 0 ? 0 : (k) >= s->srcH    ? s->srcH    - 1 : (k)) * dstW)

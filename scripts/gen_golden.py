@@ -79,6 +79,31 @@ def gen_sws_planar():
     open(os.path.join(OUT, "sws_planar_hashes.txt"), "w").write("\n".join(lines) + "\n")
 
 
+def gen_sws_fastbil():
+    from cases import SWS_FASTBIL_CASES
+    lines = []
+    for i, (w, h, dw, dh, fl, kind) in enumerate(SWS_FASTBIL_CASES):
+        y, u, v = cl.yuv_frame(w, h, 800 + i, kind)
+        rgb = cl.ref_sws(w, h, dw, dh, fl, y, u, v)
+        pl = cl.ref_sws_planar(w, h, dw, dh, fl, y, u, v)
+        lines.append(f"{i} {w} {h} {dw} {dh} {fl} {kind} {sha(rgb)} {sha(np.concatenate([p.ravel() for p in pl]))}")
+    open(os.path.join(OUT, "sws_fastbil_hashes.txt"), "w").write("\n".join(lines) + "\n")
+
+
+def gen_sws_nv():
+    from cases import SWS_NV_CASES
+    lines = []
+    for i, (w, h, dw, dh, fl, kind) in enumerate(SWS_NV_CASES):
+        y, u, v = cl.yuv_frame(w, h, 1000 + i, kind)
+        for sf, name in ((cl.PIX_FMT_NV12, "nv12"), (cl.PIX_FMT_NV21, "nv21")):
+            uv = cl.nv_interleave(u, v, sf)
+            rgb = cl.ref_sws(w, h, dw, dh, fl, y, uv, uv, src_fmt=sf)
+            bgra = cl.ref_sws(w, h, dw, dh, fl, y, uv, uv, src_fmt=sf, fmt=cl.PIX_FMT_BGRA)
+            pl = cl.ref_sws_planar(w, h, dw, dh, fl, y, uv, uv, src_fmt=sf)
+            lines.append(f"{name} {i} {w} {h} {dw} {dh} {fl} {kind} {sha(rgb)} {sha(bgra)} {sha(np.concatenate([p.ravel() for p in pl]))}")
+    open(os.path.join(OUT, "sws_nv_hashes.txt"), "w").write("\n".join(lines) + "\n")
+
+
 def gen_idct():
     R = cl.ref()
     d = {}
@@ -307,6 +332,8 @@ if __name__ == "__main__":
     gen_sws()
     gen_sws_formats()
     gen_sws_planar()
+    gen_sws_fastbil()
+    gen_sws_nv()
     gen_idct()
     gen_h264idct()
     gen_mecmp()

@@ -103,3 +103,18 @@ SWS_PLANAR_CASES = [(64, 48, 64, 48, FATE, "random"), (64, 48, 100, 70, FATE, "r
                     (64, 48, 32, 48, SWS_BICUBIC, "random"), (352, 288, 200, 100, FATE, "random"), (100, 50, 37, 21, FATE, "limited"),
                     (64, 48, 64, 47, SWS_POINT, "random"), (64, 48, 31, 17, SWS_AREA, "random"), (352, 288, 640, 360, SWS_BICUBLIN, "random"),
                     (63, 47, 80, 60, SWS_BICUBIC, "random"), (352, 288, 176, 144, FATE, "smooth")]
+
+
+# SWS_FAST_BILINEAR (ff_hyscale_fast_c / ff_hcscale_fast_c horizontal pass): (w, h, dw, dh, flags, kind); run for rgb24 and yuv420p
+SWS_FAST_BILINEAR = 1
+SWS_FASTBIL_CASES = [(64, 48, 64, 48, 1 | SWS_ACCURATE_RND, "random"), (64, 48, 64, 48, 1, "random"), (64, 48, 100, 70, 1, "limited"),
+                     (64, 48, 33, 21, 1, "random"), (352, 288, 640, 360, 1, "random"), (352, 288, 200, 100, 1 | SWS_ACCURATE_RND | SWS_BITEXACT, "random"),
+                     (66, 50, 40, 96, 1, "smooth"), (7, 48, 64, 30, 1, "random"), (64, 48, 8, 48, 1, "random"), (100, 50, 37, 21, 1, "random"),
+                     (640, 360, 1280, 720, 1, "random")]
+
+
+# nv12 / nv21 sources (plane 1 = interleaved chroma; the reference de-interleaves with nvXXtoUV_c and, having no LUT converter
+# for them, always runs the scaler): (w, h, dw, dh, flags, kind), each for nv12 and nv21, to rgb24, bgra and yuv420p
+SWS_NV_CASES = [(64, 48, 64, 48, FATE, "random"), (64, 48, 64, 48, SWS_BICUBIC, "random"), (64, 48, 100, 70, FATE, "limited"),
+                (64, 48, 33, 21, SWS_BILINEAR, "random"), (352, 288, 200, 100, FATE, "random"), (66, 50, 66, 50, SWS_BICUBIC, "random"),
+                (63, 47, 63, 47, SWS_BICUBIC, "smooth"), (64, 48, 128, 96, 1, "random"), (352, 288, 352, 288, FATE, "random")]

@@ -36,6 +36,8 @@ def oracle():
         L.orc_sws_open.argtypes = [C.c_int] * 5
         L.orc_sws_open_fmt.restype = C.c_void_p
         L.orc_sws_open_fmt.argtypes = [C.c_int] * 6
+        L.orc_sws_open_io.restype = C.c_void_p
+        L.orc_sws_open_io.argtypes = [C.c_int] * 7
         L.orc_sws_close.argtypes = [C.c_void_p]
         L.orc_sws_set_colorspace.argtypes = [C.c_void_p, i32p, C.c_int, C.c_int, C.c_int, C.c_int]
         L.orc_sws_scale.argtypes = [C.c_void_p, u8p, C.c_int, u8p, C.c_int, u8p, C.c_int, u8p, C.c_int]
@@ -81,6 +83,8 @@ def ref():
         L.ffref_sws_open.argtypes = [C.c_int] * 6
         L.ffref_sws_open_fmt.restype = C.c_void_p
         L.ffref_sws_open_fmt.argtypes = [C.c_int] * 7
+        L.ffref_sws_open_io.restype = C.c_void_p
+        L.ffref_sws_open_io.argtypes = [C.c_int] * 8
         L.ffref_sws_close.argtypes = [C.c_void_p]
         L.ffref_sws_set_colorspace.argtypes = [C.c_void_p] + [C.c_int] * 7
         L.ffref_sws_scale.argtypes = [C.c_void_p, u8p, C.c_int, u8p, C.c_int, u8p, C.c_int, C.c_int, C.c_int, u8p, C.c_int]
@@ -144,11 +148,25 @@ def fmt_bpp(fmt):
     return 3 if fmt in (PIX_FMT_RGB24, PIX_FMT_BGR24) else 4
 
 
-def _sws_run(lib, pre, w, h, dw, dh, flags, y, u, v, dst_pad=0, threads=1, colorspace=None, fmt=PIX_FMT_RGB24):
+PIX_FMT_NV12, PIX_FMT_NV21 = 23, 24
+
+
+def nv_interleave(u, v, src_fmt, pad=0):
+    """U and V planes -> the interleaved plane 1 of an nv12 / nv21 picture (row stride 2*cw + pad)."""
+    ch, cw = u.shape[0], u.shape[1]
+    uv = np.full((ch, 2 * cw + pad), 0x5C, np.uint8)
+    a, b = (u, v) if src_fmt == PIX_FMT_NV12 else (v, u)
+    uv[:, 0:2 * cw:2] = a
+    uv[:, 1:2 * cw:2] = b
+    return uv
+
+
+def _sws_run(lib, pre, w, h, dw, dh, flags, y, u, v, dst_pad=0, threads=1, colorspace=None, fmt=PIX_FMT_RGB24, src_fmt=0):
+    """src_fmt nv12 / nv21: `u` is the interleaved chroma plane, `v` is ignored"""
     if pre == "ffref":
-        ctx = lib.ffref_sws_open_fmt(w, h, dw, dh, fmt, flags, threads)
+        ctx = lib.ffref_sws_open_io(src_fmt, w, h, fmt, dw, dh, flags, threads)
     else:
-        ctx = lib.orc_sws_open_fmt(w, h, dw, dh, fmt, flags)
+        ctx = lib.orc_sws_open_io(src_fmt, w, h, fmt, dw, dh, flags)
     if not ctx:
         return None
     try:
@@ -173,12 +191,12 @@ def _sws_run(lib, pre, w, h, dw, dh, flags, y, u, v, dst_pad=0, threads=1, color
 PIX_FMT_YUV420P = 0
 
 
-def _sws_run_planar(lib, pre, w, h, dw, dh, flags, y, u, v, dst_pad=0, threads=1):
-    """yuv420p -> yuv420p; returns (Y, U, V) destination planes (pad bytes stay 0xA5)."""
+def _sws_run_planar(lib, pre, w, h, dw, dh, flags, y, u, v, dst_pad=0, threads=1, src_fmt=0):
+    """yuv420p / nv12 / nv21 -> yuv420p; returns (Y, U, V) destination planes (pad bytes stay 0xA5)."""
     if pre == "ffref":
-        ctx = lib.ffref_sws_open_fmt(w, h, dw, dh, PIX_FMT_YUV420P, flags, threads)
+        ctx = lib.ffref_sws_open_io(src_fmt, w, h, PIX_FMT_YUV420P, dw, dh, flags, threads)
     else:
-        ctx = lib.orc_sws_open_fmt(w, h, dw, dh, PIX_FMT_YUV420P, flags)
+        ctx = lib.orc_sws_open_io(src_fmt, w, h, PIX_FMT_YUV420P, dw, dh, flags)
     if not ctx:
         return None
     try:

@@ -88,6 +88,35 @@ def test_sws_oracle_planar_vs_ref():
         assert all(np.array_equal(p, q) for p, q in zip(a, b)), (w, h, dw, dh, hex(fl))
 
 
+def test_sws_oracle_fast_bilinear_golden_hashes():
+    """SWS_FAST_BILINEAR (hyscale_fast / hcscale_fast) against the reference's outputs, rgb24 and yuv420p destinations."""
+    n = 0
+    for line in open(os.path.join(G, "sws_fastbil_hashes.txt")):
+        i, w, h, dw, dh, fl, kind, hrgb, hyuv = line.split()
+        i, w, h, dw, dh, fl = map(int, (i, w, h, dw, dh, fl))
+        y, u, v = cl.yuv_frame(w, h, 800 + i, kind)
+        assert sha(cl.orc_sws(w, h, dw, dh, fl, y, u, v)) == hrgb, (i, w, h, dw, dh, hex(fl))
+        assert sha(np.concatenate([p.ravel() for p in cl.orc_sws_planar(w, h, dw, dh, fl, y, u, v)])) == hyuv, (i, w, h, dw, dh, hex(fl))
+        n += 1
+    assert n == 11
+
+
+def test_sws_oracle_nv12_nv21_golden_hashes():
+    """nv12 / nv21 sources to rgb24, bgra and yuv420p against the reference's outputs."""
+    n = 0
+    for line in open(os.path.join(G, "sws_nv_hashes.txt")):
+        name, i, w, h, dw, dh, fl, kind, hrgb, hbgra, hyuv = line.split()
+        i, w, h, dw, dh, fl = map(int, (i, w, h, dw, dh, fl))
+        sf = cl.PIX_FMT_NV12 if name == "nv12" else cl.PIX_FMT_NV21
+        y, u, v = cl.yuv_frame(w, h, 1000 + i, kind)
+        uv = cl.nv_interleave(u, v, sf)
+        assert sha(cl.orc_sws(w, h, dw, dh, fl, y, uv, uv, src_fmt=sf)) == hrgb, (name, i)
+        assert sha(cl.orc_sws(w, h, dw, dh, fl, y, uv, uv, src_fmt=sf, fmt=cl.PIX_FMT_BGRA)) == hbgra, (name, i)
+        assert sha(np.concatenate([p.ravel() for p in cl.orc_sws_planar(w, h, dw, dh, fl, y, uv, uv, src_fmt=sf)])) == hyuv, (name, i)
+        n += 1
+    assert n == 18
+
+
 def test_sws_oracle_colorspace_golden():
     g = np.load(os.path.join(G, "sws_colorspace.npz"))
     y, u, v = g["y"], g["u"], g["v"]

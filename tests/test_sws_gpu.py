@@ -17,9 +17,9 @@ def sha(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
 
-def gpu_sws(device, w, h, dw, dh, fl, y, u, v, dst_pad=0, colorspace=None, fmt=cl.PIX_FMT_RGB24):
+def gpu_sws(device, w, h, dw, dh, fl, y, u, v, dst_pad=0, colorspace=None, fmt=cl.PIX_FMT_RGB24, src_fmt=0):
     from ffmpeg_b200 import swscale as sw
-    ctx = sw.sws_getContext(device, w, h, sw.AV_PIX_FMT_YUV420P, dw, dh, fmt, fl)
+    ctx = sw.sws_getContext(device, w, h, src_fmt, dw, dh, fmt, fl)
     try:
         if colorspace is not None:
             ctx.setColorspaceDetails(cl.COEFFS[colorspace[0]], colorspace[1], cl.COEFFS[colorspace[2]], colorspace[3],
@@ -131,9 +131,9 @@ def test_other_formats_slices_and_batch(device):
         sw.sws_getContext(device, 64, 48, 0, 64, 48, 4, FATE)           # AV_PIX_FMT_YUV422P as destination: not this path
 
 
-def gpu_sws_planar(device, w, h, dw, dh, fl, y, u, v, dst_pad=0):
+def gpu_sws_planar(device, w, h, dw, dh, fl, y, u, v, dst_pad=0, src_fmt=0):
     from ffmpeg_b200 import swscale as sw
-    ctx = sw.sws_getContext(device, w, h, sw.AV_PIX_FMT_YUV420P, dw, dh, sw.AV_PIX_FMT_YUV420P, fl)
+    ctx = sw.sws_getContext(device, w, h, src_fmt, dw, dh, sw.AV_PIX_FMT_YUV420P, fl)
     try:
         return ctx.convert_planar(y, u, v, dst_pad=dst_pad)
     finally:
@@ -196,6 +196,83 @@ def test_planar_batch_device_and_errors(device):
     with pytest.raises(fb.B200Error):
         rgb.scale_batch_device_planar([0, 0, 0], [w, cw, cw], [0, 0, 0], [0, 0, 0], [dw, cdw, cdw], [0, 0, 0], 1)
     rgb.free()
+
+
+def test_fast_bilinear_golden_hashes_and_oracle(device):
+    """SWS_FAST_BILINEAR: reference fixtures for both destinations, plus larger oracle comparisons (4K -> 1080p, upscales)."""
+    n = 0
+    for line in open(os.path.join(G, "sws_fastbil_hashes.txt")):
+        i, w, h, dw, dh, fl, kind, hrgb, hyuv = line.split()
+        i, w, h, dw, dh, fl = map(int, (i, w, h, dw, dh, fl))
+        y, u, v = cl.yuv_frame(w, h, 800 + i, kind)
+        assert sha(gpu_sws(device, w, h, dw, dh, fl, y, u, v)) == hrgb, (i, w, h, dw, dh, hex(fl))
+        assert sha(np.concatenate([p.ravel() for p in gpu_sws_planar(device, w, h, dw, dh, fl, y, u, v)])) == hyuv, (i, w, h, dw, dh, hex(fl))
+        n += 1
+    assert n == 11
+    for (w, h, dw, dh, fl) in ((3840, 2160, 1920, 1080, 1), (1280, 720, 1920, 1080, 1 | cl.SWS_ACCURATE_RND), (641, 361, 333, 201, 1)):
+        y, u, v = cl.yuv_frame(w, h, 5, "random", pad=3)
+        assert np.array_equal(cl.orc_sws(w, h, dw, dh, fl, y, u, v), gpu_sws(device, w, h, dw, dh, fl, y, u, v)), (w, h, dw, dh)
+        a, b = cl.orc_sws_planar(w, h, dw, dh, fl, y, u, v), gpu_sws_planar(device, w, h, dw, dh, fl, y, u, v)
+        assert all(np.array_equal(p, q) for p, q in zip(a, b)), (w, h, dw, dh)
+
+
+def test_nv12_nv21_golden_hashes(device):
+    n = 0
+    for line in open(os.path.join(G, "sws_nv_hashes.txt")):
+        name, i, w, h, dw, dh, fl, kind, hrgb, hbgra, hyuv = line.split()
+        i, w, h, dw, dh, fl = map(int, (i, w, h, dw, dh, fl))
+        sf = cl.PIX_FMT_NV12 if name == "nv12" else cl.PIX_FMT_NV21
+        y, u, v = cl.yuv_frame(w, h, 1000 + i, kind)
+        uv = cl.nv_interleave(u, v, sf)
+        assert sha(gpu_sws(device, w, h, dw, dh, fl, y, uv, uv, src_fmt=sf)) == hrgb, (name, i)
+        assert sha(gpu_sws(device, w, h, dw, dh, fl, y, uv, uv, src_fmt=sf, fmt=cl.PIX_FMT_BGRA)) == hbgra, (name, i)
+        assert sha(np.concatenate([p.ravel() for p in gpu_sws_planar(device, w, h, dw, dh, fl, y, uv, uv, src_fmt=sf)])) == hyuv, (name, i)
+        n += 1
+    assert n == 18
+
+
+def test_nv12_4k_slices_batches_and_bottom_up(device):
+    """The decoder-output case: nv12 4K frames to rgb24 (vector kernels after the chroma split), through every entry point:
+    whole frame, top-down slices, bottom-up strides, batched device pointers, batched host pointers."""
+    import torch
+    from ffmpeg_b200 import swscale as sw
+    w, h, n = 3840, 2160, 3
+    frames = [cl.yuv_frame(w, h, 60 + i, "random") for i in range(n)]
+    uvs = [cl.nv_interleave(f[1], f[2], cl.PIX_FMT_NV12, pad=32) for f in frames]
+    refs = [cl.orc_sws(w, h, w, h, FATE, frames[i][0], uvs[i], uvs[i], src_fmt=cl.PIX_FMT_NV12) for i in range(n)]
+    # the split must give what the planar source gives
+    assert np.array_equal(refs[0], cl.orc_sws(w, h, w, h, FATE, *frames[0]))
+    ctx = sw.sws_getContext(device, w, h, sw.AV_PIX_FMT_NV12, w, h, sw.AV_PIX_FMT_RGB24, FATE)
+    assert np.array_equal(ctx.convert(frames[0][0], uvs[0], uvs[0]), refs[0])
+    out = np.zeros((h, w * 3), np.uint8)
+    total = 0
+    for sy in range(0, h, 540):
+        total += ctx.scale([frames[1][0][sy:], uvs[1][sy // 2:]], [w, uvs[1].strides[0]], sy, 540, [out], [w * 3])
+    assert total == h and np.array_equal(out, refs[1])
+    # bottom-up source (negative strides): the picture is read upside down, like the reference does
+    yf, uvf = np.ascontiguousarray(frames[2][0][::-1]), np.ascontiguousarray(uvs[2][::-1])
+    ref_flipped = cl.orc_sws(w, h, w, h, FATE, yf, uvf, uvf, src_fmt=cl.PIX_FMT_NV12)
+    out = np.zeros((h, w * 3), np.uint8)
+    uvst = uvs[2].strides[0]
+    assert ctx.scale([frames[2][0].ctypes.data + (h - 1) * w, uvs[2].ctypes.data + (h // 2 - 1) * uvst], [-w, -uvst], 0, h, [out], [w * 3]) == h
+    assert np.array_equal(out, ref_flipped)
+    Y = np.stack([f[0] for f in frames]); UV = np.stack([np.ascontiguousarray(x[:, :w]) for x in uvs])
+    with torch.cuda.stream(torch.cuda.ExternalStream(device.stream)):
+        dY, dUV = torch.from_numpy(Y).cuda(), torch.from_numpy(UV).cuda()
+        do = torch.zeros((n, h, w * 3), dtype=torch.uint8, device="cuda")
+        ctx.scale_batch_device([dY, dUV], [w, w], [w * h, w * h // 2], do, w * 3, w * h * 3, n)
+        device.sync()
+        got = do.cpu().numpy()
+    ho = np.zeros((n, h, w * 3), np.uint8)
+    ctx.scale_batch_host([Y.ctypes.data, UV.ctypes.data], [w, w], [w * h, w * h // 2], ho.ctypes.data, w * 3, w * h * 3, n)
+    for i in range(n):
+        assert np.array_equal(got[i], refs[i]) and np.array_equal(ho[i], refs[i]), i
+    ctx.free()
+    # nv12 -> yuv420p: scaled, and the same-size de-interleave (nv12ToPlanarWrapper)
+    for (dw, dh) in ((1920, 1080), (w, h)):
+        a = cl.orc_sws_planar(w, h, dw, dh, FATE, frames[0][0], uvs[0], uvs[0], src_fmt=cl.PIX_FMT_NV12)
+        b = gpu_sws_planar(device, w, h, dw, dh, FATE, frames[0][0], uvs[0], uvs[0], src_fmt=cl.PIX_FMT_NV12)
+        assert all(np.array_equal(p, q) for p, q in zip(a, b)), (dw, dh)
 
 
 def test_bottom_up_strides(device):
