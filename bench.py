@@ -445,6 +445,26 @@ def run_b200(args, rank, world, local_rank):
     results["variant_flags_bicubic"] = {"value": fps2, "unit": "frames/s", "roofline": {
         "bound": "hbm", "achieved": ach2, "peak": peak, "unit": "GB/s", "frac": ach2 / peak, "kernel": "sws_unscaled_kernel",
         "launch_ms": k2, "traffic": ncu_traffic("sws_unscaled_kernel")}}
+    # variant: nv12 source (the decoder-output layout), FATE flags: interleaved chroma read straight by the vector kernel
+    with torch.cuda.stream(stream):
+        UV = torch.stack((U, V), dim=3).reshape(BATCH, H4K // 2, W4K).contiguous()
+    ctxn = sw.sws_getContext(dev, W4K, H4K, sw.AV_PIX_FMT_NV12, W4K, H4K, sw.AV_PIX_FMT_RGB24, FLAGS_FATE)
+    with torch.cuda.stream(stream):
+        calln = lambda: ctxn.scale_batch_device([Y, UV], [W4K, W4K], [W4K * H4K, W4K * H4K // 2], OUT, W4K * 3, W4K * H4K * 3, BATCH)
+        for _ in range(3):
+            calln()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(5):
+            calln()
+        e1.record(stream)
+    barrier()
+    msn = reduce_max(e0.elapsed_time(e1)) / 5
+    results["variant_nv12"] = {"value": world * BATCH / (msn / 1e3), "unit": "frames/s", "ms_per_step": msn, "roofline": {
+        "bound": "hbm", "achieved": FRAME_BYTES * BATCH / (msn / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+        "frac": FRAME_BYTES * BATCH / (msn / 1e3) / 1e9 / peak, "kernel": "sws_vscale_rgb24_fast_kernel<true,true,RGB24,NV12>"}}
+    ctxn.free()
+    del UV
     # variant: the scaler proper, 4K -> 1080p with FATE flags (horizontal pass -> int16 lines -> vertical pass), yuv420p and rgb24 out
     NS = 32
     sc = {}

@@ -250,9 +250,25 @@ __device__ __forceinline__ void fold2(int k2, const uint2 &r0, const uint2 &r1, 
     acc[4] = dp2a_lo_su(k2, lo, acc[4]); acc[5] = dp2a_hi_su(k2, lo, acc[5]); acc[6] = dp2a_lo_su(k2, hi, acc[6]); acc[7] = dp2a_hi_su(k2, hi, acc[7]);
 }
 
+// nv12 / nv21 chroma: the two source lines come as 16 interleaved bytes (U,V pairs; V,U for nv21); PRMT picks the U (or V)
+// bytes of both lines at once, so de-interleaving costs nothing over the planar case (same 8 PRMT + 16 IDP.2A per tap pair).
+template <int NV>
+__device__ __forceinline__ void fold2_nv(int k2, const uint4 &r0, const uint4 &r1, int *aU, int *aV)
+{
+    constexpr unsigned SU = NV == 1 ? 0x6240 : 0x7351, SV = NV == 1 ? 0x7351 : 0x6240;
+    const unsigned w0[4] = { r0.x, r0.y, r0.z, r0.w }, w1[4] = { r1.x, r1.y, r1.z, r1.w };
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const unsigned wu = __byte_perm(w0[j], w1[j], SU), wv = __byte_perm(w0[j], w1[j], SV);
+        aU[2 * j] = dp2a_lo_su(k2, wu, aU[2 * j]); aU[2 * j + 1] = dp2a_hi_su(k2, wu, aU[2 * j + 1]);
+        aV[2 * j] = dp2a_lo_su(k2, wv, aV[2 * j]); aV[2 * j + 1] = dp2a_hi_su(k2, wv, aV[2 * j + 1]);
+    }
+}
+
 // CFS4: the chroma bank has exactly 4 taps (bicubic 2x vertical chroma up-sampling, the BASELINE case): fully unrolled.
 // Line offsets are 32-bit (the host guarantees |stride| * lines < 2^31); coefficient pairs come pre-packed (t.vChr2/vLum2).
-template <bool LUMID, bool CFS4, int KIND>
+// NV: 0 planar chroma (a.u, a.v), 1 nv12 / 2 nv21 (a.u = interleaved plane; only instantiated with CFS4)
+template <bool LUMID, bool CFS4, int KIND, int NV = 0>
 __global__ void __launch_bounds__(128, LUMID ? (KIND <= SWS_OUT_BGR24 ? 12 : 10) : 8)
 sws_vscale_rgb24_fast_kernel(SwsFrameArgs a, SwsDevTables t, SwsColorConst c, int ngroups)
 {
@@ -271,7 +287,15 @@ sws_vscale_rgb24_fast_kernel(SwsFrameArgs a, SwsDevTables t, SwsColorConst c, in
     int aU[8], aV[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) aU[i] = aV[i] = 1 << 11;
-    if (CFS4) {
+    if (CFS4 && NV) {
+        const int2 k = __ldg(reinterpret_cast<const int2 *>(t.vChr2 + 2 * dy));
+        const int l0 = min(max(firstChr, 0), chmax), l1 = min(max(firstChr + 1, 0), chmax);
+        const int l2 = min(max(firstChr + 2, 0), chmax), l3 = min(max(firstChr + 3, 0), chmax);
+        const uint8_t *uvb = a.u + f * a.ufs + xg * 16;
+        const uint4 q0 = __ldg(reinterpret_cast<const uint4 *>(uvb + l0 * us)), q1 = __ldg(reinterpret_cast<const uint4 *>(uvb + l1 * us));
+        const uint4 q2 = __ldg(reinterpret_cast<const uint4 *>(uvb + l2 * us)), q3 = __ldg(reinterpret_cast<const uint4 *>(uvb + l3 * us));
+        fold2_nv<NV ? NV : 1>(k.x, q0, q1, aU, aV); fold2_nv<NV ? NV : 1>(k.y, q2, q3, aU, aV);
+    } else if (CFS4) {
         const int2 k = __ldg(reinterpret_cast<const int2 *>(t.vChr2 + 2 * dy));
         const int l0 = min(max(firstChr, 0), chmax), l1 = min(max(firstChr + 1, 0), chmax);
         const int l2 = min(max(firstChr + 2, 0), chmax), l3 = min(max(firstChr + 3, 0), chmax);
@@ -751,6 +775,26 @@ static void launch_vscale_fast(bool lumid, bool c4, dim3 grid, dim3 block, cudaS
     else              sws_vscale_rgb24_fast_kernel<false, false, KIND><<<grid, block, 0, stream>>>(b, dt, col, ngroups);
 }
 
+template <int KIND>
+static void launch_vscale_fast_nv_k(int nv, dim3 grid, dim3 block, cudaStream_t stream, const SwsFrameArgs &b, const SwsDevTables &dt,
+                                    const SwsColorConst &col, int ngroups)
+{
+    if (nv == 1) sws_vscale_rgb24_fast_kernel<true, true, KIND, 1><<<grid, block, 0, stream>>>(b, dt, col, ngroups);
+    else         sws_vscale_rgb24_fast_kernel<true, true, KIND, 2><<<grid, block, 0, stream>>>(b, dt, col, ngroups);
+}
+static void launch_vscale_fast_nv(int kind, int nv, dim3 grid, dim3 block, cudaStream_t stream, const SwsFrameArgs &b,
+                                  const SwsDevTables &dt, const SwsColorConst &col, int ngroups)
+{
+    switch (kind) {
+    case SWS_OUT_RGB24: launch_vscale_fast_nv_k<SWS_OUT_RGB24>(nv, grid, block, stream, b, dt, col, ngroups); break;
+    case SWS_OUT_BGR24: launch_vscale_fast_nv_k<SWS_OUT_BGR24>(nv, grid, block, stream, b, dt, col, ngroups); break;
+    case SWS_OUT_RGBA:  launch_vscale_fast_nv_k<SWS_OUT_RGBA>(nv, grid, block, stream, b, dt, col, ngroups); break;
+    case SWS_OUT_BGRA:  launch_vscale_fast_nv_k<SWS_OUT_BGRA>(nv, grid, block, stream, b, dt, col, ngroups); break;
+    case SWS_OUT_ARGB:  launch_vscale_fast_nv_k<SWS_OUT_ARGB>(nv, grid, block, stream, b, dt, col, ngroups); break;
+    default:            launch_vscale_fast_nv_k<SWS_OUT_ABGR>(nv, grid, block, stream, b, dt, col, ngroups); break;
+    }
+}
+
 // enqueue the conversion of nframes frames on `stream`
 // Which lines a launch covers.  Whole frames: everything.  Slice calls: the output lines that became computable and the
 // source lines that were just uploaded (only those need the horizontal pass).
@@ -767,7 +811,12 @@ static int launch_batch(B200SwsContext *c, cudaStream_t stream, const uint8_t *c
     if (R.ndy <= 0 && R.nly <= 0 && R.ncy <= 0) return 0;
     const uint8_t *src[3] = { src_in[0], src_in[1], src_in[2] };
     long long sstr[3] = { sstr_in[0], sstr_in[1], sstr_in[2] }, sfs[3] = { sfs_in[0], sfs_in[1], sfs_in[2] };
-    if (p.src_nv) {
+    // nv12 / nv21 straight into the vector kernel (no split pass) when the whole line is covered by 16-pixel groups
+    auto fits32_ = [](long long stride, long long lines) { return (stride < 0 ? -stride : stride) * (lines + 1) < (1LL << 31); };
+    const bool nv_direct = p.src_nv && !p.unscaled_lut && c->h_identity && c->fast_x && c->lum_identity && p.vChr.size == 4 &&
+                           p.dstW % 16 == 0 && R.ndy > 0 && aligned16(src[0], sstr[0], sfs[0]) && aligned16(src[1], sstr[1], sfs[1]) &&
+                           aligned16(dst, ds, dfs) && fits32_(sstr[0], p.srcH) && fits32_(sstr[1], p.chrSrcH) && fits32_(ds, p.dstH);
+    if (p.src_nv && !nv_direct) {
         int ret = nv_split(c, stream, nv_scratch, nframes, R.cy0, R.ncy, src, sstr, sfs);
         if (ret < 0) return ret;
     }
@@ -811,6 +860,12 @@ static int launch_batch(B200SwsContext *c, cudaStream_t stream, const uint8_t *c
             auto fits32 = [](long long stride, long long lines) { return (stride < 0 ? -stride : stride) * (lines + 1) < (1LL << 31); };
             const bool off32 = fits32(b.ys, p.srcH) && fits32(b.us, p.chrSrcH) && fits32(b.vs, p.chrSrcH) && fits32(b.ds, p.dstH);
             const int ngroups = (vecOK && c->fast_x && off32 && R.ndy > 0) ? p.dstW / 16 : 0;
+            if (nv_direct) {
+                dim3 block(128), grid(b200_ceil_div(p.dstW / 16, 128), R.ndy, nf);
+                launch_vscale_fast_nv(p.out.kind, p.src_nv, grid, block, stream, b, c->dt, p.color, p.dstW / 16);
+                B200_LAUNCHED();
+                continue;
+            }
             if (ngroups) {
                 dim3 block(128), grid(b200_ceil_div(ngroups, 128), R.ndy, nf);
                 const bool c4 = p.vChr.size == 4;
