@@ -69,6 +69,15 @@ class H264IDCTContext(C.Structure):
     _fields_ = [("idct_add", _H264IDCT), ("idct8_add", _H264IDCT), ("idct_dc_add", _H264IDCT), ("idct8_dc_add", _H264IDCT)]
 
 
+_H264W = C.CFUNCTYPE(None, C.c_void_p, C.c_ssize_t, C.c_int, C.c_int, C.c_int, C.c_int)
+_H264BW = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_ssize_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int)
+
+
+class H264WeightContext(C.Structure):
+    """weight_pixels_tab / biweight_pixels_tab of H264DSPContext, libavcodec/h264dsp.h:33-45"""
+    _fields_ = [("weight_pixels_tab", _H264W * 4), ("biweight_pixels_tab", _H264BW * 4)]
+
+
 _CHROMA = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_ssize_t, C.c_int, C.c_int, C.c_int)
 
 
@@ -130,6 +139,8 @@ PROTOTYPES = {
     "b200_hpel_batch_device": (C.c_int, [vp, C.c_int64, vp, vp, vp, vp, vp, vp, C.c_ssize_t]),
     "b200_h264_idct_init": (C.c_int, [C.POINTER(H264IDCTContext), C.c_int, C.c_int]),
     "b200_h264_idct_batch_device": (C.c_int, [vp, C.c_int, C.c_int64, vp, vp, vp, vp, C.c_ssize_t]),
+    "b200_h264_weight_init": (C.c_int, [C.POINTER(H264WeightContext), C.c_int]),
+    "b200_h264_weight_batch_device": (C.c_int, [vp, C.c_int64, vp, vp, vp, vp, vp, C.c_ssize_t]),
     "b200_videodsp_init": (C.c_int, [C.POINTER(VideoDSPContext), C.c_int]),
     "b200_emulated_edge_mc_batch_device": (C.c_int, [vp, C.c_int64, vp, vp, C.c_ssize_t, vp, vp, C.c_ssize_t, vp, C.c_int, C.c_int]),
     "b200_h264chroma_init": (C.c_int, [C.POINTER(H264ChromaContext), C.c_int]),

@@ -2,7 +2,7 @@
 libavcodec/h264qpel.c:50-120; H264ChromaContext from ff_h264chroma_init, libavcodec/h264chroma.c:36-65; HpelDSPContext from
 ff_hpeldsp_init, libavcodec/hpeldsp.c:337-352) and the batched entry points."""
 import ctypes as C
-from ._lib import lib, check, vp, H264QpelContext, HpelDSPContext, H264ChromaContext, VideoDSPContext
+from ._lib import lib, check, vp, H264QpelContext, HpelDSPContext, H264ChromaContext, VideoDSPContext, H264WeightContext
 
 
 def _dptr(x):
@@ -67,3 +67,22 @@ def emulated_edge_mc_batch_device(device, n, buf, buf_off, buf_linesize, src, or
     return check(lib().b200_emulated_edge_mc_batch_device(device.handle, n, vp(_dptr(buf)), vp(_dptr(buf_off)), buf_linesize,
                                                           vp(_dptr(src)), vp(_dptr(origin)), src_linesize, vp(_dptr(geom)), w, h),
                  "emulated_edge_mc_batch_device")
+
+
+def ff_h264dsp_weight_init(bit_depth=8):
+    """weight_pixels_tab / biweight_pixels_tab as ff_h264dsp_init installs them (libavcodec/h264dsp.c:103-110)."""
+    c = H264WeightContext()
+    check(lib().b200_h264_weight_init(C.byref(c), bit_depth), "ff_h264dsp_init (weight)")
+    return c
+
+
+def weight_params(idx, height, log2_denom, weight, weights, offset):
+    return [idx | (height << 8) | (log2_denom << 16), weight, weights, offset]
+
+
+def h264_weight_batch_device(device, n, params, dst, dst_off, src, src_off, stride):
+    """src None: weight in place; else biweight.  params: int32 [n, 4] built with weight_params()."""
+    return check(lib().b200_h264_weight_batch_device(device.handle, n, vp(_dptr(params)), vp(_dptr(dst)), vp(_dptr(dst_off)),
+                                                     vp(_dptr(src)) if src is not None else None,
+                                                     vp(_dptr(src_off)) if src_off is not None else None, stride),
+                 "h264_weight_batch_device")

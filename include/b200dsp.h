@@ -194,6 +194,23 @@ int  b200_h264_idct_init(B200H264IDCTContext *c, int bit_depth, int chroma_forma
 int  b200_h264_idct_batch_device(B200Device *dev, int kind, int64_t n, int16_t *blocks, const int64_t *blk_off,
                                  uint8_t *dst, const int64_t *dst_off, ptrdiff_t stride);
 
+/* H.264 explicit weighted prediction, 8 bit: weight_pixels_tab / biweight_pixels_tab of H264DSPContext (libavcodec/h264dsp.h:33-45)
+ * as installed by ff_h264dsp_init(c, 8, ...) (libavcodec/h264dsp.c:103-110; functions in h264dsp_template.c:30-99).
+ * Index = width: [0] 16, [1] 8, [2] 4, [3] 2. */
+typedef void (*b200_h264_weight_func)(uint8_t *block, ptrdiff_t stride, int height, int log2_denom, int weight, int offset);
+typedef void (*b200_h264_biweight_func)(uint8_t *dst, uint8_t *src, ptrdiff_t stride, int height, int log2_denom,
+                                        int weightd, int weights, int offset);
+typedef struct B200H264WeightContext {
+    b200_h264_weight_func   weight_pixels_tab[4];
+    b200_h264_biweight_func biweight_pixels_tab[4];
+} B200H264WeightContext;
+int  b200_h264_weight_init(B200H264WeightContext *c, int bit_depth);            /* bit_depth must be 8 */
+/* batched, DEVICE pointers.  params: 4 int32 per block (16-byte aligned array): [0] = width index | height << 8 | log2_denom << 16,
+ * [1] = weight (the destination weight for biweight), [2] = source weight (biweight), [3] = offset.  src == NULL: weight
+ * (in place on dst + dst_off[i]); src != NULL: biweight of dst + dst_off[i] with src + src_off[i].  One stride for both. */
+int  b200_h264_weight_batch_device(B200Device *dev, int64_t n, const int32_t *params, uint8_t *dst, const int64_t *dst_off,
+                                   const uint8_t *src, const int64_t *src_off, ptrdiff_t stride);
+
 /* ------------------------------------------------------------------------------------------------ me_cmp
  * Replaces MECmpContext (libavcodec/me_cmp.h:53-77) as filled by ff_me_cmp_init (libavcodec/me_cmp.c:961-1027) for the
  * SAD / SSE entries: sad[0..1] = pix_abs16_c / pix_abs8_c, sse[0..2] = sse16_c / sse8_c / sse4_c,

@@ -88,6 +88,9 @@ void orc_h264qpel(int avg, int size_idx, int pos, uint8_t *dst, const uint8_t *s
 int  orc_hpel(int tab, int size_idx, int xy, uint8_t *block, const uint8_t *pixels, ptrdiff_t line_size, int h);
 void orc_emulated_edge_mc(uint8_t *buf, const uint8_t *src, ptrdiff_t buf_linesize, ptrdiff_t src_linesize,
                           int block_w, int block_h, int src_x, int src_y, int w, int h);
+void orc_h264_weight(int idx, uint8_t *block, ptrdiff_t stride, int height, int log2_denom, int weight, int offset);
+void orc_h264_biweight(int idx, uint8_t *dst, const uint8_t *src, ptrdiff_t stride, int height, int log2_denom,
+                       int weightd, int weights, int offset);
 int  orc_h264chroma(int avg, int idx, uint8_t *dst, const uint8_t *src, ptrdiff_t stride, int h, int x, int y);
 
 /* ------------------------------------------------------------------ tx (float FFT / MDCT, power-of-two) */

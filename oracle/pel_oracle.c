@@ -22,6 +22,9 @@
  *                                                                    (src_x, src_y); samples outside the w x h picture replicate the
  *                                                                    nearest border sample (the reference clamps the window so at least
  *                                                                    one row and column is inside, then copies and smears the edges)
+ *   h264 weight / biweight . libavcodec/h264dsp_template.c:30-99        explicit weighted prediction on the motion-compensated block:
+ *                                                                    clip((p*w + o') >> d) with o' = (o << d) + (d ? 1 << (d-1) : 0); and
+ *                                                                    clip((s*ws + p*wd + o'') >> (d+1)) with o'' = ((o + 1) | 1) << d
  */
 #include "oracle.h"
 
@@ -140,4 +143,24 @@ void orc_emulated_edge_mc(uint8_t *buf, const uint8_t *src, ptrdiff_t buf_linesi
             buf[y * buf_linesize + x] = origin[py * src_linesize + px];
         }
     }
+}
+
+static int clip255(int a) { return a < 0 ? 0 : a > 255 ? 255 : a; }
+
+void orc_h264_weight(int idx, uint8_t *block, ptrdiff_t stride, int height, int log2_denom, int weight, int offset)
+{
+    const int w = 16 >> idx;
+    offset = (int)((unsigned)offset << log2_denom);
+    if (log2_denom) offset += 1 << (log2_denom - 1);
+    for (int y = 0; y < height; y++, block += stride)
+        for (int x = 0; x < w; x++) block[x] = (uint8_t)clip255((block[x] * weight + offset) >> log2_denom);
+}
+
+void orc_h264_biweight(int idx, uint8_t *dst, const uint8_t *src, ptrdiff_t stride, int height, int log2_denom,
+                       int weightd, int weights, int offset)
+{
+    const int w = 16 >> idx;
+    offset = (int)((unsigned)((offset + 1) | 1) << log2_denom);
+    for (int y = 0; y < height; y++, dst += stride, src += stride)
+        for (int x = 0; x < w; x++) dst[x] = (uint8_t)clip255((src[x] * weights + dst[x] * weightd + offset) >> (log2_denom + 1));
 }

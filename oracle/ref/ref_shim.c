@@ -342,6 +342,21 @@ API int ffref_h264_idct(int kind, uint8_t *dst, int16_t *block, ptrdiff_t stride
     return -1;
 }
 
+/* H.264 weighted prediction: idx 0..3 = widths 16, 8, 4, 2 */
+API void ffref_h264_weight(int idx, uint8_t *block, ptrdiff_t stride, int height, int log2_denom, int weight, int offset)
+{
+    static H264DSPContext c; static int ok;
+    if (!ok) { ff_h264dsp_init(&c, 8, 1); ok = 1; }
+    c.weight_pixels_tab[idx](block, stride, height, log2_denom, weight, offset);
+}
+API void ffref_h264_biweight(int idx, uint8_t *dst, uint8_t *src, ptrdiff_t stride, int height, int log2_denom,
+                             int weightd, int weights, int offset)
+{
+    static H264DSPContext c; static int ok;
+    if (!ok) { ff_h264dsp_init(&c, 8, 1); ok = 1; }
+    c.biweight_pixels_tab[idx](dst, src, stride, height, log2_denom, weightd, weights, offset);
+}
+
 /* ------------------------------------------------------------------ tx ------------------------------------------ */
 
 typedef struct { AVTXContext *ctx; av_tx_fn fn; } RefTx;

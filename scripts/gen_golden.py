@@ -156,6 +156,26 @@ def gen_h264idct():
     np.savez_compressed(os.path.join(OUT, "h264idct.npz"), **d)
 
 
+def gen_h264weight():
+    """weight / biweight for every width, a grid of (log2_denom, weights, offset) incl. the extremes the bitstream allows"""
+    R = cl.ref()
+    rng = np.random.default_rng(25)
+    src = rng.integers(0, 256, (20, 32), dtype=np.uint8)
+    dst0 = rng.integers(0, 256, (20, 32), dtype=np.uint8)
+    cases = []
+    for idx in range(4):
+        for (d, w1, w2, off) in ((0, 1, 1, 0), (5, 32, 32, 0), (7, -128, 127, -128), (6, 127, -128, 127), (3, 10, -3, 5), (1, -1, 3, -7), (7, 64, 64, 1), (2, 0, 0, 9)):
+            cases.append((idx, (2, 4, 8, 16)[(idx + d) % 4], d, w1, w2, off))
+    d = {"src": src, "dst0": dst0, "cases": np.array(cases, np.int32)}
+    ps = C.cast(src.ctypes.data + 2 * 32 + 8, cl.u8p)
+    for k, (idx, h, ld, w1, w2, off) in enumerate(cases):
+        a, b = dst0.copy(), dst0.copy()
+        R.ffref_h264_weight(idx, C.cast(a.ctypes.data + 2 * 32 + 8, cl.u8p), 32, h, ld, w1, off)
+        R.ffref_h264_biweight(idx, C.cast(b.ctypes.data + 2 * 32 + 8, cl.u8p), ps, 32, h, ld, w1, w2, off)
+        d[f"w{k}"], d[f"b{k}"] = a, b
+    np.savez_compressed(os.path.join(OUT, "h264weight.npz"), **d)
+
+
 def gen_mecmp():
     R = cl.ref()
     rng = np.random.default_rng(21)
@@ -336,6 +356,7 @@ if __name__ == "__main__":
     gen_sws_nv()
     gen_idct()
     gen_h264idct()
+    gen_h264weight()
     gen_mecmp()
     gen_pel()
     gen_chroma()

@@ -59,6 +59,11 @@ def oracle():
         if hasattr(L, "orc_emulated_edge_mc"):
             L.orc_emulated_edge_mc.argtypes = [u8p, C.c_void_p, C.c_ssize_t, C.c_ssize_t] + [C.c_int] * 6
             L.orc_emulated_edge_mc.restype = None
+        if hasattr(L, "orc_h264_weight"):
+            L.orc_h264_weight.argtypes = [C.c_int, u8p, C.c_ssize_t] + [C.c_int] * 4
+            L.orc_h264_weight.restype = None
+            L.orc_h264_biweight.argtypes = [C.c_int, u8p, u8p, C.c_ssize_t] + [C.c_int] * 5
+            L.orc_h264_biweight.restype = None
         if hasattr(L, "orc_h264chroma"):
             L.orc_h264chroma.argtypes = [C.c_int, C.c_int, u8p, u8p, C.c_ssize_t, C.c_int, C.c_int, C.c_int]
         if hasattr(L, "orc_tx_open"):
@@ -107,6 +112,11 @@ def ref():
         if hasattr(L, "ffref_emulated_edge_mc"):
             L.ffref_emulated_edge_mc.argtypes = [u8p, C.c_void_p, C.c_ssize_t, C.c_ssize_t] + [C.c_int] * 6
             L.ffref_emulated_edge_mc.restype = None
+        if hasattr(L, "ffref_h264_weight"):
+            L.ffref_h264_weight.argtypes = [C.c_int, u8p, C.c_ssize_t] + [C.c_int] * 4
+            L.ffref_h264_weight.restype = None
+            L.ffref_h264_biweight.argtypes = [C.c_int, u8p, u8p, C.c_ssize_t] + [C.c_int] * 5
+            L.ffref_h264_biweight.restype = None
         if hasattr(L, "ffref_h264chroma"):
             L.ffref_h264chroma.argtypes = [C.c_int, C.c_int, u8p, u8p, C.c_ssize_t, C.c_int, C.c_int, C.c_int]
         L.ffref_tx_open.restype = C.c_void_p

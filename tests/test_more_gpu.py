@@ -335,6 +335,60 @@ def test_emulated_edge_mc_batch_vs_oracle(device):
     assert np.array_equal(got, exp), int((got != exp).sum())
 
 
+def test_h264_weight_pointer_table_golden(device):
+    from ffmpeg_b200 import pel
+    g = np.load(os.path.join(G, "h264weight.npz"))
+    t = pel.ff_h264dsp_weight_init(8)
+    src, dst0 = g["src"], g["dst0"]
+    for k, (idx, h, ld, w1, w2, off) in enumerate(g["cases"].tolist()):
+        a, b = dst0.copy(), dst0.copy()
+        t.weight_pixels_tab[idx](a.ctypes.data + 2 * 32 + 8, 32, h, ld, w1, off)
+        t.biweight_pixels_tab[idx](b.ctypes.data + 2 * 32 + 8, src.ctypes.data + 2 * 32 + 8, 32, h, ld, w1, w2, off)
+        assert np.array_equal(a, g[f"w{k}"]), ("weight", k)
+        assert np.array_equal(b, g[f"b{k}"]), ("biweight", k)
+    with pytest.raises(Exception):
+        pel.ff_h264dsp_weight_init(10)
+
+
+def test_h264_weight_batch_vs_oracle(device):
+    """Weighted and bi-weighted prediction over a frame of partitions (all widths, heights, denominators, unaligned x)."""
+    import torch
+    from ffmpeg_b200 import pel
+    O = cl.oracle()
+    rng = np.random.default_rng(17)
+    W, H = 352, 208
+    src = rng.integers(0, 256, (H, W), dtype=np.uint8)
+    dst0 = rng.integers(0, 256, (H, W), dtype=np.uint8)
+    params, doffs, soffs = [], [], []
+    for by in range(H // 16):
+        for bx in range(W // 16 - 1):
+            idx = int(rng.integers(0, 4))
+            h = int(rng.choice([2, 4, 8, 16]))
+            ld = int(rng.integers(0, 8))
+            w1, w2, off = (int(v) for v in rng.integers(-128, 128, 3))
+            params.append(pel.weight_params(idx, h, ld, w1, w2, off))
+            jx = 0 if idx == 0 else int(rng.integers(0, 4)) * (1 if idx < 3 else 2)      # destinations of one call must not overlap
+            doffs.append(by * 16 * W + bx * 16 + jx); soffs.append(by * 16 * W + bx * 16 + int(rng.integers(0, 8)))
+    n = len(params)
+    pa = np.array(params, np.int32)
+    for bi in (False, True):
+        exp = dst0.copy()
+        for (p0, w1, w2, off), do, so in zip(params, doffs, soffs):
+            idx, h, ld = p0 & 3, (p0 >> 8) & 255, (p0 >> 16) & 31
+            if bi:
+                O.orc_h264_biweight(idx, C.cast(exp.ctypes.data + do, cl.u8p), C.cast(src.ctypes.data + so, cl.u8p), W, h, ld, w1, w2, off)
+            else:
+                O.orc_h264_weight(idx, C.cast(exp.ctypes.data + do, cl.u8p), W, h, ld, w1, off)
+        with on_stream(device):
+            t = lambda a, dt: torch.from_numpy(np.array(a, dt)).cuda()
+            d_dst, d_src = torch.from_numpy(dst0).cuda(), torch.from_numpy(src).cuda()
+            pel.h264_weight_batch_device(device, n, torch.from_numpy(pa).cuda(), d_dst, t(doffs, np.int64), d_src if bi else None,
+                                         t(soffs, np.int64) if bi else None, W)
+            device.sync()
+            got = d_dst.cpu().numpy()
+        assert np.array_equal(got, exp), (bi, int((got != exp).sum()))
+
+
 # ---------------------------------------------------------------------------------------------- tx
 def ulp_diff(a, b):
     ai, bi = a.view(np.int32).astype(np.int64), b.view(np.int32).astype(np.int64)

@@ -139,6 +139,18 @@ def test_h264_idct_oracle_vs_ref():
         assert np.array_equal(d1, d2) and np.array_equal(b1, b2), (kind, it)
 
 
+def test_h264_weight_oracle_golden():
+    g = np.load(os.path.join(G, "h264weight.npz"))
+    O = cl.oracle()
+    src, dst0 = g["src"], g["dst0"]
+    ps = C.cast(src.ctypes.data + 2 * 32 + 8, cl.u8p)
+    for k, (idx, h, ld, w1, w2, off) in enumerate(g["cases"].tolist()):
+        a, b = dst0.copy(), dst0.copy()
+        O.orc_h264_weight(idx, C.cast(a.ctypes.data + 2 * 32 + 8, cl.u8p), 32, h, ld, w1, off)
+        O.orc_h264_biweight(idx, C.cast(b.ctypes.data + 2 * 32 + 8, cl.u8p), ps, 32, h, ld, w1, w2, off)
+        assert np.array_equal(a, g[f"w{k}"]) and np.array_equal(b, g[f"b{k}"]), k
+
+
 def test_pel_oracle_golden():
     g = np.load(os.path.join(G, "pel.npz"))
     O = cl.oracle()
