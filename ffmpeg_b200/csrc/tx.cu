@@ -561,13 +561,18 @@ static int tx_build(B200TXContext *c, float scale)
     d.leaf16 = (const int *)(b + o_l16); d.n_leaf16 = (int)leaf16.size();
     d.leaf8 = (const int *)(b + o_l8); d.n_leaf8 = (int)leaf8.size();
     c->tb = n <= 1024 ? 4 : n <= 2048 ? 2 : 1;                     // transforms per CTA (about 35 KB of shared memory up to n = 2048)
+    if (const char *e = getenv("B200_TX_TB")) {                    // tuning knob (1, 2 or 4); the default above is what the bench uses
+        const int v = atoi(e);
+        if ((v == 1 || v == 2 || v == 4) && (size_t)v * (n + (n >> 4) + 1) * sizeof(float2) <= 200 * 1024) c->tb = v;
+    }
     c->smem = (size_t)c->tb * (n + (n >> 4) + 1) * sizeof(float2);
     if (c->smem > 48 * 1024) {
-        B200_CUDA_OK(cudaFuncSetAttribute(tx_fft_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem));
-        B200_CUDA_OK(cudaFuncSetAttribute(tx_mdct_inv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem));
-        B200_CUDA_OK(cudaFuncSetAttribute(tx_mdct_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem));
-        B200_CUDA_OK(cudaFuncSetAttribute(tx_rdft_r2c_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem));
-        B200_CUDA_OK(cudaFuncSetAttribute(tx_rdft_c2r_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem));
+#define TX_SMEM(K) B200_CUDA_OK(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem))
+#define TX_SMEM_ALL(TB) do { TX_SMEM(tx_fft_kernel<TB>); TX_SMEM(tx_mdct_inv_kernel<TB>); TX_SMEM(tx_mdct_fwd_kernel<TB>); \
+                             TX_SMEM(tx_rdft_r2c_kernel<TB>); TX_SMEM(tx_rdft_c2r_kernel<TB>); } while (0)
+        if (c->tb == 4) TX_SMEM_ALL(4); else if (c->tb == 2) TX_SMEM_ALL(2); else TX_SMEM_ALL(1);
+#undef TX_SMEM_ALL
+#undef TX_SMEM
     }
     return 0;
 }
@@ -576,7 +581,13 @@ static int tx_launch(B200TXContext *c, cudaStream_t st, void *out, const void *i
                      ptrdiff_t out_step, ptrdiff_t in_step, void *c2r_writeback = nullptr)
 {
     if (count <= 0) return 0;
-    const int threads = c->d.n * c->tb >= 1024 ? 256 : c->d.n * c->tb >= 256 ? 128 : 64;
+    // measured on B200 (scripts/quick_bench.py tx with B200_TX_TB / B200_TX_THREADS): 256 threads pay off from 1024 points per
+    // transform on; 512-point transforms (iMDCT-1024) run 18 % faster with 128-thread CTAs
+    int threads = c->d.n >= 1024 ? 256 : c->d.n >= 256 ? 128 : 64;
+    if (const char *e = getenv("B200_TX_THREADS")) {               // tuning knob
+        const int v = atoi(e);
+        if (v == 64 || v == 128 || v == 256) threads = v;
+    }
     const long long per = 0x7fffffffLL / 4 * c->tb;              // transforms per launch (grid.x limit)
     for (int64_t c0 = 0; c0 < count; c0 += per) {
         const long long cnt = count - c0 < per ? count - c0 : per;
