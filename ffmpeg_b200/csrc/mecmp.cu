@@ -3,6 +3,7 @@
 // Reference semantics reproduced bit-for-bit (checker: oracle/mecmp_oracle.c):
 //   pix_abs16_c / pix_abs8_c, *_x2 / _y2 / _xy2   libavcodec/me_cmp.c:114-385
 //   sse16_c / sse8_c / sse4_c                     libavcodec/me_cmp.c:37-103
+//   hadamard8_diff8x8_c, hadamard8_diff16_c       libavcodec/me_cmp.c:514-562, 933-950 (SATD)
 //   ff_me_cmp_sad, ff_me_search_esa               libavfilter/motion_estimation.c:60-97 (driver vf_mestimate.c:85-127)
 //
 // ESA kernel: one CTA per macroblock.  The current block and the clipped search window of the reference frame are
@@ -42,6 +43,45 @@ me_cmp_kernel(int fn, int w, int mode, const uint8_t *f1, const uint8_t *f2, lon
         const int d = pa - pb;
         s += fn == B200_MECMP_SSE ? d * d : abs(d);
     }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[i] = s;
+}
+
+// hadamard8_diff (SATD): one warp per comparison, 8 lanes per 8x8 block, lane = one row of differences.  The row transform
+// runs in the lane's registers, the column transform across the 8 lanes with xor-shuffles; the sum of absolute values of
+// the 64 coefficients does not depend on the butterfly order (exact integers), so this equals the reference's result.
+// nblk = 1 (8 wide), 2 (16 wide, h = 8) or 4 (16 wide, h = 16).
+__global__ void __launch_bounds__(256)
+me_satd_kernel(int nblk, const uint8_t *f1, const uint8_t *f2, long long stride, const int64_t *off1, const int64_t *off2,
+               long long n, int32_t *out)
+{
+    const long long i = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= n) return;
+    const int lane = threadIdx.x & 31, blk = lane >> 3, row = lane & 7;
+    int s = 0;
+    const bool on = blk < nblk;
+    int v[8];
+    {
+        const long long o = (long long)((blk >> 1) * 8 + row) * stride + (blk & 1) * 8;
+        const uint8_t *a = f1 + off1[i] + o, *b = f2 + off2[i] + o;
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = on ? (int)b[k] - (int)a[k] : 0;      // src - dst, like the reference
+    }
+#pragma unroll
+    for (int span = 1; span < 8; span <<= 1)
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            if (!(k & span)) { const int x = v[k], y = v[k + span]; v[k] = x + y; v[k + span] = x - y; }
+#pragma unroll
+    for (int span = 1; span < 8; span <<= 1)
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int other = __shfl_xor_sync(0xffffffffu, v[k], span);
+            v[k] = (row & span) ? other - v[k] : v[k] + other;
+        }
+#pragma unroll
+    for (int k = 0; k < 8; k++) s += abs(v[k]);
 #pragma unroll
     for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0) out[i] = s;
@@ -162,6 +202,7 @@ int decode(int fn, int idx, int *w, int *mode)
     if (fn == B200_MECMP_SAD) { if (idx < 0 || idx > 1) return B200_EINVAL; *w = 16 >> idx; return 0; }
     if (fn == B200_MECMP_SSE) { if (idx < 0 || idx > 2) return B200_EINVAL; *w = 16 >> idx; return 0; }
     if (fn == B200_MECMP_PIX_ABS) { if (idx < 0 || idx > 7) return B200_EINVAL; *w = idx < 4 ? 16 : 8; *mode = idx & 3; return 0; }
+    if (fn == B200_MECMP_HADAMARD8) { if (idx < 0 || idx > 1) return B200_EINVAL; *w = 16 >> idx; return 0; }
     return B200_EINVAL;
 }
 
@@ -178,6 +219,9 @@ B200_API int b200_me_cmp_batch_device(B200Device *dev, int fn, int idx, const ui
     B200_CUDA_OK(cudaSetDevice(dev->ordinal));
     const long long blocks = (n + 7) / 8;
     if (blocks > 0x7fffffffLL) return B200_EINVAL;
+    if (fn == B200_MECMP_HADAMARD8)                               // 8 wide ignores h; 16 wide: two blocks, four when h == 16
+        me_satd_kernel<<<(unsigned)blocks, 256, 0, dev->stream>>>(w == 8 ? 1 : h == 16 ? 4 : 2, frame1, frame2, stride, off1, off2, n, out);
+    else
     me_cmp_kernel<<<(unsigned)blocks, 256, 0, dev->stream>>>(fn, w, mode, frame1, frame2, stride, h, off1, off2, n, out);
     B200_LAUNCHED();
     B200_CUDA_OK(cudaGetLastError());
@@ -212,6 +256,7 @@ int host_cmp(int fn, int idx, const uint8_t *blk1, const uint8_t *blk2, ptrdiff_
     if (!dev) fail("no device");
     int w, mode;
     if (decode(fn, idx, &w, &mode) < 0) fail("bad index");
+    if (fn == B200_MECMP_HADAMARD8) h = (w == 16 && h == 16) ? 16 : 8;         // the reference reads 8 rows unless 16 wide with h == 16
     if (cudaSetDevice(dev->ordinal) != cudaSuccess) fail("cudaSetDevice");
     const int cw = w + 1, ch = h + 1;                             // x2/y2/xy2 read one extra column / row of blk2
     const size_t pitch = 32;
@@ -227,7 +272,8 @@ int host_cmp(int fn, int idx, const uint8_t *blk1, const uint8_t *blk2, ptrdiff_
     const int bw = mode & 1 ? cw : w, bh = mode & 2 ? ch : h;
     if (cudaMemcpy2DAsync(d2, pitch, blk2, as, bw, bh, cudaMemcpyHostToDevice, st) != cudaSuccess) fail("h2d");
     if (cudaMemsetAsync(offs, 0, 16, st) != cudaSuccess) fail("memset");
-    me_cmp_kernel<<<1, 32, 0, st>>>(fn, w, mode, d1, d2, (long long)pitch, h, offs, offs + 1, 1, dout);
+    if (fn == B200_MECMP_HADAMARD8) me_satd_kernel<<<1, 32, 0, st>>>(w == 8 ? 1 : h == 16 ? 4 : 2, d1, d2, (long long)pitch, offs, offs + 1, 1, dout);
+    else me_cmp_kernel<<<1, 32, 0, st>>>(fn, w, mode, d1, d2, (long long)pitch, h, offs, offs + 1, 1, dout);
     B200_LAUNCHED();
     int32_t res = 0;
     if (cudaMemcpyAsync(&res, dout, 4, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) fail("d2h");
@@ -251,5 +297,6 @@ B200_API int b200_me_cmp_init(B200MECmpContext *c, int codec_flags)
     c->pix_abs[0][2] = tab_fn<B200_MECMP_PIX_ABS, 2>; c->pix_abs[0][3] = tab_fn<B200_MECMP_PIX_ABS, 3>;
     c->pix_abs[1][0] = tab_fn<B200_MECMP_PIX_ABS, 4>; c->pix_abs[1][1] = tab_fn<B200_MECMP_PIX_ABS, 5>;
     c->pix_abs[1][2] = tab_fn<B200_MECMP_PIX_ABS, 6>; c->pix_abs[1][3] = tab_fn<B200_MECMP_PIX_ABS, 7>;
+    c->hadamard8_diff[0] = tab_fn<B200_MECMP_HADAMARD8, 0>; c->hadamard8_diff[1] = tab_fn<B200_MECMP_HADAMARD8, 1>;
     return 0;
 }

@@ -3,7 +3,7 @@ and of the exhaustive search libavfilter drives it with (libavfilter/motion_esti
 import ctypes as C
 from ._lib import lib, check, vp, MECmpContext
 
-SAD, SSE, PIX_ABS = 0, 1, 2
+SAD, SSE, PIX_ABS, HADAMARD8 = 0, 1, 2, 3
 AV_CODEC_FLAG_BITEXACT = 1 << 23
 
 

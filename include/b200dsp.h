@@ -242,6 +242,7 @@ int  b200_me_cmp_init(B200MECmpContext *c, int codec_flags);
 #define B200_MECMP_SAD     0   /* idx 0: 16 wide, 1: 8 wide */
 #define B200_MECMP_SSE     1   /* idx 0: 16, 1: 8, 2: 4 wide */
 #define B200_MECMP_PIX_ABS 2   /* idx = 4*size(0:16,1:8) + (0 full, 1 x2, 2 y2, 3 xy2) */
+#define B200_MECMP_HADAMARD8 3 /* hadamard8_diff (SATD, me_cmp.c:514-562,933-950): idx 0: 16 wide (h = 8 or 16), 1: 8x8 (h ignored) */
 /* batched, DEVICE pointers: out[i] = fn(frame1 + off1[i], frame2 + off2[i], stride, h) */
 int  b200_me_cmp_batch_device(B200Device *dev, int fn, int idx, const uint8_t *frame1, const uint8_t *frame2,
                               ptrdiff_t stride, int h, const int64_t *off1, const int64_t *off2, int64_t n, int32_t *out);

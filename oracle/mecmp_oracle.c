@@ -45,8 +45,37 @@ static int sse_wh(const uint8_t *a, const uint8_t *b, ptrdiff_t stride, int w, i
     return s;
 }
 
+/* hadamard8_diff8x8_c (me_cmp.c:514-562): sum of the absolute values of the 8x8 Hadamard transform of src - dst; the result is
+ * the same whatever order the butterflies run in (exact integers).  The 16-wide entry is the WRAPPER8_16_SQ of it (:933-950):
+ * two 8x8 blocks side by side, two more below them when h == 16; the 8-wide entry ignores h. */
+static int satd8x8(const uint8_t *dst, const uint8_t *src, ptrdiff_t stride)
+{
+    int t[64], sum = 0;
+    for (int i = 0; i < 8; i++)
+        for (int j = 0; j < 8; j++) t[8 * i + j] = src[stride * i + j] - dst[stride * i + j];
+    for (int pass = 0; pass < 2; pass++) {                         /* rows, then columns */
+        const int es = pass ? 8 : 1, ls = pass ? 1 : 8;
+        for (int l = 0; l < 8; l++)
+            for (int span = 1; span < 8; span <<= 1)
+                for (int a = 0; a < 8; a++)
+                    if (!(a & span)) {
+                        const int x = t[l * ls + a * es], y = t[l * ls + (a + span) * es];
+                        t[l * ls + a * es] = x + y; t[l * ls + (a + span) * es] = x - y;
+                    }
+    }
+    for (int i = 0; i < 64; i++) sum += abs(t[i]);
+    return sum;
+}
+
 int orc_me_cmp(int fn, int idx, const uint8_t *blk1, const uint8_t *blk2, ptrdiff_t stride, int h)
 {
+    if (fn == 3) {
+        if (idx == 1) return satd8x8(blk1, blk2, stride);
+        if (idx != 0) return -1;
+        int s = satd8x8(blk1, blk2, stride) + satd8x8(blk1 + 8, blk2 + 8, stride);
+        if (h == 16) s += satd8x8(blk1 + 8 * stride, blk2 + 8 * stride, stride) + satd8x8(blk1 + 8 * stride + 8, blk2 + 8 * stride + 8, stride);
+        return s;
+    }
     if (fn == 0) return idx == 0 ? sad_wh(blk1, blk2, stride, 16, h, 0) : idx == 1 ? sad_wh(blk1, blk2, stride, 8, h, 0) : -1;
     if (fn == 1) return idx <= 2 ? sse_wh(blk1, blk2, stride, 16 >> idx, h) : -1;
     if (fn == 2) return idx < 8 ? sad_wh(blk1, blk2, stride, idx < 4 ? 16 : 8, h, idx & 3) : -1;

@@ -223,11 +223,11 @@ static void mecmp_init(void)
     g_mecmp_ok = 1;
 }
 
-/* fn: 0 sad[idx], 1 sse[idx], 2 pix_abs[idx>>2][idx&3] */
+/* fn: 0 sad[idx], 1 sse[idx], 2 pix_abs[idx>>2][idx&3], 3 hadamard8_diff[idx] */
 API int ffref_me_cmp(int fn, int idx, const uint8_t *blk1, const uint8_t *blk2, ptrdiff_t stride, int h)
 {
     mecmp_init();
-    me_cmp_func f = fn == 0 ? g_mecmp.sad[idx] : fn == 1 ? g_mecmp.sse[idx] : g_mecmp.pix_abs[idx >> 2][idx & 3];
+    me_cmp_func f = fn == 0 ? g_mecmp.sad[idx] : fn == 1 ? g_mecmp.sse[idx] : fn == 3 ? g_mecmp.hadamard8_diff[idx] : g_mecmp.pix_abs[idx >> 2][idx & 3];
     if (!f) return -1;
     return f(NULL, blk1, blk2, stride, h);
 }
@@ -237,7 +237,7 @@ API void ffref_me_cmp_batch(int fn, int idx, const uint8_t *f1, const uint8_t *f
                             const int64_t *off1, const int64_t *off2, int n, int32_t *out)
 {
     mecmp_init();
-    me_cmp_func f = fn == 0 ? g_mecmp.sad[idx] : fn == 1 ? g_mecmp.sse[idx] : g_mecmp.pix_abs[idx >> 2][idx & 3];
+    me_cmp_func f = fn == 0 ? g_mecmp.sad[idx] : fn == 1 ? g_mecmp.sse[idx] : fn == 3 ? g_mecmp.hadamard8_diff[idx] : g_mecmp.pix_abs[idx >> 2][idx & 3];
     for (int i = 0; i < n; i++) out[i] = f(NULL, f1 + off1[i], f2 + off2[i], stride, h);
 }
 

@@ -241,6 +241,22 @@ def gen_edge():
     np.savez_compressed(os.path.join(OUT, "edge.npz"), **d)
 
 
+def gen_satd():
+    """hadamard8_diff[0] (16 wide, h 8 / 16) and [1] (8x8) on the checkasm-style 64x64 random images of mecmp.npz"""
+    R = cl.ref()
+    g = np.load(os.path.join(OUT, "mecmp.npz"))
+    img1, img2 = g["img1"], g["img2"]
+    rng = np.random.default_rng(26)
+    rows = []
+    for idx in (0, 1):
+        for _ in range(40):
+            x1, y1, x2, y2 = (int(v) for v in rng.integers(0, 40, 4))
+            h = int(rng.choice([8, 16]))
+            v = R.ffref_me_cmp(3, idx, C.cast(img1.ctypes.data + y1 * 64 + x1, cl.u8p), C.cast(img2.ctypes.data + y2 * 64 + x2, cl.u8p), 64, h)
+            rows.append((3, idx, x1, y1, x2, y2, h, v))
+    np.savez_compressed(os.path.join(OUT, "satd.npz"), cases=np.array(rows, np.int32))
+
+
 def gen_pel():
     R = cl.ref()
     rng = np.random.default_rng(22)
@@ -358,6 +374,7 @@ if __name__ == "__main__":
     gen_h264idct()
     gen_h264weight()
     gen_mecmp()
+    gen_satd()
     gen_pel()
     gen_chroma()
     gen_edge()

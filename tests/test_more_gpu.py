@@ -25,7 +25,7 @@ def test_mecmp_pointer_table_golden(device):
     g = np.load(os.path.join(G, "mecmp.npz"))
     c = me_cmp.ff_me_cmp_init()
     img1, img2 = g["img1"], g["img2"]
-    assert not c.hadamard8_diff[0] and not c.sad[2]            # entries not implemented stay NULL
+    assert not c.dct_sad[0] and not c.sad[2]                   # entries not implemented stay NULL
     for fn, idx, x1, y1, x2, y2, h, v in g["cases"]:
         f = c.sad[idx] if fn == 0 else c.sse[idx] if fn == 1 else c.pix_abs[idx >> 2][idx & 3]
         got = f(None, C.cast(img1.ctypes.data + int(y1) * 64 + int(x1), u8p), C.cast(img2.ctypes.data + int(y2) * 64 + int(x2), u8p), 64, int(h))
@@ -56,6 +56,38 @@ def test_mecmp_batch_vs_oracle(device):
                     exp = np.array([O.orc_me_cmp(fn, idx, C.cast(f1.ctypes.data + int(a), cl.u8p), C.cast(f2.ctypes.data + int(b), cl.u8p), W, h)
                                     for a, b in zip(off1[:400], off2[:400])])
                     assert np.array_equal(got[:400], exp), (fn, idx, h)
+
+
+def test_satd_pointer_table_and_batch(device):
+    """hadamard8_diff (SATD): drop-in entries against the reference fixture, batched entry against the oracle."""
+    import torch
+    from ffmpeg_b200 import me_cmp
+    from ffmpeg_b200._lib import u8p
+    g, cases = np.load(os.path.join(G, "mecmp.npz")), np.load(os.path.join(G, "satd.npz"))["cases"]
+    c = me_cmp.ff_me_cmp_init()
+    img1, img2 = g["img1"], g["img2"]
+    for fn, idx, x1, y1, x2, y2, h, v in cases[::3]:
+        got = c.hadamard8_diff[idx](None, C.cast(img1.ctypes.data + int(y1) * 64 + int(x1), u8p), C.cast(img2.ctypes.data + int(y2) * 64 + int(x2), u8p), 64, int(h))
+        assert got == v, (idx, h)
+    O = cl.oracle()
+    rng = np.random.default_rng(6)
+    W, H, n = 256, 128, 2000
+    f1 = rng.integers(0, 256, (H, W), dtype=np.uint8)
+    f2 = np.clip(f1.astype(np.int32) + rng.integers(-20, 21, (H, W)), 0, 255).astype(np.uint8)
+    off1 = (rng.integers(0, H - 20, n) * W + rng.integers(0, W - 20, n)).astype(np.int64)
+    off2 = (rng.integers(0, H - 20, n) * W + rng.integers(0, W - 20, n)).astype(np.int64)
+    with on_stream(device):
+        d1, d2 = torch.from_numpy(f1).cuda(), torch.from_numpy(f2).cuda()
+        o1, o2 = torch.from_numpy(off1).cuda(), torch.from_numpy(off2).cuda()
+        out = torch.zeros(n, dtype=torch.int32, device="cuda")
+        for idx in (0, 1):
+            for h in (8, 16):
+                me_cmp.me_cmp_batch_device(device, me_cmp.HADAMARD8, idx, d1, d2, W, h, o1, o2, n, out)
+                device.sync()
+                got = out.cpu().numpy()
+                exp = np.array([O.orc_me_cmp(3, idx, C.cast(f1.ctypes.data + int(a), cl.u8p), C.cast(f2.ctypes.data + int(b), cl.u8p), W, h)
+                                for a, b in zip(off1[:500], off2[:500])])
+                assert np.array_equal(got[:500], exp), (idx, h)
 
 
 def gpu_esa(device, cur, ref_, mb, sp):

@@ -151,6 +151,16 @@ def test_h264_weight_oracle_golden():
         assert np.array_equal(a, g[f"w{k}"]) and np.array_equal(b, g[f"b{k}"]), k
 
 
+def test_satd_oracle_golden():
+    g, c = np.load(os.path.join(G, "mecmp.npz")), np.load(os.path.join(G, "satd.npz"))["cases"]
+    O = cl.oracle()
+    img1, img2 = g["img1"], g["img2"]
+    for fn, idx, x1, y1, x2, y2, h, v in c:
+        got = O.orc_me_cmp(int(fn), int(idx), C.cast(img1.ctypes.data + int(y1) * 64 + int(x1), cl.u8p),
+                           C.cast(img2.ctypes.data + int(y2) * 64 + int(x2), cl.u8p), 64, int(h))
+        assert got == v, (fn, idx, h)
+
+
 def test_pel_oracle_golden():
     g = np.load(os.path.join(G, "pel.npz"))
     O = cl.oracle()
