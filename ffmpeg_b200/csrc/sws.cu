@@ -209,6 +209,46 @@ sws_hscale_kernel(const uint8_t *src, long long sstride, long long sfs, int16_t 
     dst[(long long)blockIdx.z * dfs + (long long)line * dstW + i] = (int16_t)min(acc >> 7, 32767);
 }
 
+// Same filter, one thread = one output column over HROWS consecutive lines: position and tap pairs of a column are the same
+// on every line, so they are fetched once and held in registers (NP pairs, filter sizes up to 2*NP); per line only the
+// source words are loaded.  Adjacent threads read adjacent source bytes and write adjacent int16 samples.
+constexpr int HROWS = 8;
+template <int NP>
+__global__ void __launch_bounds__(256)
+sws_hscale_rows_kernel(const uint8_t *src, long long sstride, long long sfs, int16_t *dst, int dstW, long long dfs,
+                       const int32_t *coef2, const int32_t *pos, int fs, int line0, int nlines)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= dstW) return;
+    const int np = (fs + 1) >> 1, p0 = __ldg(pos + i);
+    int k[NP];
+#pragma unroll
+    for (int j = 0; j < NP; j++) k[j] = j < np ? __ldg(coef2 + (long long)i * np + j) : 0;
+    const int r0 = blockIdx.y * HROWS, r1 = min(r0 + HROWS, nlines);
+    const uint8_t *base = src + (long long)blockIdx.z * sfs + p0;
+    int16_t *out = dst + (long long)blockIdx.z * dfs + i;
+    for (int r = r0; r < r1; r++) {
+        const int line = r + line0;
+        const uint8_t *s = base + (long long)line * sstride;
+        const unsigned sh = (unsigned)(reinterpret_cast<uintptr_t>(s) & 3);
+        const unsigned *w = reinterpret_cast<const unsigned *>(s - sh);
+        const int need = (int)sh + fs;
+        unsigned prev = __ldg(w);
+        int acc = 0;
+#pragma unroll
+        for (int q = 0; q < (NP + 1) / 2; q++) {               // window word q = taps 4q .. 4q+3 (zero pairs beyond the filter)
+            if (q * 4 < fs) {
+                const unsigned next = ((q + 1) * 4 < need) ? __ldg(w + q + 1) : 0u;
+                const unsigned win = __funnelshift_r(prev, next, sh * 8);
+                prev = next;
+                acc = dp2a_lo_su(k[2 * q], win, acc);
+                if (2 * q + 1 < NP) acc = dp2a_hi_su(k[2 * q + 1], win, acc);
+            }
+        }
+        out[(long long)line * dstW] = (int16_t)min(acc >> 7, 32767);
+    }
+}
+
 // SWS_FAST_BILINEAR horizontal pass (ff_hyscale_fast_c / ff_hcscale_fast_c, hscale_fast_bilinear.c:27-67): 16.16 stepping with
 // 7-bit blend weights; outputs whose left sample is the last source sample (or beyond) are src[srcW-1] * 128, which is what
 // the fix-up loop at the end of both reference functions leaves (so the sample right of the row end is never read).
@@ -524,6 +564,48 @@ sws_vscale_planar4_kernel(const int16_t *src, int sls, long long sfs, int nlines
     *reinterpret_cast<unsigned *>(dst + f * dfs + (long long)dy * ds + x) = __byte_perm(lo, hi, 0x6420);
 }
 
+// eight adjacent samples per thread: 128-bit loads of the int16 lines, one 64-bit store (w % 8 == 0, 8-aligned destination)
+__global__ void __launch_bounds__(256)
+sws_vscale_planar8_kernel(const int16_t *src, int sls, long long sfs, int nlines, uint8_t *dst, long long ds, long long dfs,
+                          int w, const int16_t *coef, const int32_t *pos, int fs, int line0)
+{
+    const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+    if (x >= w) return;
+    const int dy = blockIdx.y + line0;
+    const long long f = blockIdx.z;
+    const int16_t *p = reinterpret_cast<const int16_t *>(reinterpret_cast<const char *>(src) + f * sfs) + x;
+    const int first = max(1 - fs, __ldg(pos + dy));
+    int v[8];
+    if (fs == 1) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4 *>(p + (long long)min(max(first, 0), nlines - 1) * sls));
+        const unsigned ww[4] = { q.x, q.y, q.z, q.w };
+#pragma unroll
+        for (int j = 0; j < 4; j++) { v[2 * j] = ((int)(short)(ww[j] & 0xffff) + 64) >> 7; v[2 * j + 1] = (((int)ww[j] >> 16) + 64) >> 7; }
+    } else {
+        unsigned a[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) a[j] = 64u << 12;
+        const int16_t *k = coef + (long long)dy * fs;
+        for (int t = 0; t < fs; t++) {
+            const uint4 q = __ldg(reinterpret_cast<const uint4 *>(p + (long long)min(max(first + t, 0), nlines - 1) * sls));
+            const unsigned ww[4] = { q.x, q.y, q.z, q.w };
+            const int c = (int)__ldg(k + t);
+#pragma unroll
+            for (int j = 0; j < 4; j++) { a[2 * j] += (unsigned)((int)(short)(ww[j] & 0xffff) * c); a[2 * j + 1] += (unsigned)(((int)ww[j] >> 16) * c); }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[j] = (int)a[j] >> 19;
+    }
+    unsigned o[2];
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const unsigned lo = __vimin_s16x2_relu(__byte_perm((unsigned)v[4 * h], (unsigned)v[4 * h + 1], 0x5410), 0x00ff00ffu);
+        const unsigned hi = __vimin_s16x2_relu(__byte_perm((unsigned)v[4 * h + 2], (unsigned)v[4 * h + 3], 0x5410), 0x00ff00ffu);
+        o[h] = __byte_perm(lo, hi, 0x6420);
+    }
+    *reinterpret_cast<uint2 *>(dst + f * dfs + (long long)dy * ds + x) = make_uint2(o[0], o[1]);
+}
+
 // planarCopyWrapper (swscale_unscaled.c:2220-2333, 8-bit planes): row copies, 16 bytes per thread when everything is aligned
 __global__ void __launch_bounds__(256)
 sws_plane_copy_kernel(const uint8_t *src, long long ss, long long sfs, uint8_t *dst, long long ds, long long dfs, int w, int vec)
@@ -775,6 +857,23 @@ static void launch_vscale_fast(bool lumid, bool c4, dim3 grid, dim3 block, cudaS
     else              sws_vscale_rgb24_fast_kernel<false, false, KIND><<<grid, block, 0, stream>>>(b, dt, col, ngroups);
 }
 
+// horizontal pass of `nlines` lines starting at line0 (filter sizes up to 16 take the register-resident variant)
+static void launch_hscale(cudaStream_t stream, const uint8_t *src, long long sstride, long long sfs, int16_t *dst, int dstW, long long dfs,
+                          const int32_t *coef2, const int32_t *pos, int fs, int line0, int nlines, int nf)
+{
+    dim3 block(256);
+    if (fs <= 16) {
+        dim3 grid(b200_ceil_div(dstW, 256), b200_ceil_div(nlines, HROWS), nf);
+        if (fs <= 2)      sws_hscale_rows_kernel<1><<<grid, block, 0, stream>>>(src, sstride, sfs, dst, dstW, dfs, coef2, pos, fs, line0, nlines);
+        else if (fs <= 4) sws_hscale_rows_kernel<2><<<grid, block, 0, stream>>>(src, sstride, sfs, dst, dstW, dfs, coef2, pos, fs, line0, nlines);
+        else if (fs <= 8) sws_hscale_rows_kernel<4><<<grid, block, 0, stream>>>(src, sstride, sfs, dst, dstW, dfs, coef2, pos, fs, line0, nlines);
+        else              sws_hscale_rows_kernel<8><<<grid, block, 0, stream>>>(src, sstride, sfs, dst, dstW, dfs, coef2, pos, fs, line0, nlines);
+    } else {
+        dim3 grid(b200_ceil_div(dstW, 256), nlines, nf);
+        sws_hscale_kernel<<<grid, block, 0, stream>>>(src, sstride, sfs, dst, dstW, dfs, coef2, pos, fs, line0);
+    }
+}
+
 template <int KIND>
 static void launch_vscale_fast_nv_k(int nv, dim3 grid, dim3 block, cudaStream_t stream, const SwsFrameArgs &b, const SwsDevTables &dt,
                                     const SwsColorConst &col, int ngroups)
@@ -903,16 +1002,16 @@ static int launch_batch(B200SwsContext *c, cudaStream_t stream, const uint8_t *c
             if (R.nly > 0) {
                 dim3 grid(b200_ceil_div(p.dstW, 256), R.nly, nf);
                 if (p.fast_bilinear) sws_hscale_fast_kernel<false><<<grid, block, 0, stream>>>(b.y, b.ys, b.yfs, mY, p.dstW, mfs, p.srcW, p.lumXInc, R.ly0);
-                else sws_hscale_kernel<<<grid, block, 0, stream>>>(b.y, b.ys, b.yfs, mY, p.dstW, mfs, c->dt.hLum2, c->dt.hLumPos, c->dt.hLumSize, R.ly0);
+                else launch_hscale(stream, b.y, b.ys, b.yfs, mY, p.dstW, mfs, c->dt.hLum2, c->dt.hLumPos, c->dt.hLumSize, R.ly0, R.nly, nf);
                 B200_LAUNCHED();
             }
             if (R.ncy > 0) {
                 dim3 gridc(b200_ceil_div(p.chrDstW, 256), R.ncy, nf);
                 if (p.fast_bilinear) sws_hscale_fast_kernel<true><<<gridc, block, 0, stream>>>(b.u, b.us, b.ufs, mU, p.chrDstW, mfs, p.chrSrcW, p.chrXInc, R.cy0);
-                else sws_hscale_kernel<<<gridc, block, 0, stream>>>(b.u, b.us, b.ufs, mU, p.chrDstW, mfs, c->dt.hChr2, c->dt.hChrPos, c->dt.hChrSize, R.cy0);
+                else launch_hscale(stream, b.u, b.us, b.ufs, mU, p.chrDstW, mfs, c->dt.hChr2, c->dt.hChrPos, c->dt.hChrSize, R.cy0, R.ncy, nf);
                 B200_LAUNCHED();
                 if (p.fast_bilinear) sws_hscale_fast_kernel<true><<<gridc, block, 0, stream>>>(b.v, b.vs, b.vfs, mV, p.chrDstW, mfs, p.chrSrcW, p.chrXInc, R.cy0);
-                else sws_hscale_kernel<<<gridc, block, 0, stream>>>(b.v, b.vs, b.vfs, mV, p.chrDstW, mfs, c->dt.hChr2, c->dt.hChrPos, c->dt.hChrSize, R.cy0);
+                else launch_hscale(stream, b.v, b.vs, b.vfs, mV, p.chrDstW, mfs, c->dt.hChr2, c->dt.hChrPos, c->dt.hChrSize, R.cy0, R.ncy, nf);
                 B200_LAUNCHED();
             }
             if (R.ndy <= 0) continue;
@@ -999,13 +1098,19 @@ static int launch_planar(B200SwsContext *c, cudaStream_t stream, const uint8_t *
                 sws_hscale_fast_kernel<true><<<gh, block, 0, stream>>>(src[pl] + (long long)f0 * sfs[pl], sstr[pl], sfs[pl], m[pl], dw[pl],
                                                                        (long long)(perFrame / 2), sw[pl], p.chrXInc, 0);
             else
-                sws_hscale_kernel<<<gh, block, 0, stream>>>(src[pl] + (long long)f0 * sfs[pl], sstr[pl], sfs[pl], m[pl], dw[pl],
-                                                            (long long)(perFrame / 2), hc[pl], hp[pl], hs[pl], 0);
+                launch_hscale(stream, src[pl] + (long long)f0 * sfs[pl], sstr[pl], sfs[pl], m[pl], dw[pl], (long long)(perFrame / 2),
+                              hc[pl], hp[pl], hs[pl], 0, sh[pl], nf);
             B200_LAUNCHED();
             uint8_t *dpl = dst[pl] + (long long)f0 * dfs[pl];
             const bool v4 = dw[pl] % 4 == 0 && (plane[0] % 8 == 0) && (plane[1] % 8 == 0) &&
                             (((uintptr_t)dpl | (uintptr_t)dstr[pl] | (uintptr_t)dfs[pl]) & 3) == 0;
-            if (v4) {
+            const bool v8 = v4 && dw[pl] % 8 == 0 && (plane[0] % 16 == 0) && (plane[1] % 16 == 0) &&
+                            (((uintptr_t)dpl | (uintptr_t)dstr[pl] | (uintptr_t)dfs[pl]) & 7) == 0;
+            if (v8) {
+                dim3 g8(b200_ceil_div(dw[pl] / 8, 256), dh[pl], nf);
+                sws_vscale_planar8_kernel<<<g8, block, 0, stream>>>(m[pl], dw[pl], (long long)perFrame, sh[pl], dpl, dstr[pl], dfs[pl],
+                                                                    dw[pl], vc[pl], vp[pl], vs[pl], 0);
+            } else if (v4) {
                 dim3 g4(b200_ceil_div(dw[pl] / 4, 256), dh[pl], nf);
                 sws_vscale_planar4_kernel<<<g4, block, 0, stream>>>(m[pl], dw[pl], (long long)perFrame, sh[pl], dpl, dstr[pl], dfs[pl],
                                                                     dw[pl], vc[pl], vp[pl], vs[pl], 0);
