@@ -446,6 +446,65 @@ sws_vscale_rgb24_slow_kernel(SwsFrameArgs a, SwsDevTables t, SwsColorConst c, in
     put_pair_bytes(a.dst + f * a.dfs + (long long)dy * a.ds + (long long)p * (2 * a.bpp), a, c, cb, Y0, Y1, second);
 }
 
+// ------------------------------------------------------------------------------------------------ kernel: vertical FIR + packed RGB from int16 lines (vector)
+// The scaled path's `_X` writer (yuv2rgb_X_c_template) on the int16 line planes the horizontal pass leaves: one thread = 8
+// pixels (4 chroma pairs) of one output line, 128-bit luma and 64-bit chroma line loads, sums mod 2^32 like the reference.
+// Used when every line takes the `_X` writer, dstW % 8 == 0 and everything is aligned; other cases stay on the scalar kernel.
+template <int KIND>
+__global__ void __launch_bounds__(128)
+sws_vscale_rgb24_x8_kernel(SwsFrameArgs a, SwsDevTables t, SwsColorConst c, int ngroups)
+{
+    constexpr int PW = OutWords<KIND>::per_pair, BPP = OutWords<KIND>::bpp;
+    const int xg = blockIdx.x * blockDim.x + threadIdx.x;
+    if (xg >= ngroups) return;
+    const int dy = blockIdx.y + a.y0;
+    const long long f = blockIdx.z;
+    const int lfs = t.vLumSize, cfs = t.vChrSize;
+    const int16_t *lf = t.vLum + (long long)dy * lfs, *cf = t.vChr + (long long)dy * cfs;
+    const int firstLum = max(1 - lfs, __ldg(t.vLumPos + dy));
+    const int firstChr = max(1 - cfs, __ldg(t.vChrPos + dy));
+    const uint8_t *yb = a.y + f * a.yfs + xg * 16, *ub = a.u + f * a.ufs + xg * 8, *vb = a.v + f * a.vfs + xg * 8;
+    unsigned sY[8], sU[4], sV[4];
+#pragma unroll
+    for (int i = 0; i < 8; i++) sY[i] = 1u << 18;
+#pragma unroll
+    for (int i = 0; i < 4; i++) sU[i] = sV[i] = 1u << 18;
+    for (int j = 0; j < lfs; j++) {
+        const int line = min(max(firstLum + j, 0), a.srcH - 1);
+        const uint4 q = __ldg(reinterpret_cast<const uint4 *>(yb + (long long)line * a.ys));
+        const unsigned k = (unsigned)(int)__ldg(lf + j);
+        const unsigned w[4] = { q.x, q.y, q.z, q.w };
+#pragma unroll
+        for (int i = 0; i < 4; i++) { sY[2 * i] += (unsigned)(int)(short)(w[i] & 0xffff) * k; sY[2 * i + 1] += (unsigned)((int)w[i] >> 16) * k; }
+    }
+    for (int j = 0; j < cfs; j++) {
+        const int line = min(max(firstChr + j, 0), a.chrSrcH - 1);
+        const uint2 qu = __ldg(reinterpret_cast<const uint2 *>(ub + (long long)line * a.us));
+        const uint2 qv = __ldg(reinterpret_cast<const uint2 *>(vb + (long long)line * a.vs));
+        const unsigned k = (unsigned)(int)__ldg(cf + j);
+        sU[0] += (unsigned)(int)(short)(qu.x & 0xffff) * k; sU[1] += (unsigned)((int)qu.x >> 16) * k;
+        sU[2] += (unsigned)(int)(short)(qu.y & 0xffff) * k; sU[3] += (unsigned)((int)qu.y >> 16) * k;
+        sV[0] += (unsigned)(int)(short)(qv.x & 0xffff) * k; sV[1] += (unsigned)((int)qv.x >> 16) * k;
+        sV[2] += (unsigned)(int)(short)(qv.y & 0xffff) * k; sV[3] += (unsigned)((int)qv.y >> 16) * k;
+    }
+    unsigned m[4 * PW];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const ChromaBase cb = chroma_base(c, (int)sU[i] >> 19, (int)sV[i] >> 19);
+        pair_out<KIND>(c.cy, cb, (int)sY[2 * i] >> 19, (int)sY[2 * i + 1] >> 19, m + PW * i);
+    }
+    uint8_t *d = a.dst + f * a.dfs + (long long)dy * a.ds + (long long)xg * (8 * BPP);
+    if (KIND <= SWS_OUT_BGR24) {                              // 4 pairs = 12 packed words -> 6 output words (24 bytes)
+        uint2 *d2 = reinterpret_cast<uint2 *>(d);
+#pragma unroll
+        for (int k2 = 0; k2 < 3; k2++)
+            d2[k2] = make_uint2(__byte_perm(m[4 * k2], m[4 * k2 + 1], 0x6420), __byte_perm(m[4 * k2 + 2], m[4 * k2 + 3], 0x6420));
+    } else {
+        uint4 *d4 = reinterpret_cast<uint4 *>(d);
+        d4[0] = make_uint4(m[0], m[1], m[2], m[3]); d4[1] = make_uint4(m[4], m[5], m[6], m[7]);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ kernel: full-chroma writer
 // chrDstW == dstW (SWS_FULL_CHR_H_INT, forced for odd widths).  One thread per pixel; taps always from int16 planes.
 __global__ void __launch_bounds__(256)
@@ -641,6 +700,7 @@ struct B200SwsContext {
     bool h_identity = false;         // both horizontal banks are the identity -> u8-source kernels
     bool fast_x = false;             // every line uses the _X writer and no 32-bit sum can wrap -> vector kernel
     bool lum_identity = false;       // vertical luma bank is a single tap of 4096 on every line
+    bool all_x = false;              // every output line takes the `_X` writer (rowMode 0)
     // intermediate int16 line planes for the scaled path (grown on demand, per batch)
     void *mid = nullptr; size_t mid_bytes = 0;
     // de-interleaved chroma of an nv12 / nv21 source (persistent: slice calls keep earlier bands here)
@@ -710,6 +770,8 @@ static int upload_tables(B200SwsContext *c)
     c->dt.hLum = (const int16_t *)(b + o_hl); c->dt.hLumPos = (const int32_t *)(b + o_hlp); c->dt.hLumSize = p.hLum.size;
     c->dt.hChr = (const int16_t *)(b + o_hc); c->dt.hChrPos = (const int32_t *)(b + o_hcp); c->dt.hChrSize = p.hChr.size;
     c->h_identity = !p.fast_bilinear && p.chrDstHSub == 1 && p.hLum.identity() && p.hChr.identity();
+    c->all_x = !p.planar;
+    for (int y = 0; y < p.dstH && c->all_x; y++) if (p.rowMode[(size_t)y * 4] != 0) c->all_x = false;
     c->fast_x = c->h_identity && !p.planar;
     c->lum_identity = p.vLum.size == 1;
     for (int y = 0; y < p.dstH && c->fast_x; y++) {
@@ -1019,7 +1081,18 @@ static int launch_batch(B200SwsContext *c, cudaStream_t stream, const uint8_t *c
             m.y = (const uint8_t *)mY; m.u = (const uint8_t *)mU; m.v = (const uint8_t *)mV;
             m.ys = (long long)p.dstW * 2; m.us = m.vs = (long long)p.chrDstW * 2;
             m.yfs = m.ufs = m.vfs = (long long)perFrame;
-            if (p.chrDstHSub) {
+            if (p.chrDstHSub && c->all_x && p.dstW % 8 == 0 && aligned16(dst, ds, dfs) && lumPlane % 16 == 0 && chrPlane % 8 == 0) {
+                const int ng = p.dstW / 8;
+                dim3 block2(128), grid(b200_ceil_div(ng, 128), R.ndy, nf);
+                switch (p.out.kind) {
+                case SWS_OUT_RGB24: sws_vscale_rgb24_x8_kernel<SWS_OUT_RGB24><<<grid, block2, 0, stream>>>(m, c->dt, p.color, ng); break;
+                case SWS_OUT_BGR24: sws_vscale_rgb24_x8_kernel<SWS_OUT_BGR24><<<grid, block2, 0, stream>>>(m, c->dt, p.color, ng); break;
+                case SWS_OUT_RGBA:  sws_vscale_rgb24_x8_kernel<SWS_OUT_RGBA><<<grid, block2, 0, stream>>>(m, c->dt, p.color, ng); break;
+                case SWS_OUT_BGRA:  sws_vscale_rgb24_x8_kernel<SWS_OUT_BGRA><<<grid, block2, 0, stream>>>(m, c->dt, p.color, ng); break;
+                case SWS_OUT_ARGB:  sws_vscale_rgb24_x8_kernel<SWS_OUT_ARGB><<<grid, block2, 0, stream>>>(m, c->dt, p.color, ng); break;
+                default:            sws_vscale_rgb24_x8_kernel<SWS_OUT_ABGR><<<grid, block2, 0, stream>>>(m, c->dt, p.color, ng); break;
+                }
+            } else if (p.chrDstHSub) {
                 const int np = (p.dstW + 1) / 2;
                 dim3 block2(128), grid(b200_ceil_div(np, 128), R.ndy, nf);
                 sws_vscale_rgb24_slow_kernel<false><<<grid, block2, 0, stream>>>(m, c->dt, p.color, 0, np);
