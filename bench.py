@@ -97,6 +97,48 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU arms
+def gpu_numa_cpus(index):
+    """CPUs of the NUMA node the GPU hangs off (what `numactl --cpunodebind` would use), or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:                     # nvml prints an 8-digit domain, sysfs uses 4
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        return cpus or None
+    except Exception:
+        return None
+
+
+class near_gpu:
+    """Run the block on the CPUs next to the GPU, so that pinned host buffers allocated inside land on that NUMA node."""
+    def __init__(self, index):
+        self.cpus = gpu_numa_cpus(index)
+
+    def __enter__(self):
+        self.old = None
+        if self.cpus:
+            try:
+                self.old = os.sched_getaffinity(0)
+                os.sched_setaffinity(0, self.cpus & self.old or self.cpus)
+            except Exception:
+                self.old = None
+        return self
+
+    def __exit__(self, *a):
+        if self.old:
+            os.sched_setaffinity(0, self.old)
+
+
 def cpu_lib():
     import cpulibs as cl
     if cl.have_ref():
@@ -560,10 +602,12 @@ def run_b200(args, rank, world, local_rank):
     # ---- e2e: the C-ABI host entry point with pinned host buffers (H2D + kernels + D2H inside the timed region)
     e2e = None
     try:
-        hY = torch.empty((BATCH, H4K, W4K), dtype=torch.uint8).pin_memory()
-        hU = torch.empty((BATCH, H4K // 2, W4K // 2), dtype=torch.uint8).pin_memory()
-        hV = torch.empty((BATCH, H4K // 2, W4K // 2), dtype=torch.uint8).pin_memory()
-        hO = torch.empty((BATCH, H4K, W4K * 3), dtype=torch.uint8).pin_memory()
+        with near_gpu(local_rank) as ng:                 # host buffers on the GPU's NUMA node (numactl-style placement)
+            hY = torch.empty((BATCH, H4K, W4K), dtype=torch.uint8).pin_memory()
+            hU = torch.empty((BATCH, H4K // 2, W4K // 2), dtype=torch.uint8).pin_memory()
+            hV = torch.empty((BATCH, H4K // 2, W4K // 2), dtype=torch.uint8).pin_memory()
+            hO = torch.empty((BATCH, H4K, W4K * 3), dtype=torch.uint8).pin_memory()
+            hO.zero_()                                   # first touch here
         hY.copy_(Y.cpu()); hU.copy_(U.cpu()); hV.copy_(V.cpu())
         ctx = sw.sws_getContext(dev, W4K, H4K, sw.AV_PIX_FMT_YUV420P, W4K, H4K, sw.AV_PIX_FMT_RGB24, FLAGS_FATE)
         call = lambda: ctx.scale_batch_host([hY.data_ptr(), hU.data_ptr(), hV.data_ptr()], sstr, sfs, hO.data_ptr(),
@@ -584,7 +628,8 @@ def run_b200(args, rank, world, local_rank):
         ctx.free()
         e2e = {"value": world * BATCH * e2e_steps / dt, "unit": "frames/s", "h2d_bytes_per_step": FRAME_BYTES_IN * BATCH,
                "d2h_bytes_per_step": FRAME_BYTES_OUT * BATCH, "steps": e2e_steps, "matches_device_path": same,
-               "api": "b200_sws_scale_batch_host (C ABI, pinned host buffers)"}
+               "api": "b200_sws_scale_batch_host (C ABI, pinned host buffers)",
+               "host_buffers": "allocated on the GPU's NUMA node" if ng.cpus else "default placement"}
         del hY, hU, hV, hO
     except Exception as ex:                       # pinned allocation can fail on small hosts: report, do not fake
         e2e = {"value": None, "unit": "frames/s", "error": str(ex)[:200]}
