@@ -139,6 +139,17 @@ class near_gpu:
             os.sched_setaffinity(0, self.old)
 
 
+_STDOUT_FD = None
+
+
+def emit_line(line):
+    """The one JSON line, on the real stdout."""
+    sys.stdout.flush()
+    if _STDOUT_FD is not None:
+        os.dup2(_STDOUT_FD, 1)
+    print(json.dumps(line), flush=True)
+
+
 def cpu_lib():
     import cpulibs as cl
     if cl.have_ref():
@@ -654,7 +665,7 @@ def run_b200(args, rank, world, local_rank):
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "idct": idct, "mux_gather": mux, **results,
         }
-        print(json.dumps(line), flush=True)
+        emit_line(line)
     dev.close()
 
 
@@ -674,6 +685,12 @@ def main():
     if world > 1:
         import torch
         import torch.distributed as dist
+        # NCCL prints its version banner on stdout when the communicator comes up; stdout must carry the JSON line only, so
+        # everything before that line goes to stderr (emit_line() switches back)
+        global _STDOUT_FD
+        sys.stdout.flush()
+        _STDOUT_FD = os.dup(1)
+        os.dup2(2, 1)
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
