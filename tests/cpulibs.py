@@ -235,6 +235,39 @@ def orc_sws_planar(w, h, dw, dh, flags, y, u, v, **kw):
     return _sws_run_planar(oracle(), "orc", w, h, dw, dh, flags, y, u, v, **kw)
 
 
+NUT_PATH = os.path.join(ROOT, "oracle", "_ref", "libffnut.so")
+_nut = None
+
+
+def have_nut():
+    return os.path.exists(NUT_PATH)
+
+
+def nut_md5(buf, w, h, pix_fmt):
+    """md5 of the NUT stream FATE's `-vcodec rawvideo -f nut md5:` writes for one frame (oracle/ref/ref_nut.c drives the
+    reference's own NUT muxer); buf = the rawvideo packet (planes back to back, no padding)."""
+    global _nut
+    if _nut is None:
+        _nut = C.CDLL(NUT_PATH)
+        _nut.ffref_nut_md5.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    buf = np.ascontiguousarray(buf)
+    m = (C.c_uint8 * 16)()
+    n = _nut.ffref_nut_md5(buf.ctypes.data, buf.size, w, h, pix_fmt, m)
+    assert n > buf.size, n
+    return bytes(m).hex()
+
+
+def fate_pixfmts_goldens():
+    rows = []
+    for line in open(os.path.join(ROOT, "tests", "golden", "fate_pixfmts.txt")):
+        if line.startswith("#") or not line.strip():
+            continue
+        where, test, fmt, size, md5 = line.split()
+        w, h = (int(v) for v in size.split("x"))
+        rows.append((where, test, fmt, w, h, md5))
+    return rows
+
+
 COEFFS = {  # libswscale/yuv2rgb.c:47-59, indexed by SWS_CS_*
     0: (104597, 132201, 25675, 53279), 1: (117489, 138438, 13975, 34925), 2: (104597, 132201, 25675, 53279),
     3: (104597, 132201, 25675, 53279), 4: (104448, 132798, 24759, 53109), 5: (104597, 132201, 25675, 53279),

@@ -388,3 +388,20 @@ def test_vsynth1_frame0(device):
     assert np.array_equal(gpu_sws(device, 352, 288, 352, 288, FATE, y, u, v), g["rgb_same"])
     assert np.array_equal(gpu_sws(device, 352, 288, 200, 100, FATE, y, u, v), g["rgb_200x100"])
     assert np.array_equal(gpu_sws(device, 352, 288, 352, 288, cl.SWS_BICUBIC, y, u, v), g["rgb_lut"])
+
+
+def test_fate_filter_pixfmts_md5(device):
+    """The CUDA path's frames, wrapped by the reference's NUT muxer exactly as FATE does, hash to the md5 sums the
+    reference tree commits for filter-pixfmts-null / -scale (tests/golden/fate_pixfmts.txt cites each line)."""
+    import functools
+    from test_fate_golden import fate_frame, FMT_ID
+    if not cl.have_nut():
+        pytest.skip("oracle/_ref/libffnut.so not built")
+    try:
+        cl.nut_md5(np.zeros(16 * 16 * 3, np.uint8), 16, 16, cl.PIX_FMT_RGB24)
+    except (OSError, AssertionError) as e:
+        pytest.skip(f"libffnut.so not usable on this box: {e}")
+    rgb, planar = functools.partial(gpu_sws, device), functools.partial(gpu_sws_planar, device)
+    for where, test, fmt, w, h, md5 in cl.fate_pixfmts_goldens():
+        frame, _ = fate_frame(rgb, planar, fmt, w, h)
+        assert cl.nut_md5(frame, w, h, FMT_ID[fmt]) == md5, (where, test, fmt)
