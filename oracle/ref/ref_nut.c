@@ -26,6 +26,7 @@
 #include "libavutil/dict.h"
 #include "libavutil/log.h"
 #include "libavutil/pixdesc.h"
+#include "libavutil/mathematics.h"
 #include "libavcodec/packet.h"
 #include "libavcodec/codec_par.h"
 #include "libavcodec/raw.h"
@@ -35,8 +36,10 @@
 
 extern const FFOutputFormat ff_nut_muxer;
 
-/* frame: the rawvideo packet (planes back to back, line size = width * bytes per pixel); returns the NUT stream size */
-API int ffref_nut_md5(const uint8_t *frame, int size, int w, int h, int pix_fmt, uint8_t md5[16])
+/* frames: nframes rawvideo packets of `size` bytes back to back (each: planes back to back, line size = width * bytes
+ * per pixel), pts 0,1,2...; returns the NUT stream size.  nframes = 1 is the filter-pixfmts-* command, nframes = 5 the
+ * filter-pixdesc-* one (tests/fate-run.sh:599-618, `-frames:v 5`). */
+API int ffref_nut_md5_frames(const uint8_t *frames, int size, int nframes, int w, int h, int pix_fmt, uint8_t md5[16])
 {
     AVFormatContext *s = avformat_alloc_context();
     AVPacket *pkt = NULL;
@@ -68,13 +71,19 @@ API int ffref_nut_md5(const uint8_t *frame, int size, int w, int h, int pix_fmt,
     if (avio_open_dyn_buf(&s->pb) < 0) goto end;
     if ((ret = avformat_write_header(s, NULL)) < 0) goto end;
     pkt = av_packet_alloc();
-    if (!pkt || av_new_packet(pkt, size) < 0) { ret = -1; goto end; }
-    memcpy(pkt->data, frame, size);
-    pkt->pts = pkt->dts = 0;
-    pkt->duration = 1;
-    pkt->flags |= AV_PKT_FLAG_KEY;
-    pkt->stream_index = 0;
-    if ((ret = av_write_frame(s, pkt)) < 0) goto end;
+    if (!pkt) { ret = -1; goto end; }
+    for (int i = 0; i < nframes; i++) {
+        if (av_new_packet(pkt, size) < 0) { ret = -1; goto end; }
+        memcpy(pkt->data, frames + (size_t)i * size, size);
+        /* the muxer picked its own stream time base in write_header (nutenc.c:753-756); the tool rescales the
+         * encoder's 1/25 timestamps to it (fftools/ffmpeg_mux.c) */
+        pkt->pts = pkt->dts = av_rescale_q(i, (AVRational){ 1, 25 }, st->time_base);
+        pkt->duration = av_rescale_q(1, (AVRational){ 1, 25 }, st->time_base);
+        pkt->flags |= AV_PKT_FLAG_KEY;
+        pkt->stream_index = 0;
+        if ((ret = av_write_frame(s, pkt)) < 0) goto end;
+        av_packet_unref(pkt);
+    }
     av_write_trailer(s);
     n = avio_close_dyn_buf(s->pb, &buf);
     s->pb = NULL;
@@ -86,6 +95,11 @@ end:
     if (s && s->pb) { uint8_t *b2 = NULL; avio_close_dyn_buf(s->pb, &b2); av_free(b2); s->pb = NULL; }
     avformat_free_context(s);
     return ret;
+}
+
+API int ffref_nut_md5(const uint8_t *frame, int size, int w, int h, int pix_fmt, uint8_t md5[16])
+{
+    return ffref_nut_md5_frames(frame, size, 1, w, h, pix_fmt, md5);
 }
 
 /* ------------------------------------------------------------------ never reached for one rawvideo stream */
@@ -110,8 +124,11 @@ const char *avio_find_protocol_name(const char *url) { return NULL; }
 int avio_close(AVIOContext *s) { return 0; }
 const AVOutputFormat *av_muxer_iterate(void **opaque) { return NULL; }
 const AVInputFormat *av_demuxer_iterate(void **opaque) { return NULL; }
-int av_index_search_timestamp(AVStream *st, int64_t ts, int flags) { return -1; }
-int av_add_index_entry(AVStream *st, int64_t pos, int64_t ts, int size, int distance, int flags) { return 0; }
+/* seek.c (the stream index the muxer keeps for syncpoint back pointers) reaches these only when demuxing; a muxed stream
+ * has pts_wrap_behavior = AV_PTS_WRAP_IGNORE, for which libavformat/demux.c:52-54 returns the timestamp unchanged */
+int64_t ff_wrap_timestamp(const AVStream *st, int64_t timestamp) { return timestamp; }
+int av_read_frame(AVFormatContext *s, AVPacket *pkt) { return -1; }
+int avformat_queue_attached_pictures(AVFormatContext *s) { return -1; }
 /* avformat_new_stream() wants an internal codec context; the NUT muxing path never looks inside it */
 AVCodecContext *avcodec_alloc_context3(const AVCodec *c) { return av_mallocz(16384); }
 void ff_parse_specific_params(AVStream *st, int *au_rate, int *au_ssize, int *au_scale) { *au_rate = 1; *au_ssize = 1; *au_scale = 1; }

@@ -243,16 +243,18 @@ def have_nut():
     return os.path.exists(NUT_PATH)
 
 
-def nut_md5(buf, w, h, pix_fmt):
-    """md5 of the NUT stream FATE's `-vcodec rawvideo -f nut md5:` writes for one frame (oracle/ref/ref_nut.c drives the
-    reference's own NUT muxer); buf = the rawvideo packet (planes back to back, no padding)."""
+def nut_md5(frames, w, h, pix_fmt):
+    """md5 of the NUT stream FATE's `-vcodec rawvideo -f nut md5:` writes (oracle/ref/ref_nut.c drives the reference's own
+    NUT muxer); frames = one rawvideo packet (planes back to back, no padding) or a list of them."""
     global _nut
     if _nut is None:
         _nut = C.CDLL(NUT_PATH)
-        _nut.ffref_nut_md5.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
-    buf = np.ascontiguousarray(buf)
+        _nut.ffref_nut_md5_frames.argtypes = [C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]
+    if not isinstance(frames, (list, tuple)):
+        frames = [frames]
+    buf = np.concatenate([np.ascontiguousarray(f).ravel() for f in frames])
     m = (C.c_uint8 * 16)()
-    n = _nut.ffref_nut_md5(buf.ctypes.data, buf.size, w, h, pix_fmt, m)
+    n = _nut.ffref_nut_md5_frames(buf.ctypes.data, buf.size // len(frames), len(frames), w, h, pix_fmt, m)
     assert n > buf.size, n
     return bytes(m).hex()
 
@@ -262,10 +264,29 @@ def fate_pixfmts_goldens():
     for line in open(os.path.join(ROOT, "tests", "golden", "fate_pixfmts.txt")):
         if line.startswith("#") or not line.strip():
             continue
-        where, test, fmt, size, md5 = line.split()
+        where, test, fmt, size, nframes, md5 = line.split()
         w, h = (int(v) for v in size.split("x"))
-        rows.append((where, test, fmt, w, h, md5))
+        rows.append((where, test, fmt, w, h, int(nframes), md5))
     return rows
+
+
+VIDEOGEN = os.path.join(ROOT, "oracle", "_ref", "videogen")
+
+
+def vsynth1_frames(n):
+    """frames 0..n-1 of FATE's vsynth1 as (y, u, v): runs the reference's generator (tests/videogen.c, compiled by
+    oracle/ref/Makefile) and unpacks its pgmyuv files (Y plane, then rows of U|V)"""
+    import subprocess, tempfile
+    out = []
+    with tempfile.TemporaryDirectory() as td:
+        subprocess.run([VIDEOGEN, td + "/"], check=True, stdout=subprocess.DEVNULL)
+        for i in range(n):
+            raw = open(os.path.join(td, f"{i:02d}.pgm"), "rb").read()
+            hdr, rest = raw.split(b"\n255\n", 1)
+            assert hdr.split() == [b"P5", b"352", b"432"], hdr
+            a = np.frombuffer(rest, np.uint8).reshape(432, 352)
+            out.append(tuple(np.ascontiguousarray(p) for p in (a[:288], a[288:, :176], a[288:, 176:])))
+    return out
 
 
 COEFFS = {  # libswscale/yuv2rgb.c:47-59, indexed by SWS_CS_*

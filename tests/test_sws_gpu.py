@@ -392,16 +392,15 @@ def test_vsynth1_frame0(device):
 
 def test_fate_filter_pixfmts_md5(device):
     """The CUDA path's frames, wrapped by the reference's NUT muxer exactly as FATE does, hash to the md5 sums the
-    reference tree commits for filter-pixfmts-null / -scale (tests/golden/fate_pixfmts.txt cites each line)."""
+    reference tree commits for filter-pixfmts-{null,copy,vflip,hflip,crop,scale} and filter-pixdesc-* (5 frames) —
+    tests/golden/fate_pixfmts.txt cites each line."""
     import functools
-    from test_fate_golden import fate_frame, FMT_ID
-    if not cl.have_nut():
-        pytest.skip("oracle/_ref/libffnut.so not built")
+    import test_fate_golden as fg
+    if not (cl.have_nut() and os.path.exists(cl.VIDEOGEN)):
+        pytest.skip("oracle/_ref/libffnut.so / videogen not built")
     try:
         cl.nut_md5(np.zeros(16 * 16 * 3, np.uint8), 16, 16, cl.PIX_FMT_RGB24)
-    except (OSError, AssertionError) as e:
-        pytest.skip(f"libffnut.so not usable on this box: {e}")
-    rgb, planar = functools.partial(gpu_sws, device), functools.partial(gpu_sws_planar, device)
-    for where, test, fmt, w, h, md5 in cl.fate_pixfmts_goldens():
-        frame, _ = fate_frame(rgb, planar, fmt, w, h)
-        assert cl.nut_md5(frame, w, h, FMT_ID[fmt]) == md5, (where, test, fmt)
+        cl.vsynth1_frames(1)
+    except Exception as e:                                                # checker tools, not the product: skip, never fail
+        pytest.skip(f"oracle/_ref tools not usable on this box: {e}")
+    fg.check_all(functools.partial(gpu_sws, device), functools.partial(gpu_sws_planar, device))
