@@ -591,6 +591,20 @@ sws_vscale_planar_kernel(const int16_t *src, int sls, long long sfs, int nlines,
     dst[f * dfs + (long long)dy * ds + x] = (uint8_t)clamp_u8(val);
 }
 
+// lumRangeToJpeg_c / lumRangeFromJpeg_c / chrRange*_c (swscale.c:163-209) applied in place to the horizontally scaled lines,
+// where the reference calls them (hscale.c:61-63, :195-197): v = (v * coeff + offset) >> 14, limited -> full clips at 2^15-1.
+// One thread per sample; grid x over the line, y over lines, z over frames (dfs in int16 elements).
+__global__ void __launch_bounds__(256)
+sws_range_kernel(int16_t *mid, int w, long long dfs, int coeff, int offset, int clip)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= w) return;
+    int16_t *p = mid + (long long)blockIdx.z * dfs + (long long)blockIdx.y * w + x;
+    int v = ((int)*p * coeff + offset) >> 14;
+    if (clip) v = min(v, 32767);
+    *p = (int16_t)v;
+}
+
 // four adjacent samples per thread: 64-bit loads of the int16 lines, one 32-bit store (w % 4 == 0, 4-aligned destination)
 __global__ void __launch_bounds__(256)
 sws_vscale_planar4_kernel(const int16_t *src, int sls, long long sfs, int nlines, uint8_t *dst, long long ds, long long dfs,
@@ -788,6 +802,12 @@ static int upload_tables(B200SwsContext *c)
 B200_API B200SwsContext *b200_sws_getContext(B200Device *dev, int srcW, int srcH, int srcFormat,
                                              int dstW, int dstH, int dstFormat, int flags)
 {
+    return b200_sws_getContext_range(dev, srcW, srcH, srcFormat, 0, dstW, dstH, dstFormat, 0, flags);
+}
+
+B200_API B200SwsContext *b200_sws_getContext_range(B200Device *dev, int srcW, int srcH, int srcFormat, int srcRange,
+                                                   int dstW, int dstH, int dstFormat, int dstRange, int flags)
+{
     if (!dev) { b200_set_error("b200_sws_getContext: no device"); return nullptr; }
     SwsOutFmt out;
     const bool src_ok = srcFormat == B200_PIX_FMT_YUV420P || srcFormat == B200_PIX_FMT_NV12 || srcFormat == B200_PIX_FMT_NV21;
@@ -800,7 +820,7 @@ B200_API B200SwsContext *b200_sws_getContext(B200Device *dev, int srcW, int srcH
     c->dev = dev;
     c->plan.out = out;
     c->plan.src_nv = srcFormat == B200_PIX_FMT_NV12 ? 1 : srcFormat == B200_PIX_FMT_NV21 ? 2 : 0;
-    int ret = sws_plan_build(c->plan, srcW, srcH, dstW, dstH, flags);
+    int ret = sws_plan_build(c->plan, srcW, srcH, dstW, dstH, flags, srcRange, dstRange);
     if (ret < 0) { b200_set_error("b200_sws_getContext: unsupported configuration (%d)", ret); delete c; return nullptr; }
     cudaSetDevice(dev->ordinal);
     if (upload_tables(c) < 0) { delete c; return nullptr; }
@@ -822,9 +842,11 @@ B200_API void b200_sws_freeContext(B200SwsContext *c)
 B200_API int b200_sws_setColorspaceDetails(B200SwsContext *c, const int inv_table[4], int srcRange,
                                            const int table[4], int dstRange, int brightness, int contrast, int saturation)
 {
-    (void)table; (void)dstRange;          // dst is RGB: range_override_needed(), utils.c:844-880
-    if (!c || !inv_table) return B200_EINVAL;
-    return sws_plan_colorspace(c->plan, inv_table, srcRange, brightness, contrast, saturation);
+    if (!c || !inv_table || !table) return B200_EINVAL;
+    const int ret = sws_plan_colorspace_details(c->plan, inv_table, srcRange, table, dstRange, brightness, contrast, saturation);
+    if (ret == B200_ENOSYS)
+        b200_set_error("sws_setColorspaceDetails: yuv -> yuv with different matrices (the reference cascades through bgr24) is not implemented");
+    return ret;
 }
 
 B200_API int b200_sws_info(const B200SwsContext *c, int *o)
@@ -1174,6 +1196,11 @@ static int launch_planar(B200SwsContext *c, cudaStream_t stream, const uint8_t *
                 launch_hscale(stream, src[pl] + (long long)f0 * sfs[pl], sstr[pl], sfs[pl], m[pl], dw[pl], (long long)(perFrame / 2),
                               hc[pl], hp[pl], hs[pl], 0, sh[pl], nf);
             B200_LAUNCHED();
+            if (p.range_conv) {
+                sws_range_kernel<<<gh, block, 0, stream>>>(m[pl], dw[pl], (long long)(perFrame / 2), pl ? p.chrRangeCoeff : p.lumRangeCoeff,
+                                                           pl ? p.chrRangeOffset : p.lumRangeOffset, p.range_conv == 1);
+                B200_LAUNCHED();
+            }
             uint8_t *dpl = dst[pl] + (long long)f0 * dfs[pl];
             const bool v4 = dw[pl] % 4 == 0 && (plane[0] % 8 == 0) && (plane[1] % 8 == 0) &&
                             (((uintptr_t)dpl | (uintptr_t)dstr[pl] | (uintptr_t)dfs[pl]) & 3) == 0;

@@ -10,6 +10,7 @@
 #include "sws_plan.h"
 #include "b200dsp.h"
 #include <cstdlib>
+#include <cstring>
 #include <cmath>
 #include <algorithm>
 #include <limits>
@@ -256,6 +257,50 @@ int sws_plan_colorspace(SwsPlan &p, const int inv_table[4], int fullRange, int b
     return 0;
 }
 
+// solve_range_convert (swscale.c:577-589) for an 8-bit destination: src_bits 15, src_shift 7, mult_shift 14
+// (init_range_convert_constants, :591-600); the line functions narrow the coefficient to uint16 and the offset to int32
+static void solve_range(unsigned srcMin, unsigned srcMax, unsigned dstMin, unsigned dstMax, int &coeff, int &offset)
+{
+    const int srcShift = 7, multShift = 14, totalShift = srcShift + multShift;
+    const uint64_t srcRange = srcMax - srcMin, dstRange = dstMax - dstMin;
+    const uint64_t q = (dstRange << totalShift) / srcRange;
+    const uint32_t c = (uint32_t)((q + (1u << srcShift) - 1) >> srcShift);                      // AV_CEIL_RSHIFT
+    const i64 o = ((i64)dstMax << totalShift) - ((i64)srcMax << srcShift) * c + (1u << (multShift - 1));
+    coeff = (uint16_t)c;
+    offset = (int32_t)o;
+}
+
+// ff_sws_init_range_convert (swscale.c:626-660): only a yuv destination converts, and only when the ranges differ
+static void plan_range_convert(SwsPlan &p)
+{
+    p.range_conv = 0;
+    if (p.src_range == p.dst_range || p.out.kind != SWS_OUT_YUV420P) return;
+    if (p.src_range) {
+        solve_range(0, 255, 16, 235, p.lumRangeCoeff, p.lumRangeOffset);
+        solve_range(0, 255, 16, 240, p.chrRangeCoeff, p.chrRangeOffset);
+        p.range_conv = 2;
+    } else {
+        solve_range(16, 235, 0, 255, p.lumRangeCoeff, p.lumRangeOffset);
+        solve_range(16, 240, 0, 255, p.chrRangeCoeff, p.chrRangeOffset);
+        p.range_conv = 1;
+    }
+}
+
+int sws_plan_colorspace_details(SwsPlan &p, const int inv_table[4], int srcRange, const int table[4], int dstRange,
+                                int brightness, int contrast, int saturation)
+{
+    const bool yuvDst = p.out.kind == SWS_OUT_YUV420P;
+    if (!yuvDst) dstRange = 0;                                                   // range_override_needed(dst), utils.c:877-878
+    memcpy(p.src_cs, inv_table, sizeof(p.src_cs));
+    memcpy(p.dst_cs, table, sizeof(p.dst_cs));
+    p.src_range = srcRange;
+    p.dst_range = dstRange;
+    plan_range_convert(p);
+    if (yuvDst)     // utils.c:910-989: with different matrices the reference cascades yuv -> bgr24 -> yuv; that needs the rgb readers
+        return memcmp(p.src_cs, p.dst_cs, sizeof(p.src_cs)) ? B200_ENOSYS : 0;
+    return sws_plan_colorspace(p, inv_table, srcRange, brightness, contrast, saturation);
+}
+
 bool sws_out_format(int f, SwsOutFmt &o)
 {
     switch (f) {
@@ -270,7 +315,7 @@ bool sws_out_format(int f, SwsOutFmt &o)
     return false;
 }
 
-int sws_plan_build(SwsPlan &p, int srcW, int srcH, int dstW, int dstH, int flags)
+int sws_plan_build(SwsPlan &p, int srcW, int srcH, int dstW, int dstH, int flags, int srcRange, int dstRange)
 {
     if (srcW < 1 || srcH < 1 || dstW < 1 || dstH < 1) return B200_EINVAL;
     int algo = flags & 0x7FF;                                                    // scaler bits, utils.c:1196-1222
@@ -291,11 +336,13 @@ int sws_plan_build(SwsPlan &p, int srcW, int srcH, int dstW, int dstH, int flags
     p.chrDstW = chroma_shift_up(dstW, p.chrDstHSub);
     p.chrDstH = chroma_shift_up(dstH, chrDstVSub);                               // packed RGB has no vertical chroma subsampling
     static const int bt601[4] = { 104597, 132201, 25675, 53279 };                // ff_yuv2rgb_coeffs[SWS_CS_DEFAULT], yuv2rgb.c:47-59
-    int ret = sws_plan_colorspace(p, bt601, 0, 0, 1 << 16, 1 << 16);
+    // utils.c:1164-1167: the ranges the context holds at initialisation go through sws_setColorspaceDetails
+    int ret = sws_plan_colorspace_details(p, bt601, srcRange, bt601, dstRange, 0, 1 << 16, 1 << 16);
     if (ret < 0) return ret;
 
-    // unscaled special converter gate: swscale_unscaled.c:2426-2431 reached from utils.c:1623-1637
-    p.planar_copy = p.planar && srcW == dstW && srcH == dstH;
+    // unscaled special converter gate: swscale_unscaled.c:2426-2431 reached from utils.c:1623-1637; a yuv destination only
+    // looks for one when no range conversion is due (utils.c:1624-1626)
+    p.planar_copy = p.planar && srcW == dstW && srcH == dstH && p.src_range == p.dst_range;
     if (p.planar_copy) return 0;
     // (only planar yuv420p / yuv422p sources have the LUT converter; nv12 / nv21 go through the scaler)
     p.unscaled_lut = !p.planar && !p.src_nv && srcW == dstW && srcH == dstH && !(flags & B200_SWS_ACCURATE_RND) && !(dstH & 1);

@@ -40,6 +40,11 @@ struct SwsPlan {
     int lumXInc = 0, chrXInc = 0; // 16.16 horizontal steps (utils.c:1250,1425)
     bool planar = false;          // destination yuv420p (yuv2planeX / yuv2plane1 writers, vscale.c:34-107)
     bool planar_copy = false;     // same size yuv420p -> yuv420p: planarCopyWrapper (swscale_unscaled.c:2220,2675-2693)
+    // yuv -> yuv range conversion of the 15-bit lines between the two passes (swscale.c:163-209; constants :577-624)
+    int src_range = 0, dst_range = 0;            // SwsContext.src_range / .dst_range (0 limited, non-zero full)
+    int range_conv = 0;           // 0 none, 1 limited -> full (lum/chrRangeToJpeg_c: clips at 2^15-1), 2 full -> limited (FromJpeg)
+    int lumRangeCoeff = 0, lumRangeOffset = 0, chrRangeCoeff = 0, chrRangeOffset = 0;
+    int src_cs[4] = { 104597, 132201, 25675, 53279 }, dst_cs[4] = { 104597, 132201, 25675, 53279 };   // colorspace tables as last set
     SwsFilterBank hLum, hChr, vLum, vChr;
     SwsColorConst color{};
     // per output line: writer selected by packed_vscale (vscale.c:144-169): 0 = _X, 1 = _1, 2 = _2, plus alphas
@@ -47,5 +52,9 @@ struct SwsPlan {
 };
 
 // returns 0 or a negative B200_E* code
-int sws_plan_build(SwsPlan &p, int srcW, int srcH, int dstW, int dstH, int flags);
+// srcRange / dstRange: the values SwsContext.src_range / .dst_range hold when sws_init_context runs
+int sws_plan_build(SwsPlan &p, int srcW, int srcH, int dstW, int dstH, int flags, int srcRange = 0, int dstRange = 0);
+// sws_setColorspaceDetails (utils.c:849-1004): RGB destination -> look-up constants; yuv destination -> ranges + range conversion
+int sws_plan_colorspace_details(SwsPlan &p, const int inv_table[4], int srcRange, const int table[4], int dstRange,
+                                int brightness, int contrast, int saturation);
 int sws_plan_colorspace(SwsPlan &p, const int inv_table[4], int fullRange, int brightness, int contrast, int saturation);

@@ -28,13 +28,14 @@ def _dptr(x):
 
 
 class SwsContext:
-    def __init__(self, device, srcW, srcH, srcFormat, dstW, dstH, dstFormat, flags):
+    def __init__(self, device, srcW, srcH, srcFormat, dstW, dstH, dstFormat, flags, src_range=0, dst_range=0):
+        """src_range / dst_range: SwsContext.src_range / .dst_range as set before sws_init_context (0 limited, 1 full)"""
         self.device = device
         self.srcW, self.srcH, self.dstW, self.dstH, self.flags = srcW, srcH, dstW, dstH, flags
         self.srcFormat, self.dstFormat = srcFormat, dstFormat
         self.planar = dstFormat == AV_PIX_FMT_YUV420P
         self.bpp = 1 if self.planar else 3 if dstFormat in (AV_PIX_FMT_RGB24, AV_PIX_FMT_BGR24) else 4
-        h = lib().b200_sws_getContext(device.handle, srcW, srcH, srcFormat, dstW, dstH, dstFormat, flags)
+        h = lib().b200_sws_getContext_range(device.handle, srcW, srcH, srcFormat, src_range, dstW, dstH, dstFormat, dst_range, flags)
         if not h:
             raise B200Error("sws_getContext failed: " + lib().b200_last_error().decode())
         self._h = vp(h)
@@ -125,5 +126,5 @@ class SwsContext:
             pass
 
 
-def sws_getContext(device, srcW, srcH, srcFormat, dstW, dstH, dstFormat, flags):
-    return SwsContext(device, srcW, srcH, srcFormat, dstW, dstH, dstFormat, flags)
+def sws_getContext(device, srcW, srcH, srcFormat, dstW, dstH, dstFormat, flags, src_range=0, dst_range=0):
+    return SwsContext(device, srcW, srcH, srcFormat, dstW, dstH, dstFormat, flags, src_range, dst_range)

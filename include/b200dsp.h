@@ -93,8 +93,20 @@ typedef struct B200SwsContext B200SwsContext;
 /* like sws_getContext(); srcFilter/dstFilter/param are not supported (must be the defaults). NULL on failure. */
 B200SwsContext *b200_sws_getContext(B200Device *dev, int srcW, int srcH, int srcFormat,
                                     int dstW, int dstH, int dstFormat, int flags);
+/* The same with SwsContext.src_range / .dst_range (libswscale/swscale.h, AVOption "src_range" / "dst_range"; 0 = limited,
+ * 1 = full) set before sws_init_context(), the way vf_scale's in_range / out_range reach the scaler (libswscale/utils.c:
+ * 1164-1167).  With a yuv420p destination and different ranges the 15-bit lines are range-converted between the horizontal
+ * and the vertical pass (lumRangeToJpeg_c ... chrRangeFromJpeg_c, libswscale/swscale.c:163-209, :577-660) and the same-size
+ * case goes through the scaler instead of planarCopyWrapper (utils.c:1623-1626).  For RGB destinations dstRange is ignored
+ * and srcRange selects the look-up tables, as in the reference. */
+B200SwsContext *b200_sws_getContext_range(B200Device *dev, int srcW, int srcH, int srcFormat, int srcRange,
+                                          int dstW, int dstH, int dstFormat, int dstRange, int flags);
 void b200_sws_freeContext(B200SwsContext *c);
-/* like sws_setColorspaceDetails(); `table`/dstRange are accepted and ignored for RGB output like the reference */
+/* like sws_setColorspaceDetails() (libswscale/utils.c:849-1004).  RGB destination: `table` / dstRange are accepted and
+ * ignored like the reference.  yuv420p destination: the ranges are stored and the range conversion is re-selected
+ * (brightness / contrast / saturation do not apply); a context that was initialised as a plain copy (same size, equal
+ * ranges) stays one, as in the reference, where convert_unscaled is chosen once at init.  inv_table != table for
+ * yuv -> yuv makes the reference cascade through bgr24: not implemented, B200_ENOSYS. */
 int  b200_sws_setColorspaceDetails(B200SwsContext *c, const int inv_table[4], int srcRange,
                                    const int table[4], int dstRange, int brightness, int contrast, int saturation);
 /* drop-in for sws_scale(): HOST pointers, strides in bytes (negative allowed), returns output lines.

@@ -49,10 +49,17 @@ OrcSws *orc_sws_open(int srcW, int srcH, int dstW, int dstH, int flags);        
 OrcSws *orc_sws_open_fmt(int srcW, int srcH, int dstW, int dstH, int dstFormat, int flags);                 /* yuv420p source */
 /* srcFormat yuv420p, nv12 or nv21: for the semi-planar sources the scale calls take the interleaved plane as `u` (`v` unused) */
 OrcSws *orc_sws_open_io(int srcFormat, int srcW, int srcH, int dstFormat, int dstW, int dstH, int flags);
+/* src_range / dst_range (0 = limited "mpeg", 1 = full "jpeg") given before initialisation, like SwsContext.src_range /
+ * .dst_range set ahead of sws_init_context; only a yuv destination converts ranges (swscale.c:626-660) */
+OrcSws *orc_sws_open_range(int srcFormat, int srcW, int srcH, int srcRange, int dstFormat, int dstW, int dstH, int dstRange, int flags);
 void    orc_sws_close(OrcSws *s);
 /* inv_table = 4 coefficients as ff_yuv2rgb_coeffs rows; contrast/saturation 16.16 */
 int     orc_sws_set_colorspace(OrcSws *s, const int inv_table[4], int srcRange,
                                int brightness, int contrast, int saturation);
+/* the full sws_setColorspaceDetails(): for a yuv destination the ranges are kept and the range conversion between the two
+ * passes is re-selected; different matrices for yuv -> yuv (the reference cascades through bgr24) are not restated: -1 */
+int     orc_sws_set_colorspace_details(OrcSws *s, const int inv_table[4], int srcRange, const int table[4], int dstRange,
+                                       int brightness, int contrast, int saturation);
 /* whole-frame conversion; returns number of output lines or <0 */
 int     orc_sws_scale(OrcSws *s, const uint8_t *y, int ys, const uint8_t *u, int us,
                       const uint8_t *v, int vs, uint8_t *dst, int ds);

@@ -76,6 +76,23 @@ API void *ffref_sws_open_io(int srcFormat, int srcW, int srcH, int dstFormat, in
     return c;
 }
 
+/* src_range / dst_range set on the context before sws_init_context (SwsContext fields, swscale.h), the way vf_scale's
+ * in_range / out_range reach the scaler: with a yuv destination and different ranges the range conversion of
+ * swscale.c:163-209 runs between the horizontal and the vertical pass */
+API void *ffref_sws_open_range(int srcFormat, int srcW, int srcH, int srcRange, int dstFormat, int dstW, int dstH, int dstRange,
+                               int flags, int threads)
+{
+    SwsContext *c = sws_alloc_context();
+    if (!c) return NULL;
+    c->src_w = srcW; c->src_h = srcH; c->dst_w = dstW; c->dst_h = dstH;
+    c->src_format = srcFormat; c->dst_format = dstFormat;
+    c->src_range = srcRange; c->dst_range = dstRange;
+    c->flags = flags;
+    c->threads = threads;
+    if (sws_init_context(c, NULL, NULL) < 0) { sws_freeContext(c); return NULL; }
+    return c;
+}
+
 API void ffref_sws_close(void *h) { sws_freeContext((SwsContext *)h); }
 
 /* colorspace details pass-through (sws_setColorspaceDetails); table index = SWS_CS_* */

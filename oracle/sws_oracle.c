@@ -41,6 +41,11 @@ struct OrcSws {
     uint8_t ytab[YTAB_SIZE];
     int offR[NTAB], offGU[NTAB], offGV[NTAB], offB[NTAB];
     int y_offset, y_coeff, v2r, v2g, u2g, u2b;   /* int16 values for the full-chroma writer */
+    /* yuv -> yuv range conversion on the 15-bit lines between the two passes (swscale.c:163-209, :577-660) */
+    int src_range, dst_range;
+    int range_conv;            /* 0 none, 1 limited -> full (lum/chrRangeToJpeg_c, clips at 2^15-1), 2 full -> limited (FromJpeg) */
+    int lum_coeff, lum_offset, chr_coeff, chr_offset;
+    int src_cs[4], dst_cs[4];
 };
 
 static int64_t i64abs(int64_t a) { return a < 0 ? -a : a; }
@@ -280,6 +285,50 @@ int orc_sws_set_colorspace(OrcSws *s, const int inv_table[4], int fullRange,
 
 static const int default_coeffs[4] = { 104597, 132201, 25675, 53279 };  /* yuv2rgb.c:47-59 row SWS_CS_DEFAULT */
 
+/* solve_range_convert (swscale.c:577-589) for an 8-bit destination: src_bits 15, src_shift 7, mult_shift 14
+ * (init_range_convert_constants, :591-600).  The line functions take the coefficient as uint16 and the offset as int32. */
+static void solve_range(unsigned src_min, unsigned src_max, unsigned dst_min, unsigned dst_max, int *coeff, int *offset)
+{
+    const int src_shift = 7, mult_shift = 14, total_shift = mult_shift + src_shift;
+    const uint64_t src_range = src_max - src_min, dst_range = dst_max - dst_min;
+    const uint64_t q = (dst_range << total_shift) / src_range;
+    const uint32_t c = (uint32_t)((q + (1u << src_shift) - 1) >> src_shift);                   /* AV_CEIL_RSHIFT */
+    const int64_t  o = ((int64_t)dst_max << total_shift) - ((int64_t)src_max << src_shift) * c + (1u << (mult_shift - 1));
+    *coeff  = (uint16_t)c;
+    *offset = (int32_t)o;
+}
+
+/* ff_sws_init_range_convert (swscale.c:626-660) */
+static void init_range_convert(OrcSws *s)
+{
+    s->range_conv = 0;
+    if (s->src_range == s->dst_range || !s->planar) return;
+    if (s->src_range) {                                              /* full -> limited */
+        solve_range(0, 255, 16, 235, &s->lum_coeff, &s->lum_offset);
+        solve_range(0, 255, 16, 240, &s->chr_coeff, &s->chr_offset);
+        s->range_conv = 2;
+    } else {                                                         /* limited -> full */
+        solve_range(16, 235, 0, 255, &s->lum_coeff, &s->lum_offset);
+        solve_range(16, 240, 0, 255, &s->chr_coeff, &s->chr_offset);
+        s->range_conv = 1;
+    }
+}
+
+/* sws_setColorspaceDetails (utils.c:849-1004) */
+int orc_sws_set_colorspace_details(OrcSws *s, const int inv_table[4], int srcRange, const int table[4], int dstRange,
+                                   int brightness, int contrast, int saturation)
+{
+    if (!s->planar) dstRange = 0;                                    /* range_override_needed(dst), utils.c:877-878 */
+    memcpy(s->src_cs, inv_table, sizeof(s->src_cs));
+    memcpy(s->dst_cs, table, sizeof(s->dst_cs));
+    s->src_range = srcRange;
+    s->dst_range = dstRange;
+    init_range_convert(s);
+    if (s->planar)                                                   /* utils.c:910-989: other matrices would cascade via bgr24 */
+        return memcmp(s->src_cs, s->dst_cs, sizeof(s->src_cs)) ? -1 : 0;
+    return orc_sws_set_colorspace(s, inv_table, srcRange, brightness, contrast, saturation);
+}
+
 OrcSws *orc_sws_open(int srcW, int srcH, int dstW, int dstH, int flags)
 {
     return orc_sws_open_fmt(srcW, srcH, dstW, dstH, ORC_PIX_FMT_RGB24, flags);
@@ -312,6 +361,11 @@ OrcSws *orc_sws_open_fmt(int srcW, int srcH, int dstW, int dstH, int dstFormat, 
 
 OrcSws *orc_sws_open_io(int srcFormat, int srcW, int srcH, int dstFormat, int dstW, int dstH, int flags)
 {
+    return orc_sws_open_range(srcFormat, srcW, srcH, 0, dstFormat, dstW, dstH, 0, flags);
+}
+
+OrcSws *orc_sws_open_range(int srcFormat, int srcW, int srcH, int srcRange, int dstFormat, int dstW, int dstH, int dstRange, int flags)
+{
     if (srcW < 1 || srcH < 1 || dstW < 1 || dstH < 1) return NULL;
     if (srcFormat != ORC_PIX_FMT_YUV420P && srcFormat != ORC_PIX_FMT_NV12 && srcFormat != ORC_PIX_FMT_NV21) return NULL;
     OrcSws *s = calloc(1, sizeof(*s));
@@ -332,15 +386,18 @@ OrcSws *orc_sws_open_io(int srcFormat, int srcW, int srcH, int dstFormat, int ds
     const int chrDstVSub = s->planar ? 1 : 0;                      /* av_pix_fmt_get_chroma_sub_sample(dstFormat), utils.c:1266 */
     s->chrSrcW = ceil_rshift(srcW, 1); s->chrSrcH = ceil_rshift(srcH, 1);
     s->chrDstW = ceil_rshift(dstW, s->chrDstHSub); s->chrDstH = ceil_rshift(dstH, chrDstVSub);
-    orc_sws_set_colorspace(s, default_coeffs, 0, 0, 1 << 16, 1 << 16);
+    /* utils.c:1164-1167: the ranges given before initialisation go through sws_setColorspaceDetails */
+    orc_sws_set_colorspace_details(s, default_coeffs, srcRange != 0, default_coeffs, dstRange != 0, 0, 1 << 16, 1 << 16);
 
-    if (s->planar && srcW == dstW && srcH == dstH) {               /* planarCopyWrapper (swscale_unscaled.c:2675-2693) or, for a
+    /* the unscaled converters are only looked for when no range conversion is due (utils.c:1623-1626) */
+    if (s->planar && srcW == dstW && srcH == dstH && s->src_range == s->dst_range) {               /* planarCopyWrapper (swscale_unscaled.c:2675-2693) or, for a
                                                                     * semi-planar source, nv12ToPlanarWrapper (:167-188, :2415-2419):
                                                                     * both are a luma copy plus a chroma copy / de-interleave */
         s->unscaled_lut = 2;
         return s;
     }
-    /* swscale_unscaled.c:2426-2431 through utils.c:1623-1637: only planar yuv420p/422p sources have the LUT converter */
+    /* swscale_unscaled.c:2426-2431 through utils.c:1623-1637: only planar yuv420p/422p sources have the LUT converter
+     * (packed RGB destination: dst_range was forced to 0 above; isAnyRGB(dst) passes the range test of utils.c:1625) */
     if (!s->planar && !s->src_nv && srcW == dstW && srcH == dstH && !(flags & ORC_SWS_ACCURATE_RND) && !(dstH & 1)) {
         s->unscaled_lut = 1;
         return s;
@@ -497,6 +554,17 @@ static void vscale_plane_line(uint8_t *dst, int w, const int16_t *plane, int pw,
     }
 }
 
+/* lumRangeToJpeg_c / lumRangeFromJpeg_c / chrRange*_c (swscale.c:163-209), called per line right after the horizontal
+ * pass (hscale.c:61-63, :195-197) */
+static void range_line(int16_t *d, int w, int coeff, int offset, int clip)
+{
+    for (int i = 0; i < w; i++) {
+        int v = (d[i] * coeff + offset) >> 14;
+        if (clip && v > 32767) v = 32767;
+        d[i] = (int16_t)v;
+    }
+}
+
 /* yuv420p -> yuv420p: horizontal pass per plane, then lum_planar_vscale / chr_planar_vscale (vscale.c:34-107) */
 /* nvXXtoUV_c (input.c:921-948): plane 1 of an nv12 / nv21 picture split into U and V planes of chrSrcW x chrSrcH */
 static uint8_t *split_nv(const OrcSws *s, const uint8_t *uv, int uvs)
@@ -545,6 +613,14 @@ int orc_sws_scale_planar(OrcSws *s, const uint8_t *y, int ys, const uint8_t *u, 
     for (int r = 0; r < s->chrSrcH; r++) {
         hpass(s, CU + (size_t)r * cW, cW, u + (ptrdiff_t)r * us, s->chrSrcW, 1);
         hpass(s, CV + (size_t)r * cW, cW, v + (ptrdiff_t)r * vs, s->chrSrcW, 1);
+    }
+    if (s->range_conv) {
+        const int clip = s->range_conv == 1;
+        for (int r = 0; r < s->srcH; r++) range_line(L + (size_t)r * dstW, dstW, s->lum_coeff, s->lum_offset, clip);
+        for (int r = 0; r < s->chrSrcH; r++) {
+            range_line(CU + (size_t)r * cW, cW, s->chr_coeff, s->chr_offset, clip);
+            range_line(CV + (size_t)r * cW, cW, s->chr_coeff, s->chr_offset, clip);
+        }
     }
     for (int d = 0; d < s->dstH; d++) {
         int first = s->vLumPos[d] > 1 - s->vLumSize ? s->vLumPos[d] : 1 - s->vLumSize;

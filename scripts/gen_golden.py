@@ -79,6 +79,17 @@ def gen_sws_planar():
     open(os.path.join(OUT, "sws_planar_hashes.txt"), "w").write("\n".join(lines) + "\n")
 
 
+def gen_sws_range():
+    """yuv420p -> yuv420p with range conversion: the reference's outputs for SWS_RANGE_CASES."""
+    from cases import SWS_RANGE_CASES
+    lines = []
+    for i, (w, h, dw, dh, fl, kind, ranges, details) in enumerate(SWS_RANGE_CASES):
+        y, u, v = cl.yuv_frame(w, h, 1200 + i, kind)
+        out = cl.ref_sws_planar(w, h, dw, dh, fl, y, u, v, ranges=ranges, details=details)
+        lines.append(f"{i} {w} {h} {dw} {dh} {fl} {kind} {sha(np.concatenate([p.ravel() for p in out]))}")
+    open(os.path.join(OUT, "sws_range_hashes.txt"), "w").write("\n".join(lines) + "\n")
+
+
 def gen_sws_fastbil():
     from cases import SWS_FASTBIL_CASES
     lines = []
@@ -381,5 +392,6 @@ if __name__ == "__main__":
     gen_tx()
     gen_vsynth1()
     gen_sws_slices()
+    gen_sws_range()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -118,3 +118,25 @@ SWS_FASTBIL_CASES = [(64, 48, 64, 48, 1 | SWS_ACCURATE_RND, "random"), (64, 48, 
 SWS_NV_CASES = [(64, 48, 64, 48, FATE, "random"), (64, 48, 64, 48, SWS_BICUBIC, "random"), (64, 48, 100, 70, FATE, "limited"),
                 (64, 48, 33, 21, SWS_BILINEAR, "random"), (352, 288, 200, 100, FATE, "random"), (66, 50, 66, 50, SWS_BICUBIC, "random"),
                 (63, 47, 63, 47, SWS_BICUBIC, "smooth"), (64, 48, 128, 96, 1, "random"), (352, 288, 352, 288, FATE, "random")]
+
+
+# yuv -> yuv range conversion (lum/chrRangeToJpeg_c, FromJpeg_c between the two passes, swscale.c:163-209):
+# (w, h, dw, dh, flags, kind, (src_range, dst_range) at init, sws_setColorspaceDetails() call after init or None)
+# details = (src_cs, src_range, dst_cs, dst_range, brightness, contrast, saturation), cs = SWS_CS_* index
+_ID = (5, 0, 5, 0, 0, 1 << 16, 1 << 16)
+SWS_RANGE_CASES = [
+    (352, 288, 352, 288, FATE, "random", (0, 1), None),              # the geometry of FATE's sws-yuv-range: same size, through the scaler
+    (352, 288, 352, 288, FATE, "limited", (1, 0), None),
+    (64, 48, 100, 70, FATE, "random", (0, 1), None),
+    (64, 48, 100, 70, FATE, "random", (1, 0), None),
+    (66, 50, 40, 96, SWS_BILINEAR, "limited", (0, 1), None),
+    (352, 288, 200, 100, SWS_BICUBIC, "smooth", (1, 0), None),
+    (64, 48, 33, 21, SWS_FAST_BILINEAR, "random", (0, 1), None),
+    (64, 48, 128, 96, SWS_FAST_BILINEAR, "random", (1, 0), None),
+    (64, 48, 64, 48, SWS_BICUBIC, "random", (1, 1), None),           # equal ranges: plain copy
+    (64, 48, 100, 70, FATE, "random", (0, 0), (5, 0, 5, 1, 0, 1 << 16, 1 << 16)),       # ranges changed after init: conversion switched on
+    (64, 48, 100, 70, FATE, "random", (0, 1), (5, 1, 5, 1, 0, 1 << 16, 1 << 16)),       # ... and off
+    (64, 48, 100, 70, FATE, "random", (0, 1), (5, 1, 5, 0, 2000, 70000, 80000)),        # direction flipped; brightness etc. do not apply
+    (64, 48, 64, 48, FATE, "random", (0, 0), (5, 0, 5, 1, 0, 1 << 16, 1 << 16)),        # initialised as a copy: stays a copy
+    (64, 48, 64, 48, FATE, "random", (0, 1), _ID),                                       # initialised through the scaler: stays there
+]

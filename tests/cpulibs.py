@@ -38,6 +38,9 @@ def oracle():
         L.orc_sws_open_fmt.argtypes = [C.c_int] * 6
         L.orc_sws_open_io.restype = C.c_void_p
         L.orc_sws_open_io.argtypes = [C.c_int] * 7
+        L.orc_sws_open_range.restype = C.c_void_p
+        L.orc_sws_open_range.argtypes = [C.c_int] * 9
+        L.orc_sws_set_colorspace_details.argtypes = [C.c_void_p, i32p, C.c_int, i32p, C.c_int, C.c_int, C.c_int, C.c_int]
         L.orc_sws_close.argtypes = [C.c_void_p]
         L.orc_sws_set_colorspace.argtypes = [C.c_void_p, i32p, C.c_int, C.c_int, C.c_int, C.c_int]
         L.orc_sws_scale.argtypes = [C.c_void_p, u8p, C.c_int, u8p, C.c_int, u8p, C.c_int, u8p, C.c_int]
@@ -90,6 +93,8 @@ def ref():
         L.ffref_sws_open_fmt.argtypes = [C.c_int] * 7
         L.ffref_sws_open_io.restype = C.c_void_p
         L.ffref_sws_open_io.argtypes = [C.c_int] * 8
+        L.ffref_sws_open_range.restype = C.c_void_p
+        L.ffref_sws_open_range.argtypes = [C.c_int] * 10
         L.ffref_sws_close.argtypes = [C.c_void_p]
         L.ffref_sws_set_colorspace.argtypes = [C.c_void_p] + [C.c_int] * 7
         L.ffref_sws_scale.argtypes = [C.c_void_p, u8p, C.c_int, u8p, C.c_int, u8p, C.c_int, C.c_int, C.c_int, u8p, C.c_int]
@@ -201,15 +206,24 @@ def _sws_run(lib, pre, w, h, dw, dh, flags, y, u, v, dst_pad=0, threads=1, color
 PIX_FMT_YUV420P = 0
 
 
-def _sws_run_planar(lib, pre, w, h, dw, dh, flags, y, u, v, dst_pad=0, threads=1, src_fmt=0):
-    """yuv420p / nv12 / nv21 -> yuv420p; returns (Y, U, V) destination planes (pad bytes stay 0xA5)."""
+def _sws_run_planar(lib, pre, w, h, dw, dh, flags, y, u, v, dst_pad=0, threads=1, src_fmt=0, ranges=(0, 0), details=None):
+    """yuv420p / nv12 / nv21 -> yuv420p; returns (Y, U, V) destination planes (pad bytes stay 0xA5).
+    ranges = (src_range, dst_range) given before initialisation; details = (src_cs, src_range, dst_cs, dst_range,
+    brightness, contrast, saturation) for a sws_setColorspaceDetails() call after it."""
     if pre == "ffref":
-        ctx = lib.ffref_sws_open_io(src_fmt, w, h, PIX_FMT_YUV420P, dw, dh, flags, threads)
+        ctx = lib.ffref_sws_open_range(src_fmt, w, h, ranges[0], PIX_FMT_YUV420P, dw, dh, ranges[1], flags, threads)
     else:
-        ctx = lib.orc_sws_open_io(src_fmt, w, h, PIX_FMT_YUV420P, dw, dh, flags)
+        ctx = lib.orc_sws_open_range(src_fmt, w, h, ranges[0], PIX_FMT_YUV420P, dw, dh, ranges[1], flags)
     if not ctx:
         return None
     try:
+        if details is not None:
+            if pre == "ffref":
+                r = lib.ffref_sws_set_colorspace(ctx, *details)
+            else:
+                ta, tb = (np.array(COEFFS[k], dtype=np.int32) for k in (details[0], details[2]))
+                r = lib.orc_sws_set_colorspace_details(ctx, ptr(ta, i32p), details[1], ptr(tb, i32p), details[3], *details[4:])
+            assert r == 0, r
         cw, ch = (dw + 1) // 2, (dh + 1) // 2
         dy = np.full((dh, dw + dst_pad), 0xA5, np.uint8)
         du = np.full((ch, cw + dst_pad), 0xA5, np.uint8)

@@ -198,3 +198,58 @@ def test_sws_oracle_vsynth1_frame0():
     assert np.array_equal(cl.orc_sws(352, 288, 352, 288, FATE, y, u, v), g["rgb_same"])
     assert np.array_equal(cl.orc_sws(352, 288, 200, 100, FATE, y, u, v), g["rgb_200x100"])
     assert np.array_equal(cl.orc_sws(352, 288, 352, 288, cl.SWS_BICUBIC, y, u, v), g["rgb_lut"])
+
+
+def test_sws_oracle_range_golden_hashes():
+    """yuv -> yuv range conversion (lum/chrRangeToJpeg_c, FromJpeg_c) against the reference's outputs, ranges given at
+    initialisation or through sws_setColorspaceDetails() afterwards (incl. the context that stays a plain copy)."""
+    from cases import SWS_RANGE_CASES
+    lines = open(os.path.join(G, "sws_range_hashes.txt")).read().split("\n")[:-1]
+    assert len(lines) == len(SWS_RANGE_CASES) == 14
+    for line, (w, h, dw, dh, fl, kind, ranges, details) in zip(lines, SWS_RANGE_CASES):
+        i, hout = int(line.split()[0]), line.split()[-1]
+        y, u, v = cl.yuv_frame(w, h, 1200 + i, kind)
+        out = cl.orc_sws_planar(w, h, dw, dh, fl, y, u, v, ranges=ranges, details=details)
+        assert sha(np.concatenate([p.ravel() for p in out])) == hout, (i, w, h, dw, dh, hex(fl), ranges, details)
+
+
+def test_sws_oracle_range_vs_ref():
+    if not cl.have_ref():
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(81)
+    for it in range(24):
+        w, h = int(rng.integers(8, 120)), int(rng.integers(8, 90))
+        dw, dh = (w, h) if it % 4 == 0 else (int(rng.integers(8, 160)), int(rng.integers(8, 120)))
+        fl = int(rng.choice([FATE, cl.SWS_BICUBIC, cl.SWS_BILINEAR, cl.SWS_POINT, 1]))
+        ranges = [(0, 1), (1, 0), (0, 0), (1, 1)][int(rng.integers(0, 4))]
+        details = None if it % 3 else (5, int(rng.integers(0, 2)), 5, int(rng.integers(0, 2)), 0, 1 << 16, 1 << 16)
+        y, u, v = cl.yuv_frame(w, h, 1300 + it, ["random", "limited"][it & 1], pad=int(rng.integers(0, 9)))
+        a = cl.ref_sws_planar(w, h, dw, dh, fl, y, u, v, dst_pad=3, ranges=ranges, details=details)
+        b = cl.orc_sws_planar(w, h, dw, dh, fl, y, u, v, dst_pad=3, ranges=ranges, details=details)
+        assert all(np.array_equal(p, q) for p, q in zip(a, b)), (w, h, dw, dh, hex(fl), ranges, details)
+
+
+FATE_SWS_YUV_RANGE = 0xbc7a0fa2     # tests/ref/fate/sws-yuv-range:6 (framecrc: av_adler32_update(0, ...) over the 152064-byte frame)
+
+
+def fate_sws_yuv_range_crc(run_planar):
+    """tests/fate/libswscale.mak:28-32: vsynth1 frame 0, scale=in_range=limited:out_range=full:flags=+accurate_rnd+bitexact"""
+    import zlib
+    g = np.load(os.path.join(G, "vsynth1_f0.npz"))
+    out = run_planar(352, 288, 352, 288, cl.SWS_BICUBIC | cl.SWS_ACCURATE_RND | cl.SWS_BITEXACT, g["y"], g["u"], g["v"], ranges=(0, 1))
+    return zlib.adler32(np.concatenate([p.ravel() for p in out]).tobytes(), 0)
+
+
+def test_sws_oracle_fate_sws_yuv_range():
+    assert fate_sws_yuv_range_crc(cl.orc_sws_planar) == FATE_SWS_YUV_RANGE
+    if cl.have_ref():
+        assert fate_sws_yuv_range_crc(cl.ref_sws_planar) == FATE_SWS_YUV_RANGE
+
+
+def test_sws_oracle_yuv_matrix_change_not_restated():
+    """different matrices for yuv -> yuv: the reference cascades through bgr24; the oracle says so instead of guessing"""
+    L = cl.oracle()
+    ctx = L.orc_sws_open_range(0, 64, 48, 0, 0, 100, 70, 0, FATE)
+    ta, tb = (np.array(cl.COEFFS[k], dtype=np.int32) for k in (1, 5))
+    assert L.orc_sws_set_colorspace_details(ctx, cl.ptr(ta, cl.i32p), 0, cl.ptr(tb, cl.i32p), 1, 0, 1 << 16, 1 << 16) == -1
+    L.orc_sws_close(ctx)
