@@ -889,6 +889,42 @@ B200_API int b200_sws_plan_probe(int srcW, int srcH, int dstW, int dstH, int fla
     return n;
 }
 
+// The general form: any source / destination format and ranges this path takes, plus an optional sws_setColorspaceDetails()
+// call after the build.  cfg = { srcW, srcH, srcFormat, srcRange, dstW, dstH, dstFormat, dstRange, flags };
+// details = NULL or { inv_table[4], srcRange, table[4], dstRange, brightness, contrast, saturation } (13 ints);
+// info32: [0..15] as b200_sws_info, [16] plain copy, [17] range conversion (0 none, 1 limited->full, 2 full->limited),
+// [18..21] luma coefficient, luma offset, chroma coefficient, chroma offset, [22] fast-bilinear horizontal pass,
+// [23] semi-planar source kind, [24] what the details call returned, [25] src_range, [26] dst_range.
+B200_API int b200_sws_plan_probe2(const int cfg[9], const int *details, int which, int16_t *filter, int32_t *pos, int cap, int *o)
+{
+    if (!cfg) return B200_EINVAL;
+    SwsPlan p;
+    const int srcFormat = cfg[2];
+    if (!(srcFormat == B200_PIX_FMT_YUV420P || srcFormat == B200_PIX_FMT_NV12 || srcFormat == B200_PIX_FMT_NV21) ||
+        !sws_out_format(cfg[6], p.out)) return B200_ENOSYS;
+    p.src_nv = srcFormat == B200_PIX_FMT_NV12 ? 1 : srcFormat == B200_PIX_FMT_NV21 ? 2 : 0;
+    int ret = sws_plan_build(p, cfg[0], cfg[1], cfg[4], cfg[5], cfg[8], cfg[3], cfg[7]);
+    if (ret < 0) return ret;
+    int dret = 0;
+    if (details)
+        dret = sws_plan_colorspace_details(p, details, details[4], details + 5, details[9], details[10], details[11], details[12]);
+    if (o) {
+        o[0] = p.hLum.size; o[1] = p.hChr.size; o[2] = p.vLum.size; o[3] = p.vChr.size;
+        o[4] = p.chrSrcW; o[5] = p.chrSrcH; o[6] = p.chrDstW; o[7] = p.chrDstH;
+        o[8] = p.unscaled_lut; o[9] = 1; o[10] = 1; o[11] = p.chrDstHSub; o[12] = p.planar ? 1 : 0;
+        o[13] = p.dstW; o[14] = p.dstH; o[15] = 0;
+        o[16] = p.planar_copy; o[17] = p.range_conv;
+        o[18] = p.lumRangeCoeff; o[19] = p.lumRangeOffset; o[20] = p.chrRangeCoeff; o[21] = p.chrRangeOffset;
+        o[22] = p.fast_bilinear; o[23] = p.src_nv; o[24] = dret; o[25] = p.src_range; o[26] = p.dst_range;
+        for (int i = 27; i < 32; i++) o[i] = 0;
+    }
+    const SwsFilterBank &b = which == 0 ? p.hLum : which == 1 ? p.hChr : which == 2 ? p.vLum : p.vChr;
+    int n = b.n < cap ? b.n : cap;
+    if (filter && n) memcpy(filter, b.coef.data(), (size_t)n * b.size * 2);
+    if (pos && n) memcpy(pos, b.pos.data(), (size_t)n * 4);
+    return n;
+}
+
 static bool aligned16(const void *p, long long stride, long long fstride)
 {
     return (((uintptr_t)p) & 15) == 0 && (stride & 15) == 0 && (fstride & 15) == 0;

@@ -143,6 +143,13 @@ int  b200_sws_get_filter(const B200SwsContext *c, int which, int16_t *filter, in
  * the filter generation against the reference).  info16 as b200_sws_info; filter/pos may be NULL. Returns n or <0. */
 int  b200_sws_plan_probe(int srcW, int srcH, int dstW, int dstH, int flags, int which,
                          int16_t *filter, int32_t *pos, int cap, int *info16);
+/* the general form: cfg = { srcW, srcH, srcFormat, srcRange, dstW, dstH, dstFormat, dstRange, flags }; details = NULL or the 13
+ * ints of a sws_setColorspaceDetails() call made after initialisation { inv_table[4], srcRange, table[4], dstRange,
+ * brightness, contrast, saturation }.  info32: [0..15] as b200_sws_info ([12] = vertical chroma shift of the destination),
+ * [16] plain-copy context, [17] range conversion (0 none, 1 limited->full, 2 full->limited), [18..21] its luma coefficient,
+ * luma offset, chroma coefficient, chroma offset (libswscale/swscale.c:577-624), [22] fast-bilinear horizontal pass,
+ * [23] semi-planar source kind, [24] return value of the details call, [25] src_range, [26] dst_range. */
+int  b200_sws_plan_probe2(const int cfg[9], const int *details, int which, int16_t *filter, int32_t *pos, int cap, int *info32);
 
 /* ------------------------------------------------------------------------------------------------ idctdsp
  * Replaces IDCTDSPContext (libavcodec/idctdsp.h:43-91) as filled by ff_idctdsp_init (libavcodec/idctdsp.c:228-314)

@@ -68,6 +68,9 @@ int     orc_sws_scale_planar(OrcSws *s, const uint8_t *y, int ys, const uint8_t 
                              uint8_t *dy, int dys, uint8_t *du, int dus, uint8_t *dv, int dvs);
 /* 16 ints, same layout as ffref_sws_info */
 int     orc_sws_info(const OrcSws *s, int *out);
+/* 6 ints, same layout as ffref_sws_range_info: conversion kind (0 none, 1 limited->full, 2 full->limited), luma coefficient
+ * and offset, chroma coefficient and offset, unscaled converter installed */
+int     orc_sws_range_info(const OrcSws *s, int *out);
 /* which: 0 hLum 1 hChr 2 vLum 3 vChr; returns n entries copied */
 int     orc_sws_get_filter(const OrcSws *s, int which, int16_t *filter, int32_t *pos, int cap);
 /* the bare horizontal FIR */

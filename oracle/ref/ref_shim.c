@@ -138,6 +138,20 @@ API int ffref_sws_info(void *h, int *out /* 16 ints */)
     return 0;
 }
 
+/* Range conversion the context ended up with (swscale.c:626-660): out[0] = 0 none, 1 limited -> full (src_range == 0),
+ * 2 full -> limited; [1..4] = luma / chroma coefficient and offset narrowed the way the 8-bit line functions narrow them
+ * (uint16 / int32, swscale.c:163-209); [5] = an unscaled converter is installed. */
+API int ffref_sws_range_info(void *h, int *out)
+{
+    SwsInternal *c = sws_internal((SwsContext *)h);
+    const int on = c->lumConvertRange != NULL;
+    out[0] = !on ? 0 : c->opts.src_range ? 2 : 1;
+    out[1] = on ? (uint16_t)c->lumConvertRange_coeff : 0; out[2] = on ? (int32_t)c->lumConvertRange_offset : 0;
+    out[3] = on ? (uint16_t)c->chrConvertRange_coeff : 0; out[4] = on ? (int32_t)c->chrConvertRange_offset : 0;
+    out[5] = c->convert_unscaled != NULL;
+    return 0;
+}
+
 /* which: 0 hLum 1 hChr 2 vLum 3 vChr.  Copies filter (n*size int16) and pos (n int32). Returns n. */
 API int ffref_sws_get_filter(void *h, int which, int16_t *filter, int32_t *pos, int cap)
 {

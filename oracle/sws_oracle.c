@@ -440,6 +440,17 @@ int orc_sws_info(const OrcSws *s, int *out)
     return 0;
 }
 
+/* out[0] range conversion in use (0 none, 1 limited -> full, 2 full -> limited), [1..4] luma coefficient, luma offset,
+ * chroma coefficient, chroma offset as the line functions see them, [5] an unscaled converter was installed */
+int orc_sws_range_info(const OrcSws *s, int *out)
+{
+    out[0] = s->range_conv;
+    out[1] = s->range_conv ? s->lum_coeff : 0; out[2] = s->range_conv ? s->lum_offset : 0;
+    out[3] = s->range_conv ? s->chr_coeff : 0; out[4] = s->range_conv ? s->chr_offset : 0;
+    out[5] = s->unscaled_lut != 0;
+    return 0;
+}
+
 int orc_sws_get_filter(const OrcSws *s, int which, int16_t *filter, int32_t *pos, int cap)
 {
     const int16_t *f; const int32_t *p; int n, fs;

@@ -4,6 +4,7 @@
 import hashlib
 import os
 
+import ctypes as C
 import numpy as np
 import pytest
 
@@ -253,3 +254,94 @@ def test_sws_oracle_yuv_matrix_change_not_restated():
     ta, tb = (np.array(cl.COEFFS[k], dtype=np.int32) for k in (1, 5))
     assert L.orc_sws_set_colorspace_details(ctx, cl.ptr(ta, cl.i32p), 0, cl.ptr(tb, cl.i32p), 1, 0, 1 << 16, 1 << 16) == -1
     L.orc_sws_close(ctx)
+
+
+def _all_sws_configs():
+    """(src_fmt, w, h, src_range, dst_fmt, dw, dh, dst_range, flags, details) over every case list of tests/cases.py"""
+    from cases import SWS_FORMAT_CASES, SWS_PLANAR_CASES, SWS_FASTBIL_CASES, SWS_NV_CASES, SWS_RANGE_CASES
+    out = []
+    for (w, h, dw, dh, fl, _k) in SWS_FORMAT_CASES:
+        for f in cl.PACKED_RGB_FORMATS.values():
+            out.append((0, w, h, 0, f, dw, dh, 0, fl, None))
+    for (w, h, dw, dh, fl, _k) in SWS_PLANAR_CASES:
+        out.append((0, w, h, 0, 0, dw, dh, 0, fl, None))
+    for (w, h, dw, dh, fl, _k) in SWS_FASTBIL_CASES:
+        out += [(0, w, h, 0, cl.PIX_FMT_RGB24, dw, dh, 0, fl, None), (0, w, h, 0, 0, dw, dh, 0, fl, None)]
+    for (w, h, dw, dh, fl, _k) in SWS_NV_CASES:
+        for sf in (cl.PIX_FMT_NV12, cl.PIX_FMT_NV21):
+            out += [(sf, w, h, 0, cl.PIX_FMT_RGB24, dw, dh, 0, fl, None), (sf, w, h, 0, 0, dw, dh, 0, fl, None)]
+    for (w, h, dw, dh, fl, _k, ranges, details) in SWS_RANGE_CASES:
+        out.append((0, w, h, ranges[0], 0, dw, dh, ranges[1], fl, details))
+        out.append((cl.PIX_FMT_NV12, w, h, ranges[0], 0, dw, dh, ranges[1], fl, details))
+        out.append((0, w, h, ranges[0], cl.PIX_FMT_RGB24, dw, dh, ranges[1], fl, None))      # RGB destination: dst_range is ignored
+    out += [(0, 3840, 2160, 0, 0, 1920, 1080, 1, FATE, None), (0, 3840, 2160, 1, 0, 3840, 2160, 0, FATE, None)]
+    return out
+
+
+def test_host_plan_matches_oracle_and_reference_all_formats():
+    """The product's host-side set-up (sws_plan.cpp: converter gates, filter banks, range-conversion constants) for every
+    source / destination format, range and flag combination of the case lists, against the oracle and, where built, the
+    reference's initialised context.  No GPU involved."""
+    import ffmpeg_b200 as fb
+    L, O = fb.lib(), cl.oracle()
+    R = cl.ref() if cl.have_ref() else None
+    O.orc_sws_range_info.argtypes = [C.c_void_p, cl.i32p]
+    if R is not None:
+        R.ffref_sws_range_info.argtypes = [C.c_void_p, cl.i32p]
+    cfgs = _all_sws_configs()
+    assert len(cfgs) > 150
+    for (sf, w, h, sr, df, dw, dh, dr, fl, details) in cfgs:
+        key = (sf, w, h, sr, df, dw, dh, dr, hex(fl), details)
+        cfg = np.array([w, h, sf, sr, dw, dh, df, dr, fl], np.int32)
+        det = None
+        if details is not None:
+            det = np.array(list(cl.COEFFS[details[0]]) + [details[1]] + list(cl.COEFFS[details[2]]) + list(details[3:]), np.int32)
+        octx = O.orc_sws_open_range(sf, w, h, sr, df, dw, dh, dr, fl)
+        assert octx, key
+        rctx = R.ffref_sws_open_range(sf, w, h, sr, df, dw, dh, dr, fl, 1) if R is not None else None
+        if details is not None:
+            ta, tb = (np.array(cl.COEFFS[k], dtype=np.int32) for k in (details[0], details[2]))
+            assert O.orc_sws_set_colorspace_details(octx, cl.ptr(ta, cl.i32p), details[1], cl.ptr(tb, cl.i32p), details[3], *details[4:]) == 0
+            if rctx:
+                assert R.ffref_sws_set_colorspace(rctx, *details) == 0
+        oi, ori = np.zeros(16, np.int32), np.zeros(6, np.int32)
+        O.orc_sws_info(octx, cl.ptr(oi, cl.i32p))
+        O.orc_sws_range_info(octx, cl.ptr(ori, cl.i32p))
+        if rctx:
+            rri = np.zeros(6, np.int32)
+            R.ffref_sws_range_info(rctx, cl.ptr(rri, cl.i32p))
+            assert list(rri) == list(ori), (key, list(rri), list(ori))
+        for which in range(4):
+            pi = np.zeros(32, np.int32)
+            n = L.b200_sws_plan_probe2(cl.ptr(cfg, cl.i32p), cl.ptr(det, cl.i32p) if det is not None else None, which, None, None, 0,
+                                       cl.ptr(pi, cl.i32p))
+            assert n >= 0 and pi[24] == 0, key
+            assert list(pi[:8]) == list(oi[:8]) and pi[11] == oi[11], (key, list(pi[:16]), list(oi))
+            assert bool(pi[8] or pi[16]) == bool(ori[5]), (key, "unscaled converter gate")
+            assert [int(pi[17]), int(pi[18]) if pi[17] else 0, int(pi[19]) if pi[17] else 0, int(pi[20]) if pi[17] else 0,
+                    int(pi[21]) if pi[17] else 0] == list(ori[:5]), (key, list(pi[16:27]), list(ori))
+            size, cnt = int(pi[which]), [dw, int(pi[6]), dh, int(pi[7])][which]
+            if size == 0:
+                continue
+            f1, p1 = np.zeros(cnt * size, np.int16), np.zeros(cnt, np.int32)
+            f2, p2 = f1.copy(), p1.copy()
+            L.b200_sws_plan_probe2(cl.ptr(cfg, cl.i32p), cl.ptr(det, cl.i32p) if det is not None else None, which,
+                                   cl.ptr(f1, cl.i16p), cl.ptr(p1, cl.i32p), cnt, None)
+            O.orc_sws_get_filter(octx, which, cl.ptr(f2, cl.i16p), cl.ptr(p2, cl.i32p), cnt)
+            assert np.array_equal(f1, f2) and np.array_equal(p1, p2), (key, which)
+        O.orc_sws_close(octx)
+        if rctx:
+            R.ffref_sws_close(rctx)
+
+
+def test_host_plan_refuses_yuv_matrix_change():
+    import ffmpeg_b200 as fb
+    L = fb.lib()
+    cfg = np.array([64, 48, 0, 0, 100, 70, 0, 0, FATE], np.int32)
+    det = np.array(list(cl.COEFFS[1]) + [0] + list(cl.COEFFS[5]) + [1, 0, 1 << 16, 1 << 16], np.int32)
+    pi = np.zeros(32, np.int32)
+    assert L.b200_sws_plan_probe2(cl.ptr(cfg, cl.i32p), cl.ptr(det, cl.i32p), 0, None, None, 0, cl.ptr(pi, cl.i32p)) >= 0
+    assert pi[24] == -38                                            # B200_ENOSYS: the reference would cascade through bgr24
+    cfg[6] = cl.PIX_FMT_RGB24                                       # RGB destination: `table` is ignored, like the reference
+    assert L.b200_sws_plan_probe2(cl.ptr(cfg, cl.i32p), cl.ptr(det, cl.i32p), 0, None, None, 0, cl.ptr(pi, cl.i32p)) >= 0
+    assert pi[24] == 0
