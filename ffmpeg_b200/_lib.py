@@ -78,6 +78,13 @@ class H264WeightContext(C.Structure):
     _fields_ = [("weight_pixels_tab", _H264W * 4), ("biweight_pixels_tab", _H264BW * 4)]
 
 
+class MpvUnquant(C.Structure):
+    """B200MpvUnquant: the MPVContext fields the inverse quantisers read (libavcodec/mpegvideo.h:70-77,201-203,258)"""
+    _fields_ = [("intra_matrix", C.c_uint16 * 64), ("inter_matrix", C.c_uint16 * 64), ("permutated", C.c_uint8 * 64),
+                ("raster_end", C.c_uint8 * 64), ("y_dc_scale", C.c_int32), ("c_dc_scale", C.c_int32), ("q_scale_type", C.c_int32),
+                ("h263_aic", C.c_int32), ("ac_pred", C.c_int32)]
+
+
 _CHROMA = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_ssize_t, C.c_int, C.c_int, C.c_int)
 
 
@@ -143,6 +150,7 @@ PROTOTYPES = {
     "b200_h264_idct_batch_device": (C.c_int, [vp, C.c_int, C.c_int64, vp, vp, vp, vp, C.c_ssize_t]),
     "b200_h264_weight_init": (C.c_int, [C.POINTER(H264WeightContext), C.c_int]),
     "b200_h264_weight_batch_device": (C.c_int, [vp, C.c_int64, vp, vp, vp, vp, vp, C.c_ssize_t]),
+    "b200_mpv_unquantize_batch_device": (C.c_int, [vp, C.c_int, vp, vp, C.c_int64, vp, vp, vp]),
     "b200_videodsp_init": (C.c_int, [C.POINTER(VideoDSPContext), C.c_int]),
     "b200_emulated_edge_mc_batch_device": (C.c_int, [vp, C.c_int64, vp, vp, C.c_ssize_t, vp, vp, C.c_ssize_t, vp, C.c_int, C.c_int]),
     "b200_h264chroma_init": (C.c_int, [C.POINTER(H264ChromaContext), C.c_int]),

@@ -191,6 +191,31 @@ int  b200_idct_mb420_device(B200Device *dev, int kind, const int16_t *blocks, in
 int  b200_idct_mb420_host(B200Device *dev, int kind, const int16_t *blocks, int mb_w, int mb_h, int nframes,
                           uint8_t *const planes[3], const int linesize[3], const int64_t frame_stride[3]);
 
+/* mpegvideo inverse quantisers: the members of MPVUnquantDSPContext (libavcodec/mpegvideo_unquantize.h:31-44) as
+ * ff_mpv_unquantize_init() installs them (libavcodec/mpegvideo_unquantize.c:50-290), i.e. what runs in front of the IDCT in
+ * mpv_reconstruct_mb's put_dct / add_dequant_dct (libavcodec/mpegvideo_dec.c).  The reference functions take the whole
+ * MPVContext; B200MpvUnquant carries the fields they read (mpegvideo.h:70-77 y/c_dc_scale, ac_pred, h263_aic, the scan
+ * tables; :201-203 intra_matrix / inter_matrix; :258 q_scale_type).  variant 3 is the function the reference installs for
+ * AV_CODEC_FLAG_BITEXACT (with mismatch control); variant 2 the plain one. */
+#define B200_UNQUANT_MPEG1_INTRA          0
+#define B200_UNQUANT_MPEG1_INTER          1
+#define B200_UNQUANT_MPEG2_INTRA          2
+#define B200_UNQUANT_MPEG2_INTRA_BITEXACT 3
+#define B200_UNQUANT_MPEG2_INTER          4
+#define B200_UNQUANT_H263_INTRA           5
+#define B200_UNQUANT_H263_INTER           6
+typedef struct B200MpvUnquant {
+    uint16_t intra_matrix[64], inter_matrix[64];     /* raster order after the IDCT permutation, as MPVContext holds them */
+    uint8_t  permutated[64], raster_end[64];         /* ScanTable (ff_init_scantable, mpegvideo_unquantize.c:36-48) of the scan in use */
+    int32_t  y_dc_scale, c_dc_scale, q_scale_type, h263_aic, ac_pred;
+} B200MpvUnquant;
+/* batched, DEVICE pointers, in place: block i = blocks + 64*i (int16, 4-byte aligned), its number inside the macroblock
+ * blk_n[i] (0-3 luma, 4+ chroma: selects the DC scale; NULL = macroblock stream order, i % 6), quantiser qscale[i] and
+ * block_last_index last_index[i] (-1 = no coded coefficient; the H.263 variants need >= 0 like the reference asserts).
+ * Coefficients beyond the coded part of the scan are left untouched, as by the reference. */
+int  b200_mpv_unquantize_batch_device(B200Device *dev, int variant, const B200MpvUnquant *p, int16_t *blocks, int64_t nblocks,
+                                      const uint8_t *blk_n, const uint8_t *qscale, const int8_t *last_index);
+
 /* H.264 residual transforms, 8 bit: the IDCT members of H264DSPContext (libavcodec/h264dsp.h:81-88) as installed by
  * ff_h264dsp_init(c, 8, chroma_format_idc) (libavcodec/h264dsp.c:66-139): ff_h264_idct_add_8_c, ff_h264_idct8_add_8_c,
  * ff_h264_idct_dc_add_8_c, ff_h264_idct8_dc_add_8_c (libavcodec/h264idct_template.c:33-181).  The add16/add8/add4 wrappers

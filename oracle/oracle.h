@@ -83,6 +83,21 @@ void orc_idct_put(uint8_t *dest, ptrdiff_t line_size, int16_t *block);
 void orc_idct_add(uint8_t *dest, ptrdiff_t line_size, int16_t *block);
 void orc_idct_batch(int kind, int16_t *blocks, int nblocks, uint8_t *dest, ptrdiff_t line_size,
                     const int64_t *dest_off);
+/* inverse quantisers of libavcodec/mpegvideo_unquantize.c (MPVUnquantDSPContext), in place on int16[64] blocks */
+enum { ORC_UNQUANT_MPEG1_INTRA, ORC_UNQUANT_MPEG1_INTER, ORC_UNQUANT_MPEG2_INTRA, ORC_UNQUANT_MPEG2_INTRA_BITEXACT,
+       ORC_UNQUANT_MPEG2_INTER, ORC_UNQUANT_H263_INTRA, ORC_UNQUANT_H263_INTER };
+typedef struct OrcMpvUnquant {            /* what the functions read from MPVContext (libavcodec/mpegvideo.h:70-77,201-203,258) */
+    uint16_t intra_matrix[64], inter_matrix[64];
+    uint8_t  permutated[64], raster_end[64];      /* ScanTable of the scan in use (intra and inter tables are the same scan) */
+    int32_t  y_dc_scale, c_dc_scale, q_scale_type, h263_aic, ac_pred;
+} OrcMpvUnquant;
+/* ff_init_scantable: permutation = IDCTDSPContext.idct_permutation, scan = ff_zigzag_direct / ff_alternate_vertical_scan */
+void orc_mpv_init_scantable(const uint8_t permutation[64], const uint8_t scan[64], uint8_t permutated[64], uint8_t raster_end[64]);
+/* n = block number inside the macroblock (0-3 luma, 4+ chroma: picks the DC scale), last_index = block_last_index[n] */
+void orc_mpv_unquantize(int variant, const OrcMpvUnquant *p, int16_t *block, int n, int qscale, int last_index);
+/* blk_n NULL: blocks come in macroblock order, n = index % 6 */
+void orc_mpv_unquantize_batch(int variant, const OrcMpvUnquant *p, int16_t *blocks, int64_t nblocks, const uint8_t *blk_n,
+                              const uint8_t *qscale, const int8_t *last_index);
 /* H.264 residual add, 8 bit: kind 0 idct_add (4x4), 1 idct8_add, 2 idct_dc_add, 3 idct8_dc_add; clears the coefficients */
 int  orc_h264_idct(int kind, uint8_t *dst, int16_t *block, ptrdiff_t stride);
 void orc_pixels_clamped(int kind, const int16_t *block, uint8_t *pixels, ptrdiff_t line_size);

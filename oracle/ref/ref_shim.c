@@ -409,3 +409,40 @@ API void ffref_tx_run(void *h, void *out, void *in, ptrdiff_t stride, int count,
     for (int i = 0; i < count; i++)
         t->fn(t->ctx, (uint8_t *)out + i * out_step, (uint8_t *)in + i * in_step, stride);
 }
+
+/* ------------------------------------------------------------------ mpegvideo inverse quantisers ---------------- */
+#include "libavcodec/mpegvideo.h"
+#include "libavcodec/mpegvideodata.h"
+#include "libavcodec/mathops.h"
+#include "libavcodec/mpegvideo_unquantize.h"
+
+/* variant: 0 mpeg1 intra, 1 mpeg1 inter, 2 mpeg2 intra, 3 mpeg2 intra (bitexact flavour), 4 mpeg2 inter, 5 h263 intra,
+ * 6 h263 inter — the members of MPVUnquantDSPContext as ff_mpv_unquantize_init() fills them.  The MPVContext holds only what
+ * the functions read; scan tables are built by ff_init_scantable with the identity permutation of the C simple IDCT. */
+API int ffref_mpv_unquantize_batch(int variant, const uint16_t *intra_matrix, const uint16_t *inter_matrix, int alternate_scan,
+                                   int y_dc_scale, int c_dc_scale, int q_scale_type, int h263_aic, int ac_pred,
+                                   int16_t *blocks, int64_t nblocks, const uint8_t *blk_n, const uint8_t *qscale,
+                                   const int8_t *last_index)
+{
+    MPVUnquantDSPContext dsp;
+    MPVContext *s = av_mallocz(sizeof(*s));
+    uint8_t perm[64];
+    if (!s) return -1;
+    ff_mpv_unquantize_init(&dsp, variant == 3, q_scale_type);
+    for (int i = 0; i < 64; i++) { perm[i] = i; s->intra_matrix[i] = intra_matrix[i]; s->inter_matrix[i] = inter_matrix[i]; }
+    ff_init_scantable(perm, &s->intra_scantable, alternate_scan ? ff_alternate_vertical_scan : ff_zigzag_direct);
+    ff_init_scantable(perm, &s->inter_scantable, alternate_scan ? ff_alternate_vertical_scan : ff_zigzag_direct);
+    s->y_dc_scale = y_dc_scale; s->c_dc_scale = c_dc_scale; s->q_scale_type = q_scale_type;
+    s->h263_aic = h263_aic; s->ac_pred = ac_pred;
+    void (*fn)(const MPVContext *, int16_t *, int, int) =
+        variant == 0 ? dsp.dct_unquantize_mpeg1_intra : variant == 1 ? dsp.dct_unquantize_mpeg1_inter :
+        variant == 2 || variant == 3 ? dsp.dct_unquantize_mpeg2_intra : variant == 4 ? dsp.dct_unquantize_mpeg2_inter :
+        variant == 5 ? dsp.dct_unquantize_h263_intra : dsp.dct_unquantize_h263_inter;
+    for (int64_t b = 0; b < nblocks; b++) {
+        const int n = blk_n ? blk_n[b] : (int)(b % 6);
+        s->block_last_index[n] = last_index[b];
+        fn(s, blocks + 64 * b, n, qscale[b]);
+    }
+    av_free(s);
+    return 0;
+}

@@ -90,6 +90,16 @@ def gen_sws_range():
     open(os.path.join(OUT, "sws_range_hashes.txt"), "w").write("\n".join(lines) + "\n")
 
 
+def gen_unquant():
+    """mpegvideo inverse quantisers: the reference's outputs for unquant_case(seed, variant)."""
+    d = {}
+    for variant in range(7):
+        for seed in (11, 12):
+            cfg, blocks, blk_n, q, last = cl.unquant_case(seed * 7 + variant, variant, nblocks=48)
+            d[f"v{variant}_s{seed}"] = cl.ref_unquant(variant, cfg, blocks, blk_n, q, last)
+    np.savez_compressed(os.path.join(OUT, "unquant.npz"), **d)
+
+
 def gen_sws_fastbil():
     from cases import SWS_FASTBIL_CASES
     lines = []
@@ -393,5 +403,6 @@ if __name__ == "__main__":
     gen_vsynth1()
     gen_sws_slices()
     gen_sws_range()
+    gen_unquant()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -249,6 +249,85 @@ def orc_sws_planar(w, h, dw, dh, flags, y, u, v, **kw):
     return _sws_run_planar(oracle(), "orc", w, h, dw, dh, flags, y, u, v, **kw)
 
 
+# ---------------------------------------------------------------- mpegvideo inverse quantisers (mpegvideo_unquantize.c)
+UNQUANT_VARIANTS = ["mpeg1_intra", "mpeg1_inter", "mpeg2_intra", "mpeg2_intra_bitexact", "mpeg2_inter", "h263_intra", "h263_inter"]
+ZIGZAG = np.array([0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21,
+                   28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61,
+                   54, 47, 55, 62, 63], np.uint8)                                        # ISO zig-zag scan
+ALTERNATE_VERTICAL = np.array([0, 8, 16, 24, 1, 9, 2, 10, 17, 25, 32, 40, 48, 56, 57, 49, 41, 33, 26, 18, 3, 11, 4, 12, 19, 27, 34,
+                               42, 50, 58, 35, 43, 51, 59, 20, 28, 5, 13, 6, 14, 21, 29, 36, 44, 52, 60, 37, 45, 53, 61, 22, 30, 7,
+                               15, 23, 31, 38, 46, 54, 62, 39, 47, 55, 63], np.uint8)    # ISO 13818-2 figure 7-3
+
+
+class OrcMpvUnquant(C.Structure):
+    _fields_ = [("intra_matrix", C.c_uint16 * 64), ("inter_matrix", C.c_uint16 * 64), ("permutated", C.c_uint8 * 64),
+                ("raster_end", C.c_uint8 * 64), ("y_dc_scale", C.c_int32), ("c_dc_scale", C.c_int32), ("q_scale_type", C.c_int32),
+                ("h263_aic", C.c_int32), ("ac_pred", C.c_int32)]
+
+
+def unquant_params(intra_matrix, inter_matrix, alternate_scan, y_dc_scale, c_dc_scale, q_scale_type, h263_aic, ac_pred, struct=OrcMpvUnquant):
+    """the oracle's (or, with struct=..., the product's) parameter block; scan tables as ff_init_scantable builds them"""
+    p = struct()
+    scan = ALTERNATE_VERTICAL if alternate_scan else ZIGZAG
+    end = -1
+    for i in range(64):
+        p.intra_matrix[i], p.inter_matrix[i] = int(intra_matrix[i]), int(inter_matrix[i])
+        p.permutated[i] = int(scan[i])
+        end = max(end, int(scan[i]))
+        p.raster_end[i] = end
+    p.y_dc_scale, p.c_dc_scale, p.q_scale_type, p.h263_aic, p.ac_pred = y_dc_scale, c_dc_scale, q_scale_type, h263_aic, ac_pred
+    return p
+
+
+def unquant_case(seed, variant, nblocks=96):
+    """seeded quantised blocks the way a decoder leaves them: non-zero only up to last_index in scan order"""
+    rng = np.random.default_rng(seed)
+    alt = int(rng.integers(0, 2))
+    scan = ALTERNATE_VERTICAL if alt else ZIGZAG
+    cfg = dict(intra_matrix=rng.integers(8, 84, 64).astype(np.uint16), inter_matrix=rng.integers(8, 60, 64).astype(np.uint16),
+               alternate_scan=alt, y_dc_scale=int(rng.integers(1, 9)), c_dc_scale=int(rng.integers(1, 9)),
+               q_scale_type=int(rng.integers(0, 2)), h263_aic=int(rng.integers(0, 2)) if variant == 5 else 0,
+               ac_pred=int(rng.integers(0, 2)) if variant == 5 else 0)
+    cfg["intra_matrix"][0] = 8
+    blocks = np.zeros((nblocks, 64), np.int16)
+    last = rng.integers(-1 if variant not in (5, 6) else 0, 64, nblocks).astype(np.int8)
+    last[:4] = [63, 0, 62, 1]
+    for b in range(nblocks):
+        k = int(last[b]) + 1
+        amp = [3, 40, 300, 2047][b & 3]
+        v = rng.integers(-amp, amp + 1, k).astype(np.int16)
+        v[rng.random(k) < 0.45] = 0
+        blocks[b, scan[:k]] = v
+        if b % 7 == 3:
+            blocks[b, 63] = int(rng.integers(-5, 6))                  # a coefficient beyond last_index: left alone (unless reached)
+    qscale = rng.integers(1, 32, nblocks).astype(np.uint8)
+    blk_n = (np.arange(nblocks) % 6).astype(np.uint8) if seed & 1 else rng.integers(0, 6, nblocks).astype(np.uint8)
+    return cfg, blocks, blk_n, qscale, last
+
+
+def orc_unquant(variant, cfg, blocks, blk_n, qscale, last):
+    L = oracle()
+    L.orc_mpv_unquantize_batch.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_mpv_unquantize_batch.restype = None
+    p = unquant_params(**cfg)
+    out = np.ascontiguousarray(blocks).copy()
+    L.orc_mpv_unquantize_batch(variant, C.byref(p), out.ctypes.data, out.shape[0], blk_n.ctypes.data if blk_n is not None else None,
+                               qscale.ctypes.data, last.ctypes.data)
+    return out
+
+
+def ref_unquant(variant, cfg, blocks, blk_n, qscale, last):
+    L = ref()
+    L.ffref_mpv_unquantize_batch.argtypes = [C.c_int, C.c_void_p, C.c_void_p] + [C.c_int] * 6 + [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    out = np.ascontiguousarray(blocks).copy()
+    im, nm = np.ascontiguousarray(cfg["intra_matrix"], np.uint16), np.ascontiguousarray(cfg["inter_matrix"], np.uint16)
+    r = L.ffref_mpv_unquantize_batch(variant, im.ctypes.data, nm.ctypes.data, cfg["alternate_scan"], cfg["y_dc_scale"], cfg["c_dc_scale"],
+                                     cfg["q_scale_type"], cfg["h263_aic"], cfg["ac_pred"], out.ctypes.data, out.shape[0],
+                                     blk_n.ctypes.data if blk_n is not None else None, qscale.ctypes.data, last.ctypes.data)
+    assert r == 0
+    return out
+
+
 NUT_PATH = os.path.join(ROOT, "oracle", "_ref", "libffnut.so")
 _nut = None
 

@@ -270,3 +270,56 @@ def test_more_oracles_vs_reference_live():
         xc = np.ascontiguousarray(x[:, :n + 2])
         assert np.array_equal(_tx(R, "ffref", 6, 1, n, 0.5, xc.copy(), n).view(np.uint32), _tx(O, "orc", 6, 1, n, 0.5, xc.copy(), n).view(np.uint32))
         assert np.array_equal(_tx(R, "ffref", 1, 0, n, -1.0, x, n).view(np.uint32), _tx(O, "orc", 1, 0, n, -1.0, x, n).view(np.uint32))
+
+
+# ---------------------------------------------------------------------------------------------- mpegvideo inverse quantisers
+def test_unquant_oracle_golden():
+    """the seven dct_unquantize_* functions (mpegvideo_unquantize.c) against the reference's outputs"""
+    g = np.load(os.path.join(G, "unquant.npz"))
+    for variant in range(7):
+        for seed in (11, 12):
+            cfg, blocks, blk_n, q, last = cl.unquant_case(seed * 7 + variant, variant, nblocks=48)
+            out = cl.orc_unquant(variant, cfg, blocks, blk_n, q, last)
+            assert np.array_equal(out, g[f"v{variant}_s{seed}"]), (cl.UNQUANT_VARIANTS[variant], seed)
+            assert not np.array_equal(out, blocks)
+
+
+def test_unquant_oracle_vs_ref():
+    if not cl.have_ref():
+        pytest.skip("oracle/_ref not built")
+    for variant in range(7):
+        for seed in range(30):
+            cfg, blocks, blk_n, q, last = cl.unquant_case(100 + seed * 7 + variant, variant)
+            a = cl.ref_unquant(variant, cfg, blocks, blk_n, q, last)
+            b = cl.orc_unquant(variant, cfg, blocks, blk_n if seed % 3 else None, q, last) if seed % 3 else None
+            if b is None:                                            # macroblock stream order: n = index % 6
+                n6 = (np.arange(blocks.shape[0]) % 6).astype(np.uint8)
+                a = cl.ref_unquant(variant, cfg, blocks, n6, q, last)
+                b = cl.orc_unquant(variant, cfg, blocks, None, q, last)
+            assert np.array_equal(a, b), (cl.UNQUANT_VARIANTS[variant], seed)
+
+
+def test_unquant_properties():
+    """mismatch control leaves an odd coefficient sum (ISO 13818-2 7.4.4); untouched tail; mpeg1 results are odd"""
+    for variant in (3, 4):
+        cfg, blocks, blk_n, q, last = cl.unquant_case(900 + variant, variant, nblocks=200)
+        blocks[:, 63] = 0
+        for b in range(blocks.shape[0]):
+            if last[b] == 63:
+                last[b] = 62
+        scan = cl.ALTERNATE_VERTICAL if cfg["alternate_scan"] else cl.ZIGZAG
+        out = cl.orc_unquant(variant, cfg, blocks, blk_n, q, last).astype(np.int64)
+        for b in range(out.shape[0]):
+            coded = scan[:int(last[b]) + 1]
+            s = int(out[b, coded].sum()) + int(out[b, 63]) + (int(out[b, 0]) if variant == 3 and 0 not in coded else 0)
+            assert s & 1, (variant, b)
+    for variant in (0, 1):
+        cfg, blocks, blk_n, q, last = cl.unquant_case(950 + variant, variant, nblocks=100)
+        out = cl.orc_unquant(variant, cfg, blocks, blk_n, q, last)
+        scan = cl.ALTERNATE_VERTICAL if cfg["alternate_scan"] else cl.ZIGZAG
+        for b in range(out.shape[0]):
+            coded = scan[(1 if variant == 0 else 0):int(last[b]) + 1]
+            v = out[b, coded]
+            assert np.all((v[v != 0] & 1) == 1)
+            rest = scan[int(last[b]) + 1:]
+            assert np.array_equal(out[b, rest], blocks[b, rest])
