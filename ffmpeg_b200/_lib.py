@@ -78,6 +78,23 @@ class H264WeightContext(C.Structure):
     _fields_ = [("weight_pixels_tab", _H264W * 4), ("biweight_pixels_tab", _H264BW * 4)]
 
 
+class FloatDSPContext(C.Structure):
+    """AVFloatDSPContext, libavutil/float_dsp.h:24-210 (same member order)"""
+    _F, _D = C.POINTER(C.c_float), C.POINTER(C.c_double)
+    _fields_ = [("vector_fmul", C.CFUNCTYPE(None, _F, _F, _F, C.c_int)),
+                ("vector_fmac_scalar", C.CFUNCTYPE(None, _F, _F, C.c_float, C.c_int)),
+                ("vector_dmac_scalar", C.CFUNCTYPE(None, _D, _D, C.c_double, C.c_int)),
+                ("vector_fmul_scalar", C.CFUNCTYPE(None, _F, _F, C.c_float, C.c_int)),
+                ("vector_dmul_scalar", C.CFUNCTYPE(None, _D, _D, C.c_double, C.c_int)),
+                ("vector_fmul_window", C.CFUNCTYPE(None, _F, _F, _F, _F, C.c_int)),
+                ("vector_fmul_add", C.CFUNCTYPE(None, _F, _F, _F, _F, C.c_int)),
+                ("vector_fmul_reverse", C.CFUNCTYPE(None, _F, _F, _F, C.c_int)),
+                ("butterflies_float", C.CFUNCTYPE(None, _F, _F, C.c_int)),
+                ("scalarproduct_float", C.CFUNCTYPE(C.c_float, _F, _F, C.c_int)),
+                ("vector_dmul", C.CFUNCTYPE(None, _D, _D, _D, C.c_int)),
+                ("scalarproduct_double", C.CFUNCTYPE(C.c_double, _D, _D, C.c_size_t))]
+
+
 class MpvUnquant(C.Structure):
     """B200MpvUnquant: the MPVContext fields the inverse quantisers read (libavcodec/mpegvideo.h:70-77,201-203,258)"""
     _fields_ = [("intra_matrix", C.c_uint16 * 64), ("inter_matrix", C.c_uint16 * 64), ("permutated", C.c_uint8 * 64),
@@ -151,6 +168,8 @@ PROTOTYPES = {
     "b200_h264_weight_init": (C.c_int, [C.POINTER(H264WeightContext), C.c_int]),
     "b200_h264_weight_batch_device": (C.c_int, [vp, C.c_int64, vp, vp, vp, vp, vp, C.c_ssize_t]),
     "b200_mpv_unquantize_batch_device": (C.c_int, [vp, C.c_int, vp, vp, C.c_int64, vp, vp, vp]),
+    "b200_float_dsp_init": (C.c_int, [vp]),
+    "b200_float_dsp_batch_device": (C.c_int, [vp, C.c_int, C.c_int64, C.c_int, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, C.c_double]),
     "b200_videodsp_init": (C.c_int, [C.POINTER(VideoDSPContext), C.c_int]),
     "b200_emulated_edge_mc_batch_device": (C.c_int, [vp, C.c_int64, vp, vp, C.c_ssize_t, vp, vp, C.c_ssize_t, vp, C.c_int, C.c_int]),
     "b200_h264chroma_init": (C.c_int, [C.POINTER(H264ChromaContext), C.c_int]),

@@ -216,6 +216,48 @@ typedef struct B200MpvUnquant {
 int  b200_mpv_unquantize_batch_device(B200Device *dev, int variant, const B200MpvUnquant *p, int16_t *blocks, int64_t nblocks,
                                       const uint8_t *blk_n, const uint8_t *qscale, const int8_t *last_index);
 
+/* ------------------------------------------------------------------------------------------------ float_dsp
+ * Replaces AVFloatDSPContext (libavutil/float_dsp.h:24-210) as avpriv_float_dsp_alloc() fills it with the C functions
+ * (libavutil/float_dsp.c:27-141, float_scalarproduct.c:25-33): the element-wise float work around the transforms, e.g.
+ * vector_fmul_window after every iMDCT of the AAC decoder (libavcodec/aac/aacdec_dsp_template.c).  Same member order as the
+ * reference struct.  The table entries take HOST pointers (copy in, kernel, copy out). */
+typedef struct B200FloatDSPContext {
+    void   (*vector_fmul)(float *dst, const float *src0, const float *src1, int len);
+    void   (*vector_fmac_scalar)(float *dst, const float *src, float mul, int len);
+    void   (*vector_dmac_scalar)(double *dst, const double *src, double mul, int len);
+    void   (*vector_fmul_scalar)(float *dst, const float *src, float mul, int len);
+    void   (*vector_dmul_scalar)(double *dst, const double *src, double mul, int len);
+    void   (*vector_fmul_window)(float *dst, const float *src0, const float *src1, const float *win, int len);
+    void   (*vector_fmul_add)(float *dst, const float *src0, const float *src1, const float *src2, int len);
+    void   (*vector_fmul_reverse)(float *dst, const float *src0, const float *src1, int len);
+    void   (*butterflies_float)(float *v1, float *v2, int len);
+    float  (*scalarproduct_float)(const float *v1, const float *v2, int len);
+    void   (*vector_dmul)(double *dst, const double *src0, const double *src1, int len);
+    double (*scalarproduct_double)(const double *v1, const double *v2, size_t len);
+} B200FloatDSPContext;
+int  b200_float_dsp_init(B200FloatDSPContext *c);        /* like avpriv_float_dsp_alloc(), into caller storage */
+/* ops, numbered in the struct's member order */
+#define B200_FDSP_VECTOR_FMUL          0
+#define B200_FDSP_VECTOR_FMAC_SCALAR   1
+#define B200_FDSP_VECTOR_DMAC_SCALAR   2
+#define B200_FDSP_VECTOR_FMUL_SCALAR   3
+#define B200_FDSP_VECTOR_DMUL_SCALAR   4
+#define B200_FDSP_VECTOR_FMUL_WINDOW   5
+#define B200_FDSP_VECTOR_FMUL_ADD      6
+#define B200_FDSP_VECTOR_FMUL_REVERSE  7
+#define B200_FDSP_BUTTERFLIES_FLOAT    8
+#define B200_FDSP_SCALARPRODUCT_FLOAT  9
+#define B200_FDSP_VECTOR_DMUL          10
+#define B200_FDSP_SCALARPRODUCT_DOUBLE 11
+/* batched, DEVICE pointers: nvec vectors of len elements (float, or double for the D ops); vector v of each operand starts at
+ * base + v*stride (strides in elements; 0 = one vector shared by all, e.g. the window).  Operand roles as in the reference:
+ * vector_fmul_window: src2 = window of 2*len, dst gets 2*len; butterflies_float: dst = v1, src0 = v2, both rewritten;
+ * the scalar products put one value per vector at dst[v*dst_stride] and, like the C loops, sum left to right (one thread per
+ * vector: exact, not fast).  fmac / butterflies read dst; otherwise dst may alias an input only element for element. */
+int  b200_float_dsp_batch_device(B200Device *dev, int op, int64_t nvec, int len, void *dst, int64_t dst_stride,
+                                 const void *src0, int64_t src0_stride, const void *src1, int64_t src1_stride,
+                                 const void *src2, int64_t src2_stride, double mul);
+
 /* H.264 residual transforms, 8 bit: the IDCT members of H264DSPContext (libavcodec/h264dsp.h:81-88) as installed by
  * ff_h264dsp_init(c, 8, chroma_format_idc) (libavcodec/h264dsp.c:66-139): ff_h264_idct_add_8_c, ff_h264_idct8_add_8_c,
  * ff_h264_idct_dc_add_8_c, ff_h264_idct8_dc_add_8_c (libavcodec/h264idct_template.c:33-181).  The add16/add8/add4 wrappers

@@ -98,6 +98,13 @@ void orc_mpv_unquantize(int variant, const OrcMpvUnquant *p, int16_t *block, int
 /* blk_n NULL: blocks come in macroblock order, n = index % 6 */
 void orc_mpv_unquantize_batch(int variant, const OrcMpvUnquant *p, int16_t *blocks, int64_t nblocks, const uint8_t *blk_n,
                               const uint8_t *qscale, const int8_t *last_index);
+/* AVFloatDSPContext (libavutil/float_dsp.h:24-210), ops numbered in the struct's member order.  dst/src are float (double for
+ * the D ops); vector_fmul_window: src2 = the 2*len window, dst has 2*len elements; butterflies: dst = v1, src0 = v2, both
+ * written; the scalar products leave their result in dst[0]. */
+enum { ORC_FDSP_VECTOR_FMUL, ORC_FDSP_VECTOR_FMAC_SCALAR, ORC_FDSP_VECTOR_DMAC_SCALAR, ORC_FDSP_VECTOR_FMUL_SCALAR,
+       ORC_FDSP_VECTOR_DMUL_SCALAR, ORC_FDSP_VECTOR_FMUL_WINDOW, ORC_FDSP_VECTOR_FMUL_ADD, ORC_FDSP_VECTOR_FMUL_REVERSE,
+       ORC_FDSP_BUTTERFLIES_FLOAT, ORC_FDSP_SCALARPRODUCT_FLOAT, ORC_FDSP_VECTOR_DMUL, ORC_FDSP_SCALARPRODUCT_DOUBLE };
+int  orc_float_dsp(int op, void *dst, const void *src0, const void *src1, const void *src2, double mul, int len);
 /* H.264 residual add, 8 bit: kind 0 idct_add (4x4), 1 idct8_add, 2 idct_dc_add, 3 idct8_dc_add; clears the coefficients */
 int  orc_h264_idct(int kind, uint8_t *dst, int16_t *block, ptrdiff_t stride);
 void orc_pixels_clamped(int kind, const int16_t *block, uint8_t *pixels, ptrdiff_t line_size);

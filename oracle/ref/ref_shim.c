@@ -446,3 +446,29 @@ API int ffref_mpv_unquantize_batch(int variant, const uint16_t *intra_matrix, co
     av_free(s);
     return 0;
 }
+
+/* ------------------------------------------------------------------ AVFloatDSPContext ---------------------------- */
+#include "libavutil/float_dsp.h"
+
+/* op = member index in AVFloatDSPContext (float_dsp.h:24-210); argument meaning as orc_float_dsp */
+API int ffref_float_dsp(int op, void *dst, const void *src0, const void *src1, const void *src2, double mul, int len)
+{
+    static AVFloatDSPContext *f;
+    if (!f) f = avpriv_float_dsp_alloc(0);
+    if (!f) return -1;
+    switch (op) {
+    case 0:  f->vector_fmul(dst, src0, src1, len); return 0;
+    case 1:  f->vector_fmac_scalar(dst, src0, (float)mul, len); return 0;
+    case 2:  f->vector_dmac_scalar(dst, src0, mul, len); return 0;
+    case 3:  f->vector_fmul_scalar(dst, src0, (float)mul, len); return 0;
+    case 4:  f->vector_dmul_scalar(dst, src0, mul, len); return 0;
+    case 5:  f->vector_fmul_window(dst, src0, src1, src2, len); return 0;
+    case 6:  f->vector_fmul_add(dst, src0, src1, src2, len); return 0;
+    case 7:  f->vector_fmul_reverse(dst, src0, src1, len); return 0;
+    case 8:  f->butterflies_float(dst, (float *)src0, len); return 0;
+    case 9:  *(float *)dst = f->scalarproduct_float(src0, src1, len); return 0;
+    case 10: f->vector_dmul(dst, src0, src1, len); return 0;
+    case 11: *(double *)dst = f->scalarproduct_double(src0, src1, len); return 0;
+    }
+    return -1;
+}

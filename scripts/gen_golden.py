@@ -100,6 +100,18 @@ def gen_unquant():
     np.savez_compressed(os.path.join(OUT, "unquant.npz"), **d)
 
 
+def gen_fdsp():
+    """AVFloatDSPContext C functions: the reference's outputs for fdsp_case(seed, op, length)."""
+    d = {}
+    for op in range(12):
+        for length in (16, 100, 1024):
+            r, a = cl.ref_fdsp(op, *cl.fdsp_case(40 + op, op, length), length)
+            d[f"op{op}_n{length}"] = r
+            if op == 8:
+                d[f"op{op}_n{length}_v2"] = a
+    np.savez_compressed(os.path.join(OUT, "fdsp.npz"), **d)
+
+
 def gen_sws_fastbil():
     from cases import SWS_FASTBIL_CASES
     lines = []
@@ -404,5 +416,6 @@ if __name__ == "__main__":
     gen_sws_slices()
     gen_sws_range()
     gen_unquant()
+    gen_fdsp()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

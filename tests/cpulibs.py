@@ -328,6 +328,44 @@ def ref_unquant(variant, cfg, blocks, blk_n, qscale, last):
     return out
 
 
+# ---------------------------------------------------------------- AVFloatDSPContext (libavutil/float_dsp.c)
+FDSP_OPS = ["vector_fmul", "vector_fmac_scalar", "vector_dmac_scalar", "vector_fmul_scalar", "vector_dmul_scalar", "vector_fmul_window",
+            "vector_fmul_add", "vector_fmul_reverse", "butterflies_float", "scalarproduct_float", "vector_dmul", "scalarproduct_double"]
+FDSP_DOUBLE = (2, 4, 10, 11)
+
+
+def fdsp_case(seed, op, length):
+    """(dst, src0, src1, src2, mul): dst/src2 have 2*length elements for vector_fmul_window; mixed magnitudes, a few
+    denormals and signed zeros"""
+    rng = np.random.default_rng(seed)
+    dt = np.float64 if op in FDSP_DOUBLE else np.float32
+    n2 = 2 * length if op == 5 else length
+
+    def mk(n):
+        a = (rng.standard_normal(n) * rng.choice([1e-3, 1.0, 1e3], n)).astype(dt)
+        if n > 8:
+            a[rng.integers(0, n, 3)] = [0.0, -0.0, np.finfo(dt).tiny / 4]
+        return a
+    return mk(n2), mk(length), mk(length), mk(n2), float(np.float32(rng.standard_normal()))
+
+
+def _fdsp_run(L, name, op, dst, src0, src1, src2, mul, length):
+    f = getattr(L, name)
+    f.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int]
+    d, a = dst.copy(), src0.copy()
+    assert f(op, d.ctypes.data, a.ctypes.data, src1.ctypes.data, src2.ctypes.data, mul, length) == 0
+    return (d[:1] if op in (9, 11) else d), a
+
+
+def orc_fdsp(op, dst, src0, src1, src2, mul, length):
+    """returns (dst after, src0 after) — src0 changes only for butterflies_float; the scalar products return dst[:1]"""
+    return _fdsp_run(oracle(), "orc_float_dsp", op, dst, src0, src1, src2, mul, length)
+
+
+def ref_fdsp(op, dst, src0, src1, src2, mul, length):
+    return _fdsp_run(ref(), "ffref_float_dsp", op, dst, src0, src1, src2, mul, length)
+
+
 NUT_PATH = os.path.join(ROOT, "oracle", "_ref", "libffnut.so")
 _nut = None
 

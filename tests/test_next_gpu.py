@@ -63,3 +63,60 @@ def test_unquant_errors(device):
         with pytest.raises(fb.B200Error):
             mv.unquantize_batch_device(device, 7, p, db, 8, None, dq, dl)
         assert mv.unquantize_batch_device(device, 0, p, db, 0, None, dq, dl) == 0
+
+
+# ---------------------------------------------------------------------------------------------- AVFloatDSPContext
+def test_fdsp_pointer_table_golden(device):
+    """AVFloatDSPContext entries called with host pointers, against the reference's outputs (fdsp.npz), bit for bit"""
+    import ctypes as C
+    from ffmpeg_b200 import float_dsp as fd
+    g = np.load(os.path.join(G, "fdsp.npz"))
+    c = fd.avpriv_float_dsp_alloc(0)
+    F, D = C.POINTER(C.c_float), C.POINTER(C.c_double)
+    for op in range(12):
+        P = D if op in cl.FDSP_DOUBLE else F
+        for length in (16, 100, 1024):
+            dst, s0, s1, s2, mul = cl.fdsp_case(40 + op, op, length)
+            p = lambda a: a.ctypes.data_as(P)
+            name = cl.FDSP_OPS[op]
+            fn = getattr(c, name)
+            if op in (0, 7, 10):
+                fn(p(dst), p(s0), p(s1), length)
+            elif op in (1, 2, 3, 4):
+                fn(p(dst), p(s0), mul, length)
+            elif op in (5, 6):
+                fn(p(dst), p(s0), p(s1), p(s2), length)
+            elif op == 8:
+                fn(p(dst), p(s0), length)
+                assert s0.tobytes() == g[f"op{op}_n{length}_v2"].tobytes()
+            else:
+                dst = np.array([fn(p(s0), p(s1), length)], dst.dtype)
+            got = dst[:1] if op in (9, 11) else dst
+            assert got.tobytes() == g[f"op{op}_n{length}"].tobytes(), (name, length)
+
+
+def test_fdsp_batch_vs_oracle(device):
+    """batched device entry point: many vectors, shared window / operand (stride 0), odd lengths, more than 65535 vectors"""
+    import torch
+    from ffmpeg_b200 import float_dsp as fd
+    for op in range(12):
+        for length, nvec in ((1024, 40), (77, 9), (8, 70000 if op in (0, 9) else 300)):
+            dt = np.float64 if op in cl.FDSP_DOUBLE else np.float32
+            n2 = 2 * length if op == 5 else length
+            cases = [cl.fdsp_case(700 + op * 31 + v % 50, op, length) for v in range(min(nvec, 50))]
+            idx = np.arange(nvec) % len(cases)
+            dst = np.stack([cases[i][0] for i in idx]); s0 = np.stack([cases[i][1] for i in idx]); s1 = np.stack([cases[i][2] for i in idx])
+            s2 = cases[0][3]                                            # one window / addend for all vectors (stride 0)
+            mul = cases[0][4]
+            exp = [cl.orc_fdsp(op, cases[i][0], cases[i][1], cases[i][2], s2, mul, length) for i in range(len(cases))]
+            dot = op in (9, 11)
+            with on_stream(device):
+                dd = torch.from_numpy(np.zeros(nvec, dt) if dot else dst).cuda()
+                d0, d1, d2 = torch.from_numpy(s0).cuda(), torch.from_numpy(s1).cuda(), torch.from_numpy(s2).cuda()
+                fd.float_dsp_batch_device(device, op, nvec, length, dd, 1 if dot else n2, d0, length, d1, length, d2, 0, mul)
+                device.sync()
+                got, got0 = dd.cpu().numpy(), d0.cpu().numpy()
+            for v in range(nvec):
+                e, e0 = exp[idx[v]]
+                assert (got[v:v + 1] if dot else got[v]).tobytes() == e.tobytes(), (cl.FDSP_OPS[op], length, v)
+                assert got0[v].tobytes() == e0.tobytes(), (cl.FDSP_OPS[op], length, v, "src0")

@@ -323,3 +323,25 @@ def test_unquant_properties():
             assert np.all((v[v != 0] & 1) == 1)
             rest = scan[int(last[b]) + 1:]
             assert np.array_equal(out[b, rest], blocks[b, rest])
+
+
+# ---------------------------------------------------------------------------------------------- AVFloatDSPContext
+def test_fdsp_oracle_golden():
+    """the twelve AVFloatDSPContext C functions against the reference's outputs, bit for bit"""
+    g = np.load(os.path.join(G, "fdsp.npz"))
+    for op in range(12):
+        for length in (16, 100, 1024):
+            r, a = cl.orc_fdsp(op, *cl.fdsp_case(40 + op, op, length), length)
+            assert r.tobytes() == g[f"op{op}_n{length}"].tobytes(), (cl.FDSP_OPS[op], length)
+            if op == 8:
+                assert a.tobytes() == g[f"op{op}_n{length}_v2"].tobytes()
+
+
+def test_fdsp_oracle_vs_ref():
+    if not cl.have_ref():
+        pytest.skip("oracle/_ref not built")
+    for op in range(12):
+        for k, length in enumerate((1, 3, 17, 64, 333, 2048)):
+            case = cl.fdsp_case(500 + 13 * op + k, op, length)
+            (r1, a1), (r2, a2) = cl.ref_fdsp(op, *case, length), cl.orc_fdsp(op, *case, length)
+            assert r1.tobytes() == r2.tobytes() and a1.tobytes() == a2.tobytes(), (cl.FDSP_OPS[op], length)
