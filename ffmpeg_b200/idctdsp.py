@@ -21,6 +21,21 @@ def ff_idctdsp_init(idct_algo=FF_IDCT_SIMPLE, bits_per_raw_sample=8, lowres=0):
     return c
 
 
+def ff_idctdsp_init_hbd(idct_algo=FF_IDCT_SIMPLE, bits_per_raw_sample=10, lowres=0):
+    """ff_idctdsp_init for bits_per_raw_sample 9 / 10 / 12 (idctdsp.c:248-266): uint16 pixels, line sizes in bytes."""
+    c = IDCTDSPContext()
+    check(lib().b200_idctdsp_init_hbd(C.byref(c), idct_algo, bits_per_raw_sample, lowres), "ff_idctdsp_init_hbd")
+    return c
+
+
+def idct_hbd_batch_device(device, depth, kind, blocks, nblocks, dest=None, dest_off=None, line_size=None, uniform_line_size=0):
+    return check(lib().b200_idct_hbd_batch_device(device.handle, depth, kind, vp(_dptr(blocks)), nblocks,
+                                                  vp(_dptr(dest)) if dest is not None else None,
+                                                  vp(_dptr(dest_off)) if dest_off is not None else None,
+                                                  vp(_dptr(line_size)) if line_size is not None else None, uniform_line_size),
+                 "idct_hbd_batch_device")
+
+
 def idct_batch_device(device, kind, blocks, nblocks, dest=None, dest_off=None, line_size=None, uniform_line_size=0):
     return check(lib().b200_idct_batch_device(device.handle, kind, vp(_dptr(blocks)), nblocks, vp(_dptr(dest)) if dest is not None else None,
                                               vp(_dptr(dest_off)) if dest_off is not None else None,

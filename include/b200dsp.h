@@ -191,6 +191,15 @@ int  b200_idct_mb420_device(B200Device *dev, int kind, const int16_t *blocks, in
 int  b200_idct_mb420_host(B200Device *dev, int kind, const int16_t *blocks, int mb_w, int mb_h, int nframes,
                           uint8_t *const planes[3], const int linesize[3], const int64_t frame_stride[3]);
 
+/* The same table for bits_per_raw_sample 9 / 10 / 12: ff_simple_idct_{,put_,add_}int16_10bit resp. _12bit
+ * (libavcodec/idctdsp.c:248-266, libavcodec/simple_idct_template.c:63-104,329-368); uint16 pixels, line sizes in bytes.  Kept as a
+ * separate entry until it has run on hardware, then b200_idctdsp_init() takes the depth.  The clamp helpers stay the 8-bit ones
+ * like the reference's.  As with the 8-bit batch call the coefficient blocks are NOT clobbered by put / add. */
+int  b200_idctdsp_init_hbd(B200IDCTDSPContext *c, int idct_algo, int bits_per_raw_sample, int lowres);
+/* batched, DEVICE pointers: as b200_idct_batch_device with depth 10 (9 maps to it) or 12; dest_off / line sizes in bytes, even */
+int  b200_idct_hbd_batch_device(B200Device *dev, int depth, int kind, int16_t *blocks, int64_t nblocks, uint8_t *dest,
+                                const int64_t *dest_off, const int32_t *line_size, int uniform_line_size);
+
 /* mpegvideo inverse quantisers: the members of MPVUnquantDSPContext (libavcodec/mpegvideo_unquantize.h:31-44) as
  * ff_mpv_unquantize_init() installs them (libavcodec/mpegvideo_unquantize.c:50-290), i.e. what runs in front of the IDCT in
  * mpv_reconstruct_mb's put_dct / add_dequant_dct (libavcodec/mpegvideo_dec.c).  The reference functions take the whole

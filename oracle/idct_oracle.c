@@ -102,6 +102,85 @@ void orc_idct_batch(int kind, int16_t *blocks, int nblocks, uint8_t *dest, ptrdi
     }
 }
 
+/* ------------------------------------------------------------------ simple IDCT, 10 and 12 bit (int16 coefficients)
+ * libavcodec/simple_idct_template.c:63-104 (constants: 10 bit W3 = 19265, W4 = 16384, ROW_SHIFT 12, COL_SHIFT 19, DC_SHIFT 2;
+ * 12 bit W = 45451 ... 9041, ROW_SHIFT 16, COL_SHIFT 17, DC_SHIFT -1), :114-206 row pass with the DC-only shortcut
+ * ((row[0] << 2) for 10 bit, (row[0] + 1) >> 1 for 12 bit, both & 0xffff), :209-257 columns, :281-368 put / add / in place on
+ * uint16 pixels clipped to the bit depth.  Installed by ff_idctdsp_init for bits_per_raw_sample 9, 10 and 12
+ * (idctdsp.c:248-266).  All sums mod 2^32 as in the reference (SUINT / unsigned MUL, MAC). */
+typedef struct { uint32_t w[8]; int row_shift, col_shift, dc_shift, depth; } HbdConst;
+static const HbdConst HBD10 = { { 0, 22725, 21407, 19265, 16384, 12873, 8867, 4520 }, 12, 19, 2, 10 };
+static const HbdConst HBD12 = { { 0, 45451, 42813, 38531, 32767, 25746, 17734, 9041 }, 16, 17, -1, 12 };
+
+static void hbd_row(const HbdConst *k, int16_t *r)
+{
+    const uint32_t *W = k->w;
+    if (!(r[1] | r[2] | r[3] | r[4] | r[5] | r[6] | r[7])) {
+        int t = k->dc_shift >= 0 ? r[0] * (1 << k->dc_shift) : (r[0] + (1 << (-k->dc_shift - 1))) >> -k->dc_shift;
+        int16_t dc = (int16_t)(uint16_t)(t & 0xffff);
+        for (int i = 0; i < 8; i++) r[i] = dc;
+        return;
+    }
+    uint32_t a0 = W[4] * (uint32_t)r[0] + (1u << (k->row_shift - 1)), a1 = a0, a2 = a0, a3 = a0;
+    a0 += W[2] * (uint32_t)r[2]; a1 += W[6] * (uint32_t)r[2]; a2 -= W[6] * (uint32_t)r[2]; a3 -= W[2] * (uint32_t)r[2];
+    uint32_t b0 = W[1] * (uint32_t)r[1] + W[3] * (uint32_t)r[3];
+    uint32_t b1 = W[3] * (uint32_t)r[1] - W[7] * (uint32_t)r[3];
+    uint32_t b2 = W[5] * (uint32_t)r[1] - W[1] * (uint32_t)r[3];
+    uint32_t b3 = W[7] * (uint32_t)r[1] - W[5] * (uint32_t)r[3];
+    a0 += W[4] * (uint32_t)r[4] + W[6] * (uint32_t)r[6];
+    a1 += -W[4] * (uint32_t)r[4] - W[2] * (uint32_t)r[6];
+    a2 += -W[4] * (uint32_t)r[4] + W[2] * (uint32_t)r[6];
+    a3 += W[4] * (uint32_t)r[4] - W[6] * (uint32_t)r[6];
+    b0 += W[5] * (uint32_t)r[5] + W[7] * (uint32_t)r[7];
+    b1 += -W[1] * (uint32_t)r[5] - W[5] * (uint32_t)r[7];
+    b2 += W[7] * (uint32_t)r[5] + W[3] * (uint32_t)r[7];
+    b3 += W[3] * (uint32_t)r[5] - W[1] * (uint32_t)r[7];
+    const int sh = k->row_shift;
+    r[0] = (int16_t)((int32_t)(a0 + b0) >> sh); r[7] = (int16_t)((int32_t)(a0 - b0) >> sh);
+    r[1] = (int16_t)((int32_t)(a1 + b1) >> sh); r[6] = (int16_t)((int32_t)(a1 - b1) >> sh);
+    r[2] = (int16_t)((int32_t)(a2 + b2) >> sh); r[5] = (int16_t)((int32_t)(a2 - b2) >> sh);
+    r[3] = (int16_t)((int32_t)(a3 + b3) >> sh); r[4] = (int16_t)((int32_t)(a3 - b3) >> sh);
+}
+
+static void hbd_col(const HbdConst *k, const int16_t *c, int out[8])
+{
+    const uint32_t *W = k->w;
+    uint32_t a0 = W[4] * (uint32_t)(c[0] + (int)((1u << (k->col_shift - 1)) / W[4])), a1 = a0, a2 = a0, a3 = a0;
+    a0 += W[2] * (uint32_t)c[16]; a1 += W[6] * (uint32_t)c[16]; a2 -= W[6] * (uint32_t)c[16]; a3 -= W[2] * (uint32_t)c[16];
+    uint32_t b0 = W[1] * (uint32_t)c[8], b1 = W[3] * (uint32_t)c[8], b2 = W[5] * (uint32_t)c[8], b3 = W[7] * (uint32_t)c[8];
+    b0 += W[3] * (uint32_t)c[24]; b1 -= W[7] * (uint32_t)c[24]; b2 -= W[1] * (uint32_t)c[24]; b3 -= W[5] * (uint32_t)c[24];
+    a0 += W[4] * (uint32_t)c[32]; a1 -= W[4] * (uint32_t)c[32]; a2 -= W[4] * (uint32_t)c[32]; a3 += W[4] * (uint32_t)c[32];
+    b0 += W[5] * (uint32_t)c[40]; b1 -= W[1] * (uint32_t)c[40]; b2 += W[7] * (uint32_t)c[40]; b3 += W[3] * (uint32_t)c[40];
+    a0 += W[6] * (uint32_t)c[48]; a1 -= W[2] * (uint32_t)c[48]; a2 += W[2] * (uint32_t)c[48]; a3 -= W[6] * (uint32_t)c[48];
+    b0 += W[7] * (uint32_t)c[56]; b1 -= W[5] * (uint32_t)c[56]; b2 += W[3] * (uint32_t)c[56]; b3 -= W[1] * (uint32_t)c[56];
+    const int sh = k->col_shift;
+    out[0] = (int32_t)(a0 + b0) >> sh; out[1] = (int32_t)(a1 + b1) >> sh; out[2] = (int32_t)(a2 + b2) >> sh; out[3] = (int32_t)(a3 + b3) >> sh;
+    out[4] = (int32_t)(a3 - b3) >> sh; out[5] = (int32_t)(a2 - b2) >> sh; out[6] = (int32_t)(a1 - b1) >> sh; out[7] = (int32_t)(a0 - b0) >> sh;
+}
+
+/* depth 10 (also what 9-bit content uses) or 12; kind 0 in place, 1 put, 2 add; dest = uint16 pixels, line_size in bytes */
+int orc_idct_hbd(int depth, int kind, uint8_t *dest_, ptrdiff_t line_size, int16_t *block)
+{
+    const HbdConst *k = depth == 10 ? &HBD10 : depth == 12 ? &HBD12 : 0;
+    if (!k || kind < 0 || kind > 2) return -1;
+    uint16_t *dest = (uint16_t *)dest_;
+    const ptrdiff_t ls = line_size / 2;
+    const int maxv = (1 << depth) - 1;
+    int o[8];
+    for (int i = 0; i < 8; i++) hbd_row(k, block + 8 * i);
+    for (int i = 0; i < 8; i++) {
+        hbd_col(k, block + i, o);
+        for (int j = 0; j < 8; j++) {
+            if (kind == 0) block[8 * j + i] = (int16_t)o[j];
+            else {
+                int v = kind == 1 ? o[j] : dest[j * ls + i] + o[j];
+                dest[j * ls + i] = (uint16_t)(v < 0 ? 0 : v > maxv ? maxv : v);
+            }
+        }
+    }
+    return 0;
+}
+
 /* idctdsp.c:73-165; kind 0 put, 1 put_signed, 2 add */
 void orc_pixels_clamped(int kind, const int16_t *block, uint8_t *pixels, ptrdiff_t ls)
 {

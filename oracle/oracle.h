@@ -83,6 +83,9 @@ void orc_idct_put(uint8_t *dest, ptrdiff_t line_size, int16_t *block);
 void orc_idct_add(uint8_t *dest, ptrdiff_t line_size, int16_t *block);
 void orc_idct_batch(int kind, int16_t *blocks, int nblocks, uint8_t *dest, ptrdiff_t line_size,
                     const int64_t *dest_off);
+/* simple IDCT at 10 / 12 bit (ff_simple_idct_{,put_,add_}int16_{10,12}bit): kind 0 in place, 1 put, 2 add; dest = uint16 pixels,
+ * line_size in bytes; the block is clobbered like the reference's */
+int  orc_idct_hbd(int depth, int kind, uint8_t *dest, ptrdiff_t line_size, int16_t *block);
 /* inverse quantisers of libavcodec/mpegvideo_unquantize.c (MPVUnquantDSPContext), in place on int16[64] blocks */
 enum { ORC_UNQUANT_MPEG1_INTRA, ORC_UNQUANT_MPEG1_INTER, ORC_UNQUANT_MPEG2_INTRA, ORC_UNQUANT_MPEG2_INTRA_BITEXACT,
        ORC_UNQUANT_MPEG2_INTER, ORC_UNQUANT_H263_INTRA, ORC_UNQUANT_H263_INTER };

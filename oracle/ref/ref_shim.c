@@ -472,3 +472,30 @@ API int ffref_float_dsp(int op, void *dst, const void *src0, const void *src1, c
     }
     return -1;
 }
+
+/* ------------------------------------------------------------------ simple IDCT, 10 / 12 bit ---------------------- */
+#include "libavcodec/avcodec.h"
+#include "libavcodec/idctdsp.h"
+
+/* through ff_idctdsp_init() with bits_per_raw_sample = depth (9, 10 or 12), idct_algo = FF_IDCT_SIMPLE: whatever it installs
+ * (idctdsp.c:248-266).  kind 0 idct, 1 idct_put, 2 idct_add; dest = uint16 pixels, line_size in bytes. */
+API int ffref_idct_hbd(int depth, int kind, uint8_t *dest, ptrdiff_t line_size, int16_t *block)
+{
+    static IDCTDSPContext c[13];
+    static int done[13];
+    if (depth < 9 || depth > 12) return -1;
+    if (!done[depth]) {
+        AVCodecContext *avctx = av_mallocz(sizeof(*avctx));
+        if (!avctx) return -1;
+        avctx->bits_per_raw_sample = depth;
+        avctx->idct_algo = FF_IDCT_SIMPLE;
+        ff_idctdsp_init(&c[depth], avctx);
+        av_free(avctx);
+        done[depth] = 1;
+    }
+    if (c[depth].perm_type != FF_IDCT_PERM_NONE) return -2;
+    if (kind == 0) c[depth].idct(block);
+    else if (kind == 1) c[depth].idct_put(dest, line_size, block);
+    else c[depth].idct_add(dest, line_size, block);
+    return 0;
+}

@@ -112,6 +112,18 @@ def gen_fdsp():
     np.savez_compressed(os.path.join(OUT, "fdsp.npz"), **d)
 
 
+def gen_idct_hbd():
+    """10 / 12 bit simple IDCT: the reference's outputs (through ff_idctdsp_init) for idct_hbd_blocks(seed, depth, 60)."""
+    d = {}
+    for depth in (10, 12):
+        blocks = cl.idct_hbd_blocks(70 + depth, depth, 60)
+        dest = np.random.default_rng(depth).integers(0, 1 << depth, (8, 60 * 8), dtype=np.uint16)
+        for kind in (0, 1, 2):
+            b, o = cl.ref_idct_hbd(depth, kind, blocks, dest, dest.strides[0])
+            d[f"d{depth}_k{kind}"] = b if kind == 0 else o
+    np.savez_compressed(os.path.join(OUT, "idct_hbd.npz"), **d)
+
+
 def gen_sws_fastbil():
     from cases import SWS_FASTBIL_CASES
     lines = []
@@ -417,5 +429,6 @@ if __name__ == "__main__":
     gen_sws_range()
     gen_unquant()
     gen_fdsp()
+    gen_idct_hbd()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

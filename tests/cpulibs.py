@@ -328,6 +328,50 @@ def ref_unquant(variant, cfg, blocks, blk_n, qscale, last):
     return out
 
 
+# ---------------------------------------------------------------- simple IDCT, 10 / 12 bit
+def idct_hbd_blocks(seed, depth, n):
+    """n coefficient blocks: dense small, full int16 range, sparse, DC only, DC-only rows, decoder-like range"""
+    rng = np.random.default_rng(seed)
+    out = np.zeros((n, 64), np.int16)
+    for i in range(n):
+        mode = i % 6
+        if mode == 0:
+            b = rng.integers(-512, 513, 64)
+        elif mode == 1:
+            b = rng.integers(-32768, 32768, 64)
+        elif mode == 2:
+            b = np.zeros(64, np.int64)
+            b[rng.integers(0, 64, int(rng.integers(1, 6)))] = rng.integers(-4000, 4000)
+        elif mode == 3:
+            b = np.zeros(64, np.int64)
+            b[0] = rng.integers(-32768, 32768)
+        elif mode == 4:
+            b = np.zeros(64, np.int64)
+            b[::8] = rng.integers(-3000, 3000, 8)
+        else:
+            b = rng.integers(-(1 << (depth + 3)), 1 << (depth + 3), 64)
+        out[i] = b
+    return out
+
+
+def _idct_hbd_run(L, name, depth, kind, blocks, dest, line_size):
+    """blocks [n, 64] int16, dest uint16 [8, n*8 (+pad)]: block i at column 8*i.  Returns (blocks after, dest after)."""
+    f = getattr(L, name)
+    f.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_ssize_t, C.c_void_p]
+    b, d = blocks.copy(), dest.copy()
+    for i in range(b.shape[0]):
+        assert f(depth, kind, d.ctypes.data + 16 * i, line_size, b[i].ctypes.data) == 0
+    return b, d
+
+
+def orc_idct_hbd(depth, kind, blocks, dest, line_size):
+    return _idct_hbd_run(oracle(), "orc_idct_hbd", depth, kind, blocks, dest, line_size)
+
+
+def ref_idct_hbd(depth, kind, blocks, dest, line_size):
+    return _idct_hbd_run(ref(), "ffref_idct_hbd", depth, kind, blocks, dest, line_size)
+
+
 # ---------------------------------------------------------------- AVFloatDSPContext (libavutil/float_dsp.c)
 FDSP_OPS = ["vector_fmul", "vector_fmac_scalar", "vector_dmac_scalar", "vector_fmul_scalar", "vector_dmul_scalar", "vector_fmul_window",
             "vector_fmul_add", "vector_fmul_reverse", "butterflies_float", "scalarproduct_float", "vector_dmul", "scalarproduct_double"]

@@ -120,3 +120,59 @@ def test_fdsp_batch_vs_oracle(device):
                 e, e0 = exp[idx[v]]
                 assert (got[v:v + 1] if dot else got[v]).tobytes() == e.tobytes(), (cl.FDSP_OPS[op], length, v)
                 assert got0[v].tobytes() == e0.tobytes(), (cl.FDSP_OPS[op], length, v, "src0")
+
+
+# ---------------------------------------------------------------------------------------------- simple IDCT, 10 / 12 bit
+def gpu_idct_hbd(device, depth, kind, blocks, dest):
+    """blocks [n, 64], dest uint16 [8, >= n*8]: block i at column 8*i -> (blocks after, dest after)"""
+    import torch
+    from ffmpeg_b200 import idctdsp
+    n = blocks.shape[0]
+    off = (np.arange(n, dtype=np.int64) * 16)
+    with on_stream(device):
+        db, dd, do = torch.from_numpy(blocks.copy()).cuda(), torch.from_numpy(dest.view(np.int16).copy()).cuda(), torch.from_numpy(off).cuda()
+        idctdsp.idct_hbd_batch_device(device, depth, kind, db, n, dd, do, None, dest.strides[0])
+        device.sync()
+        return db.cpu().numpy(), dd.cpu().numpy().view(np.uint16)
+
+
+def test_idct_hbd_golden_and_oracle(device):
+    g = np.load(os.path.join(G, "idct_hbd.npz"))
+    for depth in (10, 12):
+        blocks = cl.idct_hbd_blocks(70 + depth, depth, 60)
+        dest = np.random.default_rng(depth).integers(0, 1 << depth, (8, 60 * 8), dtype=np.uint16)
+        for kind in (0, 1, 2):
+            b, o = gpu_idct_hbd(device, depth, kind, blocks, dest)
+            assert np.array_equal(b if kind == 0 else o, g[f"d{depth}_k{kind}"]), (depth, kind)
+            if kind:
+                assert np.array_equal(b, blocks)                            # put / add leave the coefficients alone
+        for kind in (0, 1, 2):
+            blocks = cl.idct_hbd_blocks(400 + depth + kind, depth, 5000)
+            dest = np.random.default_rng(kind).integers(0, 1 << depth, (8, 5000 * 8 + 4), dtype=np.uint16)
+            b, o = gpu_idct_hbd(device, depth, kind, blocks, dest)
+            eb, eo = cl.orc_idct_hbd(depth, kind, blocks, dest, dest.strides[0])
+            assert np.array_equal(o, eo) and (kind != 0 or np.array_equal(b, eb)), (depth, kind)
+
+
+def test_idct_hbd_pointer_table(device):
+    """IDCTDSPContext for bits_per_raw_sample 9 / 10 / 12 called with host pointers"""
+    import ctypes as C
+    import ffmpeg_b200 as fb
+    from ffmpeg_b200 import idctdsp
+    from ffmpeg_b200._lib import u8p, i16p
+    for bits, depth in ((9, 10), (10, 10), (12, 12)):
+        c = idctdsp.ff_idctdsp_init_hbd(idctdsp.FF_IDCT_SIMPLE, bits, 0)
+        blocks = cl.idct_hbd_blocks(bits, depth, 12)
+        dest = np.random.default_rng(bits).integers(0, 1 << depth, (8, 12 * 8 + 3), dtype=np.uint16)
+        for kind in (0, 1, 2):
+            b, d = blocks.copy(), dest.copy()
+            for i in range(12):
+                blk = b[i].ctypes.data_as(i16p)
+                if kind == 0:
+                    c.idct(blk)
+                else:
+                    (c.idct_put if kind == 1 else c.idct_add)(C.cast(d.ctypes.data + 16 * i, u8p), d.strides[0], blk)
+            eb, ed = cl.orc_idct_hbd(depth, kind, blocks, dest, dest.strides[0])
+            assert np.array_equal(d, ed) and (kind != 0 or np.array_equal(b, eb)), (bits, kind)
+    with pytest.raises(fb.B200Error):
+        idctdsp.ff_idctdsp_init_hbd(idctdsp.FF_IDCT_SIMPLE, 8, 0)

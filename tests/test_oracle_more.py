@@ -345,3 +345,30 @@ def test_fdsp_oracle_vs_ref():
             case = cl.fdsp_case(500 + 13 * op + k, op, length)
             (r1, a1), (r2, a2) = cl.ref_fdsp(op, *case, length), cl.orc_fdsp(op, *case, length)
             assert r1.tobytes() == r2.tobytes() and a1.tobytes() == a2.tobytes(), (cl.FDSP_OPS[op], length)
+
+
+# ---------------------------------------------------------------------------------------------- simple IDCT, 10 / 12 bit
+def test_idct_hbd_oracle_golden():
+    g = np.load(os.path.join(G, "idct_hbd.npz"))
+    for depth in (10, 12):
+        blocks = cl.idct_hbd_blocks(70 + depth, depth, 60)
+        dest = np.random.default_rng(depth).integers(0, 1 << depth, (8, 60 * 8), dtype=np.uint16)
+        for kind in (0, 1, 2):
+            b, o = cl.orc_idct_hbd(depth, kind, blocks, dest, dest.strides[0])
+            assert np.array_equal(b if kind == 0 else o, g[f"d{depth}_k{kind}"]), (depth, kind)
+            assert o.max() < (1 << depth)
+
+
+def test_idct_hbd_oracle_vs_ref():
+    if not cl.have_ref():
+        pytest.skip("oracle/_ref not built")
+    for depth in (10, 12):
+        for kind in (0, 1, 2):
+            blocks = cl.idct_hbd_blocks(200 + depth + kind, depth, 300)
+            dest = np.random.default_rng(kind).integers(0, 1 << depth, (8, 300 * 8 + 5), dtype=np.uint16)
+            (b1, d1), (b2, d2) = cl.ref_idct_hbd(depth, kind, blocks, dest, dest.strides[0]), cl.orc_idct_hbd(depth, kind, blocks, dest, dest.strides[0])
+            assert np.array_equal(d1, d2) and np.array_equal(b1, b2), (depth, kind)
+    # 9-bit content gets the 10-bit functions (idctdsp.c:248)
+    blocks = cl.idct_hbd_blocks(9, 10, 30)
+    dest = np.zeros((8, 240), np.uint16)
+    assert np.array_equal(cl.ref_idct_hbd(9, 1, blocks, dest, 480)[1], cl.orc_idct_hbd(10, 1, blocks, dest, 480)[1])
