@@ -1,6 +1,6 @@
 // idct_hbd.cu — libavcodec's "simple" IDCT at 10 and 12 bit (int16 coefficients, uint16 pixels) on sm_100a.
 //
-// Reference semantics reproduced bit-for-bit (checker: oracle/idct_oracle.c, orc_idct_hbd), libavcodec/simple_idct_template.c:
+// Reference semantics reproduced bit-for-bit (checker: the 10 / 12 bit part of oracle/idct_oracle.c), libavcodec/simple_idct_template.c:
 //   :63-104   constants (10 bit: W3 = 19265, W4 = 16384, ROW_SHIFT 12, COL_SHIFT 19, DC_SHIFT 2; 12 bit: W1..W7 = 45451 ... 9041,
 //             ROW_SHIFT 16, COL_SHIFT 17, DC_SHIFT -1)
 //   :114-206  idctRowCondDC: rows without AC terms become (row[0] << 2) resp. (row[0] + 1) >> 1, & 0xffff; results back in int16
