@@ -30,6 +30,7 @@ extern "C" {
 #define ORC_SWS_AREA          0x20
 #define ORC_SWS_BICUBLIN      0x40
 #define ORC_SWS_FULL_CHR_H_INT 0x2000
+#define ORC_SWS_FULL_CHR_H_INP 0x4000
 #define ORC_SWS_ACCURATE_RND  0x40000
 #define ORC_SWS_BITEXACT      0x80000
 
@@ -47,7 +48,10 @@ typedef struct OrcSws OrcSws;
 #define ORC_PIX_FMT_BGRA  28
 OrcSws *orc_sws_open(int srcW, int srcH, int dstW, int dstH, int flags);                      /* rgb24 */
 OrcSws *orc_sws_open_fmt(int srcW, int srcH, int dstW, int dstH, int dstFormat, int flags);                 /* yuv420p source */
-/* srcFormat yuv420p, nv12 or nv21: for the semi-planar sources the scale calls take the interleaved plane as `u` (`v` unused) */
+/* srcFormat yuv420p, nv12 or nv21: for the semi-planar sources the scale calls take the interleaved plane as `u` (`v` unused).
+ * srcFormat rgb24 / bgr24 / rgba / bgra / argb / abgr (packed RGB source, the input readers of libswscale/input.c): the scale calls
+ * take the packed picture as `y` (`u`, `v` unused).  Not restated (open returns NULL): same-size RGB -> RGB (the reference's
+ * rgb2rgb shuffles) and a source with alpha scaled to a destination with alpha (the alpha plane then goes through the scaler). */
 OrcSws *orc_sws_open_io(int srcFormat, int srcW, int srcH, int dstFormat, int dstW, int dstH, int flags);
 /* src_range / dst_range (0 = limited "mpeg", 1 = full "jpeg") given before initialisation, like SwsContext.src_range /
  * .dst_range set ahead of sws_init_context; only a yuv destination converts ranges (swscale.c:626-660) */

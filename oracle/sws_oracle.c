@@ -46,6 +46,12 @@ struct OrcSws {
     int range_conv;            /* 0 none, 1 limited -> full (lum/chrRangeToJpeg_c, clips at 2^15-1), 2 full -> limited (FromJpeg) */
     int lum_coeff, lum_offset, chr_coeff, chr_offset;
     int src_cs[4], dst_cs[4];
+    /* packed RGB source (input.c readers -> 16-bit lines -> hScale16To15_c) */
+    int src_rgb;               /* 0: yuv source; 3 / 4: bytes per source pixel */
+    int sro, sgo, sbo;         /* byte positions of R, G, B in a source pixel */
+    int chrSrcHSub, chrSrcVSub;
+    int rgb2yuv[9];            /* input_rgb2yuv_table: RY GY BY RU GU BU RV GV BV (swscale_internal.h:468-477), 15-bit */
+    int bgr24_yv12;            /* 1: reference installs bgr24ToYv12Wrapper (ff_rgb24toyv12_c) as convert_unscaled */
 };
 
 static int64_t i64abs(int64_t a) { return a < 0 ? -a : a; }
@@ -314,18 +320,42 @@ static void init_range_convert(OrcSws *s)
     }
 }
 
+/* fill_rgb2yuv_table (utils.c:614-700): always the limited-range matrix ("range = 1 is handled elsewhere", i.e. by the range
+ * conversion between the passes); the default BT.601 table gets the hand-rounded constants of :692-702 */
+static void fill_rgb2yuv(OrcSws *s, const int table[4])
+{
+    const int64_t ONE = 65536;
+    int64_t vr = table[0], ub = table[1], ug = -table[2], vg = -table[3], cy = ONE * 255 / 219;
+    int64_t W = rounded_div(ONE * ONE * ug, ub), V = rounded_div(ONE * ONE * vg, vr), Z = ONE * ONE - W - V;
+    int64_t Cy = rounded_div(cy * Z, ONE), Cu = rounded_div(ub * Z, ONE), Cv = rounded_div(vr * Z, ONE);
+    int *t = s->rgb2yuv;
+    t[0] = (int)-rounded_div((1 << 15) * V, Cy);       t[1] = (int)rounded_div((1 << 15) * ONE * ONE, Cy);  t[2] = (int)-rounded_div((1 << 15) * W, Cy);
+    t[3] = (int)rounded_div((1 << 15) * V, Cu);        t[4] = (int)-rounded_div((1 << 15) * ONE * ONE, Cu); t[5] = (int)rounded_div((1 << 15) * (Z + W), Cu);
+    t[6] = (int)rounded_div((1 << 15) * (V + Z), Cv);  t[7] = (int)-rounded_div((1 << 15) * ONE * ONE, Cv); t[8] = (int)rounded_div((1 << 15) * W, Cv);
+    if (!memcmp(table, default_coeffs, sizeof(default_coeffs))) {
+        t[2] =  (int)(0.114 * 219 / 255 * (1 << 15) + 0.5); t[8] = -(int)(0.081 * 224 / 255 * (1 << 15) + 0.5);
+        t[5] =  (int)(0.500 * 224 / 255 * (1 << 15) + 0.5); t[1] =  (int)(0.587 * 219 / 255 * (1 << 15) + 0.5);
+        t[7] = -(int)(0.419 * 224 / 255 * (1 << 15) + 0.5); t[4] = -(int)(0.331 * 224 / 255 * (1 << 15) + 0.5);
+        t[0] =  (int)(0.299 * 219 / 255 * (1 << 15) + 0.5); t[6] =  (int)(0.500 * 224 / 255 * (1 << 15) + 0.5);
+        t[3] = -(int)(0.169 * 224 / 255 * (1 << 15) + 0.5);
+    }
+}
+
 /* sws_setColorspaceDetails (utils.c:849-1004) */
 int orc_sws_set_colorspace_details(OrcSws *s, const int inv_table[4], int srcRange, const int table[4], int dstRange,
                                    int brightness, int contrast, int saturation)
 {
     if (!s->planar) dstRange = 0;                                    /* range_override_needed(dst), utils.c:877-878 */
+    if (s->src_rgb) srcRange = 0;                                    /* range_override_needed(src), utils.c:879-880 */
+    fill_rgb2yuv(s, table);                                          /* utils.c:1002 */
     memcpy(s->src_cs, inv_table, sizeof(s->src_cs));
     memcpy(s->dst_cs, table, sizeof(s->dst_cs));
     s->src_range = srcRange;
     s->dst_range = dstRange;
     init_range_convert(s);
-    if (s->planar)                                                   /* utils.c:910-989: other matrices would cascade via bgr24 */
+    if (s->planar && !s->src_rgb)                                    /* utils.c:910-989: other matrices would cascade via bgr24 */
         return memcmp(s->src_cs, s->dst_cs, sizeof(s->src_cs)) ? -1 : 0;
+    if (s->planar) return 0;                                         /* RGB -> yuv: only the rgb2yuv table and the ranges matter */
     return orc_sws_set_colorspace(s, inv_table, srcRange, brightness, contrast, saturation);
 }
 
@@ -367,10 +397,15 @@ OrcSws *orc_sws_open_io(int srcFormat, int srcW, int srcH, int dstFormat, int ds
 OrcSws *orc_sws_open_range(int srcFormat, int srcW, int srcH, int srcRange, int dstFormat, int dstW, int dstH, int dstRange, int flags)
 {
     if (srcW < 1 || srcH < 1 || dstW < 1 || dstH < 1) return NULL;
-    if (srcFormat != ORC_PIX_FMT_YUV420P && srcFormat != ORC_PIX_FMT_NV12 && srcFormat != ORC_PIX_FMT_NV21) return NULL;
     OrcSws *s = calloc(1, sizeof(*s));
     if (!s) return NULL;
+    if (set_format(s, srcFormat) == 0 && !s->planar) {              /* packed RGB source: remember its byte layout */
+        s->src_rgb = s->bpp; s->sro = s->ro; s->sgo = s->go; s->sbo = s->bo;
+    } else if (srcFormat != ORC_PIX_FMT_YUV420P && srcFormat != ORC_PIX_FMT_NV12 && srcFormat != ORC_PIX_FMT_NV21) { free(s); return NULL; }
     if (set_format(s, dstFormat) < 0) { free(s); return NULL; }
+    if (s->src_rgb && !s->planar && srcW == dstW && srcH == dstH) { free(s); return NULL; }    /* rgb2rgb shuffles: not this path */
+    if (s->src_rgb == 4 && !s->planar && s->bpp == 4) { free(s); return NULL; }                /* alpha carried through the scaler
+                                                                                                 * (alpToYV12 + the A writers): not restated */
     s->src_nv = srcFormat == ORC_PIX_FMT_NV12 ? 1 : srcFormat == ORC_PIX_FMT_NV21 ? 2 : 0;
     int algo = flags & 0x7FF;
     if (!algo) { algo = ORC_SWS_BICUBIC; flags |= algo; }           /* utils.c:1209-1217 */
@@ -379,18 +414,35 @@ OrcSws *orc_sws_open_range(int srcFormat, int srcW, int srcH, int srcRange, int 
         algo = ORC_SWS_BILINEAR;
         flags ^= ORC_SWS_FAST_BILINEAR | algo;
     }
-    s->fast_bilinear = algo == ORC_SWS_FAST_BILINEAR;              /* hyscale_fast / hcscale_fast, swscale.c:676-681 */
+    s->fast_bilinear = algo == ORC_SWS_FAST_BILINEAR && !s->src_rgb;  /* hyscale_fast / hcscale_fast exist for 8-bit input lines only
+                                                                    * (swscale.c:675-681); RGB sources are srcBpc 16 (utils.c:1407-1408)
+                                                                    * and use the 2-tap filter initFilter builds for the flag */
     if (!s->planar && (dstW & 1)) flags |= ORC_SWS_FULL_CHR_H_INT; /* utils.c:1271-1276 (RGB destinations only) */
+    if (!s->planar && s->src_rgb && !(flags & ORC_SWS_FAST_BILINEAR))
+        flags |= ORC_SWS_FULL_CHR_H_INT;                           /* utils.c:1277-1285: source chroma is not subsampled */
     s->srcW = srcW; s->srcH = srcH; s->dstW = dstW; s->dstH = dstH; s->flags = flags;
     s->chrDstHSub = (!s->planar && (flags & ORC_SWS_FULL_CHR_H_INT)) ? 0 : 1;      /* utils.c:1359-1360 */
     const int chrDstVSub = s->planar ? 1 : 0;                      /* av_pix_fmt_get_chroma_sub_sample(dstFormat), utils.c:1266 */
-    s->chrSrcW = ceil_rshift(srcW, 1); s->chrSrcH = ceil_rshift(srcH, 1);
+    s->chrSrcHSub = 1; s->chrSrcVSub = 1;
+    if (s->src_rgb) {                                              /* utils.c:1366-1393: every other pixel for chroma unless asked otherwise */
+        s->chrSrcVSub = 0;
+        s->chrSrcHSub = !(srcW & 1) && !(flags & ORC_SWS_FULL_CHR_H_INP) &&
+                        ((dstW >> s->chrDstHSub) <= (srcW >> 1) || (flags & ORC_SWS_FAST_BILINEAR));
+    }
+    s->chrSrcW = ceil_rshift(srcW, s->chrSrcHSub); s->chrSrcH = ceil_rshift(srcH, s->chrSrcVSub);
     s->chrDstW = ceil_rshift(dstW, s->chrDstHSub); s->chrDstH = ceil_rshift(dstH, chrDstVSub);
     /* utils.c:1164-1167: the ranges given before initialisation go through sws_setColorspaceDetails */
     orc_sws_set_colorspace_details(s, default_coeffs, srcRange != 0, default_coeffs, dstRange != 0, 0, 1 << 16, 1 << 16);
 
     /* the unscaled converters are only looked for when no range conversion is due (utils.c:1623-1626) */
-    if (s->planar && srcW == dstW && srcH == dstH && s->src_range == s->dst_range) {               /* planarCopyWrapper (swscale_unscaled.c:2675-2693) or, for a
+    /* bgr24ToYv12Wrapper (swscale_unscaled.c:2453-2457): bgr24 only, not with accurate_rnd, even width */
+    if (s->planar && s->src_rgb == 3 && s->sbo == 0 && srcW == dstW && srcH == dstH && s->src_range == s->dst_range &&
+        !(flags & ORC_SWS_ACCURATE_RND) && !(dstW & 1)) {
+        s->bgr24_yv12 = 1;
+        s->unscaled_lut = 3;
+        return s;
+    }
+    if (s->planar && !s->src_rgb && srcW == dstW && srcH == dstH && s->src_range == s->dst_range) {               /* planarCopyWrapper (swscale_unscaled.c:2675-2693) or, for a
                                                                     * semi-planar source, nv12ToPlanarWrapper (:167-188, :2415-2419):
                                                                     * both are a luma copy plus a chroma copy / de-interleave */
         s->unscaled_lut = 2;
@@ -412,11 +464,11 @@ OrcSws *orc_sws_open_range(int srcFormat, int srcW, int srcH, int srcRange, int 
     if (make_filter(&s->hLum, &s->hLumPos, &s->hLumSize, (int)lumXInc, srcW, dstW, 1 << 14, lum_scaler, flags,
                     local_pos(0, 0), local_pos(0, 0)) < 0) goto fail;
     if (make_filter(&s->hChr, &s->hChrPos, &s->hChrSize, (int)chrXInc, s->chrSrcW, s->chrDstW, 1 << 14, chr_scaler, flags,
-                    local_pos(1, -513), local_pos(s->chrDstHSub, -513)) < 0) goto fail;
+                    local_pos(s->chrSrcHSub, -513), local_pos(s->chrDstHSub, -513)) < 0) goto fail;
     if (make_filter(&s->vLum, &s->vLumPos, &s->vLumSize, (int)lumYInc, srcH, dstH, 1 << 12, lum_scaler, flags,
                     local_pos(0, 0), local_pos(0, 0)) < 0) goto fail;
     if (make_filter(&s->vChr, &s->vChrPos, &s->vChrSize, (int)chrYInc, s->chrSrcH, s->chrDstH, 1 << 12, chr_scaler, flags,
-                    local_pos(1, -513), local_pos(chrDstVSub, -513)) < 0) goto fail;
+                    local_pos(s->chrSrcVSub, -513), local_pos(chrDstVSub, -513)) < 0) goto fail;
     return s;
 fail:
     orc_sws_close(s);
@@ -492,11 +544,103 @@ static void hscale_fast(int16_t *dst, int dstW, const uint8_t *src, int srcW, in
         else dst[i] = (int16_t)((src[xx] << 7) + (src[xx + 1] - src[xx]) * xalpha);
     }
 }
+/* hScale16To15_c (swscale.c:99-125) for an RGB source: sh = 13; the reader's int16 line is read as uint16 */
+static void hscale16to15(int16_t *dst, int dstW, const int16_t *src, const int16_t *filter, const int32_t *pos, int fs)
+{
+    for (int i = 0; i < dstW; i++) {
+        int val = 0;
+        for (int j = 0; j < fs; j++) val += (int)(uint16_t)src[pos[i] + j] * filter[fs * i + j];
+        val >>= 13;
+        dst[i] = (int16_t)(val < 32767 ? val : 32767);
+    }
+}
+
+/* rgb24ToY_c / bgr24ToY_c (input.c:1068-1134) and the 32-bit templates (input.c:264-287, instantiated :390-393 with the
+ * coefficients shifted by 8 and S = RGB2YUV_SHIFT + 8): the same value for all six byte orders */
+static void rgb_to_y(const OrcSws *s, int16_t *dst, const uint8_t *src, int w)
+{
+    const int ry = s->rgb2yuv[0], gy = s->rgb2yuv[1], by = s->rgb2yuv[2];
+    for (int i = 0; i < w; i++) {
+        const uint8_t *p = src + (size_t)i * s->src_rgb;
+        dst[i] = (int16_t)((ry * p[s->sro] + gy * p[s->sgo] + by * p[s->sbo] + (32 << 14) + (1 << 8)) >> 9);
+    }
+}
+/* rgb24ToUV_c / rgb24ToUV_half_c and friends (input.c:1083-1172, :289-352): half = two neighbouring pixels summed */
+static void rgb_to_uv(const OrcSws *s, int16_t *dU, int16_t *dV, const uint8_t *src, int w)
+{
+    const int ru = s->rgb2yuv[3], gu = s->rgb2yuv[4], bu = s->rgb2yuv[5], rv = s->rgb2yuv[6], gv = s->rgb2yuv[7], bv = s->rgb2yuv[8];
+    for (int i = 0; i < w; i++) {
+        if (s->chrSrcHSub) {
+            const uint8_t *p = src + (size_t)2 * i * s->src_rgb, *q = p + s->src_rgb;
+            const int r = p[s->sro] + q[s->sro], g = p[s->sgo] + q[s->sgo], b = p[s->sbo] + q[s->sbo];
+            dU[i] = (int16_t)((ru * r + gu * g + bu * b + (256 << 15) + (1 << 9)) >> 10);
+            dV[i] = (int16_t)((rv * r + gv * g + bv * b + (256 << 15) + (1 << 9)) >> 10);
+        } else {
+            const uint8_t *p = src + (size_t)i * s->src_rgb;
+            const int r = p[s->sro], g = p[s->sgo], b = p[s->sbo];
+            dU[i] = (int16_t)((ru * r + gu * g + bu * b + (256 << 14) + (1 << 8)) >> 9);
+            dV[i] = (int16_t)((rv * r + gv * g + bv * b + (256 << 14) + (1 << 8)) >> 9);
+        }
+    }
+}
+
+/* ff_rgb24toyv12_c (rgb2rgb_template.c:580-641) on a bgr24 picture: truncating luma, chroma from the 2x2 box average */
+static void bgr24_to_yv12(const OrcSws *s, const uint8_t *src, int ss, uint8_t *dy, int dys, uint8_t *du, int dus, uint8_t *dv, int dvs)
+{
+    const int *t = s->rgb2yuv;
+    for (int y = 0; y < s->srcH; y += 2) {
+        const uint8_t *s1 = src + (ptrdiff_t)y * ss, *s2 = y + 1 == s->srcH ? s1 : s1 + ss;
+        uint8_t *y1 = dy + (ptrdiff_t)y * dys, *y2 = y + 1 == s->srcH ? y1 : y1 + dys;
+        for (int i = 0; i < s->srcW >> 1; i++) {
+            unsigned px[4][3];                                      /* b, g, r of the four pixels */
+            for (int k = 0; k < 3; k++) { px[0][k] = s1[6 * i + k]; px[1][k] = s1[6 * i + 3 + k]; px[2][k] = s2[6 * i + k]; px[3][k] = s2[6 * i + 3 + k]; }
+            uint8_t *yo[4] = { y1 + 2 * i, y1 + 2 * i + 1, y2 + 2 * i, y2 + 2 * i + 1 };
+            for (int k = 0; k < 4; k++)
+                *yo[k] = (uint8_t)((((unsigned)t[0] * px[k][2] + (unsigned)t[1] * px[k][1] + (unsigned)t[2] * px[k][0]) >> 15) + 16);
+            const unsigned bx = (px[0][0] + px[1][0] + px[2][0] + px[3][0]) >> 2, gx = (px[0][1] + px[1][1] + px[2][1] + px[3][1]) >> 2,
+                           rx = (px[0][2] + px[1][2] + px[2][2] + px[3][2]) >> 2;
+            du[(ptrdiff_t)(y >> 1) * dus + i] = (uint8_t)((((unsigned)t[3] * rx + (unsigned)t[4] * gx + (unsigned)t[5] * bx) >> 15) + 128);
+            dv[(ptrdiff_t)(y >> 1) * dvs + i] = (uint8_t)((((unsigned)t[6] * rx + (unsigned)t[7] * gx + (unsigned)t[8] * bx) >> 15) + 128);
+        }
+    }
+}
+
 static void hpass(const OrcSws *s, int16_t *dst, int dstW, const uint8_t *src, int srcW, int chroma)
 {
     if (s->fast_bilinear) hscale_fast(dst, dstW, src, srcW, chroma ? s->chrXInc : s->lumXInc, chroma);
     else if (chroma) orc_hscale8to15(dst, dstW, src, s->hChr, s->hChrPos, s->hChrSize);
     else orc_hscale8to15(dst, dstW, src, s->hLum, s->hLumPos, s->hLumSize);
+}
+
+/* the horizontal pass over a whole picture: L = srcH lines of dstW, CU / CV = chrSrcH lines of chrDstW.  For a packed RGB source
+ * every line first goes through the input readers (lum_convert / chr_convert, hscale.c:103-160,229-290) */
+static int hlines(const OrcSws *s, const uint8_t *y, int ys, const uint8_t *u, int us, const uint8_t *v, int vs,
+                  int16_t *L, int16_t *CU, int16_t *CV)
+{
+    const int dstW = s->dstW, cW = s->chrDstW;
+    if (s->src_rgb) {
+        int16_t *t = calloc((size_t)3 * (s->srcW + 16), sizeof(int16_t));
+        if (!t) return -1;
+        int16_t *tY = t, *tU = t + s->srcW + 16, *tV = tU + s->srcW + 16;
+        for (int r = 0; r < s->srcH; r++) {
+            rgb_to_y(s, tY, y + (ptrdiff_t)r * ys, s->srcW);
+            hscale16to15(L + (size_t)r * dstW, dstW, tY, s->hLum, s->hLumPos, s->hLumSize);
+        }
+        for (int r = 0; r < s->chrSrcH; r++) {
+            rgb_to_uv(s, tU, tV, y + (ptrdiff_t)r * ys, s->chrSrcW);
+            hscale16to15(CU + (size_t)r * cW, cW, tU, s->hChr, s->hChrPos, s->hChrSize);
+            hscale16to15(CV + (size_t)r * cW, cW, tV, s->hChr, s->hChrPos, s->hChrSize);
+        }
+        free(t);
+        return 0;
+    }
+    for (int r = 0; r < s->srcH; r++)
+        hpass(s, L + (size_t)r * dstW, dstW, y + (ptrdiff_t)r * ys, s->srcW, 0);
+    for (int r = 0; r < s->chrSrcH; r++) {
+        hpass(s, CU + (size_t)r * cW, cW, u + (ptrdiff_t)r * us, s->chrSrcW, 1);
+        hpass(s, CV + (size_t)r * cW, cW, v + (ptrdiff_t)r * vs, s->chrSrcW, 1);
+    }
+    return 0;
 }
 
 /* yuv2rgb_write, 24 and 32 bpp branches (output.c:1676-1713): one chroma pair -> LUT bases, two lumas -> two pixels */
@@ -606,6 +750,10 @@ int orc_sws_scale_planar(OrcSws *s, const uint8_t *y, int ys, const uint8_t *u, 
         free(t);
         return r;
     }
+    if (s->unscaled_lut == 3) {
+        bgr24_to_yv12(s, y, ys, dy, dys, du, dus, dv, dvs);
+        return s->srcH;
+    }
     if (s->unscaled_lut == 2) {
         for (int r = 0; r < s->srcH; r++) memcpy(dy + (ptrdiff_t)r * dys, y + (ptrdiff_t)r * ys, s->srcW);
         for (int r = 0; r < s->chrSrcH; r++) {
@@ -619,12 +767,7 @@ int orc_sws_scale_planar(OrcSws *s, const uint8_t *y, int ys, const uint8_t *u, 
     int16_t *CU = malloc((size_t)s->chrSrcH * cW * sizeof(int16_t));
     int16_t *CV = malloc((size_t)s->chrSrcH * cW * sizeof(int16_t));
     if (!L || !CU || !CV) { free(L); free(CU); free(CV); return -ENOMEM; }
-    for (int r = 0; r < s->srcH; r++)
-        hpass(s, L + (size_t)r * dstW, dstW, y + (ptrdiff_t)r * ys, s->srcW, 0);
-    for (int r = 0; r < s->chrSrcH; r++) {
-        hpass(s, CU + (size_t)r * cW, cW, u + (ptrdiff_t)r * us, s->chrSrcW, 1);
-        hpass(s, CV + (size_t)r * cW, cW, v + (ptrdiff_t)r * vs, s->chrSrcW, 1);
-    }
+    if (hlines(s, y, ys, u, us, v, vs, L, CU, CV) < 0) { free(L); free(CU); free(CV); return -ENOMEM; }
     if (s->range_conv) {
         const int clip = s->range_conv == 1;
         for (int r = 0; r < s->srcH; r++) range_line(L + (size_t)r * dstW, dstW, s->lum_coeff, s->lum_offset, clip);
@@ -669,12 +812,7 @@ int orc_sws_scale(OrcSws *s, const uint8_t *y, int ys, const uint8_t *u, int us,
     int16_t *CU = malloc((size_t)s->chrSrcH * cW * sizeof(int16_t));
     int16_t *CV = malloc((size_t)s->chrSrcH * cW * sizeof(int16_t));
     if (!L || !CU || !CV) { free(L); free(CU); free(CV); return -ENOMEM; }
-    for (int r = 0; r < s->srcH; r++)
-        hpass(s, L + (size_t)r * dstW, dstW, y + (ptrdiff_t)r * ys, s->srcW, 0);
-    for (int r = 0; r < s->chrSrcH; r++) {
-        hpass(s, CU + (size_t)r * cW, cW, u + (ptrdiff_t)r * us, s->chrSrcW, 1);
-        hpass(s, CV + (size_t)r * cW, cW, v + (ptrdiff_t)r * vs, s->chrSrcW, 1);
-    }
+    if (hlines(s, y, ys, u, us, v, vs, L, CU, CV) < 0) { free(L); free(CU); free(CV); return -ENOMEM; }
     const int lfs = s->vLumSize, cfs = s->vChrSize, full = !s->chrDstHSub;
 #define LROW(k) (L  + (size_t)((k) < 0 ? 0 : (k) >= s->srcH    ? s->srcH    - 1 : (k)) * dstW)
 #define UROW(k) (CU + (size_t)((k) < 0 ? 0 : (k) >= s->chrSrcH ? s->chrSrcH - 1 : (k)) * cW)

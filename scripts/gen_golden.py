@@ -124,6 +124,21 @@ def gen_idct_hbd():
     np.savez_compressed(os.path.join(OUT, "idct_hbd.npz"), **d)
 
 
+def gen_sws_rgbsrc():
+    """packed RGB sources: the reference's outputs for SWS_RGBSRC_CASES (sha256; yuv420p planes concatenated / the rgb24 picture)."""
+    from cases import SWS_RGBSRC_CASES
+    lines = []
+    for i, (w, h, dw, dh, fl, kind) in enumerate(SWS_RGBSRC_CASES):
+        for name, sf in cl.PACKED_RGB_FORMATS.items():
+            src = cl.rgb_frame(w, h, 2000 + i, cl.fmt_bpp(sf), kind)
+            for ranges in ((0, 0), (0, 1)):
+                pl = cl.ref_sws_planar(w, h, dw, dh, fl, src, src, src, src_fmt=sf, ranges=ranges)
+                lines.append(f"{i} {name} yuv420p {ranges[1]} {sha(np.concatenate([p.ravel() for p in pl]))}")
+            if (w, h) != (dw, dh) and cl.fmt_bpp(sf) == 3:
+                lines.append(f"{i} {name} rgb24 0 {sha(cl.ref_sws(w, h, dw, dh, fl, src, src, src, fmt=cl.PIX_FMT_RGB24, src_fmt=sf))}")
+    open(os.path.join(OUT, "sws_rgbsrc_hashes.txt"), "w").write("\n".join(lines) + "\n")
+
+
 def gen_sws_fastbil():
     from cases import SWS_FASTBIL_CASES
     lines = []
@@ -430,5 +445,6 @@ if __name__ == "__main__":
     gen_unquant()
     gen_fdsp()
     gen_idct_hbd()
+    gen_sws_rgbsrc()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -140,3 +140,15 @@ SWS_RANGE_CASES = [
     (64, 48, 64, 48, FATE, "random", (0, 0), (5, 0, 5, 1, 0, 1 << 16, 1 << 16)),        # initialised as a copy: stays a copy
     (64, 48, 64, 48, FATE, "random", (0, 1), _ID),                                       # initialised through the scaler: stays there
 ]
+
+
+# packed RGB sources (the input readers rgb24ToY_c / ...ToUV_c / ...ToUV_half_c and the 32-bit templates,
+# input.c:264-393,1068-1172; hScale16To15_c; bgr24ToYv12Wrapper): (w, h, dw, dh, flags, kind); every case runs for the six source
+# byte orders -> yuv420p, and (when the size changes) -> rgb24 for the 3-byte sources
+SWS_FULL_CHR_H_INP = 0x4000
+SWS_RGBSRC_CASES = [(64, 48, 64, 48, FATE, "random"), (64, 48, 64, 48, SWS_BICUBIC, "random"), (64, 48, 100, 70, FATE, "smooth"),
+                    (64, 48, 33, 21, SWS_BILINEAR, "random"), (352, 288, 200, 100, FATE, "random"), (63, 47, 63, 47, SWS_BICUBIC, "random"),
+                    (63, 47, 80, 60, FATE, "random"), (64, 48, 128, 96, SWS_BICUBIC | SWS_FULL_CHR_H_INP, "random"),
+                    (64, 48, 40, 30, SWS_POINT, "random"), (64, 48, 100, 70, SWS_FAST_BILINEAR, "random"),
+                    (64, 48, 40, 30, SWS_FAST_BILINEAR, "smooth"), (352, 288, 640, 360, SWS_BICUBLIN, "random"),
+                    (66, 50, 66, 50, FATE | SWS_FULL_CHR_H_INP, "random"), (64, 48, 64, 30, FATE, "random"), (64, 48, 32, 48, SWS_AREA, "random")]

@@ -176,6 +176,18 @@ def nv_interleave(u, v, src_fmt, pad=0):
     return uv
 
 
+def rgb_frame(w, h, seed, bpp, kind="random", pad=0):
+    """packed RGB source picture: (h, w*bpp + pad) uint8"""
+    rng = np.random.default_rng(seed)
+    if kind == "random":
+        return rng.integers(0, 256, (h, w * bpp + pad), dtype=np.uint8)
+    yy, xx = np.mgrid[0:h, 0:w]
+    a = np.full((h, w * bpp + pad), 0x3C, np.uint8)
+    for k in range(bpp):
+        a[:, k:w * bpp:bpp] = ((xx * 3 + yy * 2 + k * 40) % 256).astype(np.uint8)
+    return a
+
+
 def _sws_run(lib, pre, w, h, dw, dh, flags, y, u, v, dst_pad=0, threads=1, colorspace=None, fmt=PIX_FMT_RGB24, src_fmt=0):
     """src_fmt nv12 / nv21: `u` is the interleaved chroma plane, `v` is ignored"""
     if pre == "ffref":

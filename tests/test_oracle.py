@@ -345,3 +345,54 @@ def test_host_plan_refuses_yuv_matrix_change():
     cfg[6] = cl.PIX_FMT_RGB24                                       # RGB destination: `table` is ignored, like the reference
     assert L.b200_sws_plan_probe2(cl.ptr(cfg, cl.i32p), cl.ptr(det, cl.i32p), 0, None, None, 0, cl.ptr(pi, cl.i32p)) >= 0
     assert pi[24] == 0
+
+
+def rgbsrc_rows():
+    """(case index, case, source name, source format, destination 'yuv420p' / 'rgb24', dst_range, sha256) of sws_rgbsrc_hashes.txt"""
+    from cases import SWS_RGBSRC_CASES
+    rows = []
+    for line in open(os.path.join(G, "sws_rgbsrc_hashes.txt")):
+        i, name, dst, dr, h = line.split()
+        rows.append((int(i), SWS_RGBSRC_CASES[int(i)], name, cl.PACKED_RGB_FORMATS[name], dst, int(dr), h))
+    return rows
+
+
+def run_rgbsrc_row(run_rgb, run_planar, row):
+    i, (w, h, dw, dh, fl, kind), name, sf, dst, dr, _ = row
+    src = cl.rgb_frame(w, h, 2000 + i, cl.fmt_bpp(sf), kind)
+    if dst == "yuv420p":
+        return np.concatenate([p.ravel() for p in run_planar(w, h, dw, dh, fl, src, src, src, src_fmt=sf, ranges=(0, dr))])
+    return run_rgb(w, h, dw, dh, fl, src, src, src, fmt=cl.PIX_FMT_RGB24, src_fmt=sf)
+
+
+def test_sws_oracle_rgb_sources_golden_hashes():
+    """packed RGB sources (input readers, 16-bit horizontal pass, bgr24 -> yv12 special converter) against the reference"""
+    rows = rgbsrc_rows()
+    assert len(rows) == 15 * 6 * 2 + 11 * 2
+    for row in rows:
+        assert sha(run_rgbsrc_row(cl.orc_sws, cl.orc_sws_planar, row)) == row[-1], row[:6]
+
+
+def test_sws_oracle_rgb_sources_vs_ref():
+    if not cl.have_ref():
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(91)
+    names = list(cl.PACKED_RGB_FORMATS)
+    for it in range(40):
+        w, h = int(rng.integers(8, 120)), int(rng.integers(8, 90))
+        dw, dh = (w, h) if it % 5 == 0 else (int(rng.integers(8, 160)), int(rng.integers(8, 120)))
+        fl = int(rng.choice([FATE, cl.SWS_BICUBIC, cl.SWS_BILINEAR, cl.SWS_POINT, 1, cl.SWS_BICUBIC | 0x4000]))
+        sf = cl.PACKED_RGB_FORMATS[names[it % 6]]
+        src = cl.rgb_frame(w, h, 2100 + it, cl.fmt_bpp(sf), "random", pad=int(rng.integers(0, 7)))
+        ranges = (0, int(rng.integers(0, 2)))
+        a = cl.ref_sws_planar(w, h, dw, dh, fl, src, src, src, dst_pad=3, src_fmt=sf, ranges=ranges)
+        b = cl.orc_sws_planar(w, h, dw, dh, fl, src, src, src, dst_pad=3, src_fmt=sf, ranges=ranges)
+        assert all(np.array_equal(p, q) for p, q in zip(a, b)), (w, h, dw, dh, hex(fl), names[it % 6], ranges)
+        if (w, h) != (dw, dh):
+            df = cl.PIX_FMT_BGR24 if it & 1 else (cl.PIX_FMT_RGBA if cl.fmt_bpp(sf) == 3 else cl.PIX_FMT_RGB24)
+            a = cl.ref_sws(w, h, dw, dh, fl, src, src, src, fmt=df, src_fmt=sf, dst_pad=2)
+            b = cl.orc_sws(w, h, dw, dh, fl, src, src, src, fmt=df, src_fmt=sf, dst_pad=2)
+            assert np.array_equal(a, b), (w, h, dw, dh, hex(fl), names[it % 6], df)
+    O = cl.oracle()
+    assert not O.orc_sws_open_io(cl.PIX_FMT_RGB24, 64, 48, cl.PIX_FMT_BGR24, 64, 48, FATE)      # same-size rgb -> rgb: rgb2rgb, not this path
+    assert not O.orc_sws_open_io(cl.PIX_FMT_RGBA, 64, 48, cl.PIX_FMT_BGRA, 32, 24, FATE)        # alpha through the scaler: not restated
