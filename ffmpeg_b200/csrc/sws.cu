@@ -591,6 +591,95 @@ sws_vscale_planar_kernel(const int16_t *src, int sls, long long sfs, int nlines,
     dst[f * dfs + (long long)dy * ds + x] = (uint8_t)clamp_u8(val);
 }
 
+// ------------------------------------------------------------------------------------------------ kernels: packed RGB source
+// Input readers fused into the horizontal pass.  The reference converts every source line to a 16-bit line first
+// (rgb24ToY_c / bgr24ToY_c / the 32-bit templates, input.c:264-393,1068-1134: identical values for all six byte orders; chroma
+// rgb24ToUV_c or, when the scaler samples chroma from every other pixel, rgb24ToUV_half_c on the sum of two pixels,
+// input.c:1083-1172) and then runs hScale16To15_c (swscale.c:99-125: taps read as uint16, sum >> 13, clamp to 2^15-1).
+// Here each thread produces one output sample and evaluates the reader for the taps it needs; first version, not tuned
+// (neighbouring threads re-read overlapping source pixels from L1).
+struct RgbIn { int bpp, ro, go, bo, half; int c[9]; };
+
+__global__ void __launch_bounds__(256)
+sws_rgbin_hscale_y_kernel(const uint8_t *src, long long sstride, long long sfs, int16_t *dst, int dstW, long long dfs,
+                          const int16_t *filter, const int32_t *pos, int fs, const RgbIn R)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= dstW) return;
+    const int line = blockIdx.y;
+    const uint8_t *s = src + (long long)blockIdx.z * sfs + (long long)line * sstride;
+    const int p0 = __ldg(pos + i);
+    const int16_t *f = filter + (long long)i * fs;
+    int acc = 0;
+    for (int j = 0; j < fs; j++) {
+        const uint8_t *px = s + (long long)(p0 + j) * R.bpp;
+        const int v = (R.c[0] * (int)__ldg(px + R.ro) + R.c[1] * (int)__ldg(px + R.go) + R.c[2] * (int)__ldg(px + R.bo) + (32 << 14) + (1 << 8)) >> 9;
+        acc += (int)(uint16_t)(int16_t)v * (int)__ldg(f + j);
+    }
+    dst[(long long)blockIdx.z * dfs + (long long)line * dstW + i] = (int16_t)min(acc >> 13, 32767);
+}
+
+__global__ void __launch_bounds__(256)
+sws_rgbin_hscale_uv_kernel(const uint8_t *src, long long sstride, long long sfs, int16_t *dstU, int16_t *dstV, int dstW, long long dfs,
+                           const int16_t *filter, const int32_t *pos, int fs, const RgbIn R)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= dstW) return;
+    const int line = blockIdx.y;
+    const uint8_t *s = src + (long long)blockIdx.z * sfs + (long long)line * sstride;
+    const int p0 = __ldg(pos + i);
+    const int16_t *f = filter + (long long)i * fs;
+    int accU = 0, accV = 0;
+    for (int j = 0; j < fs; j++) {
+        int r, g, b, u, v;
+        if (R.half) {
+            const uint8_t *px = s + (long long)(p0 + j) * 2 * R.bpp, *q = px + R.bpp;
+            r = (int)__ldg(px + R.ro) + (int)__ldg(q + R.ro); g = (int)__ldg(px + R.go) + (int)__ldg(q + R.go); b = (int)__ldg(px + R.bo) + (int)__ldg(q + R.bo);
+            u = (R.c[3] * r + R.c[4] * g + R.c[5] * b + (256 << 15) + (1 << 9)) >> 10;
+            v = (R.c[6] * r + R.c[7] * g + R.c[8] * b + (256 << 15) + (1 << 9)) >> 10;
+        } else {
+            const uint8_t *px = s + (long long)(p0 + j) * R.bpp;
+            r = __ldg(px + R.ro); g = __ldg(px + R.go); b = __ldg(px + R.bo);
+            u = (R.c[3] * r + R.c[4] * g + R.c[5] * b + (256 << 14) + (1 << 8)) >> 9;
+            v = (R.c[6] * r + R.c[7] * g + R.c[8] * b + (256 << 14) + (1 << 8)) >> 9;
+        }
+        const int k = __ldg(f + j);
+        accU += (int)(uint16_t)(int16_t)u * k;
+        accV += (int)(uint16_t)(int16_t)v * k;
+    }
+    const long long o = (long long)blockIdx.z * dfs + (long long)line * dstW + i;
+    dstU[o] = (int16_t)min(accU >> 13, 32767);
+    dstV[o] = (int16_t)min(accV >> 13, 32767);
+}
+
+// bgr24 -> yuv420p, same size, without accurate_rnd: the reference's special converter ff_rgb24toyv12_c
+// (rgb2rgb_template.c:580-641): Y = (dot >> 15) + 16 (truncating), U / V from the 2x2 box average of each channel; sums are
+// formed in unsigned arithmetic and the byte store keeps the low 8 bits.  One thread per 2x2 pixel block.
+__global__ void __launch_bounds__(256)
+sws_bgr24_yv12_kernel(const uint8_t *src, long long sstride, long long sfs, uint8_t *dy, long long dys, long long dyf,
+                      uint8_t *du, long long dus, long long duf, uint8_t *dv, long long dvs, long long dvf, int w, int h, const RgbIn R)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (w >> 1)) return;
+    const int y = 2 * blockIdx.y;
+    const long long f = blockIdx.z;
+    const bool last = y + 1 == h;                                           // odd height: the last line pairs with itself
+    const uint8_t *s1 = src + f * sfs + (long long)y * sstride + 6 * i, *s2 = last ? s1 : s1 + sstride;
+    unsigned px[4][3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) { px[0][k] = __ldg(s1 + k); px[1][k] = __ldg(s1 + 3 + k); px[2][k] = __ldg(s2 + k); px[3][k] = __ldg(s2 + 3 + k); }
+    unsigned Y[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) Y[k] = (((unsigned)R.c[0] * px[k][2] + (unsigned)R.c[1] * px[k][1] + (unsigned)R.c[2] * px[k][0]) >> 15) + 16;
+    uint8_t *y1 = dy + f * dyf + (long long)y * dys + 2 * i;
+    y1[0] = (uint8_t)Y[0]; y1[1] = (uint8_t)Y[1];
+    if (!last) { y1[dys] = (uint8_t)Y[2]; y1[dys + 1] = (uint8_t)Y[3]; }
+    const unsigned bx = (px[0][0] + px[1][0] + px[2][0] + px[3][0]) >> 2, gx = (px[0][1] + px[1][1] + px[2][1] + px[3][1]) >> 2,
+                   rx = (px[0][2] + px[1][2] + px[2][2] + px[3][2]) >> 2;
+    du[f * duf + (long long)blockIdx.y * dus + i] = (uint8_t)((((unsigned)R.c[3] * rx + (unsigned)R.c[4] * gx + (unsigned)R.c[5] * bx) >> 15) + 128);
+    dv[f * dvf + (long long)blockIdx.y * dvs + i] = (uint8_t)((((unsigned)R.c[6] * rx + (unsigned)R.c[7] * gx + (unsigned)R.c[8] * bx) >> 15) + 128);
+}
+
 // lumRangeToJpeg_c / lumRangeFromJpeg_c / chrRange*_c (swscale.c:163-209) applied in place to the horizontally scaled lines,
 // where the reference calls them (hscale.c:61-63, :195-197): v = (v * coeff + offset) >> 14, limited -> full clips at 2^15-1.
 // One thread per sample; grid x over the line, y over lines, z over frames (dfs in int16 elements).
@@ -799,6 +888,18 @@ static int upload_tables(B200SwsContext *c)
     return 0;
 }
 
+// source side of a plan: yuv420p, nv12 / nv21, or packed 8-bit RGB (input readers); false = not a source this path reads
+static bool set_source_format(SwsPlan &p, int srcFormat)
+{
+    p.src_nv = srcFormat == B200_PIX_FMT_NV12 ? 1 : srcFormat == B200_PIX_FMT_NV21 ? 2 : 0;
+    p.src_rgb = 0;
+    if (srcFormat == B200_PIX_FMT_YUV420P || p.src_nv) return true;
+    SwsOutFmt f;
+    if (!sws_out_format(srcFormat, f) || f.kind == SWS_OUT_YUV420P) return false;
+    p.src_rgb = f.bpp; p.sro = f.ro; p.sgo = f.go; p.sbo = f.bo;
+    return true;
+}
+
 B200_API B200SwsContext *b200_sws_getContext(B200Device *dev, int srcW, int srcH, int srcFormat,
                                              int dstW, int dstH, int dstFormat, int flags)
 {
@@ -810,16 +911,21 @@ B200_API B200SwsContext *b200_sws_getContext_range(B200Device *dev, int srcW, in
 {
     if (!dev) { b200_set_error("b200_sws_getContext: no device"); return nullptr; }
     SwsOutFmt out;
-    const bool src_ok = srcFormat == B200_PIX_FMT_YUV420P || srcFormat == B200_PIX_FMT_NV12 || srcFormat == B200_PIX_FMT_NV21;
-    if (!src_ok || !sws_out_format(dstFormat, out)) {
-        b200_set_error("b200_sws_getContext: only yuv420p -> rgb24 / bgr24 / rgba / bgra / argb / abgr / yuv420p is implemented");
-        return nullptr;
-    }
     B200SwsContext *c = new (std::nothrow) B200SwsContext();
     if (!c) return nullptr;
+    if (!set_source_format(c->plan, srcFormat) || !sws_out_format(dstFormat, out)) {
+        b200_set_error("b200_sws_getContext: only yuv420p / nv12 / nv21 -> rgb24 / bgr24 / rgba / bgra / argb / abgr / yuv420p and "
+                       "packed 8-bit RGB -> yuv420p are implemented");
+        delete c;
+        return nullptr;
+    }
+    if (c->plan.src_rgb && out.kind != SWS_OUT_YUV420P) {
+        b200_set_error("b200_sws_getContext: packed RGB source -> packed RGB destination is not implemented on the device yet");
+        delete c;
+        return nullptr;
+    }
     c->dev = dev;
     c->plan.out = out;
-    c->plan.src_nv = srcFormat == B200_PIX_FMT_NV12 ? 1 : srcFormat == B200_PIX_FMT_NV21 ? 2 : 0;
     int ret = sws_plan_build(c->plan, srcW, srcH, dstW, dstH, flags, srcRange, dstRange);
     if (ret < 0) { b200_set_error("b200_sws_getContext: unsupported configuration (%d)", ret); delete c; return nullptr; }
     cudaSetDevice(dev->ordinal);
@@ -894,15 +1000,14 @@ B200_API int b200_sws_plan_probe(int srcW, int srcH, int dstW, int dstH, int fla
 // details = NULL or { inv_table[4], srcRange, table[4], dstRange, brightness, contrast, saturation } (13 ints);
 // info32: [0..15] as b200_sws_info, [16] plain copy, [17] range conversion (0 none, 1 limited->full, 2 full->limited),
 // [18..21] luma coefficient, luma offset, chroma coefficient, chroma offset, [22] fast-bilinear horizontal pass,
-// [23] semi-planar source kind, [24] what the details call returned, [25] src_range, [26] dst_range.
+// [23] semi-planar source kind, [24] what the details call returned, [25] src_range, [26] dst_range, [27] packed RGB source
+// (bytes per pixel), [28] / [29] horizontal / vertical chroma shift of the source as scaled, [30] bgr24 -> yv12 converter,
+// [32..40] the rgb -> yuv table (needs room for 48 ints).
 B200_API int b200_sws_plan_probe2(const int cfg[9], const int *details, int which, int16_t *filter, int32_t *pos, int cap, int *o)
 {
     if (!cfg) return B200_EINVAL;
     SwsPlan p;
-    const int srcFormat = cfg[2];
-    if (!(srcFormat == B200_PIX_FMT_YUV420P || srcFormat == B200_PIX_FMT_NV12 || srcFormat == B200_PIX_FMT_NV21) ||
-        !sws_out_format(cfg[6], p.out)) return B200_ENOSYS;
-    p.src_nv = srcFormat == B200_PIX_FMT_NV12 ? 1 : srcFormat == B200_PIX_FMT_NV21 ? 2 : 0;
+    if (!set_source_format(p, cfg[2]) || !sws_out_format(cfg[6], p.out)) return B200_ENOSYS;
     int ret = sws_plan_build(p, cfg[0], cfg[1], cfg[4], cfg[5], cfg[8], cfg[3], cfg[7]);
     if (ret < 0) return ret;
     int dret = 0;
@@ -916,7 +1021,8 @@ B200_API int b200_sws_plan_probe2(const int cfg[9], const int *details, int whic
         o[16] = p.planar_copy; o[17] = p.range_conv;
         o[18] = p.lumRangeCoeff; o[19] = p.lumRangeOffset; o[20] = p.chrRangeCoeff; o[21] = p.chrRangeOffset;
         o[22] = p.fast_bilinear; o[23] = p.src_nv; o[24] = dret; o[25] = p.src_range; o[26] = p.dst_range;
-        for (int i = 27; i < 32; i++) o[i] = 0;
+        o[27] = p.src_rgb; o[28] = p.chrSrcHSub; o[29] = p.chrSrcVSub; o[30] = p.bgr24_yv12; o[31] = 0;
+        for (int i = 0; i < 9; i++) o[32 + i] = p.rgb2yuv[i];
     }
     const SwsFilterBank &b = which == 0 ? p.hLum : which == 1 ? p.hChr : which == 2 ? p.vLum : p.vChr;
     int n = b.n < cap ? b.n : cap;
@@ -1192,8 +1298,20 @@ static int launch_planar(B200SwsContext *c, cudaStream_t stream, const uint8_t *
     }
     const int sw[3] = { p.srcW, p.chrSrcW, p.chrSrcW }, sh[3] = { p.srcH, p.chrSrcH, p.chrSrcH };
     const int dw[3] = { p.dstW, p.chrDstW, p.chrDstW }, dh[3] = { p.dstH, p.chrDstH, p.chrDstH };
+    RgbIn R;
+    R.bpp = p.src_rgb; R.ro = p.sro; R.go = p.sgo; R.bo = p.sbo; R.half = p.chrSrcHSub;
+    for (int i = 0; i < 9; i++) R.c[i] = p.rgb2yuv[i];
     for (int f0 = 0; f0 < nframes; f0 += 65535) {
         const int nf = nframes - f0 < 65535 ? nframes - f0 : 65535;
+        if (p.bgr24_yv12) {
+            dim3 block(256), grid(b200_ceil_div(p.srcW >> 1, 256), (p.srcH + 1) / 2, nf);
+            sws_bgr24_yv12_kernel<<<grid, block, 0, stream>>>(src[0] + (long long)f0 * sfs[0], sstr[0], sfs[0],
+                                                               dst[0] + (long long)f0 * dfs[0], dstr[0], dfs[0],
+                                                               dst[1] + (long long)f0 * dfs[1], dstr[1], dfs[1],
+                                                               dst[2] + (long long)f0 * dfs[2], dstr[2], dfs[2], p.srcW, p.srcH, R);
+            B200_LAUNCHED();
+            continue;
+        }
         if (p.planar_copy) {
             for (int pl = 0; pl < 3; pl++) {
                 const uint8_t *s = src[pl] + (long long)f0 * sfs[pl];
@@ -1222,7 +1340,15 @@ static int launch_planar(B200SwsContext *c, cudaStream_t stream, const uint8_t *
         const int vs[3] = { c->dt.vLumSize, c->dt.vChrSize, c->dt.vChrSize };
         for (int pl = 0; pl < 3; pl++) {
             dim3 block(256), gh(b200_ceil_div(dw[pl], 256), sh[pl], nf), gv(b200_ceil_div(dw[pl], 256), dh[pl], nf);
-            if (p.fast_bilinear && pl == 0)
+            if (p.src_rgb) {                    // packed source in src[0]: luma lines, then both chroma planes in one launch
+                if (pl == 0)
+                    sws_rgbin_hscale_y_kernel<<<gh, block, 0, stream>>>(src[0] + (long long)f0 * sfs[0], sstr[0], sfs[0], m[0], dw[0],
+                                                                        (long long)(perFrame / 2), c->dt.hLum, c->dt.hLumPos, c->dt.hLumSize, R);
+                else if (pl == 1)
+                    sws_rgbin_hscale_uv_kernel<<<gh, block, 0, stream>>>(src[0] + (long long)f0 * sfs[0], sstr[0], sfs[0], m[1], m[2], dw[1],
+                                                                         (long long)(perFrame / 2), c->dt.hChr, c->dt.hChrPos, c->dt.hChrSize, R);
+            }
+            else if (p.fast_bilinear && pl == 0)
                 sws_hscale_fast_kernel<false><<<gh, block, 0, stream>>>(src[pl] + (long long)f0 * sfs[pl], sstr[pl], sfs[pl], m[pl], dw[pl],
                                                                         (long long)(perFrame / 2), sw[pl], p.lumXInc, 0);
             else if (p.fast_bilinear)
@@ -1231,7 +1357,7 @@ static int launch_planar(B200SwsContext *c, cudaStream_t stream, const uint8_t *
             else
                 launch_hscale(stream, src[pl] + (long long)f0 * sfs[pl], sstr[pl], sfs[pl], m[pl], dw[pl], (long long)(perFrame / 2),
                               hc[pl], hp[pl], hs[pl], 0, sh[pl], nf);
-            B200_LAUNCHED();
+            if (!(p.src_rgb && pl == 2)) B200_LAUNCHED();
             if (p.range_conv) {
                 sws_range_kernel<<<gh, block, 0, stream>>>(m[pl], dw[pl], (long long)(perFrame / 2), pl ? p.chrRangeCoeff : p.lumRangeCoeff,
                                                            pl ? p.chrRangeOffset : p.lumRangeOffset, p.range_conv == 1);
@@ -1267,11 +1393,11 @@ B200_API int b200_sws_scale_batch_device_planar(B200SwsContext *c, const uint8_t
 {
     if (!c || !src || !srcStride || !srcFrameStride || !dst || !dstStride || !dstFrameStride) return B200_EINVAL;
     if (!c->plan.planar) return B200_EINVAL;
-    const int nsp = c->plan.src_nv ? 2 : 3;
+    const int nsp = c->plan.src_rgb ? 1 : c->plan.src_nv ? 2 : 3;           // packed RGB: plane 0 only; nv12 / nv21: planes 0 and 1
     for (int i = 0; i < 3; i++) if ((i < nsp && (!src[i] || srcStride[i] < 0)) || !dst[i] || dstStride[i] < 0) return B200_EINVAL;
     B200_CUDA_OK(cudaSetDevice(c->dev->ordinal));
-    const long long ss[3] = { srcStride[0], srcStride[1], nsp == 3 ? srcStride[2] : 0 };
-    const long long fs[3] = { srcFrameStride[0], srcFrameStride[1], nsp == 3 ? srcFrameStride[2] : 0 };
+    const long long ss[3] = { srcStride[0], nsp >= 2 ? srcStride[1] : 0, nsp == 3 ? srcStride[2] : 0 };
+    const long long fs[3] = { srcFrameStride[0], nsp >= 2 ? srcFrameStride[1] : 0, nsp == 3 ? srcFrameStride[2] : 0 };
     const long long ds[3] = { dstStride[0], dstStride[1], dstStride[2] };
     const long long df[3] = { dstFrameStride[0], dstFrameStride[1], dstFrameStride[2] };
     return launch_planar(c, c->dev->stream, src, ss, fs, dst, ds, df, nframes);
@@ -1286,14 +1412,15 @@ static int sws_scale_planar_host(B200SwsContext *c, const uint8_t *const srcSlic
         b200_set_error("yuv420p destination: only whole-frame calls are implemented");
         return B200_ENOSYS;
     }
-    const int nsp = p.src_nv ? 2 : 3;                             // nv12 / nv21: plane 1 carries both chroma components
+    const int nsp = p.src_rgb ? 1 : p.src_nv ? 2 : 3;             // packed RGB: one plane; nv12 / nv21: plane 1 carries both chroma components
     for (int i = 0; i < 3; i++) {
         if (!dst[i] || (i < nsp && !srcSlice[i])) return B200_EINVAL;
         if (dstStride[i] < 0 || (i < nsp && srcStride[i] < 0)) return B200_ENOSYS;
     }
     B200Device *d = c->dev;
     B200_CUDA_OK(cudaSetDevice(d->ordinal));
-    const int sw[3] = { p.srcW, p.src_nv ? 2 * p.chrSrcW : p.chrSrcW, p.src_nv ? 0 : p.chrSrcW }, sh[3] = { p.srcH, p.chrSrcH, p.chrSrcH };
+    const int sw[3] = { p.src_rgb ? p.srcW * p.src_rgb : p.srcW, p.src_rgb ? 0 : p.src_nv ? 2 * p.chrSrcW : p.chrSrcW, (p.src_nv || p.src_rgb) ? 0 : p.chrSrcW },
+              sh[3] = { p.srcH, p.src_rgb ? 0 : p.chrSrcH, p.src_rgb ? 0 : p.chrSrcH };
     const int dw[3] = { p.dstW, p.chrDstW, p.chrDstW }, dh[3] = { p.dstH, p.chrDstH, p.chrDstH };
     size_t spitch[3], dpitch[3], soff[3], doff[3], total = 0;
     for (int i = 0; i < 3; i++) { spitch[i] = ((size_t)sw[i] + 255) & ~(size_t)255; soff[i] = total; total += spitch[i] * sh[i]; }

@@ -286,18 +286,47 @@ static void plan_range_convert(SwsPlan &p)
     }
 }
 
+static i64 rounded_div(i64 a, i64 b) { return a >= 0 ? (a + (b >> 1)) / b : (a - (b >> 1)) / b; }
+
+// fill_rgb2yuv_table (utils.c:614-700): always the limited-range matrix (full range comes from the range conversion between
+// the passes); the default BT.601 table gets the hand-rounded constants of utils.c:692-702
+static void plan_rgb2yuv(SwsPlan &p, const int table[4])
+{
+    static const int bt601[4] = { 104597, 132201, 25675, 53279 };
+    const i64 ONE = 65536;
+    const i64 vr = table[0], ub = table[1], ug = -(i64)table[2], vg = -(i64)table[3], cy = ONE * 255 / 219;
+    if (!vr || !ub) return;                                                       // (the reference would divide by zero)
+    const i64 W = rounded_div(ONE * ONE * ug, ub), V = rounded_div(ONE * ONE * vg, vr), Z = ONE * ONE - W - V;
+    const i64 Cy = rounded_div(cy * Z, ONE), Cu = rounded_div(ub * Z, ONE), Cv = rounded_div(vr * Z, ONE);
+    if (!Cy || !Cu || !Cv) return;
+    int *t = p.rgb2yuv;
+    t[0] = (int)-rounded_div((1 << 15) * V, Cy);      t[1] = (int)rounded_div((1 << 15) * ONE * ONE, Cy);  t[2] = (int)-rounded_div((1 << 15) * W, Cy);
+    t[3] = (int)rounded_div((1 << 15) * V, Cu);       t[4] = (int)-rounded_div((1 << 15) * ONE * ONE, Cu); t[5] = (int)rounded_div((1 << 15) * (Z + W), Cu);
+    t[6] = (int)rounded_div((1 << 15) * (V + Z), Cv); t[7] = (int)-rounded_div((1 << 15) * ONE * ONE, Cv); t[8] = (int)rounded_div((1 << 15) * W, Cv);
+    if (!memcmp(table, bt601, sizeof(bt601))) {
+        t[2] =  (int)(0.114 * 219 / 255 * (1 << 15) + 0.5); t[8] = -(int)(0.081 * 224 / 255 * (1 << 15) + 0.5);
+        t[5] =  (int)(0.500 * 224 / 255 * (1 << 15) + 0.5); t[1] =  (int)(0.587 * 219 / 255 * (1 << 15) + 0.5);
+        t[7] = -(int)(0.419 * 224 / 255 * (1 << 15) + 0.5); t[4] = -(int)(0.331 * 224 / 255 * (1 << 15) + 0.5);
+        t[0] =  (int)(0.299 * 219 / 255 * (1 << 15) + 0.5); t[6] =  (int)(0.500 * 224 / 255 * (1 << 15) + 0.5);
+        t[3] = -(int)(0.169 * 224 / 255 * (1 << 15) + 0.5);
+    }
+}
+
 int sws_plan_colorspace_details(SwsPlan &p, const int inv_table[4], int srcRange, const int table[4], int dstRange,
                                 int brightness, int contrast, int saturation)
 {
     const bool yuvDst = p.out.kind == SWS_OUT_YUV420P;
     if (!yuvDst) dstRange = 0;                                                   // range_override_needed(dst), utils.c:877-878
+    if (p.src_rgb) srcRange = 0;                                                 // range_override_needed(src), utils.c:879-880
+    plan_rgb2yuv(p, table);                                                      // utils.c:1002
     memcpy(p.src_cs, inv_table, sizeof(p.src_cs));
     memcpy(p.dst_cs, table, sizeof(p.dst_cs));
     p.src_range = srcRange;
     p.dst_range = dstRange;
     plan_range_convert(p);
-    if (yuvDst)     // utils.c:910-989: with different matrices the reference cascades yuv -> bgr24 -> yuv; that needs the rgb readers
+    if (yuvDst && !p.src_rgb)   // utils.c:910-989: with different matrices the reference cascades yuv -> bgr24 -> yuv: not built
         return memcmp(p.src_cs, p.dst_cs, sizeof(p.src_cs)) ? B200_ENOSYS : 0;
+    if (yuvDst) return 0;       // RGB -> yuv: only the rgb2yuv table and the ranges matter
     return sws_plan_colorspace(p, inv_table, srcRange, brightness, contrast, saturation);
 }
 
@@ -325,14 +354,26 @@ int sws_plan_build(SwsPlan &p, int srcW, int srcH, int dstW, int dstH, int flags
         algo = B200_SWS_BILINEAR;
         flags ^= B200_SWS_FAST_BILINEAR | algo;
     }
-    p.fast_bilinear = algo == B200_SWS_FAST_BILINEAR;                            // swscale.c:676-681
+    // the fast horizontal functions exist for 8-bit input lines only (swscale.c:675-681); RGB sources are srcBpc 16
+    // (utils.c:1407-1408) and use the 2-tap filter initFilter builds for the flag
+    p.fast_bilinear = algo == B200_SWS_FAST_BILINEAR && !p.src_rgb;
     p.planar = p.out.kind == SWS_OUT_YUV420P;
+    if (p.src_rgb && !p.planar && srcW == dstW && srcH == dstH) return B200_ENOSYS;          // the reference's rgb2rgb shuffles: not this path
+    if (p.src_rgb == 4 && !p.planar && p.out.bpp == 4) return B200_ENOSYS;                   // alpha carried through the scaler: not built
     if (!p.planar && (dstW & 1)) flags |= B200_SWS_FULL_CHR_H_INT;               // utils.c:1271-1276 (RGB destinations only)
+    if (!p.planar && p.src_rgb && !(flags & B200_SWS_FAST_BILINEAR))
+        flags |= B200_SWS_FULL_CHR_H_INT;                                        // utils.c:1277-1285: source chroma is not subsampled
     p.srcW = srcW; p.srcH = srcH; p.dstW = dstW; p.dstH = dstH; p.flags = flags;
     p.chrDstHSub = (!p.planar && (flags & B200_SWS_FULL_CHR_H_INT)) ? 0 : 1;     // utils.c:1359-1360
     const int chrDstVSub = p.planar ? 1 : 0;                                     // av_pix_fmt_get_chroma_sub_sample(dstFormat), utils.c:1266
-    p.chrSrcW = chroma_shift_up(srcW, 1);
-    p.chrSrcH = chroma_shift_up(srcH, 1);
+    p.chrSrcHSub = 1; p.chrSrcVSub = 1;
+    if (p.src_rgb) {                                                             // utils.c:1366-1393: every other pixel for chroma unless asked otherwise
+        p.chrSrcVSub = 0;
+        p.chrSrcHSub = (!(srcW & 1) && !(flags & B200_SWS_FULL_CHR_H_INP) &&
+                        ((dstW >> p.chrDstHSub) <= (srcW >> 1) || (flags & B200_SWS_FAST_BILINEAR))) ? 1 : 0;
+    }
+    p.chrSrcW = chroma_shift_up(srcW, p.chrSrcHSub);
+    p.chrSrcH = chroma_shift_up(srcH, p.chrSrcVSub);
     p.chrDstW = chroma_shift_up(dstW, p.chrDstHSub);
     p.chrDstH = chroma_shift_up(dstH, chrDstVSub);                               // packed RGB has no vertical chroma subsampling
     static const int bt601[4] = { 104597, 132201, 25675, 53279 };                // ff_yuv2rgb_coeffs[SWS_CS_DEFAULT], yuv2rgb.c:47-59
@@ -342,10 +383,14 @@ int sws_plan_build(SwsPlan &p, int srcW, int srcH, int dstW, int dstH, int flags
 
     // unscaled special converter gate: swscale_unscaled.c:2426-2431 reached from utils.c:1623-1637; a yuv destination only
     // looks for one when no range conversion is due (utils.c:1624-1626)
-    p.planar_copy = p.planar && srcW == dstW && srcH == dstH && p.src_range == p.dst_range;
+    // bgr24ToYv12Wrapper (swscale_unscaled.c:2453-2457): bgr24 only, not with accurate_rnd, even width
+    p.bgr24_yv12 = p.planar && p.src_rgb == 3 && p.sbo == 0 && srcW == dstW && srcH == dstH && p.src_range == p.dst_range &&
+                   !(flags & B200_SWS_ACCURATE_RND) && !(dstW & 1);
+    if (p.bgr24_yv12) return 0;
+    p.planar_copy = p.planar && !p.src_rgb && srcW == dstW && srcH == dstH && p.src_range == p.dst_range;
     if (p.planar_copy) return 0;
     // (only planar yuv420p / yuv422p sources have the LUT converter; nv12 / nv21 go through the scaler)
-    p.unscaled_lut = !p.planar && !p.src_nv && srcW == dstW && srcH == dstH && !(flags & B200_SWS_ACCURATE_RND) && !(dstH & 1);
+    p.unscaled_lut = !p.planar && !p.src_nv && !p.src_rgb && srcW == dstW && srcH == dstH && !(flags & B200_SWS_ACCURATE_RND) && !(dstH & 1);
     if (p.unscaled_lut) return 0;
 
     const int lumScaler = algo == B200_SWS_BICUBLIN ? B200_SWS_BICUBIC : algo;
@@ -360,10 +405,10 @@ int sws_plan_build(SwsPlan &p, int srcW, int srcH, int dstW, int dstH, int flags
     p.lumXInc = (int)lumXInc; p.chrXInc = (int)chrXInc;
     if ((ret = build_bank(p.hLum, lumScaler, (int)lumXInc, srcW, dstW, 1 << 14, sample_origin(0, 0), sample_origin(0, 0))) < 0) return ret;
     if ((ret = build_bank(p.hChr, chrScaler, (int)chrXInc, p.chrSrcW, p.chrDstW, 1 << 14,
-                          sample_origin(1, -513), sample_origin(p.chrDstHSub, -513))) < 0) return ret;
+                          sample_origin(p.chrSrcHSub, -513), sample_origin(p.chrDstHSub, -513))) < 0) return ret;
     if ((ret = build_bank(p.vLum, lumScaler, (int)lumYInc, srcH, dstH, 1 << 12, sample_origin(0, 0), sample_origin(0, 0))) < 0) return ret;
     if ((ret = build_bank(p.vChr, chrScaler, (int)chrYInc, p.chrSrcH, p.chrDstH, 1 << 12,
-                          sample_origin(1, -513), sample_origin(chrDstVSub, -513))) < 0) return ret;
+                          sample_origin(p.chrSrcVSub, -513), sample_origin(chrDstVSub, -513))) < 0) return ret;
     if (p.planar) return 0;
 
     // writer per output line, as packed_vscale decides it (vscale.c:144-169); coefficients are read as uint16 there

@@ -45,6 +45,12 @@ struct SwsPlan {
     int range_conv = 0;           // 0 none, 1 limited -> full (lum/chrRangeToJpeg_c: clips at 2^15-1), 2 full -> limited (FromJpeg)
     int lumRangeCoeff = 0, lumRangeOffset = 0, chrRangeCoeff = 0, chrRangeOffset = 0;
     int src_cs[4] = { 104597, 132201, 25675, 53279 }, dst_cs[4] = { 104597, 132201, 25675, 53279 };   // colorspace tables as last set
+    // packed RGB source: input readers (input.c:264-393,1068-1172) -> 16-bit lines -> hScale16To15_c (swscale.c:99-125)
+    int src_rgb = 0;              // 0: yuv source; 3 / 4: bytes per source pixel (set, with the offsets, before sws_plan_build)
+    int sro = 0, sgo = 0, sbo = 0;                // byte positions of R, G, B in a source pixel
+    int chrSrcHSub = 1, chrSrcVSub = 1;           // chroma sampling of the source as the scaler sees it (utils.c:1366-1396)
+    int rgb2yuv[9] = { 0 };       // input_rgb2yuv_table RY GY BY RU GU BU RV GV BV (swscale_internal.h:468-477; utils.c:614-700)
+    bool bgr24_yv12 = false;      // reference installs bgr24ToYv12Wrapper (ff_rgb24toyv12_c, rgb2rgb_template.c:580-641)
     SwsFilterBank hLum, hChr, vLum, vChr;
     SwsColorConst color{};
     // per output line: writer selected by packed_vscale (vscale.c:144-169): 0 = _X, 1 = _1, 2 = _2, plus alphas

@@ -1,4 +1,5 @@
-"""Host-side mirror of the libswscale interface for the accelerated path (yuv420p -> rgb24 / bgr24 / rgba / bgra / argb / abgr / yuv420p).
+"""Host-side mirror of the libswscale interface for the accelerated path (yuv420p / nv12 / nv21 -> rgb24 / bgr24 / rgba / bgra / argb /
+abgr / yuv420p, and packed 8-bit RGB -> yuv420p: pass the packed picture as plane 0).
 
 Names and argument meaning follow libswscale/swscale.h: sws_getContext (:utils.c:1919), sws_setColorspaceDetails
 (utils.c:849), sws_scale (swscale.c:1626), sws_freeContext.  Arrays are numpy (host) for sws_scale / scale_batch_host
@@ -12,7 +13,7 @@ AV_PIX_FMT_YUV420P, AV_PIX_FMT_RGB24, AV_PIX_FMT_BGR24 = 0, 2, 3                
 AV_PIX_FMT_ARGB, AV_PIX_FMT_RGBA, AV_PIX_FMT_ABGR, AV_PIX_FMT_BGRA = 25, 26, 27, 28
 AV_PIX_FMT_NV12, AV_PIX_FMT_NV21 = 23, 24                                                # source only: src[1] = interleaved chroma
 SWS_FAST_BILINEAR, SWS_BILINEAR, SWS_BICUBIC, SWS_POINT, SWS_AREA, SWS_BICUBLIN = 1, 2, 4, 0x10, 0x20, 0x40
-SWS_FULL_CHR_H_INT, SWS_ACCURATE_RND, SWS_BITEXACT = 0x2000, 0x40000, 0x80000
+SWS_FULL_CHR_H_INT, SWS_FULL_CHR_H_INP, SWS_ACCURATE_RND, SWS_BITEXACT = 0x2000, 0x4000, 0x40000, 0x80000
 # libswscale/yuv2rgb.c:47-59 (sws_getCoefficients)
 SWS_CS_ITU709, SWS_CS_FCC, SWS_CS_ITU601, SWS_CS_SMPTE240M, SWS_CS_DEFAULT, SWS_CS_BT2020 = 1, 4, 5, 7, 5, 9
 _COEFFS = {0: (104597, 132201, 25675, 53279), 1: (117489, 138438, 13975, 34925), 4: (104448, 132798, 24759, 53109),

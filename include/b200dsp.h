@@ -85,12 +85,16 @@ uint64_t b200_launch_count(void);
 #define B200_SWS_AREA          0x20
 #define B200_SWS_BICUBLIN      0x40
 #define B200_SWS_FULL_CHR_H_INT 0x2000
+#define B200_SWS_FULL_CHR_H_INP 0x4000   /* packed RGB source: chroma from every pixel instead of every other one */
 #define B200_SWS_ACCURATE_RND  0x40000
 #define B200_SWS_BITEXACT      0x80000
 
 typedef struct B200SwsContext B200SwsContext;
 
-/* like sws_getContext(); srcFilter/dstFilter/param are not supported (must be the defaults). NULL on failure. */
+/* like sws_getContext(); srcFilter/dstFilter/param are not supported (must be the defaults). NULL on failure.
+ * Sources: yuv420p, nv12, nv21 (-> packed 8-bit RGB or yuv420p) and rgb24 / bgr24 / rgba / bgra / argb / abgr (-> yuv420p; the input
+ * readers of libswscale/input.c:264-393,1068-1172, hScale16To15_c, and the bgr24ToYv12Wrapper special converter,
+ * libswscale/swscale_unscaled.c:2453-2457); a packed RGB source is passed as plane 0 (src[1], src[2] unused). */
 B200SwsContext *b200_sws_getContext(B200Device *dev, int srcW, int srcH, int srcFormat,
                                     int dstW, int dstH, int dstFormat, int flags);
 /* The same with SwsContext.src_range / .dst_range (libswscale/swscale.h, AVOption "src_range" / "dst_range"; 0 = limited,
@@ -148,8 +152,10 @@ int  b200_sws_plan_probe(int srcW, int srcH, int dstW, int dstH, int flags, int 
  * brightness, contrast, saturation }.  info32: [0..15] as b200_sws_info ([12] = vertical chroma shift of the destination),
  * [16] plain-copy context, [17] range conversion (0 none, 1 limited->full, 2 full->limited), [18..21] its luma coefficient,
  * luma offset, chroma coefficient, chroma offset (libswscale/swscale.c:577-624), [22] fast-bilinear horizontal pass,
- * [23] semi-planar source kind, [24] return value of the details call, [25] src_range, [26] dst_range. */
-int  b200_sws_plan_probe2(const int cfg[9], const int *details, int which, int16_t *filter, int32_t *pos, int cap, int *info32);
+ * [23] semi-planar source kind, [24] return value of the details call, [25] src_range, [26] dst_range, [27] packed RGB source
+ * (bytes per pixel), [28] / [29] horizontal / vertical chroma shift of the source as the scaler sees it, [30] bgr24 -> yv12
+ * converter installed, [32..40] input_rgb2yuv_table.  The array must hold 48 ints. */
+int  b200_sws_plan_probe2(const int cfg[9], const int *details, int which, int16_t *filter, int32_t *pos, int cap, int *info48);
 
 /* ------------------------------------------------------------------------------------------------ idctdsp
  * Replaces IDCTDSPContext (libavcodec/idctdsp.h:43-91) as filled by ff_idctdsp_init (libavcodec/idctdsp.c:228-314)

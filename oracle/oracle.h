@@ -75,6 +75,9 @@ int     orc_sws_info(const OrcSws *s, int *out);
 /* 6 ints, same layout as ffref_sws_range_info: conversion kind (0 none, 1 limited->full, 2 full->limited), luma coefficient
  * and offset, chroma coefficient and offset, unscaled converter installed */
 int     orc_sws_range_info(const OrcSws *s, int *out);
+/* 13 ints, same layout as ffref_sws_rgb_info: bytes per pixel of a packed RGB source (0 = yuv source), horizontal / vertical chroma
+ * shift of the source as scaled, bgr24 -> yv12 converter installed, input_rgb2yuv_table[9] */
+int     orc_sws_rgb_info(const OrcSws *s, int *out);
 /* which: 0 hLum 1 hChr 2 vLum 3 vChr; returns n entries copied */
 int     orc_sws_get_filter(const OrcSws *s, int which, int16_t *filter, int32_t *pos, int cap);
 /* the bare horizontal FIR */

@@ -152,6 +152,18 @@ API int ffref_sws_range_info(void *h, int *out)
     return 0;
 }
 
+/* Source side of the initialised context: out[0] = bytes per pixel if the source is packed 8-bit RGB else 0, [1] / [2] =
+ * chrSrcHSubSample / chrSrcVSubSample, [3] = an unscaled converter is installed, [4..12] = input_rgb2yuv_table. */
+API int ffref_sws_rgb_info(void *h, int *out)
+{
+    SwsInternal *c = sws_internal((SwsContext *)h);
+    const AVPixFmtDescriptor *d = av_pix_fmt_desc_get(c->opts.src_format);
+    out[0] = isAnyRGB(c->opts.src_format) ? av_get_bits_per_pixel(d) / 8 : 0;
+    out[1] = c->chrSrcHSubSample; out[2] = c->chrSrcVSubSample; out[3] = c->convert_unscaled != NULL;
+    for (int i = 0; i < 9; i++) out[4 + i] = c->input_rgb2yuv_table[i];
+    return 0;
+}
+
 /* which: 0 hLum 1 hChr 2 vLum 3 vChr.  Copies filter (n*size int16) and pos (n int32). Returns n. */
 API int ffref_sws_get_filter(void *h, int which, int16_t *filter, int32_t *pos, int cap)
 {

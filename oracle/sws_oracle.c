@@ -503,6 +503,15 @@ int orc_sws_range_info(const OrcSws *s, int *out)
     return 0;
 }
 
+/* out[0] bytes per pixel of a packed RGB source (0: yuv source), [1] / [2] horizontal / vertical chroma shift of the source as
+ * scaled, [3] bgr24 -> yv12 converter installed, [4..12] input_rgb2yuv_table */
+int orc_sws_rgb_info(const OrcSws *s, int *out)
+{
+    out[0] = s->src_rgb; out[1] = s->chrSrcHSub; out[2] = s->chrSrcVSub; out[3] = s->bgr24_yv12;
+    for (int i = 0; i < 9; i++) out[4 + i] = s->rgb2yuv[i];
+    return 0;
+}
+
 int orc_sws_get_filter(const OrcSws *s, int which, int16_t *filter, int32_t *pos, int cap)
 {
     const int16_t *f; const int32_t *p; int n, fs;

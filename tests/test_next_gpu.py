@@ -176,3 +176,57 @@ def test_idct_hbd_pointer_table(device):
             assert np.array_equal(d, ed) and (kind != 0 or np.array_equal(b, eb)), (bits, kind)
     with pytest.raises(fb.B200Error):
         idctdsp.ff_idctdsp_init_hbd(idctdsp.FF_IDCT_SIMPLE, 8, 0)
+
+
+# ---------------------------------------------------------------------------------------------- swscale: packed RGB sources
+def test_sws_rgb_sources_golden_and_oracle(device):
+    """rgb24 / bgr24 / rgba / bgra / argb / abgr -> yuv420p (input readers fused into the horizontal pass, the bgr24 -> yv12
+    converter, range conversion behind them) against the reference's outputs and the oracle"""
+    import functools
+    from test_oracle import rgbsrc_rows, run_rgbsrc_row, sha
+    from test_sws_gpu import gpu_sws_planar
+    rows = [r for r in rgbsrc_rows() if r[4] == "yuv420p"]
+    assert len(rows) == 15 * 6 * 2
+    gp = functools.partial(gpu_sws_planar, device)
+    for row in rows:
+        got = run_rgbsrc_row(None, gp, row)
+        assert np.array_equal(got, run_rgbsrc_row(None, cl.orc_sws_planar, row)), row[:6]
+        assert sha(got) == row[-1], row[:6]
+
+
+def test_sws_rgb_sources_large_padded_batch(device):
+    import torch
+    import ffmpeg_b200 as fb
+    from ffmpeg_b200 import swscale as sw
+    from test_sws_gpu import gpu_sws_planar
+    from cases import FATE
+    for (w, h, dw, dh, fl, name) in [(1920, 1080, 1920, 1080, FATE, "bgra"), (1920, 1080, 1280, 720, cl.SWS_BICUBIC, "rgb24"),
+                                     (1280, 720, 1280, 720, cl.SWS_BICUBIC, "bgr24"), (641, 361, 1280, 720, cl.SWS_BILINEAR, "argb"),
+                                     (1281, 721, 1281, 721, cl.SWS_BICUBIC, "bgr24")]:
+        sf = cl.PACKED_RGB_FORMATS[name]
+        src = cl.rgb_frame(w, h, 2300 + w, cl.fmt_bpp(sf), "random", pad=5)
+        out = gpu_sws_planar(device, w, h, dw, dh, fl, src, src, src, dst_pad=3, src_fmt=sf)
+        exp = cl.orc_sws_planar(w, h, dw, dh, fl, src, src, src, dst_pad=3, src_fmt=sf)
+        assert all(np.array_equal(p, q) for p, q in zip(out, exp)), (w, h, dw, dh, hex(fl), name)
+    # batched device entry point, 3 frames of rgba -> yuv420p (scaled) and of bgr24 through the special converter
+    for (name, dw, dh, fl) in (("rgba", 480, 270, FATE), ("bgr24", 320, 180, cl.SWS_BICUBIC)):
+        sf, w, h, n = cl.PACKED_RGB_FORMATS[name], 320, 180, 3
+        bpp = cl.fmt_bpp(sf)
+        frames = [cl.rgb_frame(w, h, 2400 + k, bpp) for k in range(n)]
+        ctx = sw.sws_getContext(device, w, h, sf, dw, dh, sw.AV_PIX_FMT_YUV420P, fl)
+        with torch.cuda.stream(torch.cuda.ExternalStream(device.stream)):
+            S = torch.from_numpy(np.stack(frames)).cuda()
+            DY = torch.zeros((n, dh, dw), dtype=torch.uint8, device="cuda")
+            DU = torch.zeros((n, dh // 2, dw // 2), dtype=torch.uint8, device="cuda")
+            DV = torch.zeros((n, dh // 2, dw // 2), dtype=torch.uint8, device="cuda")
+            ctx.scale_batch_device_planar([S], [w * bpp], [w * bpp * h], [DY, DU, DV], [dw, dw // 2, dw // 2],
+                                          [dw * dh, dw * dh // 4, dw * dh // 4], n)
+            device.sync()
+            got = [t.cpu().numpy() for t in (DY, DU, DV)]
+        for i in range(n):
+            exp = cl.orc_sws_planar(w, h, dw, dh, fl, frames[i], frames[i], frames[i], src_fmt=sf)
+            for k in range(3):
+                assert np.array_equal(got[k][i], exp[k]), (name, i, k)
+        ctx.free()
+    with pytest.raises(fb.B200Error):                                  # packed RGB -> packed RGB is not on the device yet
+        sw.sws_getContext(device, 64, 48, sw.AV_PIX_FMT_RGB24, 32, 24, sw.AV_PIX_FMT_BGR24, FATE)

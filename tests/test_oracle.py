@@ -275,6 +275,14 @@ def _all_sws_configs():
         out.append((cl.PIX_FMT_NV12, w, h, ranges[0], 0, dw, dh, ranges[1], fl, details))
         out.append((0, w, h, ranges[0], cl.PIX_FMT_RGB24, dw, dh, ranges[1], fl, None))      # RGB destination: dst_range is ignored
     out += [(0, 3840, 2160, 0, 0, 1920, 1080, 1, FATE, None), (0, 3840, 2160, 1, 0, 3840, 2160, 0, FATE, None)]
+    from cases import SWS_RGBSRC_CASES
+    for (w, h, dw, dh, fl, _k) in SWS_RGBSRC_CASES:
+        for sf in cl.PACKED_RGB_FORMATS.values():
+            out += [(sf, w, h, 0, 0, dw, dh, 0, fl, None), (sf, w, h, 0, 0, dw, dh, 1, fl, None)]
+            if (w, h) != (dw, dh) and cl.fmt_bpp(sf) == 3:
+                out.append((sf, w, h, 0, cl.PIX_FMT_BGRA, dw, dh, 0, fl, None))
+        out.append((cl.PIX_FMT_BGR24, w, h, 0, 0, dw, dh, 0, fl, (1, 0, 1, 1, 0, 1 << 16, 1 << 16)))     # bt709 table, full range out
+    out += [(cl.PIX_FMT_RGB24, 3840, 2160, 0, 0, 3840, 2160, 0, FATE, None), (cl.PIX_FMT_BGRA, 3840, 2160, 0, 0, 1920, 1080, 0, cl.SWS_BICUBIC, None)]
     return out
 
 
@@ -286,8 +294,10 @@ def test_host_plan_matches_oracle_and_reference_all_formats():
     L, O = fb.lib(), cl.oracle()
     R = cl.ref() if cl.have_ref() else None
     O.orc_sws_range_info.argtypes = [C.c_void_p, cl.i32p]
+    O.orc_sws_rgb_info.argtypes = [C.c_void_p, cl.i32p]
     if R is not None:
         R.ffref_sws_range_info.argtypes = [C.c_void_p, cl.i32p]
+        R.ffref_sws_rgb_info.argtypes = [C.c_void_p, cl.i32p]
     cfgs = _all_sws_configs()
     assert len(cfgs) > 150
     for (sf, w, h, sr, df, dw, dh, dr, fl, details) in cfgs:
@@ -307,17 +317,25 @@ def test_host_plan_matches_oracle_and_reference_all_formats():
         oi, ori = np.zeros(16, np.int32), np.zeros(6, np.int32)
         O.orc_sws_info(octx, cl.ptr(oi, cl.i32p))
         O.orc_sws_range_info(octx, cl.ptr(ori, cl.i32p))
+        ogi = np.zeros(13, np.int32)
+        O.orc_sws_rgb_info(octx, cl.ptr(ogi, cl.i32p))
         if rctx:
-            rri = np.zeros(6, np.int32)
+            rri, rgi = np.zeros(6, np.int32), np.zeros(13, np.int32)
             R.ffref_sws_range_info(rctx, cl.ptr(rri, cl.i32p))
+            R.ffref_sws_rgb_info(rctx, cl.ptr(rgi, cl.i32p))
             assert list(rri) == list(ori), (key, list(rri), list(ori))
+            assert list(rgi[:3]) == list(ogi[:3]), (key, list(rgi), list(ogi))
+            if ogi[0]:                      # (for yuv -> yuv the reference returns before it fills the table, utils.c:910-989)
+                assert list(rgi[4:]) == list(ogi[4:]), (key, list(rgi), list(ogi))
+                assert bool(rgi[3]) == bool(ogi[3]), (key, "bgr24 -> yv12 gate")
         for which in range(4):
-            pi = np.zeros(32, np.int32)
+            pi = np.zeros(48, np.int32)
             n = L.b200_sws_plan_probe2(cl.ptr(cfg, cl.i32p), cl.ptr(det, cl.i32p) if det is not None else None, which, None, None, 0,
                                        cl.ptr(pi, cl.i32p))
             assert n >= 0 and pi[24] == 0, key
             assert list(pi[:8]) == list(oi[:8]) and pi[11] == oi[11], (key, list(pi[:16]), list(oi))
-            assert bool(pi[8] or pi[16]) == bool(ori[5]), (key, "unscaled converter gate")
+            assert bool(pi[8] or pi[16] or pi[30]) == bool(ori[5]), (key, "unscaled converter gate")
+            assert [int(pi[27]), int(pi[28]), int(pi[29]), int(pi[30])] + [int(x) for x in pi[32:41]] == [int(x) for x in ogi], (key, list(pi[27:41]), list(ogi))
             assert [int(pi[17]), int(pi[18]) if pi[17] else 0, int(pi[19]) if pi[17] else 0, int(pi[20]) if pi[17] else 0,
                     int(pi[21]) if pi[17] else 0] == list(ori[:5]), (key, list(pi[16:27]), list(ori))
             size, cnt = int(pi[which]), [dw, int(pi[6]), dh, int(pi[7])][which]
@@ -339,7 +357,7 @@ def test_host_plan_refuses_yuv_matrix_change():
     L = fb.lib()
     cfg = np.array([64, 48, 0, 0, 100, 70, 0, 0, FATE], np.int32)
     det = np.array(list(cl.COEFFS[1]) + [0] + list(cl.COEFFS[5]) + [1, 0, 1 << 16, 1 << 16], np.int32)
-    pi = np.zeros(32, np.int32)
+    pi = np.zeros(48, np.int32)
     assert L.b200_sws_plan_probe2(cl.ptr(cfg, cl.i32p), cl.ptr(det, cl.i32p), 0, None, None, 0, cl.ptr(pi, cl.i32p)) >= 0
     assert pi[24] == -38                                            # B200_ENOSYS: the reference would cascade through bgr24
     cfg[6] = cl.PIX_FMT_RGB24                                       # RGB destination: `table` is ignored, like the reference
