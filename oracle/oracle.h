@@ -67,7 +67,8 @@ int     orc_sws_set_colorspace_details(OrcSws *s, const int inv_table[4], int sr
 /* whole-frame conversion; returns number of output lines or <0 */
 int     orc_sws_scale(OrcSws *s, const uint8_t *y, int ys, const uint8_t *u, int us,
                       const uint8_t *v, int vs, uint8_t *dst, int ds);
-/* planar destination (context opened with ORC_PIX_FMT_YUV420P) */
+/* planar destination (context opened with ORC_PIX_FMT_YUV420P, or ORC_PIX_FMT_NV12 / NV21: then `du` receives the interleaved
+ * chroma plane of 2 * chrDstW bytes per line and `dv` is unused) */
 int     orc_sws_scale_planar(OrcSws *s, const uint8_t *y, int ys, const uint8_t *u, int us, const uint8_t *v, int vs,
                              uint8_t *dy, int dys, uint8_t *du, int dus, uint8_t *dv, int dvs);
 /* 16 ints, same layout as ffref_sws_info */

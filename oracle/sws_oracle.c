@@ -52,6 +52,7 @@ struct OrcSws {
     int chrSrcHSub, chrSrcVSub;
     int rgb2yuv[9];            /* input_rgb2yuv_table: RY GY BY RU GU BU RV GV BV (swscale_internal.h:468-477), 15-bit */
     int bgr24_yv12;            /* 1: reference installs bgr24ToYv12Wrapper (ff_rgb24toyv12_c) as convert_unscaled */
+    int dst_nv;                /* 0: three destination planes; 1: nv12, 2: nv21 destination (plane 1 = U,V / V,U interleaved) */
 };
 
 static int64_t i64abs(int64_t a) { return a < 0 ? -a : a; }
@@ -373,6 +374,8 @@ static int set_format(OrcSws *s, int fmt)
     s->planar = 0;
     switch (fmt) {
     case ORC_PIX_FMT_YUV420P: s->planar = 1; s->bpp = 1; s->ro = s->go = s->bo = 0; s->ao = -1; break;
+    case ORC_PIX_FMT_NV12: case ORC_PIX_FMT_NV21:                   /* as a destination: yuv420p with the chroma planes interleaved */
+        s->planar = 1; s->bpp = 1; s->ro = s->go = s->bo = 0; s->ao = -1; break;
     case ORC_PIX_FMT_RGB24: s->bpp = 3; s->ro = 0; s->go = 1; s->bo = 2; s->ao = -1; break;
     case ORC_PIX_FMT_BGR24: s->bpp = 3; s->ro = 2; s->go = 1; s->bo = 0; s->ao = -1; break;
     case ORC_PIX_FMT_RGBA:  s->bpp = 4; s->ro = 0; s->go = 1; s->bo = 2; s->ao = 3;  break;
@@ -403,6 +406,7 @@ OrcSws *orc_sws_open_range(int srcFormat, int srcW, int srcH, int srcRange, int 
         s->src_rgb = s->bpp; s->sro = s->ro; s->sgo = s->go; s->sbo = s->bo;
     } else if (srcFormat != ORC_PIX_FMT_YUV420P && srcFormat != ORC_PIX_FMT_NV12 && srcFormat != ORC_PIX_FMT_NV21) { free(s); return NULL; }
     if (set_format(s, dstFormat) < 0) { free(s); return NULL; }
+    s->dst_nv = dstFormat == ORC_PIX_FMT_NV12 ? 1 : dstFormat == ORC_PIX_FMT_NV21 ? 2 : 0;
     if (s->src_rgb && !s->planar && srcW == dstW && srcH == dstH) { free(s); return NULL; }    /* rgb2rgb shuffles: not this path */
     if (s->src_rgb == 4 && !s->planar && s->bpp == 4) { free(s); return NULL; }                /* alpha carried through the scaler
                                                                                                  * (alpToYV12 + the A writers): not restated */
@@ -436,7 +440,7 @@ OrcSws *orc_sws_open_range(int srcFormat, int srcW, int srcH, int srcRange, int 
 
     /* the unscaled converters are only looked for when no range conversion is due (utils.c:1623-1626) */
     /* bgr24ToYv12Wrapper (swscale_unscaled.c:2453-2457): bgr24 only, not with accurate_rnd, even width */
-    if (s->planar && s->src_rgb == 3 && s->sbo == 0 && srcW == dstW && srcH == dstH && s->src_range == s->dst_range &&
+    if (s->planar && !s->dst_nv && s->src_rgb == 3 && s->sbo == 0 && srcW == dstW && srcH == dstH && s->src_range == s->dst_range &&
         !(flags & ORC_SWS_ACCURATE_RND) && !(dstW & 1)) {
         s->bgr24_yv12 = 1;
         s->unscaled_lut = 3;
@@ -749,6 +753,25 @@ int orc_sws_scale_planar(OrcSws *s, const uint8_t *y, int ys, const uint8_t *u, 
                          uint8_t *dy, int dys, uint8_t *du, int dus, uint8_t *dv, int dvs)
 {
     if (!s->planar) return -EINVAL;
+    if (s->dst_nv) {
+        /* nv12 / nv21 destination: what the three-plane path writes, with the chroma planes interleaved — planarToNv12Wrapper
+         * (swscale_unscaled.c:147-165) when unscaled; through the scaler yuv2nv12cX_c (output.c:495-528) forms the same sums
+         * with the same flat dither as yuv2planeX_8_c / yuv2plane1_8_c and stores u, v (v, u for nv21) side by side */
+        const int cw = s->chrDstW, ch = s->chrDstH, nv = s->dst_nv;
+        uint8_t *t = malloc((size_t)2 * cw * ch);
+        if (!t) return -ENOMEM;
+        s->dst_nv = 0;
+        int r = orc_sws_scale_planar(s, y, ys, u, us, v, vs, dy, dys, t, cw, t + (size_t)cw * ch, cw);
+        s->dst_nv = nv;
+        const uint8_t *a = nv == 1 ? t : t + (size_t)cw * ch, *b = nv == 1 ? t + (size_t)cw * ch : t;
+        for (int j = 0; j < ch && r >= 0; j++)
+            for (int i = 0; i < cw; i++) {
+                du[(ptrdiff_t)j * dus + 2 * i] = a[(size_t)j * cw + i];
+                du[(ptrdiff_t)j * dus + 2 * i + 1] = b[(size_t)j * cw + i];
+            }
+        free(t);
+        return r;
+    }
     if (s->src_nv) {
         uint8_t *t = split_nv(s, u, us);
         if (!t) return -ENOMEM;

@@ -218,14 +218,16 @@ def _sws_run(lib, pre, w, h, dw, dh, flags, y, u, v, dst_pad=0, threads=1, color
 PIX_FMT_YUV420P = 0
 
 
-def _sws_run_planar(lib, pre, w, h, dw, dh, flags, y, u, v, dst_pad=0, threads=1, src_fmt=0, ranges=(0, 0), details=None):
+def _sws_run_planar(lib, pre, w, h, dw, dh, flags, y, u, v, dst_pad=0, threads=1, src_fmt=0, ranges=(0, 0), details=None,
+                    dst_fmt=PIX_FMT_YUV420P):
     """yuv420p / nv12 / nv21 -> yuv420p; returns (Y, U, V) destination planes (pad bytes stay 0xA5).
     ranges = (src_range, dst_range) given before initialisation; details = (src_cs, src_range, dst_cs, dst_range,
-    brightness, contrast, saturation) for a sws_setColorspaceDetails() call after it."""
+    brightness, contrast, saturation) for a sws_setColorspaceDetails() call after it.
+    dst_fmt nv12 / nv21: returns (Y, UV) with UV the interleaved plane."""
     if pre == "ffref":
-        ctx = lib.ffref_sws_open_range(src_fmt, w, h, ranges[0], PIX_FMT_YUV420P, dw, dh, ranges[1], flags, threads)
+        ctx = lib.ffref_sws_open_range(src_fmt, w, h, ranges[0], dst_fmt, dw, dh, ranges[1], flags, threads)
     else:
-        ctx = lib.orc_sws_open_range(src_fmt, w, h, ranges[0], PIX_FMT_YUV420P, dw, dh, ranges[1], flags)
+        ctx = lib.orc_sws_open_range(src_fmt, w, h, ranges[0], dst_fmt, dw, dh, ranges[1], flags)
     if not ctx:
         return None
     try:
@@ -238,7 +240,8 @@ def _sws_run_planar(lib, pre, w, h, dw, dh, flags, y, u, v, dst_pad=0, threads=1
             assert r == 0, r
         cw, ch = (dw + 1) // 2, (dh + 1) // 2
         dy = np.full((dh, dw + dst_pad), 0xA5, np.uint8)
-        du = np.full((ch, cw + dst_pad), 0xA5, np.uint8)
+        nvd = dst_fmt in (PIX_FMT_NV12, PIX_FMT_NV21)
+        du = np.full((ch, (2 * cw if nvd else cw) + dst_pad), 0xA5, np.uint8)
         dv = np.full((ch, cw + dst_pad), 0xA5, np.uint8)
         if pre == "ffref":
             n = lib.ffref_sws_scale_planar(ctx, ptr(y), y.strides[0], ptr(u), u.strides[0], ptr(v), v.strides[0], 0, h,
@@ -247,7 +250,7 @@ def _sws_run_planar(lib, pre, w, h, dw, dh, flags, y, u, v, dst_pad=0, threads=1
             n = lib.orc_sws_scale_planar(ctx, ptr(y), y.strides[0], ptr(u), u.strides[0], ptr(v), v.strides[0],
                                          ptr(dy), dy.strides[0], ptr(du), du.strides[0], ptr(dv), dv.strides[0])
         assert n == dh, n
-        return dy, du, dv
+        return (dy, du) if nvd else (dy, du, dv)
     finally:
         (lib.ffref_sws_close if pre == "ffref" else lib.orc_sws_close)(ctx)
 

@@ -11,16 +11,17 @@ import pytest
 import cpulibs as cl
 from cases import FATE
 
-FMT_ID = dict(cl.PACKED_RGB_FORMATS, yuv420p=cl.PIX_FMT_YUV420P)
+FMT_ID = dict(cl.PACKED_RGB_FORMATS, yuv420p=cl.PIX_FMT_YUV420P, nv12=cl.PIX_FMT_NV12, nv21=cl.PIX_FMT_NV21)
+NV = ("nv12", "nv21")
 needs_nut = pytest.mark.skipif(not (cl.have_nut() and os.path.exists(cl.VIDEOGEN)), reason="oracle/_ref/libffnut.so / videogen not built")
 
 
 def filtered(planes, test, fmt):
     """the byte moves of FATE's vflip / hflip / crop=100:100:100:100 filters on a converted picture"""
-    bpp = cl.fmt_bpp(FMT_ID[fmt]) if fmt != "yuv420p" else 1
+    bpp = 1 if fmt == "yuv420p" or fmt in NV else cl.fmt_bpp(FMT_ID[fmt])
     out = []
     for k, p in enumerate(planes):
-        px = p.reshape(p.shape[0], -1, bpp)
+        px = p.reshape(p.shape[0], -1, 2 if (fmt in NV and k) else bpp)          # nv12 / nv21 chroma: one (u, v) pair per sample
         o = 100 >> (k > 0)                                             # chroma planes: half the offset and size
         if test == "vflip":
             px = px[::-1]
@@ -38,6 +39,10 @@ def fate_stream(run_rgb, run_planar, frames, test, fmt, w, h):
     for y, u, v in frames:
         if fmt == "yuv420p":
             planes = run_planar(352, 288, w, h, FATE, y, u, v) if test == "scale" else (y, u, v)
+        elif fmt in NV:
+            planes = run_planar(352, 288, 352, 288, FATE, y, u, v, dst_fmt=FMT_ID[fmt])
+            if test == "scale":                                     # the second scaler: semi-planar in, the same format out
+                planes = run_planar(352, 288, w, h, FATE, planes[0], planes[1], planes[1], src_fmt=FMT_ID[fmt], dst_fmt=FMT_ID[fmt])
         else:
             pic = run_rgb(352, 288, 352, 288, FATE, y, u, v, fmt=FMT_ID[fmt])
             if test == "scale":                                     # the second scaler: packed RGB in, the same format out
@@ -47,12 +52,15 @@ def fate_stream(run_rgb, run_planar, frames, test, fmt, w, h):
     return pkts
 
 
-def check_all(run_rgb, run_planar, rgb_sources=True):
-    """rgb_sources=False: skip the rows whose second scaler reads packed RGB (a path the caller does not have yet)"""
+def check_all(run_rgb, run_planar, rgb_sources=True, nv_dest=True):
+    """rgb_sources=False: skip the rows whose second scaler reads packed RGB; nv_dest=False: skip the nv12 / nv21 rows (paths the
+    caller does not have yet)"""
     rows = cl.fate_pixfmts_goldens()
-    assert len(rows) == 45
+    assert len(rows) == 59
     if not rgb_sources:
-        rows = [r for r in rows if not (r[1] == "scale" and r[2] != "yuv420p")]
+        rows = [r for r in rows if not (r[1] == "scale" and r[2] in cl.PACKED_RGB_FORMATS)]
+    if not nv_dest:
+        rows = [r for r in rows if r[2] not in NV]
     src = cl.vsynth1_frames(5)
     g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vsynth1_f0.npz"))
     assert all(np.array_equal(a, g[k]) for a, k in zip(src[0], "yuv"))              # the generator gives the committed frame 0

@@ -414,3 +414,32 @@ def test_sws_oracle_rgb_sources_vs_ref():
     O = cl.oracle()
     assert not O.orc_sws_open_io(cl.PIX_FMT_RGB24, 64, 48, cl.PIX_FMT_BGR24, 64, 48, FATE)      # same-size rgb -> rgb: rgb2rgb, not this path
     assert not O.orc_sws_open_io(cl.PIX_FMT_RGBA, 64, 48, cl.PIX_FMT_BGRA, 32, 24, FATE)        # alpha through the scaler: not restated
+
+
+def test_sws_oracle_nv_destinations_vs_ref():
+    """nv12 / nv21 as the destination (planarToNv12Wrapper when unscaled, yuv2nv12cX_c through the scaler) from every source kind"""
+    if not cl.have_ref():
+        pytest.skip("oracle/_ref not built")
+    from cases import SWS_PLANAR_CASES, SWS_RANGE_CASES, SWS_NV_CASES, SWS_RGBSRC_CASES
+    n = 0
+
+    def same(*a, **k):
+        r, o = cl.ref_sws_planar(*a, **k), cl.orc_sws_planar(*a, **k)
+        assert r is not None and o is not None and len(r) == len(o) == 2, (a[:5], k.get("dst_fmt"))
+        assert all(np.array_equal(p, q) for p, q in zip(r, o)), (a[:5], {x: k[x] for x in k if x != "details"})
+    for df in (cl.PIX_FMT_NV12, cl.PIX_FMT_NV21):
+        for i, (w, h, dw, dh, fl, kind) in enumerate(SWS_PLANAR_CASES):
+            same(w, h, dw, dh, fl, *cl.yuv_frame(w, h, 2500 + i, kind), dst_fmt=df, dst_pad=i % 3)
+        for i, (w, h, dw, dh, fl, kind, ranges, det) in enumerate(SWS_RANGE_CASES):
+            same(w, h, dw, dh, fl, *cl.yuv_frame(w, h, 2600 + i, kind), dst_fmt=df, ranges=ranges, details=det)
+        for i, (w, h, dw, dh, fl, kind) in enumerate(SWS_NV_CASES[:6]):
+            y, u, v = cl.yuv_frame(w, h, 2700 + i, kind)
+            for sf in (cl.PIX_FMT_NV12, cl.PIX_FMT_NV21):
+                uv = cl.nv_interleave(u, v, sf)
+                same(w, h, dw, dh, fl, y, uv, uv, src_fmt=sf, dst_fmt=df)
+        for i, (w, h, dw, dh, fl, kind) in enumerate(SWS_RGBSRC_CASES):
+            name = list(cl.PACKED_RGB_FORMATS)[(i + n) % 6]
+            sf = cl.PACKED_RGB_FORMATS[name]
+            src = cl.rgb_frame(w, h, 2800 + i, cl.fmt_bpp(sf), kind)
+            same(w, h, dw, dh, fl, src, src, src, src_fmt=sf, dst_fmt=df)
+        n += 1

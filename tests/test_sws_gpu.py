@@ -405,7 +405,7 @@ def test_fate_filter_pixfmts_md5(device):
         cl.vsynth1_frames(1)
     except Exception as e:                                                # checker tools, not the product: skip, never fail
         pytest.skip(f"oracle/_ref tools not usable on this box: {e}")
-    fg.check_all(functools.partial(gpu_sws, device), functools.partial(gpu_sws_planar, device), rgb_sources=False)
+    fg.check_all(functools.partial(gpu_sws, device), functools.partial(gpu_sws_planar, device), rgb_sources=False, nv_dest=False)
 
 
 def test_range_conversion_golden_hashes_and_oracle(device):
