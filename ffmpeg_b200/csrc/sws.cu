@@ -808,6 +808,8 @@ struct B200SwsContext {
     void *mid = nullptr; size_t mid_bytes = 0;
     // de-interleaved chroma of an nv12 / nv21 source (persistent: slice calls keep earlier bands here)
     void *nv_buf = nullptr; size_t nv_bytes = 0;
+    // chroma planes of an nv12 / nv21 destination before they are interleaved
+    void *nvout_buf = nullptr; size_t nvout_bytes = 0;
     // slice calls (sws_scale with srcSliceH < srcH): device copies of the source planes and of the picture being built,
     // plus the next output line (SwsInternal.dstY, swscale.c:297,551)
     void *slice_buf = nullptr;
@@ -819,7 +821,7 @@ static int upload_tables(B200SwsContext *c)
 {
     const SwsPlan &p = c->plan;
     if (c->tables) { cudaFree(c->tables); c->tables = nullptr; }
-    if (p.unscaled_lut || p.planar_copy) return 0;
+    if (p.unscaled_lut || p.planar_copy || p.bgr24_yv12) return 0;
     auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
     size_t off = 0;
     size_t o_vl = off;  off += al(p.vLum.coef.size() * 2);
@@ -895,7 +897,7 @@ static bool set_source_format(SwsPlan &p, int srcFormat)
     p.src_rgb = 0;
     if (srcFormat == B200_PIX_FMT_YUV420P || p.src_nv) return true;
     SwsOutFmt f;
-    if (!sws_out_format(srcFormat, f) || f.kind == SWS_OUT_YUV420P) return false;
+    if (!sws_out_format(srcFormat, f) || sws_out_is_yuv(f.kind)) return false;
     p.src_rgb = f.bpp; p.sro = f.ro; p.sgo = f.go; p.sbo = f.bo;
     return true;
 }
@@ -919,7 +921,7 @@ B200_API B200SwsContext *b200_sws_getContext_range(B200Device *dev, int srcW, in
         delete c;
         return nullptr;
     }
-    if (c->plan.src_rgb && out.kind != SWS_OUT_YUV420P) {
+    if (c->plan.src_rgb && !sws_out_is_yuv(out.kind)) {
         b200_set_error("b200_sws_getContext: packed RGB source -> packed RGB destination is not implemented on the device yet");
         delete c;
         return nullptr;
@@ -941,6 +943,7 @@ B200_API void b200_sws_freeContext(B200SwsContext *c)
     if (c->tables) cudaFree(c->tables);
     if (c->mid) cudaFree(c->mid);
     if (c->nv_buf) cudaFree(c->nv_buf);
+    if (c->nvout_buf) cudaFree(c->nvout_buf);
     if (c->slice_buf) cudaFree(c->slice_buf);
     delete c;
 }
@@ -1001,7 +1004,7 @@ B200_API int b200_sws_plan_probe(int srcW, int srcH, int dstW, int dstH, int fla
 // info32: [0..15] as b200_sws_info, [16] plain copy, [17] range conversion (0 none, 1 limited->full, 2 full->limited),
 // [18..21] luma coefficient, luma offset, chroma coefficient, chroma offset, [22] fast-bilinear horizontal pass,
 // [23] semi-planar source kind, [24] what the details call returned, [25] src_range, [26] dst_range, [27] packed RGB source
-// (bytes per pixel), [28] / [29] horizontal / vertical chroma shift of the source as scaled, [30] bgr24 -> yv12 converter,
+// (bytes per pixel), [28] / [29] horizontal / vertical chroma shift of the source as scaled, [30] bgr24 -> yv12 converter, [31] nv12 / nv21 destination,
 // [32..40] the rgb -> yuv table (needs room for 48 ints).
 B200_API int b200_sws_plan_probe2(const int cfg[9], const int *details, int which, int16_t *filter, int32_t *pos, int cap, int *o)
 {
@@ -1021,7 +1024,7 @@ B200_API int b200_sws_plan_probe2(const int cfg[9], const int *details, int whic
         o[16] = p.planar_copy; o[17] = p.range_conv;
         o[18] = p.lumRangeCoeff; o[19] = p.lumRangeOffset; o[20] = p.chrRangeCoeff; o[21] = p.chrRangeOffset;
         o[22] = p.fast_bilinear; o[23] = p.src_nv; o[24] = dret; o[25] = p.src_range; o[26] = p.dst_range;
-        o[27] = p.src_rgb; o[28] = p.chrSrcHSub; o[29] = p.chrSrcVSub; o[30] = p.bgr24_yv12; o[31] = 0;
+        o[27] = p.src_rgb; o[28] = p.chrSrcHSub; o[29] = p.chrSrcVSub; o[30] = p.bgr24_yv12; o[31] = p.dst_nv;
         for (int i = 0; i < 9; i++) o[32 + i] = p.rgb2yuv[i];
     }
     const SwsFilterBank &b = which == 0 ? p.hLum : which == 1 ? p.hChr : which == 2 ? p.vLum : p.vChr;
@@ -1285,8 +1288,8 @@ B200_API int b200_sws_scale_batch_device(B200SwsContext *c, const uint8_t *const
 }
 
 // yuv420p -> yuv420p: horizontal pass of the three planes into int16 line planes, then one vertical pass per plane
-static int launch_planar(B200SwsContext *c, cudaStream_t stream, const uint8_t *const src_in[3], const long long sstr_in[3],
-                         const long long sfs_in[3], uint8_t *const dst[3], const long long dstr[3], const long long dfs[3], int nframes)
+static int launch_planar3(B200SwsContext *c, cudaStream_t stream, const uint8_t *const src_in[3], const long long sstr_in[3],
+                          const long long sfs_in[3], uint8_t *const dst[3], const long long dstr[3], const long long dfs[3], int nframes)
 {
     const SwsPlan &p = c->plan;
     if (nframes <= 0) return 0;
@@ -1387,6 +1390,53 @@ static int launch_planar(B200SwsContext *c, cudaStream_t stream, const uint8_t *
     return 0;
 }
 
+// nv12 / nv21 destination: U and V of planarToNv12Wrapper / yuv2nv12cX_c are what the three-plane writers produce (same sums, same
+// flat dither), stored side by side (V first for nv21): one byte pair per thread
+__global__ void __launch_bounds__(256)
+sws_nv_interleave_kernel(const uint8_t *u, const uint8_t *v, long long cs, long long cfs, uint8_t *dst, long long ds, long long dfs, int cw)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cw) return;
+    const long long o = (long long)blockIdx.z * cfs + (long long)blockIdx.y * cs + i;
+    uint8_t *d = dst + (long long)blockIdx.z * dfs + (long long)blockIdx.y * ds + 2 * i;
+    d[0] = __ldg(u + o);
+    d[1] = __ldg(v + o);
+}
+
+// yuv destinations: three planes, or (nv12 / nv21) the same into scratch chroma planes followed by the interleave
+static int launch_planar(B200SwsContext *c, cudaStream_t stream, const uint8_t *const src[3], const long long sstr[3],
+                         const long long sfs[3], uint8_t *const dst[3], const long long dstr[3], const long long dfs[3], int nframes)
+{
+    const SwsPlan &p = c->plan;
+    if (!p.dst_nv) return launch_planar3(c, stream, src, sstr, sfs, dst, dstr, dfs, nframes);
+    if (nframes <= 0) return 0;
+    const size_t cplane = (size_t)p.chrDstW * p.chrDstH;
+    long long chunk = (long long)((size_t)(64u << 20) / (2 * cplane ? 2 * cplane : 1));
+    if (chunk < 1) chunk = 1;
+    if (chunk > nframes) chunk = nframes;
+    const size_t need = 2 * cplane * (size_t)chunk;
+    if (c->nvout_bytes < need) {
+        if (c->nvout_buf) { cudaStreamSynchronize(stream); cudaFree(c->nvout_buf); c->nvout_buf = nullptr; c->nvout_bytes = 0; }
+        B200_CUDA_OK(cudaMalloc(&c->nvout_buf, need));
+        c->nvout_bytes = need;
+    }
+    uint8_t *buf = (uint8_t *)c->nvout_buf;
+    for (long long f0 = 0; f0 < nframes; f0 += chunk) {
+        const int nf = (int)(nframes - f0 < chunk ? nframes - f0 : chunk);
+        const uint8_t *s3[3] = { src[0] ? src[0] + f0 * sfs[0] : nullptr, src[1] ? src[1] + f0 * sfs[1] : nullptr, src[2] ? src[2] + f0 * sfs[2] : nullptr };
+        uint8_t *d3[3] = { dst[0] + f0 * dfs[0], buf, buf + cplane };
+        const long long ds3[3] = { dstr[0], p.chrDstW, p.chrDstW }, df3[3] = { dfs[0], (long long)(2 * cplane), (long long)(2 * cplane) };
+        const int ret = launch_planar3(c, stream, s3, sstr, sfs, d3, ds3, df3, nf);
+        if (ret < 0) return ret;
+        dim3 block(256), grid(b200_ceil_div(p.chrDstW, 256), p.chrDstH, nf);
+        sws_nv_interleave_kernel<<<grid, block, 0, stream>>>(p.dst_nv == 1 ? d3[1] : d3[2], p.dst_nv == 1 ? d3[2] : d3[1], p.chrDstW,
+                                                             (long long)(2 * cplane), dst[1] + f0 * dfs[1], dstr[1], dfs[1], p.chrDstW);
+        B200_LAUNCHED();
+    }
+    B200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 B200_API int b200_sws_scale_batch_device_planar(B200SwsContext *c, const uint8_t *const src[3], const int srcStride[3],
                                                 const int64_t srcFrameStride[3], uint8_t *const dst[3], const int dstStride[3],
                                                 const int64_t dstFrameStride[3], int nframes)
@@ -1394,12 +1444,13 @@ B200_API int b200_sws_scale_batch_device_planar(B200SwsContext *c, const uint8_t
     if (!c || !src || !srcStride || !srcFrameStride || !dst || !dstStride || !dstFrameStride) return B200_EINVAL;
     if (!c->plan.planar) return B200_EINVAL;
     const int nsp = c->plan.src_rgb ? 1 : c->plan.src_nv ? 2 : 3;           // packed RGB: plane 0 only; nv12 / nv21: planes 0 and 1
-    for (int i = 0; i < 3; i++) if ((i < nsp && (!src[i] || srcStride[i] < 0)) || !dst[i] || dstStride[i] < 0) return B200_EINVAL;
+    const int ndp = c->plan.dst_nv ? 2 : 3;                                 // nv12 / nv21 destination: dst[1] is the interleaved plane
+    for (int i = 0; i < 3; i++) if ((i < nsp && (!src[i] || srcStride[i] < 0)) || (i < ndp && (!dst[i] || dstStride[i] < 0))) return B200_EINVAL;
     B200_CUDA_OK(cudaSetDevice(c->dev->ordinal));
     const long long ss[3] = { srcStride[0], nsp >= 2 ? srcStride[1] : 0, nsp == 3 ? srcStride[2] : 0 };
     const long long fs[3] = { srcFrameStride[0], nsp >= 2 ? srcFrameStride[1] : 0, nsp == 3 ? srcFrameStride[2] : 0 };
-    const long long ds[3] = { dstStride[0], dstStride[1], dstStride[2] };
-    const long long df[3] = { dstFrameStride[0], dstFrameStride[1], dstFrameStride[2] };
+    const long long ds[3] = { dstStride[0], dstStride[1], ndp == 3 ? dstStride[2] : 0 };
+    const long long df[3] = { dstFrameStride[0], dstFrameStride[1], ndp == 3 ? dstFrameStride[2] : 0 };
     return launch_planar(c, c->dev->stream, src, ss, fs, dst, ds, df, nframes);
 }
 
@@ -1413,15 +1464,16 @@ static int sws_scale_planar_host(B200SwsContext *c, const uint8_t *const srcSlic
         return B200_ENOSYS;
     }
     const int nsp = p.src_rgb ? 1 : p.src_nv ? 2 : 3;             // packed RGB: one plane; nv12 / nv21: plane 1 carries both chroma components
+    const int ndp = p.dst_nv ? 2 : 3;                             // nv12 / nv21 destination: two planes
     for (int i = 0; i < 3; i++) {
-        if (!dst[i] || (i < nsp && !srcSlice[i])) return B200_EINVAL;
-        if (dstStride[i] < 0 || (i < nsp && srcStride[i] < 0)) return B200_ENOSYS;
+        if ((i < ndp && !dst[i]) || (i < nsp && !srcSlice[i])) return B200_EINVAL;
+        if ((i < ndp && dstStride[i] < 0) || (i < nsp && srcStride[i] < 0)) return B200_ENOSYS;
     }
     B200Device *d = c->dev;
     B200_CUDA_OK(cudaSetDevice(d->ordinal));
     const int sw[3] = { p.src_rgb ? p.srcW * p.src_rgb : p.srcW, p.src_rgb ? 0 : p.src_nv ? 2 * p.chrSrcW : p.chrSrcW, (p.src_nv || p.src_rgb) ? 0 : p.chrSrcW },
               sh[3] = { p.srcH, p.src_rgb ? 0 : p.chrSrcH, p.src_rgb ? 0 : p.chrSrcH };
-    const int dw[3] = { p.dstW, p.chrDstW, p.chrDstW }, dh[3] = { p.dstH, p.chrDstH, p.chrDstH };
+    const int dw[3] = { p.dstW, p.dst_nv ? 2 * p.chrDstW : p.chrDstW, p.dst_nv ? 0 : p.chrDstW }, dh[3] = { p.dstH, p.chrDstH, p.dst_nv ? 0 : p.chrDstH };
     size_t spitch[3], dpitch[3], soff[3], doff[3], total = 0;
     for (int i = 0; i < 3; i++) { spitch[i] = ((size_t)sw[i] + 255) & ~(size_t)255; soff[i] = total; total += spitch[i] * sh[i]; }
     for (int i = 0; i < 3; i++) { dpitch[i] = ((size_t)dw[i] + 255) & ~(size_t)255; doff[i] = total; total += dpitch[i] * dh[i]; }
@@ -1437,7 +1489,7 @@ static int sws_scale_planar_host(B200SwsContext *c, const uint8_t *const srcSlic
     }
     int ret = launch_planar(c, st, sp, ss, zero, dp, ds, zero, 1);
     if (ret < 0) return ret;
-    for (int i = 0; i < 3; i++)
+    for (int i = 0; i < ndp; i++)
         B200_CUDA_OK(cudaMemcpy2DAsync(dst[i], (size_t)dstStride[i], dp[i], dpitch[i], dw[i], dh[i], cudaMemcpyDeviceToHost, st));
     B200_CUDA_OK(cudaStreamSynchronize(st));
     return p.dstH;

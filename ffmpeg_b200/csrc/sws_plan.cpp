@@ -274,7 +274,7 @@ static void solve_range(unsigned srcMin, unsigned srcMax, unsigned dstMin, unsig
 static void plan_range_convert(SwsPlan &p)
 {
     p.range_conv = 0;
-    if (p.src_range == p.dst_range || p.out.kind != SWS_OUT_YUV420P) return;
+    if (p.src_range == p.dst_range || !sws_out_is_yuv(p.out.kind)) return;
     if (p.src_range) {
         solve_range(0, 255, 16, 235, p.lumRangeCoeff, p.lumRangeOffset);
         solve_range(0, 255, 16, 240, p.chrRangeCoeff, p.chrRangeOffset);
@@ -315,7 +315,7 @@ static void plan_rgb2yuv(SwsPlan &p, const int table[4])
 int sws_plan_colorspace_details(SwsPlan &p, const int inv_table[4], int srcRange, const int table[4], int dstRange,
                                 int brightness, int contrast, int saturation)
 {
-    const bool yuvDst = p.out.kind == SWS_OUT_YUV420P;
+    const bool yuvDst = sws_out_is_yuv(p.out.kind);
     if (!yuvDst) dstRange = 0;                                                   // range_override_needed(dst), utils.c:877-878
     if (p.src_rgb) srcRange = 0;                                                 // range_override_needed(src), utils.c:879-880
     plan_rgb2yuv(p, table);                                                      // utils.c:1002
@@ -340,6 +340,8 @@ bool sws_out_format(int f, SwsOutFmt &o)
     case B200_PIX_FMT_ARGB:  o = { SWS_OUT_ARGB,  4, 1, 2, 3, 0 };  return true;
     case B200_PIX_FMT_ABGR:  o = { SWS_OUT_ABGR,  4, 3, 2, 1, 0 };  return true;
     case B200_PIX_FMT_YUV420P: o = { SWS_OUT_YUV420P, 1, 0, 0, 0, -1 }; return true;
+    case B200_PIX_FMT_NV12:    o = { SWS_OUT_NV12, 1, 0, 0, 0, -1 }; return true;
+    case B200_PIX_FMT_NV21:    o = { SWS_OUT_NV21, 1, 0, 0, 0, -1 }; return true;
     }
     return false;
 }
@@ -357,7 +359,8 @@ int sws_plan_build(SwsPlan &p, int srcW, int srcH, int dstW, int dstH, int flags
     // the fast horizontal functions exist for 8-bit input lines only (swscale.c:675-681); RGB sources are srcBpc 16
     // (utils.c:1407-1408) and use the 2-tap filter initFilter builds for the flag
     p.fast_bilinear = algo == B200_SWS_FAST_BILINEAR && !p.src_rgb;
-    p.planar = p.out.kind == SWS_OUT_YUV420P;
+    p.planar = sws_out_is_yuv(p.out.kind);
+    p.dst_nv = p.out.kind == SWS_OUT_NV12 ? 1 : p.out.kind == SWS_OUT_NV21 ? 2 : 0;
     if (p.src_rgb && !p.planar && srcW == dstW && srcH == dstH) return B200_ENOSYS;          // the reference's rgb2rgb shuffles: not this path
     if (p.src_rgb == 4 && !p.planar && p.out.bpp == 4) return B200_ENOSYS;                   // alpha carried through the scaler: not built
     if (!p.planar && (dstW & 1)) flags |= B200_SWS_FULL_CHR_H_INT;               // utils.c:1271-1276 (RGB destinations only)
@@ -384,7 +387,7 @@ int sws_plan_build(SwsPlan &p, int srcW, int srcH, int dstW, int dstH, int flags
     // unscaled special converter gate: swscale_unscaled.c:2426-2431 reached from utils.c:1623-1637; a yuv destination only
     // looks for one when no range conversion is due (utils.c:1624-1626)
     // bgr24ToYv12Wrapper (swscale_unscaled.c:2453-2457): bgr24 only, not with accurate_rnd, even width
-    p.bgr24_yv12 = p.planar && p.src_rgb == 3 && p.sbo == 0 && srcW == dstW && srcH == dstH && p.src_range == p.dst_range &&
+    p.bgr24_yv12 = p.planar && !p.dst_nv && p.src_rgb == 3 && p.sbo == 0 && srcW == dstW && srcH == dstH && p.src_range == p.dst_range &&
                    !(flags & B200_SWS_ACCURATE_RND) && !(dstW & 1);
     if (p.bgr24_yv12) return 0;
     p.planar_copy = p.planar && !p.src_rgb && srcW == dstW && srcH == dstH && p.src_range == p.dst_range;

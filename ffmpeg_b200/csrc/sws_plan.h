@@ -25,7 +25,9 @@ struct SwsColorConst {
 // Packed 8-bit RGB outputs: bytes per pixel and the byte position of each channel (ao < 0: no alpha byte).
 // 32-bit formats carry alpha = 255 (yuv2rgb.c:947-960 adds 255 << abase to the ramp; output.c:2066-2095 stores 255).
 enum SwsOutKind { SWS_OUT_RGB24, SWS_OUT_BGR24, SWS_OUT_RGBA, SWS_OUT_BGRA, SWS_OUT_ARGB, SWS_OUT_ABGR,
-                  SWS_OUT_YUV420P /* planar destination: three planes, bpp = 1 */ };
+                  SWS_OUT_YUV420P /* planar destination: three planes, bpp = 1 */,
+                  SWS_OUT_NV12, SWS_OUT_NV21 /* luma plane + interleaved chroma plane (U,V / V,U): yuv420p with the chroma interleaved */ };
+inline bool sws_out_is_yuv(int kind) { return kind == SWS_OUT_YUV420P || kind == SWS_OUT_NV12 || kind == SWS_OUT_NV21; }
 struct SwsOutFmt { int kind, bpp, ro, go, bo, ao; };
 bool sws_out_format(int av_pix_fmt, SwsOutFmt &o);
 
@@ -38,7 +40,8 @@ struct SwsPlan {
     int src_nv = 0;               // 0: yuv420p source; 1: nv12, 2: nv21 (plane 1 holds U,V / V,U interleaved; nvXXtoUV_c, input.c:921-948)
     bool fast_bilinear = false;   // SWS_FAST_BILINEAR: horizontal pass = ff_hyscale_fast_c / ff_hcscale_fast_c (hscale_fast_bilinear.c:27-67)
     int lumXInc = 0, chrXInc = 0; // 16.16 horizontal steps (utils.c:1250,1425)
-    bool planar = false;          // destination yuv420p (yuv2planeX / yuv2plane1 writers, vscale.c:34-107)
+    bool planar = false;          // destination yuv420p / nv12 / nv21 (yuv2planeX / yuv2plane1 / yuv2nv12cX writers, vscale.c:34-107)
+    int dst_nv = 0;               // 1: nv12, 2: nv21 destination (planarToNv12Wrapper swscale_unscaled.c:147-165; yuv2nv12cX_c output.c:495-528)
     bool planar_copy = false;     // same size yuv420p -> yuv420p: planarCopyWrapper (swscale_unscaled.c:2220,2675-2693)
     // yuv -> yuv range conversion of the 15-bit lines between the two passes (swscale.c:163-209; constants :577-624)
     int src_range = 0, dst_range = 0;            // SwsContext.src_range / .dst_range (0 limited, non-zero full)

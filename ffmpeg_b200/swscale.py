@@ -34,7 +34,8 @@ class SwsContext:
         self.device = device
         self.srcW, self.srcH, self.dstW, self.dstH, self.flags = srcW, srcH, dstW, dstH, flags
         self.srcFormat, self.dstFormat = srcFormat, dstFormat
-        self.planar = dstFormat == AV_PIX_FMT_YUV420P
+        self.dst_nv = dstFormat in (AV_PIX_FMT_NV12, AV_PIX_FMT_NV21)          # destination: luma plane + interleaved chroma plane
+        self.planar = dstFormat == AV_PIX_FMT_YUV420P or self.dst_nv
         self.bpp = 1 if self.planar else 3 if dstFormat in (AV_PIX_FMT_RGB24, AV_PIX_FMT_BGR24) else 4
         h = lib().b200_sws_getContext_range(device.handle, srcW, srcH, srcFormat, src_range, dstW, dstH, dstFormat, dst_range, flags)
         if not h:
@@ -80,21 +81,22 @@ class SwsContext:
         return out
 
     def convert_planar(self, y, u, v, dst_pad=0):
-        """yuv420p destination: whole frame, returns (Y, U, V) arrays."""
+        """yuv420p destination: whole frame, returns (Y, U, V) arrays; nv12 / nv21 destination: (Y, UV)."""
         cw, ch = (self.dstW + 1) // 2, (self.dstH + 1) // 2
         dy = np.full((self.dstH, self.dstW + dst_pad), 0xA5, np.uint8)
-        du = np.full((ch, cw + dst_pad), 0xA5, np.uint8)
+        du = np.full((ch, (2 * cw if self.dst_nv else cw) + dst_pad), 0xA5, np.uint8)
         dv = np.full((ch, cw + dst_pad), 0xA5, np.uint8)
-        n = self.scale([y, u, v], [y.strides[0], u.strides[0], v.strides[0]], 0, self.srcH, [dy, du, dv],
-                       [dy.strides[0], du.strides[0], dv.strides[0]])
+        dst = [dy, du] if self.dst_nv else [dy, du, dv]
+        n = self.scale([y, u, v], [y.strides[0], u.strides[0], v.strides[0]], 0, self.srcH, dst, [a.strides[0] for a in dst])
         assert n == self.dstH
-        return dy, du, dv
+        return tuple(dst)
 
     def scale_batch_device_planar(self, src, srcStride, srcFrameStride, dst, dstStride, dstFrameStride, nframes):
         src, srcStride, srcFrameStride = (list(src) + [0] * 3)[:3], (list(srcStride) + [0] * 3)[:3], (list(srcFrameStride) + [0] * 3)[:3]
         sp = (vp * 3)(*[_dptr(a) for a in src])
         ss = (C.c_int32 * 3)(*srcStride)
         fs = (C.c_int64 * 3)(*srcFrameStride)
+        dst, dstStride, dstFrameStride = (list(dst) + [0] * 3)[:3], (list(dstStride) + [0] * 3)[:3], (list(dstFrameStride) + [0] * 3)[:3]
         dp = (vp * 3)(*[_dptr(a) for a in dst])
         ds = (C.c_int32 * 3)(*dstStride)
         df = (C.c_int64 * 3)(*dstFrameStride)

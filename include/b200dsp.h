@@ -94,7 +94,10 @@ typedef struct B200SwsContext B200SwsContext;
 /* like sws_getContext(); srcFilter/dstFilter/param are not supported (must be the defaults). NULL on failure.
  * Sources: yuv420p, nv12, nv21 (-> packed 8-bit RGB or yuv420p) and rgb24 / bgr24 / rgba / bgra / argb / abgr (-> yuv420p; the input
  * readers of libswscale/input.c:264-393,1068-1172, hScale16To15_c, and the bgr24ToYv12Wrapper special converter,
- * libswscale/swscale_unscaled.c:2453-2457); a packed RGB source is passed as plane 0 (src[1], src[2] unused). */
+ * libswscale/swscale_unscaled.c:2453-2457); a packed RGB source is passed as plane 0 (src[1], src[2] unused).
+ * Destinations nv12 / nv21 (what NVENC reads) are yuv420p with the chroma planes interleaved: planarToNv12Wrapper
+ * (libswscale/swscale_unscaled.c:147-165) unscaled, yuv2nv12cX_c (libswscale/output.c:495-528) through the scaler; dst[1] is the
+ * interleaved plane, dst[2] unused. */
 B200SwsContext *b200_sws_getContext(B200Device *dev, int srcW, int srcH, int srcFormat,
                                     int dstW, int dstH, int dstFormat, int flags);
 /* The same with SwsContext.src_range / .dst_range (libswscale/swscale.h, AVOption "src_range" / "dst_range"; 0 = limited,
@@ -154,7 +157,7 @@ int  b200_sws_plan_probe(int srcW, int srcH, int dstW, int dstH, int flags, int 
  * luma offset, chroma coefficient, chroma offset (libswscale/swscale.c:577-624), [22] fast-bilinear horizontal pass,
  * [23] semi-planar source kind, [24] return value of the details call, [25] src_range, [26] dst_range, [27] packed RGB source
  * (bytes per pixel), [28] / [29] horizontal / vertical chroma shift of the source as the scaler sees it, [30] bgr24 -> yv12
- * converter installed, [32..40] input_rgb2yuv_table.  The array must hold 48 ints. */
+ * converter installed, [31] semi-planar destination kind (1 nv12, 2 nv21), [32..40] input_rgb2yuv_table.  The array must hold 48 ints. */
 int  b200_sws_plan_probe2(const int cfg[9], const int *details, int which, int16_t *filter, int32_t *pos, int cap, int *info48);
 
 /* ------------------------------------------------------------------------------------------------ idctdsp

@@ -230,3 +230,53 @@ def test_sws_rgb_sources_large_padded_batch(device):
         ctx.free()
     with pytest.raises(fb.B200Error):                                  # packed RGB -> packed RGB is not on the device yet
         sw.sws_getContext(device, 64, 48, sw.AV_PIX_FMT_RGB24, 32, 24, sw.AV_PIX_FMT_BGR24, FATE)
+
+
+# ---------------------------------------------------------------------------------------------- swscale: nv12 / nv21 destinations
+def test_sws_nv_destinations(device):
+    """nv12 / nv21 as the destination (the layout NVENC reads) from planar, semi-planar and packed RGB sources, against the oracle;
+    then FATE's own md5 sums for these formats (null, copy, vflip, hflip, crop, scale, pixdesc) on the CUDA path's frames"""
+    import functools
+    import torch
+    from ffmpeg_b200 import swscale as sw
+    from test_sws_gpu import gpu_sws_planar, gpu_sws
+    from cases import SWS_PLANAR_CASES, SWS_RANGE_CASES, SWS_RGBSRC_CASES, FATE
+    import test_fate_golden as fg
+    for df in (cl.PIX_FMT_NV12, cl.PIX_FMT_NV21):
+        for i, (w, h, dw, dh, fl, kind) in enumerate(SWS_PLANAR_CASES):
+            y, u, v = cl.yuv_frame(w, h, 2500 + i, kind)
+            out = gpu_sws_planar(device, w, h, dw, dh, fl, y, u, v, dst_fmt=df, dst_pad=i % 3)
+            exp = cl.orc_sws_planar(w, h, dw, dh, fl, y, u, v, dst_fmt=df, dst_pad=i % 3)
+            assert len(out) == 2 and all(np.array_equal(p, q) for p, q in zip(out, exp)), ("planar", i, df)
+        for i, (w, h, dw, dh, fl, kind, ranges, det) in enumerate(SWS_RANGE_CASES[:9]):
+            y, u, v = cl.yuv_frame(w, h, 2600 + i, kind)
+            out = gpu_sws_planar(device, w, h, dw, dh, fl, y, u, v, dst_fmt=df, ranges=ranges)
+            exp = cl.orc_sws_planar(w, h, dw, dh, fl, y, u, v, dst_fmt=df, ranges=ranges)
+            assert all(np.array_equal(p, q) for p, q in zip(out, exp)), ("range", i, df)
+        y, u, v = cl.yuv_frame(640, 360, 2700, "random")
+        uv = cl.nv_interleave(u, v, cl.PIX_FMT_NV12)
+        for (dw, dh) in ((640, 360), (800, 450)):
+            out = gpu_sws_planar(device, 640, 360, dw, dh, FATE, y, uv, uv, src_fmt=cl.PIX_FMT_NV12, dst_fmt=df)
+            exp = cl.orc_sws_planar(640, 360, dw, dh, FATE, y, uv, uv, src_fmt=cl.PIX_FMT_NV12, dst_fmt=df)
+            assert all(np.array_equal(p, q) for p, q in zip(out, exp)), ("nv12 source", dw, df)
+    fg.check_all(functools.partial(gpu_sws, device), functools.partial(gpu_sws_planar, device), rgb_sources=False, nv_dest=True)
+    # the encoder feed: bgra 1080p -> nv12 (packed RGB source kernels too), and the batched device entry point with two destination planes
+    src = cl.rgb_frame(1920, 1080, 2900, 4)
+    out = gpu_sws_planar(device, 1920, 1080, 1920, 1080, FATE, src, src, src, src_fmt=cl.PIX_FMT_BGRA, dst_fmt=cl.PIX_FMT_NV12)
+    exp = cl.orc_sws_planar(1920, 1080, 1920, 1080, FATE, src, src, src, src_fmt=cl.PIX_FMT_BGRA, dst_fmt=cl.PIX_FMT_NV12)
+    assert all(np.array_equal(p, q) for p, q in zip(out, exp))
+    w, h, dw, dh, n = 320, 180, 480, 270, 3
+    frames = [cl.yuv_frame(w, h, 2950 + k, "random") for k in range(n)]
+    ctx = sw.sws_getContext(device, w, h, 0, dw, dh, sw.AV_PIX_FMT_NV12, FATE)
+    with on_stream(device):
+        Y, U, V = (torch.from_numpy(np.stack([f[k] for f in frames])).cuda() for k in range(3))
+        DY = torch.zeros((n, dh, dw), dtype=torch.uint8, device="cuda")
+        DUV = torch.zeros((n, dh // 2, dw), dtype=torch.uint8, device="cuda")
+        ctx.scale_batch_device_planar([Y, U, V], [w, w // 2, w // 2], [w * h, w * h // 4, w * h // 4], [DY, DUV], [dw, dw],
+                                      [dw * dh, dw * dh // 2], n)
+        device.sync()
+        gy, guv = DY.cpu().numpy(), DUV.cpu().numpy()
+    for i in range(n):
+        ey, euv = cl.orc_sws_planar(w, h, dw, dh, FATE, *frames[i], dst_fmt=cl.PIX_FMT_NV12)
+        assert np.array_equal(gy[i], ey) and np.array_equal(guv[i], euv), i
+    ctx.free()

@@ -283,6 +283,11 @@ def _all_sws_configs():
                 out.append((sf, w, h, 0, cl.PIX_FMT_BGRA, dw, dh, 0, fl, None))
         out.append((cl.PIX_FMT_BGR24, w, h, 0, 0, dw, dh, 0, fl, (1, 0, 1, 1, 0, 1 << 16, 1 << 16)))     # bt709 table, full range out
     out += [(cl.PIX_FMT_RGB24, 3840, 2160, 0, 0, 3840, 2160, 0, FATE, None), (cl.PIX_FMT_BGRA, 3840, 2160, 0, 0, 1920, 1080, 0, cl.SWS_BICUBIC, None)]
+    for df in (cl.PIX_FMT_NV12, cl.PIX_FMT_NV21):                  # semi-planar destinations from planar and packed sources
+        for (w, h, dw, dh, fl, _k) in SWS_PLANAR_CASES:
+            out += [(0, w, h, 0, df, dw, dh, 0, fl, None), (0, w, h, 0, df, dw, dh, 1, fl, None)]
+        for (w, h, dw, dh, fl, _k) in SWS_RGBSRC_CASES:
+            out += [(cl.PIX_FMT_BGR24, w, h, 0, df, dw, dh, 0, fl, None), (cl.PIX_FMT_RGBA, w, h, 0, df, dw, dh, 0, fl, None)]
     return out
 
 

@@ -131,9 +131,9 @@ def test_other_formats_slices_and_batch(device):
         sw.sws_getContext(device, 64, 48, 0, 64, 48, 4, FATE)           # AV_PIX_FMT_YUV422P as destination: not this path
 
 
-def gpu_sws_planar(device, w, h, dw, dh, fl, y, u, v, dst_pad=0, src_fmt=0, ranges=(0, 0), details=None):
+def gpu_sws_planar(device, w, h, dw, dh, fl, y, u, v, dst_pad=0, src_fmt=0, ranges=(0, 0), details=None, dst_fmt=0):
     from ffmpeg_b200 import swscale as sw
-    ctx = sw.sws_getContext(device, w, h, src_fmt, dw, dh, sw.AV_PIX_FMT_YUV420P, fl, src_range=ranges[0], dst_range=ranges[1])
+    ctx = sw.sws_getContext(device, w, h, src_fmt, dw, dh, dst_fmt, fl, src_range=ranges[0], dst_range=ranges[1])
     try:
         if details is not None:
             assert ctx.setColorspaceDetails(cl.COEFFS[details[0]], details[1], cl.COEFFS[details[2]], details[3], *details[4:]) == 0
