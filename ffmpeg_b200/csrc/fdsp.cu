@@ -14,6 +14,7 @@
 
 namespace {
 
+// [device-code fdsp] (tests/cuda_emu runs this block on the CPU against the checker; comment markers only)
 template <typename T> __device__ __forceinline__ T mul_rn(T a, T b);
 template <> __device__ __forceinline__ float  mul_rn(float a, float b)   { return __fmul_rn(a, b); }
 template <> __device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
@@ -70,6 +71,7 @@ fdsp_dot_kernel(Operands o, long long nvec, int len)
     static_cast<T *>(o.dst)[v * o.dstS] = p;
 }
 
+// [/device-code fdsp]
 template <typename T, int OP>
 int launch_op(cudaStream_t st, const Operands &o, long long nvec, int len, double mul)
 {

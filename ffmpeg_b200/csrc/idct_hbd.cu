@@ -15,6 +15,7 @@
 
 namespace {
 
+// [device-code idct_hbd] (tests/cuda_emu runs this block on the CPU against the checker; comment markers only)
 template <int DEPTH> struct K;
 template <> struct K<10> { static constexpr unsigned W1 = 22725, W2 = 21407, W3 = 19265, W4 = 16384, W5 = 12873, W6 = 8867, W7 = 4520;
                            static constexpr int ROW = 12, COL = 19, DC = 2; };
@@ -121,6 +122,7 @@ idct_hbd_kernel(int16_t *blocks, long long n, uint8_t *dest, const int64_t *dest
     }
 }
 
+// [/device-code idct_hbd]
 template <int DEPTH>
 int launch(cudaStream_t st, int kind, int16_t *blocks, long long n, uint8_t *dest, const int64_t *off, const int32_t *ls, int uls)
 {

@@ -591,6 +591,7 @@ sws_vscale_planar_kernel(const int16_t *src, int sls, long long sfs, int nlines,
     dst[f * dfs + (long long)dy * ds + x] = (uint8_t)clamp_u8(val);
 }
 
+// [device-code sws_new] (tests/cuda_emu runs this block on the CPU against the checker; comment markers only)
 // ------------------------------------------------------------------------------------------------ kernels: packed RGB source
 // Input readers fused into the horizontal pass.  The reference converts every source line to a 16-bit line first
 // (rgb24ToY_c / bgr24ToY_c / the 32-bit templates, input.c:264-393,1068-1134: identical values for all six byte orders; chroma
@@ -694,6 +695,7 @@ sws_range_kernel(int16_t *mid, int w, long long dfs, int coeff, int offset, int 
     *p = (int16_t)v;
 }
 
+// [/device-code sws_new]
 // four adjacent samples per thread: 64-bit loads of the int16 lines, one 32-bit store (w % 4 == 0, 4-aligned destination)
 __global__ void __launch_bounds__(256)
 sws_vscale_planar4_kernel(const int16_t *src, int sls, long long sfs, int nlines, uint8_t *dst, long long ds, long long dfs,
@@ -1390,6 +1392,7 @@ static int launch_planar3(B200SwsContext *c, cudaStream_t stream, const uint8_t 
     return 0;
 }
 
+// [device-code sws_nvout]
 // nv12 / nv21 destination: U and V of planarToNv12Wrapper / yuv2nv12cX_c are what the three-plane writers produce (same sums, same
 // flat dither), stored side by side (V first for nv21): one byte pair per thread
 __global__ void __launch_bounds__(256)
@@ -1403,6 +1406,7 @@ sws_nv_interleave_kernel(const uint8_t *u, const uint8_t *v, long long cs, long 
     d[1] = __ldg(v + o);
 }
 
+// [/device-code sws_nvout]
 // yuv destinations: three planes, or (nv12 / nv21) the same into scratch chroma planes followed by the interleave
 static int launch_planar(B200SwsContext *c, cudaStream_t stream, const uint8_t *const src[3], const long long sstr[3],
                          const long long sfs[3], uint8_t *const dst[3], const long long dstr[3], const long long dfs[3], int nframes)

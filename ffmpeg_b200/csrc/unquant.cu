@@ -18,6 +18,7 @@ namespace {
 
 constexpr int WARPS = 4;
 
+// [device-code unquant] (tests/cuda_emu runs this block on the CPU against the checker; comment markers only)
 struct UnquantDev {                       // passed by value (416 bytes of kernel parameters)
     uint16_t intra[64], inter[64];
     uint8_t scanpos[64];                  // scan index of each raster coefficient (inverse of ScanTable.permutated)
@@ -91,6 +92,7 @@ mpv_unquant_kernel(const UnquantDev P, int16_t *blocks, long long nblocks, const
     *wp = ((unsigned)lv[0] & 0xffffu) | ((unsigned)lv[1] << 16);
 }
 
+// [/device-code unquant]
 } // namespace
 
 B200_API int b200_mpv_unquantize_batch_device(B200Device *dev, int variant, const B200MpvUnquant *p, int16_t *blocks, int64_t nblocks,

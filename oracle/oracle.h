@@ -71,6 +71,11 @@ int     orc_sws_scale(OrcSws *s, const uint8_t *y, int ys, const uint8_t *u, int
  * chroma plane of 2 * chrDstW bytes per line and `dv` is unused) */
 int     orc_sws_scale_planar(OrcSws *s, const uint8_t *y, int ys, const uint8_t *u, int us, const uint8_t *v, int vs,
                              uint8_t *dy, int dys, uint8_t *du, int dus, uint8_t *dv, int dvs);
+/* single stages, for checking single kernels: the horizontal pass over a whole picture (L: srcH x dstW, CU / CV: chrSrcH x chrDstW
+ * int16; a packed RGB source goes through the input readers first) and the range conversion of n lines of width w in place */
+int     orc_sws_hlines(const OrcSws *s, const uint8_t *y, int ys, const uint8_t *u, int us, const uint8_t *v, int vs,
+                       int16_t *L, int16_t *CU, int16_t *CV);
+void    orc_sws_range_lines(const OrcSws *s, int16_t *lines, int w, int n, int chroma);
 /* 16 ints, same layout as ffref_sws_info */
 int     orc_sws_info(const OrcSws *s, int *out);
 /* 6 ints, same layout as ffref_sws_range_info: conversion kind (0 none, 1 limited->full, 2 full->limited), luma coefficient

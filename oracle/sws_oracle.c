@@ -656,6 +656,21 @@ static int hlines(const OrcSws *s, const uint8_t *y, int ys, const uint8_t *u, i
     return 0;
 }
 
+static void range_line(int16_t *d, int w, int coeff, int offset, int clip);
+/* the two stages in front of the vertical pass, exposed so that single kernels can be checked against them */
+int orc_sws_hlines(const OrcSws *s, const uint8_t *y, int ys, const uint8_t *u, int us, const uint8_t *v, int vs,
+                   int16_t *L, int16_t *CU, int16_t *CV)
+{
+    if (s->unscaled_lut) return -EINVAL;
+    return hlines(s, y, ys, u, us, v, vs, L, CU, CV);
+}
+void orc_sws_range_lines(const OrcSws *s, int16_t *lines, int w, int n, int chroma)
+{
+    if (!s->range_conv) return;
+    for (int r = 0; r < n; r++)
+        range_line(lines + (size_t)r * w, w, chroma ? s->chr_coeff : s->lum_coeff, chroma ? s->chr_offset : s->lum_offset, s->range_conv == 1);
+}
+
 /* yuv2rgb_write, 24 and 32 bpp branches (output.c:1676-1713): one chroma pair -> LUT bases, two lumas -> two pixels */
 static void put_pair(const OrcSws *s, uint8_t *d, int Y1, int Y2, int U, int V)
 {

@@ -1,0 +1,186 @@
+"""CPU tier: the device code of the kernels that have not run on a GPU yet, executed on the host by a small CUDA emulation
+(tests/cuda_emu/emu.h: one CUDA thread after the other, an OS thread per lane for the warp collective) and compared with the
+oracle.  The [device-code ...] blocks are cut out of ffmpeg_b200/csrc/*.cu as they are and compiled with g++; the launch geometry
+in tests/cuda_emu/emu_kernels.cpp repeats the library's host code.  This checks arithmetic and indexing of the kernels and the
+tables the host set-up feeds them — not memory-space rules, races or speed, which need the hardware."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import cpulibs as cl
+from cases import FATE
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMU = os.path.join(ROOT, "tests", "cuda_emu")
+
+
+@pytest.fixture(scope="module")
+def emu():
+    gen = os.path.join(EMU, "_gen")
+    os.makedirs(gen, exist_ok=True)
+    found = {}
+    src_dir = os.path.join(ROOT, "ffmpeg_b200", "csrc")
+    for f in sorted(os.listdir(src_dir)):
+        if f.endswith(".cu"):
+            txt = open(os.path.join(src_dir, f)).read()
+            for m in re.finditer(r"// \[device-code (\w+)\][^\n]*\n(.*?)// \[/device-code \1\]", txt, re.S):
+                found[m.group(1)] = m.group(2)
+    assert sorted(found) == ["fdsp", "idct_hbd", "sws_new", "sws_nvout", "unquant"], sorted(found)
+    for k, v in found.items():
+        open(os.path.join(gen, k + ".inc"), "w").write(v)
+    so = os.path.join(gen, "libemu.so")
+    cxx = "/opt/gcc/bin/g++" if os.path.exists("/opt/gcc/bin/g++") else "g++"
+    r = subprocess.run([cxx, "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread", "-ffp-contract=off", "-w", "-I" + os.path.join(ROOT, "include"),
+                        "-I" + EMU, os.path.join(EMU, "emu_kernels.cpp"), "-o", so], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    return C.CDLL(so)
+
+
+def vp(a):
+    return C.c_void_p(a.ctypes.data) if a is not None else None
+
+
+def plan(cfg, details=None):
+    """(info48, [filter banks (coef int16 [n, size], pos int32 [n])]) from the product's host set-up, no GPU"""
+    import ffmpeg_b200 as fb
+    L = fb.lib()
+    c = np.array(cfg, np.int32)
+    info = np.zeros(48, np.int32)
+    banks = []
+    for which in range(4):
+        assert L.b200_sws_plan_probe2(cl.ptr(c, cl.i32p), None, which, None, None, 0, cl.ptr(info, cl.i32p)) >= 0
+        size, n = int(info[which]), [cfg[4], int(info[6]), cfg[5], int(info[7])][which]
+        f, p = np.zeros(max(n * size, 1), np.int16), np.zeros(max(n, 1), np.int32)
+        if size:
+            L.b200_sws_plan_probe2(cl.ptr(c, cl.i32p), None, which, cl.ptr(f, cl.i16p), cl.ptr(p, cl.i32p), n, None)
+        banks.append((f, p, size))
+    return info, banks
+
+
+RGB_OFFSETS = {"rgb24": (3, 0, 1, 2), "bgr24": (3, 2, 1, 0), "rgba": (4, 0, 1, 2), "bgra": (4, 2, 1, 0), "argb": (4, 1, 2, 3), "abgr": (4, 3, 2, 1)}
+
+
+def test_emu_rgb_source_horizontal_pass_and_range(emu):
+    """sws_rgbin_hscale_{y,uv}_kernel with the filter banks and the rgb -> yuv table of the product's own host set-up, against the
+    oracle's reader + 16-bit horizontal pass; then sws_range_kernel on those lines against the oracle's range conversion"""
+    O = cl.oracle()
+    O.orc_sws_hlines.argtypes = [C.c_void_p] + [C.c_void_p, C.c_int] * 3 + [C.c_void_p] * 3
+    O.orc_sws_range_lines.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+    n = 0
+    for (w, h, dw, dh, fl) in [(64, 48, 100, 70, FATE), (64, 48, 33, 21, cl.SWS_BILINEAR), (63, 47, 63, 47, cl.SWS_BICUBIC), (64, 48, 128, 96, cl.SWS_BICUBIC | 0x4000),
+                               (64, 48, 40, 30, 1), (352, 288, 200, 100, FATE), (64, 48, 64, 48, FATE)]:
+        for name, sf in cl.PACKED_RGB_FORMATS.items():
+            for dr in (0, 1):
+                bpp, ro, go, bo = RGB_OFFSETS[name]
+                src = cl.rgb_frame(w, h, 3000 + n, bpp, "random", pad=(n % 3) * 3)
+                n += 1
+                info, banks = plan([w, h, sf, 0, dw, dh, 0, dr, fl])
+                assert info[27] == bpp and not info[30] and not info[16]
+                cw, csh = int(info[6]), int(info[5])                   # chroma: chrDstW samples per line, chrSrcH lines
+                rgbin = np.array([bpp, ro, go, bo, int(info[28])] + [int(x) for x in info[32:41]], np.int32)
+                L, CU, CV = np.zeros((h, dw), np.int16), np.zeros((csh, cw), np.int16), np.zeros((csh, cw), np.int16)
+                emu.emu_sws_rgbin_y(vp(src), C.c_longlong(src.strides[0]), C.c_longlong(0), vp(L), dw, C.c_longlong(0), vp(banks[0][0]), vp(banks[0][1]),
+                                    banks[0][2], vp(rgbin), h, 1)
+                emu.emu_sws_rgbin_uv(vp(src), C.c_longlong(src.strides[0]), C.c_longlong(0), vp(CU), vp(CV), cw, C.c_longlong(0), vp(banks[1][0]),
+                                     vp(banks[1][1]), banks[1][2], vp(rgbin), csh, 1)
+                octx = O.orc_sws_open_range(sf, w, h, 0, 0, dw, dh, dr, fl)
+                assert octx
+                eL, eU, eV = np.zeros_like(L), np.zeros_like(CU), np.zeros_like(CV)
+                assert O.orc_sws_hlines(octx, vp(src), src.strides[0], vp(src), 0, vp(src), 0, vp(eL), vp(eU), vp(eV)) == 0
+                assert np.array_equal(L, eL) and np.array_equal(CU, eU) and np.array_equal(CV, eV), (w, h, dw, dh, hex(fl), name)
+                if dr:                                                  # limited -> full behind an RGB source
+                    assert info[17] == 1
+                    emu.emu_sws_range(vp(L), dw, h, 1, C.c_longlong(0), int(info[18]), int(info[19]), 1)
+                    emu.emu_sws_range(vp(CU), cw, csh, 1, C.c_longlong(0), int(info[20]), int(info[21]), 1)
+                    O.orc_sws_range_lines(octx, vp(eL), dw, h, 0)
+                    O.orc_sws_range_lines(octx, vp(eU), cw, csh, 1)
+                    assert np.array_equal(L, eL) and np.array_equal(CU, eU), ("range", w, h, dw, dh, name)
+                O.orc_sws_close(octx)
+
+
+def test_emu_range_kernel_both_directions(emu):
+    O = cl.oracle()
+    O.orc_sws_range_lines.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+    rng = np.random.default_rng(7)
+    for (sr, dr) in ((0, 1), (1, 0)):
+        info, _ = plan([64, 48, 0, sr, 100, 70, 0, dr, FATE])
+        assert info[17] == (1 if dr else 2)
+        octx = O.orc_sws_open_range(0, 64, 48, sr, 0, 100, 70, dr, FATE)
+        for chroma in (0, 1):
+            frames, rows, w = 3, 5, 301
+            a = rng.integers(-2000, 32768, (frames, rows + 2, w)).astype(np.int16)      # frame stride larger than rows * w
+            e = a.copy()
+            emu.emu_sws_range(vp(a), w, rows, frames, C.c_longlong((rows + 2) * w), int(info[18 + 2 * chroma]), int(info[19 + 2 * chroma]), int(dr))
+            for f in range(frames):
+                O.orc_sws_range_lines(octx, C.c_void_p(e.ctypes.data + f * (rows + 2) * w * 2), w, rows, chroma)
+            assert np.array_equal(a, e), (sr, dr, chroma)
+            assert not np.array_equal(a[:, :rows], rng.integers(0, 1, 1))              # (something happened)
+        O.orc_sws_close(octx)
+
+
+def test_emu_bgr24_yv12_and_nv_interleave(emu):
+    for (w, h) in ((64, 48), (66, 51), (352, 288)):
+        src = cl.rgb_frame(w, h, 3100 + w, 3, "random", pad=5)
+        info, _ = plan([w, h, cl.PIX_FMT_BGR24, 0, w, h, 0, 0, cl.SWS_BICUBIC])
+        assert info[30] == 1
+        rgbin = np.array([3, 2, 1, 0, 0] + [int(x) for x in info[32:41]], np.int32)
+        cw, ch = w // 2, (h + 1) // 2
+        dy, du, dv = np.zeros((h, w + 3), np.uint8), np.zeros((ch, cw + 1), np.uint8), np.zeros((ch, cw + 2), np.uint8)
+        emu.emu_sws_bgr24_yv12(vp(src), C.c_longlong(src.strides[0]), vp(dy), C.c_longlong(dy.strides[0]), vp(du), C.c_longlong(du.strides[0]),
+                               vp(dv), C.c_longlong(dv.strides[0]), w, h, vp(rgbin))
+        ey, eu, ev = cl.orc_sws_planar(w, h, w, h, cl.SWS_BICUBIC, src, src, src, src_fmt=cl.PIX_FMT_BGR24)
+        assert np.array_equal(dy[:, :w], ey) and np.array_equal(du[:, :cw], eu) and np.array_equal(dv[:, :cw], ev), (w, h)
+        uv = np.zeros((ch, 2 * cw + 4), np.uint8)
+        emu.emu_sws_nv_interleave(vp(eu), vp(ev), C.c_longlong(eu.strides[0]), vp(uv), C.c_longlong(uv.strides[0]), cw, ch)
+        assert np.array_equal(uv[:, :2 * cw], cl.nv_interleave(eu, ev, cl.PIX_FMT_NV12)) and not uv[:, 2 * cw:].any()
+
+
+def test_emu_float_dsp(emu):
+    emu.emu_fdsp.argtypes = [C.c_int, C.c_longlong, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong,
+                             C.c_void_p, C.c_longlong, C.c_double]
+    for op in range(12):
+        for length, nvec in ((1024, 3), (77, 9), (8, 40), (1, 2)):
+            dt = np.float64 if op in cl.FDSP_DOUBLE else np.float32
+            n2 = 2 * length if op == 5 else length
+            cases = [cl.fdsp_case(700 + op * 31 + v, op, length) for v in range(nvec)]
+            dst, s0, s1 = (np.stack([c[k] for c in cases]) for k in range(3))
+            s2, mul = cases[0][3], cases[0][4]
+            dot = op in (9, 11)
+            d = np.zeros(nvec, dt) if dot else dst.copy()
+            a = s0.copy()
+            assert emu.emu_fdsp(op, nvec, length, d.ctypes.data, 1 if dot else n2, a.ctypes.data, length, s1.ctypes.data, length, s2.ctypes.data, 0, mul) == 0
+            for v in range(nvec):
+                e, e0 = cl.orc_fdsp(op, cases[v][0], cases[v][1], cases[v][2], s2, mul, length)
+                assert (d[v:v + 1] if dot else d[v]).tobytes() == e.tobytes() and a[v].tobytes() == e0.tobytes(), (cl.FDSP_OPS[op], length, v)
+
+
+def test_emu_idct_hbd(emu):
+    emu.emu_idct_hbd.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_int]
+    for depth in (10, 12):
+        for kind in (0, 1, 2):
+            n = 300
+            blocks = cl.idct_hbd_blocks(600 + depth + kind, depth, n)
+            dest = np.random.default_rng(kind).integers(0, 1 << depth, (8, n * 8 + 4), dtype=np.uint16)
+            b, d = blocks.copy(), dest.copy()
+            off = np.arange(n, dtype=np.int64) * 16
+            assert emu.emu_idct_hbd(depth, kind, b.ctypes.data, n, d.ctypes.data, off.ctypes.data, dest.strides[0]) == 0
+            eb, ed = cl.orc_idct_hbd(depth, kind, blocks, dest, dest.strides[0])
+            assert np.array_equal(d, ed) and np.array_equal(b, eb if kind == 0 else blocks), (depth, kind)
+
+
+def test_emu_unquant(emu):
+    from ffmpeg_b200._lib import MpvUnquant
+    emu.emu_unquant.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p]
+    for variant in range(7):
+        for seed in range(3):
+            cfg, blocks, blk_n, q, last = cl.unquant_case(800 + seed * 7 + variant, variant, nblocks=50 + seed)
+            p = cl.unquant_params(struct=MpvUnquant, **cfg)
+            use_n = blk_n if seed != 1 else None
+            b = np.ascontiguousarray(blocks).copy()
+            assert emu.emu_unquant(variant, C.byref(p), b.ctypes.data, b.shape[0], use_n.ctypes.data if use_n is not None else None,
+                                   q.ctypes.data, last.ctypes.data) == 0
+            assert np.array_equal(b, cl.orc_unquant(variant, cfg, blocks, use_n, q, last)), (cl.UNQUANT_VARIANTS[variant], seed)
