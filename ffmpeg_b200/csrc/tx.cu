@@ -14,6 +14,7 @@
 // skips the multiplication by (1, 0); that distinction is kept.
 // HBM traffic per transform is the algorithmic 8N in + 8N out (FFT) or 4*len in + 4*len out (iMDCT).
 #include "common.h"
+#include "tx_pfa.h"
 #include <vector>
 #include <cmath>
 #include <cstring>
@@ -427,6 +428,7 @@ void collect_blocks(std::vector<std::vector<int>> &lv, int L, int off)   // bloc
 
 struct B200TXContext {
     B200Device *dev = nullptr;
+    TxPfa *pfa = nullptr;            // compound 15 x M MDCT (tx_pfa.cu): everything below d is unused then
     int type = 0, inv = 0, len = 0;
     TxDev d{};
     void *blob = nullptr;
@@ -581,6 +583,7 @@ static int tx_launch(B200TXContext *c, cudaStream_t st, void *out, const void *i
                      ptrdiff_t out_step, ptrdiff_t in_step, void *c2r_writeback = nullptr)
 {
     if (count <= 0) return 0;
+    if (c->pfa) return tx_pfa_launch(c->pfa, st, out, in, stride, count, out_step, in_step);
     // measured on B200 (scripts/quick_bench.py tx with B200_TX_TB / B200_TX_THREADS): 256 threads pay off from 1024 points per
     // transform on; 512-point transforms (iMDCT-1024) run 18 % faster with 128-thread CTAs
     int threads = c->d.n >= 1024 ? 256 : c->d.n >= 256 ? 128 : 64;
@@ -648,7 +651,20 @@ B200_API int b200_tx_init_device(B200Device *dev, B200TXContext **ctx, b200_tx_f
     if (!dev) return B200_ENODEV;
     if (type != B200_TX_FLOAT_FFT && type != B200_TX_FLOAT_MDCT && type != B200_TX_FLOAT_RDFT) return B200_ENOSYS;
     if (flags & ~(uint64_t)B200_TX_UNALIGNED) return B200_ENOSYS;    // INPLACE / FULL_IMDCT / REAL_TO_* not implemented
-    if (len < 2 || (len & (len - 1))) return B200_ENOSYS;            // PFA (3/5/7/9/15 x 2^n) lengths not implemented
+    if (type == B200_TX_FLOAT_MDCT && tx_pfa_length_ok(len)) {       // 15 x 2^k: the compound MDCT av_tx_init() picks (Opus CELT sizes)
+        float scp = 1.0f;
+        if (scale) scp = *(const float *)scale;
+        B200TXContext *cp = new (std::nothrow) B200TXContext();
+        if (!cp) return B200_ENOMEM;
+        cp->dev = dev; cp->type = type; cp->inv = !!inv; cp->len = len;
+        if (cudaSetDevice(dev->ordinal) != cudaSuccess) { delete cp; return B200_EEXTERNAL; }
+        cp->pfa = tx_pfa_create(cp->inv, len, scp);
+        if (!cp->pfa) { delete cp; return B200_EEXTERNAL; }
+        *ctx = cp;
+        if (tx) *tx = tx_host_fn;
+        return 0;
+    }
+    if (len < 2 || (len & (len - 1))) return B200_ENOSYS;            // other PFA lengths (3/5/7/9 x 2^n) are not implemented
     if (type == B200_TX_FLOAT_RDFT && len < 4) return B200_ENOSYS;   // ff_tx_rdft_*_def: min_len 4
     const int n = type == 0 ? len : len >> 1;
     if (n < 1 || n > 16384) return B200_ENOSYS;                      // one transform must fit a CTA's shared memory
@@ -677,6 +693,7 @@ B200_API void b200_tx_uninit(B200TXContext **ctx)
     cudaSetDevice(c->dev->ordinal);
     cudaStreamSynchronize(c->dev->stream);
     if (c->blob) cudaFree(c->blob);
+    tx_pfa_free(c->pfa);
     delete c;
     *ctx = nullptr;
 }

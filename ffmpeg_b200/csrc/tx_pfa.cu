@@ -1,0 +1,437 @@
+// tx_pfa.cu — libavutil/tx compound 15 x M float MDCT on sm_100a: what av_tx_init(AV_TX_FLOAT_MDCT, len = 15 * 2^k) resolves to
+// (mdct_pfa_15xM_{inv,fwd} carry the largest factor, libavutil/tx.c:391-395), i.e. the Opus CELT transforms of 120 ... 960
+// (libavcodec/opus/dec_celt.c:569, enc.c:690).
+//
+// Reference semantics reproduced bit for bit (checker: the compound part of oracle/tx_oracle.c), libavutil/tx_template.c:
+//   :172-209 fft3, :211-250 fft5 / fft5_m1..m3, :465-476 fft15 (float branches), table ff_tx_tab_53 :91-108
+//   :1430-1469 ff_tx_mdct_pfa_init (compound map libavutil/tx.c:75-123, 3x5 input map embedded tx_priv.h:275-284, twiddles
+//              ff_tx_mdct_gen_exp :2107-2134, scatter permutation of the M-point transform tx.c:136-154)
+//   :1471-1511 ff_tx_mdct_pfa_15xM_inv, :1533-1579 ff_tx_mdct_pfa_15xM_fwd, M-point split-radix transforms :540-722
+// Every product and sum is rounded on its own (library built with --fmad=false), in the reference's order.
+//
+// First version, correctness before speed: ONE THREAD PER TRANSFORM, the 15 x M work array in a global scratch line per
+// thread; the tuned version will put one transform per warp / CTA in shared memory like tx.cu does for powers of two.
+#include "tx_pfa.h"
+#include <vector>
+#include <cmath>
+#include <cstring>
+
+namespace {
+
+// [device-code tx_pfa] (tests/cuda_emu runs this block on the CPU against the checker; comment markers only)
+struct PfaDev {
+    const int *in_map, *out_map, *sub_map;     // in_map holds doubled positions (tx_template.c:1460-1462)
+    const float2 *exp;
+    const float *tab53;
+    const float *tabs[8];                      // tabs[k]: cosine table of the 2^k-point transform (k = 3 ... 7)
+    int m, log2m, len;
+};
+
+__device__ __forceinline__ void butterflies(float2 &a0, float2 &a1, float2 &a2, float2 &a3, float t1, float t2, float t5, float t6)
+{
+    const float r0 = a0.x, i0 = a0.y, r1 = a1.x, i1 = a1.y;
+    const float t3 = t5 - t1; t5 = t5 + t1;
+    a2.x = r0 - t5; a0.x = r0 + t5;
+    a3.y = i1 - t3; a1.y = i1 + t3;
+    const float t4 = t2 - t6; t6 = t2 + t6;
+    a3.x = r1 - t4; a1.x = r1 + t4;
+    a2.y = i0 - t6; a0.y = i0 + t6;
+}
+
+__device__ __forceinline__ void transform(float2 &a0, float2 &a1, float2 &a2, float2 &a3, float wre, float wim)
+{
+    const float t1 = a2.x * wre - a2.y * (-wim);
+    const float t2 = a2.x * (-wim) + a2.y * wre;
+    const float t5 = a3.x * wre - a3.y * wim;
+    const float t6 = a3.x * wim + a3.y * wre;
+    butterflies(a0, a1, a2, a3, t1, t2, t5, t6);
+}
+
+__device__ __forceinline__ void fft4(float2 *d)
+{
+    float t1, t2, t3, t4, t5, t6, t7, t8;
+    t3 = d[0].x - d[1].x; t1 = d[0].x + d[1].x;
+    t8 = d[3].x - d[2].x; t6 = d[3].x + d[2].x;
+    const float d2re = t1 - t6, d0re = t1 + t6;
+    t4 = d[0].y - d[1].y; t2 = d[0].y + d[1].y;
+    t7 = d[2].y - d[3].y; t5 = d[2].y + d[3].y;
+    d[2].x = d2re; d[0].x = d0re;
+    d[3].y = t4 - t8; d[1].y = t4 + t8;
+    d[3].x = t3 - t7; d[1].x = t3 + t7;
+    d[2].y = t2 - t5; d[0].y = t2 + t5;
+}
+
+// in-place 2^K-point transform without the input permutation (ff_tx_fft{N}_ns); the recursion is unrolled at compile time
+template <int K> __device__ void fft_ns(float2 *d, const PfaDev &P)
+{
+    constexpr int n = 1 << K, n4 = n / 4;
+    fft_ns<K - 1>(d, P);
+    fft_ns<K - 2>(d + 2 * n4, P);
+    fft_ns<K - 2>(d + 3 * n4, P);
+    constexpr int len = n4 >> 1, o1 = 2 * len, o2 = 4 * len, o3 = 6 * len;        // ff_tx_fft_sr_combine(d, tab_n, n / 8)
+    const float *cs = P.tabs[K], *wim = cs + o1 - 7;
+    float2 *z = d;
+    for (int i = 0; i < len; i += 4) {
+        transform(z[0], z[o1 + 0], z[o2 + 0], z[o3 + 0], cs[0], wim[7]);
+        transform(z[2], z[o1 + 2], z[o2 + 2], z[o3 + 2], cs[2], wim[5]);
+        transform(z[4], z[o1 + 4], z[o2 + 4], z[o3 + 4], cs[4], wim[3]);
+        transform(z[6], z[o1 + 6], z[o2 + 6], z[o3 + 6], cs[6], wim[1]);
+        transform(z[1], z[o1 + 1], z[o2 + 1], z[o3 + 1], cs[1], wim[6]);
+        transform(z[3], z[o1 + 3], z[o2 + 3], z[o3 + 3], cs[3], wim[4]);
+        transform(z[5], z[o1 + 5], z[o2 + 5], z[o3 + 5], cs[5], wim[2]);
+        transform(z[7], z[o1 + 7], z[o2 + 7], z[o3 + 7], cs[7], wim[0]);
+        z += 8; cs += 8; wim -= 8;
+    }
+}
+template <> __device__ void fft_ns<1>(float2 *d, const PfaDev &)
+{
+    const float re = d[0].x - d[1].x, im = d[0].y - d[1].y;
+    d[0].x = d[0].x + d[1].x; d[0].y = d[0].y + d[1].y;
+    d[1].x = re; d[1].y = im;
+}
+template <> __device__ void fft_ns<2>(float2 *d, const PfaDev &) { fft4(d); }
+template <> __device__ void fft_ns<3>(float2 *d, const PfaDev &P)
+{
+    const float c = P.tabs[3][1];
+    fft4(d);
+    const float t1 = d[4].x - (-d[5].x), d5re = d[4].x + (-d[5].x);
+    const float t2 = d[4].y - (-d[5].y), d5im = d[4].y + (-d[5].y);
+    const float t5 = d[6].x - (-d[7].x), d7re = d[6].x + (-d[7].x);
+    const float t6 = d[6].y - (-d[7].y), d7im = d[6].y + (-d[7].y);
+    d[5].x = d5re; d[5].y = d5im; d[7].x = d7re; d[7].y = d7im;
+    butterflies(d[0], d[2], d[4], d[6], t1, t2, t5, t6);
+    transform(d[1], d[3], d[5], d[7], c, c);
+}
+template <> __device__ void fft_ns<4>(float2 *d, const PfaDev &P)
+{
+    const float *c = P.tabs[4];
+    fft_ns<3>(d, P);
+    fft4(d + 8);
+    fft4(d + 12);
+    butterflies(d[0], d[4], d[8], d[12], d[8].x, d[8].y, d[12].x, d[12].y);
+    transform(d[2], d[6], d[10], d[14], c[2], c[2]);
+    transform(d[1], d[5], d[9], d[13], c[1], c[3]);
+    transform(d[3], d[7], d[11], d[15], c[3], c[1]);
+}
+
+__device__ void fft_ns_any(float2 *d, const PfaDev &P)
+{
+    switch (P.log2m) {
+    case 1: fft_ns<1>(d, P); break;
+    case 2: fft_ns<2>(d, P); break;
+    case 3: fft_ns<3>(d, P); break;
+    case 4: fft_ns<4>(d, P); break;
+    case 5: fft_ns<5>(d, P); break;
+    case 6: fft_ns<6>(d, P); break;
+    default: fft_ns<7>(d, P); break;
+    }
+}
+
+__device__ __forceinline__ void fft3(const float *tab, float2 *out, const float2 *in, int stride)
+{
+    float2 t0 = in[0], t1, t2;
+    t1.x = in[1].y - in[2].y; t2.y = in[1].y + in[2].y;
+    t1.y = in[1].x - in[2].x; t2.x = in[1].x + in[2].x;
+    out[0 * stride].x = t0.x + t2.x;
+    out[0 * stride].y = t0.y + t2.y;
+    t1.x = tab[8] * t1.x; t1.y = tab[9] * t1.y; t2.x = tab[10] * t2.x; t2.y = tab[10] * t2.y;
+    out[1 * stride].x = t0.x - t2.x + t1.x;
+    out[1 * stride].y = t0.y - t2.y - t1.y;
+    out[2 * stride].x = t0.x - t2.x - t1.x;
+    out[2 * stride].y = t0.y - t2.y + t1.y;
+}
+
+template <int D0, int D1, int D2, int D3, int D4>
+__device__ __forceinline__ void fft5(const float *tab, float2 *out, const float2 *in, int stride)
+{
+    const float2 dc = in[0];
+    float2 z0[4], t[6];
+    t[1].y = in[1].x - in[4].x; t[0].x = in[1].x + in[4].x;
+    t[1].x = in[1].y - in[4].y; t[0].y = in[1].y + in[4].y;
+    t[3].y = in[2].x - in[3].x; t[2].x = in[2].x + in[3].x;
+    t[3].x = in[2].y - in[3].y; t[2].y = in[2].y + in[3].y;
+    out[D0 * stride].x = dc.x + t[0].x + t[2].x;
+    out[D0 * stride].y = dc.y + t[0].y + t[2].y;
+    { const float a = tab[0] * t[2].x - tab[2] * t[0].x, b = tab[0] * t[0].x - tab[2] * t[2].x; t[4].x = a; t[0].x = b; }
+    { const float a = tab[0] * t[2].y - tab[2] * t[0].y, b = tab[0] * t[0].y - tab[2] * t[2].y; t[4].y = a; t[0].y = b; }
+    { const float a = tab[4] * t[3].x - tab[6] * t[1].x, b = tab[4] * t[1].x + tab[6] * t[3].x; t[5].x = a; t[1].x = b; }
+    { const float a = tab[4] * t[3].y - tab[6] * t[1].y, b = tab[4] * t[1].y + tab[6] * t[3].y; t[5].y = a; t[1].y = b; }
+    z0[0].x = t[0].x - t[1].x; z0[3].x = t[0].x + t[1].x;
+    z0[0].y = t[0].y - t[1].y; z0[3].y = t[0].y + t[1].y;
+    z0[2].x = t[4].x - t[5].x; z0[1].x = t[4].x + t[5].x;
+    z0[2].y = t[4].y - t[5].y; z0[1].y = t[4].y + t[5].y;
+    out[D1 * stride].x = dc.x + z0[3].x; out[D1 * stride].y = dc.y + z0[0].y;
+    out[D2 * stride].x = dc.x + z0[2].x; out[D2 * stride].y = dc.y + z0[1].y;
+    out[D3 * stride].x = dc.x + z0[1].x; out[D3 * stride].y = dc.y + z0[2].y;
+    out[D4 * stride].x = dc.x + z0[0].x; out[D4 * stride].y = dc.y + z0[3].y;
+}
+
+__device__ __forceinline__ void fft15(const float *tab, float2 *out, const float2 *in, int stride)
+{
+    float2 tmp[15];
+#pragma unroll
+    for (int i = 0; i < 5; i++) fft3(tab, tmp + i, in + i * 3, 5);
+    fft5<0, 6, 12, 3, 9>(tab, out, tmp + 0, stride);
+    fft5<10, 1, 7, 13, 4>(tab, out, tmp + 5, stride);
+    fft5<5, 11, 2, 8, 14>(tab, out, tmp + 10, stride);
+}
+
+// ff_tx_mdct_pfa_15xM_inv: one thread = one transform; in: len floats with a stride (in floats), out: len floats
+__global__ void __launch_bounds__(64)
+tx_mdct_pfa15_inv_kernel(const PfaDev P, float *out, const float *in, long long stride, long long out_step, long long in_step, long long count,
+                         float2 *scratch)
+{
+    const long long tr = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tr >= count) return;
+    const int len4 = P.len >> 2, len2 = P.len >> 1, m = P.m;
+    float2 *tmp = scratch + tr * len2;
+    float2 *z = reinterpret_cast<float2 *>(reinterpret_cast<char *>(out) + tr * out_step);
+    const float *src = reinterpret_cast<const float *>(reinterpret_cast<const char *>(in) + tr * in_step);
+    const float *in1 = src, *in2 = src + ((15 * m * 2) - 1) * stride;
+    const float2 *e = P.exp;
+    const int *in_map = P.in_map, *sub_map = P.sub_map;
+    for (int i = 0; i < len2; i += 15) {
+        float2 f15[15];
+#pragma unroll
+        for (int j = 0; j < 15; j++) {
+            const int k = in_map[j];
+            const float are = in2[-k * stride], aim = in1[k * stride];
+            f15[j].x = are * e[j].x - aim * e[j].y;
+            f15[j].y = are * e[j].y + aim * e[j].x;
+        }
+        fft15(P.tab53, tmp + *(sub_map++), f15, m);
+        e += 15; in_map += 15;
+    }
+    for (int i = 0; i < 15; i++) fft_ns_any(tmp + m * i, P);
+    for (int i = 0; i < len4; i++) {
+        const int i0 = len4 + i, i1 = len4 - i - 1, s0 = P.out_map[i0], s1 = P.out_map[i1];
+        const float2 src1 = make_float2(tmp[s1].y, tmp[s1].x), src0 = make_float2(tmp[s0].y, tmp[s0].x);
+        z[i1].x = src1.x * e[i1].y - src1.y * e[i1].x;
+        z[i0].y = src1.x * e[i1].x + src1.y * e[i1].y;
+        z[i0].x = src0.x * e[i0].y - src0.y * e[i0].x;
+        z[i1].y = src0.x * e[i0].x + src0.y * e[i0].y;
+    }
+}
+
+// ff_tx_mdct_pfa_15xM_fwd: in: 2*len floats, out: len floats with a stride (in floats)
+__global__ void __launch_bounds__(64)
+tx_mdct_pfa15_fwd_kernel(const PfaDev P, float *out, const float *in, long long stride, long long out_step, long long in_step, long long count,
+                         float2 *scratch)
+{
+    const long long tr = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tr >= count) return;
+    const int m = P.m, len4 = 15 * m, len3 = len4 * 3, len8 = P.len >> 2;
+    float2 *tmp = scratch + tr * len4;
+    float *dst = reinterpret_cast<float *>(reinterpret_cast<char *>(out) + tr * out_step);
+    const float *src = reinterpret_cast<const float *>(reinterpret_cast<const char *>(in) + tr * in_step);
+    const float2 *e = P.exp;
+    for (int i = 0; i < m; i++) {
+        float2 f15[15];
+#pragma unroll
+        for (int j = 0; j < 15; j++) {
+            const int k = P.in_map[i * 15 + j];
+            float re, im;
+            if (k < len4) { re = -src[len4 + k] + src[1 * len4 - 1 - k]; im = -src[len3 + k] + -src[1 * len3 - 1 - k]; }
+            else          { re = -src[len4 + k] + -src[5 * len4 - 1 - k]; im = src[-len4 + k] + -src[1 * len3 - 1 - k]; }
+            f15[j].y = re * e[k >> 1].x - im * e[k >> 1].y;
+            f15[j].x = re * e[k >> 1].y + im * e[k >> 1].x;
+        }
+        fft15(P.tab53, tmp + P.sub_map[i], f15, m);
+    }
+    for (int i = 0; i < 15; i++) fft_ns_any(tmp + m * i, P);
+    for (int i = 0; i < len8; i++) {
+        const int i0 = len8 + i, i1 = len8 - i - 1, s0 = P.out_map[i0], s1 = P.out_map[i1];
+        const float2 src1 = tmp[s1], src0 = tmp[s0];
+        dst[(2 * i1 + 1) * stride] = src0.x * e[i0].y - src0.y * e[i0].x;
+        dst[2 * i0 * stride]       = src0.x * e[i0].x + src0.y * e[i0].y;
+        dst[(2 * i0 + 1) * stride] = src1.x * e[i1].y - src1.y * e[i1].x;
+        dst[2 * i1 * stride]       = src1.x * e[i1].x + src1.y * e[i1].y;
+    }
+}
+// [/device-code tx_pfa]
+
+int sr_perm(int i, int len, int inv)                               // split_radix_permutation, libavutil/tx.c:125-134
+{
+    len >>= 1;
+    if (len <= 1) return i & 1;
+    if (!(i & len)) return sr_perm(i, len, inv) * 2;
+    len >>= 1;
+    return sr_perm(i, len, inv) * 4 + 1 - 2 * (!(i & len) ^ inv);
+}
+int mulinv(int n, int m)                                           // libavutil/tx.c:34-42
+{
+    n = n % m;
+    for (int x = 1; x < m; x++) if (((n * x) % m) == 1) return x;
+    return 0;
+}
+
+} // namespace
+
+struct TxPfa {
+    int inv = 0, len = 0, m = 0;
+    PfaDev d{};
+    void *blob = nullptr;
+    void *scratch = nullptr; size_t scratch_bytes = 0;
+};
+
+// the host tables of one transform (also used by the CPU test tier through b200_tx_pfa_tables)
+struct PfaHost {
+    std::vector<int> in_map, out_map, sub_map;
+    std::vector<float> exp;            // interleaved re, im: inverse = 2 * l2 entries (pre-shuffled, then natural), forward = l2
+    float tab53[12];
+    std::vector<float> cosk[8];
+    int m = 0, log2m = 0;
+};
+
+bool tx_pfa_length_ok(int len)
+{
+    if (len < 120 || len % 30) return false;                        // m >= 4: the 4-point transform is the smallest codelet we carry
+    const int m = len / 30;
+    return !(m & (m - 1)) && m <= 128;
+}
+
+static void pfa_host_tables(PfaHost &H, int inv, int len, float scale)
+{
+    const int n = 15, l2 = len >> 1, m = l2 / n;
+    H.m = m; H.log2m = 0;
+    while ((1 << H.log2m) < m) H.log2m++;
+    H.in_map.assign(l2, 0); H.out_map.assign(l2, 0); H.sub_map.assign(m, 0);
+    const int m_inv = mulinv(m, n), n_inv = mulinv(n, m);
+    for (int j = 0; j < m; j++)                                     // ff_tx_gen_compound_mapping, gather direction (tx.c:104-110)
+        for (int i = 0; i < n; i++) {
+            H.in_map[j * n + i] = (i * m + j * n) % l2;
+            H.out_map[(i * m * m_inv + j * n * n_inv) % l2] = i * m + j;
+        }
+    if (inv)
+        for (int i = 0; i < m; i++) {
+            int *in = &H.in_map[i * n + 1];
+            for (int j = 0; j < ((n - 1) >> 1); j++) std::swap(in[j], in[n - j - 2]);
+        }
+    for (int k = 0; k < l2; k += 15) {                              // TX_EMBED_INPUT_PFA_MAP(map, len, 3, 5)
+        int mt[15];
+        memcpy(mt, &H.in_map[k], sizeof(mt));
+        for (int b = 0; b < 5; b++) for (int a = 0; a < 3; a++) H.in_map[k + b * 3 + a] = mt[(b * 3 + a * 5) % 15];
+    }
+    const double theta = (scale < 0 ? l2 : 0) + 1.0 / 8.0, sc = sqrt(fabs((double)scale));      // ff_tx_mdct_gen_exp
+    std::vector<float> full(2 * (size_t)l2);
+    for (int i = 0; i < l2; i++) {
+        const double alpha = M_PI_2 * (i + theta) / l2;
+        full[2 * i] = (float)(cos(alpha) * sc);
+        full[2 * i + 1] = (float)(sin(alpha) * sc);
+    }
+    if (inv) {
+        H.exp.assign(4 * (size_t)l2, 0.f);
+        memcpy(&H.exp[2 * (size_t)l2], full.data(), sizeof(float) * 2 * l2);
+        for (int i = 0; i < l2; i++) { H.exp[2 * i] = full[2 * H.in_map[i]]; H.exp[2 * i + 1] = full[2 * H.in_map[i] + 1]; }
+    } else
+        H.exp = full;
+    for (int i = 0; i < l2; i++) H.in_map[i] <<= 1;
+    for (int i = 0; i < m; i++) H.sub_map[(-sr_perm(i, m, inv)) & (m - 1)] = i;
+    const double c5 = cos(2 * M_PI / 5), c10 = cos(2 * M_PI / 10), s5 = sin(2 * M_PI / 5), s10 = sin(2 * M_PI / 10);
+    H.tab53[0] = H.tab53[1] = (float)c5; H.tab53[2] = H.tab53[3] = (float)c10;
+    H.tab53[4] = H.tab53[5] = (float)s5; H.tab53[6] = H.tab53[7] = (float)s10;
+    H.tab53[8] = H.tab53[9] = (float)cos(2 * M_PI / 12); H.tab53[10] = (float)cos(2 * M_PI / 6); H.tab53[11] = (float)cos(8 * M_PI / 6);
+    for (int k = 3; k <= H.log2m; k++) {                            // ff_tx_init_tab_N (tx_template.c:65-77)
+        const int nn = 1 << k;
+        H.cosk[k].assign(nn / 4 + 1, 0.f);
+        const double freq = 2 * M_PI / nn;
+        for (int i = 0; i < nn / 4; i++) H.cosk[k][i] = (float)cos(i * freq);
+    }
+}
+
+// host-only: the tables of a transform, flattened, for the CPU test tier: [in_map l2][out_map l2][sub_map m] as int32, then
+// floats: exp, tab53[12], cosine tables k = 3 .. log2m.  Returns the number of 32-bit words (or what it would need if cap is short).
+B200_API int b200_tx_pfa_tables(int inv, int len, float scale, int32_t *words, int cap, int32_t *layout8)
+{
+    if (!tx_pfa_length_ok(len)) return B200_ENOSYS;
+    PfaHost H;
+    pfa_host_tables(H, inv, len, scale);
+    std::vector<int32_t> w;
+    auto addi = [&](const std::vector<int> &v) { for (int x : v) w.push_back(x); };
+    auto addf = [&](const float *f, size_t n) { for (size_t i = 0; i < n; i++) { int32_t b; memcpy(&b, f + i, 4); w.push_back(b); } };
+    int32_t lay[8] = { 0 };
+    lay[0] = (int32_t)w.size(); addi(H.in_map);
+    lay[1] = (int32_t)w.size(); addi(H.out_map);
+    lay[2] = (int32_t)w.size(); addi(H.sub_map);
+    lay[3] = (int32_t)w.size(); addf(H.exp.data(), H.exp.size());
+    lay[4] = (int32_t)w.size(); addf(H.tab53, 12);
+    lay[5] = (int32_t)w.size();
+    for (int k = 3; k <= H.log2m; k++) addf(H.cosk[k].data(), H.cosk[k].size());
+    lay[6] = H.m; lay[7] = H.log2m;
+    if (layout8) memcpy(layout8, lay, sizeof(lay));
+    if (words && cap >= (int)w.size()) memcpy(words, w.data(), w.size() * 4);
+    return (int)w.size();
+}
+
+TxPfa *tx_pfa_create(int inv, int len, float scale)
+{
+    if (!tx_pfa_length_ok(len)) return nullptr;
+    PfaHost H;
+    pfa_host_tables(H, inv, len, scale);
+    const int l2 = len >> 1, m = H.m;
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    size_t off = 0;
+    const size_t o_in = off;  off += al(sizeof(int) * l2);
+    const size_t o_out = off; off += al(sizeof(int) * l2);
+    const size_t o_sub = off; off += al(sizeof(int) * m);
+    const size_t o_exp = off; off += al(sizeof(float) * H.exp.size());
+    const size_t o_53 = off;  off += al(sizeof(float) * 12);
+    size_t o_cos[8] = { 0 };
+    for (int k = 3; k <= H.log2m; k++) { o_cos[k] = off; off += al(sizeof(float) * H.cosk[k].size()); }
+    std::vector<uint8_t> host(off, 0);
+    memcpy(&host[o_in], H.in_map.data(), sizeof(int) * l2);
+    memcpy(&host[o_out], H.out_map.data(), sizeof(int) * l2);
+    memcpy(&host[o_sub], H.sub_map.data(), sizeof(int) * m);
+    memcpy(&host[o_exp], H.exp.data(), sizeof(float) * H.exp.size());
+    memcpy(&host[o_53], H.tab53, sizeof(float) * 12);
+    for (int k = 3; k <= H.log2m; k++) memcpy(&host[o_cos[k]], H.cosk[k].data(), sizeof(float) * H.cosk[k].size());
+    TxPfa *p = new (std::nothrow) TxPfa();
+    if (!p) return nullptr;
+    p->inv = inv; p->len = len; p->m = m;
+    if (cudaMalloc(&p->blob, off) != cudaSuccess || cudaMemcpy(p->blob, host.data(), off, cudaMemcpyHostToDevice) != cudaSuccess) {
+        b200_set_error("tx_pfa_create: device tables");
+        if (p->blob) cudaFree(p->blob);
+        delete p;
+        return nullptr;
+    }
+    uint8_t *b = (uint8_t *)p->blob;
+    PfaDev &d = p->d;
+    d.in_map = (const int *)(b + o_in); d.out_map = (const int *)(b + o_out); d.sub_map = (const int *)(b + o_sub);
+    d.exp = (const float2 *)(b + o_exp); d.tab53 = (const float *)(b + o_53);
+    for (int k = 0; k < 8; k++) d.tabs[k] = k >= 3 && k <= H.log2m ? (const float *)(b + o_cos[k]) : nullptr;
+    d.m = m; d.log2m = H.log2m; d.len = len;
+    return p;
+}
+
+void tx_pfa_free(TxPfa *p)
+{
+    if (!p) return;
+    if (p->blob) cudaFree(p->blob);
+    if (p->scratch) cudaFree(p->scratch);
+    delete p;
+}
+
+int tx_pfa_launch(TxPfa *p, cudaStream_t st, void *out, const void *in, ptrdiff_t stride, int64_t count, ptrdiff_t out_step, ptrdiff_t in_step)
+{
+    if (count <= 0) return 0;
+    const size_t l2 = (size_t)p->len >> 1;
+    const int64_t chunk_max = (int64_t)((size_t)(256u << 20) / (l2 * sizeof(float2)));          // scratch of at most 256 MB
+    const int64_t chunk = count < chunk_max ? count : chunk_max;
+    const size_t need = (size_t)chunk * l2 * sizeof(float2);
+    if (p->scratch_bytes < need) {
+        if (p->scratch) { cudaStreamSynchronize(st); cudaFree(p->scratch); p->scratch = nullptr; p->scratch_bytes = 0; }
+        B200_CUDA_OK(cudaMalloc(&p->scratch, need));
+        p->scratch_bytes = need;
+    }
+    for (int64_t c0 = 0; c0 < count; c0 += chunk) {
+        const long long cnt = count - c0 < chunk ? count - c0 : chunk;
+        const unsigned nb = (unsigned)((cnt + 63) / 64);
+        char *o = (char *)out + c0 * out_step;
+        const char *i = (const char *)in + c0 * in_step;
+        if (p->inv) tx_mdct_pfa15_inv_kernel<<<nb, 64, 0, st>>>(p->d, (float *)o, (const float *)i, (long long)(stride / 4), out_step, in_step, cnt, (float2 *)p->scratch);
+        else        tx_mdct_pfa15_fwd_kernel<<<nb, 64, 0, st>>>(p->d, (float *)o, (const float *)i, (long long)(stride / 4), out_step, in_step, cnt, (float2 *)p->scratch);
+        B200_LAUNCHED();
+    }
+    B200_CUDA_OK(cudaGetLastError());
+    return 0;
+}

@@ -1,0 +1,10 @@
+// tx_pfa.h — compound 15 x M float MDCT (tx_pfa.cu), used by tx.cu for the lengths av_tx_init() gives to mdct_pfa_15xM
+#pragma once
+#include "common.h"
+
+struct TxPfa;
+// len = MDCT length (15 * 2^k, k >= 2), scale as for av_tx_init; returns nullptr (and sets the error string) on failure
+TxPfa *tx_pfa_create(int inv, int len, float scale);
+void   tx_pfa_free(TxPfa *p);
+bool   tx_pfa_length_ok(int len);
+int    tx_pfa_launch(TxPfa *p, cudaStream_t st, void *out, const void *in, ptrdiff_t stride, int64_t count, ptrdiff_t out_step, ptrdiff_t in_step);

@@ -32,6 +32,12 @@ struct OrcTx {
     cpx *exp;                   /* MDCT twiddles */
     float *rexp;                /* RDFT: 8 factors, then cos and sin-like tables of len/4 entries each */
     float *tab[18];             /* tab[k] = cosine table of size 2^k */
+    /* compound 15 x M MDCT (ff_tx_mdct_pfa_15xM_{inv,fwd}, tx_template.c:1471-1599): len/2 = 15 * m complex points */
+    int pfa_m;                  /* 0: power-of-two transform; else m (power of two >= 2) */
+    int *pfa_in, *pfa_out;      /* compound input map (15-point groups, 3x5 map embedded; doubled for the inverse) and CRT output map */
+    int *pfa_sub;               /* scatter permutation of the m-point FFT (ff_tx_gen_ptwo_revtab, FF_TX_MAP_SCATTER) */
+    cpx *pfa_tmp;
+    float tab53[12];            /* ff_tx_tab_53 (tx_template.c:91-108) */
 };
 
 static void make_tab(OrcTx *t, int k)
@@ -140,8 +146,182 @@ static int sr_perm(int i, int len, int inv)
 
 static int ilog2i(int n) { int k = 0; while ((1 << k) < n) k++; return k; }
 
+/* ---- compound 15 x M MDCT: what av_tx_init(AV_TX_FLOAT_MDCT, len = 15 * 2^k) selects (mdct_pfa_15xM has the largest factor,
+ * tx.c:391-395), e.g. the Opus CELT sizes 120 ... 960 (libavcodec/opus/dec_celt.c:569) -------------------------------------- */
+static int mulinv(int n, int m)                                /* tx.c:34-42 */
+{
+    n = n % m;
+    for (int x = 1; x < m; x++) if (((n * x) % m) == 1) return x;
+    return 0;
+}
+
+static OrcTx *open_mdct_pfa15(int inv, int len, float scale)
+{
+    OrcTx *t = calloc(1, sizeof(*t));
+    const int n = 15, l2 = len >> 1, m = l2 / n;
+    t->type = 1; t->inv = !!inv; t->len = len; t->n = m; t->pfa_m = m;
+    for (int j = 3; (1 << j) <= m; j++) make_tab(t, j);
+    /* ff_tx_gen_compound_mapping(s, opts = NULL -> gather, inv, 15, m), tx.c:75-123 */
+    int *in_map = t->pfa_in = malloc(sizeof(int) * l2), *out_map = t->pfa_out = malloc(sizeof(int) * l2);
+    const int m_inv = mulinv(m, n), n_inv = mulinv(n, m);
+    for (int j = 0; j < m; j++)
+        for (int i = 0; i < n; i++) {
+            in_map[j * n + i] = (i * m + j * n) % l2;
+            out_map[(i * m * m_inv + j * n * n_inv) % l2] = i * m + j;
+        }
+    if (inv)
+        for (int i = 0; i < m; i++) {
+            int *in = &in_map[i * n + 1];                      /* skip the DC */
+            for (int j = 0; j < ((n - 1) >> 1); j++) { int x = in[j]; in[j] = in[n - j - 2]; in[n - j - 2] = x; }
+        }
+    /* TX_EMBED_INPUT_PFA_MAP(map, len, 3, 5), tx_priv.h:275-284: the 15-point transform is itself a 3 x 5 compound */
+    for (int k = 0; k < l2; k += 15) {
+        int mt[15];
+        memcpy(mt, &in_map[k], sizeof(mt));
+        for (int b = 0; b < 5; b++) for (int a = 0; a < 3; a++) in_map[k + b * 3 + a] = mt[(b * 3 + a * 5) % 15];
+    }
+    /* ff_tx_mdct_gen_exp(s, inv ? s->map : NULL), tx_template.c:2107-2134 */
+    const int len4 = l2;
+    const double theta = (scale < 0 ? len4 : 0) + 1.0 / 8.0, sc = sqrt(fabs((double)scale));
+    cpx *full = malloc(sizeof(cpx) * len4);
+    for (int i = 0; i < len4; i++) {
+        const double alpha = M_PI_2 * (i + theta) / len4;
+        full[i].re = (float)(cos(alpha) * sc);
+        full[i].im = (float)(sin(alpha) * sc);
+    }
+    if (inv) {
+        t->exp = malloc(sizeof(cpx) * 2 * len4);
+        memcpy(t->exp + len4, full, sizeof(cpx) * len4);
+        for (int i = 0; i < len4; i++) t->exp[i] = full[in_map[i]];
+        free(full);
+    } else
+        t->exp = full;
+    for (int i = 0; i < l2; i++) in_map[i] <<= 1;              /* "saves multiplies in loops" (tx_template.c:1460-1462) */
+    /* sub-transform: m-point FFT, in place, pre-shuffled, scatter map (ff_tx_mdct_pfa_init sub_opts; tx.c:136-154) */
+    t->pfa_sub = malloc(sizeof(int) * m);
+    for (int i = 0; i < m; i++) t->pfa_sub[(-sr_perm(i, m, t->inv)) & (m - 1)] = i;
+    t->pfa_tmp = malloc(sizeof(cpx) * l2);
+    const double c5 = cos(2 * M_PI / 5), c10 = cos(2 * M_PI / 10), s5 = sin(2 * M_PI / 5), s10 = sin(2 * M_PI / 10);
+    t->tab53[0] = t->tab53[1] = (float)c5; t->tab53[2] = t->tab53[3] = (float)c10;
+    t->tab53[4] = t->tab53[5] = (float)s5; t->tab53[6] = t->tab53[7] = (float)s10;
+    t->tab53[8] = t->tab53[9] = (float)cos(2 * M_PI / 12); t->tab53[10] = (float)cos(2 * M_PI / 6); t->tab53[11] = (float)cos(8 * M_PI / 6);
+    return t;
+}
+
+/* fft3 (tx_template.c:172-209, float branch): out with stride */
+static void pfa_fft3(const float *tab, cpx *out, const cpx *in, int stride)
+{
+    cpx t0 = in[0], t1, t2;
+    t1.re = in[1].im - in[2].im; t2.im = in[1].im + in[2].im;
+    t1.im = in[1].re - in[2].re; t2.re = in[1].re + in[2].re;
+    out[0 * stride].re = t0.re + t2.re;
+    out[0 * stride].im = t0.im + t2.im;
+    t1.re = tab[8] * t1.re; t1.im = tab[9] * t1.im; t2.re = tab[10] * t2.re; t2.im = tab[10] * t2.im;
+    out[1 * stride].re = t0.re - t2.re + t1.re;
+    out[1 * stride].im = t0.im - t2.im - t1.im;
+    out[2 * stride].re = t0.re - t2.re - t1.re;
+    out[2 * stride].im = t0.im - t2.im + t1.im;
+}
+
+/* DECL_FFT5 (tx_template.c:211-250): d[] = the five output slots of the variant (fft5_m1 / _m2 / _m3) */
+static void pfa_fft5(const float *tab, cpx *out, const cpx *in, int stride, const int d[5])
+{
+    cpx dc = in[0], z0[4], t[6];
+    t[1].im = in[1].re - in[4].re; t[0].re = in[1].re + in[4].re;
+    t[1].re = in[1].im - in[4].im; t[0].im = in[1].im + in[4].im;
+    t[3].im = in[2].re - in[3].re; t[2].re = in[2].re + in[3].re;
+    t[3].re = in[2].im - in[3].im; t[2].im = in[2].im + in[3].im;
+    out[d[0] * stride].re = dc.re + t[0].re + t[2].re;
+    out[d[0] * stride].im = dc.im + t[0].im + t[2].im;
+    { const float a = tab[0] * t[2].re - tab[2] * t[0].re, b = tab[0] * t[0].re - tab[2] * t[2].re; t[4].re = a; t[0].re = b; }   /* SMUL */
+    { const float a = tab[0] * t[2].im - tab[2] * t[0].im, b = tab[0] * t[0].im - tab[2] * t[2].im; t[4].im = a; t[0].im = b; }
+    { const float a = tab[4] * t[3].re - tab[6] * t[1].re, b = tab[4] * t[1].re + tab[6] * t[3].re; t[5].re = a; t[1].re = b; }   /* CMUL */
+    { const float a = tab[4] * t[3].im - tab[6] * t[1].im, b = tab[4] * t[1].im + tab[6] * t[3].im; t[5].im = a; t[1].im = b; }
+    z0[0].re = t[0].re - t[1].re; z0[3].re = t[0].re + t[1].re;
+    z0[0].im = t[0].im - t[1].im; z0[3].im = t[0].im + t[1].im;
+    z0[2].re = t[4].re - t[5].re; z0[1].re = t[4].re + t[5].re;
+    z0[2].im = t[4].im - t[5].im; z0[1].im = t[4].im + t[5].im;
+    out[d[1] * stride].re = dc.re + z0[3].re; out[d[1] * stride].im = dc.im + z0[0].im;
+    out[d[2] * stride].re = dc.re + z0[2].re; out[d[2] * stride].im = dc.im + z0[1].im;
+    out[d[3] * stride].re = dc.re + z0[1].re; out[d[3] * stride].im = dc.im + z0[2].im;
+    out[d[4] * stride].re = dc.re + z0[0].re; out[d[4] * stride].im = dc.im + z0[3].im;
+}
+
+/* fft15 (tx_template.c:465-476) */
+static void pfa_fft15(const float *tab, cpx *out, const cpx *in, int stride)
+{
+    static const int m1[5] = { 0, 6, 12, 3, 9 }, m2[5] = { 10, 1, 7, 13, 4 }, m3[5] = { 5, 11, 2, 8, 14 };
+    cpx tmp[15];
+    for (int i = 0; i < 5; i++) pfa_fft3(tab, tmp + i, in + i * 3, 5);
+    pfa_fft5(tab, out, tmp + 0, stride, m1);
+    pfa_fft5(tab, out, tmp + 5, stride, m2);
+    pfa_fft5(tab, out, tmp + 10, stride, m3);
+}
+
+static void fft_ns(OrcTx *t, int k, cpx *d, const cpx *s);
+
+/* ff_tx_mdct_pfa_15xM_inv (DECL_COMP_IMDCT, tx_template.c:1471-1511): len floats with a stride in, len/2 complex (= len floats) out */
+static void run_mdct_pfa_inv(OrcTx *t, float *out, const float *in, ptrdiff_t stride)
+{
+    cpx *z = (cpx *)out, f15[15];
+    const cpx *e = t->exp;
+    const int len4 = t->len >> 2, len2 = t->len >> 1, m = t->pfa_m;
+    const int *in_map = t->pfa_in, *sub_map = t->pfa_sub;
+    const float *in1 = in, *in2 = in + ((15 * m * 2) - 1) * stride;
+    for (int i = 0; i < len2; i += 15) {
+        for (int j = 0; j < 15; j++) {
+            const int k = in_map[j];
+            const float are = in2[-k * stride], aim = in1[k * stride];
+            f15[j].re = are * e[j].re - aim * e[j].im;                  /* CMUL3 */
+            f15[j].im = are * e[j].im + aim * e[j].re;
+        }
+        pfa_fft15(t->tab53, t->pfa_tmp + *(sub_map++), f15, m);
+        e += 15; in_map += 15;
+    }
+    for (int i = 0; i < 15; i++) fft_ns(t, ilog2i(m), t->pfa_tmp + m * i, t->pfa_tmp + m * i);
+    for (int i = 0; i < len4; i++) {
+        const int i0 = len4 + i, i1 = len4 - i - 1, s0 = t->pfa_out[i0], s1 = t->pfa_out[i1];
+        const cpx src1 = { t->pfa_tmp[s1].im, t->pfa_tmp[s1].re }, src0 = { t->pfa_tmp[s0].im, t->pfa_tmp[s0].re };
+        z[i1].re = src1.re * e[i1].im - src1.im * e[i1].re;
+        z[i0].im = src1.re * e[i1].re + src1.im * e[i1].im;
+        z[i0].re = src0.re * e[i0].im - src0.im * e[i0].re;
+        z[i1].im = src0.re * e[i0].re + src0.im * e[i0].im;
+    }
+}
+
+/* ff_tx_mdct_pfa_15xM_fwd (DECL_COMP_MDCT, tx_template.c:1533-1579): 2*len floats in, len floats with a stride out */
+static void run_mdct_pfa_fwd(OrcTx *t, float *dst, const float *src, ptrdiff_t stride)
+{
+    cpx f15[15];
+    const cpx *e = t->exp;
+    const int m = t->pfa_m, len4 = 15 * m, len3 = len4 * 3, len8 = t->len >> 2;
+    const int *in_map = t->pfa_in, *sub_map = t->pfa_sub;
+    for (int i = 0; i < m; i++) {
+        for (int j = 0; j < 15; j++) {
+            const int k = in_map[i * 15 + j];
+            float re, im;
+            if (k < len4) { re = -src[len4 + k] + src[1 * len4 - 1 - k]; im = -src[len3 + k] + -src[1 * len3 - 1 - k]; }
+            else          { re = -src[len4 + k] + -src[5 * len4 - 1 - k]; im = src[-len4 + k] + -src[1 * len3 - 1 - k]; }
+            f15[j].im = re * e[k >> 1].re - im * e[k >> 1].im;
+            f15[j].re = re * e[k >> 1].im + im * e[k >> 1].re;
+        }
+        pfa_fft15(t->tab53, t->pfa_tmp + sub_map[i], f15, m);
+    }
+    for (int i = 0; i < 15; i++) fft_ns(t, ilog2i(m), t->pfa_tmp + m * i, t->pfa_tmp + m * i);
+    for (int i = 0; i < len8; i++) {
+        const int i0 = len8 + i, i1 = len8 - i - 1, s0 = t->pfa_out[i0], s1 = t->pfa_out[i1];
+        const cpx src1 = t->pfa_tmp[s1], src0 = t->pfa_tmp[s0];
+        dst[2 * i1 * stride + stride] = src0.re * e[i0].im - src0.im * e[i0].re;
+        dst[2 * i0 * stride]          = src0.re * e[i0].re + src0.im * e[i0].im;
+        dst[2 * i0 * stride + stride] = src1.re * e[i1].im - src1.im * e[i1].re;
+        dst[2 * i1 * stride]          = src1.re * e[i1].re + src1.im * e[i1].im;
+    }
+}
+
 OrcTx *orc_tx_open(int type, int inv, int len, float scale, unsigned flags)
 {
+    if (!flags && type == 1 && len >= 60 && len % 30 == 0 && !(((len / 30)) & ((len / 30) - 1)))
+        return open_mdct_pfa15(inv, len, scale);
     if (flags || (type != 0 && type != 1 && type != 6) || len < 2 || (len & (len - 1))) return NULL;
     if (type == 6 && len < 4) return NULL;                     /* ff_tx_rdft_*_def: min_len 4 */
     OrcTx *t = calloc(1, sizeof(*t));
@@ -199,7 +379,8 @@ void orc_tx_close(OrcTx *t)
 {
     if (!t) return;
     for (int i = 0; i < 18; i++) free(t->tab[i]);
-    free(t->map); free(t->sub_map); free(t->exp); free(t->rexp); free(t);
+    free(t->map); free(t->sub_map); free(t->exp); free(t->rexp);
+    free(t->pfa_in); free(t->pfa_out); free(t->pfa_sub); free(t->pfa_tmp); free(t);
 }
 
 static void run_fft(OrcTx *t, cpx *dst, const cpx *src)
@@ -313,6 +494,8 @@ void orc_tx_run(OrcTx *t, void *out, void *in, ptrdiff_t stride, int count, ptrd
         void *o = (uint8_t *)out + c * out_step, *i = (uint8_t *)in + c * in_step;
         if (t->type == 0) run_fft(t, o, i);
         else if (t->type == 6) run_rdft(t, o, i);
+        else if (t->pfa_m && t->inv) run_mdct_pfa_inv(t, o, i, stride / (ptrdiff_t)sizeof(float));
+        else if (t->pfa_m) run_mdct_pfa_fwd(t, o, i, stride / (ptrdiff_t)sizeof(float));
         else if (t->inv) run_mdct_inv(t, o, i, stride / (ptrdiff_t)sizeof(float));
         else run_mdct_fwd(t, o, i, stride / (ptrdiff_t)sizeof(float));
     }

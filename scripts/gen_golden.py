@@ -139,6 +139,24 @@ def gen_sws_rgbsrc():
     open(os.path.join(OUT, "sws_rgbsrc_hashes.txt"), "w").write("\n".join(lines) + "\n")
 
 
+def gen_tx_pfa():
+    """compound 15 x M float MDCT (Opus CELT sizes): the reference's outputs, inverse and forward, two scales."""
+    R = cl.ref()
+    d = {}
+    rng = np.random.default_rng(77)
+    for n in (120, 240, 480, 960):
+        for inv in (1, 0):
+            x = (rng.random((2, n if inv else 2 * n), dtype=np.float32) * 2 - 1).astype(np.float32)
+            d[f"in_{n}_{inv}"] = x
+            for j, sc in enumerate((1.0 / n, -1.0)):
+                h = R.ffref_tx_open(1, inv, n, sc, 0)
+                out = np.zeros((2, n), np.float32)
+                R.ffref_tx_run(h, out.ctypes.data, x.ctypes.data, 4, 2, out.strides[0], x.strides[0])
+                R.ffref_tx_close(h)
+                d[f"out_{n}_{inv}_{j}"] = out
+    np.savez_compressed(os.path.join(OUT, "tx_pfa.npz"), **d)
+
+
 def gen_sws_fastbil():
     from cases import SWS_FASTBIL_CASES
     lines = []
@@ -446,5 +464,6 @@ if __name__ == "__main__":
     gen_fdsp()
     gen_idct_hbd()
     gen_sws_rgbsrc()
+    gen_tx_pfa()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

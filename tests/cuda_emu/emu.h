@@ -14,6 +14,8 @@
 
 struct dim3 { unsigned x, y, z; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
 struct uint4 { unsigned x, y, z, w; };
+struct float2 { float x, y; };
+static inline float2 make_float2(float a, float b) { float2 r = { a, b }; return r; }
 static thread_local dim3 threadIdx, blockIdx, blockDim, gridDim;
 
 #define __global__

@@ -29,7 +29,7 @@ def emu():
             txt = open(os.path.join(src_dir, f)).read()
             for m in re.finditer(r"// \[device-code (\w+)\][^\n]*\n(.*?)// \[/device-code \1\]", txt, re.S):
                 found[m.group(1)] = m.group(2)
-    assert sorted(found) == ["fdsp", "idct_hbd", "sws_new", "sws_nvout", "unquant"], sorted(found)
+    assert sorted(found) == ["fdsp", "idct_hbd", "sws_new", "sws_nvout", "tx_pfa", "unquant"], sorted(found)
     for k, v in found.items():
         open(os.path.join(gen, k + ".inc"), "w").write(v)
     so = os.path.join(gen, "libemu.so")
@@ -184,3 +184,43 @@ def test_emu_unquant(emu):
             assert emu.emu_unquant(variant, C.byref(p), b.ctypes.data, b.shape[0], use_n.ctypes.data if use_n is not None else None,
                                    q.ctypes.data, last.ctypes.data) == 0
             assert np.array_equal(b, cl.orc_unquant(variant, cfg, blocks, use_n, q, last)), (cl.UNQUANT_VARIANTS[variant], seed)
+
+
+def test_emu_tx_mdct_pfa15(emu):
+    """the compound 15 x M MDCT kernels (Opus CELT sizes) with the tables of the library's own host set-up, against the oracle,
+    bit for bit; strided input (inverse) and output (forward), several transforms per launch"""
+    import ffmpeg_b200 as fb
+    from test_oracle_more import _tx
+    L, O = fb.lib(), cl.oracle()
+    L.b200_tx_pfa_tables.argtypes = [C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_int, C.c_void_p]
+    emu.emu_tx_pfa.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_longlong,
+                               C.c_longlong, C.c_void_p]
+    rng = np.random.default_rng(11)
+    assert L.b200_tx_pfa_tables(1, 60, 1.0, None, 0, None) < 0 and L.b200_tx_pfa_tables(1, 1024, 1.0, None, 0, None) < 0
+    for n in (120, 240, 480, 960, 1920):
+        for inv in (1, 0):
+            for sc in (1.0 / n, -1.0, -1.0 / 32768):
+                lay = np.zeros(8, np.int32)
+                nw = L.b200_tx_pfa_tables(inv, n, sc, None, 0, lay.ctypes.data)
+                assert nw > 0
+                words = np.zeros(nw, np.int32)
+                assert L.b200_tx_pfa_tables(inv, n, sc, words.ctypes.data, nw, lay.ctypes.data) == nw
+                cnt = 5
+                x = (rng.random((cnt, n if inv else 2 * n), dtype=np.float32) * 2 - 1).astype(np.float32)
+                exp = _tx(O, "orc", 1, inv, n, sc, x, n)
+                out = np.zeros((cnt, n), np.float32)
+                scratch = np.zeros((cnt, n // 2, 2), np.float32)
+                assert emu.emu_tx_pfa(inv, n, words.ctypes.data, lay.ctypes.data, out.ctypes.data, x.ctypes.data, 1, out.strides[0], x.strides[0],
+                                      cnt, scratch.ctypes.data) == 0
+                assert np.array_equal(out.view(np.uint32), exp.view(np.uint32)), (n, inv, sc)
+        # stride 2 floats: the inverse reads every other input float, the forward writes every other output float
+        lay = np.zeros(8, np.int32)
+        nw = L.b200_tx_pfa_tables(1, n, 1.0, None, 0, lay.ctypes.data)
+        words = np.zeros(nw, np.int32)
+        L.b200_tx_pfa_tables(1, n, 1.0, words.ctypes.data, nw, lay.ctypes.data)
+        x = (rng.random((2, n), dtype=np.float32) * 2 - 1).astype(np.float32)
+        xs = np.zeros((2, 2 * n), np.float32)
+        xs[:, ::2] = x
+        out, scratch = np.zeros((2, n), np.float32), np.zeros((2, n // 2, 2), np.float32)
+        emu.emu_tx_pfa(1, n, words.ctypes.data, lay.ctypes.data, out.ctypes.data, xs.ctypes.data, 2, out.strides[0], xs.strides[0], 2, scratch.ctypes.data)
+        assert np.array_equal(out.view(np.uint32), _tx(O, "orc", 1, 1, n, 1.0, x, n).view(np.uint32)), (n, "strided inverse")

@@ -280,3 +280,41 @@ def test_sws_nv_destinations(device):
         ey, euv = cl.orc_sws_planar(w, h, dw, dh, FATE, *frames[i], dst_fmt=cl.PIX_FMT_NV12)
         assert np.array_equal(gy[i], ey) and np.array_equal(guv[i], euv), i
     ctx.free()
+
+
+# ---------------------------------------------------------------------------------------------- tx: compound 15 x M MDCT (Opus CELT)
+def test_tx_mdct_pfa15(device):
+    """av_tx_init(AV_TX_FLOAT_MDCT, 15 * 2^k): host av_tx_fn against the reference's outputs, batched device call against the oracle"""
+    import torch
+    import ffmpeg_b200 as fb
+    from ffmpeg_b200 import tx
+    from test_oracle_more import _tx
+    g = np.load(os.path.join(G, "tx_pfa.npz"))
+    O = cl.oracle()
+    for n in (120, 240, 480, 960):
+        for inv in (1, 0):
+            for j, sc in enumerate((1.0 / n, -1.0)):
+                c = tx.av_tx_init(tx.AV_TX_FLOAT_MDCT, inv, n, scale=sc)
+                x = g[f"in_{n}_{inv}"]
+                out = np.zeros((x.shape[0], n), np.float32)
+                for r in range(x.shape[0]):
+                    c.fn(out[r], x[r].copy(), 4)
+                assert np.array_equal(out.view(np.uint32), g[f"out_{n}_{inv}_{j}"].view(np.uint32)), (n, inv, j)
+                c.uninit()
+    rng = np.random.default_rng(21)
+    for n in (120, 960, 1920):
+        for inv in (1, 0):
+            cnt = 3000
+            x = (rng.random((cnt, n if inv else 2 * n), dtype=np.float32) * 2 - 1).astype(np.float32)
+            c = tx.av_tx_init(tx.AV_TX_FLOAT_MDCT, inv, n, scale=1.0 / n, device=device)
+            with on_stream(device):
+                di, do = torch.from_numpy(x).cuda(), torch.zeros((cnt, n), dtype=torch.float32, device="cuda")
+                c.batch_device(do, di, 4, cnt, 4 * n, x.strides[0])
+                device.sync()
+                got = do.cpu().numpy()
+            assert np.array_equal(got.view(np.uint32), _tx(O, "orc", 1, inv, n, 1.0 / n, x, n).view(np.uint32)), (n, inv)
+            c.uninit()
+    with pytest.raises(fb.B200Error):
+        tx.av_tx_init(tx.AV_TX_FLOAT_MDCT, 1, 60, scale=1.0)            # 15 x 2: below the smallest sub-transform carried
+    with pytest.raises(fb.B200Error):
+        tx.av_tx_init(tx.AV_TX_FLOAT_FFT, 0, 960)                       # compound FFTs are not built
