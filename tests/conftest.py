@@ -9,17 +9,19 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with `-m gpu`)")
-    config.addinivalue_line("markers", "hw_unverified: GPU test of a kernel written after the round's GPU budget ran out; it has "
-                            "never run on hardware, so it only runs with B200_RUN_UNVERIFIED=1 (first thing next round)")
+    config.addinivalue_line("markers", "hw_unverified: GPU test of a kernel written after the round's GPU budget ran out: its device code has "
+                            "only run under the host emulation (tests/test_cuda_emu.py).  Such tests live in the file that sorts last, "
+                            "run as non-strict expected failures (their hardware result is recorded as XPASS / XFAIL without deciding the "
+                            "tier's status) and become ordinary tests with B200_RUN_UNVERIFIED=1")
 
 
 def pytest_collection_modifyitems(config, items):
     if os.environ.get("B200_RUN_UNVERIFIED") == "1":
         return
-    skip = pytest.mark.skip(reason="kernel not yet run on hardware (written without GPU access); set B200_RUN_UNVERIFIED=1")
     for item in items:
         if "hw_unverified" in item.keywords:
-            item.add_marker(skip)
+            item.add_marker(pytest.mark.xfail(strict=False, reason="first hardware run of this kernel (host-emulation verified only)"))
+            item.add_marker(pytest.mark.timeout(600))
 
 
 @pytest.fixture(scope="session")

@@ -1,8 +1,13 @@
-"""GPU tier, NOT YET RUN ON HARDWARE: kernels written after round 1's GPU budget was spent.
-Their oracles are pinned to the compiled reference on CPU (tests/test_oracle_more.py); these tests compare the CUDA path with
-the oracle and the reference-generated fixtures and are skipped unless B200_RUN_UNVERIFIED=1 (tests/conftest.py) — to be run,
-fixed if needed and un-gated at the start of the next round."""
+"""GPU tier, NOT YET RUN ON HARDWARE when committed: kernels written after round 1's GPU budget was spent.
+Their oracles are pinned to the compiled reference on CPU (tests/test_oracle*.py) and their device code runs bit-identically to the
+oracle under the host emulation (tests/test_cuda_emu.py).  These tests compare the CUDA path with the oracle and the
+reference-generated fixtures.  The file sorts last and its tests run as non-strict expected failures (tests/conftest.py): the first
+hardware result is recorded (XPASS / XFAIL) without deciding the status of the tier, and a fault here cannot disturb the verified
+tests before it.  B200_RUN_UNVERIFIED=1 turns them into ordinary tests."""
+import functools
 import os
+import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -11,6 +16,21 @@ import cpulibs as cl
 
 pytestmark = [pytest.mark.gpu, pytest.mark.hw_unverified]
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def isolated(fn):
+    """Run the test body in a child pytest process: the function tables of the library abort() on a CUDA error (like the void C
+    functions they replace cannot report one), and a faulting kernel poisons its CUDA context — neither may take the tier down."""
+    @functools.wraps(fn)
+    def wrapper(device):
+        if os.environ.get("B200_ISOLATED_CHILD") == "1":
+            return fn(device)
+        env = dict(os.environ, B200_ISOLATED_CHILD="1", B200_RUN_UNVERIFIED="1")
+        r = subprocess.run([sys.executable, "-m", "pytest", f"{os.path.abspath(__file__)}::{fn.__name__}", "-m", "gpu", "-q", "-x",
+                            "-p", "no:cacheprovider"], env=env, capture_output=True, text=True, timeout=900,
+                           cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        assert r.returncode == 0, "child run failed:\n" + r.stdout[-4000:] + r.stderr[-2000:]
+    return wrapper
 
 
 def on_stream(device):
@@ -33,6 +53,7 @@ def gpu_unquant(device, variant, cfg, blocks, blk_n, q, last):
         return db.cpu().numpy()
 
 
+@isolated
 def test_unquant_golden_and_oracle(device):
     g = np.load(os.path.join(G, "unquant.npz"))
     for variant in range(7):
@@ -47,6 +68,7 @@ def test_unquant_golden_and_oracle(device):
             assert np.array_equal(out, cl.orc_unquant(variant, cfg, blocks, use_n, q, last)), (cl.UNQUANT_VARIANTS[variant], seed)
 
 
+@isolated
 def test_unquant_errors(device):
     import torch
     import ffmpeg_b200 as fb
@@ -66,6 +88,7 @@ def test_unquant_errors(device):
 
 
 # ---------------------------------------------------------------------------------------------- AVFloatDSPContext
+@isolated
 def test_fdsp_pointer_table_golden(device):
     """AVFloatDSPContext entries called with host pointers, against the reference's outputs (fdsp.npz), bit for bit"""
     import ctypes as C
@@ -95,6 +118,7 @@ def test_fdsp_pointer_table_golden(device):
             assert got.tobytes() == g[f"op{op}_n{length}"].tobytes(), (name, length)
 
 
+@isolated
 def test_fdsp_batch_vs_oracle(device):
     """batched device entry point: many vectors, shared window / operand (stride 0), odd lengths, more than 65535 vectors"""
     import torch
@@ -136,6 +160,7 @@ def gpu_idct_hbd(device, depth, kind, blocks, dest):
         return db.cpu().numpy(), dd.cpu().numpy().view(np.uint16)
 
 
+@isolated
 def test_idct_hbd_golden_and_oracle(device):
     g = np.load(os.path.join(G, "idct_hbd.npz"))
     for depth in (10, 12):
@@ -154,6 +179,7 @@ def test_idct_hbd_golden_and_oracle(device):
             assert np.array_equal(o, eo) and (kind != 0 or np.array_equal(b, eb)), (depth, kind)
 
 
+@isolated
 def test_idct_hbd_pointer_table(device):
     """IDCTDSPContext for bits_per_raw_sample 9 / 10 / 12 called with host pointers"""
     import ctypes as C
@@ -179,6 +205,7 @@ def test_idct_hbd_pointer_table(device):
 
 
 # ---------------------------------------------------------------------------------------------- swscale: packed RGB sources
+@isolated
 def test_sws_rgb_sources_golden_and_oracle(device):
     """rgb24 / bgr24 / rgba / bgra / argb / abgr -> yuv420p (input readers fused into the horizontal pass, the bgr24 -> yv12
     converter, range conversion behind them) against the reference's outputs and the oracle"""
@@ -194,6 +221,7 @@ def test_sws_rgb_sources_golden_and_oracle(device):
         assert sha(got) == row[-1], row[:6]
 
 
+@isolated
 def test_sws_rgb_sources_large_padded_batch(device):
     import torch
     import ffmpeg_b200 as fb
@@ -233,6 +261,7 @@ def test_sws_rgb_sources_large_padded_batch(device):
 
 
 # ---------------------------------------------------------------------------------------------- swscale: nv12 / nv21 destinations
+@isolated
 def test_sws_nv_destinations(device):
     """nv12 / nv21 as the destination (the layout NVENC reads) from planar, semi-planar and packed RGB sources, against the oracle;
     then FATE's own md5 sums for these formats (null, copy, vflip, hflip, crop, scale, pixdesc) on the CUDA path's frames"""
@@ -283,6 +312,7 @@ def test_sws_nv_destinations(device):
 
 
 # ---------------------------------------------------------------------------------------------- tx: compound 15 x M MDCT (Opus CELT)
+@isolated
 def test_tx_mdct_pfa15(device):
     """av_tx_init(AV_TX_FLOAT_MDCT, 15 * 2^k): host av_tx_fn against the reference's outputs, batched device call against the oracle"""
     import torch
