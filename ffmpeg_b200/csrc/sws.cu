@@ -923,11 +923,6 @@ B200_API B200SwsContext *b200_sws_getContext_range(B200Device *dev, int srcW, in
         delete c;
         return nullptr;
     }
-    if (c->plan.src_rgb && !sws_out_is_yuv(out.kind)) {
-        b200_set_error("b200_sws_getContext: packed RGB source -> packed RGB destination is not implemented on the device yet");
-        delete c;
-        return nullptr;
-    }
     c->dev = dev;
     c->plan.out = out;
     int ret = sws_plan_build(c->plan, srcW, srcH, dstW, dstH, flags, srcRange, dstRange);
@@ -1276,6 +1271,77 @@ static int launch_batch(B200SwsContext *c, cudaStream_t stream, const uint8_t *c
     return 0;
 }
 
+// packed RGB source -> packed RGB destination (always through the scaler: the same-size case is the reference's rgb2rgb shuffle and
+// is refused at context creation): input readers + 16-bit horizontal pass into the int16 line planes, then the same vertical
+// writers as the yuv-source scaled path (the stage after the horizontal pass in launch_batch)
+static int launch_rgbsrc_packed(B200SwsContext *c, cudaStream_t stream, const uint8_t *src, long long sstr, long long sfs,
+                                uint8_t *dst, long long ds, long long dfs, int nframes)
+{
+    const SwsPlan &p = c->plan;
+    if (nframes <= 0) return 0;
+    RgbIn Rg;
+    Rg.bpp = p.src_rgb; Rg.ro = p.sro; Rg.go = p.sgo; Rg.bo = p.sbo; Rg.half = p.chrSrcHSub;
+    for (int i = 0; i < 9; i++) Rg.c[i] = p.rgb2yuv[i];
+    const size_t lumPlane = (size_t)p.srcH * p.dstW * 2, chrPlane = (size_t)p.chrSrcH * p.chrDstW * 2;
+    const size_t perFrame = ((lumPlane + 2 * chrPlane) + 255) & ~(size_t)255;
+    long long chunk = (long long)((size_t)(512u << 20) / perFrame);
+    if (chunk < 1) chunk = 1;
+    if (chunk > nframes) chunk = nframes;
+    if (chunk > 65535) chunk = 65535;
+    const size_t need = perFrame * (size_t)chunk;
+    if (c->mid_bytes < need) {
+        if (c->mid) { cudaStreamSynchronize(stream); cudaFree(c->mid); c->mid = nullptr; c->mid_bytes = 0; }
+        B200_CUDA_OK(cudaMalloc(&c->mid, need));
+        c->mid_bytes = need;
+    }
+    int16_t *mY = (int16_t *)c->mid;
+    int16_t *mU = (int16_t *)((uint8_t *)c->mid + lumPlane);
+    int16_t *mV = (int16_t *)((uint8_t *)c->mid + lumPlane + chrPlane);
+    const long long mfs = (long long)(perFrame / 2);
+    for (long long f0 = 0; f0 < nframes; f0 += chunk) {
+        const int nf = (int)(nframes - f0 < chunk ? nframes - f0 : chunk);
+        const uint8_t *s = src + f0 * sfs;
+        uint8_t *d = dst + f0 * dfs;
+        dim3 block(256);
+        sws_rgbin_hscale_y_kernel<<<dim3(b200_ceil_div(p.dstW, 256), p.srcH, nf), block, 0, stream>>>(s, sstr, sfs, mY, p.dstW, mfs, c->dt.hLum, c->dt.hLumPos,
+                                                                                                        c->dt.hLumSize, Rg);
+        B200_LAUNCHED();
+        sws_rgbin_hscale_uv_kernel<<<dim3(b200_ceil_div(p.chrDstW, 256), p.chrSrcH, nf), block, 0, stream>>>(s, sstr, sfs, mU, mV, p.chrDstW, mfs, c->dt.hChr,
+                                                                                                               c->dt.hChrPos, c->dt.hChrSize, Rg);
+        B200_LAUNCHED();
+        SwsFrameArgs m{};
+        m.y = (const uint8_t *)mY; m.u = (const uint8_t *)mU; m.v = (const uint8_t *)mV;
+        m.ys = (long long)p.dstW * 2; m.us = m.vs = (long long)p.chrDstW * 2;
+        m.yfs = m.ufs = m.vfs = (long long)perFrame;
+        m.dst = d; m.ds = ds; m.dfs = dfs;
+        m.srcH = p.srcH; m.chrSrcH = p.chrSrcH; m.dstW = p.dstW; m.dstH = p.dstH; m.chrDstW = p.chrDstW;
+        m.y0 = 0;
+        m.bpp = p.out.bpp; m.ro = p.out.ro; m.go = p.out.go; m.bo = p.out.bo; m.ao = p.out.ao;
+        if (p.chrDstHSub && c->all_x && p.dstW % 8 == 0 && aligned16(d, ds, dfs) && lumPlane % 16 == 0 && chrPlane % 8 == 0) {
+            const int ng = p.dstW / 8;
+            dim3 block2(128), grid(b200_ceil_div(ng, 128), p.dstH, nf);
+            switch (p.out.kind) {
+            case SWS_OUT_RGB24: sws_vscale_rgb24_x8_kernel<SWS_OUT_RGB24><<<grid, block2, 0, stream>>>(m, c->dt, p.color, ng); break;
+            case SWS_OUT_BGR24: sws_vscale_rgb24_x8_kernel<SWS_OUT_BGR24><<<grid, block2, 0, stream>>>(m, c->dt, p.color, ng); break;
+            case SWS_OUT_RGBA:  sws_vscale_rgb24_x8_kernel<SWS_OUT_RGBA><<<grid, block2, 0, stream>>>(m, c->dt, p.color, ng); break;
+            case SWS_OUT_BGRA:  sws_vscale_rgb24_x8_kernel<SWS_OUT_BGRA><<<grid, block2, 0, stream>>>(m, c->dt, p.color, ng); break;
+            case SWS_OUT_ARGB:  sws_vscale_rgb24_x8_kernel<SWS_OUT_ARGB><<<grid, block2, 0, stream>>>(m, c->dt, p.color, ng); break;
+            default:            sws_vscale_rgb24_x8_kernel<SWS_OUT_ABGR><<<grid, block2, 0, stream>>>(m, c->dt, p.color, ng); break;
+            }
+        } else if (p.chrDstHSub) {
+            const int np = (p.dstW + 1) / 2;
+            dim3 block2(128), grid(b200_ceil_div(np, 128), p.dstH, nf);
+            sws_vscale_rgb24_slow_kernel<false><<<grid, block2, 0, stream>>>(m, c->dt, p.color, 0, np);
+        } else {
+            dim3 block2(256), grid(b200_ceil_div(p.dstW, 256), p.dstH, nf);
+            sws_vscale_rgb24_full_kernel<<<grid, block2, 0, stream>>>(m, c->dt, p.color);
+        }
+        B200_LAUNCHED();
+    }
+    B200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 B200_API int b200_sws_scale_batch_device(B200SwsContext *c, const uint8_t *const src[3], const int srcStride[3],
                                          const int64_t srcFrameStride[3], uint8_t *dst, int dstStride,
                                          int64_t dstFrameStride, int nframes)
@@ -1283,6 +1349,10 @@ B200_API int b200_sws_scale_batch_device(B200SwsContext *c, const uint8_t *const
     if (!c || !src || !srcStride || !srcFrameStride || !dst) return B200_EINVAL;
     if (c->plan.planar) return B200_EINVAL;                   // three destination planes: b200_sws_scale_batch_device_planar
     B200_CUDA_OK(cudaSetDevice(c->dev->ordinal));
+    if (c->plan.src_rgb) {                                    // packed source: plane 0 only
+        if (!src[0] || srcStride[0] < 0 || dstStride < 0) return B200_EINVAL;
+        return launch_rgbsrc_packed(c, c->dev->stream, src[0], srcStride[0], srcFrameStride[0], dst, dstStride, dstFrameStride, nframes);
+    }
     const bool nv = c->plan.src_nv != 0;                      // nv12 / nv21: src[2] and its strides are not read
     const long long ss[3] = { srcStride[0], srcStride[1], nv ? 0 : srcStride[2] };
     const long long fs[3] = { srcFrameStride[0], srcFrameStride[1], nv ? 0 : srcFrameStride[2] };
@@ -1521,6 +1591,7 @@ B200_API int b200_sws_scale_batch_host(B200SwsContext *c, const uint8_t *const s
 {
     if (!c || !src || !srcStride || !srcFrameStride || !dst || nframes < 0) return B200_EINVAL;
     if (c->plan.planar) return B200_EINVAL;
+    if (c->plan.src_rgb) { b200_set_error("b200_sws_scale_batch_host: packed RGB sources are not wired into this entry point"); return B200_ENOSYS; }
     B200Device *d = c->dev;
     B200_CUDA_OK(cudaSetDevice(d->ordinal));
     const SwsPlan &p = c->plan;
@@ -1644,6 +1715,24 @@ B200_API int b200_sws_scale(B200SwsContext *c, const uint8_t *const srcSlice[], 
     if (!c || !srcSlice || !srcStride || !dst || !dstStride) return B200_EINVAL;
     const SwsPlan &p = c->plan;
     if (p.planar) return sws_scale_planar_host(c, srcSlice, srcStride, srcSliceY, srcSliceH, dst, dstStride);
+    if (p.src_rgb) {                                              // packed RGB -> packed RGB: whole frames, top-down
+        if (srcSliceY != 0 || srcSliceH != p.srcH) { b200_set_error("packed RGB source: only whole-frame calls are implemented"); return B200_ENOSYS; }
+        if (!srcSlice[0] || !dst[0]) return B200_EINVAL;
+        if (srcStride[0] < 0 || dstStride[0] < 0) return B200_ENOSYS;
+        B200Device *dv = c->dev;
+        B200_CUDA_OK(cudaSetDevice(dv->ordinal));
+        const size_t sPitch = ((size_t)p.srcW * p.src_rgb + 255) & ~(size_t)255, dPitch = ((size_t)p.dstW * p.out.bpp + 255) & ~(size_t)255;
+        uint8_t *scr2 = (uint8_t *)b200_scratch(dv, sPitch * p.srcH + dPitch * p.dstH);
+        if (!scr2) return B200_ENOMEM;
+        cudaStream_t st2 = dv->stream;
+        B200_CUDA_OK(cudaMemcpy2DAsync(scr2, sPitch, srcSlice[0], (size_t)srcStride[0], (size_t)p.srcW * p.src_rgb, p.srcH, cudaMemcpyHostToDevice, st2));
+        uint8_t *dd2 = scr2 + sPitch * p.srcH;
+        const int r2 = launch_rgbsrc_packed(c, st2, scr2, (long long)sPitch, 0, dd2, (long long)dPitch, 0, 1);
+        if (r2 < 0) return r2;
+        B200_CUDA_OK(cudaMemcpy2DAsync(dst[0], (size_t)dstStride[0], dd2, dPitch, (size_t)p.dstW * p.out.bpp, p.dstH, cudaMemcpyDeviceToHost, st2));
+        B200_CUDA_OK(cudaStreamSynchronize(st2));
+        return p.dstH;
+    }
     if (srcSliceY != 0 || srcSliceH != p.srcH)
         return sws_scale_slice(c, srcSlice, srcStride, srcSliceY, srcSliceH, dst, dstStride);
     c->slice_open = false;

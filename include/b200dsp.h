@@ -92,7 +92,8 @@ uint64_t b200_launch_count(void);
 typedef struct B200SwsContext B200SwsContext;
 
 /* like sws_getContext(); srcFilter/dstFilter/param are not supported (must be the defaults). NULL on failure.
- * Sources: yuv420p, nv12, nv21 (-> packed 8-bit RGB or yuv420p) and rgb24 / bgr24 / rgba / bgra / argb / abgr (-> yuv420p; the input
+ * Sources: yuv420p, nv12, nv21 (-> packed 8-bit RGB or yuv420p / nv12 / nv21) and rgb24 / bgr24 / rgba / bgra / argb / abgr (-> yuv420p /
+ * nv12 / nv21, or, when the size changes and alpha is not carried from source to destination, -> packed 8-bit RGB; the input
  * readers of libswscale/input.c:264-393,1068-1172, hScale16To15_c, and the bgr24ToYv12Wrapper special converter,
  * libswscale/swscale_unscaled.c:2453-2457); a packed RGB source is passed as plane 0 (src[1], src[2] unused).
  * Destinations nv12 / nv21 (what NVENC reads) are yuv420p with the chroma planes interleaved: planarToNv12Wrapper

@@ -211,13 +211,13 @@ def test_sws_rgb_sources_golden_and_oracle(device):
     converter, range conversion behind them) against the reference's outputs and the oracle"""
     import functools
     from test_oracle import rgbsrc_rows, run_rgbsrc_row, sha
-    from test_sws_gpu import gpu_sws_planar
-    rows = [r for r in rgbsrc_rows() if r[4] == "yuv420p"]
-    assert len(rows) == 15 * 6 * 2
-    gp = functools.partial(gpu_sws_planar, device)
-    for row in rows:
-        got = run_rgbsrc_row(None, gp, row)
-        assert np.array_equal(got, run_rgbsrc_row(None, cl.orc_sws_planar, row)), row[:6]
+    from test_sws_gpu import gpu_sws_planar, gpu_sws
+    rows = rgbsrc_rows()
+    assert len(rows) == 15 * 6 * 2 + 11 * 2
+    gp, gr = functools.partial(gpu_sws_planar, device), functools.partial(gpu_sws, device)
+    for row in rows:                                                    # -> yuv420p, and -> rgb24 through the scaler for rgb24 / bgr24
+        got = run_rgbsrc_row(gr, gp, row)
+        assert np.array_equal(got, run_rgbsrc_row(cl.orc_sws, cl.orc_sws_planar, row)), row[:6]
         assert sha(got) == row[-1], row[:6]
 
 
@@ -256,8 +256,26 @@ def test_sws_rgb_sources_large_padded_batch(device):
             for k in range(3):
                 assert np.array_equal(got[k][i], exp[k]), (name, i, k)
         ctx.free()
-    with pytest.raises(fb.B200Error):                                  # packed RGB -> packed RGB is not on the device yet
-        sw.sws_getContext(device, 64, 48, sw.AV_PIX_FMT_RGB24, 32, 24, sw.AV_PIX_FMT_BGR24, FATE)
+    # packed RGB -> packed RGB through the scaler: batched device entry point, other destination orders
+    w, h, dw, dh, n = 320, 180, 200, 100, 3
+    frames = [cl.rgb_frame(w, h, 2450 + k, 3) for k in range(n)]
+    for dname in ("bgr24", "rgba", "argb"):
+        df = cl.PACKED_RGB_FORMATS[dname]
+        bpp = cl.fmt_bpp(df)
+        ctx = sw.sws_getContext(device, w, h, sw.AV_PIX_FMT_RGB24, dw, dh, df, FATE)
+        with torch.cuda.stream(torch.cuda.ExternalStream(device.stream)):
+            S = torch.from_numpy(np.stack(frames)).cuda()
+            D = torch.zeros((n, dh, dw * bpp), dtype=torch.uint8, device="cuda")
+            ctx.scale_batch_device([S], [w * 3], [w * 3 * h], D, dw * bpp, dw * bpp * dh, n)
+            device.sync()
+            got = D.cpu().numpy()
+        for i in range(n):
+            assert np.array_equal(got[i], cl.orc_sws(w, h, dw, dh, FATE, frames[i], frames[i], frames[i], fmt=df, src_fmt=cl.PIX_FMT_RGB24)), (dname, i)
+        ctx.free()
+    with pytest.raises(fb.B200Error):                                  # same size: the reference's rgb2rgb shuffles, not this path
+        sw.sws_getContext(device, 64, 48, sw.AV_PIX_FMT_RGB24, 64, 48, sw.AV_PIX_FMT_BGR24, FATE)
+    with pytest.raises(fb.B200Error):                                  # alpha carried through the scaler: not built
+        sw.sws_getContext(device, 64, 48, sw.AV_PIX_FMT_RGBA, 32, 24, sw.AV_PIX_FMT_BGRA, FATE)
 
 
 # ---------------------------------------------------------------------------------------------- swscale: nv12 / nv21 destinations
@@ -288,7 +306,7 @@ def test_sws_nv_destinations(device):
             out = gpu_sws_planar(device, 640, 360, dw, dh, FATE, y, uv, uv, src_fmt=cl.PIX_FMT_NV12, dst_fmt=df)
             exp = cl.orc_sws_planar(640, 360, dw, dh, FATE, y, uv, uv, src_fmt=cl.PIX_FMT_NV12, dst_fmt=df)
             assert all(np.array_equal(p, q) for p, q in zip(out, exp)), ("nv12 source", dw, df)
-    fg.check_all(functools.partial(gpu_sws, device), functools.partial(gpu_sws_planar, device), rgb_sources=False, nv_dest=True)
+    fg.check_all(functools.partial(gpu_sws, device), functools.partial(gpu_sws_planar, device), rgb_sources=True, nv_dest=True)     # all 59 FATE sums
     # the encoder feed: bgra 1080p -> nv12 (packed RGB source kernels too), and the batched device entry point with two destination planes
     src = cl.rgb_frame(1920, 1080, 2900, 4)
     out = gpu_sws_planar(device, 1920, 1080, 1920, 1080, FATE, src, src, src, src_fmt=cl.PIX_FMT_BGRA, dst_fmt=cl.PIX_FMT_NV12)
