@@ -44,6 +44,53 @@ def vp(a):
     return C.c_void_p(a.ctypes.data) if a is not None else None
 
 
+WARP_KERNELS = {"mpv_unquant_kernel"}                   # kernels that use a warp collective: one OS thread per lane
+
+
+def rewrite_launches(txt):
+    """`kernel<<<grid, block, smem, stream>>>(args)` -> a call of emu_cfg_launch() (tests/cuda_emu/fake/cuda_runtime.h)"""
+    out, i = [], 0
+    pat = re.compile(r"([A-Za-z_]\w*(?:<[^;<>()]*>)?)\s*<<<(.*?)>>>\s*\(")
+    while True:
+        m = pat.search(txt, i)
+        if not m:
+            out.append(txt[i:])
+            break
+        out.append(txt[i:m.start()])
+        j, depth = m.end(), 1
+        while depth:
+            depth += (txt[j] == "(") - (txt[j] == ")")
+            j += 1
+        kern, cfg, args = m.group(1), m.group(2), txt[m.end():j - 1]
+        warp = "true" if re.match(r"\w+", kern).group(0) in WARP_KERNELS else "false"
+        out.append(f"emu_cfg_launch({warp}, [&] {{ {kern}({args}); }}, {cfg})")
+        i = j
+    return "".join(out)
+
+
+@pytest.fixture(scope="module")
+def emuhost():
+    """libemuhost.so: the translation units without inline PTX (fdsp, unquant, idct_hbd, tx_pfa), HOST CODE INCLUDED, compiled with
+    g++ against a stand-in CUDA runtime (tests/cuda_emu/fake/cuda_runtime.h): the library's own entry points run on the CPU"""
+    gen = os.path.join(EMU, "_gen")
+    os.makedirs(gen, exist_ok=True)
+    cs = os.path.join(ROOT, "ffmpeg_b200", "csrc")
+    srcs = []
+    for f in ("fdsp.cu", "unquant.cu", "idct_hbd.cu", "tx_pfa.cu"):
+        t = rewrite_launches(open(os.path.join(cs, f)).read())
+        assert "<<<" not in t
+        p = os.path.join(gen, "host_" + f[:-3] + ".cpp")
+        open(p, "w").write(t)
+        srcs.append(p)
+    so = os.path.join(gen, "libemuhost.so")
+    cxx = "/opt/gcc/bin/g++" if os.path.exists("/opt/gcc/bin/g++") else "g++"
+    r = subprocess.run([cxx, "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread", "-ffp-contract=off", "-w", "-I" + os.path.join(EMU, "fake"), "-I" + cs,
+                        "-I" + os.path.join(ROOT, "include"), "-I" + EMU] + srcs + [os.path.join(EMU, "fake_device.cpp"), "-o", so],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    return C.CDLL(so)
+
+
 def plan(cfg, details=None):
     """(info48, [filter banks (coef int16 [n, size], pos int32 [n])]) from the product's host set-up, no GPU"""
     import ffmpeg_b200 as fb
@@ -224,3 +271,125 @@ def test_emu_tx_mdct_pfa15(emu):
         out, scratch = np.zeros((2, n), np.float32), np.zeros((2, n // 2, 2), np.float32)
         emu.emu_tx_pfa(1, n, words.ctypes.data, lay.ctypes.data, out.ctypes.data, xs.ctypes.data, 2, out.strides[0], xs.strides[0], 2, scratch.ctypes.data)
         assert np.array_equal(out.view(np.uint32), _tx(O, "orc", 1, 1, n, 1.0, x, n).view(np.uint32)), (n, "strided inverse")
+
+
+# ------------------------------------------------------------------ the library's own host code on the stand-in runtime
+def test_host_float_dsp_entry_points(emuhost):
+    """b200_float_dsp_batch_device (strides, shared operand, more vectors than one grid holds, argument checks) and the
+    AVFloatDSPContext function table (host pointers: copy in, launch, copy out), all through the library's real code"""
+    from ffmpeg_b200._lib import FloatDSPContext
+    L = emuhost
+    L.b200_float_dsp_batch_device.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                              C.c_void_p, C.c_int64, C.c_double]
+    for op in range(12):
+        for length, nvec in ((64, 5), (9, 3), (4, 66000 if op in (0, 9) else 7)):
+            dt = np.float64 if op in cl.FDSP_DOUBLE else np.float32
+            n2 = 2 * length if op == 5 else length
+            cases = [cl.fdsp_case(900 + op * 17 + v, op, length) for v in range(min(nvec, 6))]
+            idx = np.arange(nvec) % len(cases)
+            dst, s0, s1 = (np.stack([cases[i][k] for i in idx]) for k in range(3))
+            s2, mul = cases[0][3], cases[0][4]
+            dot = op in (9, 11)
+            d = np.zeros(nvec, dt) if dot else dst.copy()
+            a = s0.copy()
+            assert L.b200_float_dsp_batch_device(None, op, nvec, length, d.ctypes.data, 1 if dot else n2, a.ctypes.data, length, s1.ctypes.data, length,
+                                                 s2.ctypes.data, 0, mul) == 0
+            exp = [cl.orc_fdsp(op, c[0], c[1], c[2], s2, mul, length) for c in cases]
+            for v in range(nvec):
+                e, e0 = exp[idx[v]]
+                assert (d[v:v + 1] if dot else d[v]).tobytes() == e.tobytes() and a[v].tobytes() == e0.tobytes(), (cl.FDSP_OPS[op], length, v)
+    x = np.zeros(8, np.float32)
+    assert L.b200_float_dsp_batch_device(None, 12, 1, 8, x.ctypes.data, 8, x.ctypes.data, 8, x.ctypes.data, 8, None, 0, 0.0) < 0       # unknown op
+    assert L.b200_float_dsp_batch_device(None, 6, 1, 8, x.ctypes.data, 8, x.ctypes.data, 8, x.ctypes.data, 8, None, 0, 0.0) < 0        # fmul_add needs src2
+    assert L.b200_float_dsp_batch_device(None, 0, 1, 8, x.ctypes.data + 2, 8, x.ctypes.data, 8, x.ctypes.data, 8, None, 0, 0.0) < 0    # misaligned
+    assert L.b200_float_dsp_batch_device(None, 0, 0, 8, None, 8, None, 8, None, 8, None, 0, 0.0) == 0                                 # nothing to do
+    c = FloatDSPContext()
+    assert L.b200_float_dsp_init(C.byref(c)) == 0
+    F, D = C.POINTER(C.c_float), C.POINTER(C.c_double)
+    for op in range(12):
+        P = D if op in cl.FDSP_DOUBLE else F
+        for length in (16, 100):
+            dst, s0, s1, s2, mul = cl.fdsp_case(40 + op, op, length)
+            e, e0 = cl.orc_fdsp(op, dst, s0, s1, s2, mul, length)
+            p = lambda z: z.ctypes.data_as(P)
+            fn = getattr(c, cl.FDSP_OPS[op])
+            if op in (0, 7, 10):
+                fn(p(dst), p(s0), p(s1), length)
+            elif op in (1, 2, 3, 4):
+                fn(p(dst), p(s0), mul, length)
+            elif op in (5, 6):
+                fn(p(dst), p(s0), p(s1), p(s2), length)
+            elif op == 8:
+                fn(p(dst), p(s0), length)
+            else:
+                dst = np.array([fn(p(s0), p(s1), length)], dst.dtype)
+            assert (dst[:1] if op in (9, 11) else dst).tobytes() == e.tobytes() and s0.tobytes() == e0.tobytes(), (cl.FDSP_OPS[op], length)
+
+
+def test_host_unquant_entry_point(emuhost):
+    from ffmpeg_b200._lib import MpvUnquant
+    L = emuhost
+    L.b200_mpv_unquantize_batch_device.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    for variant in range(7):
+        cfg, blocks, blk_n, q, last = cl.unquant_case(1100 + variant, variant, nblocks=37)
+        p = cl.unquant_params(struct=MpvUnquant, **cfg)
+        for use_n in (blk_n, None):
+            b = np.ascontiguousarray(blocks).copy()
+            assert L.b200_mpv_unquantize_batch_device(None, variant, C.byref(p), b.ctypes.data, b.shape[0], use_n.ctypes.data if use_n is not None else None,
+                                                      q.ctypes.data, last.ctypes.data) == 0
+            assert np.array_equal(b, cl.orc_unquant(variant, cfg, blocks, use_n, q, last)), (cl.UNQUANT_VARIANTS[variant], use_n is None)
+    b = np.ascontiguousarray(blocks).copy()
+    assert L.b200_mpv_unquantize_batch_device(None, 7, C.byref(p), b.ctypes.data, 4, None, q.ctypes.data, last.ctypes.data) < 0
+    assert L.b200_mpv_unquantize_batch_device(None, 0, C.byref(p), b.ctypes.data, 0, None, q.ctypes.data, last.ctypes.data) == 0
+    p.permutated[5] = p.permutated[6]
+    assert L.b200_mpv_unquantize_batch_device(None, 0, C.byref(p), b.ctypes.data, 4, None, q.ctypes.data, last.ctypes.data) < 0
+    assert np.array_equal(b, blocks)
+
+
+def test_host_idct_hbd_entry_points(emuhost):
+    from ffmpeg_b200._lib import IDCTDSPContext, u8p, i16p
+    L = emuhost
+    L.b200_idct_hbd_batch_device.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    for depth_arg, depth in ((9, 10), (10, 10), (12, 12)):
+        for kind in (0, 1, 2):
+            n = 70
+            blocks = cl.idct_hbd_blocks(1200 + depth + kind, depth, n)
+            dest = np.random.default_rng(kind).integers(0, 1 << depth, (8, n * 8 + 4), dtype=np.uint16)
+            b, d = blocks.copy(), dest.copy()
+            off = np.arange(n, dtype=np.int64) * 16
+            assert L.b200_idct_hbd_batch_device(None, depth_arg, kind, b.ctypes.data, n, d.ctypes.data, off.ctypes.data, None, dest.strides[0]) == 0
+            eb, ed = cl.orc_idct_hbd(depth, kind, blocks, dest, dest.strides[0])
+            assert np.array_equal(d, ed) and np.array_equal(b, eb if kind == 0 else blocks), (depth_arg, kind)
+        c = IDCTDSPContext()
+        assert L.b200_idctdsp_init_hbd(C.byref(c), 2, depth_arg, 0) == 0
+        blocks = cl.idct_hbd_blocks(depth_arg, depth, 6)
+        dest = np.random.default_rng(depth_arg).integers(0, 1 << depth, (8, 6 * 8 + 3), dtype=np.uint16)
+        for kind in (0, 1, 2):
+            b, d = blocks.copy(), dest.copy()
+            for i in range(6):
+                blk = b[i].ctypes.data_as(i16p)
+                if kind == 0:
+                    c.idct(blk)
+                else:
+                    (c.idct_put if kind == 1 else c.idct_add)(C.cast(d.ctypes.data + 16 * i, u8p), d.strides[0], blk)
+            eb, ed = cl.orc_idct_hbd(depth, kind, blocks, dest, dest.strides[0])
+            assert np.array_equal(d, ed) and (kind != 0 or np.array_equal(b, eb)), (depth_arg, kind, "table")
+    c = IDCTDSPContext()
+    assert L.b200_idctdsp_init_hbd(C.byref(c), 2, 8, 0) < 0 and L.b200_idctdsp_init_hbd(C.byref(c), 2, 10, 1) < 0
+    x = np.zeros(64, np.int16)
+    assert L.b200_idct_hbd_batch_device(None, 11, 0, x.ctypes.data, 1, None, None, None, 0) < 0
+
+
+def test_host_tx_pfa_create_and_launch(emuhost):
+    from test_oracle_more import _tx
+    L, O = emuhost, cl.oracle()
+    L.emu_host_tx_pfa.argtypes = [C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_longlong, C.c_longlong]
+    rng = np.random.default_rng(31)
+    for n in (120, 960):
+        for inv in (1, 0):
+            cnt = 70                                                    # more than one 64-thread block
+            x = (rng.random((cnt, n if inv else 2 * n), dtype=np.float32) * 2 - 1).astype(np.float32)
+            out = np.zeros((cnt, n), np.float32)
+            assert L.emu_host_tx_pfa(inv, n, 1.0 / n, out.ctypes.data, x.ctypes.data, 4, cnt, out.strides[0], x.strides[0]) == 0
+            assert np.array_equal(out.view(np.uint32), _tx(O, "orc", 1, inv, n, 1.0 / n, x, n).view(np.uint32)), (n, inv)
+    assert L.emu_host_tx_pfa(1, 60, 1.0, None, None, 4, 1, 0, 0) < 0
