@@ -14,6 +14,10 @@
 
 struct dim3 { unsigned x, y, z; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
 struct uint4 { unsigned x, y, z, w; };
+struct uint2 { unsigned x, y; };
+struct int2 { int x, y; };
+static inline uint2 make_uint2(unsigned a, unsigned b) { uint2 r = { a, b }; return r; }
+static inline uint4 make_uint4(unsigned a, unsigned b, unsigned c, unsigned d) { uint4 r = { a, b, c, d }; return r; }
 struct float2 { float x, y; };
 static inline float2 make_float2(float a, float b) { float2 r = { a, b }; return r; }
 static thread_local dim3 threadIdx, blockIdx, blockDim, gridDim;
@@ -32,6 +36,44 @@ static inline float  __fmul_rn(float a, float b)   { volatile float r = a * b; r
 static inline float  __fadd_rn(float a, float b)   { volatile float r = a + b; return r; }
 static inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
 static inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
+
+// integer SIMD-in-a-word intrinsics of the swscale kernels, by their PTX definitions
+static inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s)          // PRMT, default mode: nibble n picks byte n of {y,x}; bit 3 = replicate its sign
+{
+    const unsigned long long v = ((unsigned long long)y << 32) | x;
+    unsigned r = 0;
+    for (int i = 0; i < 4; i++) {
+        const unsigned sel = (s >> (4 * i)) & 0xF;
+        unsigned b = (unsigned)(v >> (8 * (sel & 7))) & 0xFF;
+        if (sel & 8) b = (b & 0x80) ? 0xFF : 0x00;
+        r |= b << (8 * i);
+    }
+    return r;
+}
+static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned sh)   // SHF.R.WRAP: low word of {hi,lo} >> (sh & 31)
+{
+    return (unsigned)(((((unsigned long long)hi) << 32) | lo) >> (sh & 31));
+}
+static inline int __vimin_s32_relu(int a, int b) { const int m = a < b ? a : b; return m < 0 ? 0 : m; }
+static inline unsigned __vimin_s16x2_relu(unsigned a, unsigned b)               // per signed halfword: max(min(a, b), 0)
+{
+    unsigned r = 0;
+    for (int i = 0; i < 2; i++) {
+        const int x = (int16_t)(a >> (16 * i)), y = (int16_t)(b >> (16 * i));
+        int m = x < y ? x : y;
+        if (m < 0) m = 0;
+        r |= ((unsigned)m & 0xFFFF) << (16 * i);
+    }
+    return r;
+}
+// dp2a.{lo,hi}.s32.u32 d, a, b, c with a as two signed halfwords and b as unsigned bytes (what the two asm helpers of sws.cu emit):
+// d = c + a.h0 * b.byte[0 | 2] + a.h1 * b.byte[1 | 3]
+static inline int emu_dp2a_su(int a, unsigned b, int c, int hi)
+{
+    const int h0 = (int16_t)(a & 0xFFFF), h1 = (int16_t)((unsigned)a >> 16);
+    const int b0 = (b >> (hi ? 16 : 0)) & 0xFF, b1 = (b >> (hi ? 24 : 8)) & 0xFF;
+    return (int)((unsigned)c + (unsigned)(h0 * b0) + (unsigned)(h1 * b1));
+}
 
 // warp collective for kernels launched with emu_launch_warps: every lane is an OS thread, the barrier makes them meet
 struct EmuWarp { std::barrier<> *bar; unsigned slots[32]; };

@@ -11,6 +11,7 @@ extern "C" const char *b200_last_error(void) { return g_err; }
 extern "C" uint64_t emu_launch_count(void) { return g_b200_launches.load(); }
 static B200Device g_dev;
 B200Device *b200_default_device() { return &g_dev; }
+extern "C" int b200_device_open(B200Device **out, int, void *) { *out = &g_dev; return 0; }        // one stand-in device
 void *b200_scratch(B200Device *d, size_t bytes)
 {
     if (d->scratch_bytes < bytes) { free(d->scratch); d->scratch = malloc(bytes + 64); d->scratch_bytes = bytes; }

@@ -273,6 +273,195 @@ def test_emu_tx_mdct_pfa15(emu):
         assert np.array_equal(out.view(np.uint32), _tx(O, "orc", 1, 1, n, 1.0, x, n).view(np.uint32)), (n, "strided inverse")
 
 
+# ------------------------------------------------------------------ all of swscale (sws.cu + sws_plan.cpp) on the stand-in runtime
+@pytest.fixture(scope="module")
+def emusws():
+    """libemusws.so: ffmpeg_b200/csrc/sws.cu — every kernel and all host code — plus sws_plan.cpp on the stand-in runtime.  The only
+    edit besides the launch rewrite: the bodies of the two inline-PTX helpers (dp2a.lo / dp2a.hi) are replaced by their definition."""
+    gen = os.path.join(EMU, "_gen")
+    os.makedirs(gen, exist_ok=True)
+    cs = os.path.join(ROOT, "ffmpeg_b200", "csrc")
+    t = open(os.path.join(cs, "sws.cu")).read()
+    t, n1 = re.subn(r'\{ int d; asm\("dp2a\.lo\.s32\.u32[^\n]*\n', "{ return emu_dp2a_su(a, b, c, 0); }\n", t)
+    t, n2 = re.subn(r'\{ int d; asm\("dp2a\.hi\.s32\.u32[^\n]*\n', "{ return emu_dp2a_su(a, b, c, 1); }\n", t)
+    assert n1 == 1 and n2 == 1 and not re.search(r"\basm\b", t)
+    t = rewrite_launches(t)
+    assert "<<<" not in t
+    open(os.path.join(gen, "host_sws.cpp"), "w").write(t)
+    open(os.path.join(gen, "host_tx_pfa.cpp"), "w").write(rewrite_launches(open(os.path.join(cs, "tx_pfa.cu")).read()))    # fake_device.cpp refers to it
+    so = os.path.join(gen, "libemusws.so")
+    cxx = "/opt/gcc/bin/g++" if os.path.exists("/opt/gcc/bin/g++") else "g++"
+    r = subprocess.run([cxx, "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread", "-ffp-contract=off", "-w", "-I" + os.path.join(EMU, "fake"), "-I" + cs,
+                        "-I" + os.path.join(ROOT, "include"), "-I" + EMU, os.path.join(gen, "host_sws.cpp"), os.path.join(cs, "sws_plan.cpp"),
+                        os.path.join(EMU, "fake_device.cpp"), os.path.join(gen, "host_tx_pfa.cpp"), "-o", so], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    L = C.CDLL(so)
+    L.b200_sws_getContext_range.restype = C.c_void_p
+    L.b200_sws_getContext_range.argtypes = [C.c_void_p] + [C.c_int] * 9
+    L.b200_sws_freeContext.argtypes = [C.c_void_p]
+    L.b200_sws_setColorspaceDetails.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.b200_sws_scale.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.b200_sws_scale_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int]
+    L.b200_sws_scale_batch_device_planar.argtypes = [C.c_void_p] + [C.c_void_p] * 6 + [C.c_int]
+    L.b200_last_error.restype = C.c_char_p
+    dev = C.c_void_p()
+    assert L.b200_device_open(C.byref(dev), 0, None) == 0
+    L.dev = dev
+    return L
+
+
+def _emu_ctx(L, w, h, src_fmt, dw, dh, dst_fmt, fl, ranges=(0, 0), details=None):
+    ctx = L.b200_sws_getContext_range(L.dev, w, h, src_fmt, ranges[0], dw, dh, dst_fmt, ranges[1], fl)
+    if ctx and details is not None:
+        ta, tb = (np.array(cl.COEFFS[k], np.int32) for k in (details[0], details[2]))
+        assert L.b200_sws_setColorspaceDetails(ctx, ta.ctypes.data, details[1], tb.ctypes.data, details[3], *details[4:]) == 0
+    return ctx
+
+
+def _emu_scale(L, ctx, planes, h, dst):
+    sp = (C.c_void_p * 4)(*[a.ctypes.data for a in planes] + [None] * (4 - len(planes)))
+    ss = (C.c_int32 * 4)(*[a.strides[0] for a in planes] + [0] * (4 - len(planes)))
+    dp = (C.c_void_p * 4)(*[a.ctypes.data for a in dst] + [None] * (4 - len(dst)))
+    ds = (C.c_int32 * 4)(*[a.strides[0] for a in dst] + [0] * (4 - len(dst)))
+    return L.b200_sws_scale(ctx, sp, ss, 0, h, dp, ds)
+
+
+def emu_sws(L, w, h, dw, dh, fl, y, u, v, dst_pad=0, colorspace=None, fmt=cl.PIX_FMT_RGB24, src_fmt=0):
+    """the library's sws_scale() path for a packed RGB destination, on the emulated device (same signature as cpulibs.orc_sws)"""
+    det = None if colorspace is None else (colorspace[0], colorspace[1], colorspace[2], colorspace[3], colorspace[4], colorspace[5], colorspace[6])
+    ctx = _emu_ctx(L, w, h, src_fmt, dw, dh, fmt, fl, details=det)
+    if not ctx:
+        return None
+    out = np.full((dh, dw * cl.fmt_bpp(fmt) + dst_pad), 0xA5, np.uint8)
+    planes = [y] if src_fmt in cl.PACKED_RGB_FORMATS.values() else [y, u] if src_fmt in (cl.PIX_FMT_NV12, cl.PIX_FMT_NV21) else [y, u, v]
+    n = _emu_scale(L, ctx, planes, h, [out])
+    L.b200_sws_freeContext(ctx)
+    assert n == dh, (n, L.b200_last_error())
+    return out
+
+
+def emu_sws_planar(L, w, h, dw, dh, fl, y, u, v, dst_pad=0, src_fmt=0, ranges=(0, 0), details=None, dst_fmt=0):
+    ctx = _emu_ctx(L, w, h, src_fmt, dw, dh, dst_fmt, fl, ranges, details)
+    if not ctx:
+        return None
+    cw, ch = (dw + 1) // 2, (dh + 1) // 2
+    nvd = dst_fmt in (cl.PIX_FMT_NV12, cl.PIX_FMT_NV21)
+    dst = [np.full((dh, dw + dst_pad), 0xA5, np.uint8), np.full((ch, (2 * cw if nvd else cw) + dst_pad), 0xA5, np.uint8)]
+    if not nvd:
+        dst.append(np.full((ch, cw + dst_pad), 0xA5, np.uint8))
+    planes = [y] if src_fmt in cl.PACKED_RGB_FORMATS.values() else [y, u] if src_fmt in (cl.PIX_FMT_NV12, cl.PIX_FMT_NV21) else [y, u, v]
+    n = _emu_scale(L, ctx, planes, h, dst)
+    L.b200_sws_freeContext(ctx)
+    assert n == dh, (n, L.b200_last_error())
+    return tuple(dst)
+
+
+def test_sws_emulation_agrees_with_hardware_verified_paths(emusws):
+    """calibration of the emulation itself: paths that already passed on a B200 (vector kernels with dp2a / prmt / vimin, LUT converter,
+    scaled path, nv12 source, planar scaling) must give the oracle's bytes here too"""
+    import functools
+    from cases import SWS_FORMAT_CASES, SWS_PLANAR_CASES, SWS_NV_CASES, SWS_FASTBIL_CASES
+    er, ep = functools.partial(emu_sws, emusws), functools.partial(emu_sws_planar, emusws)
+    for i, (w, h, dw, dh, fl, kind) in enumerate(SWS_FORMAT_CASES):
+        y, u, v = cl.yuv_frame(w, h, 3300 + i, kind)
+        for name in ("rgb24", "bgra", "argb"):
+            f = cl.PACKED_RGB_FORMATS[name]
+            assert np.array_equal(er(w, h, dw, dh, fl, y, u, v, fmt=f, dst_pad=i % 3), cl.orc_sws(w, h, dw, dh, fl, y, u, v, fmt=f, dst_pad=i % 3)), (i, name)
+    for i, (w, h, dw, dh, fl, kind) in enumerate(SWS_PLANAR_CASES + SWS_FASTBIL_CASES[:6]):
+        y, u, v = cl.yuv_frame(w, h, 3400 + i, kind)
+        assert all(np.array_equal(a, b) for a, b in zip(ep(w, h, dw, dh, fl, y, u, v), cl.orc_sws_planar(w, h, dw, dh, fl, y, u, v))), ("planar", i)
+    for i, (w, h, dw, dh, fl, kind) in enumerate(SWS_NV_CASES[:6]):
+        y, u, v = cl.yuv_frame(w, h, 3500 + i, kind)
+        uv = cl.nv_interleave(u, v, cl.PIX_FMT_NV12)
+        assert np.array_equal(er(w, h, dw, dh, fl, y, uv, uv, src_fmt=cl.PIX_FMT_NV12), cl.orc_sws(w, h, dw, dh, fl, y, uv, uv, src_fmt=cl.PIX_FMT_NV12)), ("nv12", i)
+    y, u, v = cl.yuv_frame(640, 352, 3600, "random")                     # 16-pixel-group vector kernels, FATE flags and LUT path
+    for fl in (FATE, cl.SWS_BICUBIC):
+        assert np.array_equal(er(640, 352, 640, 352, fl, y, u, v), cl.orc_sws(640, 352, 640, 352, fl, y, u, v)), hex(fl)
+
+
+def test_sws_range_conversion_whole_path(emusws):
+    """the range-conversion GPU tests of tests/test_sws_gpu.py, through the library's real entry points on the emulated device"""
+    import functools
+    from cases import SWS_RANGE_CASES
+    from test_oracle import fate_sws_yuv_range_crc, FATE_SWS_YUV_RANGE, sha
+    ep = functools.partial(emu_sws_planar, emusws)
+    lines = open(os.path.join(ROOT, "tests", "golden", "sws_range_hashes.txt")).read().split("\n")[:-1]
+    for line, (w, h, dw, dh, fl, kind, ranges, details) in zip(lines, SWS_RANGE_CASES):
+        i, hout = int(line.split()[0]), line.split()[-1]
+        y, u, v = cl.yuv_frame(w, h, 1200 + i, kind)
+        out = ep(w, h, dw, dh, fl, y, u, v, ranges=ranges, details=details)
+        assert sha(np.concatenate([p.ravel() for p in out])) == hout, (i, ranges, details)
+    assert fate_sws_yuv_range_crc(ep) == FATE_SWS_YUV_RANGE
+    y, u, v = cl.yuv_frame(351, 287, 1751, "random", pad=5)
+    assert all(np.array_equal(a, b) for a, b in zip(ep(351, 287, 351, 287, cl.SWS_BICUBIC, y, u, v, dst_pad=7, ranges=(1, 0)),
+                                                    cl.orc_sws_planar(351, 287, 351, 287, cl.SWS_BICUBIC, y, u, v, dst_pad=7, ranges=(1, 0))))
+    # batched device entry point with range conversion (host arrays stand in for device memory), and the refused matrix change
+    L = emusws
+    w, h, dw, dh, n = 320, 180, 480, 270, 3
+    frames = [cl.yuv_frame(w, h, 1600 + k, "random") for k in range(n)]
+    Y, U, V = (np.ascontiguousarray(np.stack([f[k] for f in frames])) for k in range(3))
+    DY, DU, DV = np.zeros((n, dh, dw), np.uint8), np.zeros((n, dh // 2, dw // 2), np.uint8), np.zeros((n, dh // 2, dw // 2), np.uint8)
+    ctx = _emu_ctx(L, w, h, 0, dw, dh, 0, FATE, (1, 0))
+    arr = lambda t, vals: (t * 3)(*vals)
+    assert L.b200_sws_scale_batch_device_planar(ctx, arr(C.c_void_p, [Y.ctypes.data, U.ctypes.data, V.ctypes.data]), arr(C.c_int32, [w, w // 2, w // 2]),
+                                                arr(C.c_int64, [w * h, w * h // 4, w * h // 4]), arr(C.c_void_p, [DY.ctypes.data, DU.ctypes.data, DV.ctypes.data]),
+                                                arr(C.c_int32, [dw, dw // 2, dw // 2]), arr(C.c_int64, [dw * dh, dw * dh // 4, dw * dh // 4]), n) == 0
+    for i in range(n):
+        e = cl.orc_sws_planar(w, h, dw, dh, FATE, *frames[i], ranges=(1, 0))
+        assert np.array_equal(DY[i], e[0]) and np.array_equal(DU[i], e[1]) and np.array_equal(DV[i], e[2]), i
+    ta, tb = np.array(cl.COEFFS[1], np.int32), np.array(cl.COEFFS[5], np.int32)
+    assert L.b200_sws_setColorspaceDetails(ctx, ta.ctypes.data, 0, tb.ctypes.data, 1, 0, 1 << 16, 1 << 16) == -38
+    L.b200_sws_freeContext(ctx)
+
+
+def test_sws_rgb_sources_nv_destinations_and_all_fate_sums(emusws):
+    """packed RGB sources, nv12 / nv21 destinations and RGB -> RGB scaling through the library's real entry points, against the
+    reference's outputs; then all 59 FATE md5 sums from the emulated device's frames"""
+    import functools
+    from test_oracle import rgbsrc_rows, run_rgbsrc_row, sha
+    from cases import SWS_PLANAR_CASES
+    import test_fate_golden as fg
+    er, ep = functools.partial(emu_sws, emusws), functools.partial(emu_sws_planar, emusws)
+    for row in rgbsrc_rows():
+        assert sha(run_rgbsrc_row(er, ep, row)) == row[-1], row[:6]
+    for df in (cl.PIX_FMT_NV12, cl.PIX_FMT_NV21):
+        for i, (w, h, dw, dh, fl, kind) in enumerate(SWS_PLANAR_CASES):
+            y, u, v = cl.yuv_frame(w, h, 2500 + i, kind)
+            out, exp = ep(w, h, dw, dh, fl, y, u, v, dst_fmt=df, dst_pad=i % 3), cl.orc_sws_planar(w, h, dw, dh, fl, y, u, v, dst_fmt=df, dst_pad=i % 3)
+            assert len(out) == 2 and all(np.array_equal(a, b) for a, b in zip(out, exp)), (i, df)
+        src = cl.rgb_frame(64, 48, 2990, 4)
+        out, exp = (f(64, 48, 100, 70, FATE, src, src, src, src_fmt=cl.PIX_FMT_BGRA, dst_fmt=df, ranges=(0, 1)) for f in (ep, cl.orc_sws_planar))
+        assert all(np.array_equal(a, b) for a, b in zip(out, exp)), ("bgra -> nv, full range", df)
+    if cl.have_nut() and os.path.exists(cl.VIDEOGEN):
+        fg.check_all(er, ep, rgb_sources=True, nv_dest=True)
+    assert er(64, 48, 64, 48, FATE, src, src, src, fmt=cl.PIX_FMT_BGR24, src_fmt=cl.PIX_FMT_RGB24) is None          # same-size rgb -> rgb: refused
+    assert er(64, 48, 32, 24, FATE, src, src, src, fmt=cl.PIX_FMT_BGRA, src_fmt=cl.PIX_FMT_RGBA) is None           # alpha through the scaler: refused
+    # batched device entry points: rgba -> nv12 (two destination planes) and rgb24 -> bgra
+    L = emusws
+    w, h, dw, dh, n = 64, 48, 100, 70, 2
+    frames = [cl.rgb_frame(w, h, 2960 + k, 4) for k in range(n)]
+    S = np.ascontiguousarray(np.stack(frames))
+    DY, DUV = np.zeros((n, dh, dw), np.uint8), np.zeros((n, dh // 2, dw), np.uint8)
+    ctx = _emu_ctx(L, w, h, cl.PIX_FMT_RGBA, dw, dh, cl.PIX_FMT_NV12, FATE)
+    arr = lambda t, vals: (t * 3)(*vals)
+    assert L.b200_sws_scale_batch_device_planar(ctx, arr(C.c_void_p, [S.ctypes.data, None, None]), arr(C.c_int32, [w * 4, 0, 0]), arr(C.c_int64, [w * 4 * h, 0, 0]),
+                                                arr(C.c_void_p, [DY.ctypes.data, DUV.ctypes.data, None]), arr(C.c_int32, [dw, dw, 0]),
+                                                arr(C.c_int64, [dw * dh, dw * dh // 2, 0]), n) == 0
+    L.b200_sws_freeContext(ctx)
+    for i in range(n):
+        ey, euv = cl.orc_sws_planar(w, h, dw, dh, FATE, frames[i], frames[i], frames[i], src_fmt=cl.PIX_FMT_RGBA, dst_fmt=cl.PIX_FMT_NV12)
+        assert np.array_equal(DY[i], ey) and np.array_equal(DUV[i], euv), i
+    frames = [cl.rgb_frame(w, h, 2970 + k, 3) for k in range(n)]
+    S = np.ascontiguousarray(np.stack(frames))
+    D = np.zeros((n, dh, dw * 4), np.uint8)
+    ctx = _emu_ctx(L, w, h, cl.PIX_FMT_RGB24, dw, dh, cl.PIX_FMT_BGRA, FATE)
+    assert L.b200_sws_scale_batch_device(ctx, arr(C.c_void_p, [S.ctypes.data, None, None]), arr(C.c_int32, [w * 3, 0, 0]), arr(C.c_int64, [w * 3 * h, 0, 0]),
+                                         D.ctypes.data, dw * 4, dw * 4 * dh, n) == 0
+    L.b200_sws_freeContext(ctx)
+    for i in range(n):
+        assert np.array_equal(D[i], cl.orc_sws(w, h, dw, dh, FATE, frames[i], frames[i], frames[i], fmt=cl.PIX_FMT_BGRA, src_fmt=cl.PIX_FMT_RGB24)), i
+
+
 # ------------------------------------------------------------------ the library's own host code on the stand-in runtime
 def test_host_float_dsp_entry_points(emuhost):
     """b200_float_dsp_batch_device (strides, shared operand, more vectors than one grid holds, argument checks) and the
