@@ -89,6 +89,28 @@ static inline unsigned __reduce_xor_sync(unsigned, unsigned v)
     return r;
 }
 
+// block-synchronous kernels (dynamic shared memory + __syncthreads): every thread of a block is an OS thread, one block at a time;
+// a thread that returns drops out of the barrier like an exited CUDA thread
+static thread_local std::barrier<> *emu_block_bar = nullptr;
+static thread_local void *emu_smem = nullptr;
+static inline void __syncthreads() { emu_block_bar->arrive_and_wait(); }
+template <typename F> static void emu_launch_blocks(dim3 grid, dim3 block, size_t smem, F body)
+{
+    std::vector<unsigned char> shared(smem + 64);
+    for (unsigned bz = 0; bz < grid.z; bz++) for (unsigned by = 0; by < grid.y; by++) for (unsigned bx = 0; bx < grid.x; bx++) {
+        std::barrier<> bar(block.x * block.y * block.z);
+        std::vector<std::thread> th;
+        for (unsigned tz = 0; tz < block.z; tz++) for (unsigned ty = 0; ty < block.y; ty++) for (unsigned tx = 0; tx < block.x; tx++)
+            th.emplace_back([&, tx, ty, tz] {
+                gridDim = grid; blockDim = block; blockIdx = dim3(bx, by, bz); threadIdx = dim3(tx, ty, tz);
+                emu_block_bar = &bar; emu_smem = shared.data();
+                body();
+                bar.arrive_and_drop();
+            });
+        for (auto &t : th) t.join();
+    }
+}
+
 // sequential launch: kernels without collectives or shared memory
 template <typename F> static void emu_launch(dim3 grid, dim3 block, F body)
 {

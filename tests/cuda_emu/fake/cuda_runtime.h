@@ -26,7 +26,12 @@ static inline cudaError_t cudaMemcpy2DAsync(void *d, size_t dp, const void *s, s
 }
 
 // what `kernel<<<grid, block, smem, stream>>>(args)` is rewritten into by tests/test_cuda_emu.py
-template <typename F> static void emu_cfg_launch(bool warp_collectives, F body, dim3 grid, dim3 block, size_t = 0, cudaStream_t = nullptr)
+// mode 0: threads one after the other; 1: an OS thread per lane (warp collectives); 2: an OS thread per thread of a block (__syncthreads)
+template <typename F> static void emu_cfg_launch(int mode, F body, dim3 grid, dim3 block, size_t smem = 0, cudaStream_t = nullptr)
 {
-    if (warp_collectives) emu_launch_warps(grid, block, body); else emu_launch(grid, block, body);
+    if (mode == 1) emu_launch_warps(grid, block, body);
+    else if (mode == 2) emu_launch_blocks(grid, block, smem, body);
+    else emu_launch(grid, block, body);
 }
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+template <typename K> static inline cudaError_t cudaFuncSetAttribute(K, cudaFuncAttribute, int) { return cudaSuccess; }

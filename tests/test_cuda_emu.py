@@ -45,6 +45,7 @@ def vp(a):
 
 
 WARP_KERNELS = {"mpv_unquant_kernel"}                   # kernels that use a warp collective: one OS thread per lane
+BLOCK_KERNELS = {"tx_fft_kernel", "tx_mdct_inv_kernel", "tx_mdct_fwd_kernel", "tx_rdft_r2c_kernel", "tx_rdft_c2r_kernel"}    # __syncthreads
 
 
 def rewrite_launches(txt):
@@ -62,8 +63,9 @@ def rewrite_launches(txt):
             depth += (txt[j] == "(") - (txt[j] == ")")
             j += 1
         kern, cfg, args = m.group(1), m.group(2), txt[m.end():j - 1]
-        warp = "true" if re.match(r"\w+", kern).group(0) in WARP_KERNELS else "false"
-        out.append(f"emu_cfg_launch({warp}, [&] {{ {kern}({args}); }}, {cfg})")
+        name = re.match(r"\w+", kern).group(0)
+        mode = 1 if name in WARP_KERNELS else 2 if name in BLOCK_KERNELS else 0
+        out.append(f"emu_cfg_launch({mode}, [&] {{ {kern}({args}); }}, {cfg})")
         i = j
     return "".join(out)
 
@@ -460,6 +462,80 @@ def test_sws_rgb_sources_nv_destinations_and_all_fate_sums(emusws):
     L.b200_sws_freeContext(ctx)
     for i in range(n):
         assert np.array_equal(D[i], cl.orc_sws(w, h, dw, dh, FATE, frames[i], frames[i], frames[i], fmt=cl.PIX_FMT_BGRA, src_fmt=cl.PIX_FMT_RGB24)), i
+
+
+# ------------------------------------------------------------------ all of libavutil/tx (tx.cu + tx_pfa.cu) on the stand-in runtime
+@pytest.fixture(scope="module")
+def emutx():
+    """libemutx.so: ffmpeg_b200/csrc/tx.cu (shared-memory kernels: one OS thread per CUDA thread of a block, __syncthreads = barrier) and
+    tx_pfa.cu with their host code.  Edits besides the launch rewrite: `extern __shared__ float2 z[]` becomes a pointer to the block's buffer."""
+    gen = os.path.join(EMU, "_gen")
+    os.makedirs(gen, exist_ok=True)
+    cs = os.path.join(ROOT, "ffmpeg_b200", "csrc")
+    t = open(os.path.join(cs, "tx.cu")).read()
+    t, n = re.subn(r"extern __shared__ float2 z\[\];", "float2 *z = (float2 *)emu_smem;", t)
+    assert n == 5 and "__shared__" not in t and not re.search(r"\basm\b", t)
+    t = rewrite_launches(t)
+    assert "<<<" not in t
+    open(os.path.join(gen, "host_tx.cpp"), "w").write(t)
+    open(os.path.join(gen, "host_tx_pfa.cpp"), "w").write(rewrite_launches(open(os.path.join(cs, "tx_pfa.cu")).read()))
+    so = os.path.join(gen, "libemutx.so")
+    cxx = "/opt/gcc/bin/g++" if os.path.exists("/opt/gcc/bin/g++") else "g++"
+    r = subprocess.run([cxx, "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread", "-ffp-contract=off", "-w", "-I" + os.path.join(EMU, "fake"), "-I" + cs,
+                        "-I" + os.path.join(ROOT, "include"), "-I" + EMU, os.path.join(gen, "host_tx.cpp"), os.path.join(gen, "host_tx_pfa.cpp"),
+                        os.path.join(EMU, "fake_device.cpp"), "-o", so], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    L = C.CDLL(so)
+    L.b200_tx_init_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_uint64]
+    L.b200_tx_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_ssize_t, C.c_int64, C.c_ssize_t, C.c_ssize_t]
+    L.b200_tx_uninit.argtypes = [C.c_void_p]
+    dev = C.c_void_p()
+    assert L.b200_device_open(C.byref(dev), 0, None) == 0
+    L.dev = dev
+    return L
+
+
+def _emu_tx(L, typ, inv, n, scale, x, out_floats, host_fn=False):
+    """b200_tx_init_device + b200_tx_batch_device (or the av_tx_fn host entry, one transform at a time) on the emulated device"""
+    from ffmpeg_b200._lib import TX_FN
+    ctx, fn = C.c_void_p(), TX_FN()
+    sc = C.c_float(scale)
+    ret = L.b200_tx_init_device(L.dev, C.byref(ctx), C.byref(fn), typ, inv, n, C.byref(sc), 0)
+    if ret < 0:
+        return ret
+    out = np.zeros((x.shape[0], out_floats), np.float32)
+    xin = x.copy()
+    if host_fn:
+        for r in range(x.shape[0]):
+            fn(ctx, out[r].ctypes.data, xin[r].ctypes.data, 8 if typ == 0 else 4)
+    else:
+        assert L.b200_tx_batch_device(ctx, out.ctypes.data, xin.ctypes.data, 8 if typ == 0 else 4, x.shape[0], out.strides[0], xin.strides[0]) == 0
+    L.b200_tx_uninit(C.byref(ctx))
+    return out
+
+
+def test_tx_whole_path_on_emulated_device(emutx):
+    """calibration on the hardware-verified transforms (power-of-two FFT / MDCT / RDFT: the emulated shared-memory kernels give the
+    oracle's bits), then the compound 15 x M MDCT through b200_tx_init_device — the path tx.cu now dispatches to tx_pfa.cu"""
+    from test_oracle_more import _tx
+    O = cl.oracle()
+    rng = np.random.default_rng(41)
+    for n in (16, 64, 256, 1024):
+        x = (rng.random((5, 2 * n), dtype=np.float32) * 2 - 1).astype(np.float32)
+        for inv in (0, 1):
+            assert np.array_equal(_emu_tx(emutx, 0, inv, n, 1.0, x, 2 * n).view(np.uint32), _tx(O, "orc", 0, inv, n, 1.0, x, 2 * n).view(np.uint32)), ("fft", n, inv)
+        xi = np.ascontiguousarray(x[:, :n])
+        assert np.array_equal(_emu_tx(emutx, 1, 1, n, 1.0 / n, xi, n).view(np.uint32), _tx(O, "orc", 1, 1, n, 1.0 / n, xi, n).view(np.uint32)), ("imdct", n)
+        assert np.array_equal(_emu_tx(emutx, 1, 0, n, 1.0, x, n).view(np.uint32), _tx(O, "orc", 1, 0, n, 1.0, x, n).view(np.uint32)), ("mdct", n)
+        assert np.array_equal(_emu_tx(emutx, 6, 0, n, 1.0, xi, n + 2).view(np.uint32), _tx(O, "orc", 6, 0, n, 1.0, xi.copy(), n + 2).view(np.uint32)), ("r2c", n)
+    for n in (120, 240, 960):
+        for inv in (1, 0):
+            x = (rng.random((70, n if inv else 2 * n), dtype=np.float32) * 2 - 1).astype(np.float32)
+            exp = _tx(O, "orc", 1, inv, n, 1.0 / n, x, n)
+            assert np.array_equal(_emu_tx(emutx, 1, inv, n, 1.0 / n, x, n).view(np.uint32), exp.view(np.uint32)), ("pfa batch", n, inv)
+            assert np.array_equal(_emu_tx(emutx, 1, inv, n, 1.0 / n, x[:3], n, host_fn=True).view(np.uint32), exp[:3].view(np.uint32)), ("pfa av_tx_fn", n, inv)
+    x = np.zeros((1, 1920), np.float32)
+    assert _emu_tx(emutx, 0, 0, 960, 1.0, x, 1920) == -38 and _emu_tx(emutx, 1, 1, 60, 1.0, x, 60) == -38 and _emu_tx(emutx, 6, 0, 96, 1.0, x, 98) == -38
 
 
 # ------------------------------------------------------------------ the library's own host code on the stand-in runtime
