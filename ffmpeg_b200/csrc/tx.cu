@@ -15,6 +15,7 @@
 // HBM traffic per transform is the algorithmic 8N in + 8N out (FFT) or 4*len in + 4*len out (iMDCT).
 #include "common.h"
 #include "tx_pfa.h"
+#include "tx_dct.h"
 #include <vector>
 #include <cmath>
 #include <cstring>
@@ -429,6 +430,7 @@ void collect_blocks(std::vector<std::vector<int>> &lv, int L, int off)   // bloc
 struct B200TXContext {
     B200Device *dev = nullptr;
     TxPfa *pfa = nullptr;            // compound 15 x M MDCT (tx_pfa.cu): everything below d is unused then
+    TxDct *dct = nullptr;            // AV_TX_FLOAT_DCT (tx_dct.cu): stages around a child RDFT context
     int type = 0, inv = 0, len = 0;
     TxDev d{};
     void *blob = nullptr;
@@ -584,6 +586,7 @@ static int tx_launch(B200TXContext *c, cudaStream_t st, void *out, const void *i
 {
     if (count <= 0) return 0;
     if (c->pfa) return tx_pfa_launch(c->pfa, st, out, in, stride, count, out_step, in_step);
+    if (c->dct) return tx_dct_launch(c->dct, st, out, in, count, out_step, in_step);
     // measured on B200 (scripts/quick_bench.py tx with B200_TX_TB / B200_TX_THREADS): 256 threads pay off from 1024 points per
     // transform on; 512-point transforms (iMDCT-1024) run 18 % faster with 128-thread CTAs
     int threads = c->d.n >= 1024 ? 256 : c->d.n >= 256 ? 128 : 64;
@@ -621,7 +624,8 @@ static void tx_host_fn(B200TXContext *c, void *out, void *in, ptrdiff_t stride)
     if (cudaSetDevice(d->ordinal) != cudaSuccess) fail("cudaSetDevice");
     const size_t n = c->d.n, len = c->len;
     size_t in_elems, out_elems;            // floats
-    if (c->type == 0) { in_elems = out_elems = 2 * n; }
+    if (c->dct) { in_elems = out_elems = (size_t)tx_dct_points(c->dct); }     // DCT-II: len in / len out; DCT-III: 2*len in / 2*len out
+    else if (c->type == 0) { in_elems = out_elems = 2 * n; }
     else if (c->type == 6) { in_elems = c->inv ? len + 2 : len; out_elems = c->inv ? len : len + 2; }
     else if (c->inv) { in_elems = len; out_elems = len; }
     else { in_elems = 2 * len; out_elems = len; }
@@ -649,8 +653,22 @@ B200_API int b200_tx_init_device(B200Device *dev, B200TXContext **ctx, b200_tx_f
     if (!ctx || !len) return B200_EINVAL;                            // av_tx_init, tx.c:903-940
     *ctx = nullptr;
     if (!dev) return B200_ENODEV;
-    if (type != B200_TX_FLOAT_FFT && type != B200_TX_FLOAT_MDCT && type != B200_TX_FLOAT_RDFT) return B200_ENOSYS;
+    if (type != B200_TX_FLOAT_FFT && type != B200_TX_FLOAT_MDCT && type != B200_TX_FLOAT_RDFT && type != B200_TX_FLOAT_DCT) return B200_ENOSYS;
     if (flags & ~(uint64_t)B200_TX_UNALIGNED) return B200_ENOSYS;    // INPLACE / FULL_IMDCT / REAL_TO_* not implemented
+    if (type == B200_TX_FLOAT_DCT) {                                 // DCT-II / DCT-III around a child real-DFT context (tx_dct.cu)
+        if (!tx_dct_length_ok(!!inv, len)) return B200_ENOSYS;
+        float scd = 1.0f;
+        if (scale) scd = *(const float *)scale;
+        B200TXContext *cd = new (std::nothrow) B200TXContext();
+        if (!cd) return B200_ENOMEM;
+        cd->dev = dev; cd->type = type; cd->inv = !!inv; cd->len = len;
+        if (cudaSetDevice(dev->ordinal) != cudaSuccess) { delete cd; return B200_EEXTERNAL; }
+        cd->dct = tx_dct_create(dev, cd->inv, len, scd);
+        if (!cd->dct) { delete cd; return B200_EEXTERNAL; }
+        *ctx = cd;
+        if (tx) *tx = tx_host_fn;
+        return 0;
+    }
     if (type == B200_TX_FLOAT_MDCT && tx_pfa_length_ok(len)) {       // 15 x 2^k: the compound MDCT av_tx_init() picks (Opus CELT sizes)
         float scp = 1.0f;
         if (scale) scp = *(const float *)scale;
@@ -694,6 +712,7 @@ B200_API void b200_tx_uninit(B200TXContext **ctx)
     cudaStreamSynchronize(c->dev->stream);
     if (c->blob) cudaFree(c->blob);
     tx_pfa_free(c->pfa);
+    tx_dct_free(c->dct);
     delete c;
     *ctx = nullptr;
 }

@@ -3,7 +3,7 @@ for AV_TX_FLOAT_FFT, AV_TX_FLOAT_MDCT and AV_TX_FLOAT_RDFT, plus the batched dev
 import ctypes as C
 from ._lib import lib, check, vp, TX_FN
 
-AV_TX_FLOAT_FFT, AV_TX_FLOAT_MDCT, AV_TX_FLOAT_RDFT = 0, 1, 6
+AV_TX_FLOAT_FFT, AV_TX_FLOAT_MDCT, AV_TX_FLOAT_RDFT, AV_TX_FLOAT_DCT = 0, 1, 6, 9
 
 
 def _dptr(x):

@@ -433,6 +433,10 @@ int  b200_emulated_edge_mc_batch_device(B200Device *dev, int64_t n, uint8_t *buf
                                    * (tx_template.c:1655-1724) the host av_tx_fn rewrites its input on the inverse; the
                                    * batched device entry point leaves the input untouched.  AV_TX_REAL_TO_REAL /
                                    * AV_TX_REAL_TO_IMAGINARY are not implemented. */
+#define B200_TX_FLOAT_DCT   9     /* AV_TX_FLOAT_DCT: forward = DCT-II of len points, inverse = DCT-III of 2 * len points (the reference's
+                                   * ff_tx_dct_init doubles the length it is given, libavutil/tx_template.c:1844-1848; callers pass N / 2).
+                                   * ff_tx_dctII / ff_tx_dctIII (tx_template.c:1874-1968).  Input and output are N floats per transform;
+                                   * unlike the reference neither the input is overwritten nor 2 floats of padding are needed. */
 #define B200_TX_UNALIGNED   2     /* AV_TX_UNALIGNED (accepted, no effect) */
 typedef struct B200TXContext B200TXContext;
 typedef void (*b200_tx_fn)(B200TXContext *s, void *out, void *in, ptrdiff_t stride);   /* av_tx_fn: HOST pointers */
@@ -444,6 +448,8 @@ int  b200_tx_init(B200TXContext **ctx, b200_tx_fn *tx, int type, int inv, int le
 /* host-only: the tables ff_tx_mdct_pfa_init() builds for a 15 x M MDCT, flattened into 32-bit words, for the CPU test tier
  * (layout8: word offsets of in_map, out_map, sub_map, exp, tab_53, cosine tables; then M and log2 M).  Returns the word count. */
 int  b200_tx_pfa_tables(int inv, int len, float scale, int32_t *words, int cap, int32_t *layout8);
+/* host-only: the factor table of ff_tx_dct_init (N rotation factors, then N / 2 butterfly factors), for the CPU test tier */
+int  b200_tx_dct_table(int inv, int len, float *tab, int cap);
 int  b200_tx_init_device(B200Device *dev, B200TXContext **ctx, b200_tx_fn *tx, int type, int inv, int len,
                          const void *scale, uint64_t flags);
 void b200_tx_uninit(B200TXContext **ctx);

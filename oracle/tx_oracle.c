@@ -38,6 +38,10 @@ struct OrcTx {
     int *pfa_sub;               /* scatter permutation of the m-point FFT (ff_tx_gen_ptwo_revtab, FF_TX_MAP_SCATTER) */
     cpx *pfa_tmp;
     float tab53[12];            /* ff_tx_tab_53 (tx_template.c:91-108) */
+    /* AV_TX_FLOAT_DCT (type 9): DCT-II forward / DCT-III inverse around a real DFT (ff_tx_dctII / ff_tx_dctIII, tx_template.c:1832-1968) */
+    OrcTx *dct_sub;             /* the r2c (forward) or c2r (inverse) transform of dct_n points */
+    int dct_n;                  /* points: len forward, 2 * len inverse (ff_tx_dct_init doubles it) */
+    float *dct_exp;             /* dct_n rotation factors, then dct_n / 2 pre- or post-scaling factors */
 };
 
 static void make_tab(OrcTx *t, int k)
@@ -318,8 +322,77 @@ static void run_mdct_pfa_fwd(OrcTx *t, float *dst, const float *src, ptrdiff_t s
     }
 }
 
+/* ff_tx_dct_init (tx_template.c:1832-1872): the inverse is defined on twice the length it is asked for (callers pass N / 2) */
+static OrcTx *open_dct(int inv, int len, float scale)
+{
+    float rsc = scale;
+    if (inv) { len *= 2; rsc *= 0.5f; }
+    if (len < 4 || (len & (len - 1))) return NULL;
+    OrcTx *sub = orc_tx_open(6, inv, len, rsc, 0);
+    if (!sub) return NULL;
+    OrcTx *t = calloc(1, sizeof(*t));
+    t->type = 9; t->inv = !!inv; t->len = len; t->dct_n = len; t->dct_sub = sub;
+    float *tab = t->dct_exp = malloc(sizeof(float) * (len / 2) * 3);
+    const double freq = M_PI / (len * 2);
+    for (int i = 0; i < len; i++) tab[i] = (float)(cos(i * freq) * (!inv + 1));
+    for (int i = 0; i < len / 2; i++)
+        tab[len + i] = inv ? (float)(0.5 / sin((2 * i + 1) * freq)) : (float)cos((len - 2 * i - 1) * freq);
+    return t;
+}
+
+static void run_rdft(OrcTx *t, void *out, void *in);
+
+/* ff_tx_dctII (tx_template.c:1874-1925): len floats in (overwritten), len + 2 floats of room in dst, len results */
+static void run_dct2(OrcTx *t, float *dst, float *src)
+{
+    const int len = t->dct_n, len2 = len >> 1;
+    const float *e = t->dct_exp;
+    for (int i = 0; i < len2; i++) {
+        const float in1 = src[i], in2 = src[len - i - 1], s = e[len + i];
+        const float tmp1 = (in1 + in2) * 0.5f, tmp2 = (in1 - in2) * s;
+        src[i] = tmp1 + tmp2;
+        src[len - i - 1] = tmp1 - tmp2;
+    }
+    run_rdft(t->dct_sub, dst, src);
+    float next = dst[len];
+    for (int i = len - 2; i > 0; i -= 2) {
+        const float are = e[len - i], aim = e[i], bre = dst[i + 0], bim = dst[i + 1];
+        const float tmp = are * bre - aim * bim;                     /* CMUL(tmp, dst[i], exp[len - i], exp[i], dst[i], dst[i + 1]) */
+        dst[i] = are * bim + aim * bre;
+        dst[i + 1] = next;
+        next += tmp;
+    }
+    dst[0] = e[0] * dst[0];
+    dst[1] = next;
+}
+
+/* ff_tx_dctIII (tx_template.c:1927-1968): len + 2 floats in (len coefficients, two of padding; overwritten), len floats out */
+static void run_dct3(OrcTx *t, float *dst, float *src)
+{
+    const int len = t->dct_n, len2 = len >> 1;
+    const float *e = t->dct_exp;
+    float tmp2 = 2 * src[len - 1];
+    src[len] = tmp2;
+    for (int i = len - 2; i >= 2; i -= 2) {
+        const float val1 = src[i - 0], val2 = src[i - 1] - src[i + 1];
+        const float are = e[len - i], aim = e[i];
+        src[i + 1] = are * val1 - aim * val2;                        /* CMUL(src[i + 1], src[i], exp[len - i], exp[i], val1, val2) */
+        src[i] = are * val2 + aim * val1;
+    }
+    run_rdft(t->dct_sub, dst, src);
+    for (int i = 0; i < len2; i++) {
+        const float in1 = dst[i], in2 = dst[len - i - 1], c = e[len + i];
+        const float tmp1 = in1 + in2;
+        tmp2 = in1 - in2;
+        tmp2 *= c;
+        dst[i] = tmp1 + tmp2;
+        dst[len - i - 1] = tmp1 - tmp2;
+    }
+}
+
 OrcTx *orc_tx_open(int type, int inv, int len, float scale, unsigned flags)
 {
+    if (!flags && type == 9) return open_dct(inv, len, scale);
     if (!flags && type == 1 && len >= 60 && len % 30 == 0 && !(((len / 30)) & ((len / 30) - 1)))
         return open_mdct_pfa15(inv, len, scale);
     if (flags || (type != 0 && type != 1 && type != 6) || len < 2 || (len & (len - 1))) return NULL;
@@ -380,7 +453,8 @@ void orc_tx_close(OrcTx *t)
     if (!t) return;
     for (int i = 0; i < 18; i++) free(t->tab[i]);
     free(t->map); free(t->sub_map); free(t->exp); free(t->rexp);
-    free(t->pfa_in); free(t->pfa_out); free(t->pfa_sub); free(t->pfa_tmp); free(t);
+    free(t->pfa_in); free(t->pfa_out); free(t->pfa_sub); free(t->pfa_tmp);
+    orc_tx_close(t->dct_sub); free(t->dct_exp); free(t);
 }
 
 static void run_fft(OrcTx *t, cpx *dst, const cpx *src)
@@ -492,7 +566,8 @@ void orc_tx_run(OrcTx *t, void *out, void *in, ptrdiff_t stride, int count, ptrd
 {
     for (int c = 0; c < count; c++) {
         void *o = (uint8_t *)out + c * out_step, *i = (uint8_t *)in + c * in_step;
-        if (t->type == 0) run_fft(t, o, i);
+        if (t->type == 9) { if (t->inv) run_dct3(t, o, i); else run_dct2(t, o, i); }
+        else if (t->type == 0) run_fft(t, o, i);
         else if (t->type == 6) run_rdft(t, o, i);
         else if (t->pfa_m && t->inv) run_mdct_pfa_inv(t, o, i, stride / (ptrdiff_t)sizeof(float));
         else if (t->pfa_m) run_mdct_pfa_fwd(t, o, i, stride / (ptrdiff_t)sizeof(float));

@@ -157,6 +157,25 @@ def gen_tx_pfa():
     np.savez_compressed(os.path.join(OUT, "tx_pfa.npz"), **d)
 
 
+def gen_tx_dct():
+    """AV_TX_FLOAT_DCT: the reference's DCT-II (len points) and DCT-III (asked for len / 2) outputs, two scales."""
+    R = cl.ref()
+    d = {}
+    rng = np.random.default_rng(78)
+    for n in (8, 64, 512):
+        x = (rng.random((2, n + 2), dtype=np.float32) * 2 - 1).astype(np.float32)
+        x[:, n:] = 0
+        d[f"in_{n}"] = x
+        for inv, asked in ((0, n), (1, n // 2)):
+            for j, sc in enumerate((1.0, 0.5 / n)):
+                h = R.ffref_tx_open(9, inv, asked, sc, 0)
+                out, xin = np.zeros((2, n + 2), np.float32), x.copy()
+                R.ffref_tx_run(h, out.ctypes.data, xin.ctypes.data, 4, 2, out.strides[0], xin.strides[0])
+                R.ffref_tx_close(h)
+                d[f"out_{n}_{inv}_{j}"] = out[:, :n].copy()
+    np.savez_compressed(os.path.join(OUT, "tx_dct.npz"), **d)
+
+
 def gen_sws_fastbil():
     from cases import SWS_FASTBIL_CASES
     lines = []
@@ -465,5 +484,6 @@ if __name__ == "__main__":
     gen_idct_hbd()
     gen_sws_rgbsrc()
     gen_tx_pfa()
+    gen_tx_dct()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

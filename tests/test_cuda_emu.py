@@ -29,7 +29,7 @@ def emu():
             txt = open(os.path.join(src_dir, f)).read()
             for m in re.finditer(r"// \[device-code (\w+)\][^\n]*\n(.*?)// \[/device-code \1\]", txt, re.S):
                 found[m.group(1)] = m.group(2)
-    assert sorted(found) == ["fdsp", "idct_hbd", "sws_new", "sws_nvout", "tx_pfa", "unquant"], sorted(found)
+    assert sorted(found) == ["fdsp", "idct_hbd", "sws_new", "sws_nvout", "tx_dct", "tx_pfa", "unquant"], sorted(found)
     for k, v in found.items():
         open(os.path.join(gen, k + ".inc"), "w").write(v)
     so = os.path.join(gen, "libemu.so")
@@ -479,11 +479,12 @@ def emutx():
     assert "<<<" not in t
     open(os.path.join(gen, "host_tx.cpp"), "w").write(t)
     open(os.path.join(gen, "host_tx_pfa.cpp"), "w").write(rewrite_launches(open(os.path.join(cs, "tx_pfa.cu")).read()))
+    open(os.path.join(gen, "host_tx_dct.cpp"), "w").write(rewrite_launches(open(os.path.join(cs, "tx_dct.cu")).read()))
     so = os.path.join(gen, "libemutx.so")
     cxx = "/opt/gcc/bin/g++" if os.path.exists("/opt/gcc/bin/g++") else "g++"
     r = subprocess.run([cxx, "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread", "-ffp-contract=off", "-w", "-I" + os.path.join(EMU, "fake"), "-I" + cs,
                         "-I" + os.path.join(ROOT, "include"), "-I" + EMU, os.path.join(gen, "host_tx.cpp"), os.path.join(gen, "host_tx_pfa.cpp"),
-                        os.path.join(EMU, "fake_device.cpp"), "-o", so], capture_output=True, text=True)
+                        os.path.join(gen, "host_tx_dct.cpp"), os.path.join(EMU, "fake_device.cpp"), "-o", so], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
     L = C.CDLL(so)
     L.b200_tx_init_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_uint64]
@@ -534,7 +535,23 @@ def test_tx_whole_path_on_emulated_device(emutx):
             exp = _tx(O, "orc", 1, inv, n, 1.0 / n, x, n)
             assert np.array_equal(_emu_tx(emutx, 1, inv, n, 1.0 / n, x, n).view(np.uint32), exp.view(np.uint32)), ("pfa batch", n, inv)
             assert np.array_equal(_emu_tx(emutx, 1, inv, n, 1.0 / n, x[:3], n, host_fn=True).view(np.uint32), exp[:3].view(np.uint32)), ("pfa av_tx_fn", n, inv)
+    # AV_TX_FLOAT_DCT: DCT-II forward (len points), DCT-III inverse (asked for len, works on 2 * len), batch and av_tx_fn entries;
+    # the input is left alone
+    for n in (4, 16, 64, 512):
+        for sc in (1.0, 0.5 / n):
+            x = (rng.random((70 if n == 64 else 3, n), dtype=np.float32) * 2 - 1).astype(np.float32)
+            xp = np.concatenate([x, np.zeros((x.shape[0], 2), np.float32)], axis=1)       # the reference wants two floats of padding
+            for inv, asked in ((0, n), (1, n // 2)):
+                h = O.orc_tx_open(9, inv, asked, sc, 0)
+                e, xin = np.zeros((x.shape[0], n + 2), np.float32), xp.copy()
+                O.orc_tx_run(h, e.ctypes.data, xin.ctypes.data, 4, x.shape[0], e.strides[0], xin.strides[0])
+                O.orc_tx_close(h)
+                got = _emu_tx(emutx, 9, inv, asked, sc, x, n)
+                assert np.array_equal(got.view(np.uint32), e[:, :n].view(np.uint32)), ("dct batch", n, inv, sc)
+                got = _emu_tx(emutx, 9, inv, asked, sc, x[:2], n, host_fn=True)
+                assert np.array_equal(got.view(np.uint32), e[:2, :n].view(np.uint32)), ("dct av_tx_fn", n, inv, sc)
     x = np.zeros((1, 1920), np.float32)
+    assert _emu_tx(emutx, 9, 0, 96, 1.0, x, 96) == -38 and _emu_tx(emutx, 9, 0, 2, 1.0, x, 2) == -38 and _emu_tx(emutx, 9, 1, 1, 1.0, x, 2) == -38
     assert _emu_tx(emutx, 0, 0, 960, 1.0, x, 1920) == -38 and _emu_tx(emutx, 1, 1, 60, 1.0, x, 60) == -38 and _emu_tx(emutx, 6, 0, 96, 1.0, x, 98) == -38
 
 

@@ -405,3 +405,37 @@ def test_tx_pfa15_oracle_vs_ref_and_round_trip():
     for i in range(2 * n):                                          # direct MDCT definition, float64
         ref += x[0, i] * np.cos(np.pi / n * (i + 0.5 + n / 2) * (k + 0.5))
     assert np.allclose(coef[0], ref, atol=2e-3), float(np.abs(coef[0] - ref).max())
+
+
+# ---------------------------------------------------------------------------------------------- tx: DCT-II / DCT-III
+def _dct(L, pre, inv, asked, sc, x_padded, n):
+    h = getattr(L, pre + "_tx_open")(9, inv, asked, sc, 0)
+    assert h
+    out, xin = np.zeros((x_padded.shape[0], n + 2), np.float32), x_padded.copy()
+    getattr(L, pre + "_tx_run")(h, out.ctypes.data, xin.ctypes.data, 4, x_padded.shape[0], out.strides[0], xin.strides[0])
+    getattr(L, pre + "_tx_close")(h)
+    return out[:, :n]
+
+
+def test_tx_dct_oracle_golden_and_definition():
+    """ff_tx_dctII / ff_tx_dctIII against the reference's outputs bit for bit, and against the textbook DCT-II"""
+    g = np.load(os.path.join(G, "tx_dct.npz"))
+    O = cl.oracle()
+    for n in (8, 64, 512):
+        for inv, asked in ((0, n), (1, n // 2)):
+            for j, sc in enumerate((1.0, 0.5 / n)):
+                got = _dct(O, "orc", inv, asked, sc, g[f"in_{n}"], n)
+                assert np.array_equal(got.view(np.uint32), g[f"out_{n}_{inv}_{j}"].view(np.uint32)), (n, inv, j)
+    if cl.have_ref():
+        R = cl.ref()
+        rng = np.random.default_rng(13)
+        for n in (4, 16, 256, 2048):
+            x = (rng.random((2, n + 2), dtype=np.float32) * 2 - 1).astype(np.float32)
+            for inv, asked in ((0, n), (1, n // 2)):
+                assert np.array_equal(_dct(R, "ffref", inv, asked, -1.0, x, n).view(np.uint32), _dct(O, "orc", inv, asked, -1.0, x, n).view(np.uint32)), (n, inv)
+    n = 64
+    x = np.random.default_rng(3).random((1, n + 2)).astype(np.float32)
+    k, i = np.arange(n)[:, None], np.arange(n)[None, :]
+    ref = (np.cos(np.pi / n * (i + 0.5) * k) * x[0, :n].astype(np.float64)).sum(axis=1)
+    got = _dct(O, "orc", 0, n, 1.0, x, n)[0]
+    assert np.allclose(got, ref, atol=1e-3) or np.allclose(got, 2 * ref, atol=1e-3) or np.allclose(got, ref / 2, atol=1e-3), float(np.abs(got - ref).max())

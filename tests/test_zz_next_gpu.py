@@ -366,3 +366,42 @@ def test_tx_mdct_pfa15(device):
         tx.av_tx_init(tx.AV_TX_FLOAT_MDCT, 1, 60, scale=1.0)            # 15 x 2: below the smallest sub-transform carried
     with pytest.raises(fb.B200Error):
         tx.av_tx_init(tx.AV_TX_FLOAT_FFT, 0, 960)                       # compound FFTs are not built
+
+
+# ---------------------------------------------------------------------------------------------- tx: DCT-II / DCT-III
+@isolated
+def test_tx_dct(device):
+    """AV_TX_FLOAT_DCT: host av_tx_fn against the reference's outputs, batched device call against the oracle"""
+    import torch
+    import ffmpeg_b200 as fb
+    from ffmpeg_b200 import tx
+    from test_oracle_more import _dct
+    g = np.load(os.path.join(G, "tx_dct.npz"))
+    O = cl.oracle()
+    for n in (8, 64, 512):
+        for inv, asked in ((0, n), (1, n // 2)):
+            for j, sc in enumerate((1.0, 0.5 / n)):
+                c = tx.av_tx_init(tx.AV_TX_FLOAT_DCT, inv, asked, scale=sc)
+                x = g[f"in_{n}"]
+                out = np.zeros((x.shape[0], n), np.float32)
+                for r in range(x.shape[0]):
+                    xin = x[r, :n].copy()
+                    c.fn(out[r], xin, 4)
+                    assert np.array_equal(xin, x[r, :n])                                 # the input is left alone
+                assert np.array_equal(out.view(np.uint32), g[f"out_{n}_{inv}_{j}"].view(np.uint32)), (n, inv, j)
+                c.uninit()
+    rng = np.random.default_rng(22)
+    for n in (16, 1024):
+        for inv, asked in ((0, n), (1, n // 2)):
+            cnt = 2000
+            x = (rng.random((cnt, n + 2), dtype=np.float32) * 2 - 1).astype(np.float32)
+            c = tx.av_tx_init(tx.AV_TX_FLOAT_DCT, inv, asked, scale=1.0, device=device)
+            with on_stream(device):
+                di, do = torch.from_numpy(np.ascontiguousarray(x[:, :n])).cuda(), torch.zeros((cnt, n), dtype=torch.float32, device="cuda")
+                c.batch_device(do, di, 4, cnt, 4 * n, 4 * n)
+                device.sync()
+                got = do.cpu().numpy()
+            assert np.array_equal(got.view(np.uint32), _dct(O, "orc", inv, asked, 1.0, x, n).view(np.uint32)), (n, inv)
+            c.uninit()
+    with pytest.raises(fb.B200Error):
+        tx.av_tx_init(tx.AV_TX_FLOAT_DCT, 0, 96, scale=1.0)
