@@ -172,6 +172,7 @@ PROTOTYPES = {
     "b200_idct_hbd_batch_device": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int64, vp, vp, vp, C.c_int]),
     "b200_tx_pfa_tables": (C.c_int, [C.c_int, C.c_int, C.c_float, vp, C.c_int, vp]),
     "b200_tx_dct_table": (C.c_int, [C.c_int, C.c_int, vp, C.c_int]),
+    "b200_tx_i32_tables": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_float, vp, C.c_int, vp]),
     "b200_float_dsp_init": (C.c_int, [vp]),
     "b200_float_dsp_batch_device": (C.c_int, [vp, C.c_int, C.c_int64, C.c_int, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, C.c_double]),
     "b200_videodsp_init": (C.c_int, [C.POINTER(VideoDSPContext), C.c_int]),

@@ -16,6 +16,7 @@
 #include "common.h"
 #include "tx_pfa.h"
 #include "tx_dct.h"
+#include "tx_int32.h"
 #include <vector>
 #include <cmath>
 #include <cstring>
@@ -431,6 +432,7 @@ struct B200TXContext {
     B200Device *dev = nullptr;
     TxPfa *pfa = nullptr;            // compound 15 x M MDCT (tx_pfa.cu): everything below d is unused then
     TxDct *dct = nullptr;            // AV_TX_FLOAT_DCT (tx_dct.cu): stages around a child RDFT context
+    TxI32 *i32 = nullptr;            // AV_TX_INT32_FFT / _MDCT (tx_int32.cu)
     int type = 0, inv = 0, len = 0;
     TxDev d{};
     void *blob = nullptr;
@@ -587,6 +589,7 @@ static int tx_launch(B200TXContext *c, cudaStream_t st, void *out, const void *i
     if (count <= 0) return 0;
     if (c->pfa) return tx_pfa_launch(c->pfa, st, out, in, stride, count, out_step, in_step);
     if (c->dct) return tx_dct_launch(c->dct, st, out, in, count, out_step, in_step);
+    if (c->i32) return tx_i32_launch(c->i32, st, out, in, stride, count, out_step, in_step);
     // measured on B200 (scripts/quick_bench.py tx with B200_TX_TB / B200_TX_THREADS): 256 threads pay off from 1024 points per
     // transform on; 512-point transforms (iMDCT-1024) run 18 % faster with 128-thread CTAs
     int threads = c->d.n >= 1024 ? 256 : c->d.n >= 256 ? 128 : 64;
@@ -619,6 +622,7 @@ static int tx_launch(B200TXContext *c, cudaStream_t st, void *out, const void *i
 // av_tx_fn shaped entry: HOST pointers, one transform
 static void tx_host_fn(B200TXContext *c, void *out, void *in, ptrdiff_t stride)
 {
+    if (c->i32) { tx_i32_host_fn(c->i32, out, in, stride); return; }
     auto fail = [](const char *what) { fprintf(stderr, "libb200dsp: av_tx_fn failed: %s (%s)\n", what, b200_last_error()); abort(); };
     B200Device *d = c->dev;
     if (cudaSetDevice(d->ordinal) != cudaSuccess) fail("cudaSetDevice");
@@ -653,8 +657,23 @@ B200_API int b200_tx_init_device(B200Device *dev, B200TXContext **ctx, b200_tx_f
     if (!ctx || !len) return B200_EINVAL;                            // av_tx_init, tx.c:903-940
     *ctx = nullptr;
     if (!dev) return B200_ENODEV;
-    if (type != B200_TX_FLOAT_FFT && type != B200_TX_FLOAT_MDCT && type != B200_TX_FLOAT_RDFT && type != B200_TX_FLOAT_DCT) return B200_ENOSYS;
+    if (type != B200_TX_FLOAT_FFT && type != B200_TX_FLOAT_MDCT && type != B200_TX_FLOAT_RDFT && type != B200_TX_FLOAT_DCT &&
+        type != B200_TX_INT32_FFT && type != B200_TX_INT32_MDCT) return B200_ENOSYS;
     if (flags & ~(uint64_t)B200_TX_UNALIGNED) return B200_ENOSYS;    // INPLACE / FULL_IMDCT / REAL_TO_* not implemented
+    if (type == B200_TX_INT32_FFT || type == B200_TX_INT32_MDCT) {   // 32-bit fixed point (tx_int32.cu)
+        if (!tx_i32_length_ok(type, len)) return B200_ENOSYS;
+        float sci = 1.0f;
+        if (type == B200_TX_INT32_MDCT && scale) sci = *(const float *)scale;
+        B200TXContext *ci = new (std::nothrow) B200TXContext();
+        if (!ci) return B200_ENOMEM;
+        ci->dev = dev; ci->type = type; ci->inv = !!inv; ci->len = len;
+        if (cudaSetDevice(dev->ordinal) != cudaSuccess) { delete ci; return B200_EEXTERNAL; }
+        ci->i32 = tx_i32_create(dev, type, ci->inv, len, sci);
+        if (!ci->i32) { delete ci; return B200_EEXTERNAL; }
+        *ctx = ci;
+        if (tx) *tx = tx_host_fn;
+        return 0;
+    }
     if (type == B200_TX_FLOAT_DCT) {                                 // DCT-II / DCT-III around a child real-DFT context (tx_dct.cu)
         if (!tx_dct_length_ok(!!inv, len)) return B200_ENOSYS;
         float scd = 1.0f;
@@ -713,6 +732,7 @@ B200_API void b200_tx_uninit(B200TXContext **ctx)
     if (c->blob) cudaFree(c->blob);
     tx_pfa_free(c->pfa);
     tx_dct_free(c->dct);
+    tx_i32_free(c->i32);
     delete c;
     *ctx = nullptr;
 }
@@ -721,7 +741,7 @@ B200_API int b200_tx_batch_device(B200TXContext *c, void *out, const void *in, p
                                   ptrdiff_t out_step, ptrdiff_t in_step)
 {
     if (!c || !out || !in || count < 0) return B200_EINVAL;
-    if (c->type == 1 && (stride & 3)) return B200_EINVAL;
+    if ((c->type == 1 || c->type == B200_TX_INT32_MDCT) && (stride & 3)) return B200_EINVAL;
     B200_CUDA_OK(cudaSetDevice(c->dev->ordinal));
-    return tx_launch(c, c->dev->stream, out, in, c->type == 1 ? stride : 8, count, out_step, in_step);
+    return tx_launch(c, c->dev->stream, out, in, (c->type == 1 || c->type == B200_TX_INT32_MDCT) ? stride : 8, count, out_step, in_step);
 }

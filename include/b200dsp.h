@@ -433,6 +433,8 @@ int  b200_emulated_edge_mc_batch_device(B200Device *dev, int64_t n, uint8_t *buf
                                    * (tx_template.c:1655-1724) the host av_tx_fn rewrites its input on the inverse; the
                                    * batched device entry point leaves the input untouched.  AV_TX_REAL_TO_REAL /
                                    * AV_TX_REAL_TO_IMAGINARY are not implemented. */
+#define B200_TX_INT32_FFT   4     /* AV_TX_INT32_FFT: AVComplexInt32 in / out, power-of-two lengths (libavutil/tx_int32.c) */
+#define B200_TX_INT32_MDCT  5     /* AV_TX_INT32_MDCT: int32 samples, scale as const float *, power-of-two lengths (fixed-point AAC / AC-3) */
 #define B200_TX_FLOAT_DCT   9     /* AV_TX_FLOAT_DCT: forward = DCT-II of len points, inverse = DCT-III of 2 * len points (the reference's
                                    * ff_tx_dct_init doubles the length it is given, libavutil/tx_template.c:1844-1848; callers pass N / 2).
                                    * ff_tx_dctII / ff_tx_dctIII (tx_template.c:1874-1968).  Input and output are N floats per transform;
@@ -450,6 +452,8 @@ int  b200_tx_init(B200TXContext **ctx, b200_tx_fn *tx, int type, int inv, int le
 int  b200_tx_pfa_tables(int inv, int len, float scale, int32_t *words, int cap, int32_t *layout8);
 /* host-only: the factor table of ff_tx_dct_init (N rotation factors, then N / 2 butterfly factors), for the CPU test tier */
 int  b200_tx_dct_table(int inv, int len, float *tab, int cap);
+/* host-only: the tables of an int32 transform flattened into words (layout4: offsets of map, exp, cosine tables; then log2 n) */
+int  b200_tx_i32_tables(int type, int inv, int len, float scale, int32_t *words, int cap, int32_t *layout4);
 int  b200_tx_init_device(B200Device *dev, B200TXContext **ctx, b200_tx_fn *tx, int type, int inv, int len,
                          const void *scale, uint64_t flags);
 void b200_tx_uninit(B200TXContext **ctx);

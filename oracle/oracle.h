@@ -146,6 +146,11 @@ typedef struct OrcTx OrcTx;
 OrcTx *orc_tx_open(int type /*0 FFT, 1 MDCT, 6 RDFT (r2c forward, c2r inverse)*/, int inv, int len, float scale, unsigned flags);
 void   orc_tx_close(OrcTx *t);
 void   orc_tx_run(OrcTx *t, void *out, void *in, ptrdiff_t stride, int count, ptrdiff_t out_step, ptrdiff_t in_step);
+/* the 32-bit fixed-point transforms (txi_oracle.c): type 4 AV_TX_INT32_FFT, 5 AV_TX_INT32_MDCT, power-of-two lengths */
+typedef struct OrcTxI OrcTxI;
+OrcTxI *orc_txi_open(int type, int inv, int len, float scale, unsigned flags);
+void    orc_txi_close(OrcTxI *t);
+void    orc_txi_run(OrcTxI *t, void *out, void *in, ptrdiff_t stride, int count, ptrdiff_t out_step, ptrdiff_t in_step);
 
 #ifdef __cplusplus
 }

@@ -176,6 +176,32 @@ def gen_tx_dct():
     np.savez_compressed(os.path.join(OUT, "tx_dct.npz"), **d)
 
 
+def gen_tx_int32():
+    """AV_TX_INT32_FFT / AV_TX_INT32_MDCT: the reference's outputs (full-range FFT inputs, so the wrapping sums are exercised)."""
+    R = cl.ref()
+    d = {}
+    rng = np.random.default_rng(79)
+    for n in (8, 64, 1024):
+        x = rng.integers(-(1 << 31), 1 << 31, (2, 2 * n)).astype(np.int32)
+        d[f"in_{n}"] = x
+        for inv in (0, 1):
+            h = R.ffref_tx_open(4, inv, n, 1.0, 0)
+            out, xin = np.zeros((2, 2 * n), np.int32), x.copy()
+            R.ffref_tx_run(h, out.ctypes.data, xin.ctypes.data, 8, 2, out.strides[0], xin.strides[0])
+            R.ffref_tx_close(h)
+            d[f"fft_{n}_{inv}"] = out
+        xs = (x >> 6).astype(np.int32)
+        for j, sc in enumerate((1.0 / n, -1.0 / 32768)):
+            for inv in (1, 0):
+                xi = np.ascontiguousarray(xs[:, :n]) if inv else xs
+                h = R.ffref_tx_open(5, inv, n, sc, 0)
+                out, xin = np.zeros((2, n), np.int32), xi.copy()
+                R.ffref_tx_run(h, out.ctypes.data, xin.ctypes.data, 4, 2, out.strides[0], xin.strides[0])
+                R.ffref_tx_close(h)
+                d[f"mdct_{n}_{inv}_{j}"] = out
+    np.savez_compressed(os.path.join(OUT, "tx_int32.npz"), **d)
+
+
 def gen_sws_fastbil():
     from cases import SWS_FASTBIL_CASES
     lines = []
@@ -485,5 +511,6 @@ if __name__ == "__main__":
     gen_sws_rgbsrc()
     gen_tx_pfa()
     gen_tx_dct()
+    gen_tx_int32()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

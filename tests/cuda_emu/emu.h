@@ -17,6 +17,7 @@ struct uint4 { unsigned x, y, z, w; };
 struct uint2 { unsigned x, y; };
 struct int2 { int x, y; };
 static inline uint2 make_uint2(unsigned a, unsigned b) { uint2 r = { a, b }; return r; }
+static inline int2 make_int2(int a, int b) { int2 r = { a, b }; return r; }
 static inline uint4 make_uint4(unsigned a, unsigned b, unsigned c, unsigned d) { uint4 r = { a, b, c, d }; return r; }
 struct float2 { float x, y; };
 static inline float2 make_float2(float a, float b) { float2 r = { a, b }; return r; }

@@ -24,6 +24,9 @@ constexpr int WARPS = 4;
 namespace pfa {
 #include "_gen/tx_pfa.inc"
 }
+namespace txi {
+#include "_gen/tx_int32.inc"         // likewise
+}
 namespace dct {
 #include "_gen/tx_dct.inc"           // exercised through the library's entry points in test_tx_whole_path_on_emulated_device
 }

@@ -29,7 +29,7 @@ def emu():
             txt = open(os.path.join(src_dir, f)).read()
             for m in re.finditer(r"// \[device-code (\w+)\][^\n]*\n(.*?)// \[/device-code \1\]", txt, re.S):
                 found[m.group(1)] = m.group(2)
-    assert sorted(found) == ["fdsp", "idct_hbd", "sws_new", "sws_nvout", "tx_dct", "tx_pfa", "unquant"], sorted(found)
+    assert sorted(found) == ["fdsp", "idct_hbd", "sws_new", "sws_nvout", "tx_dct", "tx_int32", "tx_pfa", "unquant"], sorted(found)
     for k, v in found.items():
         open(os.path.join(gen, k + ".inc"), "w").write(v)
     so = os.path.join(gen, "libemu.so")
@@ -480,11 +480,13 @@ def emutx():
     open(os.path.join(gen, "host_tx.cpp"), "w").write(t)
     open(os.path.join(gen, "host_tx_pfa.cpp"), "w").write(rewrite_launches(open(os.path.join(cs, "tx_pfa.cu")).read()))
     open(os.path.join(gen, "host_tx_dct.cpp"), "w").write(rewrite_launches(open(os.path.join(cs, "tx_dct.cu")).read()))
+    open(os.path.join(gen, "host_tx_int32.cpp"), "w").write(rewrite_launches(open(os.path.join(cs, "tx_int32.cu")).read()))
     so = os.path.join(gen, "libemutx.so")
     cxx = "/opt/gcc/bin/g++" if os.path.exists("/opt/gcc/bin/g++") else "g++"
     r = subprocess.run([cxx, "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread", "-ffp-contract=off", "-w", "-I" + os.path.join(EMU, "fake"), "-I" + cs,
                         "-I" + os.path.join(ROOT, "include"), "-I" + EMU, os.path.join(gen, "host_tx.cpp"), os.path.join(gen, "host_tx_pfa.cpp"),
-                        os.path.join(gen, "host_tx_dct.cpp"), os.path.join(EMU, "fake_device.cpp"), "-o", so], capture_output=True, text=True)
+                        os.path.join(gen, "host_tx_dct.cpp"), os.path.join(gen, "host_tx_int32.cpp"), os.path.join(EMU, "fake_device.cpp"), "-o", so],
+                       capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
     L = C.CDLL(so)
     L.b200_tx_init_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_uint64]
@@ -496,6 +498,21 @@ def emutx():
     return L
 
 
+def orc_txi(typ, inv, n, scale, x, out_words):
+    """the int32 oracle (txi_oracle.c): type 4 FFT / 5 MDCT"""
+    O = cl.oracle()
+    O.orc_txi_open.restype = C.c_void_p
+    O.orc_txi_open.argtypes = [C.c_int, C.c_int, C.c_int, C.c_float, C.c_uint]
+    O.orc_txi_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_ssize_t, C.c_int, C.c_ssize_t, C.c_ssize_t]
+    O.orc_txi_close.argtypes = [C.c_void_p]
+    h = O.orc_txi_open(typ, inv, n, scale, 0)
+    assert h
+    out, xin = np.zeros((x.shape[0], out_words), np.int32), x.copy()
+    O.orc_txi_run(h, out.ctypes.data, xin.ctypes.data, 8 if typ == 4 else 4, x.shape[0], out.strides[0], xin.strides[0])
+    O.orc_txi_close(h)
+    return out
+
+
 def _emu_tx(L, typ, inv, n, scale, x, out_floats, host_fn=False):
     """b200_tx_init_device + b200_tx_batch_device (or the av_tx_fn host entry, one transform at a time) on the emulated device"""
     from ffmpeg_b200._lib import TX_FN
@@ -504,13 +521,14 @@ def _emu_tx(L, typ, inv, n, scale, x, out_floats, host_fn=False):
     ret = L.b200_tx_init_device(L.dev, C.byref(ctx), C.byref(fn), typ, inv, n, C.byref(sc), 0)
     if ret < 0:
         return ret
-    out = np.zeros((x.shape[0], out_floats), np.float32)
+    out = np.zeros((x.shape[0], out_floats), x.dtype)
     xin = x.copy()
+    st = 8 if typ in (0, 4) else 4
     if host_fn:
         for r in range(x.shape[0]):
-            fn(ctx, out[r].ctypes.data, xin[r].ctypes.data, 8 if typ == 0 else 4)
+            fn(ctx, out[r].ctypes.data, xin[r].ctypes.data, st)
     else:
-        assert L.b200_tx_batch_device(ctx, out.ctypes.data, xin.ctypes.data, 8 if typ == 0 else 4, x.shape[0], out.strides[0], xin.strides[0]) == 0
+        assert L.b200_tx_batch_device(ctx, out.ctypes.data, xin.ctypes.data, st, x.shape[0], out.strides[0], xin.strides[0]) == 0
     L.b200_tx_uninit(C.byref(ctx))
     return out
 
@@ -550,7 +568,23 @@ def test_tx_whole_path_on_emulated_device(emutx):
                 assert np.array_equal(got.view(np.uint32), e[:, :n].view(np.uint32)), ("dct batch", n, inv, sc)
                 got = _emu_tx(emutx, 9, inv, asked, sc, x[:2], n, host_fn=True)
                 assert np.array_equal(got.view(np.uint32), e[:2, :n].view(np.uint32)), ("dct av_tx_fn", n, inv, sc)
+    # AV_TX_INT32_FFT / AV_TX_INT32_MDCT (one thread per transform), batch and av_tx_fn entries, full-range inputs (sums wrap)
+    for n in (2, 8, 32, 256, 2048):
+        xi32 = rng.integers(-(1 << 31), 1 << 31, (70 if n == 32 else 3, 2 * n)).astype(np.int32)
+        for inv in (0, 1):
+            e = orc_txi(4, inv, n, 1.0, xi32, 2 * n)
+            assert np.array_equal(_emu_tx(emutx, 4, inv, n, 1.0, xi32, 2 * n), e), ("int32 fft", n, inv)
+            assert np.array_equal(_emu_tx(emutx, 4, inv, n, 1.0, xi32[:2], 2 * n, host_fn=True), e[:2]), ("int32 fft av_tx_fn", n, inv)
+        if n >= 8:
+            xs = (xi32 >> 6).astype(np.int32)
+            for sc in (1.0, 1.0 / n, -1.0 / 32768):
+                e = orc_txi(5, 1, n, sc, np.ascontiguousarray(xs[:, :n]), n)
+                assert np.array_equal(_emu_tx(emutx, 5, 1, n, sc, np.ascontiguousarray(xs[:, :n]), n), e), ("int32 imdct", n, sc)
+                e = orc_txi(5, 0, n, sc, xs, n)
+                assert np.array_equal(_emu_tx(emutx, 5, 0, n, sc, xs, n), e), ("int32 mdct", n, sc)
+                assert np.array_equal(_emu_tx(emutx, 5, 0, n, sc, xs[:2], n, host_fn=True), e[:2]), ("int32 mdct av_tx_fn", n, sc)
     x = np.zeros((1, 1920), np.float32)
+    assert _emu_tx(emutx, 4, 0, 96, 1.0, x, 192) == -38 and _emu_tx(emutx, 5, 1, 960, 1.0, x, 960) == -38 and _emu_tx(emutx, 2, 0, 64, 1.0, x, 128) == -38
     assert _emu_tx(emutx, 9, 0, 96, 1.0, x, 96) == -38 and _emu_tx(emutx, 9, 0, 2, 1.0, x, 2) == -38 and _emu_tx(emutx, 9, 1, 1, 1.0, x, 2) == -38
     assert _emu_tx(emutx, 0, 0, 960, 1.0, x, 1920) == -38 and _emu_tx(emutx, 1, 1, 60, 1.0, x, 60) == -38 and _emu_tx(emutx, 6, 0, 96, 1.0, x, 98) == -38
 

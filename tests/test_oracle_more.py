@@ -439,3 +439,47 @@ def test_tx_dct_oracle_golden_and_definition():
     ref = (np.cos(np.pi / n * (i + 0.5) * k) * x[0, :n].astype(np.float64)).sum(axis=1)
     got = _dct(O, "orc", 0, n, 1.0, x, n)[0]
     assert np.allclose(got, ref, atol=1e-3) or np.allclose(got, 2 * ref, atol=1e-3) or np.allclose(got, ref / 2, atol=1e-3), float(np.abs(got - ref).max())
+
+
+# ---------------------------------------------------------------------------------------------- tx: 32-bit fixed point
+def _txi(L, pre, typ, inv, n, sc, x, outn):
+    if pre == "orc":
+        L.orc_txi_open.restype = C.c_void_p
+        L.orc_txi_open.argtypes = [C.c_int, C.c_int, C.c_int, C.c_float, C.c_uint]
+        L.orc_txi_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_ssize_t, C.c_int, C.c_ssize_t, C.c_ssize_t]
+        L.orc_txi_close.argtypes = [C.c_void_p]
+        op, ru, clo = L.orc_txi_open, L.orc_txi_run, L.orc_txi_close
+    else:
+        op, ru, clo = L.ffref_tx_open, L.ffref_tx_run, L.ffref_tx_close
+    h = op(typ, inv, n, sc, 0)
+    assert h
+    out, xin = np.zeros((x.shape[0], outn), np.int32), x.copy()
+    ru(h, out.ctypes.data, xin.ctypes.data, 8 if typ == 4 else 4, x.shape[0], out.strides[0], xin.strides[0])
+    clo(h)
+    return out
+
+
+def test_tx_int32_oracle_golden_and_ref():
+    """AV_TX_INT32_FFT / _MDCT (TX_INT32 instantiation of tx_template.c) against the reference's outputs"""
+    g = np.load(os.path.join(G, "tx_int32.npz"))
+    O = cl.oracle()
+    for n in (8, 64, 1024):
+        x = g[f"in_{n}"]
+        xs = (x >> 6).astype(np.int32)
+        for inv in (0, 1):
+            assert np.array_equal(_txi(O, "orc", 4, inv, n, 1.0, x, 2 * n), g[f"fft_{n}_{inv}"]), (n, inv)
+        for j, sc in enumerate((1.0 / n, -1.0 / 32768)):
+            for inv in (1, 0):
+                xi = np.ascontiguousarray(xs[:, :n]) if inv else xs
+                assert np.array_equal(_txi(O, "orc", 5, inv, n, sc, xi, n), g[f"mdct_{n}_{inv}_{j}"]), (n, inv, j)
+    if cl.have_ref():
+        R = cl.ref()
+        rng = np.random.default_rng(14)
+        for n in (2, 4, 16, 32, 256, 2048):
+            x = rng.integers(-(1 << 31), 1 << 31, (2, 2 * n)).astype(np.int32)
+            for inv in (0, 1):
+                assert np.array_equal(_txi(R, "ffref", 4, inv, n, 1.0, x, 2 * n), _txi(O, "orc", 4, inv, n, 1.0, x, 2 * n)), (n, inv)
+            if n >= 8:
+                for inv in (1, 0):
+                    xi = np.ascontiguousarray((x >> 5)[:, :n]) if inv else (x >> 5)
+                    assert np.array_equal(_txi(R, "ffref", 5, inv, n, 1.0, xi, n), _txi(O, "orc", 5, inv, n, 1.0, xi, n)), (n, inv)

@@ -405,3 +405,46 @@ def test_tx_dct(device):
             c.uninit()
     with pytest.raises(fb.B200Error):
         tx.av_tx_init(tx.AV_TX_FLOAT_DCT, 0, 96, scale=1.0)
+
+
+# ---------------------------------------------------------------------------------------------- tx: 32-bit fixed point
+@isolated
+def test_tx_int32(device):
+    """AV_TX_INT32_FFT / AV_TX_INT32_MDCT: host av_tx_fn against the reference's outputs, batched device call against the oracle"""
+    import torch
+    from ffmpeg_b200 import tx
+    from test_oracle_more import _txi
+    g = np.load(os.path.join(G, "tx_int32.npz"))
+    O = cl.oracle()
+    for n in (8, 64, 1024):
+        x = g[f"in_{n}"]
+        xs = (x >> 6).astype(np.int32)
+        for inv in (0, 1):
+            c = tx.av_tx_init(tx.AV_TX_INT32_FFT, inv, n)
+            out = np.zeros_like(x)
+            for r in range(2):
+                c.fn(out[r], x[r].copy(), 8)
+            assert np.array_equal(out, g[f"fft_{n}_{inv}"]), (n, inv)
+            c.uninit()
+        for j, sc in enumerate((1.0 / n, -1.0 / 32768)):
+            for inv in (1, 0):
+                xi = np.ascontiguousarray(xs[:, :n]) if inv else xs
+                c = tx.av_tx_init(tx.AV_TX_INT32_MDCT, inv, n, scale=sc)
+                out = np.zeros((2, n), np.int32)
+                for r in range(2):
+                    c.fn(out[r], xi[r].copy(), 4)
+                assert np.array_equal(out, g[f"mdct_{n}_{inv}_{j}"]), (n, inv, j)
+                c.uninit()
+    rng = np.random.default_rng(23)
+    for n in (16, 1024):
+        cnt = 2000
+        x = rng.integers(-(1 << 29), 1 << 29, (cnt, 2 * n)).astype(np.int32)
+        for typ, inv, xin, outn in ((4, 0, x, 2 * n), (4, 1, x, 2 * n), (5, 1, np.ascontiguousarray(x[:, :n]), n), (5, 0, x, n)):
+            c = tx.av_tx_init(typ, inv, n, scale=1.0 / n, device=device)
+            with on_stream(device):
+                di, do = torch.from_numpy(xin).cuda(), torch.zeros((cnt, outn), dtype=torch.int32, device="cuda")
+                c.batch_device(do, di, 8 if typ == 4 else 4, cnt, 4 * outn, xin.strides[0])
+                device.sync()
+                got = do.cpu().numpy()
+            assert np.array_equal(got, _txi(O, "orc", typ, inv, n, 1.0 / n, xin, outn)), (typ, inv, n)
+            c.uninit()
