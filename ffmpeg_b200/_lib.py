@@ -95,6 +95,13 @@ class FloatDSPContext(C.Structure):
                 ("scalarproduct_double", C.CFUNCTYPE(C.c_double, _D, _D, C.c_size_t))]
 
 
+class ProresDSPContext(C.Structure):
+    """libavcodec/proresdsp.h:28-35"""
+    _fields_ = [("idct_permutation_type", C.c_int), ("idct_permutation", C.c_uint8 * 64),
+                ("idct_put", C.CFUNCTYPE(None, C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_void_p)),
+                ("idct_put_bayer", C.c_void_p)]
+
+
 class MpvUnquant(C.Structure):
     """B200MpvUnquant: the MPVContext fields the inverse quantisers read (libavcodec/mpegvideo.h:70-77,201-203,258)"""
     _fields_ = [("intra_matrix", C.c_uint16 * 64), ("inter_matrix", C.c_uint16 * 64), ("permutated", C.c_uint8 * 64),
@@ -173,6 +180,8 @@ PROTOTYPES = {
     "b200_tx_pfa_tables": (C.c_int, [C.c_int, C.c_int, C.c_float, vp, C.c_int, vp]),
     "b200_tx_dct_table": (C.c_int, [C.c_int, C.c_int, vp, C.c_int]),
     "b200_tx_i32_tables": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_float, vp, C.c_int, vp]),
+    "b200_proresdsp_init": (C.c_int, [vp, C.c_int]),
+    "b200_prores_idct_put_batch_device": (C.c_int, [vp, C.c_int, vp, C.c_int64, vp, vp, vp, vp, C.c_int]),
     "b200_float_dsp_init": (C.c_int, [vp]),
     "b200_float_dsp_batch_device": (C.c_int, [vp, C.c_int, C.c_int64, C.c_int, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, vp, C.c_int64, C.c_double]),
     "b200_videodsp_init": (C.c_int, [C.POINTER(VideoDSPContext), C.c_int]),

@@ -21,6 +21,10 @@ template <> struct K<10> { static constexpr unsigned W1 = 22725, W2 = 21407, W3 
                            static constexpr int ROW = 12, COL = 19, DC = 2; };
 template <> struct K<12> { static constexpr unsigned W1 = 45451, W2 = 42813, W3 = 38531, W4 = 32767, W5 = 25746, W6 = 17734, W7 = 9041;
                            static constexpr int ROW = 16, COL = 17, DC = -1; };
+// the EXTRA_SHIFT instantiation proresdsp.c makes of the 10-bit constants (simple_idct_template.c:73-76: ROW_SHIFT 13, COL_SHIFT 18,
+// DC_SHIFT 1) with the two extra bits its row pass is called with (proresdsp.c:61-62) folded in: ROW 13 + 2, DC 1 - 2
+template <> struct K<110> { static constexpr unsigned W1 = 22725, W2 = 21407, W3 = 19265, W4 = 16384, W5 = 12873, W6 = 8867, W7 = 4520;
+                            static constexpr int ROW = 15, COL = 18, DC = -1; };
 
 template <int DEPTH> __device__ __forceinline__ void row_pass(int *r)     // r[0..7]: one row, values are int16 in int registers
 {
@@ -122,7 +126,37 @@ idct_hbd_kernel(int16_t *blocks, long long n, uint8_t *dest, const int64_t *dest
     }
 }
 
+// ProresDSPContext.idct_put (libavcodec/proresdsp.c:56-82,102-167): coefficients * qmat (int16 wrap), row pass, 8192 added to the first
+// row, in-place column pass (int16), pixels clipped to [4, 2^bits - 5].  VARIANT 110: 10 bit, 12: 12 bit.  One thread per block;
+// the coefficient blocks are left untouched (the reference overwrites them).
+template <int VARIANT>
+__global__ void __launch_bounds__(128)
+prores_idct_put_kernel(const int16_t *blocks, long long n, const int16_t *qmat, uint8_t *dest, const int64_t *dest_off, const int32_t *line_size,
+                       int uniform_ls)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int v[64];
+#pragma unroll
+    for (int k = 0; k < 64; k++) v[k] = (int)(int16_t)((int)blocks[64 * i + k] * (int)qmat[k]);
+#pragma unroll
+    for (int r = 0; r < 8; r++) row_pass<VARIANT>(v + 8 * r);
+    constexpr int BITS = VARIANT == 110 ? 10 : 12, LO = 4, HI = (1 << BITS) - 4 - 1;
+    uint16_t *d = reinterpret_cast<uint16_t *>(dest + dest_off[i]);
+    const long long ls = (line_size ? line_size[i] : uniform_ls) >> 1;
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+        int col[8], o[8];
+        v[c] = (int)(int16_t)(v[c] + 8192);
+#pragma unroll
+        for (int j = 0; j < 8; j++) col[j] = v[8 * j + c];
+        col_pass<VARIANT>(col, o);
+#pragma unroll
+        for (int j = 0; j < 8; j++) d[j * ls + c] = (uint16_t)min(max((int)(int16_t)o[j], LO), HI);
+    }
+}
 // [/device-code idct_hbd]
+
 template <int DEPTH>
 int launch(cudaStream_t st, int kind, int16_t *blocks, long long n, uint8_t *dest, const int64_t *off, const int32_t *ls, int uls)
 {
@@ -202,6 +236,72 @@ B200_API int b200_idct_hbd_batch_device(B200Device *dev, int depth, int kind, in
     B200_CUDA_OK(cudaSetDevice(dev->ordinal));
     const int ret = depth == 10 ? launch<10>(dev->stream, kind, blocks, nblocks, dest, dest_off, line_size, uniform_line_size)
                                 : launch<12>(dev->stream, kind, blocks, nblocks, dest, dest_off, line_size, uniform_line_size);
+    if (ret < 0) return ret;
+    B200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ---- ProresDSPContext (libavcodec/proresdsp.h:28-35, ff_proresdsp_init proresdsp.c:169-194)
+namespace {
+
+int launch_prores(cudaStream_t st, int bits, const int16_t *blocks, long long n, const int16_t *qmat, uint8_t *dest, const int64_t *off,
+                  const int32_t *ls, int uls)
+{
+    const long long grid = (n + 127) / 128;
+    if (grid > 0x7fffffffLL) return B200_EINVAL;
+    if (bits == 10) prores_idct_put_kernel<110><<<(unsigned)grid, 128, 0, st>>>(blocks, n, qmat, dest, off, ls, uls);
+    else            prores_idct_put_kernel<12><<<(unsigned)grid, 128, 0, st>>>(blocks, n, qmat, dest, off, ls, uls);
+    B200_LAUNCHED();
+    return 0;
+}
+
+template <int BITS>
+void prores_tab_put(uint16_t *out, ptrdiff_t linesize, int16_t *block, const int16_t *qmat)
+{
+    B200Device *dev = b200_default_device();
+    if (!dev) die("no device");
+    if (linesize < 16 || (linesize & 1)) die("line size must be even and >= 16 bytes");
+    if (cudaSetDevice(dev->ordinal) != cudaSuccess) die("cudaSetDevice");
+    uint8_t *scr = (uint8_t *)b200_scratch(dev, 128 + 128 + 128 + 16);
+    if (!scr) die("scratch");
+    int16_t *dblk = (int16_t *)scr, *dq = (int16_t *)(scr + 128);
+    uint8_t *ddst = scr + 256;
+    int64_t *doff = (int64_t *)(scr + 384);
+    cudaStream_t st = dev->stream;
+    const int64_t zero = 0;
+    if (cudaMemcpyAsync(dblk, block, 128, cudaMemcpyHostToDevice, st) != cudaSuccess) die("h2d block");
+    if (cudaMemcpyAsync(dq, qmat, 128, cudaMemcpyHostToDevice, st) != cudaSuccess) die("h2d qmat");
+    if (cudaMemcpyAsync(doff, &zero, 8, cudaMemcpyHostToDevice, st) != cudaSuccess) die("h2d off");
+    if (launch_prores(st, BITS, dblk, 1, dq, ddst, doff, nullptr, 16) < 0 || cudaGetLastError() != cudaSuccess) die("launch");
+    if (cudaMemcpy2DAsync(out, (size_t)linesize, ddst, 16, 16, 8, cudaMemcpyDeviceToHost, st) != cudaSuccess) die("d2h");
+    if (cudaStreamSynchronize(st) != cudaSuccess) die("sync");
+}
+
+} // namespace
+
+B200_API int b200_proresdsp_init(B200ProresDSPContext *c, int bits_per_raw_sample)
+{
+    if (!c) return B200_EINVAL;
+    if (bits_per_raw_sample != 10 && bits_per_raw_sample != 12) return B200_ENOSYS;
+    if (!b200_default_device()) return B200_ENODEV;
+    memset(c, 0, sizeof(*c));
+    c->idct_permutation_type = 0;                                    // FF_IDCT_PERM_NONE
+    for (int i = 0; i < 64; i++) c->idct_permutation[i] = (uint8_t)i;
+    c->idct_put = bits_per_raw_sample == 10 ? prores_tab_put<10> : prores_tab_put<12>;
+    c->idct_put_bayer = nullptr;                                     // ProRes RAW (32-bit coefficients + linearisation curve): not built
+    return 0;
+}
+
+B200_API int b200_prores_idct_put_batch_device(B200Device *dev, int bits, const int16_t *blocks, int64_t nblocks, const int16_t *qmat,
+                                               uint8_t *dest, const int64_t *dest_off, const int32_t *line_size, int uniform_line_size)
+{
+    if (!dev) dev = b200_default_device();
+    if (!dev) return B200_ENODEV;
+    if ((bits != 10 && bits != 12) || nblocks < 0) return B200_EINVAL;
+    if (nblocks == 0) return 0;
+    if (!blocks || !qmat || !dest || !dest_off || (reinterpret_cast<uintptr_t>(dest) & 1) || (!line_size && (uniform_line_size & 1))) return B200_EINVAL;
+    B200_CUDA_OK(cudaSetDevice(dev->ordinal));
+    const int ret = launch_prores(dev->stream, bits, blocks, nblocks, qmat, dest, dest_off, line_size, uniform_line_size);
     if (ret < 0) return ret;
     B200_CUDA_OK(cudaGetLastError());
     return 0;

@@ -36,6 +36,20 @@ def idct_hbd_batch_device(device, depth, kind, blocks, nblocks, dest=None, dest_
                  "idct_hbd_batch_device")
 
 
+def ff_proresdsp_init(bits_per_raw_sample):
+    """ProresDSPContext (libavcodec/proresdsp.h): c.idct_put(out, linesize, block, qmat) on HOST pointers"""
+    from ._lib import ProresDSPContext
+    c = ProresDSPContext()
+    check(lib().b200_proresdsp_init(C.byref(c), bits_per_raw_sample), "ff_proresdsp_init")
+    return c
+
+
+def prores_idct_put_batch_device(device, bits, blocks, nblocks, qmat, dest, dest_off, line_size=None, uniform_line_size=0):
+    return check(lib().b200_prores_idct_put_batch_device(device.handle, bits, vp(_dptr(blocks)), nblocks, vp(_dptr(qmat)), vp(_dptr(dest)),
+                                                         vp(_dptr(dest_off)), vp(_dptr(line_size)) if line_size is not None else None,
+                                                         uniform_line_size), "prores_idct_put_batch_device")
+
+
 def idct_batch_device(device, kind, blocks, nblocks, dest=None, dest_off=None, line_size=None, uniform_line_size=0):
     return check(lib().b200_idct_batch_device(device.handle, kind, vp(_dptr(blocks)), nblocks, vp(_dptr(dest)) if dest is not None else None,
                                               vp(_dptr(dest_off)) if dest_off is not None else None,

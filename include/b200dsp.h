@@ -210,6 +210,22 @@ int  b200_idctdsp_init_hbd(B200IDCTDSPContext *c, int idct_algo, int bits_per_ra
 int  b200_idct_hbd_batch_device(B200Device *dev, int depth, int kind, int16_t *blocks, int64_t nblocks, uint8_t *dest,
                                 const int64_t *dest_off, const int32_t *line_size, int uniform_line_size);
 
+/* ProresDSPContext (libavcodec/proresdsp.h:28-35) as ff_proresdsp_init(dsp, bits_per_raw_sample) fills it for 10 and 12 bit
+ * (libavcodec/proresdsp.c:56-82,102-194): idct_put = dequantise by qmat + inverse transform + bias + clip to [4, 2^bits - 5], the
+ * fused "dequant + IDCT" of the ProRes decoder (libavcodec/proresdec.c:559-598).  Same member order as the reference struct;
+ * idct_put_bayer (ProRes RAW) is left NULL. */
+typedef struct B200ProresDSPContext {
+    int idct_permutation_type;             /* FF_IDCT_PERM_NONE */
+    uint8_t idct_permutation[64];
+    void (*idct_put)(uint16_t *out, ptrdiff_t linesize, int16_t *block, const int16_t *qmat);     /* HOST pointers; block is not clobbered */
+    void (*idct_put_bayer)(uint16_t *out, ptrdiff_t linesize, int32_t *block, const int16_t *qmat, const uint16_t *lin_curve);
+} B200ProresDSPContext;
+int  b200_proresdsp_init(B200ProresDSPContext *c, int bits_per_raw_sample);
+/* batched, DEVICE pointers: block i = blocks + 64*i goes, dequantised by qmat[64] (device), to dest + dest_off[i] (bytes; uint16 pixels)
+ * with line size line_size[i] or uniform_line_size (bytes, even) */
+int  b200_prores_idct_put_batch_device(B200Device *dev, int bits, const int16_t *blocks, int64_t nblocks, const int16_t *qmat,
+                                       uint8_t *dest, const int64_t *dest_off, const int32_t *line_size, int uniform_line_size);
+
 /* mpegvideo inverse quantisers: the members of MPVUnquantDSPContext (libavcodec/mpegvideo_unquantize.h:31-44) as
  * ff_mpv_unquantize_init() installs them (libavcodec/mpegvideo_unquantize.c:50-290), i.e. what runs in front of the IDCT in
  * mpv_reconstruct_mb's put_dct / add_dequant_dct (libavcodec/mpegvideo_dec.c).  The reference functions take the whole

@@ -108,20 +108,24 @@ void orc_idct_batch(int kind, int16_t *blocks, int nblocks, uint8_t *dest, ptrdi
  * ((row[0] << 2) for 10 bit, (row[0] + 1) >> 1 for 12 bit, both & 0xffff), :209-257 columns, :281-368 put / add / in place on
  * uint16 pixels clipped to the bit depth.  Installed by ff_idctdsp_init for bits_per_raw_sample 9, 10 and 12
  * (idctdsp.c:248-266).  All sums mod 2^32 as in the reference (SUINT / unsigned MUL, MAC). */
-typedef struct { uint32_t w[8]; int row_shift, col_shift, dc_shift, depth; } HbdConst;
-static const HbdConst HBD10 = { { 0, 22725, 21407, 19265, 16384, 12873, 8867, 4520 }, 12, 19, 2, 10 };
-static const HbdConst HBD12 = { { 0, 45451, 42813, 38531, 32767, 25746, 17734, 9041 }, 16, 17, -1, 12 };
+typedef struct { uint32_t w[8]; int row_shift, col_shift, dc_shift, depth, extra; } HbdConst;
+static const HbdConst HBD10 = { { 0, 22725, 21407, 19265, 16384, 12873, 8867, 4520 }, 12, 19, 2, 10, 0 };
+static const HbdConst HBD12 = { { 0, 45451, 42813, 38531, 32767, 25746, 17734, 9041 }, 16, 17, -1, 12, 0 };
+/* the EXTRA_SHIFT instantiation of the 10-bit constants that proresdsp.c makes (simple_idct_template.c:73-76: ROW_SHIFT 13,
+ * COL_SHIFT 18, DC_SHIFT 1), run with extra_shift = 2 in the row pass (proresdsp.c:61-62) */
+static const HbdConst PRORES10 = { { 0, 22725, 21407, 19265, 16384, 12873, 8867, 4520 }, 13, 18, 1, 10, 2 };
 
 static void hbd_row(const HbdConst *k, int16_t *r)
 {
     const uint32_t *W = k->w;
     if (!(r[1] | r[2] | r[3] | r[4] | r[5] | r[6] | r[7])) {
-        int t = k->dc_shift >= 0 ? r[0] * (1 << k->dc_shift) : (r[0] + (1 << (-k->dc_shift - 1))) >> -k->dc_shift;
+        const int dsh = k->dc_shift - k->extra;
+        int t = dsh >= 0 ? r[0] * (1 << dsh) : (r[0] + (1 << (-dsh - 1))) >> -dsh;
         int16_t dc = (int16_t)(uint16_t)(t & 0xffff);
         for (int i = 0; i < 8; i++) r[i] = dc;
         return;
     }
-    uint32_t a0 = W[4] * (uint32_t)r[0] + (1u << (k->row_shift - 1)), a1 = a0, a2 = a0, a3 = a0;
+    uint32_t a0 = W[4] * (uint32_t)r[0] + (1u << (k->row_shift + k->extra - 1)), a1 = a0, a2 = a0, a3 = a0;
     a0 += W[2] * (uint32_t)r[2]; a1 += W[6] * (uint32_t)r[2]; a2 -= W[6] * (uint32_t)r[2]; a3 -= W[2] * (uint32_t)r[2];
     uint32_t b0 = W[1] * (uint32_t)r[1] + W[3] * (uint32_t)r[3];
     uint32_t b1 = W[3] * (uint32_t)r[1] - W[7] * (uint32_t)r[3];
@@ -135,7 +139,7 @@ static void hbd_row(const HbdConst *k, int16_t *r)
     b1 += -W[1] * (uint32_t)r[5] - W[5] * (uint32_t)r[7];
     b2 += W[7] * (uint32_t)r[5] + W[3] * (uint32_t)r[7];
     b3 += W[3] * (uint32_t)r[5] - W[1] * (uint32_t)r[7];
-    const int sh = k->row_shift;
+    const int sh = k->row_shift + k->extra;
     r[0] = (int16_t)((int32_t)(a0 + b0) >> sh); r[7] = (int16_t)((int32_t)(a0 - b0) >> sh);
     r[1] = (int16_t)((int32_t)(a1 + b1) >> sh); r[6] = (int16_t)((int32_t)(a1 - b1) >> sh);
     r[2] = (int16_t)((int32_t)(a2 + b2) >> sh); r[5] = (int16_t)((int32_t)(a2 - b2) >> sh);
@@ -178,6 +182,32 @@ int orc_idct_hbd(int depth, int kind, uint8_t *dest_, ptrdiff_t line_size, int16
             }
         }
     }
+    return 0;
+}
+
+/* ProresDSPContext.idct_put (libavcodec/proresdsp.c:56-82,102-167): block[i] *= qmat[i] (int16 wrap), the row pass (10 bit: the
+ * extra-shift constants with two more bits of shift; 12 bit: the plain 12-bit rows), 8192 added to the first row, the in-place column
+ * pass, then pixels clipped to [4, 2^bits - 5].  out = uint16 pixels, linesize in bytes. */
+int orc_prores_idct_put(int bits, uint8_t *out_, ptrdiff_t linesize, int16_t *block, const int16_t *qmat)
+{
+    const HbdConst *k = bits == 10 ? &PRORES10 : bits == 12 ? &HBD12 : 0;
+    if (!k) return -1;
+    uint16_t *out = (uint16_t *)out_;
+    const ptrdiff_t ls = linesize >> 1;
+    const int lo = 4, hi = (1 << bits) - 4 - 1;
+    int o[8];
+    for (int i = 0; i < 64; i++) block[i] = (int16_t)(block[i] * qmat[i]);
+    for (int i = 0; i < 8; i++) hbd_row(k, block + 8 * i);
+    for (int i = 0; i < 8; i++) {
+        block[i] = (int16_t)(block[i] + 8192);
+        hbd_col(k, block + i, o);
+        for (int j = 0; j < 8; j++) block[8 * j + i] = (int16_t)o[j];
+    }
+    for (int y = 0; y < 8; y++)
+        for (int x = 0; x < 8; x++) {
+            const int v = block[8 * y + x];
+            out[y * ls + x] = (uint16_t)(v < lo ? lo : v > hi ? hi : v);
+        }
     return 0;
 }
 

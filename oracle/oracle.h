@@ -99,6 +99,9 @@ void orc_idct_batch(int kind, int16_t *blocks, int nblocks, uint8_t *dest, ptrdi
 /* simple IDCT at 10 / 12 bit (ff_simple_idct_{,put_,add_}int16_{10,12}bit): kind 0 in place, 1 put, 2 add; dest = uint16 pixels,
  * line_size in bytes; the block is clobbered like the reference's */
 int  orc_idct_hbd(int depth, int kind, uint8_t *dest, ptrdiff_t line_size, int16_t *block);
+/* ProresDSPContext.idct_put for bits_per_raw_sample 10 / 12 (libavcodec/proresdsp.c): dequantise by qmat, inverse transform, bias,
+ * clip to [4, 2^bits - 5]; out = uint16 pixels, linesize in bytes; the block is left holding the transformed values like the reference's */
+int  orc_prores_idct_put(int bits, uint8_t *out, ptrdiff_t linesize, int16_t *block, const int16_t *qmat);
 /* inverse quantisers of libavcodec/mpegvideo_unquantize.c (MPVUnquantDSPContext), in place on int16[64] blocks */
 enum { ORC_UNQUANT_MPEG1_INTRA, ORC_UNQUANT_MPEG1_INTER, ORC_UNQUANT_MPEG2_INTRA, ORC_UNQUANT_MPEG2_INTRA_BITEXACT,
        ORC_UNQUANT_MPEG2_INTER, ORC_UNQUANT_H263_INTRA, ORC_UNQUANT_H263_INTER };

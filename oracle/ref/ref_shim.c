@@ -511,3 +511,19 @@ API int ffref_idct_hbd(int depth, int kind, uint8_t *dest, ptrdiff_t line_size, 
     else c[depth].idct_add(dest, line_size, block);
     return 0;
 }
+
+/* ------------------------------------------------------------------ ProresDSPContext ------------------------------ */
+#include "libavcodec/proresdsp.h"
+
+/* ff_proresdsp_init(bits).idct_put: out = uint16 pixels, linesize in bytes */
+API int ffref_prores_idct_put(int bits, uint8_t *out, ptrdiff_t linesize, int16_t *block, const int16_t *qmat)
+{
+    static ProresDSPContext c[2];
+    static int done[2];
+    if (bits != 10 && bits != 12) return -1;
+    const int i = bits == 12;
+    if (!done[i]) { ff_proresdsp_init(&c[i], bits); done[i] = 1; }
+    if (c[i].idct_permutation_type != FF_IDCT_PERM_NONE) return -2;
+    c[i].idct_put((uint16_t *)out, linesize, block, qmat);
+    return 0;
+}

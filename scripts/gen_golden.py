@@ -202,6 +202,17 @@ def gen_tx_int32():
     np.savez_compressed(os.path.join(OUT, "tx_int32.npz"), **d)
 
 
+def gen_prores():
+    """ProresDSPContext.idct_put at 10 and 12 bit: the reference's pixels for prores_case(seed, bits, 60)."""
+    d = {}
+    for bits in (10, 12):
+        for seed in (0, 1, 2):
+            blocks, qmat = cl.prores_case(90 + seed, bits, 60)
+            _, px = cl.ref_prores(bits, blocks, qmat, np.zeros((8, 60 * 8), np.uint16), 60 * 16)
+            d[f"b{bits}_s{seed}"] = px
+    np.savez_compressed(os.path.join(OUT, "prores.npz"), **d)
+
+
 def gen_sws_fastbil():
     from cases import SWS_FASTBIL_CASES
     lines = []
@@ -512,5 +523,6 @@ if __name__ == "__main__":
     gen_tx_pfa()
     gen_tx_dct()
     gen_tx_int32()
+    gen_prores()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -387,6 +387,46 @@ def ref_idct_hbd(depth, kind, blocks, dest, line_size):
     return _idct_hbd_run(ref(), "ffref_idct_hbd", depth, kind, blocks, dest, line_size)
 
 
+def prores_case(seed, bits, n):
+    """(blocks [n, 64] int16, qmat [64] int16): quantised ProRes-like coefficients, several magnitudes, sparse and DC-only blocks"""
+    rng = np.random.default_rng(seed)
+    blocks = np.zeros((n, 64), np.int16)
+    for i in range(n):
+        mode = i % 5
+        if mode == 0:
+            b = rng.integers(-64, 65, 64)
+        elif mode == 1:
+            b = rng.integers(-2048, 2048, 64)
+        elif mode == 2:
+            b = np.zeros(64, np.int64)
+            b[rng.integers(0, 64, int(rng.integers(1, 6)))] = rng.integers(-500, 500)
+        elif mode == 3:
+            b = np.zeros(64, np.int64)
+            b[0] = rng.integers(-4096, 4096)
+        else:
+            b = np.zeros(64, np.int64)
+            b[::8] = rng.integers(-300, 300, 8)
+        blocks[i] = b
+    return blocks, rng.integers(1, [64, 5, 255][seed % 3] + 1, 64).astype(np.int16)
+
+
+def _prores_run(L, name, bits, blocks, qmat, dest, line_size):
+    f = getattr(L, name)
+    f.argtypes = [C.c_int, C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_void_p]
+    b, d = blocks.copy(), dest.copy()
+    for i in range(b.shape[0]):
+        assert f(bits, d.ctypes.data + 16 * i, line_size, b[i].ctypes.data, qmat.ctypes.data) == 0
+    return b, d
+
+
+def orc_prores(bits, blocks, qmat, dest, line_size):
+    return _prores_run(oracle(), "orc_prores_idct_put", bits, blocks, qmat, dest, line_size)
+
+
+def ref_prores(bits, blocks, qmat, dest, line_size):
+    return _prores_run(ref(), "ffref_prores_idct_put", bits, blocks, qmat, dest, line_size)
+
+
 # ---------------------------------------------------------------- AVFloatDSPContext (libavutil/float_dsp.c)
 FDSP_OPS = ["vector_fmul", "vector_fmac_scalar", "vector_dmac_scalar", "vector_fmul_scalar", "vector_dmul_scalar", "vector_fmul_window",
             "vector_fmul_add", "vector_fmul_reverse", "butterflies_float", "scalarproduct_float", "vector_dmul", "scalarproduct_double"]

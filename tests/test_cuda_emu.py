@@ -696,6 +696,33 @@ def test_host_idct_hbd_entry_points(emuhost):
     assert L.b200_idct_hbd_batch_device(None, 11, 0, x.ctypes.data, 1, None, None, None, 0) < 0
 
 
+def test_host_prores_entry_points(emuhost):
+    """b200_prores_idct_put_batch_device and the ProresDSPContext table (dequantise + transform + bias + clip) against the oracle"""
+    from ffmpeg_b200._lib import ProresDSPContext
+    L = emuhost
+    L.b200_prores_idct_put_batch_device.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    for bits in (10, 12):
+        n = 150
+        blocks, qmat = cl.prores_case(500 + bits, bits, n)
+        dest = np.zeros((8, n * 8 + 5), np.uint16)
+        d, b = dest.copy(), blocks.copy()
+        off = np.arange(n, dtype=np.int64) * 16
+        assert L.b200_prores_idct_put_batch_device(None, bits, b.ctypes.data, n, qmat.ctypes.data, d.ctypes.data, off.ctypes.data, None, dest.strides[0]) == 0
+        _, e = cl.orc_prores(bits, blocks, qmat, dest, dest.strides[0])
+        assert np.array_equal(d, e) and np.array_equal(b, blocks), bits
+        c = ProresDSPContext()
+        assert L.b200_proresdsp_init(C.byref(c), bits) == 0 and c.idct_permutation_type == 0 and list(c.idct_permutation) == list(range(64))
+        d = dest.copy()
+        for i in range(8):
+            blk = blocks[i].copy()
+            c.idct_put(d.ctypes.data + 16 * i, d.strides[0], blk.ctypes.data, qmat.ctypes.data)
+            assert np.array_equal(blk, blocks[i])
+        assert np.array_equal(d[:, :64], e[:, :64]), (bits, "table")
+    c = ProresDSPContext()
+    assert L.b200_proresdsp_init(C.byref(c), 8) < 0
+    assert L.b200_prores_idct_put_batch_device(None, 11, blocks.ctypes.data, 1, qmat.ctypes.data, dest.ctypes.data, off.ctypes.data, None, 16) < 0
+
+
 def test_host_tx_pfa_create_and_launch(emuhost):
     from test_oracle_more import _tx
     L, O = emuhost, cl.oracle()

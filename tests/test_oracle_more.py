@@ -483,3 +483,19 @@ def test_tx_int32_oracle_golden_and_ref():
                 for inv in (1, 0):
                     xi = np.ascontiguousarray((x >> 5)[:, :n]) if inv else (x >> 5)
                     assert np.array_equal(_txi(R, "ffref", 5, inv, n, 1.0, xi, n), _txi(O, "orc", 5, inv, n, 1.0, xi, n)), (n, inv)
+
+
+# ---------------------------------------------------------------------------------------------- ProresDSPContext
+def test_prores_idct_put_oracle_golden_and_ref():
+    g = np.load(os.path.join(G, "prores.npz"))
+    for bits in (10, 12):
+        for seed in (0, 1, 2):
+            blocks, qmat = cl.prores_case(90 + seed, bits, 60)
+            b, px = cl.orc_prores(bits, blocks, qmat, np.zeros((8, 60 * 8), np.uint16), 60 * 16)
+            assert np.array_equal(px, g[f"b{bits}_s{seed}"]), (bits, seed)
+            assert px.min() >= 4 and px.max() <= (1 << bits) - 5
+        if cl.have_ref():
+            blocks, qmat = cl.prores_case(300 + bits, bits, 400)
+            dest = np.zeros((8, 400 * 8 + 3), np.uint16)
+            (b1, d1), (b2, d2) = cl.ref_prores(bits, blocks, qmat, dest, dest.strides[0]), cl.orc_prores(bits, blocks, qmat, dest, dest.strides[0])
+            assert np.array_equal(d1, d2) and np.array_equal(b1, b2), bits

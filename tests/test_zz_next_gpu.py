@@ -448,3 +448,32 @@ def test_tx_int32(device):
                 got = do.cpu().numpy()
             assert np.array_equal(got, _txi(O, "orc", typ, inv, n, 1.0 / n, xin, outn)), (typ, inv, n)
             c.uninit()
+
+
+# ---------------------------------------------------------------------------------------------- ProresDSPContext
+@isolated
+def test_prores_idct_put(device):
+    """ProresDSPContext.idct_put (dequant + IDCT + bias + clip) at 10 and 12 bit: function table against the reference's pixels,
+    batched device call against the oracle"""
+    import torch
+    from ffmpeg_b200 import idctdsp
+    g = np.load(os.path.join(G, "prores.npz"))
+    for bits in (10, 12):
+        c = idctdsp.ff_proresdsp_init(bits)
+        for seed in (0, 1, 2):
+            blocks, qmat = cl.prores_case(90 + seed, bits, 60)
+            px = np.zeros((8, 60 * 8), np.uint16)
+            for i in range(60):
+                c.idct_put(px.ctypes.data + 16 * i, px.strides[0], blocks[i].copy().ctypes.data, qmat.ctypes.data)
+            assert np.array_equal(px, g[f"b{bits}_s{seed}"]), (bits, seed)
+        n = 20000
+        blocks, qmat = cl.prores_case(700 + bits, bits, n)
+        dest = np.zeros((8, n * 8 + 4), np.uint16)
+        off = np.arange(n, dtype=np.int64) * 16
+        with on_stream(device):
+            db, dq = torch.from_numpy(blocks).cuda(), torch.from_numpy(qmat).cuda()
+            dd, do = torch.from_numpy(dest.view(np.int16).copy()).cuda(), torch.from_numpy(off).cuda()
+            idctdsp.prores_idct_put_batch_device(device, bits, db, n, dq, dd, do, None, dest.strides[0])
+            device.sync()
+            got = dd.cpu().numpy().view(np.uint16)
+        assert np.array_equal(got, cl.orc_prores(bits, blocks, qmat, dest, dest.strides[0])[1]), bits
