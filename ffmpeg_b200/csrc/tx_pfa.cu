@@ -1,4 +1,4 @@
-// tx_pfa.cu — libavutil/tx compound 15 x M float MDCT on sm_100a: what av_tx_init(AV_TX_FLOAT_MDCT, len = 15 * 2^k) resolves to
+// tx_pfa.cu — libavutil/tx compound N x M float MDCT (N = 15, 5, 3) on sm_100a: what av_tx_init(AV_TX_FLOAT_MDCT, len = 2 * N * 2^k) resolves to
 // (mdct_pfa_15xM_{inv,fwd} carry the largest factor, libavutil/tx.c:391-395), i.e. the Opus CELT transforms of 120 ... 960
 // (libavcodec/opus/dec_celt.c:569, enc.c:690).
 //
@@ -23,8 +23,9 @@ struct PfaDev {
     const int *in_map, *out_map, *sub_map;     // in_map holds doubled positions (tx_template.c:1460-1462)
     const float2 *exp;
     const float *tab53;
-    const float *tabs[8];                      // tabs[k]: cosine table of the 2^k-point transform (k = 3 ... 7)
+    const float *tabs[12];                     // tabs[k]: cosine table of the 2^k-point transform (k = 3 ... 9)
     int m, log2m, len;
+    int nfac;                                  // the odd factor: 15, 5 or 3
 };
 
 __device__ __forceinline__ void butterflies(float2 &a0, float2 &a1, float2 &a2, float2 &a3, float t1, float t2, float t5, float t6)
@@ -123,7 +124,9 @@ __device__ void fft_ns_any(float2 *d, const PfaDev &P)
     case 4: fft_ns<4>(d, P); break;
     case 5: fft_ns<5>(d, P); break;
     case 6: fft_ns<6>(d, P); break;
-    default: fft_ns<7>(d, P); break;
+    case 7: fft_ns<7>(d, P); break;
+    case 8: fft_ns<8>(d, P); break;
+    default: fft_ns<9>(d, P); break;
     }
 }
 
@@ -166,6 +169,14 @@ __device__ __forceinline__ void fft5(const float *tab, float2 *out, const float2
     out[D4 * stride].x = dc.x + z0[0].x; out[D4 * stride].y = dc.y + z0[3].y;
 }
 
+__device__ __forceinline__ void fft15(const float *tab, float2 *out, const float2 *in, int stride);
+// the N-point transform DECL_COMP_IMDCT / DECL_COMP_MDCT instantiate for N = 3, 5, 15
+__device__ __forceinline__ void fftN(int n, const float *tab, float2 *out, const float2 *in, int stride)
+{
+    if (n == 3) fft3(tab, out, in, stride);
+    else if (n == 5) fft5<0, 1, 2, 3, 4>(tab, out, in, stride);
+    else fft15(tab, out, in, stride);
+}
 __device__ __forceinline__ void fft15(const float *tab, float2 *out, const float2 *in, int stride)
 {
     float2 tmp[15];
@@ -183,26 +194,28 @@ tx_mdct_pfa15_inv_kernel(const PfaDev P, float *out, const float *in, long long 
 {
     const long long tr = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (tr >= count) return;
-    const int len4 = P.len >> 2, len2 = P.len >> 1, m = P.m;
+    const int len4 = P.len >> 2, len2 = P.len >> 1, m = P.m, N = P.nfac;
     float2 *tmp = scratch + tr * len2;
     float2 *z = reinterpret_cast<float2 *>(reinterpret_cast<char *>(out) + tr * out_step);
     const float *src = reinterpret_cast<const float *>(reinterpret_cast<const char *>(in) + tr * in_step);
-    const float *in1 = src, *in2 = src + ((15 * m * 2) - 1) * stride;
+    const float *in1 = src, *in2 = src + ((N * m * 2) - 1) * stride;
     const float2 *e = P.exp;
     const int *in_map = P.in_map, *sub_map = P.sub_map;
-    for (int i = 0; i < len2; i += 15) {
+    for (int i = 0; i < len2; i += N) {
         float2 f15[15];
 #pragma unroll
         for (int j = 0; j < 15; j++) {
-            const int k = in_map[j];
-            const float are = in2[-k * stride], aim = in1[k * stride];
-            f15[j].x = are * e[j].x - aim * e[j].y;
-            f15[j].y = are * e[j].y + aim * e[j].x;
+            if (j < N) {
+                const int k = in_map[j];
+                const float are = in2[-k * stride], aim = in1[k * stride];
+                f15[j].x = are * e[j].x - aim * e[j].y;
+                f15[j].y = are * e[j].y + aim * e[j].x;
+            }
         }
-        fft15(P.tab53, tmp + *(sub_map++), f15, m);
-        e += 15; in_map += 15;
+        fftN(N, P.tab53, tmp + *(sub_map++), f15, m);
+        e += N; in_map += N;
     }
-    for (int i = 0; i < 15; i++) fft_ns_any(tmp + m * i, P);
+    for (int i = 0; i < N; i++) fft_ns_any(tmp + m * i, P);
     for (int i = 0; i < len4; i++) {
         const int i0 = len4 + i, i1 = len4 - i - 1, s0 = P.out_map[i0], s1 = P.out_map[i1];
         const float2 src1 = make_float2(tmp[s1].y, tmp[s1].x), src0 = make_float2(tmp[s0].y, tmp[s0].x);
@@ -220,7 +233,7 @@ tx_mdct_pfa15_fwd_kernel(const PfaDev P, float *out, const float *in, long long 
 {
     const long long tr = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (tr >= count) return;
-    const int m = P.m, len4 = 15 * m, len3 = len4 * 3, len8 = P.len >> 2;
+    const int m = P.m, N = P.nfac, len4 = N * m, len3 = len4 * 3, len8 = P.len >> 2;
     float2 *tmp = scratch + tr * len4;
     float *dst = reinterpret_cast<float *>(reinterpret_cast<char *>(out) + tr * out_step);
     const float *src = reinterpret_cast<const float *>(reinterpret_cast<const char *>(in) + tr * in_step);
@@ -229,16 +242,18 @@ tx_mdct_pfa15_fwd_kernel(const PfaDev P, float *out, const float *in, long long 
         float2 f15[15];
 #pragma unroll
         for (int j = 0; j < 15; j++) {
-            const int k = P.in_map[i * 15 + j];
-            float re, im;
-            if (k < len4) { re = -src[len4 + k] + src[1 * len4 - 1 - k]; im = -src[len3 + k] + -src[1 * len3 - 1 - k]; }
-            else          { re = -src[len4 + k] + -src[5 * len4 - 1 - k]; im = src[-len4 + k] + -src[1 * len3 - 1 - k]; }
-            f15[j].y = re * e[k >> 1].x - im * e[k >> 1].y;
-            f15[j].x = re * e[k >> 1].y + im * e[k >> 1].x;
+            if (j < N) {
+                const int k = P.in_map[i * N + j];
+                float re, im;
+                if (k < len4) { re = -src[len4 + k] + src[1 * len4 - 1 - k]; im = -src[len3 + k] + -src[1 * len3 - 1 - k]; }
+                else          { re = -src[len4 + k] + -src[5 * len4 - 1 - k]; im = src[-len4 + k] + -src[1 * len3 - 1 - k]; }
+                f15[j].y = re * e[k >> 1].x - im * e[k >> 1].y;
+                f15[j].x = re * e[k >> 1].y + im * e[k >> 1].x;
+            }
         }
-        fft15(P.tab53, tmp + P.sub_map[i], f15, m);
+        fftN(N, P.tab53, tmp + P.sub_map[i], f15, m);
     }
-    for (int i = 0; i < 15; i++) fft_ns_any(tmp + m * i, P);
+    for (int i = 0; i < N; i++) fft_ns_any(tmp + m * i, P);
     for (int i = 0; i < len8; i++) {
         const int i0 = len8 + i, i1 = len8 - i - 1, s0 = P.out_map[i0], s1 = P.out_map[i1];
         const float2 src1 = tmp[s1], src0 = tmp[s0];
@@ -279,20 +294,27 @@ struct PfaHost {
     std::vector<int> in_map, out_map, sub_map;
     std::vector<float> exp;            // interleaved re, im: inverse = 2 * l2 entries (pre-shuffled, then natural), forward = l2
     float tab53[12];
-    std::vector<float> cosk[8];
-    int m = 0, log2m = 0;
+    std::vector<float> cosk[12];
+    int m = 0, log2m = 0, nfac = 0;
 };
 
-bool tx_pfa_length_ok(int len)
+// the odd factor av_tx_init() ends up with for this MDCT length: the largest of 15, 5, 3 that leaves a power of two (tx.c:391-395); 0 = none
+static int pfa_factor(int len)
 {
-    if (len < 120 || len % 30) return false;                        // m >= 4: the 4-point transform is the smallest codelet we carry
-    const int m = len / 30;
-    return !(m & (m - 1)) && m <= 128;
+    if (len < 12 || (len & 1)) return 0;
+    static const int factors[3] = { 15, 5, 3 };
+    for (int n : factors) {
+        const int l2 = len >> 1, m = l2 / n;
+        if (l2 % n == 0 && m >= 2 && m <= 512 && !(m & (m - 1))) return n;
+    }
+    return 0;
 }
+bool tx_pfa_length_ok(int len) { return pfa_factor(len) != 0; }
 
 static void pfa_host_tables(PfaHost &H, int inv, int len, float scale)
 {
-    const int n = 15, l2 = len >> 1, m = l2 / n;
+    const int n = pfa_factor(len), l2 = len >> 1, m = l2 / n;
+    H.nfac = n;
     H.m = m; H.log2m = 0;
     while ((1 << H.log2m) < m) H.log2m++;
     H.in_map.assign(l2, 0); H.out_map.assign(l2, 0); H.sub_map.assign(m, 0);
@@ -307,7 +329,7 @@ static void pfa_host_tables(PfaHost &H, int inv, int len, float scale)
             int *in = &H.in_map[i * n + 1];
             for (int j = 0; j < ((n - 1) >> 1); j++) std::swap(in[j], in[n - j - 2]);
         }
-    for (int k = 0; k < l2; k += 15) {                              // TX_EMBED_INPUT_PFA_MAP(map, len, 3, 5)
+    for (int k = 0; n == 15 && k < l2; k += 15) {                   // TX_EMBED_INPUT_PFA_MAP(map, len, 3, 5): the 15-point transform is 3 x 5
         int mt[15];
         memcpy(mt, &H.in_map[k], sizeof(mt));
         for (int b = 0; b < 5; b++) for (int a = 0; a < 3; a++) H.in_map[k + b * 3 + a] = mt[(b * 3 + a * 5) % 15];
@@ -357,7 +379,7 @@ B200_API int b200_tx_pfa_tables(int inv, int len, float scale, int32_t *words, i
     lay[4] = (int32_t)w.size(); addf(H.tab53, 12);
     lay[5] = (int32_t)w.size();
     for (int k = 3; k <= H.log2m; k++) addf(H.cosk[k].data(), H.cosk[k].size());
-    lay[6] = H.m; lay[7] = H.log2m;
+    lay[6] = H.m; lay[7] = H.log2m | (H.nfac << 8);
     if (layout8) memcpy(layout8, lay, sizeof(lay));
     if (words && cap >= (int)w.size()) memcpy(words, w.data(), w.size() * 4);
     return (int)w.size();
@@ -376,7 +398,7 @@ TxPfa *tx_pfa_create(int inv, int len, float scale)
     const size_t o_sub = off; off += al(sizeof(int) * m);
     const size_t o_exp = off; off += al(sizeof(float) * H.exp.size());
     const size_t o_53 = off;  off += al(sizeof(float) * 12);
-    size_t o_cos[8] = { 0 };
+    size_t o_cos[12] = { 0 };
     for (int k = 3; k <= H.log2m; k++) { o_cos[k] = off; off += al(sizeof(float) * H.cosk[k].size()); }
     std::vector<uint8_t> host(off, 0);
     memcpy(&host[o_in], H.in_map.data(), sizeof(int) * l2);
@@ -398,8 +420,8 @@ TxPfa *tx_pfa_create(int inv, int len, float scale)
     PfaDev &d = p->d;
     d.in_map = (const int *)(b + o_in); d.out_map = (const int *)(b + o_out); d.sub_map = (const int *)(b + o_sub);
     d.exp = (const float2 *)(b + o_exp); d.tab53 = (const float *)(b + o_53);
-    for (int k = 0; k < 8; k++) d.tabs[k] = k >= 3 && k <= H.log2m ? (const float *)(b + o_cos[k]) : nullptr;
-    d.m = m; d.log2m = H.log2m; d.len = len;
+    for (int k = 0; k < 12; k++) d.tabs[k] = k >= 3 && k <= H.log2m ? (const float *)(b + o_cos[k]) : nullptr;
+    d.m = m; d.log2m = H.log2m; d.len = len; d.nfac = H.nfac;
     return p;
 }
 

@@ -3,7 +3,7 @@
 #include "common.h"
 
 struct TxPfa;
-// len = MDCT length (15 * 2^k, k >= 2), scale as for av_tx_init; returns nullptr (and sets the error string) on failure
+// len = MDCT length (2 * N * 2^k with N = 15, 5 or 3 and k >= 1), scale as for av_tx_init; returns nullptr (and sets the error string) on failure
 TxPfa *tx_pfa_create(int inv, int len, float scale);
 void   tx_pfa_free(TxPfa *p);
 bool   tx_pfa_length_ok(int len);

@@ -34,6 +34,7 @@ struct OrcTx {
     float *tab[18];             /* tab[k] = cosine table of size 2^k */
     /* compound 15 x M MDCT (ff_tx_mdct_pfa_15xM_{inv,fwd}, tx_template.c:1471-1599): len/2 = 15 * m complex points */
     int pfa_m;                  /* 0: power-of-two transform; else m (power of two >= 2) */
+    int pfa_n;                  /* the odd factor: 15, 5 or 3 (ff_tx_mdct_pfa_{15,5,3}xM) */
     int *pfa_in, *pfa_out;      /* compound input map (15-point groups, 3x5 map embedded; doubled for the inverse) and CRT output map */
     int *pfa_sub;               /* scatter permutation of the m-point FFT (ff_tx_gen_ptwo_revtab, FF_TX_MAP_SCATTER) */
     cpx *pfa_tmp;
@@ -159,11 +160,11 @@ static int mulinv(int n, int m)                                /* tx.c:34-42 */
     return 0;
 }
 
-static OrcTx *open_mdct_pfa15(int inv, int len, float scale)
+static OrcTx *open_mdct_pfa(int n, int inv, int len, float scale)
 {
     OrcTx *t = calloc(1, sizeof(*t));
-    const int n = 15, l2 = len >> 1, m = l2 / n;
-    t->type = 1; t->inv = !!inv; t->len = len; t->n = m; t->pfa_m = m;
+    const int l2 = len >> 1, m = l2 / n;
+    t->type = 1; t->inv = !!inv; t->len = len; t->n = m; t->pfa_m = m; t->pfa_n = n;
     for (int j = 3; (1 << j) <= m; j++) make_tab(t, j);
     /* ff_tx_gen_compound_mapping(s, opts = NULL -> gather, inv, 15, m), tx.c:75-123 */
     int *in_map = t->pfa_in = malloc(sizeof(int) * l2), *out_map = t->pfa_out = malloc(sizeof(int) * l2);
@@ -179,7 +180,7 @@ static OrcTx *open_mdct_pfa15(int inv, int len, float scale)
             for (int j = 0; j < ((n - 1) >> 1); j++) { int x = in[j]; in[j] = in[n - j - 2]; in[n - j - 2] = x; }
         }
     /* TX_EMBED_INPUT_PFA_MAP(map, len, 3, 5), tx_priv.h:275-284: the 15-point transform is itself a 3 x 5 compound */
-    for (int k = 0; k < l2; k += 15) {
+    for (int k = 0; n == 15 && k < l2; k += 15) {
         int mt[15];
         memcpy(mt, &in_map[k], sizeof(mt));
         for (int b = 0; b < 5; b++) for (int a = 0; a < 3; a++) in_map[k + b * 3 + a] = mt[(b * 3 + a * 5) % 15];
@@ -262,6 +263,15 @@ static void pfa_fft15(const float *tab, cpx *out, const cpx *in, int stride)
     pfa_fft5(tab, out, tmp + 10, stride, m3);
 }
 
+/* fft3 / fft5 / fft15 as the DECL_COMP_* macros instantiate them for N = 3, 5, 15 */
+static void pfa_fftN(int n, const float *tab, cpx *out, const cpx *in, int stride)
+{
+    static const int d5[5] = { 0, 1, 2, 3, 4 };
+    if (n == 3) pfa_fft3(tab, out, in, stride);
+    else if (n == 5) pfa_fft5(tab, out, in, stride, d5);
+    else pfa_fft15(tab, out, in, stride);
+}
+
 static void fft_ns(OrcTx *t, int k, cpx *d, const cpx *s);
 
 /* ff_tx_mdct_pfa_15xM_inv (DECL_COMP_IMDCT, tx_template.c:1471-1511): len floats with a stride in, len/2 complex (= len floats) out */
@@ -269,20 +279,20 @@ static void run_mdct_pfa_inv(OrcTx *t, float *out, const float *in, ptrdiff_t st
 {
     cpx *z = (cpx *)out, f15[15];
     const cpx *e = t->exp;
-    const int len4 = t->len >> 2, len2 = t->len >> 1, m = t->pfa_m;
+    const int len4 = t->len >> 2, len2 = t->len >> 1, m = t->pfa_m, N = t->pfa_n;
     const int *in_map = t->pfa_in, *sub_map = t->pfa_sub;
-    const float *in1 = in, *in2 = in + ((15 * m * 2) - 1) * stride;
-    for (int i = 0; i < len2; i += 15) {
-        for (int j = 0; j < 15; j++) {
+    const float *in1 = in, *in2 = in + ((N * m * 2) - 1) * stride;
+    for (int i = 0; i < len2; i += N) {
+        for (int j = 0; j < N; j++) {
             const int k = in_map[j];
             const float are = in2[-k * stride], aim = in1[k * stride];
             f15[j].re = are * e[j].re - aim * e[j].im;                  /* CMUL3 */
             f15[j].im = are * e[j].im + aim * e[j].re;
         }
-        pfa_fft15(t->tab53, t->pfa_tmp + *(sub_map++), f15, m);
-        e += 15; in_map += 15;
+        pfa_fftN(N, t->tab53, t->pfa_tmp + *(sub_map++), f15, m);
+        e += N; in_map += N;
     }
-    for (int i = 0; i < 15; i++) fft_ns(t, ilog2i(m), t->pfa_tmp + m * i, t->pfa_tmp + m * i);
+    for (int i = 0; i < N; i++) fft_ns(t, ilog2i(m), t->pfa_tmp + m * i, t->pfa_tmp + m * i);
     for (int i = 0; i < len4; i++) {
         const int i0 = len4 + i, i1 = len4 - i - 1, s0 = t->pfa_out[i0], s1 = t->pfa_out[i1];
         const cpx src1 = { t->pfa_tmp[s1].im, t->pfa_tmp[s1].re }, src0 = { t->pfa_tmp[s0].im, t->pfa_tmp[s0].re };
@@ -298,20 +308,20 @@ static void run_mdct_pfa_fwd(OrcTx *t, float *dst, const float *src, ptrdiff_t s
 {
     cpx f15[15];
     const cpx *e = t->exp;
-    const int m = t->pfa_m, len4 = 15 * m, len3 = len4 * 3, len8 = t->len >> 2;
+    const int m = t->pfa_m, N = t->pfa_n, len4 = N * m, len3 = len4 * 3, len8 = t->len >> 2;
     const int *in_map = t->pfa_in, *sub_map = t->pfa_sub;
     for (int i = 0; i < m; i++) {
-        for (int j = 0; j < 15; j++) {
-            const int k = in_map[i * 15 + j];
+        for (int j = 0; j < N; j++) {
+            const int k = in_map[i * N + j];
             float re, im;
             if (k < len4) { re = -src[len4 + k] + src[1 * len4 - 1 - k]; im = -src[len3 + k] + -src[1 * len3 - 1 - k]; }
             else          { re = -src[len4 + k] + -src[5 * len4 - 1 - k]; im = src[-len4 + k] + -src[1 * len3 - 1 - k]; }
             f15[j].im = re * e[k >> 1].re - im * e[k >> 1].im;
             f15[j].re = re * e[k >> 1].im + im * e[k >> 1].re;
         }
-        pfa_fft15(t->tab53, t->pfa_tmp + sub_map[i], f15, m);
+        pfa_fftN(N, t->tab53, t->pfa_tmp + sub_map[i], f15, m);
     }
-    for (int i = 0; i < 15; i++) fft_ns(t, ilog2i(m), t->pfa_tmp + m * i, t->pfa_tmp + m * i);
+    for (int i = 0; i < N; i++) fft_ns(t, ilog2i(m), t->pfa_tmp + m * i, t->pfa_tmp + m * i);
     for (int i = 0; i < len8; i++) {
         const int i0 = len8 + i, i1 = len8 - i - 1, s0 = t->pfa_out[i0], s1 = t->pfa_out[i1];
         const cpx src1 = t->pfa_tmp[s1], src0 = t->pfa_tmp[s0];
@@ -393,8 +403,13 @@ static void run_dct3(OrcTx *t, float *dst, float *src)
 OrcTx *orc_tx_open(int type, int inv, int len, float scale, unsigned flags)
 {
     if (!flags && type == 9) return open_dct(inv, len, scale);
-    if (!flags && type == 1 && len >= 60 && len % 30 == 0 && !(((len / 30)) & ((len / 30) - 1)))
-        return open_mdct_pfa15(inv, len, scale);
+    if (!flags && type == 1 && len >= 12 && !(len & 1)) {          /* compound MDCT: the largest odd factor wins (tx.c:391-395) */
+        static const int factors[3] = { 15, 5, 3 };
+        for (int f = 0; f < 3; f++) {
+            const int n = factors[f], l2 = len >> 1, m = l2 / n;
+            if (l2 % n == 0 && m >= 2 && !(m & (m - 1))) return open_mdct_pfa(n, inv, len, scale);
+        }
+    }
     if (flags || (type != 0 && type != 1 && type != 6) || len < 2 || (len & (len - 1))) return NULL;
     if (type == 6 && len < 4) return NULL;                     /* ff_tx_rdft_*_def: min_len 4 */
     OrcTx *t = calloc(1, sizeof(*t));

@@ -41,9 +41,9 @@ int emu_tx_pfa(int inv, int len, const int32_t *words, const int32_t *lay, float
     P.in_map = words + lay[0]; P.out_map = words + lay[1]; P.sub_map = words + lay[2];
     P.exp = (const float2 *)(words + lay[3]); P.tab53 = (const float *)(words + lay[4]);
     const float *c = (const float *)(words + lay[5]);
-    for (int k = 0; k < 8; k++) P.tabs[k] = nullptr;
-    for (int k = 3; k <= lay[7]; k++) { P.tabs[k] = c; c += (1 << k) / 4 + 1; }
-    P.m = lay[6]; P.log2m = lay[7]; P.len = len;
+    for (int k = 0; k < 12; k++) P.tabs[k] = nullptr;
+    for (int k = 3; k <= (lay[7] & 255); k++) { P.tabs[k] = c; c += (1 << k) / 4 + 1; }
+    P.m = lay[6]; P.log2m = lay[7] & 255; P.nfac = lay[7] >> 8; P.len = len;
     const dim3 g(ceil_div(count, 64)), t(64);
     if (inv) emu_launch(g, t, [&] { pfa::tx_mdct_pfa15_inv_kernel(P, out, in, stride_floats, out_step, in_step, count, scratch); });
     else     emu_launch(g, t, [&] { pfa::tx_mdct_pfa15_fwd_kernel(P, out, in, stride_floats, out_step, in_step, count, scratch); });

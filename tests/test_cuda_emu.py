@@ -245,8 +245,8 @@ def test_emu_tx_mdct_pfa15(emu):
     emu.emu_tx_pfa.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_longlong,
                                C.c_longlong, C.c_void_p]
     rng = np.random.default_rng(11)
-    assert L.b200_tx_pfa_tables(1, 60, 1.0, None, 0, None) < 0 and L.b200_tx_pfa_tables(1, 1024, 1.0, None, 0, None) < 0
-    for n in (120, 240, 480, 960, 1920):
+    assert L.b200_tx_pfa_tables(1, 84, 1.0, None, 0, None) < 0 and L.b200_tx_pfa_tables(1, 1024, 1.0, None, 0, None) < 0      # 7 x M, power of two
+    for n in (120, 240, 480, 960, 1920, 60, 12, 96, 1536, 20, 160, 640):            # 15 x M, then 3 x M and 5 x M
         for inv in (1, 0):
             for sc in (1.0 / n, -1.0, -1.0 / 32768):
                 lay = np.zeros(8, np.int32)
@@ -547,7 +547,7 @@ def test_tx_whole_path_on_emulated_device(emutx):
         assert np.array_equal(_emu_tx(emutx, 1, 1, n, 1.0 / n, xi, n).view(np.uint32), _tx(O, "orc", 1, 1, n, 1.0 / n, xi, n).view(np.uint32)), ("imdct", n)
         assert np.array_equal(_emu_tx(emutx, 1, 0, n, 1.0, x, n).view(np.uint32), _tx(O, "orc", 1, 0, n, 1.0, x, n).view(np.uint32)), ("mdct", n)
         assert np.array_equal(_emu_tx(emutx, 6, 0, n, 1.0, xi, n + 2).view(np.uint32), _tx(O, "orc", 6, 0, n, 1.0, xi.copy(), n + 2).view(np.uint32)), ("r2c", n)
-    for n in (120, 240, 960):
+    for n in (120, 240, 960, 24, 384, 40, 320):
         for inv in (1, 0):
             x = (rng.random((70, n if inv else 2 * n), dtype=np.float32) * 2 - 1).astype(np.float32)
             exp = _tx(O, "orc", 1, inv, n, 1.0 / n, x, n)
@@ -584,9 +584,9 @@ def test_tx_whole_path_on_emulated_device(emutx):
                 assert np.array_equal(_emu_tx(emutx, 5, 0, n, sc, xs, n), e), ("int32 mdct", n, sc)
                 assert np.array_equal(_emu_tx(emutx, 5, 0, n, sc, xs[:2], n, host_fn=True), e[:2]), ("int32 mdct av_tx_fn", n, sc)
     x = np.zeros((1, 1920), np.float32)
-    assert _emu_tx(emutx, 4, 0, 96, 1.0, x, 192) == -38 and _emu_tx(emutx, 5, 1, 960, 1.0, x, 960) == -38 and _emu_tx(emutx, 2, 0, 64, 1.0, x, 128) == -38
+    assert _emu_tx(emutx, 4, 0, 96, 1.0, x, 192) == -38 and _emu_tx(emutx, 5, 1, 960, 1.0, x, 960) == -38 and _emu_tx(emutx, 1, 1, 84, 1.0, x, 84) == -38 and _emu_tx(emutx, 2, 0, 64, 1.0, x, 128) == -38
     assert _emu_tx(emutx, 9, 0, 96, 1.0, x, 96) == -38 and _emu_tx(emutx, 9, 0, 2, 1.0, x, 2) == -38 and _emu_tx(emutx, 9, 1, 1, 1.0, x, 2) == -38
-    assert _emu_tx(emutx, 0, 0, 960, 1.0, x, 1920) == -38 and _emu_tx(emutx, 1, 1, 60, 1.0, x, 60) == -38 and _emu_tx(emutx, 6, 0, 96, 1.0, x, 98) == -38
+    assert _emu_tx(emutx, 0, 0, 960, 1.0, x, 1920) == -38 and _emu_tx(emutx, 6, 0, 96, 1.0, x, 98) == -38
 
 
 # ------------------------------------------------------------------ the library's own host code on the stand-in runtime
@@ -728,11 +728,11 @@ def test_host_tx_pfa_create_and_launch(emuhost):
     L, O = emuhost, cl.oracle()
     L.emu_host_tx_pfa.argtypes = [C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_longlong, C.c_longlong]
     rng = np.random.default_rng(31)
-    for n in (120, 960):
+    for n in (120, 960, 48, 80):
         for inv in (1, 0):
             cnt = 70                                                    # more than one 64-thread block
             x = (rng.random((cnt, n if inv else 2 * n), dtype=np.float32) * 2 - 1).astype(np.float32)
             out = np.zeros((cnt, n), np.float32)
             assert L.emu_host_tx_pfa(inv, n, 1.0 / n, out.ctypes.data, x.ctypes.data, 4, cnt, out.strides[0], x.strides[0]) == 0
             assert np.array_equal(out.view(np.uint32), _tx(O, "orc", 1, inv, n, 1.0 / n, x, n).view(np.uint32)), (n, inv)
-    assert L.emu_host_tx_pfa(1, 60, 1.0, None, None, 4, 1, 0, 0) < 0
+    assert L.emu_host_tx_pfa(1, 84, 1.0, None, None, 4, 1, 0, 0) < 0

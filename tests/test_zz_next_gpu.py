@@ -350,7 +350,7 @@ def test_tx_mdct_pfa15(device):
                 assert np.array_equal(out.view(np.uint32), g[f"out_{n}_{inv}_{j}"].view(np.uint32)), (n, inv, j)
                 c.uninit()
     rng = np.random.default_rng(21)
-    for n in (120, 960, 1920):
+    for n in (120, 960, 1920, 96, 640):                                # 15 x M, 3 x M, 5 x M
         for inv in (1, 0):
             cnt = 3000
             x = (rng.random((cnt, n if inv else 2 * n), dtype=np.float32) * 2 - 1).astype(np.float32)
@@ -363,7 +363,7 @@ def test_tx_mdct_pfa15(device):
             assert np.array_equal(got.view(np.uint32), _tx(O, "orc", 1, inv, n, 1.0 / n, x, n).view(np.uint32)), (n, inv)
             c.uninit()
     with pytest.raises(fb.B200Error):
-        tx.av_tx_init(tx.AV_TX_FLOAT_MDCT, 1, 60, scale=1.0)            # 15 x 2: below the smallest sub-transform carried
+        tx.av_tx_init(tx.AV_TX_FLOAT_MDCT, 1, 84, scale=1.0)            # 7 x M: not built
     with pytest.raises(fb.B200Error):
         tx.av_tx_init(tx.AV_TX_FLOAT_FFT, 0, 960)                       # compound FFTs are not built
 
