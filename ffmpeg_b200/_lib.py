@@ -95,6 +95,18 @@ class FloatDSPContext(C.Structure):
                 ("scalarproduct_double", C.CFUNCTYPE(C.c_double, _D, _D, C.c_size_t))]
 
 
+_LF_TC = C.CFUNCTYPE(None, C.c_void_p, C.c_ssize_t, C.c_int, C.c_int, C.c_void_p)
+_LF_INTRA = C.CFUNCTYPE(None, C.c_void_p, C.c_ssize_t, C.c_int, C.c_int)
+
+
+class H264LoopFilterContext(C.Structure):
+    """the loop-filter members of H264DSPContext, libavcodec/h264dsp.h:48-73"""
+    _fields_ = [("v_loop_filter_luma", _LF_TC), ("h_loop_filter_luma", _LF_TC), ("h_loop_filter_luma_mbaff", _LF_TC),
+                ("v_loop_filter_luma_intra", _LF_INTRA), ("h_loop_filter_luma_intra", _LF_INTRA), ("h_loop_filter_luma_mbaff_intra", _LF_INTRA),
+                ("v_loop_filter_chroma", _LF_TC), ("h_loop_filter_chroma", _LF_TC), ("h_loop_filter_chroma_mbaff", _LF_TC),
+                ("v_loop_filter_chroma_intra", _LF_INTRA), ("h_loop_filter_chroma_intra", _LF_INTRA), ("h_loop_filter_chroma_mbaff_intra", _LF_INTRA)]
+
+
 class ProresDSPContext(C.Structure):
     """libavcodec/proresdsp.h:28-35"""
     _fields_ = [("idct_permutation_type", C.c_int), ("idct_permutation", C.c_uint8 * 64),
@@ -180,6 +192,8 @@ PROTOTYPES = {
     "b200_tx_pfa_tables": (C.c_int, [C.c_int, C.c_int, C.c_float, vp, C.c_int, vp]),
     "b200_tx_dct_table": (C.c_int, [C.c_int, C.c_int, vp, C.c_int]),
     "b200_tx_i32_tables": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_float, vp, C.c_int, vp]),
+    "b200_h264_loop_filter_init": (C.c_int, [vp, C.c_int, C.c_int]),
+    "b200_h264_loop_filter_batch_device": (C.c_int, [vp, C.c_int64, vp, vp, vp, C.c_ssize_t, vp, vp, vp]),
     "b200_proresdsp_init": (C.c_int, [vp, C.c_int]),
     "b200_prores_idct_put_batch_device": (C.c_int, [vp, C.c_int, vp, C.c_int64, vp, vp, vp, vp, C.c_int]),
     "b200_float_dsp_init": (C.c_int, [vp]),

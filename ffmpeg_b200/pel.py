@@ -86,3 +86,17 @@ def h264_weight_batch_device(device, n, params, dst, dst_off, src, src_off, stri
                                                      vp(_dptr(src)) if src is not None else None,
                                                      vp(_dptr(src_off)) if src_off is not None else None, stride),
                  "h264_weight_batch_device")
+
+
+def ff_h264dsp_loop_filter_init(bit_depth=8, chroma_format_idc=1):
+    """the loop-filter members of H264DSPContext (libavcodec/h264dsp.h:48-73) on HOST pointers"""
+    from ._lib import H264LoopFilterContext
+    c = H264LoopFilterContext()
+    check(lib().b200_h264_loop_filter_init(C.byref(c), bit_depth, chroma_format_idc), "ff_h264dsp_init (loop filter)")
+    return c
+
+
+def h264_loop_filter_batch_device(device, nedges, kinds, pix, pix_off, stride, alpha, beta, tc0):
+    """one independent set of edges; kinds / alpha / beta uint8 [n], pix_off int64 [n], tc0 int8 [n, 4] (device)"""
+    return check(lib().b200_h264_loop_filter_batch_device(device.handle, nedges, vp(_dptr(kinds)), vp(_dptr(pix)), vp(_dptr(pix_off)), stride,
+                                                          vp(_dptr(alpha)), vp(_dptr(beta)), vp(_dptr(tc0))), "h264_loop_filter_batch_device")

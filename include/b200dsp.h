@@ -226,6 +226,32 @@ int  b200_proresdsp_init(B200ProresDSPContext *c, int bits_per_raw_sample);
 int  b200_prores_idct_put_batch_device(B200Device *dev, int bits, const int16_t *blocks, int64_t nblocks, const int16_t *qmat,
                                        uint8_t *dest, const int64_t *dest_off, const int32_t *line_size, int uniform_line_size);
 
+/* H.264 in-loop deblocking, 8 bit: the loop-filter members of H264DSPContext (libavcodec/h264dsp.h:48-73) in the reference's order,
+ * as ff_h264dsp_init(c, 8, chroma_format_idc) installs them (libavcodec/h264dsp.c:109-132; functions libavcodec/h264dsp_template.c:
+ * 103-340).  pix points at the first pixel on the far side of the edge, like the reference; HOST pointers. */
+typedef struct B200H264LoopFilterContext {
+    void (*v_loop_filter_luma)(uint8_t *pix, ptrdiff_t stride, int alpha, int beta, int8_t *tc0);
+    void (*h_loop_filter_luma)(uint8_t *pix, ptrdiff_t stride, int alpha, int beta, int8_t *tc0);
+    void (*h_loop_filter_luma_mbaff)(uint8_t *pix, ptrdiff_t stride, int alpha, int beta, int8_t *tc0);
+    void (*v_loop_filter_luma_intra)(uint8_t *pix, ptrdiff_t stride, int alpha, int beta);
+    void (*h_loop_filter_luma_intra)(uint8_t *pix, ptrdiff_t stride, int alpha, int beta);
+    void (*h_loop_filter_luma_mbaff_intra)(uint8_t *pix, ptrdiff_t stride, int alpha, int beta);
+    void (*v_loop_filter_chroma)(uint8_t *pix, ptrdiff_t stride, int alpha, int beta, int8_t *tc0);
+    void (*h_loop_filter_chroma)(uint8_t *pix, ptrdiff_t stride, int alpha, int beta, int8_t *tc0);
+    void (*h_loop_filter_chroma_mbaff)(uint8_t *pix, ptrdiff_t stride, int alpha, int beta, int8_t *tc0);
+    void (*v_loop_filter_chroma_intra)(uint8_t *pix, ptrdiff_t stride, int alpha, int beta);
+    void (*h_loop_filter_chroma_intra)(uint8_t *pix, ptrdiff_t stride, int alpha, int beta);
+    void (*h_loop_filter_chroma_mbaff_intra)(uint8_t *pix, ptrdiff_t stride, int alpha, int beta);
+} B200H264LoopFilterContext;
+int  b200_h264_loop_filter_init(B200H264LoopFilterContext *c, int bit_depth, int chroma_format_idc);     /* bit_depth must be 8 */
+/* kinds for the batched call: 0 v_luma, 1 h_luma, 2 h_luma_mbaff, 3-5 their _intra forms, 6 v_chroma, 7 h_chroma, 8 h_chroma_mbaff,
+ * 9-11 their _intra forms, 12 / 13 h_chroma / h_chroma_mbaff of 4:2:2 content, 14 / 15 their _intra forms */
+/* batched, DEVICE pointers: edge e of kind kinds[e] at pix + pix_off[e] with alpha[e], beta[e] and tc0[4*e .. 4*e+3] (ignored by the
+ * intra kinds).  The edges of one call must not read or write each other's pixels (p3..q3 across, the edge's lines along): the
+ * decoder's sequential order becomes one call per independent set of edges. */
+int  b200_h264_loop_filter_batch_device(B200Device *dev, int64_t nedges, const uint8_t *kinds, uint8_t *pix, const int64_t *pix_off,
+                                        ptrdiff_t stride, const uint8_t *alpha, const uint8_t *beta, const int8_t *tc0);
+
 /* mpegvideo inverse quantisers: the members of MPVUnquantDSPContext (libavcodec/mpegvideo_unquantize.h:31-44) as
  * ff_mpv_unquantize_init() installs them (libavcodec/mpegvideo_unquantize.c:50-290), i.e. what runs in front of the IDCT in
  * mpv_reconstruct_mb's put_dct / add_dequant_dct (libavcodec/mpegvideo_dec.c).  The reference functions take the whole

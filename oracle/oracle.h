@@ -102,6 +102,10 @@ int  orc_idct_hbd(int depth, int kind, uint8_t *dest, ptrdiff_t line_size, int16
 /* ProresDSPContext.idct_put for bits_per_raw_sample 10 / 12 (libavcodec/proresdsp.c): dequantise by qmat, inverse transform, bias,
  * clip to [4, 2^bits - 5]; out = uint16 pixels, linesize in bytes; the block is left holding the transformed values like the reference's */
 int  orc_prores_idct_put(int bits, uint8_t *out, ptrdiff_t linesize, int16_t *block, const int16_t *qmat);
+/* H.264 deblocking, 8 bit: kind 0 v_luma, 1 h_luma, 2 h_luma_mbaff, 3-5 the same three _intra (tc0 unused), 6 v_chroma, 7 h_chroma,
+ * 8 h_chroma_mbaff, 9-11 their _intra forms, 12 / 13 h_chroma / h_chroma_mbaff of 4:2:2 content, 14 / 15 their _intra forms.
+ * pix points at q0 of the first line (the first pixel on the far side of the edge), as in H264DSPContext */
+int  orc_h264_loop_filter(int kind, uint8_t *pix, ptrdiff_t stride, int alpha, int beta, const int8_t *tc0);
 /* inverse quantisers of libavcodec/mpegvideo_unquantize.c (MPVUnquantDSPContext), in place on int16[64] blocks */
 enum { ORC_UNQUANT_MPEG1_INTRA, ORC_UNQUANT_MPEG1_INTER, ORC_UNQUANT_MPEG2_INTRA, ORC_UNQUANT_MPEG2_INTRA_BITEXACT,
        ORC_UNQUANT_MPEG2_INTER, ORC_UNQUANT_H263_INTRA, ORC_UNQUANT_H263_INTER };

@@ -527,3 +527,32 @@ API int ffref_prores_idct_put(int bits, uint8_t *out, ptrdiff_t linesize, int16_
     c[i].idct_put((uint16_t *)out, linesize, block, qmat);
     return 0;
 }
+
+/* ------------------------------------------------------------------ H.264 deblocking ----------------------------- */
+/* the loop-filter members of H264DSPContext, 8 bit; kinds 0-11 from ff_h264dsp_init(c, 8, 1) in the member order of h264dsp.h:48-73,
+ * kinds 12-15 = h_loop_filter_chroma, h_loop_filter_chroma_mbaff and their _intra forms from ff_h264dsp_init(c, 8, 2) (4:2:2) */
+API int ffref_h264_loop_filter(int kind, uint8_t *pix, ptrdiff_t stride, int alpha, int beta, int8_t *tc0)
+{
+    static H264DSPContext c420, c422; static int ok;
+    if (!ok) { ff_h264dsp_init(&c420, 8, 1); ff_h264dsp_init(&c422, 8, 2); ok = 1; }
+    switch (kind) {
+    case 0:  c420.v_loop_filter_luma(pix, stride, alpha, beta, tc0); break;
+    case 1:  c420.h_loop_filter_luma(pix, stride, alpha, beta, tc0); break;
+    case 2:  c420.h_loop_filter_luma_mbaff(pix, stride, alpha, beta, tc0); break;
+    case 3:  c420.v_loop_filter_luma_intra(pix, stride, alpha, beta); break;
+    case 4:  c420.h_loop_filter_luma_intra(pix, stride, alpha, beta); break;
+    case 5:  c420.h_loop_filter_luma_mbaff_intra(pix, stride, alpha, beta); break;
+    case 6:  c420.v_loop_filter_chroma(pix, stride, alpha, beta, tc0); break;
+    case 7:  c420.h_loop_filter_chroma(pix, stride, alpha, beta, tc0); break;
+    case 8:  c420.h_loop_filter_chroma_mbaff(pix, stride, alpha, beta, tc0); break;
+    case 9:  c420.v_loop_filter_chroma_intra(pix, stride, alpha, beta); break;
+    case 10: c420.h_loop_filter_chroma_intra(pix, stride, alpha, beta); break;
+    case 11: c420.h_loop_filter_chroma_mbaff_intra(pix, stride, alpha, beta); break;
+    case 12: c422.h_loop_filter_chroma(pix, stride, alpha, beta, tc0); break;
+    case 13: c422.h_loop_filter_chroma_mbaff(pix, stride, alpha, beta, tc0); break;
+    case 14: c422.h_loop_filter_chroma_intra(pix, stride, alpha, beta); break;
+    case 15: c422.h_loop_filter_chroma_mbaff_intra(pix, stride, alpha, beta); break;
+    default: return -1;
+    }
+    return 0;
+}

@@ -202,6 +202,21 @@ def gen_tx_int32():
     np.savez_compressed(os.path.join(OUT, "tx_int32.npz"), **d)
 
 
+def gen_h264lf():
+    """H264DSPContext loop filters, 8 bit: the reference's picture after the 512 edges of h264lf_case(seed, 512) (sha256, plus the first
+    64 x 512 pixels of seed 0 for a readable diff)."""
+    import hashlib
+    d = {}
+    for seed in (0, 1, 2):
+        pic, kinds, off, alpha, beta, tc0 = cl.h264lf_case(40 + seed, 512)
+        out = cl.ref_h264lf(pic, kinds, off, alpha, beta, tc0)
+        assert not np.array_equal(out, pic)
+        d[f"sha_{seed}"] = np.frombuffer(hashlib.sha256(out.tobytes()).digest(), np.uint8)
+        if seed == 0:
+            d["head_0"] = out[:64].copy()
+    np.savez_compressed(os.path.join(OUT, "h264lf.npz"), **d)
+
+
 def gen_prores():
     """ProresDSPContext.idct_put at 10 and 12 bit: the reference's pixels for prores_case(seed, bits, 60)."""
     d = {}
@@ -513,6 +528,7 @@ if __name__ == "__main__":
     gen_chroma()
     gen_edge()
     gen_tx()
+    gen_h264lf()
     gen_vsynth1()
     gen_sws_slices()
     gen_sws_range()

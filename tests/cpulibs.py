@@ -427,6 +427,55 @@ def ref_prores(bits, blocks, qmat, dest, line_size):
     return _prores_run(ref(), "ffref_prores_idct_put", bits, blocks, qmat, dest, line_size)
 
 
+# ---------------------------------------------------------------- H.264 deblocking (libavcodec/h264dsp_template.c:103-340)
+LF_CELL = 32          # one edge per 32 x 32 cell, q0 of its first line at (8, 8): p3..q3 across and 16 lines along stay inside the cell
+
+
+def h264lf_case(seed, n, cols=16):
+    """(pic uint8 [rows*32, cols*32], kinds uint8 [n], off int64 [n], alpha uint8 [n], beta uint8 [n], tc0 int8 [n, 4]): n independent
+    edges of all 16 kinds over noisy, gently and very gently varying content (so that every branch of the filters is taken)"""
+    rng = np.random.default_rng(seed)
+    rows = (n + cols - 1) // cols
+    pic = np.zeros((rows * LF_CELL, cols * LF_CELL), np.uint8)
+    for i in range(rows * cols):
+        y, x = (i // cols) * LF_CELL, (i % cols) * LF_CELL
+        m = (i // 16) % 4
+        if m == 0:
+            c = rng.integers(0, 256, (LF_CELL, LF_CELL))
+        else:
+            c = int(rng.integers(0, 256)) + rng.integers(-3 * m, 3 * m + 1, (LF_CELL, LF_CELL))
+            if m == 3:
+                c[:, 8:] += int(rng.integers(-12, 13))
+                c[8:, :] += int(rng.integers(-12, 13))
+        pic[y:y + LF_CELL, x:x + LF_CELL] = np.clip(c, 0, 255)
+    i = np.arange(n)
+    kinds = (i % 16).astype(np.uint8)
+    off = ((i // cols) * LF_CELL + 8) * pic.strides[0] + (i % cols) * LF_CELL + 8
+    alpha = rng.integers(0, 256, n).astype(np.uint8)
+    alpha[rng.random(n) < 0.3] = 255
+    beta = rng.integers(0, 19, n).astype(np.uint8)
+    tc0 = rng.integers(-1, 14, (n, 4)).astype(np.int8)
+    return pic, kinds, off.astype(np.int64), alpha, beta, tc0
+
+
+def _h264lf_run(L, name, pic, kinds, off, alpha, beta, tc0):
+    f = getattr(L, name)
+    f.argtypes = [C.c_int, C.c_void_p, C.c_ssize_t, C.c_int, C.c_int, C.c_void_p]
+    out = pic.copy()
+    for e in range(len(kinds)):
+        t = tc0[e].copy()
+        assert f(int(kinds[e]), out.ctypes.data + int(off[e]), out.strides[0], int(alpha[e]), int(beta[e]), t.ctypes.data) == 0
+    return out
+
+
+def orc_h264lf(pic, kinds, off, alpha, beta, tc0):
+    return _h264lf_run(oracle(), "orc_h264_loop_filter", pic, kinds, off, alpha, beta, tc0)
+
+
+def ref_h264lf(pic, kinds, off, alpha, beta, tc0):
+    return _h264lf_run(ref(), "ffref_h264_loop_filter", pic, kinds, off, alpha, beta, tc0)
+
+
 # ---------------------------------------------------------------- AVFloatDSPContext (libavutil/float_dsp.c)
 FDSP_OPS = ["vector_fmul", "vector_fmac_scalar", "vector_dmac_scalar", "vector_fmul_scalar", "vector_dmul_scalar", "vector_fmul_window",
             "vector_fmul_add", "vector_fmul_reverse", "butterflies_float", "scalarproduct_float", "vector_dmul", "scalarproduct_double"]

@@ -29,7 +29,7 @@ def emu():
             txt = open(os.path.join(src_dir, f)).read()
             for m in re.finditer(r"// \[device-code (\w+)\][^\n]*\n(.*?)// \[/device-code \1\]", txt, re.S):
                 found[m.group(1)] = m.group(2)
-    assert sorted(found) == ["fdsp", "idct_hbd", "sws_new", "sws_nvout", "tx_dct", "tx_int32", "tx_pfa", "unquant"], sorted(found)
+    assert sorted(found) == ["fdsp", "h264lf", "idct_hbd", "sws_new", "sws_nvout", "tx_dct", "tx_int32", "tx_pfa", "unquant"], sorted(found)
     for k, v in found.items():
         open(os.path.join(gen, k + ".inc"), "w").write(v)
     so = os.path.join(gen, "libemu.so")
@@ -72,13 +72,13 @@ def rewrite_launches(txt):
 
 @pytest.fixture(scope="module")
 def emuhost():
-    """libemuhost.so: the translation units without inline PTX (fdsp, unquant, idct_hbd, tx_pfa), HOST CODE INCLUDED, compiled with
+    """libemuhost.so: the translation units without inline PTX (fdsp, unquant, idct_hbd, tx_pfa, h264lf), HOST CODE INCLUDED, compiled with
     g++ against a stand-in CUDA runtime (tests/cuda_emu/fake/cuda_runtime.h): the library's own entry points run on the CPU"""
     gen = os.path.join(EMU, "_gen")
     os.makedirs(gen, exist_ok=True)
     cs = os.path.join(ROOT, "ffmpeg_b200", "csrc")
     srcs = []
-    for f in ("fdsp.cu", "unquant.cu", "idct_hbd.cu", "tx_pfa.cu"):
+    for f in ("fdsp.cu", "unquant.cu", "idct_hbd.cu", "tx_pfa.cu", "h264lf.cu"):
         t = rewrite_launches(open(os.path.join(cs, f)).read())
         assert "<<<" not in t
         p = os.path.join(gen, "host_" + f[:-3] + ".cpp")
@@ -721,6 +721,42 @@ def test_host_prores_entry_points(emuhost):
     c = ProresDSPContext()
     assert L.b200_proresdsp_init(C.byref(c), 8) < 0
     assert L.b200_prores_idct_put_batch_device(None, 11, blocks.ctypes.data, 1, qmat.ctypes.data, dest.ctypes.data, off.ctypes.data, None, 16) < 0
+
+
+def test_host_h264_loop_filter_entry_points(emuhost):
+    """b200_h264_loop_filter_batch_device over 2048 independent edges of all 16 kinds, and the H264DSPContext loop-filter table edge
+    by edge (4:2:0 and 4:2:2 selections), against the oracle"""
+    from ffmpeg_b200._lib import H264LoopFilterContext
+    L = emuhost
+    L.b200_h264_loop_filter_batch_device.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 3 + [C.c_ssize_t] + [C.c_void_p] * 3
+    pic, kinds, off, alpha, beta, tc0 = cl.h264lf_case(21, 2048)
+    d = pic.copy()
+    assert L.b200_h264_loop_filter_batch_device(None, 2048, kinds.ctypes.data, d.ctypes.data, off.ctypes.data, d.strides[0], alpha.ctypes.data,
+                                                beta.ctypes.data, tc0.ctypes.data) == 0
+    e = cl.orc_h264lf(pic, kinds, off, alpha, beta, tc0)
+    assert np.array_equal(d, e) and not np.array_equal(d, pic)
+    names = [f[0] for f in H264LoopFilterContext._fields_]
+    for idc in (1, 2):
+        c = H264LoopFilterContext()
+        assert L.b200_h264_loop_filter_init(C.byref(c), 8, idc) == 0
+        # member -> kind, as ff_h264dsp_init selects (h264dsp.c:116-132)
+        kind_of = dict(zip(names, range(12)))
+        if idc == 2:
+            kind_of.update(h_loop_filter_chroma=12, h_loop_filter_chroma_mbaff=13, h_loop_filter_chroma_intra=14, h_loop_filter_chroma_mbaff_intra=15)
+        pic, kinds, off, alpha, beta, tc0 = cl.h264lf_case(30 + idc, 192)
+        members = [names[i % 12] for i in range(192)]
+        kinds = np.array([kind_of[m] for m in members], np.uint8)
+        d = pic.copy()
+        for i, m in enumerate(members):
+            t = tc0[i].copy()
+            args = (d.ctypes.data + int(off[i]), d.strides[0], int(alpha[i]), int(beta[i]))
+            getattr(c, m)(*args, t.ctypes.data) if "intra" not in m else getattr(c, m)(*args)
+            assert np.array_equal(t, tc0[i])
+        assert np.array_equal(d, cl.orc_h264lf(pic, kinds, off, alpha, beta, tc0)), idc
+    c = H264LoopFilterContext()
+    assert L.b200_h264_loop_filter_init(C.byref(c), 10, 1) < 0 and L.b200_h264_loop_filter_init(None, 8, 1) < 0
+    assert L.b200_h264_loop_filter_batch_device(None, 0, None, None, None, 0, None, None, None) == 0
+    assert L.b200_h264_loop_filter_batch_device(None, 1, None, d.ctypes.data, off.ctypes.data, 16, alpha.ctypes.data, beta.ctypes.data, tc0.ctypes.data) < 0
 
 
 def test_host_tx_pfa_create_and_launch(emuhost):

@@ -499,3 +499,33 @@ def test_prores_idct_put_oracle_golden_and_ref():
             dest = np.zeros((8, 400 * 8 + 3), np.uint16)
             (b1, d1), (b2, d2) = cl.ref_prores(bits, blocks, qmat, dest, dest.strides[0]), cl.orc_prores(bits, blocks, qmat, dest, dest.strides[0])
             assert np.array_equal(d1, d2) and np.array_equal(b1, b2), bits
+
+
+# ---------------------------------------------------------------------------------------------- H.264 deblocking filters
+def test_h264_loop_filter_oracle_golden_and_ref():
+    """oracle/h264lf_oracle.c against the reference's ff_h264dsp_init(8, 1 / 2) loop filters: fixture hashes, then bit-exact over 16
+    kinds x noisy / smooth content x the whole alpha / beta / tc0 range (tc0 = -1 skips a group, 0 filters p0 / q0 only)"""
+    import hashlib
+    g = np.load(os.path.join(G, "h264lf.npz"))
+    for seed in (0, 1, 2):
+        case = cl.h264lf_case(40 + seed, 512)
+        out = cl.orc_h264lf(*case)
+        assert hashlib.sha256(out.tobytes()).digest() == g[f"sha_{seed}"].tobytes(), seed
+        if seed == 0:
+            assert np.array_equal(out[:64], g["head_0"])
+    for seed in (7, 8):
+        case = cl.h264lf_case(seed, 2048)
+        a, b = cl.orc_h264lf(*case), cl.ref_h264lf(*case)
+        assert np.array_equal(a, b) and not np.array_equal(a, case[0])
+    # nothing outside p2..q2 of the edge's own lines is ever written
+    pic, kinds, off, alpha, beta, tc0 = cl.h264lf_case(9, 256)
+    out = cl.orc_h264lf(pic, kinds, off, alpha, beta, tc0)
+    keep = np.ones(pic.shape, bool)
+    for e in range(256):
+        y, x = divmod(int(off[e]), pic.strides[0])
+        vert = kinds[e] in (0, 3, 6, 9)
+        if vert:
+            keep[y - 3:y + 3, x:x + 16] = False
+        else:
+            keep[y:y + 16, x - 3:x + 3] = False
+    assert np.array_equal(out[keep], pic[keep])

@@ -477,3 +477,43 @@ def test_prores_idct_put(device):
             device.sync()
             got = dd.cpu().numpy().view(np.uint16)
         assert np.array_equal(got, cl.orc_prores(bits, blocks, qmat, dest, dest.strides[0])[1]), bits
+
+
+# ---------------------------------------------------------------------------------------------- H.264 deblocking filters
+@isolated
+def test_h264_loop_filter(device):
+    """H264DSPContext loop filters, 8 bit: the function table on host pointers reproduces the reference's fixture picture; the batched
+    device call over 65536 independent edges matches the oracle"""
+    import hashlib
+    import torch
+    from ffmpeg_b200 import pel
+    from ffmpeg_b200._lib import H264LoopFilterContext
+    g = np.load(os.path.join(G, "h264lf.npz"))
+    names = [f[0] for f in H264LoopFilterContext._fields_]
+    c420, c422 = pel.ff_h264dsp_loop_filter_init(8, 1), pel.ff_h264dsp_loop_filter_init(8, 2)
+    member = {k: (c420, names[k]) for k in range(12)}
+    member.update({12: (c422, "h_loop_filter_chroma"), 13: (c422, "h_loop_filter_chroma_mbaff"), 14: (c422, "h_loop_filter_chroma_intra"),
+                   15: (c422, "h_loop_filter_chroma_mbaff_intra")})
+    pic, kinds, off, alpha, beta, tc0 = cl.h264lf_case(40, 512)
+    d = pic.copy()
+    for e in range(512):
+        c, m = member[int(kinds[e])]
+        args = (d.ctypes.data + int(off[e]), d.strides[0], int(alpha[e]), int(beta[e]))
+        getattr(c, m)(*args, tc0[e].copy().ctypes.data) if "intra" not in m else getattr(c, m)(*args)
+    assert np.array_equal(d[:64], g["head_0"])
+    assert hashlib.sha256(d.tobytes()).digest() == g["sha_0"].tobytes()
+    for seed in (0, 1, 2):
+        n = 512 if seed else 65536
+        pic, kinds, off, alpha, beta, tc0 = cl.h264lf_case(40 + seed, n) if seed else cl.h264lf_case(77, n, cols=64)
+        with on_stream(device):
+            dp = torch.from_numpy(pic).cuda()
+            dk, do, da, db, dt = (torch.from_numpy(x).cuda() for x in (kinds, off, alpha, beta, tc0))
+            pel.h264_loop_filter_batch_device(device, n, dk, dp, do, pic.strides[0], da, db, dt)
+            device.sync()
+            got = dp.cpu().numpy()
+        if seed:
+            assert hashlib.sha256(got.tobytes()).digest() == g[f"sha_{seed}"].tobytes(), seed
+        else:
+            assert np.array_equal(got, cl.orc_h264lf(pic, kinds, off, alpha, beta, tc0))
+    with pytest.raises(Exception):
+        pel.ff_h264dsp_loop_filter_init(10, 1)
