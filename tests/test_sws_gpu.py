@@ -406,66 +406,3 @@ def test_fate_filter_pixfmts_md5(device):
     except Exception as e:                                                # checker tools, not the product: skip, never fail
         pytest.skip(f"oracle/_ref tools not usable on this box: {e}")
     fg.check_all(functools.partial(gpu_sws, device), functools.partial(gpu_sws_planar, device), rgb_sources=False, nv_dest=False)
-
-
-def test_range_conversion_golden_hashes_and_oracle(device):
-    """yuv -> yuv range conversion (SWS_RANGE_CASES) against the reference's outputs and the oracle; ranges at initialisation
-    or changed through sws_setColorspaceDetails(), incl. the same-size context that stays a plain copy."""
-    from cases import SWS_RANGE_CASES
-    lines = open(os.path.join(G, "sws_range_hashes.txt")).read().split("\n")[:-1]
-    assert len(lines) == len(SWS_RANGE_CASES)
-    for line, (w, h, dw, dh, fl, kind, ranges, details) in zip(lines, SWS_RANGE_CASES):
-        i, hout = int(line.split()[0]), line.split()[-1]
-        y, u, v = cl.yuv_frame(w, h, 1200 + i, kind)
-        out = gpu_sws_planar(device, w, h, dw, dh, fl, y, u, v, ranges=ranges, details=details)
-        exp = cl.orc_sws_planar(w, h, dw, dh, fl, y, u, v, ranges=ranges, details=details)
-        assert all(np.array_equal(p, q) for p, q in zip(out, exp)), (i, [int((p != q).sum()) for p, q in zip(out, exp)])
-        assert sha(np.concatenate([p.ravel() for p in out])) == hout, (i, w, h, dw, dh, hex(fl), ranges, details)
-
-
-def test_range_conversion_fate_crc_padded_nv12(device):
-    """FATE's sws-yuv-range checksum on the CUDA path; padded strides and an nv12 source."""
-    from test_oracle import fate_sws_yuv_range_crc, FATE_SWS_YUV_RANGE
-    import functools
-    assert fate_sws_yuv_range_crc(functools.partial(gpu_sws_planar, device)) == FATE_SWS_YUV_RANGE
-    for (w, h, dw, dh, fl, ranges) in [(640, 360, 1280, 720, FATE, (0, 1)), (351, 287, 351, 287, cl.SWS_BICUBIC, (1, 0)),
-                                       (1920, 1080, 1280, 720, cl.SWS_BILINEAR, (1, 0))]:
-        y, u, v = cl.yuv_frame(w, h, 1400 + w, "random", pad=5)
-        out = gpu_sws_planar(device, w, h, dw, dh, fl, y, u, v, dst_pad=7, ranges=ranges)
-        exp = cl.orc_sws_planar(w, h, dw, dh, fl, y, u, v, dst_pad=7, ranges=ranges)
-        assert all(np.array_equal(p, q) for p, q in zip(out, exp)), (w, h, dw, dh, hex(fl), ranges)
-    # nv12 source, limited -> full
-    w, h, dw, dh = 640, 360, 800, 450
-    y, u, v = cl.yuv_frame(w, h, 1500, "limited")
-    uv = cl.nv_interleave(u, v, cl.PIX_FMT_NV12)
-    out = gpu_sws_planar(device, w, h, dw, dh, FATE, y, uv, uv, src_fmt=cl.PIX_FMT_NV12, ranges=(0, 1))
-    exp = cl.orc_sws_planar(w, h, dw, dh, FATE, y, uv, uv, src_fmt=cl.PIX_FMT_NV12, ranges=(0, 1))
-    assert all(np.array_equal(p, q) for p, q in zip(out, exp))
-
-
-def test_range_conversion_batch_device(device):
-    """batched device entry point with range conversion (3 frames, full -> limited), and the refusal of a matrix change"""
-    import torch
-    import ffmpeg_b200 as fb
-    from ffmpeg_b200 import swscale as sw
-    w, h, dw, dh, n = 320, 180, 480, 270, 3
-    frames = [cl.yuv_frame(w, h, 1600 + k, "random") for k in range(n)]
-    cw, ch, dcw, dch = w // 2, h // 2, dw // 2, dh // 2
-    ctx = sw.sws_getContext(device, w, h, 0, dw, dh, sw.AV_PIX_FMT_YUV420P, FATE, src_range=1, dst_range=0)
-    with torch.cuda.stream(torch.cuda.ExternalStream(device.stream)):
-        Y, U, V = (torch.from_numpy(np.stack([f[k] for f in frames])).cuda() for k in range(3))
-        DY = torch.zeros((n, dh, dw), dtype=torch.uint8, device="cuda")
-        DU = torch.zeros((n, dch, dcw), dtype=torch.uint8, device="cuda")
-        DV = torch.zeros((n, dch, dcw), dtype=torch.uint8, device="cuda")
-        ctx.scale_batch_device_planar([Y, U, V], [w, cw, cw], [w * h, cw * ch, cw * ch], [DY, DU, DV], [dw, dcw, dcw],
-                                      [dw * dh, dcw * dch, dcw * dch], n)
-        device.sync()
-        got = [t.cpu().numpy() for t in (DY, DU, DV)]
-    for i in range(n):
-        exp = cl.orc_sws_planar(w, h, dw, dh, FATE, *frames[i], ranges=(1, 0))
-        for k in range(3):
-            assert np.array_equal(got[k][i], exp[k]), (i, k)
-    # different matrices for yuv -> yuv: the reference cascades through bgr24; this path refuses loudly
-    with pytest.raises(fb.B200Error):
-        ctx.setColorspaceDetails(cl.COEFFS[1], 0, cl.COEFFS[5], 1, 0, 1 << 16, 1 << 16)
-    ctx.free()
