@@ -3,7 +3,7 @@
 // (libavcodec/opus/dec_celt.c:569, enc.c:690).
 //
 // Reference semantics reproduced bit for bit (checker: the compound part of oracle/tx_oracle.c), libavutil/tx_template.c:
-//   :172-209 fft3, :211-250 fft5 / fft5_m1..m3, :465-476 fft15 (float branches), table ff_tx_tab_53 :91-108
+//   :172-209 fft3, :211-250 fft5 / fft5_m1..m3, :252-339 fft7, :341-463 fft9, :465-476 fft15 (float branches), tables ff_tx_tab_53 / _7 / _9 :91-130
 //   :1430-1469 ff_tx_mdct_pfa_init (compound map libavutil/tx.c:75-123, 3x5 input map embedded tx_priv.h:275-284, twiddles
 //              ff_tx_mdct_gen_exp :2107-2134, scatter permutation of the M-point transform tx.c:136-154)
 //   :1471-1511 ff_tx_mdct_pfa_15xM_inv, :1533-1579 ff_tx_mdct_pfa_15xM_fwd, M-point split-radix transforms :540-722
@@ -22,10 +22,10 @@ namespace {
 struct PfaDev {
     const int *in_map, *out_map, *sub_map;     // in_map holds doubled positions (tx_template.c:1460-1462)
     const float2 *exp;
-    const float *tab53;
+    const float *tab53;                        // ff_tx_tab_53 [12], then ff_tx_tab_7 [6] and ff_tx_tab_9 [8]
     const float *tabs[12];                     // tabs[k]: cosine table of the 2^k-point transform (k = 3 ... 9)
     int m, log2m, len;
-    int nfac;                                  // the odd factor: 15, 5 or 3
+    int nfac;                                  // the odd factor: 15, 9, 7, 5 or 3
 };
 
 __device__ __forceinline__ void butterflies(float2 &a0, float2 &a1, float2 &a2, float2 &a3, float t1, float t2, float t5, float t6)
@@ -169,12 +169,89 @@ __device__ __forceinline__ void fft5(const float *tab, float2 *out, const float2
     out[D4 * stride].x = dc.x + z0[0].x; out[D4 * stride].y = dc.y + z0[3].y;
 }
 
+// fft7 (tx_template.c:252-339, float branch).  S[k] / D[k]: sum / difference of in[k + 1] and in[6 - k]; T = ff_tx_tab_7 as three
+// (re, im) pairs.  The products and sums keep the reference's left-to-right order (the library is built without contraction).
+__device__ __forceinline__ void fft7(const float *T, float2 *out, const float2 *in, int stride)
+{
+    const float c0 = T[0], s0 = T[1], c1 = T[2], s1 = T[3], c2 = T[4], s2 = T[5];
+    const float2 dc = in[0];
+    float2 S[3], D[3], z[3], u[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        S[k].x = in[k + 1].x + in[6 - k].x; D[k].x = in[k + 1].x - in[6 - k].x;
+        S[k].y = in[k + 1].y + in[6 - k].y; D[k].y = in[k + 1].y - in[6 - k].y;
+    }
+    out[0].x = dc.x + S[0].x + S[1].x + S[2].x;
+    out[0].y = dc.y + S[0].y + S[1].y + S[2].y;
+    z[0].x = c0 * S[0].x - c2 * S[2].x - c1 * S[1].x;
+    z[1].x = c0 * S[2].x - c1 * S[0].x - c2 * S[1].x;
+    z[2].x = c0 * S[1].x - c2 * S[0].x - c1 * S[2].x;
+    z[0].y = c0 * S[0].y - c1 * S[1].y - c2 * S[2].y;
+    z[1].y = c0 * S[2].y - c1 * S[0].y - c2 * S[1].y;
+    z[2].y = c0 * S[1].y - c2 * S[0].y - c1 * S[2].y;
+    u[0].x = s2 * D[0].y + s1 * D[2].y - s0 * D[1].y;
+    u[1].x = s0 * D[2].y + s2 * D[1].y - s1 * D[0].y;
+    u[2].x = s2 * D[2].y + s1 * D[1].y + s0 * D[0].y;
+    u[0].y = s0 * D[0].x + s1 * D[1].x + s2 * D[2].x;
+    u[1].y = s2 * D[1].x + s0 * D[2].x - s1 * D[0].x;
+    u[2].y = s2 * D[0].x + s1 * D[2].x - s0 * D[1].x;
+    out[1 * stride].x = dc.x + (z[0].x + u[2].x); out[1 * stride].y = dc.y + (z[0].y - u[0].y);
+    out[2 * stride].x = dc.x + (z[1].x - u[1].x); out[2 * stride].y = dc.y + (z[1].y + u[1].y);
+    out[3 * stride].x = dc.x + (z[2].x + u[0].x); out[3 * stride].y = dc.y + (z[2].y - u[2].y);
+    out[4 * stride].x = dc.x + (z[2].x - u[0].x); out[4 * stride].y = dc.y + (z[2].y + u[2].y);
+    out[5 * stride].x = dc.x + (z[1].x + u[1].x); out[5 * stride].y = dc.y + (z[1].y - u[1].y);
+    out[6 * stride].x = dc.x + (z[0].x - u[2].x); out[6 * stride].y = dc.y + (z[0].y + u[0].y);
+}
+
+// fft9 (tx_template.c:341-463, float branch).  S[k] / D[k]: sum / difference of in[k + 1] and in[8 - k]; T = ff_tx_tab_9 as four pairs.
+__device__ __forceinline__ void fft9(const float *T, float2 *out, const float2 *in, int stride)
+{
+    const float2 dc = in[0];
+    float2 S[4], D[4], w[4], x[5], y[5], z0, z1;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        S[k].x = in[k + 1].x + in[8 - k].x; D[k].x = in[k + 1].x - in[8 - k].x;
+        S[k].y = in[k + 1].y + in[8 - k].y; D[k].y = in[k + 1].y - in[8 - k].y;
+    }
+    w[0].x = S[0].x - S[3].x; w[0].y = S[0].y - S[3].y;
+    w[1].x = S[1].x - S[3].x; w[1].y = S[1].y - S[3].y;
+    w[2].x = D[0].x - D[3].x; w[2].y = D[0].y - D[3].y;
+    w[3].x = D[1].x + D[3].x; w[3].y = D[1].y + D[3].y;
+    z0.x = dc.x + S[2].x; z0.y = dc.y + S[2].y;
+    z1.x = S[0].x + S[1].x + S[3].x; z1.y = S[0].y + S[1].y + S[3].y;
+    out[0].x = z0.x + z1.x; out[0].y = z0.y + z1.y;
+    y[3].x = T[1] * (D[0].x - D[1].x + D[3].x);
+    y[3].y = T[1] * (D[0].y - D[1].y + D[3].y);
+    x[3].x = z0.x + T[0] * z1.x; x[3].y = z0.y + T[0] * z1.y;
+    z0.x = dc.x + T[0] * S[2].x; z0.y = dc.y + T[0] * S[2].y;
+    x[1].x = T[2] * w[0].x + T[5] * w[1].x; x[1].y = T[2] * w[0].y + T[5] * w[1].y;
+    x[2].x = T[5] * w[0].x - T[6] * w[1].x; x[2].y = T[5] * w[0].y - T[6] * w[1].y;
+    y[1].x = T[3] * w[2].x + T[4] * w[3].x; y[1].y = T[3] * w[2].y + T[4] * w[3].y;
+    y[2].x = T[4] * w[2].x - T[7] * w[3].x; y[2].y = T[4] * w[2].y - T[7] * w[3].y;
+    y[0].x = T[1] * D[2].x; y[0].y = T[1] * D[2].y;
+    x[4].x = x[1].x + x[2].x; x[4].y = x[1].y + x[2].y;
+    y[4].x = y[1].x - y[2].x; y[4].y = y[1].y - y[2].y;
+    x[1].x = z0.x + x[1].x; x[1].y = z0.y + x[1].y;
+    y[1].x = y[0].x + y[1].x; y[1].y = y[0].y + y[1].y;
+    x[2].x = z0.x + x[2].x; x[2].y = z0.y + x[2].y;
+    y[2].x = y[2].x - y[0].x; y[2].y = y[2].y - y[0].y;
+    x[4].x = z0.x - x[4].x; x[4].y = z0.y - x[4].y;
+    y[4].x = y[0].x - y[4].x; y[4].y = y[0].y - y[4].y;
+#pragma unroll
+    for (int k = 1; k <= 4; k++) {
+        out[k * stride].x = x[k].x + y[k].y; out[k * stride].y = x[k].y - y[k].x;
+        out[(9 - k) * stride].x = x[k].x - y[k].y; out[(9 - k) * stride].y = x[k].y + y[k].x;
+    }
+}
+
 __device__ __forceinline__ void fft15(const float *tab, float2 *out, const float2 *in, int stride);
-// the N-point transform DECL_COMP_IMDCT / DECL_COMP_MDCT instantiate for N = 3, 5, 15
+// the N-point transform DECL_COMP_IMDCT / DECL_COMP_MDCT instantiate for N = 3, 5, 7, 9, 15
 __device__ __forceinline__ void fftN(int n, const float *tab, float2 *out, const float2 *in, int stride)
 {
     if (n == 3) fft3(tab, out, in, stride);
     else if (n == 5) fft5<0, 1, 2, 3, 4>(tab, out, in, stride);
+    else if (n == 7) fft7(tab + 12, out, in, stride);
+    else if (n == 9) fft9(tab + 18, out, in, stride);
     else fft15(tab, out, in, stride);
 }
 __device__ __forceinline__ void fft15(const float *tab, float2 *out, const float2 *in, int stride)
@@ -293,16 +370,16 @@ struct TxPfa {
 struct PfaHost {
     std::vector<int> in_map, out_map, sub_map;
     std::vector<float> exp;            // interleaved re, im: inverse = 2 * l2 entries (pre-shuffled, then natural), forward = l2
-    float tab53[12];
+    float tab53[26];                   // ff_tx_tab_53 [12], ff_tx_tab_7 [6], ff_tx_tab_9 [8]
     std::vector<float> cosk[12];
     int m = 0, log2m = 0, nfac = 0;
 };
 
-// the odd factor av_tx_init() ends up with for this MDCT length: the largest of 15, 5, 3 that leaves a power of two (tx.c:391-395); 0 = none
+// the odd factor av_tx_init() ends up with for this MDCT length: the largest of 15, 9, 7, 5, 3 that leaves a power of two (tx.c:391-395); 0 = none
 static int pfa_factor(int len)
 {
     if (len < 12 || (len & 1)) return 0;
-    static const int factors[3] = { 15, 5, 3 };
+    static const int factors[5] = { 15, 9, 7, 5, 3 };
     for (int n : factors) {
         const int l2 = len >> 1, m = l2 / n;
         if (l2 % n == 0 && m >= 2 && m <= 512 && !(m & (m - 1))) return n;
@@ -353,6 +430,11 @@ static void pfa_host_tables(PfaHost &H, int inv, int len, float scale)
     H.tab53[0] = H.tab53[1] = (float)c5; H.tab53[2] = H.tab53[3] = (float)c10;
     H.tab53[4] = H.tab53[5] = (float)s5; H.tab53[6] = H.tab53[7] = (float)s10;
     H.tab53[8] = H.tab53[9] = (float)cos(2 * M_PI / 12); H.tab53[10] = (float)cos(2 * M_PI / 6); H.tab53[11] = (float)cos(8 * M_PI / 6);
+    float *t7 = H.tab53 + 12, *t9 = H.tab53 + 18;                   // ff_tx_init_tab_7 / _9 (tx_template.c:110-130)
+    t7[0] = (float)cos(2 * M_PI / 7); t7[1] = (float)sin(2 * M_PI / 7); t7[2] = (float)sin(2 * M_PI / 28);
+    t7[3] = (float)cos(2 * M_PI / 28); t7[4] = (float)cos(2 * M_PI / 14); t7[5] = (float)sin(2 * M_PI / 14);
+    t9[0] = (float)cos(2 * M_PI / 3); t9[1] = (float)sin(2 * M_PI / 3); t9[2] = (float)cos(2 * M_PI / 9); t9[3] = (float)sin(2 * M_PI / 9);
+    t9[4] = (float)cos(2 * M_PI / 36); t9[5] = (float)sin(2 * M_PI / 36); t9[6] = t9[2] + t9[5]; t9[7] = t9[3] - t9[4];
     for (int k = 3; k <= H.log2m; k++) {                            // ff_tx_init_tab_N (tx_template.c:65-77)
         const int nn = 1 << k;
         H.cosk[k].assign(nn / 4 + 1, 0.f);
@@ -362,7 +444,7 @@ static void pfa_host_tables(PfaHost &H, int inv, int len, float scale)
 }
 
 // host-only: the tables of a transform, flattened, for the CPU test tier: [in_map l2][out_map l2][sub_map m] as int32, then
-// floats: exp, tab53[12], cosine tables k = 3 .. log2m.  Returns the number of 32-bit words (or what it would need if cap is short).
+// floats: exp, tab53[12] + tab7[6] + tab9[8], cosine tables k = 3 .. log2m.  Returns the number of 32-bit words (or what it would need if cap is short).
 B200_API int b200_tx_pfa_tables(int inv, int len, float scale, int32_t *words, int cap, int32_t *layout8)
 {
     if (!tx_pfa_length_ok(len)) return B200_ENOSYS;
@@ -376,7 +458,7 @@ B200_API int b200_tx_pfa_tables(int inv, int len, float scale, int32_t *words, i
     lay[1] = (int32_t)w.size(); addi(H.out_map);
     lay[2] = (int32_t)w.size(); addi(H.sub_map);
     lay[3] = (int32_t)w.size(); addf(H.exp.data(), H.exp.size());
-    lay[4] = (int32_t)w.size(); addf(H.tab53, 12);
+    lay[4] = (int32_t)w.size(); addf(H.tab53, 26);
     lay[5] = (int32_t)w.size();
     for (int k = 3; k <= H.log2m; k++) addf(H.cosk[k].data(), H.cosk[k].size());
     lay[6] = H.m; lay[7] = H.log2m | (H.nfac << 8);
@@ -397,7 +479,7 @@ TxPfa *tx_pfa_create(int inv, int len, float scale)
     const size_t o_out = off; off += al(sizeof(int) * l2);
     const size_t o_sub = off; off += al(sizeof(int) * m);
     const size_t o_exp = off; off += al(sizeof(float) * H.exp.size());
-    const size_t o_53 = off;  off += al(sizeof(float) * 12);
+    const size_t o_53 = off;  off += al(sizeof(float) * 26);
     size_t o_cos[12] = { 0 };
     for (int k = 3; k <= H.log2m; k++) { o_cos[k] = off; off += al(sizeof(float) * H.cosk[k].size()); }
     std::vector<uint8_t> host(off, 0);
@@ -405,7 +487,7 @@ TxPfa *tx_pfa_create(int inv, int len, float scale)
     memcpy(&host[o_out], H.out_map.data(), sizeof(int) * l2);
     memcpy(&host[o_sub], H.sub_map.data(), sizeof(int) * m);
     memcpy(&host[o_exp], H.exp.data(), sizeof(float) * H.exp.size());
-    memcpy(&host[o_53], H.tab53, sizeof(float) * 12);
+    memcpy(&host[o_53], H.tab53, sizeof(float) * 26);
     for (int k = 3; k <= H.log2m; k++) memcpy(&host[o_cos[k]], H.cosk[k].data(), sizeof(float) * H.cosk[k].size());
     TxPfa *p = new (std::nothrow) TxPfa();
     if (!p) return nullptr;

@@ -485,12 +485,12 @@ int  b200_emulated_edge_mc_batch_device(B200Device *dev, int64_t n, uint8_t *buf
 typedef struct B200TXContext B200TXContext;
 typedef void (*b200_tx_fn)(B200TXContext *s, void *out, void *in, ptrdiff_t stride);   /* av_tx_fn: HOST pointers */
 /* like av_tx_init(); uses the process-wide default device.  scale: const float * (MDCT), ignored for FFT.
- * Lengths: powers of two, and for AV_TX_FLOAT_MDCT also 2 * N * 2^k with N = 15, 5 or 3: the compound transform av_tx_init() resolves
- * to for those (ff_tx_mdct_pfa_{15,5,3}xM_{inv,fwd}_float_c, libavutil/tx_template.c:1471-1599; 15 x M covers the Opus CELT sizes).
+ * Lengths: powers of two, and for AV_TX_FLOAT_MDCT also 2 * N * 2^k with N = 15, 9, 7, 5 or 3: the compound transform av_tx_init() resolves
+ * to for those (ff_tx_mdct_pfa_{15,9,7,5,3}xM_{inv,fwd}_float_c, libavutil/tx_template.c:1471-1599; 15 x M covers the Opus CELT sizes).
  * Returns 0 or B200_ENOSYS (unsupported type / flags / length), B200_EINVAL, B200_ENODEV. */
 int  b200_tx_init(B200TXContext **ctx, b200_tx_fn *tx, int type, int inv, int len, const void *scale, uint64_t flags);
 /* host-only: the tables ff_tx_mdct_pfa_init() builds for a 15 x M MDCT, flattened into 32-bit words, for the CPU test tier
- * (layout8: word offsets of in_map, out_map, sub_map, exp, tab_53, cosine tables; then M and log2 M | N << 8).  Returns the word count. */
+ * (layout8: word offsets of in_map, out_map, sub_map, exp, tab_53 + tab_7 + tab_9 (26 floats), cosine tables; then M and log2 M | N << 8).  Returns the word count. */
 int  b200_tx_pfa_tables(int inv, int len, float scale, int32_t *words, int cap, int32_t *layout8);
 /* host-only: the factor table of ff_tx_dct_init (N rotation factors, then N / 2 butterfly factors), for the CPU test tier */
 int  b200_tx_dct_table(int inv, int len, float *tab, int cap);

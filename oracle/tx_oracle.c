@@ -34,11 +34,11 @@ struct OrcTx {
     float *tab[18];             /* tab[k] = cosine table of size 2^k */
     /* compound 15 x M MDCT (ff_tx_mdct_pfa_15xM_{inv,fwd}, tx_template.c:1471-1599): len/2 = 15 * m complex points */
     int pfa_m;                  /* 0: power-of-two transform; else m (power of two >= 2) */
-    int pfa_n;                  /* the odd factor: 15, 5 or 3 (ff_tx_mdct_pfa_{15,5,3}xM) */
+    int pfa_n;                  /* the odd factor: 15, 9, 7, 5 or 3 (ff_tx_mdct_pfa_{15,9,7,5,3}xM) */
     int *pfa_in, *pfa_out;      /* compound input map (15-point groups, 3x5 map embedded; doubled for the inverse) and CRT output map */
     int *pfa_sub;               /* scatter permutation of the m-point FFT (ff_tx_gen_ptwo_revtab, FF_TX_MAP_SCATTER) */
     cpx *pfa_tmp;
-    float tab53[12];            /* ff_tx_tab_53 (tx_template.c:91-108) */
+    float tab53[12 + 6 + 8];    /* ff_tx_tab_53 (tx_template.c:91-108), then ff_tx_tab_7 (:110-118) and ff_tx_tab_9 (:120-130) */
     /* AV_TX_FLOAT_DCT (type 9): DCT-II forward / DCT-III inverse around a real DFT (ff_tx_dctII / ff_tx_dctIII, tx_template.c:1832-1968) */
     OrcTx *dct_sub;             /* the r2c (forward) or c2r (inverse) transform of dct_n points */
     int dct_n;                  /* points: len forward, 2 * len inverse (ff_tx_dct_init doubles it) */
@@ -210,6 +210,11 @@ static OrcTx *open_mdct_pfa(int n, int inv, int len, float scale)
     t->tab53[0] = t->tab53[1] = (float)c5; t->tab53[2] = t->tab53[3] = (float)c10;
     t->tab53[4] = t->tab53[5] = (float)s5; t->tab53[6] = t->tab53[7] = (float)s10;
     t->tab53[8] = t->tab53[9] = (float)cos(2 * M_PI / 12); t->tab53[10] = (float)cos(2 * M_PI / 6); t->tab53[11] = (float)cos(8 * M_PI / 6);
+    float *t7 = t->tab53 + 12, *t9 = t->tab53 + 18;
+    t7[0] = (float)cos(2 * M_PI / 7); t7[1] = (float)sin(2 * M_PI / 7); t7[2] = (float)sin(2 * M_PI / 28);
+    t7[3] = (float)cos(2 * M_PI / 28); t7[4] = (float)cos(2 * M_PI / 14); t7[5] = (float)sin(2 * M_PI / 14);
+    t9[0] = (float)cos(2 * M_PI / 3); t9[1] = (float)sin(2 * M_PI / 3); t9[2] = (float)cos(2 * M_PI / 9); t9[3] = (float)sin(2 * M_PI / 9);
+    t9[4] = (float)cos(2 * M_PI / 36); t9[5] = (float)sin(2 * M_PI / 36); t9[6] = t9[2] + t9[5]; t9[7] = t9[3] - t9[4];
     return t;
 }
 
@@ -263,12 +268,86 @@ static void pfa_fft15(const float *tab, cpx *out, const cpx *in, int stride)
     pfa_fft5(tab, out, tmp + 10, stride, m3);
 }
 
-/* fft3 / fft5 / fft15 as the DECL_COMP_* macros instantiate them for N = 3, 5, 15 */
+/* fft7 (tx_template.c:252-339, float branch).  S[k] / D[k]: sum / difference of in[k + 1] and in[6 - k]; T = ff_tx_tab_7 as three
+ * (re, im) pairs.  Every expression keeps the reference's left-to-right order of products and sums. */
+static void pfa_fft7(const float *T, cpx *out, const cpx *in, int stride)
+{
+    const float c0 = T[0], s0 = T[1], c1 = T[2], s1 = T[3], c2 = T[4], s2 = T[5];
+    const cpx dc = in[0];
+    cpx S[3], D[3], z[3], u[3];
+    for (int k = 0; k < 3; k++) {
+        S[k].re = in[k + 1].re + in[6 - k].re; D[k].re = in[k + 1].re - in[6 - k].re;
+        S[k].im = in[k + 1].im + in[6 - k].im; D[k].im = in[k + 1].im - in[6 - k].im;
+    }
+    out[0].re = dc.re + S[0].re + S[1].re + S[2].re;
+    out[0].im = dc.im + S[0].im + S[1].im + S[2].im;
+    z[0].re = c0 * S[0].re - c2 * S[2].re - c1 * S[1].re;
+    z[1].re = c0 * S[2].re - c1 * S[0].re - c2 * S[1].re;
+    z[2].re = c0 * S[1].re - c2 * S[0].re - c1 * S[2].re;
+    z[0].im = c0 * S[0].im - c1 * S[1].im - c2 * S[2].im;
+    z[1].im = c0 * S[2].im - c1 * S[0].im - c2 * S[1].im;
+    z[2].im = c0 * S[1].im - c2 * S[0].im - c1 * S[2].im;
+    u[0].re = s2 * D[0].im + s1 * D[2].im - s0 * D[1].im;
+    u[1].re = s0 * D[2].im + s2 * D[1].im - s1 * D[0].im;
+    u[2].re = s2 * D[2].im + s1 * D[1].im + s0 * D[0].im;
+    u[0].im = s0 * D[0].re + s1 * D[1].re + s2 * D[2].re;
+    u[1].im = s2 * D[1].re + s0 * D[2].re - s1 * D[0].re;
+    u[2].im = s2 * D[0].re + s1 * D[2].re - s0 * D[1].re;
+    out[1 * stride].re = dc.re + (z[0].re + u[2].re); out[1 * stride].im = dc.im + (z[0].im - u[0].im);
+    out[2 * stride].re = dc.re + (z[1].re - u[1].re); out[2 * stride].im = dc.im + (z[1].im + u[1].im);
+    out[3 * stride].re = dc.re + (z[2].re + u[0].re); out[3 * stride].im = dc.im + (z[2].im - u[2].im);
+    out[4 * stride].re = dc.re + (z[2].re - u[0].re); out[4 * stride].im = dc.im + (z[2].im + u[2].im);
+    out[5 * stride].re = dc.re + (z[1].re + u[1].re); out[5 * stride].im = dc.im + (z[1].im - u[1].im);
+    out[6 * stride].re = dc.re + (z[0].re - u[2].re); out[6 * stride].im = dc.im + (z[0].im + u[0].im);
+}
+
+/* fft9 (tx_template.c:341-463, float branch).  S[k] / D[k]: sum / difference of in[k + 1] and in[8 - k]; T = ff_tx_tab_9 as four pairs. */
+static void pfa_fft9(const float *T, cpx *out, const cpx *in, int stride)
+{
+    const cpx dc = in[0];
+    cpx S[4], D[4], w[4], x[5], y[5], z0, z1;
+    for (int k = 0; k < 4; k++) {
+        S[k].re = in[k + 1].re + in[8 - k].re; D[k].re = in[k + 1].re - in[8 - k].re;
+        S[k].im = in[k + 1].im + in[8 - k].im; D[k].im = in[k + 1].im - in[8 - k].im;
+    }
+    w[0].re = S[0].re - S[3].re; w[0].im = S[0].im - S[3].im;
+    w[1].re = S[1].re - S[3].re; w[1].im = S[1].im - S[3].im;
+    w[2].re = D[0].re - D[3].re; w[2].im = D[0].im - D[3].im;
+    w[3].re = D[1].re + D[3].re; w[3].im = D[1].im + D[3].im;
+    z0.re = dc.re + S[2].re; z0.im = dc.im + S[2].im;
+    z1.re = S[0].re + S[1].re + S[3].re; z1.im = S[0].im + S[1].im + S[3].im;
+    out[0].re = z0.re + z1.re; out[0].im = z0.im + z1.im;
+    y[3].re = T[1] * (D[0].re - D[1].re + D[3].re);
+    y[3].im = T[1] * (D[0].im - D[1].im + D[3].im);
+    x[3].re = z0.re + T[0] * z1.re; x[3].im = z0.im + T[0] * z1.im;
+    z0.re = dc.re + T[0] * S[2].re; z0.im = dc.im + T[0] * S[2].im;
+    x[1].re = T[2] * w[0].re + T[5] * w[1].re; x[1].im = T[2] * w[0].im + T[5] * w[1].im;
+    x[2].re = T[5] * w[0].re - T[6] * w[1].re; x[2].im = T[5] * w[0].im - T[6] * w[1].im;
+    y[1].re = T[3] * w[2].re + T[4] * w[3].re; y[1].im = T[3] * w[2].im + T[4] * w[3].im;
+    y[2].re = T[4] * w[2].re - T[7] * w[3].re; y[2].im = T[4] * w[2].im - T[7] * w[3].im;
+    y[0].re = T[1] * D[2].re; y[0].im = T[1] * D[2].im;
+    x[4].re = x[1].re + x[2].re; x[4].im = x[1].im + x[2].im;
+    y[4].re = y[1].re - y[2].re; y[4].im = y[1].im - y[2].im;
+    x[1].re = z0.re + x[1].re; x[1].im = z0.im + x[1].im;
+    y[1].re = y[0].re + y[1].re; y[1].im = y[0].im + y[1].im;
+    x[2].re = z0.re + x[2].re; x[2].im = z0.im + x[2].im;
+    y[2].re = y[2].re - y[0].re; y[2].im = y[2].im - y[0].im;
+    x[4].re = z0.re - x[4].re; x[4].im = z0.im - x[4].im;
+    y[4].re = y[0].re - y[4].re; y[4].im = y[0].im - y[4].im;
+    for (int k = 1; k <= 4; k++) {
+        out[k * stride].re = x[k].re + y[k].im; out[k * stride].im = x[k].im - y[k].re;
+        out[(9 - k) * stride].re = x[k].re - y[k].im; out[(9 - k) * stride].im = x[k].im + y[k].re;
+    }
+}
+
+/* fft3 / fft5 / fft7 / fft9 / fft15 as the DECL_COMP_* macros instantiate them */
 static void pfa_fftN(int n, const float *tab, cpx *out, const cpx *in, int stride)
 {
     static const int d5[5] = { 0, 1, 2, 3, 4 };
     if (n == 3) pfa_fft3(tab, out, in, stride);
     else if (n == 5) pfa_fft5(tab, out, in, stride, d5);
+    else if (n == 7) pfa_fft7(tab + 12, out, in, stride);
+    else if (n == 9) pfa_fft9(tab + 18, out, in, stride);
     else pfa_fft15(tab, out, in, stride);
 }
 
@@ -404,8 +483,8 @@ OrcTx *orc_tx_open(int type, int inv, int len, float scale, unsigned flags)
 {
     if (!flags && type == 9) return open_dct(inv, len, scale);
     if (!flags && type == 1 && len >= 12 && !(len & 1)) {          /* compound MDCT: the largest odd factor wins (tx.c:391-395) */
-        static const int factors[3] = { 15, 5, 3 };
-        for (int f = 0; f < 3; f++) {
+        static const int factors[5] = { 15, 9, 7, 5, 3 };
+        for (int f = 0; f < 5; f++) {
             const int n = factors[f], l2 = len >> 1, m = l2 / n;
             if (l2 % n == 0 && m >= 2 && !(m & (m - 1))) return open_mdct_pfa(n, inv, len, scale);
         }

@@ -140,11 +140,11 @@ def gen_sws_rgbsrc():
 
 
 def gen_tx_pfa():
-    """compound 15 x M float MDCT (Opus CELT sizes): the reference's outputs, inverse and forward, two scales."""
+    """compound 15 x M float MDCT (Opus CELT sizes), then 7 x M and 9 x M: the reference's outputs, inverse and forward, two scales."""
     R = cl.ref()
     d = {}
     rng = np.random.default_rng(77)
-    for n in (120, 240, 480, 960):
+    for n in (120, 240, 480, 960, 112, 448, 144, 576):
         for inv in (1, 0):
             x = (rng.random((2, n if inv else 2 * n), dtype=np.float32) * 2 - 1).astype(np.float32)
             d[f"in_{n}_{inv}"] = x

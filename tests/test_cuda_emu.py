@@ -245,8 +245,8 @@ def test_emu_tx_mdct_pfa15(emu):
     emu.emu_tx_pfa.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_longlong,
                                C.c_longlong, C.c_void_p]
     rng = np.random.default_rng(11)
-    assert L.b200_tx_pfa_tables(1, 84, 1.0, None, 0, None) < 0 and L.b200_tx_pfa_tables(1, 1024, 1.0, None, 0, None) < 0      # 7 x M, power of two
-    for n in (120, 240, 480, 960, 1920, 60, 12, 96, 1536, 20, 160, 640):            # 15 x M, then 3 x M and 5 x M
+    assert L.b200_tx_pfa_tables(1, 84, 1.0, None, 0, None) < 0 and L.b200_tx_pfa_tables(1, 1024, 1.0, None, 0, None) < 0      # 7 x 6, power of two
+    for n in (120, 240, 480, 960, 1920, 60, 12, 96, 1536, 20, 160, 640, 28, 112, 448, 36, 144, 2304):  # 15 x M; 3 x M and 5 x M; 7 x M and 9 x M
         for inv in (1, 0):
             for sc in (1.0 / n, -1.0, -1.0 / 32768):
                 lay = np.zeros(8, np.int32)
@@ -547,7 +547,7 @@ def test_tx_whole_path_on_emulated_device(emutx):
         assert np.array_equal(_emu_tx(emutx, 1, 1, n, 1.0 / n, xi, n).view(np.uint32), _tx(O, "orc", 1, 1, n, 1.0 / n, xi, n).view(np.uint32)), ("imdct", n)
         assert np.array_equal(_emu_tx(emutx, 1, 0, n, 1.0, x, n).view(np.uint32), _tx(O, "orc", 1, 0, n, 1.0, x, n).view(np.uint32)), ("mdct", n)
         assert np.array_equal(_emu_tx(emutx, 6, 0, n, 1.0, xi, n + 2).view(np.uint32), _tx(O, "orc", 6, 0, n, 1.0, xi.copy(), n + 2).view(np.uint32)), ("r2c", n)
-    for n in (120, 240, 960, 24, 384, 40, 320):
+    for n in (120, 240, 960, 24, 384, 40, 320, 56, 72):
         for inv in (1, 0):
             x = (rng.random((70, n if inv else 2 * n), dtype=np.float32) * 2 - 1).astype(np.float32)
             exp = _tx(O, "orc", 1, inv, n, 1.0 / n, x, n)
@@ -764,7 +764,7 @@ def test_host_tx_pfa_create_and_launch(emuhost):
     L, O = emuhost, cl.oracle()
     L.emu_host_tx_pfa.argtypes = [C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_longlong, C.c_longlong]
     rng = np.random.default_rng(31)
-    for n in (120, 960, 48, 80):
+    for n in (120, 960, 48, 80, 224, 288):
         for inv in (1, 0):
             cnt = 70                                                    # more than one 64-thread block
             x = (rng.random((cnt, n if inv else 2 * n), dtype=np.float32) * 2 - 1).astype(np.float32)

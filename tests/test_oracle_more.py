@@ -379,7 +379,7 @@ def test_tx_pfa15_oracle_golden_bitexact():
     """ff_tx_mdct_pfa_15xM_{inv,fwd}_float_c at the Opus CELT sizes against the reference's outputs, bit for bit"""
     g = np.load(os.path.join(G, "tx_pfa.npz"))
     O = cl.oracle()
-    for n in (120, 240, 480, 960):
+    for n in (120, 240, 480, 960, 112, 448, 144, 576):                # 15 x M, then 7 x M and 9 x M
         for inv in (1, 0):
             for j, sc in enumerate((1.0 / n, -1.0)):
                 got = _tx(O, "orc", 1, inv, n, sc, g[f"in_{n}_{inv}"], n)
@@ -391,7 +391,7 @@ def test_tx_pfa15_oracle_vs_ref_and_round_trip():
     rng = np.random.default_rng(12)
     if cl.have_ref():
         R = cl.ref()
-        for n in (60, 120, 480, 1920, 3840):
+        for n in (60, 120, 480, 1920, 3840, 28, 56, 1792, 7168, 36, 72, 2304, 9216):    # 15 x M; 7 x M; 9 x M
             for inv in (1, 0):
                 x = (rng.random((2, n if inv else 2 * n), dtype=np.float32) * 2 - 1).astype(np.float32)
                 for sc in (1.0, -1.0 / 32768):

@@ -409,7 +409,7 @@ def test_tx_mdct_pfa15(device):
     from test_oracle_more import _tx
     g = np.load(os.path.join(G, "tx_pfa.npz"))
     O = cl.oracle()
-    for n in (120, 240, 480, 960):
+    for n in (120, 240, 480, 960, 112, 448, 144, 576):
         for inv in (1, 0):
             for j, sc in enumerate((1.0 / n, -1.0)):
                 c = tx.av_tx_init(tx.AV_TX_FLOAT_MDCT, inv, n, scale=sc)
@@ -420,7 +420,7 @@ def test_tx_mdct_pfa15(device):
                 assert np.array_equal(out.view(np.uint32), g[f"out_{n}_{inv}_{j}"].view(np.uint32)), (n, inv, j)
                 c.uninit()
     rng = np.random.default_rng(21)
-    for n in (120, 960, 1920, 96, 640):                                # 15 x M, 3 x M, 5 x M
+    for n in (120, 960, 1920, 96, 640, 224, 1152):                     # 15 x M, 3 x M, 5 x M, 7 x M, 9 x M
         for inv in (1, 0):
             cnt = 3000
             x = (rng.random((cnt, n if inv else 2 * n), dtype=np.float32) * 2 - 1).astype(np.float32)
@@ -433,7 +433,7 @@ def test_tx_mdct_pfa15(device):
             assert np.array_equal(got.view(np.uint32), _tx(O, "orc", 1, inv, n, 1.0 / n, x, n).view(np.uint32)), (n, inv)
             c.uninit()
     with pytest.raises(fb.B200Error):
-        tx.av_tx_init(tx.AV_TX_FLOAT_MDCT, 1, 84, scale=1.0)            # 7 x M: not built
+        tx.av_tx_init(tx.AV_TX_FLOAT_MDCT, 1, 84, scale=1.0)            # 7 x 6: the sub-transform would be a compound FFT, not built
     with pytest.raises(fb.B200Error):
         tx.av_tx_init(tx.AV_TX_FLOAT_FFT, 0, 960)                       # compound FFTs are not built
 
