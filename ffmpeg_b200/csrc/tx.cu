@@ -434,6 +434,7 @@ struct B200TXContext {
     TxDct *dct = nullptr;            // AV_TX_FLOAT_DCT (tx_dct.cu): stages around a child RDFT context
     TxI32 *i32 = nullptr;            // AV_TX_INT32_FFT / _MDCT (tx_int32.cu)
     int type = 0, inv = 0, len = 0;
+    bool full = false;               // AV_TX_FULL_IMDCT: ff_tx_mdct_inv_full around the inverse MDCT (tx_template.c:1372-1413)
     TxDev d{};
     void *blob = nullptr;
     size_t smem = 0;
@@ -583,8 +584,44 @@ static int tx_build(B200TXContext *c, float scale)
     return 0;
 }
 
+// ff_tx_mdct_inv_full (tx_template.c:1386-1398): the inverse MDCT has put its n outputs at out[n/2 .. 3n/2); the first and the last
+// quarter of the 2n outputs are mirrors of them (the first one negated).  One thread per mirrored pair.
+__global__ void __launch_bounds__(256)
+tx_imdct_full_mirror_kernel(float *out, long long out_step_floats, int n, long long count)
+{
+    const int n2 = n >> 1;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count * n2) return;
+    float *d = out + (t / n2) * out_step_floats;
+    const int k = (int)(t % n2);
+    d[k] = -d[n - k - 1];
+    d[2 * n - k - 1] = d[n + k];
+}
+
+static int tx_launch_half(B200TXContext *c, cudaStream_t st, void *out, const void *in, ptrdiff_t stride, int64_t count,
+                          ptrdiff_t out_step, ptrdiff_t in_step, void *c2r_writeback);
+
 static int tx_launch(B200TXContext *c, cudaStream_t st, void *out, const void *in, ptrdiff_t stride, int64_t count,
                      ptrdiff_t out_step, ptrdiff_t in_step, void *c2r_writeback = nullptr)
+{
+    if (!c->full) return tx_launch_half(c, st, out, in, stride, count, out_step, in_step, c2r_writeback);
+    if (count <= 0) return 0;
+    if (out_step & 3) return B200_EINVAL;
+    const int ret = tx_launch_half(c, st, (float *)out + (c->len >> 1), in, stride, count, out_step, in_step, nullptr);
+    if (ret < 0) return ret;
+    const long long per = 0x7fffffffLL * 256 / (c->len >> 1);        // transforms per launch (grid.x limit)
+    for (int64_t c0 = 0; c0 < count; c0 += per) {
+        const long long cnt = count - c0 < per ? count - c0 : per;
+        const long long threads = cnt * (c->len >> 1);
+        tx_imdct_full_mirror_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>((float *)((char *)out + c0 * out_step), out_step / 4, c->len, cnt);
+        B200_LAUNCHED();
+    }
+    B200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+static int tx_launch_half(B200TXContext *c, cudaStream_t st, void *out, const void *in, ptrdiff_t stride, int64_t count,
+                          ptrdiff_t out_step, ptrdiff_t in_step, void *c2r_writeback)
 {
     if (count <= 0) return 0;
     if (c->pfa) return tx_pfa_launch(c->pfa, st, out, in, stride, count, out_step, in_step);
@@ -631,8 +668,9 @@ static void tx_host_fn(B200TXContext *c, void *out, void *in, ptrdiff_t stride)
     if (c->dct) { in_elems = out_elems = (size_t)tx_dct_points(c->dct); }     // DCT-II: len in / len out; DCT-III: 2*len in / 2*len out
     else if (c->type == 0) { in_elems = out_elems = 2 * n; }
     else if (c->type == 6) { in_elems = c->inv ? len + 2 : len; out_elems = c->inv ? len : len + 2; }
-    else if (c->inv) { in_elems = len; out_elems = len; }
+    else if (c->inv) { in_elems = len; out_elems = c->full ? 2 * len : len; }
     else { in_elems = 2 * len; out_elems = len; }
+    if (c->full && stride != 4) fail("AV_TX_FULL_IMDCT takes stride == sizeof(float) (the reference mirrors with the input stride)");
     float *scr = (float *)b200_scratch(d, (in_elems + out_elems) * 4 + 512);
     if (!scr) fail("scratch");
     float *din = scr, *dout = scr + ((in_elems + 63) & ~(size_t)63);
@@ -659,7 +697,9 @@ B200_API int b200_tx_init_device(B200Device *dev, B200TXContext **ctx, b200_tx_f
     if (!dev) return B200_ENODEV;
     if (type != B200_TX_FLOAT_FFT && type != B200_TX_FLOAT_MDCT && type != B200_TX_FLOAT_RDFT && type != B200_TX_FLOAT_DCT &&
         type != B200_TX_INT32_FFT && type != B200_TX_INT32_MDCT) return B200_ENOSYS;
-    if (flags & ~(uint64_t)B200_TX_UNALIGNED) return B200_ENOSYS;    // INPLACE / FULL_IMDCT / REAL_TO_* not implemented
+    if (flags & ~(uint64_t)(B200_TX_UNALIGNED | B200_TX_FULL_IMDCT)) return B200_ENOSYS;    // INPLACE / REAL_TO_* not implemented
+    const bool full = (flags & B200_TX_FULL_IMDCT) != 0;
+    if (full && !(type == B200_TX_FLOAT_MDCT && inv)) return B200_ENOSYS;      // only the inverse MDCT has such a codelet (tx.c:762-771)
     if (type == B200_TX_INT32_FFT || type == B200_TX_INT32_MDCT) {   // 32-bit fixed point (tx_int32.cu)
         if (!tx_i32_length_ok(type, len)) return B200_ENOSYS;
         float sci = 1.0f;
@@ -693,7 +733,7 @@ B200_API int b200_tx_init_device(B200Device *dev, B200TXContext **ctx, b200_tx_f
         if (scale) scp = *(const float *)scale;
         B200TXContext *cp = new (std::nothrow) B200TXContext();
         if (!cp) return B200_ENOMEM;
-        cp->dev = dev; cp->type = type; cp->inv = !!inv; cp->len = len;
+        cp->dev = dev; cp->type = type; cp->inv = !!inv; cp->len = len; cp->full = full;
         if (cudaSetDevice(dev->ordinal) != cudaSuccess) { delete cp; return B200_EEXTERNAL; }
         cp->pfa = tx_pfa_create(cp->inv, len, scp);
         if (!cp->pfa) { delete cp; return B200_EEXTERNAL; }
@@ -703,13 +743,14 @@ B200_API int b200_tx_init_device(B200Device *dev, B200TXContext **ctx, b200_tx_f
     }
     if (len < 2 || (len & (len - 1))) return B200_ENOSYS;            // other PFA lengths (3/5/7/9 x 2^n) are not implemented
     if (type == B200_TX_FLOAT_RDFT && len < 4) return B200_ENOSYS;   // ff_tx_rdft_*_def: min_len 4
+    if (type == B200_TX_FLOAT_MDCT && len < 4) return B200_ENOSYS;   // len 2: the reference falls back to its naive MDCT (no 1-point FFT)
     const int n = type == 0 ? len : len >> 1;
     if (n < 1 || n > 16384) return B200_ENOSYS;                      // one transform must fit a CTA's shared memory
     float sc = 1.0f;                                                 // default_scale_f
     if (type != B200_TX_FLOAT_FFT && scale) sc = *(const float *)scale;
     B200TXContext *c = new (std::nothrow) B200TXContext();
     if (!c) return B200_ENOMEM;
-    c->dev = dev; c->type = type; c->inv = !!inv; c->len = len;
+    c->dev = dev; c->type = type; c->inv = !!inv; c->len = len; c->full = full;
     if (cudaSetDevice(dev->ordinal) != cudaSuccess) { delete c; return B200_EEXTERNAL; }
     int ret = tx_build(c, sc);
     if (ret < 0) { if (c->blob) cudaFree(c->blob); delete c; return ret; }
@@ -742,6 +783,7 @@ B200_API int b200_tx_batch_device(B200TXContext *c, void *out, const void *in, p
 {
     if (!c || !out || !in || count < 0) return B200_EINVAL;
     if ((c->type == 1 || c->type == B200_TX_INT32_MDCT) && (stride & 3)) return B200_EINVAL;
+    if (c->full && stride != 4) return B200_EINVAL;                  // the reference mirrors with the input stride: only sizeof(float) is meaningful
     B200_CUDA_OK(cudaSetDevice(c->dev->ordinal));
     return tx_launch(c, c->dev->stream, out, in, (c->type == 1 || c->type == B200_TX_INT32_MDCT) ? stride : 8, count, out_step, in_step);
 }

@@ -33,6 +33,7 @@ struct OrcTx {
     float *rexp;                /* RDFT: 8 factors, then cos and sin-like tables of len/4 entries each */
     float *tab[18];             /* tab[k] = cosine table of size 2^k */
     /* compound 15 x M MDCT (ff_tx_mdct_pfa_15xM_{inv,fwd}, tx_template.c:1471-1599): len/2 = 15 * m complex points */
+    int full;                   /* AV_TX_FULL_IMDCT: ff_tx_mdct_inv_full around the inverse MDCT (tx_template.c:1372-1413) */
     int pfa_m;                  /* 0: power-of-two transform; else m (power of two >= 2) */
     int pfa_n;                  /* the odd factor: 15, 9, 7, 5 or 3 (ff_tx_mdct_pfa_{15,9,7,5,3}xM) */
     int *pfa_in, *pfa_out;      /* compound input map (15-point groups, 3x5 map embedded; doubled for the inverse) and CRT output map */
@@ -481,6 +482,12 @@ static void run_dct3(OrcTx *t, float *dst, float *src)
 
 OrcTx *orc_tx_open(int type, int inv, int len, float scale, unsigned flags)
 {
+    if (flags == 4) {                                          /* AV_TX_FULL_IMDCT: only the inverse MDCT has such a codelet (tx.c:762-771) */
+        if (type != 1 || !inv) return NULL;
+        OrcTx *sub = orc_tx_open(type, inv, len, scale, 0);
+        if (sub) sub->full = 1;
+        return sub;
+    }
     if (!flags && type == 9) return open_dct(inv, len, scale);
     if (!flags && type == 1 && len >= 12 && !(len & 1)) {          /* compound MDCT: the largest odd factor wins (tx.c:391-395) */
         static const int factors[5] = { 15, 9, 7, 5, 3 };
@@ -491,6 +498,7 @@ OrcTx *orc_tx_open(int type, int inv, int len, float scale, unsigned flags)
     }
     if (flags || (type != 0 && type != 1 && type != 6) || len < 2 || (len & (len - 1))) return NULL;
     if (type == 6 && len < 4) return NULL;                     /* ff_tx_rdft_*_def: min_len 4 */
+    if (type == 1 && len < 4) return NULL;                     /* a 2-point MDCT has no 1-point FFT to sit on: the reference falls back to its naive MDCT */
     OrcTx *t = calloc(1, sizeof(*t));
     t->type = type; t->inv = !!inv; t->len = len;
     t->n = type == 0 ? len : len >> 1;
@@ -660,7 +668,17 @@ void orc_tx_run(OrcTx *t, void *out, void *in, ptrdiff_t stride, int count, ptrd
 {
     for (int c = 0; c < count; c++) {
         void *o = (uint8_t *)out + c * out_step, *i = (uint8_t *)in + c * in_step;
-        if (t->type == 9) { if (t->inv) run_dct3(t, o, i); else run_dct2(t, o, i); }
+        if (t->full) {                                         /* ff_tx_mdct_inv_full: the half transform into the middle, then the two mirrors */
+            float *d = o;
+            const int n = t->len, n2 = n >> 1;
+            const ptrdiff_t st = stride / (ptrdiff_t)sizeof(float);
+            if (t->pfa_m) run_mdct_pfa_inv(t, d + n2, i, st); else run_mdct_inv(t, d + n2, i, st);
+            for (int k = 0; k < n2; k++) {
+                d[k * st] = -d[(n - k - 1) * st];
+                d[(2 * n - k - 1) * st] = d[(n + k) * st];
+            }
+        }
+        else if (t->type == 9) { if (t->inv) run_dct3(t, o, i); else run_dct2(t, o, i); }
         else if (t->type == 0) run_fft(t, o, i);
         else if (t->type == 6) run_rdft(t, o, i);
         else if (t->pfa_m && t->inv) run_mdct_pfa_inv(t, o, i, stride / (ptrdiff_t)sizeof(float));

@@ -157,6 +157,24 @@ def gen_tx_pfa():
     np.savez_compressed(os.path.join(OUT, "tx_pfa.npz"), **d)
 
 
+def gen_tx_full_imdct():
+    """AV_TX_FULL_IMDCT: the reference's 2 * len outputs of the inverse float MDCT, power-of-two and compound lengths, two scales."""
+    R = cl.ref()
+    d = {}
+    rng = np.random.default_rng(79)
+    for n in (4, 64, 256, 1024, 120, 144):
+        x = (rng.random((2, n), dtype=np.float32) * 2 - 1).astype(np.float32)
+        d[f"in_{n}"] = x
+        for j, sc in enumerate((1.0 / n, -1.0)):
+            h = R.ffref_tx_open(1, 1, n, sc, 4)
+            assert h
+            out = np.zeros((2, 2 * n), np.float32)
+            R.ffref_tx_run(h, out.ctypes.data, x.ctypes.data, 4, 2, out.strides[0], x.strides[0])
+            R.ffref_tx_close(h)
+            d[f"out_{n}_{j}"] = out
+    np.savez_compressed(os.path.join(OUT, "tx_full_imdct.npz"), **d)
+
+
 def gen_tx_dct():
     """AV_TX_FLOAT_DCT: the reference's DCT-II (len points) and DCT-III (asked for len / 2) outputs, two scales."""
     R = cl.ref()
@@ -537,6 +555,7 @@ if __name__ == "__main__":
     gen_idct_hbd()
     gen_sws_rgbsrc()
     gen_tx_pfa()
+    gen_tx_full_imdct()
     gen_tx_dct()
     gen_tx_int32()
     gen_prores()

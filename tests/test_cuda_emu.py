@@ -513,12 +513,12 @@ def orc_txi(typ, inv, n, scale, x, out_words):
     return out
 
 
-def _emu_tx(L, typ, inv, n, scale, x, out_floats, host_fn=False):
+def _emu_tx(L, typ, inv, n, scale, x, out_floats, host_fn=False, flags=0):
     """b200_tx_init_device + b200_tx_batch_device (or the av_tx_fn host entry, one transform at a time) on the emulated device"""
     from ffmpeg_b200._lib import TX_FN
     ctx, fn = C.c_void_p(), TX_FN()
     sc = C.c_float(scale)
-    ret = L.b200_tx_init_device(L.dev, C.byref(ctx), C.byref(fn), typ, inv, n, C.byref(sc), 0)
+    ret = L.b200_tx_init_device(L.dev, C.byref(ctx), C.byref(fn), typ, inv, n, C.byref(sc), flags)
     if ret < 0:
         return ret
     out = np.zeros((x.shape[0], out_floats), x.dtype)
@@ -553,6 +553,15 @@ def test_tx_whole_path_on_emulated_device(emutx):
             exp = _tx(O, "orc", 1, inv, n, 1.0 / n, x, n)
             assert np.array_equal(_emu_tx(emutx, 1, inv, n, 1.0 / n, x, n).view(np.uint32), exp.view(np.uint32)), ("pfa batch", n, inv)
             assert np.array_equal(_emu_tx(emutx, 1, inv, n, 1.0 / n, x[:3], n, host_fn=True).view(np.uint32), exp[:3].view(np.uint32)), ("pfa av_tx_fn", n, inv)
+    # AV_TX_FULL_IMDCT around the power-of-two and the compound inverse MDCT: batch and av_tx_fn entries; refused elsewhere
+    for n in (4, 64, 1024, 120, 144, 96):
+        x = (rng.random((70 if n == 64 else 4, n), dtype=np.float32) * 2 - 1).astype(np.float32)
+        exp = _tx(O, "orc", 1, 1, n, 1.0 / n, x, 2 * n, flags=4)
+        assert np.array_equal(_emu_tx(emutx, 1, 1, n, 1.0 / n, x, 2 * n, flags=4).view(np.uint32), exp.view(np.uint32)), ("full imdct", n)
+        assert np.array_equal(_emu_tx(emutx, 1, 1, n, 1.0 / n, x[:2], 2 * n, host_fn=True, flags=6).view(np.uint32), exp[:2].view(np.uint32)), ("full imdct fn", n)
+    assert _emu_tx(emutx, 1, 0, 64, 1.0, x, 64, flags=4) == -38 and _emu_tx(emutx, 0, 1, 64, 1.0, x, 128, flags=4) == -38
+    assert _emu_tx(emutx, 5, 1, 64, 1.0, x, 128, flags=4) == -38 and _emu_tx(emutx, 1, 1, 64, 1.0, x, 128, flags=1) == -38
+    assert _emu_tx(emutx, 1, 1, 2, 1.0, x, 2) == -38                      # 2-point MDCT: the reference's naive fallback, not built
     # AV_TX_FLOAT_DCT: DCT-II forward (len points), DCT-III inverse (asked for len, works on 2 * len), batch and av_tx_fn entries;
     # the input is left alone
     for n in (4, 16, 64, 512):

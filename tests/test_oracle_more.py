@@ -183,8 +183,8 @@ def test_pel_oracle_golden():
     assert n > 150
 
 
-def _tx(L, pre, typ, inv, n, scale, x, out_floats):
-    h = getattr(L, pre + "_tx_open")(typ, inv, n, scale, 0)
+def _tx(L, pre, typ, inv, n, scale, x, out_floats, flags=0):
+    h = getattr(L, pre + "_tx_open")(typ, inv, n, scale, flags)
     assert h
     out = np.zeros((x.shape[0], out_floats), np.float32)
     getattr(L, pre + "_tx_run")(h, out.ctypes.data, x.ctypes.data, 8 if typ == 0 else 4, x.shape[0], out.strides[0], x.strides[0])
@@ -405,6 +405,32 @@ def test_tx_pfa15_oracle_vs_ref_and_round_trip():
     for i in range(2 * n):                                          # direct MDCT definition, float64
         ref += x[0, i] * np.cos(np.pi / n * (i + 0.5 + n / 2) * (k + 0.5))
     assert np.allclose(coef[0], ref, atol=2e-3), float(np.abs(coef[0] - ref).max())
+
+
+def test_tx_full_imdct_oracle_golden_and_ref():
+    """AV_TX_FULL_IMDCT (ff_tx_mdct_inv_full: cook, atrac3, atrac3+, dolby_e, dca_lbr ask for it): 2 * len outputs, power-of-two and
+    compound lengths, against the reference's outputs; refused for anything but the inverse MDCT, like av_tx_init does"""
+    g = np.load(os.path.join(G, "tx_full_imdct.npz"))
+    O = cl.oracle()
+    for n in (4, 64, 256, 1024, 120, 144):
+        for j, sc in enumerate((1.0 / n, -1.0)):
+            got = _tx(O, "orc", 1, 1, n, sc, g[f"in_{n}"], 2 * n, flags=4)
+            assert np.array_equal(got.view(np.uint32), g[f"out_{n}_{j}"].view(np.uint32)), (n, j)
+    assert not O.orc_tx_open(1, 0, 64, 1.0, 4) and not O.orc_tx_open(0, 1, 64, 1.0, 4) and not O.orc_tx_open(6, 1, 64, 1.0, 4)
+    if cl.have_ref():
+        R = cl.ref()
+        rng = np.random.default_rng(19)
+        assert not R.ffref_tx_open(1, 0, 64, 1.0, 4) and not R.ffref_tx_open(0, 1, 64, 1.0, 4)
+        for n in (8, 128, 2048, 32768, 960, 112, 96, 640):
+            x = (rng.random((2, n), dtype=np.float32) * 2 - 1).astype(np.float32)
+            for sc in (1.0, -1.0 / 32768):
+                a, b = _tx(R, "ffref", 1, 1, n, sc, x, 2 * n, flags=4), _tx(O, "orc", 1, 1, n, sc, x, 2 * n, flags=4)
+                assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (n, sc)
+    # the middle half is the plain inverse MDCT
+    x = g["in_256"]
+    full, half = _tx(O, "orc", 1, 1, 256, 1.0, x, 512, flags=4), _tx(O, "orc", 1, 1, 256, 1.0, x, 256)
+    assert np.array_equal(full[:, 128:384].view(np.uint32), half.view(np.uint32))
+    assert np.array_equal(full[:, :128], -half[:, 127::-1]) and np.array_equal(full[:, 384:], half[:, :127:-1])
 
 
 # ---------------------------------------------------------------------------------------------- tx: DCT-II / DCT-III

@@ -399,6 +399,45 @@ def test_sws_nv_destinations(device):
     ctx.free()
 
 
+# ---------------------------------------------------------------------------------------------- tx: AV_TX_FULL_IMDCT
+@isolated
+def test_tx_full_imdct(device):
+    """av_tx_init(AV_TX_FLOAT_MDCT, inverse, flags = AV_TX_FULL_IMDCT): host av_tx_fn against the reference's outputs, batched device
+    call against the oracle (power-of-two and compound lengths)"""
+    import torch
+    import ffmpeg_b200 as fb
+    from ffmpeg_b200 import tx
+    from test_oracle_more import _tx
+    g = np.load(os.path.join(G, "tx_full_imdct.npz"))
+    O = cl.oracle()
+    for n in (4, 64, 256, 1024, 120, 144):
+        for j, sc in enumerate((1.0 / n, -1.0)):
+            c = tx.av_tx_init(tx.AV_TX_FLOAT_MDCT, 1, n, scale=sc, flags=tx.AV_TX_FULL_IMDCT)
+            x = g[f"in_{n}"]
+            out = np.zeros((x.shape[0], 2 * n), np.float32)
+            for r in range(x.shape[0]):
+                c.fn(out[r], x[r].copy(), 4)
+            assert np.array_equal(out.view(np.uint32), g[f"out_{n}_{j}"].view(np.uint32)), (n, j)
+            c.uninit()
+    rng = np.random.default_rng(23)
+    for n in (1024, 2048, 960, 640):
+        cnt = 3000
+        x = (rng.random((cnt, n), dtype=np.float32) * 2 - 1).astype(np.float32)
+        c = tx.av_tx_init(tx.AV_TX_FLOAT_MDCT, 1, n, scale=1.0 / n, flags=tx.AV_TX_FULL_IMDCT, device=device)
+        with on_stream(device):
+            di, do = torch.from_numpy(x).cuda(), torch.zeros((cnt, 2 * n), dtype=torch.float32, device="cuda")
+            c.batch_device(do, di, 4, cnt, 8 * n, 4 * n)
+            device.sync()
+            got = do.cpu().numpy()
+        assert np.array_equal(got.view(np.uint32), _tx(O, "orc", 1, 1, n, 1.0 / n, x, 2 * n, flags=4).view(np.uint32)), n
+        with pytest.raises(fb.B200Error):
+            c.batch_device(do, di, 8, cnt, 8 * n, 4 * n)                # the mirror step only makes sense with stride == sizeof(float)
+        c.uninit()
+    for typ, inv in ((tx.AV_TX_FLOAT_MDCT, 0), (tx.AV_TX_FLOAT_FFT, 1), (tx.AV_TX_INT32_MDCT, 1)):
+        with pytest.raises(fb.B200Error):
+            tx.av_tx_init(typ, inv, 64, scale=1.0, flags=tx.AV_TX_FULL_IMDCT)
+
+
 # ---------------------------------------------------------------------------------------------- tx: compound 15 x M MDCT (Opus CELT)
 @isolated
 def test_tx_mdct_pfa15(device):
