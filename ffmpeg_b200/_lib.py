@@ -192,6 +192,8 @@ PROTOTYPES = {
     "b200_tx_pfa_tables": (C.c_int, [C.c_int, C.c_int, C.c_float, vp, C.c_int, vp]),
     "b200_tx_dct_table": (C.c_int, [C.c_int, C.c_int, vp, C.c_int]),
     "b200_tx_i32_tables": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_float, vp, C.c_int, vp]),
+    "b200_pixelutils_get_sad_fn": (vp, [C.c_int, C.c_int, C.c_int, vp]),
+    "b200_pixelutils_sad_batch_device": (C.c_int, [vp, C.c_int, vp, C.c_ssize_t, vp, C.c_ssize_t, vp, vp, C.c_int64, vp]),
     "b200_h264_loop_filter_init": (C.c_int, [vp, C.c_int, C.c_int]),
     "b200_h264_loop_filter_batch_device": (C.c_int, [vp, C.c_int64, vp, vp, vp, C.c_ssize_t, vp, vp, vp]),
     "b200_proresdsp_init": (C.c_int, [vp, C.c_int]),

@@ -25,3 +25,17 @@ def me_cmp_batch_device(device, fn, idx, frame1, frame2, stride, h, off1, off2, 
 def me_esa_device(device, cur, ref, linesize, width, height, frame_stride, nframes, mb_size, search_param, out_mv, out_cost):
     return check(lib().b200_me_esa_device(device.handle, vp(_dptr(cur)), vp(_dptr(ref)), linesize, width, height, frame_stride,
                                           nframes, mb_size, search_param, vp(_dptr(out_mv)), vp(_dptr(out_cost))), "me_esa_device")
+
+
+PIXELUTILS_SAD_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_ssize_t)
+
+
+def av_pixelutils_get_sad_fn(w_bits, h_bits, aligned=0, log_ctx=None):
+    """av_pixelutils_get_sad_fn (libavutil/pixelutils.h:31-52): a function on HOST pointers, or None like the reference's NULL"""
+    p = lib().b200_pixelutils_get_sad_fn(w_bits, h_bits, aligned, log_ctx)
+    return PIXELUTILS_SAD_FN(p) if p else None
+
+
+def pixelutils_sad_batch_device(device, w_bits, frame1, stride1, frame2, stride2, off1, off2, n, out):
+    return check(lib().b200_pixelutils_sad_batch_device(device.handle, w_bits, vp(_dptr(frame1)), stride1, vp(_dptr(frame2)), stride2,
+                                                        vp(_dptr(off1)), vp(_dptr(off2)), n, vp(_dptr(out))), "pixelutils_sad_batch_device")

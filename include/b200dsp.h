@@ -401,6 +401,14 @@ int  b200_me_cmp_batch_device(B200Device *dev, int fn, int idx, const uint8_t *f
 int  b200_me_esa_device(B200Device *dev, const uint8_t *cur, const uint8_t *ref, int linesize, int width, int height,
                         int64_t frame_stride, int nframes, int mb_size, int search_param, int32_t *out_mv, uint64_t *out_cost);
 
+/* libavutil's public block SAD: av_pixelutils_get_sad_fn (libavutil/pixelutils.h:31-52, pixelutils.c:43-111).  Square blocks of
+ * 1 << w_bits pixels, w_bits = h_bits = 1 ... 5; NULL for anything else, like the reference (and when no device is set). */
+typedef int (*b200_pixelutils_sad_fn)(const uint8_t *src1, ptrdiff_t stride1, const uint8_t *src2, ptrdiff_t stride2);   /* HOST pointers */
+b200_pixelutils_sad_fn b200_pixelutils_get_sad_fn(int w_bits, int h_bits, int aligned, void *log_ctx);
+/* batched, DEVICE pointers: out[i] = sad(frame1 + off1[i], stride1, frame2 + off2[i], stride2) over a (1 << w_bits)^2 block */
+int  b200_pixelutils_sad_batch_device(B200Device *dev, int w_bits, const uint8_t *frame1, ptrdiff_t stride1, const uint8_t *frame2,
+                                      ptrdiff_t stride2, const int64_t *off1, const int64_t *off2, int64_t n, int32_t *out);
+
 /* ------------------------------------------------------------------------------------------------ h264qpel / hpeldsp
  * Replaces H264QpelContext (libavcodec/h264qpel.h:27-30) as filled by ff_h264qpel_init(c, 8) (libavcodec/h264qpel.c:50-120)
  * and HpelDSPContext (libavcodec/hpeldsp.h:39-97) as filled by ff_hpeldsp_init (libavcodec/hpeldsp.c:337-352), 8 bit.

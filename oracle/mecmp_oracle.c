@@ -119,3 +119,17 @@ void orc_esa_frame(const uint8_t *cur, const uint8_t *ref, int linesize, int wid
             out_cost[by * b_w + bx] = best;
         }
 }
+
+/* av_pixelutils_get_sad_fn(bits, bits, ...) (libavutil/pixelutils.c:43-111): square blocks of 1 << bits pixels, one stride per block */
+int orc_pixelutils_sad(int bits, const uint8_t *src1, ptrdiff_t stride1, const uint8_t *src2, ptrdiff_t stride2)
+{
+    if (bits < 1 || bits > 5) return -1;
+    const int size = 1 << bits;
+    int sum = 0;
+    for (int y = 0; y < size; y++)
+        for (int x = 0; x < size; x++) {
+            const int d = src1[y * stride1 + x] - src2[y * stride2 + x];
+            sum += d < 0 ? -d : d;
+        }
+    return sum;
+}

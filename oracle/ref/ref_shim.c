@@ -275,6 +275,14 @@ API int ffref_me_cmp(int fn, int idx, const uint8_t *blk1, const uint8_t *blk2, 
     return f(NULL, blk1, blk2, stride, h);
 }
 
+/* av_pixelutils_get_sad_fn(bits, bits, aligned = 0): -1 where the reference has no function */
+#include "libavutil/pixelutils.h"
+API int ffref_pixelutils_sad(int bits, const uint8_t *src1, ptrdiff_t stride1, const uint8_t *src2, ptrdiff_t stride2)
+{
+    av_pixelutils_sad_fn f = av_pixelutils_get_sad_fn(bits, bits, 0, NULL);
+    return f ? f(src1, stride1, src2, stride2) : -1;
+}
+
 /* many calls in one go (for the CPU baseline): offsets into two frames */
 API void ffref_me_cmp_batch(int fn, int idx, const uint8_t *f1, const uint8_t *f2, ptrdiff_t stride, int h,
                             const int64_t *off1, const int64_t *off2, int n, int32_t *out)

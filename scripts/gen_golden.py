@@ -220,6 +220,14 @@ def gen_tx_int32():
     np.savez_compressed(os.path.join(OUT, "tx_int32.npz"), **d)
 
 
+def gen_pixelutils():
+    """av_pixelutils_get_sad_fn: the reference's sums for pixelutils_case(50 + bits, bits, 200), sizes 2 ... 32."""
+    d = {}
+    for bits in range(1, 6):
+        d[f"sad_{bits}"] = cl.ref_pixelutils(bits, *cl.pixelutils_case(50 + bits, bits, 200))
+    np.savez_compressed(os.path.join(OUT, "pixelutils.npz"), **d)
+
+
 def gen_h264lf():
     """H264DSPContext loop filters, 8 bit: the reference's picture after the 512 edges of h264lf_case(seed, 512) (sha256, plus the first
     64 x 512 pixels of seed 0 for a readable diff)."""
@@ -547,6 +555,7 @@ if __name__ == "__main__":
     gen_edge()
     gen_tx()
     gen_h264lf()
+    gen_pixelutils()
     gen_vsynth1()
     gen_sws_slices()
     gen_sws_range()

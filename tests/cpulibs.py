@@ -427,6 +427,36 @@ def ref_prores(bits, blocks, qmat, dest, line_size):
     return _prores_run(ref(), "ffref_prores_idct_put", bits, blocks, qmat, dest, line_size)
 
 
+# ---------------------------------------------------------------- av_pixelutils_get_sad_fn (libavutil/pixelutils.c:43-111)
+def pixelutils_case(seed, bits, n):
+    """(frame1 [h, s1], frame2 [h, s2], off1, off2): n block pairs of (1 << bits)^2 pixels at random positions, different strides;
+    every fourth pair compares a block with a slightly noisy copy of itself"""
+    rng = np.random.default_rng(seed)
+    size = 1 << bits
+    f1 = rng.integers(0, 256, (96, 160)).astype(np.uint8)
+    f2 = rng.integers(0, 256, (96, 203)).astype(np.uint8)
+    y1, x1 = rng.integers(0, 96 - size + 1, n), rng.integers(0, 160 - size + 1, n)
+    y2, x2 = rng.integers(0, 96 - size + 1, n), rng.integers(0, 203 - size + 1, n)
+    for i in range(0, min(n, 40), 4):
+        blk = f1[y1[i]:y1[i] + size, x1[i]:x1[i] + size].astype(np.int64) + rng.integers(-2, 3, (size, size))
+        f2[y2[i]:y2[i] + size, x2[i]:x2[i] + size] = np.clip(blk, 0, 255)
+    return f1, f2, (y1 * 160 + x1).astype(np.int64), (y2 * 203 + x2).astype(np.int64)
+
+
+def _pixelutils_run(L, name, bits, f1, f2, off1, off2):
+    f = getattr(L, name)
+    f.argtypes = [C.c_int, C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_ssize_t]
+    return np.array([f(bits, f1.ctypes.data + int(a), f1.strides[0], f2.ctypes.data + int(b), f2.strides[0]) for a, b in zip(off1, off2)], np.int32)
+
+
+def orc_pixelutils(bits, f1, f2, off1, off2):
+    return _pixelutils_run(oracle(), "orc_pixelutils_sad", bits, f1, f2, off1, off2)
+
+
+def ref_pixelutils(bits, f1, f2, off1, off2):
+    return _pixelutils_run(ref(), "ffref_pixelutils_sad", bits, f1, f2, off1, off2)
+
+
 # ---------------------------------------------------------------- H.264 deblocking (libavcodec/h264dsp_template.c:103-340)
 LF_CELL = 32          # one edge per 32 x 32 cell, q0 of its first line at (8, 8): p3..q3 across and 16 lines along stay inside the cell
 

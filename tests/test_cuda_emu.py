@@ -29,7 +29,7 @@ def emu():
             txt = open(os.path.join(src_dir, f)).read()
             for m in re.finditer(r"// \[device-code (\w+)\][^\n]*\n(.*?)// \[/device-code \1\]", txt, re.S):
                 found[m.group(1)] = m.group(2)
-    assert sorted(found) == ["fdsp", "h264lf", "idct_hbd", "sws_new", "sws_nvout", "tx_dct", "tx_int32", "tx_pfa", "unquant"], sorted(found)
+    assert sorted(found) == ["fdsp", "h264lf", "idct_hbd", "pixelutils", "sws_new", "sws_nvout", "tx_dct", "tx_int32", "tx_pfa", "unquant"], sorted(found)
     for k, v in found.items():
         open(os.path.join(gen, k + ".inc"), "w").write(v)
     so = os.path.join(gen, "libemu.so")
@@ -72,13 +72,13 @@ def rewrite_launches(txt):
 
 @pytest.fixture(scope="module")
 def emuhost():
-    """libemuhost.so: the translation units without inline PTX (fdsp, unquant, idct_hbd, tx_pfa, h264lf), HOST CODE INCLUDED, compiled with
+    """libemuhost.so: the translation units without inline PTX (fdsp, unquant, idct_hbd, tx_pfa, h264lf, pixelutils), HOST CODE INCLUDED, compiled with
     g++ against a stand-in CUDA runtime (tests/cuda_emu/fake/cuda_runtime.h): the library's own entry points run on the CPU"""
     gen = os.path.join(EMU, "_gen")
     os.makedirs(gen, exist_ok=True)
     cs = os.path.join(ROOT, "ffmpeg_b200", "csrc")
     srcs = []
-    for f in ("fdsp.cu", "unquant.cu", "idct_hbd.cu", "tx_pfa.cu", "h264lf.cu"):
+    for f in ("fdsp.cu", "unquant.cu", "idct_hbd.cu", "tx_pfa.cu", "h264lf.cu", "pixelutils.cu"):
         t = rewrite_launches(open(os.path.join(cs, f)).read())
         assert "<<<" not in t
         p = os.path.join(gen, "host_" + f[:-3] + ".cpp")
@@ -766,6 +766,28 @@ def test_host_h264_loop_filter_entry_points(emuhost):
     assert L.b200_h264_loop_filter_init(C.byref(c), 10, 1) < 0 and L.b200_h264_loop_filter_init(None, 8, 1) < 0
     assert L.b200_h264_loop_filter_batch_device(None, 0, None, None, None, 0, None, None, None) == 0
     assert L.b200_h264_loop_filter_batch_device(None, 1, None, d.ctypes.data, off.ctypes.data, 16, alpha.ctypes.data, beta.ctypes.data, tc0.ctypes.data) < 0
+
+
+def test_host_pixelutils_entry_points(emuhost):
+    """b200_pixelutils_sad_batch_device (two strides, 2x2 ... 32x32) and the functions av_pixelutils_get_sad_fn hands out, against the oracle"""
+    from ffmpeg_b200.me_cmp import PIXELUTILS_SAD_FN
+    L = emuhost
+    L.b200_pixelutils_sad_batch_device.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    L.b200_pixelutils_get_sad_fn.restype = C.c_void_p
+    L.b200_pixelutils_get_sad_fn.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p]
+    for bits in range(1, 6):
+        f1, f2, o1, o2 = cl.pixelutils_case(70 + bits, bits, 700)
+        out = np.full(700, -5, np.int32)
+        assert L.b200_pixelutils_sad_batch_device(None, bits, f1.ctypes.data, f1.strides[0], f2.ctypes.data, f2.strides[0], o1.ctypes.data, o2.ctypes.data,
+                                                  700, out.ctypes.data) == 0
+        exp = cl.orc_pixelutils(bits, f1, f2, o1, o2)
+        assert np.array_equal(out, exp), bits
+        fn = PIXELUTILS_SAD_FN(L.b200_pixelutils_get_sad_fn(bits, bits, 0, None))
+        for i in range(6):
+            assert fn(f1.ctypes.data + int(o1[i]), f1.strides[0], f2.ctypes.data + int(o2[i]), f2.strides[0]) == exp[i]
+    assert not L.b200_pixelutils_get_sad_fn(0, 0, 0, None) and not L.b200_pixelutils_get_sad_fn(6, 6, 0, None) and not L.b200_pixelutils_get_sad_fn(3, 4, 0, None)
+    assert L.b200_pixelutils_sad_batch_device(None, 6, f1.ctypes.data, 160, f2.ctypes.data, 203, o1.ctypes.data, o2.ctypes.data, 1, out.ctypes.data) < 0
+    assert L.b200_pixelutils_sad_batch_device(None, 3, None, 160, None, 203, None, None, 0, None) == 0
 
 
 def test_host_tx_pfa_create_and_launch(emuhost):

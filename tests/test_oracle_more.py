@@ -555,3 +555,20 @@ def test_h264_loop_filter_oracle_golden_and_ref():
         else:
             keep[y:y + 16, x - 3:x + 3] = False
     assert np.array_equal(out[keep], pic[keep])
+
+
+# ---------------------------------------------------------------------------------------------- av_pixelutils_get_sad_fn
+def test_pixelutils_sad_oracle_golden_and_ref():
+    g = np.load(os.path.join(G, "pixelutils.npz"))
+    for bits in range(1, 6):
+        case = cl.pixelutils_case(50 + bits, bits, 200)
+        got = cl.orc_pixelutils(bits, *case)
+        assert np.array_equal(got, g[f"sad_{bits}"]) and got.min() >= 0 and got[0] < got[1:].max()
+        if cl.have_ref():
+            case = cl.pixelutils_case(150 + bits, bits, 500)
+            assert np.array_equal(cl.orc_pixelutils(bits, *case), cl.ref_pixelutils(bits, *case)), bits
+    f = np.zeros((64, 64), np.uint8)
+    for bits in (0, 6):                                                   # no such block size: the reference returns NULL
+        assert cl.oracle().orc_pixelutils_sad(bits, f.ctypes.data, 64, f.ctypes.data, 64) == -1
+        if cl.have_ref():
+            assert cl.ref().ffref_pixelutils_sad(bits, f.ctypes.data, 64, f.ctypes.data, 64) == -1

@@ -13,6 +13,7 @@ import numpy as np
 import pytest
 
 import cpulibs as cl
+from ctypes import c_int as C_int, c_void_p as C_vp, c_ssize_t as C_ss
 
 pytestmark = [pytest.mark.gpu, pytest.mark.hw_unverified]
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -626,3 +627,32 @@ def test_h264_loop_filter(device):
             assert np.array_equal(got, cl.orc_h264lf(pic, kinds, off, alpha, beta, tc0))
     with pytest.raises(Exception):
         pel.ff_h264dsp_loop_filter_init(10, 1)
+
+
+# ---------------------------------------------------------------------------------------------- av_pixelutils_get_sad_fn
+@isolated
+def test_pixelutils_sad(device):
+    """av_pixelutils_get_sad_fn: the functions on host pointers reproduce the reference's sums; the batched device call (two strides,
+    100000 block pairs) matches the oracle"""
+    import torch
+    from ffmpeg_b200 import me_cmp
+    g = np.load(os.path.join(G, "pixelutils.npz"))
+    for bits in range(1, 6):
+        f1, f2, o1, o2 = cl.pixelutils_case(50 + bits, bits, 200)
+        fn = me_cmp.av_pixelutils_get_sad_fn(bits, bits)
+        got = [fn(f1.ctypes.data + int(a), f1.strides[0], f2.ctypes.data + int(b), f2.strides[0]) for a, b in zip(o1[:40], o2[:40])]
+        assert got == list(g[f"sad_{bits}"][:40]), bits
+        n = 100000
+        f1, f2, o1, o2 = cl.pixelutils_case(250 + bits, bits, n)
+        with on_stream(device):
+            d1, d2, do1, do2 = (torch.from_numpy(x).cuda() for x in (f1, f2, o1, o2))
+            out = torch.full((n,), -1, dtype=torch.int32, device="cuda")
+            me_cmp.pixelutils_sad_batch_device(device, bits, d1, f1.strides[0], d2, f2.strides[0], do1, do2, n, out)
+            device.sync()
+            res = out.cpu().numpy()
+        O = cl.oracle()
+        O.orc_pixelutils_sad.argtypes = [C_int, C_vp, C_ss, C_vp, C_ss]
+        idx = np.random.default_rng(bits).integers(0, n, 3000)
+        exp = cl.orc_pixelutils(bits, f1, f2, o1[idx], o2[idx])
+        assert np.array_equal(res[idx], exp), bits
+    assert me_cmp.av_pixelutils_get_sad_fn(3, 4) is None and me_cmp.av_pixelutils_get_sad_fn(6, 6) is None
