@@ -697,7 +697,10 @@ B200_API int b200_tx_init_device(B200Device *dev, B200TXContext **ctx, b200_tx_f
     if (!dev) return B200_ENODEV;
     if (type != B200_TX_FLOAT_FFT && type != B200_TX_FLOAT_MDCT && type != B200_TX_FLOAT_RDFT && type != B200_TX_FLOAT_DCT &&
         type != B200_TX_INT32_FFT && type != B200_TX_INT32_MDCT) return B200_ENOSYS;
-    if (flags & ~(uint64_t)(B200_TX_UNALIGNED | B200_TX_FULL_IMDCT)) return B200_ENOSYS;    // INPLACE / REAL_TO_* not implemented
+    if (flags & ~(uint64_t)(B200_TX_INPLACE | B200_TX_UNALIGNED | B200_TX_FULL_IMDCT)) return B200_ENOSYS;    // REAL_TO_* not implemented
+    // AV_TX_INPLACE: the complex FFT kernels stage a whole transform in shared memory before they store, so out == in is always
+    // fine for them and gives the bits of the out-of-place call (as ff_tx_fft_inplace does, tx_template.c:780-812); other types refuse
+    if ((flags & B200_TX_INPLACE) && !(type == B200_TX_FLOAT_FFT && len >= 2 && !(len & (len - 1)))) return B200_ENOSYS;
     const bool full = (flags & B200_TX_FULL_IMDCT) != 0;
     if (full && !(type == B200_TX_FLOAT_MDCT && inv)) return B200_ENOSYS;      // only the inverse MDCT has such a codelet (tx.c:762-771)
     if (type == B200_TX_INT32_FFT || type == B200_TX_INT32_MDCT) {   // 32-bit fixed point (tx_int32.cu)

@@ -5,7 +5,7 @@ from ._lib import lib, check, vp, TX_FN
 
 AV_TX_FLOAT_FFT, AV_TX_FLOAT_MDCT, AV_TX_FLOAT_RDFT, AV_TX_FLOAT_DCT = 0, 1, 6, 9
 AV_TX_INT32_FFT, AV_TX_INT32_MDCT = 4, 5
-AV_TX_UNALIGNED, AV_TX_FULL_IMDCT = 2, 4          # flags (libavutil/tx.h:155-180)
+AV_TX_INPLACE, AV_TX_UNALIGNED, AV_TX_FULL_IMDCT = 1, 2, 4          # flags (libavutil/tx.h:155-180)
 
 
 def _dptr(x):

@@ -489,6 +489,7 @@ int  b200_emulated_edge_mc_batch_device(B200Device *dev, int64_t n, uint8_t *buf
                                    * ff_tx_dct_init doubles the length it is given, libavutil/tx_template.c:1844-1848; callers pass N / 2).
                                    * ff_tx_dctII / ff_tx_dctIII (tx_template.c:1874-1968).  Input and output are N floats per transform;
                                    * unlike the reference neither the input is overwritten nor 2 floats of padding are needed. */
+#define B200_TX_INPLACE     1     /* AV_TX_INPLACE: AV_TX_FLOAT_FFT only; out == in is allowed (batch: out_step == in_step) */
 #define B200_TX_UNALIGNED   2     /* AV_TX_UNALIGNED (accepted, no effect) */
 #define B200_TX_FULL_IMDCT  4     /* AV_TX_FULL_IMDCT (libavutil/tx.h:175-180; ff_tx_mdct_inv_full, tx_template.c:1372-1413): inverse
                                    * AV_TX_FLOAT_MDCT only; 2 * len outputs, stride must be sizeof(float) */

@@ -562,6 +562,21 @@ def test_tx_whole_path_on_emulated_device(emutx):
     assert _emu_tx(emutx, 1, 0, 64, 1.0, x, 64, flags=4) == -38 and _emu_tx(emutx, 0, 1, 64, 1.0, x, 128, flags=4) == -38
     assert _emu_tx(emutx, 5, 1, 64, 1.0, x, 128, flags=4) == -38 and _emu_tx(emutx, 1, 1, 64, 1.0, x, 128, flags=1) == -38
     assert _emu_tx(emutx, 1, 1, 2, 1.0, x, 2) == -38                      # 2-point MDCT: the reference's naive fallback, not built
+    # AV_TX_INPLACE: complex FFT only, out == in through the batch entry and through av_tx_fn
+    from ffmpeg_b200._lib import TX_FN
+    for n in (2, 16, 1024):
+        x = (rng.random((6, 2 * n), dtype=np.float32) * 2 - 1).astype(np.float32)
+        exp = _tx(O, "orc", 0, 0, n, 1.0, x, 2 * n)
+        ctx, fn, sc = C.c_void_p(), TX_FN(), C.c_float(1.0)
+        assert emutx.b200_tx_init_device(emutx.dev, C.byref(ctx), C.byref(fn), 0, 0, n, C.byref(sc), 1) == 0
+        buf = x.copy()
+        assert emutx.b200_tx_batch_device(ctx, buf.ctypes.data, buf.ctypes.data, 8, 6, buf.strides[0], buf.strides[0]) == 0
+        assert np.array_equal(buf.view(np.uint32), exp.view(np.uint32)), ("in place", n)
+        buf = x[:1].copy()
+        fn(ctx, buf.ctypes.data, buf.ctypes.data, 8)
+        assert np.array_equal(buf.view(np.uint32), exp[:1].view(np.uint32)), ("in place fn", n)
+        emutx.b200_tx_uninit(C.byref(ctx))
+    assert _emu_tx(emutx, 1, 1, 64, 1.0, x, 64, flags=1) == -38 and _emu_tx(emutx, 6, 0, 64, 1.0, x, 66, flags=1) == -38
     # AV_TX_FLOAT_DCT: DCT-II forward (len points), DCT-III inverse (asked for len, works on 2 * len), batch and av_tx_fn entries;
     # the input is left alone
     for n in (4, 16, 64, 512):

@@ -439,6 +439,37 @@ def test_tx_full_imdct(device):
             tx.av_tx_init(typ, inv, 64, scale=1.0, flags=tx.AV_TX_FULL_IMDCT)
 
 
+@isolated
+def test_tx_inplace_fft(device):
+    """AV_TX_INPLACE: complex FFT with out == in, batched (several transforms per CTA) and through av_tx_fn; other types refuse the flag"""
+    import torch
+    import ffmpeg_b200 as fb
+    from ffmpeg_b200 import tx
+    from test_oracle_more import _tx
+    O = cl.oracle()
+    rng = np.random.default_rng(29)
+    for n in (2, 64, 1024, 4096):
+        cnt = 1001
+        x = (rng.random((cnt, 2 * n), dtype=np.float32) * 2 - 1).astype(np.float32)
+        exp = _tx(O, "orc", 0, 1, n, 1.0, x, 2 * n)
+        c = tx.av_tx_init(tx.AV_TX_FLOAT_FFT, 1, n, flags=tx.AV_TX_INPLACE, device=device)
+        with on_stream(device):
+            d = torch.from_numpy(x).cuda()
+            c.batch_device(d, d, 8, cnt, 8 * n, 8 * n)
+            device.sync()
+            got = d.cpu().numpy()
+        assert np.array_equal(got.view(np.uint32), exp.view(np.uint32)), n
+        c.uninit()
+        c = tx.av_tx_init(tx.AV_TX_FLOAT_FFT, 1, n, flags=tx.AV_TX_INPLACE)
+        buf = x[0].copy()
+        c.fn(buf, buf, 8)
+        assert np.array_equal(buf.view(np.uint32), exp[0].view(np.uint32)), n
+        c.uninit()
+    for typ in (tx.AV_TX_FLOAT_MDCT, tx.AV_TX_FLOAT_RDFT, tx.AV_TX_FLOAT_DCT):
+        with pytest.raises(fb.B200Error):
+            tx.av_tx_init(typ, 0, 64, scale=1.0, flags=tx.AV_TX_INPLACE)
+
+
 # ---------------------------------------------------------------------------------------------- tx: compound 15 x M MDCT (Opus CELT)
 @isolated
 def test_tx_mdct_pfa15(device):
