@@ -313,6 +313,11 @@ void tx_i32_free(TxI32 *p)
 int tx_i32_launch(TxI32 *p, cudaStream_t st, void *out, const void *in, ptrdiff_t stride, int64_t count, ptrdiff_t out_step, ptrdiff_t in_step)
 {
     if (count <= 0) return 0;
+    // the kernels move complex values as 8-byte words: the complex side(s) of a transform must be 8-byte aligned (the reference
+    // asks for 32 unless AV_TX_UNALIGNED), the real side 4
+    const uintptr_t oa = reinterpret_cast<uintptr_t>(out) | (uintptr_t)out_step, ia = reinterpret_cast<uintptr_t>(in) | (uintptr_t)in_step;
+    const bool cplx_out = p->type == B200_TX_INT32_FFT || p->inv, cplx_in = p->type == B200_TX_INT32_FFT;
+    if ((oa & (cplx_out ? 7 : 3)) || (ia & (cplx_in ? 7 : 3))) return B200_EINVAL;
     const bool fwd_mdct = p->type == B200_TX_INT32_MDCT && !p->inv;
     const size_t l2 = (size_t)p->len >> 1;
     int64_t chunk = count;

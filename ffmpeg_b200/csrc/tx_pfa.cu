@@ -518,6 +518,9 @@ void tx_pfa_free(TxPfa *p)
 int tx_pfa_launch(TxPfa *p, cudaStream_t st, void *out, const void *in, ptrdiff_t stride, int64_t count, ptrdiff_t out_step, ptrdiff_t in_step)
 {
     if (count <= 0) return 0;
+    // the inverse writes its outputs as complex pairs (8-byte words); everything else moves single floats
+    if (((reinterpret_cast<uintptr_t>(out) | (uintptr_t)out_step) & (p->inv ? 7 : 3)) || ((reinterpret_cast<uintptr_t>(in) | (uintptr_t)in_step) & 3))
+        return B200_EINVAL;
     const size_t l2 = (size_t)p->len >> 1;
     const int64_t chunk_max = (int64_t)((size_t)(256u << 20) / (l2 * sizeof(float2)));          // scratch of at most 256 MB
     const int64_t chunk = count < chunk_max ? count : chunk_max;
