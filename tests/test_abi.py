@@ -61,3 +61,16 @@ def test_idct_struct_layout():
     # 6 pointers, 64-byte permutation, two ints: the reference's layout on LP64 (libavcodec/idctdsp.h:43-91)
     assert C.sizeof(IDCTDSPContext) == 6 * 8 + 64 + 8
     assert IDCTDSPContext.idct_permutation.offset == 48
+
+
+def test_tables_match_reference_structs():
+    """oracle/ref/ref_layout_check.c puts include/b200dsp.h next to the reference's own headers and asserts, at compile time, that
+    every function table has the reference struct's size, member offsets and function-pointer types (IDCTDSPContext, MECmpContext,
+    H264QpelContext, HpelDSPContext, H264ChromaContext, VideoDSPContext, the H264DSPContext runs, ProresDSPContext,
+    AVFloatDSPContext, av_pixelutils_sad_fn, the tx enums).  The unit is part of libffref.so: the marker proves it was compiled."""
+    import ctypes as C
+    import cpulibs as cl
+    if not cl.have_ref():
+        pytest.skip("oracle/_ref/libffref.so not built")
+    marker = C.c_char_p.in_dll(cl.ref(), "ffref_layout_check")
+    assert C.string_at(C.addressof(marker)).startswith(b"b200dsp.h tables match")
