@@ -572,3 +572,54 @@ def test_pixelutils_sad_oracle_golden_and_ref():
         assert cl.oracle().orc_pixelutils_sad(bits, f.ctypes.data, 64, f.ctypes.data, 64) == -1
         if cl.have_ref():
             assert cl.ref().ffref_pixelutils_sad(bits, f.ctypes.data, 64, f.ctypes.data, 64) == -1
+
+
+# ---------------------------------------------------------------------------------------------- IDCT accuracy (libavcodec/tests/dct.c)
+def _ref_dct_matrix():
+    c = np.zeros((8, 8))
+    c[0, :] = np.sqrt(0.125)                                              # ff_ref_dct_init, libavcodec/dctref.c:40-50
+    for i in range(1, 8):
+        c[i, :] = 0.5 * np.cos(i * (np.arange(8) + 0.5) * np.pi / 8)
+    return c
+
+
+def test_idct_accuracy_like_reference_dct_test():
+    """The accuracy criteria of the reference's own IDCT test (libavcodec/tests/dct.c:176-270, 20000 blocks per input class)
+    applied to the checker's 8-bit simple IDCT, and — 10 / 12 bit use the same test with more input bits there — to the 10-bit
+    one: double-precision reference transform with its rounding (dctref.c:60-125), peak error <= 1, mean square error <= 0.02,
+    mean error <= 0.0015 (class 2), per-coefficient square error <= 0.06 and systematic error <= 0.015 (classes 0 and 1)."""
+    O = cl.oracle()
+    cm = _ref_dct_matrix()
+    n = 20000
+    for bits, run in ((8, "orc8"), (10, "orc10")):
+        vals = 1 << bits
+        rng = np.random.default_rng(bits)
+        for test in (0, 1, 2):
+            blocks = np.zeros((n, 8, 8), np.int64)
+            if test == 0:                                                 # spatial noise, forward reference DCT, >> 3
+                px = rng.integers(-vals, vals, (n, 8, 8))
+                out = np.einsum("ik,nkj->nij", cm, px.astype(np.float64)) * 8
+                blocks = np.floor(np.einsum("nik,jk->nij", out, cm) + 0.499999999999).astype(np.int64) >> 3
+            elif test == 1:                                               # 1 ... 10 non-zero coefficients
+                flat = blocks.reshape(n, 64)
+                for b in range(n):
+                    k = int(rng.integers(1, 11))
+                    flat[b, rng.integers(0, 64, k)] = rng.integers(-vals, vals, k)
+            else:                                                         # DC plus the parity coefficient
+                blocks[:, 0, 0] = rng.integers(-8 * vals, 8 * vals, n)
+                blocks[:, 7, 7] = (blocks[:, 0, 0] & 1) ^ 1
+            b16 = np.ascontiguousarray(blocks.reshape(n, 64).astype(np.int16))
+            exp = np.floor(np.einsum("ki,nkj->nij", cm, np.einsum("nik,kj->nij", b16.reshape(n, 8, 8).astype(np.float64), cm)) + 0.5)
+            got = b16.copy()
+            if run == "orc8":
+                for b in range(n):
+                    O.orc_idct(cl.ptr(got[b], cl.i16p))
+            else:
+                got, _ = cl.orc_idct_hbd(10, 0, b16, np.zeros((8, 8), np.uint16), 16)
+            err = got.reshape(n, 64).astype(np.int64) - exp.reshape(n, 64).astype(np.int64)
+            err_inf, omse, ome = int(np.abs(err).max()), float((err ** 2).mean()), float(err.mean())
+            per_coef_sq, per_coef_sys = float((err ** 2).sum(0).max()) / n, float(np.abs(err.sum(0)).max()) / n
+            if test < 2:
+                assert per_coef_sq <= 0.06 and per_coef_sys <= 0.015, (bits, test, per_coef_sq, per_coef_sys)
+            else:
+                assert err_inf <= 1 and omse <= 0.02 and abs(ome) <= 0.0015, (bits, test, err_inf, omse, ome)
