@@ -1585,6 +1585,14 @@ static PackedLayout packed_layout(const SwsPlan &p)
     return L;
 }
 
+
+// bytes of a destination row the reference writes: its unscaled LUT converters work on pixel pairs and never touch an odd last
+// column (yuv2rgb.c:137-236: (dstW >> 3) * 8 + (dstW & 4) + (dstW & 2) pixels per line), so the host entry points must not either
+static inline size_t sws_written_row_bytes(const SwsPlan &p)
+{
+    return (size_t)(p.unscaled_lut ? (p.dstW & ~1) : p.dstW) * p.out.bpp;
+}
+
 B200_API int b200_sws_scale_batch_host(B200SwsContext *c, const uint8_t *const src[3], const int srcStride[3],
                                        const int64_t srcFrameStride[3], uint8_t *dst, int dstStride,
                                        int64_t dstFrameStride, int nframes)
@@ -1632,12 +1640,12 @@ B200_API int b200_sws_scale_batch_host(B200SwsContext *c, const uint8_t *const s
         int ret = launch_batch(c, st, sp, ss, fs, dbase, (long long)L.dPitch, (long long)L.dstBytes, nf, nullptr,
                                p.src_nv ? dbase + L.dstBytes * chunk : nullptr);
         if (ret < 0) return ret;
-        const size_t rowBytes = (size_t)p.dstW * p.out.bpp;
-        if ((size_t)dstStride == rowBytes && L.dPitch == rowBytes && dstFrameStride == (int64_t)(rowBytes * p.dstH)) {
+        const size_t rowBytes = sws_written_row_bytes(p);
+        if (rowBytes == (size_t)p.dstW * p.out.bpp && (size_t)dstStride == rowBytes && L.dPitch == rowBytes && dstFrameStride == (int64_t)(rowBytes * p.dstH)) {
             // contiguous on both sides: the whole chunk comes back as one linear copy
             B200_CUDA_OK(cudaMemcpyAsync(dst + (int64_t)f0 * dstFrameStride, dbase, L.dstBytes * nf, cudaMemcpyDeviceToHost, st));
         } else {
-            for (int f = 0; f < nf; f++)
+            for (int f = 0; f < nf && rowBytes; f++)
                 B200_CUDA_OK(cudaMemcpy2DAsync(dst + (int64_t)(f0 + f) * dstFrameStride, (size_t)dstStride,
                                                dbase + (size_t)f * L.dstBytes, L.dPitch, rowBytes, p.dstH, cudaMemcpyDeviceToHost, st));
         }
@@ -1701,9 +1709,9 @@ static int sws_scale_slice(B200SwsContext *c, const uint8_t *const srcSlice[], c
     const SwsRows R = { y0, y1 - y0, srcSliceY, srcSliceH, chrY, chrH };
     int ret = launch_batch(c, st, sp, ss, fs, db, (long long)L.dPitch, 0, 1, &R);
     if (ret < 0) return ret;
-    if (y1 > y0)
+    if (y1 > y0 && sws_written_row_bytes(p))
         B200_CUDA_OK(cudaMemcpy2DAsync(dst[0] + (long long)y0 * dstStride[0], (size_t)dstStride[0], db + (size_t)y0 * L.dPitch, L.dPitch,
-                                       (size_t)p.dstW * p.out.bpp, y1 - y0, cudaMemcpyDeviceToHost, st));
+                                       sws_written_row_bytes(p), y1 - y0, cudaMemcpyDeviceToHost, st));
     B200_CUDA_OK(cudaStreamSynchronize(st));
     if (srcSliceY + srcSliceH == p.srcH) c->slice_open = false;
     return p.unscaled_lut ? srcSliceH : y1 - y0;
@@ -1761,12 +1769,15 @@ B200_API int b200_sws_scale(B200SwsContext *c, const uint8_t *const srcSlice[], 
     if (ret < 0) return ret;
     const long long dsl = dstStride[0];
     const long long dabs = dsl < 0 ? -dsl : dsl;
-    if (dsl < 0) {
+    const size_t wb = sws_written_row_bytes(p);
+    if (!wb) {
+        // a one-pixel-wide picture through the pair-wise converter: nothing is written
+    } else if (dsl < 0) {
         // flip while copying back: row r of the device picture goes to dst[0] + r*dsl
         for (int r = 0; r < p.dstH; r++)
-            B200_CUDA_OK(cudaMemcpyAsync(dst[0] + (long long)r * dsl, dd + (size_t)r * L.dPitch, (size_t)p.dstW * p.out.bpp, cudaMemcpyDeviceToHost, st));
+            B200_CUDA_OK(cudaMemcpyAsync(dst[0] + (long long)r * dsl, dd + (size_t)r * L.dPitch, wb, cudaMemcpyDeviceToHost, st));
     } else {
-        B200_CUDA_OK(cudaMemcpy2DAsync(dst[0], (size_t)dabs, dd, L.dPitch, (size_t)p.dstW * p.out.bpp, p.dstH, cudaMemcpyDeviceToHost, st));
+        B200_CUDA_OK(cudaMemcpy2DAsync(dst[0], (size_t)dabs, dd, L.dPitch, wb, p.dstH, cudaMemcpyDeviceToHost, st));
     }
     B200_CUDA_OK(cudaStreamSynchronize(st));
     return p.dstH;

@@ -376,6 +376,14 @@ def test_sws_emulation_agrees_with_hardware_verified_paths(emusws):
         y, u, v = cl.yuv_frame(w, h, 3500 + i, kind)
         uv = cl.nv_interleave(u, v, cl.PIX_FMT_NV12)
         assert np.array_equal(er(w, h, dw, dh, fl, y, uv, uv, src_fmt=cl.PIX_FMT_NV12), cl.orc_sws(w, h, dw, dh, fl, y, uv, uv, src_fmt=cl.PIX_FMT_NV12)), ("nv12", i)
+    # odd widths through the unscaled LUT converter: the reference works on pixel pairs and leaves the last column of the
+    # destination alone (yuv2rgb.c:137-236) — the host entry point must not copy that column back either
+    for (w, h) in ((7, 6), (17, 10), (33, 6), (1, 2)):
+        y, u, v = cl.yuv_frame(w, h, 3700 + w, "random")
+        for name in ("rgb24", "bgra"):
+            f = cl.PACKED_RGB_FORMATS[name]
+            got, exp = er(w, h, w, h, cl.SWS_BICUBIC, y, u, v, fmt=f, dst_pad=2), cl.orc_sws(w, h, w, h, cl.SWS_BICUBIC, y, u, v, fmt=f, dst_pad=2)
+            assert np.array_equal(got, exp) and (got[:, (w - 1) * cl.fmt_bpp(f):] == 0xA5).all(), (w, h, name)
     y, u, v = cl.yuv_frame(640, 352, 3600, "random")                     # 16-pixel-group vector kernels, FATE flags and LUT path
     for fl in (FATE, cl.SWS_BICUBIC):
         assert np.array_equal(er(640, 352, 640, 352, fl, y, u, v), cl.orc_sws(640, 352, 640, 352, fl, y, u, v)), hex(fl)

@@ -120,6 +120,19 @@ def test_range_conversion_batch_device(device):
     ctx.free()
 
 
+@isolated
+def test_sws_odd_width_unscaled_leaves_last_column(device):
+    """same-size yuv420p -> rgb without accurate_rnd at an odd width: the reference's pair-wise LUT converter never writes the last
+    column (yuv2rgb.c:137-236); found by differential fuzzing on the emulated device, the host entry points used to copy it back"""
+    from test_sws_gpu import gpu_sws
+    for (w, h) in ((7, 6), (17, 10), (351, 288)):
+        y, u, v = cl.yuv_frame(w, h, 3700 + w, "random")
+        for name in ("rgb24", "bgra"):
+            f = cl.PACKED_RGB_FORMATS[name]
+            got, exp = gpu_sws(device, w, h, w, h, cl.SWS_BICUBIC, y, u, v, fmt=f, dst_pad=2), cl.orc_sws(w, h, w, h, cl.SWS_BICUBIC, y, u, v, fmt=f, dst_pad=2)
+            assert np.array_equal(got, exp), (w, h, name)
+
+
 # ---------------------------------------------------------------------------------------------- mpegvideo inverse quantisers
 def gpu_unquant(device, variant, cfg, blocks, blk_n, q, last):
     import torch
