@@ -390,7 +390,10 @@ int sws_plan_build(SwsPlan &p, int srcW, int srcH, int dstW, int dstH, int flags
     p.bgr24_yv12 = p.planar && !p.dst_nv && p.src_rgb == 3 && p.sbo == 0 && srcW == dstW && srcH == dstH && p.src_range == p.dst_range &&
                    !(flags & B200_SWS_ACCURATE_RND) && !(dstW & 1);
     if (p.bgr24_yv12) return 0;
-    p.planar_copy = p.planar && !p.src_rgb && srcW == dstW && srcH == dstH && p.src_range == p.dst_range;
+    // same-size yuv -> yuv: planarCopyWrapper, planarToNv12Wrapper or nv12ToPlanarWrapper (swscale_unscaled.c:2415-2419,2675-2693,147-188);
+    // nv12 <-> nv21 has no such converter and goes through the scaler (it matters once sws_setColorspaceDetails changes a range)
+    p.planar_copy = p.planar && !p.src_rgb && srcW == dstW && srcH == dstH && p.src_range == p.dst_range &&
+                    !(p.src_nv && p.dst_nv && p.src_nv != p.dst_nv);
     if (p.planar_copy) return 0;
     // (only planar yuv420p / yuv422p sources have the LUT converter; nv12 / nv21 go through the scaler)
     p.unscaled_lut = !p.planar && !p.src_nv && !p.src_rgb && srcW == dstW && srcH == dstH && !(flags & B200_SWS_ACCURATE_RND) && !(dstH & 1);

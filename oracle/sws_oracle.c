@@ -446,9 +446,11 @@ OrcSws *orc_sws_open_range(int srcFormat, int srcW, int srcH, int srcRange, int 
         s->unscaled_lut = 3;
         return s;
     }
-    if (s->planar && !s->src_rgb && srcW == dstW && srcH == dstH && s->src_range == s->dst_range) {               /* planarCopyWrapper (swscale_unscaled.c:2675-2693) or, for a
-                                                                    * semi-planar source, nv12ToPlanarWrapper (:167-188, :2415-2419):
-                                                                    * both are a luma copy plus a chroma copy / de-interleave */
+    /* planarCopyWrapper (swscale_unscaled.c:2675-2693), planarToNv12Wrapper (:147-165) or, for a semi-planar source,
+     * nv12ToPlanarWrapper (:167-188, :2415-2419): all a luma copy plus a chroma copy / interleave / de-interleave.  nv12 <-> nv21
+     * has no such converter: it goes through the scaler (same bytes, until sws_setColorspaceDetails changes a range) */
+    if (s->planar && !s->src_rgb && srcW == dstW && srcH == dstH && s->src_range == s->dst_range &&
+        !(s->src_nv && s->dst_nv && s->src_nv != s->dst_nv)) {
         s->unscaled_lut = 2;
         return s;
     }

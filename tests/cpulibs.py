@@ -201,8 +201,10 @@ def _sws_run(lib, pre, w, h, dw, dh, flags, y, u, v, dst_pad=0, threads=1, color
             if pre == "ffref":
                 lib.ffref_sws_set_colorspace(ctx, *colorspace)
             else:
-                tab = np.array(COEFFS[colorspace[0]], dtype=np.int32)
-                lib.orc_sws_set_colorspace(ctx, ptr(tab, i32p), colorspace[1], colorspace[4], colorspace[5], colorspace[6])
+                tab, tab2 = np.array(COEFFS[colorspace[0]], dtype=np.int32), np.array(COEFFS[colorspace[2]], dtype=np.int32)
+                lib.orc_sws_set_colorspace_details.argtypes = [C.c_void_p, i32p, C.c_int, i32p, C.c_int, C.c_int, C.c_int, C.c_int]
+                lib.orc_sws_set_colorspace_details(ctx, ptr(tab, i32p), colorspace[1], ptr(tab2, i32p), colorspace[3], colorspace[4], colorspace[5],
+                                                   colorspace[6])
         ds = dw * fmt_bpp(fmt) + dst_pad
         dst = np.full((dh, ds), 0xA5, dtype=np.uint8)
         if pre == "ffref":

@@ -472,6 +472,66 @@ def test_sws_rgb_sources_nv_destinations_and_all_fate_sums(emusws):
         assert np.array_equal(D[i], cl.orc_sws(w, h, dw, dh, FATE, frames[i], frames[i], frames[i], fmt=cl.PIX_FMT_BGRA, src_fmt=cl.PIX_FMT_RGB24)), i
 
 
+def test_sws_differential_fuzz(emusws):
+    """seeded random contexts (sizes incl. odd ones, every source / destination format of the library, scaler flags, ranges,
+    sws_setColorspaceDetails with other matrices / brightness / contrast / saturation, padded destinations) through the library's
+    real entry points on the emulated device, against the checker and — where it is built — the compiled reference.  This is the
+    loop that found the odd-column write-back of the unscaled converter and the nv12 <-> nv21 copy shortcut; what the library
+    refuses, the checker must refuse too."""
+    import functools
+    import random
+    er, ep = functools.partial(emu_sws, emusws), functools.partial(emu_sws_planar, emusws)
+    rnd = random.Random(20260923)
+    flags = [cl.SWS_BICUBIC, cl.SWS_BILINEAR, FATE, cl.SWS_BICUBIC | 0x40000, cl.SWS_BILINEAR | 0x80000, 1, cl.SWS_BICUBIC | 0x2000, FATE | 0x2000,
+             cl.SWS_BICUBIC | 0x4000, 0x10, 0x200, 0x400]
+    fmts = [0, cl.PIX_FMT_NV12, cl.PIX_FMT_NV21] + list(cl.PACKED_RGB_FORMATS.values())
+    ran = refused = 0
+    for it in range(90):
+        w, h = rnd.choice([2, 4, 6, 8, 10, 16, 18, 34, 66, 100, 130]), rnd.choice([2, 4, 6, 8, 10, 16, 18, 34, 50])
+        w, h = w + (rnd.random() < 0.3), h + (rnd.random() < 0.3)
+        dw, dh = (w, h) if rnd.random() < 0.35 else (rnd.choice([2, 3, 8, 17, 32, 64, 100, 200]), rnd.choice([2, 3, 8, 17, 32, 64, 100]))
+        fl, sf, df = rnd.choice(flags), rnd.choice(fmts), rnd.choice(fmts)
+        rgbsrc, rgbdst = sf in cl.PACKED_RGB_FORMATS.values(), df in cl.PACKED_RGB_FORMATS.values()
+        ranges = (0, 0) if rgbdst else rnd.choice([(0, 0), (0, 0), (0, 1), (1, 0), (1, 1)])
+        dpad = rnd.choice([0, 0, 1, 5, 13])
+        cs = None
+        if rnd.random() < 0.4:
+            cs = (rnd.choice([1, 2, 4, 5, 6, 7, 9]), rnd.choice([0, 1]), rnd.choice([1, 5, 6, 7, 9]), rnd.choice([0, 1]), rnd.choice([0, 1 << 12, -(1 << 13)]),
+                  rnd.choice([1 << 16, 70000, 50000]), rnd.choice([1 << 16, 80000, 40000]))
+        if rgbsrc:
+            y = u = v = cl.rgb_frame(w, h, 9000 + it, cl.fmt_bpp(sf))
+        else:
+            y, u, v = cl.yuv_frame(w, h, 9000 + it, rnd.choice(["random", "limited", "smooth"]))
+            if sf:
+                u = v = cl.nv_interleave(u, v, sf)
+        kw = dict(fmt=df, src_fmt=sf, dst_pad=dpad, colorspace=cs) if rgbdst else dict(src_fmt=sf, dst_fmt=df, ranges=ranges, dst_pad=dpad, details=cs)
+        orc, ref, emu = (cl.orc_sws, cl.ref_sws, er) if rgbdst else (cl.orc_sws_planar, cl.ref_sws_planar, ep)
+        desc = (it, w, h, dw, dh, hex(fl), sf, df, ranges, dpad, cs)
+        try:
+            exp = orc(w, h, dw, dh, fl, y, u, v, **kw)
+        except Exception:
+            exp = None                                                    # the checker refuses (e.g. other matrices for yuv -> yuv)
+        ctx = _emu_ctx(emusws, w, h, sf, dw, dh, df, fl, ranges, None)
+        if ctx and cs is not None:
+            ta, tb = (np.array(cl.COEFFS[k], np.int32) for k in (cs[0], cs[2]))
+            if emusws.b200_sws_setColorspaceDetails(ctx, ta.ctypes.data, cs[1], tb.ctypes.data, cs[3], *cs[4:]) != 0:
+                emusws.b200_sws_freeContext(ctx)
+                ctx = None
+        if not ctx:
+            assert exp is None, ("refused by the library only", desc)
+            refused += 1
+            continue
+        emusws.b200_sws_freeContext(ctx)
+        assert exp is not None, ("refused by the checker only", desc)
+        got = emu(w, h, dw, dh, fl, y, u, v, **kw)
+        same = (lambda a, b: np.array_equal(a, b)) if rgbdst else (lambda a, b: all(np.array_equal(p, q) for p, q in zip(a, b)))
+        assert same(got, exp), ("library != checker", desc)
+        if cl.have_ref():
+            assert same(ref(w, h, dw, dh, fl, y, u, v, **kw), exp), ("checker != reference", desc)
+        ran += 1
+    assert ran >= 40 and refused >= 10, (ran, refused)
+
+
 # ------------------------------------------------------------------ all of libavutil/tx (tx.cu + tx_pfa.cu) on the stand-in runtime
 @pytest.fixture(scope="module")
 def emutx():
