@@ -53,6 +53,35 @@ i64 cubic_weight(i64 d)
     return (-B - 6 * C) * ddd + (6 * B + 30 * C) * dd + (-12 * B - 48 * C) * d + (8 * B + 24 * C) * ((i64)1 << 30);
 }
 
+// the kernels initFilter evaluates in double precision (utils.c:325-368), default parameters; d = distance in 2.30 fixed point.
+// The products and quotients keep the reference's order: these run on the host with the host's libm, like the reference's do.
+i64 float_kernel_weight(int scaler, i64 d, i64 unit)
+{
+    const double fd = d * (1.0 / (1 << 30));
+    i64 w;
+    if (scaler == B200_SWS_X) {
+        double c = fd < 1.0 ? cos(fd * M_PI) : -1.0;
+        c = c < 0.0 ? -pow(-c, 1.0) : pow(c, 1.0);
+        w = (c * 0.5 + 0.5) * unit;
+    } else if (scaler == B200_SWS_GAUSS) {
+        w = exp2(-3.0 * fd * fd) * unit;
+    } else if (scaler == B200_SWS_SINC) {
+        w = (d ? sin(fd * M_PI) / (fd * M_PI) : 1.0) * unit;
+    } else if (scaler == B200_SWS_LANCZOS) {
+        const double p = 3.0;
+        w = (d ? sin(fd * M_PI) * sin(fd * M_PI / p) / (fd * fd * M_PI * M_PI / p) : 1.0) * unit;
+        if (fd > p) w = 0;
+    } else {                                                                     // spline: getSplineCoeff(1, 0, p, -p - 1, dist), utils.c:155-167
+        double a = 1.0, b = 0.0, c = -2.196152422706632, e = 2.196152422706632 - 1.0, dist = fd;
+        while (dist > 1.0) {
+            const double nb = b + 2.0 * c + 3.0 * e, nc = c + 3.0 * e, ne = -b - 3.0 * c - 6.0 * e;
+            a = 0.0; b = nb; c = nc; e = ne; dist -= 1.0;
+        }
+        w = (((e * dist + c) * dist + b) * dist + a) * unit;
+    }
+    return w;
+}
+
 int raw_taps(RawTaps &r, int scaler, int inc, int srcN, int dstN, int srcOrg, int dstOrg, i64 unit)
 {
     r.first.assign((size_t)dstN + 3, 0);
@@ -86,7 +115,10 @@ int raw_taps(RawTaps &r, int scaler, int inc, int srcN, int dstN, int srcOrg, in
     case B200_SWS_BICUBIC:  support = 4; break;
     case B200_SWS_BILINEAR: support = 2; break;
     case B200_SWS_AREA:     support = 1; break;
-    default: return B200_ENOSYS;                                                 // float kernels (gauss, sinc, ...) not built
+    case B200_SWS_X: case B200_SWS_GAUSS:     support = 8; break;
+    case B200_SWS_SINC: case B200_SWS_SPLINE: support = 20; break;
+    case B200_SWS_LANCZOS:  support = 6; break;                                  // 2 * param[0], default 3 (utils.c:278-279)
+    default: return B200_ENOSYS;
     }
     int taps = inc <= (1 << 16) ? 1 + support : 1 + (int)(((i64)support * srcN + dstN - 1) / dstN);
     taps = std::max(1, std::min(taps, srcN - 2));
@@ -108,8 +140,10 @@ int raw_taps(RawTaps &r, int scaler, int inc, int srcN, int dstN, int srcOrg, in
                 else if (d2 * inc < ((i64)1 << 45))  w = -d2 * inc + ((i64)1 << 45);
                 else                                 w = 0;
                 w *= unit >> 46;
-            } else {
+            } else if (scaler == B200_SWS_BILINEAR) {
                 w = std::max<i64>(0, (1 << 30) - d) * (unit >> 30);
+            } else {
+                w = float_kernel_weight(scaler, d, unit);
             }
             r.w[(size_t)i * taps + j] = w;
         }

@@ -81,9 +81,14 @@ uint64_t b200_launch_count(void);
 #define B200_SWS_FAST_BILINEAR 0x1
 #define B200_SWS_BILINEAR      0x2
 #define B200_SWS_BICUBIC       0x4
+#define B200_SWS_X             0x8
 #define B200_SWS_POINT         0x10
 #define B200_SWS_AREA          0x20
 #define B200_SWS_BICUBLIN      0x40
+#define B200_SWS_GAUSS         0x80     /* X, GAUSS, SINC, LANCZOS, SPLINE: default parameters (param[] = SWS_PARAM_DEFAULT) */
+#define B200_SWS_SINC          0x100
+#define B200_SWS_LANCZOS       0x200
+#define B200_SWS_SPLINE        0x400
 #define B200_SWS_FULL_CHR_H_INT 0x2000
 #define B200_SWS_FULL_CHR_H_INP 0x4000   /* packed RGB source: chroma from every pixel instead of every other one */
 #define B200_SWS_ACCURATE_RND  0x40000

@@ -26,9 +26,14 @@ extern "C" {
 #define ORC_SWS_FAST_BILINEAR 0x1
 #define ORC_SWS_BILINEAR      0x2
 #define ORC_SWS_BICUBIC       0x4
+#define ORC_SWS_X             0x8
 #define ORC_SWS_POINT         0x10
 #define ORC_SWS_AREA          0x20
 #define ORC_SWS_BICUBLIN      0x40
+#define ORC_SWS_GAUSS         0x80
+#define ORC_SWS_SINC          0x100
+#define ORC_SWS_LANCZOS       0x200
+#define ORC_SWS_SPLINE        0x400
 #define ORC_SWS_FULL_CHR_H_INT 0x2000
 #define ORC_SWS_FULL_CHR_H_INP 0x4000
 #define ORC_SWS_ACCURATE_RND  0x40000

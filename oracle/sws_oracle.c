@@ -17,6 +17,7 @@
  */
 #include "oracle.h"
 #include <stdlib.h>
+#include <math.h>
 #include <string.h>
 #include <errno.h>
 
@@ -108,10 +109,12 @@ static int make_filter(int16_t **outFilter, int32_t **outPos, int *outSize, int 
             x += xInc;
         }
     } else {                                                       /* :272-383 */
-        int sizeFactor = scaler == ORC_SWS_BICUBIC ? 4 : scaler == ORC_SWS_BILINEAR ? 2 :
-                         scaler == ORC_SWS_AREA ? 1 : -1;
+        /* scale_algorithms[] (utils.c:183-195); Lanczos: 2 * param[0] with the default 3 (:278-279) */
+        int sizeFactor = scaler == ORC_SWS_BICUBIC ? 4 : scaler == ORC_SWS_BILINEAR ? 2 : scaler == ORC_SWS_AREA ? 1 :
+                         scaler == ORC_SWS_GAUSS || scaler == ORC_SWS_X ? 8 : scaler == ORC_SWS_SINC || scaler == ORC_SWS_SPLINE ? 20 :
+                         scaler == ORC_SWS_LANCZOS ? 6 : -1;
         int64_t x;
-        if (sizeFactor < 0) { free(pos); return -ENOSYS; }        /* float-kernel scalers not restated */
+        if (sizeFactor < 0) { free(pos); return -ENOSYS; }
         if (xInc <= 1 << 16) fs = 1 + sizeFactor;
         else                 fs = 1 + (int)(((int64_t)sizeFactor * srcW + dstW - 1) / dstW);
         if (fs > srcW - 2) fs = srcW - 2;
@@ -149,10 +152,32 @@ static int make_filter(int16_t **outFilter, int32_t **outPos, int *outSize, int 
                     else if (d2 * xInc < (1LL << (29 + 16)))  coeff = -d2 * xInc + (1LL << (29 + 16));
                     else                                      coeff = 0;
                     coeff *= fone >> (30 + 16);
-                } else {                                           /* bilinear */
+                } else if (scaler == ORC_SWS_BILINEAR) {
                     coeff = (1 << 30) - d;
                     if (coeff < 0) coeff = 0;
                     coeff *= fone >> 30;
+                } else {                                           /* the kernels evaluated in double precision (:325-368), default parameters */
+                    const double fd = d * (1.0 / (1 << 30));
+                    if (scaler == ORC_SWS_X) {
+                        double c = fd < 1.0 ? cos(fd * M_PI) : -1.0;
+                        c = c < 0.0 ? -pow(-c, 1.0) : pow(c, 1.0);
+                        coeff = (c * 0.5 + 0.5) * fone;
+                    } else if (scaler == ORC_SWS_GAUSS) {
+                        coeff = exp2(-3.0 * fd * fd) * fone;
+                    } else if (scaler == ORC_SWS_SINC) {
+                        coeff = (d ? sin(fd * M_PI) / (fd * M_PI) : 1.0) * fone;
+                    } else if (scaler == ORC_SWS_LANCZOS) {
+                        const double p = 3.0;
+                        coeff = (d ? sin(fd * M_PI) * sin(fd * M_PI / p) / (fd * fd * M_PI * M_PI / p) : 1.0) * fone;
+                        if (fd > p) coeff = 0;
+                    } else {                                       /* spline: getSplineCoeff(1, 0, p, -p - 1, dist), utils.c:155-167 */
+                        double a = 1.0, b = 0.0, c = -2.196152422706632, e = 2.196152422706632 - 1.0, dist = fd;
+                        while (dist > 1.0) {
+                            const double nb = b + 2.0 * c + 3.0 * e, nc = c + 3.0 * e, ne = -b - 3.0 * c - 6.0 * e;
+                            a = 0.0; b = nb; c = nc; e = ne; dist -= 1.0;
+                        }
+                        coeff = (((e * dist + c) * dist + b) * dist + a) * fone;
+                    }
                 }
                 f[i * fs + j] = coeff;
                 xx++;

@@ -228,6 +228,18 @@ def gen_pixelutils():
     np.savez_compressed(os.path.join(OUT, "pixelutils.npz"), **d)
 
 
+def gen_sws_float_kernels():
+    """gauss / sinc / lanczos / spline / experimental scalers: sha256 of the reference's rgb24 and yuv420p outputs per case."""
+    import hashlib
+    from cases import SWS_FLOAT_KERNEL_CASES
+    with open(os.path.join(OUT, "sws_float_kernel_hashes.txt"), "w") as f:
+        for i, (w, h, dw, dh, fl, kind) in enumerate(SWS_FLOAT_KERNEL_CASES):
+            y, u, v = cl.yuv_frame(w, h, 4100 + i, kind)
+            rgb = cl.ref_sws(w, h, dw, dh, fl, y, u, v)
+            yuv = np.concatenate([p.ravel() for p in cl.ref_sws_planar(w, h, dw, dh, fl, y, u, v)])
+            f.write(f"{i} {hashlib.sha256(rgb.tobytes()).hexdigest()} {hashlib.sha256(yuv.tobytes()).hexdigest()}\n")
+
+
 def gen_h264lf():
     """H264DSPContext loop filters, 8 bit: the reference's picture after the 512 edges of h264lf_case(seed, 512) (sha256, plus the first
     64 x 512 pixels of seed 0 for a readable diff)."""
@@ -555,6 +567,7 @@ if __name__ == "__main__":
     gen_edge()
     gen_tx()
     gen_h264lf()
+    gen_sws_float_kernels()
     gen_pixelutils()
     gen_vsynth1()
     gen_sws_slices()

@@ -152,3 +152,11 @@ SWS_RGBSRC_CASES = [(64, 48, 64, 48, FATE, "random"), (64, 48, 64, 48, SWS_BICUB
                     (64, 48, 40, 30, SWS_POINT, "random"), (64, 48, 100, 70, SWS_FAST_BILINEAR, "random"),
                     (64, 48, 40, 30, SWS_FAST_BILINEAR, "smooth"), (352, 288, 640, 360, SWS_BICUBLIN, "random"),
                     (66, 50, 66, 50, FATE | SWS_FULL_CHR_H_INP, "random"), (64, 48, 64, 30, FATE, "random"), (64, 48, 32, 48, SWS_AREA, "random")]
+
+
+# the scalers initFilter evaluates in double precision (libswscale/utils.c:325-368): experimental, Gaussian, sinc, Lanczos, spline
+SWS_X, SWS_GAUSS, SWS_SINC, SWS_LANCZOS, SWS_SPLINE = 0x8, 0x80, 0x100, 0x200, 0x400
+SWS_FLOAT_KERNEL_CASES = [(w, h, dw, dh, fl | extra, "random")
+                          for fl in (SWS_X, SWS_GAUSS, SWS_SINC, SWS_LANCZOS, SWS_SPLINE)
+                          for (w, h, dw, dh, extra) in ((64, 48, 100, 30, 0), (100, 50, 32, 64, 0xc0000), (352, 288, 200, 100, 0xc0000),
+                                                        (34, 16, 200, 151, 0x2000), (130, 98, 17, 8, 0))]

@@ -483,7 +483,7 @@ def test_sws_differential_fuzz(emusws):
     er, ep = functools.partial(emu_sws, emusws), functools.partial(emu_sws_planar, emusws)
     rnd = random.Random(20260923)
     flags = [cl.SWS_BICUBIC, cl.SWS_BILINEAR, FATE, cl.SWS_BICUBIC | 0x40000, cl.SWS_BILINEAR | 0x80000, 1, cl.SWS_BICUBIC | 0x2000, FATE | 0x2000,
-             cl.SWS_BICUBIC | 0x4000, 0x10, 0x200, 0x400]
+             cl.SWS_BICUBIC | 0x4000, 0x10, 0x20, 0x40, 0x8, 0x80, 0x100, 0x200, 0x400, 0x200 | 0xc0000]
     fmts = [0, cl.PIX_FMT_NV12, cl.PIX_FMT_NV21] + list(cl.PACKED_RGB_FORMATS.values())
     ran = refused = 0
     for it in range(90):

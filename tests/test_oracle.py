@@ -288,6 +288,9 @@ def _all_sws_configs():
             out += [(0, w, h, 0, df, dw, dh, 0, fl, None), (0, w, h, 0, df, dw, dh, 1, fl, None)]
         for (w, h, dw, dh, fl, _k) in SWS_RGBSRC_CASES:
             out += [(cl.PIX_FMT_BGR24, w, h, 0, df, dw, dh, 0, fl, None), (cl.PIX_FMT_RGBA, w, h, 0, df, dw, dh, 0, fl, None)]
+    from cases import SWS_FLOAT_KERNEL_CASES
+    for (w, h, dw, dh, fl, _k) in SWS_FLOAT_KERNEL_CASES:           # gauss / sinc / lanczos / spline / experimental scalers
+        out += [(0, w, h, 0, cl.PIX_FMT_RGB24, dw, dh, 0, fl, None), (0, w, h, 0, 0, dw, dh, 0, fl, None), (cl.PIX_FMT_NV12, w, h, 0, cl.PIX_FMT_BGRA, dw, dh, 0, fl, None)]
     return out
 
 
@@ -448,3 +451,24 @@ def test_sws_oracle_nv_destinations_vs_ref():
             src = cl.rgb_frame(w, h, 2800 + i, cl.fmt_bpp(sf), kind)
             same(w, h, dw, dh, fl, src, src, src, src_fmt=sf, dst_fmt=df)
         n += 1
+
+
+def test_float_kernel_scalers_oracle_golden_and_ref():
+    """SWS_X / GAUSS / SINC / LANCZOS / SPLINE (filter taps from double-precision kernels, utils.c:325-368) against the reference's
+    outputs: fixture hashes for both destinations, then the compiled reference on more sizes"""
+    from cases import SWS_FLOAT_KERNEL_CASES
+    lines = open(os.path.join(G, "sws_float_kernel_hashes.txt")).read().split("\n")[:-1]
+    assert len(lines) == len(SWS_FLOAT_KERNEL_CASES)
+    for line, (w, h, dw, dh, fl, kind) in zip(lines, SWS_FLOAT_KERNEL_CASES):
+        i, hrgb, hyuv = line.split()
+        y, u, v = cl.yuv_frame(w, h, 4100 + int(i), kind)
+        assert sha(cl.orc_sws(w, h, dw, dh, fl, y, u, v)) == hrgb, (i, hex(fl))
+        assert sha(np.concatenate([p.ravel() for p in cl.orc_sws_planar(w, h, dw, dh, fl, y, u, v)])) == hyuv, (i, hex(fl))
+    if cl.have_ref():
+        for fl in (0x8, 0x80, 0x100, 0x200, 0x400):
+            for (w, h, dw, dh) in ((64, 48, 64, 30), (20, 10, 300, 7), (351, 287, 97, 301)):
+                y, u, v = cl.yuv_frame(w, h, 4200 + w, "limited")
+                assert np.array_equal(cl.orc_sws(w, h, dw, dh, fl | FATE, y, u, v), cl.ref_sws(w, h, dw, dh, fl | FATE, y, u, v)), (hex(fl), w, h, dw, dh)
+                src = cl.rgb_frame(w, h, 4300 + w, 4)
+                a, b = (f(w, h, dw, dh, fl, src, src, src, src_fmt=cl.PIX_FMT_BGRA, dst_fmt=cl.PIX_FMT_NV12) for f in (cl.orc_sws_planar, cl.ref_sws_planar))
+                assert all(np.array_equal(p, q) for p, q in zip(a, b)), (hex(fl), "bgra -> nv12")

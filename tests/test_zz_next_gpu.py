@@ -121,6 +121,22 @@ def test_range_conversion_batch_device(device):
 
 
 @isolated
+def test_sws_float_kernel_scalers(device):
+    """SWS_X / GAUSS / SINC / LANCZOS / SPLINE: only the host-side filter banks are new (up to 59 taps vertically here); same kernels"""
+    from cases import SWS_FLOAT_KERNEL_CASES
+    from test_sws_gpu import gpu_sws, gpu_sws_planar, sha
+    lines = open(os.path.join(G, "sws_float_kernel_hashes.txt")).read().split("\n")[:-1]
+    for line, (w, h, dw, dh, fl, kind) in zip(lines, SWS_FLOAT_KERNEL_CASES):
+        i, hrgb, hyuv = line.split()
+        y, u, v = cl.yuv_frame(w, h, 4100 + int(i), kind)
+        assert sha(gpu_sws(device, w, h, dw, dh, fl, y, u, v)) == hrgb, (i, hex(fl))
+        assert sha(np.concatenate([p.ravel() for p in gpu_sws_planar(device, w, h, dw, dh, fl, y, u, v)])) == hyuv, (i, hex(fl))
+    y, u, v = cl.yuv_frame(1920, 1080, 4400, "random")                  # lanczos 1080p -> 720p, the common quality downscale
+    fl = 0x200 | 0xc0000
+    assert np.array_equal(gpu_sws(device, 1920, 1080, 1280, 720, fl, y, u, v), cl.orc_sws(1920, 1080, 1280, 720, fl, y, u, v))
+
+
+@isolated
 def test_sws_odd_width_unscaled_leaves_last_column(device):
     """same-size yuv420p -> rgb without accurate_rnd at an odd width: the reference's pair-wise LUT converter never writes the last
     column (yuv2rgb.c:137-236); found by differential fuzzing on the emulated device, the host entry points used to copy it back"""
