@@ -160,6 +160,7 @@ PROTOTYPES = {
     "b200_launch_count": (C.c_uint64, []),
     "b200_sws_getContext": (vp, [vp] + [C.c_int] * 7),
     "b200_sws_getContext_range": (vp, [vp] + [C.c_int] * 9),
+    "b200_sws_getContext_params": (vp, [vp] + [C.c_int] * 9 + [vp]),
     "b200_sws_freeContext": (None, [vp]),
     "b200_sws_setColorspaceDetails": (C.c_int, [vp, i32p, C.c_int, i32p, C.c_int, C.c_int, C.c_int, C.c_int]),
     "b200_sws_scale": (C.c_int, [vp, C.POINTER(vp), i32p, C.c_int, C.c_int, C.POINTER(vp), i32p]),

@@ -913,6 +913,12 @@ B200_API B200SwsContext *b200_sws_getContext(B200Device *dev, int srcW, int srcH
 B200_API B200SwsContext *b200_sws_getContext_range(B200Device *dev, int srcW, int srcH, int srcFormat, int srcRange,
                                                    int dstW, int dstH, int dstFormat, int dstRange, int flags)
 {
+    return b200_sws_getContext_params(dev, srcW, srcH, srcFormat, srcRange, dstW, dstH, dstFormat, dstRange, flags, nullptr);
+}
+
+B200_API B200SwsContext *b200_sws_getContext_params(B200Device *dev, int srcW, int srcH, int srcFormat, int srcRange,
+                                                    int dstW, int dstH, int dstFormat, int dstRange, int flags, const double *param)
+{
     if (!dev) { b200_set_error("b200_sws_getContext: no device"); return nullptr; }
     SwsOutFmt out;
     B200SwsContext *c = new (std::nothrow) B200SwsContext();
@@ -925,6 +931,7 @@ B200_API B200SwsContext *b200_sws_getContext_range(B200Device *dev, int srcW, in
     }
     c->dev = dev;
     c->plan.out = out;
+    if (param) { c->plan.param[0] = param[0]; c->plan.param[1] = param[1]; }
     int ret = sws_plan_build(c->plan, srcW, srcH, dstW, dstH, flags, srcRange, dstRange);
     if (ret < 0) { b200_set_error("b200_sws_getContext: unsupported configuration (%d)", ret); delete c; return nullptr; }
     cudaSetDevice(dev->ordinal);

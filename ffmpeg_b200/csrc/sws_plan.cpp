@@ -41,10 +41,11 @@ struct RawTaps {
 };
 
 // The weight of a source sample at distance d (Q30 after the <<13) from the output sample centre.
-i64 cubic_weight(i64 d)
+constexpr double kParamDefault = 123456.0;                                       // SWS_PARAM_DEFAULT, swscale.h
+i64 cubic_weight(i64 d, const double *param)
 {
-    // Mitchell-Netravali with B = 0, C = 0.6 in Q24 (the reference's SWS_PARAM_DEFAULT), utils.c:312-332
-    const i64 B = 0, C = (i64)(0.6 * (1 << 24));
+    // Mitchell-Netravali, B = param[0] (default 0), C = param[1] (default 0.6) in Q24, utils.c:312-332
+    const i64 B = (param[0] != kParamDefault ? param[0] : 0) * (1 << 24), C = (param[1] != kParamDefault ? param[1] : 0.6) * (1 << 24);
     if (d >= (i64)1 << 31) return 0;
     const i64 dd = (d * d) >> 30, ddd = (dd * d) >> 30;
     if (d < (i64)1 << 30)
@@ -53,22 +54,24 @@ i64 cubic_weight(i64 d)
     return (-B - 6 * C) * ddd + (6 * B + 30 * C) * dd + (-12 * B - 48 * C) * d + (8 * B + 24 * C) * ((i64)1 << 30);
 }
 
-// the kernels initFilter evaluates in double precision (utils.c:325-368), default parameters; d = distance in 2.30 fixed point.
+// the kernels initFilter evaluates in double precision (utils.c:325-368); d = distance in 2.30 fixed point.
 // The products and quotients keep the reference's order: these run on the host with the host's libm, like the reference's do.
-i64 float_kernel_weight(int scaler, i64 d, i64 unit)
+i64 float_kernel_weight(int scaler, i64 d, i64 unit, const double *param)
 {
     const double fd = d * (1.0 / (1 << 30));
     i64 w;
     if (scaler == B200_SWS_X) {
         double c = fd < 1.0 ? cos(fd * M_PI) : -1.0;
-        c = c < 0.0 ? -pow(-c, 1.0) : pow(c, 1.0);
+        const double A = param[0] != kParamDefault ? param[0] : 1.0;
+        c = c < 0.0 ? -pow(-c, A) : pow(c, A);
         w = (c * 0.5 + 0.5) * unit;
     } else if (scaler == B200_SWS_GAUSS) {
-        w = exp2(-3.0 * fd * fd) * unit;
+        const double p = param[0] != kParamDefault ? param[0] : 3.0;
+        w = exp2(-p * fd * fd) * unit;
     } else if (scaler == B200_SWS_SINC) {
         w = (d ? sin(fd * M_PI) / (fd * M_PI) : 1.0) * unit;
     } else if (scaler == B200_SWS_LANCZOS) {
-        const double p = 3.0;
+        const double p = param[0] != kParamDefault ? param[0] : 3.0;
         w = (d ? sin(fd * M_PI) * sin(fd * M_PI / p) / (fd * fd * M_PI * M_PI / p) : 1.0) * unit;
         if (fd > p) w = 0;
     } else {                                                                     // spline: getSplineCoeff(1, 0, p, -p - 1, dist), utils.c:155-167
@@ -82,7 +85,7 @@ i64 float_kernel_weight(int scaler, i64 d, i64 unit)
     return w;
 }
 
-int raw_taps(RawTaps &r, int scaler, int inc, int srcN, int dstN, int srcOrg, int dstOrg, i64 unit)
+int raw_taps(RawTaps &r, int scaler, int inc, int srcN, int dstN, int srcOrg, int dstOrg, i64 unit, const double *param)
 {
     r.first.assign((size_t)dstN + 3, 0);
     if (std::abs(inc - 0x10000) < 10 && srcOrg == dstOrg) {                      // utils.c:221-231
@@ -117,9 +120,10 @@ int raw_taps(RawTaps &r, int scaler, int inc, int srcN, int dstN, int srcOrg, in
     case B200_SWS_AREA:     support = 1; break;
     case B200_SWS_X: case B200_SWS_GAUSS:     support = 8; break;
     case B200_SWS_SINC: case B200_SWS_SPLINE: support = 20; break;
-    case B200_SWS_LANCZOS:  support = 6; break;                                  // 2 * param[0], default 3 (utils.c:278-279)
+    case B200_SWS_LANCZOS:  support = param[0] != kParamDefault ? (int)ceil(2 * param[0]) : 6; break;   // utils.c:278-279
     default: return B200_ENOSYS;
     }
+    if (support > 50 || support <= 0) return B200_EINVAL;                        // utils.c:280-285 (0 would trip the reference's assert)
     int taps = inc <= (1 << 16) ? 1 + support : 1 + (int)(((i64)support * srcN + dstN - 1) / dstN);
     taps = std::max(1, std::min(taps, srcN - 2));
     r.taps = taps;
@@ -133,7 +137,7 @@ int raw_taps(RawTaps &r, int scaler, int inc, int srcN, int dstN, int srcOrg, in
             if (inc > (1 << 16)) d = d * dstN / srcN;
             i64 w;
             if (scaler == B200_SWS_BICUBIC) {
-                w = cubic_weight(d) / (((i64)1 << 54) / unit);
+                w = cubic_weight(d, param) / (((i64)1 << 54) / unit);
             } else if (scaler == B200_SWS_AREA) {
                 const i64 d2 = d - (1 << 29);
                 if (d2 * inc < -((i64)1 << 45))      w = (i64)1 << 46;
@@ -143,7 +147,7 @@ int raw_taps(RawTaps &r, int scaler, int inc, int srcN, int dstN, int srcOrg, in
             } else if (scaler == B200_SWS_BILINEAR) {
                 w = std::max<i64>(0, (1 << 30) - d) * (unit >> 30);
             } else {
-                w = float_kernel_weight(scaler, d, unit);
+                w = float_kernel_weight(scaler, d, unit, param);
             }
             r.w[(size_t)i * taps + j] = w;
         }
@@ -151,11 +155,11 @@ int raw_taps(RawTaps &r, int scaler, int inc, int srcN, int dstN, int srcOrg, in
     return 0;
 }
 
-int build_bank(SwsFilterBank &bank, int scaler, int inc, int srcN, int dstN, int one, int srcOrg, int dstOrg)
+int build_bank(SwsFilterBank &bank, int scaler, int inc, int srcN, int dstN, int one, int srcOrg, int dstOrg, const double *param)
 {
     const i64 unit = (i64)1 << (54 - std::min(floor_log2((unsigned)(srcN / dstN)), 8));
     RawTaps r;
-    int ret = raw_taps(r, scaler, inc, srcN, dstN, srcOrg, dstOrg, unit);
+    int ret = raw_taps(r, scaler, inc, srcN, dstN, srcOrg, dstOrg, unit, param);
     if (ret < 0) return ret;
     const int T = r.taps;
     const double cutoff = 0.002 * (double)unit;                                  // SWS_MAX_REDUCE_CUTOFF, swscale.h:447
@@ -443,12 +447,12 @@ int sws_plan_build(SwsPlan &p, int srcW, int srcH, int dstW, int dstH, int flags
         lumXInc > INT32_MAX || lumYInc > INT32_MAX || chrXInc > INT32_MAX || chrYInc > INT32_MAX)
         return B200_ENOSYS;
     p.lumXInc = (int)lumXInc; p.chrXInc = (int)chrXInc;
-    if ((ret = build_bank(p.hLum, lumScaler, (int)lumXInc, srcW, dstW, 1 << 14, sample_origin(0, 0), sample_origin(0, 0))) < 0) return ret;
+    if ((ret = build_bank(p.hLum, lumScaler, (int)lumXInc, srcW, dstW, 1 << 14, sample_origin(0, 0), sample_origin(0, 0), p.param)) < 0) return ret;
     if ((ret = build_bank(p.hChr, chrScaler, (int)chrXInc, p.chrSrcW, p.chrDstW, 1 << 14,
-                          sample_origin(p.chrSrcHSub, -513), sample_origin(p.chrDstHSub, -513))) < 0) return ret;
-    if ((ret = build_bank(p.vLum, lumScaler, (int)lumYInc, srcH, dstH, 1 << 12, sample_origin(0, 0), sample_origin(0, 0))) < 0) return ret;
+                          sample_origin(p.chrSrcHSub, -513), sample_origin(p.chrDstHSub, -513), p.param)) < 0) return ret;
+    if ((ret = build_bank(p.vLum, lumScaler, (int)lumYInc, srcH, dstH, 1 << 12, sample_origin(0, 0), sample_origin(0, 0), p.param)) < 0) return ret;
     if ((ret = build_bank(p.vChr, chrScaler, (int)chrYInc, p.chrSrcH, p.chrDstH, 1 << 12,
-                          sample_origin(p.chrSrcVSub, -513), sample_origin(chrDstVSub, -513))) < 0) return ret;
+                          sample_origin(p.chrSrcVSub, -513), sample_origin(chrDstVSub, -513), p.param)) < 0) return ret;
     if (p.planar) return 0;
 
     // writer per output line, as packed_vscale decides it (vscale.c:144-169); coefficients are read as uint16 there

@@ -54,6 +54,7 @@ struct SwsPlan {
     int chrSrcHSub = 1, chrSrcVSub = 1;           // chroma sampling of the source as the scaler sees it (utils.c:1366-1396)
     int rgb2yuv[9] = { 0 };       // input_rgb2yuv_table RY GY BY RU GU BU RV GV BV (swscale_internal.h:468-477; utils.c:614-700)
     bool bgr24_yv12 = false;      // reference installs bgr24ToYv12Wrapper (ff_rgb24toyv12_c, rgb2rgb_template.c:580-641)
+    double param[2] = { 123456.0, 123456.0 };     // SwsContext.scaler_params; SWS_PARAM_DEFAULT = 123456 (set before sws_plan_build)
     SwsFilterBank hLum, hChr, vLum, vChr;
     SwsColorConst color{};
     // per output line: writer selected by packed_vscale (vscale.c:144-169): 0 = _X, 1 = _1, 2 = _2, plus alphas

@@ -29,15 +29,17 @@ def _dptr(x):
 
 
 class SwsContext:
-    def __init__(self, device, srcW, srcH, srcFormat, dstW, dstH, dstFormat, flags, src_range=0, dst_range=0):
-        """src_range / dst_range: SwsContext.src_range / .dst_range as set before sws_init_context (0 limited, 1 full)"""
+    def __init__(self, device, srcW, srcH, srcFormat, dstW, dstH, dstFormat, flags, src_range=0, dst_range=0, param=None):
+        """src_range / dst_range: SwsContext.src_range / .dst_range as set before sws_init_context (0 limited, 1 full);
+        param: sws_getContext's scaler parameters (two doubles, 123456 = SWS_PARAM_DEFAULT) or None"""
         self.device = device
         self.srcW, self.srcH, self.dstW, self.dstH, self.flags = srcW, srcH, dstW, dstH, flags
         self.srcFormat, self.dstFormat = srcFormat, dstFormat
         self.dst_nv = dstFormat in (AV_PIX_FMT_NV12, AV_PIX_FMT_NV21)          # destination: luma plane + interleaved chroma plane
         self.planar = dstFormat == AV_PIX_FMT_YUV420P or self.dst_nv
         self.bpp = 1 if self.planar else 3 if dstFormat in (AV_PIX_FMT_RGB24, AV_PIX_FMT_BGR24) else 4
-        h = lib().b200_sws_getContext_range(device.handle, srcW, srcH, srcFormat, src_range, dstW, dstH, dstFormat, dst_range, flags)
+        pp = (C.c_double * 2)(*param) if param is not None else None
+        h = lib().b200_sws_getContext_params(device.handle, srcW, srcH, srcFormat, src_range, dstW, dstH, dstFormat, dst_range, flags, pp)
         if not h:
             raise B200Error("sws_getContext failed: " + lib().b200_last_error().decode())
         self._h = vp(h)
@@ -129,5 +131,5 @@ class SwsContext:
             pass
 
 
-def sws_getContext(device, srcW, srcH, srcFormat, dstW, dstH, dstFormat, flags, src_range=0, dst_range=0):
-    return SwsContext(device, srcW, srcH, srcFormat, dstW, dstH, dstFormat, flags, src_range, dst_range)
+def sws_getContext(device, srcW, srcH, srcFormat, dstW, dstH, dstFormat, flags, src_range=0, dst_range=0, param=None):
+    return SwsContext(device, srcW, srcH, srcFormat, dstW, dstH, dstFormat, flags, src_range, dst_range, param)

@@ -114,6 +114,11 @@ B200SwsContext *b200_sws_getContext(B200Device *dev, int srcW, int srcH, int src
  * and srcRange selects the look-up tables, as in the reference. */
 B200SwsContext *b200_sws_getContext_range(B200Device *dev, int srcW, int srcH, int srcFormat, int srcRange,
                                           int dstW, int dstH, int dstFormat, int dstRange, int flags);
+/* The same with SwsContext.scaler_params — the `param` argument of sws_getContext() (libswscale/swscale.h; utils.c:312-360):
+ * bicubic B / C (default 0 / 0.6), Gaussian exponent (3), Lanczos width (3), the experimental scaler's power (1).  NULL, or
+ * 123456 (SWS_PARAM_DEFAULT) in either slot, selects the default. */
+B200SwsContext *b200_sws_getContext_params(B200Device *dev, int srcW, int srcH, int srcFormat, int srcRange,
+                                           int dstW, int dstH, int dstFormat, int dstRange, int flags, const double *param);
 void b200_sws_freeContext(B200SwsContext *c);
 /* like sws_setColorspaceDetails() (libswscale/utils.c:849-1004).  RGB destination: `table` / dstRange are accepted and
  * ignored like the reference.  yuv420p destination: the ranges are stored and the range conversion is re-selected

@@ -93,6 +93,22 @@ API void *ffref_sws_open_range(int srcFormat, int srcW, int srcH, int srcRange, 
     return c;
 }
 
+/* the same with SwsContext.scaler_params (what sws_getContext copies from its `param` argument) */
+API void *ffref_sws_open_params(int srcFormat, int srcW, int srcH, int srcRange, int dstFormat, int dstW, int dstH, int dstRange,
+                                int flags, int threads, const double *param)
+{
+    SwsContext *c = sws_alloc_context();
+    if (!c) return NULL;
+    c->src_w = srcW; c->src_h = srcH; c->dst_w = dstW; c->dst_h = dstH;
+    c->src_format = srcFormat; c->dst_format = dstFormat;
+    c->src_range = srcRange; c->dst_range = dstRange;
+    c->flags = flags;
+    c->threads = threads;
+    if (param) { c->scaler_params[0] = param[0]; c->scaler_params[1] = param[1]; }
+    if (sws_init_context(c, NULL, NULL) < 0) { sws_freeContext(c); return NULL; }
+    return c;
+}
+
 API void ffref_sws_close(void *h) { sws_freeContext((SwsContext *)h); }
 
 /* colorspace details pass-through (sws_setColorspaceDetails); table index = SWS_CS_* */

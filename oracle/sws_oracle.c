@@ -72,6 +72,11 @@ static int local_pos(int chr_subsample, int pos)
 }
 
 /* utils.c:197-612 with srcFilter = dstFilter = NULL, param = defaults, filterAlign = 1 */
+/* SwsContext.scaler_params (sws_getContext's `param`, swscale.h): SWS_PARAM_DEFAULT = 123456 selects each kernel's default.
+ * The checker is single threaded: orc_sws_open_params() sets them around the open call. */
+#define ORC_PARAM_DEFAULT 123456
+static double g_param[2] = { ORC_PARAM_DEFAULT, ORC_PARAM_DEFAULT };
+
 static int make_filter(int16_t **outFilter, int32_t **outPos, int *outSize, int xInc, int srcW, int dstW,
                        int one, int scaler, int flags, int srcPos, int dstPos)
 {
@@ -112,9 +117,10 @@ static int make_filter(int16_t **outFilter, int32_t **outPos, int *outSize, int 
         /* scale_algorithms[] (utils.c:183-195); Lanczos: 2 * param[0] with the default 3 (:278-279) */
         int sizeFactor = scaler == ORC_SWS_BICUBIC ? 4 : scaler == ORC_SWS_BILINEAR ? 2 : scaler == ORC_SWS_AREA ? 1 :
                          scaler == ORC_SWS_GAUSS || scaler == ORC_SWS_X ? 8 : scaler == ORC_SWS_SINC || scaler == ORC_SWS_SPLINE ? 20 :
-                         scaler == ORC_SWS_LANCZOS ? 6 : -1;
+                         scaler == ORC_SWS_LANCZOS ? (g_param[0] != ORC_PARAM_DEFAULT ? (int)ceil(2 * g_param[0]) : 6) : -1;
         int64_t x;
         if (sizeFactor < 0) { free(pos); return -ENOSYS; }
+        if (sizeFactor > 50 || sizeFactor == 0) { free(pos); return -EINVAL; }   /* :282-285 (0 trips the reference's assert) */
         if (xInc <= 1 << 16) fs = 1 + sizeFactor;
         else                 fs = 1 + (int)(((int64_t)sizeFactor * srcW + dstW - 1) / dstW);
         if (fs > srcW - 2) fs = srcW - 2;
@@ -130,8 +136,8 @@ static int make_filter(int16_t **outFilter, int32_t **outPos, int *outSize, int 
                 if (xInc > 1 << 16)
                     d = d * dstW / srcW;
                 if (scaler == ORC_SWS_BICUBIC) {                   /* B = 0, C = 0.6 in 8.24 */
-                    int64_t B = 0;
-                    int64_t C = (int64_t)(0.6 * (1 << 24));
+                    int64_t B = (g_param[0] != ORC_PARAM_DEFAULT ? g_param[0] : 0) * (1 << 24);
+                    int64_t C = (g_param[1] != ORC_PARAM_DEFAULT ? g_param[1] : 0.6) * (1 << 24);
                     if (d >= 1LL << 31) {
                         coeff = 0;
                     } else {
@@ -160,14 +166,16 @@ static int make_filter(int16_t **outFilter, int32_t **outPos, int *outSize, int 
                     const double fd = d * (1.0 / (1 << 30));
                     if (scaler == ORC_SWS_X) {
                         double c = fd < 1.0 ? cos(fd * M_PI) : -1.0;
-                        c = c < 0.0 ? -pow(-c, 1.0) : pow(c, 1.0);
+                        const double A = g_param[0] != ORC_PARAM_DEFAULT ? g_param[0] : 1.0;
+                        c = c < 0.0 ? -pow(-c, A) : pow(c, A);
                         coeff = (c * 0.5 + 0.5) * fone;
                     } else if (scaler == ORC_SWS_GAUSS) {
-                        coeff = exp2(-3.0 * fd * fd) * fone;
+                        const double p = g_param[0] != ORC_PARAM_DEFAULT ? g_param[0] : 3.0;
+                        coeff = exp2(-p * fd * fd) * fone;
                     } else if (scaler == ORC_SWS_SINC) {
                         coeff = (d ? sin(fd * M_PI) / (fd * M_PI) : 1.0) * fone;
                     } else if (scaler == ORC_SWS_LANCZOS) {
-                        const double p = 3.0;
+                        const double p = g_param[0] != ORC_PARAM_DEFAULT ? g_param[0] : 3.0;
                         coeff = (d ? sin(fd * M_PI) * sin(fd * M_PI / p) / (fd * fd * M_PI * M_PI / p) : 1.0) * fone;
                         if (fd > p) coeff = 0;
                     } else {                                       /* spline: getSplineCoeff(1, 0, p, -p - 1, dist), utils.c:155-167 */
@@ -420,6 +428,15 @@ OrcSws *orc_sws_open_fmt(int srcW, int srcH, int dstW, int dstH, int dstFormat, 
 OrcSws *orc_sws_open_io(int srcFormat, int srcW, int srcH, int dstFormat, int dstW, int dstH, int flags)
 {
     return orc_sws_open_range(srcFormat, srcW, srcH, 0, dstFormat, dstW, dstH, 0, flags);
+}
+
+OrcSws *orc_sws_open_params(int srcFormat, int srcW, int srcH, int srcRange, int dstFormat, int dstW, int dstH, int dstRange, int flags,
+                            const double *param)
+{
+    if (param) { g_param[0] = param[0]; g_param[1] = param[1]; }
+    OrcSws *s = orc_sws_open_range(srcFormat, srcW, srcH, srcRange, dstFormat, dstW, dstH, dstRange, flags);
+    g_param[0] = g_param[1] = ORC_PARAM_DEFAULT;
+    return s;
 }
 
 OrcSws *orc_sws_open_range(int srcFormat, int srcW, int srcH, int srcRange, int dstFormat, int dstW, int dstH, int dstRange, int flags)

@@ -160,3 +160,7 @@ SWS_FLOAT_KERNEL_CASES = [(w, h, dw, dh, fl | extra, "random")
                           for fl in (SWS_X, SWS_GAUSS, SWS_SINC, SWS_LANCZOS, SWS_SPLINE)
                           for (w, h, dw, dh, extra) in ((64, 48, 100, 30, 0), (100, 50, 32, 64, 0xc0000), (352, 288, 200, 100, 0xc0000),
                                                         (34, 16, 200, 151, 0x2000), (130, 98, 17, 8, 0))]
+
+# sws_getContext's `param` (SwsContext.scaler_params; 123456 = SWS_PARAM_DEFAULT): (scaler flag, (param0, param1))
+SWS_PARAM_CASES = [(4, (0.0, 0.5)), (4, (1 / 3, 1 / 3)), (4, (1.0, 0.0)), (4, (123456.0, 0.75)), (0x40, (0.0, 0.75)), (0x80, (2.0, 123456.0)),
+                   (0x80, (4.5, 123456.0)), (0x200, (2.0, 123456.0)), (0x200, (5.0, 123456.0)), (0x8, (0.5, 123456.0)), (0x8, (2.0, 123456.0)), (2, (0.3, 0.3))]

@@ -188,9 +188,17 @@ def rgb_frame(w, h, seed, bpp, kind="random", pad=0):
     return a
 
 
-def _sws_run(lib, pre, w, h, dw, dh, flags, y, u, v, dst_pad=0, threads=1, colorspace=None, fmt=PIX_FMT_RGB24, src_fmt=0):
-    """src_fmt nv12 / nv21: `u` is the interleaved chroma plane, `v` is ignored"""
-    if pre == "ffref":
+def _sws_run(lib, pre, w, h, dw, dh, flags, y, u, v, dst_pad=0, threads=1, colorspace=None, fmt=PIX_FMT_RGB24, src_fmt=0, param=None):
+    """src_fmt nv12 / nv21: `u` is the interleaved chroma plane, `v` is ignored; param: sws_getContext's two scaler parameters"""
+    if param is not None:
+        pa = (C.c_double * 2)(*param)
+        if pre == "ffref":
+            lib.ffref_sws_open_params.restype, lib.ffref_sws_open_params.argtypes = C.c_void_p, [C.c_int] * 10 + [C.c_void_p]
+            ctx = lib.ffref_sws_open_params(src_fmt, w, h, 0, fmt, dw, dh, 0, flags, threads, pa)
+        else:
+            lib.orc_sws_open_params.restype, lib.orc_sws_open_params.argtypes = C.c_void_p, [C.c_int] * 9 + [C.c_void_p]
+            ctx = lib.orc_sws_open_params(src_fmt, w, h, 0, fmt, dw, dh, 0, flags, pa)
+    elif pre == "ffref":
         ctx = lib.ffref_sws_open_io(src_fmt, w, h, fmt, dw, dh, flags, threads)
     else:
         ctx = lib.orc_sws_open_io(src_fmt, w, h, fmt, dw, dh, flags)

@@ -472,6 +472,37 @@ def test_sws_rgb_sources_nv_destinations_and_all_fate_sums(emusws):
         assert np.array_equal(D[i], cl.orc_sws(w, h, dw, dh, FATE, frames[i], frames[i], frames[i], fmt=cl.PIX_FMT_BGRA, src_fmt=cl.PIX_FMT_RGB24)), i
 
 
+def test_sws_scaler_params(emusws):
+    """sws_getContext's `param` (bicubic B / C, Gaussian exponent, Lanczos width, the experimental scaler's power) through
+    b200_sws_getContext_params on the emulated device, against the checker and the compiled reference; a Lanczos width whose
+    filter would exceed the reference's limit of 50 is refused by all three"""
+    from cases import SWS_PARAM_CASES
+    L = emusws
+    L.b200_sws_getContext_params.restype = C.c_void_p
+    L.b200_sws_getContext_params.argtypes = [C.c_void_p] + [C.c_int] * 9 + [C.c_void_p]
+
+    def emu(w, h, dw, dh, fl, y, u, v, prm):
+        ctx = L.b200_sws_getContext_params(L.dev, w, h, 0, 0, dw, dh, cl.PIX_FMT_RGB24, 0, fl, (C.c_double * 2)(*prm))
+        if not ctx:
+            return None
+        out = np.full((dh, dw * 3), 0xA5, np.uint8)
+        assert _emu_scale(L, ctx, [y, u, v], h, [out]) == dh
+        L.b200_sws_freeContext(ctx)
+        return out
+    for i, (fl, prm) in enumerate(SWS_PARAM_CASES):
+        for (w, h, dw, dh, extra) in ((64, 48, 100, 30, 0), (352, 288, 200, 100, 0xc0000), (34, 16, 200, 151, 0x2000)):
+            y, u, v = cl.yuv_frame(w, h, 4500 + i, "random")
+            exp = cl.orc_sws(w, h, dw, dh, fl | extra, y, u, v, param=prm)
+            assert np.array_equal(emu(w, h, dw, dh, fl | extra, y, u, v, prm), exp), (hex(fl), prm, w, h)
+            if cl.have_ref():
+                assert np.array_equal(cl.ref_sws(w, h, dw, dh, fl | extra, y, u, v, param=prm), exp), ("checker != reference", hex(fl), prm, w, h)
+    # the parameters change the picture, and the default marker in both slots is the plain context
+    y, u, v = cl.yuv_frame(64, 48, 4600, "random")
+    base = cl.orc_sws(64, 48, 100, 30, 4, y, u, v)
+    assert np.array_equal(emu(64, 48, 100, 30, 4, y, u, v, (123456.0, 123456.0)), base) and not np.array_equal(emu(64, 48, 100, 30, 4, y, u, v, (1.0, 0.0)), base)
+    assert emu(64, 48, 100, 30, 0x200, y, u, v, (26.0, 123456.0)) is None and cl.orc_sws(64, 48, 100, 30, 0x200, y, u, v, param=(26.0, 123456.0)) is None
+
+
 def test_sws_differential_fuzz(emusws):
     """seeded random contexts (sizes incl. odd ones, every source / destination format of the library, scaler flags, ranges,
     sws_setColorspaceDetails with other matrices / brightness / contrast / saturation, padded destinations) through the library's

@@ -137,6 +137,20 @@ def test_sws_float_kernel_scalers(device):
 
 
 @isolated
+def test_sws_scaler_params(device):
+    """sws_getContext's `param`: only the host-side filter banks depend on it"""
+    from cases import SWS_PARAM_CASES
+    from ffmpeg_b200 import swscale as sw
+    for i, (fl, prm) in enumerate(SWS_PARAM_CASES):
+        w, h, dw, dh = 352, 288, 200, 100
+        y, u, v = cl.yuv_frame(w, h, 4500 + i, "random")
+        ctx = sw.sws_getContext(device, w, h, 0, dw, dh, cl.PIX_FMT_RGB24, fl | 0xc0000, param=prm)
+        got = ctx.convert(y, u, v)
+        ctx.free()
+        assert np.array_equal(got, cl.orc_sws(w, h, dw, dh, fl | 0xc0000, y, u, v, param=prm)), (hex(fl), prm)
+
+
+@isolated
 def test_sws_odd_width_unscaled_leaves_last_column(device):
     """same-size yuv420p -> rgb without accurate_rnd at an odd width: the reference's pair-wise LUT converter never writes the last
     column (yuv2rgb.c:137-236); found by differential fuzzing on the emulated device, the host entry points used to copy it back"""
