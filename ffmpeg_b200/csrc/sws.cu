@@ -1540,9 +1540,22 @@ static int sws_scale_planar_host(B200SwsContext *c, const uint8_t *const srcSlic
                                  int srcSliceY, int srcSliceH, uint8_t *const dst[], const int dstStride[])
 {
     const SwsPlan &p = c->plan;
-    if (srcSliceY != 0 || srcSliceH != p.srcH) {
-        b200_set_error("yuv420p destination: only whole-frame calls are implemented");
+    const bool whole = srcSliceY == 0 && srcSliceH == p.srcH && !c->slice_open;
+    if (!whole && (p.src_rgb || p.bgr24_yv12)) {
+        b200_set_error("packed RGB source: only whole-frame calls are implemented");
         return B200_ENOSYS;
+    }
+    if (!whole) {
+        // parameter checks of scale_internal (macro_height_src = 2 for yuv420p), as in the packed-RGB slice path below
+        if ((srcSliceY & 1) || ((srcSliceH & 1) && srcSliceY + srcSliceH != p.srcH) || srcSliceY + srcSliceH > p.srcH || srcSliceY < 0 || srcSliceH < 0) {
+            b200_set_error("Slice parameters %d, %d are invalid", srcSliceY, srcSliceH);
+            return B200_EINVAL;
+        }
+        if (srcSliceH == 0) return 0;
+        if (!c->slice_open && srcSliceY != 0) {
+            b200_set_error("slices must start at line 0 (bottom-up slice order is not implemented)");
+            return srcSliceY + srcSliceH == p.srcH ? B200_ENOSYS : B200_EINVAL;
+        }
     }
     const int nsp = p.src_rgb ? 1 : p.src_nv ? 2 : 3;             // packed RGB: one plane; nv12 / nv21: plane 1 carries both chroma components
     const int ndp = p.dst_nv ? 2 : 3;                             // nv12 / nv21 destination: two planes
@@ -1558,11 +1571,54 @@ static int sws_scale_planar_host(B200SwsContext *c, const uint8_t *const srcSlic
     size_t spitch[3], dpitch[3], soff[3], doff[3], total = 0;
     for (int i = 0; i < 3; i++) { spitch[i] = ((size_t)sw[i] + 255) & ~(size_t)255; soff[i] = total; total += spitch[i] * sh[i]; }
     for (int i = 0; i < 3; i++) { dpitch[i] = ((size_t)dw[i] + 255) & ~(size_t)255; doff[i] = total; total += dpitch[i] * dh[i]; }
-    uint8_t *scr = (uint8_t *)b200_scratch(d, total);
-    if (!scr) return B200_ENOMEM;
     cudaStream_t st = d->stream;
     const uint8_t *sp[3]; uint8_t *dp[3]; long long ss[3], ds[3];
     const long long zero[3] = { 0, 0, 0 };
+    if (!whole) {
+        // Slice sequence (top-down): the bands accumulate in a device copy of the picture that lives in the context; after each band
+        // the whole picture is converted again — an output line only depends on source lines that have arrived once ff_swscale's
+        // "enough lines" test (swscale.c:463-465) passes for it — and the lines that became complete are copied back: the return
+        // value and the lines written per call are the reference's.
+        if (!c->slice_buf) B200_CUDA_OK(cudaMalloc(&c->slice_buf, total));
+        uint8_t *sb = (uint8_t *)c->slice_buf;
+        if (srcSliceY == 0) { c->next_dst_y = 0; c->slice_open = true; }
+        const int chrY = srcSliceY >> 1, chrH = -((-srcSliceH) >> 1);
+        const int by[3] = { srcSliceY, chrY, chrY }, bh[3] = { srcSliceH, chrH, chrH };
+        for (int i = 0; i < 3; i++) {
+            if (i < nsp)
+                B200_CUDA_OK(cudaMemcpy2DAsync(sb + soff[i] + (size_t)by[i] * spitch[i], spitch[i], srcSlice[i], (size_t)srcStride[i], sw[i], bh[i], cudaMemcpyHostToDevice, st));
+            sp[i] = sb + soff[i]; dp[i] = sb + doff[i]; ss[i] = (long long)spitch[i]; ds[i] = (long long)dpitch[i];
+        }
+        int y0, y1;
+        if (p.planar_copy) {                                   // the copy wrappers handle exactly the band they are given
+            y0 = srcSliceY; y1 = srcSliceY + srcSliceH;
+        } else {
+            y0 = c->next_dst_y;
+            const int avail_l = srcSliceY + srcSliceH, avail_c = -((-(srcSliceY + srcSliceH)) >> 1);
+            for (y1 = y0; y1 < p.dstH; y1++) {
+                // luma availability is tested for the last luma line of the chroma line's pair: firstLumSrcY2 (swscale.c:419-421)
+                const int firstLum = std::max(1 - p.vLum.size, p.vLum.pos[std::min(y1 | 1, p.dstH - 1)]);
+                const int firstChr = std::max(1 - p.vChr.size, p.vChr.pos[y1 >> 1]);      // chrDstY = dstY >> 1 (swscale.c:414)
+                const int lastLum = std::min(p.srcH, firstLum + p.vLum.size) - 1;
+                const int lastChr = std::min(p.chrSrcH, firstChr + p.vChr.size) - 1;
+                if (!(lastLum < avail_l && lastChr < avail_c)) break;
+            }
+            c->next_dst_y = y1;
+        }
+        if (y1 > y0) {
+            int ret = launch_planar(c, st, sp, ss, zero, dp, ds, zero, 1);
+            if (ret < 0) return ret;
+            const int c0 = (y0 + 1) >> 1, c1 = (y1 + 1) >> 1;           // chroma lines are written with the even luma lines (vscale.c:34-107)
+            B200_CUDA_OK(cudaMemcpy2DAsync(dst[0] + (long long)y0 * dstStride[0], (size_t)dstStride[0], dp[0] + (size_t)y0 * dpitch[0], dpitch[0], dw[0], y1 - y0, cudaMemcpyDeviceToHost, st));
+            for (int i = 1; i < ndp && c1 > c0; i++)
+                B200_CUDA_OK(cudaMemcpy2DAsync(dst[i] + (long long)c0 * dstStride[i], (size_t)dstStride[i], dp[i] + (size_t)c0 * dpitch[i], dpitch[i], dw[i], c1 - c0, cudaMemcpyDeviceToHost, st));
+        }
+        B200_CUDA_OK(cudaStreamSynchronize(st));
+        if (srcSliceY + srcSliceH == p.srcH) c->slice_open = false;
+        return y1 - y0;
+    }
+    uint8_t *scr = (uint8_t *)b200_scratch(d, total);
+    if (!scr) return B200_ENOMEM;
     for (int i = 0; i < 3; i++) {
         if (i < nsp)
             B200_CUDA_OK(cudaMemcpy2DAsync(scr + soff[i], spitch[i], srcSlice[i], (size_t)srcStride[i], sw[i], sh[i], cudaMemcpyHostToDevice, st));

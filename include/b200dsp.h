@@ -129,9 +129,9 @@ int  b200_sws_setColorspaceDetails(B200SwsContext *c, const int inv_table[4], in
                                    const int table[4], int dstRange, int brightness, int contrast, int saturation);
 /* drop-in for sws_scale(): HOST pointers, strides in bytes (negative allowed), returns output lines.
  * Top-down slice sequences are supported (bands uploaded into a device copy of the picture, lines emitted as soon as
- * their vertical taps are complete, same return values as the reference) for packed RGB destinations from planar / semi-planar
- * sources; bottom-up slice order, and slice calls with a yuv420p / nv12 / nv21 destination or a packed RGB source, return
- * B200_ENOSYS (whole-frame calls only there). */
+ * their vertical taps are complete, same return values as the reference) from planar / semi-planar sources, into packed RGB and
+ * into yuv420p / nv12 / nv21 destinations; bottom-up slice order, and slice calls with a packed RGB source, return B200_ENOSYS
+ * (whole-frame calls only there). */
 int  b200_sws_scale(B200SwsContext *c, const uint8_t *const srcSlice[], const int srcStride[],
                     int srcSliceY, int srcSliceH, uint8_t *const dst[], const int dstStride[]);
 /* SwsFunc-shaped entry (first argument is the context): what a maintainer installs as convert_unscaled */

@@ -472,6 +472,44 @@ def test_sws_rgb_sources_nv_destinations_and_all_fate_sums(emusws):
         assert np.array_equal(D[i], cl.orc_sws(w, h, dw, dh, FATE, frames[i], frames[i], frames[i], fmt=cl.PIX_FMT_BGRA, src_fmt=cl.PIX_FMT_RGB24)), i
 
 
+def test_sws_slice_calls_planar_destination(emusws):
+    """sws_scale() band by band into yuv420p / nv12 on the emulated device: per-call return values and the final planes equal the
+    compiled reference's (the luma test of ff_swscale's "enough lines" uses the last line of the chroma pair, swscale.c:419-421)"""
+    if not cl.have_ref():
+        pytest.skip("oracle/_ref/libffref.so not built")
+    import random
+    L, R = emusws, cl.ref()
+    R.ffref_sws_scale_planar.argtypes = [C.c_void_p] + [C.c_void_p, C.c_int] * 3 + [C.c_int, C.c_int] + [C.c_void_p, C.c_int] * 3
+    rnd = random.Random(77)
+    for it in range(40):
+        w, h = rnd.choice([16, 34, 64, 100]), rnd.choice([8, 16, 34, 48, 66])
+        dw, dh = (w, h) if it % 4 == 0 else (rnd.choice([8, 18, 32, 64, 100]), rnd.choice([8, 18, 32, 64, 100]))
+        if h > 2 * dh:
+            dh = (h // 2 + 2) & ~1                                         # steep vertical reductions trip the reference's own assert (swscale.c:474) when sliced
+        fl, df, ranges = rnd.choice([cl.SWS_BICUBIC, cl.SWS_BILINEAR, FATE, 0x10]), rnd.choice([0, cl.PIX_FMT_NV12]), rnd.choice([(0, 0), (0, 1), (1, 0)])
+        y, u, v = cl.yuv_frame(w, h, 7700 + it, "random")
+        cuts = sorted(set([0, h] + [2 * rnd.randrange(1, h // 2) for _ in range(rnd.randrange(1, 4))]))
+        bands = [(a, b - a) for a, b in zip(cuts[:-1], cuts[1:])]
+        cw, ch = (dw + 1) // 2, (dh + 1) // 2
+        mk = lambda: [np.full((dh, dw), 0xA5, np.uint8), np.full((ch, 2 * cw if df else cw), 0xA5, np.uint8), np.full((ch, cw), 0xA5, np.uint8)]
+        rp, gp, rr, gr = mk(), mk(), [], []
+        rc = R.ffref_sws_open_range(0, w, h, ranges[0], df, dw, dh, ranges[1], fl, 1)
+        ctx = _emu_ctx(L, w, h, 0, dw, dh, df, fl, ranges)
+        assert rc and ctx
+        for (sy, sh) in bands:
+            rr.append(R.ffref_sws_scale_planar(rc, y[sy:].ctypes.data, y.strides[0], u[sy // 2:].ctypes.data, u.strides[0], v[sy // 2:].ctypes.data, v.strides[0],
+                                               sy, sh, rp[0].ctypes.data, rp[0].strides[0], rp[1].ctypes.data, rp[1].strides[0], rp[2].ctypes.data, rp[2].strides[0]))
+        for rep in range(2):                                              # the library's context is reusable for the next picture
+            gr = [L.b200_sws_scale(ctx, (C.c_void_p * 4)(y[sy:].ctypes.data, u[sy // 2:].ctypes.data, v[sy // 2:].ctypes.data, None),
+                                   (C.c_int32 * 4)(y.strides[0], u.strides[0], v.strides[0], 0), sy, sh,
+                                   (C.c_void_p * 4)(gp[0].ctypes.data, gp[1].ctypes.data, gp[2].ctypes.data, None),
+                                   (C.c_int32 * 4)(gp[0].strides[0], gp[1].strides[0], gp[2].strides[0], 0)) for (sy, sh) in bands]
+            assert gr == rr and sum(gr) == dh, (it, bands, gr, rr)
+        R.ffref_sws_close(rc)
+        L.b200_sws_freeContext(ctx)
+        assert all(np.array_equal(a, b) for a, b in zip(gp[:2 if df else 3], rp[:2 if df else 3])), (it, w, h, dw, dh, hex(fl), df, ranges, bands)
+
+
 def test_sws_scaler_params(emusws):
     """sws_getContext's `param` (bicubic B / C, Gaussian exponent, Lanczos width, the experimental scaler's power) through
     b200_sws_getContext_params on the emulated device, against the checker and the compiled reference; a Lanczos width whose
