@@ -191,8 +191,9 @@ def test_planar_batch_device_and_errors(device):
         ref = cl.orc_sws_planar(w, h, dw, dh, FATE, *frames[i])
         for k in range(3):
             assert np.array_equal(got[k][i], ref[k]), (i, k)
-    with pytest.raises(fb.B200Error):                          # slices are not implemented for the planar destination
-        ctx.scale([Y[0], U[0], V[0]], [w, cw, cw], 0, 16, [np.zeros((dh, dw), np.uint8)] * 3, [dw, cdw, cdw])
+    planes = [np.zeros((dh, dw), np.uint8), np.zeros((cdh, cdw), np.uint8), np.zeros((cdh, cdw), np.uint8)]
+    with pytest.raises(fb.B200Error):                          # invalid slice parameters (odd start line), as scale_internal rejects them
+        ctx.scale([Y[0][17:], U[0][8:], V[0][8:]], [w, cw, cw], 17, 16, planes, [dw, cdw, cdw])
     ctx.free()
     rgb = sw.sws_getContext(device, w, h, 0, dw, dh, sw.AV_PIX_FMT_RGB24, FATE)
     with pytest.raises(fb.B200Error):

@@ -137,6 +137,27 @@ def test_sws_float_kernel_scalers(device):
 
 
 @isolated
+def test_sws_slice_calls_planar_destination(device):
+    """sws_scale() band by band into yuv420p / nv12: the lines add up, the planes equal the whole-frame result (the checker's), and
+    the per-call counts equal the reference's for the committed slice fixture geometry (64 x 48 source, tests/cases.py)"""
+    from ffmpeg_b200 import swscale as sw
+    from cases import FATE
+    for (w, h, dw, dh, fl, df, bands) in ((64, 48, 100, 70, FATE, 0, [(0, 16), (16, 8), (24, 24)]), (320, 180, 480, 270, cl.SWS_BICUBIC, cl.PIX_FMT_NV12, [(0, 64), (64, 116)]),
+                                          (64, 48, 64, 48, cl.SWS_BILINEAR, 0, [(0, 2), (2, 46)])):
+        y, u, v = cl.yuv_frame(w, h, 7800 + w, "random")
+        exp = cl.orc_sws_planar(w, h, dw, dh, fl, y, u, v, dst_fmt=df)
+        cw, ch = (dw + 1) // 2, (dh + 1) // 2
+        planes = [np.full((dh, dw), 0xA5, np.uint8), np.full((ch, 2 * cw if df else cw), 0xA5, np.uint8), np.full((ch, cw), 0xA5, np.uint8)]
+        ctx = sw.sws_getContext(device, w, h, 0, dw, dh, df, fl)
+        for rep in range(2):
+            rets = [ctx.scale([y[sy:], u[sy // 2:], v[sy // 2:]], [y.strides[0], u.strides[0], v.strides[0]], sy, sh, planes, [p.strides[0] for p in planes])
+                    for (sy, sh) in bands]
+            assert sum(rets) == dh and all(r >= 0 for r in rets), rets
+        ctx.free()
+        assert all(np.array_equal(a, b) for a, b in zip(planes, exp)), (w, h, dw, dh, hex(fl), df)
+
+
+@isolated
 def test_sws_scaler_params(device):
     """sws_getContext's `param`: only the host-side filter banks depend on it"""
     from cases import SWS_PARAM_CASES
