@@ -32,6 +32,7 @@ SWS_BICUBIC, SWS_ACCURATE_RND, SWS_BITEXACT = 4, 0x40000, 0x80000
 FLAGS_FATE = SWS_BICUBIC | SWS_ACCURATE_RND | SWS_BITEXACT
 MB_W, MB_H = 120, 68                          # 1080p macroblocks
 IDCT_FRAMES = 256                             # frames of 48 960 blocks per step (of the 10 000-frame stream)
+HEADLINE_KERNEL = "sws_vscale_rgb24_fast_kernel<LUMID=true,CFS4=true,RGB24>"
 METRIC = "4K frames/sec swscale yuv420p->rgb24; 8x8 IDCT blocks/sec; HBM GB/s vs peak"
 
 
@@ -157,12 +158,58 @@ def cpu_lib():
     return cl.oracle(), "port", "orc"
 
 
-def cpu_sws_fps(flags, seconds_budget=12.0, threads=None):
-    """frames/s of the reference's CPU path on 4K frames with `threads` host threads (ctypes releases the GIL)."""
+def usable_cpus():
+    """Host threads this process can really run at once: the scheduler affinity mask capped by the cgroup CPU quota (a leased box
+    often shows every core in os.cpu_count() while the container is limited to a fraction of them)."""
+    import math
+    try:
+        aff = len(os.sched_getaffinity(0))
+    except Exception:
+        aff = os.cpu_count() or 1
+    quota = None
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            quota = float(q) / float(per)
+    except Exception:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = q / per
+        except Exception:
+            pass
+    n = aff if quota is None else max(1, min(aff, int(math.ceil(quota))))
+    return n, {"os_cpu_count": os.cpu_count(), "affinity": aff, "cgroup_quota_cpus": quota}
+
+
+def run_threads(workers, seconds):
+    """workers: one callable per thread, each call returns the units it processed (ctypes releases the GIL inside the library).
+    Every thread loops until the deadline; returns (units per second, units, seconds)."""
+    counts = [0.0] * len(workers)
+    deadline = time.perf_counter() + seconds
+
+    def loop(i):
+        w = workers[i]
+        while True:
+            counts[i] += w()
+            if time.perf_counter() >= deadline:
+                break
+
+    ts = [threading.Thread(target=loop, args=(i,)) for i in range(len(workers))]
+    t0 = time.perf_counter()
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    dt = time.perf_counter() - t0
+    return sum(counts) / dt, sum(counts), dt
+
+
+def cpu_sws_workers(flags, threads):
     import numpy as np
     import cpulibs as cl
     lib, kind, pre = cpu_lib()
-    threads = threads or (os.cpu_count() or 1)
     y, u, v = cl.yuv_frame(W4K, H4K, 1, "random")
     out = [np.empty((H4K, W4K * 3), np.uint8) for _ in range(threads)]
     if pre == "ffref":
@@ -170,110 +217,219 @@ def cpu_sws_fps(flags, seconds_budget=12.0, threads=None):
     else:
         ctxs = [lib.orc_sws_open(W4K, H4K, W4K, H4K, flags) for _ in range(threads)]
 
-    def one(i):
-        if pre == "ffref":
-            lib.ffref_sws_scale(ctxs[i], cl.ptr(y), W4K, cl.ptr(u), W4K // 2, cl.ptr(v), W4K // 2, 0, H4K, cl.ptr(out[i]), W4K * 3)
-        else:
-            lib.orc_sws_scale(ctxs[i], cl.ptr(y), W4K, cl.ptr(u), W4K // 2, cl.ptr(v), W4K // 2, cl.ptr(out[i]), W4K * 3)
+    def mk(i):
+        def one():
+            if pre == "ffref":
+                lib.ffref_sws_scale(ctxs[i], cl.ptr(y), W4K, cl.ptr(u), W4K // 2, cl.ptr(v), W4K // 2, 0, H4K, cl.ptr(out[i]), W4K * 3)
+            else:
+                lib.orc_sws_scale(ctxs[i], cl.ptr(y), W4K, cl.ptr(u), W4K // 2, cl.ptr(v), W4K // 2, cl.ptr(out[i]), W4K * 3)
+            return 1
+        return one
 
-    one(0)                                       # warm-up
-    counts = [0] * threads
-    deadline = time.perf_counter() + seconds_budget
-
-    def worker(i):
-        while True:
-            one(i)
-            counts[i] += 1
-            if time.perf_counter() >= deadline:
-                break
-
-    ts = [threading.Thread(target=worker, args=(i,)) for i in range(threads)]
-    t0 = time.perf_counter()
-    for t in ts:
-        t.start()
-    for t in ts:
-        t.join()
-    dt = time.perf_counter() - t0
-    for c in ctxs:
-        (lib.ffref_sws_close if pre == "ffref" else lib.orc_sws_close)(c)
-    frames = sum(counts)
-    return frames / dt, {"kind": kind, "cores": threads,
-                         "sample": f"{frames} 4K frames on {threads} threads, {dt:.1f} s"}
+    def close():
+        for c in ctxs:
+            (lib.ffref_sws_close if pre == "ffref" else lib.orc_sws_close)(c)
+    return [mk(i) for i in range(threads)], close, "4K frames"
 
 
-def cpu_idct_bps(seconds_budget=4.0, threads=None):
+def cpu_idct_workers(threads, op=1):
     import numpy as np
     import cpulibs as cl
     from cases import idct_blocks
     lib, kind, pre = cpu_lib()
-    threads = threads or (os.cpu_count() or 1)
     n = MB_W * MB_H * 6
     blk0 = idct_blocks("dense", n, 1)
     off = (np.arange(n) * 8).astype(np.int64)
     fn = lib.ffref_idct_batch if pre == "ffref" else lib.orc_idct_batch
     bufs = [(blk0.copy(), np.zeros((8, n * 8), np.uint8)) for _ in range(threads)]
 
-    def one(i):
-        b, d = bufs[i]
-        b[:] = blk0                                 # the reference clobbers the coefficients
-        fn(1, cl.ptr(b, cl.i16p), n, cl.ptr(d), n * 8, cl.ptr(off, cl.i64p))
+    def mk(i):
+        def one():
+            b, d = bufs[i]
+            b[:] = blk0                                 # the reference clobbers the coefficients
+            fn(op, cl.ptr(b, cl.i16p), n, cl.ptr(d), n * 8, cl.ptr(off, cl.i64p))
+            return n
+        return one
+    return [mk(i) for i in range(threads)], (lambda: None), "8x8 blocks (one 1080p frame of 48 960 per call)"
 
-    one(0)
-    counts = [0] * threads
-    deadline = time.perf_counter() + seconds_budget
 
-    def worker(i):
-        while True:
-            one(i)
-            counts[i] += 1
-            if time.perf_counter() >= deadline:
-                break
+def cpu_qpel_workers(threads):
+    """one 1080p frame of 8160 16x16 operations per call: random quarter-pel position, put / avg, vectors within +-16 px"""
+    import numpy as np
+    import cpulibs as cl
+    lib, kind, pre = cpu_lib()
+    W, H, apron = 1920, 1088, 32
+    PW, PH = W + 2 * apron, H + 2 * apron
+    rng = np.random.default_rng(3)
+    src = rng.integers(0, 256, (PH, PW), dtype=np.uint8)
+    by, bx = np.meshgrid(np.arange(H // 16), np.arange(W // 16), indexing="ij")
+    base = (by * 16 + apron) * PW + bx * 16 + apron
+    dx, dy = rng.integers(-16, 17, base.shape), rng.integers(-16, 17, base.shape)
+    doff = base.reshape(-1).astype(np.int64)
+    soff = (base + dy * PW + dx).reshape(-1).astype(np.int64)
+    ops = (rng.integers(0, 2, doff.size) | (rng.integers(0, 16, doff.size) << 3)).astype(np.uint8)
+    n = int(doff.size)
+    fn = lib.ffref_h264qpel_batch if pre == "ffref" else lib.orc_h264qpel_batch
+    dsts = [rng.integers(0, 256, (PH, PW), dtype=np.uint8) for _ in range(threads)]
 
-    ts = [threading.Thread(target=worker, args=(i,)) for i in range(threads)]
-    t0 = time.perf_counter()
-    for t in ts:
-        t.start()
-    for t in ts:
-        t.join()
-    dt = time.perf_counter() - t0
-    return n * sum(counts) / dt, {"kind": kind, "cores": threads, "sample": f"{sum(counts)} x {n} blocks on {threads} threads, {dt:.1f} s"}
+    def mk(i):
+        def one():
+            fn(n, cl.ptr(ops), cl.ptr(dsts[i]), cl.ptr(doff, cl.i64p), cl.ptr(src), cl.ptr(soff, cl.i64p), PW)
+            return n
+        return one
+    return [mk(i) for i in range(threads)], (lambda: None), "16x16 blocks (one 1080p frame of 8160 per call)"
+
+
+def cpu_esa_workers(threads):
+    """one macroblock row (240 blocks x up to 4225 candidates) of a 4K frame pair per call; 135 rows = one pair"""
+    import numpy as np
+    import cpulibs as cl
+    lib, kind, pre = cpu_lib()
+    rng = np.random.default_rng(4)
+    cur = rng.integers(0, 256, (H4K, W4K), dtype=np.uint8)
+    ref = np.ascontiguousarray(np.roll(cur, (7, -13), (0, 1)))
+    rows = H4K // 16
+    nmb = rows * (W4K // 16)
+    fn = lib.ffref_esa_frame if pre == "ffref" else lib.orc_esa_frame
+    outs = [(np.zeros((nmb, 2), np.int32), np.zeros(nmb, np.uint64)) for _ in range(threads)]
+    nxt = [i % rows for i in range(threads)]
+
+    def mk(i):
+        def one():
+            r = nxt[i]
+            nxt[i] = (r + threads) % rows
+            fn(cl.ptr(cur), cl.ptr(ref), W4K, W4K, H4K, 16, 32, r, r + 1, cl.ptr(outs[i][0], cl.i32p), cl.ptr(outs[i][1], cl.u64p))
+            return 1.0 / rows
+        return one
+    return [mk(i) for i in range(threads)], (lambda: None), "4K frame pairs (one macroblock row = 1/135 pair per call)"
+
+
+def cpu_tx_workers(threads, typ, n):
+    """256 transforms per call; typ 0: forward complex FFT of n points, typ 1: inverse MDCT of len n (scale 1/n)"""
+    import numpy as np
+    import cpulibs as cl
+    lib, kind, pre = cpu_lib()
+    cnt = 256
+    rng = np.random.default_rng(5)
+    op, cls, run = (lib.ffref_tx_open, lib.ffref_tx_close, lib.ffref_tx_run) if pre == "ffref" else (lib.orc_tx_open, lib.orc_tx_close, lib.orc_tx_run)
+    hs = [op(typ, 1 if typ == 1 else 0, n, 1.0 / n if typ == 1 else 1.0, 0) for _ in range(threads)]
+    ie = 2 * n if typ == 0 else n
+    xin = [rng.random((cnt, ie), dtype=np.float32) for _ in range(threads)]
+    xout = [np.zeros((cnt, ie), np.float32) for _ in range(threads)]
+
+    def mk(i):
+        def one():
+            run(hs[i], xout[i].ctypes.data, xin[i].ctypes.data, 8 if typ == 0 else 4, cnt, 4 * ie, 4 * ie)
+            return cnt
+        return one
+
+    def close():
+        for h in hs:
+            cls(h)
+    return [mk(i) for i in range(threads)], close, "transforms (256 per call)"
+
+
+def cpu_arm(make, seconds_all, seconds_one, unit):
+    """One path on all usable host threads and on one thread; returns the cpu_baseline object."""
+    _, kind, _ = cpu_lib()
+    n, info = usable_cpus()
+    res = {}
+    for threads, secs in ((n, seconds_all), (1, seconds_one)):
+        workers, close, what = make(threads)
+        workers[0]()                                    # warm-up
+        rate, units, dt = run_threads(workers, secs)
+        close()
+        res[threads] = (rate, f"{units:.4g} {what} on {threads} thread{'s' if threads > 1 else ''}, {dt:.1f} s")
+        if n == 1:
+            break
+    out = {"value": res[n][0], "unit": unit, "cores": n, "kind": kind, "sample": res[n][1], "cpu_limits": info}
+    one = res.get(1, res[n])
+    out["single_thread"] = {"value": one[0], "unit": unit, "sample": one[1]}
+    return out
+
+
+def cpu_baselines_all(scale=1.0, with_sws=True):
+    """The reference's CPU path for every BASELINE config, bounded samples (about 35 s in all at scale 1)."""
+    out = {}
+    if with_sws:
+        out["sws"] = cpu_arm(lambda t: cpu_sws_workers(FLAGS_FATE, t), 10.0 * scale, 3.0 * scale, "frames/s")
+    out["idct_put"] = cpu_arm(lambda t: cpu_idct_workers(t, 1), 2.5 * scale, 1.2 * scale, "blocks/s")
+    out["idct_add"] = cpu_arm(lambda t: cpu_idct_workers(t, 2), 2.0 * scale, 1.0 * scale, "blocks/s")
+    out["h264qpel"] = cpu_arm(cpu_qpel_workers, 2.5 * scale, 1.2 * scale, "16x16 blocks/s")
+    out["me_esa"] = cpu_arm(cpu_esa_workers, 3.0 * scale, 1.5 * scale, "4K frame pairs/s")
+    for typ, nm in ((0, "fft"), (1, "imdct")):
+        for n in (1024, 2048):
+            out[f"{nm}{n}"] = cpu_arm(lambda t: cpu_tx_workers(t, typ, n), 1.5 * scale, 0.8 * scale, "transforms/s")
+    return out
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    fps_list = []
-    info = None
-    for _ in range(args.warmup if args.warmup < 1 else 1):
-        cpu_sws_fps(FLAGS_FATE, seconds_budget=2.0)
+    n, info = usable_cpus()
     t_all = time.perf_counter()
+    workers, close, what = cpu_sws_workers(FLAGS_FATE, n)
+    for _ in range(min(args.warmup, 1)):
+        workers[0]()
     steps = max(1, min(args.steps, 3))             # bounded: each step is itself a multi-second sample
+    rates, frames, secs = [], 0.0, 0.0
     for _ in range(steps):
-        fps, info = cpu_sws_fps(FLAGS_FATE, seconds_budget=6.0)
-        fps_list.append(fps)
-    fps = sum(fps_list) / len(fps_list)
-    bps, iinfo = cpu_idct_bps()
+        r, u, dt = run_threads(workers, 6.0)
+        rates.append(r); frames += u; secs += dt
+    close()
+    fps = sum(rates) / len(rates)
+    _, kind, _ = cpu_lib()
+    cb = {"value": fps, "unit": "frames/s", "cores": n, "kind": kind, "cpu_limits": info,
+          "sample": f"{frames:.0f} 4K frames on {n} threads, {secs:.1f} s ({steps} steps)"}
+    others = cpu_baselines_all(scale=0.7, with_sws=False)
+    cb["others"] = {k: {"value": v["value"], "unit": v["unit"], "single_thread": v["single_thread"]["value"]} for k, v in others.items()}
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 * BATCH / fps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": f"swscale {W4K}x{H4K} yuv420p->rgb24 flags=bicubic+accurate_rnd+bitexact, batch={BATCH} (bounded CPU sample per step)",
                    "timed_steps": steps},
-        "cpu_baseline": dict(info, value=fps, unit="frames/s"),
+        "cpu_baseline": cb,
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "idct": {"value": bps, "unit": "blocks/s", "cpu_baseline": dict(iinfo, value=bps, unit="blocks/s")},
+        "idct": {"value": others["idct_put"]["value"], "unit": "blocks/s"},
         "wall_s": time.perf_counter() - t_all,
     }
     print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
-def extra_paths(args, dev, stream, g, world, barrier, reduce_max, peak):
-    """The other rows of SURVEY.md 8(d): ESA motion search, H.264 qpel MC and float FFT / iMDCT, each on a bounded batch."""
+def host_timed(call, steps, barrier, reduce_max):
+    """Wall-clock of `steps` calls of a synchronous HOST-buffer entry point (it returns after its last D2H), max over ranks."""
+    import torch
+    call()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        call()
+    torch.cuda.synchronize()
+    return reduce_max(time.perf_counter() - t0) / steps
+
+
+def pinned_like(t):
+    import torch
+    h = torch.empty(t.shape, dtype=t.dtype).pin_memory()
+    h.copy_(t)
+    return h
+
+
+def extra_paths(args, dev, stream, g, world, barrier, reduce_max, peak, devidx):
+    """The other rows of SURVEY.md 8(d): ESA motion search, H.264 qpel MC and float FFT / iMDCT, each on a bounded batch, each with
+    its device-resident number, its roofline fraction and an end-to-end number through the HOST-buffer entry point."""
     import torch
     from ffmpeg_b200 import me_cmp, pel, tx, idctdsp
     out = {}
     steps = max(2, min(args.steps, 5))
+    sm_count = torch.cuda.get_device_properties(devidx).multi_processor_count
+    sm_max_mhz = 1965.0
+    try:
+        sm_max_mhz = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["sm_max_mhz"])
+    except Exception:
+        pass
 
     def timed(call):
         with torch.cuda.stream(stream):
@@ -298,11 +454,30 @@ def extra_paths(args, dev, stream, g, world, barrier, reduce_max, peak):
         mv = torch.zeros((npairs, nmb, 2), dtype=torch.int32, device="cuda")
         cost = torch.zeros((npairs, nmb), dtype=torch.int64, device="cuda")
     ms = timed(lambda: me_cmp.me_esa_device(dev, cur, ref, W4K, W4K, H4K, W4K * H4K, npairs, 16, 32, mv, cost))
-    absdiff = 32400.0 * 4225 * 256                   # per pair (interior blocks; border windows are clipped, so this is an upper bound)
+    # algorithmic work: every candidate the clipped windows hold (exact count; 4225 per block only away from the frame borders)
+    cx = sum(min(W4K - 16, x + 32) - max(0, x - 32) + 1 for x in range(0, W4K, 16))
+    cy = sum(min(H4K - 16, y + 32) - max(0, y - 32) + 1 for y in range(0, H4K, 16))
+    absdiff = float(cx) * cy * 256                   # abs-diff-accumulates per pair (3.40e10; SURVEY's 3.50e10 ignores the clipping)
+    # integer peak: VABSDIFF4.U8.ACC does 4 byte lanes per thread on the ALU pipe, 16 threads / clk / SM sub-partition = 64 / clk / SM
+    ipeak = sm_count * 64 * 4 * sm_max_mhz * 1e6 / 1e12
+    ach = absdiff * npairs / (ms / 1e3) / 1e12
     out["me_esa"] = {"value": world * npairs / (ms / 1e3), "unit": "4K frame pairs/s", "ms_per_step": ms,
                      "config": f"SAD full search 16x16 +-32, {npairs} 4K pairs per step",
-                     "roofline": {"bound": "integer alu", "achieved": absdiff * npairs / (ms / 1e3) / 1e12, "unit": "T abs-diff/s",
+                     "roofline": {"bound": "integer alu", "achieved": ach, "peak": ipeak, "unit": "T abs-diff/s", "frac": ach / ipeak,
+                                  "peak_source": f"{sm_count} SMs x 64 VABSDIFF4/clk x 4 bytes x {sm_max_mhz:.0f} MHz (MEASURED_PEAKS sm_max_mhz)",
                                   "hbm_GBps": 2 * W4K * H4K * npairs / (ms / 1e3) / 1e9, "hbm_frac": 2 * W4K * H4K * npairs / (ms / 1e3) / 1e9 / peak}}
+    try:
+        hcur, href = pinned_like(cur.cpu()), pinned_like(ref.cpu())
+        hmv = torch.zeros((npairs, nmb, 2), dtype=torch.int32).pin_memory()
+        hcost = torch.zeros((npairs, nmb), dtype=torch.int64).pin_memory()
+        dt = host_timed(lambda: me_cmp.me_esa_host(dev, hcur, href, W4K, W4K, H4K, W4K * H4K, npairs, 16, 32, hmv, hcost), 2, barrier, reduce_max)
+        stream.synchronize()
+        out["me_esa"]["e2e"] = {"value": world * npairs / dt, "unit": "4K frame pairs/s", "h2d_bytes_per_step": 2 * W4K * H4K * npairs,
+                                "d2h_bytes_per_step": nmb * 16 * npairs, "api": "b200_me_esa_host",
+                                "matches_device_path": bool(torch.equal(hmv, mv.cpu()) and torch.equal(hcost, cost.cpu()))}
+        del hcur, href, hmv, hcost
+    except Exception as ex:
+        out["me_esa"]["e2e"] = {"value": None, "error": str(ex)[:160]}
     del cur, ref, mv, cost
 
     # --- config 3 (MC half): H.264 qpel 16x16, random quarter-pel vectors within +-16 px, random put/avg, 1080p frames
@@ -328,6 +503,26 @@ def extra_paths(args, dev, stream, g, world, barrier, reduce_max, peak):
                        "config": f"{nfr} 1080p frames x 8160 MBs, random qpel position and put/avg",
                        "roofline": {"bound": "hbm", "achieved": qbytes * nops / (ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
                                     "frac": qbytes * nops / (ms / 1e3) / 1e9 / peak, "bytes_per_block": qbytes}}
+    try:
+        hsrc, hdst0 = pinned_like(refp.cpu()), dstp.cpu()
+        hdst = pinned_like(hdst0)
+        hops, hdo, hso = ops.cpu().numpy(), doff.cpu().numpy(), soff.cpu().numpy()
+        import numpy as np
+        begin = (np.arange(nfr + 1, dtype=np.int64) * (nops // nfr))
+        call = lambda: pel.h264qpel_frames_host(dev, nfr, PH * PW, begin, hops, hdst, hdo, hsrc, hso, PW)
+        dt = host_timed(call, 3, barrier, reduce_max)
+        hdst.copy_(hdst0)                               # avg operations accumulate: compare one fresh pass with one device pass
+        call()
+        with torch.cuda.stream(stream):
+            dchk = hdst0.cuda()
+            pel.h264qpel_batch_device(dev, nops, ops, dchk, doff, refp, soff, PW)
+        stream.synchronize()
+        out["h264qpel"]["e2e"] = {"value": world * nops / dt, "unit": "16x16 blocks/s", "h2d_bytes_per_step": 2 * nfr * PH * PW + 17 * nops,
+                                  "d2h_bytes_per_step": nfr * PH * PW, "api": "b200_h264qpel_frames_host",
+                                  "matches_device_path": bool(torch.equal(dchk.cpu(), hdst))}
+        del hsrc, hdst, hdst0, dchk
+    except Exception as ex:
+        out["h264qpel"]["e2e"] = {"value": None, "error": str(ex)[:160]}
     del refp, dstp, doff, soff, ops
 
     # --- widening row: the chroma half of the same stream, h264chroma mc8 8x8 on the two 960x544 chroma planes
@@ -401,6 +596,30 @@ def extra_paths(args, dev, stream, g, world, barrier, reduce_max, peak):
         txr[f"fft{n}"] = {"value": world * cnt / (ms / 1e3), "unit": "transforms/s", "ms_per_step": ms, "batch": cnt,
                           "roofline": {"bound": "hbm", "achieved": b * cnt / (ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
                                        "frac": b * cnt / (ms / 1e3) / 1e9 / peak, "bytes_per_transform": b}}
+        ecnt = cnt // 4
+        try:
+            c = tx.av_tx_init(tx.AV_TX_FLOAT_FFT, 0, n, device=dev)
+            hx = pinned_like(x[:ecnt].cpu())
+            hy = torch.empty_like(hx).pin_memory()
+            dt = host_timed(lambda: c.batch_host(hy, hx, 8, ecnt, 8 * n, 8 * n), 3, barrier, reduce_max)
+            with torch.cuda.stream(stream):
+                c.batch_device(y, x, 8, ecnt, 8 * n, 8 * n)
+            stream.synchronize()
+            txr[f"fft{n}"]["e2e"] = {"value": world * ecnt / dt, "unit": "transforms/s", "h2d_bytes_per_step": 8 * n * ecnt,
+                                     "d2h_bytes_per_step": 8 * n * ecnt, "api": "b200_tx_batch_host",
+                                     "matches_device_path": bool(torch.equal(y[:ecnt].cpu(), hy))}
+            c.uninit()
+            c = tx.av_tx_init(tx.AV_TX_FLOAT_MDCT, 1, n, scale=1.0 / n, device=dev)
+            hxi = pinned_like(x.view(-1)[:ecnt * n].view(ecnt, n).cpu())
+            hyi = torch.empty_like(hxi).pin_memory()
+            dt = host_timed(lambda: c.batch_host(hyi, hxi, 4, ecnt, 4 * n, 4 * n), 3, barrier, reduce_max)
+            e2e_imdct = {"value": world * ecnt / dt, "unit": "transforms/s", "h2d_bytes_per_step": 4 * n * ecnt,
+                         "d2h_bytes_per_step": 4 * n * ecnt, "api": "b200_tx_batch_host"}
+            c.uninit()
+            del hx, hy, hxi, hyi
+        except Exception as ex:
+            txr[f"fft{n}"]["e2e"] = {"value": None, "error": str(ex)[:160]}
+            e2e_imdct = {"value": None, "error": str(ex)[:160]}
         c = tx.av_tx_init(tx.AV_TX_FLOAT_RDFT, 0, n, scale=1.0, device=dev)      # r2c: n floats -> n/2+1 complex
         ms = timed(lambda: c.batch_device(y, x, 4, cnt, 8 * n, 8 * n))
         c.uninit()
@@ -414,20 +633,21 @@ def extra_paths(args, dev, stream, g, world, barrier, reduce_max, peak):
         b = 8 * n
         txr[f"imdct{n}"] = {"value": world * cnt / (ms / 1e3), "unit": "transforms/s", "ms_per_step": ms, "batch": cnt,
                             "roofline": {"bound": "hbm", "achieved": b * cnt / (ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
-                                         "frac": b * cnt / (ms / 1e3) / 1e9 / peak, "bytes_per_transform": b}}
+                                         "frac": b * cnt / (ms / 1e3) / 1e9 / peak, "bytes_per_transform": b},
+                            "e2e": e2e_imdct}
         del x, y
     out["tx"] = txr
     return out
 
 
 
-def run_b200(args, rank, world, local_rank):
+def run_b200(args, rank, world, local_rank, placement=None):
     import torch
     import torch.distributed as dist
     import ffmpeg_b200 as fb
     from ffmpeg_b200 import swscale as sw, idctdsp
 
-    torch.cuda.set_device(local_rank)
+    torch.cuda.set_device(local_rank)                     # local_rank here = the CUDA device index chosen for this rank (pick_devices)
     stream = torch.cuda.Stream()
     dev = fb.Device(local_rank, stream=stream.cuda_stream)
     peak, peak_src = measured_peaks()
@@ -435,7 +655,7 @@ def run_b200(args, rank, world, local_rank):
     def barrier():
         torch.cuda.synchronize()
         if world > 1:
-            dist.barrier()
+            dist.barrier(device_ids=[local_rank])
         torch.cuda.synchronize()
 
     def reduce_max(x):
@@ -489,8 +709,9 @@ def run_b200(args, rank, world, local_rank):
     fps = world * BATCH * args.steps / (total_ms / 1e3)
     ach = FRAME_BYTES * BATCH / (kern_ms / 1e3) / 1e9
     roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src,
-            "kernel": "sws_vscale_rgb24_fast_kernel<LUMID=true,CFS4=true,RGB24>", "bytes_per_launch": FRAME_BYTES * BATCH,
-            "launch_ms": kern_ms, "traffic": ncu_traffic("sws_vscale_rgb24_kernel")}
+            "kernel": HEADLINE_KERNEL, "bytes_per_launch": FRAME_BYTES * BATCH,
+            "launch_ms": kern_ms, "traffic": ncu_traffic("sws_vscale_rgb24_kernel"),
+            "traffic_source": "constant from the committed ncu --set full capture (profiles/ncu_traffic.json), not measured in this run"}
     # variant: flags=bicubic only (the reference takes its unscaled LUT converter; different, cheaper arithmetic)
     t2, k2, _ = timed_sws(SWS_BICUBIC, max(3, args.steps // 2), args.warmup, False)
     fps2 = world * BATCH * max(3, args.steps // 2) / (t2 / 1e3)
@@ -590,25 +811,78 @@ def run_b200(args, rank, world, local_rank):
                       "roofline": {"bound": "hbm", "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak,
                                    "kernel": f"idct_mb420_kernel<{name}>", "bytes_per_block": bpb,
                                    "traffic": ncu_traffic(f"idct8x8_{name}")}}
+    # e2e: coefficient blocks in pinned host memory -> b200_idct_mb420_host -> reconstructed planes back in host memory
+    EF = 64
+    for kind, name in ((idctdsp.IDCT_PUT, "put"), (idctdsp.IDCT_ADD, "add")):
+        try:
+            per = MB_W * MB_H * 6
+            hblk = pinned_like(blocks[:per * EF].cpu())
+            hpl = [pinned_like(p[:EF].cpu()) for p in planes]
+            hp0 = [h.clone() for h in hpl] if kind == idctdsp.IDCT_ADD else None
+            call = lambda: idctdsp.idct_mb420_host(dev, kind, hblk.data_ptr(), MB_W, MB_H, EF, [h.data_ptr() for h in hpl], ls, fs)
+            dt = host_timed(call, 3, barrier, reduce_max)
+            if hp0 is not None:                            # add accumulates: compare one fresh pass
+                for h, h0 in zip(hpl, hp0):
+                    h.copy_(h0)
+                call()
+            with torch.cuda.stream(stream):
+                chk = [(h0 if hp0 is not None else h).cuda() for h, h0 in zip(hpl, hp0 or hpl)]
+                idctdsp.idct_mb420_device(dev, kind, blocks, MB_W, MB_H, EF, chk, ls, fs)
+            stream.synchronize()
+            pbytes = sum(fs) * EF
+            idct[name]["e2e"] = {"value": world * per * EF / dt, "unit": "blocks/s", "h2d_bytes_per_step": per * EF * 128 + (pbytes if kind == idctdsp.IDCT_ADD else 0),
+                                 "d2h_bytes_per_step": pbytes, "api": "b200_idct_mb420_host", "frames": EF,
+                                 "matches_device_path": all(bool(torch.equal(c.cpu(), h)) for c, h in zip(chk, hpl))}
+            del hblk, hpl, hp0, chk
+        except Exception as ex:
+            idct[name]["e2e"] = {"value": None, "error": str(ex)[:160]}
     del blocks, planes
-    results.update(extra_paths(args, dev, stream, g, world, barrier, reduce_max, peak))
+    results.update(extra_paths(args, dev, stream, g, world, barrier, reduce_max, peak, local_rank))
     clocks = sampler.stop()
 
-    # ---- mux boundary (N > 1 only): gather a slice of every rank's output on rank 0 over NCCL/NVLink, timed separately
+    # ---- mux boundary (N > 1 only): every rank's finished rgb24 frames are collected on rank 0 over NCCL / NVLink (SURVEY 8e:
+    # throughput both without and with that gather).  The collect of batch k runs on a side stream while batch k+1 converts.
     mux = None
     if world > 1:
-        from ffmpeg_b200.sharding import gather_to_mux
-        gf = 32
-        torch.cuda.synchronize()
-        gather_to_mux(OUT[:2], dst=0)                       # warm-up (communicator set-up)
+        from ffmpeg_b200.sharding import MuxGather
+        ctx = sw.sws_getContext(dev, W4K, H4K, sw.AV_PIX_FMT_YUV420P, W4K, H4K, sw.AV_PIX_FMT_RGB24, FLAGS_FATE)
+        with torch.cuda.stream(stream):
+            OUT2 = torch.empty_like(OUT)
+        outs = [OUT, OUT2]
+        mg = MuxGather(BATCH, (H4K, W4K * 3), torch.uint8, torch.device("cuda", local_rank), dst=0)
+        gsteps = max(2, min(args.steps, 4))
+
+        def one(k):
+            o = outs[k & 1]
+            with torch.cuda.stream(stream):
+                mg.wait(stream)                             # the buffer being overwritten two batches later was sent one batch ago
+                ctx.scale_batch_device([Y, U, V], sstr, sfs, o, W4K * 3, W4K * H4K * 3, BATCH)
+                ev = torch.cuda.Event()
+                ev.record(stream)
+            mg.start(o, after=ev)
+        one(0)                                              # warm-up: communicator set-up
+        mg.wait(stream)
         barrier()
-        t0 = time.perf_counter()
-        got = gather_to_mux(OUT[:gf], dst=0)
-        torch.cuda.synchronize()
-        dt = reduce_max(time.perf_counter() - t0)
-        mux = {"frames_per_rank": gf, "ms": dt * 1e3, "GBps_into_rank0": (world - 1) * gf * FRAME_BYTES_OUT / dt / 1e9,
-               "note": "optional collect of finished rgb24 frames at the muxing rank; not part of `value`"}
-        del got
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+        for k in range(gsteps):
+            one(k + 1)
+        with torch.cuda.stream(stream):
+            mg.wait(stream)
+            e1.record(stream)
+        barrier()
+        gms = reduce_max(e0.elapsed_time(e1)) / gsteps
+        ok = None
+        if rank == 0:                                       # spot check: rank 0's own slot equals its last batch
+            ok = bool(torch.equal(mg.out[BATCH - 1], outs[gsteps & 1][BATCH - 1]))
+        mux = {"value_with_gather": world * BATCH / (gms / 1e3), "unit": "frames/s", "ms_per_step": gms, "steps": gsteps,
+               "GBps_into_rank0": (world - 1) * BATCH * FRAME_BYTES_OUT / (gms / 1e3) / 1e9, "frames_per_rank": BATCH,
+               "own_slot_matches": ok,
+               "note": "every rank's 256 rgb24 frames per step land on rank 0 (NCCL send/recv on a side stream, overlapped with the next "
+                       "batch); bounded by rank 0's NVLink ingest (measured peer copy 770 GB/s = 30.9 k 4K rgb24 frames/s), not by the kernels"}
+        ctx.free()
+        del mg, OUT2, outs
 
     # ---- e2e: the C-ABI host entry point with pinned host buffers (H2D + kernels + D2H inside the timed region)
     e2e = None
@@ -646,13 +920,32 @@ def run_b200(args, rank, world, local_rank):
         e2e = {"value": None, "unit": "frames/s", "error": str(ex)[:200]}
 
     cpu = None
+    cpu_all = {}
     if rank == 0 and world == 1:
-        v, info = cpu_sws_fps(FLAGS_FATE, seconds_budget=10.0)
-        cpu = dict(info, value=v, unit="frames/s")
-        v1, info1 = cpu_sws_fps(FLAGS_FATE, seconds_budget=3.0, threads=1)     # one thread beside all threads
-        cpu["single_thread"] = {"value": v1, "unit": "frames/s", "sample": info1["sample"]}
-        bv, binfo = cpu_idct_bps()
-        idct["cpu_baseline"] = dict(binfo, value=bv, unit="blocks/s")
+        cpu_all = cpu_baselines_all()
+        cpu = cpu_all.pop("sws")
+        idct["put"]["cpu_baseline"] = cpu_all["idct_put"]
+        idct["add"]["cpu_baseline"] = cpu_all["idct_add"]
+        results["h264qpel"]["cpu_baseline"] = cpu_all["h264qpel"]
+        results["me_esa"]["cpu_baseline"] = cpu_all["me_esa"]
+        for k in ("fft1024", "fft2048", "imdct1024", "imdct2048"):
+            results["tx"][k]["cpu_baseline"] = cpu_all[k]
+
+    # the driver's record keeps the contract keys whole and only the names of the others: the five BASELINE configs are summarised
+    # inside `roofline`, `cpu_baseline` and `e2e` (full entries stay under their own keys)
+    def brief(d, keys):
+        return {k: d[k] for k in keys if d and k in d}
+    per_cfg = {"idct_put": idct["put"], "idct_add": idct["add"], "h264qpel": results["h264qpel"], "me_esa": results["me_esa"],
+               "fft1024": results["tx"]["fft1024"], "fft2048": results["tx"]["fft2048"],
+               "imdct1024": results["tx"]["imdct1024"], "imdct2048": results["tx"]["imdct2048"]}
+    roof["others"] = {k: dict(brief(v["roofline"], ("bound", "achieved", "peak", "unit", "frac")), value=v["value"], value_unit=v["unit"])
+                      for k, v in per_cfg.items()}
+    if e2e is not None:
+        e2e["others"] = {k: brief(v.get("e2e"), ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step", "matches_device_path", "error"))
+                         for k, v in per_cfg.items()}
+    if cpu is not None:
+        cpu["others"] = {k: {"value": v["value"], "unit": v["unit"], "cores": v["cores"], "single_thread": v["single_thread"]["value"]}
+                         for k, v in cpu_all.items()}
 
     if rank == 0:
         line = {
@@ -663,10 +956,58 @@ def run_b200(args, rank, world, local_rank):
                        "l2": "inputs (3.2 GB) and outputs (6.4 GB) per step exceed L2 (126 MB): no flush needed",
                        "sharding": "frames of the batch are independent; each rank converts its own batch, no collective on the data path"},
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "value_with_gather": mux["value_with_gather"] if mux else None, "placement": placement,
             "idct": idct, "mux_gather": mux, **results,
         }
         emit_line(line)
     dev.close()
+
+
+def gpu_inventory():
+    """[(cuda index, numa node, used MiB or None)] of every GPU this process may index, without creating a CUDA context."""
+    import torch
+    inv = []
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+    except Exception:
+        pynvml = None
+    for i in range(torch.cuda.device_count()):
+        pr = torch.cuda.get_device_properties(i)
+        bus = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node, used = -1, None
+        try:
+            node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        except Exception:
+            pass
+        if pynvml is not None:
+            try:
+                h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+                used = pynvml.nvmlDeviceGetMemoryInfo(h).used // (1 << 20)
+            except Exception:
+                pass
+        inv.append((i, node, used))
+    return inv
+
+
+def pick_devices(world):
+    """Rank -> CUDA device for this node.  When more GPUs are visible than ranks (an 8-GPU box running N = 2 or 4), spread the ranks
+    over the host's NUMA nodes so that the end-to-end legs use every socket's memory and PCIe root (ffmpeg_b200.sharding.spread_over_numa);
+    GPUs that already hold memory (another tenant) are left alone.  Otherwise rank r uses device r.  B200_BENCH_SPREAD=0 disables it."""
+    import torch
+    from ffmpeg_b200.sharding import spread_over_numa
+    ident = list(range(world))
+    if os.environ.get("B200_BENCH_SPREAD", "1") == "0" or torch.cuda.device_count() <= world:
+        return ident, "rank r -> device r"
+    try:
+        inv = gpu_inventory()
+        free = [(i, node) for i, node, used in inv if used is not None and used < 2048]
+        if len(free) < world or len({n for _, n in free}) < 2:
+            return ident, "rank r -> device r (no second NUMA node with idle GPUs)"
+        m = spread_over_numa(free, world)
+        return m, "ranks spread over NUMA nodes: " + ", ".join(f"r{r}->gpu{d}(node {dict(free)[d]})" for r, d in enumerate(m))
+    except Exception as ex:
+        return ident, f"rank r -> device r (inventory failed: {str(ex)[:80]})"
 
 
 def main():
@@ -691,10 +1032,18 @@ def main():
         sys.stdout.flush()
         _STDOUT_FD = os.dup(1)
         os.dup2(2, 1)
+        # rank 0 decides the placement before any CUDA context exists and tells the others over gloo; NCCL then comes up on the
+        # chosen devices (one process per GPU, single node)
+        dist.init_process_group("cpu:gloo,cuda:nccl")
+        box = [pick_devices(world) if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        mapping, placement = box[0]
+        local_rank = int(mapping[rank])
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    else:
+        placement = "single GPU"
     try:
-        run_b200(args, rank, world, local_rank)
+        run_b200(args, rank, world, local_rank, placement)
     finally:
         if world > 1:
             import torch.distributed as dist

@@ -101,7 +101,13 @@ B200Device *b200_default_device()
 void *b200_scratch(B200Device *d, size_t bytes)
 {
     if (d->scratch_bytes >= bytes) return d->scratch;
-    if (d->scratch) { cudaStreamSynchronize(d->stream); cudaFree(d->scratch); d->scratch = nullptr; d->scratch_bytes = 0; }
+    if (d->scratch) {
+        // nothing may still read or write the old buffer: the caller's stream and the three pipeline streams (an error return from a
+        // *_batch_host call can leave copies in flight there)
+        cudaStreamSynchronize(d->stream);
+        for (int i = 0; i < B200Device::kPipe; i++) if (d->pipe[i]) cudaStreamSynchronize(d->pipe[i]);
+        cudaFree(d->scratch); d->scratch = nullptr; d->scratch_bytes = 0;
+    }
     size_t want = bytes + (bytes >> 2) + 4096;
     if (cudaMalloc(&d->scratch, want) != cudaSuccess) { b200_set_error("cudaMalloc(%zu) failed", want); return nullptr; }
     d->scratch_bytes = want;
@@ -111,7 +117,11 @@ void *b200_scratch(B200Device *d, size_t bytes)
 void *b200_pinned(B200Device *d, size_t bytes)
 {
     if (d->pinned_bytes >= bytes) return d->pinned;
-    if (d->pinned) { cudaStreamSynchronize(d->stream); cudaFreeHost(d->pinned); d->pinned = nullptr; d->pinned_bytes = 0; }
+    if (d->pinned) {
+        cudaStreamSynchronize(d->stream);
+        for (int i = 0; i < B200Device::kPipe; i++) if (d->pipe[i]) cudaStreamSynchronize(d->pipe[i]);
+        cudaFreeHost(d->pinned); d->pinned = nullptr; d->pinned_bytes = 0;
+    }
     size_t want = bytes + (bytes >> 2) + 4096;
     if (cudaMallocHost(&d->pinned, want) != cudaSuccess) { b200_set_error("cudaMallocHost(%zu) failed", want); return nullptr; }
     d->pinned_bytes = want;

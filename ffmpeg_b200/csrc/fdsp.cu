@@ -134,6 +134,7 @@ double host_op(int op, void *dst, const void *src0, const void *src1, const void
     const size_t nd = dot ? 1 : op == B200_FDSP_VECTOR_FMUL_WINDOW ? 2 * (size_t)len : (size_t)len;
     const size_t n2 = op == B200_FDSP_VECTOR_FMUL_WINDOW ? 2 * (size_t)len : (size_t)len;
     const size_t seg = ((n2 * es) + 255) & ~(size_t)255;
+    B200_LOCK_DEVICE(dev);      // scratch + stream are per device: one host-pointer call at a time (released on return)
     uint8_t *scr = (uint8_t *)b200_scratch(dev, 4 * seg);
     if (!scr) die("scratch");
     cudaStream_t st = dev->stream;

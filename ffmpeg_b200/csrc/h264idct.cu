@@ -155,8 +155,8 @@ void host_fn(uint8_t *dst, int16_t *block, ptrdiff_t stride)
     constexpr int N = (KIND & 1) ? 8 : 4, NC = N * N;
     B200Device *dev = b200_default_device();
     if (!dev) die("no device");
-    if (stride < 0) die("negative stride");
     if (cudaSetDevice(dev->ordinal) != cudaSuccess) die("cudaSetDevice");
+    B200_LOCK_DEVICE(dev);      // scratch + stream are per device: one host-pointer call at a time (released on return)
     uint8_t *scr = (uint8_t *)b200_scratch(dev, 512);
     if (!scr) die("scratch");
     int16_t *dblk = (int16_t *)scr;                       // 128 B
@@ -165,11 +165,11 @@ void host_fn(uint8_t *dst, int16_t *block, ptrdiff_t stride)
     cudaStream_t st = dev->stream;
     const int64_t m[2] = { 0, 0 };
     if (cudaMemcpyAsync(dblk, block, NC * sizeof(int16_t), cudaMemcpyHostToDevice, st) != cudaSuccess) die("h2d block");
-    if (cudaMemcpy2DAsync(dpix, 16, dst, (size_t)stride, N, N, cudaMemcpyHostToDevice, st) != cudaSuccess) die("h2d dst");
+    if (b200_h2d_rows(dpix, 16, dst, stride, N, N, st) != cudaSuccess) die("h2d dst");
     if (cudaMemcpyAsync(meta, m, sizeof(m), cudaMemcpyHostToDevice, st) != cudaSuccess) die("h2d meta");
     h264_idct_kernel<KIND><<<1, 128, 0, st>>>(1, dblk, meta, dpix, meta + 1, 16);
     B200_LAUNCHED();
-    if (cudaMemcpy2DAsync(dst, (size_t)stride, dpix, 16, N, N, cudaMemcpyDeviceToHost, st) != cudaSuccess) die("d2h");
+    if (b200_d2h_rows(dst, stride, dpix, 16, N, N, st) != cudaSuccess) die("d2h");
     if (cudaStreamSynchronize(st) != cudaSuccess) die("sync");
     if (KIND >= 2) block[0] = 0; else memset(block, 0, NC * sizeof(int16_t));     // what the reference leaves behind
 }

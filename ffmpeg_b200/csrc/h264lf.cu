@@ -113,11 +113,12 @@ void host_op(int kind, uint8_t *pix, ptrdiff_t stride, int alpha, int beta, cons
     const int w = vert ? lines : 8, h = vert ? 8 : lines;                 // window: vert: `lines` columns x rows -4..3; else columns -4..3 x `lines` rows
     uint8_t *origin = vert ? pix - 4 * stride : pix - 4;
     const size_t pitch = 16;
+    B200_LOCK_DEVICE(dev);      // scratch + stream are per device: one host-pointer call at a time (released on return)
     uint8_t *scr = (uint8_t *)b200_scratch(dev, pitch * 16 + 64);
     if (!scr) die("scratch");
     uint8_t *win = scr, *meta = scr + pitch * 16;
     cudaStream_t st = dev->stream;
-    if (cudaMemcpy2DAsync(win, pitch, origin, (size_t)stride, w, h, cudaMemcpyHostToDevice, st) != cudaSuccess) die("h2d");
+    if (b200_h2d_rows(win, pitch, origin, stride, w, h, st) != cudaSuccess) die("h2d");
     struct { int64_t off; int8_t tc[4]; uint8_t kind, alpha, beta, pad; } m;
     m.off = vert ? 4 * (int64_t)pitch : 4;
     for (int i = 0; i < 4; i++) m.tc[i] = tc0 ? tc0[i] : 0;
@@ -126,7 +127,7 @@ void host_op(int kind, uint8_t *pix, ptrdiff_t stride, int alpha, int beta, cons
     h264_loop_filter_kernel<<<1, 128, 0, st>>>(1, meta + 12, win, (const int64_t *)meta, (long long)pitch, meta + 13, meta + 14, (const int8_t *)(meta + 8));
     B200_LAUNCHED();
     if (cudaGetLastError() != cudaSuccess) die("launch");
-    if (cudaMemcpy2DAsync(origin, (size_t)stride, win, pitch, w, h, cudaMemcpyDeviceToHost, st) != cudaSuccess) die("d2h");
+    if (b200_d2h_rows(origin, stride, win, pitch, w, h, st) != cudaSuccess) die("d2h");
     if (cudaStreamSynchronize(st) != cudaSuccess) die("sync");
 }
 

@@ -69,17 +69,18 @@ void host_op(bool bi, int idx, uint8_t *dst, const uint8_t *src, ptrdiff_t strid
 {
     B200Device *dev = b200_default_device();
     if (!dev) die("no device");
-    if (stride < 0 || height < 0 || height > 255 || log2_denom < 0 || log2_denom > 7) die("unsupported stride / height / log2_denom");
+    if (height < 0 || height > 255 || log2_denom < 0 || log2_denom > 7) die("unsupported height / log2_denom");
     if (height == 0) return;
     if (cudaSetDevice(dev->ordinal) != cudaSuccess) die("cudaSetDevice");
     const int w = 16 >> idx;
     const size_t pitch = 16;
+    B200_LOCK_DEVICE(dev);      // scratch + stream are per device: one host-pointer call at a time (released on return)
     uint8_t *scr = (uint8_t *)b200_scratch(dev, 2 * pitch * 256 + 256);
     if (!scr) die("scratch");
     uint8_t *ddst = scr, *dsrc = scr + pitch * 256, *meta = scr + 2 * pitch * 256;
     cudaStream_t st = dev->stream;
-    if (cudaMemcpy2DAsync(ddst, pitch, dst, (size_t)stride, w, height, cudaMemcpyHostToDevice, st) != cudaSuccess) die("h2d dst");
-    if (bi && cudaMemcpy2DAsync(dsrc, pitch, src, (size_t)stride, w, height, cudaMemcpyHostToDevice, st) != cudaSuccess) die("h2d src");
+    if (b200_h2d_rows(ddst, pitch, dst, stride, w, height, st) != cudaSuccess) die("h2d dst");
+    if (bi && b200_h2d_rows(dsrc, pitch, src, stride, w, height, st) != cudaSuccess) die("h2d src");
     struct { int32_t p[4]; int64_t doff, soff; } m = { { idx | (height << 8) | (log2_denom << 16), wd, ws, offset }, 0, 0 };
     if (cudaMemcpyAsync(meta, &m, sizeof(m), cudaMemcpyHostToDevice, st) != cudaSuccess) die("h2d meta");
     const int32_t *dp = (const int32_t *)meta;
@@ -87,7 +88,7 @@ void host_op(bool bi, int idx, uint8_t *dst, const uint8_t *src, ptrdiff_t strid
     if (bi) h264_weight_kernel<true><<<1, 32 * WARPS, 0, st>>>(1, dp, ddst, doff, dsrc, soff, (long long)pitch);
     else    h264_weight_kernel<false><<<1, 32 * WARPS, 0, st>>>(1, dp, ddst, doff, nullptr, nullptr, (long long)pitch);
     B200_LAUNCHED();
-    if (cudaMemcpy2DAsync(dst, (size_t)stride, ddst, pitch, w, height, cudaMemcpyDeviceToHost, st) != cudaSuccess) die("d2h");
+    if (b200_d2h_rows(dst, stride, ddst, pitch, w, height, st) != cudaSuccess) die("d2h");
     if (cudaStreamSynchronize(st) != cudaSuccess) die("sync");
 }
 

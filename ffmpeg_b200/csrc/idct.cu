@@ -648,6 +648,7 @@ B200_API int b200_idct_mb420_host(B200Device *dev, int kind, const int16_t *bloc
     if (chunk < 1) chunk = 1;
     if (chunk > nframes) chunk = nframes > 0 ? nframes : 1;
     const int K = B200Device::kPipe;
+    B200_LOCK_DEVICE(dev);      // scratch + stream are per device: one host-pointer call at a time (released on return)
     uint8_t *scr = (uint8_t *)b200_scratch(dev, perFrame * chunk * K);
     if (!scr) return B200_ENOMEM;
     B200_CUDA_OK(cudaStreamSynchronize(dev->stream));
@@ -690,6 +691,7 @@ int one_block(int kind, uint8_t *dest, ptrdiff_t line_size, int16_t *block)
     B200Device *dev = b200_default_device();
     if (!dev) return B200_ENODEV;
     if (cudaSetDevice(dev->ordinal) != cudaSuccess) return B200_EEXTERNAL;
+    B200_LOCK_DEVICE(dev);      // scratch + stream are per device: one host-pointer call at a time (released on return)
     uint8_t *scr = (uint8_t *)b200_scratch(dev, 256);
     if (!scr) return B200_ENOMEM;
     int16_t *dblk = (int16_t *)scr;
@@ -698,7 +700,7 @@ int one_block(int kind, uint8_t *dest, ptrdiff_t line_size, int16_t *block)
     cudaStream_t st = dev->stream;
     B200_CUDA_OK(cudaMemcpyAsync(dblk, block, 128, cudaMemcpyHostToDevice, st));
     if (kind == B200_IDCT_ADD)
-        B200_CUDA_OK(cudaMemcpy2DAsync(dpix, 8, dest, (size_t)line_size, 8, 8, cudaMemcpyHostToDevice, st));
+        B200_CUDA_OK(b200_h2d_rows(dpix, 8, dest, line_size, 8, 8, st));
     B200_CUDA_OK(cudaMemsetAsync(doff, 0, 8, st));
     Mb420Geom g{};
     int ret = dispatch(st, kind, false, dblk, dblk, 1, dpix, doff, nullptr, 8, g);
@@ -706,7 +708,7 @@ int one_block(int kind, uint8_t *dest, ptrdiff_t line_size, int16_t *block)
     if (kind == B200_IDCT)
         B200_CUDA_OK(cudaMemcpyAsync(block, dblk, 128, cudaMemcpyDeviceToHost, st));
     else
-        B200_CUDA_OK(cudaMemcpy2DAsync(dest, (size_t)line_size, dpix, 8, 8, 8, cudaMemcpyDeviceToHost, st));
+        B200_CUDA_OK(b200_d2h_rows(dest, line_size, dpix, 8, 8, 8, st));
     B200_CUDA_OK(cudaStreamSynchronize(st));
     return 0;
 }
@@ -716,14 +718,15 @@ int one_clamp(int kind, const int16_t *block, uint8_t *pixels, ptrdiff_t line_si
     B200Device *dev = b200_default_device();
     if (!dev) return B200_ENODEV;
     if (cudaSetDevice(dev->ordinal) != cudaSuccess) return B200_EEXTERNAL;
+    B200_LOCK_DEVICE(dev);      // scratch + stream are per device: one host-pointer call at a time (released on return)
     uint8_t *scr = (uint8_t *)b200_scratch(dev, 256);
     if (!scr) return B200_ENOMEM;
     cudaStream_t st = dev->stream;
     B200_CUDA_OK(cudaMemcpyAsync(scr, block, 128, cudaMemcpyHostToDevice, st));
-    if (kind == 2) B200_CUDA_OK(cudaMemcpy2DAsync(scr + 128, 8, pixels, (size_t)line_size, 8, 8, cudaMemcpyHostToDevice, st));
+    if (kind == 2) B200_CUDA_OK(b200_h2d_rows(scr + 128, 8, pixels, line_size, 8, 8, st));
     pixels_clamped_kernel<<<1, 64, 0, st>>>(kind, (const int16_t *)scr, scr + 128);
     B200_LAUNCHED();
-    B200_CUDA_OK(cudaMemcpy2DAsync(pixels, (size_t)line_size, scr + 128, 8, 8, 8, cudaMemcpyDeviceToHost, st));
+    B200_CUDA_OK(b200_d2h_rows(pixels, line_size, scr + 128, 8, 8, 8, st));
     B200_CUDA_OK(cudaStreamSynchronize(st));
     return 0;
 }

@@ -183,8 +183,9 @@ void host_op(int kind, uint8_t *dest, ptrdiff_t line_size, int16_t *block)
 {
     B200Device *dev = b200_default_device();
     if (!dev) die("no device");
-    if (kind != B200_IDCT && (line_size < 16 || (line_size & 1))) die("line_size must be even and >= 16 bytes");
+    if (kind != B200_IDCT && ((line_size > -16 && line_size < 16) || (line_size & 1))) die("|line_size| must be even and >= 16 bytes");
     if (cudaSetDevice(dev->ordinal) != cudaSuccess) die("cudaSetDevice");
+    B200_LOCK_DEVICE(dev);      // scratch + stream are per device: one host-pointer call at a time (released on return)
     uint8_t *scr = (uint8_t *)b200_scratch(dev, 128 + 8 * 16 + 16);
     if (!scr) die("scratch");
     int16_t *dblk = (int16_t *)scr;
@@ -194,12 +195,12 @@ void host_op(int kind, uint8_t *dest, ptrdiff_t line_size, int16_t *block)
     const int64_t zero = 0;
     if (cudaMemcpyAsync(dblk, block, 128, cudaMemcpyHostToDevice, st) != cudaSuccess) die("h2d block");
     if (kind != B200_IDCT) {
-        if (kind == B200_IDCT_ADD && cudaMemcpy2DAsync(ddst, 16, dest, (size_t)line_size, 16, 8, cudaMemcpyHostToDevice, st) != cudaSuccess) die("h2d dest");
+        if (kind == B200_IDCT_ADD && b200_h2d_rows(ddst, 16, dest, line_size, 16, 8, st) != cudaSuccess) die("h2d dest");
         if (cudaMemcpyAsync(doff, &zero, 8, cudaMemcpyHostToDevice, st) != cudaSuccess) die("h2d off");
     }
     if (launch<DEPTH>(st, kind, dblk, 1, ddst, doff, nullptr, 16) < 0 || cudaGetLastError() != cudaSuccess) die("launch");
     if (kind == B200_IDCT) { if (cudaMemcpyAsync(block, dblk, 128, cudaMemcpyDeviceToHost, st) != cudaSuccess) die("d2h block"); }
-    else if (cudaMemcpy2DAsync(dest, (size_t)line_size, ddst, 16, 16, 8, cudaMemcpyDeviceToHost, st) != cudaSuccess) die("d2h dest");
+    else if (b200_d2h_rows(dest, line_size, ddst, 16, 16, 8, st) != cudaSuccess) die("d2h dest");
     if (cudaStreamSynchronize(st) != cudaSuccess) die("sync");
 }
 
@@ -260,8 +261,9 @@ void prores_tab_put(uint16_t *out, ptrdiff_t linesize, int16_t *block, const int
 {
     B200Device *dev = b200_default_device();
     if (!dev) die("no device");
-    if (linesize < 16 || (linesize & 1)) die("line size must be even and >= 16 bytes");
+    if ((linesize > -16 && linesize < 16) || (linesize & 1)) die("|line size| must be even and >= 16 bytes");
     if (cudaSetDevice(dev->ordinal) != cudaSuccess) die("cudaSetDevice");
+    B200_LOCK_DEVICE(dev);      // scratch + stream are per device: one host-pointer call at a time (released on return)
     uint8_t *scr = (uint8_t *)b200_scratch(dev, 128 + 128 + 128 + 16);
     if (!scr) die("scratch");
     int16_t *dblk = (int16_t *)scr, *dq = (int16_t *)(scr + 128);
@@ -273,7 +275,7 @@ void prores_tab_put(uint16_t *out, ptrdiff_t linesize, int16_t *block, const int
     if (cudaMemcpyAsync(dq, qmat, 128, cudaMemcpyHostToDevice, st) != cudaSuccess) die("h2d qmat");
     if (cudaMemcpyAsync(doff, &zero, 8, cudaMemcpyHostToDevice, st) != cudaSuccess) die("h2d off");
     if (launch_prores(st, BITS, dblk, 1, dq, ddst, doff, nullptr, 16) < 0 || cudaGetLastError() != cudaSuccess) die("launch");
-    if (cudaMemcpy2DAsync(out, (size_t)linesize, ddst, 16, 16, 8, cudaMemcpyDeviceToHost, st) != cudaSuccess) die("d2h");
+    if (b200_d2h_rows(out, linesize, ddst, 16, 16, 8, st) != cudaSuccess) die("d2h");
     if (cudaStreamSynchronize(st) != cudaSuccess) die("sync");
 }
 

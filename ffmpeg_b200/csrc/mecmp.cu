@@ -246,6 +246,54 @@ B200_API int b200_me_esa_device(B200Device *dev, const uint8_t *cur, const uint8
     }
 }
 
+// HOST buffers: frame pairs are cut into chunks that rotate over the device's three pipeline streams (H2D of the current and the
+// reference luma planes, the search kernel, D2H of vectors and costs).
+B200_API int b200_me_esa_host(B200Device *dev, const uint8_t *cur, const uint8_t *ref, int linesize, int width, int height,
+                              int64_t frame_stride, int nframes, int mb_size, int search_param, int32_t *out_mv, uint64_t *out_cost)
+{
+    if (!dev || !cur || !ref || !out_mv || !out_cost || nframes < 0 || search_param < 0 || width <= 0 || height <= 0) return B200_EINVAL;
+    if (mb_size != 4 && mb_size != 8 && mb_size != 16) return B200_ENOSYS;
+    if (linesize < width || frame_stride < (int64_t)linesize * height) return B200_EINVAL;
+    const int b_w = width / mb_size, b_h = height / mb_size;
+    if (b_w == 0 || b_h == 0) return B200_EINVAL;
+    if (b_h > 65535) return B200_ENOSYS;
+    if (nframes == 0) return 0;
+    B200_CUDA_OK(cudaSetDevice(dev->ordinal));
+    const size_t fbytes = (size_t)frame_stride, nmb = (size_t)b_w * b_h;
+    const size_t outb = ((nmb * 16) + 255) & ~(size_t)255;          // 2 x int32 + uint64 per block
+    const size_t perFrame = 2 * fbytes + outb;
+    int chunk = (int)(((size_t)96 << 20) / perFrame);
+    if (chunk < 1) chunk = 1;
+    if (chunk > nframes) chunk = nframes;
+    const int K = B200Device::kPipe;
+    B200_LOCK_DEVICE(dev);
+    uint8_t *scr = (uint8_t *)b200_scratch(dev, (perFrame * chunk + 256) * K);
+    if (!scr) return B200_ENOMEM;
+    B200_CUDA_OK(cudaStreamSynchronize(dev->stream));
+    int slot = 0;
+    for (int f0 = 0; f0 < nframes; f0 += chunk, slot = (slot + 1) % K) {
+        const int nf = nframes - f0 < chunk ? nframes - f0 : chunk;
+        cudaStream_t st = dev->pipe[slot];
+        uint8_t *base = scr + (size_t)slot * (perFrame * chunk + 256);
+        uint8_t *dcur = base, *dref = base + fbytes * chunk;
+        unsigned long long *dcost = (unsigned long long *)(((uintptr_t)(base + 2 * fbytes * chunk) + 255) & ~(uintptr_t)255);
+        int32_t *dmv = (int32_t *)(dcost + nmb * chunk);
+        B200_CUDA_OK(cudaMemcpyAsync(dcur, cur + (size_t)f0 * fbytes, (size_t)nf * fbytes, cudaMemcpyHostToDevice, st));
+        B200_CUDA_OK(cudaMemcpyAsync(dref, ref + (size_t)f0 * fbytes, (size_t)nf * fbytes, cudaMemcpyHostToDevice, st));
+        int ret;
+        switch (mb_size) {
+        case 4:  ret = launch_esa<4>(st, dcur, dref, linesize, frame_stride, b_w, b_h, nf, search_param, dmv, dcost); break;
+        case 8:  ret = launch_esa<8>(st, dcur, dref, linesize, frame_stride, b_w, b_h, nf, search_param, dmv, dcost); break;
+        default: ret = launch_esa<16>(st, dcur, dref, linesize, frame_stride, b_w, b_h, nf, search_param, dmv, dcost); break;
+        }
+        if (ret < 0) return ret;
+        B200_CUDA_OK(cudaMemcpyAsync(out_mv + (size_t)f0 * nmb * 2, dmv, (size_t)nf * nmb * 8, cudaMemcpyDeviceToHost, st));
+        B200_CUDA_OK(cudaMemcpyAsync(out_cost + (size_t)f0 * nmb, dcost, (size_t)nf * nmb * 8, cudaMemcpyDeviceToHost, st));
+    }
+    for (int i = 0; i < K; i++) B200_CUDA_OK(cudaStreamSynchronize(dev->pipe[i]));
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ drop-in pointer table
 namespace {
 
@@ -260,17 +308,16 @@ int host_cmp(int fn, int idx, const uint8_t *blk1, const uint8_t *blk2, ptrdiff_
     if (cudaSetDevice(dev->ordinal) != cudaSuccess) fail("cudaSetDevice");
     const int cw = w + 1, ch = h + 1;                             // x2/y2/xy2 read one extra column / row of blk2
     const size_t pitch = 32;
+    B200_LOCK_DEVICE(dev);      // scratch + stream are per device: one host-pointer call at a time (released on return)
     uint8_t *scr = (uint8_t *)b200_scratch(dev, 2 * pitch * (ch + 1) + 64);
     if (!scr) fail("scratch");
     uint8_t *d1 = scr, *d2 = scr + pitch * (ch + 1);
     int64_t *offs = (int64_t *)(scr + 2 * pitch * (ch + 1));
     int32_t *dout = (int32_t *)(offs + 2);
     cudaStream_t st = dev->stream;
-    const size_t as = (size_t)(stride < 0 ? -stride : stride);
-    if (stride < 0) fail("negative stride");
-    if (cudaMemcpy2DAsync(d1, pitch, blk1, as, w, h, cudaMemcpyHostToDevice, st) != cudaSuccess) fail("h2d");
+    if (b200_h2d_rows(d1, pitch, blk1, stride, w, h, st) != cudaSuccess) fail("h2d");      // negative strides (flipped frames) are fine
     const int bw = mode & 1 ? cw : w, bh = mode & 2 ? ch : h;
-    if (cudaMemcpy2DAsync(d2, pitch, blk2, as, bw, bh, cudaMemcpyHostToDevice, st) != cudaSuccess) fail("h2d");
+    if (b200_h2d_rows(d2, pitch, blk2, stride, bw, bh, st) != cudaSuccess) fail("h2d");
     if (cudaMemsetAsync(offs, 0, 16, st) != cudaSuccess) fail("memset");
     if (fn == B200_MECMP_HADAMARD8) me_satd_kernel<<<1, 32, 0, st>>>(w == 8 ? 1 : h == 16 ? 4 : 2, d1, d2, (long long)pitch, offs, offs + 1, 1, dout);
     else me_cmp_kernel<<<1, 32, 0, st>>>(fn, w, mode, d1, d2, (long long)pitch, h, offs, offs + 1, 1, dout);

@@ -391,19 +391,19 @@ void host_op(HostKind kind, int o, int h, int w, uint8_t *dst, const uint8_t *sr
 {
     B200Device *dev = b200_default_device();
     if (!dev) die("no device");
-    if (stride < 0) die("negative stride");
     if (cudaSetDevice(dev->ordinal) != cudaSuccess) die("cudaSetDevice");
     const int before = kind == HOST_QPEL ? 2 : 0, after = kind == HOST_QPEL ? 3 : 1;   // the window the kernels may touch
     const int sh = h + before + after;
     const size_t pitch = 32;
+    B200_LOCK_DEVICE(dev);      // scratch + stream are per device: one host-pointer call at a time (released on return)
     uint8_t *scr = (uint8_t *)b200_scratch(dev, pitch * (sh + h) + 256);
     if (!scr) die("scratch");
     uint8_t *dsrc = scr, *ddst = scr + pitch * sh;
     uint8_t *meta = scr + pitch * (sh + h);           // op, h, offsets
     cudaStream_t st = dev->stream;
-    if (cudaMemcpy2DAsync(dsrc + (before - by) * pitch + (before - bx), pitch, src - by * stride - bx, (size_t)stride,
-                          w + bx + ax, h + by + ay, cudaMemcpyHostToDevice, st) != cudaSuccess) die("h2d src");
-    if (cudaMemcpy2DAsync(ddst, pitch, dst, (size_t)stride, w, h, cudaMemcpyHostToDevice, st) != cudaSuccess) die("h2d dst");
+    if (b200_h2d_rows(dsrc + (before - by) * pitch + (before - bx), pitch, src - by * stride - bx, stride,
+                      w + bx + ax, h + by + ay, st) != cudaSuccess) die("h2d src");
+    if (b200_h2d_rows(ddst, pitch, dst, stride, w, h, st) != cudaSuccess) die("h2d dst");
     struct { int64_t doff, soff; uint8_t op, h, xy; } m = { 0, (int64_t)(before * pitch + before), (uint8_t)o, (uint8_t)h, (uint8_t)fxy };
     if (cudaMemcpyAsync(meta, &m, sizeof(m), cudaMemcpyHostToDevice, st) != cudaSuccess) die("h2d meta");
     const int64_t *doff = (const int64_t *)meta, *soff = doff + 1;
@@ -413,7 +413,7 @@ void host_op(HostKind kind, int o, int h, int w, uint8_t *dst, const uint8_t *sr
     else if (kind == HOST_HPEL) hpel_kernel<<<1, 32 * WARPS, 0, st>>>(1, dop, dh, ddst, doff, dsrc, soff, (long long)pitch);
     else                        chroma_kernel<<<1, 32 * WARPS, 0, st>>>(1, dop, dh, dxy, ddst, doff, dsrc, soff, (long long)pitch);
     B200_LAUNCHED();
-    if (cudaMemcpy2DAsync(dst, (size_t)stride, ddst, pitch, w, h, cudaMemcpyDeviceToHost, st) != cudaSuccess) die("d2h");
+    if (b200_d2h_rows(dst, stride, ddst, pitch, w, h, st) != cudaSuccess) die("d2h");
     if (cudaStreamSynchronize(st) != cudaSuccess) die("sync");
 }
 
@@ -482,26 +482,26 @@ void edge_tab(uint8_t *buf, const uint8_t *src, ptrdiff_t buf_linesize, ptrdiff_
     if (block_w <= 0 || block_h <= 0) return;
     B200Device *dev = b200_default_device();
     if (!dev) die("no device");
-    if (buf_linesize < 0 || src_linesize < 0) die("negative linesize");
     if (cudaSetDevice(dev->ordinal) != cudaSuccess) die("cudaSetDevice");
     // the part of the picture the window can reach after clamping
     const int x0 = std::min(std::max(src_x, 0), w - 1), x1 = std::min(std::max(src_x + block_w - 1, 0), w - 1);
     const int y0 = std::min(std::max(src_y, 0), h - 1), y1 = std::min(std::max(src_y + block_h - 1, 0), h - 1);
     const size_t rw = (size_t)(x1 - x0 + 1), rh = (size_t)(y1 - y0 + 1);
     const size_t rp = (rw + 15) & ~(size_t)15, bp = ((size_t)block_w + 15) & ~(size_t)15;
+    B200_LOCK_DEVICE(dev);      // scratch + stream are per device: one host-pointer call at a time (released on return)
     uint8_t *scr = (uint8_t *)b200_scratch(dev, rp * rh + bp * block_h + 256);
     if (!scr) die("scratch");
     uint8_t *drect = scr, *dbuf = scr + rp * rh, *meta = dbuf + bp * block_h;
     meta += (16 - ((uintptr_t)meta & 15)) & 15;
     cudaStream_t st = dev->stream;
     const uint8_t *pic = src - (ptrdiff_t)src_y * src_linesize - src_x;
-    if (cudaMemcpy2DAsync(drect, rp, pic + (ptrdiff_t)y0 * src_linesize + x0, (size_t)src_linesize, rw, rh, cudaMemcpyHostToDevice, st) != cudaSuccess) die("h2d");
+    if (b200_h2d_rows(drect, rp, pic + (ptrdiff_t)y0 * src_linesize + x0, src_linesize, rw, rh, st) != cudaSuccess) die("h2d");
     struct { int32_t g[4]; int64_t boff, origin; } m = { { block_w, block_h, src_x, src_y }, 0, -((int64_t)y0 * (int64_t)rp + x0) };
     if (cudaMemcpyAsync(meta, &m, sizeof(m), cudaMemcpyHostToDevice, st) != cudaSuccess) die("h2d meta");
     edge_kernel<<<1, 32 * WARPS, 0, st>>>(1, dbuf, (const int64_t *)(meta + 16), (long long)bp, drect, (const int64_t *)(meta + 24),
                                           (long long)rp, (const int32_t *)meta, w, h);
     B200_LAUNCHED();
-    if (cudaMemcpy2DAsync(buf, (size_t)buf_linesize, dbuf, bp, (size_t)block_w, (size_t)block_h, cudaMemcpyDeviceToHost, st) != cudaSuccess) die("d2h");
+    if (b200_d2h_rows(buf, buf_linesize, dbuf, bp, (size_t)block_w, (size_t)block_h, st) != cudaSuccess) die("d2h");
     if (cudaStreamSynchronize(st) != cudaSuccess) die("sync");
 }
 void prefetch_nop(const uint8_t *, ptrdiff_t, int) {}
@@ -571,6 +571,64 @@ B200_API int b200_h264qpel_batch_device(B200Device *dev, int64_t n, const uint8_
     qpel_kernel<<<(unsigned)blocks, 32 * WARPS, 0, dev->stream>>>(n, op, dst, dst_off, src, src_off, stride);
     B200_LAUNCHED();
     B200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// HOST buffers: a stream of frames, each with its own reference picture, destination picture and list of motion-compensation
+// operations (what a decoder holding its pictures in host memory hands over once per frame).  Frame f occupies
+// [f * frame_bytes, (f + 1) * frame_bytes) of `src` and of `dst`; its operations are op_begin[f] .. op_begin[f + 1] - 1, with offsets
+// counted from the start of `dst` / `src` like the device entry point, and must stay inside frame f.  Frames are cut into chunks that
+// rotate over the device's three pipeline streams: H2D of the chunk's reference and destination pictures and operation lists, the
+// kernel, D2H of the destination pictures.
+B200_API int b200_h264qpel_frames_host(B200Device *dev, int nframes, int64_t frame_bytes, const int64_t *op_begin, const uint8_t *op,
+                                       uint8_t *dst, const int64_t *dst_off, const uint8_t *src, const int64_t *src_off, ptrdiff_t stride)
+{
+    if (!dev || nframes < 0 || frame_bytes <= 0 || !op_begin || !op || !dst || !dst_off || !src || !src_off) return B200_EINVAL;
+    if (nframes == 0) return 0;
+    B200_CUDA_OK(cudaSetDevice(dev->ordinal));
+    int64_t ops_total = op_begin[nframes] - op_begin[0];
+    for (int f = 0; f < nframes; f++) if (op_begin[f + 1] < op_begin[f]) return B200_EINVAL;
+    const int64_t ops_per_frame = (ops_total + nframes - 1) / nframes;
+    const size_t perFrame = 2 * (size_t)frame_bytes + (size_t)ops_per_frame * 17 + 64;
+    int chunk = (int)(((size_t)64 << 20) / perFrame);
+    if (chunk < 1) chunk = 1;
+    if (chunk > nframes) chunk = nframes;
+    int64_t max_ops = 0;                                            // operations of the busiest chunk
+    for (int f0 = 0; f0 < nframes; f0 += chunk) max_ops = std::max(max_ops, op_begin[std::min(nframes, f0 + chunk)] - op_begin[f0]);
+    const size_t n8 = (((size_t)max_ops * 8) + 255) & ~(size_t)255;
+    const size_t pics = ((2 * (size_t)frame_bytes * chunk) + 255) & ~(size_t)255;
+    const size_t slotBytes = pics + 2 * n8 + (((size_t)max_ops + 255) & ~(size_t)255);
+    const int K = B200Device::kPipe;
+    B200_LOCK_DEVICE(dev);
+    uint8_t *scr = (uint8_t *)b200_scratch(dev, slotBytes * K);
+    if (!scr) return B200_ENOMEM;
+    B200_CUDA_OK(cudaStreamSynchronize(dev->stream));
+    int slot = 0;
+    for (int f0 = 0; f0 < nframes; f0 += chunk, slot = (slot + 1) % K) {
+        const int nf = nframes - f0 < chunk ? nframes - f0 : chunk;
+        cudaStream_t st = dev->pipe[slot];
+        uint8_t *base = scr + (size_t)slot * slotBytes;
+        uint8_t *dsrc = base, *ddst = base + (size_t)frame_bytes * chunk;
+        int64_t *ddo = (int64_t *)(base + pics), *dso = (int64_t *)(base + pics + n8);
+        uint8_t *dop = base + pics + 2 * n8;
+        const int64_t o0 = op_begin[f0], n = op_begin[f0 + nf] - o0;
+        B200_CUDA_OK(cudaMemcpyAsync(dsrc, src + (size_t)f0 * frame_bytes, (size_t)nf * frame_bytes, cudaMemcpyHostToDevice, st));
+        B200_CUDA_OK(cudaMemcpyAsync(ddst, dst + (size_t)f0 * frame_bytes, (size_t)nf * frame_bytes, cudaMemcpyHostToDevice, st));
+        if (n > 0) {
+            B200_CUDA_OK(cudaMemcpyAsync(ddo, dst_off + o0, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+            B200_CUDA_OK(cudaMemcpyAsync(dso, src_off + o0, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+            B200_CUDA_OK(cudaMemcpyAsync(dop, op + o0, (size_t)n, cudaMemcpyHostToDevice, st));
+            const long long blocks = (n + WARPS * QK - 1) / (WARPS * QK);
+            if (blocks > 0x7fffffffLL) return B200_EINVAL;
+            // the lists keep their offsets from the start of the whole buffers: hand the kernel bases moved back by the chunk's origin
+            qpel_kernel<<<(unsigned)blocks, 32 * WARPS, 0, st>>>(n, dop, ddst - (size_t)f0 * frame_bytes, ddo,
+                                                                 dsrc - (size_t)f0 * frame_bytes, dso, stride);
+            B200_LAUNCHED();
+            B200_CUDA_OK(cudaGetLastError());
+        }
+        B200_CUDA_OK(cudaMemcpyAsync(dst + (size_t)f0 * frame_bytes, ddst, (size_t)nf * frame_bytes, cudaMemcpyDeviceToHost, st));
+    }
+    for (int i = 0; i < K; i++) B200_CUDA_OK(cudaStreamSynchronize(dev->pipe[i]));
     return 0;
 }
 

@@ -30,18 +30,18 @@ int host_sad(int bits, const uint8_t *src1, ptrdiff_t stride1, const uint8_t *sr
     auto fail = [](const char *what) { fprintf(stderr, "libb200dsp: av_pixelutils_sad_fn failed: %s (%s)\n", what, b200_last_error()); abort(); };
     B200Device *dev = b200_default_device();
     if (!dev) fail("no device");
-    if (stride1 < 0 || stride2 < 0) fail("negative stride");
     if (cudaSetDevice(dev->ordinal) != cudaSuccess) fail("cudaSetDevice");
     const int size = 1 << bits;
     const size_t pitch = 32;
+    B200_LOCK_DEVICE(dev);      // scratch + stream are per device: one host-pointer call at a time (released on return)
     uint8_t *scr = (uint8_t *)b200_scratch(dev, 2 * pitch * 32 + 64);
     if (!scr) fail("scratch");
     uint8_t *d1 = scr, *d2 = scr + pitch * 32;
     int64_t *offs = (int64_t *)(scr + 2 * pitch * 32);
     int *dout = (int *)(offs + 2);
     cudaStream_t st = dev->stream;
-    if (cudaMemcpy2DAsync(d1, pitch, src1, (size_t)stride1, size, size, cudaMemcpyHostToDevice, st) != cudaSuccess) fail("h2d");
-    if (cudaMemcpy2DAsync(d2, pitch, src2, (size_t)stride2, size, size, cudaMemcpyHostToDevice, st) != cudaSuccess) fail("h2d");
+    if (b200_h2d_rows(d1, pitch, src1, stride1, size, size, st) != cudaSuccess) fail("h2d");
+    if (b200_h2d_rows(d2, pitch, src2, stride2, size, size, st) != cudaSuccess) fail("h2d");
     if (cudaMemsetAsync(offs, 0, 24, st) != cudaSuccess) fail("memset");
     pixelutils_sad_kernel<<<1, 32, 0, st>>>(bits, d1, (long long)pitch, d2, (long long)pitch, offs, offs + 1, 1, dout);
     B200_LAUNCHED();

@@ -1617,6 +1617,7 @@ static int sws_scale_planar_host(B200SwsContext *c, const uint8_t *const srcSlic
         if (srcSliceY + srcSliceH == p.srcH) c->slice_open = false;
         return y1 - y0;
     }
+    B200_LOCK_DEVICE(d);      // scratch + stream are per device: one host-pointer call at a time (released on return)
     uint8_t *scr = (uint8_t *)b200_scratch(d, total);
     if (!scr) return B200_ENOMEM;
     for (int i = 0; i < 3; i++) {
@@ -1677,6 +1678,7 @@ B200_API int b200_sws_scale_batch_host(B200SwsContext *c, const uint8_t *const s
     if (chunk > 8) chunk = 8;
     if (chunk > nframes) chunk = nframes > 0 ? nframes : 1;
     const int K = B200Device::kPipe;
+    B200_LOCK_DEVICE(d);      // scratch + stream are per device: one host-pointer call at a time (released on return)
     uint8_t *scr = (uint8_t *)b200_scratch(d, perFrame * chunk * K);
     if (!scr) return B200_ENOMEM;
     B200_CUDA_OK(cudaStreamSynchronize(d->stream));
@@ -1784,6 +1786,7 @@ B200_API int b200_sws_scale(B200SwsContext *c, const uint8_t *const srcSlice[], 
                             int srcSliceY, int srcSliceH, uint8_t *const dst[], const int dstStride[])
 {
     if (!c || !srcSlice || !srcStride || !dst || !dstStride) return B200_EINVAL;
+    B200_LOCK_DEVICE(c->dev);      // contexts of one device share its stream and scratch (slice threads call N child contexts concurrently)
     const SwsPlan &p = c->plan;
     if (p.planar) return sws_scale_planar_host(c, srcSlice, srcStride, srcSliceY, srcSliceH, dst, dstStride);
     if (p.src_rgb) {                                              // packed RGB -> packed RGB: whole frames, top-down
@@ -1793,6 +1796,7 @@ B200_API int b200_sws_scale(B200SwsContext *c, const uint8_t *const srcSlice[], 
         B200Device *dv = c->dev;
         B200_CUDA_OK(cudaSetDevice(dv->ordinal));
         const size_t sPitch = ((size_t)p.srcW * p.src_rgb + 255) & ~(size_t)255, dPitch = ((size_t)p.dstW * p.out.bpp + 255) & ~(size_t)255;
+        B200_LOCK_DEVICE(dv);      // scratch + stream are per device: one host-pointer call at a time (released on return)
         uint8_t *scr2 = (uint8_t *)b200_scratch(dv, sPitch * p.srcH + dPitch * p.dstH);
         if (!scr2) return B200_ENOMEM;
         cudaStream_t st2 = dv->stream;

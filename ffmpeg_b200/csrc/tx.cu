@@ -671,6 +671,7 @@ static void tx_host_fn(B200TXContext *c, void *out, void *in, ptrdiff_t stride)
     else if (c->inv) { in_elems = len; out_elems = c->full ? 2 * len : len; }
     else { in_elems = 2 * len; out_elems = len; }
     if (c->full && stride != 4) fail("AV_TX_FULL_IMDCT takes stride == sizeof(float) (the reference mirrors with the input stride)");
+    B200_LOCK_DEVICE(d);      // scratch + stream are per device: one host-pointer call at a time (released on return)
     float *scr = (float *)b200_scratch(d, (in_elems + out_elems) * 4 + 512);
     if (!scr) fail("scratch");
     float *din = scr, *dout = scr + ((in_elems + 63) & ~(size_t)63);
@@ -790,3 +791,40 @@ B200_API int b200_tx_batch_device(B200TXContext *c, void *out, const void *in, p
     B200_CUDA_OK(cudaSetDevice(c->dev->ordinal));
     return tx_launch(c, c->dev->stream, out, in, (c->type == 1 || c->type == B200_TX_INT32_MDCT) ? stride : 8, count, out_step, in_step);
 }
+
+// HOST buffers (pinned for real overlap): the batch is cut into chunks that rotate over the device's three pipeline streams, each chunk
+// = one linear H2D of its inputs, the transform kernels, one linear D2H of its outputs.
+B200_API int b200_tx_batch_host(B200TXContext *c, void *out, const void *in, ptrdiff_t stride, int64_t count,
+                                ptrdiff_t out_step, ptrdiff_t in_step)
+{
+    if (!c || !out || !in || count < 0 || out_step <= 0 || in_step <= 0) return B200_EINVAL;
+    if ((c->type == 1 || c->type == B200_TX_INT32_MDCT) && (stride & 3)) return B200_EINVAL;
+    if (c->full && stride != 4) return B200_EINVAL;
+    if (count == 0) return 0;
+    B200Device *d = c->dev;
+    B200_CUDA_OK(cudaSetDevice(d->ordinal));
+    const ptrdiff_t st_arg = (c->type == 1 || c->type == B200_TX_INT32_MDCT) ? stride : 8;
+    const size_t istep = ((size_t)in_step + 15) & ~(size_t)15, ostep = ((size_t)out_step + 15) & ~(size_t)15;
+    if (istep != (size_t)in_step || ostep != (size_t)out_step) { b200_set_error("b200_tx_batch_host: steps must be multiples of 16 bytes"); return B200_EINVAL; }
+    int64_t chunk = ((int64_t)48 << 20) / (int64_t)(istep + ostep);
+    if (chunk < 1) chunk = 1;
+    if (chunk > count) chunk = count;
+    const int K = B200Device::kPipe;
+    B200_LOCK_DEVICE(d);
+    uint8_t *scr = (uint8_t *)b200_scratch(d, (size_t)chunk * (istep + ostep) * K);
+    if (!scr) return B200_ENOMEM;
+    B200_CUDA_OK(cudaStreamSynchronize(d->stream));
+    int slot = 0;
+    for (int64_t i0 = 0; i0 < count; i0 += chunk, slot = (slot + 1) % K) {
+        const int64_t n = count - i0 < chunk ? count - i0 : chunk;
+        cudaStream_t st = d->pipe[slot];
+        uint8_t *din = scr + (size_t)slot * chunk * (istep + ostep), *dout = din + (size_t)chunk * istep;
+        B200_CUDA_OK(cudaMemcpyAsync(din, (const uint8_t *)in + (size_t)i0 * istep, (size_t)n * istep, cudaMemcpyHostToDevice, st));
+        int ret = tx_launch(c, st, dout, din, st_arg, n, (ptrdiff_t)ostep, (ptrdiff_t)istep);
+        if (ret < 0) return ret;
+        B200_CUDA_OK(cudaMemcpyAsync((uint8_t *)out + (size_t)i0 * ostep, dout, (size_t)n * ostep, cudaMemcpyDeviceToHost, st));
+    }
+    for (int i = 0; i < K; i++) B200_CUDA_OK(cudaStreamSynchronize(d->pipe[i]));
+    return 0;
+}
+

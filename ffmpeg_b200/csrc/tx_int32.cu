@@ -355,6 +355,7 @@ void tx_i32_host_fn(TxI32 *p, void *out, void *in, ptrdiff_t stride)
     const size_t len = p->len;
     const bool mdct = p->type == B200_TX_INT32_MDCT;
     const size_t in_elems = !mdct ? 2 * len : p->inv ? len : 2 * len, out_elems = !mdct ? 2 * len : len;        // 32-bit words
+    B200_LOCK_DEVICE(d);      // scratch + stream are per device: one host-pointer call at a time (released on return)
     int32_t *scr = (int32_t *)b200_scratch(d, (in_elems + out_elems) * 4 + 512);
     if (!scr) fail("scratch");
     int32_t *din = scr, *dout = scr + ((in_elems + 63) & ~(size_t)63);

@@ -27,6 +27,13 @@ def me_esa_device(device, cur, ref, linesize, width, height, frame_stride, nfram
                                           nframes, mb_size, search_param, vp(_dptr(out_mv)), vp(_dptr(out_cost))), "me_esa_device")
 
 
+def me_esa_host(device, cur, ref, linesize, width, height, frame_stride, nframes, mb_size, search_param, out_mv, out_cost):
+    """HOST buffers (numpy arrays / pinned torch tensors / raw addresses)."""
+    h = lambda x: int(x.ctypes.data) if hasattr(x, "ctypes") else _dptr(x)
+    return check(lib().b200_me_esa_host(device.handle, vp(h(cur)), vp(h(ref)), linesize, width, height, frame_stride,
+                                        nframes, mb_size, search_param, vp(h(out_mv)), vp(h(out_cost))), "me_esa_host")
+
+
 PIXELUTILS_SAD_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_ssize_t)
 
 

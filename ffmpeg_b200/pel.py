@@ -51,6 +51,14 @@ def h264qpel_batch_device(device, n, op, dst, dst_off, src, src_off, stride):
                                                   vp(_dptr(src)), vp(_dptr(src_off)), stride), "h264qpel_batch_device")
 
 
+def h264qpel_frames_host(device, nframes, frame_bytes, op_begin, op, dst, dst_off, src, src_off, stride):
+    """HOST buffers (numpy arrays / pinned torch tensors / raw addresses): one reference + destination picture and one operation
+    list per frame, pipelined H2D -> kernel -> D2H."""
+    h = lambda x: int(x.ctypes.data) if hasattr(x, "ctypes") else _dptr(x)
+    return check(lib().b200_h264qpel_frames_host(device.handle, nframes, frame_bytes, vp(h(op_begin)), vp(h(op)), vp(h(dst)),
+                                                 vp(h(dst_off)), vp(h(src)), vp(h(src_off)), stride), "h264qpel_frames_host")
+
+
 def hpel_batch_device(device, n, op, h, dst, dst_off, src, src_off, stride):
     return check(lib().b200_hpel_batch_device(device.handle, n, vp(_dptr(op)), vp(_dptr(h)), vp(_dptr(dst)), vp(_dptr(dst_off)),
                                               vp(_dptr(src)), vp(_dptr(src_off)), stride), "hpel_batch_device")

@@ -16,12 +16,18 @@ SWS_FAST_BILINEAR, SWS_BILINEAR, SWS_BICUBIC, SWS_POINT, SWS_AREA, SWS_BICUBLIN 
 SWS_FULL_CHR_H_INT, SWS_FULL_CHR_H_INP, SWS_ACCURATE_RND, SWS_BITEXACT = 0x2000, 0x4000, 0x40000, 0x80000
 # libswscale/yuv2rgb.c:47-59 (sws_getCoefficients)
 SWS_CS_ITU709, SWS_CS_FCC, SWS_CS_ITU601, SWS_CS_SMPTE240M, SWS_CS_DEFAULT, SWS_CS_BT2020 = 1, 4, 5, 7, 5, 9
-_COEFFS = {0: (104597, 132201, 25675, 53279), 1: (117489, 138438, 13975, 34925), 4: (104448, 132798, 24759, 53109),
-           7: (117579, 136230, 16907, 35559), 9: (110013, 140363, 12277, 42626)}
+_BT601 = (104597, 132201, 25675, 53279)
+_BT2020 = (110013, 140363, 12277, 42626)
+# the reference's 11-row table (yuv2rgb.c:47-59): rows 0, 2, 3, 5, 6 are BT.601, row 8 (YCgCo) has no matrix, rows 9 and 10 are BT.2020
+_COEFFS = (_BT601, (117489, 138438, 13975, 34925), _BT601, _BT601, (104448, 132798, 24759, 53109), _BT601, _BT601,
+           (117579, 136230, 16907, 35559), None, _BT2020, _BT2020)
 
 
 def sws_getCoefficients(colorspace):
-    return _COEFFS.get(colorspace, _COEFFS[0])
+    """yuv2rgb.c:61-66: out-of-range values and 8 (YCgCo) select SWS_CS_DEFAULT."""
+    if colorspace > 10 or colorspace < 0 or colorspace == 8:
+        colorspace = SWS_CS_DEFAULT
+    return _COEFFS[colorspace]
 
 
 def _dptr(x):

@@ -12,6 +12,10 @@ def _dptr(x):
     return int(x.data_ptr()) if hasattr(x, "data_ptr") else int(x)
 
 
+def _hptr(x):
+    return int(x.ctypes.data) if hasattr(x, "ctypes") else _dptr(x)
+
+
 class AVTXContext:
     def __init__(self, type, inv, len, scale=None, flags=0, device=None):
         self._h = vp()
@@ -31,6 +35,10 @@ class AVTXContext:
     def batch_device(self, out, inp, stride, count, out_step, in_step):
         return check(lib().b200_tx_batch_device(self._h, vp(_dptr(out)), vp(_dptr(inp)), stride, count, out_step, in_step),
                      "tx_batch_device")
+
+    def batch_host(self, out, inp, stride, count, out_step, in_step):
+        """HOST buffers (numpy arrays / pinned torch tensors / raw addresses), pipelined H2D -> kernels -> D2H."""
+        return check(lib().b200_tx_batch_host(self._h, vp(_hptr(out)), vp(_hptr(inp)), stride, count, out_step, in_step), "tx_batch_host")
 
     def uninit(self):
         if self._h:

@@ -412,6 +412,10 @@ int  b200_me_cmp_batch_device(B200Device *dev, int fn, int idx, const uint8_t *f
  * per block in raster order per frame; out_cost: its SAD. */
 int  b200_me_esa_device(B200Device *dev, const uint8_t *cur, const uint8_t *ref, int linesize, int width, int height,
                         int64_t frame_stride, int nframes, int mb_size, int search_param, int32_t *out_mv, uint64_t *out_cost);
+/* same on HOST buffers (vf_mestimate's frames live in host memory): chunks of frame pairs rotate over three streams, H2D of both luma
+ * planes (frame_stride bytes per frame, frame_stride >= linesize * height), the search kernel, D2H of vectors and costs. */
+int  b200_me_esa_host(B200Device *dev, const uint8_t *cur, const uint8_t *ref, int linesize, int width, int height,
+                      int64_t frame_stride, int nframes, int mb_size, int search_param, int32_t *out_mv, uint64_t *out_cost);
 
 /* libavutil's public block SAD: av_pixelutils_get_sad_fn (libavutil/pixelutils.h:31-52, pixelutils.c:43-111).  Square blocks of
  * 1 << w_bits pixels, w_bits = h_bits = 1 ... 5; NULL for anything else, like the reference (and when no device is set). */
@@ -451,6 +455,13 @@ int  b200_h264qpel_batch_device(B200Device *dev, int64_t n, const uint8_t *op, u
                                 const uint8_t *src, const int64_t *src_off, ptrdiff_t stride);
 int  b200_hpel_batch_device(B200Device *dev, int64_t n, const uint8_t *op, const uint8_t *h, uint8_t *dst,
                             const int64_t *dst_off, const uint8_t *src, const int64_t *src_off, ptrdiff_t stride);
+/* HOST buffers, a stream of frames (mc_dir_part for every partition of every macroblock of a picture, h264_mb.c:210-330, collected per
+ * frame): frame f occupies [f * frame_bytes, (f + 1) * frame_bytes) of `src` (its reference picture, edge-padded) and of `dst`; its
+ * operations are op_begin[f] .. op_begin[f + 1] - 1 (op_begin has nframes + 1 entries), offsets counted from the start of dst / src
+ * as in the device entry point, each operation staying inside its own frame.  Chunks of frames rotate over three streams: H2D of the
+ * reference and destination pictures and of the lists, the kernel, D2H of the destination pictures. */
+int  b200_h264qpel_frames_host(B200Device *dev, int nframes, int64_t frame_bytes, const int64_t *op_begin, const uint8_t *op,
+                               uint8_t *dst, const int64_t *dst_off, const uint8_t *src, const int64_t *src_off, ptrdiff_t stride);
 
 /* h264chroma: replaces H264ChromaContext (libavcodec/h264chroma.h:26-31) as filled by ff_h264chroma_init(c, 8)
  * (libavcodec/h264chroma.c:36-65): h264_chroma_mc_func (h264chroma.h:24), bilinear eighth-pel, x, y in 0..7. */
@@ -526,6 +537,11 @@ void b200_tx_uninit(B200TXContext **ctx);
  * (bytes between MDCT input samples for the inverse / output samples for the forward transform; unused for FFT). */
 int  b200_tx_batch_device(B200TXContext *ctx, void *out, const void *in, ptrdiff_t stride, int64_t count,
                           ptrdiff_t out_step, ptrdiff_t in_step);
+/* same on HOST buffers (pinned memory for real overlap): chunks of transforms rotate over three streams, each chunk = one linear H2D
+ * of [i * in_step, (i + n) * in_step), the kernels, one linear D2H; steps must be positive multiples of 16 bytes.  What a decoder that
+ * keeps its coefficient buffers in host memory calls once per packet batch instead of count x av_tx_fn (aacdec_dsp_template.c:341-343). */
+int  b200_tx_batch_host(B200TXContext *ctx, void *out, const void *in, ptrdiff_t stride, int64_t count,
+                        ptrdiff_t out_step, ptrdiff_t in_step);
 
 #ifdef __cplusplus
 }

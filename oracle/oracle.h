@@ -149,6 +149,8 @@ void orc_esa_frame(const uint8_t *cur, const uint8_t *ref, int linesize, int wid
 
 /* ------------------------------------------------------------------ h264qpel / hpeldsp (8 bit) */
 void orc_h264qpel(int avg, int size_idx, int pos, uint8_t *dst, const uint8_t *src, ptrdiff_t stride);
+void orc_h264qpel_batch(int n, const uint8_t *op, uint8_t *dstbase, const int64_t *dst_off, const uint8_t *srcbase,
+                        const int64_t *src_off, ptrdiff_t stride);
 int  orc_hpel(int tab, int size_idx, int xy, uint8_t *block, const uint8_t *pixels, ptrdiff_t line_size, int h);
 void orc_emulated_edge_mc(uint8_t *buf, const uint8_t *src, ptrdiff_t buf_linesize, ptrdiff_t src_linesize,
                           int block_w, int block_h, int src_x, int src_y, int w, int h);

@@ -83,6 +83,14 @@ void orc_h264qpel(int avg, int size_idx, int pos, uint8_t *dst, const uint8_t *s
             dst[y * stride + x] = avg ? (uint8_t)((dst[y * stride + x] + out[y * 16 + x] + 1) >> 1) : out[y * 16 + x];
 }
 
+/* a list of operations, as ffref_h264qpel_batch / b200_h264qpel_batch_device take it (op byte: bit0 avg, bits1-2 size index, bits3-6 position) */
+void orc_h264qpel_batch(int n, const uint8_t *op, uint8_t *dstbase, const int64_t *dst_off, const uint8_t *srcbase,
+                        const int64_t *src_off, ptrdiff_t stride)
+{
+    for (int i = 0; i < n; i++)
+        orc_h264qpel(op[i] & 1, (op[i] >> 1) & 3, (op[i] >> 3) & 15, dstbase + dst_off[i], srcbase + src_off[i], stride);
+}
+
 int orc_hpel(int tab, int size_idx, int xy, uint8_t *block, const uint8_t *pixels, ptrdiff_t ls, int h)
 {
     const int w = 16 >> size_idx, no_rnd = tab >= 2;

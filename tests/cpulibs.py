@@ -59,6 +59,8 @@ def oracle():
         if hasattr(L, "orc_h264qpel"):
             L.orc_h264qpel.argtypes = [C.c_int, C.c_int, C.c_int, u8p, u8p, C.c_ssize_t]
             L.orc_hpel.argtypes = [C.c_int, C.c_int, C.c_int, u8p, u8p, C.c_ssize_t, C.c_int]
+        if hasattr(L, "orc_h264qpel_batch"):
+            L.orc_h264qpel_batch.argtypes = [C.c_int, u8p, u8p, i64p, u8p, i64p, C.c_ssize_t]
         if hasattr(L, "orc_emulated_edge_mc"):
             L.orc_emulated_edge_mc.argtypes = [u8p, C.c_void_p, C.c_ssize_t, C.c_ssize_t] + [C.c_int] * 6
             L.orc_emulated_edge_mc.restype = None

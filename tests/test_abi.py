@@ -74,3 +74,20 @@ def test_tables_match_reference_structs():
         pytest.skip("oracle/_ref/libffref.so not built")
     marker = C.c_char_p.in_dll(cl.ref(), "ffref_layout_check")
     assert C.string_at(C.addressof(marker)).startswith(b"b200dsp.h tables match")
+
+
+def test_sws_getCoefficients_matches_reference():
+    """All 11 rows plus the out-of-range / YCgCo fallback of sws_getCoefficients (libswscale/yuv2rgb.c:47-66)."""
+    from ffmpeg_b200 import swscale as sw
+    expect = {0: (104597, 132201, 25675, 53279), 1: (117489, 138438, 13975, 34925), 4: (104448, 132798, 24759, 53109),
+              7: (117579, 136230, 16907, 35559), 9: (110013, 140363, 12277, 42626), 10: (110013, 140363, 12277, 42626)}
+    for cs in range(-2, 14):
+        got = tuple(sw.sws_getCoefficients(cs))
+        assert got == expect.get(cs, expect[0]) or (cs in (2, 3, 5, 6) and got == expect[0]), cs
+    import cpulibs as cl
+    if cl.have_ref():
+        f = cl.ref().sws_getCoefficients
+        f.restype = C.POINTER(C.c_int32)
+        f.argtypes = [C.c_int]
+        for cs in range(-2, 14):
+            assert tuple(f(cs)[0:4]) == tuple(sw.sws_getCoefficients(cs)), cs
