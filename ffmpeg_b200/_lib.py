@@ -209,6 +209,7 @@ PROTOTYPES = {
     "b200_tx_init_device": (C.c_int, [vp, C.POINTER(vp), C.POINTER(TX_FN), C.c_int, C.c_int, C.c_int, vp, C.c_uint64]),
     "b200_tx_uninit": (None, [C.POINTER(vp)]),
     "b200_tx_batch_device": (C.c_int, [vp, vp, vp, C.c_ssize_t, C.c_int64, C.c_ssize_t, C.c_ssize_t]),
+    "b200_tx_r16_plan": (C.c_int, [C.c_int, C.c_int, vp, C.c_int]),
     "b200_tx_batch_host": (C.c_int, [vp, vp, vp, C.c_ssize_t, C.c_int64, C.c_ssize_t, C.c_ssize_t]),
     "b200_h264qpel_frames_host": (C.c_int, [vp, C.c_int, C.c_int64, vp, vp, vp, vp, vp, vp, C.c_ssize_t]),
     "b200_me_esa_host": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, vp, vp]),

@@ -386,6 +386,84 @@ sws_vscale_rgb24_fast_kernel(SwsFrameArgs a, SwsDevTables t, SwsColorConst c, in
     store_out<KIND>(a.dst + f * a.dfs + (long long)dy * (int)a.ds + xg * (16 * OutWords<KIND>::bpp), m);
 }
 
+// ------------------------------------------------------------------------------------------------ kernel: two output lines per thread
+// Same arithmetic as sws_vscale_rgb24_fast_kernel<true, true, KIND, NV> (identity luma bank, 4 chroma taps), for a pair of output lines
+// whose chroma windows coincide.  With 2x vertical chroma up-sampling the bicubic window of output lines 2k+1 and 2k+2 starts at the same
+// chroma line (vChrFilterPos equal, only the coefficients differ; the host checks this for the whole bank), so one thread loads the four
+// chroma lines once, interleaves them once (PRMT) and evaluates both lines from the same registers: 16 px x 2 lines per thread,
+// half the chroma loads, interleaves, address arithmetic and set-up of the one-line kernel.
+__device__ __forceinline__ void interleave2(const uint2 &r0, const uint2 &r1, unsigned *w)
+{
+    w[0] = __byte_perm(r0.x, r1.x, 0x5140); w[1] = __byte_perm(r0.x, r1.x, 0x7362);
+    w[2] = __byte_perm(r0.y, r1.y, 0x5140); w[3] = __byte_perm(r0.y, r1.y, 0x7362);
+}
+template <int NV>
+__device__ __forceinline__ void interleave2_nv(const uint4 &r0, const uint4 &r1, unsigned *wu, unsigned *wv)
+{
+    constexpr unsigned SU = NV == 1 ? 0x6240 : 0x7351, SV = NV == 1 ? 0x7351 : 0x6240;
+    wu[0] = __byte_perm(r0.x, r1.x, SU); wv[0] = __byte_perm(r0.x, r1.x, SV);
+    wu[1] = __byte_perm(r0.y, r1.y, SU); wv[1] = __byte_perm(r0.y, r1.y, SV);
+    wu[2] = __byte_perm(r0.z, r1.z, SU); wv[2] = __byte_perm(r0.z, r1.z, SV);
+    wu[3] = __byte_perm(r0.w, r1.w, SU); wv[3] = __byte_perm(r0.w, r1.w, SV);
+}
+
+template <int KIND, int NV>
+__global__ void __launch_bounds__(128, 6)
+sws_vscale_rgb24_pair_kernel(SwsFrameArgs a, SwsDevTables t, SwsColorConst c, int ngroups)
+{
+    constexpr int PW = OutWords<KIND>::per_pair;
+    const int xg = blockIdx.x * blockDim.x + threadIdx.x;
+    if (xg >= ngroups) return;
+    const int dA = a.y0 + 2 * blockIdx.y;                                   // lines dA and dA + 1
+    const long long f = blockIdx.z;
+    const int firstChr = max(-3, __ldg(t.vChrPos + dA));                    // == vChrPos[dA + 1]
+    const int chmax = a.chrSrcH - 1;
+    const int l0 = min(max(firstChr, 0), chmax), l1 = min(max(firstChr + 1, 0), chmax);
+    const int l2 = min(max(firstChr + 2, 0), chmax), l3 = min(max(firstChr + 3, 0), chmax);
+    const int us = (int)a.us, vs = (int)a.vs, ys = (int)a.ys;
+    unsigned IU[2][4], IV[2][4];                                            // [tap pair][word]: two chroma samples x two lines each
+    if (NV) {
+        const uint8_t *uvb = a.u + f * a.ufs + xg * 16;
+        const uint4 q0 = __ldg(reinterpret_cast<const uint4 *>(uvb + l0 * us)), q1 = __ldg(reinterpret_cast<const uint4 *>(uvb + l1 * us));
+        const uint4 q2 = __ldg(reinterpret_cast<const uint4 *>(uvb + l2 * us)), q3 = __ldg(reinterpret_cast<const uint4 *>(uvb + l3 * us));
+        interleave2_nv<NV ? NV : 1>(q0, q1, IU[0], IV[0]);
+        interleave2_nv<NV ? NV : 1>(q2, q3, IU[1], IV[1]);
+    } else {
+        const uint8_t *ub = a.u + f * a.ufs + xg * 8, *vb = a.v + f * a.vfs + xg * 8;
+        const uint2 u0 = __ldg(reinterpret_cast<const uint2 *>(ub + l0 * us)), u1 = __ldg(reinterpret_cast<const uint2 *>(ub + l1 * us));
+        const uint2 u2 = __ldg(reinterpret_cast<const uint2 *>(ub + l2 * us)), u3 = __ldg(reinterpret_cast<const uint2 *>(ub + l3 * us));
+        const uint2 v0 = __ldg(reinterpret_cast<const uint2 *>(vb + l0 * vs)), v1 = __ldg(reinterpret_cast<const uint2 *>(vb + l1 * vs));
+        const uint2 v2 = __ldg(reinterpret_cast<const uint2 *>(vb + l2 * vs)), v3 = __ldg(reinterpret_cast<const uint2 *>(vb + l3 * vs));
+        interleave2(u0, u1, IU[0]); interleave2(u2, u3, IU[1]);
+        interleave2(v0, v1, IV[0]); interleave2(v2, v3, IV[1]);
+    }
+    const uint8_t *yb = a.y + f * a.yfs + xg * 16;
+    const int lyA = min(max(__ldg(t.vLumPos + dA), 0), a.srcH - 1), lyB = min(max(__ldg(t.vLumPos + dA + 1), 0), a.srcH - 1);
+    const uint4 qy[2] = { __ldg(reinterpret_cast<const uint4 *>(yb + lyA * ys)), __ldg(reinterpret_cast<const uint4 *>(yb + lyB * ys)) };
+    const int2 kA = __ldg(reinterpret_cast<const int2 *>(t.vChr2 + 2 * dA)), kB = __ldg(reinterpret_cast<const int2 *>(t.vChr2 + 2 * dA + 2));
+    uint8_t *drow = a.dst + f * a.dfs + (long long)dA * (int)a.ds + xg * (16 * OutWords<KIND>::bpp);
+#pragma unroll
+    for (int L = 0; L < 2; L++) {
+        const int kx = L ? kB.x : kA.x, ky = L ? kB.y : kA.y;
+        int aU[8], aV[8];
+#pragma unroll
+        for (int w = 0; w < 4; w++) {
+            aU[2 * w]     = dp2a_lo_su(ky, IU[1][w], dp2a_lo_su(kx, IU[0][w], 1 << 11));
+            aU[2 * w + 1] = dp2a_hi_su(ky, IU[1][w], dp2a_hi_su(kx, IU[0][w], 1 << 11));
+            aV[2 * w]     = dp2a_lo_su(ky, IV[1][w], dp2a_lo_su(kx, IV[0][w], 1 << 11));
+            aV[2 * w + 1] = dp2a_hi_su(ky, IV[1][w], dp2a_hi_su(kx, IV[0][w], 1 << 11));
+        }
+        const unsigned yw[4] = { qy[L].x, qy[L].y, qy[L].z, qy[L].w };
+        unsigned m[8 * PW];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const ChromaBase cb = chroma_base(c, aU[i] >> 12, aV[i] >> 12);
+            pair_out<KIND>(c.cy, cb, byte_of(yw[(2 * i) >> 2], (2 * i) & 3), byte_of(yw[(2 * i + 1) >> 2], (2 * i + 1) & 3), m + PW * i);
+        }
+        store_out<KIND>(drow + (long long)L * (int)a.ds, m);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ kernel: vertical FIR + rgb24 (slow, general)
 // All three writers (_X, _1, _2), u8 (identity horizontal pass) or int16 line-plane sources, any alignment.
 // One thread = one pixel pair of one output line; covers pairs [p0, p1).  Grid: x over pairs, y over lines, z over frames.
@@ -806,6 +884,7 @@ struct B200SwsContext {
     bool fast_x = false;             // every line uses the _X writer and no 32-bit sum can wrap -> vector kernel
     bool lum_identity = false;       // vertical luma bank is a single tap of 4096 on every line
     bool all_x = false;              // every output line takes the `_X` writer (rowMode 0)
+    bool pair_ok = false;            // identity luma bank, 4 chroma taps, and output lines 2k+1 / 2k+2 share their chroma window
     // intermediate int16 line planes for the scaled path (grown on demand, per batch)
     void *mid = nullptr; size_t mid_bytes = 0;
     // de-interleaved chroma of an nv12 / nv21 source (persistent: slice calls keep earlier bands here)
@@ -889,6 +968,9 @@ static int upload_tables(B200SwsContext *c)
         if (sl > 60000 || sc > 60000) c->fast_x = false;         // (2^18 + 32640 * sum|coef|) must stay below 2^31
         if (p.vLum.size != 1 || p.vLum.coef[y] != 4096) c->lum_identity = false;
     }
+    c->pair_ok = c->fast_x && c->lum_identity && p.vChr.size == 4 && p.dstH >= 4 && !getenv("B200_SWS_NO_PAIR");
+    for (int y = 1; y + 1 < p.dstH && c->pair_ok; y += 2)
+        if (p.vChr.pos[y] != p.vChr.pos[y + 1]) c->pair_ok = false;
     return 0;
 }
 
@@ -1132,6 +1214,22 @@ static void launch_vscale_fast_nv(int kind, int nv, dim3 grid, dim3 block, cudaS
 // source lines that were just uploaded (only those need the horizontal pass).
 struct SwsRows { int dy0, ndy, ly0, nly, cy0, ncy; };
 
+
+// the two-line kernel over output lines [first, first + 2 * npairs), first odd
+template <int NV>
+static void launch_vscale_pair(int kind, dim3 grid, dim3 block, cudaStream_t stream, const SwsFrameArgs &b, const SwsDevTables &dt,
+                               const SwsColorConst &col, int ngroups)
+{
+    switch (kind) {
+    case SWS_OUT_RGB24: sws_vscale_rgb24_pair_kernel<SWS_OUT_RGB24, NV><<<grid, block, 0, stream>>>(b, dt, col, ngroups); break;
+    case SWS_OUT_BGR24: sws_vscale_rgb24_pair_kernel<SWS_OUT_BGR24, NV><<<grid, block, 0, stream>>>(b, dt, col, ngroups); break;
+    case SWS_OUT_RGBA:  sws_vscale_rgb24_pair_kernel<SWS_OUT_RGBA, NV><<<grid, block, 0, stream>>>(b, dt, col, ngroups); break;
+    case SWS_OUT_BGRA:  sws_vscale_rgb24_pair_kernel<SWS_OUT_BGRA, NV><<<grid, block, 0, stream>>>(b, dt, col, ngroups); break;
+    case SWS_OUT_ARGB:  sws_vscale_rgb24_pair_kernel<SWS_OUT_ARGB, NV><<<grid, block, 0, stream>>>(b, dt, col, ngroups); break;
+    default:            sws_vscale_rgb24_pair_kernel<SWS_OUT_ABGR, NV><<<grid, block, 0, stream>>>(b, dt, col, ngroups); break;
+    }
+}
+
 static int launch_batch(B200SwsContext *c, cudaStream_t stream, const uint8_t *const src_in[3], const long long sstr_in[3],
                         const long long sfs_in[3], uint8_t *dst, long long ds, long long dfs, int nframes,
                         const SwsRows *rows = nullptr, uint8_t *nv_scratch = nullptr)
@@ -1192,14 +1290,34 @@ static int launch_batch(B200SwsContext *c, cudaStream_t stream, const uint8_t *c
             auto fits32 = [](long long stride, long long lines) { return (stride < 0 ? -stride : stride) * (lines + 1) < (1LL << 31); };
             const bool off32 = fits32(b.ys, p.srcH) && fits32(b.us, p.chrSrcH) && fits32(b.vs, p.chrSrcH) && fits32(b.ds, p.dstH);
             const int ngroups = (vecOK && c->fast_x && off32 && R.ndy > 0) ? p.dstW / 16 : 0;
+            // lines [R.dy0, R.dy0 + R.ndy) = at most one leading line, pairs (odd, even) for the two-line kernel, at most one trailing line
+            const bool pairs_on = c->pair_ok && R.ndy >= 3 && (nv_direct || ngroups);
+            const int pfirst = pairs_on ? (R.dy0 | 1) : R.dy0, npairs = pairs_on ? (R.dy0 + R.ndy - pfirst) / 2 : 0;
+            if (npairs > 0) {
+                const int ng = nv_direct ? p.dstW / 16 : ngroups;
+                SwsFrameArgs bp = b;
+                bp.y0 = pfirst;
+                dim3 block(128), grid(b200_ceil_div(ng, 128), npairs, nf);
+                if (!nv_direct) launch_vscale_pair<0>(p.out.kind, grid, block, stream, bp, c->dt, p.color, ng);
+                else if (p.src_nv == 1) launch_vscale_pair<1>(p.out.kind, grid, block, stream, bp, c->dt, p.color, ng);
+                else launch_vscale_pair<2>(p.out.kind, grid, block, stream, bp, c->dt, p.color, ng);
+                B200_LAUNCHED();
+            }
+            // the one-line kernel: everything when no pairs were formed, else the lines left over at either end
+            const int seg0[2] = { R.dy0, pfirst + 2 * npairs }, segn[2] = { npairs > 0 ? pfirst - R.dy0 : R.ndy, npairs > 0 ? R.dy0 + R.ndy - (pfirst + 2 * npairs) : 0 };
+            for (int sg = 0; sg < 2; sg++) {
+            if (segn[sg] <= 0) continue;
+            SwsFrameArgs b1 = b;
+            b1.y0 = seg0[sg];
+            const SwsFrameArgs &b = b1;
             if (nv_direct) {
-                dim3 block(128), grid(b200_ceil_div(p.dstW / 16, 128), R.ndy, nf);
+                dim3 block(128), grid(b200_ceil_div(p.dstW / 16, 128), segn[sg], nf);
                 launch_vscale_fast_nv(p.out.kind, p.src_nv, grid, block, stream, b, c->dt, p.color, p.dstW / 16);
                 B200_LAUNCHED();
                 continue;
             }
             if (ngroups) {
-                dim3 block(128), grid(b200_ceil_div(ngroups, 128), R.ndy, nf);
+                dim3 block(128), grid(b200_ceil_div(ngroups, 128), segn[sg], nf);
                 const bool c4 = p.vChr.size == 4;
                 switch (p.out.kind) {
                 case SWS_OUT_RGB24: launch_vscale_fast<SWS_OUT_RGB24>(c->lum_identity, c4, grid, block, stream, b, c->dt, p.color, ngroups); break;
@@ -1211,6 +1329,8 @@ static int launch_batch(B200SwsContext *c, cudaStream_t stream, const uint8_t *c
                 }
                 B200_LAUNCHED();
             }
+            }
+            if (nv_direct) continue;
             const int p0 = ngroups * 8, p1 = (p.dstW + 1) / 2;
             if (p1 > p0 && R.ndy > 0) {
                 dim3 block(128), grid(b200_ceil_div(p1 - p0, 128), R.ndy, nf);

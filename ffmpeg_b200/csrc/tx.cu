@@ -17,6 +17,7 @@
 #include "tx_pfa.h"
 #include "tx_dct.h"
 #include "tx_int32.h"
+#include "tx_r16.h"
 #include <vector>
 #include <cmath>
 #include <cstring>
@@ -433,6 +434,7 @@ struct B200TXContext {
     TxPfa *pfa = nullptr;            // compound 15 x M MDCT (tx_pfa.cu): everything below d is unused then
     TxDct *dct = nullptr;            // AV_TX_FLOAT_DCT (tx_dct.cu): stages around a child RDFT context
     TxI32 *i32 = nullptr;            // AV_TX_INT32_FFT / _MDCT (tx_int32.cu)
+    TxR16 *r16 = nullptr;            // 512 ... 4096-point FFT / inverse MDCT: register-resident passes (tx_r16.cu), else the kernels below
     int type = 0, inv = 0, len = 0;
     bool full = false;               // AV_TX_FULL_IMDCT: ff_tx_mdct_inv_full around the inverse MDCT (tx_template.c:1372-1413)
     TxDev d{};
@@ -496,11 +498,13 @@ static int tx_build(B200TXContext *c, float scale)
         if (c->inv) {
             ex.resize(2 * (size_t)len4);
             for (int i = 0; i < len4; i++) { ex[len4 + i] = full[i]; ex[i] = full[gather[i]]; sub_map[i] = gather[i] << 1; }
+            c->r16 = tx_r16_create(1, n, gather.data(), full.data(), c->dev->sm_count);
         } else {
             ex = full;
             for (int i = 0; i < len4; i++) sub_map[i] = gather[i];
         }
     }
+    if (c->type == 0) c->r16 = tx_r16_create(0, n, gather.data(), nullptr, c->dev->sm_count);
     auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
     size_t off = 0;
     const size_t o_blk = off; off += al(blk.size() * 4);
@@ -627,6 +631,8 @@ static int tx_launch_half(B200TXContext *c, cudaStream_t st, void *out, const vo
     if (c->pfa) return tx_pfa_launch(c->pfa, st, out, in, stride, count, out_step, in_step);
     if (c->dct) return tx_dct_launch(c->dct, st, out, in, count, out_step, in_step);
     if (c->i32) return tx_i32_launch(c->i32, st, out, in, stride, count, out_step, in_step);
+    if (c->r16 && (c->type == 0 || stride == 4) && tx_r16_accepts(c->r16, out, in, out_step, in_step))
+        return tx_r16_launch(c->r16, st, out, in, out_step, in_step, count);
     // measured on B200 (scripts/quick_bench.py tx with B200_TX_TB / B200_TX_THREADS): 256 threads pay off from 1024 points per
     // transform on; 512-point transforms (iMDCT-1024) run 18 % faster with 128-thread CTAs
     int threads = c->d.n >= 1024 ? 256 : c->d.n >= 256 ? 128 : 64;
@@ -757,7 +763,7 @@ B200_API int b200_tx_init_device(B200Device *dev, B200TXContext **ctx, b200_tx_f
     c->dev = dev; c->type = type; c->inv = !!inv; c->len = len; c->full = full;
     if (cudaSetDevice(dev->ordinal) != cudaSuccess) { delete c; return B200_EEXTERNAL; }
     int ret = tx_build(c, sc);
-    if (ret < 0) { if (c->blob) cudaFree(c->blob); delete c; return ret; }
+    if (ret < 0) { if (c->blob) cudaFree(c->blob); tx_r16_destroy(c->r16); delete c; return ret; }
     *ctx = c;
     if (tx) *tx = tx_host_fn;
     return 0;
@@ -778,6 +784,7 @@ B200_API void b200_tx_uninit(B200TXContext **ctx)
     tx_pfa_free(c->pfa);
     tx_dct_free(c->dct);
     tx_i32_free(c->i32);
+    tx_r16_destroy(c->r16);
     delete c;
     *ctx = nullptr;
 }

@@ -530,6 +530,10 @@ int  b200_tx_pfa_tables(int inv, int len, float scale, int32_t *words, int cap, 
 int  b200_tx_dct_table(int inv, int len, float *tab, int cap);
 /* host-only: the tables of an int32 transform flattened into words (layout4: offsets of map, exp, cosine tables; then log2 n) */
 int  b200_tx_i32_tables(int type, int inv, int len, float scale, int32_t *words, int cap, int32_t *layout4);
+/* host-only: the per-thread plan of the register-resident 512 ... 4096-point kernel (csrc/tx_r16.cu; word w of thread tg at
+ * words[w * (n / 16) + tg]), for the CPU test tier, which replays the schedule in numpy and compares it with the checker.
+ * Returns the word count, B200_ENOSYS for sizes the kernel does not cover. */
+int  b200_tx_r16_plan(int n, int inv, uint32_t *words, int cap);
 int  b200_tx_init_device(B200Device *dev, B200TXContext **ctx, b200_tx_fn *tx, int type, int inv, int len,
                          const void *scale, uint64_t flags);
 void b200_tx_uninit(B200TXContext **ctx);
