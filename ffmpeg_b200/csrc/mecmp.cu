@@ -13,6 +13,7 @@
 // vector tested first is exactly "smallest key".  This search is integer-ALU bound (about 2100 op/byte), not HBM bound.
 #include "common.h"
 #include <cstring>
+#include <cstdlib>
 
 namespace {
 
@@ -175,10 +176,180 @@ esa_kernel(const uint8_t *cur, const uint8_t *ref, int linesize, long long frame
     }
 }
 
+// ---------------------------------------------------------------- exhaustive search, second kernel
+// The first kernel spends 2.3 instructions per VABSDIFF4 in its inner loop: every candidate row is re-assembled from two window words
+// with PRMT and every window / current-block word is fetched again for every group of four candidates.  Here
+//  * the window is kept in shared memory four times, once per byte phase (copy s holds the window shifted left by s bytes, built from
+//    copy 0 with funnel shifts), so a candidate at any column reads aligned words and needs no PRMT at all;
+//  * a task is ESA2_NV vertically adjacent candidates of one column: a window row, once loaded, is compared with the ESA2_NV rows of
+//    the current block it can face (rows i, i-1, ... of the block for candidates 0, 1, ...), and each row of the current block is
+//    loaded once per task (a broadcast LDS.128) and kept in a ring of ESA2_NV rows.  Per window row of a task: 4 + 1 loads, 32
+//    VABSDIFF4.U8.ACC: 1.2 instructions per useful one;
+//  * a CTA owns MBS horizontally adjacent macroblocks: their windows overlap by all but 16 columns, and 2 x 585 tasks spread over
+//    256 threads leave fewer idle slots in the last round than 585 do.
+// Key, tie-breaks and outputs are those of esa_kernel.
+constexpr int ESA2_THREADS = 256;
+constexpr int ESA2_NV = 8;
+
+template <int MB, int MBS>
+__global__ void __launch_bounds__(ESA2_THREADS)
+esa2_kernel(const uint8_t *cur, const uint8_t *ref, int linesize, long long frame_stride, int b_w, int b_h, int search,
+            int pitch /* words per window row */, int copy_words /* words per phase copy */, int32_t *out_mv, unsigned long long *out_cost)
+{
+    constexpr int WPR = MB / 4;                                    // words per block row
+    extern __shared__ unsigned smem[];
+    unsigned *scur = smem;                                         // [MBS][MB][WPR]
+    unsigned *swin = smem + MBS * MB * WPR;                        // [4][copy_words]
+    __shared__ unsigned long long best[MBS][ESA2_THREADS / 32];
+
+    const int bx0 = blockIdx.x * MBS, by = blockIdx.y;
+    const long long f = blockIdx.z;
+    const int nm = min(MBS, b_w - bx0);
+    const int y_mb = by * MB;
+    const int gx_max = (b_w - 1) * MB, gy_max = (b_h - 1) * MB;
+    const int y0 = max(y_mb - search, 0), y1 = min(y_mb + search, gy_max), ny = y1 - y0 + 1;
+    int xmb[MBS], x0[MBS], nx[MBS];
+#pragma unroll
+    for (int m = 0; m < MBS; m++) {
+        xmb[m] = (bx0 + min(m, nm - 1)) * MB;
+        x0[m] = max(xmb[m] - search, 0);
+        nx[m] = min(xmb[m] + search, gx_max) - x0[m] + 1;
+    }
+    const int xs = x0[0];
+    const int wcols = x0[nm - 1] + nx[nm - 1] - 1 + MB - xs;      // bytes of the joint window
+    const int wrows = ny + MB - 1, trows = wrows + ESA2_NV - 1;    // rows a task of the last group may touch (the extra ones are zero)
+    const uint8_t *r = ref + f * frame_stride + (long long)y0 * linesize + xs;
+
+    // ---- stage the current blocks and phase 0 of the window
+    for (int i = threadIdx.x; i < nm * MB * WPR; i += ESA2_THREADS) {
+        const int m = i / (MB * WPR), rem = i - m * (MB * WPR), row = rem / WPR, q = rem - row * WPR;
+        const uint8_t *c = cur + f * frame_stride + (long long)(y_mb + row) * linesize + xmb[m] + 4 * q;
+        scur[i] = (unsigned)c[0] | (unsigned)c[1] << 8 | (unsigned)c[2] << 16 | (unsigned)c[3] << 24;
+    }
+    const bool al4 = ((reinterpret_cast<uintptr_t>(r) | (unsigned)linesize) & 3) == 0;
+    for (int i = threadIdx.x; i < trows * pitch; i += ESA2_THREADS) {
+        const int yy = i / pitch, k = i - yy * pitch;
+        unsigned w = 0;
+        if (yy < wrows) {
+            const uint8_t *p = r + (long long)yy * linesize + 4 * k;
+            if (al4 && 4 * k + 3 < wcols) w = __ldg(reinterpret_cast<const unsigned *>(p));
+            else
+                for (int b = 0; b < 4; b++) if (4 * k + b < wcols) w |= (unsigned)__ldg(p + b) << (8 * b);
+        }
+        swin[i] = w;
+    }
+    if (threadIdx.x == 0) swin[trows * pitch] = 0;                  // the word the last funnel shift reads
+    __syncthreads();
+    for (int i = threadIdx.x; i < trows * pitch; i += ESA2_THREADS) {
+        const unsigned w0 = swin[i], w1 = swin[i + 1];
+        swin[copy_words + i] = __funnelshift_r(w0, w1, 8);
+        swin[2 * copy_words + i] = __funnelshift_r(w0, w1, 16);
+        swin[3 * copy_words + i] = __funnelshift_r(w0, w1, 24);
+    }
+    __syncthreads();
+
+    // ---- tasks: (macroblock m, row group gy, column cx), columns fastest so that a warp reads consecutive words of the four copies
+    const int ng = (ny + ESA2_NV - 1) / ESA2_NV;
+    const int ntask0 = nx[0] * ng, ntasks = ntask0 + (nm > 1 ? nx[MBS - 1] * ng : 0);
+    unsigned long long mine[MBS];
+#pragma unroll
+    for (int m = 0; m < MBS; m++) mine[m] = ~0ull;
+    for (int t = threadIdx.x; t < ntasks; t += ESA2_THREADS) {
+        const int m = (MBS > 1 && t >= ntask0) ? 1 : 0;
+        const int local = t - (m ? ntask0 : 0);
+        const int nxm = m ? nx[MBS - 1] : nx[0], x0m = m ? x0[MBS - 1] : x0[0], xmbm = m ? xmb[MBS - 1] : xmb[0];
+        const int gy = local / nxm, cx = local - gy * nxm;
+        const int wx = x0m - xs + cx;
+        const unsigned *wrow = swin + (wx & 3) * copy_words + gy * ESA2_NV * pitch + (wx >> 2);
+        const unsigned *crow = scur + m * (MB * WPR);
+        unsigned sad[ESA2_NV], C[ESA2_NV][WPR];
+#pragma unroll
+        for (int c = 0; c < ESA2_NV; c++) sad[c] = 0;
+#pragma unroll
+        for (int i = 0; i < MB + ESA2_NV - 1; i++) {
+            unsigned W[WPR];
+#pragma unroll
+            for (int q = 0; q < WPR; q++) W[q] = wrow[q];
+            wrow += pitch;
+            if (i < MB) {
+#pragma unroll
+                for (int q = 0; q < WPR; q++) C[i % ESA2_NV][q] = crow[i * WPR + q];
+            }
+#pragma unroll
+            for (int c = 0; c < ESA2_NV; c++) {
+                const int j = i - c;
+                if (j >= 0 && j < MB) {
+#pragma unroll
+                    for (int q = 0; q < WPR; q++) sad[c] = __vsadu4(W[q], C[j % ESA2_NV][q]) + sad[c];
+                }
+            }
+        }
+        unsigned long long bestk = ~0ull;
+#pragma unroll
+        for (int c = 0; c < ESA2_NV; c++) {
+            const int cy = gy * ESA2_NV + c;
+            if (cy < ny) {
+                const int ax = x0m + cx, ay = y0 + cy;
+                const unsigned notzero = (ax == xmbm && ay == y_mb) ? 0u : 1u;
+                const unsigned long long key = ((unsigned long long)sad[c] << 32) | ((unsigned long long)notzero << 31) | (unsigned)(cy * nxm + cx);
+                bestk = key < bestk ? key : bestk;
+            }
+        }
+        if (MBS > 1 && m) mine[MBS - 1] = bestk < mine[MBS - 1] ? bestk : mine[MBS - 1];
+        else mine[0] = bestk < mine[0] ? bestk : mine[0];
+    }
+#pragma unroll
+    for (int m = 0; m < MBS; m++) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, mine[m], o);
+            mine[m] = other < mine[m] ? other : mine[m];
+        }
+        if ((threadIdx.x & 31) == 0) best[m][threadIdx.x >> 5] = mine[m];
+    }
+    __syncthreads();
+    if (threadIdx.x < nm) {
+        const int m = threadIdx.x;
+        unsigned long long mm = best[m][0];
+        for (int i = 1; i < ESA2_THREADS / 32; i++) mm = best[m][i] < mm ? best[m][i] : mm;
+        const int nxm = m ? nx[MBS - 1] : nx[0], x0m = m ? x0[MBS - 1] : x0[0];
+        const int k = (int)(mm & 0x7fffffffu);
+        const int cy = k / nxm, cx = k - cy * nxm;
+        const long long o = (f * b_h + by) * b_w + bx0 + m;
+        out_mv[2 * o] = x0m + cx;
+        out_mv[2 * o + 1] = y0 + cy;
+        out_cost[o] = mm >> 32;
+    }
+}
+
 template <int MB>
 int launch_esa(cudaStream_t st, const uint8_t *cur, const uint8_t *ref, int linesize, long long fs, int b_w, int b_h,
                int nframes, int search, int32_t *mv, unsigned long long *cost)
 {
+    static int v2 = -1;                                          // B200_ESA2=0: the first kernel
+    if (v2 < 0) { const char *e = getenv("B200_ESA2"); v2 = e ? atoi(e) : 1; }
+    if (v2) {
+        constexpr int MBS = 2;
+        const int wc = 2 * search + MB * MBS;                    // widest joint window in bytes
+        const int pitch = (wc + 3) / 4 + 1;
+        const int trows = 2 * search + MB + ESA2_NV - 1;
+        int copy_words = trows * pitch + 1;
+        copy_words += (8 - (copy_words & 31) + 32) & 31;         // copies 8 banks apart: the four phases of 8 neighbouring columns hit 32 banks
+        const size_t smem2 = ((size_t)MBS * MB * (MB / 4) + 4 * (size_t)copy_words) * 4;
+        if (smem2 <= 100 * 1024) {
+            if (smem2 > 48 * 1024)
+                B200_CUDA_OK(cudaFuncSetAttribute(esa2_kernel<MB, MBS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            for (int f0 = 0; f0 < nframes; f0 += 65535) {
+                const int nf = nframes - f0 < 65535 ? nframes - f0 : 65535;
+                dim3 grid((b_w + MBS - 1) / MBS, b_h, nf);
+                esa2_kernel<MB, MBS><<<grid, ESA2_THREADS, smem2, st>>>(cur + (long long)f0 * fs, ref + (long long)f0 * fs, linesize, fs, b_w, b_h,
+                                                                        search, pitch, copy_words, mv + 2LL * f0 * b_w * b_h, cost + (long long)f0 * b_w * b_h);
+                B200_LAUNCHED();
+            }
+            B200_CUDA_OK(cudaGetLastError());
+            return 0;
+        }
+    }
     const int wcols = 2 * search + MB;                           // widest window in bytes
     const int win_pitch = (wcols + 3) / 4 + 1;                   // +1 word: the PRMT pair read one past the last needed word
     const size_t smem = ((size_t)MB * (MB / 4) + (size_t)(2 * search + MB) * win_pitch) * 4;

@@ -11,6 +11,7 @@
 #include "common.h"
 #include <algorithm>
 #include <cstring>
+#include <cstdlib>
 
 namespace {
 
@@ -246,6 +247,201 @@ qpel_kernel(long long n, const uint8_t *op, uint8_t *dst, const int64_t *dst_off
     }
 }
 
+// ------------------------------------------------------------------------------------------------ qpel on TMA-staged windows
+// Same arithmetic as qpel_kernel; what changes is how a window reaches shared memory: one cp.async.bulk.tensor.2d (UTMALDG) per
+// operation — a box of 32 bytes x (size + 5) rows whose origin is the operation's own (column - 8, row - 2) in a tensor map laid
+// over the reference plane — completes on the operation's mbarrier.  A warp issues the boxes of all its TQK operations before it
+// computes the first one, so nothing of the load path runs on the LSU any more (no per-row 16-byte loads, no register -> shared
+// staging, no funnel-shift re-alignment: the box lands with block column 0 at byte 8 of each 32-byte row).  The tile uses the
+// 32-byte swizzle (the two 16-byte halves of rows 4..7 of every 8 are swapped), which makes the 8-byte row-segment reads of a warp
+// conflict-free; WinT applies it on the word index.  Operations whose box would leave the row (a block closer than 8 bytes to the
+// left end or 24 to the right end of a line: never the case inside an edge-padded H.264 picture) are filled by plain loads instead.
+constexpr int TQK = 8;                  // operations per warp
+constexpr int TILE_BYTES = 768;         // 21 rows x 32 bytes, rounded up to the 256-byte swizzle period
+template <bool SWZ>
+struct WinT {
+    const unsigned *t;
+    __device__ __forceinline__ unsigned w(int row, int k) const { return t[row * 8 + (SWZ ? (k ^ (row & 4)) : k)]; }
+};
+template <bool SWZ>
+__device__ __forceinline__ uint2 t_row8p(const WinT<SWZ> &W, int row, int x0, int dx)
+{
+    const int k = (QX + x0) >> 2;
+    unsigned w0 = W.w(row, k), w1 = W.w(row, k + 1);
+    if (dx) { const unsigned w2 = W.w(row, k + 2); w0 = __funnelshift_r(w0, w1, 8); w1 = __funnelshift_r(w1, w2, 8); }
+    return make_uint2(w0, w1);
+}
+template <bool SWZ>
+__device__ __forceinline__ void t_hsum8(const WinT<SWZ> &W, int row, int x0, int init, int *o)
+{
+    const int k = (QX + x0 - 4) >> 2;
+    const unsigned A[5] = { W.w(row, k), W.w(row, k + 1), W.w(row, k + 2), W.w(row, k + 3), W.w(row, k + 4) };
+    unsigned S[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        const int b = 2 + i;
+        S[i] = (b & 3) ? __funnelshift_r(A[b >> 2], A[(b >> 2) + 1], (b & 3) * 8) : A[b >> 2];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) o[i] = dp4a_us(S[i + 4], TAP4_B, dp4a_us(S[i], TAP4_A, init));
+}
+
+__device__ __forceinline__ uint32_t pel_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void pel_mbar_wait(uint32_t a, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void pel_tma_2d(uint32_t dst, const CUtensorMap *tm, int c0, int c1, uint32_t mbar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 :: "r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(mbar) : "memory");
+}
+
+struct __align__(1024) QpelTmaSmem {
+    uint8_t tile[WARPS][TQK][TILE_BYTES];
+    short hraw[WARPS][21 * 16];
+    unsigned long long mbar[WARPS][TQK];
+};
+
+template <bool SWZ>
+__global__ void __launch_bounds__(32 * WARPS)
+qpel_tma_kernel(const __grid_constant__ CUtensorMap tm16, const __grid_constant__ CUtensorMap tm8, const __grid_constant__ CUtensorMap tm4,
+                long long n, const uint8_t *op, uint8_t *dst, const int64_t *dst_off, const uint8_t *src, const int64_t *src_off,
+                long long stride, unsigned long long magic)
+{
+    __shared__ QpelTmaSmem sm;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long first_op = ((long long)blockIdx.x * WARPS + warp) * TQK;
+    if (first_op >= n) return;
+    // lanes 0 .. TQK-1 each own one operation's descriptor and issue its box
+    int mo = -1, inb = 0;
+    long long msoff = 0, mdoff = 0;
+    if (lane < TQK) {
+        const uint32_t mb = pel_smem_u32(&sm.mbar[warp][lane]);
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(mb) : "memory");
+        if (first_op + lane < n) {
+            mo = __ldg(op + first_op + lane); msoff = __ldg(src_off + first_op + lane); mdoff = __ldg(dst_off + first_op + lane);
+        }
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+    if (mo >= 0 && msoff >= 0) {
+        // row and column of the block inside the plane: soff = y * stride + x (reciprocal multiply, corrected)
+        unsigned long long y = __umul64hi((unsigned long long)msoff, magic);
+        long long x = msoff - (long long)y * stride;
+        while (x >= stride) { x -= stride; y++; }
+        const int size = 16 >> ((mo >> 1) & 3);
+        if (x >= 8 && x + 24 <= stride && y >= 2 && y < 0x7fffff00ULL) {
+            inb = 1;
+            const CUtensorMap *tm = size == 16 ? &tm16 : size == 8 ? &tm8 : &tm4;
+            pel_tma_2d(pel_smem_u32(&sm.tile[warp][lane][0]), tm, (int)x - 8, (int)y - 2, pel_smem_u32(&sm.mbar[warp][lane]), 32u * (size + 5));
+        }
+    }
+    short *hraw = sm.hraw[warp];
+    for (int t = 0; t < TQK; t++) {
+        const int o = __shfl_sync(0xffffffffu, mo, t);
+        if (o < 0) break;                                                                  // past the end (warp-uniform)
+        const long long doff = __shfl_sync(0xffffffffu, mdoff, t);
+        const int avg = o & 1, size = 16 >> ((o >> 1) & 3), qx = (o >> 3) & 3, qy = (o >> 5) & 3;
+        uint8_t *dp = dst + doff;
+        const int wdim = size + 5;
+        const int npx = size < 8 ? size : 8, segs = size >> 3 ? size >> 3 : 1;
+        const bool mine = lane < size * segs;
+        const int y = lane / segs, x0 = (lane - y * segs) * 8;
+        uint8_t *d = dp + (long long)y * stride + x0;
+        const bool vec = npx == 8 && ((reinterpret_cast<uintptr_t>(d)) & 7) == 0;
+        uint2 pv = make_uint2(0, 0);
+        if (mine && avg && vec) pv = *reinterpret_cast<const uint2 *>(d);                  // destination row requested early
+        uint8_t *tile = sm.tile[warp][t];
+        if (__shfl_sync(0xffffffffu, inb, t)) {
+            pel_mbar_wait(pel_smem_u32(&sm.mbar[warp][t]), 0);
+        } else {                                                                           // box would leave the line: plain loads
+            const long long soff = __shfl_sync(0xffffffffu, msoff, t);
+            if (lane < wdim) {
+                const uint8_t *rp = src + soff + (long long)(lane - 2) * stride - 2;
+                for (int k = 0; k < wdim; k++) {
+                    const int b = QX - 2 + k;
+                    tile[lane * 32 + (SWZ ? (b ^ ((lane & 4) << 2)) : b)] = __ldg(rp + k);
+                }
+            }
+            __syncwarp();
+        }
+        const WinT<SWZ> W{ reinterpret_cast<const unsigned *>(tile) };
+        const bool need_j = (qx == 2 && qy != 0) || (qy == 2 && qx != 0);
+        if (need_j) {
+            for (int k = lane; k < wdim * segs; k += 32) {
+                const int r = k / segs, xx = (k - r * segs) * 8;
+                int h[8];
+                t_hsum8(W, r, xx, 0, h);
+                uint4 pk;
+                pk.x = __byte_perm(h[0], h[1], 0x5410); pk.y = __byte_perm(h[2], h[3], 0x5410);
+                pk.z = __byte_perm(h[4], h[5], 0x5410); pk.w = __byte_perm(h[6], h[7], 0x5410);
+                *reinterpret_cast<uint4 *>(&hraw[r * 16 + xx]) = pk;
+            }
+            __syncwarp();
+        }
+        if (mine) {
+            const bool useF = (qy == 0 && qx != 2) || (qx == 0 && (qy & 1));
+            const bool useH = qx != 0 && qy != 2;
+            const bool useV = qy != 0 && qx != 2;
+            uint2 res = make_uint2(0, 0);
+            bool have = false;
+            auto add = [&](const uint2 &c) {
+                if (have) { res.x = __vavgu4(res.x, c.x); res.y = __vavgu4(res.y, c.y); }
+                else { res = c; have = true; }
+            };
+            if (useF) add(t_row8p(W, y + 2 + (qy == 3), x0, qx == 3));
+            if (useH) {
+                int h[8];
+                t_hsum8(W, y + 2 + (qy == 3), x0, 16, h);
+                add(clip_pack8<5>(h));
+            }
+            if (useV) {
+                const int dx = qx == 3;
+                int a8[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) a8[k] = 16;
+#pragma unroll
+                for (int j = 0; j < 3; j++)
+                    vfold(tap2_16(j), t_row8p(W, y + 2 * j, x0, dx), t_row8p(W, y + 2 * j + 1, x0, dx), a8);
+                add(clip_pack8<5>(a8));
+            }
+            if (need_j) {
+                int j6[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) j6[k] = 512;
+#pragma unroll
+                for (int j = 0; j < 3; j++) {
+                    const uint4 pa = *reinterpret_cast<const uint4 *>(&hraw[(y + 2 * j) * 16 + x0]);
+                    const uint4 pb = *reinterpret_cast<const uint4 *>(&hraw[(y + 2 * j + 1) * 16 + x0]);
+                    const unsigned wa[4] = { pa.x, pa.y, pa.z, pa.w }, wb[4] = { pb.x, pb.y, pb.z, pb.w };
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        j6[2 * k]     = dp2a_lo_ss(__byte_perm(wa[k], wb[k], 0x5410), tap2_8(j), j6[2 * k]);
+                        j6[2 * k + 1] = dp2a_lo_ss(__byte_perm(wa[k], wb[k], 0x7632), tap2_8(j), j6[2 * k + 1]);
+                    }
+                }
+                add(clip_pack8<10>(j6));
+            }
+            if (vec) {
+                if (avg) { res.x = __vavgu4(res.x, pv.x); res.y = __vavgu4(res.y, pv.y); }
+                *reinterpret_cast<uint2 *>(d) = res;
+            } else {
+                for (int k = 0; k < npx; k++) {
+                    const int v = (int)__byte_perm(k < 4 ? res.x : res.y, 0, 0x4440 | (k & 3));
+                    d[k] = (uint8_t)(avg ? (d[k] + v + 1) >> 1 : v);
+                }
+            }
+        }
+        __syncwarp();                                                                      // hraw is reused by the next operation
+    }
+}
+
 // hpel: one warp per operation, direct global reads (at most 4 taps per pixel, rows are contiguous)
 __global__ void __launch_bounds__(32 * WARPS)
 hpel_kernel(long long n, const uint8_t *op, const uint8_t *hh, uint8_t *dst, const int64_t *dst_off, const uint8_t *src,
@@ -349,6 +545,112 @@ chroma_kernel(long long n, const uint8_t *op, const uint8_t *hh, const uint8_t *
             for (int k = 0; k < w; k++) {
                 const int px = (int)__byte_perm(k < 4 ? w0 : w1, 0, 0x4440 | (k & 3));
                 d[k] = (uint8_t)(avg ? (d[k] + px + 1) >> 1 : px);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ h264chroma on TMA-staged windows
+// Same arithmetic as chroma_kernel.  Every operation's source window arrives as one cp.async.bulk.tensor.2d box of 16 bytes x
+// (h + 1) rows (h rows when y == 0: the row below the block is never touched then, as in the reference) placed at the block's own
+// column and row of a tensor map over the reference plane, so a row costs no LSU work at all (the LDG kernel pays a 32-byte sector and
+// two funnel shifts for 9 useful bytes).  A warp owns CQ x 4 operations (8 lanes each, lane = row) and issues all their boxes before
+// it computes the first: 16 windows in flight per warp.  Heights other than 2 / 4 / 8 / 16, and blocks within 16 bytes of the end of
+// a line, take plain loads into the same tile.  The box may read up to 7 bytes right of the reference's own window inside the line.
+constexpr int CQ = 4;                   // operations per 8-lane group
+constexpr int CTILE = 384;              // 17 rows x 16 bytes, rounded to the 128-byte alignment TMA wants
+struct ChromaMaps { CUtensorMap m[8]; };                                // [2 * log2(h / 2) + (y != 0)]: box heights 2,3, 4,5, 8,9, 16,17
+struct __align__(128) ChromaTmaSmem {
+    uint8_t tile[WARPS][4 * CQ][CTILE];
+    unsigned long long mbar[WARPS][4 * CQ];
+};
+
+__global__ void __launch_bounds__(32 * WARPS)
+chroma_tma_kernel(const __grid_constant__ ChromaMaps maps, long long n, const uint8_t *op, const uint8_t *hh, const uint8_t *xy, uint8_t *dst,
+                  const int64_t *dst_off, const uint8_t *src, const int64_t *src_off, long long stride, unsigned long long magic)
+{
+    __shared__ ChromaTmaSmem sm;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, grp = lane >> 3, sub = lane & 7;
+    constexpr int PER_WARP = 4 * CQ;
+    const long long first_op = ((long long)blockIdx.x * WARPS + warp) * PER_WARP;
+    if (first_op >= n) return;
+    // lanes 0 .. 15 own one operation's descriptor each (slot = lane: group lane / CQ, round lane % CQ) and issue its box
+    int mo = -1, mh = 0, mpq = 0, inb = 0;
+    long long msoff = 0, mdoff = 0;
+    if (lane < PER_WARP) {
+        const uint32_t mb = pel_smem_u32(&sm.mbar[warp][lane]);
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(mb) : "memory");
+        const long long i = first_op + lane;
+        if (i < n) { mo = __ldg(op + i); mh = __ldg(hh + i); mpq = __ldg(xy + i); msoff = __ldg(src_off + i); mdoff = __ldg(dst_off + i); }
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+    if (mo >= 0 && msoff >= 0 && (mh == 2 || mh == 4 || mh == 8 || mh == 16)) {
+        unsigned long long y = __umul64hi((unsigned long long)msoff, magic);
+        long long x = msoff - (long long)y * stride;
+        while (x >= stride) { x -= stride; y++; }
+        if (x + 16 <= stride && y < 0x7fffff00ULL) {
+            inb = 1;
+            const int fy = (mpq >> 3) & 7, rows = mh + (fy != 0);
+            const int mi = 2 * (mh == 2 ? 0 : mh == 4 ? 1 : mh == 8 ? 2 : 3) + (fy != 0);
+            pel_tma_2d(pel_smem_u32(&sm.tile[warp][lane][0]), &maps.m[mi], (int)x, (int)y, pel_smem_u32(&sm.mbar[warp][lane]), 16u * rows);
+        }
+    }
+    for (int r = 0; r < CQ; r++) {
+        const int slot = grp * CQ + r;
+        const int o = __shfl_sync(0xffffffffu, mo, slot);
+        const bool valid = o >= 0;
+        const int h = __shfl_sync(0xffffffffu, mh, slot), pq = __shfl_sync(0xffffffffu, mpq, slot);
+        const long long doff = __shfl_sync(0xffffffffu, mdoff, slot), soff = __shfl_sync(0xffffffffu, msoff, slot);
+        const int tma = __shfl_sync(0xffffffffu, inb, slot);
+        const int fx = pq & 7, fy = (pq >> 3) & 7;
+        const int avg = o & 1, w = 8 >> ((o >> 1) & 3);
+        const int kab = 4 * ((8 - fx) * (8 - fy)) | (4 * (fx * (8 - fy))) << 16;      // s16 pairs (4A, 4B) and (4C, 4D)
+        const int kcd = 4 * ((8 - fx) * fy) | (4 * (fx * fy)) << 16;
+        uint8_t *dp = dst + doff;
+        uint8_t *tile = sm.tile[warp][slot];
+        const int nbytes = w + (fx != 0);
+        if (valid && tma) pel_mbar_wait(pel_smem_u32(&sm.mbar[warp][slot]), 0);
+        if (!valid) continue;
+        for (int y0 = 0; y0 < h; y0 += 16) {
+            if (!tma) {                                                                  // plain loads: rows y0 .. y0 + 16 of the window
+                __syncwarp(0xffu << (8 * grp));
+                const int rows = min(h - y0, 16) + (fy != 0);
+                for (int rr = sub; rr < rows; rr += 8) {
+                    const uint8_t *rp = src + soff + (long long)(y0 + rr) * stride;
+                    for (int k = 0; k < nbytes; k++) tile[rr * 16 + k] = __ldg(rp + k);
+                }
+                __syncwarp(0xffu << (8 * grp));
+            }
+#pragma unroll 1
+            for (int yy = sub; yy < min(h - y0, 16); yy += 8) {
+                const uint4 tq = *reinterpret_cast<const uint4 *>(tile + yy * 16);
+                const uint4 bq = *reinterpret_cast<const uint4 *>(tile + (yy + 1) * 16);
+                const unsigned ta = __funnelshift_r(tq.x, tq.y, 8), tb = __funnelshift_r(tq.y, tq.z, 8);
+                const unsigned ba = __funnelshift_r(bq.x, bq.y, 8), bb = __funnelshift_r(bq.y, bq.z, 8);
+                int v[8];
+                v[0] = dp2a_lo_su(kcd, bq.x, dp2a_lo_su(kab, tq.x, 128)); v[1] = dp2a_lo_su(kcd, ba, dp2a_lo_su(kab, ta, 128));
+                v[2] = dp2a_hi_su(kcd, bq.x, dp2a_hi_su(kab, tq.x, 128)); v[3] = dp2a_hi_su(kcd, ba, dp2a_hi_su(kab, ta, 128));
+                v[4] = dp2a_lo_su(kcd, bq.y, dp2a_lo_su(kab, tq.y, 128)); v[5] = dp2a_lo_su(kcd, bb, dp2a_lo_su(kab, tb, 128));
+                v[6] = dp2a_hi_su(kcd, bq.y, dp2a_hi_su(kab, tq.y, 128)); v[7] = dp2a_hi_su(kcd, bb, dp2a_hi_su(kab, tb, 128));
+                unsigned w0 = __byte_perm(__byte_perm(v[0], v[1], 0x5151), __byte_perm(v[2], v[3], 0x5151), 0x5410);
+                unsigned w1 = __byte_perm(__byte_perm(v[4], v[5], 0x5151), __byte_perm(v[6], v[7], 0x5151), 0x5410);
+                uint8_t *d = dp + (long long)(y0 + yy) * stride;
+                const unsigned al = (unsigned)(reinterpret_cast<uintptr_t>(d) & 7);
+                if (w == 8 && al == 0) {
+                    uint2 *d8 = reinterpret_cast<uint2 *>(d);
+                    if (avg) { const uint2 pv = *d8; w0 = __vavgu4(pv.x, w0); w1 = __vavgu4(pv.y, w1); }
+                    *d8 = make_uint2(w0, w1);
+                } else if (w >= 4 && (al & 3) == 0) {
+                    unsigned *d4 = reinterpret_cast<unsigned *>(d);
+                    d4[0] = avg ? __vavgu4(d4[0], w0) : w0;
+                    if (w == 8) d4[1] = avg ? __vavgu4(d4[1], w1) : w1;
+                } else {
+                    for (int k = 0; k < w; k++) {
+                        const int px = (int)__byte_perm(k < 4 ? w0 : w1, 0, 0x4440 | (k & 3));
+                        d[k] = (uint8_t)(avg ? (d[k] + px + 1) >> 1 : px);
+                    }
+                }
             }
         }
     }
@@ -551,10 +853,48 @@ B200_API int b200_h264chroma_batch_device(B200Device *dev, int64_t n, const uint
     if (!dev || n < 0 || !op || !h || !xy || !dst || !dst_off || !src || !src_off) return B200_EINVAL;
     if (n == 0) return 0;
     B200_CUDA_OK(cudaSetDevice(dev->ordinal));
-    const int per_cta = 32 * WARPS / CH_LANES;
-    const long long blocks = (n + per_cta - 1) / per_cta;
-    if (blocks > 0x7fffffffLL) return B200_EINVAL;
-    chroma_kernel<<<(unsigned)blocks, 32 * WARPS, 0, dev->stream>>>(n, op, h, xy, dst, dst_off, src, src_off, stride);
+    static int mode = -1;                                         // B200_CHROMA_TMA=0: the LDG kernel
+    if (mode < 0) { const char *e = getenv("B200_CHROMA_TMA"); mode = e ? atoi(e) : 1; }
+    ChromaMaps maps;
+    bool tma = mode > 0 && stride >= 16;
+    for (int k = 0; k < 8 && tma; k++)
+        tma = b200_tmap_2d_u8(&maps.m[k], src, (unsigned long long)stride, 16, (2u << (k >> 1)) + (k & 1), (int)CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (tma) {
+        const long long blocks = (n + WARPS * 4 * CQ - 1) / (WARPS * 4 * CQ);
+        if (blocks > 0x7fffffffLL) return B200_EINVAL;
+        chroma_tma_kernel<<<(unsigned)blocks, 32 * WARPS, 0, dev->stream>>>(maps, n, op, h, xy, dst, dst_off, src, src_off, stride,
+                                                                            ~0ULL / (unsigned long long)stride);
+    } else {
+        const int per_cta = 32 * WARPS / CH_LANES;
+        const long long blocks = (n + per_cta - 1) / per_cta;
+        if (blocks > 0x7fffffffLL) return B200_EINVAL;
+        chroma_kernel<<<(unsigned)blocks, 32 * WARPS, 0, dev->stream>>>(n, op, h, xy, dst, dst_off, src, src_off, stride);
+    }
+    B200_LAUNCHED();
+    B200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// B200_QPEL_TMA: 0 = LDG-staged kernel, 1 = TMA boxes without swizzle, 2 (default) = TMA boxes with the 32-byte swizzle
+static int qpel_launch(cudaStream_t st, int64_t n, const uint8_t *op, uint8_t *dst, const int64_t *dst_off, const uint8_t *src,
+                       const int64_t *src_off, ptrdiff_t stride)
+{
+    static int mode = -1;
+    if (mode < 0) { const char *e = getenv("B200_QPEL_TMA"); mode = e ? atoi(e) : 2; }
+    CUtensorMap tm16, tm8, tm4;
+    const int swz = mode == 2 ? (int)CU_TENSOR_MAP_SWIZZLE_32B : (int)CU_TENSOR_MAP_SWIZZLE_NONE;
+    if (mode > 0 && stride >= 32 && b200_tmap_2d_u8(&tm16, src, (unsigned long long)stride, 32, 21, swz) &&
+        b200_tmap_2d_u8(&tm8, src, (unsigned long long)stride, 32, 13, swz) && b200_tmap_2d_u8(&tm4, src, (unsigned long long)stride, 32, 9, swz)) {
+        const long long blocks = (n + WARPS * TQK - 1) / (WARPS * TQK);
+        if (blocks > 0x7fffffffLL) return B200_EINVAL;
+        const unsigned long long magic = ~0ULL / (unsigned long long)stride;              // floor((2^64 - 1) / stride): the quotient estimate is never too large
+        if (mode == 2) qpel_tma_kernel<true><<<(unsigned)blocks, 32 * WARPS, 0, st>>>(tm16, tm8, tm4, n, op, dst, dst_off, src, src_off, stride, magic);
+        else           qpel_tma_kernel<false><<<(unsigned)blocks, 32 * WARPS, 0, st>>>(tm16, tm8, tm4, n, op, dst, dst_off, src, src_off, stride, magic);
+    } else {
+        const long long blocks = (n + WARPS * QK - 1) / (WARPS * QK);
+        if (blocks > 0x7fffffffLL) return B200_EINVAL;
+        qpel_kernel<<<(unsigned)blocks, 32 * WARPS, 0, st>>>(n, op, dst, dst_off, src, src_off, stride);
+    }
     B200_LAUNCHED();
     B200_CUDA_OK(cudaGetLastError());
     return 0;
@@ -566,12 +906,7 @@ B200_API int b200_h264qpel_batch_device(B200Device *dev, int64_t n, const uint8_
     if (!dev || n < 0 || !op || !dst || !dst_off || !src || !src_off) return B200_EINVAL;
     if (n == 0) return 0;
     B200_CUDA_OK(cudaSetDevice(dev->ordinal));
-    const long long blocks = (n + WARPS * QK - 1) / (WARPS * QK);
-    if (blocks > 0x7fffffffLL) return B200_EINVAL;
-    qpel_kernel<<<(unsigned)blocks, 32 * WARPS, 0, dev->stream>>>(n, op, dst, dst_off, src, src_off, stride);
-    B200_LAUNCHED();
-    B200_CUDA_OK(cudaGetLastError());
-    return 0;
+    return qpel_launch(dev->stream, n, op, dst, dst_off, src, src_off, stride);
 }
 
 // HOST buffers: a stream of frames, each with its own reference picture, destination picture and list of motion-compensation

@@ -60,6 +60,20 @@ __device__ __forceinline__ ChromaBase chroma_base(const SwsColorConst &c, int U,
     return o;
 }
 
+// The same constants from the vertical sums themselves (12 fraction bits, before any shift): clamping the sum to [0, 2^20) and clearing
+// its fraction gives u8 << 12, and hi32((u8 << 12) * (coef << 4)) = (u8 * coef) >> 16 with the base folded into the same multiply-add
+// (IMAD.HI on the FMA pipe): no shift and no shift-add on the ALU pipe, which is the busy one in the vector kernels.
+// Needs |coef| < 2^27 (the host checks it before it selects a vector kernel).
+__device__ __forceinline__ ChromaBase chroma_base_q12(const SwsColorConst &c, int Usum, int Vsum)
+{
+    const int su = __vimin_s32_relu(Usum, 0xFFFFF) & ~0xFFF, sv = __vimin_s32_relu(Vsum, 0xFFFFF) & ~0xFFF;
+    ChromaBase o;
+    o.r = c.yb0 + (__mulhi(sv, c.crv << 4) + c.baseR) * c.cy;
+    o.g = c.yb0 + (__mulhi(su, c.cgu << 4) + (__mulhi(sv, c.cgv << 4) + c.baseG)) * c.cy;
+    o.b = c.yb0 + (__mulhi(su, c.cbu << 4) + c.baseB) * c.cy;
+    return o;
+}
+
 // Two pixels sharing one chroma sample -> three words holding (r0,g0) (b0,r1) (g1,b1) as clamped s16x2 (bytes 0 and 2).
 // (A + Y*cy) >> 16 is the high half of the 32-bit sum: PRMT picks the high halves, VIMNMX.S16x2.RELU clamps both to 0..255.
 __device__ __forceinline__ void pair_rgb_packed(int cy, const ChromaBase &cb, int Y0, int Y1, unsigned *m)
@@ -380,7 +394,7 @@ sws_vscale_rgb24_fast_kernel(SwsFrameArgs a, SwsDevTables t, SwsColorConst c, in
     unsigned m[8 * PW];
 #pragma unroll
     for (int i = 0; i < 8; i++) {
-        const ChromaBase cb = chroma_base(c, aU[i] >> 12, aV[i] >> 12);
+        const ChromaBase cb = chroma_base_q12(c, aU[i], aV[i]);
         pair_out<KIND>(c.cy, cb, Y[2 * i], Y[2 * i + 1], m + PW * i);
     }
     store_out<KIND>(a.dst + f * a.dfs + (long long)dy * (int)a.ds + xg * (16 * OutWords<KIND>::bpp), m);
@@ -408,7 +422,7 @@ __device__ __forceinline__ void interleave2_nv(const uint4 &r0, const uint4 &r1,
 }
 
 template <int KIND, int NV>
-__global__ void __launch_bounds__(128, 6)
+__global__ void __launch_bounds__(128, 8)
 sws_vscale_rgb24_pair_kernel(SwsFrameArgs a, SwsDevTables t, SwsColorConst c, int ngroups)
 {
     constexpr int PW = OutWords<KIND>::per_pair;
@@ -457,7 +471,7 @@ sws_vscale_rgb24_pair_kernel(SwsFrameArgs a, SwsDevTables t, SwsColorConst c, in
         unsigned m[8 * PW];
 #pragma unroll
         for (int i = 0; i < 8; i++) {
-            const ChromaBase cb = chroma_base(c, aU[i] >> 12, aV[i] >> 12);
+            const ChromaBase cb = chroma_base_q12(c, aU[i], aV[i]);
             pair_out<KIND>(c.cy, cb, byte_of(yw[(2 * i) >> 2], (2 * i) & 3), byte_of(yw[(2 * i + 1) >> 2], (2 * i + 1) & 3), m + PW * i);
         }
         store_out<KIND>(drow + (long long)L * (int)a.ds, m);
@@ -959,6 +973,11 @@ static int upload_tables(B200SwsContext *c)
     c->all_x = !p.planar;
     for (int y = 0; y < p.dstH && c->all_x; y++) if (p.rowMode[(size_t)y * 4] != 0) c->all_x = false;
     c->fast_x = c->h_identity && !p.planar;
+    {   // chroma_base_q12 multiplies by coef << 4
+        const long long lim = 1LL << 27;
+        auto big = [&](int v) { return (long long)v >= lim || (long long)v <= -lim; };
+        if (big(p.color.crv) || big(p.color.cgu) || big(p.color.cgv) || big(p.color.cbu)) c->fast_x = false;
+    }
     c->lum_identity = p.vLum.size == 1;
     for (int y = 0; y < p.dstH && c->fast_x; y++) {
         if (p.rowMode[(size_t)y * 4] != 0) c->fast_x = false;
@@ -1118,6 +1137,198 @@ B200_API int b200_sws_plan_probe2(const int cfg[9], const int *details, int whic
     if (filter && n) memcpy(filter, b.coef.data(), (size_t)n * b.size * 2);
     if (pos && n) memcpy(pos, b.pos.data(), (size_t)n * 4);
     return n;
+}
+
+// ------------------------------------------------------------------------------------------------ kernels: fused horizontal + vertical scaler
+// The two-pass scaler writes every horizontally scaled line to HBM as int16 and the vertical pass reads each of them back once per
+// tap (through L2 mostly): about 2.6 x the algorithmic traffic, and both passes are load-bound.  Here a CTA owns a tile of FT_W output
+// columns x TR output lines: it runs the horizontal FIR (same code and arithmetic as sws_hscale_rows_kernel) over exactly the source
+// lines the tile's vertical taps reach — the reference's ring buffer of scaled lines (swscale.c:412-535), tile-sized, in shared
+// memory — and then the vertical FIR + writer (same arithmetic as sws_vscale_planar8_kernel / sws_vscale_rgb24_x8_kernel) out of
+// shared memory.  Source bytes are read from HBM once (plus the vertical halo, 8 lines in 72 for 4K -> 1080p), nothing else moves.
+constexpr int FT_W = 128;               // output columns per CTA = threads per CTA
+
+// horizontal FIR of output column `col` over source lines ra .. rb into lines[(r - ra) * FT_W + slot]
+template <int NP, int PITCH>
+__device__ __forceinline__ void fused_hstage(const uint8_t *plane, long long sstride, const int32_t *coef2, const int32_t *pos, int fs,
+                                             int col, int ra, int rb, int16_t *lines, int slot)
+{
+    const int np = (fs + 1) >> 1, p0 = __ldg(pos + col);
+    int k[NP];
+#pragma unroll
+    for (int j = 0; j < NP; j++) k[j] = j < np ? __ldg(coef2 + (long long)col * np + j) : 0;
+    const uint8_t *base = plane + p0;
+    for (int r = ra; r <= rb; r++) {
+        const uint8_t *s = base + (long long)r * sstride;
+        const unsigned sh = (unsigned)(reinterpret_cast<uintptr_t>(s) & 3);
+        const unsigned *w = reinterpret_cast<const unsigned *>(s - sh);
+        const int need = (int)sh + fs;
+        unsigned prev = __ldg(w);
+        int acc = 0;
+#pragma unroll
+        for (int q = 0; q < (NP + 1) / 2; q++) {
+            if (q * 4 < fs) {
+                const unsigned next = ((q + 1) * 4 < need) ? __ldg(w + q + 1) : 0u;
+                const unsigned win = __funnelshift_r(prev, next, sh * 8);
+                prev = next;
+                acc = dp2a_lo_su(k[2 * q], win, acc);
+                if (2 * q + 1 < NP) acc = dp2a_hi_su(k[2 * q + 1], win, acc);
+            }
+        }
+        lines[(r - ra) * PITCH + slot] = (int16_t)min(acc >> 7, 32767);
+    }
+}
+
+// one 8-bit plane -> one 8-bit plane (yuv2planeX_8_c / yuv2plane1_8_c with the flat dither of SWS_BITEXACT, output.c:468-493)
+template <int NP>
+__global__ void __launch_bounds__(FT_W)
+sws_fused_plane_kernel(const uint8_t *src, long long sstride, long long sfs, int srcH, uint8_t *dst, long long ds, long long dfs,
+                       int dstW, int dstH, const int32_t *hcoef2, const int32_t *hpos, int hfs, const int16_t *vcoef,
+                       const int32_t *vpos, int vfs, int TR)
+{
+    extern __shared__ __align__(16) int16_t fused_lines[];
+    const int tid = threadIdx.x, x0 = blockIdx.x * FT_W, dy0 = blockIdx.y * TR, dy1 = min(dy0 + TR, dstH) - 1;
+    const long long f = blockIdx.z;
+    const int ra = min(max(max(1 - vfs, __ldg(vpos + dy0)), 0), srcH - 1);
+    const int rb = min(max(max(1 - vfs, __ldg(vpos + dy1)) + vfs - 1, 0), srcH - 1);
+    if (x0 + tid < dstW) fused_hstage<NP, FT_W>(src + f * sfs, sstride, hcoef2, hpos, hfs, x0 + tid, ra, rb, fused_lines, tid);
+    __syncthreads();
+    const int nrows = dy1 - dy0 + 1;
+    for (int it = tid; it < nrows * (FT_W / 8); it += FT_W) {
+        const int row = it / (FT_W / 8), g = it - row * (FT_W / 8), x = x0 + g * 8;
+        if (x >= dstW) continue;
+        const int dy = dy0 + row;
+        const int first = max(1 - vfs, __ldg(vpos + dy));
+        int v[8];
+        if (vfs == 1) {
+            const uint4 q = *reinterpret_cast<const uint4 *>(fused_lines + (min(max(first, 0), srcH - 1) - ra) * FT_W + g * 8);
+            const unsigned ww[4] = { q.x, q.y, q.z, q.w };
+#pragma unroll
+            for (int j = 0; j < 4; j++) { v[2 * j] = ((int)(short)(ww[j] & 0xffff) + 64) >> 7; v[2 * j + 1] = (((int)ww[j] >> 16) + 64) >> 7; }
+        } else {
+            unsigned a[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) a[j] = 64u << 12;
+            const int16_t *k = vcoef + (long long)dy * vfs;
+            for (int t = 0; t < vfs; t++) {
+                const uint4 q = *reinterpret_cast<const uint4 *>(fused_lines + (min(max(first + t, 0), srcH - 1) - ra) * FT_W + g * 8);
+                const unsigned ww[4] = { q.x, q.y, q.z, q.w };
+                const int c = (int)__ldg(k + t);
+#pragma unroll
+                for (int j = 0; j < 4; j++) { a[2 * j] += (unsigned)((int)(short)(ww[j] & 0xffff) * c); a[2 * j + 1] += (unsigned)(((int)ww[j] >> 16) * c); }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++) v[j] = (int)a[j] >> 19;
+        }
+        unsigned o[2];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const unsigned lo = __vimin_s16x2_relu(__byte_perm((unsigned)v[4 * h], (unsigned)v[4 * h + 1], 0x5410), 0x00ff00ffu);
+            const unsigned hi = __vimin_s16x2_relu(__byte_perm((unsigned)v[4 * h + 2], (unsigned)v[4 * h + 3], 0x5410), 0x00ff00ffu);
+            o[h] = __byte_perm(lo, hi, 0x6420);
+        }
+        *reinterpret_cast<uint2 *>(dst + f * dfs + (long long)dy * ds + x) = make_uint2(o[0], o[1]);
+    }
+}
+
+// yuv420p -> packed RGB through the `_X` writer (yuv2rgb_X_c_template, output.c:1789-1840): luma tile FT_W x TR, chroma FT_W/2 columns
+// of both planes; smem = luma lines (pitch FT_W), then U lines, then V lines (pitch FT_W/2); rowsL, rowsC: the largest tile's need
+template <int KIND, int NP>
+__global__ void __launch_bounds__(FT_W)
+sws_fused_rgb_kernel(SwsFrameArgs a, SwsDevTables t, SwsColorConst c, int TR, int rowsL, int rowsC)
+{
+    constexpr int PW = OutWords<KIND>::per_pair, BPP = OutWords<KIND>::bpp, CW = FT_W / 2;
+    extern __shared__ __align__(16) int16_t fused_lines[];
+    int16_t *lumL = fused_lines, *chrU = lumL + rowsL * FT_W, *chrV = chrU + rowsC * CW;
+    const int tid = threadIdx.x, x0 = blockIdx.x * FT_W, dy0 = blockIdx.y * TR, dy1 = min(dy0 + TR, a.dstH) - 1;
+    const long long f = blockIdx.z;
+    const int lfs = t.vLumSize, cfs = t.vChrSize;
+    const int la = min(max(max(1 - lfs, __ldg(t.vLumPos + dy0)), 0), a.srcH - 1);
+    const int lb = min(max(max(1 - lfs, __ldg(t.vLumPos + dy1)) + lfs - 1, 0), a.srcH - 1);
+    const int ca = min(max(max(1 - cfs, __ldg(t.vChrPos + dy0)), 0), a.chrSrcH - 1);
+    const int cb_ = min(max(max(1 - cfs, __ldg(t.vChrPos + dy1)) + cfs - 1, 0), a.chrSrcH - 1);
+    if (x0 + tid < a.dstW) fused_hstage<NP, FT_W>(a.y + f * a.yfs, a.ys, t.hLum2, t.hLumPos, t.hLumSize, x0 + tid, la, lb, lumL, tid);
+    {
+        const int cc = tid & (CW - 1), ccol = x0 / 2 + cc;
+        if (ccol < a.chrDstW) {
+            if (tid < CW) fused_hstage<NP, CW>(a.u + f * a.ufs, a.us, t.hChr2, t.hChrPos, t.hChrSize, ccol, ca, cb_, chrU, cc);
+            else          fused_hstage<NP, CW>(a.v + f * a.vfs, a.vs, t.hChr2, t.hChrPos, t.hChrSize, ccol, ca, cb_, chrV, cc);
+        }
+    }
+    __syncthreads();
+    const int nrows = dy1 - dy0 + 1;
+    for (int it = tid; it < nrows * (FT_W / 8); it += FT_W) {
+        const int row = it / (FT_W / 8), g = it - row * (FT_W / 8), x = x0 + g * 8;
+        if (x >= a.dstW) continue;
+        const int dy = dy0 + row;
+        const int16_t *lf = t.vLum + (long long)dy * lfs, *cf = t.vChr + (long long)dy * cfs;
+        const int firstLum = max(1 - lfs, __ldg(t.vLumPos + dy));
+        const int firstChr = max(1 - cfs, __ldg(t.vChrPos + dy));
+        unsigned sY[8], sU[4], sV[4];
+#pragma unroll
+        for (int i = 0; i < 8; i++) sY[i] = 1u << 18;
+#pragma unroll
+        for (int i = 0; i < 4; i++) sU[i] = sV[i] = 1u << 18;
+        for (int j = 0; j < lfs; j++) {
+            const int line = min(max(firstLum + j, 0), a.srcH - 1) - la;
+            const uint4 q = *reinterpret_cast<const uint4 *>(lumL + line * FT_W + g * 8);
+            const unsigned k = (unsigned)(int)__ldg(lf + j);
+            const unsigned w[4] = { q.x, q.y, q.z, q.w };
+#pragma unroll
+            for (int i = 0; i < 4; i++) { sY[2 * i] += (unsigned)(int)(short)(w[i] & 0xffff) * k; sY[2 * i + 1] += (unsigned)((int)w[i] >> 16) * k; }
+        }
+        for (int j = 0; j < cfs; j++) {
+            const int line = min(max(firstChr + j, 0), a.chrSrcH - 1) - ca;
+            const uint2 qu = *reinterpret_cast<const uint2 *>(chrU + line * CW + g * 4);
+            const uint2 qv = *reinterpret_cast<const uint2 *>(chrV + line * CW + g * 4);
+            const unsigned k = (unsigned)(int)__ldg(cf + j);
+            sU[0] += (unsigned)(int)(short)(qu.x & 0xffff) * k; sU[1] += (unsigned)((int)qu.x >> 16) * k;
+            sU[2] += (unsigned)(int)(short)(qu.y & 0xffff) * k; sU[3] += (unsigned)((int)qu.y >> 16) * k;
+            sV[0] += (unsigned)(int)(short)(qv.x & 0xffff) * k; sV[1] += (unsigned)((int)qv.x >> 16) * k;
+            sV[2] += (unsigned)(int)(short)(qv.y & 0xffff) * k; sV[3] += (unsigned)((int)qv.y >> 16) * k;
+        }
+        unsigned m[4 * PW];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const ChromaBase cb = chroma_base(c, (int)sU[i] >> 19, (int)sV[i] >> 19);
+            pair_out<KIND>(c.cy, cb, (int)sY[2 * i] >> 19, (int)sY[2 * i + 1] >> 19, m + PW * i);
+        }
+        uint8_t *d = a.dst + f * a.dfs + (long long)dy * a.ds + (long long)x * BPP;
+        if (KIND <= SWS_OUT_BGR24) {
+            uint2 *d2 = reinterpret_cast<uint2 *>(d);
+#pragma unroll
+            for (int k2 = 0; k2 < 3; k2++)
+                d2[k2] = make_uint2(__byte_perm(m[4 * k2], m[4 * k2 + 1], 0x6420), __byte_perm(m[4 * k2 + 2], m[4 * k2 + 3], 0x6420));
+        } else {
+            uint4 *d4 = reinterpret_cast<uint4 *>(d);
+            d4[0] = make_uint4(m[0], m[1], m[2], m[3]); d4[1] = make_uint4(m[4], m[5], m[6], m[7]);
+        }
+    }
+}
+
+// rows of the horizontally scaled plane the vertical taps of output lines [dy0, dy1] reach (the kernels compute the same range)
+static int fused_rows_needed(const SwsFilterBank &v, int srcH, int dstH, int TR)
+{
+    int mx = 0;
+    for (int dy0 = 0; dy0 < dstH; dy0 += TR) {
+        const int dy1 = std::min(dy0 + TR, dstH) - 1;
+        const int ra = std::min(std::max(std::max(1 - v.size, v.pos[dy0]), 0), srcH - 1);
+        const int rb = std::min(std::max(std::max(1 - v.size, v.pos[dy1]) + v.size - 1, 0), srcH - 1);
+        if (rb < ra) return -1;                      // not monotone: leave it to the two-pass path
+        mx = std::max(mx, rb - ra + 1);
+        for (int dy = dy0; dy <= dy1; dy++) {         // every line of the tile must stay inside [ra, rb]
+            const int fa = std::min(std::max(std::max(1 - v.size, v.pos[dy]), 0), srcH - 1);
+            const int fb = std::min(std::max(std::max(1 - v.size, v.pos[dy]) + v.size - 1, 0), srcH - 1);
+            if (fa < ra || fb > rb) return -1;
+        }
+    }
+    return mx;
+}
+static bool fused_enabled()
+{
+    static int on = -1;
+    if (on < 0) { const char *e = getenv("B200_SWS_FUSED"); on = e ? atoi(e) : 1; }
+    return on != 0;
 }
 
 static bool aligned16(const void *p, long long stride, long long fstride)
@@ -1338,7 +1549,43 @@ static int launch_batch(B200SwsContext *c, cudaStream_t stream, const uint8_t *c
                 B200_LAUNCHED();
             }
         } else {
-            // scaled path: horizontal pass into int16 line planes, then the vertical pass
+            // scaled path.  Whole frames through the `_X` writer: one fused kernel (no int16 planes in HBM)
+            if (!rows && fused_enabled() && !p.fast_bilinear && p.chrDstHSub && c->all_x && p.dstW % 8 == 0 && aligned16(dst, ds, dfs) &&
+                p.hLum.size <= 16 && p.hChr.size <= 16) {
+                int TR = 32;
+                int rl = fused_rows_needed(p.vLum, p.srcH, p.dstH, TR), rc = fused_rows_needed(p.vChr, p.chrSrcH, p.dstH, TR);
+                if (rl > 0 && rc > 0 && (size_t)(rl * FT_W + rc * FT_W) * 2 > 64 * 1024) {
+                    TR = 16;
+                    rl = fused_rows_needed(p.vLum, p.srcH, p.dstH, TR); rc = fused_rows_needed(p.vChr, p.chrSrcH, p.dstH, TR);
+                }
+                const size_t smem = rl > 0 && rc > 0 ? (size_t)(rl * FT_W + rc * FT_W) * 2 : 0;
+                if (smem && smem <= 64 * 1024) {
+                    dim3 gf(b200_ceil_div(p.dstW, FT_W), b200_ceil_div(p.dstH, TR), nf);
+                    const bool np4 = p.hLum.size <= 8 && p.hChr.size <= 8;
+#define B200_FUSED_RGB(K)                                                                                                         \
+                    do {                                                                                                          \
+                        if (np4) {                                                                                                \
+                            if (smem > 48 * 1024) B200_CUDA_OK(cudaFuncSetAttribute(sws_fused_rgb_kernel<K, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+                            sws_fused_rgb_kernel<K, 4><<<gf, FT_W, smem, stream>>>(b, c->dt, p.color, TR, rl, rc);                   \
+                        } else {                                                                                                  \
+                            if (smem > 48 * 1024) B200_CUDA_OK(cudaFuncSetAttribute(sws_fused_rgb_kernel<K, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+                            sws_fused_rgb_kernel<K, 8><<<gf, FT_W, smem, stream>>>(b, c->dt, p.color, TR, rl, rc);                   \
+                        }                                                                                                         \
+                    } while (0)
+                    switch (p.out.kind) {
+                    case SWS_OUT_RGB24: B200_FUSED_RGB(SWS_OUT_RGB24); break;
+                    case SWS_OUT_BGR24: B200_FUSED_RGB(SWS_OUT_BGR24); break;
+                    case SWS_OUT_RGBA:  B200_FUSED_RGB(SWS_OUT_RGBA); break;
+                    case SWS_OUT_BGRA:  B200_FUSED_RGB(SWS_OUT_BGRA); break;
+                    case SWS_OUT_ARGB:  B200_FUSED_RGB(SWS_OUT_ARGB); break;
+                    default:            B200_FUSED_RGB(SWS_OUT_ABGR); break;
+                    }
+#undef B200_FUSED_RGB
+                    B200_LAUNCHED();
+                    continue;
+                }
+            }
+            // two passes: horizontal pass into int16 line planes, then the vertical pass
             const size_t lumPlane = (size_t)p.srcH * p.dstW * 2, chrPlane = (size_t)p.chrSrcH * p.chrDstW * 2;
             const size_t perFrame = ((lumPlane + 2 * chrPlane) + 255) & ~(size_t)255;
             const size_t need = perFrame * nf;
@@ -1556,9 +1803,33 @@ static int launch_planar3(B200SwsContext *c, cudaStream_t stream, const uint8_t 
             else if (p.fast_bilinear)
                 sws_hscale_fast_kernel<true><<<gh, block, 0, stream>>>(src[pl] + (long long)f0 * sfs[pl], sstr[pl], sfs[pl], m[pl], dw[pl],
                                                                        (long long)(perFrame / 2), sw[pl], p.chrXInc, 0);
-            else
+            else {
+                // fused horizontal + vertical pass for this plane when the writer below would be the 8-sample one
+                uint8_t *dplf = dst[pl] + (long long)f0 * dfs[pl];
+                const SwsFilterBank &vb = pl ? p.vChr : p.vLum;
+                const bool f8 = fused_enabled() && !p.range_conv && hs[pl] <= 16 && dw[pl] % 8 == 0 &&
+                                (((uintptr_t)dplf | (uintptr_t)dstr[pl] | (uintptr_t)dfs[pl]) & 7) == 0;
+                int TR = 32, need_rows = f8 ? fused_rows_needed(vb, sh[pl], dh[pl], TR) : -1;
+                if (need_rows > 96) { TR = 16; need_rows = fused_rows_needed(vb, sh[pl], dh[pl], TR); }
+                if (need_rows > 0 && need_rows <= 96) {
+                    const size_t smem = (size_t)need_rows * FT_W * 2;
+                    dim3 gf(b200_ceil_div(dw[pl], FT_W), b200_ceil_div(dh[pl], TR), nf);
+                    const uint8_t *sp = src[pl] + (long long)f0 * sfs[pl];
+                    if (hs[pl] <= 8) {
+                        if (smem > 48 * 1024) B200_CUDA_OK(cudaFuncSetAttribute(sws_fused_plane_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                        sws_fused_plane_kernel<4><<<gf, FT_W, smem, stream>>>(sp, sstr[pl], sfs[pl], sh[pl], dplf, dstr[pl], dfs[pl], dw[pl], dh[pl],
+                                                                              hc[pl], hp[pl], hs[pl], vc[pl], vp[pl], vs[pl], TR);
+                    } else {
+                        if (smem > 48 * 1024) B200_CUDA_OK(cudaFuncSetAttribute(sws_fused_plane_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                        sws_fused_plane_kernel<8><<<gf, FT_W, smem, stream>>>(sp, sstr[pl], sfs[pl], sh[pl], dplf, dstr[pl], dfs[pl], dw[pl], dh[pl],
+                                                                              hc[pl], hp[pl], hs[pl], vc[pl], vp[pl], vs[pl], TR);
+                    }
+                    B200_LAUNCHED();
+                    continue;
+                }
                 launch_hscale(stream, src[pl] + (long long)f0 * sfs[pl], sstr[pl], sfs[pl], m[pl], dw[pl], (long long)(perFrame / 2),
                               hc[pl], hp[pl], hs[pl], 0, sh[pl], nf);
+            }
             if (!(p.src_rgb && pl == 2)) B200_LAUNCHED();
             if (p.range_conv) {
                 sws_range_kernel<<<gh, block, 0, stream>>>(m[pl], dw[pl], (long long)(perFrame / 2), pl ? p.chrRangeCoeff : p.lumRangeCoeff,

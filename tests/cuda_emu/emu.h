@@ -56,6 +56,7 @@ static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned sh)   
     return (unsigned)(((((unsigned long long)hi) << 32) | lo) >> (sh & 31));
 }
 static inline int atomicAdd(int *p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+static inline int __mulhi(int a, int b) { return (int)(((long long)a * (long long)b) >> 32); }
 static inline int __vimin_s32_relu(int a, int b) { const int m = a < b ? a : b; return m < 0 ? 0 : m; }
 static inline unsigned __vimin_s16x2_relu(unsigned a, unsigned b)               // per signed halfword: max(min(a, b), 0)
 {

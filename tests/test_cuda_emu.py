@@ -45,7 +45,8 @@ def vp(a):
 
 
 WARP_KERNELS = {"mpv_unquant_kernel"}                   # kernels that use a warp collective: one OS thread per lane
-BLOCK_KERNELS = {"tx_fft_kernel", "tx_mdct_inv_kernel", "tx_mdct_fwd_kernel", "tx_rdft_r2c_kernel", "tx_rdft_c2r_kernel"}    # __syncthreads
+BLOCK_KERNELS = {"tx_fft_kernel", "tx_mdct_inv_kernel", "tx_mdct_fwd_kernel", "tx_rdft_r2c_kernel", "tx_rdft_c2r_kernel",
+                 "sws_fused_plane_kernel", "sws_fused_rgb_kernel"}    # __syncthreads + dynamic shared memory
 
 
 def rewrite_launches(txt):
@@ -287,6 +288,8 @@ def emusws():
     t, n1 = re.subn(r'\{ int d; asm\("dp2a\.lo\.s32\.u32[^\n]*\n', "{ return emu_dp2a_su(a, b, c, 0); }\n", t)
     t, n2 = re.subn(r'\{ int d; asm\("dp2a\.hi\.s32\.u32[^\n]*\n', "{ return emu_dp2a_su(a, b, c, 1); }\n", t)
     assert n1 == 1 and n2 == 1 and not re.search(r"\basm\b", t)
+    t, n3 = re.subn(r"extern __shared__ __align__\(16\) int16_t fused_lines\[\];", "int16_t *fused_lines = (int16_t *)emu_smem;", t)   # fused scaler tiles
+    assert n3 == 2 and "__shared__" not in t
     t = rewrite_launches(t)
     assert "<<<" not in t
     open(os.path.join(gen, "host_sws.cpp"), "w").write(t)
