@@ -26,6 +26,9 @@ struct PfaDev {
     const float *tabs[12];                     // tabs[k]: cosine table of the 2^k-point transform (k = 3 ... 9)
     int m, log2m, len;
     int nfac;                                  // the odd factor: 15, 9, 7, 5 or 3
+    const int *blk;                            // offsets of the split-radix blocks of an m-point transform, level after level
+    int lvl_start[12], lvl_cnt[12];            // level L (block size 2^L): blk[lvl_start[L] .. + lvl_cnt[L])
+    int ms;                                    // pitch of one m-point sub-transform in shared memory: m + m / 16 + 1
 };
 
 __device__ __forceinline__ void butterflies(float2 &a0, float2 &a1, float2 &a2, float2 &a3, float t1, float t2, float t5, float t6)
@@ -48,85 +51,40 @@ __device__ __forceinline__ void transform(float2 &a0, float2 &a1, float2 &a2, fl
     butterflies(a0, a1, a2, a3, t1, t2, t5, t6);
 }
 
-__device__ __forceinline__ void fft4(float2 *d)
+// The nfac power-of-two sub-transforms of a compound MDCT, all at once and level by level, on data held in shared memory:
+// z[j * ms + PADI(k)] is sample k of sub-transform j.  The reference's recursion  fft(S) = fft(S/2) | fft(S/4) | fft(S/4) ; combine(S)
+// (ff_tx_fft{N}_ns / ff_tx_fft_sr_combine, tx_template.c:562-722) is flattened: all blocks of one size are independent, so the CTA
+// sweeps S = 2, 4, ..., m with one barrier per size, every thread taking butterflies of any block of any sub-transform.  The
+// hard-coded sizes 4, 8, 16 are instances of the same rule except that their j = 0 butterfly skips the multiplication by (1, 0).
+__device__ __forceinline__ int PADI(int i) { return i + (i >> 4); }
+__device__ void pfa_sub_ffts(const PfaDev &P, float2 *z)
 {
-    float t1, t2, t3, t4, t5, t6, t7, t8;
-    t3 = d[0].x - d[1].x; t1 = d[0].x + d[1].x;
-    t8 = d[3].x - d[2].x; t6 = d[3].x + d[2].x;
-    const float d2re = t1 - t6, d0re = t1 + t6;
-    t4 = d[0].y - d[1].y; t2 = d[0].y + d[1].y;
-    t7 = d[2].y - d[3].y; t5 = d[2].y + d[3].y;
-    d[2].x = d2re; d[0].x = d0re;
-    d[3].y = t4 - t8; d[1].y = t4 + t8;
-    d[3].x = t3 - t7; d[1].x = t3 + t7;
-    d[2].y = t2 - t5; d[0].y = t2 + t5;
-}
-
-// in-place 2^K-point transform without the input permutation (ff_tx_fft{N}_ns); the recursion is unrolled at compile time
-template <int K> __device__ void fft_ns(float2 *d, const PfaDev &P)
-{
-    constexpr int n = 1 << K, n4 = n / 4;
-    fft_ns<K - 1>(d, P);
-    fft_ns<K - 2>(d + 2 * n4, P);
-    fft_ns<K - 2>(d + 3 * n4, P);
-    constexpr int len = n4 >> 1, o1 = 2 * len, o2 = 4 * len, o3 = 6 * len;        // ff_tx_fft_sr_combine(d, tab_n, n / 8)
-    const float *cs = P.tabs[K], *wim = cs + o1 - 7;
-    float2 *z = d;
-    for (int i = 0; i < len; i += 4) {
-        transform(z[0], z[o1 + 0], z[o2 + 0], z[o3 + 0], cs[0], wim[7]);
-        transform(z[2], z[o1 + 2], z[o2 + 2], z[o3 + 2], cs[2], wim[5]);
-        transform(z[4], z[o1 + 4], z[o2 + 4], z[o3 + 4], cs[4], wim[3]);
-        transform(z[6], z[o1 + 6], z[o2 + 6], z[o3 + 6], cs[6], wim[1]);
-        transform(z[1], z[o1 + 1], z[o2 + 1], z[o3 + 1], cs[1], wim[6]);
-        transform(z[3], z[o1 + 3], z[o2 + 3], z[o3 + 3], cs[3], wim[4]);
-        transform(z[5], z[o1 + 5], z[o2 + 5], z[o3 + 5], cs[5], wim[2]);
-        transform(z[7], z[o1 + 7], z[o2 + 7], z[o3 + 7], cs[7], wim[0]);
-        z += 8; cs += 8; wim -= 8;
-    }
-}
-template <> __device__ void fft_ns<1>(float2 *d, const PfaDev &)
-{
-    const float re = d[0].x - d[1].x, im = d[0].y - d[1].y;
-    d[0].x = d[0].x + d[1].x; d[0].y = d[0].y + d[1].y;
-    d[1].x = re; d[1].y = im;
-}
-template <> __device__ void fft_ns<2>(float2 *d, const PfaDev &) { fft4(d); }
-template <> __device__ void fft_ns<3>(float2 *d, const PfaDev &P)
-{
-    const float c = P.tabs[3][1];
-    fft4(d);
-    const float t1 = d[4].x - (-d[5].x), d5re = d[4].x + (-d[5].x);
-    const float t2 = d[4].y - (-d[5].y), d5im = d[4].y + (-d[5].y);
-    const float t5 = d[6].x - (-d[7].x), d7re = d[6].x + (-d[7].x);
-    const float t6 = d[6].y - (-d[7].y), d7im = d[6].y + (-d[7].y);
-    d[5].x = d5re; d[5].y = d5im; d[7].x = d7re; d[7].y = d7im;
-    butterflies(d[0], d[2], d[4], d[6], t1, t2, t5, t6);
-    transform(d[1], d[3], d[5], d[7], c, c);
-}
-template <> __device__ void fft_ns<4>(float2 *d, const PfaDev &P)
-{
-    const float *c = P.tabs[4];
-    fft_ns<3>(d, P);
-    fft4(d + 8);
-    fft4(d + 12);
-    butterflies(d[0], d[4], d[8], d[12], d[8].x, d[8].y, d[12].x, d[12].y);
-    transform(d[2], d[6], d[10], d[14], c[2], c[2]);
-    transform(d[1], d[5], d[9], d[13], c[1], c[3]);
-    transform(d[3], d[7], d[11], d[15], c[3], c[1]);
-}
-
-__device__ void fft_ns_any(float2 *d, const PfaDev &P)
-{
-    switch (P.log2m) {
-    case 1: fft_ns<1>(d, P); break;
-    case 2: fft_ns<2>(d, P); break;
-    case 3: fft_ns<3>(d, P); break;
-    case 4: fft_ns<4>(d, P); break;
-    case 5: fft_ns<5>(d, P); break;
-    case 6: fft_ns<6>(d, P); break;
-    case 7: fft_ns<7>(d, P); break;
-    case 8: fft_ns<8>(d, P); break;
-    default: fft_ns<9>(d, P); break;
+    const int N = P.nfac;
+    for (int L = 1; L <= P.log2m; L++) {
+        const int *off = P.blk + P.lvl_start[L];
+        const int cnt = P.lvl_cnt[L];
+        if (L == 1) {
+            for (int it = threadIdx.x; it < N * cnt; it += blockDim.x) {
+                const int j = it / cnt, o = off[it - j * cnt];
+                float2 &a = z[j * P.ms + PADI(o)], &b = z[j * P.ms + PADI(o + 1)];
+                const float2 s0 = a, s1 = b;
+                a = make_float2(s0.x + s1.x, s0.y + s1.y);
+                b = make_float2(s0.x - s1.x, s0.y - s1.y);
+            }
+        } else {
+            const int lq = L - 2, q = 1 << lq, per = cnt << lq;
+            const float *tab = P.tabs[L];
+            for (int it = threadIdx.x; it < N * per; it += blockDim.x) {
+                const int j = it / per, r = it - j * per, o = off[r >> lq], jj = r & (q - 1);
+                float2 *zj = z + j * P.ms;
+                const int i0 = PADI(o + jj), i1 = PADI(o + q + jj), i2 = PADI(o + 2 * q + jj), i3 = PADI(o + 3 * q + jj);
+                float2 a0 = zj[i0], a1 = zj[i1], a2 = zj[i2], a3 = zj[i3];
+                if (L <= 4 && jj == 0) butterflies(a0, a1, a2, a3, a2.x, a2.y, a3.x, a3.y);
+                else transform(a0, a1, a2, a3, tab[jj], tab[q - jj]);
+                zj[i0] = a0; zj[i1] = a1; zj[i2] = a2; zj[i3] = a3;
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -264,80 +222,88 @@ __device__ __forceinline__ void fft15(const float *tab, float2 *out, const float
     fft5<5, 11, 2, 8, 14>(tab, out, tmp + 10, stride);
 }
 
-// ff_tx_mdct_pfa_15xM_inv: one thread = one transform; in: len floats with a stride (in floats), out: len floats
-__global__ void __launch_bounds__(64)
-tx_mdct_pfa15_inv_kernel(const PfaDev P, float *out, const float *in, long long stride, long long out_step, long long in_step, long long count,
-                         float2 *scratch)
+// ff_tx_mdct_pfa_{15,9,7,5,3}xM_inv (tx_template.c:1430-1508): one CTA per transform.  Pre-rotation and the m small odd-size
+// transforms (one per thread, straight into the shared-memory layout of the sub-transforms), the nfac m-point transforms
+// cooperatively, then the post-rotation.  in: len floats with a stride (in floats), out: len floats.
+constexpr int PFA_THREADS = 128;
+__global__ void __launch_bounds__(PFA_THREADS)
+tx_mdct_pfa_inv_kernel(const PfaDev P, float *out, const float *in, long long stride, long long out_step, long long in_step, long long count)
 {
-    const long long tr = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (tr >= count) return;
+    extern __shared__ float2 pfa_z[];
     const int len4 = P.len >> 2, len2 = P.len >> 1, m = P.m, N = P.nfac;
-    float2 *tmp = scratch + tr * len2;
-    float2 *z = reinterpret_cast<float2 *>(reinterpret_cast<char *>(out) + tr * out_step);
-    const float *src = reinterpret_cast<const float *>(reinterpret_cast<const char *>(in) + tr * in_step);
-    const float *in1 = src, *in2 = src + ((N * m * 2) - 1) * stride;
-    const float2 *e = P.exp;
-    const int *in_map = P.in_map, *sub_map = P.sub_map;
-    for (int i = 0; i < len2; i += N) {
-        float2 f15[15];
+    for (long long tr = blockIdx.x; tr < count; tr += gridDim.x) {
+        float2 *z = reinterpret_cast<float2 *>(reinterpret_cast<char *>(out) + tr * out_step);
+        const float *src = reinterpret_cast<const float *>(reinterpret_cast<const char *>(in) + tr * in_step);
+        const float *in1 = src, *in2 = src + ((N * m * 2) - 1) * stride;
+        for (int b = threadIdx.x; b < m; b += blockDim.x) {
+            const float2 *e = P.exp + b * N;
+            const int *in_map = P.in_map + b * N;
+            float2 f15[15];
 #pragma unroll
-        for (int j = 0; j < 15; j++) {
-            if (j < N) {
-                const int k = in_map[j];
-                const float are = in2[-k * stride], aim = in1[k * stride];
-                f15[j].x = are * e[j].x - aim * e[j].y;
-                f15[j].y = are * e[j].y + aim * e[j].x;
+            for (int j = 0; j < 15; j++) {
+                if (j < N) {
+                    const int k = in_map[j];
+                    const float are = in2[-k * stride], aim = in1[k * stride];
+                    f15[j].x = are * e[j].x - aim * e[j].y;
+                    f15[j].y = are * e[j].y + aim * e[j].x;
+                }
             }
+            fftN(N, P.tab53, pfa_z + PADI(P.sub_map[b]), f15, P.ms);
         }
-        fftN(N, P.tab53, tmp + *(sub_map++), f15, m);
-        e += N; in_map += N;
-    }
-    for (int i = 0; i < N; i++) fft_ns_any(tmp + m * i, P);
-    for (int i = 0; i < len4; i++) {
-        const int i0 = len4 + i, i1 = len4 - i - 1, s0 = P.out_map[i0], s1 = P.out_map[i1];
-        const float2 src1 = make_float2(tmp[s1].y, tmp[s1].x), src0 = make_float2(tmp[s0].y, tmp[s0].x);
-        z[i1].x = src1.x * e[i1].y - src1.y * e[i1].x;
-        z[i0].y = src1.x * e[i1].x + src1.y * e[i1].y;
-        z[i0].x = src0.x * e[i0].y - src0.y * e[i0].x;
-        z[i1].y = src0.x * e[i0].x + src0.y * e[i0].y;
+        __syncthreads();
+        pfa_sub_ffts(P, pfa_z);
+        const float2 *e = P.exp + len2;
+        for (int i = threadIdx.x; i < len4; i += blockDim.x) {
+            const int i0 = len4 + i, i1 = len4 - i - 1, s0 = P.out_map[i0], s1 = P.out_map[i1];
+            const float2 t1 = pfa_z[(s1 >> P.log2m) * P.ms + PADI(s1 & (m - 1))], t0 = pfa_z[(s0 >> P.log2m) * P.ms + PADI(s0 & (m - 1))];
+            const float2 src1 = make_float2(t1.y, t1.x), src0 = make_float2(t0.y, t0.x);
+            float2 o1, o0;
+            o1.x = src1.x * e[i1].y - src1.y * e[i1].x;
+            o0.y = src1.x * e[i1].x + src1.y * e[i1].y;
+            o0.x = src0.x * e[i0].y - src0.y * e[i0].x;
+            o1.y = src0.x * e[i0].x + src0.y * e[i0].y;
+            z[i1] = o1; z[i0] = o0;
+        }
+        __syncthreads();                                   // the next transform reuses the buffer
     }
 }
 
-// ff_tx_mdct_pfa_15xM_fwd: in: 2*len floats, out: len floats with a stride (in floats)
-__global__ void __launch_bounds__(64)
-tx_mdct_pfa15_fwd_kernel(const PfaDev P, float *out, const float *in, long long stride, long long out_step, long long in_step, long long count,
-                         float2 *scratch)
+// ff_tx_mdct_pfa_{15,9,7,5,3}xM_fwd (tx_template.c:1510-1599): in: 2*len floats, out: len floats with a stride (in floats)
+__global__ void __launch_bounds__(PFA_THREADS)
+tx_mdct_pfa_fwd_kernel(const PfaDev P, float *out, const float *in, long long stride, long long out_step, long long in_step, long long count)
 {
-    const long long tr = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (tr >= count) return;
+    extern __shared__ float2 pfa_z[];
     const int m = P.m, N = P.nfac, len4 = N * m, len3 = len4 * 3, len8 = P.len >> 2;
-    float2 *tmp = scratch + tr * len4;
-    float *dst = reinterpret_cast<float *>(reinterpret_cast<char *>(out) + tr * out_step);
-    const float *src = reinterpret_cast<const float *>(reinterpret_cast<const char *>(in) + tr * in_step);
     const float2 *e = P.exp;
-    for (int i = 0; i < m; i++) {
-        float2 f15[15];
+    for (long long tr = blockIdx.x; tr < count; tr += gridDim.x) {
+        float *dst = reinterpret_cast<float *>(reinterpret_cast<char *>(out) + tr * out_step);
+        const float *src = reinterpret_cast<const float *>(reinterpret_cast<const char *>(in) + tr * in_step);
+        for (int b = threadIdx.x; b < m; b += blockDim.x) {
+            float2 f15[15];
 #pragma unroll
-        for (int j = 0; j < 15; j++) {
-            if (j < N) {
-                const int k = P.in_map[i * N + j];
-                float re, im;
-                if (k < len4) { re = -src[len4 + k] + src[1 * len4 - 1 - k]; im = -src[len3 + k] + -src[1 * len3 - 1 - k]; }
-                else          { re = -src[len4 + k] + -src[5 * len4 - 1 - k]; im = src[-len4 + k] + -src[1 * len3 - 1 - k]; }
-                f15[j].y = re * e[k >> 1].x - im * e[k >> 1].y;
-                f15[j].x = re * e[k >> 1].y + im * e[k >> 1].x;
+            for (int j = 0; j < 15; j++) {
+                if (j < N) {
+                    const int k = P.in_map[b * N + j];
+                    float re, im;
+                    if (k < len4) { re = -src[len4 + k] + src[1 * len4 - 1 - k]; im = -src[len3 + k] + -src[1 * len3 - 1 - k]; }
+                    else          { re = -src[len4 + k] + -src[5 * len4 - 1 - k]; im = src[-len4 + k] + -src[1 * len3 - 1 - k]; }
+                    f15[j].y = re * e[k >> 1].x - im * e[k >> 1].y;
+                    f15[j].x = re * e[k >> 1].y + im * e[k >> 1].x;
+                }
             }
+            fftN(N, P.tab53, pfa_z + PADI(P.sub_map[b]), f15, P.ms);
         }
-        fftN(N, P.tab53, tmp + P.sub_map[i], f15, m);
-    }
-    for (int i = 0; i < N; i++) fft_ns_any(tmp + m * i, P);
-    for (int i = 0; i < len8; i++) {
-        const int i0 = len8 + i, i1 = len8 - i - 1, s0 = P.out_map[i0], s1 = P.out_map[i1];
-        const float2 src1 = tmp[s1], src0 = tmp[s0];
-        dst[(2 * i1 + 1) * stride] = src0.x * e[i0].y - src0.y * e[i0].x;
-        dst[2 * i0 * stride]       = src0.x * e[i0].x + src0.y * e[i0].y;
-        dst[(2 * i0 + 1) * stride] = src1.x * e[i1].y - src1.y * e[i1].x;
-        dst[2 * i1 * stride]       = src1.x * e[i1].x + src1.y * e[i1].y;
+        __syncthreads();
+        pfa_sub_ffts(P, pfa_z);
+        for (int i = threadIdx.x; i < len8; i += blockDim.x) {
+            const int i0 = len8 + i, i1 = len8 - i - 1, s0 = P.out_map[i0], s1 = P.out_map[i1];
+            const float2 src1 = pfa_z[(s1 >> P.log2m) * P.ms + PADI(s1 & (m - 1))], src0 = pfa_z[(s0 >> P.log2m) * P.ms + PADI(s0 & (m - 1))];
+            dst[(2 * i1 + 1) * stride] = src0.x * e[i0].y - src0.y * e[i0].x;
+            dst[2 * i0 * stride]       = src0.x * e[i0].x + src0.y * e[i0].y;
+            dst[(2 * i0 + 1) * stride] = src1.x * e[i1].y - src1.y * e[i1].x;
+            dst[2 * i1 * stride]       = src1.x * e[i1].x + src1.y * e[i1].y;
+        }
+        __syncthreads();
     }
 }
 // [/device-code tx_pfa]
@@ -363,7 +329,8 @@ struct TxPfa {
     int inv = 0, len = 0, m = 0;
     PfaDev d{};
     void *blob = nullptr;
-    void *scratch = nullptr; size_t scratch_bytes = 0;
+    size_t smem = 0;
+    int grid_cap = 0;
 };
 
 // the host tables of one transform (also used by the CPU test tier through b200_tx_pfa_tables)
@@ -373,7 +340,21 @@ struct PfaHost {
     float tab53[26];                   // ff_tx_tab_53 [12], ff_tx_tab_7 [6], ff_tx_tab_9 [8]
     std::vector<float> cosk[12];
     int m = 0, log2m = 0, nfac = 0;
+    std::vector<int> blk;              // split-radix block offsets of an m-point transform, level after level
+    int lvl_start[12] = { 0 }, lvl_cnt[12] = { 0 };
 };
+
+static void pfa_collect_blocks(std::vector<std::vector<int>> &lv, int L, int off)   // block of size 2^L at `off` and everything below it
+{
+    if (L < 1) return;
+    lv[L].push_back(off);
+    const int S = 1 << L;
+    pfa_collect_blocks(lv, L - 1, off);
+    if (L >= 2) {
+        pfa_collect_blocks(lv, L - 2, off + S / 2);
+        pfa_collect_blocks(lv, L - 2, off + 3 * S / 4);
+    }
+}
 
 // the odd factor av_tx_init() ends up with for this MDCT length: the largest of 15, 9, 7, 5, 3 that leaves a power of two (tx.c:391-395); 0 = none
 static int pfa_factor(int len)
@@ -394,6 +375,15 @@ static void pfa_host_tables(PfaHost &H, int inv, int len, float scale)
     H.nfac = n;
     H.m = m; H.log2m = 0;
     while ((1 << H.log2m) < m) H.log2m++;
+    {
+        std::vector<std::vector<int>> lv(12);
+        pfa_collect_blocks(lv, H.log2m, 0);
+        H.blk.clear();
+        for (int L = 0; L < 12; L++) {
+            H.lvl_start[L] = (int)H.blk.size(); H.lvl_cnt[L] = (int)lv[L].size();
+            H.blk.insert(H.blk.end(), lv[L].begin(), lv[L].end());
+        }
+    }
     H.in_map.assign(l2, 0); H.out_map.assign(l2, 0); H.sub_map.assign(m, 0);
     const int m_inv = mulinv(m, n), n_inv = mulinv(n, m);
     for (int j = 0; j < m; j++)                                     // ff_tx_gen_compound_mapping, gather direction (tx.c:104-110)
@@ -462,6 +452,9 @@ B200_API int b200_tx_pfa_tables(int inv, int len, float scale, int32_t *words, i
     lay[5] = (int32_t)w.size();
     for (int k = 3; k <= H.log2m; k++) addf(H.cosk[k].data(), H.cosk[k].size());
     lay[6] = H.m; lay[7] = H.log2m | (H.nfac << 8);
+    for (int L = 0; L < 12; L++) w.push_back(H.lvl_start[L]);      // after the cosine tables: 12 level starts, 12 level counts, the offsets
+    for (int L = 0; L < 12; L++) w.push_back(H.lvl_cnt[L]);
+    addi(H.blk);
     if (layout8) memcpy(layout8, lay, sizeof(lay));
     if (words && cap >= (int)w.size()) memcpy(words, w.data(), w.size() * 4);
     return (int)w.size();
@@ -482,7 +475,9 @@ TxPfa *tx_pfa_create(int inv, int len, float scale)
     const size_t o_53 = off;  off += al(sizeof(float) * 26);
     size_t o_cos[12] = { 0 };
     for (int k = 3; k <= H.log2m; k++) { o_cos[k] = off; off += al(sizeof(float) * H.cosk[k].size()); }
+    const size_t o_blk = off; off += al(sizeof(int) * H.blk.size() + 4);
     std::vector<uint8_t> host(off, 0);
+    memcpy(&host[o_blk], H.blk.data(), sizeof(int) * H.blk.size());
     memcpy(&host[o_in], H.in_map.data(), sizeof(int) * l2);
     memcpy(&host[o_out], H.out_map.data(), sizeof(int) * l2);
     memcpy(&host[o_sub], H.sub_map.data(), sizeof(int) * m);
@@ -504,6 +499,22 @@ TxPfa *tx_pfa_create(int inv, int len, float scale)
     d.exp = (const float2 *)(b + o_exp); d.tab53 = (const float *)(b + o_53);
     for (int k = 0; k < 12; k++) d.tabs[k] = k >= 3 && k <= H.log2m ? (const float *)(b + o_cos[k]) : nullptr;
     d.m = m; d.log2m = H.log2m; d.len = len; d.nfac = H.nfac;
+    d.blk = (const int *)(b + o_blk);
+    for (int L = 0; L < 12; L++) { d.lvl_start[L] = H.lvl_start[L]; d.lvl_cnt[L] = H.lvl_cnt[L]; }
+    d.ms = m + (m >> 4) + 1;
+    p->smem = (size_t)H.nfac * d.ms * sizeof(float2);
+    if (p->smem > 48 * 1024 &&
+        (cudaFuncSetAttribute(tx_mdct_pfa_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem) != cudaSuccess ||
+         cudaFuncSetAttribute(tx_mdct_pfa_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem) != cudaSuccess)) {
+        b200_set_error("tx_pfa_create: %zu bytes of shared memory per transform", p->smem);
+        cudaFree(p->blob);
+        delete p;
+        return nullptr;
+    }
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    p->grid_cap = (sms > 0 ? sms : 148) * 8;
     return p;
 }
 
@@ -511,7 +522,6 @@ void tx_pfa_free(TxPfa *p)
 {
     if (!p) return;
     if (p->blob) cudaFree(p->blob);
-    if (p->scratch) cudaFree(p->scratch);
     delete p;
 }
 
@@ -521,24 +531,11 @@ int tx_pfa_launch(TxPfa *p, cudaStream_t st, void *out, const void *in, ptrdiff_
     // the inverse writes its outputs as complex pairs (8-byte words); everything else moves single floats
     if (((reinterpret_cast<uintptr_t>(out) | (uintptr_t)out_step) & (p->inv ? 7 : 3)) || ((reinterpret_cast<uintptr_t>(in) | (uintptr_t)in_step) & 3))
         return B200_EINVAL;
-    const size_t l2 = (size_t)p->len >> 1;
-    const int64_t chunk_max = (int64_t)((size_t)(256u << 20) / (l2 * sizeof(float2)));          // scratch of at most 256 MB
-    const int64_t chunk = count < chunk_max ? count : chunk_max;
-    const size_t need = (size_t)chunk * l2 * sizeof(float2);
-    if (p->scratch_bytes < need) {
-        if (p->scratch) { cudaStreamSynchronize(st); cudaFree(p->scratch); p->scratch = nullptr; p->scratch_bytes = 0; }
-        B200_CUDA_OK(cudaMalloc(&p->scratch, need));
-        p->scratch_bytes = need;
-    }
-    for (int64_t c0 = 0; c0 < count; c0 += chunk) {
-        const long long cnt = count - c0 < chunk ? count - c0 : chunk;
-        const unsigned nb = (unsigned)((cnt + 63) / 64);
-        char *o = (char *)out + c0 * out_step;
-        const char *i = (const char *)in + c0 * in_step;
-        if (p->inv) tx_mdct_pfa15_inv_kernel<<<nb, 64, 0, st>>>(p->d, (float *)o, (const float *)i, (long long)(stride / 4), out_step, in_step, cnt, (float2 *)p->scratch);
-        else        tx_mdct_pfa15_fwd_kernel<<<nb, 64, 0, st>>>(p->d, (float *)o, (const float *)i, (long long)(stride / 4), out_step, in_step, cnt, (float2 *)p->scratch);
-        B200_LAUNCHED();
-    }
+    // one CTA per transform, CTAs stride over the batch
+    const unsigned nb = (unsigned)(count < p->grid_cap ? count : p->grid_cap);
+    if (p->inv) tx_mdct_pfa_inv_kernel<<<nb, PFA_THREADS, p->smem, st>>>(p->d, (float *)out, (const float *)in, (long long)(stride / 4), out_step, in_step, count);
+    else        tx_mdct_pfa_fwd_kernel<<<nb, PFA_THREADS, p->smem, st>>>(p->d, (float *)out, (const float *)in, (long long)(stride / 4), out_step, in_step, count);
+    B200_LAUNCHED();
     B200_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -33,9 +33,11 @@ namespace dct {
 
 extern "C" {
 
-// tables = what b200_tx_pfa_tables() of the library returns (host-only), layout8 as it reports it
+// tables = what b200_tx_pfa_tables() of the library returns (host-only), layout8 as it reports it; after the cosine tables the words
+// hold 12 level starts, 12 level counts and the block offsets of the m-point split-radix transform.  One CTA per transform
+// (block-synchronous emulation: an OS thread per CUDA thread, dynamic shared memory = nfac sub-transforms).
 int emu_tx_pfa(int inv, int len, const int32_t *words, const int32_t *lay, float *out, const float *in, long long stride_floats, long long out_step,
-               long long in_step, long long count, float2 *scratch)
+               long long in_step, long long count, float2 *)
 {
     pfa::PfaDev P;
     P.in_map = words + lay[0]; P.out_map = words + lay[1]; P.sub_map = words + lay[2];
@@ -43,10 +45,15 @@ int emu_tx_pfa(int inv, int len, const int32_t *words, const int32_t *lay, float
     const float *c = (const float *)(words + lay[5]);
     for (int k = 0; k < 12; k++) P.tabs[k] = nullptr;
     for (int k = 3; k <= (lay[7] & 255); k++) { P.tabs[k] = c; c += (1 << k) / 4 + 1; }
+    const int32_t *lv = (const int32_t *)c;
+    for (int L = 0; L < 12; L++) { P.lvl_start[L] = lv[L]; P.lvl_cnt[L] = lv[12 + L]; }
+    P.blk = lv + 24;
     P.m = lay[6]; P.log2m = lay[7] & 255; P.nfac = lay[7] >> 8; P.len = len;
-    const dim3 g(ceil_div(count, 64)), t(64);
-    if (inv) emu_launch(g, t, [&] { pfa::tx_mdct_pfa15_inv_kernel(P, out, in, stride_floats, out_step, in_step, count, scratch); });
-    else     emu_launch(g, t, [&] { pfa::tx_mdct_pfa15_fwd_kernel(P, out, in, stride_floats, out_step, in_step, count, scratch); });
+    P.ms = P.m + (P.m >> 4) + 1;
+    const size_t smem = (size_t)P.nfac * P.ms * sizeof(float2);
+    const dim3 g((unsigned)(count < 3 ? count : 3)), t(pfa::PFA_THREADS);            // fewer CTAs than transforms: the batch loop runs too
+    if (inv) emu_launch_blocks(g, t, smem, [&] { pfa::tx_mdct_pfa_inv_kernel(P, out, in, stride_floats, out_step, in_step, count); });
+    else     emu_launch_blocks(g, t, smem, [&] { pfa::tx_mdct_pfa_fwd_kernel(P, out, in, stride_floats, out_step, in_step, count); });
     return 0;
 }
 
