@@ -319,7 +319,7 @@ qpel_tma_kernel(const __grid_constant__ CUtensorMap tm16, const __grid_constant_
     const long long first_op = ((long long)blockIdx.x * WARPS + warp) * TQK;
     if (first_op >= n) return;
     // lanes 0 .. TQK-1 each own one operation's descriptor and issue its box
-    int mo = -1, inb = 0;
+    int mo = -1, inb = 0, bx = 0, by = 0;
     long long msoff = 0, mdoff = 0;
     if (lane < TQK) {
         const uint32_t mb = pel_smem_u32(&sm.mbar[warp][lane]);
@@ -335,11 +335,15 @@ qpel_tma_kernel(const __grid_constant__ CUtensorMap tm16, const __grid_constant_
         unsigned long long y = __umul64hi((unsigned long long)msoff, magic);
         long long x = msoff - (long long)y * stride;
         while (x >= stride) { x -= stride; y++; }
-        const int size = 16 >> ((mo >> 1) & 3);
-        if (x >= 8 && x + 24 <= stride && y >= 2 && y < 0x7fffff00ULL) {
-            inb = 1;
-            const CUtensorMap *tm = size == 16 ? &tm16 : size == 8 ? &tm8 : &tm4;
-            pel_tma_2d(pel_smem_u32(&sm.tile[warp][lane][0]), tm, (int)x - 8, (int)y - 2, pel_smem_u32(&sm.mbar[warp][lane]), 32u * (size + 5));
+        if (x >= 8 && x + 24 <= stride && y >= 2 && y < 0x7fffff00ULL) { inb = 1; bx = (int)x - 8; by = (int)y - 2; }
+    }
+    // the copies are issued by one lane (TMA operands live in uniform registers): lane 0 walks the warp's operations
+    for (int k = 0; k < TQK; k++) {
+        const int kin = __shfl_sync(0xffffffffu, inb, k), kx = __shfl_sync(0xffffffffu, bx, k), ky = __shfl_sync(0xffffffffu, by, k);
+        const int ksize = 16 >> ((__shfl_sync(0xffffffffu, mo, k) >> 1) & 3);
+        if (kin && lane == 0) {
+            const CUtensorMap *tm = ksize == 16 ? &tm16 : ksize == 8 ? &tm8 : &tm4;
+            pel_tma_2d(pel_smem_u32(&sm.tile[warp][k][0]), tm, kx, ky, pel_smem_u32(&sm.mbar[warp][k]), 32u * (ksize + 5));
         }
     }
     short *hraw = sm.hraw[warp];
@@ -575,7 +579,7 @@ chroma_tma_kernel(const __grid_constant__ ChromaMaps maps, long long n, const ui
     const long long first_op = ((long long)blockIdx.x * WARPS + warp) * PER_WARP;
     if (first_op >= n) return;
     // lanes 0 .. 15 own one operation's descriptor each (slot = lane: group lane / CQ, round lane % CQ) and issue its box
-    int mo = -1, mh = 0, mpq = 0, inb = 0;
+    int mo = -1, mh = 0, mpq = 0, inb = 0, bx = 0, by = 0;
     long long msoff = 0, mdoff = 0;
     if (lane < PER_WARP) {
         const uint32_t mb = pel_smem_u32(&sm.mbar[warp][lane]);
@@ -589,11 +593,15 @@ chroma_tma_kernel(const __grid_constant__ ChromaMaps maps, long long n, const ui
         unsigned long long y = __umul64hi((unsigned long long)msoff, magic);
         long long x = msoff - (long long)y * stride;
         while (x >= stride) { x -= stride; y++; }
-        if (x + 16 <= stride && y < 0x7fffff00ULL) {
-            inb = 1;
-            const int fy = (mpq >> 3) & 7, rows = mh + (fy != 0);
-            const int mi = 2 * (mh == 2 ? 0 : mh == 4 ? 1 : mh == 8 ? 2 : 3) + (fy != 0);
-            pel_tma_2d(pel_smem_u32(&sm.tile[warp][lane][0]), &maps.m[mi], (int)x, (int)y, pel_smem_u32(&sm.mbar[warp][lane]), 16u * rows);
+        if (x + 16 <= stride && y < 0x7fffff00ULL) { inb = 1; bx = (int)x; by = (int)y; }
+    }
+    for (int k = 0; k < PER_WARP; k++) {                            // issued by one lane: TMA operands live in uniform registers
+        const int kin = __shfl_sync(0xffffffffu, inb, k), kx = __shfl_sync(0xffffffffu, bx, k), ky = __shfl_sync(0xffffffffu, by, k);
+        const int kh = __shfl_sync(0xffffffffu, mh, k), kfy = (__shfl_sync(0xffffffffu, mpq, k) >> 3) & 7;
+        if (kin && lane == 0) {
+            const int rows = kh + (kfy != 0);
+            const int mi = 2 * (kh == 2 ? 0 : kh == 4 ? 1 : kh == 8 ? 2 : 3) + (kfy != 0);
+            pel_tma_2d(pel_smem_u32(&sm.tile[warp][k][0]), &maps.m[mi], kx, ky, pel_smem_u32(&sm.mbar[warp][k]), 16u * rows);
         }
     }
     for (int r = 0; r < CQ; r++) {

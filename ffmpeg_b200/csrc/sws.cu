@@ -60,20 +60,8 @@ __device__ __forceinline__ ChromaBase chroma_base(const SwsColorConst &c, int U,
     return o;
 }
 
-// The same constants from the vertical sums themselves (12 fraction bits, before any shift): clamping the sum to [0, 2^20) and clearing
-// its fraction gives u8 << 12, and hi32((u8 << 12) * (coef << 4)) = (u8 * coef) >> 16 with the base folded into the same multiply-add
-// (IMAD.HI on the FMA pipe): no shift and no shift-add on the ALU pipe, which is the busy one in the vector kernels.
-// Needs |coef| < 2^27 (the host checks it before it selects a vector kernel).
-__device__ __forceinline__ ChromaBase chroma_base_q12(const SwsColorConst &c, int Usum, int Vsum)
-{
-    const int su = __vimin_s32_relu(Usum, 0xFFFFF) & ~0xFFF, sv = __vimin_s32_relu(Vsum, 0xFFFFF) & ~0xFFF;
-    ChromaBase o;
-    o.r = c.yb0 + (__mulhi(sv, c.crv << 4) + c.baseR) * c.cy;
-    o.g = c.yb0 + (__mulhi(su, c.cgu << 4) + (__mulhi(sv, c.cgv << 4) + c.baseG)) * c.cy;
-    o.b = c.yb0 + (__mulhi(su, c.cbu << 4) + c.baseB) * c.cy;
-    return o;
-}
-
+// (Measured on a B200, round 2: folding the ">> 16, add base" pairs into IMAD.HI — hi32((u8 << 12) * (coef << 4)) + base — removes 64 ALU-pipe
+// shift-adds per 32 pixels but runs 9 % slower: IMAD.HI is not a full-rate instruction.  The plain form below stays.)
 // Two pixels sharing one chroma sample -> three words holding (r0,g0) (b0,r1) (g1,b1) as clamped s16x2 (bytes 0 and 2).
 // (A + Y*cy) >> 16 is the high half of the 32-bit sum: PRMT picks the high halves, VIMNMX.S16x2.RELU clamps both to 0..255.
 __device__ __forceinline__ void pair_rgb_packed(int cy, const ChromaBase &cb, int Y0, int Y1, unsigned *m)
@@ -394,7 +382,7 @@ sws_vscale_rgb24_fast_kernel(SwsFrameArgs a, SwsDevTables t, SwsColorConst c, in
     unsigned m[8 * PW];
 #pragma unroll
     for (int i = 0; i < 8; i++) {
-        const ChromaBase cb = chroma_base_q12(c, aU[i], aV[i]);
+        const ChromaBase cb = chroma_base(c, aU[i] >> 12, aV[i] >> 12);
         pair_out<KIND>(c.cy, cb, Y[2 * i], Y[2 * i + 1], m + PW * i);
     }
     store_out<KIND>(a.dst + f * a.dfs + (long long)dy * (int)a.ds + xg * (16 * OutWords<KIND>::bpp), m);
@@ -471,7 +459,7 @@ sws_vscale_rgb24_pair_kernel(SwsFrameArgs a, SwsDevTables t, SwsColorConst c, in
         unsigned m[8 * PW];
 #pragma unroll
         for (int i = 0; i < 8; i++) {
-            const ChromaBase cb = chroma_base_q12(c, aU[i], aV[i]);
+            const ChromaBase cb = chroma_base(c, aU[i] >> 12, aV[i] >> 12);
             pair_out<KIND>(c.cy, cb, byte_of(yw[(2 * i) >> 2], (2 * i) & 3), byte_of(yw[(2 * i + 1) >> 2], (2 * i + 1) & 3), m + PW * i);
         }
         store_out<KIND>(drow + (long long)L * (int)a.ds, m);
@@ -973,11 +961,6 @@ static int upload_tables(B200SwsContext *c)
     c->all_x = !p.planar;
     for (int y = 0; y < p.dstH && c->all_x; y++) if (p.rowMode[(size_t)y * 4] != 0) c->all_x = false;
     c->fast_x = c->h_identity && !p.planar;
-    {   // chroma_base_q12 multiplies by coef << 4
-        const long long lim = 1LL << 27;
-        auto big = [&](int v) { return (long long)v >= lim || (long long)v <= -lim; };
-        if (big(p.color.crv) || big(p.color.cgu) || big(p.color.cgv) || big(p.color.cbu)) c->fast_x = false;
-    }
     c->lum_identity = p.vLum.size == 1;
     for (int y = 0; y < p.dstH && c->fast_x; y++) {
         if (p.rowMode[(size_t)y * 4] != 0) c->fast_x = false;

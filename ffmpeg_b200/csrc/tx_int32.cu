@@ -7,8 +7,11 @@
 //   tables tx_template.c:65-77; butterflies / transform / combine :540-586; base cases :631-704; recursion :615-629; FFT wrapper :763-778;
 //   MDCT :1223-1342; twiddles :2107-2134; permutation libavutil/tx.c:125-154.
 //
-// First version, correctness before speed: ONE THREAD PER TRANSFORM working in global memory (the float kernels of tx.cu, one
-// transform per CTA in shared memory, are the model for the tuned version; IMAD.WIDE carries the 64-bit products).
+// One CTA per transform, the transform in shared memory (as tx.cu's float kernels): the reference's recursion
+// fft(S) = fft(S/2) | fft(S/4) | fft(S/4) ; combine(S) is flattened into levels — all blocks of one size are independent — and the
+// CTA sweeps S = 2, 4, ..., n with one barrier per size; the hard-coded sizes 4, 8, 16 follow the same rule except that their j = 0
+// butterfly skips the multiplication by (1, 0).  Every sum wraps modulo 2^32 and every product is rounded exactly as the reference
+// does it, so the schedule does not matter for the bits.  IMAD.WIDE carries the 64-bit products.
 #include "tx_int32.h"
 #include <vector>
 #include <cmath>
@@ -22,6 +25,8 @@ struct TxiDev {
     const int2 *exp;                // MDCT twiddles (inverse: pre-shuffled copy first, natural order after it)
     const int *tabs[18];            // tabs[k]: cosine table of the 2^k-point transform
     int n, log2n, len;              // n: complex points of the FFT that runs
+    const int *blk;                 // offsets of the split-radix blocks, level after level
+    int lvl_start[18], lvl_cnt[18]; // level L (block size 2^L): blk[lvl_start[L] .. + lvl_cnt[L])
 };
 
 __device__ __forceinline__ int mulr(long long accu) { return (int)((accu + 0x40000000LL) >> 31); }
@@ -48,139 +53,102 @@ __device__ __forceinline__ void transform(int2 &a0, int2 &a1, int2 &a2, int2 &a3
     cmul(t5, t6, a3.x, a3.y, wre, wim);
     butterflies(a0, a1, a2, a3, t1, t2, t5, t6);
 }
-__device__ __forceinline__ void fft4(int2 *d)
+__device__ __forceinline__ int PADI(int i) { return i + (i >> 4); }
+// all levels of one transform held in z[PADI(0 .. n)) (shared memory)
+__device__ void i32_levels(const TxiDev &P, int2 *z)
 {
-    const unsigned s0r = d[0].x, s1r = d[1].x, s2r = d[2].x, s3r = d[3].x, s0i = d[0].y, s1i = d[1].y, s2i = d[2].y, s3i = d[3].y;
-    const unsigned t3 = s0r - s1r, t1 = s0r + s1r, t8 = s3r - s2r, t6 = s3r + s2r;
-    const unsigned t4 = s0i - s1i, t2 = s0i + s1i, t7 = s2i - s3i, t5 = s2i + s3i;
-    d[2].x = (int)(t1 - t6); d[0].x = (int)(t1 + t6);
-    d[3].y = (int)(t4 - t8); d[1].y = (int)(t4 + t8);
-    d[3].x = (int)(t3 - t7); d[1].x = (int)(t3 + t7);
-    d[2].y = (int)(t2 - t5); d[0].y = (int)(t2 + t5);
-}
-
-// in-place 2^K-point transform without the input permutation; the recursion is unrolled at compile time into calls
-template <int K> __device__ void fft_ns(int2 *d, const TxiDev &P)
-{
-    constexpr int n = 1 << K, n4 = n / 4;
-    fft_ns<K - 1>(d, P);
-    fft_ns<K - 2>(d + 2 * n4, P);
-    fft_ns<K - 2>(d + 3 * n4, P);
-    constexpr int len = n4 >> 1, o1 = 2 * len, o2 = 4 * len, o3 = 6 * len;
-    const int *cs = P.tabs[K], *wim = cs + o1 - 7;
-    int2 *z = d;
-    for (int i = 0; i < len; i += 4) {
-        transform(z[0], z[o1 + 0], z[o2 + 0], z[o3 + 0], cs[0], wim[7]);
-        transform(z[2], z[o1 + 2], z[o2 + 2], z[o3 + 2], cs[2], wim[5]);
-        transform(z[4], z[o1 + 4], z[o2 + 4], z[o3 + 4], cs[4], wim[3]);
-        transform(z[6], z[o1 + 6], z[o2 + 6], z[o3 + 6], cs[6], wim[1]);
-        transform(z[1], z[o1 + 1], z[o2 + 1], z[o3 + 1], cs[1], wim[6]);
-        transform(z[3], z[o1 + 3], z[o2 + 3], z[o3 + 3], cs[3], wim[4]);
-        transform(z[5], z[o1 + 5], z[o2 + 5], z[o3 + 5], cs[5], wim[2]);
-        transform(z[7], z[o1 + 7], z[o2 + 7], z[o3 + 7], cs[7], wim[0]);
-        z += 8; cs += 8; wim -= 8;
-    }
-}
-template <> __device__ void fft_ns<0>(int2 *, const TxiDev &) {}
-template <> __device__ void fft_ns<1>(int2 *d, const TxiDev &)
-{
-    const unsigned re = (unsigned)d[0].x - (unsigned)d[1].x, im = (unsigned)d[0].y - (unsigned)d[1].y;
-    d[0].x = (int)((unsigned)d[0].x + (unsigned)d[1].x); d[0].y = (int)((unsigned)d[0].y + (unsigned)d[1].y);
-    d[1].x = (int)re; d[1].y = (int)im;
-}
-template <> __device__ void fft_ns<2>(int2 *d, const TxiDev &) { fft4(d); }
-template <> __device__ void fft_ns<3>(int2 *d, const TxiDev &P)
-{
-    const int c = P.tabs[3][1];
-    const int2 s4 = d[4], s5 = d[5], s6 = d[6], s7 = d[7];
-    fft4(d);
-    const unsigned t1 = (unsigned)s4.x - (unsigned)(-s5.x), t2 = (unsigned)s4.y - (unsigned)(-s5.y);
-    const unsigned t5 = (unsigned)s6.x - (unsigned)(-s7.x), t6 = (unsigned)s6.y - (unsigned)(-s7.y);
-    d[5].x = (int)((unsigned)s4.x + (unsigned)(-s5.x)); d[5].y = (int)((unsigned)s4.y + (unsigned)(-s5.y));
-    d[7].x = (int)((unsigned)s6.x + (unsigned)(-s7.x)); d[7].y = (int)((unsigned)s6.y + (unsigned)(-s7.y));
-    butterflies(d[0], d[2], d[4], d[6], t1, t2, t5, t6);
-    transform(d[1], d[3], d[5], d[7], c, c);
-}
-template <> __device__ void fft_ns<4>(int2 *d, const TxiDev &P)
-{
-    const int *c = P.tabs[4];
-    fft_ns<3>(d, P);
-    fft4(d + 8);
-    fft4(d + 12);
-    butterflies(d[0], d[4], d[8], d[12], (unsigned)d[8].x, (unsigned)d[8].y, (unsigned)d[12].x, (unsigned)d[12].y);
-    transform(d[2], d[6], d[10], d[14], c[2], c[2]);
-    transform(d[1], d[5], d[9], d[13], c[1], c[3]);
-    transform(d[3], d[7], d[11], d[15], c[3], c[1]);
-}
-__device__ void fft_ns_any(int2 *d, const TxiDev &P)
-{
-    switch (P.log2n) {
-    case 0: break;
-    case 1: fft_ns<1>(d, P); break;   case 2: fft_ns<2>(d, P); break;   case 3: fft_ns<3>(d, P); break;
-    case 4: fft_ns<4>(d, P); break;   case 5: fft_ns<5>(d, P); break;   case 6: fft_ns<6>(d, P); break;
-    case 7: fft_ns<7>(d, P); break;   case 8: fft_ns<8>(d, P); break;   case 9: fft_ns<9>(d, P); break;
-    case 10: fft_ns<10>(d, P); break; case 11: fft_ns<11>(d, P); break; default: fft_ns<12>(d, P); break;
+    for (int L = 1; L <= P.log2n; L++) {
+        const int *off = P.blk + P.lvl_start[L];
+        const int cnt = P.lvl_cnt[L];
+        if (L == 1) {
+            for (int b = threadIdx.x; b < cnt; b += blockDim.x) {
+                const int o = off[b];
+                const int2 s0 = z[PADI(o)], s1 = z[PADI(o + 1)];
+                z[PADI(o)] = make_int2((int)((unsigned)s0.x + (unsigned)s1.x), (int)((unsigned)s0.y + (unsigned)s1.y));
+                z[PADI(o + 1)] = make_int2((int)((unsigned)s0.x - (unsigned)s1.x), (int)((unsigned)s0.y - (unsigned)s1.y));
+            }
+        } else {
+            const int lq = L - 2, q = 1 << lq, total = cnt << lq;
+            const int *tab = P.tabs[L];
+            for (int r = threadIdx.x; r < total; r += blockDim.x) {
+                const int o = off[r >> lq], j = r & (q - 1);
+                const int i0 = PADI(o + j), i1 = PADI(o + q + j), i2 = PADI(o + 2 * q + j), i3 = PADI(o + 3 * q + j);
+                int2 a0 = z[i0], a1 = z[i1], a2 = z[i2], a3 = z[i3];
+                if (L <= 4 && j == 0) butterflies(a0, a1, a2, a3, (unsigned)a2.x, (unsigned)a2.y, (unsigned)a3.x, (unsigned)a3.y);
+                else transform(a0, a1, a2, a3, tab[j], tab[q - j]);
+                z[i0] = a0; z[i1] = a1; z[i2] = a2; z[i3] = a3;
+            }
+        }
+        __syncthreads();
     }
 }
 
 __device__ __forceinline__ int fold(int x, int y) { return (int)((unsigned)x + (unsigned)y + 32u) >> 6; }
 
-// kind 0: FFT (out-of-place gather + in-place transform), 1: inverse MDCT, 2: forward MDCT.  One thread per transform.
+// kind 0: FFT, 1: inverse MDCT, 2: forward MDCT.  One CTA per transform (CTAs stride over the batch).
+constexpr int I32_THREADS = 128;
 template <int KIND>
-__global__ void __launch_bounds__(64)
-tx_i32_kernel(const TxiDev P, int *out, const int *in, long long stride, long long out_step, long long in_step, long long count, int2 *scratch)
+__global__ void __launch_bounds__(I32_THREADS)
+tx_i32_kernel(const TxiDev P, int *out, const int *in, long long stride, long long out_step, long long in_step, long long count)
 {
-    const long long tr = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (tr >= count) return;
-    int *dst = reinterpret_cast<int *>(reinterpret_cast<char *>(out) + tr * out_step);
-    const int *src = reinterpret_cast<const int *>(reinterpret_cast<const char *>(in) + tr * in_step);
-    if (KIND == 0) {
-        int2 *d = reinterpret_cast<int2 *>(dst);
-        const int2 *s = reinterpret_cast<const int2 *>(src);
-        for (int j = 0; j < P.n; j++) d[j] = s[P.map[j]];
-        fft_ns_any(d, P);
-        return;
-    }
+    extern __shared__ int2 i32_z[];
+    int2 *z = i32_z;
     const int len2 = P.len >> 1, len4 = P.len >> 2;
-    const int2 *e = P.exp;
-    if (KIND == 1) {
-        int2 *z = reinterpret_cast<int2 *>(dst);
-        const int *in1 = src, *in2 = src + (len2 * 2 - 1) * stride;
-        for (int i = 0; i < len2; i++) {
-            const int k = P.map[i];
-            unsigned re, im;
-            cmul(re, im, in2[-k * stride], in1[k * stride], e[i].x, e[i].y);
-            z[i].x = (int)re; z[i].y = (int)im;
+    for (long long tr = blockIdx.x; tr < count; tr += gridDim.x) {
+        int *dst = reinterpret_cast<int *>(reinterpret_cast<char *>(out) + tr * out_step);
+        const int *src = reinterpret_cast<const int *>(reinterpret_cast<const char *>(in) + tr * in_step);
+        const int2 *e = P.exp;
+        if (KIND == 0) {
+            const int2 *s = reinterpret_cast<const int2 *>(src);
+            for (int j = threadIdx.x; j < P.n; j += blockDim.x) z[PADI(j)] = s[P.map[j]];
+        } else if (KIND == 1) {
+            const int *in1 = src, *in2 = src + (len2 * 2 - 1) * stride;
+            for (int i = threadIdx.x; i < len2; i += blockDim.x) {
+                const int k = P.map[i];
+                unsigned re, im;
+                cmul(re, im, in2[-k * stride], in1[k * stride], e[i].x, e[i].y);
+                z[PADI(i)] = make_int2((int)re, (int)im);
+            }
+        } else {
+            const int len3 = len2 * 3;
+            for (int i = threadIdx.x; i < len2; i += blockDim.x) {
+                const int k = 2 * i, idx = P.map[i];
+                int re, im;
+                if (k < len2) { re = fold(-src[len2 + k], src[1 * len2 - 1 - k]); im = fold(-src[len3 + k], -src[1 * len3 - 1 - k]); }
+                else          { re = fold(-src[len2 + k], -src[5 * len2 - 1 - k]); im = fold(src[-len2 + k], -src[1 * len3 - 1 - k]); }
+                unsigned a, b;
+                cmul(a, b, re, im, e[i].x, e[i].y);
+                z[PADI(idx)] = make_int2((int)b, (int)a);
+            }
         }
-        fft_ns_any(z, P);
-        e += len2;
-        for (int i = 0; i < len4; i++) {
-            const int i0 = len4 + i, i1 = len4 - i - 1;
-            const int2 s1 = make_int2(z[i1].y, z[i1].x), s0 = make_int2(z[i0].y, z[i0].x);
-            unsigned a, b;
-            cmul(a, b, s1.x, s1.y, e[i1].y, e[i1].x); z[i1].x = (int)a; z[i0].y = (int)b;
-            cmul(a, b, s0.x, s0.y, e[i0].y, e[i0].x); z[i0].x = (int)a; z[i1].y = (int)b;
+        __syncthreads();
+        i32_levels(P, z);
+        if (KIND == 0) {
+            int2 *d = reinterpret_cast<int2 *>(dst);
+            for (int j = threadIdx.x; j < P.n; j += blockDim.x) d[j] = z[PADI(j)];
+        } else if (KIND == 1) {
+            int2 *d = reinterpret_cast<int2 *>(dst);
+            e += len2;
+            for (int i = threadIdx.x; i < len4; i += blockDim.x) {
+                const int i0 = len4 + i, i1 = len4 - i - 1;
+                const int2 z1 = z[PADI(i1)], z0 = z[PADI(i0)];
+                const int2 s1 = make_int2(z1.y, z1.x), s0 = make_int2(z0.y, z0.x);
+                unsigned a, b, c2, d2;
+                cmul(a, b, s1.x, s1.y, e[i1].y, e[i1].x);            // z[i1].re, z[i0].im
+                cmul(c2, d2, s0.x, s0.y, e[i0].y, e[i0].x);          // z[i0].re, z[i1].im
+                d[i1] = make_int2((int)a, (int)d2);
+                d[i0] = make_int2((int)c2, (int)b);
+            }
+        } else {
+            for (int i = threadIdx.x; i < len4; i += blockDim.x) {
+                const int i0 = len4 + i, i1 = len4 - i - 1;
+                const int2 s1 = z[PADI(i1)], s0 = z[PADI(i0)];
+                unsigned a, b;
+                cmul(a, b, s0.x, s0.y, e[i0].y, e[i0].x); dst[(2 * i1 + 1) * stride] = (int)a; dst[2 * i0 * stride] = (int)b;
+                cmul(a, b, s1.x, s1.y, e[i1].y, e[i1].x); dst[(2 * i0 + 1) * stride] = (int)a; dst[2 * i1 * stride] = (int)b;
+            }
         }
-    } else {
-        int2 *z = scratch + tr * len2;
-        const int len3 = len2 * 3;
-        for (int i = 0; i < len2; i++) {
-            const int k = 2 * i, idx = P.map[i];
-            int re, im;
-            if (k < len2) { re = fold(-src[len2 + k], src[1 * len2 - 1 - k]); im = fold(-src[len3 + k], -src[1 * len3 - 1 - k]); }
-            else          { re = fold(-src[len2 + k], -src[5 * len2 - 1 - k]); im = fold(src[-len2 + k], -src[1 * len3 - 1 - k]); }
-            unsigned a, b;
-            cmul(a, b, re, im, e[i].x, e[i].y);
-            z[idx].y = (int)a; z[idx].x = (int)b;
-        }
-        fft_ns_any(z, P);
-        for (int i = 0; i < len4; i++) {
-            const int i0 = len4 + i, i1 = len4 - i - 1;
-            const int2 s1 = z[i1], s0 = z[i0];
-            unsigned a, b;
-            cmul(a, b, s0.x, s0.y, e[i0].y, e[i0].x); dst[(2 * i1 + 1) * stride] = (int)a; dst[2 * i0 * stride] = (int)b;
-            cmul(a, b, s1.x, s1.y, e[i1].y, e[i1].x); dst[(2 * i0 + 1) * stride] = (int)a; dst[2 * i1 * stride] = (int)b;
-        }
+        __syncthreads();                                   // the buffer is reused by the next transform of this CTA
     }
 }
 // [/device-code tx_int32]
@@ -209,7 +177,8 @@ struct TxI32 {
     int type = 0, inv = 0, len = 0;
     TxiDev d{};
     void *blob = nullptr;
-    void *scratch = nullptr; size_t scratch_bytes = 0;
+    size_t smem = 0;
+    int grid_cap = 0;
 };
 
 bool tx_i32_length_ok(int type, int len)
@@ -262,6 +231,21 @@ static int i32_host_tables(std::vector<int32_t> &w, int32_t lay[4], int type, in
         w.push_back(0);
     }
     lay[3] = k;
+    {   // after the cosine tables: 18 level starts, 18 level counts, then the block offsets of every level
+        std::vector<std::vector<int>> lv(18);
+        struct R { static void go(std::vector<std::vector<int>> &lv, int L, int off) {
+            if (L < 1) return;
+            lv[L].push_back(off);
+            const int S = 1 << L;
+            go(lv, L - 1, off);
+            if (L >= 2) { go(lv, L - 2, off + S / 2); go(lv, L - 2, off + 3 * S / 4); }
+        } };
+        R::go(lv, k, 0);
+        int start = 0;
+        for (int L = 0; L < 18; L++) { w.push_back(start); start += (int)lv[L].size(); }
+        for (int L = 0; L < 18; L++) w.push_back((int)lv[L].size());
+        for (int L = 0; L < 18; L++) for (int o : lv[L]) w.push_back(o);
+    }
     return (int)w.size();
 }
 
@@ -299,6 +283,18 @@ TxI32 *tx_i32_create(B200Device *dev, int type, int inv, int len, float scale)
     const int32_t *c = b + lay[2];
     for (int k = 0; k < 18; k++) d.tabs[k] = nullptr;
     for (int k = 3; k <= d.log2n; k++) { d.tabs[k] = c; c += (1 << k) / 4 + 1; }
+    d.blk = c + 36;
+    for (int L = 0; L < 18; L++) { d.lvl_start[L] = w[(size_t)(c - b) + L]; d.lvl_cnt[L] = w[(size_t)(c - b) + 18 + L]; }
+    p->smem = (size_t)(d.n + (d.n >> 4) + 1) * sizeof(int2);
+    if (p->smem > 48 * 1024 &&
+        (cudaFuncSetAttribute(tx_i32_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem) != cudaSuccess ||
+         cudaFuncSetAttribute(tx_i32_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem) != cudaSuccess ||
+         cudaFuncSetAttribute(tx_i32_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem) != cudaSuccess)) {
+        cudaFree(p->blob);
+        delete p;
+        return nullptr;
+    }
+    p->grid_cap = (dev && dev->sm_count > 0 ? dev->sm_count : 148) * 8;
     return p;
 }
 
@@ -306,7 +302,6 @@ void tx_i32_free(TxI32 *p)
 {
     if (!p) return;
     if (p->blob) cudaFree(p->blob);
-    if (p->scratch) cudaFree(p->scratch);
     delete p;
 }
 
@@ -318,31 +313,12 @@ int tx_i32_launch(TxI32 *p, cudaStream_t st, void *out, const void *in, ptrdiff_
     const uintptr_t oa = reinterpret_cast<uintptr_t>(out) | (uintptr_t)out_step, ia = reinterpret_cast<uintptr_t>(in) | (uintptr_t)in_step;
     const bool cplx_out = p->type == B200_TX_INT32_FFT || p->inv, cplx_in = p->type == B200_TX_INT32_FFT;
     if ((oa & (cplx_out ? 7 : 3)) || (ia & (cplx_in ? 7 : 3))) return B200_EINVAL;
-    const bool fwd_mdct = p->type == B200_TX_INT32_MDCT && !p->inv;
-    const size_t l2 = (size_t)p->len >> 1;
-    int64_t chunk = count;
-    if (fwd_mdct) {                                                  // the forward MDCT builds its complex array in scratch
-        const int64_t chunk_max = (int64_t)((size_t)(256u << 20) / (l2 * sizeof(int2)));
-        if (chunk > chunk_max) chunk = chunk_max;
-        const size_t need = (size_t)chunk * l2 * sizeof(int2);
-        if (p->scratch_bytes < need) {
-            if (p->scratch) { cudaStreamSynchronize(st); cudaFree(p->scratch); p->scratch = nullptr; p->scratch_bytes = 0; }
-            B200_CUDA_OK(cudaMalloc(&p->scratch, need));
-            p->scratch_bytes = need;
-        }
-    }
-    if (chunk > 0x7fffffffLL / 2) chunk = 0x7fffffffLL / 2;
-    for (int64_t c0 = 0; c0 < count; c0 += chunk) {
-        const long long cnt = count - c0 < chunk ? count - c0 : chunk;
-        const unsigned nb = (unsigned)((cnt + 63) / 64);
-        int *o = (int *)((char *)out + c0 * out_step);
-        const int *i = (const int *)((const char *)in + c0 * in_step);
-        const long long sf = (long long)(stride / 4);
-        if (p->type == B200_TX_INT32_FFT) tx_i32_kernel<0><<<nb, 64, 0, st>>>(p->d, o, i, sf, out_step, in_step, cnt, nullptr);
-        else if (p->inv)                  tx_i32_kernel<1><<<nb, 64, 0, st>>>(p->d, o, i, sf, out_step, in_step, cnt, nullptr);
-        else                              tx_i32_kernel<2><<<nb, 64, 0, st>>>(p->d, o, i, sf, out_step, in_step, cnt, (int2 *)p->scratch);
-        B200_LAUNCHED();
-    }
+    const unsigned nb = (unsigned)(count < p->grid_cap ? count : p->grid_cap);
+    const long long sf = (long long)(stride / 4);
+    if (p->type == B200_TX_INT32_FFT) tx_i32_kernel<0><<<nb, I32_THREADS, p->smem, st>>>(p->d, (int *)out, (const int *)in, sf, out_step, in_step, count);
+    else if (p->inv)                  tx_i32_kernel<1><<<nb, I32_THREADS, p->smem, st>>>(p->d, (int *)out, (const int *)in, sf, out_step, in_step, count);
+    else                              tx_i32_kernel<2><<<nb, I32_THREADS, p->smem, st>>>(p->d, (int *)out, (const int *)in, sf, out_step, in_step, count);
+    B200_LAUNCHED();
     B200_CUDA_OK(cudaGetLastError());
     return 0;
 }

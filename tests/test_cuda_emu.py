@@ -32,6 +32,8 @@ def emu():
     assert sorted(found) == ["fdsp", "h264lf", "idct_hbd", "pixelutils", "sws_new", "sws_nvout", "tx_dct", "tx_int32", "tx_pfa", "unquant"], sorted(found)
     found["tx_pfa"], n_sh = re.subn(r"extern __shared__ float2 pfa_z\[\];", "float2 *pfa_z = (float2 *)emu_smem;", found["tx_pfa"])
     assert n_sh == 2
+    found["tx_int32"], n_sh = re.subn(r"extern __shared__ int2 i32_z\[\];", "int2 *i32_z = (int2 *)emu_smem;", found["tx_int32"])
+    assert n_sh == 1
     for k, v in found.items():
         open(os.path.join(gen, k + ".inc"), "w").write(v)
     so = os.path.join(gen, "libemu.so")
@@ -48,7 +50,7 @@ def vp(a):
 
 WARP_KERNELS = {"mpv_unquant_kernel"}                   # kernels that use a warp collective: one OS thread per lane
 BLOCK_KERNELS = {"tx_fft_kernel", "tx_mdct_inv_kernel", "tx_mdct_fwd_kernel", "tx_rdft_r2c_kernel", "tx_rdft_c2r_kernel",
-                 "sws_fused_plane_kernel", "sws_fused_rgb_kernel", "tx_mdct_pfa_inv_kernel", "tx_mdct_pfa_fwd_kernel"}    # __syncthreads + dynamic shared memory
+                 "sws_fused_plane_kernel", "sws_fused_rgb_kernel", "tx_mdct_pfa_inv_kernel", "tx_mdct_pfa_fwd_kernel", "tx_i32_kernel"}    # __syncthreads + dynamic shared memory
 
 
 def rewrite_launches(txt):
@@ -623,7 +625,8 @@ def emutx():
     open(os.path.join(gen, "host_tx.cpp"), "w").write(t)
     open(os.path.join(gen, "host_tx_pfa.cpp"), "w").write(rewrite_launches(open(os.path.join(cs, "tx_pfa.cu")).read()).replace("extern __shared__ float2 pfa_z[];", "float2 *pfa_z = (float2 *)emu_smem;"))
     open(os.path.join(gen, "host_tx_dct.cpp"), "w").write(rewrite_launches(open(os.path.join(cs, "tx_dct.cu")).read()))
-    open(os.path.join(gen, "host_tx_int32.cpp"), "w").write(rewrite_launches(open(os.path.join(cs, "tx_int32.cu")).read()))
+    open(os.path.join(gen, "host_tx_int32.cpp"), "w").write(rewrite_launches(open(os.path.join(cs, "tx_int32.cu")).read()).replace(
+        "extern __shared__ int2 i32_z[];", "int2 *i32_z = (int2 *)emu_smem;"))
     # tx_r16.cu (bulk async copies + mbarriers in inline PTX) cannot run here: the emulated library keeps tx.cu's level-by-level kernels,
     # which stay the fallback of the product; the register-resident schedule is checked by tests/test_tx_r16_plan.py and on the GPU
     open(os.path.join(gen, "host_tx_r16_stub.cpp"), "w").write(
