@@ -170,8 +170,10 @@ PROTOTYPES = {
     "b200_sws_scale_batch_host": (C.c_int, [vp, C.POINTER(vp), i32p, i64p, vp, C.c_int, C.c_int64, C.c_int]),
     "b200_sws_info": (C.c_int, [vp, i32p]),
     "b200_sws_get_filter": (C.c_int, [vp, C.c_int, i16p, i32p, C.c_int]),
+    "b200_sws_last_path": (C.c_int, [vp]),
     "b200_sws_plan_probe": (C.c_int, [C.c_int] * 6 + [i16p, i32p, C.c_int, i32p]),
     "b200_sws_plan_probe2": (C.c_int, [i32p, i32p, C.c_int, i16p, i32p, C.c_int, i32p]),
+    "b200_sws_mma_probe": (C.c_int, [i16p, i32p, C.c_int, C.c_int, i32p, C.c_int, C.POINTER(C.c_uint32), C.c_int, i32p]),
     "b200_idctdsp_init": (C.c_int, [C.POINTER(IDCTDSPContext), C.c_int, C.c_int, C.c_int]),
     "b200_idct_batch_device": (C.c_int, [vp, C.c_int, vp, C.c_int64, vp, vp, vp, C.c_int]),
     "b200_idct_mb420_device": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.POINTER(vp), i32p, i64p]),

@@ -249,39 +249,41 @@ qpel_kernel(long long n, const uint8_t *op, uint8_t *dst, const int64_t *dst_off
 
 // ------------------------------------------------------------------------------------------------ qpel on TMA-staged windows
 // Same arithmetic as qpel_kernel; what changes is how a window reaches shared memory: one cp.async.bulk.tensor.2d (UTMALDG) per
-// operation — a box of 32 bytes x (size + 5) rows whose origin is the operation's own (column - 8, row - 2) in a tensor map laid
-// over the reference plane — completes on the operation's mbarrier.  A warp issues the boxes of all its TQK operations before it
-// computes the first one, so nothing of the load path runs on the LSU any more (no per-row 16-byte loads, no register -> shared
-// staging, no funnel-shift re-alignment: the box lands with block column 0 at byte 8 of each 32-byte row).  The tile uses the
-// 32-byte swizzle (the two 16-byte halves of rows 4..7 of every 8 are swapped), which makes the 8-byte row-segment reads of a warp
-// conflict-free; WinT applies it on the word index.  Operations whose box would leave the row (a block closer than 8 bytes to the
-// left end or 24 to the right end of a line: never the case inside an edge-padded H.264 picture) are filled by plain loads instead.
+// operation completes on the operation's mbarrier.  A warp issues the boxes of all its TQK operations before it computes the first
+// one, so nothing of the load path runs on the LSU any more (no per-row 16-byte loads, no register -> shared staging).
+// The hardware wants the box origin on a 16-byte column (measured on the B200: any other start column raises an illegal-instruction
+// fault, scripts/probe/tma_probe.cu), so the box of a block at column x starts at (x - 2) & ~15 and is 48 bytes wide for 16-pixel blocks
+// (window of 21 bytes at phase 0..15) and 32 bytes for 8- and 4-pixel blocks (13 / 9 bytes); the window's byte phase inside the tile
+// row, ph = (x - 2) & 15, is folded into the word index and one funnel shift of the row readers.  Boxes that hang over the end of a
+// line are legal (the tensor map's column extent is the line pitch: the missing bytes arrive as zeros and are never used).
+// Blocks closer than 2 bytes to the start of a line or 2 rows to the start of the plane are filled by plain loads instead.
 constexpr int TQK = 8;                  // operations per warp
-constexpr int TILE_BYTES = 768;         // 21 rows x 32 bytes, rounded up to the 256-byte swizzle period
-template <bool SWZ>
+constexpr int TILE_BYTES = 1024;        // 21 rows x 48 bytes, rounded up to the 128-byte alignment the copy engine wants
 struct WinT {
     const unsigned *t;
-    __device__ __forceinline__ unsigned w(int row, int k) const { return t[row * 8 + (SWZ ? (k ^ (row & 4)) : k)]; }
+    int pw;                             // words per tile row (12 or 8)
+    int off0;                           // byte of block column 0 inside a tile row (ph + 2)
+    __device__ __forceinline__ unsigned w(int row, int k) const { return t[row * pw + k]; }
 };
-template <bool SWZ>
-__device__ __forceinline__ uint2 t_row8p(const WinT<SWZ> &W, int row, int x0, int dx)
+// 8 pixels of `row` starting at block column x0 + dx
+__device__ __forceinline__ uint2 t_row8p(const WinT &W, int row, int x0, int dx)
 {
-    const int k = (QX + x0) >> 2;
-    unsigned w0 = W.w(row, k), w1 = W.w(row, k + 1);
-    if (dx) { const unsigned w2 = W.w(row, k + 2); w0 = __funnelshift_r(w0, w1, 8); w1 = __funnelshift_r(w1, w2, 8); }
-    return make_uint2(w0, w1);
+    const int o = W.off0 + x0 + dx, k = o >> 2;
+    const unsigned sh = (unsigned)(o & 3) * 8u;
+    const unsigned w0 = W.w(row, k), w1 = W.w(row, k + 1), w2 = W.w(row, k + 2);
+    return make_uint2(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh));
 }
-template <bool SWZ>
-__device__ __forceinline__ void t_hsum8(const WinT<SWZ> &W, int row, int x0, int init, int *o)
+// raw 6-tap horizontal sums of the 8 pixels at block columns x0 .. x0 + 7
+__device__ __forceinline__ void t_hsum8(const WinT &W, int row, int x0, int init, int *o)
 {
-    const int k = (QX + x0 - 4) >> 2;
-    const unsigned A[5] = { W.w(row, k), W.w(row, k + 1), W.w(row, k + 2), W.w(row, k + 3), W.w(row, k + 4) };
-    unsigned S[12];
+    const int s = W.off0 + x0 - 2, k = s >> 2;
+    const unsigned q = (unsigned)(s & 3) * 8u;
+    const unsigned R[5] = { W.w(row, k), W.w(row, k + 1), W.w(row, k + 2), W.w(row, k + 3), W.w(row, k + 4) };
+    const unsigned A[4] = { __funnelshift_r(R[0], R[1], q), __funnelshift_r(R[1], R[2], q), __funnelshift_r(R[2], R[3], q), __funnelshift_r(R[3], R[4], q) };
+    unsigned S[12];                     // S[i] = window bytes i .. i + 3, byte 0 = block column x0 - 2
 #pragma unroll
-    for (int i = 0; i < 12; i++) {
-        const int b = 2 + i;
-        S[i] = (b & 3) ? __funnelshift_r(A[b >> 2], A[(b >> 2) + 1], (b & 3) * 8) : A[b >> 2];
-    }
+    for (int i = 0; i < 12; i++)
+        S[i] = (i & 3) ? __funnelshift_r(A[i >> 2], A[(i >> 2) + ((i >> 2) < 3 ? 1 : 0)], (i & 3) * 8) : A[i >> 2];
 #pragma unroll
     for (int i = 0; i < 8; i++) o[i] = dp4a_us(S[i + 4], TAP4_B, dp4a_us(S[i], TAP4_A, init));
 }
@@ -308,7 +310,6 @@ struct __align__(1024) QpelTmaSmem {
     unsigned long long mbar[WARPS][TQK];
 };
 
-template <bool SWZ>
 __global__ void __launch_bounds__(32 * WARPS)
 qpel_tma_kernel(const __grid_constant__ CUtensorMap tm16, const __grid_constant__ CUtensorMap tm8, const __grid_constant__ CUtensorMap tm4,
                 long long n, const uint8_t *op, uint8_t *dst, const int64_t *dst_off, const uint8_t *src, const int64_t *src_off,
@@ -318,8 +319,8 @@ qpel_tma_kernel(const __grid_constant__ CUtensorMap tm16, const __grid_constant_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long first_op = ((long long)blockIdx.x * WARPS + warp) * TQK;
     if (first_op >= n) return;
-    // lanes 0 .. TQK-1 each own one operation's descriptor and issue its box
-    int mo = -1, inb = 0, bx = 0, by = 0;
+    // lanes 0 .. TQK-1 each own one operation's descriptor
+    int mo = -1, inb = 0, bx = 0, by = 0, mph = 0;
     long long msoff = 0, mdoff = 0;
     if (lane < TQK) {
         const uint32_t mb = pel_smem_u32(&sm.mbar[warp][lane]);
@@ -335,7 +336,7 @@ qpel_tma_kernel(const __grid_constant__ CUtensorMap tm16, const __grid_constant_
         unsigned long long y = __umul64hi((unsigned long long)msoff, magic);
         long long x = msoff - (long long)y * stride;
         while (x >= stride) { x -= stride; y++; }
-        if (x >= 8 && x + 24 <= stride && y >= 2 && y < 0x7fffff00ULL) { inb = 1; bx = (int)x - 8; by = (int)y - 2; }
+        if (x >= 2 && y >= 2 && y < 0x7fffff00ULL) { inb = 1; mph = (int)(x - 2) & 15; bx = (int)(x - 2) - mph; by = (int)y - 2; }
     }
     // the copies are issued by one lane (TMA operands live in uniform registers): lane 0 walks the warp's operations
     for (int k = 0; k < TQK; k++) {
@@ -343,7 +344,7 @@ qpel_tma_kernel(const __grid_constant__ CUtensorMap tm16, const __grid_constant_
         const int ksize = 16 >> ((__shfl_sync(0xffffffffu, mo, k) >> 1) & 3);
         if (kin && lane == 0) {
             const CUtensorMap *tm = ksize == 16 ? &tm16 : ksize == 8 ? &tm8 : &tm4;
-            pel_tma_2d(pel_smem_u32(&sm.tile[warp][k][0]), tm, kx, ky, pel_smem_u32(&sm.mbar[warp][k]), 32u * (ksize + 5));
+            pel_tma_2d(pel_smem_u32(&sm.tile[warp][k][0]), tm, kx, ky, pel_smem_u32(&sm.mbar[warp][k]), (ksize == 16 ? 48u : 32u) * (ksize + 5));
         }
     }
     short *hraw = sm.hraw[warp];
@@ -362,20 +363,19 @@ qpel_tma_kernel(const __grid_constant__ CUtensorMap tm16, const __grid_constant_
         uint2 pv = make_uint2(0, 0);
         if (mine && avg && vec) pv = *reinterpret_cast<const uint2 *>(d);                  // destination row requested early
         uint8_t *tile = sm.tile[warp][t];
+        const int pwb = size == 16 ? 48 : 32;                                              // bytes per tile row
+        const int ph = __shfl_sync(0xffffffffu, mph, t);                                   // 0 for the plain-load fill
         if (__shfl_sync(0xffffffffu, inb, t)) {
             pel_mbar_wait(pel_smem_u32(&sm.mbar[warp][t]), 0);
-        } else {                                                                           // box would leave the line: plain loads
+        } else {                                                                           // first columns / rows of the plane: plain loads
             const long long soff = __shfl_sync(0xffffffffu, msoff, t);
             if (lane < wdim) {
                 const uint8_t *rp = src + soff + (long long)(lane - 2) * stride - 2;
-                for (int k = 0; k < wdim; k++) {
-                    const int b = QX - 2 + k;
-                    tile[lane * 32 + (SWZ ? (b ^ ((lane & 4) << 2)) : b)] = __ldg(rp + k);
-                }
+                for (int k = 0; k < wdim; k++) tile[lane * pwb + k] = __ldg(rp + k);
             }
             __syncwarp();
         }
-        const WinT<SWZ> W{ reinterpret_cast<const unsigned *>(tile) };
+        const WinT W{ reinterpret_cast<const unsigned *>(tile), pwb >> 2, ph + 2 };
         const bool need_j = (qx == 2 && qy != 0) || (qy == 2 && qx != 0);
         if (need_j) {
             for (int k = lane; k < wdim * segs; k += 32) {
@@ -554,15 +554,100 @@ chroma_kernel(long long n, const uint8_t *op, const uint8_t *hh, const uint8_t *
     }
 }
 
+// The batched form of chroma_kernel: the same arithmetic, CK operations per 8-lane group with every global load of the CK windows
+// (descriptors first, then window rows and — for avg — destination rows) issued before the first result is computed.  chroma_kernel
+// has one 9-byte window per 8 lanes in flight and three dependent round trips to memory per operation (ncu: long_scoreboard 38 per
+// issue, issue slots 32 % busy); here a warp keeps 4 * CK windows in flight.  Group g of a warp handles operations first + 4 * j + g.
+template <int CK, int MINB>
+__global__ void __launch_bounds__(32 * WARPS, MINB)
+chroma_kernel_k(long long n, const uint8_t *op, const uint8_t *hh, const uint8_t *xy, uint8_t *dst, const int64_t *dst_off,
+                const uint8_t *src, const int64_t *src_off, long long stride)
+{
+    const int lane = threadIdx.x & 31, grp = lane >> 3, sub = lane & (CH_LANES - 1);
+    const long long first = ((long long)blockIdx.x * WARPS + (threadIdx.x >> 5)) * (4 * CK);
+    if (first >= n) return;
+    int o[CK], h[CK], pq[CK];
+    long long so[CK], dof[CK];
+    bool valid[CK];
+#pragma unroll
+    for (int j = 0; j < CK; j++) {
+        const long long gi = first + 4 * j + grp;
+        valid[j] = gi < n;
+        const long long i = valid[j] ? gi : n - 1;
+        o[j] = __ldg(op + i); h[j] = __ldg(hh + i); pq[j] = __ldg(xy + i); so[j] = __ldg(src_off + i); dof[j] = __ldg(dst_off + i);
+    }
+    int hm = 0;
+#pragma unroll
+    for (int j = 0; j < CK; j++) hm = max(hm, valid[j] ? h[j] : 0);
+    const int hmax = __reduce_max_sync(0xffffffffu, hm);
+    for (int y0 = 0; y0 < hmax; y0 += CH_LANES) {
+        const int y = y0 + sub;
+        ChRow t[CK], bl[CK];
+        uint2 pv[CK];
+        bool mine[CK], vec[CK];
+        // every load of the CK windows
+#pragma unroll
+        for (int j = 0; j < CK; j++) {
+            const int fx = pq[j] & 7, fy = (pq[j] >> 3) & 7, w = 8 >> ((o[j] >> 1) & 3);
+            const int nbytes = w + (fx != 0);
+            mine[j] = valid[j] && y < h[j];
+            const uint8_t *rowp = src + so[j] + (long long)y * stride;
+            t[j] = chroma_row(rowp, nbytes, mine[j]);
+            const bool last = sub == CH_LANES - 1 || y == h[j] - 1;      // the row below is not held by the next lane
+            bl[j] = chroma_row(rowp + stride, nbytes, mine[j] && last && fy != 0);
+            const uint8_t *d = dst + dof[j] + (long long)y * stride;
+            vec[j] = w == 8 && (reinterpret_cast<uintptr_t>(d) & 7) == 0;
+            pv[j] = make_uint2(0, 0);
+            if (mine[j] && vec[j] && (o[j] & 1)) pv[j] = *reinterpret_cast<const uint2 *>(d);
+        }
+#pragma unroll
+        for (int j = 0; j < CK; j++) {
+            const int fx = pq[j] & 7, fy = (pq[j] >> 3) & 7, avg = o[j] & 1, w = 8 >> ((o[j] >> 1) & 3);
+            const int kab = 4 * ((8 - fx) * (8 - fy)) | (4 * (fx * (8 - fy))) << 16;      // s16 pairs (4A, 4B) and (4C, 4D)
+            const int kcd = 4 * ((8 - fx) * fy) | (4 * (fx * fy)) << 16;
+            ChRow b;
+            b.r0 = __shfl_down_sync(0xffffffffu, t[j].r0, 1, CH_LANES); b.r1 = __shfl_down_sync(0xffffffffu, t[j].r1, 1, CH_LANES);
+            b.r2 = __shfl_down_sync(0xffffffffu, t[j].r2, 1, CH_LANES);
+            if (sub == CH_LANES - 1 || y == h[j] - 1) b = bl[j];
+            if (!mine[j]) continue;
+            const ChRow &tt = t[j];
+            const unsigned ta = __funnelshift_r(tt.r0, tt.r1, 8), tb = __funnelshift_r(tt.r1, tt.r2, 8);
+            const unsigned ba = __funnelshift_r(b.r0, b.r1, 8), bb = __funnelshift_r(b.r1, b.r2, 8);
+            int v[8];
+            v[0] = dp2a_lo_su(kcd, b.r0, dp2a_lo_su(kab, tt.r0, 128)); v[1] = dp2a_lo_su(kcd, ba, dp2a_lo_su(kab, ta, 128));
+            v[2] = dp2a_hi_su(kcd, b.r0, dp2a_hi_su(kab, tt.r0, 128)); v[3] = dp2a_hi_su(kcd, ba, dp2a_hi_su(kab, ta, 128));
+            v[4] = dp2a_lo_su(kcd, b.r1, dp2a_lo_su(kab, tt.r1, 128)); v[5] = dp2a_lo_su(kcd, bb, dp2a_lo_su(kab, tb, 128));
+            v[6] = dp2a_hi_su(kcd, b.r1, dp2a_hi_su(kab, tt.r1, 128)); v[7] = dp2a_hi_su(kcd, bb, dp2a_hi_su(kab, tb, 128));
+            unsigned w0 = __byte_perm(__byte_perm(v[0], v[1], 0x5151), __byte_perm(v[2], v[3], 0x5151), 0x5410);
+            unsigned w1 = __byte_perm(__byte_perm(v[4], v[5], 0x5151), __byte_perm(v[6], v[7], 0x5151), 0x5410);
+            uint8_t *d = dst + dof[j] + (long long)y * stride;
+            if (vec[j]) {
+                if (avg) { w0 = __vavgu4(pv[j].x, w0); w1 = __vavgu4(pv[j].y, w1); }
+                *reinterpret_cast<uint2 *>(d) = make_uint2(w0, w1);
+            } else if (w >= 4 && (reinterpret_cast<uintptr_t>(d) & 3) == 0) {
+                unsigned *d4 = reinterpret_cast<unsigned *>(d);
+                d4[0] = avg ? __vavgu4(d4[0], w0) : w0;
+                if (w == 8) d4[1] = avg ? __vavgu4(d4[1], w1) : w1;
+            } else {
+                for (int k = 0; k < w; k++) {
+                    const int px = (int)__byte_perm(k < 4 ? w0 : w1, 0, 0x4440 | (k & 3));
+                    d[k] = (uint8_t)(avg ? (d[k] + px + 1) >> 1 : px);
+                }
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ h264chroma on TMA-staged windows
-// Same arithmetic as chroma_kernel.  Every operation's source window arrives as one cp.async.bulk.tensor.2d box of 16 bytes x
-// (h + 1) rows (h rows when y == 0: the row below the block is never touched then, as in the reference) placed at the block's own
-// column and row of a tensor map over the reference plane, so a row costs no LSU work at all (the LDG kernel pays a 32-byte sector and
-// two funnel shifts for 9 useful bytes).  A warp owns CQ x 4 operations (8 lanes each, lane = row) and issues all their boxes before
-// it computes the first: 16 windows in flight per warp.  Heights other than 2 / 4 / 8 / 16, and blocks within 16 bytes of the end of
-// a line, take plain loads into the same tile.  The box may read up to 7 bytes right of the reference's own window inside the line.
+// Same arithmetic as chroma_kernel.  Every operation's source window arrives as one cp.async.bulk.tensor.2d box of 32 bytes x
+// (h + 1) rows (h rows when y == 0: the row below the block is never touched then, as in the reference) whose origin is the block's
+// row and its column rounded down to 16 (the copy engine only takes 16-byte-aligned box columns, see the qpel kernel above): the 9
+// window bytes sit at phase ph = x & 15 of each 32-byte tile row, and the row readers fold ph into a word index and one funnel shift.
+// A warp owns CQ x 4 operations (8 lanes each, lane = row) and issues all their boxes before it computes the first: 16 windows in
+// flight per warp.  Heights other than 2 / 4 / 8 / 16 take plain loads into the same tile.  The box may read up to 31 bytes around
+// the reference's own window inside the line (zeros beyond the line pitch).
 constexpr int CQ = 4;                   // operations per 8-lane group
-constexpr int CTILE = 384;              // 17 rows x 16 bytes, rounded to the 128-byte alignment TMA wants
+constexpr int CTILE = 640;              // 17 rows x 32 bytes, rounded to the 128-byte alignment TMA wants
 struct ChromaMaps { CUtensorMap m[8]; };                                // [2 * log2(h / 2) + (y != 0)]: box heights 2,3, 4,5, 8,9, 16,17
 struct __align__(128) ChromaTmaSmem {
     uint8_t tile[WARPS][4 * CQ][CTILE];
@@ -579,7 +664,7 @@ chroma_tma_kernel(const __grid_constant__ ChromaMaps maps, long long n, const ui
     const long long first_op = ((long long)blockIdx.x * WARPS + warp) * PER_WARP;
     if (first_op >= n) return;
     // lanes 0 .. 15 own one operation's descriptor each (slot = lane: group lane / CQ, round lane % CQ) and issue its box
-    int mo = -1, mh = 0, mpq = 0, inb = 0, bx = 0, by = 0;
+    int mo = -1, mh = 0, mpq = 0, inb = 0, bx = 0, by = 0, mph = 0;
     long long msoff = 0, mdoff = 0;
     if (lane < PER_WARP) {
         const uint32_t mb = pel_smem_u32(&sm.mbar[warp][lane]);
@@ -593,7 +678,7 @@ chroma_tma_kernel(const __grid_constant__ ChromaMaps maps, long long n, const ui
         unsigned long long y = __umul64hi((unsigned long long)msoff, magic);
         long long x = msoff - (long long)y * stride;
         while (x >= stride) { x -= stride; y++; }
-        if (x + 16 <= stride && y < 0x7fffff00ULL) { inb = 1; bx = (int)x; by = (int)y; }
+        if (y < 0x7fffff00ULL) { inb = 1; mph = (int)x & 15; bx = (int)x - mph; by = (int)y; }
     }
     for (int k = 0; k < PER_WARP; k++) {                            // issued by one lane: TMA operands live in uniform registers
         const int kin = __shfl_sync(0xffffffffu, inb, k), kx = __shfl_sync(0xffffffffu, bx, k), ky = __shfl_sync(0xffffffffu, by, k);
@@ -601,7 +686,7 @@ chroma_tma_kernel(const __grid_constant__ ChromaMaps maps, long long n, const ui
         if (kin && lane == 0) {
             const int rows = kh + (kfy != 0);
             const int mi = 2 * (kh == 2 ? 0 : kh == 4 ? 1 : kh == 8 ? 2 : 3) + (kfy != 0);
-            pel_tma_2d(pel_smem_u32(&sm.tile[warp][k][0]), &maps.m[mi], kx, ky, pel_smem_u32(&sm.mbar[warp][k]), 16u * rows);
+            pel_tma_2d(pel_smem_u32(&sm.tile[warp][k][0]), &maps.m[mi], kx, ky, pel_smem_u32(&sm.mbar[warp][k]), 32u * rows);
         }
     }
     for (int r = 0; r < CQ; r++) {
@@ -611,6 +696,7 @@ chroma_tma_kernel(const __grid_constant__ ChromaMaps maps, long long n, const ui
         const int h = __shfl_sync(0xffffffffu, mh, slot), pq = __shfl_sync(0xffffffffu, mpq, slot);
         const long long doff = __shfl_sync(0xffffffffu, mdoff, slot), soff = __shfl_sync(0xffffffffu, msoff, slot);
         const int tma = __shfl_sync(0xffffffffu, inb, slot);
+        const int ph = __shfl_sync(0xffffffffu, mph, slot);                               // 0 for the plain-load fill
         const int fx = pq & 7, fy = (pq >> 3) & 7;
         const int avg = o & 1, w = 8 >> ((o >> 1) & 3);
         const int kab = 4 * ((8 - fx) * (8 - fy)) | (4 * (fx * (8 - fy))) << 16;      // s16 pairs (4A, 4B) and (4C, 4D)
@@ -626,14 +712,20 @@ chroma_tma_kernel(const __grid_constant__ ChromaMaps maps, long long n, const ui
                 const int rows = min(h - y0, 16) + (fy != 0);
                 for (int rr = sub; rr < rows; rr += 8) {
                     const uint8_t *rp = src + soff + (long long)(y0 + rr) * stride;
-                    for (int k = 0; k < nbytes; k++) tile[rr * 16 + k] = __ldg(rp + k);
+                    for (int k = 0; k < nbytes; k++) tile[rr * 32 + k] = __ldg(rp + k);
                 }
                 __syncwarp(0xffu << (8 * grp));
             }
 #pragma unroll 1
             for (int yy = sub; yy < min(h - y0, 16); yy += 8) {
-                const uint4 tq = *reinterpret_cast<const uint4 *>(tile + yy * 16);
-                const uint4 bq = *reinterpret_cast<const uint4 *>(tile + (yy + 1) * 16);
+                uint4 tq, bq;                                                            // .x .y .z = window bytes 0..3, 4..7, 8..11
+                {
+                    const unsigned *tw = reinterpret_cast<const unsigned *>(tile + yy * 32) + (ph >> 2), *bw = tw + 8;
+                    const unsigned sh = (unsigned)(ph & 3) * 8u;
+                    const unsigned t0 = tw[0], t1 = tw[1], t2 = tw[2], t3 = tw[3], b0 = bw[0], b1 = bw[1], b2 = bw[2], b3 = bw[3];
+                    tq.x = __funnelshift_r(t0, t1, sh); tq.y = __funnelshift_r(t1, t2, sh); tq.z = __funnelshift_r(t2, t3, sh); tq.w = 0;
+                    bq.x = __funnelshift_r(b0, b1, sh); bq.y = __funnelshift_r(b1, b2, sh); bq.z = __funnelshift_r(b2, b3, sh); bq.w = 0;
+                }
                 const unsigned ta = __funnelshift_r(tq.x, tq.y, 8), tb = __funnelshift_r(tq.y, tq.z, 8);
                 const unsigned ba = __funnelshift_r(bq.x, bq.y, 8), bb = __funnelshift_r(bq.y, bq.z, 8);
                 int v[8];
@@ -861,17 +953,28 @@ B200_API int b200_h264chroma_batch_device(B200Device *dev, int64_t n, const uint
     if (!dev || n < 0 || !op || !h || !xy || !dst || !dst_off || !src || !src_off) return B200_EINVAL;
     if (n == 0) return 0;
     B200_CUDA_OK(cudaSetDevice(dev->ordinal));
-    static int mode = -1;                                         // B200_CHROMA_TMA=0: the LDG kernel
-    if (mode < 0) { const char *e = getenv("B200_CHROMA_TMA"); mode = e ? atoi(e) : 1; }
+    static int mode = -1;                                         // B200_CHROMA_TMA: 0 (default) batched LDG kernel, 1 TMA boxes, 2 one-window LDG kernel
+    if (mode < 0) { const char *e = getenv("B200_CHROMA_TMA"); mode = e ? atoi(e) : 0; }
     ChromaMaps maps;
-    bool tma = mode > 0 && stride >= 16;
+    bool tma = mode == 1 && stride >= 32;
     for (int k = 0; k < 8 && tma; k++)
-        tma = b200_tmap_2d_u8(&maps.m[k], src, (unsigned long long)stride, 16, (2u << (k >> 1)) + (k & 1), (int)CU_TENSOR_MAP_SWIZZLE_NONE);
+        tma = b200_tmap_2d_u8(&maps.m[k], src, (unsigned long long)stride, 32, (2u << (k >> 1)) + (k & 1), (int)CU_TENSOR_MAP_SWIZZLE_NONE);
     if (tma) {
         const long long blocks = (n + WARPS * 4 * CQ - 1) / (WARPS * 4 * CQ);
         if (blocks > 0x7fffffffLL) return B200_EINVAL;
         chroma_tma_kernel<<<(unsigned)blocks, 32 * WARPS, 0, dev->stream>>>(maps, n, op, h, xy, dst, dst_off, src, src_off, stride,
                                                                             ~0ULL / (unsigned long long)stride);
+    } else if (mode == 0) {
+        static int var = -1;                                      // tuning knob: windows per 8-lane group / register budget
+        if (var < 0) { const char *e = getenv("B200_CHROMA_VAR"); var = e ? atoi(e) : 0; }
+        const int ck = var == 1 ? 2 : var == 3 ? 8 : 4;
+        const int per_cta = WARPS * 4 * ck;
+        const long long blocks = (n + per_cta - 1) / per_cta;
+        if (blocks > 0x7fffffffLL) return B200_EINVAL;
+        if (var == 1)      chroma_kernel_k<2, 12><<<(unsigned)blocks, 32 * WARPS, 0, dev->stream>>>(n, op, h, xy, dst, dst_off, src, src_off, stride);
+        else if (var == 2) chroma_kernel_k<4, 8><<<(unsigned)blocks, 32 * WARPS, 0, dev->stream>>>(n, op, h, xy, dst, dst_off, src, src_off, stride);
+        else if (var == 3) chroma_kernel_k<8, 2><<<(unsigned)blocks, 32 * WARPS, 0, dev->stream>>>(n, op, h, xy, dst, dst_off, src, src_off, stride);
+        else               chroma_kernel_k<4, 4><<<(unsigned)blocks, 32 * WARPS, 0, dev->stream>>>(n, op, h, xy, dst, dst_off, src, src_off, stride);
     } else {
         const int per_cta = 32 * WARPS / CH_LANES;
         const long long blocks = (n + per_cta - 1) / per_cta;
@@ -883,21 +986,20 @@ B200_API int b200_h264chroma_batch_device(B200Device *dev, int64_t n, const uint
     return 0;
 }
 
-// B200_QPEL_TMA: 0 = LDG-staged kernel, 1 = TMA boxes without swizzle, 2 (default) = TMA boxes with the 32-byte swizzle
+// B200_QPEL_TMA: 0 = LDG-staged kernel, otherwise (default) TMA boxes
 static int qpel_launch(cudaStream_t st, int64_t n, const uint8_t *op, uint8_t *dst, const int64_t *dst_off, const uint8_t *src,
                        const int64_t *src_off, ptrdiff_t stride)
 {
     static int mode = -1;
-    if (mode < 0) { const char *e = getenv("B200_QPEL_TMA"); mode = e ? atoi(e) : 2; }
+    if (mode < 0) { const char *e = getenv("B200_QPEL_TMA"); mode = e ? atoi(e) : 1; }
     CUtensorMap tm16, tm8, tm4;
-    const int swz = mode == 2 ? (int)CU_TENSOR_MAP_SWIZZLE_32B : (int)CU_TENSOR_MAP_SWIZZLE_NONE;
-    if (mode > 0 && stride >= 32 && b200_tmap_2d_u8(&tm16, src, (unsigned long long)stride, 32, 21, swz) &&
+    const int swz = (int)CU_TENSOR_MAP_SWIZZLE_NONE;
+    if (mode > 0 && stride >= 48 && b200_tmap_2d_u8(&tm16, src, (unsigned long long)stride, 48, 21, swz) &&
         b200_tmap_2d_u8(&tm8, src, (unsigned long long)stride, 32, 13, swz) && b200_tmap_2d_u8(&tm4, src, (unsigned long long)stride, 32, 9, swz)) {
         const long long blocks = (n + WARPS * TQK - 1) / (WARPS * TQK);
         if (blocks > 0x7fffffffLL) return B200_EINVAL;
         const unsigned long long magic = ~0ULL / (unsigned long long)stride;              // floor((2^64 - 1) / stride): the quotient estimate is never too large
-        if (mode == 2) qpel_tma_kernel<true><<<(unsigned)blocks, 32 * WARPS, 0, st>>>(tm16, tm8, tm4, n, op, dst, dst_off, src, src_off, stride, magic);
-        else           qpel_tma_kernel<false><<<(unsigned)blocks, 32 * WARPS, 0, st>>>(tm16, tm8, tm4, n, op, dst, dst_off, src, src_off, stride, magic);
+        qpel_tma_kernel<<<(unsigned)blocks, 32 * WARPS, 0, st>>>(tm16, tm8, tm4, n, op, dst, dst_off, src, src_off, stride, magic);
     } else {
         const long long blocks = (n + WARPS * QK - 1) / (WARPS * QK);
         if (blocks > 0x7fffffffLL) return B200_EINVAL;

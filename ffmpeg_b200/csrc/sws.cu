@@ -30,6 +30,13 @@ struct SwsDevTables {            // device copies of the vertical banks and the 
     const int32_t *hLum2, *hChr2;     // horizontal banks, tap pairs packed the same way
 };
 
+struct SwsMmaBank {                  // one horizontal filter bank in tensor-core form (device pointers)
+    const int2 *ginfo;               // per group of 8 output columns: { first source column of the group's window (multiple of 4), index of its first chunk };
+                                     // entry [ngroups] closes the chunk count
+    const uint4 *bfrag;              // per chunk: 32 lanes x { hi b0, hi b1, lo b0, lo b1 }
+    int ngroups;
+};
+
 struct SwsFrameArgs {
     const uint8_t *y, *u, *v;         // u8 source planes (or int16 planes reinterpret_cast for the scaled path)
     long long ys, us, vs;             // strides in BYTES (may be negative for u8 planes)
@@ -882,6 +889,10 @@ struct B200SwsContext {
     SwsPlan plan;
     void *tables = nullptr;          // one device allocation holding all banks
     SwsDevTables dt{};
+    void *mma_tables = nullptr;      // horizontal banks as tensor-core operands (sws_mma.cuh)
+    SwsMmaBank mmaL{}, mmaC{};
+    int last_path = 0;               // kernels the last scaled-path launch used: 1 two passes, 2 fused CUDA-core, 4 fused tensor-core (b200_sws_last_path)
+    int mma_pitchL = 0, mma_pitchC = 0, mma_pitchC8 = 0;   // staged-line pitches: luma / chroma tiles of 16 groups, chroma tiles of 8 groups
     bool h_identity = false;         // both horizontal banks are the identity -> u8-source kernels
     bool fast_x = false;             // every line uses the _X writer and no 32-bit sum can wrap -> vector kernel
     bool lum_identity = false;       // vertical luma bank is a single tap of 4096 on every line
@@ -900,10 +911,12 @@ struct B200SwsContext {
     bool slice_open = false;
 };
 
+static int upload_mma_tables(B200SwsContext *c);
 static int upload_tables(B200SwsContext *c)
 {
     const SwsPlan &p = c->plan;
     if (c->tables) { cudaFree(c->tables); c->tables = nullptr; }
+    if (c->mma_tables) { cudaFree(c->mma_tables); c->mma_tables = nullptr; c->mmaL = SwsMmaBank{}; c->mmaC = SwsMmaBank{}; }
     if (p.unscaled_lut || p.planar_copy || p.bgr24_yv12) return 0;
     auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
     size_t off = 0;
@@ -973,7 +986,7 @@ static int upload_tables(B200SwsContext *c)
     c->pair_ok = c->fast_x && c->lum_identity && p.vChr.size == 4 && p.dstH >= 4 && !getenv("B200_SWS_NO_PAIR");
     for (int y = 1; y + 1 < p.dstH && c->pair_ok; y += 2)
         if (p.vChr.pos[y] != p.vChr.pos[y + 1]) c->pair_ok = false;
-    return 0;
+    return upload_mma_tables(c);
 }
 
 // source side of a plan: yuv420p, nv12 / nv21, or packed 8-bit RGB (input readers); false = not a source this path reads
@@ -1029,6 +1042,7 @@ B200_API void b200_sws_freeContext(B200SwsContext *c)
     cudaSetDevice(c->dev->ordinal);
     cudaStreamSynchronize(c->dev->stream);
     if (c->tables) cudaFree(c->tables);
+    if (c->mma_tables) cudaFree(c->mma_tables);
     if (c->mid) cudaFree(c->mid);
     if (c->nv_buf) cudaFree(c->nv_buf);
     if (c->nvout_buf) cudaFree(c->nvout_buf);
@@ -1055,6 +1069,14 @@ B200_API int b200_sws_info(const B200SwsContext *c, int *o)
     o[8] = p.unscaled_lut; o[9] = 1; o[10] = 1; o[11] = p.chrDstHSub; o[12] = 0;
     o[13] = p.dstW; o[14] = p.dstH; o[15] = 0;
     return 0;
+}
+
+B200_API int b200_sws_last_path(B200SwsContext *c)
+{
+    if (!c) return B200_EINVAL;
+    const int v = c->last_path;
+    c->last_path = 0;
+    return v;
 }
 
 B200_API int b200_sws_get_filter(const B200SwsContext *c, int which, int16_t *filter, int32_t *pos, int cap)
@@ -1289,6 +1311,100 @@ sws_fused_rgb_kernel(SwsFrameArgs a, SwsDevTables t, SwsColorConst c, int TR, in
     }
 }
 
+#include "sws_mma.cuh"
+
+// Host side of the tensor-core horizontal pass: a filter bank regrouped into the B operands of mma.m16n8k32 (see sws_mma.cuh).
+struct SwsMmaHost { std::vector<int32_t> ginfo; std::vector<uint32_t> bfrag; int ngroups = 0; };
+static void sws_mma_build(const SwsFilterBank &b, SwsMmaHost &o)
+{
+    const int ng = (b.n + 7) / 8;
+    o.ngroups = ng;
+    o.ginfo.assign((size_t)(ng + 1) * 2, 0);
+    o.bfrag.clear();
+    int chunk = 0;
+    for (int G = 0; G < ng; G++) {
+        int lo = 0x7fffffff, hi = 0;
+        for (int i = 8 * G; i < std::min(8 * G + 8, b.n); i++) { lo = std::min(lo, (int)b.pos[i]); hi = std::max(hi, (int)b.pos[i] + b.size); }
+        const int kstart = lo & ~3, nch = (hi - kstart + 31) / 32;
+        o.ginfo[2 * G] = kstart;
+        o.ginfo[2 * G + 1] = chunk;
+        o.bfrag.resize((size_t)(chunk + nch) * 128, 0);
+        for (int c = 0; c < nch; c++)
+            for (int lane = 0; lane < 32; lane++) {
+                const int g = lane >> 2, t = lane & 3, i = 8 * G + g;      // B fragment: column n = lane / 4, rows k = 4 * (lane % 4) .. + 3 (b0) and 16 + the same (b1)
+                uint32_t w[4] = { 0, 0, 0, 0 };
+                if (i < b.n)
+                    for (int half = 0; half < 2; half++)
+                        for (int bb = 0; bb < 4; bb++) {
+                            const int k = 32 * c + 16 * half + 4 * t + bb, j = kstart + k - b.pos[i];
+                            if (j < 0 || j >= b.size) continue;
+                            const int cf = b.coef[(size_t)i * b.size + j];
+                            w[half] |= (uint32_t)((cf >> 8) & 0xff) << (8 * bb);         // signed high byte
+                            w[2 + half] |= (uint32_t)(cf & 0xff) << (8 * bb);            // unsigned low byte
+                        }
+                memcpy(&o.bfrag[((size_t)(chunk + c) * 32 + lane) * 4], w, 16);
+            }
+        chunk += nch;
+    }
+    o.ginfo[2 * ng] = 0;
+    o.ginfo[2 * ng + 1] = chunk;
+}
+// byte pitch of the staged source lines for tiles of `tile_groups` groups: the widest tile's span in 16-byte segments, made odd
+static int sws_mma_pitch(const SwsMmaHost &m, int tile_groups)
+{
+    int mx = 1;
+    for (int G0 = 0; G0 < m.ngroups; G0 += tile_groups) {
+        int s = 0x7fffffff, e = 0;
+        for (int G = G0; G < std::min(G0 + tile_groups, m.ngroups); G++) {
+            s = std::min(s, (int)m.ginfo[2 * G]);
+            e = std::max(e, (int)m.ginfo[2 * G] + 32 * (int)(m.ginfo[2 * G + 3] - m.ginfo[2 * G + 1]));
+        }
+        mx = std::max(mx, (e - (s & ~15) + 15) >> 4);
+    }
+    return (mx | 1) * 16;
+}
+
+static int upload_mma_tables(B200SwsContext *c)
+{
+    const SwsPlan &p = c->plan;
+    if (c->h_identity || p.fast_bilinear || p.src_rgb || p.hLum.n <= 0 || p.hChr.n <= 0) return 0;
+    SwsMmaHost L, C;
+    sws_mma_build(p.hLum, L);
+    sws_mma_build(p.hChr, C);
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t o_lg = 0, o_lb = o_lg + al(L.ginfo.size() * 4), o_cg = o_lb + al(L.bfrag.size() * 4), o_cb = o_cg + al(C.ginfo.size() * 4),
+                 total = o_cb + al(C.bfrag.size() * 4);
+    std::vector<uint8_t> host(total, 0);
+    memcpy(&host[o_lg], L.ginfo.data(), L.ginfo.size() * 4); memcpy(&host[o_lb], L.bfrag.data(), L.bfrag.size() * 4);
+    memcpy(&host[o_cg], C.ginfo.data(), C.ginfo.size() * 4); memcpy(&host[o_cb], C.bfrag.data(), C.bfrag.size() * 4);
+    B200_CUDA_OK(cudaMalloc(&c->mma_tables, total));
+    B200_CUDA_OK(cudaMemcpy(c->mma_tables, host.data(), total, cudaMemcpyHostToDevice));
+    const uint8_t *b = (const uint8_t *)c->mma_tables;
+    c->mmaL = SwsMmaBank{ (const int2 *)(b + o_lg), (const uint4 *)(b + o_lb), L.ngroups };
+    c->mmaC = SwsMmaBank{ (const int2 *)(b + o_cg), (const uint4 *)(b + o_cb), C.ngroups };
+    c->mma_pitchL = sws_mma_pitch(L, MT_W / 8);
+    c->mma_pitchC = sws_mma_pitch(C, MT_W / 8);
+    c->mma_pitchC8 = sws_mma_pitch(C, MT_W / 16);
+    return 0;
+}
+
+// host-only: the tensor-core operand tables of an arbitrary filter bank (CPU test tier: replayed lane by lane against hScale8To15_c)
+B200_API int b200_sws_mma_probe(const int16_t *coef, const int32_t *pos, int n, int size, int32_t *ginfo, int ginfo_cap,
+                                uint32_t *bfrag, int bfrag_cap, int *pitch)
+{
+    if (!coef || !pos || n <= 0 || size <= 0) return B200_EINVAL;
+    SwsFilterBank b;
+    b.coef.assign(coef, coef + (size_t)n * size);
+    b.pos.assign(pos, pos + n);
+    b.size = size; b.n = n;
+    SwsMmaHost m;
+    sws_mma_build(b, m);
+    if (ginfo) { if ((int)m.ginfo.size() > ginfo_cap) return B200_EINVAL; memcpy(ginfo, m.ginfo.data(), m.ginfo.size() * 4); }
+    if (bfrag) { if ((int)m.bfrag.size() > bfrag_cap) return B200_EINVAL; memcpy(bfrag, m.bfrag.data(), m.bfrag.size() * 4); }
+    if (pitch) { pitch[0] = sws_mma_pitch(m, MT_W / 8); pitch[1] = sws_mma_pitch(m, MT_W / 16); }
+    return (int)m.bfrag.size();                       // words of B fragments (128 per chunk)
+}
+
 // rows of the horizontally scaled plane the vertical taps of output lines [dy0, dy1] reach (the kernels compute the same range)
 static int fused_rows_needed(const SwsFilterBank &v, int srcH, int dstH, int TR)
 {
@@ -1307,11 +1423,19 @@ static int fused_rows_needed(const SwsFilterBank &v, int srcH, int dstH, int TR)
     }
     return mx;
 }
-static bool fused_enabled()
+// B200_SWS_FUSED: 0 = two passes through int16 line planes, 1 = fused CUDA-core kernels, 2 (default) = fused with the tensor-core horizontal pass
+static int fused_mode()
 {
     static int on = -1;
-    if (on < 0) { const char *e = getenv("B200_SWS_FUSED"); on = e ? atoi(e) : 1; }
-    return on != 0;
+    if (on < 0) { const char *e = getenv("B200_SWS_FUSED"); on = e ? atoi(e) : 2; }
+    return on;
+}
+static bool fused_enabled() { return fused_mode() != 0; }
+static int fused_tr(int dflt)
+{
+    static int tr = -1;
+    if (tr < 0) { const char *e = getenv("B200_SWS_TR"); tr = e ? atoi(e) : 0; }
+    return tr > 0 ? tr : dflt;
 }
 
 static bool aligned16(const void *p, long long stride, long long fstride)
@@ -1533,6 +1657,54 @@ static int launch_batch(B200SwsContext *c, cudaStream_t stream, const uint8_t *c
             }
         } else {
             // scaled path.  Whole frames through the `_X` writer: one fused kernel (no int16 planes in HBM)
+            if (!rows && fused_mode() == 2 && c->mma_tables && p.chrDstHSub && c->all_x && p.dstW % 16 == 0 && p.chrDstW * 2 == p.dstW &&
+                aligned16(dst, ds, dfs) && aligned16(b.y, b.ys, b.yfs) && aligned16(b.u, b.us, b.ufs) && aligned16(b.v, b.vs, b.vfs)) {
+                auto need = [&](int rl_, int rc_) {
+                    const size_t RL = (size_t)((rl_ + 15) & ~15), RC = (size_t)((rc_ + 15) & ~15);
+                    return MT_HDR + RL * (c->mma_pitchL + MT_TPB) + 2 * RC * (c->mma_pitchC8 + MT_CPB);
+                };
+                // output lines per tile: the horizontal pass works in blocks of 16 staged lines, so pick the height whose windows waste the
+                // fewest of them (e.g. 29 lines at 2:1 with 8 taps = exactly 64 source lines) among those that leave room for 4 CTAs per SM
+                // (measured, 4K -> 1080p rgb24: 16 lines 0.197 of the HBM roofline, 29 lines 0.179 — three planes' tiles leave 2 CTAs per SM —
+                // 13 lines 0.172: 16 is tried first, the search below only runs when 16 does not fit)
+                int TR = fused_tr(16), rl = -1, rc = -1;
+                rl = fused_rows_needed(p.vLum, p.srcH, p.dstH, TR); rc = fused_rows_needed(p.vChr, p.chrSrcH, p.dstH, TR);
+                if (rl <= 0 || rc <= 0 || need(rl, rc) > 80 * 1024) {
+                    TR = 0; rl = rc = -1;
+                    double best = 1e30;
+                    for (int cand = 32; cand >= 8; cand--) {
+                        const int a_ = fused_rows_needed(p.vLum, p.srcH, p.dstH, cand), b_ = fused_rows_needed(p.vChr, p.chrSrcH, p.dstH, cand);
+                        if (a_ <= 0 || b_ <= 0) continue;
+                        const size_t sm_ = need(a_, b_);
+                        if (sm_ > 112 * 1024) continue;
+                        const double cost = (double)(((a_ + 15) >> 4) + ((b_ + 15) >> 4)) / cand * (1.0 + (sm_ > 56 * 1024 ? 0.15 : 0.0) + (sm_ > 75 * 1024 ? 0.15 : 0.0));
+                        if (cost < best - 1e-9) { best = cost; TR = cand; rl = a_; rc = b_; }
+                    }
+                }
+                const size_t smem = rl > 0 && rc > 0 ? need(rl, rc) : 0;
+                if (smem && smem <= 112 * 1024) {
+                    dim3 gf(b200_ceil_div(p.dstW, MT_W), b200_ceil_div(p.dstH, TR), nf);
+                    const int RL = (rl + 15) & ~15, RC = (rc + 15) & ~15;
+#define B200_MMA_RGB(K)                                                                                                           \
+                    do {                                                                                                          \
+                        if (smem > 48 * 1024) B200_CUDA_OK(cudaFuncSetAttribute(sws_mma_rgb_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+                        sws_mma_rgb_kernel<K><<<gf, MT_THREADS, smem, stream>>>(b, c->dt, p.color, c->mmaL, c->mmaC, p.srcW, p.chrSrcW, TR, RL, RC,   \
+                                                                                c->mma_pitchL, c->mma_pitchC8);                  \
+                    } while (0)
+                    switch (p.out.kind) {
+                    case SWS_OUT_RGB24: B200_MMA_RGB(SWS_OUT_RGB24); break;
+                    case SWS_OUT_BGR24: B200_MMA_RGB(SWS_OUT_BGR24); break;
+                    case SWS_OUT_RGBA:  B200_MMA_RGB(SWS_OUT_RGBA); break;
+                    case SWS_OUT_BGRA:  B200_MMA_RGB(SWS_OUT_BGRA); break;
+                    case SWS_OUT_ARGB:  B200_MMA_RGB(SWS_OUT_ARGB); break;
+                    default:            B200_MMA_RGB(SWS_OUT_ABGR); break;
+                    }
+#undef B200_MMA_RGB
+                    B200_LAUNCHED();
+                    c->last_path |= 4;
+                    continue;
+                }
+            }
             if (!rows && fused_enabled() && !p.fast_bilinear && p.chrDstHSub && c->all_x && p.dstW % 8 == 0 && aligned16(dst, ds, dfs) &&
                 p.hLum.size <= 16 && p.hChr.size <= 16) {
                 int TR = 32;
@@ -1565,10 +1737,12 @@ static int launch_batch(B200SwsContext *c, cudaStream_t stream, const uint8_t *c
                     }
 #undef B200_FUSED_RGB
                     B200_LAUNCHED();
+                    c->last_path |= 2;
                     continue;
                 }
             }
             // two passes: horizontal pass into int16 line planes, then the vertical pass
+            c->last_path |= 1;
             const size_t lumPlane = (size_t)p.srcH * p.dstW * 2, chrPlane = (size_t)p.chrSrcH * p.chrDstW * 2;
             const size_t perFrame = ((lumPlane + 2 * chrPlane) + 255) & ~(size_t)255;
             const size_t need = perFrame * nf;
@@ -1790,6 +1964,36 @@ static int launch_planar3(B200SwsContext *c, cudaStream_t stream, const uint8_t 
                 // fused horizontal + vertical pass for this plane when the writer below would be the 8-sample one
                 uint8_t *dplf = dst[pl] + (long long)f0 * dfs[pl];
                 const SwsFilterBank &vb = pl ? p.vChr : p.vLum;
+                const bool m8 = fused_mode() == 2 && c->mma_tables && !p.range_conv && dw[pl] % 8 == 0 &&
+                                (((uintptr_t)dplf | (uintptr_t)dstr[pl] | (uintptr_t)dfs[pl]) & 7) == 0 &&
+                                aligned16(src[pl] + (long long)f0 * sfs[pl], sstr[pl], sfs[pl]);
+                if (m8) {
+                    const SwsFilterBank &vbm = pl ? p.vChr : p.vLum;
+                    const int SP = pl ? c->mma_pitchC : c->mma_pitchL;
+                    auto needb = [&](int r) { return MT_HDR + (size_t)((r + 15) & ~15) * (SP + MT_TPB); };
+                    int TRm = fused_tr(0), nr = -1;
+                    if (TRm > 0) nr = fused_rows_needed(vbm, sh[pl], dh[pl], TRm);
+                    else {
+                        double best = 1e30;
+                        for (int cand = 32; cand >= 8; cand--) {                   // see the packed-RGB launch: fewest wasted 16-line blocks
+                            const int a_ = fused_rows_needed(vbm, sh[pl], dh[pl], cand);
+                            if (a_ <= 0 || needb(a_) > 112 * 1024) continue;
+                            const double cost = (double)((a_ + 15) >> 4) / cand * (1.0 + (needb(a_) > 56 * 1024 ? 0.15 : 0.0) + (needb(a_) > 75 * 1024 ? 0.15 : 0.0));
+                            if (cost < best - 1e-9) { best = cost; TRm = cand; nr = a_; }
+                        }
+                    }
+                    if (nr > 0 && needb(nr) <= 112 * 1024) {
+                        const size_t smem = needb(nr);
+                        dim3 gm(b200_ceil_div(dw[pl], MT_W), b200_ceil_div(dh[pl], TRm), nf);
+                        if (smem > 48 * 1024) B200_CUDA_OK(cudaFuncSetAttribute(sws_mma_plane_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                        sws_mma_plane_kernel<<<gm, MT_THREADS, smem, stream>>>(src[pl] + (long long)f0 * sfs[pl], sstr[pl], sfs[pl], sw[pl], sh[pl], dplf,
+                                                                              dstr[pl], dfs[pl], dw[pl], dh[pl], pl ? c->mmaC : c->mmaL, pl ? c->dt.vChr2 : c->dt.vLum2, vp[pl], vs[pl],
+                                                                              TRm, (nr + 15) & ~15, SP);
+                        B200_LAUNCHED();
+                        c->last_path |= 4;
+                        continue;
+                    }
+                }
                 const bool f8 = fused_enabled() && !p.range_conv && hs[pl] <= 16 && dw[pl] % 8 == 0 &&
                                 (((uintptr_t)dplf | (uintptr_t)dstr[pl] | (uintptr_t)dfs[pl]) & 7) == 0;
                 int TR = 32, need_rows = f8 ? fused_rows_needed(vb, sh[pl], dh[pl], TR) : -1;
@@ -1808,8 +2012,10 @@ static int launch_planar3(B200SwsContext *c, cudaStream_t stream, const uint8_t 
                                                                               hc[pl], hp[pl], hs[pl], vc[pl], vp[pl], vs[pl], TR);
                     }
                     B200_LAUNCHED();
+                    c->last_path |= 2;
                     continue;
                 }
+                c->last_path |= 1;
                 launch_hscale(stream, src[pl] + (long long)f0 * sfs[pl], sstr[pl], sfs[pl], m[pl], dw[pl], (long long)(perFrame / 2),
                               hc[pl], hp[pl], hs[pl], 0, sh[pl], nf);
             }

@@ -61,6 +61,10 @@ class SwsContext:
         check(lib().b200_sws_info(self._h, o), "b200_sws_info")
         return list(o)
 
+    def last_path(self):
+        """kernels used by the scaled-path launches since the previous call: 1 two passes, 2 fused, 4 fused with the tensor-core horizontal pass"""
+        return lib().b200_sws_last_path(self._h)
+
     def get_filter(self, which):
         info = self.info()
         size = info[which]

@@ -156,6 +156,9 @@ int  b200_sws_scale_batch_host(B200SwsContext *c, const uint8_t *const src[3], c
                                int64_t dstFrameStride, int nframes);
 /* introspection for tests: same layout as the shim used on the reference (16 ints) */
 int  b200_sws_info(const B200SwsContext *c, int *out16);
+/* diagnostics: which kernels the scaled-path launches since the previous call used (bit 0 two passes through 15-bit line planes,
+ * bit 1 fused CUDA-core kernels, bit 2 fused kernels with the tensor-core horizontal pass); reading clears it. */
+int  b200_sws_last_path(B200SwsContext *c);
 /* which: 0 hLum 1 hChr 2 vLum 3 vChr — host copies of the generated filter tables */
 int  b200_sws_get_filter(const B200SwsContext *c, int which, int16_t *filter, int32_t *pos, int cap);
 
@@ -172,6 +175,13 @@ int  b200_sws_plan_probe(int srcW, int srcH, int dstW, int dstH, int flags, int 
  * (bytes per pixel), [28] / [29] horizontal / vertical chroma shift of the source as the scaler sees it, [30] bgr24 -> yv12
  * converter installed, [31] semi-planar destination kind (1 nv12, 2 nv21), [32..40] input_rgb2yuv_table.  The array must hold 48 ints. */
 int  b200_sws_plan_probe2(const int cfg[9], const int *details, int which, int16_t *filter, int32_t *pos, int cap, int *info48);
+/* host-only: a horizontal filter bank (n outputs x size taps, first-tap positions) regrouped into the operands of the tensor-core
+ * horizontal pass (csrc/sws_mma.cuh): ginfo = (ceil(n / 8) + 1) pairs { first source column of the group's window, first chunk index },
+ * bfrag = 128 words per chunk (32 lanes x { hi b0, hi b1, lo b0, lo b1 } of mma.m16n8k32's B operand), pitch[2] = staged-line byte
+ * pitches for 128- and 64-column tiles.  Returns the number of bfrag words or <0.  Replaces nothing in the reference: the tables
+ * hold libswscale's hLumFilter / hLumFilterPos (swscale_internal.h:437-448) in another order. */
+int  b200_sws_mma_probe(const int16_t *coef, const int32_t *pos, int n, int size, int32_t *ginfo, int ginfo_cap,
+                        uint32_t *bfrag, int bfrag_cap, int *pitch);
 
 /* ------------------------------------------------------------------------------------------------ idctdsp
  * Replaces IDCTDSPContext (libavcodec/idctdsp.h:43-91) as filled by ff_idctdsp_init (libavcodec/idctdsp.c:228-314)

@@ -35,6 +35,15 @@ with torch.cuda.stream(stream):
         for _ in range(2):
             c.scale_batch_device([Y, U, V], [W, W // 2, W // 2], [W * H, W * H // 4, W * H // 4], O, 1920 * 3, 1920 * 1080 * 3, min(nf, 8))
         dev.sync(); c.free()
+    if what in ("scalep", "all"):
+        c = sw.sws_getContext(dev, W, H, 0, 1920, 1080, 0, 4 | 0x40000 | 0x80000)
+        nb = min(nf, 8)
+        oy = torch.empty((nb, 1080, 1920), dtype=torch.uint8, device="cuda")
+        ou = torch.empty((nb, 540, 960), dtype=torch.uint8, device="cuda"); ov = torch.empty_like(ou)
+        for _ in range(2):
+            c.scale_batch_device_planar([Y, U, V], [W, W // 2, W // 2], [W * H, W * H // 4, W * H // 4], [oy, ou, ov], [1920, 960, 960],
+                                        [1920 * 1080, 960 * 540, 960 * 540], nb)
+        dev.sync(); c.free()
     if what in ("idct", "all"):
         mbw, mbh, fr = 120, 68, nf
         n = mbw * mbh * 6 * fr

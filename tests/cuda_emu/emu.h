@@ -11,11 +11,15 @@
 #include <thread>
 #include <vector>
 #include <functional>
+#include <memory>
+#include <cstring>
 
 struct dim3 { unsigned x, y, z; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
 struct uint4 { unsigned x, y, z, w; };
 struct uint2 { unsigned x, y; };
 struct int2 { int x, y; };
+struct int4 { int x, y, z, w; };
+static inline int4 make_int4(int a, int b, int c, int d) { int4 r = { a, b, c, d }; return r; }
 static inline uint2 make_uint2(unsigned a, unsigned b) { uint2 r = { a, b }; return r; }
 static inline int2 make_int2(int a, int b) { int2 r = { a, b }; return r; }
 static inline uint4 make_uint4(unsigned a, unsigned b, unsigned c, unsigned d) { uint4 r = { a, b, c, d }; return r; }
@@ -97,16 +101,65 @@ static inline unsigned __reduce_xor_sync(unsigned, unsigned v)
 static thread_local std::barrier<> *emu_block_bar = nullptr;
 static thread_local void *emu_smem = nullptr;
 static inline void __syncthreads() { emu_block_bar->arrive_and_wait(); }
+// warps inside a block launch (1-D blocks whose size is a multiple of 32, no thread leaves before the last collective): a barrier and
+// 32 x 8 exchange words per warp
+struct EmuBlockWarp { std::barrier<> *bar; unsigned slots[32][8]; };
+static thread_local EmuBlockWarp *emu_bwarp = nullptr;
+static inline unsigned emu_warp_xchg(unsigned v, int from_lane)
+{
+    EmuBlockWarp *w = emu_bwarp;
+    w->slots[threadIdx.x & 31][0] = v;
+    w->bar->arrive_and_wait();
+    const unsigned r = w->slots[from_lane & 31][0];
+    w->bar->arrive_and_wait();
+    return r;
+}
+static inline int __shfl_xor_sync(unsigned, int v, int m) { return (int)emu_warp_xchg((unsigned)v, (threadIdx.x & 31) ^ m); }
+static inline unsigned __shfl_xor_sync(unsigned, unsigned v, int m) { return emu_warp_xchg(v, (threadIdx.x & 31) ^ m); }
+// mma.sync.aligned.m16n8k32.row.col.s32.u8.{s8,u8}.s32 by the PTX ISA fragment layouts: lane = 4 * groupID + tig;
+//   A (16 x 32 u8): reg0 row groupID, k 4*tig..+3; reg1 row groupID + 8; reg2 / reg3 the same rows, k + 16
+//   B (32 x 8):     reg0 k 4*tig..+3, column groupID; reg1 k + 16
+//   D (16 x 8 s32): d0, d1 row groupID, columns 2*tig, 2*tig + 1; d2, d3 row groupID + 8
+static inline void emu_mma_m16n8k32(int (&d)[4], const unsigned (&a)[4], unsigned b0, unsigned b1, bool b_signed)
+{
+    EmuBlockWarp *w = emu_bwarp;
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    for (int i = 0; i < 4; i++) w->slots[lane][i] = a[i];
+    w->slots[lane][4] = b0; w->slots[lane][5] = b1;
+    w->bar->arrive_and_wait();
+    for (int i = 0; i < 4; i++) {
+        const int row = g + (i >= 2 ? 8 : 0), col = 2 * t + (i & 1);
+        long long acc = d[i];
+        for (int k = 0; k < 32; k++) {
+            const int al = (row & 7) * 4 + ((k & 15) >> 2), ar = (row >= 8 ? 1 : 0) + (k >= 16 ? 2 : 0);
+            const int av = (w->slots[al][ar] >> (8 * (k & 3))) & 0xFF;
+            const int bl = col * 4 + ((k & 15) >> 2);
+            int bv = (w->slots[bl][4 + (k >= 16 ? 1 : 0)] >> (8 * (k & 3))) & 0xFF;
+            if (b_signed && bv >= 128) bv -= 256;
+            acc += (long long)av * bv;
+        }
+        d[i] = (int)acc;
+    }
+    w->bar->arrive_and_wait();
+}
 template <typename F> static void emu_launch_blocks(dim3 grid, dim3 block, size_t smem, F body)
 {
     std::vector<unsigned char> shared(smem + 64);
+    const unsigned nthreads = block.x * block.y * block.z, nwarps = (nthreads + 31) / 32;
     for (unsigned bz = 0; bz < grid.z; bz++) for (unsigned by = 0; by < grid.y; by++) for (unsigned bx = 0; bx < grid.x; bx++) {
-        std::barrier<> bar(block.x * block.y * block.z);
+        std::barrier<> bar(nthreads);
+        std::vector<std::unique_ptr<std::barrier<>>> wbars;
+        std::vector<EmuBlockWarp> warps(nwarps);
+        for (unsigned wi = 0; wi < nwarps; wi++) {
+            wbars.emplace_back(new std::barrier<>(std::min(32u, nthreads - 32 * wi)));
+            warps[wi].bar = wbars.back().get();
+        }
         std::vector<std::thread> th;
         for (unsigned tz = 0; tz < block.z; tz++) for (unsigned ty = 0; ty < block.y; ty++) for (unsigned tx = 0; tx < block.x; tx++)
             th.emplace_back([&, tx, ty, tz] {
                 gridDim = grid; blockDim = block; blockIdx = dim3(bx, by, bz); threadIdx = dim3(tx, ty, tz);
                 emu_block_bar = &bar; emu_smem = shared.data();
+                emu_bwarp = &warps[(tx + block.x * (ty + block.y * tz)) / 32];
                 body();
                 bar.arrive_and_drop();
             });

@@ -49,7 +49,7 @@ def vp(a):
 
 
 WARP_KERNELS = {"mpv_unquant_kernel"}                   # kernels that use a warp collective: one OS thread per lane
-BLOCK_KERNELS = {"tx_fft_kernel", "tx_mdct_inv_kernel", "tx_mdct_fwd_kernel", "tx_rdft_r2c_kernel", "tx_rdft_c2r_kernel",
+BLOCK_KERNELS = {"sws_mma_plane_kernel", "sws_mma_rgb_kernel", "tx_fft_kernel", "tx_mdct_inv_kernel", "tx_mdct_fwd_kernel", "tx_rdft_r2c_kernel", "tx_rdft_c2r_kernel",
                  "sws_fused_plane_kernel", "sws_fused_rgb_kernel", "tx_mdct_pfa_inv_kernel", "tx_mdct_pfa_fwd_kernel", "tx_i32_kernel"}    # __syncthreads + dynamic shared memory
 
 
@@ -290,6 +290,17 @@ def emusws():
     os.makedirs(gen, exist_ok=True)
     cs = os.path.join(ROOT, "ffmpeg_b200", "csrc")
     t = open(os.path.join(cs, "sws.cu")).read()
+    # the tensor-core scaler (sws_mma.cuh) joins the translation unit with its three PTX helpers replaced by their definitions:
+    # mma.sync.m16n8k32 by the fragment-layout model of emu.h, the 16-byte cp.async by a copy, its wait by nothing
+    m = open(os.path.join(cs, "sws_mma.cuh")).read()
+    m, k1 = re.subn(r'\{\s*asm volatile\("mma\.sync\.aligned\.m16n8k32\.row\.col\.s32\.u8\.s8\.s32.*?\n\s*:[^\n]*\n\}', "{ emu_mma_m16n8k32(d, a, b0, b1, true); }", m, flags=re.S)
+    m, k2 = re.subn(r'\{\s*asm volatile\("mma\.sync\.aligned\.m16n8k32\.row\.col\.s32\.u8\.u8\.s32.*?\n\s*:[^\n]*\n\}', "{ emu_mma_m16n8k32(d, a, b0, b1, false); }", m, flags=re.S)
+    m, k3 = re.subn(r'\{\s*asm volatile\("cp\.async\.cg\.shared\.global[^\n]*\n\}', "{ memcpy(smem_dst, gsrc, 16); }", m)
+    m, k4 = re.subn(r'\{ asm volatile\("cp\.async\.wait_all;" ::: "memory"\); \}', "{ }", m)
+    m, k5 = re.subn(r"extern __shared__ __align__\(16\) uint8_t mt_smem\[\];", "uint8_t *mt_smem = (uint8_t *)emu_smem;", m)
+    assert (k1, k2, k3, k4, k5) == (1, 1, 1, 1, 2), (k1, k2, k3, k4, k5)
+    assert t.count('#include "sws_mma.cuh"') == 1
+    t = t.replace('#include "sws_mma.cuh"', m)
     t, n1 = re.subn(r'\{ int d; asm\("dp2a\.lo\.s32\.u32[^\n]*\n', "{ return emu_dp2a_su(a, b, c, 0); }\n", t)
     t, n2 = re.subn(r'\{ int d; asm\("dp2a\.hi\.s32\.u32[^\n]*\n', "{ return emu_dp2a_su(a, b, c, 1); }\n", t)
     assert n1 == 1 and n2 == 1 and not re.search(r"\basm\b", t)
@@ -971,3 +982,51 @@ def test_host_tx_pfa_create_and_launch(emuhost):
             assert L.emu_host_tx_pfa(inv, n, 1.0 / n, out.ctypes.data, x.ctypes.data, 4, cnt, out.strides[0], x.strides[0]) == 0
             assert np.array_equal(out.view(np.uint32), _tx(O, "orc", 1, inv, n, 1.0 / n, x, n).view(np.uint32)), (n, inv)
     assert L.emu_host_tx_pfa(1, 84, 1.0, None, None, 4, 1, 0, 0) < 0
+
+
+def _aligned(shape, align=64):
+    """uint8 array whose first byte sits on an `align`-byte boundary (the vector / tensor-core paths want 16-byte aligned planes)"""
+    n = int(np.prod(shape))
+    raw = np.zeros(n + align, np.uint8)
+    o = (-raw.ctypes.data) % align
+    return raw[o:o + n].reshape(shape)
+
+
+@pytest.mark.parametrize("case", [(320, 96, 160, 48, FATE), (352, 64, 208, 40, FATE), (192, 48, 384, 96, cl.SWS_BICUBIC), (1024, 64, 96, 16, FATE),
+                                  (640, 40, 272, 24, cl.SWS_BILINEAR | 0x40000 | 0x80000)])
+def test_sws_tensor_core_scaler_on_the_emulated_device(emusws, case):
+    """The fused scaler with the mma.m16n8k32 horizontal pass (csrc/sws_mma.cuh): whole kernels — staging, fragment addressing, hi / lo
+    coefficient split, 15-bit lines, vertical pass and writers — through the batched device entry points, against the checker; the
+    context must report that the tensor-core kernels ran."""
+    L = emusws
+    L.b200_sws_last_path.argtypes = [C.c_void_p]
+    w, h, dw, dh, fl = case
+    n = 2
+    frames = [cl.yuv_frame(w, h, 1700 + k, kind) for k, kind in enumerate(("random", "limited"))]
+    cw, ch, cdw, cdh = (w + 1) // 2, (h + 1) // 2, (dw + 1) // 2, (dh + 1) // 2
+    Y, U, V = _aligned((n, h, w)), _aligned((n, ch, cw)), _aligned((n, ch, cw))
+    for k, f in enumerate(frames):
+        Y[k], U[k], V[k] = f
+    arr = lambda t, vals: (t * 3)(*vals)
+    srcp, srcs, srcf = arr(C.c_void_p, [Y.ctypes.data, U.ctypes.data, V.ctypes.data]), arr(C.c_int32, [w, cw, cw]), arr(C.c_int64, [w * h, cw * ch, cw * ch])
+    # three-plane destination
+    DY, DU, DV = _aligned((n, dh, dw)), _aligned((n, cdh, cdw)), _aligned((n, cdh, cdw))
+    ctx = _emu_ctx(L, w, h, 0, dw, dh, 0, fl)
+    assert L.b200_sws_scale_batch_device_planar(ctx, srcp, srcs, srcf, arr(C.c_void_p, [DY.ctypes.data, DU.ctypes.data, DV.ctypes.data]),
+                                                arr(C.c_int32, [dw, cdw, cdw]), arr(C.c_int64, [dw * dh, cdw * cdh, cdw * cdh]), n) == 0
+    assert L.b200_sws_last_path(ctx) == 4
+    L.b200_sws_freeContext(ctx)
+    for i in range(n):
+        e = cl.orc_sws_planar(w, h, dw, dh, fl, *frames[i])
+        assert np.array_equal(DY[i], e[0]) and np.array_equal(DU[i], e[1]) and np.array_equal(DV[i], e[2]), (case, i)
+    # packed destinations (rgb24 and one 32-bit order)
+    if dw % 16 == 0:
+        for fmt, bpp in ((cl.PIX_FMT_RGB24, 3), (cl.PIX_FMT_BGRA, 4)):
+            D = _aligned((n, dh, dw * bpp))
+            ctx = _emu_ctx(L, w, h, 0, dw, dh, fmt, fl)
+            assert L.b200_sws_scale_batch_device(ctx, srcp, srcs, srcf, D.ctypes.data, dw * bpp, dw * dh * bpp, n) == 0
+            path = L.b200_sws_last_path(ctx)
+            assert path == 4 or (w > 4 * dw and path == 1), path     # a 10:1 tile of three planes does not fit in shared memory: two passes
+            L.b200_sws_freeContext(ctx)
+            for i in range(n):
+                assert np.array_equal(D[i], cl.orc_sws(w, h, dw, dh, fl, *frames[i], fmt=fmt)), (case, fmt, i)
