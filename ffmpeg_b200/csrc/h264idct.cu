@@ -56,17 +56,29 @@ h264_idct_kernel(long long n, int16_t *blocks, const int64_t *blk_off, uint8_t *
         const int dc = ((int)b[0] + 32) >> 6;
         b[0] = 0;
         const unsigned z = (unsigned)dc << 6;                  // add4 shifts it back
+        unsigned dv[N][2];
+#pragma unroll
+        for (int r = 0; r < N; r++) {
+            const unsigned *p = reinterpret_cast<const unsigned *>(d + r * stride);
+            dv[r][0] = p[0]; dv[r][1] = N == 8 ? p[1] : 0u;
+        }
 #pragma unroll
         for (int r = 0; r < N; r++) {
             unsigned *p = reinterpret_cast<unsigned *>(d + r * stride);
-            p[0] = add4(p[0], z, z, z, z);
-            if (N == 8) p[1] = add4(p[1], z, z, z, z);
+            p[0] = add4(dv[r][0], z, z, z, z);
+            if (N == 8) p[1] = add4(dv[r][1], z, z, z, z);
         }
         return;
     }
     if (KIND == 0) {
         uint4 *bp = reinterpret_cast<uint4 *>(b);
         const uint4 q0 = bp[0], q1 = bp[1];
+        // every destination row is requested before the first store: written row by row (load, add, store) each row's load would sit
+        // behind the previous row's store in program order and the thread would make one trip to memory per row (ncu: 138 warps stalled
+        // on the long scoreboard per issue with the memory system at 15 %)
+        unsigned dv[4];
+#pragma unroll
+        for (int r = 0; r < 4; r++) dv[r] = *reinterpret_cast<const unsigned *>(d + r * stride);
         bp[0] = make_uint4(0, 0, 0, 0); bp[1] = make_uint4(0, 0, 0, 0);
         const unsigned w[8] = { q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w };
         int c[16];
@@ -88,18 +100,22 @@ h264_idct_kernel(long long n, int16_t *blocks, const int64_t *blk_off, uint8_t *
             o[0][x] = z0 + z3; o[1][x] = z1 + z2; o[2][x] = z1 - z2; o[3][x] = z0 - z3;
         }
 #pragma unroll
-        for (int r = 0; r < 4; r++) {
-            unsigned *p = reinterpret_cast<unsigned *>(d + r * stride);
-            *p = add4(*p, o[r][0], o[r][1], o[r][2], o[r][3]);
-        }
+        for (int r = 0; r < 4; r++)
+            *reinterpret_cast<unsigned *>(d + r * stride) = add4(dv[r], o[r][0], o[r][1], o[r][2], o[r][3]);
         return;
     }
     // 8x8
     uint4 *bp = reinterpret_cast<uint4 *>(b);
     int c[64];
+    uint4 qq[8];
+    uint2 dv[8];                                                // all loads first (see the 4x4 case)
+#pragma unroll
+    for (int r = 0; r < 8; r++) qq[r] = bp[r];
+#pragma unroll
+    for (int r = 0; r < 8; r++) dv[r] = *reinterpret_cast<const uint2 *>(d + r * stride);
 #pragma unroll
     for (int r = 0; r < 8; r++) {
-        const uint4 q = bp[r];
+        const uint4 q = qq[r];
         bp[r] = make_uint4(0, 0, 0, 0);
         const unsigned w[4] = { q.x, q.y, q.z, q.w };
 #pragma unroll
@@ -127,11 +143,10 @@ h264_idct_kernel(long long n, int16_t *blocks, const int64_t *blk_off, uint8_t *
     }
 #pragma unroll
     for (int r = 0; r < 8; r++) {
-        uint2 *p = reinterpret_cast<uint2 *>(d + r * stride);
-        uint2 v = *p;
+        uint2 v = dv[r];
         v.x = add4(v.x, o[r][0], o[r][1], o[r][2], o[r][3]);
         v.y = add4(v.y, o[r][4], o[r][5], o[r][6], o[r][7]);
-        *p = v;
+        *reinterpret_cast<uint2 *>(d + r * stride) = v;
     }
 }
 

@@ -986,12 +986,15 @@ B200_API int b200_h264chroma_batch_device(B200Device *dev, int64_t n, const uint
     return 0;
 }
 
-// B200_QPEL_TMA: 0 = LDG-staged kernel, otherwise (default) TMA boxes
+// B200_QPEL_TMA: 0 (default) = LDG-staged kernel, 1 = TMA boxes.  Measured on the B200 (profiles/r02_qpel_tma_ncu.txt): the TMA form is
+// bit-exact but slower (2.12 vs 2.25 G blocks/s): one 48 x 21-byte box per operation keeps the copy engine at about one box per 150
+// cycles per SM, and the smaller boxes of the chroma kernel at one per 80 — small 2-D boxes are bound by the engine's per-row requests,
+// not by the LSU they bypass.
 static int qpel_launch(cudaStream_t st, int64_t n, const uint8_t *op, uint8_t *dst, const int64_t *dst_off, const uint8_t *src,
                        const int64_t *src_off, ptrdiff_t stride)
 {
     static int mode = -1;
-    if (mode < 0) { const char *e = getenv("B200_QPEL_TMA"); mode = e ? atoi(e) : 1; }
+    if (mode < 0) { const char *e = getenv("B200_QPEL_TMA"); mode = e ? atoi(e) : 0; }
     CUtensorMap tm16, tm8, tm4;
     const int swz = (int)CU_TENSOR_MAP_SWIZZLE_NONE;
     if (mode > 0 && stride >= 48 && b200_tmap_2d_u8(&tm16, src, (unsigned long long)stride, 48, 21, swz) &&

@@ -56,6 +56,20 @@ with torch.cuda.stream(stream):
                 idctdsp.idct_mb420_device(dev, kind, blk, mbw, mbh, fr, pl, [mbw * 16, mbw * 8, mbw * 8],
                                           [mbw * 16 * mbh * 16, mbw * 8 * mbh * 8, mbw * 8 * mbh * 8])
             dev.sync()
+    if what in ("h264", "all"):
+        Hh, Wh, hn = 1088, 1920, 16
+        planes_h = torch.randint(0, 256, (hn, Hh, Wh), dtype=torch.uint8, device="cuda")
+        for kind, N in ((0, 4), (1, 8)):
+            nb = hn * (Hh // N) * (Wh // N)
+            coef = torch.randint(-600, 601, (nb, N * N), dtype=torch.int16, device="cuda")
+            bi = torch.arange(nb, device="cuda", dtype=torch.int64)
+            per = (Hh // N) * (Wh // N)
+            fr, r = bi // per, bi % per
+            hdoff = (fr * (Hh * Wh) + (r // (Wh // N)) * (N * Wh) + (r % (Wh // N)) * N).contiguous()
+            hboff = (bi * (N * N)).contiguous()
+            for _ in range(2):
+                idctdsp.h264_idct_batch_device(dev, kind, nb, coef, hboff, planes_h, hdoff, Wh)
+            dev.sync()
     if what in ("tx", "all"):
         from ffmpeg_b200 import tx
         n, cnt = 1024, 1 << 16

@@ -139,6 +139,19 @@ with torch.cuda.stream(stream):
             timed(lambda: c.batch_device(y, x, 8, cnt, 8 * n, 8 * n), cnt, "tx", 16 * n); c.uninit()
             c = tx.av_tx_init(1, 1, n, scale=1.0 / n, device=dev); what = f"imdct{n}"
             timed(lambda: c.batch_device(y, x, 4, cnt, 4 * n, 4 * n), cnt, "tx", 8 * n); c.uninit()
+    elif what == "h264":
+        Hh, Wh, hn = 1088, 1920, 32
+        planes_h = torch.randint(0, 256, (hn, Hh, Wh), dtype=torch.uint8, device="cuda", generator=g)
+        for kind, N in ((0, 4), (1, 8)):
+            nb = hn * (Hh // N) * (Wh // N)
+            coef = torch.randint(-600, 601, (nb, N * N), dtype=torch.int16, device="cuda", generator=g)
+            bi = torch.arange(nb, device="cuda", dtype=torch.int64)
+            per = (Hh // N) * (Wh // N)
+            fr, r = bi // per, bi % per
+            hdoff = (fr * (Hh * Wh) + (r // (Wh // N)) * (N * Wh) + (r % (Wh // N)) * N).contiguous()
+            hboff = (bi * (N * N)).contiguous()
+            what = f"h264 idct{N} add (coefficients left cleared: dc-free blocks after the first pass)"
+            timed(lambda: idctdsp.h264_idct_batch_device(dev, kind, nb, coef, hboff, planes_h, hdoff, Wh), nb, "blocks", 2 * N * N * 2 + 2 * N * N)
     elif what == "esa":
         W, H, npairs = 3840, 2160, 4
         cur = torch.randint(0, 256, (npairs, H, W), dtype=torch.uint8, device="cuda", generator=g)
