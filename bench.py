@@ -637,6 +637,59 @@ def extra_paths(args, dev, stream, g, world, barrier, reduce_max, peak, devidx):
                             "e2e": e2e_imdct}
         del x, y
     out["tx"] = txr
+    # --- widening rows that had no timing yet: 10-bit simple IDCT add, the compound MDCT of Opus CELT (15 x 64 = 960),
+    # the int32 FFT of fixed-point AAC, vector_fmul_window (what follows every AAC iMDCT).  Device-resident, roofline fraction only.
+    wid = {}
+    try:
+        nb = 1 << 20
+        with torch.cuda.stream(stream):
+            blk = torch.randint(-512, 513, (nb, 64), dtype=torch.int16, device="cuda", generator=g)
+            dest = torch.randint(0, 1024, (8, nb * 8), dtype=torch.int16, device="cuda", generator=g)
+            doff = (torch.arange(nb, device="cuda", dtype=torch.int64) * 16).contiguous()
+        ms = timed(lambda: idctdsp.idct_hbd_batch_device(dev, 10, 2, blk, nb, dest, doff, None, nb * 16))
+        b = 128 + 128 + 128
+        wid["idct10_add"] = {"value": world * nb / (ms / 1e3), "unit": "blocks/s", "ms_per_step": ms,
+                             "roofline": {"bound": "hbm", "achieved": b * nb / (ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                                          "frac": b * nb / (ms / 1e3) / 1e9 / peak, "bytes_per_block": b}}
+        del blk, dest, doff
+    except Exception as ex:
+        wid["idct10_add"] = {"error": str(ex)[:160]}
+    for name, typ, inv, n, esz, inb, outb in (("mdct960_inv_15x64", tx.AV_TX_FLOAT_MDCT, 1, 960, 4, 4 * 960, 4 * 960),
+                                              ("int32_fft1024", tx.AV_TX_INT32_FFT, 0, 1024, 8, 8 * 1024, 8 * 1024)):
+        try:
+            cnt = 1 << 16
+            with torch.cuda.stream(stream):
+                if typ == tx.AV_TX_INT32_FFT:
+                    x = torch.randint(-(1 << 20), 1 << 20, (cnt, 2 * n), dtype=torch.int32, device="cuda", generator=g)
+                else:
+                    x = torch.rand((cnt, n), device="cuda", generator=g)
+                y = torch.empty_like(x)
+            c = tx.av_tx_init(typ, inv, n, scale=(1.0 / n if typ == tx.AV_TX_FLOAT_MDCT else None), device=dev)
+            ms = timed(lambda: c.batch_device(y, x, esz, cnt, outb, inb))
+            c.uninit()
+            wid[name] = {"value": world * cnt / (ms / 1e3), "unit": "transforms/s", "ms_per_step": ms, "batch": cnt,
+                         "roofline": {"bound": "hbm", "achieved": (inb + outb) * cnt / (ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                                      "frac": (inb + outb) * cnt / (ms / 1e3) / 1e9 / peak, "bytes_per_transform": inb + outb}}
+            del x, y
+        except Exception as ex:
+            wid[name] = {"error": str(ex)[:160]}
+    try:
+        from ffmpeg_b200 import float_dsp as fd
+        nvec, length = 1 << 16, 1024
+        with torch.cuda.stream(stream):
+            dstw = torch.empty((nvec, 2 * length), device="cuda")
+            s0 = torch.rand((nvec, length), device="cuda", generator=g)
+            s1 = torch.rand((nvec, length), device="cuda", generator=g)
+            win = torch.rand((2 * length,), device="cuda", generator=g)
+        ms = timed(lambda: fd.float_dsp_batch_device(dev, 5, nvec, length, dstw, 2 * length, s0, length, s1, length, win, 0, 0.0))
+        b = 4 * length * 4                              # two inputs of `length` floats, 2 * length floats out; the window stays in cache
+        wid["vector_fmul_window_1024"] = {"value": world * nvec / (ms / 1e3), "unit": "vectors/s", "ms_per_step": ms,
+                                          "roofline": {"bound": "hbm", "achieved": b * nvec / (ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                                                       "frac": b * nvec / (ms / 1e3) / 1e9 / peak, "bytes_per_vector": b}}
+        del dstw, s0, s1, win
+    except Exception as ex:
+        wid["vector_fmul_window_1024"] = {"error": str(ex)[:160]}
+    out["widening"] = wid
     return out
 
 

@@ -103,12 +103,35 @@ idct_hbd_kernel(int16_t *blocks, long long n, uint8_t *dest, const int64_t *dest
         for (int j = 0; j < 8; j++) col[j] = v[8 * j + c];
         col_pass<DEPTH>(col, o);
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            if (KIND == 0) v[8 * j + c] = o[j];
-            else {
-                uint16_t *p = d + j * ls + c;
-                const int x = KIND == 1 ? o[j] : (int)*p + o[j];
-                *p = (uint16_t)min(max(x, 0), MAXV);
+        for (int j = 0; j < 8; j++) v[8 * j + c] = o[j];
+    }
+    if (KIND != 0) {
+        // put / add: whole rows (8 samples = 16 bytes) when the rows are 16-byte aligned; for `add` every destination row is loaded
+        // before the first store (a load - add - store per sample would make one trip to memory per sample)
+        const bool vec = ((reinterpret_cast<uintptr_t>(d) | (uintptr_t)(ls * 2)) & 15) == 0;
+        if (vec) {
+            uint4 dv[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) dv[j] = KIND == 2 ? *reinterpret_cast<const uint4 *>(d + j * ls) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const unsigned w[4] = { dv[j].x, dv[j].y, dv[j].z, dv[j].w };
+                unsigned o2[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int x0 = v[8 * j + 2 * k] + (int)(w[k] & 0xffffu), x1 = v[8 * j + 2 * k + 1] + (int)(w[k] >> 16);
+                    o2[k] = (unsigned)min(max(x0, 0), MAXV) | ((unsigned)min(max(x1, 0), MAXV) << 16);
+                }
+                *reinterpret_cast<uint4 *>(d + j * ls) = make_uint4(o2[0], o2[1], o2[2], o2[3]);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; j++) {                          // unaligned rows: a row at a time
+                int dd[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) dd[k] = KIND == 2 ? (int)d[j * ls + k] : 0;
+#pragma unroll
+                for (int k = 0; k < 8; k++) d[j * ls + k] = (uint16_t)min(max(dd[k] + v[8 * j + k], 0), MAXV);
             }
         }
     }
