@@ -404,12 +404,79 @@ idct_tpb_kernel(const int16_t *blocks, int16_t *blocks_out, long long nblocks, u
 // pixel pair straight to the shared-memory tile (2-byte stores; for `add` the same 2 bytes are read first).
 // Luma tile rows 8..15 are stored with their 64-byte halves swapped so that blocks Y0/Y2 (and Y1/Y3) of one
 // macroblock, which sit 8 rows = 1024 B apart, do not share banks.
+// ---- inverse quantisation fused in front of the transform (put_dct / add_dequant_dct, libavcodec/mpegvideo_dec.c:907-922): the
+// same arithmetic as unquant.cu's kernel (libavcodec/mpegvideo_unquantize.c:50-276), applied by the thread that owns the block to the
+// eight rows it takes out of shared memory — the dequantised coefficients never exist in HBM (128 B read + 128 B written per block saved
+// against the two-kernel sequence).  V = -1: no dequantisation (the plain IDCT kernels).
+struct FusedUnquant {                     // passed by value
+    uint16_t intra[64], inter[64];
+    uint8_t scanpos[64];                  // scan index of each raster coefficient
+    uint8_t raster_end[64];
+    int y_dc, c_dc, q_type, aic, ac_pred;
+    const uint8_t *qscale;                // per block
+    const int8_t *last_index;             // per block
+};
+__constant__ uint8_t c_fused_nonlinear_qscale[32] = {              // ff_mpeg2_non_linear_qscale
+    0, 1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 14, 16, 18, 20, 22, 24, 28, 32, 36, 40, 44, 48, 52, 56, 64, 72, 80, 88, 96, 104, 112,
+};
+template <int V> __device__ __forceinline__ int fused_dequant(int level, int q, int m)
+{
+    const unsigned a = (unsigned)(level < 0 ? -level : level);
+    int v;
+    if (V == B200_UNQUANT_MPEG1_INTRA)      { v = (int)(a * q * m) >> 3; v = (v - 1) | 1; }
+    else if (V == B200_UNQUANT_MPEG1_INTER) { v = (int)(((a << 1) + 1) * q * m) >> 4; v = (v - 1) | 1; }
+    else if (V == B200_UNQUANT_MPEG2_INTER) { v = (int)(((a << 1) + 1) * q * m) >> 5; }
+    else                                    { v = (int)(a * q * m) >> 4; }
+    return level < 0 ? -v : v;
+}
+// the eight rows of one block (row j in r[j], 8 int16 each) dequantised in place; n = block number inside its macroblock
+template <int V>
+__device__ __forceinline__ void fused_unquant_rows(uint4 (&r)[8], const FusedUnquant &P, int n, int qs, int last)
+{
+    constexpr bool H263 = V == B200_UNQUANT_H263_INTRA || V == B200_UNQUANT_H263_INTER;
+    constexpr bool INTRA = V == B200_UNQUANT_MPEG1_INTRA || V == B200_UNQUANT_MPEG2_INTRA ||
+                           V == B200_UNQUANT_MPEG2_INTRA_BITEXACT || V == B200_UNQUANT_H263_INTRA;
+    constexpr bool MISMATCH = V == B200_UNQUANT_MPEG2_INTRA_BITEXACT || V == B200_UNQUANT_MPEG2_INTER;
+    int q = qs, qadd = 0, ncoef = last, parity = 0;
+    if (H263) {
+        q = qs << 1;
+        qadd = (INTRA && P.aic) ? 0 : ((qs - 1) | 1);
+        ncoef = (INTRA && P.ac_pred) ? 63 : (last >= 0 ? (int)P.raster_end[last] : -1);
+    } else if (V >= B200_UNQUANT_MPEG2_INTRA) {
+        q = P.q_type ? (int)c_fused_nonlinear_qscale[qs & 31] : qs << 1;
+    }
+#pragma unroll
+    for (int row = 0; row < 8; row++) {
+        unsigned w[4] = { r[row].x, r[row].y, r[row].z, r[row].w };
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int j = 8 * row + k;
+            int level = (k & 1) ? (int)w[k >> 1] >> 16 : (int)(short)(w[k >> 1] & 0xffffu);
+            if (INTRA && j == 0 && !(H263 && P.aic)) {
+                level = (int)(int16_t)(level * (n < 4 ? P.y_dc : P.c_dc));
+                if (MISMATCH) parity ^= level & 1;
+            }
+            const int pos = H263 ? j : (int)P.scanpos[j];
+            if (pos >= (INTRA ? 1 : 0) && pos <= ncoef && level != 0) {
+                int v;
+                if (H263) v = level < 0 ? level * q - qadd : level * q + qadd;
+                else      v = fused_dequant<V>(level, q, (int)(INTRA ? P.intra[j] : P.inter[j]));
+                if (MISMATCH) parity ^= v & 1;
+                level = (int)(int16_t)v;
+            }
+            if (MISMATCH && j == 63) level ^= (int)(1u ^ ((unsigned)parity & 1u));      // sum starts at -1: block[63] ^= sum & 1
+            w[k >> 1] = (k & 1) ? (w[k >> 1] & 0xffffu) | ((unsigned)level << 16) : (w[k >> 1] & 0xffff0000u) | ((unsigned)level & 0xffffu);
+        }
+        r[row] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
 constexpr int MAX_SEGS = 6;
 __device__ __forceinline__ int luma_swz(int row) { return (row & 8) << 3; }               // 0 or 64
 
-template <int KIND>
-__global__ void __launch_bounds__(48 * MAX_SEGS, 4)
-idct_mb420_kernel(const int16_t *blocks, Mb420Geom g, int segs_per_cta)
+template <int KIND, int V = -1>
+__global__ void __launch_bounds__(48 * MAX_SEGS, V < 0 ? 4 : 2)
+idct_mb420_kernel(const int16_t *blocks, Mb420Geom g, int segs_per_cta, const FusedUnquant *UQ = nullptr)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint4 *sin = reinterpret_cast<uint4 *>(smem_raw);                                     // segs * 48 * 8 uint4
@@ -466,8 +533,22 @@ idct_mb420_kernel(const int16_t *blocks, Mb420Geom g, int segs_per_cta)
         const uint4 *rows = &my_in[w * 8];
         const int key = w & 7;
         unsigned R2[8][4];
+        bool skip = false;
+        if (V >= 0) {
+            const long long bi = (((f * g.mb_h + mby) * g.mb_w) + mbx0 + m) * 6 + k;
+            const int last = __ldg(UQ->last_index + bi);
+            skip = KIND == B200_IDCT_ADD && last < 0;                                     // add_dequant_dct: block_last_index < 0 leaves the pixels alone
+            uint4 rr[8];
 #pragma unroll
-        for (int j = 0; j < 8; j++) row_pass_packed(rows[j ^ key], R2[j]);
+            for (int j = 0; j < 8; j++) rr[j] = rows[j ^ key];
+            fused_unquant_rows<V < 0 ? 0 : V>(rr, *UQ, k, (int)__ldg(UQ->qscale + bi), last);
+#pragma unroll
+            for (int j = 0; j < 8; j++) row_pass_packed(rr[j], R2[j]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; j++) row_pass_packed(rows[j ^ key], R2[j]);
+        }
+        if (!skip) {
 #pragma unroll
         for (int half = 0; half < 2; half++) {             // four columns (one 32-bit tile word per row) at a time
             unsigned e0[8], e1[8], e2[8], e3[8];             // column sums before the >> 20 (rows in the order 0,1,2,3,4,5,6,7)
@@ -498,6 +579,7 @@ idct_mb420_kernel(const int16_t *blocks, Mb420Geom g, int segs_per_cta)
                     *px = __byte_perm(lo, hi, 0x6420);
                 }
             }
+        }
         }
     }
     __syncthreads();
@@ -585,6 +667,31 @@ int launch_mb420(cudaStream_t st, const int16_t *blocks, const Mb420Geom &g, int
     return 0;
 }
 
+// fused inverse quantiser + IDCT over the macroblock stream (aligned planes only: the tiled kernel)
+template <int KIND, int V>
+int launch_mb420_fused(cudaStream_t st, const int16_t *blocks, const Mb420Geom &g, int nframes, const FusedUnquant *dUQ)
+{
+    const bool ok = (((uintptr_t)g.plane[0] | (uintptr_t)g.linesize[0] | (uintptr_t)g.frame_stride[0]) & 15) == 0 &&
+                    (((uintptr_t)g.plane[1] | (uintptr_t)g.linesize[1] | (uintptr_t)g.frame_stride[1] |
+                      (uintptr_t)g.plane[2] | (uintptr_t)g.linesize[2] | (uintptr_t)g.frame_stride[2]) & 7) == 0 &&
+                    g.mb_h <= 65535 && g.linesize[0] > 0 && g.linesize[1] > 0 && g.linesize[2] > 0;
+    if (!ok) { b200_set_error("unquant + idct: planes must be 16-byte (luma) / 8-byte (chroma) aligned with positive line sizes"); return B200_EINVAL; }
+    if (nframes > 65535) return B200_EINVAL;
+    const int segs_row = (g.mb_w + 7) / 8;
+    int best = 4, waste = 1 << 30;
+    for (int s = 3; s <= MAX_SEGS; s++) {
+        const int wst = ((segs_row + s - 1) / s) * s - segs_row;
+        if (wst < waste || (wst == waste && s > best)) { waste = wst; best = s; }
+    }
+    const size_t smem = (size_t)best * (48 * 128 + 3072);
+    B200_CUDA_OK(cudaFuncSetAttribute(idct_mb420_kernel<KIND, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((segs_row + best - 1) / best, g.mb_h, nframes);
+    idct_mb420_kernel<KIND, V><<<grid, 48 * best, smem, st>>>(blocks, g, best, dUQ);
+    B200_LAUNCHED();
+    B200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 int dispatch(cudaStream_t st, int kind, bool mb420, const int16_t *blocks, int16_t *out, long long n, uint8_t *dest,
              const int64_t *off, const int32_t *ls, int uls, const Mb420Geom &g, int nframes = 0)
 {
@@ -606,6 +713,52 @@ int dispatch(cudaStream_t st, int kind, bool mb420, const int16_t *blocks, int16
 }
 
 } // namespace
+
+B200_API int b200_mpv_unquant_idct_mb420_device(B200Device *dev, int variant, const B200MpvUnquant *p, int kind, const int16_t *blocks,
+                                                const uint8_t *qscale, const int8_t *last_index, int mb_w, int mb_h, int nframes,
+                                                uint8_t *const planes[3], const int linesize[3], const int64_t frame_stride[3])
+{
+    if (!dev || !p || !blocks || !qscale || !last_index || !planes || !linesize || !frame_stride || mb_w <= 0 || mb_h <= 0 || nframes < 0)
+        return B200_EINVAL;
+    if (kind != B200_IDCT_PUT && kind != B200_IDCT_ADD) return B200_EINVAL;
+    if (variant < 0 || variant > B200_UNQUANT_H263_INTER) return B200_EINVAL;
+    if (((uintptr_t)blocks) & 15) return B200_EINVAL;
+    if (nframes == 0) return 0;
+    FusedUnquant U;
+    memcpy(U.intra, p->intra_matrix, sizeof(U.intra));
+    memcpy(U.inter, p->inter_matrix, sizeof(U.inter));
+    memcpy(U.raster_end, p->raster_end, sizeof(U.raster_end));
+    bool seen[64] = { false };
+    for (int i = 0; i < 64; i++) {
+        const int j = p->permutated[i];
+        if (j > 63 || seen[j]) { b200_set_error("b200_mpv_unquant_idct: permutated[] is not a permutation of 0..63"); return B200_EINVAL; }
+        seen[j] = true;
+        U.scanpos[j] = (uint8_t)i;
+    }
+    U.y_dc = p->y_dc_scale; U.c_dc = p->c_dc_scale; U.q_type = p->q_scale_type; U.aic = p->h263_aic; U.ac_pred = p->ac_pred;
+    U.qscale = qscale; U.last_index = last_index;
+    B200_CUDA_OK(cudaSetDevice(dev->ordinal));
+    // the parameter block travels through the device's scratch (stream-ordered copy; the kernel reads it through a pointer)
+    B200_LOCK_DEVICE(dev);
+    FusedUnquant *dU = (FusedUnquant *)b200_scratch(dev, sizeof(FusedUnquant));
+    if (!dU) return B200_ENOMEM;
+    B200_CUDA_OK(cudaMemcpyAsync(dU, &U, sizeof(U), cudaMemcpyHostToDevice, dev->stream));
+    Mb420Geom g{};
+    g.mb_w = mb_w; g.mb_h = mb_h;
+    for (int i = 0; i < 3; i++) { g.plane[i] = planes[i]; g.linesize[i] = linesize[i]; g.frame_stride[i] = frame_stride[i]; }
+    cudaStream_t st = dev->stream;
+    int ret = B200_EINVAL;
+    switch (variant * 2 + (kind == B200_IDCT_ADD)) {
+#define CASE(V) case (V) * 2: ret = launch_mb420_fused<B200_IDCT_PUT, V>(st, blocks, g, nframes, dU); break; \
+                case (V) * 2 + 1: ret = launch_mb420_fused<B200_IDCT_ADD, V>(st, blocks, g, nframes, dU); break;
+    CASE(B200_UNQUANT_MPEG1_INTRA) CASE(B200_UNQUANT_MPEG1_INTER) CASE(B200_UNQUANT_MPEG2_INTRA)
+    CASE(B200_UNQUANT_MPEG2_INTRA_BITEXACT) CASE(B200_UNQUANT_MPEG2_INTER) CASE(B200_UNQUANT_H263_INTRA) CASE(B200_UNQUANT_H263_INTER)
+#undef CASE
+    }
+    if (ret < 0) return ret;
+    B200_CUDA_OK(cudaStreamSynchronize(st));          // the scratch parameter block must outlive the kernel (the lock is released on return)
+    return 0;
+}
 
 B200_API int b200_idct_batch_device(B200Device *dev, int kind, int16_t *blocks, int64_t nblocks, uint8_t *dest,
                                     const int64_t *dest_off, const int32_t *line_size, int uniform_line_size)

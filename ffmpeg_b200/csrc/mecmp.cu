@@ -4,6 +4,8 @@
 //   pix_abs16_c / pix_abs8_c, *_x2 / _y2 / _xy2   libavcodec/me_cmp.c:114-385
 //   sse16_c / sse8_c / sse4_c                     libavcodec/me_cmp.c:37-103
 //   hadamard8_diff8x8_c, hadamard8_diff16_c       libavcodec/me_cmp.c:514-562, 933-950 (SATD)
+//   hadamard8_intra8x8_c / 16, vsad, vsse (+ intra), nsse, pix_median_abs, sum_abs_dctelem   libavcodec/me_cmp.c:105-112, 145-183,
+//                                                 292-330, 387-437, 564-612, 843-931 (the context-free members of MECmpContext)
 //   ff_me_cmp_sad, ff_me_search_esa               libavfilter/motion_estimation.c:60-97 (driver vf_mestimate.c:85-127)
 //
 // ESA kernel: one CTA per macroblock.  The current block and the clipped search window of the reference frame are
@@ -55,7 +57,7 @@ me_cmp_kernel(int fn, int w, int mode, const uint8_t *f1, const uint8_t *f2, lon
 // nblk = 1 (8 wide), 2 (16 wide, h = 8) or 4 (16 wide, h = 16).
 __global__ void __launch_bounds__(256)
 me_satd_kernel(int nblk, const uint8_t *f1, const uint8_t *f2, long long stride, const int64_t *off1, const int64_t *off2,
-               long long n, int32_t *out)
+               long long n, int32_t *out, int intra = 0)
 {
     const long long i = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (i >= n) return;
@@ -67,7 +69,7 @@ me_satd_kernel(int nblk, const uint8_t *f1, const uint8_t *f2, long long stride,
         const long long o = (long long)((blk >> 1) * 8 + row) * stride + (blk & 1) * 8;
         const uint8_t *a = f1 + off1[i] + o, *b = f2 + off2[i] + o;
 #pragma unroll
-        for (int k = 0; k < 8; k++) v[k] = on ? (int)b[k] - (int)a[k] : 0;      // src - dst, like the reference
+        for (int k = 0; k < 8; k++) v[k] = !on ? 0 : intra ? (int)a[k] : (int)b[k] - (int)a[k];      // src - dst, like the reference; intra: the block itself
     }
 #pragma unroll
     for (int span = 1; span < 8; span <<= 1)
@@ -83,6 +85,70 @@ me_satd_kernel(int nblk, const uint8_t *f1, const uint8_t *f2, long long stride,
         }
 #pragma unroll
     for (int k = 0; k < 8; k++) s += abs(v[k]);
+    if (intra && row == 0) s -= abs(v[0]);                        // hadamard8_intra: coefficient (0, 0) of each 8x8 block (the mean) is left out
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[i] = s;
+}
+
+// vsad / vsse (+ intra), nsse, median_sad: one warp per comparison, a lane per pixel (w * h <= 256 pixels in 8 rounds); every term
+// only looks at the pixel itself and its right / lower / upper-left neighbours, read straight from the frames.
+__device__ __forceinline__ int mid3(int a, int b, int c)
+{
+    return max(min(a, b), min(max(a, b), c));
+}
+__global__ void __launch_bounds__(256)
+me_cmp2_kernel(int fn, int w, int intra, int weight, const uint8_t *f1, const uint8_t *f2, long long stride, int h,
+               const int64_t *off1, const int64_t *off2, long long n, int32_t *out)
+{
+    const long long i = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= n) return;
+    const int lane = threadIdx.x & 31;
+    const uint8_t *a = f1 + off1[i], *b = f2 + off2[i];
+    int s1 = 0, s2 = 0;
+    for (int p = lane; p < w * h; p += 32) {
+        const int y = p / w, x = p - y * w;
+        const uint8_t *pa = a + y * stride + x, *pb = b + y * stride + x;
+        if (fn == B200_MECMP_VSAD || fn == B200_MECMP_VSSE) {
+            if (y + 1 < h) {
+                const int d = intra ? (int)pa[0] - (int)pa[stride] : (int)pa[0] - (int)pb[0] - (int)pa[stride] + (int)pb[stride];
+                s1 += fn == B200_MECMP_VSSE ? d * d : abs(d);
+            }
+        } else if (fn == B200_MECMP_NSSE) {
+            const int d = (int)pa[0] - (int)pb[0];
+            s1 += d * d;
+            if (y + 1 < h && x + 1 < w)
+                s2 += abs((int)pa[0] - (int)pa[stride] - (int)pa[1] + (int)pa[stride + 1]) -
+                      abs((int)pb[0] - (int)pb[stride] - (int)pb[1] + (int)pb[stride + 1]);
+        } else {                                                   // median_sad
+            const int v = (int)pa[0] - (int)pb[0];
+            int pred = 0;
+            if (y == 0) pred = x ? (int)pa[-1] - (int)pb[-1] : 0;
+            else {
+                const int top = (int)pa[-stride] - (int)pb[-stride];
+                if (x == 0) pred = top;
+                else {
+                    const int left = (int)pa[-1] - (int)pb[-1], tl = (int)pa[-stride - 1] - (int)pb[-stride - 1];
+                    pred = mid3(top, left, top + left - tl);
+                }
+            }
+            s1 += abs(v - pred);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+    if (lane == 0) out[i] = fn == B200_MECMP_NSSE ? s1 + abs(s2) * weight : s1;
+}
+
+// sum_abs_dctelem: one warp per block of 64 coefficients
+__global__ void __launch_bounds__(256)
+sum_abs_dctelem_kernel(const int16_t *blocks, long long n, int32_t *out)
+{
+    const long long i = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= n) return;
+    const int lane = threadIdx.x & 31;
+    const unsigned wv = reinterpret_cast<const unsigned *>(blocks + 64 * i)[lane];
+    int s = abs((int)(short)(wv & 0xffff)) + abs((int)wv >> 16);
 #pragma unroll
     for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0) out[i] = s;
@@ -367,13 +433,17 @@ int launch_esa(cudaStream_t st, const uint8_t *cur, const uint8_t *ref, int line
     return 0;
 }
 
+std::atomic<int> g_nsse_weight{8};                               // nsse: the reference's NULL-context weight (me_cmp.c:407-410)
+
 int decode(int fn, int idx, int *w, int *mode)
 {
     *mode = 0;
     if (fn == B200_MECMP_SAD) { if (idx < 0 || idx > 1) return B200_EINVAL; *w = 16 >> idx; return 0; }
     if (fn == B200_MECMP_SSE) { if (idx < 0 || idx > 2) return B200_EINVAL; *w = 16 >> idx; return 0; }
     if (fn == B200_MECMP_PIX_ABS) { if (idx < 0 || idx > 7) return B200_EINVAL; *w = idx < 4 ? 16 : 8; *mode = idx & 3; return 0; }
-    if (fn == B200_MECMP_HADAMARD8) { if (idx < 0 || idx > 1) return B200_EINVAL; *w = 16 >> idx; return 0; }
+    if (fn == B200_MECMP_HADAMARD8) { if (idx != 0 && idx != 1 && idx != 4 && idx != 5) return B200_EINVAL; *w = 16 >> (idx & 1); *mode = idx >= 4; return 0; }
+    if (fn == B200_MECMP_VSAD || fn == B200_MECMP_VSSE) { if (idx != 0 && idx != 1 && idx != 4 && idx != 5) return B200_EINVAL; *w = 16 >> (idx & 1); *mode = idx >= 4; return 0; }
+    if (fn == B200_MECMP_NSSE || fn == B200_MECMP_MEDIAN_SAD) { if (idx < 0 || idx > 1) return B200_EINVAL; *w = 16 >> idx; return 0; }
     return B200_EINVAL;
 }
 
@@ -391,8 +461,11 @@ B200_API int b200_me_cmp_batch_device(B200Device *dev, int fn, int idx, const ui
     const long long blocks = (n + 7) / 8;
     if (blocks > 0x7fffffffLL) return B200_EINVAL;
     if (fn == B200_MECMP_HADAMARD8)                               // 8 wide ignores h; 16 wide: two blocks, four when h == 16
-        me_satd_kernel<<<(unsigned)blocks, 256, 0, dev->stream>>>(w == 8 ? 1 : h == 16 ? 4 : 2, frame1, frame2, stride, off1, off2, n, out);
-    else
+        me_satd_kernel<<<(unsigned)blocks, 256, 0, dev->stream>>>(w == 8 ? 1 : h == 16 ? 4 : 2, frame1, frame2, stride, off1, off2, n, out, mode);
+    else if (fn >= B200_MECMP_VSAD) {
+        if (w * h > 256) return B200_EINVAL;
+        me_cmp2_kernel<<<(unsigned)blocks, 256, 0, dev->stream>>>(fn, w, mode, g_nsse_weight.load(), frame1, frame2, stride, h, off1, off2, n, out);
+    } else
     me_cmp_kernel<<<(unsigned)blocks, 256, 0, dev->stream>>>(fn, w, mode, frame1, frame2, stride, h, off1, off2, n, out);
     B200_LAUNCHED();
     B200_CUDA_OK(cudaGetLastError());
@@ -487,10 +560,11 @@ int host_cmp(int fn, int idx, const uint8_t *blk1, const uint8_t *blk2, ptrdiff_
     int32_t *dout = (int32_t *)(offs + 2);
     cudaStream_t st = dev->stream;
     if (b200_h2d_rows(d1, pitch, blk1, stride, w, h, st) != cudaSuccess) fail("h2d");      // negative strides (flipped frames) are fine
-    const int bw = mode & 1 ? cw : w, bh = mode & 2 ? ch : h;
+    const int bw = fn == B200_MECMP_PIX_ABS && (mode & 1) ? cw : w, bh = fn == B200_MECMP_PIX_ABS && (mode & 2) ? ch : h;
     if (b200_h2d_rows(d2, pitch, blk2, stride, bw, bh, st) != cudaSuccess) fail("h2d");
     if (cudaMemsetAsync(offs, 0, 16, st) != cudaSuccess) fail("memset");
-    if (fn == B200_MECMP_HADAMARD8) me_satd_kernel<<<1, 32, 0, st>>>(w == 8 ? 1 : h == 16 ? 4 : 2, d1, d2, (long long)pitch, offs, offs + 1, 1, dout);
+    if (fn == B200_MECMP_HADAMARD8) me_satd_kernel<<<1, 32, 0, st>>>(w == 8 ? 1 : h == 16 ? 4 : 2, d1, d2, (long long)pitch, offs, offs + 1, 1, dout, mode);
+    else if (fn >= B200_MECMP_VSAD) me_cmp2_kernel<<<1, 32, 0, st>>>(fn, w, mode, g_nsse_weight.load(), d1, d2, (long long)pitch, h, offs, offs + 1, 1, dout);
     else me_cmp_kernel<<<1, 32, 0, st>>>(fn, w, mode, d1, d2, (long long)pitch, h, offs, offs + 1, 1, dout);
     B200_LAUNCHED();
     int32_t res = 0;
@@ -500,6 +574,24 @@ int host_cmp(int fn, int idx, const uint8_t *blk1, const uint8_t *blk2, ptrdiff_
 
 template <int FN, int IDX>
 int tab_fn(void *, const uint8_t *a, const uint8_t *b, ptrdiff_t stride, int h) { return host_cmp(FN, IDX, a, b, stride, h); }
+
+int host_sum_abs_dctelem(const int16_t *block)
+{
+    auto fail = [](const char *what) { fprintf(stderr, "libb200dsp: sum_abs_dctelem failed: %s (%s)\n", what, b200_last_error()); abort(); };
+    B200Device *dev = b200_default_device();
+    if (!dev) fail("no device");
+    if (cudaSetDevice(dev->ordinal) != cudaSuccess) fail("cudaSetDevice");
+    B200_LOCK_DEVICE(dev);
+    uint8_t *scr = (uint8_t *)b200_scratch(dev, 256);
+    if (!scr) fail("scratch");
+    cudaStream_t st = dev->stream;
+    if (cudaMemcpyAsync(scr, block, 128, cudaMemcpyHostToDevice, st) != cudaSuccess) fail("h2d");
+    sum_abs_dctelem_kernel<<<1, 32, 0, st>>>((const int16_t *)scr, 1, (int32_t *)(scr + 128));
+    B200_LAUNCHED();
+    int32_t res = 0;
+    if (cudaMemcpyAsync(&res, scr + 128, 4, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) fail("d2h");
+    return res;
+}
 
 } // namespace
 
@@ -516,5 +608,28 @@ B200_API int b200_me_cmp_init(B200MECmpContext *c, int codec_flags)
     c->pix_abs[1][0] = tab_fn<B200_MECMP_PIX_ABS, 4>; c->pix_abs[1][1] = tab_fn<B200_MECMP_PIX_ABS, 5>;
     c->pix_abs[1][2] = tab_fn<B200_MECMP_PIX_ABS, 6>; c->pix_abs[1][3] = tab_fn<B200_MECMP_PIX_ABS, 7>;
     c->hadamard8_diff[0] = tab_fn<B200_MECMP_HADAMARD8, 0>; c->hadamard8_diff[1] = tab_fn<B200_MECMP_HADAMARD8, 1>;
+    c->hadamard8_diff[4] = tab_fn<B200_MECMP_HADAMARD8, 4>; c->hadamard8_diff[5] = tab_fn<B200_MECMP_HADAMARD8, 5>;
+    c->vsad[0] = tab_fn<B200_MECMP_VSAD, 0>; c->vsad[1] = tab_fn<B200_MECMP_VSAD, 1>;
+    c->vsad[4] = tab_fn<B200_MECMP_VSAD, 4>; c->vsad[5] = tab_fn<B200_MECMP_VSAD, 5>;
+    c->vsse[0] = tab_fn<B200_MECMP_VSSE, 0>; c->vsse[1] = tab_fn<B200_MECMP_VSSE, 1>;
+    c->vsse[4] = tab_fn<B200_MECMP_VSSE, 4>; c->vsse[5] = tab_fn<B200_MECMP_VSSE, 5>;
+    c->nsse[0] = tab_fn<B200_MECMP_NSSE, 0>; c->nsse[1] = tab_fn<B200_MECMP_NSSE, 1>;
+    c->median_sad[0] = tab_fn<B200_MECMP_MEDIAN_SAD, 0>; c->median_sad[1] = tab_fn<B200_MECMP_MEDIAN_SAD, 1>;
+    c->sum_abs_dctelem = host_sum_abs_dctelem;
+    return 0;
+}
+
+B200_API void b200_me_cmp_set_nsse_weight(int weight) { g_nsse_weight.store(weight); }
+
+B200_API int b200_sum_abs_dctelem_batch_device(B200Device *dev, const int16_t *blocks, int64_t n, int32_t *out)
+{
+    if (!dev || !blocks || !out || n < 0 || ((uintptr_t)blocks & 3)) return B200_EINVAL;
+    if (n == 0) return 0;
+    B200_CUDA_OK(cudaSetDevice(dev->ordinal));
+    const long long ctas = (n + 7) / 8;
+    if (ctas > 0x7fffffffLL) return B200_EINVAL;
+    sum_abs_dctelem_kernel<<<(unsigned)ctas, 256, 0, dev->stream>>>(blocks, n, out);
+    B200_LAUNCHED();
+    B200_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -3,7 +3,7 @@ and of the exhaustive search libavfilter drives it with (libavfilter/motion_esti
 import ctypes as C
 from ._lib import lib, check, vp, MECmpContext
 
-SAD, SSE, PIX_ABS, HADAMARD8 = 0, 1, 2, 3
+SAD, SSE, PIX_ABS, HADAMARD8, VSAD, VSSE, NSSE, MEDIAN_SAD = 0, 1, 2, 3, 4, 5, 6, 7
 AV_CODEC_FLAG_BITEXACT = 1 << 23
 
 
@@ -20,6 +20,10 @@ def ff_me_cmp_init(codec_flags=AV_CODEC_FLAG_BITEXACT):
 def me_cmp_batch_device(device, fn, idx, frame1, frame2, stride, h, off1, off2, n, out):
     return check(lib().b200_me_cmp_batch_device(device.handle, fn, idx, vp(_dptr(frame1)), vp(_dptr(frame2)), stride, h,
                                                 vp(_dptr(off1)), vp(_dptr(off2)), n, vp(_dptr(out))), "me_cmp_batch_device")
+
+
+def sum_abs_dctelem_batch_device(device, blocks, n, out):
+    return check(lib().b200_sum_abs_dctelem_batch_device(device.handle, vp(_dptr(blocks)), n, vp(_dptr(out))), "sum_abs_dctelem_batch_device")
 
 
 def me_esa_device(device, cur, ref, linesize, width, height, frame_stride, nframes, mb_size, search_param, out_mv, out_cost):

@@ -37,3 +37,13 @@ def unquantize_batch_device(device, variant, params, blocks, nblocks, blk_n, qsc
     return check(lib().b200_mpv_unquantize_batch_device(device.handle, variant, C.byref(params), vp(_dptr(blocks)), nblocks,
                                                         vp(_dptr(blk_n)) if blk_n is not None else None, vp(_dptr(qscale)),
                                                         vp(_dptr(last_index))), "mpv_unquantize_batch_device")
+
+
+def unquant_idct_mb420_device(device, variant, params, kind, blocks, qscale, last_index, mb_w, mb_h, nframes, planes, linesize, frame_stride):
+    """put_dct / add_dequant_dct (libavcodec/mpegvideo_dec.c:907-922) over a 4:2:0 macroblock stream: inverse quantiser fused into the
+    simple IDCT put (kind 1) / add (kind 2); device tensors / pointers"""
+    pl = (C.c_void_p * 3)(*[_dptr(x) for x in planes])
+    ls = (C.c_int32 * 3)(*linesize)
+    fs = (C.c_int64 * 3)(*frame_stride)
+    return check(lib().b200_mpv_unquant_idct_mb420_device(device.handle, variant, C.byref(params), kind, vp(_dptr(blocks)), vp(_dptr(qscale)),
+                                                          vp(_dptr(last_index)), mb_w, mb_h, nframes, pl, ls, fs), "unquant_idct_mb420_device")

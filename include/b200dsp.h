@@ -299,6 +299,16 @@ typedef struct B200MpvUnquant {
 int  b200_mpv_unquantize_batch_device(B200Device *dev, int variant, const B200MpvUnquant *p, int16_t *blocks, int64_t nblocks,
                                       const uint8_t *blk_n, const uint8_t *qscale, const int8_t *last_index);
 
+/* put_dct / add_dequant_dct of mpv_reconstruct_mb (libavcodec/mpegvideo_dec.c:907-922) for a whole 4:2:0 macroblock stream in one
+ * kernel: inverse quantisation (variant, p, qscale[], last_index[] per block as in b200_mpv_unquantize_batch_device, block number
+ * inside the macroblock = position in the stream % 6) straight into the simple IDCT put / add of b200_idct_mb420_device — the
+ * dequantised coefficients stay in registers.  kind = B200_IDCT_ADD skips blocks whose last_index is < 0, like add_dequant_dct.
+ * `blocks` is not modified.  Planes as for b200_idct_mb420_device, 16-byte (luma) / 8-byte (chroma) aligned.  Synchronous on
+ * the device's stream (the parameter block lives in the device's scratch). */
+int  b200_mpv_unquant_idct_mb420_device(B200Device *dev, int variant, const B200MpvUnquant *p, int kind, const int16_t *blocks,
+                                        const uint8_t *qscale, const int8_t *last_index, int mb_w, int mb_h, int nframes,
+                                        uint8_t *const planes[3], const int linesize[3], const int64_t frame_stride[3]);
+
 /* ------------------------------------------------------------------------------------------------ float_dsp
  * Replaces AVFloatDSPContext (libavutil/float_dsp.h:24-210) as avpriv_float_dsp_alloc() fills it with the C functions
  * (libavutil/float_dsp.c:27-141, float_scalarproduct.c:25-33): the element-wise float work around the transforms, e.g.
@@ -411,7 +421,17 @@ int  b200_me_cmp_init(B200MECmpContext *c, int codec_flags);
 #define B200_MECMP_SAD     0   /* idx 0: 16 wide, 1: 8 wide */
 #define B200_MECMP_SSE     1   /* idx 0: 16, 1: 8, 2: 4 wide */
 #define B200_MECMP_PIX_ABS 2   /* idx = 4*size(0:16,1:8) + (0 full, 1 x2, 2 y2, 3 xy2) */
-#define B200_MECMP_HADAMARD8 3 /* hadamard8_diff (SATD, me_cmp.c:514-562,933-950): idx 0: 16 wide (h = 8 or 16), 1: 8x8 (h ignored) */
+#define B200_MECMP_HADAMARD8 3 /* hadamard8_diff (SATD, me_cmp.c:514-562,933-950): idx 0: 16 wide (h = 8 or 16), 1: 8x8 (h ignored);
+                                * idx 4 / 5: hadamard8_intra16 / intra8x8 (me_cmp.c:564-612: the block blk1 itself, mean left out) */
+#define B200_MECMP_VSAD    4   /* vsad[idx] (me_cmp.c:843-881): idx 0: 16 wide, 1: 8, 4: vsad_intra16, 5: vsad_intra8 */
+#define B200_MECMP_VSSE    5   /* vsse[idx] (me_cmp.c:883-931): same indices */
+#define B200_MECMP_NSSE    6   /* nsse[idx] (me_cmp.c:387-437): idx 0: 16, 1: 8; weight as set by b200_me_cmp_set_nsse_weight (default 8) */
+#define B200_MECMP_MEDIAN_SAD 7 /* median_sad[idx] (me_cmp.c:145-183,292-330): idx 0: 16, 1: 8 */
+/* nsse multiplies its noise term by MPVEncContext.c.avctx->nsse_weight, or by 8 when the context argument is NULL (me_cmp.c:407-410).
+ * The table entries cannot read the caller's context (its layout is private to the encoder): the weight is set here instead. */
+void b200_me_cmp_set_nsse_weight(int weight);
+/* sum_abs_dctelem_c (me_cmp.c:105-112) for n blocks of 64 coefficients, DEVICE pointers */
+int  b200_sum_abs_dctelem_batch_device(B200Device *dev, const int16_t *blocks, int64_t n, int32_t *out);
 /* batched, DEVICE pointers: out[i] = fn(frame1 + off1[i], frame2 + off2[i], stride, h) */
 int  b200_me_cmp_batch_device(B200Device *dev, int fn, int idx, const uint8_t *frame1, const uint8_t *frame2,
                               ptrdiff_t stride, int h, const int64_t *off1, const int64_t *off2, int64_t n, int32_t *out);

@@ -7,6 +7,11 @@
  *   pix_abs{16,8}_{x2,y2,xy2}_c ..... libavcodec/me_cmp.c:145-385             blk2 interpolated: avg2 = (a+b+1)>>1,
  *                                                                             avg4 = (a+b+c+d+2)>>2 (:114-115)
  *   sse16_c / sse8_c / sse4_c ....... libavcodec/me_cmp.c:37-103               sum (a-b)^2
+ *   vsad / vsad_intra, vsse / vsse_intra  libavcodec/me_cmp.c:843-931          vertical gradient of the difference (or of the block itself)
+ *   nsse16_c / nsse8_c .............. libavcodec/me_cmp.c:387-437             SSE + weight * |difference of the two blocks' 2x2 gradient energy|
+ *   pix_median_abs16_c / 8_c ........ libavcodec/me_cmp.c:145-183, 292-330    residual of the difference after median (left, top, gradient) prediction
+ *   hadamard8_intra8x8_c / 16 ....... libavcodec/me_cmp.c:564-612, 944        SATD of the block itself minus |DC|
+ *   sum_abs_dctelem_c ............... libavcodec/me_cmp.c:105-112             sum |block[i]|, i < 64
  *   table layout .................... libavcodec/me_cmp.c:961-1027             sad[0]=16 wide, sad[1]=8; sse[0..2]=16,8,4;
  *                                                                             pix_abs[0=16,1=8][0 full,1 x2,2 y2,3 xy2]
  *   ff_me_cmp_sad, ff_me_search_esa . libavfilter/motion_estimation.c:60-97   cost(0 mv) first, return at once if it is 0,
@@ -67,8 +72,95 @@ static int satd8x8(const uint8_t *dst, const uint8_t *src, ptrdiff_t stride)
     return sum;
 }
 
+static int mid3(int a, int b, int c)            /* mid_pred (libavutil/common.h / mathops.h): median of three */
+{
+    if (a > b) { if (c > b) { b = c > a ? a : c; } }
+    else       { if (b > c) { b = c > a ? c : a; } }
+    return b;
+}
+
+/* vsad / vsse (intra = the block itself): rows 1 .. h-1 against the row above */
+static int vgrad_wh(const uint8_t *s1, const uint8_t *s2, ptrdiff_t stride, int w, int h, int intra, int sq)
+{
+    int score = 0;
+    for (int y = 1; y < h; y++, s1 += stride, s2 += stride)
+        for (int x = 0; x < w; x++) {
+            const int d = intra ? s1[x] - s1[x + stride] : s1[x] - s2[x] - s1[x + stride] + s2[x + stride];
+            score += sq ? d * d : abs(d);
+        }
+    return score;
+}
+
+static int nsse_wh(const uint8_t *s1, const uint8_t *s2, ptrdiff_t stride, int w, int h, int weight)
+{
+    int score1 = 0, score2 = 0;
+    for (int y = 0; y < h; y++, s1 += stride, s2 += stride) {
+        for (int x = 0; x < w; x++) score1 += (s1[x] - s2[x]) * (s1[x] - s2[x]);
+        if (y + 1 < h)
+            for (int x = 0; x < w - 1; x++)
+                score2 += abs(s1[x] - s1[x + stride] - s1[x + 1] + s1[x + stride + 1]) -
+                          abs(s2[x] - s2[x + stride] - s2[x + 1] + s2[x + stride + 1]);
+    }
+    return score1 + abs(score2) * weight;
+}
+
+static int median_sad_wh(const uint8_t *p1, const uint8_t *p2, ptrdiff_t stride, int w, int h)
+{
+    int s = 0;
+#define V(x) (p1[x] - p2[x])
+    s += abs(V(0));
+    for (int j = 1; j < w; j++) s += abs(V(j) - V(j - 1));
+    p1 += stride; p2 += stride;
+    for (int i = 1; i < h; i++, p1 += stride, p2 += stride) {
+        s += abs(V(0) - V(-stride));
+        for (int j = 1; j < w; j++)
+            s += abs(V(j) - mid3(V(j - stride), V(j - 1), V(j - stride) + V(j - 1) - V(j - stride - 1)));
+    }
+#undef V
+    return s;
+}
+
+/* hadamard8_intra8x8_c: the transform of the block itself; the DC term (sum of all 64 samples) is left out */
+static int satd8x8_intra(const uint8_t *src, ptrdiff_t stride)
+{
+    int t[64], sum = 0;
+    for (int i = 0; i < 8; i++)
+        for (int j = 0; j < 8; j++) t[8 * i + j] = src[stride * i + j];
+    for (int pass = 0; pass < 2; pass++) {
+        const int es = pass ? 8 : 1, ls = pass ? 1 : 8;
+        for (int l = 0; l < 8; l++)
+            for (int span = 1; span < 8; span <<= 1)
+                for (int a = 0; a < 8; a++)
+                    if (!(a & span)) {
+                        const int x = t[l * ls + a * es], y = t[l * ls + (a + span) * es];
+                        t[l * ls + a * es] = x + y; t[l * ls + (a + span) * es] = x - y;
+                    }
+    }
+    for (int i = 0; i < 64; i++) sum += abs(t[i]);
+    return sum - abs(t[0]);
+}
+
+int orc_sum_abs_dctelem(const int16_t *block)
+{
+    int sum = 0;
+    for (int i = 0; i < 64; i++) sum += abs(block[i]);
+    return sum;
+}
+
 int orc_me_cmp(int fn, int idx, const uint8_t *blk1, const uint8_t *blk2, ptrdiff_t stride, int h)
 {
+    if (fn == 3 && (idx == 4 || idx == 5)) {                       /* hadamard8_diff[4] = intra16, [5] = intra8x8 */
+        if (idx == 5) return satd8x8_intra(blk1, stride);
+        int s = satd8x8_intra(blk1, stride) + satd8x8_intra(blk1 + 8, stride);
+        if (h == 16) s += satd8x8_intra(blk1 + 8 * stride, stride) + satd8x8_intra(blk1 + 8 * stride + 8, stride);
+        return s;
+    }
+    if (fn == 4 || fn == 5) {                                      /* vsad / vsse: [0] 16, [1] 8, [4] intra16, [5] intra8 */
+        if (idx != 0 && idx != 1 && idx != 4 && idx != 5) return -1;
+        return vgrad_wh(blk1, blk2, stride, idx & 1 ? 8 : 16, h, idx >= 4, fn == 5);
+    }
+    if (fn == 6) return idx == 0 || idx == 1 ? nsse_wh(blk1, blk2, stride, 16 >> idx, h, 8) : -1;     /* NULL context: weight 8 */
+    if (fn == 7) return idx == 0 || idx == 1 ? median_sad_wh(blk1, blk2, stride, 16 >> idx, h) : -1;
     if (fn == 3) {
         if (idx == 1) return satd8x8(blk1, blk2, stride);
         if (idx != 0) return -1;

@@ -286,9 +286,16 @@ static void mecmp_init(void)
 API int ffref_me_cmp(int fn, int idx, const uint8_t *blk1, const uint8_t *blk2, ptrdiff_t stride, int h)
 {
     mecmp_init();
-    me_cmp_func f = fn == 0 ? g_mecmp.sad[idx] : fn == 1 ? g_mecmp.sse[idx] : fn == 3 ? g_mecmp.hadamard8_diff[idx] : g_mecmp.pix_abs[idx >> 2][idx & 3];
+    me_cmp_func f = fn == 0 ? g_mecmp.sad[idx] : fn == 1 ? g_mecmp.sse[idx] : fn == 3 ? g_mecmp.hadamard8_diff[idx] :
+                    fn == 4 ? g_mecmp.vsad[idx] : fn == 5 ? g_mecmp.vsse[idx] : fn == 6 ? g_mecmp.nsse[idx] :
+                    fn == 7 ? g_mecmp.median_sad[idx] : g_mecmp.pix_abs[idx >> 2][idx & 3];
     if (!f) return -1;
     return f(NULL, blk1, blk2, stride, h);
+}
+API int ffref_sum_abs_dctelem(const int16_t *block)
+{
+    mecmp_init();
+    return g_mecmp.sum_abs_dctelem(block);
 }
 
 /* av_pixelutils_get_sad_fn(bits, bits, aligned = 0): -1 where the reference has no function */

@@ -1,4 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests -m gpu -q -k "h264 or idct" > gpurun_out/t_h264.log 2>&1; echo "tests rc=$?"; tail -3 gpurun_out/t_h264.log
-timeout 120 python scripts/quick_bench.py h264 10
+timeout 900 python -m pytest tests -m gpu -q > gpurun_out/tests_gpu.log 2>&1; echo "tests rc=$?"; tail -3 gpurun_out/tests_gpu.log
+timeout 600 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench rc=$?"; tail -2 gpurun_out/bench_n1.err

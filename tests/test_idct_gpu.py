@@ -290,3 +290,50 @@ def test_h264_idct_batch_vs_oracle(device, kind):
         device.sync()
         assert np.array_equal(dd.cpu().numpy(), exp), kind
         assert np.array_equal(db.cpu().numpy(), eb), kind
+
+
+@pytest.mark.parametrize("variant", range(7))
+@pytest.mark.parametrize("op", [1, 2])
+def test_unquant_idct_fused_mb420(device, variant, op):
+    """put_dct / add_dequant_dct in one kernel (b200_mpv_unquant_idct_mb420_device) = the checker's inverse quantiser followed by the
+    checker's IDCT put / add on every block; add leaves blocks with block_last_index < 0 alone (mpegvideo_dec.c:915-922)."""
+    import torch
+    from ffmpeg_b200 import mpegvideo
+    from ffmpeg_b200._lib import MpvUnquant
+    O = cl.oracle()
+    mb_w, mb_h, nf = 21, 5, 2
+    nblk = mb_w * mb_h * 6 * nf
+    cfg, blocks, _, q, last = cl.unquant_case(4000 + variant * 3 + op, variant, nblocks=nblk)
+    deq = cl.orc_unquant(variant, cfg, blocks, None, q, last)                   # block number inside the macroblock = i % 6
+    W, H = mb_w * 16, mb_h * 16
+    ls = [W + 32, W // 2 + 16, W // 2 + 16]
+    rng = np.random.default_rng(16 + variant)
+    planes = [rng.integers(0, 256, (nf, H, ls[0]), dtype=np.uint8), rng.integers(0, 256, (nf, H // 2, ls[1]), dtype=np.uint8),
+              rng.integers(0, 256, (nf, H // 2, ls[2]), dtype=np.uint8)]
+    ref = [p.copy() for p in planes]
+    b = np.arange(nblk)
+    f, r = b // (mb_w * mb_h * 6), b % (mb_w * mb_h * 6)
+    mb, k = r // 6, r % 6
+    mby, mbx = mb // mb_w, mb % mb_w
+    live = (last >= 0) if op == 2 else np.ones(nblk, bool)
+    for pl in range(3):
+        sel = ((k < 4) if pl == 0 else (k == 3 + pl)) & live
+        if pl == 0:
+            off = f * H * ls[0] + (mby * 16 + (k >> 1) * 8) * ls[0] + mbx * 16 + (k & 1) * 8
+        else:
+            off = f * (H // 2) * ls[pl] + (mby * 8) * ls[pl] + mbx * 8
+        bs = np.ascontiguousarray(deq[sel])
+        O.orc_idct_batch(op, cl.ptr(bs, cl.i16p), int(sel.sum()), cl.ptr(ref[pl]), ls[pl], cl.ptr(np.ascontiguousarray(off[sel]).astype(np.int64), cl.i64p))
+    fs = [H * ls[0], (H // 2) * ls[1], (H // 2) * ls[2]]
+    params = cl.unquant_params(struct=MpvUnquant, **cfg)
+    st = torch.cuda.ExternalStream(device.stream)
+    with torch.cuda.stream(st):
+        db = torch.from_numpy(blocks).cuda()
+        dq, dl = torch.from_numpy(q).cuda(), torch.from_numpy(last).cuda()
+        dp = [torch.from_numpy(p).cuda() for p in planes]
+        mpegvideo.unquant_idct_mb420_device(device, variant, params, op, db, dq, dl, mb_w, mb_h, nf, dp, ls, fs)
+        device.sync()
+        assert np.array_equal(db.cpu().numpy(), blocks)                          # the coefficient stream is read-only
+        for pl in range(3):
+            got = dp[pl].cpu().numpy()
+            assert np.array_equal(got, ref[pl]), (variant, op, pl, int((got != ref[pl]).sum()))

@@ -58,6 +58,51 @@ def test_mecmp_batch_vs_oracle(device):
                     assert np.array_equal(got[:400], exp), (fn, idx, h)
 
 
+def test_mecmp_round2_families(device):
+    """vsad / vsse (+ intra), nsse, median_sad, hadamard8_intra, sum_abs_dctelem: drop-in entries against the reference fixture
+    (NULL context like checkasm), batched entry against the oracle."""
+    import torch
+    from ffmpeg_b200 import me_cmp
+    from ffmpeg_b200._lib import u8p, i16p
+    g = np.load(os.path.join(G, "mecmp2.npz"))
+    c = me_cmp.ff_me_cmp_init()
+    img1, img2 = g["img1"], g["img2"]
+    assert not c.dct_sad[0] and not c.quant_psnr[0] and not c.rd[0] and not c.bit[0] and not c.w53[0]      # these need the encoder's context: stay NULL
+    tabs = {3: c.hadamard8_diff, 4: c.vsad, 5: c.vsse, 6: c.nsse, 7: c.median_sad}
+    for fn, idx, x1, y1, x2, y2, h, v in g["cases"]:
+        f = tabs[int(fn)][int(idx)]
+        got = f(None, C.cast(img1.ctypes.data + int(y1) * 64 + int(x1), u8p), C.cast(img2.ctypes.data + int(y2) * 64 + int(x2), u8p), 64, int(h))
+        assert got == v, (fn, idx, h)
+    for b, v in zip(g["blocks"][:8], g["sums"][:8]):
+        assert c.sum_abs_dctelem(np.ascontiguousarray(b).ctypes.data_as(i16p)) == v
+    O = cl.oracle()
+    rng = np.random.default_rng(6)
+    W, H, n = 256, 128, 2000
+    f1 = rng.integers(0, 256, (H, W), dtype=np.uint8)
+    f2 = (f1.astype(int) + rng.integers(-9, 10, f1.shape)).clip(0, 255).astype(np.uint8)
+    xs1, ys1, xs2, ys2 = (rng.integers(1, d - 20, n) for d in (W, H, W, H))
+    off1 = (ys1 * W + xs1).astype(np.int64)
+    off2 = (ys2 * W + xs2).astype(np.int64)
+    with on_stream(device):
+        d1, d2 = torch.from_numpy(f1).cuda(), torch.from_numpy(f2).cuda()
+        o1, o2 = torch.from_numpy(off1).cuda(), torch.from_numpy(off2).cuda()
+        out = torch.zeros(n, dtype=torch.int32, device="cuda")
+        for fn, idxs in ((3, (4, 5)), (4, (0, 1, 4, 5)), (5, (0, 1, 4, 5)), (6, (0, 1)), (7, (0, 1))):
+            for idx in idxs:
+                for h in (8, 16):
+                    me_cmp.me_cmp_batch_device(device, fn, idx, d1, d2, W, h, o1, o2, n, out)
+                    device.sync()
+                    got = out.cpu().numpy()
+                    exp = np.array([O.orc_me_cmp(fn, idx, C.cast(f1.ctypes.data + int(a), cl.u8p), C.cast(f2.ctypes.data + int(b), cl.u8p), W, h)
+                                    for a, b in zip(off1[:300], off2[:300])])
+                    assert np.array_equal(got[:300], exp), (fn, idx, h)
+        blocks = torch.from_numpy(g["blocks"]).cuda()
+        so = torch.zeros(blocks.shape[0], dtype=torch.int32, device="cuda")
+        me_cmp.sum_abs_dctelem_batch_device(device, blocks, blocks.shape[0], so)
+        device.sync()
+        assert np.array_equal(so.cpu().numpy(), g["sums"])
+
+
 def test_satd_pointer_table_and_batch(device):
     """hadamard8_diff (SATD): drop-in entries against the reference fixture, batched entry against the oracle."""
     import torch

@@ -623,3 +623,30 @@ def test_idct_accuracy_like_reference_dct_test():
                 assert per_coef_sq <= 0.06 and per_coef_sys <= 0.015, (bits, test, per_coef_sq, per_coef_sys)
             else:
                 assert err_inf <= 1 and omse <= 0.02 and abs(ome) <= 0.0015, (bits, test, err_inf, omse, ome)
+
+
+def test_mecmp_round2_families_oracle_vs_fixture_and_reference():
+    """vsad / vsse (+ intra), nsse, median_sad, hadamard8_intra, sum_abs_dctelem: the checker against the committed reference values
+    (tests/golden/mecmp2.npz, scripts/gen_golden_mecmp2.py) and, where it is built, against the compiled reference on fresh inputs."""
+    O = cl.oracle()
+    O.orc_sum_abs_dctelem.argtypes = [cl.i16p]
+    g = np.load(os.path.join(G, "mecmp2.npz"))
+    img1, img2 = g["img1"], g["img2"]
+    for fn, idx, x1, y1, x2, y2, h, v in g["cases"]:
+        got = O.orc_me_cmp(int(fn), int(idx), C.cast(img1.ctypes.data + int(y1) * 64 + int(x1), cl.u8p),
+                           C.cast(img2.ctypes.data + int(y2) * 64 + int(x2), cl.u8p), 64, int(h))
+        assert got == v, (fn, idx, h)
+    for b, v in zip(g["blocks"], g["sums"]):
+        assert O.orc_sum_abs_dctelem(cl.ptr(np.ascontiguousarray(b), cl.i16p)) == v
+    if not cl.have_ref():
+        return
+    R = cl.ref()
+    rng = np.random.default_rng(31)
+    for trial in range(60):
+        a = rng.integers(0, 256, (40, 96), dtype=np.uint8)
+        b = rng.integers(0, 256, (40, 96), dtype=np.uint8) if trial % 2 else (a.astype(int) + rng.integers(-2, 3, a.shape)).clip(0, 255).astype(np.uint8)
+        p1, p2 = C.cast(a.ctypes.data + 96 * 2 + 8, cl.u8p), C.cast(b.ctypes.data + 96 * 3 + 5, cl.u8p)
+        for fn, idxs in ((3, (4, 5)), (4, (0, 1, 4, 5)), (5, (0, 1, 4, 5)), (6, (0, 1)), (7, (0, 1))):
+            for idx in idxs:
+                for h in (8, 16):
+                    assert R.ffref_me_cmp(fn, idx, p1, p2, 96, h) == O.orc_me_cmp(fn, idx, p1, p2, 96, h), (fn, idx, h)
