@@ -689,6 +689,44 @@ def extra_paths(args, dev, stream, g, world, barrier, reduce_max, peak, devidx):
         del dstw, s0, s1, win
     except Exception as ex:
         wid["vector_fmul_window_1024"] = {"error": str(ex)[:160]}
+    # put_dct of an MPEG-2 intra stream: inverse quantiser + IDCT put, as two kernels (128 B + 128 B of extra coefficient traffic per block)
+    # and as the fused kernel (coefficients dequantised in registers)
+    try:
+        from ffmpeg_b200 import mpegvideo
+        fr = 64
+        nbq = MB_W * MB_H * 6 * fr
+        zz = [0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21, 28,
+              35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63]
+        perm, rend = mpegvideo.ff_init_scantable(list(range(64)), zz)
+        prm = mpegvideo.unquant_params([8] + [16 + (i % 23) for i in range(1, 64)], [16] * 64, perm, rend, 8, 8)
+        with torch.cuda.stream(stream):
+            qb = torch.randint(-40, 41, (nbq, 64), dtype=torch.int16, device="cuda", generator=g)
+            qwork = torch.empty_like(qb)
+            qsc = torch.randint(1, 32, (nbq,), dtype=torch.uint8, device="cuda", generator=g)
+            lastq = torch.full((nbq,), 63, dtype=torch.int8, device="cuda")
+            pls = [torch.zeros((fr, MB_H * 16, MB_W * 16), dtype=torch.uint8, device="cuda"),
+                   torch.zeros((fr, MB_H * 8, MB_W * 8), dtype=torch.uint8, device="cuda"),
+                   torch.zeros((fr, MB_H * 8, MB_W * 8), dtype=torch.uint8, device="cuda")]
+        lsq = [MB_W * 16, MB_W * 8, MB_W * 8]
+        fsq = [MB_W * 16 * MB_H * 16, MB_W * 8 * MB_H * 8, MB_W * 8 * MB_H * 8]
+
+        def two_kernels():
+            qwork.copy_(qb)                                 # the separate quantiser works in place
+            mpegvideo.unquantize_batch_device(dev, 2, prm, qwork, nbq, None, qsc, lastq)
+            idctdsp.idct_mb420_device(dev, 1, qwork, MB_W, MB_H, fr, pls, lsq, fsq)
+        ms_copy = timed(lambda: qwork.copy_(qb))
+        ms2 = max(timed(two_kernels) - ms_copy, 1e-3)
+        msf = timed(lambda: mpegvideo.unquant_idct_mb420_device(dev, 2, prm, 1, qb, qsc, lastq, MB_W, MB_H, fr, pls, lsq, fsq))
+        bq = 128 + 64 + 2
+        wid["mpeg2_put_dct"] = {"fused": {"value": world * nbq / (msf / 1e3), "unit": "blocks/s", "ms_per_step": msf,
+                                          "roofline": {"bound": "hbm", "achieved": bq * nbq / (msf / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                                                       "frac": bq * nbq / (msf / 1e3) / 1e9 / peak, "bytes_per_block": bq},
+                                          "api": "b200_mpv_unquant_idct_mb420_device"},
+                                "two_kernels": {"value": world * nbq / (ms2 / 1e3), "unit": "blocks/s", "ms_per_step": ms2,
+                                                "note": "b200_mpv_unquantize_batch_device + b200_idct_mb420_device; time of the working-copy refill subtracted"}}
+        del qb, qwork, qsc, lastq, pls
+    except Exception as ex:
+        wid["mpeg2_put_dct"] = {"error": str(ex)[:160]}
     out["widening"] = wid
     return out
 

@@ -408,7 +408,7 @@ idct_tpb_kernel(const int16_t *blocks, int16_t *blocks_out, long long nblocks, u
 // same arithmetic as unquant.cu's kernel (libavcodec/mpegvideo_unquantize.c:50-276), applied by the thread that owns the block to the
 // eight rows it takes out of shared memory — the dequantised coefficients never exist in HBM (128 B read + 128 B written per block saved
 // against the two-kernel sequence).  V = -1: no dequantisation (the plain IDCT kernels).
-struct FusedUnquant {                     // passed by value
+struct FusedUnquant {                     // passed by value (kernel parameter: every table index is a compile-time constant)
     uint16_t intra[64], inter[64];
     uint8_t scanpos[64];                  // scan index of each raster coefficient
     uint8_t raster_end[64];
@@ -476,7 +476,7 @@ __device__ __forceinline__ int luma_swz(int row) { return (row & 8) << 3; }     
 
 template <int KIND, int V = -1>
 __global__ void __launch_bounds__(48 * MAX_SEGS, V < 0 ? 4 : 2)
-idct_mb420_kernel(const int16_t *blocks, Mb420Geom g, int segs_per_cta, const FusedUnquant *UQ = nullptr)
+idct_mb420_kernel(const int16_t *blocks, Mb420Geom g, int segs_per_cta, const __grid_constant__ FusedUnquant UQ)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint4 *sin = reinterpret_cast<uint4 *>(smem_raw);                                     // segs * 48 * 8 uint4
@@ -536,12 +536,12 @@ idct_mb420_kernel(const int16_t *blocks, Mb420Geom g, int segs_per_cta, const Fu
         bool skip = false;
         if (V >= 0) {
             const long long bi = (((f * g.mb_h + mby) * g.mb_w) + mbx0 + m) * 6 + k;
-            const int last = __ldg(UQ->last_index + bi);
+            const int last = __ldg(UQ.last_index + bi);
             skip = KIND == B200_IDCT_ADD && last < 0;                                     // add_dequant_dct: block_last_index < 0 leaves the pixels alone
             uint4 rr[8];
 #pragma unroll
             for (int j = 0; j < 8; j++) rr[j] = rows[j ^ key];
-            fused_unquant_rows<V < 0 ? 0 : V>(rr, *UQ, k, (int)__ldg(UQ->qscale + bi), last);
+            fused_unquant_rows<V < 0 ? 0 : V>(rr, UQ, k, (int)__ldg(UQ.qscale + bi), last);
 #pragma unroll
             for (int j = 0; j < 8; j++) row_pass_packed(rr[j], R2[j]);
         } else {
@@ -659,7 +659,7 @@ int launch_mb420(cudaStream_t st, const int16_t *blocks, const Mb420Geom &g, int
         Mb420Geom gg = g;
         for (int i = 0; i < 3; i++) gg.plane[i] += (long long)f0 * g.frame_stride[i];
         dim3 grid((segs_row + best - 1) / best, g.mb_h, nf);
-        idct_mb420_kernel<KIND><<<grid, 48 * best, smem, st>>>(blocks + (long long)f0 * g.mb_w * g.mb_h * 6 * 64, gg, best);
+        idct_mb420_kernel<KIND><<<grid, 48 * best, smem, st>>>(blocks + (long long)f0 * g.mb_w * g.mb_h * 6 * 64, gg, best, FusedUnquant{});
         B200_LAUNCHED();
     }
     B200_CUDA_OK(cudaGetLastError());
@@ -669,7 +669,7 @@ int launch_mb420(cudaStream_t st, const int16_t *blocks, const Mb420Geom &g, int
 
 // fused inverse quantiser + IDCT over the macroblock stream (aligned planes only: the tiled kernel)
 template <int KIND, int V>
-int launch_mb420_fused(cudaStream_t st, const int16_t *blocks, const Mb420Geom &g, int nframes, const FusedUnquant *dUQ)
+int launch_mb420_fused(cudaStream_t st, const int16_t *blocks, const Mb420Geom &g, int nframes, const FusedUnquant &UQ)
 {
     const bool ok = (((uintptr_t)g.plane[0] | (uintptr_t)g.linesize[0] | (uintptr_t)g.frame_stride[0]) & 15) == 0 &&
                     (((uintptr_t)g.plane[1] | (uintptr_t)g.linesize[1] | (uintptr_t)g.frame_stride[1] |
@@ -686,7 +686,7 @@ int launch_mb420_fused(cudaStream_t st, const int16_t *blocks, const Mb420Geom &
     const size_t smem = (size_t)best * (48 * 128 + 3072);
     B200_CUDA_OK(cudaFuncSetAttribute(idct_mb420_kernel<KIND, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((segs_row + best - 1) / best, g.mb_h, nframes);
-    idct_mb420_kernel<KIND, V><<<grid, 48 * best, smem, st>>>(blocks, g, best, dUQ);
+    idct_mb420_kernel<KIND, V><<<grid, 48 * best, smem, st>>>(blocks, g, best, UQ);
     B200_LAUNCHED();
     B200_CUDA_OK(cudaGetLastError());
     return 0;
@@ -738,26 +738,19 @@ B200_API int b200_mpv_unquant_idct_mb420_device(B200Device *dev, int variant, co
     U.y_dc = p->y_dc_scale; U.c_dc = p->c_dc_scale; U.q_type = p->q_scale_type; U.aic = p->h263_aic; U.ac_pred = p->ac_pred;
     U.qscale = qscale; U.last_index = last_index;
     B200_CUDA_OK(cudaSetDevice(dev->ordinal));
-    // the parameter block travels through the device's scratch (stream-ordered copy; the kernel reads it through a pointer)
-    B200_LOCK_DEVICE(dev);
-    FusedUnquant *dU = (FusedUnquant *)b200_scratch(dev, sizeof(FusedUnquant));
-    if (!dU) return B200_ENOMEM;
-    B200_CUDA_OK(cudaMemcpyAsync(dU, &U, sizeof(U), cudaMemcpyHostToDevice, dev->stream));
     Mb420Geom g{};
     g.mb_w = mb_w; g.mb_h = mb_h;
     for (int i = 0; i < 3; i++) { g.plane[i] = planes[i]; g.linesize[i] = linesize[i]; g.frame_stride[i] = frame_stride[i]; }
     cudaStream_t st = dev->stream;
     int ret = B200_EINVAL;
     switch (variant * 2 + (kind == B200_IDCT_ADD)) {
-#define CASE(V) case (V) * 2: ret = launch_mb420_fused<B200_IDCT_PUT, V>(st, blocks, g, nframes, dU); break; \
-                case (V) * 2 + 1: ret = launch_mb420_fused<B200_IDCT_ADD, V>(st, blocks, g, nframes, dU); break;
+#define CASE(V) case (V) * 2: ret = launch_mb420_fused<B200_IDCT_PUT, V>(st, blocks, g, nframes, U); break; \
+                case (V) * 2 + 1: ret = launch_mb420_fused<B200_IDCT_ADD, V>(st, blocks, g, nframes, U); break;
     CASE(B200_UNQUANT_MPEG1_INTRA) CASE(B200_UNQUANT_MPEG1_INTER) CASE(B200_UNQUANT_MPEG2_INTRA)
     CASE(B200_UNQUANT_MPEG2_INTRA_BITEXACT) CASE(B200_UNQUANT_MPEG2_INTER) CASE(B200_UNQUANT_H263_INTRA) CASE(B200_UNQUANT_H263_INTER)
 #undef CASE
     }
-    if (ret < 0) return ret;
-    B200_CUDA_OK(cudaStreamSynchronize(st));          // the scratch parameter block must outlive the kernel (the lock is released on return)
-    return 0;
+    return ret;
 }
 
 B200_API int b200_idct_batch_device(B200Device *dev, int kind, int16_t *blocks, int64_t nblocks, uint8_t *dest,

@@ -909,6 +909,7 @@ struct B200SwsContext {
     void *slice_buf = nullptr;
     int next_dst_y = 0;
     bool slice_open = false;
+    int slice_dir = 1;               // SwsInternal.sliceDir: 1 top-down, -1 bottom-up (the picture is flipped internally, swscale.c:1096-1159)
 };
 
 static int upload_mma_tables(B200SwsContext *c);
@@ -2133,15 +2134,15 @@ static int sws_scale_planar_host(B200SwsContext *c, const uint8_t *const srcSlic
         }
         if (srcSliceH == 0) return 0;
         if (!c->slice_open && srcSliceY != 0) {
-            b200_set_error("slices must start at line 0 (bottom-up slice order is not implemented)");
-            return srcSliceY + srcSliceH == p.srcH ? B200_ENOSYS : B200_EINVAL;
+            b200_set_error("Slices start in the middle!");
+            return B200_EINVAL;
         }
     }
     const int nsp = p.src_rgb ? 1 : p.src_nv ? 2 : 3;             // packed RGB: one plane; nv12 / nv21: plane 1 carries both chroma components
     const int ndp = p.dst_nv ? 2 : 3;                             // nv12 / nv21 destination: two planes
     for (int i = 0; i < 3; i++) {
         if ((i < ndp && !dst[i]) || (i < nsp && !srcSlice[i])) return B200_EINVAL;
-        if ((i < ndp && dstStride[i] < 0) || (i < nsp && srcStride[i] < 0)) return B200_ENOSYS;
+        if (whole && ((i < ndp && dstStride[i] < 0) || (i < nsp && srcStride[i] < 0))) return B200_ENOSYS;
     }
     B200Device *d = c->dev;
     B200_CUDA_OK(cudaSetDevice(d->ordinal));
@@ -2166,7 +2167,7 @@ static int sws_scale_planar_host(B200SwsContext *c, const uint8_t *const srcSlic
         const int by[3] = { srcSliceY, chrY, chrY }, bh[3] = { srcSliceH, chrH, chrH };
         for (int i = 0; i < 3; i++) {
             if (i < nsp)
-                B200_CUDA_OK(cudaMemcpy2DAsync(sb + soff[i] + (size_t)by[i] * spitch[i], spitch[i], srcSlice[i], (size_t)srcStride[i], sw[i], bh[i], cudaMemcpyHostToDevice, st));
+                B200_CUDA_OK(b200_h2d_rows(sb + soff[i] + (size_t)by[i] * spitch[i], spitch[i], srcSlice[i], srcStride[i], sw[i], bh[i], st));
             sp[i] = sb + soff[i]; dp[i] = sb + doff[i]; ss[i] = (long long)spitch[i]; ds[i] = (long long)dpitch[i];
         }
         int y0, y1;
@@ -2189,9 +2190,9 @@ static int sws_scale_planar_host(B200SwsContext *c, const uint8_t *const srcSlic
             int ret = launch_planar(c, st, sp, ss, zero, dp, ds, zero, 1);
             if (ret < 0) return ret;
             const int c0 = (y0 + 1) >> 1, c1 = (y1 + 1) >> 1;           // chroma lines are written with the even luma lines (vscale.c:34-107)
-            B200_CUDA_OK(cudaMemcpy2DAsync(dst[0] + (long long)y0 * dstStride[0], (size_t)dstStride[0], dp[0] + (size_t)y0 * dpitch[0], dpitch[0], dw[0], y1 - y0, cudaMemcpyDeviceToHost, st));
+            B200_CUDA_OK(b200_d2h_rows(dst[0] + (long long)y0 * dstStride[0], dstStride[0], dp[0] + (size_t)y0 * dpitch[0], dpitch[0], dw[0], y1 - y0, st));
             for (int i = 1; i < ndp && c1 > c0; i++)
-                B200_CUDA_OK(cudaMemcpy2DAsync(dst[i] + (long long)c0 * dstStride[i], (size_t)dstStride[i], dp[i] + (size_t)c0 * dpitch[i], dpitch[i], dw[i], c1 - c0, cudaMemcpyDeviceToHost, st));
+                B200_CUDA_OK(b200_d2h_rows(dst[i] + (long long)c0 * dstStride[i], dstStride[i], dp[i] + (size_t)c0 * dpitch[i], dpitch[i], dw[i], c1 - c0, st));
         }
         B200_CUDA_OK(cudaStreamSynchronize(st));
         if (srcSliceY + srcSliceH == p.srcH) c->slice_open = false;
@@ -2314,11 +2315,9 @@ static int sws_scale_slice(B200SwsContext *c, const uint8_t *const srcSlice[], c
         return B200_EINVAL;
     }
     if (srcSliceH == 0) return 0;
-    if (srcStride[0] < 0 || srcStride[1] < 0 || (!p.src_nv && srcStride[2] < 0) || dstStride[0] < 0) return B200_ENOSYS;
     if (!c->slice_open && srcSliceY != 0) {
-        // "Slices start in the middle!" unless it is a bottom-up sequence, which is not implemented here
-        b200_set_error("slices must start at line 0 (bottom-up slice order is not implemented)");
-        return srcSliceY + srcSliceH == p.srcH ? B200_ENOSYS : B200_EINVAL;
+        b200_set_error("Slices start in the middle!");
+        return B200_EINVAL;
     }
     B200Device *d = c->dev;
     B200_CUDA_OK(cudaSetDevice(d->ordinal));
@@ -2328,11 +2327,11 @@ static int sws_scale_slice(B200SwsContext *c, const uint8_t *const srcSlice[], c
     uint8_t *sb = (uint8_t *)c->slice_buf, *db = sb + L.srcBytes;
     if (srcSliceY == 0) { c->next_dst_y = 0; c->slice_open = true; }
     const int chrY = srcSliceY >> 1, chrH = -((-srcSliceH) >> 1);                       // AV_CEIL_RSHIFT
-    B200_CUDA_OK(cudaMemcpy2DAsync(sb + L.yOff + (size_t)srcSliceY * L.yPitch, L.yPitch, srcSlice[0], (size_t)srcStride[0], p.srcW, srcSliceH, cudaMemcpyHostToDevice, st));
+    B200_CUDA_OK(b200_h2d_rows(sb + L.yOff + (size_t)srcSliceY * L.yPitch, L.yPitch, srcSlice[0], srcStride[0], p.srcW, srcSliceH, st));
     const size_t cp1 = p.src_nv ? 2 * L.cPitch : L.cPitch;       // nv12 / nv21: plane 1 is twice as wide and holds both components
-    B200_CUDA_OK(cudaMemcpy2DAsync(sb + L.uOff + (size_t)chrY * cp1, cp1, srcSlice[1], (size_t)srcStride[1], p.src_nv ? 2 * p.chrSrcW : p.chrSrcW, chrH, cudaMemcpyHostToDevice, st));
+    B200_CUDA_OK(b200_h2d_rows(sb + L.uOff + (size_t)chrY * cp1, cp1, srcSlice[1], srcStride[1], p.src_nv ? 2 * p.chrSrcW : p.chrSrcW, chrH, st));
     if (!p.src_nv)
-        B200_CUDA_OK(cudaMemcpy2DAsync(sb + L.vOff + (size_t)chrY * L.cPitch, L.cPitch, srcSlice[2], (size_t)srcStride[2], p.chrSrcW, chrH, cudaMemcpyHostToDevice, st));
+        B200_CUDA_OK(b200_h2d_rows(sb + L.vOff + (size_t)chrY * L.cPitch, L.cPitch, srcSlice[2], srcStride[2], p.chrSrcW, chrH, st));
     const uint8_t *sp[3] = { sb + L.yOff, sb + L.uOff, sb + L.vOff };
     const long long ss[3] = { (long long)L.yPitch, (long long)cp1, (long long)L.cPitch };
     const long long fs[3] = { 0, 0, 0 };
@@ -2355,8 +2354,8 @@ static int sws_scale_slice(B200SwsContext *c, const uint8_t *const srcSlice[], c
     int ret = launch_batch(c, st, sp, ss, fs, db, (long long)L.dPitch, 0, 1, &R);
     if (ret < 0) return ret;
     if (y1 > y0 && sws_written_row_bytes(p))
-        B200_CUDA_OK(cudaMemcpy2DAsync(dst[0] + (long long)y0 * dstStride[0], (size_t)dstStride[0], db + (size_t)y0 * L.dPitch, L.dPitch,
-                                       sws_written_row_bytes(p), y1 - y0, cudaMemcpyDeviceToHost, st));
+        B200_CUDA_OK(b200_d2h_rows(dst[0] + (long long)y0 * dstStride[0], dstStride[0], db + (size_t)y0 * L.dPitch, L.dPitch,
+                                   sws_written_row_bytes(p), y1 - y0, st));
     B200_CUDA_OK(cudaStreamSynchronize(st));
     if (srcSliceY + srcSliceH == p.srcH) c->slice_open = false;
     return p.unscaled_lut ? srcSliceH : y1 - y0;
@@ -2368,6 +2367,32 @@ B200_API int b200_sws_scale(B200SwsContext *c, const uint8_t *const srcSlice[], 
     if (!c || !srcSlice || !srcStride || !dst || !dstStride) return B200_EINVAL;
     B200_LOCK_DEVICE(c->dev);      // contexts of one device share its stream and scratch (slice threads call N child contexts concurrently)
     const SwsPlan &p = c->plan;
+    // Slice direction (scale_internal, libswscale/swscale.c:1096-1103): a sequence that starts with the band touching the bottom
+    // of the picture runs bottom-up; the reference then flips the picture internally (:1141-1159: negated strides, pointers on the last
+    // line of the band / of the destination, srcSliceY counted from the bottom) and so does this wrapper, band by band.
+    if (!c->slice_open)
+        c->slice_dir = (srcSliceY != 0 && srcSliceH != p.srcH && srcSliceY + srcSliceH == p.srcH && !p.src_rgb && !p.bgr24_yv12) ? -1 : 1;
+    if (c->slice_dir == -1) {
+        if ((p.srcH & 1) || (srcSliceH & 1) || (srcSliceY & 1) || srcSliceH <= 0 || srcSliceY < 0 || srcSliceY + srcSliceH > p.srcH ||
+            (p.planar && (p.dstH & 1))) {
+            b200_set_error("bottom-up slices: only even heights are implemented");
+            return B200_ENOSYS;
+        }
+        const uint8_t *s2[4] = { srcSlice[0], srcSlice[1], p.src_nv ? nullptr : srcSlice[2], nullptr };
+        int ss2[4] = { -srcStride[0], -srcStride[1], p.src_nv ? 0 : -srcStride[2], 0 };
+        uint8_t *d2[4] = { dst[0], p.planar ? dst[1] : nullptr, p.planar && !p.dst_nv ? dst[2] : nullptr, nullptr };
+        int ds2[4] = { -dstStride[0], p.planar ? -dstStride[1] : 0, p.planar && !p.dst_nv ? -dstStride[2] : 0, 0 };
+        if (!s2[0] || !s2[1] || (!p.src_nv && !s2[2]) || !d2[0] || (p.planar && !d2[1]) || (p.planar && !p.dst_nv && !d2[2])) return B200_EINVAL;
+        s2[0] += (long long)(srcSliceH - 1) * srcStride[0];
+        s2[1] += (long long)((srcSliceH >> 1) - 1) * srcStride[1];
+        if (s2[2]) s2[2] += (long long)((srcSliceH >> 1) - 1) * srcStride[2];
+        d2[0] += (long long)(p.dstH - 1) * dstStride[0];
+        if (d2[1]) d2[1] += (long long)((p.dstH >> 1) - 1) * dstStride[1];
+        if (d2[2]) d2[2] += (long long)((p.dstH >> 1) - 1) * dstStride[2];
+        const int yint = p.srcH - srcSliceY - srcSliceH;
+        if (p.planar) return sws_scale_planar_host(c, s2, ss2, yint, srcSliceH, d2, ds2);
+        return sws_scale_slice(c, s2, ss2, yint, srcSliceH, d2, ds2);
+    }
     if (p.planar) return sws_scale_planar_host(c, srcSlice, srcStride, srcSliceY, srcSliceH, dst, dstStride);
     if (p.src_rgb) {                                              // packed RGB -> packed RGB: whole frames, top-down
         if (srcSliceY != 0 || srcSliceH != p.srcH) { b200_set_error("packed RGB source: only whole-frame calls are implemented"); return B200_ENOSYS; }

@@ -19,7 +19,9 @@ namespace {
 constexpr int WARPS = 4;
 
 // [device-code unquant] (tests/cuda_emu runs this block on the CPU against the checker; comment markers only)
-struct UnquantDev {                       // passed by value (416 bytes of kernel parameters)
+struct UnquantDev {                       // passed by value as a __grid_constant__ parameter: the per-lane table look-ups index the constant bank
+                                          // directly (a plain by-value parameter is copied to local memory per thread when indexed at run time:
+                                          // the round-2 launch list showed this kernel at 1.1 G blocks/s because of it)
     uint16_t intra[64], inter[64];
     uint8_t scanpos[64];                  // scan index of each raster coefficient (inverse of ScanTable.permutated)
     uint8_t raster_end[64];
@@ -43,53 +45,63 @@ template <int V> __device__ __forceinline__ int dequant(int level, int q, int m)
 
 template <int V>
 __global__ void __launch_bounds__(32 * WARPS)
-mpv_unquant_kernel(const UnquantDev P, int16_t *blocks, long long nblocks, const uint8_t *blk_n, const uint8_t *qscale,
+mpv_unquant_kernel(const __grid_constant__ UnquantDev P, int16_t *blocks, long long nblocks, const uint8_t *blk_n, const uint8_t *qscale,
                    const int8_t *last_index)
 {
     constexpr bool H263 = V == B200_UNQUANT_H263_INTRA || V == B200_UNQUANT_H263_INTER;
     constexpr bool INTRA = V == B200_UNQUANT_MPEG1_INTRA || V == B200_UNQUANT_MPEG2_INTRA ||
                            V == B200_UNQUANT_MPEG2_INTRA_BITEXACT || V == B200_UNQUANT_H263_INTRA;
     constexpr bool MISMATCH = V == B200_UNQUANT_MPEG2_INTRA_BITEXACT || V == B200_UNQUANT_MPEG2_INTER;
-    const long long b = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5);
-    if (b >= nblocks) return;                                               // whole warps leave together
     const int lane = threadIdx.x & 31;
-    const int n = blk_n ? (int)__ldg(blk_n + b) : (int)(b % 6);
-    const int qs = __ldg(qscale + b), last = __ldg(last_index + b);
-    unsigned *wp = reinterpret_cast<unsigned *>(blocks + 64 * b) + lane;
-    const unsigned word = *wp;
-    int lv[2] = { (int)(int16_t)(word & 0xffffu), (int)(int16_t)(word >> 16) };
-    int parity = 0;
-    int q = qs, qadd = 0, ncoef = last;
-    if (H263) {
-        q = qs << 1;
-        qadd = (INTRA && P.aic) ? 0 : ((qs - 1) | 1);
-        ncoef = (INTRA && P.ac_pred) ? 63 : (last >= 0 ? (int)P.raster_end[last] : -1);
-    } else if (V >= B200_UNQUANT_MPEG2_INTRA) {
-        q = P.q_type ? (int)c_nonlinear_qscale[qs & 31] : qs << 1;
-    }
+    // a lane always owns coefficients 2 * lane and 2 * lane + 1: its matrix entries and scan positions are fetched once (32 different
+    // constant-bank addresses per warp instruction are served one after the other), then the warp walks over blocks
+    int mat[2], spos[2];
 #pragma unroll
     for (int k = 0; k < 2; k++) {
         const int j = 2 * lane + k;
-        int level = lv[k];
-        if (INTRA && j == 0 && !(H263 && P.aic)) {
-            level = (int)(int16_t)(level * (n < 4 ? P.y_dc : P.c_dc));
-            if (MISMATCH) parity ^= level & 1;
-        }
-        const int pos = H263 ? j : (int)P.scanpos[j];
-        if (pos >= (INTRA ? 1 : 0) && pos <= ncoef && level != 0) {
-            int v;
-            if (H263) v = level < 0 ? level * q - qadd : level * q + qadd;
-            else      v = dequant<V>(level, q, (int)(INTRA ? P.intra[j] : P.inter[j]));
-            if (MISMATCH) parity ^= v & 1;
-            level = (int)(int16_t)v;
-        }
-        lv[k] = level;
+        mat[k] = (int)(INTRA ? P.intra[j] : P.inter[j]);
+        spos[k] = H263 ? j : (int)P.scanpos[j];
     }
-    if (MISMATCH) {
-        const unsigned par = __reduce_xor_sync(0xffffffffu, (unsigned)parity);
-        if (lane == 31) lv[1] ^= (int)(1u ^ (par & 1u));                    // sum starts at -1: block[63] ^= sum & 1
+    const long long nwarps = (long long)gridDim.x * WARPS;
+    for (long long b = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5); b < nblocks; b += nwarps) {      // whole warps leave together
+        const int n = blk_n ? (int)__ldg(blk_n + b) : (int)(b % 6);
+        const int qs = __ldg(qscale + b), last = __ldg(last_index + b);
+        unsigned *wp = reinterpret_cast<unsigned *>(blocks + 64 * b) + lane;
+        const unsigned word = *wp;
+        int lv[2] = { (int)(int16_t)(word & 0xffffu), (int)(int16_t)(word >> 16) };
+        int parity = 0;
+        int q = qs, qadd = 0, ncoef = last;
+        if (H263) {
+            q = qs << 1;
+            qadd = (INTRA && P.aic) ? 0 : ((qs - 1) | 1);
+            ncoef = (INTRA && P.ac_pred) ? 63 : (last >= 0 ? (int)P.raster_end[last] : -1);
+        } else if (V >= B200_UNQUANT_MPEG2_INTRA) {
+            q = P.q_type ? (int)c_nonlinear_qscale[qs & 31] : qs << 1;
+        }
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const int j = 2 * lane + k;
+            int level = lv[k];
+            if (INTRA && j == 0 && !(H263 && P.aic)) {
+                level = (int)(int16_t)(level * (n < 4 ? P.y_dc : P.c_dc));
+                if (MISMATCH) parity ^= level & 1;
+            }
+            const int pos = spos[k];
+            if (pos >= (INTRA ? 1 : 0) && pos <= ncoef && level != 0) {
+                int v;
+                if (H263) v = level < 0 ? level * q - qadd : level * q + qadd;
+                else      v = dequant<V>(level, q, mat[k]);
+                if (MISMATCH) parity ^= v & 1;
+                level = (int)(int16_t)v;
+            }
+            lv[k] = level;
+        }
+        if (MISMATCH) {
+            const unsigned par = __reduce_xor_sync(0xffffffffu, (unsigned)parity);
+            if (lane == 31) lv[1] ^= (int)(1u ^ (par & 1u));                    // sum starts at -1: block[63] ^= sum & 1
+        }
+        *wp = ((unsigned)lv[0] & 0xffffu) | ((unsigned)lv[1] << 16);
     }
-    *wp = ((unsigned)lv[0] & 0xffffu) | ((unsigned)lv[1] << 16);
 }
 
 // [/device-code unquant]
@@ -116,8 +128,9 @@ B200_API int b200_mpv_unquantize_batch_device(B200Device *dev, int variant, cons
     }
     P.y_dc = p->y_dc_scale; P.c_dc = p->c_dc_scale; P.q_type = p->q_scale_type; P.aic = p->h263_aic; P.ac_pred = p->ac_pred;
     B200_CUDA_OK(cudaSetDevice(dev->ordinal));
-    const long long grid = (nblocks + WARPS - 1) / WARPS;
-    if (grid > 0x7fffffffLL) return B200_EINVAL;
+    long long grid = (nblocks + WARPS - 1) / WARPS;
+    const long long cap = (long long)(dev->sm_count > 0 ? dev->sm_count : 148) * 16 * 8;      // persistent warps: each walks nblocks / (grid * WARPS) blocks
+    if (grid > cap) grid = cap;
     dim3 g((unsigned)grid), t(32 * WARPS);
     cudaStream_t st = dev->stream;
     switch (variant) {

@@ -130,7 +130,8 @@ int  b200_sws_setColorspaceDetails(B200SwsContext *c, const int inv_table[4], in
 /* drop-in for sws_scale(): HOST pointers, strides in bytes (negative allowed), returns output lines.
  * Top-down slice sequences are supported (bands uploaded into a device copy of the picture, lines emitted as soon as
  * their vertical taps are complete, same return values as the reference) from planar / semi-planar sources, into packed RGB and
- * into yuv420p / nv12 / nv21 destinations; bottom-up slice order, and slice calls with a packed RGB source, return B200_ENOSYS
+ * into yuv420p / nv12 / nv21 destinations; a sequence whose first band touches the last line runs bottom-up (the picture is flipped internally like
+ * scale_internal, swscale.c:1096-1159; even heights); slice calls with a packed RGB source return B200_ENOSYS
  * (whole-frame calls only there). */
 int  b200_sws_scale(B200SwsContext *c, const uint8_t *const srcSlice[], const int srcStride[],
                     int srcSliceY, int srcSliceH, uint8_t *const dst[], const int dstStride[]);
@@ -303,8 +304,8 @@ int  b200_mpv_unquantize_batch_device(B200Device *dev, int variant, const B200Mp
  * kernel: inverse quantisation (variant, p, qscale[], last_index[] per block as in b200_mpv_unquantize_batch_device, block number
  * inside the macroblock = position in the stream % 6) straight into the simple IDCT put / add of b200_idct_mb420_device — the
  * dequantised coefficients stay in registers.  kind = B200_IDCT_ADD skips blocks whose last_index is < 0, like add_dequant_dct.
- * `blocks` is not modified.  Planes as for b200_idct_mb420_device, 16-byte (luma) / 8-byte (chroma) aligned.  Synchronous on
- * the device's stream (the parameter block lives in the device's scratch). */
+ * `blocks` is not modified.  Planes as for b200_idct_mb420_device, 16-byte (luma) / 8-byte (chroma) aligned.  Asynchronous on
+ * the device's stream. */
 int  b200_mpv_unquant_idct_mb420_device(B200Device *dev, int variant, const B200MpvUnquant *p, int kind, const int16_t *blocks,
                                         const uint8_t *qscale, const int8_t *last_index, int mb_w, int mb_h, int nframes,
                                         uint8_t *const planes[3], const int linesize[3], const int64_t frame_stride[3]);

@@ -1,4 +1,3 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q > gpurun_out/tests_gpu.log 2>&1; echo "tests rc=$?"; tail -3 gpurun_out/tests_gpu.log
-timeout 600 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench rc=$?"; tail -2 gpurun_out/bench_n1.err
+timeout 900 python -m pytest tests -m gpu -q -k "round2 or fused or mecmp or satd or unquant" > gpurun_out/t_new.log 2>&1; echo "tests rc=$?"; tail -5 gpurun_out/t_new.log

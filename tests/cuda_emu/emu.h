@@ -33,6 +33,7 @@ static thread_local dim3 threadIdx, blockIdx, blockDim, gridDim;
 #define __launch_bounds__(...)
 #define __constant__ static const
 #define __restrict__
+#define __grid_constant__
 
 template <typename T> static inline T __ldg(const T *p) { return *p; }
 using std::min;

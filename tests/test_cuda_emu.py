@@ -1030,3 +1030,51 @@ def test_sws_tensor_core_scaler_on_the_emulated_device(emusws, case):
             L.b200_sws_freeContext(ctx)
             for i in range(n):
                 assert np.array_equal(D[i], cl.orc_sws(w, h, dw, dh, fl, *frames[i], fmt=fmt)), (case, fmt, i)
+
+
+def test_sws_bottom_up_slice_sequences(emusws):
+    """sws_scale() fed bottom-up (the band touching the last line first — what the reference flips internally, swscale.c:1096-1159):
+    per-call return values and the final picture equal the compiled reference's, planar and packed destinations, scaled and LUT paths."""
+    if not cl.have_ref():
+        pytest.skip("oracle/_ref/libffref.so not built")
+    import random
+    L, R = emusws, cl.ref()
+    R.ffref_sws_scale_planar.argtypes = [C.c_void_p] + [C.c_void_p, C.c_int] * 3 + [C.c_int, C.c_int] + [C.c_void_p, C.c_int] * 3
+    R.ffref_sws_scale.argtypes = [C.c_void_p] + [C.c_void_p, C.c_int] * 3 + [C.c_int, C.c_int, C.c_void_p, C.c_int]
+    rnd = random.Random(91)
+    for it in range(36):
+        w, h = rnd.choice([16, 34, 64, 100]), rnd.choice([8, 16, 34, 48, 66])
+        dw, dh = (w, h) if it % 3 == 0 else (rnd.choice([8, 18, 32, 64, 100]), rnd.choice([8, 18, 32, 64]))
+        if h > 2 * dh:
+            dh = (h // 2 + 2) & ~1
+        fl = rnd.choice([cl.SWS_BICUBIC, cl.SWS_BILINEAR, FATE])
+        df = rnd.choice([0, cl.PIX_FMT_NV12, cl.PIX_FMT_RGB24, cl.PIX_FMT_BGRA])
+        planar = df in (0, cl.PIX_FMT_NV12)
+        y, u, v = cl.yuv_frame(w, h, 9100 + it, "random")
+        cuts = sorted(set([0, h] + [2 * rnd.randrange(1, h // 2) for _ in range(rnd.randrange(1, 4))]))
+        bands = [(a, b - a) for a, b in zip(cuts[:-1], cuts[1:])][::-1]                 # last band first
+        cw, ch = (dw + 1) // 2, (dh + 1) // 2
+        bpp = 1 if planar else cl.fmt_bpp(df)
+        mk = lambda: ([np.full((dh, dw), 0xA5, np.uint8), np.full((ch, 2 * cw if df else cw), 0xA5, np.uint8), np.full((ch, cw), 0xA5, np.uint8)]
+                      if planar else [np.full((dh, dw * bpp), 0xA5, np.uint8)])
+        rp, gp = mk(), mk()
+        rc = R.ffref_sws_open_range(0, w, h, 0, df, dw, dh, 0, fl, 1)
+        ctx = _emu_ctx(L, w, h, 0, dw, dh, df, fl)
+        assert rc and ctx
+        rr, gr = [], []
+        for (sy, sh) in bands:
+            if planar:
+                rr.append(R.ffref_sws_scale_planar(rc, y[sy:].ctypes.data, y.strides[0], u[sy // 2:].ctypes.data, u.strides[0], v[sy // 2:].ctypes.data, v.strides[0],
+                                                   sy, sh, rp[0].ctypes.data, rp[0].strides[0], rp[1].ctypes.data, rp[1].strides[0], rp[2].ctypes.data, rp[2].strides[0]))
+            else:
+                rr.append(R.ffref_sws_scale(rc, y[sy:].ctypes.data, y.strides[0], u[sy // 2:].ctypes.data, u.strides[0], v[sy // 2:].ctypes.data, v.strides[0],
+                                            sy, sh, rp[0].ctypes.data, rp[0].strides[0]))
+            dpl = [a.ctypes.data for a in gp] + [None] * (4 - len(gp))
+            dst = [a.strides[0] for a in gp] + [0] * (4 - len(gp))
+            gr.append(L.b200_sws_scale(ctx, (C.c_void_p * 4)(y[sy:].ctypes.data, u[sy // 2:].ctypes.data, v[sy // 2:].ctypes.data, None),
+                                       (C.c_int32 * 4)(y.strides[0], u.strides[0], v.strides[0], 0), sy, sh, (C.c_void_p * 4)(*dpl), (C.c_int32 * 4)(*dst)))
+        R.ffref_sws_close(rc)
+        L.b200_sws_freeContext(ctx)
+        assert gr == rr, (it, w, h, dw, dh, hex(fl), df, bands, gr, rr)
+        n = 2 if df == cl.PIX_FMT_NV12 else len(gp)
+        assert all(np.array_equal(a, b) for a, b in zip(gp[:n], rp[:n])), (it, w, h, dw, dh, hex(fl), df, bands)

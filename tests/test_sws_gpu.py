@@ -407,3 +407,27 @@ def test_fate_filter_pixfmts_md5(device):
     except Exception as e:                                                # checker tools, not the product: skip, never fail
         pytest.skip(f"oracle/_ref tools not usable on this box: {e}")
     fg.check_all(functools.partial(gpu_sws, device), functools.partial(gpu_sws_planar, device), rgb_sources=False, nv_dest=False)
+
+
+@pytest.mark.parametrize("fmt", [cl.PIX_FMT_RGB24, 0])
+def test_bottom_up_slice_order(device, fmt):
+    """A slice sequence that starts with the band touching the last line runs bottom-up: the reference flips the picture internally
+    (swscale.c:1096-1159), i.e. the result is flip(convert(flip(source))); per-call return values add up to the picture height."""
+    from ffmpeg_b200 import swscale as sw
+    w, h, dw, dh = 128, 96, 96, 64
+    y, u, v = cl.yuv_frame(w, h, 321, "random")
+    fy, fu, fv = (np.ascontiguousarray(a[::-1]) for a in (y, u, v))
+    ctx = sw.sws_getContext(device, w, h, 0, dw, dh, fmt, FATE)
+    if fmt == 0:
+        exp = [np.ascontiguousarray(a[::-1]) for a in cl.orc_sws_planar(w, h, dw, dh, FATE, fy, fu, fv)]
+        out = [np.zeros((dh, dw), np.uint8), np.zeros((dh // 2, dw // 2), np.uint8), np.zeros((dh // 2, dw // 2), np.uint8)]
+    else:
+        exp = [np.ascontiguousarray(cl.orc_sws(w, h, dw, dh, FATE, fy, fu, fv)[::-1])]
+        out = [np.zeros((dh, dw * 3), np.uint8)]
+    total = 0
+    for sy, sh in ((64, 32), (32, 32), (8, 24), (0, 8)):
+        total += ctx.scale([y[sy:], u[sy // 2:], v[sy // 2:]], [w, w // 2, w // 2], sy, sh, out, [o.strides[0] for o in out])
+    ctx.free()
+    assert total == dh
+    for a, b in zip(out, exp):
+        assert np.array_equal(a, b), int((a != b).sum())
