@@ -2122,13 +2122,14 @@ static int sws_scale_planar_host(B200SwsContext *c, const uint8_t *const srcSlic
 {
     const SwsPlan &p = c->plan;
     const bool whole = srcSliceY == 0 && srcSliceH == p.srcH && !c->slice_open;
-    if (!whole && (p.src_rgb || p.bgr24_yv12)) {
-        b200_set_error("packed RGB source: only whole-frame calls are implemented");
+    const int macro = p.src_rgb ? 1 : 2;                         // macro_height_src: 1 for packed RGB, 2 for 4:2:0 sources (swscale.c:1063-1071)
+    if (!whole && p.bgr24_yv12 && ((srcSliceY | srcSliceH) & 1)) {
+        b200_set_error("bgr24 -> yuv420p converter: slices must cover whole line pairs");      // ff_rgb24toyv12 works on line pairs of the band it is given
         return B200_ENOSYS;
     }
     if (!whole) {
-        // parameter checks of scale_internal (macro_height_src = 2 for yuv420p), as in the packed-RGB slice path below
-        if ((srcSliceY & 1) || ((srcSliceH & 1) && srcSliceY + srcSliceH != p.srcH) || srcSliceY + srcSliceH > p.srcH || srcSliceY < 0 || srcSliceH < 0) {
+        // parameter checks of scale_internal, as in the packed-RGB slice path below
+        if ((srcSliceY & (macro - 1)) || ((srcSliceH & (macro - 1)) && srcSliceY + srcSliceH != p.srcH) || srcSliceY + srcSliceH > p.srcH || srcSliceY < 0 || srcSliceH < 0) {
             b200_set_error("Slice parameters %d, %d are invalid", srcSliceY, srcSliceH);
             return B200_EINVAL;
         }
@@ -2171,11 +2172,12 @@ static int sws_scale_planar_host(B200SwsContext *c, const uint8_t *const srcSlic
             sp[i] = sb + soff[i]; dp[i] = sb + doff[i]; ss[i] = (long long)spitch[i]; ds[i] = (long long)dpitch[i];
         }
         int y0, y1;
-        if (p.planar_copy) {                                   // the copy wrappers handle exactly the band they are given
+        if (p.planar_copy || p.bgr24_yv12) {                   // the unscaled wrappers handle exactly the band they are given
             y0 = srcSliceY; y1 = srcSliceY + srcSliceH;
         } else {
             y0 = c->next_dst_y;
-            const int avail_l = srcSliceY + srcSliceH, avail_c = -((-(srcSliceY + srcSliceH)) >> 1);
+            // chroma lines of the source that have arrived: one per luma line for packed RGB sources (chrSrcVSubSample = 0, utils.c:1366-1396)
+            const int avail_l = srcSliceY + srcSliceH, avail_c = p.src_rgb ? avail_l : -((-(srcSliceY + srcSliceH)) >> 1);
             for (y1 = y0; y1 < p.dstH; y1++) {
                 // luma availability is tested for the last luma line of the chroma line's pair: firstLumSrcY2 (swscale.c:419-421)
                 const int firstLum = std::max(1 - p.vLum.size, p.vLum.pos[std::min(y1 | 1, p.dstH - 1)]);
@@ -2394,8 +2396,39 @@ B200_API int b200_sws_scale(B200SwsContext *c, const uint8_t *const srcSlice[], 
         return sws_scale_slice(c, s2, ss2, yint, srcSliceH, d2, ds2);
     }
     if (p.planar) return sws_scale_planar_host(c, srcSlice, srcStride, srcSliceY, srcSliceH, dst, dstStride);
-    if (p.src_rgb) {                                              // packed RGB -> packed RGB: whole frames, top-down
-        if (srcSliceY != 0 || srcSliceH != p.srcH) { b200_set_error("packed RGB source: only whole-frame calls are implemented"); return B200_ENOSYS; }
+    if (p.src_rgb && (srcSliceY != 0 || srcSliceH != p.srcH || c->slice_open)) {
+        // packed RGB -> packed RGB, top-down slice sequence: bands accumulate in a device copy of the source, the picture is converted again
+        // after each band and the lines whose vertical taps are complete (ff_swscale's "enough lines", swscale.c:463-465) are copied back
+        if (srcSliceY + srcSliceH > p.srcH || srcSliceY < 0 || srcSliceH < 0) { b200_set_error("Slice parameters %d, %d are invalid", srcSliceY, srcSliceH); return B200_EINVAL; }
+        if (srcSliceH == 0) return 0;
+        if (!c->slice_open && srcSliceY != 0) { b200_set_error("Slices start in the middle!"); return B200_EINVAL; }
+        if (!srcSlice[0] || !dst[0]) return B200_EINVAL;
+        B200Device *dv = c->dev;
+        B200_CUDA_OK(cudaSetDevice(dv->ordinal));
+        const size_t sPitch = ((size_t)p.srcW * p.src_rgb + 255) & ~(size_t)255, dPitch = ((size_t)p.dstW * p.out.bpp + 255) & ~(size_t)255;
+        if (!c->slice_buf) B200_CUDA_OK(cudaMalloc(&c->slice_buf, sPitch * p.srcH + dPitch * p.dstH));
+        uint8_t *sb = (uint8_t *)c->slice_buf, *db = sb + sPitch * p.srcH;
+        cudaStream_t st2 = dv->stream;
+        if (srcSliceY == 0) { c->next_dst_y = 0; c->slice_open = true; }
+        B200_CUDA_OK(b200_h2d_rows(sb + (size_t)srcSliceY * sPitch, sPitch, srcSlice[0], srcStride[0], (size_t)p.srcW * p.src_rgb, srcSliceH, st2));
+        const int y0 = c->next_dst_y, avail = srcSliceY + srcSliceH;
+        int y1;
+        for (y1 = y0; y1 < p.dstH; y1++) {
+            const int firstLum = std::max(1 - p.vLum.size, p.vLum.pos[y1]), firstChr = std::max(1 - p.vChr.size, p.vChr.pos[y1]);
+            const int lastLum = std::min(p.srcH, firstLum + p.vLum.size) - 1, lastChr = std::min(p.chrSrcH, firstChr + p.vChr.size) - 1;
+            if (!(lastLum < avail && lastChr < avail)) break;
+        }
+        c->next_dst_y = y1;
+        if (y1 > y0) {
+            const int r2 = launch_rgbsrc_packed(c, st2, sb, (long long)sPitch, 0, db, (long long)dPitch, 0, 1);
+            if (r2 < 0) return r2;
+            B200_CUDA_OK(b200_d2h_rows(dst[0] + (long long)y0 * dstStride[0], dstStride[0], db + (size_t)y0 * dPitch, dPitch, (size_t)p.dstW * p.out.bpp, y1 - y0, st2));
+        }
+        B200_CUDA_OK(cudaStreamSynchronize(st2));
+        if (avail == p.srcH) c->slice_open = false;
+        return y1 - y0;
+    }
+    if (p.src_rgb) {                                              // packed RGB -> packed RGB: a whole frame
         if (!srcSlice[0] || !dst[0]) return B200_EINVAL;
         if (srcStride[0] < 0 || dstStride[0] < 0) return B200_ENOSYS;
         B200Device *dv = c->dev;

@@ -129,10 +129,9 @@ int  b200_sws_setColorspaceDetails(B200SwsContext *c, const int inv_table[4], in
                                    const int table[4], int dstRange, int brightness, int contrast, int saturation);
 /* drop-in for sws_scale(): HOST pointers, strides in bytes (negative allowed), returns output lines.
  * Top-down slice sequences are supported (bands uploaded into a device copy of the picture, lines emitted as soon as
- * their vertical taps are complete, same return values as the reference) from planar / semi-planar sources, into packed RGB and
+ * their vertical taps are complete, same return values as the reference) from planar / semi-planar and packed RGB sources, into packed RGB and
  * into yuv420p / nv12 / nv21 destinations; a sequence whose first band touches the last line runs bottom-up (the picture is flipped internally like
- * scale_internal, swscale.c:1096-1159; even heights); slice calls with a packed RGB source return B200_ENOSYS
- * (whole-frame calls only there). */
+ * scale_internal, swscale.c:1096-1159; even heights, yuv sources). */
 int  b200_sws_scale(B200SwsContext *c, const uint8_t *const srcSlice[], const int srcStride[],
                     int srcSliceY, int srcSliceH, uint8_t *const dst[], const int dstStride[]);
 /* SwsFunc-shaped entry (first argument is the context): what a maintainer installs as convert_unscaled */
