@@ -221,13 +221,17 @@ tx_r16_kernel(const uint32_t *__restrict__ plan, const float2 *__restrict__ exp_
     uint64_t *mbar = reinterpret_cast<uint64_t *>(expS + (MODE == 1 ? N : 0));             // [GROUPS][2]
 
     const int g = threadIdx.x / G, tg = threadIdx.x % G, lane = threadIdx.x & 31;
-    // loop-invariant per-thread state
+    // loop-invariant per-thread state.  Leaf chunk of this thread: the 16 lanes of a half-warp take chunks whose low four bits AND
+    // whose top four bits are all different -- the permuted source samples of chunk c sit at (roughly bit-reversed c) + k N/16, so the
+    // top bits of c pick the bank of the reads while the low bits pick the bank of the 17-strided writes; consecutive chunks per warp
+    // made the reads an 8-way (N = 2048) / 4-way (N = 1024) bank conflict
+    const int lt = G > 16 ? (tg & 15) + 16 * (((tg & 15) ^ (tg >> 4)) & (G / 16 - 1)) : tg;
     uint32_t off[8];
 #pragma unroll
-    for (int k = 0; k < 8; k++) off[k] = plan[(size_t)k * G + tg];
-    const bool leaf_full = plan[(size_t)8 * G + tg] != 0;
-    const float c8 = __uint_as_float(plan[(size_t)9 * G + tg]), c1 = __uint_as_float(plan[(size_t)10 * G + tg]),
-                c2 = __uint_as_float(plan[(size_t)11 * G + tg]), c3 = __uint_as_float(plan[(size_t)12 * G + tg]);
+    for (int k = 0; k < 8; k++) off[k] = plan[(size_t)k * G + lt];
+    const bool leaf_full = plan[(size_t)8 * G + lt] != 0;
+    const float c8 = __uint_as_float(plan[(size_t)9 * G + lt]), c1 = __uint_as_float(plan[(size_t)10 * G + lt]),
+                c2 = __uint_as_float(plan[(size_t)11 * G + lt]), c3 = __uint_as_float(plan[(size_t)12 * G + lt]);
     PassRegs<NL1> r1; r1.load(plan, W1, G, tg);
     PassRegs<NL2> r2; r2.load(plan, W2, G, tg);
     PassRegs<NL3 ? NL3 : 2> r3;
@@ -271,7 +275,7 @@ tx_r16_kernel(const uint32_t *__restrict__ plan, const float2 *__restrict__ exp_
         group_sync<G>(g);                              // everybody has its samples: the buffer can now hold z
         leaf16(v, leaf_full, c8, c1, c2, c3);
 #pragma unroll
-        for (int i = 0; i < 16; i++) buf[17 * tg + i] = v[i];
+        for (int i = 0; i < 16; i++) buf[17 * lt + i] = v[i];
         group_sync<G>(g);
         // ---- passes over levels 5 and up
         char *dstb = out + t * out_step;

@@ -82,6 +82,18 @@ with torch.cuda.stream(stream):
         for _ in range(3):
             c.batch_device(y, x, 4, cnt, 4 * n, 4 * n)
         dev.sync(); c.uninit()
+    if what in ("tx2048",):
+        from ffmpeg_b200 import tx
+        n, cnt = 2048, 1 << 15
+        x = torch.rand((cnt, 2 * n), device="cuda"); y = torch.empty_like(x)
+        c = tx.av_tx_init(0, 0, n, device=dev)
+        for _ in range(3):
+            c.batch_device(y, x, 8, cnt, 8 * n, 8 * n)
+        dev.sync(); c.uninit()
+        c = tx.av_tx_init(1, 1, n, scale=1.0 / n, device=dev)
+        for _ in range(3):
+            c.batch_device(y, x, 4, cnt, 4 * n, 4 * n)
+        dev.sync(); c.uninit()
     if what in ("qpel", "all"):
         from ffmpeg_b200 import pel
         nfr, Wd, Hd, ap = max(16, nf), 1920, 1088, 32
