@@ -672,7 +672,7 @@ static void tx_host_fn(B200TXContext *c, void *out, void *in, ptrdiff_t stride)
     const size_t n = c->d.n, len = c->len;
     size_t in_elems, out_elems;            // floats
     if (c->dct) { in_elems = out_elems = (size_t)tx_dct_points(c->dct); }     // DCT-II: len in / len out; DCT-III: 2*len in / 2*len out
-    else if (c->type == 0) { in_elems = out_elems = 2 * n; }
+    else if (c->type == 0) { in_elems = out_elems = 2 * (c->pfa ? len : n); }
     else if (c->type == 6) { in_elems = c->inv ? len + 2 : len; out_elems = c->inv ? len : len + 2; }
     else if (c->inv) { in_elems = len; out_elems = c->full ? 2 * len : len; }
     else { in_elems = 2 * len; out_elems = len; }
@@ -685,13 +685,15 @@ static void tx_host_fn(B200TXContext *c, void *out, void *in, ptrdiff_t stride)
     cudaError_t e;
     const bool strided_in = c->type == 1 && c->inv && stride != 4;
     const bool strided_out = c->type == 1 && !c->inv && stride != 4;
+    const bool strided_cpx = c->type == 0 && c->pfa && stride != 8;  // ff_tx_fft_pfa stores out[i * stride] (tx_template.c:1078-1079)
     if (strided_in) e = cudaMemcpy2DAsync(din, 4, in, (size_t)stride, 4, in_elems, cudaMemcpyHostToDevice, st);
     else e = cudaMemcpyAsync(din, in, in_elems * 4, cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) fail("h2d");
     const bool clobbers = c->type == 6 && c->inv;                    // ff_tx_rdft_c2r rewrites its input (tx_template.c:1670-1696)
-    if (tx_launch(c, st, dout, din, 4, 1, 0, 0, clobbers ? din : nullptr) < 0) fail("launch");
+    if (tx_launch(c, st, dout, din, c->type == 0 ? 8 : 4, 1, 0, 0, clobbers ? din : nullptr) < 0) fail("launch");
     if (clobbers && cudaMemcpyAsync(in, din, (in_elems - 2) * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) fail("d2h input");
     if (strided_out) e = cudaMemcpy2DAsync(out, (size_t)stride, dout, 4, 4, out_elems, cudaMemcpyDeviceToHost, st);
+    else if (strided_cpx) e = cudaMemcpy2DAsync(out, (size_t)stride, dout, 8, 8, out_elems / 2, cudaMemcpyDeviceToHost, st);
     else e = cudaMemcpyAsync(out, dout, out_elems * 4, cudaMemcpyDeviceToHost, st);
     if (e != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) fail("d2h");
 }
@@ -707,7 +709,7 @@ B200_API int b200_tx_init_device(B200Device *dev, B200TXContext **ctx, b200_tx_f
     if (flags & ~(uint64_t)(B200_TX_INPLACE | B200_TX_UNALIGNED | B200_TX_FULL_IMDCT)) return B200_ENOSYS;    // REAL_TO_* not implemented
     // AV_TX_INPLACE: the complex FFT kernels stage a whole transform in shared memory before they store, so out == in is always
     // fine for them and gives the bits of the out-of-place call (as ff_tx_fft_inplace does, tx_template.c:780-812); other types refuse
-    if ((flags & B200_TX_INPLACE) && !(type == B200_TX_FLOAT_FFT && len >= 2 && !(len & (len - 1)))) return B200_ENOSYS;
+    if ((flags & B200_TX_INPLACE) && !(type == B200_TX_FLOAT_FFT && len >= 2 && (!(len & (len - 1)) || tx_pfa_fft_length_ok(len)))) return B200_ENOSYS;
     const bool full = (flags & B200_TX_FULL_IMDCT) != 0;
     if (full && !(type == B200_TX_FLOAT_MDCT && inv)) return B200_ENOSYS;      // only the inverse MDCT has such a codelet (tx.c:762-771)
     if (type == B200_TX_INT32_FFT || type == B200_TX_INT32_MDCT) {   // 32-bit fixed point (tx_int32.cu)
@@ -738,6 +740,17 @@ B200_API int b200_tx_init_device(B200Device *dev, B200TXContext **ctx, b200_tx_f
         if (tx) *tx = tx_host_fn;
         return 0;
     }
+    if (type == B200_TX_FLOAT_FFT && tx_pfa_fft_length_ok(len)) {    // N x 2^k complex FFT: fft_pfa over fftN_ns (N = 15, 9, 7, 5, 3) and the split-radix transform
+        B200TXContext *cp = new (std::nothrow) B200TXContext();
+        if (!cp) return B200_ENOMEM;
+        cp->dev = dev; cp->type = type; cp->inv = !!inv; cp->len = len; cp->full = false;
+        if (cudaSetDevice(dev->ordinal) != cudaSuccess) { delete cp; return B200_EEXTERNAL; }
+        cp->pfa = tx_pfa_create_fft(cp->inv, len);
+        if (!cp->pfa) { delete cp; return B200_EEXTERNAL; }
+        *ctx = cp;
+        if (tx) *tx = tx_host_fn;
+        return 0;
+    }
     if (type == B200_TX_FLOAT_MDCT && tx_pfa_length_ok(len)) {       // 15 x 2^k: the compound MDCT av_tx_init() picks (Opus CELT sizes)
         float scp = 1.0f;
         if (scale) scp = *(const float *)scale;
@@ -751,7 +764,7 @@ B200_API int b200_tx_init_device(B200Device *dev, B200TXContext **ctx, b200_tx_f
         if (tx) *tx = tx_host_fn;
         return 0;
     }
-    if (len < 2 || (len & (len - 1))) return B200_ENOSYS;            // other PFA lengths (3/5/7/9 x 2^n) are not implemented
+    if (len < 2 || (len & (len - 1))) return B200_ENOSYS;            // nested / naive decompositions (45 x 2^n, 25 x n, primes > 7 ...) are not implemented
     if (type == B200_TX_FLOAT_RDFT && len < 4) return B200_ENOSYS;   // ff_tx_rdft_*_def: min_len 4
     if (type == B200_TX_FLOAT_MDCT && len < 4) return B200_ENOSYS;   // len 2: the reference falls back to its naive MDCT (no 1-point FFT)
     const int n = type == 0 ? len : len >> 1;
@@ -796,7 +809,7 @@ B200_API int b200_tx_batch_device(B200TXContext *c, void *out, const void *in, p
     if ((c->type == 1 || c->type == B200_TX_INT32_MDCT) && (stride & 3)) return B200_EINVAL;
     if (c->full && stride != 4) return B200_EINVAL;                  // the reference mirrors with the input stride: only sizeof(float) is meaningful
     B200_CUDA_OK(cudaSetDevice(c->dev->ordinal));
-    return tx_launch(c, c->dev->stream, out, in, (c->type == 1 || c->type == B200_TX_INT32_MDCT) ? stride : 8, count, out_step, in_step);
+    return tx_launch(c, c->dev->stream, out, in, (c->type == 1 || c->type == B200_TX_INT32_MDCT || (c->type == 0 && c->pfa)) ? stride : 8, count, out_step, in_step);
 }
 
 // HOST buffers (pinned for real overlap): the batch is cut into chunks that rotate over the device's three pipeline streams, each chunk
@@ -810,7 +823,7 @@ B200_API int b200_tx_batch_host(B200TXContext *c, void *out, const void *in, ptr
     if (count == 0) return 0;
     B200Device *d = c->dev;
     B200_CUDA_OK(cudaSetDevice(d->ordinal));
-    const ptrdiff_t st_arg = (c->type == 1 || c->type == B200_TX_INT32_MDCT) ? stride : 8;
+    const ptrdiff_t st_arg = (c->type == 1 || c->type == B200_TX_INT32_MDCT || (c->type == 0 && c->pfa)) ? stride : 8;
     const size_t istep = ((size_t)in_step + 15) & ~(size_t)15, ostep = ((size_t)out_step + 15) & ~(size_t)15;
     if (istep != (size_t)in_step || ostep != (size_t)out_step) { b200_set_error("b200_tx_batch_host: steps must be multiples of 16 bytes"); return B200_EINVAL; }
     int64_t chunk = ((int64_t)48 << 20) / (int64_t)(istep + ostep);

@@ -306,6 +306,35 @@ tx_mdct_pfa_fwd_kernel(const PfaDev P, float *out, const float *in, long long st
         __syncthreads();
     }
 }
+// ff_tx_fft_pfa (tx_template.c:1059-1080) for fftN_ns x 2^k: what av_tx_init(AV_TX_FLOAT_FFT, len = N * 2^k) resolves to (checkasm
+// lengths 120 / 960 / 1920, tests/checkasm/av_tx.c:38-40).  One CTA per transform: the gathered N-point transforms (one per
+// thread), the N power-of-two transforms cooperatively, the CRT-ordered output.  in: len complex; out: len complex with a stride
+// (in complex).  Everything is read before anything is stored: out == in is fine.
+__global__ void __launch_bounds__(PFA_THREADS)
+tx_fft_pfa_kernel(const PfaDev P, float2 *out, const float2 *in, long long stride, long long out_step, long long in_step, long long count)
+{
+    extern __shared__ float2 pfa_z[];
+    const int m = P.m, N = P.nfac, l = P.len;
+    for (long long tr = blockIdx.x; tr < count; tr += gridDim.x) {
+        float2 *dst = reinterpret_cast<float2 *>(reinterpret_cast<char *>(out) + tr * out_step);
+        const float2 *src = reinterpret_cast<const float2 *>(reinterpret_cast<const char *>(in) + tr * in_step);
+        for (int b = threadIdx.x; b < m; b += blockDim.x) {
+            const int *in_map = P.in_map + b * N;
+            float2 f15[15];
+#pragma unroll
+            for (int j = 0; j < 15; j++)
+                if (j < N) f15[j] = src[in_map[j]];
+            fftN(N, P.tab53, pfa_z + PADI(P.sub_map[b]), f15, P.ms);
+        }
+        __syncthreads();
+        pfa_sub_ffts(P, pfa_z);
+        for (int i = threadIdx.x; i < l; i += blockDim.x) {
+            const int s = P.out_map[i];
+            dst[i * stride] = pfa_z[(s >> P.log2m) * P.ms + PADI(s & (m - 1))];
+        }
+        __syncthreads();
+    }
+}
 // [/device-code tx_pfa]
 
 int sr_perm(int i, int len, int inv)                               // split_radix_permutation, libavutil/tx.c:125-134
@@ -327,6 +356,7 @@ int mulinv(int n, int m)                                           // libavutil/
 
 struct TxPfa {
     int inv = 0, len = 0, m = 0;
+    bool fft = false;                  // compound complex FFT instead of the compound MDCT
     PfaDev d{};
     void *blob = nullptr;
     size_t smem = 0;
@@ -368,10 +398,21 @@ static int pfa_factor(int len)
     return 0;
 }
 bool tx_pfa_length_ok(int len) { return pfa_factor(len) != 0; }
-
-static void pfa_host_tables(PfaHost &H, int inv, int len, float scale)
+// compound complex FFT: odd part 15, 9, 7, 5 or 3 times a power of two 2 ... 512 (the tree fft_pfa -> fftN_ns + fft2^k_ns the reference builds)
+static int pfa_fft_factor(int len)
 {
-    const int n = pfa_factor(len), l2 = len >> 1, m = l2 / n;
+    if (len < 6) return 0;
+    int m = 1;
+    while (!(len & m)) m <<= 1;
+    const int n = len / m;
+    if (m < 2 || m > 512) return 0;
+    return (n == 3 || n == 5 || n == 7 || n == 9 || n == 15) ? n : 0;
+}
+bool tx_pfa_fft_length_ok(int len) { return pfa_fft_factor(len) != 0; }
+
+static void pfa_host_tables(PfaHost &H, int inv, int len, float scale, bool fft = false)
+{
+    const int n = fft ? pfa_fft_factor(len) : pfa_factor(len), l2 = fft ? len : len >> 1, m = l2 / n;
     H.nfac = n;
     H.m = m; H.log2m = 0;
     while ((1 << H.log2m) < m) H.log2m++;
@@ -391,30 +432,54 @@ static void pfa_host_tables(PfaHost &H, int inv, int len, float scale)
             H.in_map[j * n + i] = (i * m + j * n) % l2;
             H.out_map[(i * m * m_inv + j * n * n_inv) % l2] = i * m + j;
         }
-    if (inv)
-        for (int i = 0; i < m; i++) {
-            int *in = &H.in_map[i * n + 1];
-            for (int j = 0; j < ((n - 1) >> 1); j++) std::swap(in[j], in[n - j - 2]);
+    if (fft) {
+        // ff_tx_fft_pfa_init (tx_template.c:948-1057): the compound map is generated for the forward direction; the direction comes
+        // from the map of the first sub-transform (ff_tx_fft_factor_init :478-494: 3 x 5 map for 15 points, ff_tx_gen_pfa_input_map
+        // tx.c:44-71, else ff_tx_gen_default_map tx.c:525-542; the inverse reverses all but the DC), flattened into it (:1040-1046)
+        int sub[15];
+        if (n == 15) {
+            for (int b = 0; b < 5; b++)
+                for (int a = 0; a < 3; a++) {
+                    if (inv) sub[(b * 3 + a * 5) % 15] = b * 3 + a;
+                    else     sub[b * 3 + a] = (b * 3 + a * 5) % 15;
+                }
+            if (inv) for (int w = 1; w <= 7; w++) std::swap(sub[w], sub[15 - w]);
+        } else {
+            sub[0] = 0;
+            for (int i = 1; i < n; i++) sub[i] = inv ? n - i : i;
         }
-    for (int k = 0; n == 15 && k < l2; k += 15) {                   // TX_EMBED_INPUT_PFA_MAP(map, len, 3, 5): the 15-point transform is 3 x 5
-        int mt[15];
-        memcpy(mt, &H.in_map[k], sizeof(mt));
-        for (int b = 0; b < 5; b++) for (int a = 0; a < 3; a++) H.in_map[k + b * 3 + a] = mt[(b * 3 + a * 5) % 15];
+        for (int k = 0; k < l2; k += n) {
+            int mt[15];
+            memcpy(mt, &H.in_map[k], sizeof(int) * n);
+            for (int i = 0; i < n; i++) H.in_map[k + i] = mt[sub[i]];
+        }
+        H.exp.clear();
+    } else {
+        if (inv)
+            for (int i = 0; i < m; i++) {
+                int *in = &H.in_map[i * n + 1];
+                for (int j = 0; j < ((n - 1) >> 1); j++) std::swap(in[j], in[n - j - 2]);
+            }
+        for (int k = 0; n == 15 && k < l2; k += 15) {                   // TX_EMBED_INPUT_PFA_MAP(map, len, 3, 5): the 15-point transform is 3 x 5
+            int mt[15];
+            memcpy(mt, &H.in_map[k], sizeof(mt));
+            for (int b = 0; b < 5; b++) for (int a = 0; a < 3; a++) H.in_map[k + b * 3 + a] = mt[(b * 3 + a * 5) % 15];
+        }
+        const double theta = (scale < 0 ? l2 : 0) + 1.0 / 8.0, sc = sqrt(fabs((double)scale));      // ff_tx_mdct_gen_exp
+        std::vector<float> full(2 * (size_t)l2);
+        for (int i = 0; i < l2; i++) {
+            const double alpha = M_PI_2 * (i + theta) / l2;
+            full[2 * i] = (float)(cos(alpha) * sc);
+            full[2 * i + 1] = (float)(sin(alpha) * sc);
+        }
+        if (inv) {
+            H.exp.assign(4 * (size_t)l2, 0.f);
+            memcpy(&H.exp[2 * (size_t)l2], full.data(), sizeof(float) * 2 * l2);
+            for (int i = 0; i < l2; i++) { H.exp[2 * i] = full[2 * H.in_map[i]]; H.exp[2 * i + 1] = full[2 * H.in_map[i] + 1]; }
+        } else
+            H.exp = full;
+        for (int i = 0; i < l2; i++) H.in_map[i] <<= 1;
     }
-    const double theta = (scale < 0 ? l2 : 0) + 1.0 / 8.0, sc = sqrt(fabs((double)scale));      // ff_tx_mdct_gen_exp
-    std::vector<float> full(2 * (size_t)l2);
-    for (int i = 0; i < l2; i++) {
-        const double alpha = M_PI_2 * (i + theta) / l2;
-        full[2 * i] = (float)(cos(alpha) * sc);
-        full[2 * i + 1] = (float)(sin(alpha) * sc);
-    }
-    if (inv) {
-        H.exp.assign(4 * (size_t)l2, 0.f);
-        memcpy(&H.exp[2 * (size_t)l2], full.data(), sizeof(float) * 2 * l2);
-        for (int i = 0; i < l2; i++) { H.exp[2 * i] = full[2 * H.in_map[i]]; H.exp[2 * i + 1] = full[2 * H.in_map[i] + 1]; }
-    } else
-        H.exp = full;
-    for (int i = 0; i < l2; i++) H.in_map[i] <<= 1;
     for (int i = 0; i < m; i++) H.sub_map[(-sr_perm(i, m, inv)) & (m - 1)] = i;
     const double c5 = cos(2 * M_PI / 5), c10 = cos(2 * M_PI / 10), s5 = sin(2 * M_PI / 5), s10 = sin(2 * M_PI / 10);
     H.tab53[0] = H.tab53[1] = (float)c5; H.tab53[2] = H.tab53[3] = (float)c10;
@@ -460,12 +525,12 @@ B200_API int b200_tx_pfa_tables(int inv, int len, float scale, int32_t *words, i
     return (int)w.size();
 }
 
-TxPfa *tx_pfa_create(int inv, int len, float scale)
+static TxPfa *pfa_create(bool fft, int inv, int len, float scale)
 {
-    if (!tx_pfa_length_ok(len)) return nullptr;
+    if (!(fft ? tx_pfa_fft_length_ok(len) : tx_pfa_length_ok(len))) return nullptr;
     PfaHost H;
-    pfa_host_tables(H, inv, len, scale);
-    const int l2 = len >> 1, m = H.m;
+    pfa_host_tables(H, inv, len, scale, fft);
+    const int l2 = fft ? len : len >> 1, m = H.m;
     auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
     size_t off = 0;
     const size_t o_in = off;  off += al(sizeof(int) * l2);
@@ -481,12 +546,12 @@ TxPfa *tx_pfa_create(int inv, int len, float scale)
     memcpy(&host[o_in], H.in_map.data(), sizeof(int) * l2);
     memcpy(&host[o_out], H.out_map.data(), sizeof(int) * l2);
     memcpy(&host[o_sub], H.sub_map.data(), sizeof(int) * m);
-    memcpy(&host[o_exp], H.exp.data(), sizeof(float) * H.exp.size());
+    if (!H.exp.empty()) memcpy(&host[o_exp], H.exp.data(), sizeof(float) * H.exp.size());
     memcpy(&host[o_53], H.tab53, sizeof(float) * 26);
     for (int k = 3; k <= H.log2m; k++) memcpy(&host[o_cos[k]], H.cosk[k].data(), sizeof(float) * H.cosk[k].size());
     TxPfa *p = new (std::nothrow) TxPfa();
     if (!p) return nullptr;
-    p->inv = inv; p->len = len; p->m = m;
+    p->inv = inv; p->len = len; p->m = m; p->fft = fft;
     if (cudaMalloc(&p->blob, off) != cudaSuccess || cudaMemcpy(p->blob, host.data(), off, cudaMemcpyHostToDevice) != cudaSuccess) {
         b200_set_error("tx_pfa_create: device tables");
         if (p->blob) cudaFree(p->blob);
@@ -505,7 +570,8 @@ TxPfa *tx_pfa_create(int inv, int len, float scale)
     p->smem = (size_t)H.nfac * d.ms * sizeof(float2);
     if (p->smem > 48 * 1024 &&
         (cudaFuncSetAttribute(tx_mdct_pfa_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem) != cudaSuccess ||
-         cudaFuncSetAttribute(tx_mdct_pfa_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem) != cudaSuccess)) {
+         cudaFuncSetAttribute(tx_mdct_pfa_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem) != cudaSuccess ||
+         cudaFuncSetAttribute(tx_fft_pfa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem) != cudaSuccess)) {
         b200_set_error("tx_pfa_create: %zu bytes of shared memory per transform", p->smem);
         cudaFree(p->blob);
         delete p;
@@ -518,6 +584,9 @@ TxPfa *tx_pfa_create(int inv, int len, float scale)
     return p;
 }
 
+TxPfa *tx_pfa_create(int inv, int len, float scale) { return pfa_create(false, inv, len, scale); }
+TxPfa *tx_pfa_create_fft(int inv, int len) { return pfa_create(true, inv, len, 1.0f); }
+
 void tx_pfa_free(TxPfa *p)
 {
     if (!p) return;
@@ -528,6 +597,15 @@ void tx_pfa_free(TxPfa *p)
 int tx_pfa_launch(TxPfa *p, cudaStream_t st, void *out, const void *in, ptrdiff_t stride, int64_t count, ptrdiff_t out_step, ptrdiff_t in_step)
 {
     if (count <= 0) return 0;
+    if (p->fft) {                                          // complex in, complex out with a stride in bytes
+        if (((reinterpret_cast<uintptr_t>(out) | (uintptr_t)out_step | reinterpret_cast<uintptr_t>(in) | (uintptr_t)in_step | (uintptr_t)stride) & 7) || stride <= 0)
+            return B200_EINVAL;
+        const unsigned nbf = (unsigned)(count < p->grid_cap ? count : p->grid_cap);
+        tx_fft_pfa_kernel<<<nbf, PFA_THREADS, p->smem, st>>>(p->d, (float2 *)out, (const float2 *)in, (long long)(stride / 8), out_step, in_step, count);
+        B200_LAUNCHED();
+        B200_CUDA_OK(cudaGetLastError());
+        return 0;
+    }
     // the inverse writes its outputs as complex pairs (8-byte words); everything else moves single floats
     if (((reinterpret_cast<uintptr_t>(out) | (uintptr_t)out_step) & (p->inv ? 7 : 3)) || ((reinterpret_cast<uintptr_t>(in) | (uintptr_t)in_step) & 3))
         return B200_EINVAL;

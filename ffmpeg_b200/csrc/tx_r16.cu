@@ -210,7 +210,7 @@ __device__ __forceinline__ void last_pass(const float2 *buf, const PassRegs<NL> 
 template <int LOGN, int MODE, int NL1, int NL2, int NL3>
 __global__ void __launch_bounds__(256, 2)
 tx_r16_kernel(const uint32_t *__restrict__ plan, const float2 *__restrict__ exp_nat, char *__restrict__ out, const char *__restrict__ in,
-              long long out_step, long long in_step, long long count)
+              long long out_step, long long in_step, long long count, int leaf_perm)
 {
     constexpr int N = 1 << LOGN, G = N / 16, GROUPS = 256 / G, ZS = N + N / 16;
     constexpr int Q1 = 8, Q2 = 1 << (4 + NL1 - 1), Q3 = 1 << (4 + NL1 + NL2 - 1);
@@ -225,7 +225,7 @@ tx_r16_kernel(const uint32_t *__restrict__ plan, const float2 *__restrict__ exp_
     // whose top four bits are all different -- the permuted source samples of chunk c sit at (roughly bit-reversed c) + k N/16, so the
     // top bits of c pick the bank of the reads while the low bits pick the bank of the 17-strided writes; consecutive chunks per warp
     // made the reads an 8-way (N = 2048) / 4-way (N = 1024) bank conflict
-    const int lt = G > 16 ? (tg & 15) + 16 * (((tg & 15) ^ (tg >> 4)) & (G / 16 - 1)) : tg;
+    const int lt = (G > 16 && leaf_perm) ? (tg & 15) + 16 * (((tg & 15) ^ (tg >> 4)) & (G / 16 - 1)) : tg;
     uint32_t off[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) off[k] = plan[(size_t)k * G + lt];
@@ -327,11 +327,11 @@ uint32_t fbits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 } // namespace
 
 struct TxR16 {
-    int mode = 0, n = 0, logn = 0, G = 0, groups = 0, grid_cap = 0;
+    int mode = 0, n = 0, logn = 0, G = 0, groups = 0, grid_cap = 0, leaf_perm = 1;
     size_t smem = 0;
     uint32_t *plan = nullptr;
     float2 *exp_nat = nullptr;
-    void (*kernel)(const uint32_t *, const float2 *, char *, const char *, long long, long long, long long) = nullptr;
+    void (*kernel)(const uint32_t *, const float2 *, char *, const char *, long long, long long, long long, int) = nullptr;
 };
 
 template <int LOGN, int MODE, int A, int B, int C>
@@ -425,6 +425,10 @@ TxR16 *tx_r16_create(int mode, int n, const int *gather, const float2 *exp_nat, 
     const int G = n / 16;
     TxR16 *p = new TxR16();
     p->mode = mode; p->n = n; p->logn = logn; p->G = G; p->groups = 256 / G;
+    // measured (scripts/quick_bench.py tx, B200_TX_LEAF=0/1): the conflict-free leaf assignment gains 30-45 % at 2048 points and 6 % at 512,
+    // but the 1024-point FFT (not bound by shared memory) runs 5 % slower with it
+    p->leaf_perm = !(logn == 10 && mode == 0);
+    if (const char *e = getenv("B200_TX_LEAF")) p->leaf_perm = atoi(e) != 0;                  // A/B knob
     const size_t zs = (size_t)n + n / 16;
     p->smem = (size_t)p->groups * 2 * zs * 8 + (mode == 1 ? (size_t)n * 8 : 0) + (size_t)p->groups * 2 * 8;
     int rc = -1;
@@ -465,7 +469,7 @@ int tx_r16_launch(TxR16 *p, cudaStream_t st, void *out, const void *in, long lon
     if (count <= 0) return 0;
     long long blocks = (count + p->groups - 1) / p->groups;
     if (blocks > p->grid_cap) blocks = p->grid_cap;               // persistent CTAs: every group strides over the batch
-    p->kernel<<<(unsigned)blocks, 256, p->smem, st>>>(p->plan, p->exp_nat, (char *)out, (const char *)in, out_step, in_step, count);
+    p->kernel<<<(unsigned)blocks, 256, p->smem, st>>>(p->plan, p->exp_nat, (char *)out, (const char *)in, out_step, in_step, count, p->leaf_perm);
     B200_LAUNCHED();
     B200_CUDA_OK(cudaGetLastError());
     return 0;

@@ -542,7 +542,7 @@ int  b200_emulated_edge_mc_batch_device(B200Device *dev, int64_t n, uint8_t *buf
                                    * ff_tx_dct_init doubles the length it is given, libavutil/tx_template.c:1844-1848; callers pass N / 2).
                                    * ff_tx_dctII / ff_tx_dctIII (tx_template.c:1874-1968).  Input and output are N floats per transform;
                                    * unlike the reference neither the input is overwritten nor 2 floats of padding are needed. */
-#define B200_TX_INPLACE     1     /* AV_TX_INPLACE: AV_TX_FLOAT_FFT only; out == in is allowed (batch: out_step == in_step) */
+#define B200_TX_INPLACE     1     /* AV_TX_INPLACE: AV_TX_FLOAT_FFT only (power-of-two and compound); out == in is allowed (batch: out_step == in_step) */
 #define B200_TX_UNALIGNED   2     /* AV_TX_UNALIGNED (accepted, no effect) */
 #define B200_TX_FULL_IMDCT  4     /* AV_TX_FULL_IMDCT (libavutil/tx.h:175-180; ff_tx_mdct_inv_full, tx_template.c:1372-1413): inverse
                                    * AV_TX_FLOAT_MDCT only; 2 * len outputs, stride must be sizeof(float) */
@@ -550,7 +550,10 @@ typedef struct B200TXContext B200TXContext;
 typedef void (*b200_tx_fn)(B200TXContext *s, void *out, void *in, ptrdiff_t stride);   /* av_tx_fn: HOST pointers */
 /* like av_tx_init(); uses the process-wide default device.  scale: const float * (MDCT), ignored for FFT.
  * Lengths: powers of two, and for AV_TX_FLOAT_MDCT also 2 * N * 2^k with N = 15, 9, 7, 5 or 3: the compound transform av_tx_init() resolves
- * to for those (ff_tx_mdct_pfa_{15,9,7,5,3}xM_{inv,fwd}_float_c, libavutil/tx_template.c:1471-1599; 15 x M covers the Opus CELT sizes).
+ * to for those (ff_tx_mdct_pfa_{15,9,7,5,3}xM_{inv,fwd}_float_c, libavutil/tx_template.c:1471-1599; 15 x M covers the Opus CELT sizes),
+ * and for AV_TX_FLOAT_FFT also N * 2^k (2^k = 2 ... 512): the compound transform ff_tx_fft_pfa over fftN_ns and the split-radix
+ * transform (libavutil/tx_template.c:948-1080; checkasm lengths 120 / 960 / 1920).  The compound FFT stores out[i * stride] like the
+ * reference (stride in bytes, a multiple of 8); AV_TX_INPLACE is accepted for it.
  * Returns 0 or B200_ENOSYS (unsupported type / flags / length), B200_EINVAL, B200_ENODEV. */
 int  b200_tx_init(B200TXContext **ctx, b200_tx_fn *tx, int type, int inv, int len, const void *scale, uint64_t flags);
 /* host-only: the tables ff_tx_mdct_pfa_init() builds for a 15 x M MDCT, flattened into 32-bit words, for the CPU test tier

@@ -453,6 +453,24 @@ API void ffref_tx_run(void *h, void *out, void *in, ptrdiff_t stride, int count,
         t->fn(t->ctx, (uint8_t *)out + i * out_step, (uint8_t *)in + i * in_step, stride);
 }
 
+/* the codelet tree av_tx_init() resolved to, one "depth name len flags" line per node (the float operation order of a compound
+ * transform depends on which decomposition won: tests pin the CUDA plan to the same tree) */
+#include "libavutil/tx_priv.h"
+static int tx_describe_node(const AVTXContext *s, int depth, char *buf, int cap, int pos)
+{
+    if (!s || !s->cd_self) return pos;
+    int n = snprintf(buf + pos, pos < cap ? cap - pos : 0, "%d %s %d %llx\n", depth, s->cd_self->name, s->len, (unsigned long long)s->flags);
+    pos += n > 0 ? n : 0;
+    for (int i = 0; i < s->nb_sub; i++) pos = tx_describe_node(&s->sub[i], depth + 1, buf, cap, pos);
+    return pos;
+}
+API int ffref_tx_describe(void *h, char *buf, int cap)
+{
+    RefTx *t = h;
+    if (cap > 0) buf[0] = 0;
+    return tx_describe_node(t->ctx, 0, buf, cap, 0);
+}
+
 /* ------------------------------------------------------------------ mpegvideo inverse quantisers ---------------- */
 #include "libavcodec/mpegvideo.h"
 #include "libavcodec/mpegvideodata.h"

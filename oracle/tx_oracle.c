@@ -161,6 +161,20 @@ static int mulinv(int n, int m)                                /* tx.c:34-42 */
     return 0;
 }
 
+/* ff_tx_tab_53 / _7 / _9 (tx_template.c:91-130) */
+static void init_tab_odd(OrcTx *t)
+{
+    const double c5 = cos(2 * M_PI / 5), c10 = cos(2 * M_PI / 10), s5 = sin(2 * M_PI / 5), s10 = sin(2 * M_PI / 10);
+    t->tab53[0] = t->tab53[1] = (float)c5; t->tab53[2] = t->tab53[3] = (float)c10;
+    t->tab53[4] = t->tab53[5] = (float)s5; t->tab53[6] = t->tab53[7] = (float)s10;
+    t->tab53[8] = t->tab53[9] = (float)cos(2 * M_PI / 12); t->tab53[10] = (float)cos(2 * M_PI / 6); t->tab53[11] = (float)cos(8 * M_PI / 6);
+    float *t7 = t->tab53 + 12, *t9 = t->tab53 + 18;
+    t7[0] = (float)cos(2 * M_PI / 7); t7[1] = (float)sin(2 * M_PI / 7); t7[2] = (float)sin(2 * M_PI / 28);
+    t7[3] = (float)cos(2 * M_PI / 28); t7[4] = (float)cos(2 * M_PI / 14); t7[5] = (float)sin(2 * M_PI / 14);
+    t9[0] = (float)cos(2 * M_PI / 3); t9[1] = (float)sin(2 * M_PI / 3); t9[2] = (float)cos(2 * M_PI / 9); t9[3] = (float)sin(2 * M_PI / 9);
+    t9[4] = (float)cos(2 * M_PI / 36); t9[5] = (float)sin(2 * M_PI / 36); t9[6] = t9[2] + t9[5]; t9[7] = t9[3] - t9[4];
+}
+
 static OrcTx *open_mdct_pfa(int n, int inv, int len, float scale)
 {
     OrcTx *t = calloc(1, sizeof(*t));
@@ -207,15 +221,7 @@ static OrcTx *open_mdct_pfa(int n, int inv, int len, float scale)
     t->pfa_sub = malloc(sizeof(int) * m);
     for (int i = 0; i < m; i++) t->pfa_sub[(-sr_perm(i, m, t->inv)) & (m - 1)] = i;
     t->pfa_tmp = malloc(sizeof(cpx) * l2);
-    const double c5 = cos(2 * M_PI / 5), c10 = cos(2 * M_PI / 10), s5 = sin(2 * M_PI / 5), s10 = sin(2 * M_PI / 10);
-    t->tab53[0] = t->tab53[1] = (float)c5; t->tab53[2] = t->tab53[3] = (float)c10;
-    t->tab53[4] = t->tab53[5] = (float)s5; t->tab53[6] = t->tab53[7] = (float)s10;
-    t->tab53[8] = t->tab53[9] = (float)cos(2 * M_PI / 12); t->tab53[10] = (float)cos(2 * M_PI / 6); t->tab53[11] = (float)cos(8 * M_PI / 6);
-    float *t7 = t->tab53 + 12, *t9 = t->tab53 + 18;
-    t7[0] = (float)cos(2 * M_PI / 7); t7[1] = (float)sin(2 * M_PI / 7); t7[2] = (float)sin(2 * M_PI / 28);
-    t7[3] = (float)cos(2 * M_PI / 28); t7[4] = (float)cos(2 * M_PI / 14); t7[5] = (float)sin(2 * M_PI / 14);
-    t9[0] = (float)cos(2 * M_PI / 3); t9[1] = (float)sin(2 * M_PI / 3); t9[2] = (float)cos(2 * M_PI / 9); t9[3] = (float)sin(2 * M_PI / 9);
-    t9[4] = (float)cos(2 * M_PI / 36); t9[5] = (float)sin(2 * M_PI / 36); t9[6] = t9[2] + t9[5]; t9[7] = t9[3] - t9[4];
+    init_tab_odd(t);
     return t;
 }
 
@@ -480,6 +486,61 @@ static void run_dct3(OrcTx *t, float *dst, float *src)
     }
 }
 
+/* ---- compound N x M FFT: av_tx_init(AV_TX_FLOAT_FFT, len = N * 2^k), N = 15, 9, 7, 5 or 3, resolves to fft_pfa over fftN_ns and the
+ * 2^k-point split-radix transform (codelet tree printed by the compiled reference: oracle/ref/ref_shim.c ffref_tx_describe; checkasm
+ * lengths 120 / 960 / 1920, tests/checkasm/av_tx.c:38-40).  ff_tx_fft_pfa_init (tx_template.c:948-1057), ff_tx_fft_pfa (:1059-1080). */
+static OrcTx *open_fft_pfa(int n, int inv, int len)
+{
+    OrcTx *t = calloc(1, sizeof(*t));
+    const int m = len / n;
+    t->type = 0; t->inv = !!inv; t->len = len; t->n = m; t->pfa_m = m; t->pfa_n = n;
+    for (int j = 3; (1 << j) <= m; j++) make_tab(t, j);
+    /* ff_tx_gen_compound_mapping(s, opts, 0, n, m): gather input map, CRT output map; the direction is NOT applied here */
+    int *in_map = t->pfa_in = malloc(sizeof(int) * len), *out_map = t->pfa_out = malloc(sizeof(int) * len);
+    const int m_inv = mulinv(m, n), n_inv = mulinv(n, m);
+    for (int j = 0; j < m; j++)
+        for (int i = 0; i < n; i++) {
+            in_map[j * n + i] = (i * m + j * n) % len;
+            out_map[(i * m * m_inv + j * n * n_inv) % len] = i * m + j;
+        }
+    /* the map of the first sub-transform (ff_tx_fft_factor_init, tx_template.c:478-494): 3 x 5 map for 15 points
+     * (ff_tx_gen_pfa_input_map, tx.c:44-71), else ff_tx_gen_default_map (tx.c:525-542); the inverse reverses all but the DC */
+    int sub[15];
+    if (n == 15) {
+        for (int b = 0; b < 5; b++)
+            for (int a = 0; a < 3; a++) {
+                if (inv) sub[(b * 3 + a * 5) % 15] = b * 3 + a;
+                else     sub[b * 3 + a] = (b * 3 + a * 5) % 15;
+            }
+        if (inv) for (int w = 1; w <= 7; w++) { int x = sub[w]; sub[w] = sub[15 - w]; sub[15 - w] = x; }
+    } else {
+        sub[0] = 0;
+        for (int i = 1; i < n; i++) sub[i] = inv ? n - i : i;
+    }
+    for (int k = 0; k < len; k += n) {                         /* "Flatten input map" (tx_template.c:1040-1046) */
+        int tmp[15];
+        memcpy(tmp, &in_map[k], sizeof(int) * n);
+        for (int i = 0; i < n; i++) in_map[k + i] = tmp[sub[i]];
+    }
+    t->pfa_sub = malloc(sizeof(int) * m);
+    for (int i = 0; i < m; i++) t->pfa_sub[(-sr_perm(i, m, t->inv)) & (m - 1)] = i;
+    t->pfa_tmp = malloc(sizeof(cpx) * len);
+    init_tab_odd(t);
+    return t;
+}
+
+static void run_fft_pfa(OrcTx *t, cpx *out, const cpx *in, ptrdiff_t stride)
+{
+    const int n = t->pfa_n, m = t->pfa_m, l = t->len;
+    cpx f[15];
+    for (int i = 0; i < m; i++) {
+        for (int j = 0; j < n; j++) f[j] = in[t->pfa_in[i * n + j]];
+        pfa_fftN(n, t->tab53, t->pfa_tmp + t->pfa_sub[i], f, m);
+    }
+    for (int i = 0; i < n; i++) fft_ns(t, ilog2i(m), t->pfa_tmp + m * i, t->pfa_tmp + m * i);
+    for (int i = 0; i < l; i++) out[i * stride] = t->pfa_tmp[t->pfa_out[i]];
+}
+
 OrcTx *orc_tx_open(int type, int inv, int len, float scale, unsigned flags)
 {
     if (flags == 4) {                                          /* AV_TX_FULL_IMDCT: only the inverse MDCT has such a codelet (tx.c:762-771) */
@@ -495,6 +556,12 @@ OrcTx *orc_tx_open(int type, int inv, int len, float scale, unsigned flags)
             const int n = factors[f], l2 = len >> 1, m = l2 / n;
             if (l2 % n == 0 && m >= 2 && !(m & (m - 1))) return open_mdct_pfa(n, inv, len, scale);
         }
+    }
+    if (!flags && type == 0 && len >= 6 && (len & (len - 1))) {   /* compound FFT: odd part 3, 5, 7, 9 or 15 times a power of two >= 2 */
+        int m = 1;
+        while (!(len & m)) m <<= 1;
+        const int n = len / m;
+        if (m >= 2 && (n == 3 || n == 5 || n == 7 || n == 9 || n == 15)) return open_fft_pfa(n, inv, len);
     }
     if (flags || (type != 0 && type != 1 && type != 6) || len < 2 || (len & (len - 1))) return NULL;
     if (type == 6 && len < 4) return NULL;                     /* ff_tx_rdft_*_def: min_len 4 */
@@ -679,6 +746,7 @@ void orc_tx_run(OrcTx *t, void *out, void *in, ptrdiff_t stride, int count, ptrd
             }
         }
         else if (t->type == 9) { if (t->inv) run_dct3(t, o, i); else run_dct2(t, o, i); }
+        else if (t->type == 0 && t->pfa_m) run_fft_pfa(t, o, i, stride / (ptrdiff_t)sizeof(cpx));
         else if (t->type == 0) run_fft(t, o, i);
         else if (t->type == 6) run_rdft(t, o, i);
         else if (t->pfa_m && t->inv) run_mdct_pfa_inv(t, o, i, stride / (ptrdiff_t)sizeof(float));

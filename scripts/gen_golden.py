@@ -157,6 +157,33 @@ def gen_tx_pfa():
     np.savez_compressed(os.path.join(OUT, "tx_pfa.npz"), **d)
 
 
+PFA_FFT_SIZES = (6, 12, 96, 10, 160, 14, 224, 18, 288, 30, 120, 960, 1920)
+
+
+def gen_tx_pfa_fft():
+    """compound complex FFTs (fft_pfa over fft{3,5,7,9,15}_ns x 2^k; checkasm av_tx.c lengths 120 / 960 / 1920): the reference's
+    outputs in both directions, plus the codelet tree it reports for each length (ffref_tx_describe)."""
+    R = cl.ref()
+    R.ffref_tx_describe.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+    d = {}
+    rng = np.random.default_rng(78)
+    trees = []
+    for n in PFA_FFT_SIZES:
+        x = (rng.random((2, 2 * n), dtype=np.float32) * 2 - 1).astype(np.float32)
+        d[f"in_{n}"] = x
+        for inv in (0, 1):
+            h = R.ffref_tx_open(0, inv, n, 1.0, 0)
+            buf = C.create_string_buffer(2048)
+            R.ffref_tx_describe(h, buf, 2048)
+            trees.append(f"{n} {inv}: " + buf.value.decode().strip().replace("\n", " | "))
+            out = np.zeros((2, 2 * n), np.float32)
+            R.ffref_tx_run(h, out.ctypes.data, x.ctypes.data, 8, 2, out.strides[0], x.strides[0])
+            R.ffref_tx_close(h)
+            d[f"out_{n}_{inv}"] = out
+    d["trees"] = np.array(trees)
+    np.savez_compressed(os.path.join(OUT, "tx_pfa_fft.npz"), **d)
+
+
 def gen_tx_full_imdct():
     """AV_TX_FULL_IMDCT: the reference's 2 * len outputs of the inverse float MDCT, power-of-two and compound lengths, two scales."""
     R = cl.ref()
@@ -552,6 +579,10 @@ def gen_sws_slices():
 if __name__ == "__main__":
     assert cl.have_ref(), "build oracle/_ref first: make -C oracle/ref"
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1:                                           # python scripts/gen_golden.py tx_pfa_fft ...: only those fixtures
+        for name in sys.argv[1:]:
+            globals()["gen_" + name]()
+        sys.exit(0)
     gen_sws()
     gen_sws_formats()
     gen_sws_planar()
@@ -577,6 +608,7 @@ if __name__ == "__main__":
     gen_idct_hbd()
     gen_sws_rgbsrc()
     gen_tx_pfa()
+    gen_tx_pfa_fft()
     gen_tx_full_imdct()
     gen_tx_dct()
     gen_tx_int32()

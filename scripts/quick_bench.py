@@ -132,8 +132,8 @@ with torch.cuda.stream(stream):
         c = sw.sws_getContext(dev, W, H, 0, W, H, 2, (4 | 0x40000 | 0x80000) if what == "sws" else 4)
         timed(lambda: c.scale_batch_device([Y, U, V], [W, W // 2, W // 2], [W * H, W * H // 4, W * H // 4], O, W * 3, W * H * 3, nf), nf, "frames", 37324800)
     elif what == "tx":
-        for n in (1024, 2048):
-            cnt = 1 << 17
+        for n in [int(v) for v in os.environ.get("QB_TX_SIZES", "1024,2048").split(",")]:
+            cnt = (1 << 28) // (2 * n)
             x = torch.rand((cnt, 2 * n), device="cuda", generator=g); y = torch.empty_like(x)
             c = tx.av_tx_init(0, 0, n, device=dev); what = f"fft{n}"
             timed(lambda: c.batch_device(y, x, 8, cnt, 8 * n, 8 * n), cnt, "tx", 16 * n); c.uninit()

@@ -31,7 +31,7 @@ def emu():
                 found[m.group(1)] = m.group(2)
     assert sorted(found) == ["fdsp", "h264lf", "idct_hbd", "pixelutils", "sws_new", "sws_nvout", "tx_dct", "tx_int32", "tx_pfa", "unquant"], sorted(found)
     found["tx_pfa"], n_sh = re.subn(r"extern __shared__ float2 pfa_z\[\];", "float2 *pfa_z = (float2 *)emu_smem;", found["tx_pfa"])
-    assert n_sh == 2
+    assert n_sh == 3
     found["tx_int32"], n_sh = re.subn(r"extern __shared__ int2 i32_z\[\];", "int2 *i32_z = (int2 *)emu_smem;", found["tx_int32"])
     assert n_sh == 1
     for k, v in found.items():
@@ -50,7 +50,7 @@ def vp(a):
 
 WARP_KERNELS = {"mpv_unquant_kernel"}                   # kernels that use a warp collective: one OS thread per lane
 BLOCK_KERNELS = {"sws_mma_plane_kernel", "sws_mma_rgb_kernel", "tx_fft_kernel", "tx_mdct_inv_kernel", "tx_mdct_fwd_kernel", "tx_rdft_r2c_kernel", "tx_rdft_c2r_kernel",
-                 "sws_fused_plane_kernel", "sws_fused_rgb_kernel", "tx_mdct_pfa_inv_kernel", "tx_mdct_pfa_fwd_kernel", "tx_i32_kernel"}    # __syncthreads + dynamic shared memory
+                 "sws_fused_plane_kernel", "sws_fused_rgb_kernel", "tx_mdct_pfa_inv_kernel", "tx_mdct_pfa_fwd_kernel", "tx_fft_pfa_kernel", "tx_i32_kernel"}    # __syncthreads + dynamic shared memory
 
 
 def rewrite_launches(txt):
@@ -717,6 +717,14 @@ def test_tx_whole_path_on_emulated_device(emutx):
             exp = _tx(O, "orc", 1, inv, n, 1.0 / n, x, n)
             assert np.array_equal(_emu_tx(emutx, 1, inv, n, 1.0 / n, x, n).view(np.uint32), exp.view(np.uint32)), ("pfa batch", n, inv)
             assert np.array_equal(_emu_tx(emutx, 1, inv, n, 1.0 / n, x[:3], n, host_fn=True).view(np.uint32), exp[:3].view(np.uint32)), ("pfa av_tx_fn", n, inv)
+    # compound complex FFTs (fft_pfa over fftN_ns x 2^k; checkasm lengths 120 / 960 / 1920): batch, av_tx_fn and in-place entries
+    for n in (6, 12, 96, 10, 160, 14, 224, 18, 288, 30, 120, 960, 1920):
+        for inv in (0, 1):
+            x = (rng.random((70 if n == 120 else 3, 2 * n), dtype=np.float32) * 2 - 1).astype(np.float32)
+            exp = _tx(O, "orc", 0, inv, n, 1.0, x, 2 * n)
+            assert np.array_equal(_emu_tx(emutx, 0, inv, n, 1.0, x, 2 * n).view(np.uint32), exp.view(np.uint32)), ("fft pfa batch", n, inv)
+            assert np.array_equal(_emu_tx(emutx, 0, inv, n, 1.0, x[:2], 2 * n, host_fn=True).view(np.uint32), exp[:2].view(np.uint32)), ("fft pfa av_tx_fn", n, inv)
+    assert _emu_tx(emutx, 0, 0, 90, 1.0, x, 180) == -38 and _emu_tx(emutx, 0, 0, 75, 1.0, x, 150) == -38 and _emu_tx(emutx, 0, 0, 15, 1.0, x, 30) == -38
     # AV_TX_FULL_IMDCT around the power-of-two and the compound inverse MDCT: batch and av_tx_fn entries; refused elsewhere
     for n in (4, 64, 1024, 120, 144, 96):
         x = (rng.random((70 if n == 64 else 4, n), dtype=np.float32) * 2 - 1).astype(np.float32)
@@ -774,7 +782,7 @@ def test_tx_whole_path_on_emulated_device(emutx):
     x = np.zeros((1, 1920), np.float32)
     assert _emu_tx(emutx, 4, 0, 96, 1.0, x, 192) == -38 and _emu_tx(emutx, 5, 1, 960, 1.0, x, 960) == -38 and _emu_tx(emutx, 1, 1, 84, 1.0, x, 84) == -38 and _emu_tx(emutx, 2, 0, 64, 1.0, x, 128) == -38
     assert _emu_tx(emutx, 9, 0, 96, 1.0, x, 96) == -38 and _emu_tx(emutx, 9, 0, 2, 1.0, x, 2) == -38 and _emu_tx(emutx, 9, 1, 1, 1.0, x, 2) == -38
-    assert _emu_tx(emutx, 0, 0, 960, 1.0, x, 1920) == -38 and _emu_tx(emutx, 6, 0, 96, 1.0, x, 98) == -38
+    assert _emu_tx(emutx, 0, 0, 90, 1.0, x, 180) == -38 and _emu_tx(emutx, 6, 0, 96, 1.0, x, 98) == -38
 
 
 # ------------------------------------------------------------------ the library's own host code on the stand-in runtime

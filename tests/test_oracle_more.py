@@ -407,6 +407,44 @@ def test_tx_pfa15_oracle_vs_ref_and_round_trip():
     assert np.allclose(coef[0], ref, atol=2e-3), float(np.abs(coef[0] - ref).max())
 
 
+PFA_FFT_SIZES = (6, 12, 96, 10, 160, 14, 224, 18, 288, 30, 120, 960, 1920)
+
+
+def test_tx_pfa_fft_oracle_golden_bitexact():
+    """compound complex FFTs (ff_tx_fft_pfa over fftN_ns x 2^k; checkasm lengths 120 / 960 / 1920) against the reference's outputs, bit
+    for bit; the fixture also records the codelet tree the reference chose, which is what the restatement assumes"""
+    g = np.load(os.path.join(G, "tx_pfa_fft.npz"))
+    O = cl.oracle()
+    trees = dict(t.split(": ", 1) for t in g["trees"])
+    for n in PFA_FFT_SIZES:
+        m = n & -n
+        for inv in (0, 1):
+            tree = trees[f"{n} {inv}"]
+            assert f"fft_pfa_float_c {n} " in tree and f"fft{n // m}_ns_float_c {n // m} " in tree and f"fft{m}_ns_float_c {m} " in tree, tree
+            got = _tx(O, "orc", 0, inv, n, 1.0, g[f"in_{n}"], 2 * n)
+            assert np.array_equal(got.view(np.uint32), g[f"out_{n}_{inv}"].view(np.uint32)), (n, inv)
+    assert not O.orc_tx_open(0, 0, 90, 1.0, 0) and not O.orc_tx_open(0, 0, 75, 1.0, 0) and not O.orc_tx_open(0, 0, 15, 1.0, 0)   # nested / naive trees: not restated
+
+
+def test_tx_pfa_fft_oracle_vs_ref_and_dft():
+    O = cl.oracle()
+    rng = np.random.default_rng(13)
+    if cl.have_ref():
+        R = cl.ref()
+        for n in (24, 48, 192, 384, 768, 20, 40, 80, 320, 28, 56, 448, 36, 72, 576, 60, 240, 480, 3840, 7680):
+            for inv in (0, 1):
+                x = (rng.random((2, 2 * n), dtype=np.float32) * 2 - 1).astype(np.float32)
+                assert np.array_equal(_tx(R, "ffref", 0, inv, n, 1.0, x, 2 * n).view(np.uint32), _tx(O, "orc", 0, inv, n, 1.0, x, 2 * n).view(np.uint32)), (n, inv)
+    for n in (120, 960, 224):                                       # it is a DFT (eps like checkasm av_tx.c:27), and forward then inverse = len * x
+        x = (rng.random((1, 2 * n), dtype=np.float32) * 2 - 1).astype(np.float32)
+        z = x[0, 0::2].astype(np.float64) + 1j * x[0, 1::2].astype(np.float64)
+        got = _tx(O, "orc", 0, 0, n, 1.0, x, 2 * n)
+        ref = np.fft.fft(z)
+        assert np.abs(got[0, 0::2] - ref.real).max() < 5e-4 * n and np.abs(got[0, 1::2] - ref.imag).max() < 5e-4 * n
+        back = _tx(O, "orc", 0, 1, n, 1.0, got.copy(), 2 * n)
+        assert np.abs(back[0] / n - x[0]).max() < 1e-4
+
+
 def test_tx_full_imdct_oracle_golden_and_ref():
     """AV_TX_FULL_IMDCT (ff_tx_mdct_inv_full: cook, atrac3, atrac3+, dolby_e, dca_lbr ask for it): 2 * len outputs, power-of-two and
     compound lengths, against the reference's outputs; refused for anything but the inverse MDCT, like av_tx_init does"""

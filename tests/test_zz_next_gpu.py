@@ -570,7 +570,55 @@ def test_tx_mdct_pfa15(device):
     with pytest.raises(fb.B200Error):
         tx.av_tx_init(tx.AV_TX_FLOAT_MDCT, 1, 84, scale=1.0)            # 7 x 6: the sub-transform would be a compound FFT, not built
     with pytest.raises(fb.B200Error):
-        tx.av_tx_init(tx.AV_TX_FLOAT_FFT, 0, 960)                       # compound FFTs are not built
+        tx.av_tx_init(tx.AV_TX_FLOAT_FFT, 0, 90)                        # 45 x 2: a nested compound tree in the reference, not built
+
+
+# ---------------------------------------------------------------------------------------------- tx: compound N x 2^k complex FFT
+def test_tx_fft_pfa(device):
+    """av_tx_init(AV_TX_FLOAT_FFT, N * 2^k), N = 15, 9, 7, 5, 3 (checkasm av_tx.c lengths 120 / 960 / 1920): host av_tx_fn against the
+    reference's outputs, batched device call (out of place, in place, strided output) against the oracle"""
+    import torch
+    import ffmpeg_b200 as fb
+    from ffmpeg_b200 import tx
+    from test_oracle_more import _tx, PFA_FFT_SIZES
+    g = np.load(os.path.join(G, "tx_pfa_fft.npz"))
+    O = cl.oracle()
+    for n in PFA_FFT_SIZES:
+        for inv in (0, 1):
+            c = tx.av_tx_init(tx.AV_TX_FLOAT_FFT, inv, n)
+            x = g[f"in_{n}"]
+            out = np.zeros((x.shape[0], 2 * n), np.float32)
+            for r in range(x.shape[0]):
+                c.fn(out[r], x[r].copy(), 8)
+            assert np.array_equal(out.view(np.uint32), g[f"out_{n}_{inv}"].view(np.uint32)), (n, inv)
+            c.uninit()
+    rng = np.random.default_rng(22)
+    for n in (120, 960, 1920, 7680, 96, 640, 224, 1152):               # 15 x M, 3 x M, 5 x M, 7 x M, 9 x M
+        for inv in (0, 1):
+            cnt = 2000 if n < 4000 else 300
+            x = (rng.random((cnt, 2 * n), dtype=np.float32) * 2 - 1).astype(np.float32)
+            exp = _tx(O, "orc", 0, inv, n, 1.0, x, 2 * n)
+            c = tx.av_tx_init(tx.AV_TX_FLOAT_FFT, inv, n, device=device)
+            with on_stream(device):
+                di, do = torch.from_numpy(x).cuda(), torch.zeros((cnt, 2 * n), dtype=torch.float32, device="cuda")
+                c.batch_device(do, di, 8, cnt, 8 * n, 8 * n)
+                device.sync()
+                assert np.array_equal(do.cpu().numpy().view(np.uint32), exp.view(np.uint32)), (n, inv)
+                if n in (120, 224):                                     # strided output: out[i * stride] (tx_template.c:1078-1079)
+                    d2 = torch.zeros((cnt, 4 * n), dtype=torch.float32, device="cuda")
+                    c.batch_device(d2, di, 16, cnt, 16 * n, 8 * n)
+                    device.sync()
+                    got = d2.cpu().numpy().reshape(cnt, n, 4)
+                    assert np.array_equal(got[:, :, :2].reshape(cnt, 2 * n).view(np.uint32), exp.view(np.uint32)) and not got[:, :, 2:].any(), (n, inv, "stride")
+            c.uninit()
+            if n in (960, 96):                                          # AV_TX_INPLACE
+                c = tx.av_tx_init(tx.AV_TX_FLOAT_FFT, inv, n, flags=tx.AV_TX_INPLACE, device=device)
+                with on_stream(device):
+                    di = torch.from_numpy(x).cuda()
+                    c.batch_device(di, di, 8, cnt, 8 * n, 8 * n)
+                    device.sync()
+                    assert np.array_equal(di.cpu().numpy().view(np.uint32), exp.view(np.uint32)), (n, inv, "inplace")
+                c.uninit()
 
 
 # ---------------------------------------------------------------------------------------------- tx: DCT-II / DCT-III
