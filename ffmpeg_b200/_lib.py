@@ -187,6 +187,7 @@ PROTOTYPES = {
     "b200_h264qpel_init": (C.c_int, [C.POINTER(H264QpelContext), C.c_int]),
     "b200_hpeldsp_init": (C.c_int, [C.POINTER(HpelDSPContext), C.c_int]),
     "b200_h264qpel_batch_device": (C.c_int, [vp, C.c_int64, vp, vp, vp, vp, vp, C.c_ssize_t]),
+    "b200_h264qpel_hbd_batch_device": (C.c_int, [vp, C.c_int, C.c_int64, vp, vp, vp, vp, vp, C.c_ssize_t]),
     "b200_hpel_batch_device": (C.c_int, [vp, C.c_int64, vp, vp, vp, vp, vp, vp, C.c_ssize_t]),
     "b200_h264_idct_init": (C.c_int, [C.POINTER(H264IDCTContext), C.c_int, C.c_int]),
     "b200_h264_idct_batch_device": (C.c_int, [vp, C.c_int, C.c_int64, vp, vp, vp, vp, C.c_ssize_t]),

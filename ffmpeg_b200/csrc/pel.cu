@@ -9,6 +9,7 @@
 // unrounded horizontal 6-tap sums once (size+5 rows of int16), and then every lane produces its pixels from shared
 // memory.  The 6-tap is never recomputed per output pixel and the reference block is read from HBM exactly once.
 #include "common.h"
+#include "pel_hbd.h"
 #include <algorithm>
 #include <cstring>
 #include <cstdlib>
@@ -1109,8 +1110,9 @@ void fill_hpel(b200_op_pixels_func *t)
 B200_API int b200_h264qpel_init(B200H264QpelContext *c, int bit_depth)
 {
     if (!c) return B200_EINVAL;
-    if (bit_depth != 8) return B200_ENOSYS;                        // h264qpel.c:87-103 also installs 9/10/12/14 bit tables
+    if (bit_depth != 8 && bit_depth != 9 && bit_depth != 10 && bit_depth != 12 && bit_depth != 14) return B200_ENOSYS;   // h264qpel.c:87-103
     if (!b200_default_device()) return B200_ENODEV;
+    if (bit_depth != 8) { pel_hbd_fill(c, bit_depth); return 0; }  // uint16 samples (pel_hbd.cu)
     fill_qpel<0, 0>(c->put_h264_qpel_pixels_tab[0]); fill_qpel<0, 1>(c->put_h264_qpel_pixels_tab[1]); fill_qpel<0, 2>(c->put_h264_qpel_pixels_tab[2]);
     fill_qpel<1, 0>(c->avg_h264_qpel_pixels_tab[0]); fill_qpel<1, 1>(c->avg_h264_qpel_pixels_tab[1]); fill_qpel<1, 2>(c->avg_h264_qpel_pixels_tab[2]);
     return 0;

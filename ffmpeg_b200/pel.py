@@ -51,6 +51,12 @@ def h264qpel_batch_device(device, n, op, dst, dst_off, src, src_off, stride):
                                                   vp(_dptr(src)), vp(_dptr(src_off)), stride), "h264qpel_batch_device")
 
 
+def h264qpel_hbd_batch_device(device, bit_depth, n, op, dst, dst_off, src, src_off, stride):
+    """9 / 10 / 12 / 14 bit samples (uint16): offsets and stride in bytes"""
+    return check(lib().b200_h264qpel_hbd_batch_device(device.handle, bit_depth, n, vp(_dptr(op)), vp(_dptr(dst)), vp(_dptr(dst_off)),
+                                                      vp(_dptr(src)), vp(_dptr(src_off)), stride), "h264qpel_hbd_batch_device")
+
+
 def h264qpel_frames_host(device, nframes, frame_bytes, op_begin, op, dst, dst_off, src, src_off, stride):
     """HOST buffers (numpy arrays / pinned torch tensors / raw addresses): one reference + destination picture and one operation
     list per frame, pipelined H2D -> kernel -> D2H."""

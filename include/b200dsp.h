@@ -471,7 +471,8 @@ typedef struct B200HpelDSPContext {
     b200_op_pixels_func put_no_rnd_pixels_tab[3][4];       /* only [0..1] filled, like the reference */
     b200_op_pixels_func avg_no_rnd_pixels_tab[4];
 } B200HpelDSPContext;
-int  b200_h264qpel_init(B200H264QpelContext *c, int bit_depth);    /* bit_depth must be 8, else B200_ENOSYS */
+int  b200_h264qpel_init(B200H264QpelContext *c, int bit_depth);    /* bit_depth 8, or 9 / 10 / 12 / 14 (uint16 samples, stride in bytes:
+                                                                     * h264qpel_template.c with BIT_DEPTH > 8); else B200_ENOSYS */
 int  b200_hpeldsp_init(B200HpelDSPContext *c, int flags);
 
 /* batched motion compensation, DEVICE pointers: operation i interpolates the block at src + src_off[i] into
@@ -483,6 +484,9 @@ int  b200_hpeldsp_init(B200HpelDSPContext *c, int flags);
  * result): keep the planes edge-padded by 3 pixels / rows, as H.264 reference frames are (h264_mb.c mc_dir_part). */
 int  b200_h264qpel_batch_device(B200Device *dev, int64_t n, const uint8_t *op, uint8_t *dst, const int64_t *dst_off,
                                 const uint8_t *src, const int64_t *src_off, ptrdiff_t stride);
+/* the same for 9 / 10 / 12 / 14 bit samples (uint16, native endian): op bytes as above, offsets and stride in BYTES (even) */
+int  b200_h264qpel_hbd_batch_device(B200Device *dev, int bit_depth, int64_t n, const uint8_t *op, uint8_t *dst, const int64_t *dst_off,
+                                    const uint8_t *src, const int64_t *src_off, ptrdiff_t stride);
 int  b200_hpel_batch_device(B200Device *dev, int64_t n, const uint8_t *op, const uint8_t *h, uint8_t *dst,
                             const int64_t *dst_off, const uint8_t *src, const int64_t *src_off, ptrdiff_t stride);
 /* HOST buffers, a stream of frames (mc_dir_part for every partition of every macroblock of a picture, h264_mb.c:210-330, collected per

@@ -150,6 +150,9 @@ void orc_esa_frame(const uint8_t *cur, const uint8_t *ref, int linesize, int wid
 
 /* ------------------------------------------------------------------ h264qpel / hpeldsp (8 bit) */
 void orc_h264qpel(int avg, int size_idx, int pos, uint8_t *dst, const uint8_t *src, ptrdiff_t stride);
+void orc_h264qpel_hbd(int depth /* 9, 10, 12, 14 */, int avg, int size_idx, int pos, uint8_t *dst, const uint8_t *src, ptrdiff_t stride_bytes);
+void orc_h264qpel_hbd_batch(int depth, int n, const uint8_t *op, uint8_t *dstbase, const int64_t *dst_off, const uint8_t *srcbase,
+                            const int64_t *src_off, ptrdiff_t stride_bytes);
 void orc_h264qpel_batch(int n, const uint8_t *op, uint8_t *dstbase, const int64_t *dst_off, const uint8_t *srcbase,
                         const int64_t *src_off, ptrdiff_t stride);
 int  orc_hpel(int tab, int size_idx, int xy, uint8_t *block, const uint8_t *pixels, ptrdiff_t line_size, int h);

@@ -83,6 +83,66 @@ void orc_h264qpel(int avg, int size_idx, int pos, uint8_t *dst, const uint8_t *s
             dst[y * stride + x] = avg ? (uint8_t)((dst[y * stride + x] + out[y * 16 + x] + 1) >> 1) : out[y * 16 + x];
 }
 
+/* ---- the same for 9 / 10 / 12 / 14 bit samples (h264qpel_template.c with BIT_DEPTH > 8, h264qpel.c:30-46; tables :87-103): uint16
+ * pixels, clip = av_clip_uintp2(v, depth).  The 10-bit build biases its int16 horizontal sums by -10 * 1023 and removes the bias in
+ * the vertical taps (h264qpel_template.c:131, :146-160): the sums never leave int16 either way, so no value changes.  stride in BYTES. */
+typedef struct { const uint16_t *s; ptrdiff_t st; int maxv; } HbSrc;
+static int hb_clip(const HbSrc *c, int v) { return v < 0 ? 0 : v > c->maxv ? c->maxv : v; }
+static int hbF(const HbSrc *c, int x, int y) { return c->s[y * c->st + x]; }
+static int hb_hraw(const HbSrc *c, int x, int y)
+{
+    const uint16_t *p = c->s + y * c->st + x;
+    return tap6(p[-2], p[-1], p[0], p[1], p[2], p[3]);
+}
+static int hbH(const HbSrc *c, int x, int y) { return hb_clip(c, (hb_hraw(c, x, y) + 16) >> 5); }
+static int hbV(const HbSrc *c, int x, int y)
+{
+    const uint16_t *p = c->s + y * c->st + x;
+    const ptrdiff_t st = c->st;
+    return hb_clip(c, (tap6(p[-2 * st], p[-st], p[0], p[st], p[2 * st], p[3 * st]) + 16) >> 5);
+}
+static int hbJ(const HbSrc *c, int x, int y)
+{
+    return hb_clip(c, (tap6(hb_hraw(c, x, y - 2), hb_hraw(c, x, y - 1), hb_hraw(c, x, y), hb_hraw(c, x, y + 1),
+                            hb_hraw(c, x, y + 2), hb_hraw(c, x, y + 3)) + 512) >> 10);
+}
+
+void orc_h264qpel_hbd(int depth, int avg, int size_idx, int pos, uint8_t *dst8, const uint8_t *src8, ptrdiff_t stride)
+{
+    const int size = 16 >> size_idx, qx = pos & 3, qy = pos >> 2;
+    const HbSrc c = { (const uint16_t *)src8, stride / 2, (1 << depth) - 1 };
+    uint16_t *dst = (uint16_t *)dst8, out[16 * 16];
+    for (int y = 0; y < size; y++)
+        for (int x = 0; x < size; x++) {
+            int v;
+            if (qy == 0)
+                v = qx == 0 ? hbF(&c, x, y) : qx == 2 ? hbH(&c, x, y) : (hbF(&c, x + (qx == 3), y) + hbH(&c, x, y) + 1) >> 1;
+            else if (qx == 0)
+                v = qy == 2 ? hbV(&c, x, y) : (hbF(&c, x, y + (qy == 3)) + hbV(&c, x, y) + 1) >> 1;
+            else if (qx == 2 && qy == 2)
+                v = hbJ(&c, x, y);
+            else if (qx == 2)
+                v = (hbH(&c, x, y + (qy == 3)) + hbJ(&c, x, y) + 1) >> 1;
+            else if (qy == 2)
+                v = (hbV(&c, x + (qx == 3), y) + hbJ(&c, x, y) + 1) >> 1;
+            else
+                v = (hbH(&c, x, y + (qy == 3)) + hbV(&c, x + (qx == 3), y) + 1) >> 1;
+            out[y * 16 + x] = (uint16_t)v;
+        }
+    for (int y = 0; y < size; y++)
+        for (int x = 0; x < size; x++) {
+            uint16_t *d = dst + y * c.st + x;
+            *d = avg ? (uint16_t)((*d + out[y * 16 + x] + 1) >> 1) : out[y * 16 + x];
+        }
+}
+
+void orc_h264qpel_hbd_batch(int depth, int n, const uint8_t *op, uint8_t *dstbase, const int64_t *dst_off, const uint8_t *srcbase,
+                            const int64_t *src_off, ptrdiff_t stride)
+{
+    for (int i = 0; i < n; i++)
+        orc_h264qpel_hbd(depth, op[i] & 1, (op[i] >> 1) & 3, (op[i] >> 3) & 15, dstbase + dst_off[i], srcbase + src_off[i], stride);
+}
+
 /* a list of operations, as ffref_h264qpel_batch / b200_h264qpel_batch_device take it (op byte: bit0 avg, bits1-2 size index, bits3-6 position) */
 void orc_h264qpel_batch(int n, const uint8_t *op, uint8_t *dstbase, const int64_t *dst_off, const uint8_t *srcbase,
                         const int64_t *src_off, ptrdiff_t stride)

@@ -357,6 +357,16 @@ API void ffref_h264qpel(int avg, int size_idx, int pos, uint8_t *dst, const uint
     (avg ? g_qpel.avg_h264_qpel_pixels_tab : g_qpel.put_h264_qpel_pixels_tab)[size_idx][pos](dst, src, stride);
 }
 
+/* 9 / 10 / 12 / 14 bit tables of ff_h264qpel_init (uint16 samples, stride in bytes) */
+API int ffref_h264qpel_hbd(int depth, int avg, int size_idx, int pos, uint8_t *dst, const uint8_t *src, ptrdiff_t stride)
+{
+    static H264QpelContext c[15]; static int ok[15];
+    if (depth != 9 && depth != 10 && depth != 12 && depth != 14) return -1;
+    if (!ok[depth]) { ff_h264qpel_init(&c[depth], depth); ok[depth] = 1; }
+    (avg ? c[depth].avg_h264_qpel_pixels_tab : c[depth].put_h264_qpel_pixels_tab)[size_idx][pos](dst, src, stride);
+    return 0;
+}
+
 API void ffref_h264qpel_batch(int n, const uint8_t *op /* n: bit0 avg, bits1-2 size_idx, bits 3-6 pos */,
                               uint8_t *dstbase, const int64_t *dst_off, const uint8_t *srcbase,
                               const int64_t *src_off, ptrdiff_t stride)

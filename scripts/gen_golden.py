@@ -184,6 +184,25 @@ def gen_tx_pfa_fft():
     np.savez_compressed(os.path.join(OUT, "tx_pfa_fft.npz"), **d)
 
 
+def gen_pel_hbd():
+    """h264qpel at 9 / 10 / 12 / 14 bit: the compiled reference's tables (ff_h264qpel_init(c, depth)) on one random and one two-level
+    picture per depth, every position / size / put+avg; stored as sha256 of the destination picture per case."""
+    R = cl.ref()
+    R.ffref_h264qpel_hbd.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_ssize_t]
+    lines = []
+    for depth in (9, 10, 12, 14):
+        for kind in range(2):
+            img, d0 = cl.hbd_picture(depth, kind)
+            for avg in (0, 1):
+                for si in range(3):
+                    for pos in range(16):
+                        d = d0.copy()
+                        off = (8 * 64 + 8) * 2
+                        R.ffref_h264qpel_hbd(depth, avg, si, pos, d.ctypes.data + off, img.ctypes.data + off, 128)
+                        lines.append(f"{depth} {kind} {avg} {si} {pos} {sha(d)}")
+    open(os.path.join(OUT, "pel_hbd_hashes.txt"), "w").write("\n".join(lines) + "\n")
+
+
 def gen_tx_full_imdct():
     """AV_TX_FULL_IMDCT: the reference's 2 * len outputs of the inverse float MDCT, power-of-two and compound lengths, two scales."""
     R = cl.ref()
@@ -609,6 +628,7 @@ if __name__ == "__main__":
     gen_sws_rgbsrc()
     gen_tx_pfa()
     gen_tx_pfa_fft()
+    gen_pel_hbd()
     gen_tx_full_imdct()
     gen_tx_dct()
     gen_tx_int32()

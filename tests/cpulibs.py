@@ -356,6 +356,15 @@ def ref_unquant(variant, cfg, blocks, blk_n, qscale, last):
 
 
 # ---------------------------------------------------------------- simple IDCT, 10 / 12 bit
+def hbd_picture(depth, kind):
+    """(48 x 64 uint16 reference picture, destination picture) for the high-bit-depth h264qpel cases: kind 0 random samples, kind 1 only
+    0 and the maximum (the extremes of every intermediate)"""
+    rng = np.random.default_rng(1000 * depth + kind)
+    mx = (1 << depth) - 1
+    img = rng.integers(0, mx + 1, (48, 64)).astype(np.uint16) if kind == 0 else (rng.integers(0, 2, (48, 64)) * mx).astype(np.uint16)
+    return img, rng.integers(0, mx + 1, (48, 64)).astype(np.uint16)
+
+
 def idct_hbd_blocks(seed, depth, n):
     """n coefficient blocks: dense small, full int16 range, sparse, DC only, DC-only rows, decoder-like range"""
     rng = np.random.default_rng(seed)

@@ -83,7 +83,7 @@ def emuhost():
     os.makedirs(gen, exist_ok=True)
     cs = os.path.join(ROOT, "ffmpeg_b200", "csrc")
     srcs = []
-    for f in ("fdsp.cu", "unquant.cu", "idct_hbd.cu", "tx_pfa.cu", "h264lf.cu", "pixelutils.cu"):
+    for f in ("fdsp.cu", "unquant.cu", "idct_hbd.cu", "tx_pfa.cu", "h264lf.cu", "pixelutils.cu", "pel_hbd.cu"):
         t = rewrite_launches(open(os.path.join(cs, f)).read())
         t = t.replace("extern __shared__ float2 pfa_z[];", "float2 *pfa_z = (float2 *)emu_smem;")
         assert "<<<" not in t
@@ -93,7 +93,7 @@ def emuhost():
     so = os.path.join(gen, "libemuhost.so")
     cxx = "/opt/gcc/bin/g++" if os.path.exists("/opt/gcc/bin/g++") else "g++"
     r = subprocess.run([cxx, "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread", "-ffp-contract=off", "-w", "-I" + os.path.join(EMU, "fake"), "-I" + cs,
-                        "-I" + os.path.join(ROOT, "include"), "-I" + EMU] + srcs + [os.path.join(EMU, "fake_device.cpp"), "-o", so],
+                        "-I" + os.path.join(ROOT, "include"), "-I" + EMU] + srcs + [os.path.join(EMU, "fake_device.cpp"), os.path.join(EMU, "fake_pel_hbd.cpp"), "-o", so],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
     return C.CDLL(so)
@@ -975,6 +975,54 @@ def test_host_pixelutils_entry_points(emuhost):
     assert not L.b200_pixelutils_get_sad_fn(0, 0, 0, None) and not L.b200_pixelutils_get_sad_fn(6, 6, 0, None) and not L.b200_pixelutils_get_sad_fn(3, 4, 0, None)
     assert L.b200_pixelutils_sad_batch_device(None, 6, f1.ctypes.data, 160, f2.ctypes.data, 203, o1.ctypes.data, o2.ctypes.data, 1, out.ctypes.data) < 0
     assert L.b200_pixelutils_sad_batch_device(None, 3, None, 160, None, 203, None, None, 0, None) == 0
+
+
+def test_host_h264qpel_hbd(emuhost):
+    """pel_hbd.cu (9 / 10 / 12 / 14 bit h264qpel) with its host code on the stand-in runtime: the batched device entry and the drop-in
+    table functions against the checker, every position / size / put+avg, extreme sample patterns included"""
+    L, O = emuhost, cl.oracle()
+    L.b200_h264qpel_hbd_batch_device.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_ssize_t]
+    L.emu_host_qpel_hbd_tab.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_longlong]
+    O.orc_h264qpel_hbd_batch.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_ssize_t]
+    O.orc_h264qpel_hbd.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_ssize_t]
+    dev = C.c_void_p()
+    assert L.b200_device_open(C.byref(dev), 0, None) == 0
+    rng = np.random.default_rng(9)
+    Wd, Hd = 96, 80
+    for depth in (9, 10, 12, 14):
+        mx = (1 << depth) - 1
+        for kind in range(2):
+            img = rng.integers(0, mx + 1, (Hd, Wd)).astype(np.uint16) if kind == 0 else (rng.integers(0, 2, (Hd, Wd)) * mx).astype(np.uint16)
+            ops, doff, soff = [], [], []
+            for avg in (0, 1):
+                for si in range(3):
+                    for pos in range(16):
+                        ops.append(avg | (si << 1) | (pos << 3))
+            n = len(ops)
+            for k in range(n):                                      # destination blocks on a 16 x 16 grid, sources anywhere inside the padding
+                doff.append(((k % 4) * 16 * Wd + (k // 4 % 6) * 16) * 2)
+                soff.append((int(rng.integers(3, Hd - 19)) * Wd + int(rng.integers(3, Wd - 19))) * 2)
+            # 96 operations need 96 disjoint blocks: 4 rows x 6 columns = 24 per picture -> four destination pictures
+            ops_a, doff_a, soff_a = np.array(ops, np.uint8), np.array(doff, np.int64), np.array(soff, np.int64)
+            for part in range(4):
+                sl = slice(part * 24, part * 24 + 24)
+                d0 = rng.integers(0, mx + 1, (Hd, Wd)).astype(np.uint16)
+                got, exp = d0.copy(), d0.copy()
+                assert L.b200_h264qpel_hbd_batch_device(dev, depth, 24, ops_a[sl].ctypes.data, got.ctypes.data, np.ascontiguousarray(doff_a[sl]).ctypes.data,
+                                                        img.ctypes.data, np.ascontiguousarray(soff_a[sl]).ctypes.data, Wd * 2) == 0
+                O.orc_h264qpel_hbd_batch(depth, 24, np.ascontiguousarray(ops_a[sl]).ctypes.data, exp.ctypes.data, np.ascontiguousarray(doff_a[sl]).ctypes.data,
+                                         img.ctypes.data, np.ascontiguousarray(soff_a[sl]).ctypes.data, Wd * 2)
+                assert np.array_equal(got, exp), (depth, kind, part)
+            for k in range(0, n, 7):                                # the drop-in table functions (host pointers, one block)
+                o = ops[k]
+                d0 = rng.integers(0, mx + 1, (Hd, Wd)).astype(np.uint16)
+                got, exp = d0.copy(), d0.copy()
+                off = (20 * Wd + 24) * 2
+                assert L.emu_host_qpel_hbd_tab(depth, o & 1, (o >> 1) & 3, o >> 3, got.ctypes.data + off, img.ctypes.data + off, Wd * 2) == 0
+                O.orc_h264qpel_hbd(depth, o & 1, (o >> 1) & 3, o >> 3, exp.ctypes.data + off, img.ctypes.data + off, Wd * 2)
+                assert np.array_equal(got, exp), (depth, kind, "tab", o)
+    assert L.b200_h264qpel_hbd_batch_device(dev, 11, 1, ops_a.ctypes.data, got.ctypes.data, doff_a.ctypes.data, img.ctypes.data, soff_a.ctypes.data, Wd * 2) == -38
+    assert L.emu_host_qpel_hbd_tab(8, 0, 0, 0, got.ctypes.data, img.ctypes.data, Wd * 2) == -38
 
 
 def test_host_tx_pfa_create_and_launch(emuhost):

@@ -407,6 +407,38 @@ def test_tx_pfa15_oracle_vs_ref_and_round_trip():
     assert np.allclose(coef[0], ref, atol=2e-3), float(np.abs(coef[0] - ref).max())
 
 
+def test_h264qpel_hbd_oracle_golden_and_ref():
+    """h264qpel for 9 / 10 / 12 / 14 bit samples: the restatement against the hashes of the compiled reference's outputs (every position,
+    size, put / avg, a random and a two-level picture per depth), and live against the compiled reference when it is here"""
+    import hashlib
+    O = cl.oracle()
+    sig = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_ssize_t]
+    O.orc_h264qpel_hbd.argtypes = sig
+    R = cl.ref() if cl.have_ref() else None
+    if R:
+        R.ffref_h264qpel_hbd.argtypes = sig
+    n = 0
+    pics = {}
+    for line in open(os.path.join(G, "pel_hbd_hashes.txt")):
+        depth, kind, avg, si, pos, h = line.split()
+        depth, kind, avg, si, pos = int(depth), int(kind), int(avg), int(si), int(pos)
+        if (depth, kind) not in pics:
+            pics[(depth, kind)] = cl.hbd_picture(depth, kind)
+        img, d0 = pics[(depth, kind)]
+        d = d0.copy()
+        off = (8 * 64 + 8) * 2
+        O.orc_h264qpel_hbd(depth, avg, si, pos, d.ctypes.data + off, img.ctypes.data + off, 128)
+        assert hashlib.sha256(d.tobytes()).hexdigest() == h, line
+        size = 16 >> si
+        assert np.array_equal(d[:8], d0[:8]) and np.array_equal(d[8 + size:], d0[8 + size:]) and np.array_equal(d[:, 8 + size:], d0[:, 8 + size:])
+        if R and n % 5 == 0:
+            r = d0.copy()
+            R.ffref_h264qpel_hbd(depth, avg, si, pos, r.ctypes.data + off, img.ctypes.data + off, 128)
+            assert np.array_equal(r, d), line
+        n += 1
+    assert n == 4 * 2 * 96
+
+
 PFA_FFT_SIZES = (6, 12, 96, 10, 160, 14, 224, 18, 288, 30, 120, 960, 1920)
 
 

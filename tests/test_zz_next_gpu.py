@@ -799,3 +799,59 @@ def test_pixelutils_sad(device):
         exp = cl.orc_pixelutils(bits, f1, f2, o1[idx], o2[idx])
         assert np.array_equal(res[idx], exp), bits
     assert me_cmp.av_pixelutils_get_sad_fn(3, 4) is None and me_cmp.av_pixelutils_get_sad_fn(6, 6) is None
+
+
+# ---------------------------------------------------------------------------------------------- h264qpel, 9 / 10 / 12 / 14 bit samples
+def test_h264qpel_hbd(device):
+    """ff_h264qpel_init(c, depth) for depth 9 / 10 / 12 / 14: the drop-in table functions (host pointers) against the hashes of the compiled
+    reference's outputs, and a macroblock stream through the batched device entry against the oracle"""
+    import ctypes as C
+    import hashlib
+    import torch
+    import ffmpeg_b200 as fb
+    from ffmpeg_b200 import pel
+    from ffmpeg_b200._lib import u8p
+    O = cl.oracle()
+    O.orc_h264qpel_hbd_batch.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_ssize_t]
+    tabs, pics, n = {}, {}, 0
+    for k, line in enumerate(open(os.path.join(G, "pel_hbd_hashes.txt"))):
+        if k % 3:
+            continue
+        depth, kind, avg, si, pos, h = line.split()
+        depth, kind, avg, si, pos = int(depth), int(kind), int(avg), int(si), int(pos)
+        if depth not in tabs:
+            tabs[depth] = pel.ff_h264qpel_init(depth)
+        if (depth, kind) not in pics:
+            pics[(depth, kind)] = cl.hbd_picture(depth, kind)
+        img, d0 = pics[(depth, kind)]
+        d = d0.copy()
+        off = (8 * 64 + 8) * 2
+        f = (tabs[depth].avg_h264_qpel_pixels_tab if avg else tabs[depth].put_h264_qpel_pixels_tab)[si][pos]
+        f(C.cast(d.ctypes.data + off, u8p), C.cast(img.ctypes.data + off, u8p), 128)
+        assert hashlib.sha256(d.tobytes()).hexdigest() == h, line
+        n += 1
+    assert n == 256
+    with pytest.raises(fb.B200Error):
+        pel.ff_h264qpel_init(11)
+    rng = np.random.default_rng(14)
+    W, H = 640, 368
+    for depth in (9, 10, 12, 14):
+        ref_ = rng.integers(0, 1 << depth, (H, W)).astype(np.uint16)
+        dst0 = rng.integers(0, 1 << depth, (H, W)).astype(np.uint16)
+        ops, doffs, soffs = [], [], []
+        for by in range(1, H // 16 - 1):
+            for bx in range(1, W // 16 - 1):
+                ops.append(pel.qpel_op(int(rng.integers(0, 2)), int(rng.integers(0, 3)), int(rng.integers(0, 16))))
+                dx, dy = (int(v) for v in rng.integers(-10, 11, 2))
+                doffs.append((by * 16 * W + bx * 16) * 2); soffs.append(((by * 16 + dy) * W + bx * 16 + dx) * 2)
+        cnt = len(ops)
+        ops_a, do_a, so_a = np.array(ops, np.uint8), np.array(doffs, np.int64), np.array(soffs, np.int64)
+        exp = dst0.copy()
+        O.orc_h264qpel_hbd_batch(depth, cnt, ops_a.ctypes.data, exp.ctypes.data, do_a.ctypes.data, ref_.ctypes.data, so_a.ctypes.data, W * 2)
+        with on_stream(device):
+            d_ops, d_do, d_so = torch.from_numpy(ops_a).cuda(), torch.from_numpy(do_a).cuda(), torch.from_numpy(so_a).cuda()
+            d_dst, d_src = torch.from_numpy(dst0.view(np.int16)).cuda(), torch.from_numpy(ref_.view(np.int16)).cuda()
+            pel.h264qpel_hbd_batch_device(device, depth, cnt, d_ops, d_dst, d_do, d_src, d_so, W * 2)
+            device.sync()
+            got = d_dst.cpu().numpy().view(np.uint16)
+        assert np.array_equal(got, exp), (depth, int((got != exp).sum()))
