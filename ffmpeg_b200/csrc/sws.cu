@@ -918,7 +918,7 @@ static int upload_tables(B200SwsContext *c)
     const SwsPlan &p = c->plan;
     if (c->tables) { cudaFree(c->tables); c->tables = nullptr; }
     if (c->mma_tables) { cudaFree(c->mma_tables); c->mma_tables = nullptr; c->mmaL = SwsMmaBank{}; c->mmaC = SwsMmaBank{}; }
-    if (p.unscaled_lut || p.planar_copy || p.bgr24_yv12) return 0;
+    if (p.unscaled_lut || p.planar_copy || p.bgr24_yv12 || p.rgb_shuffle) return 0;
     auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
     size_t off = 0;
     size_t o_vl = off;  off += al(p.vLum.coef.size() * 2);
@@ -1137,6 +1137,7 @@ B200_API int b200_sws_plan_probe2(const int cfg[9], const int *details, int whic
         o[22] = p.fast_bilinear; o[23] = p.src_nv; o[24] = dret; o[25] = p.src_range; o[26] = p.dst_range;
         o[27] = p.src_rgb; o[28] = p.chrSrcHSub; o[29] = p.chrSrcVSub; o[30] = p.bgr24_yv12; o[31] = p.dst_nv;
         for (int i = 0; i < 9; i++) o[32 + i] = p.rgb2yuv[i];
+        o[41] = p.rgb_shuffle; o[42] = (int)p.shuffle_sel;
     }
     const SwsFilterBank &b = which == 0 ? p.hLum : which == 1 ? p.hChr : which == 2 ? p.vLum : p.vChr;
     int n = b.n < cap ? b.n : cap;
@@ -1806,11 +1807,83 @@ static int launch_batch(B200SwsContext *c, cudaStream_t stream, const uint8_t *c
 // packed RGB source -> packed RGB destination (always through the scaler: the same-size case is the reference's rgb2rgb shuffle and
 // is refused at context creation): input readers + 16-bit horizontal pass into the int16 line planes, then the same vertical
 // writers as the yuv-source scaled path (the stage after the horizontal pass in launch_batch)
+// Same-size packed RGB -> packed RGB (rgbToRgbWrapper's byte shuffles / packedCopyWrapper, swscale_unscaled.c:2001-2060,2138-2170): every
+// destination byte is one source byte of the same pixel or the constant 255 (alpha of a 24-bit source).  A thread takes four pixels as
+// whole 32-bit words when both lines are 4-byte aligned, else (and for the last pixels of a line) one pixel byte by byte.
+template <int SB, int DB>
+__global__ void __launch_bounds__(128)
+sws_rgb_shuffle_kernel(const uint8_t *__restrict__ src, long long sstride, long long sfs, uint8_t *__restrict__ dst, long long dstride, long long dfs,
+                       int W, unsigned sel, int vec)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;           // group of four pixels
+    const uint8_t *s = src + (long long)blockIdx.z * sfs + (long long)blockIdx.y * sstride;
+    uint8_t *d = dst + (long long)blockIdx.z * dfs + (long long)blockIdx.y * dstride;
+    const int x0 = 4 * q;
+    if (x0 >= W) return;
+    if (vec && x0 + 4 <= W) {
+        unsigned px[4], o[4];
+        if (SB == 4) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(s + 16LL * q);
+            px[0] = v.x; px[1] = v.y; px[2] = v.z; px[3] = v.w;
+        } else {
+            const unsigned *w = reinterpret_cast<const unsigned *>(s + 12LL * q);
+            const unsigned w0 = w[0], w1 = w[1], w2 = w[2];
+            px[0] = w0; px[1] = __funnelshift_r(w0, w1, 24); px[2] = __funnelshift_r(w1, w2, 16); px[3] = w2 >> 8;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) o[k] = __byte_perm(px[k], 0xffu, sel);
+        if (DB == 4) {
+            *reinterpret_cast<uint4 *>(d + 16LL * q) = make_uint4(o[0], o[1], o[2], o[3]);
+        } else {
+            unsigned *w = reinterpret_cast<unsigned *>(d + 12LL * q);
+            w[0] = __byte_perm(o[0], o[1], 0x4210); w[1] = __byte_perm(o[1], o[2], 0x5421); w[2] = __byte_perm(o[2], o[3], 0x6542);
+        }
+        return;
+    }
+    for (int x = x0; x < min(x0 + 4, W); x++) {
+        unsigned px = 0;
+#pragma unroll
+        for (int b = 0; b < SB; b++) px |= (unsigned)s[(long long)x * SB + b] << (8 * b);
+        const unsigned o = __byte_perm(px, 0xffu, sel);
+#pragma unroll
+        for (int b = 0; b < DB; b++) d[(long long)x * DB + b] = (uint8_t)(o >> (8 * b));
+    }
+}
+
+static void launch_rgb_shuffle(const SwsPlan &p, cudaStream_t stream, const uint8_t *src, long long sstr, long long sfs, uint8_t *dst, long long ds,
+                               long long dfs, int lines, int nframes)
+{
+    // 16-byte accesses for 4-byte pixels, 4-byte accesses for 3-byte pixels
+    auto al = [](const void *ptr, long long a, long long b, int n) { return ((reinterpret_cast<uintptr_t>(ptr) | (uintptr_t)a | (uintptr_t)b) & (uintptr_t)(n - 1)) == 0; };
+    const int vec = al(src, sstr, sfs, p.src_rgb == 4 ? 16 : 4) && al(dst, ds, dfs, p.out.bpp == 4 ? 16 : 4);
+    for (int f0 = 0; f0 < nframes; f0 += 65535) {
+        const int nf = nframes - f0 < 65535 ? nframes - f0 : 65535;
+        const uint8_t *s = src + (long long)f0 * sfs;
+        uint8_t *d = dst + (long long)f0 * dfs;
+        for (int l0 = 0; l0 < lines; l0 += 65535) {
+            const int nl = lines - l0 < 65535 ? lines - l0 : 65535;
+            dim3 block(128), grid(b200_ceil_div(b200_ceil_div(p.srcW, 4), 128), nl, nf);
+            const uint8_t *sl = s + (long long)l0 * sstr;
+            uint8_t *dl = d + (long long)l0 * ds;
+            if (p.src_rgb == 4 && p.out.bpp == 4)      sws_rgb_shuffle_kernel<4, 4><<<grid, block, 0, stream>>>(sl, sstr, sfs, dl, ds, dfs, p.srcW, p.shuffle_sel, vec);
+            else if (p.src_rgb == 4)                   sws_rgb_shuffle_kernel<4, 3><<<grid, block, 0, stream>>>(sl, sstr, sfs, dl, ds, dfs, p.srcW, p.shuffle_sel, vec);
+            else if (p.out.bpp == 4)                   sws_rgb_shuffle_kernel<3, 4><<<grid, block, 0, stream>>>(sl, sstr, sfs, dl, ds, dfs, p.srcW, p.shuffle_sel, vec);
+            else                                       sws_rgb_shuffle_kernel<3, 3><<<grid, block, 0, stream>>>(sl, sstr, sfs, dl, ds, dfs, p.srcW, p.shuffle_sel, vec);
+            B200_LAUNCHED();
+        }
+    }
+}
+
 static int launch_rgbsrc_packed(B200SwsContext *c, cudaStream_t stream, const uint8_t *src, long long sstr, long long sfs,
                                 uint8_t *dst, long long ds, long long dfs, int nframes)
 {
     const SwsPlan &p = c->plan;
     if (nframes <= 0) return 0;
+    if (p.rgb_shuffle) {
+        launch_rgb_shuffle(p, stream, src, sstr, sfs, dst, ds, dfs, p.srcH, nframes);
+        B200_CUDA_OK(cudaGetLastError());
+        return 0;
+    }
     RgbIn Rg;
     Rg.bpp = p.src_rgb; Rg.ro = p.sro; Rg.go = p.sgo; Rg.bo = p.sbo; Rg.half = p.chrSrcHSub;
     for (int i = 0; i < 9; i++) Rg.c[i] = p.rgb2yuv[i];
@@ -2406,6 +2479,20 @@ B200_API int b200_sws_scale(B200SwsContext *c, const uint8_t *const srcSlice[], 
         B200Device *dv = c->dev;
         B200_CUDA_OK(cudaSetDevice(dv->ordinal));
         const size_t sPitch = ((size_t)p.srcW * p.src_rgb + 255) & ~(size_t)255, dPitch = ((size_t)p.dstW * p.out.bpp + 255) & ~(size_t)255;
+        if (p.rgb_shuffle) {                                      // convert_unscaled handles exactly the band it is given
+            B200_LOCK_DEVICE(dv);
+            uint8_t *scr3 = (uint8_t *)b200_scratch(dv, (sPitch + dPitch) * (size_t)srcSliceH);
+            if (!scr3) return B200_ENOMEM;
+            uint8_t *dd3 = scr3 + sPitch * (size_t)srcSliceH;
+            cudaStream_t st3 = dv->stream;
+            B200_CUDA_OK(b200_h2d_rows(scr3, sPitch, srcSlice[0], srcStride[0], (size_t)p.srcW * p.src_rgb, srcSliceH, st3));
+            launch_rgb_shuffle(p, st3, scr3, (long long)sPitch, 0, dd3, (long long)dPitch, 0, srcSliceH, 1);
+            B200_CUDA_OK(cudaGetLastError());
+            B200_CUDA_OK(b200_d2h_rows(dst[0] + (long long)srcSliceY * dstStride[0], dstStride[0], dd3, dPitch, (size_t)p.dstW * p.out.bpp, srcSliceH, st3));
+            B200_CUDA_OK(cudaStreamSynchronize(st3));
+            c->slice_open = srcSliceY + srcSliceH < p.srcH;
+            return srcSliceH;
+        }
         if (!c->slice_buf) B200_CUDA_OK(cudaMalloc(&c->slice_buf, sPitch * p.srcH + dPitch * p.dstH));
         uint8_t *sb = (uint8_t *)c->slice_buf, *db = sb + sPitch * p.srcH;
         cudaStream_t st2 = dv->stream;

@@ -399,7 +399,27 @@ int sws_plan_build(SwsPlan &p, int srcW, int srcH, int dstW, int dstH, int flags
     p.fast_bilinear = algo == B200_SWS_FAST_BILINEAR && !p.src_rgb;
     p.planar = sws_out_is_yuv(p.out.kind);
     p.dst_nv = p.out.kind == SWS_OUT_NV12 ? 1 : p.out.kind == SWS_OUT_NV21 ? 2 : 0;
-    if (p.src_rgb && !p.planar && srcW == dstW && srcH == dstH) return B200_ENOSYS;          // the reference's rgb2rgb shuffles: not this path
+    p.rgb_shuffle = false;
+    if (p.src_rgb && !p.planar && srcW == dstW && srcH == dstH) {
+        // same size, packed RGB both sides: a copy for equal formats (packedCopyWrapper, swscale_unscaled.c:2675-2690), else the byte
+        // shuffles of rgbToRgbWrapper (:2001-2060) when findRgbConvFn (:1843-1998) has one: always between the four 32-bit orders,
+        // between rgb24 and bgr24 and from 32 to 24 bits; from 24 to 32 bits unless SWS_BITEXACT asks for bgra / rgba (little endian:
+        // RGB32 / BGR32, "maintain symmetry between endianness" :1992-1995), which then goes through the scaler like any other pair
+        const bool to32 = p.src_rgb == 3 && p.out.bpp == 4;
+        const bool a_last = p.out.bpp == 4 && p.out.ao == 3;                                 // bgra (AV_PIX_FMT_RGB32) / rgba (BGR32) on little endian
+        if (!(to32 && a_last && (flags & B200_SWS_BITEXACT))) {
+            const int sao = p.src_rgb == 4 ? 6 - p.sro - p.sgo - p.sbo : 4;                  // 4 selects the constant 255
+            unsigned sel = 0;
+            sel |= (unsigned)p.sro << (4 * p.out.ro);
+            sel |= (unsigned)p.sgo << (4 * p.out.go);
+            sel |= (unsigned)p.sbo << (4 * p.out.bo);
+            if (p.out.bpp == 4) sel |= (unsigned)sao << (4 * p.out.ao);
+            p.rgb_shuffle = true; p.shuffle_sel = sel;
+            p.srcW = srcW; p.srcH = srcH; p.dstW = dstW; p.dstH = dstH; p.flags = flags;
+            p.chrSrcW = srcW; p.chrSrcH = srcH; p.chrDstW = dstW; p.chrDstH = dstH; p.chrSrcHSub = p.chrSrcVSub = 0; p.chrDstHSub = 0;
+            return 0;
+        }
+    }
     if (p.src_rgb == 4 && !p.planar && p.out.bpp == 4) return B200_ENOSYS;                   // alpha carried through the scaler: not built
     if (!p.planar && (dstW & 1)) flags |= B200_SWS_FULL_CHR_H_INT;               // utils.c:1271-1276 (RGB destinations only)
     if (!p.planar && p.src_rgb && !(flags & B200_SWS_FAST_BILINEAR))

@@ -449,7 +449,21 @@ OrcSws *orc_sws_open_range(int srcFormat, int srcW, int srcH, int srcRange, int 
     } else if (srcFormat != ORC_PIX_FMT_YUV420P && srcFormat != ORC_PIX_FMT_NV12 && srcFormat != ORC_PIX_FMT_NV21) { free(s); return NULL; }
     if (set_format(s, dstFormat) < 0) { free(s); return NULL; }
     s->dst_nv = dstFormat == ORC_PIX_FMT_NV12 ? 1 : dstFormat == ORC_PIX_FMT_NV21 ? 2 : 0;
-    if (s->src_rgb && !s->planar && srcW == dstW && srcH == dstH) { free(s); return NULL; }    /* rgb2rgb shuffles: not this path */
+    if (s->src_rgb && !s->planar && srcW == dstW && srcH == dstH) {
+        /* same size, packed RGB on both sides: packedCopyWrapper for equal formats (swscale_unscaled.c:2675-2690), else rgbToRgbWrapper
+         * (:2001-2060) whenever findRgbConvFn (:1843-1998) returns a function.  For the six 8-bit formats here it always does --
+         * shuffle_bytes_* between the 32-bit orders, rgb24tobgr24, rgb32to24 / rgb32tobgr24, rgb24to32 / rgb24tobgr32 -- except under
+         * SWS_BITEXACT from 24 bits to AV_PIX_FMT_RGB32 / BGR32 (bgra / rgba on little endian; :1992-1995), which the scaler handles.
+         * Every one of them moves R, G, B (and A) of a pixel to their places in the destination order; a destination alpha without a
+         * source alpha is 255 (rgb24to32 family, rgb2rgb_template.c; the first byte of each line for argb / abgr, :2030-2036). */
+        const int to32 = s->src_rgb == 3 && s->bpp == 4;
+        if (!(to32 && s->ao == 3 && (flags & ORC_SWS_BITEXACT))) {
+            s->srcW = srcW; s->srcH = srcH; s->dstW = dstW; s->dstH = dstH; s->flags = flags;
+            s->chrSrcW = s->chrDstW = srcW; s->chrSrcH = s->chrDstH = srcH;
+            s->unscaled_lut = 4;
+            return s;
+        }
+    }
     if (s->src_rgb == 4 && !s->planar && s->bpp == 4) { free(s); return NULL; }                /* alpha carried through the scaler
                                                                                                  * (alpToYV12 + the A writers): not restated */
     s->src_nv = srcFormat == ORC_PIX_FMT_NV12 ? 1 : srcFormat == ORC_PIX_FMT_NV21 ? 2 : 0;
@@ -498,7 +512,7 @@ OrcSws *orc_sws_open_range(int srcFormat, int srcW, int srcH, int srcRange, int 
     }
     /* swscale_unscaled.c:2426-2431 through utils.c:1623-1637: only planar yuv420p/422p sources have the LUT converter
      * (packed RGB destination: dst_range was forced to 0 above; isAnyRGB(dst) passes the range test of utils.c:1625) */
-    if (!s->planar && !s->src_nv && srcW == dstW && srcH == dstH && !(flags & ORC_SWS_ACCURATE_RND) && !(dstH & 1)) {
+    if (!s->planar && !s->src_nv && !s->src_rgb && srcW == dstW && srcH == dstH && !(flags & ORC_SWS_ACCURATE_RND) && !(dstH & 1)) {
         s->unscaled_lut = 1;
         return s;
     }
@@ -893,6 +907,17 @@ int orc_sws_scale(OrcSws *s, const uint8_t *y, int ys, const uint8_t *u, int us,
         s->src_nv = nv;
         free(t);
         return r;
+    }
+    if (s->unscaled_lut == 4) {                                    /* rgbToRgbWrapper / packedCopyWrapper: y is the packed source picture */
+        const int sao = s->src_rgb == 4 ? 6 - s->sro - s->sgo - s->sbo : -1;
+        for (int r = 0; r < s->srcH; r++)
+            for (int x = 0; x < s->srcW; x++) {
+                const uint8_t *p = y + (size_t)r * ys + (size_t)x * s->src_rgb;
+                uint8_t *q = dst + (size_t)r * ds + (size_t)x * s->bpp;
+                q[s->ro] = p[s->sro]; q[s->go] = p[s->sgo]; q[s->bo] = p[s->sbo];
+                if (s->bpp == 4) q[s->ao] = sao >= 0 ? p[sao] : 255;
+            }
+        return s->srcH;
     }
     if (s->unscaled_lut) {
         convert_unscaled(s, y, ys, u, us, v, vs, dst, ds);

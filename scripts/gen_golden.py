@@ -184,6 +184,23 @@ def gen_tx_pfa_fft():
     np.savez_compressed(os.path.join(OUT, "tx_pfa_fft.npz"), **d)
 
 
+RGB2RGB_FLAGS = (4, 4 | 0x80000, 4 | 0x80000 | 0x40000, 16)
+
+
+def gen_sws_rgb2rgb():
+    """same-size packed RGB -> packed RGB (rgbToRgbWrapper / packedCopyWrapper, or the scaler where findRgbConvFn has nothing): sha256 of
+    the reference's destination picture for every ordered pair of the six formats, two sizes, four flag sets."""
+    lines = []
+    for (w, h) in ((37, 10), (64, 8)):
+        for sn, sf in cl.PACKED_RGB_FORMATS.items():
+            src = cl.rgb_frame(w, h, 2600 + w, cl.fmt_bpp(sf), "random", pad=3)
+            for dn, df in cl.PACKED_RGB_FORMATS.items():
+                for fl in RGB2RGB_FLAGS:
+                    out = cl.ref_sws(w, h, w, h, fl, src, src, src, fmt=df, src_fmt=sf)
+                    lines.append(f"{w} {h} {sn} {dn} {fl} {sha(out)}")
+    open(os.path.join(OUT, "sws_rgb2rgb_hashes.txt"), "w").write("\n".join(lines) + "\n")
+
+
 def gen_pel_hbd():
     """h264qpel at 9 / 10 / 12 / 14 bit: the compiled reference's tables (ff_h264qpel_init(c, depth)) on one random and one two-level
     picture per depth, every position / size / put+avg; stored as sha256 of the destination picture per case."""
@@ -629,6 +646,7 @@ if __name__ == "__main__":
     gen_tx_pfa()
     gen_tx_pfa_fft()
     gen_pel_hbd()
+    gen_sws_rgb2rgb()
     gen_tx_full_imdct()
     gen_tx_dct()
     gen_tx_int32()

@@ -216,7 +216,9 @@ def _sws_run(lib, pre, w, h, dw, dh, flags, y, u, v, dst_pad=0, threads=1, color
                 lib.orc_sws_set_colorspace_details(ctx, ptr(tab, i32p), colorspace[1], ptr(tab2, i32p), colorspace[3], colorspace[4], colorspace[5],
                                                    colorspace[6])
         ds = dw * fmt_bpp(fmt) + dst_pad
-        dst = np.full((dh, ds), 0xA5, dtype=np.uint8)
+        # one spare line: rgbToRgbWrapper into argb / abgr from a 24-bit source writes one byte past the last pixel (the alpha of a "next"
+        # pixel, swscale_unscaled.c:2030-2042), which real AVFrame buffers absorb in their padding
+        dst = np.full((dh + 1, ds), 0xA5, dtype=np.uint8)[:dh]
         if pre == "ffref":
             n = lib.ffref_sws_scale(ctx, ptr(y), y.strides[0], ptr(u), u.strides[0], ptr(v), v.strides[0], 0, h, ptr(dst), ds)
         else:

@@ -420,8 +420,57 @@ def test_sws_oracle_rgb_sources_vs_ref():
             b = cl.orc_sws(w, h, dw, dh, fl, src, src, src, fmt=df, src_fmt=sf, dst_pad=2)
             assert np.array_equal(a, b), (w, h, dw, dh, hex(fl), names[it % 6], df)
     O = cl.oracle()
-    assert not O.orc_sws_open_io(cl.PIX_FMT_RGB24, 64, 48, cl.PIX_FMT_BGR24, 64, 48, FATE)      # same-size rgb -> rgb: rgb2rgb, not this path
     assert not O.orc_sws_open_io(cl.PIX_FMT_RGBA, 64, 48, cl.PIX_FMT_BGRA, 32, 24, FATE)        # alpha through the scaler: not restated
+
+
+def rgb2rgb_rows():
+    rows = []
+    for line in open(os.path.join(G, "sws_rgb2rgb_hashes.txt")):
+        w, h, sn, dn, fl, hsh = line.split()
+        rows.append((int(w), int(h), sn, dn, int(fl), hsh))
+    return rows
+
+
+def run_rgb2rgb_row(run, row):
+    w, h, sn, dn, fl, _ = row
+    sf, df = cl.PACKED_RGB_FORMATS[sn], cl.PACKED_RGB_FORMATS[dn]
+    src = cl.rgb_frame(w, h, 2600 + w, cl.fmt_bpp(sf), "random", pad=3)
+    return run(w, h, w, h, fl, src, src, src, fmt=df, src_fmt=sf)
+
+
+def test_sws_oracle_same_size_rgb_to_rgb():
+    """rgbToRgbWrapper / packedCopyWrapper (and the scaler where SWS_BITEXACT removes the 24 -> 32 bit shuffle): the restatement and the
+    product's plan against the reference's outputs for every ordered pair of the six packed formats"""
+    import ffmpeg_b200 as fb
+    L = fb.lib()
+    rows = rgb2rgb_rows()
+    assert len(rows) == 2 * 36 * 4
+    nshuf = 0
+    for row in rows:
+        w, h, sn, dn, fl, hsh = row
+        assert sha(run_rgb2rgb_row(cl.orc_sws, row)) == hsh, row[:5]
+        cfg = np.array([w, h, cl.PACKED_RGB_FORMATS[sn], 0, w, h, cl.PACKED_RGB_FORMATS[dn], 0, fl], np.int32)
+        pi = np.zeros(48, np.int32)
+        assert L.b200_sws_plan_probe2(cl.ptr(cfg, cl.i32p), None, 0, None, None, 0, cl.ptr(pi, cl.i32p)) >= 0
+        through_scaler = (fl & 0x80000) and sn in ("rgb24", "bgr24") and dn in ("rgba", "bgra")
+        assert bool(pi[41]) == (not through_scaler), row[:5]
+        nshuf += int(pi[41])
+    assert nshuf == 2 * (36 * 4 - 4 * 2)
+    if cl.have_ref():                                               # other sizes / paddings live
+        rng = np.random.default_rng(5)
+        names = list(cl.PACKED_RGB_FORMATS)
+        for it in range(60):
+            w, h = int(rng.integers(1, 70)), int(rng.integers(1, 20))
+            sn, dn = names[int(rng.integers(0, 6))], names[int(rng.integers(0, 6))]
+            sf, df = cl.PACKED_RGB_FORMATS[sn], cl.PACKED_RGB_FORMATS[dn]
+            fl = int(rng.choice([4, 4 | 0x80000, 2, 0x10]))
+            if w < 8 and (fl & 0x80000) and sn in ("rgb24", "bgr24") and dn in ("rgba", "bgra"):
+                continue                                            # tiny pictures through the scaler: not the point here
+            src = cl.rgb_frame(w, h, 2700 + it, cl.fmt_bpp(sf), "random", pad=int(rng.integers(0, 5)))
+            a = cl.ref_sws(w, h, w, h, fl, src, src, src, fmt=df, src_fmt=sf, dst_pad=2)
+            b = cl.orc_sws(w, h, w, h, fl, src, src, src, fmt=df, src_fmt=sf, dst_pad=2)
+            wb = w * cl.fmt_bpp(df)                                 # the reference may write one byte past a line (alpha of the "next" pixel)
+            assert np.array_equal(a[:, :wb], b[:, :wb]), (w, h, sn, dn, hex(fl))
 
 
 def test_sws_oracle_nv_destinations_vs_ref():

@@ -407,8 +407,6 @@ def test_sws_rgb_sources_large_padded_batch(device):
         for i in range(n):
             assert np.array_equal(got[i], cl.orc_sws(w, h, dw, dh, FATE, frames[i], frames[i], frames[i], fmt=df, src_fmt=cl.PIX_FMT_RGB24)), (dname, i)
         ctx.free()
-    with pytest.raises(fb.B200Error):                                  # same size: the reference's rgb2rgb shuffles, not this path
-        sw.sws_getContext(device, 64, 48, sw.AV_PIX_FMT_RGB24, 64, 48, sw.AV_PIX_FMT_BGR24, FATE)
     with pytest.raises(fb.B200Error):                                  # alpha carried through the scaler: not built
         sw.sws_getContext(device, 64, 48, sw.AV_PIX_FMT_RGBA, 32, 24, sw.AV_PIX_FMT_BGRA, FATE)
 
@@ -855,3 +853,51 @@ def test_h264qpel_hbd(device):
             device.sync()
             got = d_dst.cpu().numpy().view(np.uint16)
         assert np.array_equal(got, exp), (depth, int((got != exp).sum()))
+
+
+# ---------------------------------------------------------------------------------------------- swscale: same-size packed RGB -> packed RGB
+def test_sws_same_size_rgb_to_rgb(device):
+    """rgbToRgbWrapper / packedCopyWrapper (byte shuffles; the scaler where SWS_BITEXACT removes the 24 -> 32 bit shuffle): sws_scale on host
+    buffers against the reference's hashes for every ordered pair of formats, then slices, a batch on the device (vector and byte
+    paths) and a 4K frame against the oracle"""
+    import torch
+    from ffmpeg_b200 import swscale as sw
+    from test_oracle import rgb2rgb_rows, run_rgb2rgb_row, sha
+    from test_sws_gpu import gpu_sws
+    import functools
+    rows = rgb2rgb_rows()
+    assert len(rows) == 288
+    for row in rows:
+        assert sha(run_rgb2rgb_row(functools.partial(gpu_sws, device), row)) == row[-1], row[:5]
+    rng = np.random.default_rng(8)
+    names = list(cl.PACKED_RGB_FORMATS)
+    for it in range(12):                                                # band by band (convert_unscaled converts exactly the band it is given)
+        sn, dn = names[it % 6], names[(it * 5 + 1) % 6]
+        sf, df = cl.PACKED_RGB_FORMATS[sn], cl.PACKED_RGB_FORMATS[dn]
+        w, h = 50 + it, 33
+        src = cl.rgb_frame(w, h, 2800 + it, cl.fmt_bpp(sf), "random", pad=it % 4)
+        exp = cl.orc_sws(w, h, w, h, 4, src, src, src, fmt=df, src_fmt=sf)
+        ctx = sw.sws_getContext(device, w, h, sf, w, h, df, 4)
+        out = np.zeros_like(exp)
+        y = 0
+        for bh in (5, 1, 16, 11):
+            assert ctx.scale([src[y:]], [src.strides[0]], y, bh, [out], [out.strides[0]]) == bh
+            y += bh
+        assert y == h and np.array_equal(out, exp), (sn, dn)
+        ctx.free()
+    for (sn, dn, w, h, n, pad) in (("rgba", "bgra", 640, 360, 3, 0), ("rgb24", "bgr24", 640, 360, 3, 0), ("bgr24", "argb", 322, 75, 2, 2),
+                                   ("abgr", "rgb24", 641, 33, 2, 0), ("rgb24", "rgb24", 128, 16, 2, 0), ("rgba", "abgr", 3840, 2160, 1, 0)):
+        sf, df = cl.PACKED_RGB_FORMATS[sn], cl.PACKED_RGB_FORMATS[dn]
+        sb, db = cl.fmt_bpp(sf), cl.fmt_bpp(df)
+        frames = [cl.rgb_frame(w, h, 2900 + k, sb, "random", pad=pad) for k in range(n)]
+        ctx = sw.sws_getContext(device, w, h, sf, w, h, df, 4)
+        with torch.cuda.stream(torch.cuda.ExternalStream(device.stream)):
+            S = torch.from_numpy(np.stack(frames)).cuda()
+            D = torch.zeros((n, h, w * db + pad), dtype=torch.uint8, device="cuda")
+            ctx.scale_batch_device([S], [w * sb + pad], [(w * sb + pad) * h], D, w * db + pad, (w * db + pad) * h, n)
+            device.sync()
+            got = D.cpu().numpy()
+        for i in range(n):
+            exp = cl.orc_sws(w, h, w, h, 4, frames[i], frames[i], frames[i], fmt=df, src_fmt=sf)
+            assert np.array_equal(got[i][:, :w * db], exp), (sn, dn, i)
+        ctx.free()
