@@ -1,7 +1,7 @@
 // pel_hbd.cu — libavcodec h264qpel for 9, 10, 12 and 14 bit samples (uint16 pixels) on sm_100a: the tables ff_h264qpel_init(c, depth)
 // installs for depth > 8 (libavcodec/h264qpel.c:50-104; h264qpel_template.c instantiated with BIT_DEPTH 9 / 10 / 12 / 14, :30-46).
 //
-// Reference semantics reproduced bit for bit (checker: orc_h264qpel_hbd in oracle/pel_oracle.c, pinned on the compiled reference):
+// Reference semantics reproduced bit for bit (checker: the 16-bit qpel part of oracle/pel_oracle.c, pinned on the compiled reference):
 //   H264_LOWPASS h / v / hv   libavcodec/h264qpel_template.c:77-305   taps (1,-5,20,20,-5,1); h and v: clip((t + 16) >> 5); hv: the unrounded
 //                             horizontal sums over size + 5 rows, then the vertical taps and clip((t + 512) >> 10).  The 10-bit build
 //                             offsets the int16 intermediate by -10 * 1023 and takes it out again (:131, :146-160): no value changes.

@@ -707,6 +707,63 @@ sws_rgbin_hscale_y_kernel(const uint8_t *src, long long sstride, long long sfs, 
     dst[(long long)blockIdx.z * dfs + (long long)line * dstW + i] = (int16_t)min(acc >> 13, 32767);
 }
 
+// the alpha plane of a 32-bit source when the destination carries alpha too (c->needAlpha): rgbaToA_c / abgrToA_c (input.c:455-475) widen
+// the byte to 14 bits, then the luma filter like any other line (hscale.c:103-160; hScale16To15_c, shift 13 for RGB sources)
+__global__ void __launch_bounds__(256)
+sws_rgbin_hscale_a_kernel(const uint8_t *src, long long sstride, long long sfs, int16_t *dst, int dstW, long long dfs,
+                          const int16_t *filter, const int32_t *pos, int fs, int sao)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= dstW) return;
+    const int line = blockIdx.y;
+    const uint8_t *s = src + (long long)blockIdx.z * sfs + (long long)line * sstride;
+    const int p0 = __ldg(pos + i);
+    const int16_t *f = filter + (long long)i * fs;
+    int acc = 0;
+    for (int j = 0; j < fs; j++) {
+        const int a = (int)__ldg(s + (long long)(p0 + j) * 4 + sao);
+        acc += (a << 6 | a >> 2) * (int)__ldg(f + j);
+    }
+    dst[(long long)blockIdx.z * dfs + (long long)line * dstW + i] = (int16_t)min(acc >> 13, 32767);
+}
+
+// Alpha of the packed writers, run after the RGB writer has stored 255: the vertical luma filter on the alpha lines.
+//   full-chroma writers (output.c:2191-2199 _X, :2240-2244 _2, :2282-2286 _1): (1 << 18 + sum) >> 19, (a0 ya1 + a1 ya + (1 << 18)) >> 19,
+//   (a0 + 64) >> 7, each clipped only when bit 8 is set;
+//   two-pixel writers (:1818-1830 _X: both clipped when either has bit 8 set; :1867-1872 _2: no rounding term; :1903-1908 / :1928-1933 _1:
+//   (a0 * 255 + 16384) >> 15 below uvalpha 2048, else (a0 + 64) >> 7), always clipped.
+// mode / yalpha / uvalpha per output line as packed_vscale picks them (rowMode, vscale.c:144-169).  One thread per pixel.
+__global__ void __launch_bounds__(256)
+sws_vscale_alpha_kernel(const int16_t *al, long long alfs, int srcH, uint8_t *dst, long long ds, long long dfs, int dstW, int bpp, int ao,
+                        const int16_t *vLum, const int32_t *vLumPos, int lfs, const int32_t *rowMode, int full, int y0)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= dstW) return;
+    const int dy = blockIdx.y + y0;
+    const int16_t *plane = al + (long long)blockIdx.z * alfs;
+    const int16_t *lf = vLum + (long long)dy * lfs;
+    const int firstLum = max(1 - lfs, __ldg(vLumPos + dy));
+    const int mode = __ldg(rowMode + 4 * dy), yalpha = __ldg(rowMode + 4 * dy + 1), uvalpha = __ldg(rowMode + 4 * dy + 2);
+    auto A_ = [&](int line, int xx) { line = min(max(line, 0), srcH - 1); return (int)__ldg(plane + (long long)line * dstW + xx); };
+    auto sumX = [&](int xx) { unsigned s = 1u << 18; for (int j = 0; j < lfs; j++) s += (unsigned)A_(firstLum + j, xx) * (unsigned)(int)__ldg(lf + j); return (int)s >> 19; };
+    int A;
+    if (full) {
+        if (mode == 1) A = (A_(firstLum, x) + 64) >> 7;
+        else if (mode == 2) A = (A_(firstLum, x) * (4096 - yalpha) + A_(firstLum + 1, x) * yalpha + (1 << 18)) >> 19;
+        else A = sumX(x);
+        if (A & 0x100) A = min(max(A, 0), 255);
+    } else {
+        if (mode == 1) A = min(max(uvalpha < 2048 ? (A_(firstLum, x) * 255 + 16384) >> 15 : (A_(firstLum, x) + 64) >> 7, 0), 255);
+        else if (mode == 2) A = min(max((A_(firstLum, x) * (4096 - yalpha) + A_(firstLum + 1, x) * yalpha) >> 19, 0), 255);
+        else {
+            A = sumX(x);
+            const int B = (x ^ 1) < dstW ? sumX(x ^ 1) : A;
+            if ((A | B) & 0x100) A = min(max(A, 0), 255);
+        }
+    }
+    dst[(long long)blockIdx.z * dfs + (long long)dy * ds + (long long)x * bpp + ao] = (uint8_t)A;
+}
+
 __global__ void __launch_bounds__(256)
 sws_rgbin_hscale_uv_kernel(const uint8_t *src, long long sstride, long long sfs, int16_t *dstU, int16_t *dstV, int dstW, long long dfs,
                            const int16_t *filter, const int32_t *pos, int fs, const RgbIn R)
@@ -1888,7 +1945,7 @@ static int launch_rgbsrc_packed(B200SwsContext *c, cudaStream_t stream, const ui
     Rg.bpp = p.src_rgb; Rg.ro = p.sro; Rg.go = p.sgo; Rg.bo = p.sbo; Rg.half = p.chrSrcHSub;
     for (int i = 0; i < 9; i++) Rg.c[i] = p.rgb2yuv[i];
     const size_t lumPlane = (size_t)p.srcH * p.dstW * 2, chrPlane = (size_t)p.chrSrcH * p.chrDstW * 2;
-    const size_t perFrame = ((lumPlane + 2 * chrPlane) + 255) & ~(size_t)255;
+    const size_t perFrame = ((lumPlane + 2 * chrPlane + (p.need_alpha ? lumPlane : 0)) + 255) & ~(size_t)255;
     long long chunk = (long long)((size_t)(512u << 20) / perFrame);
     if (chunk < 1) chunk = 1;
     if (chunk > nframes) chunk = nframes;
@@ -1902,6 +1959,7 @@ static int launch_rgbsrc_packed(B200SwsContext *c, cudaStream_t stream, const ui
     int16_t *mY = (int16_t *)c->mid;
     int16_t *mU = (int16_t *)((uint8_t *)c->mid + lumPlane);
     int16_t *mV = (int16_t *)((uint8_t *)c->mid + lumPlane + chrPlane);
+    int16_t *mA = (int16_t *)((uint8_t *)c->mid + lumPlane + 2 * chrPlane);           // alpha lines (need_alpha only)
     const long long mfs = (long long)(perFrame / 2);
     for (long long f0 = 0; f0 < nframes; f0 += chunk) {
         const int nf = (int)(nframes - f0 < chunk ? nframes - f0 : chunk);
@@ -1914,6 +1972,11 @@ static int launch_rgbsrc_packed(B200SwsContext *c, cudaStream_t stream, const ui
         sws_rgbin_hscale_uv_kernel<<<dim3(b200_ceil_div(p.chrDstW, 256), p.chrSrcH, nf), block, 0, stream>>>(s, sstr, sfs, mU, mV, p.chrDstW, mfs, c->dt.hChr,
                                                                                                                c->dt.hChrPos, c->dt.hChrSize, Rg);
         B200_LAUNCHED();
+        if (p.need_alpha) {
+            sws_rgbin_hscale_a_kernel<<<dim3(b200_ceil_div(p.dstW, 256), p.srcH, nf), block, 0, stream>>>(s, sstr, sfs, mA, p.dstW, mfs, c->dt.hLum, c->dt.hLumPos,
+                                                                                                            c->dt.hLumSize, 6 - p.sro - p.sgo - p.sbo);
+            B200_LAUNCHED();
+        }
         SwsFrameArgs m{};
         m.y = (const uint8_t *)mY; m.u = (const uint8_t *)mU; m.v = (const uint8_t *)mV;
         m.ys = (long long)p.dstW * 2; m.us = m.vs = (long long)p.chrDstW * 2;
@@ -1942,6 +2005,11 @@ static int launch_rgbsrc_packed(B200SwsContext *c, cudaStream_t stream, const ui
             sws_vscale_rgb24_full_kernel<<<grid, block2, 0, stream>>>(m, c->dt, p.color);
         }
         B200_LAUNCHED();
+        if (p.need_alpha) {                                    // the writers stored 255: the scaled alpha goes on top
+            sws_vscale_alpha_kernel<<<dim3(b200_ceil_div(p.dstW, 256), p.dstH, nf), dim3(256), 0, stream>>>(mA, mfs, p.srcH, d, ds, dfs, p.dstW, p.out.bpp, p.out.ao,
+                c->dt.vLum, c->dt.vLumPos, c->dt.vLumSize, c->dt.rowMode, p.chrDstHSub ? 0 : 1, 0);
+            B200_LAUNCHED();
+        }
     }
     B200_CUDA_OK(cudaGetLastError());
     return 0;

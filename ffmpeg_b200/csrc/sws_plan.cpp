@@ -420,7 +420,7 @@ int sws_plan_build(SwsPlan &p, int srcW, int srcH, int dstW, int dstH, int flags
             return 0;
         }
     }
-    if (p.src_rgb == 4 && !p.planar && p.out.bpp == 4) return B200_ENOSYS;                   // alpha carried through the scaler: not built
+    p.need_alpha = p.src_rgb == 4 && !p.planar && p.out.bpp == 4;
     if (!p.planar && (dstW & 1)) flags |= B200_SWS_FULL_CHR_H_INT;               // utils.c:1271-1276 (RGB destinations only)
     if (!p.planar && p.src_rgb && !(flags & B200_SWS_FAST_BILINEAR))
         flags |= B200_SWS_FULL_CHR_H_INT;                                        // utils.c:1277-1285: source chroma is not subsampled

@@ -53,6 +53,7 @@ struct SwsPlan {
     int sro = 0, sgo = 0, sbo = 0;                // byte positions of R, G, B in a source pixel
     int chrSrcHSub = 1, chrSrcVSub = 1;           // chroma sampling of the source as the scaler sees it (utils.c:1366-1396)
     int rgb2yuv[9] = { 0 };       // input_rgb2yuv_table RY GY BY RU GU BU RV GV BV (swscale_internal.h:468-477; utils.c:614-700)
+    bool need_alpha = false;      // c->needAlpha = isALPHA(src) && isALPHA(dst) (utils.c:1405): the alpha plane goes through the scaler
     bool rgb_shuffle = false;     // same size packed RGB -> packed RGB: rgbToRgbWrapper / packedCopyWrapper (swscale_unscaled.c:2001-2060,2138-2170)
     unsigned shuffle_sel = 0;     // __byte_perm selector: nibble j = source byte of destination byte j, 4 = the constant 255
     bool bgr24_yv12 = false;      // reference installs bgr24ToYv12Wrapper (ff_rgb24toyv12_c, rgb2rgb_template.c:580-641)

@@ -49,6 +49,7 @@ struct OrcSws {
     int src_cs[4], dst_cs[4];
     /* packed RGB source (input.c readers -> 16-bit lines -> hScale16To15_c) */
     int src_rgb;               /* 0: yuv source; 3 / 4: bytes per source pixel */
+    int need_alpha;            /* c->needAlpha = isALPHA(src) && isALPHA(dst) (utils.c:1405): the alpha plane goes through the scaler */
     int sro, sgo, sbo;         /* byte positions of R, G, B in a source pixel */
     int chrSrcHSub, chrSrcVSub;
     int rgb2yuv[9];            /* input_rgb2yuv_table: RY GY BY RU GU BU RV GV BV (swscale_internal.h:468-477), 15-bit */
@@ -464,8 +465,7 @@ OrcSws *orc_sws_open_range(int srcFormat, int srcW, int srcH, int srcRange, int 
             return s;
         }
     }
-    if (s->src_rgb == 4 && !s->planar && s->bpp == 4) { free(s); return NULL; }                /* alpha carried through the scaler
-                                                                                                 * (alpToYV12 + the A writers): not restated */
+    s->need_alpha = s->src_rgb == 4 && !s->planar && s->bpp == 4;
     s->src_nv = srcFormat == ORC_PIX_FMT_NV12 ? 1 : srcFormat == ORC_PIX_FMT_NV21 ? 2 : 0;
     int algo = flags & 0x7FF;
     if (!algo) { algo = ORC_SWS_BICUBIC; flags |= algo; }           /* utils.c:1209-1217 */
@@ -676,6 +676,16 @@ static void bgr24_to_yv12(const OrcSws *s, const uint8_t *src, int ss, uint8_t *
     }
 }
 
+/* rgbaToA_c / abgrToA_c (input.c:455-475): the alpha byte widened to 14 bits */
+static void rgb_to_a(const OrcSws *s, int16_t *dst, const uint8_t *src, int w)
+{
+    const int sao = 6 - s->sro - s->sgo - s->sbo;
+    for (int i = 0; i < w; i++) {
+        const int a = src[(size_t)i * 4 + sao];
+        dst[i] = (int16_t)(a << 6 | a >> 2);
+    }
+}
+
 static void hpass(const OrcSws *s, int16_t *dst, int dstW, const uint8_t *src, int srcW, int chroma)
 {
     if (s->fast_bilinear) hscale_fast(dst, dstW, src, srcW, chroma ? s->chrXInc : s->lumXInc, chroma);
@@ -685,8 +695,16 @@ static void hpass(const OrcSws *s, int16_t *dst, int dstW, const uint8_t *src, i
 
 /* the horizontal pass over a whole picture: L = srcH lines of dstW, CU / CV = chrSrcH lines of chrDstW.  For a packed RGB source
  * every line first goes through the input readers (lum_convert / chr_convert, hscale.c:103-160,229-290) */
+static int hlines_a(const OrcSws *s, const uint8_t *y, int ys, const uint8_t *u, int us, const uint8_t *v, int vs,
+                    int16_t *L, int16_t *CU, int16_t *CV, int16_t *A);
 static int hlines(const OrcSws *s, const uint8_t *y, int ys, const uint8_t *u, int us, const uint8_t *v, int vs,
                   int16_t *L, int16_t *CU, int16_t *CV)
+{
+    return hlines_a(s, y, ys, u, us, v, vs, L, CU, CV, NULL);
+}
+/* A: the alpha lines (srcH lines of dstW) when the context carries alpha: read by alpToYV12, scaled with the luma filter (hscale.c:103-160) */
+static int hlines_a(const OrcSws *s, const uint8_t *y, int ys, const uint8_t *u, int us, const uint8_t *v, int vs,
+                    int16_t *L, int16_t *CU, int16_t *CV, int16_t *A)
 {
     const int dstW = s->dstW, cW = s->chrDstW;
     if (s->src_rgb) {
@@ -696,6 +714,10 @@ static int hlines(const OrcSws *s, const uint8_t *y, int ys, const uint8_t *u, i
         for (int r = 0; r < s->srcH; r++) {
             rgb_to_y(s, tY, y + (ptrdiff_t)r * ys, s->srcW);
             hscale16to15(L + (size_t)r * dstW, dstW, tY, s->hLum, s->hLumPos, s->hLumSize);
+            if (A && s->need_alpha) {
+                rgb_to_a(s, tY, y + (ptrdiff_t)r * ys, s->srcW);
+                hscale16to15(A + (size_t)r * dstW, dstW, tY, s->hLum, s->hLumPos, s->hLumSize);
+            }
         }
         for (int r = 0; r < s->chrSrcH; r++) {
             rgb_to_uv(s, tU, tV, y + (ptrdiff_t)r * ys, s->chrSrcW);
@@ -927,9 +949,11 @@ int orc_sws_scale(OrcSws *s, const uint8_t *y, int ys, const uint8_t *u, int us,
     int16_t *L = malloc((size_t)s->srcH * dstW * sizeof(int16_t));
     int16_t *CU = malloc((size_t)s->chrSrcH * cW * sizeof(int16_t));
     int16_t *CV = malloc((size_t)s->chrSrcH * cW * sizeof(int16_t));
-    if (!L || !CU || !CV) { free(L); free(CU); free(CV); return -ENOMEM; }
-    if (hlines(s, y, ys, u, us, v, vs, L, CU, CV) < 0) { free(L); free(CU); free(CV); return -ENOMEM; }
+    int16_t *AL = s->need_alpha ? malloc((size_t)s->srcH * dstW * sizeof(int16_t)) : NULL;
+    if (!L || !CU || !CV || (s->need_alpha && !AL)) { free(L); free(CU); free(CV); free(AL); return -ENOMEM; }
+    if (hlines_a(s, y, ys, u, us, v, vs, L, CU, CV, AL) < 0) { free(L); free(CU); free(CV); free(AL); return -ENOMEM; }
     const int lfs = s->vLumSize, cfs = s->vChrSize, full = !s->chrDstHSub;
+#define AROW(k) (AL + (size_t)((k) < 0 ? 0 : (k) >= s->srcH    ? s->srcH    - 1 : (k)) * dstW)
 #define LROW(k) (L  + (size_t)((k) < 0 ? 0 : (k) >= s->srcH    ? s->srcH    - 1 : (k)) * dstW)
 #define UROW(k) (CU + (size_t)((k) < 0 ? 0 : (k) >= s->chrSrcH ? s->chrSrcH - 1 : (k)) * cW)
 #define VROW(k) (CV + (size_t)((k) < 0 ? 0 : (k) >= s->chrSrcH ? s->chrSrcH - 1 : (k)) * cW)
@@ -983,6 +1007,29 @@ int orc_sws_scale(OrcSws *s, const uint8_t *y, int ys, const uint8_t *u, int us,
                     Y1 = (int)a1 >> 19; Y2 = (int)a2 >> 19; U = (int)au >> 19; V = (int)av >> 19;
                 }
                 put_pair(s, d + 2 * s->bpp * i, Y1, Y2, U, V);
+                if (s->need_alpha) {                               /* the A1 / A2 of the three writers (output.c:1818-1830,1867-1872,1903-1908,1928-1933) */
+                    int A1, A2;
+                    if (mode == 1) {
+                        const int16_t *a0 = AROW(firstLum);
+                        if (uvalpha < 2048) { A1 = (a0[2 * i] * 255 + 16384) >> 15; A2 = (a0[2 * i + 1] * 255 + 16384) >> 15; }
+                        else                { A1 = (a0[2 * i] + 64) >> 7;           A2 = (a0[2 * i + 1] + 64) >> 7; }
+                        A1 = clip_u8(A1); A2 = clip_u8(A2);
+                    } else if (mode == 2) {
+                        const int16_t *a0 = AROW(firstLum), *a1 = AROW(firstLum + 1);
+                        A1 = clip_u8((a0[2 * i] * (4096 - yalpha) + a1[2 * i] * yalpha) >> 19);
+                        A2 = clip_u8((a0[2 * i + 1] * (4096 - yalpha) + a1[2 * i + 1] * yalpha) >> 19);
+                    } else {
+                        unsigned s1 = 1 << 18, s2 = 1 << 18;
+                        for (int j = 0; j < lfs; j++) {
+                            s1 += (unsigned)(AROW(firstLum + j)[2 * i]     * (unsigned)(int)lf[j]);
+                            s2 += (unsigned)(AROW(firstLum + j)[2 * i + 1] * (unsigned)(int)lf[j]);
+                        }
+                        A1 = (int)s1 >> 19; A2 = (int)s2 >> 19;
+                        if ((A1 | A2) & 0x100) { A1 = clip_u8(A1); A2 = clip_u8(A2); }
+                    }
+                    d[2 * s->bpp * i + s->ao] = (uint8_t)A1;
+                    if (2 * i + 1 < dstW) d[2 * s->bpp * i + s->bpp + s->ao] = (uint8_t)A2;
+                }
             }
         } else {
             for (int i = 0; i < dstW; i++) {
@@ -1011,12 +1058,25 @@ int orc_sws_scale(OrcSws *s, const uint8_t *y, int ys, const uint8_t *u, int us,
                     Y = (int)ay >> 10; U = (int)au >> 10; V = (int)av >> 10;
                 }
                 put_full(s, d + s->bpp * i, Y, U, V);
+                if (s->need_alpha) {                               /* output.c:2191-2199,2240-2244,2282-2286 */
+                    int A;
+                    if (mode == 1) A = (AROW(firstLum)[i] + 64) >> 7;
+                    else if (mode == 2) A = (AROW(firstLum)[i] * (4096 - yalpha) + AROW(firstLum + 1)[i] * yalpha + (1 << 18)) >> 19;
+                    else {
+                        unsigned sa = 1 << 18;
+                        for (int j = 0; j < lfs; j++) sa += (unsigned)(AROW(firstLum + j)[i] * (unsigned)(int)lf[j]);
+                        A = (int)sa >> 19;
+                    }
+                    if (A & 0x100) A = clip_u8(A);
+                    d[s->bpp * i + s->ao] = (uint8_t)A;
+                }
             }
         }
     }
 #undef LROW
 #undef UROW
 #undef VROW
-    free(L); free(CU); free(CV);
+#undef AROW
+    free(L); free(CU); free(CV); free(AL);
     return s->dstH;
 }

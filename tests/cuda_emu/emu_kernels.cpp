@@ -72,6 +72,20 @@ void emu_sws_rgbin_y(const uint8_t *src, long long sstride, long long sfs, int16
                [&] { sws::sws_rgbin_hscale_y_kernel(src, sstride, sfs, dst, dstW, dfs, filter, pos, fs, R); });
 }
 
+void emu_sws_rgbin_a(const uint8_t *src, long long sstride, long long sfs, int16_t *dst, int dstW, long long dfs, const int16_t *filter,
+                     const int32_t *pos, int fs, int sao, int lines, int frames)
+{
+    emu_launch(dim3(ceil_div(dstW, 256), lines, frames), dim3(256),
+               [&] { sws::sws_rgbin_hscale_a_kernel(src, sstride, sfs, dst, dstW, dfs, filter, pos, fs, sao); });
+}
+
+void emu_sws_alpha(const int16_t *al, long long alfs, int srcH, uint8_t *dst, long long ds, long long dfs, int dstW, int dstH, int bpp, int ao,
+                   const int16_t *vLum, const int32_t *vLumPos, int lfs, const int32_t *rowMode, int full, int frames)
+{
+    emu_launch(dim3(ceil_div(dstW, 256), dstH, frames), dim3(256),
+               [&] { sws::sws_vscale_alpha_kernel(al, alfs, srcH, dst, ds, dfs, dstW, bpp, ao, vLum, vLumPos, lfs, rowMode, full, 0); });
+}
+
 void emu_sws_rgbin_uv(const uint8_t *src, long long sstride, long long sfs, int16_t *dstU, int16_t *dstV, int dstW, long long dfs,
                       const int16_t *filter, const int32_t *pos, int fs, const int *rgbin, int lines, int frames)
 {

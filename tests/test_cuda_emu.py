@@ -119,6 +119,41 @@ def plan(cfg, details=None):
 RGB_OFFSETS = {"rgb24": (3, 0, 1, 2), "bgr24": (3, 2, 1, 0), "rgba": (4, 0, 1, 2), "bgra": (4, 2, 1, 0), "argb": (4, 1, 2, 3), "abgr": (4, 3, 2, 1)}
 
 
+def test_emu_alpha_through_the_scaler(emu):
+    """sws_rgbin_hscale_a_kernel + sws_vscale_alpha_kernel (alpha of a 32-bit source scaled with the luma filters, both writer families)
+    with the product's own filter banks: the oracle's picture with its alpha bytes reset to 255 must get exactly the oracle's alpha back"""
+    rng = np.random.default_rng(17)
+    names = ["rgba", "bgra", "argb", "abgr"]
+    AO = {"rgba": 3, "bgra": 3, "argb": 0, "abgr": 0}
+    for it, (w, h, dw, dh, fl) in enumerate([(40, 24, 64, 40, 4), (64, 40, 33, 17, 4), (48, 20, 48, 31, 2), (50, 30, 100, 30, 1), (36, 28, 20, 28, 0x10),
+                                             (64, 32, 96, 48, 1 | 0x80000), (33, 21, 50, 40, 0x20), (64, 48, 32, 24, 4 | 0x80000 | 0x40000)]):
+        sn, dn = names[it % 4], names[(it * 3 + 1) % 4]
+        sf, df = cl.PACKED_RGB_FORMATS[sn], cl.PACKED_RGB_FORMATS[dn]
+        src = cl.rgb_frame(w, h, 3100 + it, 4, "random", pad=it % 3)
+        if it % 2:
+            src[:, AO[sn]:w * 4:4] = rng.integers(0, 2, (h, w)) * 255
+        exp = cl.orc_sws(w, h, dw, dh, fl, src, src, src, fmt=df, src_fmt=sf)
+        info, banks = plan([w, h, sf, 0, dw, dh, df, 0, fl])
+        (hl, hlp, hls), _, (vl, vlp, vls), (vc, vcp, vcs) = banks
+        full = 0 if info[11] else 1
+        A = np.zeros((h, dw), np.int16)
+        emu.emu_sws_rgbin_a(vp(src), src.strides[0], 0, vp(A), dw, 0, vp(hl), vp(hlp), hls, AO[sn], h, 1)
+        rm = np.zeros((dh, 4), np.int32)                            # packed_vscale's writer choice per line (vscale.c:144-169)
+        for dy in range(dh):
+            lf, cf = vl[dy * vls:(dy + 1) * vls].astype(np.uint16).astype(int), vc[dy * vcs:(dy + 1) * vcs].astype(np.uint16).astype(int)
+            if vls == 1 and vcs == 1:
+                rm[dy] = (1, 0, 0, 0)
+            elif vls == 1 and vcs == 2 and cf[0] + cf[1] == 4096 and cf[1] <= 4096:
+                rm[dy] = (1, 0, cf[1], 0)
+            elif vls == 2 and vcs == 2 and lf[0] + lf[1] == 4096 and lf[1] <= 4096 and cf[0] + cf[1] == 4096 and cf[1] <= 4096:
+                rm[dy] = (2, lf[1], cf[1], 0)
+        got = exp.copy()
+        got[:, AO[dn]::4] = 255
+        emu.emu_sws_alpha(vp(A), 0, h, vp(got), got.strides[0], 0, dw, dh, 4, AO[dn], vp(vl), vp(vlp), vls, vp(rm), full, 1)
+        assert np.array_equal(got, exp), (it, sn, dn, hex(fl), int((got != exp).sum()))
+        assert len(np.unique(exp[:, AO[dn]::4])) > 2                 # the alpha plane is not constant: the check means something
+
+
 def test_emu_rgb_source_horizontal_pass_and_range(emu):
     """sws_rgbin_hscale_{y,uv}_kernel with the filter banks and the rgb -> yuv table of the product's own host set-up, against the
     oracle's reader + 16-bit horizontal pass; then sws_range_kernel on those lines against the oracle's range conversion"""
@@ -463,8 +498,14 @@ def test_sws_rgb_sources_nv_destinations_and_all_fate_sums(emusws):
         assert all(np.array_equal(a, b) for a, b in zip(out, exp)), ("bgra -> nv, full range", df)
     if cl.have_nut() and os.path.exists(cl.VIDEOGEN):
         fg.check_all(er, ep, rgb_sources=True, nv_dest=True)
-    assert er(64, 48, 64, 48, FATE, src, src, src, fmt=cl.PIX_FMT_BGR24, src_fmt=cl.PIX_FMT_RGB24) is None          # same-size rgb -> rgb: refused
-    assert er(64, 48, 32, 24, FATE, src, src, src, fmt=cl.PIX_FMT_BGRA, src_fmt=cl.PIX_FMT_RGBA) is None           # alpha through the scaler: refused
+    # same-size rgb -> rgb (byte shuffles; the scaler for 24 -> bgra under SWS_BITEXACT) and alpha through the scaler, whole host path
+    s3 = cl.rgb_frame(64, 48, 2991, 3)
+    for (sf, df, a, fl) in ((cl.PIX_FMT_RGB24, cl.PIX_FMT_BGR24, s3, FATE), (cl.PIX_FMT_RGB24, cl.PIX_FMT_BGRA, s3, FATE), (cl.PIX_FMT_RGB24, cl.PIX_FMT_ARGB, s3, 4),
+                            (cl.PIX_FMT_RGBA, cl.PIX_FMT_ABGR, src, 4), (cl.PIX_FMT_BGRA, cl.PIX_FMT_RGB24, src, FATE), (cl.PIX_FMT_ARGB, cl.PIX_FMT_ARGB, src, 4)):
+        assert np.array_equal(er(64, 48, 64, 48, fl, a, a, a, fmt=df, src_fmt=sf), cl.orc_sws(64, 48, 64, 48, fl, a, a, a, fmt=df, src_fmt=sf)), ("same size", sf, df)
+    for (sf, df, dw2, dh2, fl) in ((cl.PIX_FMT_RGBA, cl.PIX_FMT_BGRA, 32, 24, FATE), (cl.PIX_FMT_ARGB, cl.PIX_FMT_RGBA, 100, 70, 2), (cl.PIX_FMT_BGRA, cl.PIX_FMT_ABGR, 96, 48, 1),
+                                   (cl.PIX_FMT_ABGR, cl.PIX_FMT_ARGB, 64, 70, 0x10)):
+        assert np.array_equal(er(64, 48, dw2, dh2, fl, src, src, src, fmt=df, src_fmt=sf), cl.orc_sws(64, 48, dw2, dh2, fl, src, src, src, fmt=df, src_fmt=sf)), ("alpha", sf, df)
     # batched device entry points: rgba -> nv12 (two destination planes) and rgb24 -> bgra
     L = emusws
     w, h, dw, dh, n = 64, 48, 100, 70, 2
@@ -617,7 +658,7 @@ def test_sws_differential_fuzz(emusws):
         if cl.have_ref():
             assert same(ref(w, h, dw, dh, fl, y, u, v, **kw), exp), ("checker != reference", desc)
         ran += 1
-    assert ran >= 40 and refused >= 10, (ran, refused)
+    assert ran >= 80 and ran + refused == 90, (ran, refused)          # since same-size RGB -> RGB and alpha went in, only other-matrix yuv -> yuv is refused
 
 
 # ------------------------------------------------------------------ all of libavutil/tx (tx.cu + tx_pfa.cu) on the stand-in runtime

@@ -419,8 +419,33 @@ def test_sws_oracle_rgb_sources_vs_ref():
             a = cl.ref_sws(w, h, dw, dh, fl, src, src, src, fmt=df, src_fmt=sf, dst_pad=2)
             b = cl.orc_sws(w, h, dw, dh, fl, src, src, src, fmt=df, src_fmt=sf, dst_pad=2)
             assert np.array_equal(a, b), (w, h, dw, dh, hex(fl), names[it % 6], df)
-    O = cl.oracle()
-    assert not O.orc_sws_open_io(cl.PIX_FMT_RGBA, 64, 48, cl.PIX_FMT_BGRA, 32, 24, FATE)        # alpha through the scaler: not restated
+
+
+def test_sws_oracle_alpha_through_the_scaler_vs_ref():
+    """32-bit source and 32-bit destination: c->needAlpha, the alpha plane is read (rgbaToA_c / abgrToA_c), scaled with the luma filters
+    and written by the A variants of all six packed writers"""
+    if not cl.have_ref():
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(4)
+    names = ["rgba", "bgra", "argb", "abgr"]
+    AO = {"rgba": 3, "bgra": 3, "argb": 0, "abgr": 0}
+    for it in range(60):
+        w, h = int(rng.integers(8, 90)), int(rng.integers(8, 60))
+        dw, dh = int(rng.integers(8, 120)), int(rng.integers(8, 80))
+        if it % 7 == 0:
+            dh = h
+        if it % 11 == 0:
+            dw = w
+        if (dw, dh) == (w, h):
+            dw += 1
+        fl = int(rng.choice([4, FATE, 2, 1, 0x10, 0x20, 0x200, 4 | 0x2000, 1 | 0x80000]))
+        sn, dn = names[int(rng.integers(0, 4))], names[int(rng.integers(0, 4))]
+        src = cl.rgb_frame(w, h, 3000 + it, 4, "random", pad=int(rng.integers(0, 5)))
+        if it % 4 == 0:
+            src[:, AO[sn]:w * 4:4] = rng.integers(0, 2, (h, w)) * 255
+        a = cl.ref_sws(w, h, dw, dh, fl, src, src, src, fmt=cl.PACKED_RGB_FORMATS[dn], src_fmt=cl.PACKED_RGB_FORMATS[sn], dst_pad=1)
+        b = cl.orc_sws(w, h, dw, dh, fl, src, src, src, fmt=cl.PACKED_RGB_FORMATS[dn], src_fmt=cl.PACKED_RGB_FORMATS[sn], dst_pad=1)
+        assert np.array_equal(a, b), (w, h, dw, dh, hex(fl), sn, dn)
 
 
 def rgb2rgb_rows():

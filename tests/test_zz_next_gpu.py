@@ -407,8 +407,26 @@ def test_sws_rgb_sources_large_padded_batch(device):
         for i in range(n):
             assert np.array_equal(got[i], cl.orc_sws(w, h, dw, dh, FATE, frames[i], frames[i], frames[i], fmt=df, src_fmt=cl.PIX_FMT_RGB24)), (dname, i)
         ctx.free()
-    with pytest.raises(fb.B200Error):                                  # alpha carried through the scaler: not built
-        sw.sws_getContext(device, 64, 48, sw.AV_PIX_FMT_RGBA, 32, 24, sw.AV_PIX_FMT_BGRA, FATE)
+    # alpha carried through the scaler (32-bit source and destination): host sws_scale and the batched device entry
+    from test_sws_gpu import gpu_sws
+    names4 = ["rgba", "bgra", "argb", "abgr"]
+    for it, (w, h, dw, dh, fl) in enumerate([(64, 48, 32, 24, FATE), (64, 48, 100, 70, 2), (322, 180, 1280, 720, 4), (1280, 720, 640, 360, 4), (64, 48, 96, 48, 1),
+                                             (641, 361, 320, 200, 0x10), (320, 180, 321, 181, 0x20)]):
+        sf, df = cl.PACKED_RGB_FORMATS[names4[it % 4]], cl.PACKED_RGB_FORMATS[names4[(it * 3 + 1) % 4]]
+        src = cl.rgb_frame(w, h, 3200 + it, 4, "random", pad=it % 3)
+        assert np.array_equal(gpu_sws(device, w, h, dw, dh, fl, src, src, src, fmt=df, src_fmt=sf), cl.orc_sws(w, h, dw, dh, fl, src, src, src, fmt=df, src_fmt=sf)), (it, "alpha")
+    w, h, dw, dh, n = 320, 180, 200, 100, 3
+    frames = [cl.rgb_frame(w, h, 3250 + k, 4) for k in range(n)]
+    ctx = sw.sws_getContext(device, w, h, sw.AV_PIX_FMT_RGBA, dw, dh, sw.AV_PIX_FMT_BGRA, 4)
+    with torch.cuda.stream(torch.cuda.ExternalStream(device.stream)):
+        S = torch.from_numpy(np.stack(frames)).cuda()
+        D = torch.zeros((n, dh, dw * 4), dtype=torch.uint8, device="cuda")
+        ctx.scale_batch_device([S], [w * 4], [w * 4 * h], D, dw * 4, dw * 4 * dh, n)
+        device.sync()
+        got = D.cpu().numpy()
+    for i in range(n):
+        assert np.array_equal(got[i], cl.orc_sws(w, h, dw, dh, 4, frames[i], frames[i], frames[i], fmt=cl.PIX_FMT_BGRA, src_fmt=cl.PIX_FMT_RGBA)), ("alpha batch", i)
+    ctx.free()
 
 
 # ---------------------------------------------------------------------------------------------- swscale: nv12 / nv21 destinations
