@@ -967,6 +967,15 @@ struct B200SwsContext {
     int next_dst_y = 0;
     bool slice_open = false;
     int slice_dir = 1;               // SwsInternal.sliceDir: 1 top-down, -1 bottom-up (the picture is flipped internally, swscale.c:1096-1159)
+    // yuv -> yuv with two different matrices: the reference cascades two contexts through a bgr24 picture (utils.c:914-989)
+    B200SwsContext *casc[2] = { nullptr, nullptr };
+    void *casc_tmp = nullptr;        // the intermediate picture on the device (zeroed once: the unscaled converter of context 0
+                                     // leaves an odd last column unwritten, the reference reads uninitialised memory there)
+    size_t casc_pitch = 0;
+    int casc_w = 0, casc_h = 0;
+    int open_src_fmt = 0, open_dst_fmt = 0, open_flags = 0;      // as given to sws_getContext
+    bool has_param = false;
+    double open_param[2] = { 0, 0 };
 };
 
 static int upload_mma_tables(B200SwsContext *c);
@@ -1086,7 +1095,8 @@ B200_API B200SwsContext *b200_sws_getContext_params(B200Device *dev, int srcW, i
     }
     c->dev = dev;
     c->plan.out = out;
-    if (param) { c->plan.param[0] = param[0]; c->plan.param[1] = param[1]; }
+    c->open_src_fmt = srcFormat; c->open_dst_fmt = dstFormat; c->open_flags = flags;
+    if (param) { c->plan.param[0] = param[0]; c->plan.param[1] = param[1]; c->has_param = true; c->open_param[0] = param[0]; c->open_param[1] = param[1]; }
     int ret = sws_plan_build(c->plan, srcW, srcH, dstW, dstH, flags, srcRange, dstRange);
     if (ret < 0) { b200_set_error("b200_sws_getContext: unsupported configuration (%d)", ret); delete c; return nullptr; }
     cudaSetDevice(dev->ordinal);
@@ -1105,6 +1115,9 @@ B200_API void b200_sws_freeContext(B200SwsContext *c)
     if (c->nv_buf) cudaFree(c->nv_buf);
     if (c->nvout_buf) cudaFree(c->nvout_buf);
     if (c->slice_buf) cudaFree(c->slice_buf);
+    if (c->casc_tmp) cudaFree(c->casc_tmp);
+    b200_sws_freeContext(c->casc[0]);
+    b200_sws_freeContext(c->casc[1]);
     delete c;
 }
 
@@ -1112,10 +1125,31 @@ B200_API int b200_sws_setColorspaceDetails(B200SwsContext *c, const int inv_tabl
                                            const int table[4], int dstRange, int brightness, int contrast, int saturation)
 {
     if (!c || !inv_table || !table) return B200_EINVAL;
+    if (c->casc[0])                                              // utils.c:908-909: a cascaded context hands the call to its main child
+        return b200_sws_setColorspaceDetails(c->casc[0], inv_table, srcRange, table, dstRange, brightness, contrast, saturation);
     const int ret = sws_plan_colorspace_details(c->plan, inv_table, srcRange, table, dstRange, brightness, contrast, saturation);
-    if (ret == B200_ENOSYS)
-        b200_set_error("sws_setColorspaceDetails: yuv -> yuv with different matrices (the reference cascades through bgr24) is not implemented");
-    return ret;
+    if (ret != B200_ENOSYS) return ret;
+    // yuv -> yuv with different matrices (utils.c:914-989): context 0 = source -> bgr24 at the smaller of the two sizes with these details
+    // (its RGB side ignores the destination half), context 1 = bgr24 -> destination with the ranges set before its initialisation and
+    // the details again without brightness / contrast / saturation; sws_scale then runs whole frames through both (scale_cascaded)
+    const SwsPlan &p = c->plan;
+    const bool big = (long long)p.srcW * p.srcH > (long long)p.dstW * p.dstH;
+    c->casc_w = big ? p.dstW : p.srcW; c->casc_h = big ? p.dstH : p.srcH;
+    const double *pr = c->has_param ? c->open_param : nullptr;
+    c->casc[0] = b200_sws_getContext_params(c->dev, p.srcW, p.srcH, c->open_src_fmt, 0, c->casc_w, c->casc_h, B200_PIX_FMT_BGR24, 0, c->open_flags, pr);
+    c->casc[1] = b200_sws_getContext_params(c->dev, c->casc_w, c->casc_h, B200_PIX_FMT_BGR24, srcRange, p.dstW, p.dstH, c->open_dst_fmt, dstRange, c->open_flags, pr);
+    c->casc_pitch = ((size_t)c->casc_w * 3 + 255) & ~(size_t)255;
+    if (!c->casc[0] || !c->casc[1] || cudaSetDevice(c->dev->ordinal) != cudaSuccess ||
+        cudaMalloc(&c->casc_tmp, c->casc_pitch * c->casc_h) != cudaSuccess || cudaMemsetAsync(c->casc_tmp, 0, c->casc_pitch * c->casc_h, c->dev->stream) != cudaSuccess) {
+        b200_sws_freeContext(c->casc[0]); b200_sws_freeContext(c->casc[1]);
+        c->casc[0] = c->casc[1] = nullptr;
+        if (c->casc_tmp) { cudaFree(c->casc_tmp); c->casc_tmp = nullptr; }
+        b200_set_error("sws_setColorspaceDetails: could not set up the yuv -> bgr24 -> yuv cascade for two different matrices");
+        return B200_ENOSYS;
+    }
+    b200_sws_setColorspaceDetails(c->casc[0], inv_table, srcRange, table, dstRange, brightness, contrast, saturation);
+    b200_sws_setColorspaceDetails(c->casc[1], inv_table, srcRange, table, dstRange, 0, 1 << 16, 1 << 16);
+    return 0;
 }
 
 B200_API int b200_sws_info(const B200SwsContext *c, int *o)
@@ -2246,6 +2280,22 @@ B200_API int b200_sws_scale_batch_device_planar(B200SwsContext *c, const uint8_t
 {
     if (!c || !src || !srcStride || !srcFrameStride || !dst || !dstStride || !dstFrameStride) return B200_EINVAL;
     if (!c->plan.planar) return B200_EINVAL;
+    if (c->casc[0]) {                                                       // two matrices: frame by frame through the bgr24 picture
+        const int nsp0 = c->plan.src_nv ? 2 : 3, ndp0 = c->plan.dst_nv ? 2 : 3;
+        for (int f = 0; f < nframes; f++) {
+            const uint8_t *s3[3] = { nullptr, nullptr, nullptr }; uint8_t *d3[3] = { nullptr, nullptr, nullptr };
+            for (int i = 0; i < nsp0; i++) s3[i] = src[i] + (long long)f * srcFrameStride[i];
+            for (int i = 0; i < ndp0; i++) d3[i] = dst[i] + (long long)f * dstFrameStride[i];
+            int r = b200_sws_scale_batch_device(c->casc[0], s3, srcStride, srcFrameStride, (uint8_t *)c->casc_tmp, (int)c->casc_pitch, 0, 1);
+            if (r < 0) return r;
+            const uint8_t *t3[3] = { (const uint8_t *)c->casc_tmp, nullptr, nullptr };
+            const int ts[3] = { (int)c->casc_pitch, 0, 0 };
+            const int64_t tf[3] = { 0, 0, 0 };
+            r = b200_sws_scale_batch_device_planar(c->casc[1], t3, ts, tf, d3, dstStride, dstFrameStride, 1);
+            if (r < 0) return r;
+        }
+        return 0;
+    }
     const int nsp = c->plan.src_rgb ? 1 : c->plan.src_nv ? 2 : 3;           // packed RGB: plane 0 only; nv12 / nv21: planes 0 and 1
     const int ndp = c->plan.dst_nv ? 2 : 3;                                 // nv12 / nv21 destination: dst[1] is the interleaved plane
     for (int i = 0; i < 3; i++) if ((i < nsp && (!src[i] || srcStride[i] < 0)) || (i < ndp && (!dst[i] || dstStride[i] < 0))) return B200_EINVAL;
@@ -2262,6 +2312,20 @@ static int sws_scale_planar_host(B200SwsContext *c, const uint8_t *const srcSlic
                                  int srcSliceY, int srcSliceH, uint8_t *const dst[], const int dstStride[])
 {
     const SwsPlan &p = c->plan;
+    if (c->casc[0]) {                                            // scale_cascaded (swscale.c:1001-1030; whole frames only, :1084-1086)
+        if (srcSliceY != 0 || srcSliceH != p.srcH) {
+            b200_set_error("sws_scale: a context cascaded for two yuv matrices converts whole frames only");
+            return B200_ENOSYS;
+        }
+        std::vector<uint8_t> tmp(((size_t)c->casc_w * 3 + 63 & ~(size_t)63) * c->casc_h, 0);
+        const int tstride = (int)(((size_t)c->casc_w * 3 + 63) & ~(size_t)63);
+        uint8_t *td[4] = { tmp.data(), nullptr, nullptr, nullptr };
+        const int tds[4] = { tstride, 0, 0, 0 };
+        int r = b200_sws_scale(c->casc[0], srcSlice, srcStride, 0, p.srcH, td, tds);
+        if (r < 0) return r;
+        const uint8_t *ts[4] = { tmp.data(), nullptr, nullptr, nullptr };
+        return b200_sws_scale(c->casc[1], ts, tds, 0, c->casc_h, dst, dstStride);
+    }
     const bool whole = srcSliceY == 0 && srcSliceH == p.srcH && !c->slice_open;
     const int macro = p.src_rgb ? 1 : 2;                         // macro_height_src: 1 for packed RGB, 2 for 4:2:0 sources (swscale.c:1063-1071)
     if (!whole && p.bgr24_yv12 && ((srcSliceY | srcSliceH) & 1)) {

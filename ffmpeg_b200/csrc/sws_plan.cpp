@@ -362,7 +362,7 @@ int sws_plan_colorspace_details(SwsPlan &p, const int inv_table[4], int srcRange
     p.src_range = srcRange;
     p.dst_range = dstRange;
     plan_range_convert(p);
-    if (yuvDst && !p.src_rgb)   // utils.c:910-989: with different matrices the reference cascades yuv -> bgr24 -> yuv: not built
+    if (yuvDst && !p.src_rgb)   // utils.c:910-989: with different matrices the reference cascades yuv -> bgr24 -> yuv: one plan cannot; b200_sws_setColorspaceDetails (sws.cu) builds the two contexts
         return memcmp(p.src_cs, p.dst_cs, sizeof(p.src_cs)) ? B200_ENOSYS : 0;
     if (yuvDst) return 0;       // RGB -> yuv: only the rgb2yuv table and the ranges matter
     return sws_plan_colorspace(p, inv_table, srcRange, brightness, contrast, saturation);

@@ -49,6 +49,11 @@ struct OrcSws {
     int src_cs[4], dst_cs[4];
     /* packed RGB source (input.c readers -> 16-bit lines -> hScale16To15_c) */
     int src_rgb;               /* 0: yuv source; 3 / 4: bytes per source pixel */
+    /* yuv -> yuv with two different matrices: the reference cascades through bgr24 (sws_setColorspaceDetails, utils.c:914-989) */
+    struct OrcSws *casc[2];
+    int casc_w, casc_h;
+    int open_src_fmt, open_dst_fmt, open_flags;      /* as given to the open call */
+    double open_param[2];
     int need_alpha;            /* c->needAlpha = isALPHA(src) && isALPHA(dst) (utils.c:1405): the alpha plane goes through the scaler */
     int sro, sgo, sbo;         /* byte positions of R, G, B in a source pixel */
     int chrSrcHSub, chrSrcVSub;
@@ -380,6 +385,8 @@ static void fill_rgb2yuv(OrcSws *s, const int table[4])
 int orc_sws_set_colorspace_details(OrcSws *s, const int inv_table[4], int srcRange, const int table[4], int dstRange,
                                    int brightness, int contrast, int saturation)
 {
+    if (s->casc[0])                                                  /* utils.c:908-909: a cascaded context hands the call to its main child */
+        return orc_sws_set_colorspace_details(s->casc[0], inv_table, srcRange, table, dstRange, brightness, contrast, saturation);
     if (!s->planar) dstRange = 0;                                    /* range_override_needed(dst), utils.c:877-878 */
     if (s->src_rgb) srcRange = 0;                                    /* range_override_needed(src), utils.c:879-880 */
     fill_rgb2yuv(s, table);                                          /* utils.c:1002 */
@@ -388,8 +395,22 @@ int orc_sws_set_colorspace_details(OrcSws *s, const int inv_table[4], int srcRan
     s->src_range = srcRange;
     s->dst_range = dstRange;
     init_range_convert(s);
-    if (s->planar && !s->src_rgb)                                    /* utils.c:910-989: other matrices would cascade via bgr24 */
-        return memcmp(s->src_cs, s->dst_cs, sizeof(s->src_cs)) ? -1 : 0;
+    if (s->planar && !s->src_rgb) {
+        /* utils.c:914-989: yuv -> yuv with different matrices goes through an intermediate bgr24 picture of the smaller of the two
+         * sizes: context 0 = source -> bgr24 with these details (the RGB side ignores its half), context 1 = bgr24 -> destination with
+         * the ranges set before its initialisation and the details again without brightness / contrast / saturation */
+        if (!memcmp(s->src_cs, s->dst_cs, sizeof(s->src_cs))) return 0;
+        if (s->casc[0]) return -1;                                   /* "we need to cascade more contexts to compensate" (:985-987) */
+        const int big = (int64_t)s->srcW * s->srcH > (int64_t)s->dstW * s->dstH;
+        s->casc_w = big ? s->dstW : s->srcW; s->casc_h = big ? s->dstH : s->srcH;
+        s->casc[0] = orc_sws_open_params(s->open_src_fmt, s->srcW, s->srcH, 0, ORC_PIX_FMT_BGR24, s->casc_w, s->casc_h, 0, s->open_flags, s->open_param);
+        if (!s->casc[0]) return -1;
+        orc_sws_set_colorspace_details(s->casc[0], inv_table, srcRange, table, dstRange, brightness, contrast, saturation);
+        s->casc[1] = orc_sws_open_params(ORC_PIX_FMT_BGR24, s->casc_w, s->casc_h, srcRange, s->open_dst_fmt, s->dstW, s->dstH, dstRange, s->open_flags, s->open_param);
+        if (!s->casc[1]) return -1;
+        orc_sws_set_colorspace_details(s->casc[1], inv_table, srcRange, table, dstRange, 0, 1 << 16, 1 << 16);
+        return 0;
+    }
     if (s->planar) return 0;                                         /* RGB -> yuv: only the rgb2yuv table and the ranges matter */
     return orc_sws_set_colorspace(s, inv_table, srcRange, brightness, contrast, saturation);
 }
@@ -445,6 +466,8 @@ OrcSws *orc_sws_open_range(int srcFormat, int srcW, int srcH, int srcRange, int 
     if (srcW < 1 || srcH < 1 || dstW < 1 || dstH < 1) return NULL;
     OrcSws *s = calloc(1, sizeof(*s));
     if (!s) return NULL;
+    s->open_src_fmt = srcFormat; s->open_dst_fmt = dstFormat; s->open_flags = flags;
+    s->open_param[0] = g_param[0]; s->open_param[1] = g_param[1];
     if (set_format(s, srcFormat) == 0 && !s->planar) {              /* packed RGB source: remember its byte layout */
         s->src_rgb = s->bpp; s->sro = s->ro; s->sgo = s->go; s->sbo = s->bo;
     } else if (srcFormat != ORC_PIX_FMT_YUV420P && srcFormat != ORC_PIX_FMT_NV12 && srcFormat != ORC_PIX_FMT_NV21) { free(s); return NULL; }
@@ -540,6 +563,7 @@ fail:
 void orc_sws_close(OrcSws *s)
 {
     if (!s) return;
+    orc_sws_close(s->casc[0]); orc_sws_close(s->casc[1]);
     free(s->hLum); free(s->hChr); free(s->vLum); free(s->vChr);
     free(s->hLumPos); free(s->hChrPos); free(s->vLumPos); free(s->vChrPos);
     free(s);
@@ -848,6 +872,17 @@ int orc_sws_scale_planar(OrcSws *s, const uint8_t *y, int ys, const uint8_t *u, 
                          uint8_t *dy, int dys, uint8_t *du, int dus, uint8_t *dv, int dvs)
 {
     if (!s->planar) return -EINVAL;
+    if (s->casc[0]) {                                              /* scale_cascaded (swscale.c:1001-1030): whole frames through both contexts */
+        const int ts = (s->casc_w * 3 + 63) & ~63;
+        /* zeroed: the unscaled converter of context 0 never writes an odd last column (yuv2rgb.c:137-236) and the reference then reads
+         * whatever av_image_alloc returned; the product zeroes its intermediate picture too */
+        uint8_t *t = calloc((size_t)ts * s->casc_h + 64, 1);
+        if (!t) return -ENOMEM;
+        int r = orc_sws_scale(s->casc[0], y, ys, u, us, v, vs, t, ts);
+        if (r >= 0) r = orc_sws_scale_planar(s->casc[1], t, ts, t, ts, t, ts, dy, dys, du, dus, dv, dvs);
+        free(t);
+        return r;
+    }
     if (s->dst_nv) {
         /* nv12 / nv21 destination: what the three-plane path writes, with the chroma planes interleaved — planarToNv12Wrapper
          * (swscale_unscaled.c:147-165) when unscaled; through the scaler yuv2nv12cX_c (output.c:495-528) forms the same sums

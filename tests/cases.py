@@ -164,3 +164,19 @@ SWS_FLOAT_KERNEL_CASES = [(w, h, dw, dh, fl | extra, "random")
 # sws_getContext's `param` (SwsContext.scaler_params; 123456 = SWS_PARAM_DEFAULT): (scaler flag, (param0, param1))
 SWS_PARAM_CASES = [(4, (0.0, 0.5)), (4, (1 / 3, 1 / 3)), (4, (1.0, 0.0)), (4, (123456.0, 0.75)), (0x40, (0.0, 0.75)), (0x80, (2.0, 123456.0)),
                    (0x80, (4.5, 123456.0)), (0x200, (2.0, 123456.0)), (0x200, (5.0, 123456.0)), (0x8, (0.5, 123456.0)), (0x8, (2.0, 123456.0)), (2, (0.3, 0.3))]
+
+
+# yuv -> yuv with two different matrices: (w, h, dw, dh, flags, src format, dst format, ranges before init, details).  The reference cascades
+# through a bgr24 picture of the smaller size (utils.c:914-989).  Cases whose first context would be the unscaled LUT converter on an odd
+# width are left out: it never writes the last column and the reference then reads uninitialised memory there.
+SWS_CASCADE_CASES = [
+    (64, 48, 100, 70, 4 | 0x80000 | 0x40000, 0, 0, (0, 0), (1, 0, 5, 0, 0, 1 << 16, 1 << 16)),
+    (100, 70, 64, 48, 4, 0, 0, (0, 0), (5, 0, 1, 0, 0, 1 << 16, 1 << 16)),
+    (64, 48, 64, 48, 4, 0, 0, (0, 0), (1, 1, 9, 0, 1 << 12, 70000, 80000)),
+    (66, 34, 66, 34, 2, 23, 0, (1, 0), (9, 1, 7, 1, 0, 1 << 16, 80000)),
+    (87, 66, 87, 66, 4 | 0x40000, 0, 0, (0, 0), (1, 0, 5, 0, -(1 << 13), 1 << 16, 80000)),
+    (77, 28, 90, 63, 1 | 0x40000, 0, 23, (1, 1), (1, 1, 9, 1, 0, 70000, 80000)),
+    (50, 40, 25, 20, 0x10, 24, 24, (0, 1), (7, 0, 1, 1, 0, 1 << 16, 1 << 16)),
+    (33, 21, 64, 40, 0x20 | 0x40000, 0, 23, (0, 0), (5, 0, 9, 0, 0, 50000, 1 << 16)),
+    (128, 64, 96, 80, 4 | 0x2000, 23, 0, (0, 0), (9, 0, 5, 1, 1 << 12, 1 << 16, 40000)),
+]

@@ -601,6 +601,47 @@ def test_sws_scaler_params(emusws):
     assert emu(64, 48, 100, 30, 0x200, y, u, v, (26.0, 123456.0)) is None and cl.orc_sws(64, 48, 100, 30, 0x200, y, u, v, param=(26.0, 123456.0)) is None
 
 
+def test_sws_yuv_matrix_cascade_on_emulated_device(emusws):
+    """sws_setColorspaceDetails with two different yuv matrices: b200_sws_scale on host pointers and the batched device entry run the
+    two cascaded contexts (yuv -> bgr24 -> yuv) like the reference; against the checker"""
+    import functools
+    from cases import SWS_CASCADE_CASES
+    ep = functools.partial(emu_sws_planar, emusws)
+    for i, (w, h, dw, dh, fl, sf, df, ranges, det) in enumerate(SWS_CASCADE_CASES):
+        y, u, v = cl.yuv_frame(w, h, 5200 + i, "random" if i % 2 else "smooth")
+        if sf:
+            u = v = cl.nv_interleave(u, v, sf)
+        out = ep(w, h, dw, dh, fl, y, u, v, src_fmt=sf, dst_fmt=df, ranges=ranges, details=det, dst_pad=i % 3)
+        exp = cl.orc_sws_planar(w, h, dw, dh, fl, y, u, v, src_fmt=sf, dst_fmt=df, ranges=ranges, details=det, dst_pad=i % 3)
+        assert out is not None and all(np.array_equal(p, q) for p, q in zip(out, exp)), (i, w, h, dw, dh, hex(fl))
+    # the batched device entry (two frames, yuv420p both sides), and slices are refused
+    L = emusws
+    w, h, dw, dh, fl, det = 64, 48, 100, 70, FATE, (1, 0, 5, 0, 0, 1 << 16, 1 << 16)
+    ctx = _emu_ctx(L, w, h, 0, dw, dh, 0, fl, (0, 0), det)
+    assert ctx
+    frames = [cl.yuv_frame(w, h, 5300 + k, "random") for k in range(2)]
+    Y, U, V = (np.stack([f[k] for f in frames]) for k in range(3))
+    DY, DU, DV = np.zeros((2, dh, dw), np.uint8), np.zeros((2, dh // 2, dw // 2), np.uint8), np.zeros((2, dh // 2, dw // 2), np.uint8)
+    sp = (C.c_void_p * 3)(Y.ctypes.data, U.ctypes.data, V.ctypes.data)
+    ss = (C.c_int * 3)(w, w // 2, w // 2)
+    sfs = (C.c_int64 * 3)(w * h, w * h // 4, w * h // 4)
+    dp = (C.c_void_p * 3)(DY.ctypes.data, DU.ctypes.data, DV.ctypes.data)
+    dss = (C.c_int * 3)(dw, dw // 2, dw // 2)
+    dfs = (C.c_int64 * 3)(dw * dh, dw * dh // 4, dw * dh // 4)
+    L.b200_sws_scale_batch_device_planar.argtypes = [C.c_void_p] * 7 + [C.c_int]
+    assert L.b200_sws_scale_batch_device_planar(ctx, sp, ss, sfs, dp, dss, dfs, 2) == 0
+    for k in range(2):
+        exp = cl.orc_sws_planar(w, h, dw, dh, fl, *frames[k], details=det)
+        assert np.array_equal(DY[k], exp[0]) and np.array_equal(DU[k], exp[1]) and np.array_equal(DV[k], exp[2]), k
+    sl = (C.c_void_p * 4)(Y.ctypes.data, U.ctypes.data, V.ctypes.data, None)
+    sls = (C.c_int * 4)(w, w // 2, w // 2, 0)
+    dl = (C.c_void_p * 4)(DY.ctypes.data, DU.ctypes.data, DV.ctypes.data, None)
+    dls = (C.c_int * 4)(dw, dw // 2, dw // 2, 0)
+    L.b200_sws_scale.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    assert L.b200_sws_scale(ctx, sl, sls, 0, 16, dl, dls) == -38
+    L.b200_sws_freeContext(ctx)
+
+
 def test_sws_differential_fuzz(emusws):
     """seeded random contexts (sizes incl. odd ones, every source / destination format of the library, scaler flags, ranges,
     sws_setColorspaceDetails with other matrices / brightness / contrast / saturation, padded destinations) through the library's

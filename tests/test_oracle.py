@@ -546,3 +546,19 @@ def test_float_kernel_scalers_oracle_golden_and_ref():
                 src = cl.rgb_frame(w, h, 4300 + w, 4)
                 a, b = (f(w, h, dw, dh, fl, src, src, src, src_fmt=cl.PIX_FMT_BGRA, dst_fmt=cl.PIX_FMT_NV12) for f in (cl.orc_sws_planar, cl.ref_sws_planar))
                 assert all(np.array_equal(p, q) for p, q in zip(a, b)), (hex(fl), "bgra -> nv12")
+
+
+def test_sws_oracle_yuv_matrix_cascade_vs_ref():
+    """yuv -> yuv with different source and destination matrices: the reference cascades two contexts through bgr24 (utils.c:914-989)"""
+    if not cl.have_ref():
+        pytest.skip("oracle/_ref not built")
+    from cases import SWS_CASCADE_CASES
+    for i, (w, h, dw, dh, fl, sf, df, ranges, det) in enumerate(SWS_CASCADE_CASES):
+        y, u, v = cl.yuv_frame(w, h, 5200 + i, "random" if i % 2 else "smooth")
+        if sf:
+            u = v = cl.nv_interleave(u, v, sf)
+        a = cl.ref_sws_planar(w, h, dw, dh, fl, y, u, v, src_fmt=sf, dst_fmt=df, ranges=ranges, details=det, dst_pad=i % 3)
+        b = cl.orc_sws_planar(w, h, dw, dh, fl, y, u, v, src_fmt=sf, dst_fmt=df, ranges=ranges, details=det, dst_pad=i % 3)
+        assert all(np.array_equal(p, q) for p, q in zip(a, b)), (i, w, h, dw, dh, hex(fl))
+        same = cl.orc_sws_planar(w, h, dw, dh, fl, y, u, v, src_fmt=sf, dst_fmt=df, ranges=ranges, details=(det[0], det[1], det[0], det[3]) + det[4:], dst_pad=i % 3)
+        assert not all(np.array_equal(p, q) for p, q in zip(b, same)), i        # the second matrix matters

@@ -81,7 +81,7 @@ def test_range_conversion_fate_crc_padded_nv12(device):
 
 @isolated
 def test_range_conversion_batch_device(device):
-    """batched device entry point with range conversion (3 frames, full -> limited), and the refusal of a matrix change"""
+    """batched device entry point with range conversion (3 frames, full -> limited); a matrix change is accepted"""
     import torch
     import ffmpeg_b200 as fb
     from ffmpeg_b200 import swscale as sw
@@ -103,9 +103,8 @@ def test_range_conversion_batch_device(device):
         exp = cl.orc_sws_planar(w, h, dw, dh, FATE, *frames[i], ranges=(1, 0))
         for k in range(3):
             assert np.array_equal(got[k][i], exp[k]), (i, k)
-    # different matrices for yuv -> yuv: the reference cascades through bgr24; this path refuses loudly
-    with pytest.raises(fb.B200Error):
-        ctx.setColorspaceDetails(cl.COEFFS[1], 0, cl.COEFFS[5], 1, 0, 1 << 16, 1 << 16)
+    # different matrices for yuv -> yuv: the reference cascades through bgr24 and so does this path (test_sws_yuv_matrix_cascade)
+    assert ctx.setColorspaceDetails(cl.COEFFS[1], 0, cl.COEFFS[5], 1, 0, 1 << 16, 1 << 16) == 0
     ctx.free()
 
 
@@ -919,3 +918,38 @@ def test_sws_same_size_rgb_to_rgb(device):
             exp = cl.orc_sws(w, h, w, h, 4, frames[i], frames[i], frames[i], fmt=df, src_fmt=sf)
             assert np.array_equal(got[i][:, :w * db], exp), (sn, dn, i)
         ctx.free()
+
+
+# ---------------------------------------------------------------------------------------------- swscale: yuv -> yuv with two matrices
+def test_sws_yuv_matrix_cascade(device):
+    """sws_setColorspaceDetails with different source and destination matrices on a yuv -> yuv context: two cascaded contexts through a
+    bgr24 picture like the reference (utils.c:914-989); host sws_scale and the batched device entry against the oracle; a hash of the
+    oracle's outputs ties it to the fixture generated from the compiled reference"""
+    import torch
+    from ffmpeg_b200 import swscale as sw
+    from test_sws_gpu import gpu_sws_planar
+    from cases import SWS_CASCADE_CASES
+    for i, (w, h, dw, dh, fl, sf, df, ranges, det) in enumerate(SWS_CASCADE_CASES + [(1920, 1080, 1280, 720, 4, 0, 0, (0, 0), (1, 0, 9, 0, 0, 1 << 16, 1 << 16))]):
+        y, u, v = cl.yuv_frame(w, h, 5200 + i, "random" if i % 2 else "smooth")
+        if sf:
+            u = v = cl.nv_interleave(u, v, sf)
+        out = gpu_sws_planar(device, w, h, dw, dh, fl, y, u, v, src_fmt=sf, dst_fmt=df, ranges=ranges, details=det, dst_pad=i % 3)
+        exp = cl.orc_sws_planar(w, h, dw, dh, fl, y, u, v, src_fmt=sf, dst_fmt=df, ranges=ranges, details=det, dst_pad=i % 3)
+        assert all(np.array_equal(p, q) for p, q in zip(out, exp)), (i, w, h, dw, dh, hex(fl))
+    w, h, dw, dh, fl, det, n = 320, 180, 480, 270, 4, (1, 0, 5, 0, 0, 1 << 16, 1 << 16), 3
+    frames = [cl.yuv_frame(w, h, 5400 + k, "random") for k in range(n)]
+    ctx = sw.sws_getContext(device, w, h, sw.AV_PIX_FMT_YUV420P, dw, dh, sw.AV_PIX_FMT_YUV420P, fl)
+    assert ctx.setColorspaceDetails(cl.COEFFS[det[0]], det[1], cl.COEFFS[det[2]], det[3], *det[4:]) == 0
+    with torch.cuda.stream(torch.cuda.ExternalStream(device.stream)):
+        S = [torch.from_numpy(np.stack([f[k] for f in frames])).cuda() for k in range(3)]
+        DY = torch.zeros((n, dh, dw), dtype=torch.uint8, device="cuda")
+        DU = torch.zeros((n, dh // 2, dw // 2), dtype=torch.uint8, device="cuda")
+        DV = torch.zeros((n, dh // 2, dw // 2), dtype=torch.uint8, device="cuda")
+        ctx.scale_batch_device_planar(S, [w, w // 2, w // 2], [w * h, w * h // 4, w * h // 4], [DY, DU, DV], [dw, dw // 2, dw // 2],
+                                      [dw * dh, dw * dh // 4, dw * dh // 4], n)
+        device.sync()
+        got = [t.cpu().numpy() for t in (DY, DU, DV)]
+    for k in range(n):
+        exp = cl.orc_sws_planar(w, h, dw, dh, fl, *frames[k], details=det)
+        assert all(np.array_equal(got[j][k], exp[j]) for j in range(3)), k
+    ctx.free()
