@@ -247,12 +247,13 @@ def test_sws_oracle_fate_sws_yuv_range():
         assert fate_sws_yuv_range_crc(cl.ref_sws_planar) == FATE_SWS_YUV_RANGE
 
 
-def test_sws_oracle_yuv_matrix_change_not_restated():
-    """different matrices for yuv -> yuv: the reference cascades through bgr24; the oracle says so instead of guessing"""
+def test_sws_oracle_yuv_matrix_change_cascades_once():
+    """different matrices for yuv -> yuv: the first call builds the bgr24 cascade (utils.c:914-989); later calls go to its first context"""
     L = cl.oracle()
     ctx = L.orc_sws_open_range(0, 64, 48, 0, 0, 100, 70, 0, FATE)
     ta, tb = (np.array(cl.COEFFS[k], dtype=np.int32) for k in (1, 5))
-    assert L.orc_sws_set_colorspace_details(ctx, cl.ptr(ta, cl.i32p), 0, cl.ptr(tb, cl.i32p), 1, 0, 1 << 16, 1 << 16) == -1
+    assert L.orc_sws_set_colorspace_details(ctx, cl.ptr(ta, cl.i32p), 0, cl.ptr(tb, cl.i32p), 1, 0, 1 << 16, 1 << 16) == 0
+    assert L.orc_sws_set_colorspace_details(ctx, cl.ptr(ta, cl.i32p), 0, cl.ptr(tb, cl.i32p), 1, 0, 1 << 16, 1 << 16) == 0
     L.orc_sws_close(ctx)
 
 
