@@ -14,6 +14,8 @@ $NCU -k regex:"sws_mma_rgb" -s 1 -c 1 -o gpurun_out/${R}_mma_rgb_final python sc
 $NCU -k regex:"idct_mb420" -s 1 -c 1 -o gpurun_out/${R}_idct_put_final python scripts/profile_target.py idct 32 > gpurun_out/p5.log 2>&1
 $NCU -k regex:"idct_mb420" -s 7 -c 1 -o gpurun_out/${R}_idct_add_final python scripts/profile_target.py idct 32 > gpurun_out/p6.log 2>&1
 $NCU -k regex:"tx_r16_kernel" -s 1 -c 1 -o gpurun_out/${R}_tx_fft1024 python scripts/profile_target.py tx 8 > gpurun_out/p7.log 2>&1
+$NCU -k regex:"tx_r16_kernel" -s 1 -c 1 -o gpurun_out/${R}_tx_fft2048_final python scripts/profile_target.py tx2048 8 > gpurun_out/p7b.log 2>&1
+$NCU -k regex:"tx_r16_kernel" -s 4 -c 1 -o gpurun_out/${R}_tx_imdct2048_final python scripts/profile_target.py tx2048 8 > gpurun_out/p7c.log 2>&1
 $NCU -k regex:"qpel_kernel" -s 1 -c 1 -o gpurun_out/${R}_qpel_ldg python scripts/profile_target.py qpel 16 > gpurun_out/p8.log 2>&1
 $NCU -k regex:"esa" -s 1 -c 1 -o gpurun_out/${R}_esa python scripts/profile_target.py esa 8 > gpurun_out/p9.log 2>&1
 $NCU -k regex:"h264_idct_kernel" -s 0 -c 1 -o gpurun_out/${R}_h264_idct4_final python scripts/profile_target.py h264 16 > gpurun_out/p10.log 2>&1
