@@ -1167,9 +1167,9 @@ void prefetch_nop(const uint8_t *, ptrdiff_t, int) {}
 B200_API int b200_videodsp_init(B200VideoDSPContext *c, int bpc)
 {
     if (!c) return B200_EINVAL;
-    if (bpc > 8) return B200_ENOSYS;                               // videodsp.c:41-45 installs the 16 bit template above 8
     if (!b200_default_device()) return B200_ENODEV;
     c->emulated_edge_mc = edge_tab;
+    if (bpc > 8) pel_hbd_fill_edge(c);                             // videodsp.c:41-45: the 16 bit template above 8
     c->prefetch = prefetch_nop;                                    // videodsp.c:34-36: the C prefetch is an empty function
     return 0;
 }
@@ -1193,8 +1193,8 @@ B200_API int b200_emulated_edge_mc_batch_device(B200Device *dev, int64_t n, uint
 B200_API int b200_h264chroma_init(B200H264ChromaContext *c, int bit_depth)
 {
     if (!c) return B200_EINVAL;
-    if (bit_depth != 8) return B200_ENOSYS;                        // h264chroma.c:46-50 installs the 16 bit template above 8
     if (!b200_default_device()) return B200_ENODEV;
+    if (bit_depth > 8 && bit_depth <= 16) { pel_hbd_fill_chroma(c); return 0; }       // h264chroma.c:45-50: the 16 bit template (pel_hbd.cu)
     memset(c, 0, sizeof(*c));                                      // entry [3] stays NULL like the reference's
     c->put_h264_chroma_pixels_tab[0] = chroma_tab<0, 0>; c->put_h264_chroma_pixels_tab[1] = chroma_tab<0, 1>; c->put_h264_chroma_pixels_tab[2] = chroma_tab<0, 2>;
     c->avg_h264_chroma_pixels_tab[0] = chroma_tab<1, 0>; c->avg_h264_chroma_pixels_tab[1] = chroma_tab<1, 1>; c->avg_h264_chroma_pixels_tab[2] = chroma_tab<1, 2>;

@@ -76,6 +76,20 @@ def h264chroma_batch_device(device, n, op, h, xy, dst, dst_off, src, src_off, st
                  "h264chroma_batch_device")
 
 
+def h264chroma_hbd_batch_device(device, n, op, h, xy, dst, dst_off, src, src_off, stride):
+    """16-bit samples (any depth above 8): offsets and stride in bytes"""
+    return check(lib().b200_h264chroma_hbd_batch_device(device.handle, n, vp(_dptr(op)), vp(_dptr(h)), vp(_dptr(xy)), vp(_dptr(dst)),
+                                                        vp(_dptr(dst_off)), vp(_dptr(src)), vp(_dptr(src_off)), stride),
+                 "h264chroma_hbd_batch_device")
+
+
+def emulated_edge_mc_hbd_batch_device(device, n, buf, buf_off, buf_linesize, src, origin, src_linesize, geom, w, h):
+    """16-bit samples: geom in pixels, offsets and line sizes in bytes"""
+    return check(lib().b200_emulated_edge_mc_hbd_batch_device(device.handle, n, vp(_dptr(buf)), vp(_dptr(buf_off)), buf_linesize,
+                                                              vp(_dptr(src)), vp(_dptr(origin)), src_linesize, vp(_dptr(geom)), w, h),
+                 "emulated_edge_mc_hbd_batch_device")
+
+
 def emulated_edge_mc_batch_device(device, n, buf, buf_off, buf_linesize, src, origin, src_linesize, geom, w, h):
     """geom: int32 [n, 4] = block_w, block_h, src_x, src_y; origin: int64 offset of each window's picture sample (0, 0)."""
     return check(lib().b200_emulated_edge_mc_batch_device(device.handle, n, vp(_dptr(buf)), vp(_dptr(buf_off)), buf_linesize,

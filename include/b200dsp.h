@@ -504,12 +504,16 @@ typedef struct B200H264ChromaContext {
     b200_h264_chroma_mc_func put_h264_chroma_pixels_tab[4];   /* [0: 8 wide, 1: 4, 2: 2]; [3] is NULL like the reference's */
     b200_h264_chroma_mc_func avg_h264_chroma_pixels_tab[4];
 } B200H264ChromaContext;
-int  b200_h264chroma_init(B200H264ChromaContext *c, int bit_depth);   /* bit_depth must be 8, else B200_ENOSYS */
+int  b200_h264chroma_init(B200H264ChromaContext *c, int bit_depth);   /* 9 ... 16: the uint16 tables (h264chroma.c:45-50); else 8 bit */
 /* batched, DEVICE pointers.  op byte: bit0 avg, bits1-2 width index (0:8,1:4,2:2); h[i] = rows; xy[i] = x | y << 3.
  * Like the reference, x == 0 never reads the column right of the block and y == 0 never reads the row below it. */
 int  b200_h264chroma_batch_device(B200Device *dev, int64_t n, const uint8_t *op, const uint8_t *h, const uint8_t *xy,
                                   uint8_t *dst, const int64_t *dst_off, const uint8_t *src, const int64_t *src_off,
                                   ptrdiff_t stride);
+/* the same for 16-bit samples (any depth above 8): offsets and stride in BYTES (even) */
+int  b200_h264chroma_hbd_batch_device(B200Device *dev, int64_t n, const uint8_t *op, const uint8_t *h, const uint8_t *xy,
+                                      uint8_t *dst, const int64_t *dst_off, const uint8_t *src, const int64_t *src_off,
+                                      ptrdiff_t stride);
 
 /* videodsp: replaces VideoDSPContext (libavcodec/videodsp.h:32-69) as filled by ff_videodsp_init(ctx, 8)
  * (libavcodec/videodsp.c:32-62): emulated_edge_mc copies a block_w x block_h window whose top-left sample is picture
@@ -520,13 +524,18 @@ typedef struct B200VideoDSPContext {
                              int block_w, int block_h, int src_x, int src_y, int w, int h);
     void (*prefetch)(const uint8_t *buf, ptrdiff_t stride, int h);
 } B200VideoDSPContext;
-int  b200_videodsp_init(B200VideoDSPContext *c, int bpc);             /* bpc must be <= 8, else B200_ENOSYS */
+int  b200_videodsp_init(B200VideoDSPContext *c, int bpc);             /* bpc <= 8: bytes; above: the 16-bit template (uint16 samples,
+                                                                        * geometry in pixels, line sizes in bytes), videodsp.c:41-45 */
 /* batched, DEVICE pointers: window i = geom[4i..4i+3] = {block_w, block_h, src_x, src_y} of the picture whose sample (0, 0)
  * is src + origin[i] (so one call can span many frames of equal w x h and linesize), written to buf + buf_off[i].
  * geom must be 16-byte aligned.  w == 0 or h == 0 writes nothing, like the reference. */
 int  b200_emulated_edge_mc_batch_device(B200Device *dev, int64_t n, uint8_t *buf, const int64_t *buf_off,
                                         ptrdiff_t buf_linesize, const uint8_t *src, const int64_t *origin,
                                         ptrdiff_t src_linesize, const int32_t *geom, int w, int h);
+/* the same for 16-bit samples: geom in pixels; buf_off, origin and the line sizes in BYTES (even) */
+int  b200_emulated_edge_mc_hbd_batch_device(B200Device *dev, int64_t n, uint8_t *buf, const int64_t *buf_off,
+                                            ptrdiff_t buf_linesize, const uint8_t *src, const int64_t *origin,
+                                            ptrdiff_t src_linesize, const int32_t *geom, int w, int h);
 
 /* ------------------------------------------------------------------------------------------------ libavutil/tx
  * Replaces av_tx_init / av_tx_uninit / av_tx_fn (libavutil/tx.h:151,202-208) for AV_TX_FLOAT_FFT, AV_TX_FLOAT_MDCT and

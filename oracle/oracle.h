@@ -150,6 +150,9 @@ void orc_esa_frame(const uint8_t *cur, const uint8_t *ref, int linesize, int wid
 
 /* ------------------------------------------------------------------ h264qpel / hpeldsp (8 bit) */
 void orc_h264qpel(int avg, int size_idx, int pos, uint8_t *dst, const uint8_t *src, ptrdiff_t stride);
+int  orc_h264chroma_hbd(int avg, int idx, uint8_t *dst, const uint8_t *src, ptrdiff_t stride_bytes, int h, int x, int y);
+void orc_emulated_edge_mc_hbd(uint8_t *buf, const uint8_t *src, ptrdiff_t buf_linesize, ptrdiff_t src_linesize,
+                              int block_w, int block_h, int src_x, int src_y, int w, int h);
 void orc_h264qpel_hbd(int depth /* 9, 10, 12, 14 */, int avg, int size_idx, int pos, uint8_t *dst, const uint8_t *src, ptrdiff_t stride_bytes);
 void orc_h264qpel_hbd_batch(int depth, int n, const uint8_t *op, uint8_t *dstbase, const int64_t *dst_off, const uint8_t *srcbase,
                             const int64_t *src_off, ptrdiff_t stride_bytes);

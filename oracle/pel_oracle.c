@@ -143,6 +143,47 @@ void orc_h264qpel_hbd_batch(int depth, int n, const uint8_t *op, uint8_t *dstbas
         orc_h264qpel_hbd(depth, op[i] & 1, (op[i] >> 1) & 3, (op[i] >> 3) & 15, dstbase + dst_off[i], srcbase + src_off[i], stride);
 }
 
+/* h264chroma for 16-bit samples (h264chroma_template.c:27-176 with BIT_DEPTH 16; ff_h264chroma_init installs it for every depth above 8,
+ * h264chroma.c:45-50): same weights, (sum + 32) >> 6, avg (a + b + 1) >> 1; the D == 0 and B + C == 0 forms skip the unused reads */
+int orc_h264chroma_hbd(int avg, int idx, uint8_t *dst8, const uint8_t *src8, ptrdiff_t stride, int h, int x, int y)
+{
+    if (idx < 0 || idx > 2) return -1;
+    const int w = 8 >> idx;
+    const int A = (8 - x) * (8 - y), B = x * (8 - y), C = (8 - x) * y, D = x * y;
+    const ptrdiff_t st = stride / 2;
+    uint16_t *dst = (uint16_t *)dst8;
+    const uint16_t *src = (const uint16_t *)src8;
+    for (int j = 0; j < h; j++)
+        for (int i = 0; i < w; i++) {
+            const uint16_t *s = src + j * st + i;
+            int v;
+            if (D) v = A * s[0] + B * s[1] + C * s[st] + D * s[st + 1];
+            else if (B + C) v = A * s[0] + (B + C) * s[C ? st : 1];
+            else v = A * s[0];
+            v = (v + 32) >> 6;
+            uint16_t *d = dst + j * st + i;
+            *d = (uint16_t)(avg ? (*d + v + 1) >> 1 : v);
+        }
+    return 0;
+}
+
+/* emulated_edge_mc for 16-bit samples (videodsp_template.c:24-101 with BIT_DEPTH 16): geometry in pixels, line sizes in bytes */
+void orc_emulated_edge_mc_hbd(uint8_t *buf, const uint8_t *src, ptrdiff_t buf_linesize, ptrdiff_t src_linesize,
+                              int block_w, int block_h, int src_x, int src_y, int w, int h)
+{
+    if (!w || !h) return;
+    const uint8_t *origin = src - (ptrdiff_t)src_y * src_linesize - (ptrdiff_t)src_x * 2;
+    for (int y = 0; y < block_h; y++) {
+        int py = src_y + y;
+        py = py < 0 ? 0 : py > h - 1 ? h - 1 : py;
+        for (int x = 0; x < block_w; x++) {
+            int px = src_x + x;
+            px = px < 0 ? 0 : px > w - 1 ? w - 1 : px;
+            *(uint16_t *)(buf + y * buf_linesize + 2 * x) = *(const uint16_t *)(origin + py * src_linesize + 2 * px);
+        }
+    }
+}
+
 /* a list of operations, as ffref_h264qpel_batch / b200_h264qpel_batch_device take it (op byte: bit0 avg, bits1-2 size index, bits3-6 position) */
 void orc_h264qpel_batch(int n, const uint8_t *op, uint8_t *dstbase, const int64_t *dst_off, const uint8_t *srcbase,
                         const int64_t *src_off, ptrdiff_t stride)

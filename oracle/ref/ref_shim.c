@@ -404,6 +404,25 @@ API int ffref_h264chroma(int avg, int idx, uint8_t *dst, const uint8_t *src, ptr
     return 0;
 }
 
+API int ffref_h264chroma_hbd(int depth, int avg, int idx, uint8_t *dst, const uint8_t *src, ptrdiff_t stride, int h, int x, int y)
+{
+    static H264ChromaContext c[17]; static int ok[17];
+    if (depth < 9 || depth > 16) return -1;
+    if (!ok[depth]) { ff_h264chroma_init(&c[depth], depth); ok[depth] = 1; }
+    h264_chroma_mc_func f = (avg ? c[depth].avg_h264_chroma_pixels_tab : c[depth].put_h264_chroma_pixels_tab)[idx];
+    if (!f) return -1;
+    f(dst, src, stride, h, x, y);
+    return 0;
+}
+
+API void ffref_emulated_edge_mc_hbd(uint8_t *buf, const uint8_t *src, ptrdiff_t buf_linesize, ptrdiff_t src_linesize,
+                                    int block_w, int block_h, int src_x, int src_y, int w, int h)
+{
+    static VideoDSPContext c; static int ok;
+    if (!ok) { ff_videodsp_init(&c, 10); ok = 1; }
+    c.emulated_edge_mc(buf, src, buf_linesize, src_linesize, block_w, block_h, src_x, src_y, w, h);
+}
+
 API void ffref_emulated_edge_mc(uint8_t *buf, const uint8_t *src, ptrdiff_t buf_linesize, ptrdiff_t src_linesize,
                                 int block_w, int block_h, int src_x, int src_y, int w, int h)
 {

@@ -184,6 +184,37 @@ def gen_tx_pfa_fft():
     np.savez_compressed(os.path.join(OUT, "tx_pfa_fft.npz"), **d)
 
 
+def hbd_chroma_cases():
+    """(avg, idx, x, y, h) for the 16-bit chroma fixture; (bw, bh, sx, sy) for the 16-bit edge fixture"""
+    rng = np.random.default_rng(31)
+    ch = [(avg, idx, x, y, [4, 8, 16, 2][(x + y + idx) % 4]) for avg in (0, 1) for idx in range(3) for x in range(8) for y in range(8)]
+    ed = [(int(rng.integers(1, 25)), int(rng.integers(1, 25)), int(rng.integers(-30, 60)), int(rng.integers(-30, 50))) for _ in range(80)]
+    return ch, ed
+
+
+def gen_pel_hbd_chroma():
+    """h264chroma (ff_h264chroma_init(c, 10 / 16)) and emulated_edge_mc (ff_videodsp_init(ctx, 10)) for 16-bit samples: sha256 of the
+    compiled reference's destination per case"""
+    R = cl.ref()
+    R.ffref_h264chroma_hbd.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_ssize_t, C.c_int, C.c_int, C.c_int]
+    R.ffref_emulated_edge_mc_hbd.argtypes = [C.c_void_p, C.c_void_p, C.c_ssize_t, C.c_ssize_t] + [C.c_int] * 6
+    ch, ed = hbd_chroma_cases()
+    lines = []
+    for depth in (10, 16):
+        img, d0 = cl.hbd_picture(depth, 0)
+        for (avg, idx, x, y, h) in ch:
+            d = d0.copy()
+            off = (8 * 64 + 8) * 2
+            R.ffref_h264chroma_hbd(depth, avg, idx, d.ctypes.data + off, img.ctypes.data + off, 128, h, x, y)
+            lines.append(f"c {depth} {avg} {idx} {x} {y} {h} {sha(d)}")
+    pic, _ = cl.hbd_picture(10, 0)
+    for (bw, bh, sx, sy) in ed:
+        out = np.zeros((bh, bw + 3), np.uint16)
+        R.ffref_emulated_edge_mc_hbd(out.ctypes.data, pic.ctypes.data + sy * pic.strides[0] + sx * 2, out.strides[0], pic.strides[0], bw, bh, sx, sy, 64, 48)
+        lines.append(f"e {bw} {bh} {sx} {sy} {sha(out)}")
+    open(os.path.join(OUT, "pel_hbd_chroma_hashes.txt"), "w").write("\n".join(lines) + "\n")
+
+
 RGB2RGB_FLAGS = (4, 4 | 0x80000, 4 | 0x80000 | 0x40000, 16)
 
 
@@ -646,6 +677,7 @@ if __name__ == "__main__":
     gen_tx_pfa()
     gen_tx_pfa_fft()
     gen_pel_hbd()
+    gen_pel_hbd_chroma()
     gen_sws_rgb2rgb()
     gen_tx_full_imdct()
     gen_tx_dct()

@@ -1,4 +1,3 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 1300 compute-sanitizer --tool memcheck --error-exitcode 9 --launch-timeout 0 python -m pytest tests -m gpu -q -x > gpurun_out/sanitizer_all.log 2>&1
-echo "exit $?"; grep -c "Invalid\|out of bounds" gpurun_out/sanitizer_all.log; tail -8 gpurun_out/sanitizer_all.log
+python -m pytest tests -m gpu -x -q -k "hbd or chroma or edge or pel" > gpurun_out/t_a.log 2>&1; tail -8 gpurun_out/t_a.log

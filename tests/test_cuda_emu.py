@@ -1107,6 +1107,73 @@ def test_host_h264qpel_hbd(emuhost):
     assert L.emu_host_qpel_hbd_tab(8, 0, 0, 0, got.ctypes.data, img.ctypes.data, Wd * 2) == -38
 
 
+def test_host_chroma_and_edge_hbd(emuhost):
+    """pel_hbd.cu: h264chroma and emulated_edge_mc for 16-bit samples, batched device entries and drop-in table functions on the stand-in
+    runtime against the checker (every eighth-pel phase, put / avg, widths 8 / 4 / 2; windows on and beyond every picture border)"""
+    L, O = emuhost, cl.oracle()
+    L.b200_h264chroma_hbd_batch_device.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 7 + [C.c_ssize_t]
+    L.b200_emulated_edge_mc_hbd_batch_device.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_void_p, C.c_ssize_t, C.c_void_p, C.c_int, C.c_int]
+    L.emu_host_chroma_hbd_tab.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int]
+    L.emu_host_edge_hbd_tab.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong] + [C.c_int] * 6
+    O.orc_h264chroma_hbd.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_ssize_t, C.c_int, C.c_int, C.c_int]
+    O.orc_emulated_edge_mc_hbd.argtypes = [C.c_void_p, C.c_void_p, C.c_ssize_t, C.c_ssize_t] + [C.c_int] * 6
+    dev = C.c_void_p()
+    assert L.b200_device_open(C.byref(dev), 0, None) == 0
+    rng = np.random.default_rng(19)
+    Wd, Hd = 96, 80
+    for depth in (10, 16):
+        img = rng.integers(0, 1 << depth, (Hd, Wd)).astype(np.uint16)
+        ops, hs, xys, doff, soff = [], [], [], [], []
+        k = 0
+        for avg in (0, 1):
+            for idx in range(3):
+                for x in range(8):
+                    for y in range(8):
+                        ops.append(avg | (idx << 1)); hs.append([4, 8, 16, 2][(x + y + idx) % 4]); xys.append(x | (y << 3))
+                        doff.append(((k % 4) * 16 * Wd + (k // 4 % 10) * 8) * 2); soff.append((int(rng.integers(0, Hd - 18)) * Wd + int(rng.integers(0, Wd - 10))) * 2)
+                        k += 1
+        n = len(ops)
+        ops_a, hs_a, xy_a, do_a, so_a = np.array(ops, np.uint8), np.array(hs, np.uint8), np.array(xys, np.uint8), np.array(doff, np.int64), np.array(soff, np.int64)
+        for part in range(0, n, 40):                                # 40 disjoint destination blocks per picture
+            sl = slice(part, min(part + 40, n))
+            cnt = sl.stop - sl.start
+            d0 = rng.integers(0, 1 << depth, (Hd, Wd)).astype(np.uint16)
+            got, exp = d0.copy(), d0.copy()
+            a = [np.ascontiguousarray(v[sl]) for v in (ops_a, hs_a, xy_a, do_a, so_a)]
+            assert L.b200_h264chroma_hbd_batch_device(dev, cnt, a[0].ctypes.data, a[1].ctypes.data, a[2].ctypes.data, got.ctypes.data, a[3].ctypes.data,
+                                                      img.ctypes.data, a[4].ctypes.data, Wd * 2) == 0
+            for j in range(cnt):
+                O.orc_h264chroma_hbd(int(a[0][j]) & 1, int(a[0][j]) >> 1, exp.ctypes.data + int(a[3][j]), img.ctypes.data + int(a[4][j]), Wd * 2, int(a[1][j]), int(a[2][j]) & 7, int(a[2][j]) >> 3)
+            assert np.array_equal(got, exp), (depth, part)
+        for j in range(0, n, 11):                                   # drop-in table functions
+            d0 = rng.integers(0, 1 << depth, (Hd, Wd)).astype(np.uint16)
+            got, exp = d0.copy(), d0.copy()
+            off = (20 * Wd + 24) * 2
+            args = (ops[j] & 1, ops[j] >> 1)
+            assert L.emu_host_chroma_hbd_tab(*args, got.ctypes.data + off, img.ctypes.data + off, Wd * 2, hs[j], xys[j] & 7, xys[j] >> 3) == 0
+            O.orc_h264chroma_hbd(*args, exp.ctypes.data + off, img.ctypes.data + off, Wd * 2, hs[j], xys[j] & 7, xys[j] >> 3)
+            assert np.array_equal(got, exp), (depth, "tab", j)
+    pic = rng.integers(0, 1024, (30, 41)).astype(np.uint16)
+    geoms, origins, boffs = [], [], []
+    BW = 32
+    for it in range(60):
+        bw, bh = int(rng.integers(1, 25)), int(rng.integers(1, 25))
+        sx, sy = int(rng.integers(-30, 60)), int(rng.integers(-30, 50))
+        geoms.append((bw, bh, sx, sy)); origins.append(0); boffs.append(it * 25 * BW * 2)
+        got, exp = np.zeros((bh, bw + 3), np.uint16), np.zeros((bh, bw + 3), np.uint16)
+        src = pic.ctypes.data + sy * pic.strides[0] + sx * 2
+        L.emu_host_edge_hbd_tab(got.ctypes.data, src, got.strides[0], pic.strides[0], bw, bh, sx, sy, 41, 30)
+        O.orc_emulated_edge_mc_hbd(exp.ctypes.data, src, exp.strides[0], pic.strides[0], bw, bh, sx, sy, 41, 30)
+        assert np.array_equal(got, exp), ("edge tab", bw, bh, sx, sy)
+    g = np.array(geoms, np.int32); og = np.array(origins, np.int64); bo = np.array(boffs, np.int64)
+    buf = np.zeros((60 * 25, BW), np.uint16)
+    assert L.b200_emulated_edge_mc_hbd_batch_device(dev, 60, buf.ctypes.data, bo.ctypes.data, BW * 2, pic.ctypes.data, og.ctypes.data, pic.strides[0], g.ctypes.data, 41, 30) == 0
+    for it, (bw, bh, sx, sy) in enumerate(geoms):
+        exp = np.zeros((bh, bw), np.uint16)
+        O.orc_emulated_edge_mc_hbd(exp.ctypes.data, pic.ctypes.data + sy * pic.strides[0] + sx * 2, exp.strides[0], pic.strides[0], bw, bh, sx, sy, 41, 30)
+        assert np.array_equal(buf[it * 25:it * 25 + bh, :bw], exp), ("edge batch", it)
+
+
 def test_host_tx_pfa_create_and_launch(emuhost):
     from test_oracle_more import _tx
     L, O = emuhost, cl.oracle()

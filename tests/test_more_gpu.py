@@ -302,8 +302,7 @@ def test_h264chroma_pointer_table_golden(device):
             f(C.cast(o.ctypes.data + 8 * 48 + 8, u8p), ps, 48, h, xy & 7, xy >> 3)
             assert np.array_equal(o[8:24, 8:16], g[key][xy]), (key, xy)
             assert np.array_equal(o[:8], dst0[:8]) and np.array_equal(o[8 + h:], dst0[8 + h:]) and np.array_equal(o[:, 16:], dst0[:, 16:]), key
-    with pytest.raises(Exception):
-        pel.ff_h264chroma_init(10)
+    assert pel.ff_h264chroma_init(10).put_h264_chroma_pixels_tab[0]        # the 16-bit tables (test_h264chroma_and_edge_hbd)
 
 
 def test_h264chroma_batch_vs_oracle(device):
@@ -379,8 +378,7 @@ def test_emulated_edge_mc_pointer_table_golden(device):
     v.emulated_edge_mc(b.ctypes.data, pic.ctypes.data, 32, LS, 8, 8, 0, 0, 0, H)
     assert (b == 0x5A).all()
     v.prefetch(pic.ctypes.data, LS, 4)
-    with pytest.raises(Exception):
-        pel.ff_videodsp_init(10)
+    assert pel.ff_videodsp_init(10).emulated_edge_mc                         # the 16-bit template (test_h264chroma_and_edge_hbd)
 
 
 def test_emulated_edge_mc_batch_vs_oracle(device):

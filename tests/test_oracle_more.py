@@ -439,6 +439,41 @@ def test_h264qpel_hbd_oracle_golden_and_ref():
     assert n == 4 * 2 * 96
 
 
+def hbd_chroma_rows():
+    rows = []
+    for line in open(os.path.join(G, "pel_hbd_chroma_hashes.txt")):
+        t = line.split()
+        rows.append((t[0],) + tuple(int(v) for v in t[1:-1]) + (t[-1],))
+    return rows
+
+
+def test_h264chroma_and_edge_hbd_oracle_golden():
+    """h264chroma and emulated_edge_mc for 16-bit samples: the restatement against the hashes of the compiled reference's outputs"""
+    import hashlib
+    O = cl.oracle()
+    O.orc_h264chroma_hbd.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_ssize_t, C.c_int, C.c_int, C.c_int]
+    O.orc_emulated_edge_mc_hbd.argtypes = [C.c_void_p, C.c_void_p, C.c_ssize_t, C.c_ssize_t] + [C.c_int] * 6
+    pics = {}
+    nc = ne = 0
+    for row in hbd_chroma_rows():
+        if row[0] == "c":
+            _, depth, avg, idx, x, y, h, hsh = row
+            img, d0 = pics.setdefault(depth, cl.hbd_picture(depth, 0))
+            d = d0.copy()
+            off = (8 * 64 + 8) * 2
+            O.orc_h264chroma_hbd(avg, idx, d.ctypes.data + off, img.ctypes.data + off, 128, h, x, y)
+            assert hashlib.sha256(d.tobytes()).hexdigest() == hsh, row[:7]
+            nc += 1
+        else:
+            _, bw, bh, sx, sy, hsh = row
+            pic, _ = pics.setdefault(10, cl.hbd_picture(10, 0))
+            out = np.zeros((bh, bw + 3), np.uint16)
+            O.orc_emulated_edge_mc_hbd(out.ctypes.data, pic.ctypes.data + sy * pic.strides[0] + sx * 2, out.strides[0], pic.strides[0], bw, bh, sx, sy, 64, 48)
+            assert hashlib.sha256(out.tobytes()).hexdigest() == hsh, row[:5]
+            ne += 1
+    assert nc == 2 * 384 and ne == 80
+
+
 PFA_FFT_SIZES = (6, 12, 96, 10, 160, 14, 224, 18, 288, 30, 120, 960, 1920)
 
 

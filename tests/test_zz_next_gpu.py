@@ -953,3 +953,77 @@ def test_sws_yuv_matrix_cascade(device):
         exp = cl.orc_sws_planar(w, h, dw, dh, fl, *frames[k], details=det)
         assert all(np.array_equal(got[j][k], exp[j]) for j in range(3)), k
     ctx.free()
+
+
+# ---------------------------------------------------------------------------------------------- h264chroma + emulated_edge_mc, 16-bit samples
+def test_h264chroma_and_edge_hbd(device):
+    """ff_h264chroma_init(c, depth > 8) and ff_videodsp_init(ctx, bpc > 8): drop-in table functions against the hashes of the compiled
+    reference's outputs; batched device entries against the oracle"""
+    import ctypes as C
+    import hashlib
+    import torch
+    from ffmpeg_b200 import pel
+    from ffmpeg_b200._lib import u8p
+    from test_oracle_more import hbd_chroma_rows
+    O = cl.oracle()
+    O.orc_h264chroma_hbd.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_ssize_t, C.c_int, C.c_int, C.c_int]
+    O.orc_emulated_edge_mc_hbd.argtypes = [C.c_void_p, C.c_void_p, C.c_ssize_t, C.c_ssize_t] + [C.c_int] * 6
+    tabs, pics = {}, {}
+    vd = pel.ff_videodsp_init(10)
+    for k, row in enumerate(hbd_chroma_rows()):
+        if row[0] == "c":
+            if k % 3:
+                continue
+            _, depth, avg, idx, x, y, h, hsh = row
+            c = tabs.setdefault(depth, pel.ff_h264chroma_init(depth))
+            img, d0 = pics.setdefault(depth, cl.hbd_picture(depth, 0))
+            d = d0.copy()
+            off = (8 * 64 + 8) * 2
+            (c.avg_h264_chroma_pixels_tab if avg else c.put_h264_chroma_pixels_tab)[idx](C.cast(d.ctypes.data + off, u8p), C.cast(img.ctypes.data + off, u8p), 128, h, x, y)
+            assert hashlib.sha256(d.tobytes()).hexdigest() == hsh, row[:7]
+        else:
+            _, bw, bh, sx, sy, hsh = row
+            pic, _ = pics.setdefault(10, cl.hbd_picture(10, 0))
+            out = np.zeros((bh, bw + 3), np.uint16)
+            vd.emulated_edge_mc(C.cast(out.ctypes.data, u8p), C.cast(pic.ctypes.data + sy * pic.strides[0] + sx * 2, u8p), out.strides[0], pic.strides[0], bw, bh, sx, sy, 64, 48)
+            assert hashlib.sha256(out.tobytes()).hexdigest() == hsh, row[:5]
+    assert not tabs[10].put_h264_chroma_pixels_tab[3]
+    rng = np.random.default_rng(23)
+    W, H = 640, 368
+    ref_ = rng.integers(0, 1 << 10, (H, W)).astype(np.uint16)
+    dst0 = rng.integers(0, 1 << 10, (H, W)).astype(np.uint16)
+    ops, hs, xys, doffs, soffs = [], [], [], [], []
+    for by in range(1, H // 16 - 1):
+        for bx in range(1, W // 8 - 1):
+            idx = int(rng.integers(0, 3))
+            ops.append(pel.chroma_op(int(rng.integers(0, 2)), idx)); hs.append(int(rng.choice([2, 4, 8, 16]))); xys.append(int(rng.integers(0, 64)))
+            dx, dy = (int(v) for v in rng.integers(-6, 7, 2))
+            doffs.append((by * 16 * W + bx * 8) * 2); soffs.append(((by * 16 + dy) * W + bx * 8 + dx) * 2)
+    n = len(ops)
+    a = [np.array(v, t) for v, t in ((ops, np.uint8), (hs, np.uint8), (xys, np.uint8), (doffs, np.int64), (soffs, np.int64))]
+    exp = dst0.copy()
+    for j in range(n):
+        O.orc_h264chroma_hbd(ops[j] & 1, ops[j] >> 1, exp.ctypes.data + doffs[j], ref_.ctypes.data + soffs[j], W * 2, hs[j], xys[j] & 7, xys[j] >> 3)
+    with on_stream(device):
+        d = [torch.from_numpy(v).cuda() for v in a]
+        d_dst, d_src = torch.from_numpy(dst0.view(np.int16)).cuda(), torch.from_numpy(ref_.view(np.int16)).cuda()
+        pel.h264chroma_hbd_batch_device(device, n, d[0], d[1], d[2], d_dst, d[3], d_src, d[4], W * 2)
+        device.sync()
+        got = d_dst.cpu().numpy().view(np.uint16)
+    assert np.array_equal(got, exp), int((got != exp).sum())
+    # edge emulation: windows all around a 64 x 48 picture, one call
+    pic, _ = cl.hbd_picture(10, 0)
+    geoms = [(int(rng.integers(1, 25)), int(rng.integers(1, 25)), int(rng.integers(-30, 80)), int(rng.integers(-30, 70))) for _ in range(500)]
+    BW = 32
+    g = np.array(geoms, np.int32); og = np.zeros(500, np.int64); bo = (np.arange(500, dtype=np.int64) * 25 * BW * 2)
+    with on_stream(device):
+        d_pic = torch.from_numpy(pic.view(np.int16)).cuda()
+        d_buf = torch.zeros((500 * 25, BW), dtype=torch.int16, device="cuda")
+        d_g, d_og, d_bo = torch.from_numpy(g).cuda(), torch.from_numpy(og).cuda(), torch.from_numpy(bo).cuda()
+        pel.emulated_edge_mc_hbd_batch_device(device, 500, d_buf, d_bo, BW * 2, d_pic, d_og, pic.strides[0], d_g, 64, 48)
+        device.sync()
+        buf = d_buf.cpu().numpy().view(np.uint16)
+    for it, (bw, bh, sx, sy) in enumerate(geoms):
+        e = np.zeros((bh, bw), np.uint16)
+        O.orc_emulated_edge_mc_hbd(e.ctypes.data, pic.ctypes.data + sy * pic.strides[0] + sx * 2, e.strides[0], pic.strides[0], bw, bh, sx, sy, 64, 48)
+        assert np.array_equal(buf[it * 25:it * 25 + bh, :bw], e), ("edge", it)
