@@ -7,6 +7,7 @@
 //
 // Batched kernel: one warp per block, a lane owns 4 consecutive pixels of a row (32-bit accesses when the row is 4-aligned).
 #include "common.h"
+#include "pel_hbd.h"
 #include <cstring>
 
 namespace {
@@ -108,8 +109,8 @@ void biweight_tab(uint8_t *dst, uint8_t *src, ptrdiff_t stride, int height, int 
 B200_API int b200_h264_weight_init(B200H264WeightContext *c, int bit_depth)
 {
     if (!c) return B200_EINVAL;
-    if (bit_depth != 8) return B200_ENOSYS;
     if (!b200_default_device()) return B200_ENODEV;
+    if (bit_depth != 8) return pel_hbd_fill_weight(c, bit_depth) ? 0 : B200_ENOSYS;      // 9 / 10 / 12 / 14: uint16 samples (pel_hbd.cu)
     c->weight_pixels_tab[0] = weight_tab<0>; c->weight_pixels_tab[1] = weight_tab<1>;
     c->weight_pixels_tab[2] = weight_tab<2>; c->weight_pixels_tab[3] = weight_tab<3>;
     c->biweight_pixels_tab[0] = biweight_tab<0>; c->biweight_pixels_tab[1] = biweight_tab<1>;

@@ -116,6 +116,14 @@ def h264_weight_batch_device(device, n, params, dst, dst_off, src, src_off, stri
                  "h264_weight_batch_device")
 
 
+def h264_weight_hbd_batch_device(device, bit_depth, n, params, dst, dst_off, src, src_off, stride):
+    """9 / 10 / 12 / 14 bit samples (uint16): offsets and stride in bytes"""
+    return check(lib().b200_h264_weight_hbd_batch_device(device.handle, bit_depth, n, vp(_dptr(params)), vp(_dptr(dst)), vp(_dptr(dst_off)),
+                                                         vp(_dptr(src)) if src is not None else None,
+                                                         vp(_dptr(src_off)) if src_off is not None else None, stride),
+                 "h264_weight_hbd_batch_device")
+
+
 def ff_h264dsp_loop_filter_init(bit_depth=8, chroma_format_idc=1):
     """the loop-filter members of H264DSPContext (libavcodec/h264dsp.h:48-73) on HOST pointers"""
     from ._lib import H264LoopFilterContext

@@ -383,12 +383,15 @@ typedef struct B200H264WeightContext {
     b200_h264_weight_func   weight_pixels_tab[4];
     b200_h264_biweight_func biweight_pixels_tab[4];
 } B200H264WeightContext;
-int  b200_h264_weight_init(B200H264WeightContext *c, int bit_depth);            /* bit_depth must be 8 */
+int  b200_h264_weight_init(B200H264WeightContext *c, int bit_depth);            /* 8, or 9 / 10 / 12 / 14 (uint16 samples, stride in bytes) */
 /* batched, DEVICE pointers.  params: 4 int32 per block (16-byte aligned array): [0] = width index | height << 8 | log2_denom << 16,
  * [1] = weight (the destination weight for biweight), [2] = source weight (biweight), [3] = offset.  src == NULL: weight
  * (in place on dst + dst_off[i]); src != NULL: biweight of dst + dst_off[i] with src + src_off[i].  One stride for both. */
 int  b200_h264_weight_batch_device(B200Device *dev, int64_t n, const int32_t *params, uint8_t *dst, const int64_t *dst_off,
                                    const uint8_t *src, const int64_t *src_off, ptrdiff_t stride);
+/* the same for 9 / 10 / 12 / 14 bit samples (uint16): offsets and stride in BYTES (even) */
+int  b200_h264_weight_hbd_batch_device(B200Device *dev, int bit_depth, int64_t n, const int32_t *params, uint8_t *dst, const int64_t *dst_off,
+                                       const uint8_t *src, const int64_t *src_off, ptrdiff_t stride);
 
 /* ------------------------------------------------------------------------------------------------ me_cmp
  * Replaces MECmpContext (libavcodec/me_cmp.h:53-77) as filled by ff_me_cmp_init (libavcodec/me_cmp.c:961-1027) for the

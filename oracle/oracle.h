@@ -150,6 +150,9 @@ void orc_esa_frame(const uint8_t *cur, const uint8_t *ref, int linesize, int wid
 
 /* ------------------------------------------------------------------ h264qpel / hpeldsp (8 bit) */
 void orc_h264qpel(int avg, int size_idx, int pos, uint8_t *dst, const uint8_t *src, ptrdiff_t stride);
+void orc_h264_weight_hbd(int depth, int idx, uint8_t *block, ptrdiff_t stride_bytes, int height, int log2_denom, int weight, int offset);
+void orc_h264_biweight_hbd(int depth, int idx, uint8_t *dst, const uint8_t *src, ptrdiff_t stride_bytes, int height, int log2_denom,
+                           int weightd, int weights, int offset);
 int  orc_h264chroma_hbd(int avg, int idx, uint8_t *dst, const uint8_t *src, ptrdiff_t stride_bytes, int h, int x, int y);
 void orc_emulated_edge_mc_hbd(uint8_t *buf, const uint8_t *src, ptrdiff_t buf_linesize, ptrdiff_t src_linesize,
                               int block_w, int block_h, int src_x, int src_y, int w, int h);

@@ -184,6 +184,38 @@ void orc_emulated_edge_mc_hbd(uint8_t *buf, const uint8_t *src, ptrdiff_t buf_li
     }
 }
 
+/* weight / biweight for 9 / 10 / 12 / 14 bit samples (h264dsp_template.c:30-99 instantiated per depth): the offset is scaled to the
+ * sample depth, the clip is av_clip_uintp2(v, depth) */
+void orc_h264_weight_hbd(int depth, int idx, uint8_t *block8, ptrdiff_t stride, int height, int log2_denom, int weight, int offset)
+{
+    const int w = 16 >> idx, maxv = (1 << depth) - 1;
+    uint16_t *block = (uint16_t *)block8;
+    const ptrdiff_t st = stride / 2;
+    offset = (int)((unsigned)offset << (log2_denom + (depth - 8)));
+    if (log2_denom) offset += 1 << (log2_denom - 1);
+    for (int y = 0; y < height; y++, block += st)
+        for (int x = 0; x < w; x++) {
+            const int v = (block[x] * weight + offset) >> log2_denom;
+            block[x] = (uint16_t)(v < 0 ? 0 : v > maxv ? maxv : v);
+        }
+}
+
+void orc_h264_biweight_hbd(int depth, int idx, uint8_t *dst8, const uint8_t *src8, ptrdiff_t stride, int height, int log2_denom,
+                           int weightd, int weights, int offset)
+{
+    const int w = 16 >> idx, maxv = (1 << depth) - 1;
+    uint16_t *dst = (uint16_t *)dst8;
+    const uint16_t *src = (const uint16_t *)src8;
+    const ptrdiff_t st = stride / 2;
+    offset = (int)((unsigned)offset << (depth - 8));
+    offset = (int)((unsigned)((offset + 1) | 1) << log2_denom);
+    for (int y = 0; y < height; y++, dst += st, src += st)
+        for (int x = 0; x < w; x++) {
+            const int v = (src[x] * weights + dst[x] * weightd + offset) >> (log2_denom + 1);
+            dst[x] = (uint16_t)(v < 0 ? 0 : v > maxv ? maxv : v);
+        }
+}
+
 /* a list of operations, as ffref_h264qpel_batch / b200_h264qpel_batch_device take it (op byte: bit0 avg, bits1-2 size index, bits3-6 position) */
 void orc_h264qpel_batch(int n, const uint8_t *op, uint8_t *dstbase, const int64_t *dst_off, const uint8_t *srcbase,
                         const int64_t *src_off, ptrdiff_t stride)

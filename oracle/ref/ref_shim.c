@@ -460,6 +460,30 @@ API void ffref_h264_biweight(int idx, uint8_t *dst, uint8_t *src, ptrdiff_t stri
     c.biweight_pixels_tab[idx](dst, src, stride, height, log2_denom, weightd, weights, offset);
 }
 
+/* weight / biweight tables of ff_h264dsp_init for 9 / 10 / 12 / 14 bit samples */
+static H264DSPContext *ref_h264dsp_hbd(int depth)
+{
+    static H264DSPContext c[15]; static int ok[15];
+    if (depth != 9 && depth != 10 && depth != 12 && depth != 14) return NULL;
+    if (!ok[depth]) { ff_h264dsp_init(&c[depth], depth, 1); ok[depth] = 1; }
+    return &c[depth];
+}
+API int ffref_h264_weight_hbd(int depth, int idx, uint8_t *block, ptrdiff_t stride, int height, int log2_denom, int weight, int offset)
+{
+    H264DSPContext *c = ref_h264dsp_hbd(depth);
+    if (!c) return -1;
+    c->weight_pixels_tab[idx](block, stride, height, log2_denom, weight, offset);
+    return 0;
+}
+API int ffref_h264_biweight_hbd(int depth, int idx, uint8_t *dst, uint8_t *src, ptrdiff_t stride, int height, int log2_denom,
+                                int weightd, int weights, int offset)
+{
+    H264DSPContext *c = ref_h264dsp_hbd(depth);
+    if (!c) return -1;
+    c->biweight_pixels_tab[idx](dst, src, stride, height, log2_denom, weightd, weights, offset);
+    return 0;
+}
+
 /* ------------------------------------------------------------------ tx ------------------------------------------ */
 
 typedef struct { AVTXContext *ctx; av_tx_fn fn; } RefTx;

@@ -215,6 +215,25 @@ def gen_pel_hbd_chroma():
     open(os.path.join(OUT, "pel_hbd_chroma_hashes.txt"), "w").write("\n".join(lines) + "\n")
 
 
+def gen_h264_weight_hbd():
+    """weight / biweight tables of ff_h264dsp_init(c, 9 / 10 / 12 / 14): sha256 of the compiled reference's block per case"""
+    R = cl.ref()
+    R.ffref_h264_weight_hbd.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_ssize_t] + [C.c_int] * 4
+    R.ffref_h264_biweight_hbd.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_ssize_t] + [C.c_int] * 5
+    lines = []
+    for depth in (9, 10, 12, 14):
+        img, d0 = cl.hbd_picture(depth, 0)
+        for k, (bi, idx, h, d, wd, ws, off) in enumerate(cl.hbd_weight_cases(depth)):
+            blk = d0.copy()
+            o = (8 * 64 + 8) * 2
+            if bi:
+                R.ffref_h264_biweight_hbd(depth, idx, blk.ctypes.data + o, img.ctypes.data + o, 128, h, d, wd, ws, off)
+            else:
+                R.ffref_h264_weight_hbd(depth, idx, blk.ctypes.data + o, 128, h, d, wd, off)
+            lines.append(f"{depth} {k} {sha(blk)}")
+    open(os.path.join(OUT, "h264_weight_hbd_hashes.txt"), "w").write("\n".join(lines) + "\n")
+
+
 RGB2RGB_FLAGS = (4, 4 | 0x80000, 4 | 0x80000 | 0x40000, 16)
 
 
@@ -678,6 +697,7 @@ if __name__ == "__main__":
     gen_tx_pfa_fft()
     gen_pel_hbd()
     gen_pel_hbd_chroma()
+    gen_h264_weight_hbd()
     gen_sws_rgb2rgb()
     gen_tx_full_imdct()
     gen_tx_dct()

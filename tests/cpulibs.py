@@ -367,6 +367,13 @@ def hbd_picture(depth, kind):
     return img, rng.integers(0, mx + 1, (48, 64)).astype(np.uint16)
 
 
+def hbd_weight_cases(depth, n=60):
+    """(bi, idx, height, log2_denom, wd, ws, offset) for the 16-bit weighted-prediction fixture / tests"""
+    rng = np.random.default_rng(4000 + depth)
+    return [(int(rng.integers(0, 2)), int(rng.integers(0, 4)), int(rng.choice([2, 4, 8, 16])), int(rng.integers(0, 8)),
+             int(rng.integers(-128, 128)), int(rng.integers(-128, 128)), int(rng.integers(-128, 128))) for _ in range(n)]
+
+
 def idct_hbd_blocks(seed, depth, n):
     """n coefficient blocks: dense small, full int16 range, sparse, DC only, DC-only rows, decoder-like range"""
     rng = np.random.default_rng(seed)

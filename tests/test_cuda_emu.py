@@ -1174,6 +1174,42 @@ def test_host_chroma_and_edge_hbd(emuhost):
         assert np.array_equal(buf[it * 25:it * 25 + bh, :bw], exp), ("edge batch", it)
 
 
+def test_host_h264_weight_hbd(emuhost):
+    """pel_hbd.cu: explicit weighted prediction for 9 / 10 / 12 / 14 bit samples, table functions and the batched device entry on the
+    stand-in runtime against the checker"""
+    from test_oracle_more import run_weight_hbd_case
+    L, O = emuhost, cl.oracle()
+    O.orc_h264_weight_hbd.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_ssize_t] + [C.c_int] * 4
+    O.orc_h264_biweight_hbd.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_ssize_t] + [C.c_int] * 5
+    L.emu_host_weight_hbd_tab.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_longlong] + [C.c_int] * 5
+    L.b200_h264_weight_hbd_batch_device.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_ssize_t]
+    dev = C.c_void_p()
+    assert L.b200_device_open(C.byref(dev), 0, None) == 0
+    for depth in (9, 10, 12, 14):
+        cases = cl.hbd_weight_cases(depth)
+        for case in cases[:25]:
+            exp = run_weight_hbd_case(O.orc_h264_weight_hbd, O.orc_h264_biweight_hbd, depth, case)
+            wf = lambda dp, idx, blk, st, h, d, wd, off: L.emu_host_weight_hbd_tab(dp, 0, idx, blk, None, st, h, d, wd, 0, off)
+            bf = lambda dp, idx, blk, src, st, h, d, wd, ws, off: L.emu_host_weight_hbd_tab(dp, 1, idx, blk, src, st, h, d, wd, ws, off)
+            assert np.array_equal(run_weight_hbd_case(wf, bf, depth, case), exp), (depth, case)
+        # batch: the weight cases in place, then the biweight cases, blocks on a 16 x 16 grid of a 64 x 48 picture (12 per call)
+        img, d0 = cl.hbd_picture(depth, 0)
+        for bi in (0, 1):
+            sel = [c for c in cases if c[0] == bi][:12]
+            params = np.array([[c[1] | (c[2] << 8) | (c[3] << 16), c[4], c[5], c[6]] for c in sel], np.int32)
+            doff = np.array([((k // 4) * 16 * 64 + (k % 4) * 16) * 2 for k in range(len(sel))], np.int64)
+            got, exp = d0.copy(), d0.copy()
+            assert L.b200_h264_weight_hbd_batch_device(dev, depth, len(sel), params.ctypes.data, got.ctypes.data, doff.ctypes.data,
+                                                       img.ctypes.data if bi else None, doff.ctypes.data if bi else None, 128) == 0
+            for k, c in enumerate(sel):
+                if bi:
+                    O.orc_h264_biweight_hbd(depth, c[1], exp.ctypes.data + int(doff[k]), img.ctypes.data + int(doff[k]), 128, c[2], c[3], c[4], c[5], c[6])
+                else:
+                    O.orc_h264_weight_hbd(depth, c[1], exp.ctypes.data + int(doff[k]), 128, c[2], c[3], c[4], c[6])
+            assert np.array_equal(got, exp), (depth, bi)
+    assert L.emu_host_weight_hbd_tab(11, 0, 0, None, None, 0, 0, 0, 0, 0, 0) == -38
+
+
 def test_host_tx_pfa_create_and_launch(emuhost):
     from test_oracle_more import _tx
     L, O = emuhost, cl.oracle()

@@ -474,6 +474,40 @@ def test_h264chroma_and_edge_hbd_oracle_golden():
     assert nc == 2 * 384 and ne == 80
 
 
+def run_weight_hbd_case(weight_fn, biweight_fn, depth, case):
+    bi, idx, h, d, wd, ws, off = case
+    img, d0 = cl.hbd_picture(depth, 0)
+    blk = d0.copy()
+    o = (8 * 64 + 8) * 2
+    if bi:
+        biweight_fn(depth, idx, blk.ctypes.data + o, img.ctypes.data + o, 128, h, d, wd, ws, off)
+    else:
+        weight_fn(depth, idx, blk.ctypes.data + o, 128, h, d, wd, off)
+    return blk
+
+
+def weight_hbd_hashes():
+    out = {}
+    for line in open(os.path.join(G, "h264_weight_hbd_hashes.txt")):
+        depth, k, h = line.split()
+        out[(int(depth), int(k))] = h
+    return out
+
+
+def test_h264_weight_hbd_oracle_golden():
+    """weight / biweight for 9 / 10 / 12 / 14 bit samples against the hashes of the compiled reference's outputs"""
+    import hashlib
+    O = cl.oracle()
+    O.orc_h264_weight_hbd.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_ssize_t] + [C.c_int] * 4
+    O.orc_h264_biweight_hbd.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_ssize_t] + [C.c_int] * 5
+    hs = weight_hbd_hashes()
+    assert len(hs) == 240
+    for depth in (9, 10, 12, 14):
+        for k, case in enumerate(cl.hbd_weight_cases(depth)):
+            blk = run_weight_hbd_case(O.orc_h264_weight_hbd, O.orc_h264_biweight_hbd, depth, case)
+            assert hashlib.sha256(blk.tobytes()).hexdigest() == hs[(depth, k)], (depth, case)
+
+
 PFA_FFT_SIZES = (6, 12, 96, 10, 160, 14, 224, 18, 288, 30, 120, 960, 1920)
 
 

@@ -1027,3 +1027,55 @@ def test_h264chroma_and_edge_hbd(device):
         e = np.zeros((bh, bw), np.uint16)
         O.orc_emulated_edge_mc_hbd(e.ctypes.data, pic.ctypes.data + sy * pic.strides[0] + sx * 2, e.strides[0], pic.strides[0], bw, bh, sx, sy, 64, 48)
         assert np.array_equal(buf[it * 25:it * 25 + bh, :bw], e), ("edge", it)
+
+
+# ---------------------------------------------------------------------------------------------- H.264 weighted prediction, 16-bit samples
+def test_h264_weight_hbd(device):
+    """ff_h264dsp_init(c, 9 / 10 / 12 / 14) weight / biweight tables: table functions against the hashes of the compiled reference's
+    outputs, batched device entry against the oracle"""
+    import ctypes as C
+    import hashlib
+    import torch
+    import ffmpeg_b200 as fb
+    from ffmpeg_b200 import pel
+    from ffmpeg_b200._lib import u8p
+    from test_oracle_more import run_weight_hbd_case, weight_hbd_hashes
+    O = cl.oracle()
+    O.orc_h264_weight_hbd.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_ssize_t] + [C.c_int] * 4
+    O.orc_h264_biweight_hbd.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_ssize_t] + [C.c_int] * 5
+    hs = weight_hbd_hashes()
+    for depth in (9, 10, 12, 14):
+        t = pel.ff_h264dsp_weight_init(depth)
+        wf = lambda dp, idx, blk, st, h, d, wd, off: t.weight_pixels_tab[idx](C.cast(blk, u8p), st, h, d, wd, off)
+        bf = lambda dp, idx, blk, src, st, h, d, wd, ws, off: t.biweight_pixels_tab[idx](C.cast(blk, u8p), C.cast(src, u8p), st, h, d, wd, ws, off)
+        for k, case in enumerate(cl.hbd_weight_cases(depth)):
+            if k % 2:
+                continue
+            assert hashlib.sha256(run_weight_hbd_case(wf, bf, depth, case).tobytes()).hexdigest() == hs[(depth, k)], (depth, case)
+    with pytest.raises(fb.B200Error):
+        pel.ff_h264dsp_weight_init(11)
+    rng = np.random.default_rng(29)
+    W, H, depth = 640, 368, 10
+    ref_ = rng.integers(0, 1 << depth, (H, W)).astype(np.uint16)
+    dst0 = rng.integers(0, 1 << depth, (H, W)).astype(np.uint16)
+    for bi in (0, 1):
+        prm, doffs = [], []
+        for by in range(H // 16):
+            for bx in range(W // 16):
+                idx, h, d = int(rng.integers(0, 4)), int(rng.choice([2, 4, 8, 16])), int(rng.integers(0, 8))
+                prm.append([idx | (h << 8) | (d << 16), int(rng.integers(-128, 128)), int(rng.integers(-128, 128)), int(rng.integers(-128, 128))])
+                doffs.append((by * 16 * W + bx * 16) * 2)
+        prm_a, do_a = np.array(prm, np.int32), np.array(doffs, np.int64)
+        exp = dst0.copy()
+        for p_, o_ in zip(prm, doffs):
+            if bi:
+                O.orc_h264_biweight_hbd(depth, p_[0] & 3, exp.ctypes.data + o_, ref_.ctypes.data + o_, W * 2, (p_[0] >> 8) & 255, p_[0] >> 16, p_[1], p_[2], p_[3])
+            else:
+                O.orc_h264_weight_hbd(depth, p_[0] & 3, exp.ctypes.data + o_, W * 2, (p_[0] >> 8) & 255, p_[0] >> 16, p_[1], p_[3])
+        with on_stream(device):
+            d_p, d_o = torch.from_numpy(prm_a).cuda(), torch.from_numpy(do_a).cuda()
+            d_dst, d_src = torch.from_numpy(dst0.view(np.int16)).cuda(), torch.from_numpy(ref_.view(np.int16)).cuda()
+            pel.h264_weight_hbd_batch_device(device, depth, len(prm), d_p, d_dst, d_o, d_src if bi else None, d_o if bi else None, W * 2)
+            device.sync()
+            got = d_dst.cpu().numpy().view(np.uint16)
+        assert np.array_equal(got, exp), (bi, int((got != exp).sum()))
