@@ -10,6 +10,7 @@
 // words read-modify-written (the reference requires dst 4-aligned, h264dsp.h:81); 8x8: 128 bytes in, eight 8-byte rows.
 // Every consumed coefficient block is zeroed like the reference's memset (the decoder relies on it for the next macroblock).
 #include "common.h"
+#include "h264idct_hbd.h"
 #include <cstring>
 
 namespace {
@@ -195,8 +196,8 @@ B200_API int b200_h264_idct_init(B200H264IDCTContext *c, int bit_depth, int chro
 {
     (void)chroma_format_idc;
     if (!c) return B200_EINVAL;
-    if (bit_depth != 8) return B200_ENOSYS;                      // h264dsp.c:139-158 installs the 9/10/12/14 bit templates above 8
     if (!b200_default_device()) return B200_ENODEV;
+    if (bit_depth != 8) return h264idct_hbd_fill(c, bit_depth) ? 0 : B200_ENOSYS;      // h264dsp.c:139-158: 9 / 10 / 12 / 14 (h264idct_hbd.cu)
     c->idct_add = host_fn<0>; c->idct8_add = host_fn<1>; c->idct_dc_add = host_fn<2>; c->idct8_dc_add = host_fn<3>;
     return 0;
 }

@@ -362,7 +362,8 @@ typedef struct B200H264IDCTContext {
     b200_h264_idct_fn idct_dc_add;     /* 4x4, only block[0] is read (and cleared) */
     b200_h264_idct_fn idct8_dc_add;
 } B200H264IDCTContext;
-int  b200_h264_idct_init(B200H264IDCTContext *c, int bit_depth, int chroma_format_idc);   /* bit_depth must be 8 */
+int  b200_h264_idct_init(B200H264IDCTContext *c, int bit_depth, int chroma_format_idc);   /* 8, or 9 / 10 / 12 / 14: uint16 samples and
+                                                                                              * int32 coefficients behind the int16_t * argument */
 #define B200_H264_IDCT4    0
 #define B200_H264_IDCT8    1
 #define B200_H264_IDCT4_DC 2
@@ -372,6 +373,9 @@ int  b200_h264_idct_init(B200H264IDCTContext *c, int bit_depth, int chroma_forma
  * and cleared.  dst + dst_off[i] and stride must be 4-aligned (8 for the 8x8 kinds), as the reference requires. */
 int  b200_h264_idct_batch_device(B200Device *dev, int kind, int64_t n, int16_t *blocks, const int64_t *blk_off,
                                  uint8_t *dst, const int64_t *dst_off, ptrdiff_t stride);
+/* the same for 9 / 10 / 12 / 14 bit samples: int32 coefficients (blk_off in int32 elements), uint16 samples (dst_off and stride in BYTES) */
+int  b200_h264_idct_hbd_batch_device(B200Device *dev, int bit_depth, int kind, int64_t n, int32_t *blocks, const int64_t *blk_off,
+                                     uint8_t *dst, const int64_t *dst_off, ptrdiff_t stride);
 
 /* H.264 explicit weighted prediction, 8 bit: weight_pixels_tab / biweight_pixels_tab of H264DSPContext (libavcodec/h264dsp.h:33-45)
  * as installed by ff_h264dsp_init(c, 8, ...) (libavcodec/h264dsp.c:103-110; functions in h264dsp_template.c:30-99).

@@ -297,3 +297,66 @@ int orc_h264_idct(int kind, uint8_t *dst, int16_t *block, ptrdiff_t stride)
     }
     return -1;
 }
+
+
+/* ---- H.264 residual adds for 9 / 10 / 12 / 14 bit samples: h264idct_template.c:33-181 with dctcoef = int32_t, pixel = uint16_t
+ * (h264dsp.c:66-158).  Same butterflies as the 8-bit functions on 32-bit values (the reference's SUINT sums: mod 2^32), clip to the depth. */
+static int hb_px(int v, int maxv) { return v < 0 ? 0 : v > maxv ? maxv : v; }
+static void hb_idct8_1d(const int32_t *s, int stride, int32_t *o)
+{
+    const uint32_t a0 = (uint32_t)s[0] + (uint32_t)s[4 * stride], a2 = (uint32_t)s[0] - (uint32_t)s[4 * stride];
+    const uint32_t a4 = (uint32_t)(s[2 * stride] >> 1) - (uint32_t)s[6 * stride], a6 = (uint32_t)(s[6 * stride] >> 1) + (uint32_t)s[2 * stride];
+    const uint32_t b0 = a0 + a6, b2 = a2 + a4, b4 = a2 - a4, b6 = a0 - a6;
+    const int32_t a1 = (int32_t)(-(uint32_t)s[3 * stride] + (uint32_t)s[5 * stride] - (uint32_t)s[7 * stride] - (uint32_t)(s[7 * stride] >> 1));
+    const int32_t a3 = (int32_t)((uint32_t)s[1 * stride] + (uint32_t)s[7 * stride] - (uint32_t)s[3 * stride] - (uint32_t)(s[3 * stride] >> 1));
+    const int32_t a5 = (int32_t)(-(uint32_t)s[1 * stride] + (uint32_t)s[7 * stride] + (uint32_t)s[5 * stride] + (uint32_t)(s[5 * stride] >> 1));
+    const int32_t a7 = (int32_t)((uint32_t)s[3 * stride] + (uint32_t)s[5 * stride] + (uint32_t)s[1 * stride] + (uint32_t)(s[1 * stride] >> 1));
+    const uint32_t b1 = (uint32_t)(a7 >> 2) + (uint32_t)a1, b3 = (uint32_t)a3 + (uint32_t)(a5 >> 2);
+    const uint32_t b5 = (uint32_t)(a3 >> 2) - (uint32_t)a5, b7 = (uint32_t)a7 - (uint32_t)(a1 >> 2);
+    o[0] = (int32_t)(b0 + b7); o[7] = (int32_t)(b0 - b7); o[1] = (int32_t)(b2 + b5); o[6] = (int32_t)(b2 - b5);
+    o[2] = (int32_t)(b4 + b3); o[5] = (int32_t)(b4 - b3); o[3] = (int32_t)(b6 + b1); o[4] = (int32_t)(b6 - b1);
+}
+
+int orc_h264_idct_hbd(int depth, int kind, uint8_t *dst8, int32_t *block, ptrdiff_t stride)
+{
+    if (kind < 0 || kind > 3 || (depth != 9 && depth != 10 && depth != 12 && depth != 14)) return -1;
+    uint16_t *dst = (uint16_t *)dst8;
+    const ptrdiff_t st = stride / 2;
+    const int maxv = (1 << depth) - 1, n = (kind & 1) ? 8 : 4;
+    if (kind >= 2) {
+        const int dc = (block[0] + 32) >> 6;
+        block[0] = 0;
+        for (int j = 0; j < n; j++)
+            for (int i = 0; i < n; i++) dst[j * st + i] = (uint16_t)hb_px(dst[j * st + i] + dc, maxv);
+        return 0;
+    }
+    block[0] = (int32_t)((uint32_t)block[0] + 32u);
+    if (kind == 0) {
+        for (int i = 0; i < 4; i++) {
+            const uint32_t z0 = (uint32_t)block[i] + (uint32_t)block[i + 8], z1 = (uint32_t)block[i] - (uint32_t)block[i + 8];
+            const uint32_t z2 = (uint32_t)(block[i + 4] >> 1) - (uint32_t)block[i + 12], z3 = (uint32_t)block[i + 4] + (uint32_t)(block[i + 12] >> 1);
+            block[i] = (int32_t)(z0 + z3); block[i + 4] = (int32_t)(z1 + z2); block[i + 8] = (int32_t)(z1 - z2); block[i + 12] = (int32_t)(z0 - z3);
+        }
+        for (int i = 0; i < 4; i++) {
+            const uint32_t z0 = (uint32_t)block[4 * i] + (uint32_t)block[4 * i + 2], z1 = (uint32_t)block[4 * i] - (uint32_t)block[4 * i + 2];
+            const uint32_t z2 = (uint32_t)(block[4 * i + 1] >> 1) - (uint32_t)block[4 * i + 3], z3 = (uint32_t)block[4 * i + 1] + (uint32_t)(block[4 * i + 3] >> 1);
+            dst[i + 0 * st] = (uint16_t)hb_px(dst[i + 0 * st] + ((int32_t)(z0 + z3) >> 6), maxv);
+            dst[i + 1 * st] = (uint16_t)hb_px(dst[i + 1 * st] + ((int32_t)(z1 + z2) >> 6), maxv);
+            dst[i + 2 * st] = (uint16_t)hb_px(dst[i + 2 * st] + ((int32_t)(z1 - z2) >> 6), maxv);
+            dst[i + 3 * st] = (uint16_t)hb_px(dst[i + 3 * st] + ((int32_t)(z0 - z3) >> 6), maxv);
+        }
+        memset(block, 0, 16 * sizeof(int32_t));
+    } else {
+        int32_t o[8];
+        for (int i = 0; i < 8; i++) {
+            hb_idct8_1d(block + i, 8, o);
+            for (int r = 0; r < 8; r++) block[i + 8 * r] = o[r];
+        }
+        for (int i = 0; i < 8; i++) {
+            hb_idct8_1d(block + 8 * i, 1, o);
+            for (int r = 0; r < 8; r++) dst[i + r * st] = (uint16_t)hb_px(dst[i + r * st] + (o[r] >> 6), maxv);
+        }
+        memset(block, 0, 64 * sizeof(int32_t));
+    }
+    return 0;
+}

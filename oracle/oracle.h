@@ -138,6 +138,7 @@ enum { ORC_FDSP_VECTOR_FMUL, ORC_FDSP_VECTOR_FMAC_SCALAR, ORC_FDSP_VECTOR_DMAC_S
 int  orc_float_dsp(int op, void *dst, const void *src0, const void *src1, const void *src2, double mul, int len);
 /* H.264 residual add, 8 bit: kind 0 idct_add (4x4), 1 idct8_add, 2 idct_dc_add, 3 idct8_dc_add; clears the coefficients */
 int  orc_h264_idct(int kind, uint8_t *dst, int16_t *block, ptrdiff_t stride);
+int  orc_h264_idct_hbd(int depth, int kind, uint8_t *dst, int32_t *block, ptrdiff_t stride_bytes);   /* 9 / 10 / 12 / 14 bit: int32 coefficients, uint16 samples */
 void orc_pixels_clamped(int kind, const int16_t *block, uint8_t *pixels, ptrdiff_t line_size);
 
 /* ------------------------------------------------------------------ me_cmp */

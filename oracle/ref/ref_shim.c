@@ -460,6 +460,21 @@ API void ffref_h264_biweight(int idx, uint8_t *dst, uint8_t *src, ptrdiff_t stri
     c.biweight_pixels_tab[idx](dst, src, stride, height, log2_denom, weightd, weights, offset);
 }
 
+/* residual adds of ff_h264dsp_init for 9 / 10 / 12 / 14 bit samples: block holds int32 coefficients behind the int16_t * type */
+static H264DSPContext *ref_h264dsp_hbd(int depth);
+API int ffref_h264_idct_hbd(int depth, int kind, uint8_t *dst, int32_t *block, ptrdiff_t stride)
+{
+    H264DSPContext *c = ref_h264dsp_hbd(depth);
+    if (!c) return -1;
+    switch (kind) {
+    case 0: c->idct_add(dst, (int16_t *)block, stride); return 0;
+    case 1: c->idct8_add(dst, (int16_t *)block, stride); return 0;
+    case 2: c->idct_dc_add(dst, (int16_t *)block, stride); return 0;
+    case 3: c->idct8_dc_add(dst, (int16_t *)block, stride); return 0;
+    }
+    return -1;
+}
+
 /* weight / biweight tables of ff_h264dsp_init for 9 / 10 / 12 / 14 bit samples */
 static H264DSPContext *ref_h264dsp_hbd(int depth)
 {

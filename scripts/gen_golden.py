@@ -234,6 +234,21 @@ def gen_h264_weight_hbd():
     open(os.path.join(OUT, "h264_weight_hbd_hashes.txt"), "w").write("\n".join(lines) + "\n")
 
 
+def gen_h264_idct_hbd():
+    """idct_add / idct8_add / idct_dc_add / idct8_dc_add of ff_h264dsp_init(c, 9 / 10 / 12 / 14): sha256 of the compiled reference's
+    destination picture + the block it leaves behind, per case"""
+    R = cl.ref()
+    R.ffref_h264_idct_hbd.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_ssize_t]
+    lines = []
+    for depth in (9, 10, 12, 14):
+        for kind in range(4):
+            for k, (blk, dst) in enumerate(cl.h264_idct_hbd_cases(depth, kind)):
+                b, d = blk.copy(), dst.copy()
+                R.ffref_h264_idct_hbd(depth, kind, d.ctypes.data + (2 * 16 + 4) * 2, b.ctypes.data, 32)
+                lines.append(f"{depth} {kind} {k} {sha(np.concatenate([d.view(np.uint8).ravel(), b.view(np.uint8).ravel()]))}")
+    open(os.path.join(OUT, "h264_idct_hbd_hashes.txt"), "w").write("\n".join(lines) + "\n")
+
+
 RGB2RGB_FLAGS = (4, 4 | 0x80000, 4 | 0x80000 | 0x40000, 16)
 
 
@@ -698,6 +713,7 @@ if __name__ == "__main__":
     gen_pel_hbd()
     gen_pel_hbd_chroma()
     gen_h264_weight_hbd()
+    gen_h264_idct_hbd()
     gen_sws_rgb2rgb()
     gen_tx_full_imdct()
     gen_tx_dct()

@@ -374,6 +374,20 @@ def hbd_weight_cases(depth, n=60):
              int(rng.integers(-128, 128)), int(rng.integers(-128, 128)), int(rng.integers(-128, 128))) for _ in range(n)]
 
 
+def h264_idct_hbd_cases(depth, kind, n=24):
+    """[(int32 coefficient block, uint16 12 x 16 destination picture)] for the 16-bit H.264 residual-add fixture / tests"""
+    rng = np.random.default_rng(6000 + 10 * depth + kind)
+    out = []
+    for it in range(n):
+        N = 64 if kind & 1 else 16
+        amp = [300, 4000, 1 << (depth + 6), 1 << 30][it % 4]
+        blk = rng.integers(-amp, amp, N).astype(np.int32)
+        if it % 7 == 0:
+            blk[1:] = 0
+        out.append((blk, rng.integers(0, 1 << depth, (12, 16)).astype(np.uint16)))
+    return out
+
+
 def idct_hbd_blocks(seed, depth, n):
     """n coefficient blocks: dense small, full int16 range, sparse, DC only, DC-only rows, decoder-like range"""
     rng = np.random.default_rng(seed)

@@ -83,7 +83,7 @@ def emuhost():
     os.makedirs(gen, exist_ok=True)
     cs = os.path.join(ROOT, "ffmpeg_b200", "csrc")
     srcs = []
-    for f in ("fdsp.cu", "unquant.cu", "idct_hbd.cu", "tx_pfa.cu", "h264lf.cu", "pixelutils.cu", "pel_hbd.cu"):
+    for f in ("fdsp.cu", "unquant.cu", "idct_hbd.cu", "tx_pfa.cu", "h264lf.cu", "pixelutils.cu", "pel_hbd.cu", "h264idct_hbd.cu"):
         t = rewrite_launches(open(os.path.join(cs, f)).read())
         t = t.replace("extern __shared__ float2 pfa_z[];", "float2 *pfa_z = (float2 *)emu_smem;")
         assert "<<<" not in t
@@ -93,7 +93,7 @@ def emuhost():
     so = os.path.join(gen, "libemuhost.so")
     cxx = "/opt/gcc/bin/g++" if os.path.exists("/opt/gcc/bin/g++") else "g++"
     r = subprocess.run([cxx, "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread", "-ffp-contract=off", "-w", "-I" + os.path.join(EMU, "fake"), "-I" + cs,
-                        "-I" + os.path.join(ROOT, "include"), "-I" + EMU] + srcs + [os.path.join(EMU, "fake_device.cpp"), os.path.join(EMU, "fake_pel_hbd.cpp"), "-o", so],
+                        "-I" + os.path.join(ROOT, "include"), "-I" + EMU] + srcs + [os.path.join(EMU, "fake_device.cpp"), os.path.join(EMU, "fake_pel_hbd.cpp"), os.path.join(EMU, "fake_h264idct_hbd.cpp"), "-o", so],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
     return C.CDLL(so)
@@ -1208,6 +1208,36 @@ def test_host_h264_weight_hbd(emuhost):
                     O.orc_h264_weight_hbd(depth, c[1], exp.ctypes.data + int(doff[k]), 128, c[2], c[3], c[4], c[6])
             assert np.array_equal(got, exp), (depth, bi)
     assert L.emu_host_weight_hbd_tab(11, 0, 0, None, None, 0, 0, 0, 0, 0, 0) == -38
+
+
+def test_host_h264_idct_hbd(emuhost):
+    """h264idct_hbd.cu (residual adds for 9 / 10 / 12 / 14 bit samples, int32 coefficients) with its host code on the stand-in runtime: the member
+    functions and the batched device entry against the hashes of the compiled reference's outputs and the checker"""
+    from test_oracle_more import h264_idct_hbd_hashes, run_h264_idct_hbd_case
+    L, O = emuhost, cl.oracle()
+    L.emu_host_h264_idct_hbd.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_longlong]
+    L.b200_h264_idct_hbd_batch_device.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_ssize_t]
+    O.orc_h264_idct_hbd.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_ssize_t]
+    dev = C.c_void_p()
+    assert L.b200_device_open(C.byref(dev), 0, None) == 0
+    hs = h264_idct_hbd_hashes()
+    for depth in (9, 10, 12, 14):
+        for kind in range(4):
+            cases = cl.h264_idct_hbd_cases(depth, kind)
+            for k, case in enumerate(cases[:10]):
+                assert run_h264_idct_hbd_case(L.emu_host_h264_idct_hbd, depth, kind, case) == hs[(depth, kind, k)], (depth, kind, k)
+            # batch: all 24 blocks into one 48 x 64 picture (8 x 8 grid cells), coefficient blocks back to back
+            N = 64 if kind & 1 else 16
+            blocks = np.concatenate([c[0] for c in cases]).astype(np.int32)
+            boff = np.arange(len(cases), dtype=np.int64) * N
+            doff = np.array([((k // 6) * 8 * 64 + (k % 6) * 8) * 2 for k in range(len(cases))], np.int64)
+            pic = np.random.default_rng(depth * 10 + kind).integers(0, 1 << depth, (48, 64)).astype(np.uint16)
+            got, exp, gb, eb = pic.copy(), pic.copy(), blocks.copy(), blocks.copy()
+            assert L.b200_h264_idct_hbd_batch_device(dev, depth, kind, len(cases), gb.ctypes.data, boff.ctypes.data, got.ctypes.data, doff.ctypes.data, 128) == 0
+            for k in range(len(cases)):
+                O.orc_h264_idct_hbd(depth, kind, exp.ctypes.data + int(doff[k]), eb.ctypes.data + 4 * int(boff[k]), 128)
+            assert np.array_equal(got, exp) and np.array_equal(gb, eb), (depth, kind)
+    assert L.emu_host_h264_idct_hbd(11, 0, None, None, 0) == -38
 
 
 def test_host_tx_pfa_create_and_launch(emuhost):

@@ -508,6 +508,35 @@ def test_h264_weight_hbd_oracle_golden():
             assert hashlib.sha256(blk.tobytes()).hexdigest() == hs[(depth, k)], (depth, case)
 
 
+def h264_idct_hbd_hashes():
+    out = {}
+    for line in open(os.path.join(G, "h264_idct_hbd_hashes.txt")):
+        depth, kind, k, h = line.split()
+        out[(int(depth), int(kind), int(k))] = h
+    return out
+
+
+def run_h264_idct_hbd_case(fn, depth, kind, case):
+    """fn(depth, kind, dst address, block address, stride bytes); returns sha256 of (picture, block left behind)"""
+    import hashlib
+    blk, dst = case
+    b, d = blk.copy(), dst.copy()
+    fn(depth, kind, d.ctypes.data + (2 * 16 + 4) * 2, b.ctypes.data, 32)
+    return hashlib.sha256(np.concatenate([d.view(np.uint8).ravel(), b.view(np.uint8).ravel()]).tobytes()).hexdigest()
+
+
+def test_h264_idct_hbd_oracle_golden():
+    """H.264 residual adds for 9 / 10 / 12 / 14 bit samples (int32 coefficients) against the hashes of the compiled reference's outputs"""
+    O = cl.oracle()
+    O.orc_h264_idct_hbd.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_ssize_t]
+    hs = h264_idct_hbd_hashes()
+    assert len(hs) == 4 * 4 * 24
+    for depth in (9, 10, 12, 14):
+        for kind in range(4):
+            for k, case in enumerate(cl.h264_idct_hbd_cases(depth, kind)):
+                assert run_h264_idct_hbd_case(O.orc_h264_idct_hbd, depth, kind, case) == hs[(depth, kind, k)], (depth, kind, k)
+
+
 PFA_FFT_SIZES = (6, 12, 96, 10, 160, 14, 224, 18, 288, 30, 120, 960, 1920)
 
 

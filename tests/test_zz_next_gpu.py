@@ -1079,3 +1079,48 @@ def test_h264_weight_hbd(device):
             device.sync()
             got = d_dst.cpu().numpy().view(np.uint16)
         assert np.array_equal(got, exp), (bi, int((got != exp).sum()))
+
+
+# ---------------------------------------------------------------------------------------------- H.264 residual adds, 16-bit samples
+def test_h264_idct_hbd(device):
+    """ff_h264dsp_init(c, 9 / 10 / 12 / 14) idct_add / idct8_add / idct_dc_add / idct8_dc_add (int32 coefficients): member functions against
+    the hashes of the compiled reference's outputs, batched device entry against the oracle"""
+    import ctypes as C
+    import torch
+    import ffmpeg_b200 as fb
+    from ffmpeg_b200 import idctdsp
+    from ffmpeg_b200._lib import lib, vp, check, H264IDCTContext
+    from test_oracle_more import h264_idct_hbd_hashes, run_h264_idct_hbd_case
+    O = cl.oracle()
+    O.orc_h264_idct_hbd.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_ssize_t]
+    hs = h264_idct_hbd_hashes()
+    for depth in (9, 10, 12, 14):
+        c = H264IDCTContext()
+        check(lib().b200_h264_idct_init(C.byref(c), depth, 1), "h264_idct_init")
+        members = [c.idct_add, c.idct8_add, c.idct_dc_add, c.idct8_dc_add]
+        fn = lambda dp, kind, d, b, st: members[kind](C.cast(d, C.POINTER(C.c_uint8)), C.cast(b, C.POINTER(C.c_int16)), st)
+        for kind in range(4):
+            for k, case in enumerate(cl.h264_idct_hbd_cases(depth, kind)):
+                if k % 3 == 0:
+                    assert run_h264_idct_hbd_case(fn, depth, kind, case) == hs[(depth, kind, k)], (depth, kind, k)
+    c = H264IDCTContext()
+    assert lib().b200_h264_idct_init(C.byref(c), 11, 1) < 0
+    rng = np.random.default_rng(37)
+    W, H, depth = 640, 368, 10
+    for kind in range(4):
+        N, B = (64, 8) if kind & 1 else (16, 4)
+        nb = (W // B) * (H // B)
+        blocks = rng.integers(-3000, 3000, (nb, N)).astype(np.int32)
+        pic = rng.integers(0, 1 << depth, (H, W)).astype(np.uint16)
+        boff = np.arange(nb, dtype=np.int64) * N
+        doff = np.array([((k // (W // B)) * B * W + (k % (W // B)) * B) * 2 for k in range(nb)], np.int64)
+        exp, eb = pic.copy(), blocks.copy()
+        for k in range(nb):
+            O.orc_h264_idct_hbd(depth, kind, exp.ctypes.data + int(doff[k]), eb.ctypes.data + 4 * int(boff[k]), W * 2)
+        with on_stream(device):
+            d_b, d_bo, d_do = torch.from_numpy(blocks).cuda(), torch.from_numpy(boff).cuda(), torch.from_numpy(doff).cuda()
+            d_p = torch.from_numpy(pic.view(np.int16)).cuda()
+            check(lib().b200_h264_idct_hbd_batch_device(device.handle, depth, kind, nb, vp(d_b.data_ptr()), vp(d_bo.data_ptr()), vp(d_p.data_ptr()), vp(d_do.data_ptr()), W * 2), "h264_idct_hbd_batch")
+            device.sync()
+            got, gb = d_p.cpu().numpy().view(np.uint16), d_b.cpu().numpy()
+        assert np.array_equal(got, exp) and np.array_equal(gb, eb), kind
