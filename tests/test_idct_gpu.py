@@ -256,8 +256,7 @@ def test_h264_idct_pointer_table_golden(device):
             N = 4 if kind in (0, 2) else 8
             assert np.array_equal(out[:, 8 * i:8 * i + N], g[f"k{kind}_out"][:, 8 * i:8 * i + N]), (kind, i)
             assert np.array_equal(blk[i], g[f"k{kind}_blk_after"][i]), (kind, i)
-    with pytest.raises(Exception):
-        idctdsp.ff_h264dsp_idct_init(10, 1)
+    assert idctdsp.ff_h264dsp_idct_init(10, 1).idct_add                       # the 16-bit functions (test_h264_idct_hbd)
 
 
 @pytest.mark.parametrize("kind", [0, 1, 2, 3])
