@@ -188,6 +188,7 @@ PROTOTYPES = {
     "b200_hpeldsp_init": (C.c_int, [C.POINTER(HpelDSPContext), C.c_int]),
     "b200_h264qpel_batch_device": (C.c_int, [vp, C.c_int64, vp, vp, vp, vp, vp, C.c_ssize_t]),
     "b200_h264qpel_hbd_batch_device": (C.c_int, [vp, C.c_int, C.c_int64, vp, vp, vp, vp, vp, C.c_ssize_t]),
+    "b200_h264_loop_filter_hbd_batch_device": (C.c_int, [vp, C.c_int, C.c_int64, vp, vp, vp, C.c_ssize_t, vp, vp, vp]),
     "b200_h264_idct_hbd_batch_device": (C.c_int, [vp, C.c_int, C.c_int, C.c_int64, vp, vp, vp, vp, C.c_ssize_t]),
     "b200_h264_weight_hbd_batch_device": (C.c_int, [vp, C.c_int, C.c_int64, vp, vp, vp, vp, vp, C.c_ssize_t]),
     "b200_h264chroma_hbd_batch_device": (C.c_int, [vp, C.c_int64, vp, vp, vp, vp, vp, vp, vp, C.c_ssize_t]),

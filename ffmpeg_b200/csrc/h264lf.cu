@@ -10,6 +10,7 @@
 // writes at most p2..q2.  Edges of one batch must not touch each other's pixels (the decoder's order — vertical edges of a
 // macroblock before its horizontal ones, macroblocks in raster order — becomes one batch per independent set, e.g. per anti-diagonal).
 #include "common.h"
+#include "h264lf_hbd.h"
 #include <cstring>
 
 namespace {
@@ -139,8 +140,8 @@ template <int KIND> void tab_intra(uint8_t *pix, ptrdiff_t stride, int alpha, in
 B200_API int b200_h264_loop_filter_init(B200H264LoopFilterContext *c, int bit_depth, int chroma_format_idc)
 {
     if (!c) return B200_EINVAL;
-    if (bit_depth != 8) return B200_ENOSYS;
     if (!b200_default_device()) return B200_ENODEV;
+    if (bit_depth != 8) return h264lf_hbd_fill(c, bit_depth, chroma_format_idc) ? 0 : B200_ENOSYS;      // 9 / 10 / 12 / 14: uint16 samples (h264lf_hbd.cu)
     const bool c422 = chroma_format_idc > 1;                             // h264dsp.c:116-132
     c->v_loop_filter_luma = tab_tc<0>; c->h_loop_filter_luma = tab_tc<1>; c->h_loop_filter_luma_mbaff = tab_tc<2>;
     c->v_loop_filter_luma_intra = tab_intra<3>; c->h_loop_filter_luma_intra = tab_intra<4>; c->h_loop_filter_luma_mbaff_intra = tab_intra<5>;

@@ -265,7 +265,7 @@ typedef struct B200H264LoopFilterContext {
     void (*h_loop_filter_chroma_intra)(uint8_t *pix, ptrdiff_t stride, int alpha, int beta);
     void (*h_loop_filter_chroma_mbaff_intra)(uint8_t *pix, ptrdiff_t stride, int alpha, int beta);
 } B200H264LoopFilterContext;
-int  b200_h264_loop_filter_init(B200H264LoopFilterContext *c, int bit_depth, int chroma_format_idc);     /* bit_depth must be 8 */
+int  b200_h264_loop_filter_init(B200H264LoopFilterContext *c, int bit_depth, int chroma_format_idc);     /* 8, or 9 / 10 / 12 / 14 (uint16 samples) */
 /* kinds for the batched call: 0 v_luma, 1 h_luma, 2 h_luma_mbaff, 3-5 their _intra forms, 6 v_chroma, 7 h_chroma, 8 h_chroma_mbaff,
  * 9-11 their _intra forms, 12 / 13 h_chroma / h_chroma_mbaff of 4:2:2 content, 14 / 15 their _intra forms */
 /* batched, DEVICE pointers: edge e of kind kinds[e] at pix + pix_off[e] with alpha[e], beta[e] and tc0[4*e .. 4*e+3] (ignored by the
@@ -273,6 +273,10 @@ int  b200_h264_loop_filter_init(B200H264LoopFilterContext *c, int bit_depth, int
  * decoder's sequential order becomes one call per independent set of edges. */
 int  b200_h264_loop_filter_batch_device(B200Device *dev, int64_t nedges, const uint8_t *kinds, uint8_t *pix, const int64_t *pix_off,
                                         ptrdiff_t stride, const uint8_t *alpha, const uint8_t *beta, const int8_t *tc0);
+/* the same for 9 / 10 / 12 / 14 bit samples (uint16): pix_off and stride in BYTES; alpha, beta and tc0 are the 8-bit table values the
+ * reference's callers pass (the functions scale them to the sample depth, h264dsp_template.c:109-112,241-246) */
+int  b200_h264_loop_filter_hbd_batch_device(B200Device *dev, int bit_depth, int64_t nedges, const uint8_t *kinds, uint8_t *pix,
+                                            const int64_t *pix_off, ptrdiff_t stride, const uint8_t *alpha, const uint8_t *beta, const int8_t *tc0);
 
 /* mpegvideo inverse quantisers: the members of MPVUnquantDSPContext (libavcodec/mpegvideo_unquantize.h:31-44) as
  * ff_mpv_unquantize_init() installs them (libavcodec/mpegvideo_unquantize.c:50-290), i.e. what runs in front of the IDCT in

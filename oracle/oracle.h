@@ -114,6 +114,7 @@ int  orc_prores_idct_put(int bits, uint8_t *out, ptrdiff_t linesize, int16_t *bl
  * 8 h_chroma_mbaff, 9-11 their _intra forms, 12 / 13 h_chroma / h_chroma_mbaff of 4:2:2 content, 14 / 15 their _intra forms.
  * pix points at q0 of the first line (the first pixel on the far side of the edge), as in H264DSPContext */
 int  orc_h264_loop_filter(int kind, uint8_t *pix, ptrdiff_t stride, int alpha, int beta, const int8_t *tc0);
+int  orc_h264_loop_filter_hbd(int depth, int kind, uint8_t *pix, ptrdiff_t stride_bytes, int alpha, int beta, const int8_t *tc0);   /* 9 / 10 / 12 / 14 bit */
 /* inverse quantisers of libavcodec/mpegvideo_unquantize.c (MPVUnquantDSPContext), in place on int16[64] blocks */
 enum { ORC_UNQUANT_MPEG1_INTRA, ORC_UNQUANT_MPEG1_INTER, ORC_UNQUANT_MPEG2_INTRA, ORC_UNQUANT_MPEG2_INTRA_BITEXACT,
        ORC_UNQUANT_MPEG2_INTER, ORC_UNQUANT_H263_INTRA, ORC_UNQUANT_H263_INTER };

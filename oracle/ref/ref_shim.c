@@ -673,3 +673,33 @@ API int ffref_h264_loop_filter(int kind, uint8_t *pix, ptrdiff_t stride, int alp
     }
     return 0;
 }
+
+
+/* the loop-filter members for 9 / 10 / 12 / 14 bit samples: kinds as ffref_h264_loop_filter (0-11 from chroma_format_idc 1, 12-15 from 2) */
+API int ffref_h264_loop_filter_hbd(int depth, int kind, uint8_t *pix, ptrdiff_t stride, int alpha, int beta, int8_t *tc0)
+{
+    static H264DSPContext c420[15], c422[15]; static int ok[15];
+    if (depth != 9 && depth != 10 && depth != 12 && depth != 14) return -1;
+    if (!ok[depth]) { ff_h264dsp_init(&c420[depth], depth, 1); ff_h264dsp_init(&c422[depth], depth, 2); ok[depth] = 1; }
+    H264DSPContext *a = &c420[depth], *b = &c422[depth];
+    switch (kind) {
+    case 0:  a->v_loop_filter_luma(pix, stride, alpha, beta, tc0); break;
+    case 1:  a->h_loop_filter_luma(pix, stride, alpha, beta, tc0); break;
+    case 2:  a->h_loop_filter_luma_mbaff(pix, stride, alpha, beta, tc0); break;
+    case 3:  a->v_loop_filter_luma_intra(pix, stride, alpha, beta); break;
+    case 4:  a->h_loop_filter_luma_intra(pix, stride, alpha, beta); break;
+    case 5:  a->h_loop_filter_luma_mbaff_intra(pix, stride, alpha, beta); break;
+    case 6:  a->v_loop_filter_chroma(pix, stride, alpha, beta, tc0); break;
+    case 7:  a->h_loop_filter_chroma(pix, stride, alpha, beta, tc0); break;
+    case 8:  a->h_loop_filter_chroma_mbaff(pix, stride, alpha, beta, tc0); break;
+    case 9:  a->v_loop_filter_chroma_intra(pix, stride, alpha, beta); break;
+    case 10: a->h_loop_filter_chroma_intra(pix, stride, alpha, beta); break;
+    case 11: a->h_loop_filter_chroma_mbaff_intra(pix, stride, alpha, beta); break;
+    case 12: b->h_loop_filter_chroma(pix, stride, alpha, beta, tc0); break;
+    case 13: b->h_loop_filter_chroma_mbaff(pix, stride, alpha, beta, tc0); break;
+    case 14: b->h_loop_filter_chroma_intra(pix, stride, alpha, beta); break;
+    case 15: b->h_loop_filter_chroma_mbaff_intra(pix, stride, alpha, beta); break;
+    default: return -1;
+    }
+    return 0;
+}

@@ -249,6 +249,15 @@ def gen_h264_idct_hbd():
     open(os.path.join(OUT, "h264_idct_hbd_hashes.txt"), "w").write("\n".join(lines) + "\n")
 
 
+def gen_h264lf_hbd():
+    """the loop-filter members of ff_h264dsp_init(c, 9 / 10 / 12 / 14, 1 / 2): sha256 of the picture after 1024 independent edges of all 16 kinds"""
+    lines = []
+    for depth in (9, 10, 12, 14):
+        case = cl.h264lf_hbd_case(50 + depth, 1024, depth)
+        lines.append(f"{depth} {sha(cl.ref_h264lf_hbd(depth, *case))}")
+    open(os.path.join(OUT, "h264lf_hbd_hashes.txt"), "w").write("\n".join(lines) + "\n")
+
+
 RGB2RGB_FLAGS = (4, 4 | 0x80000, 4 | 0x80000 | 0x40000, 16)
 
 
@@ -714,6 +723,7 @@ if __name__ == "__main__":
     gen_pel_hbd_chroma()
     gen_h264_weight_hbd()
     gen_h264_idct_hbd()
+    gen_h264lf_hbd()
     gen_sws_rgb2rgb()
     gen_tx_full_imdct()
     gen_tx_dct()

@@ -532,6 +532,36 @@ def h264lf_case(seed, n, cols=16):
     return pic, kinds, off.astype(np.int64), alpha, beta, tc0
 
 
+def h264lf_hbd_case(seed, n, depth, cols=16):
+    """the same layout for 9 / 10 / 12 / 14 bit samples: pic uint16, off in BYTES; the content of the 8-bit case scaled to the depth with
+    fresh low bits, so the scaled thresholds see the same mix of branches"""
+    pic8, kinds, off8, alpha, beta, tc0 = h264lf_case(seed, n, cols)
+    rng = np.random.default_rng(seed + 7777)
+    sh = depth - 8
+    pic = ((pic8.astype(np.int32) << sh) + rng.integers(0, 1 << sh, pic8.shape)).clip(0, (1 << depth) - 1).astype(np.uint16)
+    i = np.arange(n)
+    off = (((i // cols) * LF_CELL + 8) * pic.strides[0] + ((i % cols) * LF_CELL + 8) * 2).astype(np.int64)
+    return pic, kinds, off, alpha, beta, tc0
+
+
+def _h264lf_hbd_run(L, name, depth, pic, kinds, off, alpha, beta, tc0):
+    f = getattr(L, name)
+    f.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_ssize_t, C.c_int, C.c_int, C.c_void_p]
+    out = pic.copy()
+    for e in range(len(kinds)):
+        t = tc0[e].copy()
+        assert f(depth, int(kinds[e]), out.ctypes.data + int(off[e]), out.strides[0], int(alpha[e]), int(beta[e]), t.ctypes.data) == 0
+    return out
+
+
+def orc_h264lf_hbd(depth, pic, kinds, off, alpha, beta, tc0):
+    return _h264lf_hbd_run(oracle(), "orc_h264_loop_filter_hbd", depth, pic, kinds, off, alpha, beta, tc0)
+
+
+def ref_h264lf_hbd(depth, pic, kinds, off, alpha, beta, tc0):
+    return _h264lf_hbd_run(ref(), "ffref_h264_loop_filter_hbd", depth, pic, kinds, off, alpha, beta, tc0)
+
+
 def _h264lf_run(L, name, pic, kinds, off, alpha, beta, tc0):
     f = getattr(L, name)
     f.argtypes = [C.c_int, C.c_void_p, C.c_ssize_t, C.c_int, C.c_int, C.c_void_p]

@@ -83,7 +83,7 @@ def emuhost():
     os.makedirs(gen, exist_ok=True)
     cs = os.path.join(ROOT, "ffmpeg_b200", "csrc")
     srcs = []
-    for f in ("fdsp.cu", "unquant.cu", "idct_hbd.cu", "tx_pfa.cu", "h264lf.cu", "pixelutils.cu", "pel_hbd.cu", "h264idct_hbd.cu"):
+    for f in ("fdsp.cu", "unquant.cu", "idct_hbd.cu", "tx_pfa.cu", "h264lf.cu", "pixelutils.cu", "pel_hbd.cu", "h264idct_hbd.cu", "h264lf_hbd.cu"):
         t = rewrite_launches(open(os.path.join(cs, f)).read())
         t = t.replace("extern __shared__ float2 pfa_z[];", "float2 *pfa_z = (float2 *)emu_smem;")
         assert "<<<" not in t
@@ -1032,9 +1032,43 @@ def test_host_h264_loop_filter_entry_points(emuhost):
             assert np.array_equal(t, tc0[i])
         assert np.array_equal(d, cl.orc_h264lf(pic, kinds, off, alpha, beta, tc0)), idc
     c = H264LoopFilterContext()
-    assert L.b200_h264_loop_filter_init(C.byref(c), 10, 1) < 0 and L.b200_h264_loop_filter_init(None, 8, 1) < 0
+    assert L.b200_h264_loop_filter_init(C.byref(c), 11, 1) < 0 and L.b200_h264_loop_filter_init(None, 8, 1) < 0
     assert L.b200_h264_loop_filter_batch_device(None, 0, None, None, None, 0, None, None, None) == 0
     assert L.b200_h264_loop_filter_batch_device(None, 1, None, d.ctypes.data, off.ctypes.data, 16, alpha.ctypes.data, beta.ctypes.data, tc0.ctypes.data) < 0
+
+
+def test_host_h264_loop_filter_hbd(emuhost):
+    """h264lf_hbd.cu (deblocking for 9 / 10 / 12 / 14 bit samples) with its host code on the stand-in runtime: the batched device entry against
+    the hashes of the compiled reference's pictures, and the H264DSPContext members edge by edge against the checker"""
+    import hashlib
+    from ffmpeg_b200._lib import H264LoopFilterContext
+    from test_oracle_more import h264lf_hbd_hashes
+    L = emuhost
+    L.b200_h264_loop_filter_hbd_batch_device.argtypes = [C.c_void_p, C.c_int, C.c_int64] + [C.c_void_p] * 3 + [C.c_ssize_t] + [C.c_void_p] * 3
+    hs = h264lf_hbd_hashes()
+    names = [f[0] for f in H264LoopFilterContext._fields_]
+    for depth in (9, 10, 12, 14):
+        pic, kinds, off, alpha, beta, tc0 = cl.h264lf_hbd_case(50 + depth, 1024, depth)
+        d = pic.copy()
+        assert L.b200_h264_loop_filter_hbd_batch_device(None, depth, 1024, kinds.ctypes.data, d.ctypes.data, off.ctypes.data, d.strides[0], alpha.ctypes.data,
+                                                        beta.ctypes.data, tc0.ctypes.data) == 0
+        assert hashlib.sha256(d.tobytes()).hexdigest() == hs[depth], depth
+        for idc in (1, 2):
+            c = H264LoopFilterContext()
+            assert L.b200_h264_loop_filter_init(C.byref(c), depth, idc) == 0
+            kind_of = dict(zip(names, range(12)))
+            if idc == 2:
+                kind_of.update(h_loop_filter_chroma=12, h_loop_filter_chroma_mbaff=13, h_loop_filter_chroma_intra=14, h_loop_filter_chroma_mbaff_intra=15)
+            pic, kinds, off, alpha, beta, tc0 = cl.h264lf_hbd_case(60 + idc, 96, depth)
+            members = [names[i % 12] for i in range(96)]
+            kinds = np.array([kind_of[m] for m in members], np.uint8)
+            d = pic.copy()
+            for i, m in enumerate(members):
+                t = tc0[i].copy()
+                args = (d.ctypes.data + int(off[i]), d.strides[0], int(alpha[i]), int(beta[i]))
+                getattr(c, m)(*args, t.ctypes.data) if "intra" not in m else getattr(c, m)(*args)
+            assert np.array_equal(d, cl.orc_h264lf_hbd(depth, pic, kinds, off, alpha, beta, tc0)), (depth, idc)
+    assert L.b200_h264_loop_filter_hbd_batch_device(None, 11, 1, kinds.ctypes.data, d.ctypes.data, off.ctypes.data, d.strides[0], alpha.ctypes.data, beta.ctypes.data, tc0.ctypes.data) == -38
 
 
 def test_host_pixelutils_entry_points(emuhost):

@@ -537,6 +537,25 @@ def test_h264_idct_hbd_oracle_golden():
                 assert run_h264_idct_hbd_case(O.orc_h264_idct_hbd, depth, kind, case) == hs[(depth, kind, k)], (depth, kind, k)
 
 
+def h264lf_hbd_hashes():
+    return {int(l.split()[0]): l.split()[1] for l in open(os.path.join(G, "h264lf_hbd_hashes.txt"))}
+
+
+def test_h264_loop_filter_hbd_oracle_golden_and_ref():
+    """H.264 deblocking for 9 / 10 / 12 / 14 bit samples: 1024 edges of all 16 kinds per depth against the hash of the compiled reference's
+    picture, and live on another seed when the reference is here"""
+    import hashlib
+    hs = h264lf_hbd_hashes()
+    for depth in (9, 10, 12, 14):
+        case = cl.h264lf_hbd_case(50 + depth, 1024, depth)
+        out = cl.orc_h264lf_hbd(depth, *case)
+        assert hashlib.sha256(out.tobytes()).hexdigest() == hs[depth], depth
+        assert int((out != case[0]).sum()) > 3000                     # the filters did fire
+        if cl.have_ref():
+            case = cl.h264lf_hbd_case(90 + depth, 512, depth)
+            assert np.array_equal(cl.orc_h264lf_hbd(depth, *case), cl.ref_h264lf_hbd(depth, *case)), depth
+
+
 PFA_FFT_SIZES = (6, 12, 96, 10, 160, 14, 224, 18, 288, 30, 120, 960, 1920)
 
 

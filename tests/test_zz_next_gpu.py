@@ -783,8 +783,7 @@ def test_h264_loop_filter(device):
             assert hashlib.sha256(got.tobytes()).digest() == g[f"sha_{seed}"].tobytes(), seed
         else:
             assert np.array_equal(got, cl.orc_h264lf(pic, kinds, off, alpha, beta, tc0))
-    with pytest.raises(Exception):
-        pel.ff_h264dsp_loop_filter_init(10, 1)
+    assert pel.ff_h264dsp_loop_filter_init(10, 1).v_loop_filter_luma              # the 16-bit members (test_h264_loop_filter_hbd)
 
 
 # ---------------------------------------------------------------------------------------------- av_pixelutils_get_sad_fn
@@ -1124,3 +1123,37 @@ def test_h264_idct_hbd(device):
             device.sync()
             got, gb = d_p.cpu().numpy().view(np.uint16), d_b.cpu().numpy()
         assert np.array_equal(got, exp) and np.array_equal(gb, eb), kind
+
+
+# ---------------------------------------------------------------------------------------------- H.264 deblocking, 16-bit samples
+def test_h264_loop_filter_hbd(device):
+    """ff_h264dsp_init(c, 9 / 10 / 12 / 14, idc) loop-filter members: the batched device entry against the hashes of the compiled reference's
+    pictures (1024 edges of all 16 kinds per depth), the member functions edge by edge against the oracle"""
+    import ctypes as C
+    import hashlib
+    import torch
+    from ffmpeg_b200._lib import lib, vp, check, H264LoopFilterContext
+    from test_oracle_more import h264lf_hbd_hashes
+    hs = h264lf_hbd_hashes()
+    names = [f[0] for f in H264LoopFilterContext._fields_]
+    for depth in (9, 10, 12, 14):
+        pic, kinds, off, alpha, beta, tc0 = cl.h264lf_hbd_case(50 + depth, 1024, depth)
+        with on_stream(device):
+            d = [torch.from_numpy(v).cuda() for v in (kinds, off, alpha, beta, tc0)]
+            dp = torch.from_numpy(pic.view(np.int16)).cuda()
+            check(lib().b200_h264_loop_filter_hbd_batch_device(device.handle, depth, 1024, vp(d[0].data_ptr()), vp(dp.data_ptr()), vp(d[1].data_ptr()), pic.strides[0],
+                                                               vp(d[2].data_ptr()), vp(d[3].data_ptr()), vp(d[4].data_ptr())), "h264_loop_filter_hbd_batch")
+            device.sync()
+            got = dp.cpu().numpy().view(np.uint16)
+        assert hashlib.sha256(got.tobytes()).hexdigest() == hs[depth], depth
+        c = H264LoopFilterContext()
+        check(lib().b200_h264_loop_filter_init(C.byref(c), depth, 1), "h264_loop_filter_init")
+        pic, kinds, off, alpha, beta, tc0 = cl.h264lf_hbd_case(70 + depth, 48, depth)
+        members = [names[i % 12] for i in range(48)]
+        kinds = np.array([names.index(m) for m in members], np.uint8)
+        dd = pic.copy()
+        for i, m in enumerate(members):
+            t = tc0[i].copy()
+            args = (dd.ctypes.data + int(off[i]), dd.strides[0], int(alpha[i]), int(beta[i]))
+            getattr(c, m)(*args, t.ctypes.data) if "intra" not in m else getattr(c, m)(*args)
+        assert np.array_equal(dd, cl.orc_h264lf_hbd(depth, pic, kinds, off, alpha, beta, tc0)), depth
