@@ -1,3 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q -k "hbd or chroma or edge or pel" > gpurun_out/t_a.log 2>&1; tail -8 gpurun_out/t_a.log
+python -m pytest tests -m gpu -q > gpurun_out/r02_final_tests_gpu.log 2>&1; tail -6 gpurun_out/r02_final_tests_gpu.log
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/r02_final_smoke.log 2>&1; tail -2 gpurun_out/r02_final_smoke.log
