@@ -64,6 +64,16 @@ class HpelDSPContext(C.Structure):
 _H264IDCT = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_ssize_t)
 
 
+class SwsVector(C.Structure):
+    """SwsVector (libswscale/swscale.h:187-192)"""
+    _fields_ = [("coeff", C.POINTER(C.c_double)), ("length", C.c_int)]
+
+
+class SwsFilter(C.Structure):
+    """SwsFilter (libswscale/swscale.h:199-204)"""
+    _fields_ = [("lumH", C.POINTER(SwsVector)), ("lumV", C.POINTER(SwsVector)), ("chrH", C.POINTER(SwsVector)), ("chrV", C.POINTER(SwsVector))]
+
+
 class H264IDCTContext(C.Structure):
     """the IDCT members of H264DSPContext, libavcodec/h264dsp.h:81-88"""
     _fields_ = [("idct_add", _H264IDCT), ("idct8_add", _H264IDCT), ("idct_dc_add", _H264IDCT), ("idct8_dc_add", _H264IDCT)]
@@ -161,6 +171,7 @@ PROTOTYPES = {
     "b200_sws_getContext": (vp, [vp] + [C.c_int] * 7),
     "b200_sws_getContext_range": (vp, [vp] + [C.c_int] * 9),
     "b200_sws_getContext_params": (vp, [vp] + [C.c_int] * 9 + [vp]),
+    "b200_sws_getContext_filters": (vp, [vp] + [C.c_int] * 9 + [vp, vp, vp]),
     "b200_sws_freeContext": (None, [vp]),
     "b200_sws_setColorspaceDetails": (C.c_int, [vp, i32p, C.c_int, i32p, C.c_int, C.c_int, C.c_int, C.c_int]),
     "b200_sws_scale": (C.c_int, [vp, C.POINTER(vp), i32p, C.c_int, C.c_int, C.POINTER(vp), i32p]),

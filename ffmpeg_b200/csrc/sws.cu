@@ -1083,6 +1083,13 @@ B200_API B200SwsContext *b200_sws_getContext_range(B200Device *dev, int srcW, in
 B200_API B200SwsContext *b200_sws_getContext_params(B200Device *dev, int srcW, int srcH, int srcFormat, int srcRange,
                                                     int dstW, int dstH, int dstFormat, int dstRange, int flags, const double *param)
 {
+    return b200_sws_getContext_filters(dev, srcW, srcH, srcFormat, srcRange, dstW, dstH, dstFormat, dstRange, flags, nullptr, nullptr, param);
+}
+
+B200_API B200SwsContext *b200_sws_getContext_filters(B200Device *dev, int srcW, int srcH, int srcFormat, int srcRange, int dstW, int dstH, int dstFormat,
+                                                     int dstRange, int flags, const B200SwsFilter *srcFilter, const B200SwsFilter *dstFilter,
+                                                     const double *param)
+{
     if (!dev) { b200_set_error("b200_sws_getContext: no device"); return nullptr; }
     SwsOutFmt out;
     B200SwsContext *c = new (std::nothrow) B200SwsContext();
@@ -1095,6 +1102,14 @@ B200_API B200SwsContext *b200_sws_getContext_params(B200Device *dev, int srcW, i
     }
     c->dev = dev;
     c->plan.out = out;
+    {
+        const B200SwsVector *sv[4] = { srcFilter ? srcFilter->lumH : nullptr, srcFilter ? srcFilter->lumV : nullptr, srcFilter ? srcFilter->chrH : nullptr, srcFilter ? srcFilter->chrV : nullptr };
+        const B200SwsVector *dv[4] = { dstFilter ? dstFilter->lumH : nullptr, dstFilter ? dstFilter->lumV : nullptr, dstFilter ? dstFilter->chrH : nullptr, dstFilter ? dstFilter->chrV : nullptr };
+        for (int k = 0; k < 4; k++) {
+            if (sv[k] && sv[k]->coeff && sv[k]->length > 0) c->plan.srcFilt[k].assign(sv[k]->coeff, sv[k]->coeff + sv[k]->length);
+            if (dv[k] && dv[k]->length > 0) c->plan.dstFiltLen[k] = dv[k]->length;
+        }
+    }
     c->open_src_fmt = srcFormat; c->open_dst_fmt = dstFormat; c->open_flags = flags;
     if (param) { c->plan.param[0] = param[0]; c->plan.param[1] = param[1]; c->has_param = true; c->open_param[0] = param[0]; c->open_param[1] = param[1]; }
     int ret = sws_plan_build(c->plan, srcW, srcH, dstW, dstH, flags, srcRange, dstRange);

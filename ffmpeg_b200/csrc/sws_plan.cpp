@@ -155,12 +155,34 @@ int raw_taps(RawTaps &r, int scaler, int inc, int srcN, int dstN, int srcOrg, in
     return 0;
 }
 
-int build_bank(SwsFilterBank &bank, int scaler, int inc, int srcN, int dstN, int one, int srcOrg, int dstOrg, const double *param)
+int build_bank(SwsFilterBank &bank, int scaler, int inc, int srcN, int dstN, int one, int srcOrg, int dstOrg, const double *param,
+               const std::vector<double> *srcVec = nullptr, int dstVecLen = 0)
 {
     const i64 unit = (i64)1 << (54 - std::min(floor_log2((unsigned)(srcN / dstN)), 8));
     RawTaps r;
     int ret = raw_taps(r, scaler, inc, srcN, dstN, srcOrg, dstOrg, unit, param);
     if (ret < 0) return ret;
+    // srcFilter / dstFilter (utils.c:384-413): the source vector is convolved into every row -- `filter2[...] += coeff * filter[...]` on an
+    // int64 accumulator, i.e. through a double each time --, the destination vector only widens the row ("FIXME dstFilter" in the
+    // reference); the window start moves by the difference of the two half widths
+    const int sl = srcVec && !srcVec->empty() ? (int)srcVec->size() : 0;
+    if (sl || dstVecLen > 0) {
+        const int T0 = r.taps, T2 = T0 + (sl ? sl - 1 : 0) + (dstVecLen > 0 ? dstVecLen - 1 : 0);
+        std::vector<i64> w2((size_t)dstN * T2, 0);
+        for (int i = 0; i < dstN; i++) {
+            if (sl) {
+                for (int k = 0; k < sl; k++)
+                    for (int j = 0; j < T0; j++) {
+                        i64 &acc = w2[(size_t)i * T2 + k + j];
+                        acc = (i64)((double)acc + (*srcVec)[k] * (double)r.w[(size_t)i * T0 + j]);
+                    }
+            } else
+                for (int j = 0; j < T0; j++) w2[(size_t)i * T2 + j] = r.w[(size_t)i * T0 + j];
+            r.first[i] += (T0 - 1) / 2 - (T2 - 1) / 2;
+        }
+        r.w.swap(w2);
+        r.taps = T2;
+    }
     const int T = r.taps;
     const double cutoff = 0.002 * (double)unit;                                  // SWS_MAX_REDUCE_CUTOFF, swscale.h:447
 
@@ -399,8 +421,11 @@ int sws_plan_build(SwsPlan &p, int srcW, int srcH, int dstW, int dstH, int flags
     p.fast_bilinear = algo == B200_SWS_FAST_BILINEAR && !p.src_rgb;
     p.planar = sws_out_is_yuv(p.out.kind);
     p.dst_nv = p.out.kind == SWS_OUT_NV12 ? 1 : p.out.kind == SWS_OUT_NV21 ? 2 : 0;
+    // utils.c:1256-1263,1608,1624: a source or destination filter vector longer than one tap rules out every unscaled special converter
+    bool usesFilter = false;
+    for (int k = 0; k < 4; k++) usesFilter = usesFilter || p.srcFilt[k].size() > 1 || p.dstFiltLen[k] > 1;
     p.rgb_shuffle = false;
-    if (p.src_rgb && !p.planar && srcW == dstW && srcH == dstH) {
+    if (!usesFilter && p.src_rgb && !p.planar && srcW == dstW && srcH == dstH) {
         // same size, packed RGB both sides: a copy for equal formats (packedCopyWrapper, swscale_unscaled.c:2675-2690), else the byte
         // shuffles of rgbToRgbWrapper (:2001-2060) when findRgbConvFn (:1843-1998) has one: always between the four 32-bit orders,
         // between rgb24 and bgr24 and from 32 to 24 bits; from 24 to 32 bits unless SWS_BITEXACT asks for bgra / rgba (little endian:
@@ -445,16 +470,16 @@ int sws_plan_build(SwsPlan &p, int srcW, int srcH, int dstW, int dstH, int flags
     // unscaled special converter gate: swscale_unscaled.c:2426-2431 reached from utils.c:1623-1637; a yuv destination only
     // looks for one when no range conversion is due (utils.c:1624-1626)
     // bgr24ToYv12Wrapper (swscale_unscaled.c:2453-2457): bgr24 only, not with accurate_rnd, even width
-    p.bgr24_yv12 = p.planar && !p.dst_nv && p.src_rgb == 3 && p.sbo == 0 && srcW == dstW && srcH == dstH && p.src_range == p.dst_range &&
+    p.bgr24_yv12 = !usesFilter && p.planar && !p.dst_nv && p.src_rgb == 3 && p.sbo == 0 && srcW == dstW && srcH == dstH && p.src_range == p.dst_range &&
                    !(flags & B200_SWS_ACCURATE_RND) && !(dstW & 1);
     if (p.bgr24_yv12) return 0;
     // same-size yuv -> yuv: planarCopyWrapper, planarToNv12Wrapper or nv12ToPlanarWrapper (swscale_unscaled.c:2415-2419,2675-2693,147-188);
     // nv12 <-> nv21 has no such converter and goes through the scaler (it matters once sws_setColorspaceDetails changes a range)
-    p.planar_copy = p.planar && !p.src_rgb && srcW == dstW && srcH == dstH && p.src_range == p.dst_range &&
+    p.planar_copy = !usesFilter && p.planar && !p.src_rgb && srcW == dstW && srcH == dstH && p.src_range == p.dst_range &&
                     !(p.src_nv && p.dst_nv && p.src_nv != p.dst_nv);
     if (p.planar_copy) return 0;
     // (only planar yuv420p / yuv422p sources have the LUT converter; nv12 / nv21 go through the scaler)
-    p.unscaled_lut = !p.planar && !p.src_nv && !p.src_rgb && srcW == dstW && srcH == dstH && !(flags & B200_SWS_ACCURATE_RND) && !(dstH & 1);
+    p.unscaled_lut = !usesFilter && !p.planar && !p.src_nv && !p.src_rgb && srcW == dstW && srcH == dstH && !(flags & B200_SWS_ACCURATE_RND) && !(dstH & 1);
     if (p.unscaled_lut) return 0;
 
     const int lumScaler = algo == B200_SWS_BICUBLIN ? B200_SWS_BICUBIC : algo;
@@ -467,12 +492,12 @@ int sws_plan_build(SwsPlan &p, int srcW, int srcH, int dstW, int dstH, int flags
         lumXInc > INT32_MAX || lumYInc > INT32_MAX || chrXInc > INT32_MAX || chrYInc > INT32_MAX)
         return B200_ENOSYS;
     p.lumXInc = (int)lumXInc; p.chrXInc = (int)chrXInc;
-    if ((ret = build_bank(p.hLum, lumScaler, (int)lumXInc, srcW, dstW, 1 << 14, sample_origin(0, 0), sample_origin(0, 0), p.param)) < 0) return ret;
+    if ((ret = build_bank(p.hLum, lumScaler, (int)lumXInc, srcW, dstW, 1 << 14, sample_origin(0, 0), sample_origin(0, 0), p.param, &p.srcFilt[0], p.dstFiltLen[0])) < 0) return ret;
     if ((ret = build_bank(p.hChr, chrScaler, (int)chrXInc, p.chrSrcW, p.chrDstW, 1 << 14,
-                          sample_origin(p.chrSrcHSub, -513), sample_origin(p.chrDstHSub, -513), p.param)) < 0) return ret;
-    if ((ret = build_bank(p.vLum, lumScaler, (int)lumYInc, srcH, dstH, 1 << 12, sample_origin(0, 0), sample_origin(0, 0), p.param)) < 0) return ret;
+                          sample_origin(p.chrSrcHSub, -513), sample_origin(p.chrDstHSub, -513), p.param, &p.srcFilt[2], p.dstFiltLen[2])) < 0) return ret;
+    if ((ret = build_bank(p.vLum, lumScaler, (int)lumYInc, srcH, dstH, 1 << 12, sample_origin(0, 0), sample_origin(0, 0), p.param, &p.srcFilt[1], p.dstFiltLen[1])) < 0) return ret;
     if ((ret = build_bank(p.vChr, chrScaler, (int)chrYInc, p.chrSrcH, p.chrDstH, 1 << 12,
-                          sample_origin(p.chrSrcVSub, -513), sample_origin(chrDstVSub, -513), p.param)) < 0) return ret;
+                          sample_origin(p.chrSrcVSub, -513), sample_origin(chrDstVSub, -513), p.param, &p.srcFilt[3], p.dstFiltLen[3])) < 0) return ret;
     if (p.planar) return 0;
 
     // writer per output line, as packed_vscale decides it (vscale.c:144-169); coefficients are read as uint16 there

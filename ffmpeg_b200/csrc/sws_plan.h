@@ -57,6 +57,10 @@ struct SwsPlan {
     bool rgb_shuffle = false;     // same size packed RGB -> packed RGB: rgbToRgbWrapper / packedCopyWrapper (swscale_unscaled.c:2001-2060,2138-2170)
     unsigned shuffle_sel = 0;     // __byte_perm selector: nibble j = source byte of destination byte j, 4 = the constant 255
     bool bgr24_yv12 = false;      // reference installs bgr24ToYv12Wrapper (ff_rgb24toyv12_c, rgb2rgb_template.c:580-641)
+    // sws_getContext's srcFilter / dstFilter (SwsFilter, swscale.h:199-204), set before sws_plan_build: [0] lumH, [1] lumV, [2] chrH, [3] chrV.
+    // initFilter convolves the source vector into every tap row; of the destination vector only the length counts (utils.c:384-413)
+    std::vector<double> srcFilt[4];
+    int dstFiltLen[4] = { 0, 0, 0, 0 };
     double param[2] = { 123456.0, 123456.0 };     // SwsContext.scaler_params; SWS_PARAM_DEFAULT = 123456 (set before sws_plan_build)
     SwsFilterBank hLum, hChr, vLum, vChr;
     SwsColorConst color{};

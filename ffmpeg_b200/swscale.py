@@ -7,7 +7,7 @@ and torch CUDA tensors or raw device pointers for scale_batch_device.  Everythin
 """
 import ctypes as C
 import numpy as np
-from ._lib import lib, check, vp, i16p, i32p, i64p, B200Error
+from ._lib import lib, check, vp, i16p, i32p, i64p, B200Error, SwsFilter, SwsVector
 
 AV_PIX_FMT_YUV420P, AV_PIX_FMT_RGB24, AV_PIX_FMT_BGR24 = 0, 2, 3                       # libavutil/pixfmt.h
 AV_PIX_FMT_ARGB, AV_PIX_FMT_RGBA, AV_PIX_FMT_ABGR, AV_PIX_FMT_BGRA = 25, 26, 27, 28
@@ -35,7 +35,7 @@ def _dptr(x):
 
 
 class SwsContext:
-    def __init__(self, device, srcW, srcH, srcFormat, dstW, dstH, dstFormat, flags, src_range=0, dst_range=0, param=None):
+    def __init__(self, device, srcW, srcH, srcFormat, dstW, dstH, dstFormat, flags, src_range=0, dst_range=0, param=None, src_filter=None, dst_filter=None):
         """src_range / dst_range: SwsContext.src_range / .dst_range as set before sws_init_context (0 limited, 1 full);
         param: sws_getContext's scaler parameters (two doubles, 123456 = SWS_PARAM_DEFAULT) or None"""
         self.device = device
@@ -45,7 +45,26 @@ class SwsContext:
         self.planar = dstFormat == AV_PIX_FMT_YUV420P or self.dst_nv
         self.bpp = 1 if self.planar else 3 if dstFormat in (AV_PIX_FMT_RGB24, AV_PIX_FMT_BGR24) else 4
         pp = (C.c_double * 2)(*param) if param is not None else None
-        h = lib().b200_sws_getContext_params(device.handle, srcW, srcH, srcFormat, src_range, dstW, dstH, dstFormat, dst_range, flags, pp)
+        if src_filter is not None or dst_filter is not None:
+            # sws_getContext's srcFilter / dstFilter: four coefficient sequences (lumH, lumV, chrH, chrV; None = no vector) each
+            keep = []
+
+            def mk(vs):
+                if vs is None:
+                    return None
+                f = SwsFilter()
+                for name, v in zip(("lumH", "lumV", "chrH", "chrV"), vs):
+                    if v is not None and len(v):
+                        arr = (C.c_double * len(v))(*v)
+                        vec = SwsVector(C.cast(arr, C.POINTER(C.c_double)), len(v))
+                        keep.extend([arr, vec])
+                        setattr(f, name, C.pointer(vec))
+                keep.append(f)
+                return C.byref(f)
+            h = lib().b200_sws_getContext_filters(device.handle, srcW, srcH, srcFormat, src_range, dstW, dstH, dstFormat, dst_range, flags,
+                                                  mk(src_filter), mk(dst_filter), pp)
+        else:
+            h = lib().b200_sws_getContext_params(device.handle, srcW, srcH, srcFormat, src_range, dstW, dstH, dstFormat, dst_range, flags, pp)
         if not h:
             raise B200Error("sws_getContext failed: " + lib().b200_last_error().decode())
         self._h = vp(h)
@@ -141,5 +160,5 @@ class SwsContext:
             pass
 
 
-def sws_getContext(device, srcW, srcH, srcFormat, dstW, dstH, dstFormat, flags, src_range=0, dst_range=0, param=None):
-    return SwsContext(device, srcW, srcH, srcFormat, dstW, dstH, dstFormat, flags, src_range, dst_range, param)
+def sws_getContext(device, srcW, srcH, srcFormat, dstW, dstH, dstFormat, flags, src_range=0, dst_range=0, param=None, src_filter=None, dst_filter=None):
+    return SwsContext(device, srcW, srcH, srcFormat, dstW, dstH, dstFormat, flags, src_range, dst_range, param, src_filter, dst_filter)

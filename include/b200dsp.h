@@ -119,6 +119,15 @@ B200SwsContext *b200_sws_getContext_range(B200Device *dev, int srcW, int srcH, i
  * 123456 (SWS_PARAM_DEFAULT) in either slot, selects the default. */
 B200SwsContext *b200_sws_getContext_params(B200Device *dev, int srcW, int srcH, int srcFormat, int srcRange,
                                            int dstW, int dstH, int dstFormat, int dstRange, int flags, const double *param);
+/* sws_getContext's srcFilter / dstFilter (SwsFilter / SwsVector, libswscale/swscale.h:187-204): initFilter convolves the source vector of
+ * each direction into that direction's filter bank; of a destination vector only the length counts (the reference never applies it,
+ * "FIXME dstFilter", utils.c:384-413); any vector longer than one tap rules out the unscaled special converters (utils.c:1256-1263).
+ * NULL pointers = no filter.  The vectors are copied. */
+typedef struct B200SwsVector { const double *coeff; int length; } B200SwsVector;
+typedef struct B200SwsFilter { const B200SwsVector *lumH, *lumV, *chrH, *chrV; } B200SwsFilter;
+B200SwsContext *b200_sws_getContext_filters(B200Device *dev, int srcW, int srcH, int srcFormat, int srcRange, int dstW, int dstH, int dstFormat,
+                                            int dstRange, int flags, const B200SwsFilter *srcFilter, const B200SwsFilter *dstFilter,
+                                            const double *param);
 void b200_sws_freeContext(B200SwsContext *c);
 /* like sws_setColorspaceDetails() (libswscale/utils.c:849-1004).  RGB destination: `table` / dstRange are accepted and
  * ignored like the reference.  yuv420p destination: the ranges are stored and the range conversion is re-selected

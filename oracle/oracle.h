@@ -63,6 +63,8 @@ OrcSws *orc_sws_open_io(int srcFormat, int srcW, int srcH, int dstFormat, int ds
 /* with SwsContext.scaler_params (sws_getContext's `param`; NULL or 123456 = default) */
 OrcSws *orc_sws_open_params(int srcFormat, int srcW, int srcH, int srcRange, int dstFormat, int dstW, int dstH, int dstRange, int flags,
                             const double *param);
+OrcSws *orc_sws_open_filters(int srcFormat, int srcW, int srcH, int srcRange, int dstFormat, int dstW, int dstH, int dstRange, int flags,
+                             const double *const srcCoef[4], const int srcLen[4], const int dstLen[4], const double *param);
 OrcSws *orc_sws_open_range(int srcFormat, int srcW, int srcH, int srcRange, int dstFormat, int dstW, int dstH, int dstRange, int flags);
 void    orc_sws_close(OrcSws *s);
 /* inv_table = 4 coefficients as ff_yuv2rgb_coeffs rows; contrast/saturation 16.16 */

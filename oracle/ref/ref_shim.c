@@ -109,6 +109,39 @@ API void *ffref_sws_open_params(int srcFormat, int srcW, int srcH, int srcRange,
     return c;
 }
 
+/* sws_init_context with srcFilter / dstFilter: four (coefficients, length) pairs each -- lumH, lumV, chrH, chrV; NULL / 0 = no vector */
+API void *ffref_sws_open_filters(int srcFormat, int srcW, int srcH, int srcRange, int dstFormat, int dstW, int dstH, int dstRange,
+                                 int flags, int threads, const double *const srcCoef[4], const int srcLen[4], const int dstLen[4], const double *param)
+{
+    SwsContext *c = sws_alloc_context();
+    if (!c) return NULL;
+    c->src_w = srcW; c->src_h = srcH; c->dst_w = dstW; c->dst_h = dstH;
+    c->src_format = srcFormat; c->dst_format = dstFormat;
+    c->src_range = srcRange; c->dst_range = dstRange;
+    c->flags = flags;
+    c->threads = threads;
+    if (param) { c->scaler_params[0] = param[0]; c->scaler_params[1] = param[1]; }
+    SwsFilter sf = { 0 }, df = { 0 };
+    SwsVector **sv[4] = { &sf.lumH, &sf.lumV, &sf.chrH, &sf.chrV }, **dv[4] = { &df.lumH, &df.lumV, &df.chrH, &df.chrV };
+    int any_s = 0, any_d = 0;
+    for (int k = 0; k < 4; k++) {
+        if (srcCoef && srcCoef[k] && srcLen[k] > 0) {
+            *sv[k] = sws_allocVec(srcLen[k]);
+            memcpy((*sv[k])->coeff, srcCoef[k], sizeof(double) * srcLen[k]);
+            any_s = 1;
+        }
+        if (dstLen && dstLen[k] > 0) {
+            *dv[k] = sws_allocVec(dstLen[k]);
+            for (int i = 0; i < dstLen[k]; i++) (*dv[k])->coeff[i] = 1.0 / dstLen[k];
+            any_d = 1;
+        }
+    }
+    const int ret = sws_init_context(c, any_s ? &sf : NULL, any_d ? &df : NULL);
+    for (int k = 0; k < 4; k++) { sws_freeVec(*sv[k]); sws_freeVec(*dv[k]); }
+    if (ret < 0) { sws_freeContext(c); return NULL; }
+    return c;
+}
+
 API void ffref_sws_close(void *h) { sws_freeContext((SwsContext *)h); }
 
 /* colorspace details pass-through (sws_setColorspaceDetails); table index = SWS_CS_* */

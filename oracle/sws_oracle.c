@@ -82,6 +82,11 @@ static int local_pos(int chr_subsample, int pos)
  * The checker is single threaded: orc_sws_open_params() sets them around the open call. */
 #define ORC_PARAM_DEFAULT 123456
 static double g_param[2] = { ORC_PARAM_DEFAULT, ORC_PARAM_DEFAULT };
+/* sws_getContext's srcFilter / dstFilter vectors for the open call in flight ([0] lumH, [1] lumV, [2] chrH, [3] chrV), set by
+ * orc_sws_open_filters(); make_filter() is told which one applies */
+static const double *g_src_vec[4];
+static int g_src_len[4], g_dst_len[4];
+static int g_vec_sel = -1;
 
 static int make_filter(int16_t **outFilter, int32_t **outPos, int *outSize, int xInc, int srcW, int dstW,
                        int one, int scaler, int flags, int srcPos, int dstPos)
@@ -198,6 +203,25 @@ static int make_filter(int16_t **outFilter, int32_t **outPos, int *outSize, int 
             }
             x += 2LL * xInc;
         }
+    }
+
+    /* srcFilter / dstFilter, utils.c:384-413: the source vector convolved into every row (`filter2[...] += coeff * filter[...]` on an int64:
+     * through a double each time), the destination vector only widens the row ("FIXME dstFilter"); the window start moves */
+    if (g_vec_sel >= 0 && (g_src_len[g_vec_sel] > 0 || g_dst_len[g_vec_sel] > 0)) {
+        const int sl = g_src_len[g_vec_sel], dl = g_dst_len[g_vec_sel];
+        const int fs2 = fs + (sl ? sl - 1 : 0) + (dl ? dl - 1 : 0);
+        int64_t *f2 = calloc((size_t)dstW * fs2, sizeof(*f2));
+        for (i = 0; i < dstW; i++) {
+            if (sl) {
+                for (int k = 0; k < sl; k++)
+                    for (j = 0; j < fs; j++)
+                        f2[i * fs2 + k + j] += g_src_vec[g_vec_sel][k] * f[i * fs + j];
+            } else
+                for (j = 0; j < fs; j++) f2[i * fs2 + j] = f[i * fs + j];
+            pos[i] += (fs - 1) / 2 - (fs2 - 1) / 2;
+        }
+        free(f);
+        f = f2; fs = fs2;
     }
 
     /* size reduction, utils.c:417-457: strip near-zero taps left, count them right */
@@ -461,6 +485,20 @@ OrcSws *orc_sws_open_params(int srcFormat, int srcW, int srcH, int srcRange, int
     return s;
 }
 
+/* srcFilter / dstFilter as four (coefficients, length) pairs each: lumH, lumV, chrH, chrV; NULL / 0 = no vector */
+OrcSws *orc_sws_open_filters(int srcFormat, int srcW, int srcH, int srcRange, int dstFormat, int dstW, int dstH, int dstRange, int flags,
+                             const double *const srcCoef[4], const int srcLen[4], const int dstLen[4], const double *param)
+{
+    for (int k = 0; k < 4; k++) {
+        g_src_vec[k] = srcCoef ? srcCoef[k] : NULL;
+        g_src_len[k] = srcCoef && srcLen && srcCoef[k] ? srcLen[k] : 0;
+        g_dst_len[k] = dstLen ? dstLen[k] : 0;
+    }
+    OrcSws *s = orc_sws_open_params(srcFormat, srcW, srcH, srcRange, dstFormat, dstW, dstH, dstRange, flags, param);
+    for (int k = 0; k < 4; k++) { g_src_vec[k] = NULL; g_src_len[k] = g_dst_len[k] = 0; }
+    return s;
+}
+
 OrcSws *orc_sws_open_range(int srcFormat, int srcW, int srcH, int srcRange, int dstFormat, int dstW, int dstH, int dstRange, int flags)
 {
     if (srcW < 1 || srcH < 1 || dstW < 1 || dstH < 1) return NULL;
@@ -473,7 +511,9 @@ OrcSws *orc_sws_open_range(int srcFormat, int srcW, int srcH, int srcRange, int 
     } else if (srcFormat != ORC_PIX_FMT_YUV420P && srcFormat != ORC_PIX_FMT_NV12 && srcFormat != ORC_PIX_FMT_NV21) { free(s); return NULL; }
     if (set_format(s, dstFormat) < 0) { free(s); return NULL; }
     s->dst_nv = dstFormat == ORC_PIX_FMT_NV12 ? 1 : dstFormat == ORC_PIX_FMT_NV21 ? 2 : 0;
-    if (s->src_rgb && !s->planar && srcW == dstW && srcH == dstH) {
+    int uses_filter = 0;                                           /* utils.c:1256-1263: usesVFilter || usesHFilter */
+    for (int k = 0; k < 4; k++) uses_filter |= g_src_len[k] > 1 || g_dst_len[k] > 1;
+    if (!uses_filter && s->src_rgb && !s->planar && srcW == dstW && srcH == dstH) {
         /* same size, packed RGB on both sides: packedCopyWrapper for equal formats (swscale_unscaled.c:2675-2690), else rgbToRgbWrapper
          * (:2001-2060) whenever findRgbConvFn (:1843-1998) returns a function.  For the six 8-bit formats here it always does --
          * shuffle_bytes_* between the 32-bit orders, rgb24tobgr24, rgb32to24 / rgb32tobgr24, rgb24to32 / rgb24tobgr32 -- except under
@@ -519,7 +559,7 @@ OrcSws *orc_sws_open_range(int srcFormat, int srcW, int srcH, int srcRange, int 
 
     /* the unscaled converters are only looked for when no range conversion is due (utils.c:1623-1626) */
     /* bgr24ToYv12Wrapper (swscale_unscaled.c:2453-2457): bgr24 only, not with accurate_rnd, even width */
-    if (s->planar && !s->dst_nv && s->src_rgb == 3 && s->sbo == 0 && srcW == dstW && srcH == dstH && s->src_range == s->dst_range &&
+    if (!uses_filter && s->planar && !s->dst_nv && s->src_rgb == 3 && s->sbo == 0 && srcW == dstW && srcH == dstH && s->src_range == s->dst_range &&
         !(flags & ORC_SWS_ACCURATE_RND) && !(dstW & 1)) {
         s->bgr24_yv12 = 1;
         s->unscaled_lut = 3;
@@ -528,14 +568,14 @@ OrcSws *orc_sws_open_range(int srcFormat, int srcW, int srcH, int srcRange, int 
     /* planarCopyWrapper (swscale_unscaled.c:2675-2693), planarToNv12Wrapper (:147-165) or, for a semi-planar source,
      * nv12ToPlanarWrapper (:167-188, :2415-2419): all a luma copy plus a chroma copy / interleave / de-interleave.  nv12 <-> nv21
      * has no such converter: it goes through the scaler (same bytes, until sws_setColorspaceDetails changes a range) */
-    if (s->planar && !s->src_rgb && srcW == dstW && srcH == dstH && s->src_range == s->dst_range &&
+    if (!uses_filter && s->planar && !s->src_rgb && srcW == dstW && srcH == dstH && s->src_range == s->dst_range &&
         !(s->src_nv && s->dst_nv && s->src_nv != s->dst_nv)) {
         s->unscaled_lut = 2;
         return s;
     }
     /* swscale_unscaled.c:2426-2431 through utils.c:1623-1637: only planar yuv420p/422p sources have the LUT converter
      * (packed RGB destination: dst_range was forced to 0 above; isAnyRGB(dst) passes the range test of utils.c:1625) */
-    if (!s->planar && !s->src_nv && !s->src_rgb && srcW == dstW && srcH == dstH && !(flags & ORC_SWS_ACCURATE_RND) && !(dstH & 1)) {
+    if (!uses_filter && !s->planar && !s->src_nv && !s->src_rgb && srcW == dstW && srcH == dstH && !(flags & ORC_SWS_ACCURATE_RND) && !(dstH & 1)) {
         s->unscaled_lut = 1;
         return s;
     }
@@ -546,16 +586,22 @@ OrcSws *orc_sws_open_range(int srcFormat, int srcW, int srcH, int srcRange, int 
     int64_t chrXInc = (((int64_t)s->chrSrcW << 16) + (s->chrDstW >> 1)) / s->chrDstW;
     int64_t chrYInc = (((int64_t)s->chrSrcH << 16) + (s->chrDstH >> 1)) / s->chrDstH;
     s->lumXInc = (int)lumXInc; s->chrXInc = (int)chrXInc;
+    g_vec_sel = 0;
     if (make_filter(&s->hLum, &s->hLumPos, &s->hLumSize, (int)lumXInc, srcW, dstW, 1 << 14, lum_scaler, flags,
                     local_pos(0, 0), local_pos(0, 0)) < 0) goto fail;
+    g_vec_sel = 2;
     if (make_filter(&s->hChr, &s->hChrPos, &s->hChrSize, (int)chrXInc, s->chrSrcW, s->chrDstW, 1 << 14, chr_scaler, flags,
                     local_pos(s->chrSrcHSub, -513), local_pos(s->chrDstHSub, -513)) < 0) goto fail;
+    g_vec_sel = 1;
     if (make_filter(&s->vLum, &s->vLumPos, &s->vLumSize, (int)lumYInc, srcH, dstH, 1 << 12, lum_scaler, flags,
                     local_pos(0, 0), local_pos(0, 0)) < 0) goto fail;
+    g_vec_sel = 3;
     if (make_filter(&s->vChr, &s->vChrPos, &s->vChrSize, (int)chrYInc, s->chrSrcH, s->chrDstH, 1 << 12, chr_scaler, flags,
                     local_pos(s->chrSrcVSub, -513), local_pos(chrDstVSub, -513)) < 0) goto fail;
+    g_vec_sel = -1;
     return s;
 fail:
+    g_vec_sel = -1;
     orc_sws_close(s);
     return NULL;
 }

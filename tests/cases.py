@@ -180,3 +180,24 @@ SWS_CASCADE_CASES = [
     (33, 21, 64, 40, 0x20 | 0x40000, 0, 23, (0, 0), (5, 0, 9, 0, 0, 50000, 1 << 16)),
     (128, 64, 96, 80, 4 | 0x2000, 23, 0, (0, 0), (9, 0, 5, 1, 1 << 12, 1 << 16, 40000)),
 ]
+
+
+# sws_getContext with srcFilter / dstFilter: (w, h, dw, dh, flags, destination 'rgb24' / 'bgra' / 'yuv420p', source vectors (lumH, lumV, chrH,
+# chrV; None = no vector), destination vector lengths)
+def _gauss(sigma, n):
+    import math
+    v = [math.exp(-((i - (n - 1) / 2) ** 2) / (2 * sigma * sigma)) for i in range(n)]
+    t = sum(v)
+    return [x / t for x in v]
+
+
+SWS_FILTER_CASES = [
+    (64, 48, 100, 70, 4 | 0x80000 | 0x40000, "rgb24", (_gauss(0.8, 5), _gauss(0.8, 5), None, None), (0, 0, 0, 0)),
+    (100, 70, 64, 48, 4, "rgb24", (None, None, _gauss(1.5, 9), _gauss(1.5, 9)), (0, 0, 0, 0)),
+    (64, 48, 64, 48, 4, "bgra", ([-0.25, 1.5, -0.25], [-0.25, 1.5, -0.25], None, None), (0, 0, 0, 0)),        # same size: the LUT converter is ruled out
+    (66, 34, 66, 34, 2, "yuv420p", ([0.25, 0.5, 0.25], None, [0.25, 0.5, 0.25], None), (0, 0, 0, 0)),            # same size: no plane copy
+    (87, 66, 120, 90, 4 | 0x40000, "yuv420p", (_gauss(1.0, 7), _gauss(1.0, 7), _gauss(1.0, 7), _gauss(1.0, 7)), (3, 3, 3, 3)),
+    (77, 28, 90, 63, 1, "rgb24", ([0.3, 0.7], [0.3, 0.7], None, None), (0, 5, 0, 0)),                            # fast bilinear ignores the horizontal bank
+    (50, 40, 25, 20, 0x10, "bgra", (None, None, None, None), (3, 0, 3, 0)),                                      # destination vectors only: wider rows, same taps
+    (128, 64, 96, 80, 0x20, "yuv420p", ([1.0], [1.0], [1.0], [1.0]), (1, 1, 1, 1)),                              # one-tap vectors: nothing changes
+]

@@ -190,9 +190,26 @@ def rgb_frame(w, h, seed, bpp, kind="random", pad=0):
     return a
 
 
-def _sws_run(lib, pre, w, h, dw, dh, flags, y, u, v, dst_pad=0, threads=1, colorspace=None, fmt=PIX_FMT_RGB24, src_fmt=0, param=None):
+def _open_filters(lib, pre, src_fmt, w, h, sr, fmt, dw, dh, dr, flags, threads, filters, param):
+    """filters = (src, dst): src = 4 sequences of doubles (lumH, lumV, chrH, chrV; None = no vector), dst = 4 lengths"""
+    src, dst = filters
+    arrs = [np.array(v, np.float64) if v is not None and len(v) else None for v in (src or [None] * 4)]
+    coef = (C.c_void_p * 4)(*[a.ctypes.data if a is not None else None for a in arrs])
+    slen = (C.c_int * 4)(*[len(a) if a is not None else 0 for a in arrs])
+    dlen = (C.c_int * 4)(*(dst or [0] * 4))
+    pa = (C.c_double * 2)(*param) if param is not None else None
+    if pre == "ffref":
+        lib.ffref_sws_open_filters.restype, lib.ffref_sws_open_filters.argtypes = C.c_void_p, [C.c_int] * 10 + [C.c_void_p] * 4
+        return lib.ffref_sws_open_filters(src_fmt, w, h, sr, fmt, dw, dh, dr, flags, threads, coef, slen, dlen, pa)
+    lib.orc_sws_open_filters.restype, lib.orc_sws_open_filters.argtypes = C.c_void_p, [C.c_int] * 9 + [C.c_void_p] * 4
+    return lib.orc_sws_open_filters(src_fmt, w, h, sr, fmt, dw, dh, dr, flags, coef, slen, dlen, pa)
+
+
+def _sws_run(lib, pre, w, h, dw, dh, flags, y, u, v, dst_pad=0, threads=1, colorspace=None, fmt=PIX_FMT_RGB24, src_fmt=0, param=None, filters=None):
     """src_fmt nv12 / nv21: `u` is the interleaved chroma plane, `v` is ignored; param: sws_getContext's two scaler parameters"""
-    if param is not None:
+    if filters is not None:
+        ctx = _open_filters(lib, pre, src_fmt, w, h, 0, fmt, dw, dh, 0, flags, threads, filters, param)
+    elif param is not None:
         pa = (C.c_double * 2)(*param)
         if pre == "ffref":
             lib.ffref_sws_open_params.restype, lib.ffref_sws_open_params.argtypes = C.c_void_p, [C.c_int] * 10 + [C.c_void_p]
@@ -233,12 +250,14 @@ PIX_FMT_YUV420P = 0
 
 
 def _sws_run_planar(lib, pre, w, h, dw, dh, flags, y, u, v, dst_pad=0, threads=1, src_fmt=0, ranges=(0, 0), details=None,
-                    dst_fmt=PIX_FMT_YUV420P):
+                    dst_fmt=PIX_FMT_YUV420P, filters=None):
     """yuv420p / nv12 / nv21 -> yuv420p; returns (Y, U, V) destination planes (pad bytes stay 0xA5).
     ranges = (src_range, dst_range) given before initialisation; details = (src_cs, src_range, dst_cs, dst_range,
     brightness, contrast, saturation) for a sws_setColorspaceDetails() call after it.
     dst_fmt nv12 / nv21: returns (Y, UV) with UV the interleaved plane."""
-    if pre == "ffref":
+    if filters is not None:
+        ctx = _open_filters(lib, pre, src_fmt, w, h, ranges[0], dst_fmt, dw, dh, ranges[1], flags, threads, filters, None)
+    elif pre == "ffref":
         ctx = lib.ffref_sws_open_range(src_fmt, w, h, ranges[0], dst_fmt, dw, dh, ranges[1], flags, threads)
     else:
         ctx = lib.orc_sws_open_range(src_fmt, w, h, ranges[0], dst_fmt, dw, dh, ranges[1], flags)

@@ -642,6 +642,55 @@ def test_sws_yuv_matrix_cascade_on_emulated_device(emusws):
     L.b200_sws_freeContext(ctx)
 
 
+def test_sws_src_dst_filters_on_emulated_device(emusws):
+    """b200_sws_getContext_filters: source vectors convolved into the banks by the product's own host set-up, the unscaled converters ruled
+    out; whole frames through sws_scale on the emulated device against the checker"""
+    from ffmpeg_b200._lib import SwsFilter, SwsVector
+    from cases import SWS_FILTER_CASES
+    from test_oracle import run_filter_case
+    L = emusws
+    L.b200_sws_getContext_filters.restype = C.c_void_p
+    L.b200_sws_getContext_filters.argtypes = [C.c_void_p] + [C.c_int] * 9 + [C.c_void_p] * 3
+
+    def ctx_of(w, h, sf, dw, dh, df, fl, filters):
+        keep = []
+
+        def mk(vs, lens=None):
+            f = SwsFilter()
+            for k, name in enumerate(("lumH", "lumV", "chrH", "chrV")):
+                v = vs[k] if vs is not None else None
+                if lens is not None:
+                    v = [1.0 / lens[k]] * lens[k] if lens[k] else None
+                if v:
+                    arr = (C.c_double * len(v))(*v)
+                    vec = SwsVector(C.cast(arr, C.POINTER(C.c_double)), len(v))
+                    keep.extend([arr, vec])
+                    setattr(f, name, C.pointer(vec))
+            keep.append(f)
+            return C.addressof(f)
+        return L.b200_sws_getContext_filters(L.dev, w, h, sf, 0, dw, dh, df, 0, fl, mk(filters[0]), mk(None, filters[1]), None), keep
+
+    def run_rgb(w, h, dw, dh, fl, y, u, v, filters=None, fmt=cl.PIX_FMT_RGB24):
+        ctx, keep = ctx_of(w, h, 0, dw, dh, fmt, fl, filters)
+        assert ctx
+        out = np.full((dh, dw * cl.fmt_bpp(fmt)), 0xA5, np.uint8)
+        assert _emu_scale(L, ctx, [y, u, v], h, [out]) == dh
+        L.b200_sws_freeContext(ctx)
+        return out
+
+    def run_planar(w, h, dw, dh, fl, y, u, v, filters=None):
+        ctx, keep = ctx_of(w, h, 0, dw, dh, 0, fl, filters)
+        assert ctx
+        cw, ch = (dw + 1) // 2, (dh + 1) // 2
+        dst = [np.full((dh, dw), 0xA5, np.uint8), np.full((ch, cw), 0xA5, np.uint8), np.full((ch, cw), 0xA5, np.uint8)]
+        assert _emu_scale(L, ctx, [y, u, v], h, dst) == dh
+        L.b200_sws_freeContext(ctx)
+        return tuple(dst)
+    for i, case in enumerate(SWS_FILTER_CASES):
+        got, exp = run_filter_case(run_rgb, run_planar, i, case), run_filter_case(cl.orc_sws, cl.orc_sws_planar, i, case)
+        assert all(np.array_equal(p, q) for p, q in zip(got, exp)), (i, case[:6])
+
+
 def test_sws_differential_fuzz(emusws):
     """seeded random contexts (sizes incl. odd ones, every source / destination format of the library, scaler flags, ranges,
     sws_setColorspaceDetails with other matrices / brightness / contrast / saturation, padded destinations) through the library's

@@ -563,3 +563,27 @@ def test_sws_oracle_yuv_matrix_cascade_vs_ref():
         assert all(np.array_equal(p, q) for p, q in zip(a, b)), (i, w, h, dw, dh, hex(fl))
         same = cl.orc_sws_planar(w, h, dw, dh, fl, y, u, v, src_fmt=sf, dst_fmt=df, ranges=ranges, details=(det[0], det[1], det[0], det[3]) + det[4:], dst_pad=i % 3)
         assert not all(np.array_equal(p, q) for p, q in zip(b, same)), i        # the second matrix matters
+
+
+def run_filter_case(run_rgb, run_planar, i, case):
+    from cases import SWS_FILTER_CASES  # noqa: F401
+    w, h, dw, dh, fl, dst, src, dlen = case
+    y, u, v = cl.yuv_frame(w, h, 7100 + i, "random" if i % 2 else "smooth")
+    if dst == "yuv420p":
+        return run_planar(w, h, dw, dh, fl, y, u, v, filters=(src, dlen))
+    return (run_rgb(w, h, dw, dh, fl, y, u, v, filters=(src, dlen), fmt=cl.PACKED_RGB_FORMATS[dst]),)
+
+
+def test_sws_oracle_src_dst_filters_vs_ref():
+    """sws_getContext's srcFilter / dstFilter (initFilter's filter2 stage, utils.c:384-413, and the unscaled-converter gate :1256-1263)"""
+    if not cl.have_ref():
+        pytest.skip("oracle/_ref not built")
+    from cases import SWS_FILTER_CASES
+    for i, case in enumerate(SWS_FILTER_CASES):
+        a, b = run_filter_case(cl.ref_sws, cl.ref_sws_planar, i, case), run_filter_case(cl.orc_sws, cl.orc_sws_planar, i, case)
+        assert all(np.array_equal(p, q) for p, q in zip(a, b)), (i, case[:6])
+    plain = run_filter_case(lambda *a, filters=None, **k: cl.orc_sws(*a, **k), lambda *a, filters=None, **k: cl.orc_sws_planar(*a, **k), 0, SWS_FILTER_CASES[0])
+    assert not np.array_equal(plain[0], run_filter_case(cl.orc_sws, cl.orc_sws_planar, 0, SWS_FILTER_CASES[0])[0])     # the vectors matter
+    one = run_filter_case(cl.orc_sws, cl.orc_sws_planar, 7, SWS_FILTER_CASES[7])
+    none = run_filter_case(lambda *a, filters=None, **k: cl.orc_sws(*a, **k), lambda *a, filters=None, **k: cl.orc_sws_planar(*a, **k), 7, SWS_FILTER_CASES[7])
+    assert all(np.array_equal(p, q) for p, q in zip(one, none))                                                    # one-tap vectors are the identity

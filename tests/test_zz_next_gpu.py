@@ -1157,3 +1157,33 @@ def test_h264_loop_filter_hbd(device):
             args = (dd.ctypes.data + int(off[i]), dd.strides[0], int(alpha[i]), int(beta[i]))
             getattr(c, m)(*args, t.ctypes.data) if "intra" not in m else getattr(c, m)(*args)
         assert np.array_equal(dd, cl.orc_h264lf_hbd(depth, pic, kinds, off, alpha, beta, tc0)), depth
+
+
+# ---------------------------------------------------------------------------------------------- swscale: srcFilter / dstFilter
+def test_sws_src_dst_filters(device):
+    """sws_getContext with srcFilter / dstFilter vectors (blur / sharpen): whole frames against the oracle (itself equal to the compiled
+    reference on these cases), plus a 1080p blur"""
+    from ffmpeg_b200 import swscale as sw
+    from cases import SWS_FILTER_CASES, _gauss
+    from test_oracle import run_filter_case
+
+    def dvec(lens):
+        return None if not any(lens) else [[1.0 / n] * n if n else None for n in lens]
+
+    def run_rgb(w, h, dw, dh, fl, y, u, v, filters=None, fmt=cl.PIX_FMT_RGB24):
+        ctx = sw.sws_getContext(device, w, h, 0, dw, dh, fmt, fl, src_filter=filters[0], dst_filter=dvec(filters[1]))
+        try:
+            return ctx.convert(y, u, v)
+        finally:
+            ctx.free()
+
+    def run_planar(w, h, dw, dh, fl, y, u, v, filters=None):
+        ctx = sw.sws_getContext(device, w, h, 0, dw, dh, 0, fl, src_filter=filters[0], dst_filter=dvec(filters[1]))
+        try:
+            return ctx.convert_planar(y, u, v)
+        finally:
+            ctx.free()
+    cases = SWS_FILTER_CASES + [(1920, 1080, 1280, 720, 4, "rgb24", (_gauss(1.2, 7), _gauss(1.2, 7), None, None), (0, 0, 0, 0))]
+    for i, case in enumerate(cases):
+        got, exp = run_filter_case(run_rgb, run_planar, i, case), run_filter_case(cl.orc_sws, cl.orc_sws_planar, i, case)
+        assert all(np.array_equal(p, q) for p, q in zip(got, exp)), (i, case[:6])
