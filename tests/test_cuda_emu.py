@@ -366,8 +366,33 @@ def emusws():
     return L
 
 
-def _emu_ctx(L, w, h, src_fmt, dw, dh, dst_fmt, fl, ranges=(0, 0), details=None):
-    ctx = L.b200_sws_getContext_range(L.dev, w, h, src_fmt, ranges[0], dw, dh, dst_fmt, ranges[1], fl)
+def _emu_filters(filters, keep):
+    """(srcFilter address, dstFilter address) for b200_sws_getContext_filters from (four source vectors, four destination lengths)"""
+    from ffmpeg_b200._lib import SwsFilter, SwsVector
+
+    def mk(vs):
+        f = SwsFilter()
+        for name, v in zip(("lumH", "lumV", "chrH", "chrV"), vs):
+            if v:
+                arr = (C.c_double * len(v))(*v)
+                vec = SwsVector(C.cast(arr, C.POINTER(C.c_double)), len(v))
+                keep.extend([arr, vec])
+                setattr(f, name, C.pointer(vec))
+        keep.append(f)
+        return C.addressof(f)
+    src, dlen = filters
+    return mk(src or [None] * 4), mk([[1.0 / n] * n if n else None for n in (dlen or [0] * 4)])
+
+
+def _emu_ctx(L, w, h, src_fmt, dw, dh, dst_fmt, fl, ranges=(0, 0), details=None, filters=None):
+    if filters is not None:
+        keep = []
+        L.b200_sws_getContext_filters.restype = C.c_void_p
+        L.b200_sws_getContext_filters.argtypes = [C.c_void_p] + [C.c_int] * 9 + [C.c_void_p] * 3
+        sfp, dfp = _emu_filters(filters, keep)
+        ctx = L.b200_sws_getContext_filters(L.dev, w, h, src_fmt, ranges[0], dw, dh, dst_fmt, ranges[1], fl, sfp, dfp, None)
+    else:
+        ctx = L.b200_sws_getContext_range(L.dev, w, h, src_fmt, ranges[0], dw, dh, dst_fmt, ranges[1], fl)
     if ctx and details is not None:
         ta, tb = (np.array(cl.COEFFS[k], np.int32) for k in (details[0], details[2]))
         assert L.b200_sws_setColorspaceDetails(ctx, ta.ctypes.data, details[1], tb.ctypes.data, details[3], *details[4:]) == 0
@@ -382,10 +407,10 @@ def _emu_scale(L, ctx, planes, h, dst):
     return L.b200_sws_scale(ctx, sp, ss, 0, h, dp, ds)
 
 
-def emu_sws(L, w, h, dw, dh, fl, y, u, v, dst_pad=0, colorspace=None, fmt=cl.PIX_FMT_RGB24, src_fmt=0):
+def emu_sws(L, w, h, dw, dh, fl, y, u, v, dst_pad=0, colorspace=None, fmt=cl.PIX_FMT_RGB24, src_fmt=0, filters=None):
     """the library's sws_scale() path for a packed RGB destination, on the emulated device (same signature as cpulibs.orc_sws)"""
     det = None if colorspace is None else (colorspace[0], colorspace[1], colorspace[2], colorspace[3], colorspace[4], colorspace[5], colorspace[6])
-    ctx = _emu_ctx(L, w, h, src_fmt, dw, dh, fmt, fl, details=det)
+    ctx = _emu_ctx(L, w, h, src_fmt, dw, dh, fmt, fl, details=det, filters=filters)
     if not ctx:
         return None
     out = np.full((dh, dw * cl.fmt_bpp(fmt) + dst_pad), 0xA5, np.uint8)
@@ -396,8 +421,8 @@ def emu_sws(L, w, h, dw, dh, fl, y, u, v, dst_pad=0, colorspace=None, fmt=cl.PIX
     return out
 
 
-def emu_sws_planar(L, w, h, dw, dh, fl, y, u, v, dst_pad=0, src_fmt=0, ranges=(0, 0), details=None, dst_fmt=0):
-    ctx = _emu_ctx(L, w, h, src_fmt, dw, dh, dst_fmt, fl, ranges, details)
+def emu_sws_planar(L, w, h, dw, dh, fl, y, u, v, dst_pad=0, src_fmt=0, ranges=(0, 0), details=None, dst_fmt=0, filters=None):
+    ctx = _emu_ctx(L, w, h, src_fmt, dw, dh, dst_fmt, fl, ranges, details, filters)
     if not ctx:
         return None
     cw, ch = (dw + 1) // 2, (dh + 1) // 2
@@ -700,12 +725,13 @@ def test_sws_differential_fuzz(emusws):
     import functools
     import random
     er, ep = functools.partial(emu_sws, emusws), functools.partial(emu_sws_planar, emusws)
-    rnd = random.Random(20260923)
+    NIT, SEED = int(os.environ.get("B200_FUZZ_N", "90")), int(os.environ.get("B200_FUZZ_SEED", "20260923"))      # longer / other runs: set these
+    rnd = random.Random(SEED)
     flags = [cl.SWS_BICUBIC, cl.SWS_BILINEAR, FATE, cl.SWS_BICUBIC | 0x40000, cl.SWS_BILINEAR | 0x80000, 1, cl.SWS_BICUBIC | 0x2000, FATE | 0x2000,
              cl.SWS_BICUBIC | 0x4000, 0x10, 0x20, 0x40, 0x8, 0x80, 0x100, 0x200, 0x400, 0x200 | 0xc0000]
     fmts = [0, cl.PIX_FMT_NV12, cl.PIX_FMT_NV21] + list(cl.PACKED_RGB_FORMATS.values())
     ran = refused = 0
-    for it in range(90):
+    for it in range(NIT):
         w, h = rnd.choice([2, 4, 6, 8, 10, 16, 18, 34, 66, 100, 130]), rnd.choice([2, 4, 6, 8, 10, 16, 18, 34, 50])
         w, h = w + (rnd.random() < 0.3), h + (rnd.random() < 0.3)
         dw, dh = (w, h) if rnd.random() < 0.35 else (rnd.choice([2, 3, 8, 17, 32, 64, 100, 200]), rnd.choice([2, 3, 8, 17, 32, 64, 100]))
@@ -724,13 +750,18 @@ def test_sws_differential_fuzz(emusws):
             if sf:
                 u = v = cl.nv_interleave(u, v, sf)
         kw = dict(fmt=df, src_fmt=sf, dst_pad=dpad, colorspace=cs) if rgbdst else dict(src_fmt=sf, dst_fmt=df, ranges=ranges, dst_pad=dpad, details=cs)
+        filt = None
+        if rnd.random() < 0.2:                                            # srcFilter / dstFilter vectors
+            vecs = [None, [1.0], [0.25, 0.5, 0.25], [-0.25, 1.5, -0.25], [0.3, 0.7], [0.05, 0.25, 0.4, 0.25, 0.05]]
+            filt = ([rnd.choice(vecs) for _ in range(4)], [rnd.choice([0, 0, 1, 3]) for _ in range(4)])
+            kw["filters"] = filt
         orc, ref, emu = (cl.orc_sws, cl.ref_sws, er) if rgbdst else (cl.orc_sws_planar, cl.ref_sws_planar, ep)
         desc = (it, w, h, dw, dh, hex(fl), sf, df, ranges, dpad, cs)
         try:
             exp = orc(w, h, dw, dh, fl, y, u, v, **kw)
         except Exception:
             exp = None                                                    # the checker refuses (e.g. other matrices for yuv -> yuv)
-        ctx = _emu_ctx(emusws, w, h, sf, dw, dh, df, fl, ranges, None)
+        ctx = _emu_ctx(emusws, w, h, sf, dw, dh, df, fl, ranges, None, filt)
         if ctx and cs is not None:
             ta, tb = (np.array(cl.COEFFS[k], np.int32) for k in (cs[0], cs[2]))
             if emusws.b200_sws_setColorspaceDetails(ctx, ta.ctypes.data, cs[1], tb.ctypes.data, cs[3], *cs[4:]) != 0:
@@ -746,9 +777,22 @@ def test_sws_differential_fuzz(emusws):
         same = (lambda a, b: np.array_equal(a, b)) if rgbdst else (lambda a, b: all(np.array_equal(p, q) for p, q in zip(a, b)))
         assert same(got, exp), ("library != checker", desc)
         if cl.have_ref():
-            assert same(ref(w, h, dw, dh, fl, y, u, v, **kw), exp), ("checker != reference", desc)
+            r = ref(w, h, dw, dh, fl, y, u, v, **kw)
+            if rgbdst and rgbsrc and (w, h) == (dw, dh) and cl.fmt_bpp(sf) == 3 and df in (cl.PIX_FMT_ARGB, cl.PIX_FMT_ABGR):
+                # rgbToRgbWrapper writes the alpha of a "next" pixel one byte past every line (swscale_unscaled.c:2030-2042): picture area only
+                r, e2 = r[:, :dw * 4], exp[:, :dw * 4]
+            else:
+                e2 = exp
+            casc = not rgbsrc and not rgbdst and cs is not None and cl.COEFFS[cs[0]] != cl.COEFFS[cs[2]]
+            tw = dw if w * h > dw * dh else w
+            if casc and (tw & 1):
+                # two-matrix cascade through an odd-width bgr24 picture: when its first context is the unscaled LUT converter the last
+                # column is never written and the reference reads uninitialised memory there -- nothing to compare with
+                ran += 1
+                continue
+            assert same(r, e2), ("checker != reference", desc)
         ran += 1
-    assert ran >= 80 and ran + refused == 90, (ran, refused)          # since same-size RGB -> RGB and alpha went in, only other-matrix yuv -> yuv is refused
+    assert ran >= NIT * 8 // 9 and ran + refused == NIT, (ran, refused)          # since same-size RGB -> RGB and alpha went in, only other-matrix yuv -> yuv is refused
 
 
 # ------------------------------------------------------------------ all of libavutil/tx (tx.cu + tx_pfa.cu) on the stand-in runtime
