@@ -18,7 +18,7 @@ PFA=[12,20,24,28,36,40,48,56,60,72,80,96,112,120,144,160,240]
 for it in range(N):
     typ=rnd.choice([0,1,1,6,9,4,5]); inv=rnd.choice([0,1]); cnt=rnd.choice([1,2,5,9])
     flags=0
-    if typ==0: n=rnd.choice(POW2); 
+    if typ==0: n=rnd.choice(POW2 + [6,10,12,14,18,24,30,36,40,56,60,72,96,120,160,240]);     # power of two or compound N x 2^k
     elif typ==1: n=rnd.choice(POW2[1:]+PFA); flags = 4 if (inv and rnd.random()<0.3) else 0
     elif typ==6: n=rnd.choice(POW2[1:])
     elif typ==9: n=rnd.choice(POW2[1:6])
