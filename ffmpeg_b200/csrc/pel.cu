@@ -892,6 +892,103 @@ chroma_kernel_k(long long n, const uint8_t *op, const uint8_t *hh, const uint8_t
     }
 }
 
+template <int CK, int MINB>
+__global__ void __launch_bounds__(32 * WARPS, MINB)
+chroma_kernel_p(long long n, const uint8_t *op, const uint8_t *hh, const uint8_t *xy, uint8_t *dst, const int64_t *dst_off,
+                const uint8_t *src, const int64_t *src_off, long long stride)
+{
+    const int lane = threadIdx.x & 31, grp = lane >> 3, sub = lane & (CH_LANES - 1);
+    // persistent warps: batch b = 4 * CK consecutive operations; the descriptors of the next batch are requested before this one is
+    // worked on, so only the window loads are left on the critical path of a batch
+    const long long nwarps = (long long)gridDim.x * WARPS, nbatch = (n + 4 * CK - 1) / (4 * CK);
+    long long b = (long long)blockIdx.x * WARPS + (threadIdx.x >> 5);
+    if (b >= nbatch) return;
+    int nmeta[CK];
+    long long nso[CK], ndof[CK];
+    auto fetch = [&](long long bb) {
+#pragma unroll
+        for (int j = 0; j < CK; j++) {
+            const long long gi = bb * (4 * CK) + 4 * j + grp;
+            const bool ok = bb < nbatch && gi < n;
+            const long long i = ok ? gi : n - 1;
+            nmeta[j] = (int)__ldg(op + i) | (int)__ldg(hh + i) << 8 | (int)__ldg(xy + i) << 16 | (ok ? 1 << 24 : 0);
+            nso[j] = __ldg(src_off + i); ndof[j] = __ldg(dst_off + i);
+        }
+    };
+    fetch(b);
+    for (; b < nbatch; b += nwarps) {
+    int o[CK], h[CK], pq[CK];
+    long long so[CK], dof[CK];
+    bool valid[CK];
+#pragma unroll
+    for (int j = 0; j < CK; j++) {
+        o[j] = nmeta[j] & 255; h[j] = (nmeta[j] >> 8) & 255; pq[j] = (nmeta[j] >> 16) & 255; valid[j] = (nmeta[j] >> 24) & 1;
+        so[j] = nso[j]; dof[j] = ndof[j];
+    }
+    fetch(b + nwarps);
+    int hm = 0;
+#pragma unroll
+    for (int j = 0; j < CK; j++) hm = max(hm, valid[j] ? h[j] : 0);
+    const int hmax = __reduce_max_sync(0xffffffffu, hm);
+    for (int y0 = 0; y0 < hmax; y0 += CH_LANES) {
+        const int y = y0 + sub;
+        ChRow t[CK], bl[CK];
+        uint2 pv[CK];
+        bool mine[CK], vec[CK];
+        // every load of the CK windows
+#pragma unroll
+        for (int j = 0; j < CK; j++) {
+            const int fx = pq[j] & 7, fy = (pq[j] >> 3) & 7, w = 8 >> ((o[j] >> 1) & 3);
+            const int nbytes = w + (fx != 0);
+            mine[j] = valid[j] && y < h[j];
+            const uint8_t *rowp = src + so[j] + (long long)y * stride;
+            t[j] = chroma_row(rowp, nbytes, mine[j]);
+            const bool last = sub == CH_LANES - 1 || y == h[j] - 1;      // the row below is not held by the next lane
+            bl[j] = chroma_row(rowp + stride, nbytes, mine[j] && last && fy != 0);
+            const uint8_t *d = dst + dof[j] + (long long)y * stride;
+            vec[j] = w == 8 && (reinterpret_cast<uintptr_t>(d) & 7) == 0;
+            pv[j] = make_uint2(0, 0);
+            if (mine[j] && vec[j] && (o[j] & 1)) pv[j] = *reinterpret_cast<const uint2 *>(d);
+        }
+#pragma unroll
+        for (int j = 0; j < CK; j++) {
+            const int fx = pq[j] & 7, fy = (pq[j] >> 3) & 7, avg = o[j] & 1, w = 8 >> ((o[j] >> 1) & 3);
+            const int kab = 4 * ((8 - fx) * (8 - fy)) | (4 * (fx * (8 - fy))) << 16;      // s16 pairs (4A, 4B) and (4C, 4D)
+            const int kcd = 4 * ((8 - fx) * fy) | (4 * (fx * fy)) << 16;
+            ChRow b;
+            b.r0 = __shfl_down_sync(0xffffffffu, t[j].r0, 1, CH_LANES); b.r1 = __shfl_down_sync(0xffffffffu, t[j].r1, 1, CH_LANES);
+            b.r2 = __shfl_down_sync(0xffffffffu, t[j].r2, 1, CH_LANES);
+            if (sub == CH_LANES - 1 || y == h[j] - 1) b = bl[j];
+            if (!mine[j]) continue;
+            const ChRow &tt = t[j];
+            const unsigned ta = __funnelshift_r(tt.r0, tt.r1, 8), tb = __funnelshift_r(tt.r1, tt.r2, 8);
+            const unsigned ba = __funnelshift_r(b.r0, b.r1, 8), bb = __funnelshift_r(b.r1, b.r2, 8);
+            int v[8];
+            v[0] = dp2a_lo_su(kcd, b.r0, dp2a_lo_su(kab, tt.r0, 128)); v[1] = dp2a_lo_su(kcd, ba, dp2a_lo_su(kab, ta, 128));
+            v[2] = dp2a_hi_su(kcd, b.r0, dp2a_hi_su(kab, tt.r0, 128)); v[3] = dp2a_hi_su(kcd, ba, dp2a_hi_su(kab, ta, 128));
+            v[4] = dp2a_lo_su(kcd, b.r1, dp2a_lo_su(kab, tt.r1, 128)); v[5] = dp2a_lo_su(kcd, bb, dp2a_lo_su(kab, tb, 128));
+            v[6] = dp2a_hi_su(kcd, b.r1, dp2a_hi_su(kab, tt.r1, 128)); v[7] = dp2a_hi_su(kcd, bb, dp2a_hi_su(kab, tb, 128));
+            unsigned w0 = __byte_perm(__byte_perm(v[0], v[1], 0x5151), __byte_perm(v[2], v[3], 0x5151), 0x5410);
+            unsigned w1 = __byte_perm(__byte_perm(v[4], v[5], 0x5151), __byte_perm(v[6], v[7], 0x5151), 0x5410);
+            uint8_t *d = dst + dof[j] + (long long)y * stride;
+            if (vec[j]) {
+                if (avg) { w0 = __vavgu4(pv[j].x, w0); w1 = __vavgu4(pv[j].y, w1); }
+                *reinterpret_cast<uint2 *>(d) = make_uint2(w0, w1);
+            } else if (w >= 4 && (reinterpret_cast<uintptr_t>(d) & 3) == 0) {
+                unsigned *d4 = reinterpret_cast<unsigned *>(d);
+                d4[0] = avg ? __vavgu4(d4[0], w0) : w0;
+                if (w == 8) d4[1] = avg ? __vavgu4(d4[1], w1) : w1;
+            } else {
+                for (int k = 0; k < w; k++) {
+                    const int px = (int)__byte_perm(k < 4 ? w0 : w1, 0, 0x4440 | (k & 3));
+                    d[k] = (uint8_t)(avg ? (d[k] + px + 1) >> 1 : px);
+                }
+            }
+        }
+    }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ h264chroma on TMA-staged windows
 // Same arithmetic as chroma_kernel.  Every operation's source window arrives as one cp.async.bulk.tensor.2d box of 32 bytes x
 // (h + 1) rows (h rows when y == 0: the row below the block is never touched then, as in the reference) whose origin is the block's
@@ -1221,12 +1318,25 @@ B200_API int b200_h264chroma_batch_device(B200Device *dev, int64_t n, const uint
                                                                             ~0ULL / (unsigned long long)stride);
     } else if (mode == 0) {
         static int var = -1;                                      // tuning knob: windows per 8-lane group / register budget
-        if (var < 0) { const char *e = getenv("B200_CHROMA_VAR"); var = e ? atoi(e) : 2; }     // measured: 0 -> 0.239, 1 -> 0.247, 2 -> 0.253, 3 -> 0.177 of the roofline
+        // measured (scripts/quick_bench.py chroma, fraction of the HBM roofline): one-shot warps 0 -> 0.239, 1 -> 0.247, 2 -> 0.253, 3 -> 0.177;
+        // persistent warps that request the next batch's descriptors before working on the current one: <4,4> (121 registers) 0.264,
+        // <2,8> (64 registers, no spills) 0.277 = the default; every persistent shape that spills (<4,8>, <4,6>, <3,8>, <2,10>, <2,12>) loses
+        if (var < 0) { const char *e = getenv("B200_CHROMA_VAR"); var = e ? atoi(e) : 7; }
         const int ck = var == 1 ? 2 : var == 3 ? 8 : 4;
         const int per_cta = WARPS * 4 * ck;
         const long long blocks = (n + per_cta - 1) / per_cta;
         if (blocks > 0x7fffffffLL) return B200_EINVAL;
-        if (var == 1)      chroma_kernel_k<2, 12><<<(unsigned)blocks, 32 * WARPS, 0, dev->stream>>>(n, op, h, xy, dst, dst_off, src, src_off, stride);
+        if (var == 6 || var == 7) {                                // persistent warps with the next batch's descriptors in flight
+            int sms = 148;
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev->ordinal);
+            const int ckp = var == 7 ? 2 : 4, minb = var == 7 ? 8 : 4;
+            const long long nbatch = (n + 4 * ckp - 1) / (4 * ckp), want = (nbatch + WARPS - 1) / WARPS;
+            const long long cap = (long long)sms * minb;
+            const unsigned g = (unsigned)(want < cap ? want : cap);
+            if (var == 6) chroma_kernel_p<4, 4><<<g, 32 * WARPS, 0, dev->stream>>>(n, op, h, xy, dst, dst_off, src, src_off, stride);
+            else          chroma_kernel_p<2, 8><<<g, 32 * WARPS, 0, dev->stream>>>(n, op, h, xy, dst, dst_off, src, src_off, stride);
+        }
+        else if (var == 1) chroma_kernel_k<2, 12><<<(unsigned)blocks, 32 * WARPS, 0, dev->stream>>>(n, op, h, xy, dst, dst_off, src, src_off, stride);
         else if (var == 2) chroma_kernel_k<4, 8><<<(unsigned)blocks, 32 * WARPS, 0, dev->stream>>>(n, op, h, xy, dst, dst_off, src, src_off, stride);
         else if (var == 3) chroma_kernel_k<8, 2><<<(unsigned)blocks, 32 * WARPS, 0, dev->stream>>>(n, op, h, xy, dst, dst_off, src, src_off, stride);
         else               chroma_kernel_k<4, 4><<<(unsigned)blocks, 32 * WARPS, 0, dev->stream>>>(n, op, h, xy, dst, dst_off, src, src_off, stride);

@@ -1,4 +1,9 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -q > gpurun_out/r02_final_tests_gpu.log 2>&1; tail -6 gpurun_out/r02_final_tests_gpu.log
-python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/r02_final_smoke.log 2>&1; tail -2 gpurun_out/r02_final_smoke.log
+for v in 7 8 9 10; do
+  echo "== var $v"
+  B200_CHROMA_VAR=$v python -m pytest tests -m gpu -x -q -k "chroma" 2>&1 | tail -1
+  B200_CHROMA_VAR=$v python scripts/quick_bench.py chroma 2>&1 | tail -1
+  B200_CHROMA_VAR=$v python scripts/quick_bench.py chroma 2>&1 | tail -1
+done > gpurun_out/chroma_vars.log 2>&1
+cat gpurun_out/chroma_vars.log
