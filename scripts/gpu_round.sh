@@ -1,9 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for v in 7 8 9 10; do
-  echo "== var $v"
-  B200_CHROMA_VAR=$v python -m pytest tests -m gpu -x -q -k "chroma" 2>&1 | tail -1
-  B200_CHROMA_VAR=$v python scripts/quick_bench.py chroma 2>&1 | tail -1
-  B200_CHROMA_VAR=$v python scripts/quick_bench.py chroma 2>&1 | tail -1
-done > gpurun_out/chroma_vars.log 2>&1
-cat gpurun_out/chroma_vars.log
+python -m pytest tests -m gpu -q > gpurun_out/r02_final_tests_gpu.log 2>&1; tail -5 gpurun_out/r02_final_tests_gpu.log
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/r02_final_smoke.log 2>&1; tail -1 gpurun_out/r02_final_smoke.log
+python bench.py > gpurun_out/r02_final_bench_n1.json 2> gpurun_out/bench.err; tail -c 300 gpurun_out/r02_final_bench_n1.json; tail -2 gpurun_out/bench.err
