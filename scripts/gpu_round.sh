@@ -1,5 +1,3 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -q > gpurun_out/r02_final_tests_gpu.log 2>&1; tail -5 gpurun_out/r02_final_tests_gpu.log
-python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/r02_final_smoke.log 2>&1; tail -1 gpurun_out/r02_final_smoke.log
-python bench.py > gpurun_out/r02_final_bench_n1.json 2> gpurun_out/bench.err; tail -c 300 gpurun_out/r02_final_bench_n1.json; tail -2 gpurun_out/bench.err
+python bench.py > gpurun_out/r02_final_bench_n1.json 2> gpurun_out/bench.err; tail -c 200 gpurun_out/r02_final_bench_n1.json; tail -3 gpurun_out/bench.err
