@@ -1,3 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python bench.py > gpurun_out/r02_final_bench_n1.json 2> gpurun_out/bench.err; tail -c 200 gpurun_out/r02_final_bench_n1.json; tail -3 gpurun_out/bench.err
+ncu --set full --clock-control none --import-source on -k regex:"chroma_kernel_p" -s 1 -c 1 -o gpurun_out/r02_chroma_p python scripts/profile_target.py chroma 32 > gpurun_out/pc.log 2>&1
+ls -la gpurun_out/r02_chroma_p.ncu-rep; tail -2 gpurun_out/pc.log
