@@ -15,6 +15,7 @@
 // HBM traffic per transform is the algorithmic 8N in + 8N out (FFT) or 4*len in + 4*len out (iMDCT).
 #include "common.h"
 #include "tx_pfa.h"
+#include "tx_double.h"
 #include "tx_dct.h"
 #include "tx_int32.h"
 #include "tx_r16.h"
@@ -434,6 +435,7 @@ struct B200TXContext {
     TxPfa *pfa = nullptr;            // compound 15 x M MDCT (tx_pfa.cu): everything below d is unused then
     TxDct *dct = nullptr;            // AV_TX_FLOAT_DCT (tx_dct.cu): stages around a child RDFT context
     TxI32 *i32 = nullptr;            // AV_TX_INT32_FFT / _MDCT (tx_int32.cu)
+    TxDbl *dbl = nullptr;            // AV_TX_DOUBLE_FFT / _MDCT (tx_double.cu)
     TxR16 *r16 = nullptr;            // 512 ... 4096-point FFT / inverse MDCT: register-resident passes (tx_r16.cu), else the kernels below
     int type = 0, inv = 0, len = 0;
     bool full = false;               // AV_TX_FULL_IMDCT: ff_tx_mdct_inv_full around the inverse MDCT (tx_template.c:1372-1413)
@@ -631,6 +633,7 @@ static int tx_launch_half(B200TXContext *c, cudaStream_t st, void *out, const vo
     if (c->pfa) return tx_pfa_launch(c->pfa, st, out, in, stride, count, out_step, in_step);
     if (c->dct) return tx_dct_launch(c->dct, st, out, in, count, out_step, in_step);
     if (c->i32) return tx_i32_launch(c->i32, st, out, in, stride, count, out_step, in_step);
+    if (c->dbl) return tx_dbl_launch(c->dbl, st, out, in, stride, count, out_step, in_step);
     if (c->r16 && (c->type == 0 || stride == 4) && tx_r16_accepts(c->r16, out, in, out_step, in_step))
         return tx_r16_launch(c->r16, st, out, in, out_step, in_step, count);
     // measured on B200 (scripts/quick_bench.py tx with B200_TX_TB / B200_TX_THREADS): 256 threads pay off from 1024 points per
@@ -666,6 +669,7 @@ static int tx_launch_half(B200TXContext *c, cudaStream_t st, void *out, const vo
 static void tx_host_fn(B200TXContext *c, void *out, void *in, ptrdiff_t stride)
 {
     if (c->i32) { tx_i32_host_fn(c->i32, out, in, stride); return; }
+    if (c->dbl) { tx_dbl_host_fn(c->dbl, out, in, stride); return; }
     auto fail = [](const char *what) { fprintf(stderr, "libb200dsp: av_tx_fn failed: %s (%s)\n", what, b200_last_error()); abort(); };
     B200Device *d = c->dev;
     if (cudaSetDevice(d->ordinal) != cudaSuccess) fail("cudaSetDevice");
@@ -705,13 +709,28 @@ B200_API int b200_tx_init_device(B200Device *dev, B200TXContext **ctx, b200_tx_f
     *ctx = nullptr;
     if (!dev) return B200_ENODEV;
     if (type != B200_TX_FLOAT_FFT && type != B200_TX_FLOAT_MDCT && type != B200_TX_FLOAT_RDFT && type != B200_TX_FLOAT_DCT &&
-        type != B200_TX_INT32_FFT && type != B200_TX_INT32_MDCT) return B200_ENOSYS;
+        type != B200_TX_INT32_FFT && type != B200_TX_INT32_MDCT && type != B200_TX_DOUBLE_FFT && type != B200_TX_DOUBLE_MDCT) return B200_ENOSYS;
     if (flags & ~(uint64_t)(B200_TX_INPLACE | B200_TX_UNALIGNED | B200_TX_FULL_IMDCT)) return B200_ENOSYS;    // REAL_TO_* not implemented
     // AV_TX_INPLACE: the complex FFT kernels stage a whole transform in shared memory before they store, so out == in is always
     // fine for them and gives the bits of the out-of-place call (as ff_tx_fft_inplace does, tx_template.c:780-812); other types refuse
     if ((flags & B200_TX_INPLACE) && !(type == B200_TX_FLOAT_FFT && len >= 2 && (!(len & (len - 1)) || tx_pfa_fft_length_ok(len)))) return B200_ENOSYS;
     const bool full = (flags & B200_TX_FULL_IMDCT) != 0;
     if (full && !(type == B200_TX_FLOAT_MDCT && inv)) return B200_ENOSYS;      // only the inverse MDCT has such a codelet (tx.c:762-771)
+    if (type == B200_TX_DOUBLE_FFT || type == B200_TX_DOUBLE_MDCT) { // double precision (tx_double.cu); the scale of these types is a const double *
+        if (flags & ~(uint64_t)B200_TX_UNALIGNED) return B200_ENOSYS;
+        if (!tx_dbl_length_ok(type, len)) return B200_ENOSYS;
+        double scdd = 1.0;
+        if (type == B200_TX_DOUBLE_MDCT && scale) scdd = *(const double *)scale;
+        B200TXContext *cd2 = new (std::nothrow) B200TXContext();
+        if (!cd2) return B200_ENOMEM;
+        cd2->dev = dev; cd2->type = type; cd2->inv = !!inv; cd2->len = len;
+        if (cudaSetDevice(dev->ordinal) != cudaSuccess) { delete cd2; return B200_EEXTERNAL; }
+        cd2->dbl = tx_dbl_create(dev, type, cd2->inv, len, scdd);
+        if (!cd2->dbl) { delete cd2; return B200_EEXTERNAL; }
+        *ctx = cd2;
+        if (tx) *tx = tx_host_fn;
+        return 0;
+    }
     if (type == B200_TX_INT32_FFT || type == B200_TX_INT32_MDCT) {   // 32-bit fixed point (tx_int32.cu)
         if (!tx_i32_length_ok(type, len)) return B200_ENOSYS;
         float sci = 1.0f;
@@ -797,6 +816,7 @@ B200_API void b200_tx_uninit(B200TXContext **ctx)
     tx_pfa_free(c->pfa);
     tx_dct_free(c->dct);
     tx_i32_free(c->i32);
+    tx_dbl_free(c->dbl);
     tx_r16_destroy(c->r16);
     delete c;
     *ctx = nullptr;
@@ -809,7 +829,7 @@ B200_API int b200_tx_batch_device(B200TXContext *c, void *out, const void *in, p
     if ((c->type == 1 || c->type == B200_TX_INT32_MDCT) && (stride & 3)) return B200_EINVAL;
     if (c->full && stride != 4) return B200_EINVAL;                  // the reference mirrors with the input stride: only sizeof(float) is meaningful
     B200_CUDA_OK(cudaSetDevice(c->dev->ordinal));
-    return tx_launch(c, c->dev->stream, out, in, (c->type == 1 || c->type == B200_TX_INT32_MDCT || (c->type == 0 && c->pfa)) ? stride : 8, count, out_step, in_step);
+    return tx_launch(c, c->dev->stream, out, in, (c->type == 1 || c->type == B200_TX_INT32_MDCT || c->type == B200_TX_DOUBLE_MDCT || (c->type == 0 && c->pfa)) ? stride : 8, count, out_step, in_step);
 }
 
 // HOST buffers (pinned for real overlap): the batch is cut into chunks that rotate over the device's three pipeline streams, each chunk
@@ -823,7 +843,7 @@ B200_API int b200_tx_batch_host(B200TXContext *c, void *out, const void *in, ptr
     if (count == 0) return 0;
     B200Device *d = c->dev;
     B200_CUDA_OK(cudaSetDevice(d->ordinal));
-    const ptrdiff_t st_arg = (c->type == 1 || c->type == B200_TX_INT32_MDCT || (c->type == 0 && c->pfa)) ? stride : 8;
+    const ptrdiff_t st_arg = (c->type == 1 || c->type == B200_TX_INT32_MDCT || c->type == B200_TX_DOUBLE_MDCT || (c->type == 0 && c->pfa)) ? stride : 8;
     const size_t istep = ((size_t)in_step + 15) & ~(size_t)15, ostep = ((size_t)out_step + 15) & ~(size_t)15;
     if (istep != (size_t)in_step || ostep != (size_t)out_step) { b200_set_error("b200_tx_batch_host: steps must be multiples of 16 bytes"); return B200_EINVAL; }
     int64_t chunk = ((int64_t)48 << 20) / (int64_t)(istep + ostep);

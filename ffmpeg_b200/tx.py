@@ -1,10 +1,11 @@
 """Host-side mirror of libavutil/tx's public interface (av_tx_init / av_tx_fn / av_tx_uninit, libavutil/tx.h:151,202-208)
-for AV_TX_FLOAT_FFT, AV_TX_FLOAT_MDCT and AV_TX_FLOAT_RDFT, plus the batched device entry point."""
+for the float, int32 and double transform types the library builds, plus the batched device entry points."""
 import ctypes as C
 from ._lib import lib, check, vp, TX_FN
 
 AV_TX_FLOAT_FFT, AV_TX_FLOAT_MDCT, AV_TX_FLOAT_RDFT, AV_TX_FLOAT_DCT = 0, 1, 6, 9
 AV_TX_INT32_FFT, AV_TX_INT32_MDCT = 4, 5
+AV_TX_DOUBLE_FFT, AV_TX_DOUBLE_MDCT = 2, 3
 AV_TX_INPLACE, AV_TX_UNALIGNED, AV_TX_FULL_IMDCT = 1, 2, 4          # flags (libavutil/tx.h:155-180)
 
 
@@ -20,7 +21,8 @@ class AVTXContext:
     def __init__(self, type, inv, len, scale=None, flags=0, device=None):
         self._h = vp()
         self._fn = TX_FN()
-        sc = C.byref(C.c_float(scale)) if scale is not None else None
+        # the scale of the double types is a const double * (libavutil/tx.h:44-58)
+        sc = C.byref((C.c_double if type in (AV_TX_DOUBLE_FFT, AV_TX_DOUBLE_MDCT) else C.c_float)(scale)) if scale is not None else None
         if device is None:
             ret = lib().b200_tx_init(C.byref(self._h), C.byref(self._fn), type, inv, len, sc, flags)
         else:

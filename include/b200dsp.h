@@ -569,6 +569,8 @@ int  b200_emulated_edge_mc_hbd_batch_device(B200Device *dev, int64_t n, uint8_t 
                                    * (tx_template.c:1655-1724) the host av_tx_fn rewrites its input on the inverse; the
                                    * batched device entry point leaves the input untouched.  AV_TX_REAL_TO_REAL /
                                    * AV_TX_REAL_TO_IMAGINARY are not implemented. */
+#define B200_TX_DOUBLE_FFT  2     /* AV_TX_DOUBLE_FFT: AVComplexDouble in / out, power-of-two lengths up to 8192 (libavutil/tx_double.c) */
+#define B200_TX_DOUBLE_MDCT 3     /* AV_TX_DOUBLE_MDCT: doubles, scale as const double *, power-of-two lengths */
 #define B200_TX_INT32_FFT   4     /* AV_TX_INT32_FFT: AVComplexInt32 in / out, power-of-two lengths (libavutil/tx_int32.c) */
 #define B200_TX_INT32_MDCT  5     /* AV_TX_INT32_MDCT: int32 samples, scale as const float *, power-of-two lengths (fixed-point AAC / AC-3) */
 #define B200_TX_FLOAT_DCT   9     /* AV_TX_FLOAT_DCT: forward = DCT-II of len points, inverse = DCT-III of 2 * len points (the reference's

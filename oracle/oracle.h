@@ -179,6 +179,11 @@ OrcTx *orc_tx_open(int type /*0 FFT, 1 MDCT, 6 RDFT (r2c forward, c2r inverse)*/
 void   orc_tx_close(OrcTx *t);
 void   orc_tx_run(OrcTx *t, void *out, void *in, ptrdiff_t stride, int count, ptrdiff_t out_step, ptrdiff_t in_step);
 /* the 32-bit fixed-point transforms (txi_oracle.c): type 4 AV_TX_INT32_FFT, 5 AV_TX_INT32_MDCT, power-of-two lengths */
+typedef struct OrcTxD OrcTxD;
+/* AV_TX_DOUBLE_FFT (2) / AV_TX_DOUBLE_MDCT (3), power-of-two lengths */
+OrcTxD *orc_txd_open(int type, int inv, int len, double scale, unsigned flags);
+void    orc_txd_close(OrcTxD *t);
+void    orc_txd_run(OrcTxD *t, void *out, void *in, ptrdiff_t stride, int count, ptrdiff_t out_step, ptrdiff_t in_step);
 typedef struct OrcTxI OrcTxI;
 OrcTxI *orc_txi_open(int type, int inv, int len, float scale, unsigned flags);
 void    orc_txi_close(OrcTxI *t);

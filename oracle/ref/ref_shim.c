@@ -544,6 +544,14 @@ API void *ffref_tx_open(int type, int inv, int len, float scale, unsigned flags)
     if (av_tx_init(&t->ctx, &t->fn, (enum AVTXType)type, inv, len, &scale, flags) < 0) { free(t); return NULL; }
     return t;
 }
+/* the double types (AV_TX_DOUBLE_FFT = 2, AV_TX_DOUBLE_MDCT = 3, ...): av_tx_init reads the scale as a const double * */
+API void *ffref_txd_open(int type, int inv, int len, double scale, unsigned flags)
+{
+    RefTx *t = calloc(1, sizeof(*t));
+    if (!t) return NULL;
+    if (av_tx_init(&t->ctx, &t->fn, (enum AVTXType)type, inv, len, &scale, flags) < 0) { free(t); return NULL; }
+    return t;
+}
 API void ffref_tx_close(void *h) { RefTx *t = h; if (t) { av_tx_uninit(&t->ctx); free(t); } }
 
 /* count transforms; in/out advance by in_step/out_step BYTES per transform; stride is the av_tx_fn stride arg */

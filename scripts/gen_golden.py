@@ -258,6 +258,24 @@ def gen_h264lf_hbd():
     open(os.path.join(OUT, "h264lf_hbd_hashes.txt"), "w").write("\n".join(lines) + "\n")
 
 
+def gen_tx_double():
+    """AV_TX_DOUBLE_FFT / AV_TX_DOUBLE_MDCT, power-of-two lengths: the compiled reference's outputs (sha256 of the float64 bits)"""
+    R = cl.ref()
+    R.ffref_txd_open.restype, R.ffref_txd_open.argtypes = C.c_void_p, [C.c_int, C.c_int, C.c_int, C.c_double, C.c_uint]
+    R.ffref_tx_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_ssize_t, C.c_int, C.c_ssize_t, C.c_ssize_t]
+    lines = []
+    for (typ, n, inv, sc) in cl.txd_cases():
+        x = cl.txd_input(typ, n, inv)
+        oute = 2 * n if typ == 2 else n
+        out = np.zeros((x.shape[0], oute))
+        h = R.ffref_txd_open(typ, inv, n, sc, 0)
+        xin = x.copy()
+        R.ffref_tx_run(h, out.ctypes.data, xin.ctypes.data, 16 if typ == 2 else 8, x.shape[0], out.strides[0], xin.strides[0])
+        R.ffref_tx_close(h)
+        lines.append(f"{typ} {n} {inv} {sc!r} {sha(out)}")
+    open(os.path.join(OUT, "tx_double_hashes.txt"), "w").write("\n".join(lines) + "\n")
+
+
 RGB2RGB_FLAGS = (4, 4 | 0x80000, 4 | 0x80000 | 0x40000, 16)
 
 
@@ -724,6 +742,7 @@ if __name__ == "__main__":
     gen_h264_weight_hbd()
     gen_h264_idct_hbd()
     gen_h264lf_hbd()
+    gen_tx_double()
     gen_sws_rgb2rgb()
     gen_tx_full_imdct()
     gen_tx_dct()

@@ -407,6 +407,22 @@ def h264_idct_hbd_cases(depth, kind, n=24):
     return out
 
 
+def txd_cases():
+    """(type, len, inv, scale) of the double-precision tx fixture: AV_TX_DOUBLE_FFT = 2, AV_TX_DOUBLE_MDCT = 3"""
+    out = []
+    for n in (2, 4, 8, 16, 32, 64, 256, 1024, 4096):
+        for inv in (0, 1):
+            out.append((2, n, inv, 1.0))
+            if n >= 4:
+                out += [(3, n, inv, 1.0 / n), (3, n, inv, -1.0)]
+    return out
+
+
+def txd_input(typ, n, inv):
+    rng = np.random.default_rng(8000 + 10 * n + 2 * typ + inv)
+    return rng.random((3, 2 * n if typ == 2 else (n if inv else 2 * n))) * 2 - 1
+
+
 def idct_hbd_blocks(seed, depth, n):
     """n coefficient blocks: dense small, full int16 range, sparse, DC only, DC-only rows, decoder-like range"""
     rng = np.random.default_rng(seed)

@@ -25,6 +25,8 @@ static inline int2 make_int2(int a, int b) { int2 r = { a, b }; return r; }
 static inline uint4 make_uint4(unsigned a, unsigned b, unsigned c, unsigned d) { uint4 r = { a, b, c, d }; return r; }
 struct float2 { float x, y; };
 static inline float2 make_float2(float a, float b) { float2 r = { a, b }; return r; }
+struct double2 { double x, y; };
+static inline double2 make_double2(double a, double b) { double2 r = { a, b }; return r; }
 static thread_local dim3 threadIdx, blockIdx, blockDim, gridDim;
 
 #define __global__

@@ -50,7 +50,8 @@ def vp(a):
 
 WARP_KERNELS = {"mpv_unquant_kernel"}                   # kernels that use a warp collective: one OS thread per lane
 BLOCK_KERNELS = {"sws_mma_plane_kernel", "sws_mma_rgb_kernel", "tx_fft_kernel", "tx_mdct_inv_kernel", "tx_mdct_fwd_kernel", "tx_rdft_r2c_kernel", "tx_rdft_c2r_kernel",
-                 "sws_fused_plane_kernel", "sws_fused_rgb_kernel", "tx_mdct_pfa_inv_kernel", "tx_mdct_pfa_fwd_kernel", "tx_fft_pfa_kernel", "tx_i32_kernel"}    # __syncthreads + dynamic shared memory
+                 "sws_fused_plane_kernel", "sws_fused_rgb_kernel", "tx_mdct_pfa_inv_kernel", "tx_mdct_pfa_fwd_kernel", "tx_fft_pfa_kernel", "tx_i32_kernel",
+                 "tx_dbl_fft_kernel", "tx_dbl_mdct_inv_kernel", "tx_dbl_mdct_fwd_kernel"}    # __syncthreads + dynamic shared memory
 
 
 def rewrite_launches(txt):
@@ -813,6 +814,8 @@ def emutx():
     open(os.path.join(gen, "host_tx_dct.cpp"), "w").write(rewrite_launches(open(os.path.join(cs, "tx_dct.cu")).read()))
     open(os.path.join(gen, "host_tx_int32.cpp"), "w").write(rewrite_launches(open(os.path.join(cs, "tx_int32.cu")).read()).replace(
         "extern __shared__ int2 i32_z[];", "int2 *i32_z = (int2 *)emu_smem;"))
+    open(os.path.join(gen, "host_tx_double.cpp"), "w").write(rewrite_launches(open(os.path.join(cs, "tx_double.cu")).read()).replace(
+        "extern __shared__ double2 dbl_z[];", "double2 *dbl_z = (double2 *)emu_smem;"))
     # tx_r16.cu (bulk async copies + mbarriers in inline PTX) cannot run here: the emulated library keeps tx.cu's level-by-level kernels,
     # which stay the fallback of the product; the register-resident schedule is checked by tests/test_tx_r16_plan.py and on the GPU
     open(os.path.join(gen, "host_tx_r16_stub.cpp"), "w").write(
@@ -823,7 +826,7 @@ def emutx():
     cxx = "/opt/gcc/bin/g++" if os.path.exists("/opt/gcc/bin/g++") else "g++"
     r = subprocess.run([cxx, "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread", "-ffp-contract=off", "-w", "-I" + os.path.join(EMU, "fake"), "-I" + cs,
                         "-I" + os.path.join(ROOT, "include"), "-I" + EMU, os.path.join(gen, "host_tx.cpp"), os.path.join(gen, "host_tx_pfa.cpp"),
-                        os.path.join(gen, "host_tx_dct.cpp"), os.path.join(gen, "host_tx_int32.cpp"), os.path.join(gen, "host_tx_r16_stub.cpp"),
+                        os.path.join(gen, "host_tx_dct.cpp"), os.path.join(gen, "host_tx_int32.cpp"), os.path.join(gen, "host_tx_double.cpp"), os.path.join(gen, "host_tx_r16_stub.cpp"),
                         os.path.join(EMU, "fake_device.cpp"), "-o", so],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
@@ -870,6 +873,63 @@ def _emu_tx(L, typ, inv, n, scale, x, out_floats, host_fn=False, flags=0):
         assert L.b200_tx_batch_device(ctx, out.ctypes.data, xin.ctypes.data, st, x.shape[0], out.strides[0], xin.strides[0]) == 0
     L.b200_tx_uninit(C.byref(ctx))
     return out
+
+
+def _orc_txd(typ, inv, n, scale, x, out_doubles):
+    O = cl.oracle()
+    O.orc_txd_open.restype = C.c_void_p
+    O.orc_txd_open.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_uint]
+    O.orc_txd_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_ssize_t, C.c_int, C.c_ssize_t, C.c_ssize_t]
+    O.orc_txd_close.argtypes = [C.c_void_p]
+    h = O.orc_txd_open(typ, inv, n, scale, 0)
+    assert h
+    out, xin = np.zeros((x.shape[0], out_doubles), np.float64), x.copy()
+    O.orc_txd_run(h, out.ctypes.data, xin.ctypes.data, 16 if typ == 2 else 8, x.shape[0], out.strides[0], xin.strides[0])
+    O.orc_txd_close(h)
+    return out
+
+
+def test_tx_double_on_emulated_device(emutx):
+    """AV_TX_DOUBLE_FFT / AV_TX_DOUBLE_MDCT (tx_double.cu) through b200_tx_init_device: batch and av_tx_fn entries, strided MDCT samples, against the
+    double-precision checker (itself bit-identical to the compiled reference)"""
+    from ffmpeg_b200._lib import TX_FN
+    L = emutx
+    rng = np.random.default_rng(43)
+    for typ in (2, 3):
+        for n in (2, 4, 8, 16, 64, 256, 1024):
+            if typ == 3 and n < 4:
+                continue
+            for inv in (0, 1):
+                for sc in ((1.0,) if typ == 2 else (1.0 / n, -1.0)):
+                    ine = 2 * n if typ == 2 else (n if inv else 2 * n)
+                    oute = 2 * n if typ == 2 else n
+                    x = rng.random((5 if n <= 64 else 2, ine)) * 2 - 1
+                    exp = _orc_txd(typ, inv, n, sc, x, oute)
+                    ctx, fn = C.c_void_p(), TX_FN()
+                    scc = C.c_double(sc)
+                    assert L.b200_tx_init_device(L.dev, C.byref(ctx), C.byref(fn), typ, inv, n, C.byref(scc), 0) == 0, (typ, n, inv)
+                    out, xin = np.zeros((x.shape[0], oute)), x.copy()
+                    st = 16 if typ == 2 else 8
+                    assert L.b200_tx_batch_device(ctx, out.ctypes.data, xin.ctypes.data, st, x.shape[0], out.strides[0], xin.strides[0]) == 0
+                    assert np.array_equal(out.view(np.uint64), exp.view(np.uint64)), ("double batch", typ, n, inv, sc)
+                    o1, x0 = np.zeros(oute), x[0].copy()
+                    fn(ctx, o1.ctypes.data, x0.ctypes.data, st)
+                    assert np.array_equal(o1.view(np.uint64), exp[0].view(np.uint64)), ("double av_tx_fn", typ, n, inv, sc)
+                    if typ == 3 and n == 64:                       # strided samples: input of the inverse, output of the forward transform
+                        if inv:
+                            xs = np.zeros((x.shape[0], 3 * ine)); xs[:, ::3] = x
+                            o2 = np.zeros((x.shape[0], oute))
+                            assert L.b200_tx_batch_device(ctx, o2.ctypes.data, xs.ctypes.data, 24, x.shape[0], o2.strides[0], xs.strides[0]) == 0
+                            assert np.array_equal(o2.view(np.uint64), exp.view(np.uint64)), "strided in"
+                        else:
+                            o2 = np.zeros((x.shape[0], 3 * oute))
+                            assert L.b200_tx_batch_device(ctx, o2.ctypes.data, xin.ctypes.data, 24, x.shape[0], o2.strides[0], xin.strides[0]) == 0
+                            assert np.array_equal(o2[:, ::3].view(np.uint64), exp.view(np.uint64)) and not o2[:, 1::3].any(), "strided out"
+                    L.b200_tx_uninit(C.byref(ctx))
+    ctx, fn, scc = C.c_void_p(), TX_FN(), C.c_double(1.0)
+    assert L.b200_tx_init_device(L.dev, C.byref(ctx), C.byref(fn), 2, 0, 96, C.byref(scc), 0) == -38          # compound double lengths: not built
+    assert L.b200_tx_init_device(L.dev, C.byref(ctx), C.byref(fn), 3, 1, 64, C.byref(scc), 4) == -38          # AV_TX_FULL_IMDCT: float only here
+    assert L.b200_tx_init_device(L.dev, C.byref(ctx), C.byref(fn), 7, 0, 64, C.byref(scc), 0) == -38          # AV_TX_DOUBLE_RDFT: not built
 
 
 def test_tx_whole_path_on_emulated_device(emutx):
@@ -955,7 +1015,7 @@ def test_tx_whole_path_on_emulated_device(emutx):
                 assert np.array_equal(_emu_tx(emutx, 5, 0, n, sc, xs, n), e), ("int32 mdct", n, sc)
                 assert np.array_equal(_emu_tx(emutx, 5, 0, n, sc, xs[:2], n, host_fn=True), e[:2]), ("int32 mdct av_tx_fn", n, sc)
     x = np.zeros((1, 1920), np.float32)
-    assert _emu_tx(emutx, 4, 0, 96, 1.0, x, 192) == -38 and _emu_tx(emutx, 5, 1, 960, 1.0, x, 960) == -38 and _emu_tx(emutx, 1, 1, 84, 1.0, x, 84) == -38 and _emu_tx(emutx, 2, 0, 64, 1.0, x, 128) == -38
+    assert _emu_tx(emutx, 4, 0, 96, 1.0, x, 192) == -38 and _emu_tx(emutx, 5, 1, 960, 1.0, x, 960) == -38 and _emu_tx(emutx, 1, 1, 84, 1.0, x, 84) == -38 and _emu_tx(emutx, 7, 0, 64, 1.0, x, 128) == -38
     assert _emu_tx(emutx, 9, 0, 96, 1.0, x, 96) == -38 and _emu_tx(emutx, 9, 0, 2, 1.0, x, 2) == -38 and _emu_tx(emutx, 9, 1, 1, 1.0, x, 2) == -38
     assert _emu_tx(emutx, 0, 0, 90, 1.0, x, 180) == -38 and _emu_tx(emutx, 6, 0, 96, 1.0, x, 98) == -38
 

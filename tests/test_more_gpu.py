@@ -628,4 +628,4 @@ def test_tx_linearity_1m_batch(device):
     with pytest.raises(fb.B200Error):
         tx.av_tx_init(tx.AV_TX_FLOAT_FFT, 0, 90, device=device)             # 45 x 2: nested compound tree, not implemented
     with pytest.raises(fb.B200Error):
-        tx.av_tx_init(2, 0, 1024, device=device)                            # other transform types (AV_TX_DOUBLE_FFT)
+        tx.av_tx_init(7, 0, 1024, device=device)                            # other transform types (AV_TX_DOUBLE_RDFT)

@@ -556,6 +556,39 @@ def test_h264_loop_filter_hbd_oracle_golden_and_ref():
             assert np.array_equal(cl.orc_h264lf_hbd(depth, *case), cl.ref_h264lf_hbd(depth, *case)), depth
 
 
+def txd_hashes():
+    out = {}
+    for line in open(os.path.join(G, "tx_double_hashes.txt")):
+        typ, n, inv, sc, h = line.split()
+        out[(int(typ), int(n), int(inv), float(sc))] = h
+    return out
+
+
+def test_tx_double_oracle_golden_and_ref():
+    """AV_TX_DOUBLE_FFT / AV_TX_DOUBLE_MDCT: the double-precision restatement against the hashes of the compiled reference's outputs (and live)"""
+    import hashlib
+    O = cl.oracle()
+    O.orc_txd_open.restype, O.orc_txd_open.argtypes = C.c_void_p, [C.c_int, C.c_int, C.c_int, C.c_double, C.c_uint]
+    O.orc_txd_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_ssize_t, C.c_int, C.c_ssize_t, C.c_ssize_t]
+    O.orc_txd_close.argtypes = [C.c_void_p]
+    hs = txd_hashes()
+    assert len(hs) == len(cl.txd_cases())
+    for (typ, n, inv, sc) in cl.txd_cases():
+        x = cl.txd_input(typ, n, inv)
+        out = np.zeros((x.shape[0], 2 * n if typ == 2 else n))
+        h = O.orc_txd_open(typ, inv, n, sc, 0)
+        assert h
+        xin = x.copy()
+        O.orc_txd_run(h, out.ctypes.data, xin.ctypes.data, 16 if typ == 2 else 8, x.shape[0], out.strides[0], xin.strides[0])
+        O.orc_txd_close(h)
+        assert hashlib.sha256(out.tobytes()).hexdigest() == hs[(typ, n, inv, sc)], (typ, n, inv, sc)
+        if typ == 2 and n >= 16:                                    # it is a DFT
+            z = x[0, 0::2] + 1j * x[0, 1::2]
+            ref = np.fft.ifft(z) * n if inv else np.fft.fft(z)
+            assert np.abs(out[0, 0::2] - ref.real).max() < 1e-9 * n and np.abs(out[0, 1::2] - ref.imag).max() < 1e-9 * n
+    assert not O.orc_txd_open(2, 0, 96, 1.0, 0) and not O.orc_txd_open(3, 1, 2, 1.0, 0)
+
+
 PFA_FFT_SIZES = (6, 12, 96, 10, 160, 14, 224, 18, 288, 30, 120, 960, 1920)
 
 

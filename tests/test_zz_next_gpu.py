@@ -732,7 +732,8 @@ def test_prores_idct_put(device):
             blocks, qmat = cl.prores_case(90 + seed, bits, 60)
             px = np.zeros((8, 60 * 8), np.uint16)
             for i in range(60):
-                c.idct_put(px.ctypes.data + 16 * i, px.strides[0], blocks[i].copy().ctypes.data, qmat.ctypes.data)
+                blk = blocks[i].copy()                                  # kept alive across the call
+                c.idct_put(px.ctypes.data + 16 * i, px.strides[0], blk.ctypes.data, qmat.ctypes.data)
             assert np.array_equal(px, g[f"b{bits}_s{seed}"]), (bits, seed)
         n = 20000
         blocks, qmat = cl.prores_case(700 + bits, bits, n)
@@ -767,7 +768,8 @@ def test_h264_loop_filter(device):
     for e in range(512):
         c, m = member[int(kinds[e])]
         args = (d.ctypes.data + int(off[e]), d.strides[0], int(alpha[e]), int(beta[e]))
-        getattr(c, m)(*args, tc0[e].copy().ctypes.data) if "intra" not in m else getattr(c, m)(*args)
+        tcc = tc0[e].copy()                                             # kept alive across the call
+        getattr(c, m)(*args, tcc.ctypes.data) if "intra" not in m else getattr(c, m)(*args)
     assert np.array_equal(d[:64], g["head_0"])
     assert hashlib.sha256(d.tobytes()).digest() == g["sha_0"].tobytes()
     for seed in (0, 1, 2):
@@ -1187,3 +1189,47 @@ def test_sws_src_dst_filters(device):
     for i, case in enumerate(cases):
         got, exp = run_filter_case(run_rgb, run_planar, i, case), run_filter_case(cl.orc_sws, cl.orc_sws_planar, i, case)
         assert all(np.array_equal(p, q) for p, q in zip(got, exp)), (i, case[:6])
+
+
+# ---------------------------------------------------------------------------------------------- tx: double precision
+def test_tx_double(device):
+    """AV_TX_DOUBLE_FFT / AV_TX_DOUBLE_MDCT, power-of-two lengths: av_tx_fn on host buffers and the batched device entry against the hashes of
+    the compiled reference's outputs; a larger batch against the checker"""
+    import hashlib
+    import torch
+    import ffmpeg_b200 as fb
+    from ffmpeg_b200 import tx
+    from test_oracle_more import txd_hashes
+    from test_cuda_emu import _orc_txd
+    hs = txd_hashes()
+    for (typ, n, inv, sc) in cl.txd_cases():
+        x = cl.txd_input(typ, n, inv)
+        oute = 2 * n if typ == 2 else n
+        st = 16 if typ == 2 else 8
+        c = tx.av_tx_init(typ, inv, n, scale=sc, device=device)
+        out = np.zeros((x.shape[0], oute))
+        for r in range(x.shape[0]):
+            xr = x[r].copy()
+            c.fn(out[r], xr, st)
+        assert hashlib.sha256(out.tobytes()).hexdigest() == hs[(typ, n, inv, sc)], ("av_tx_fn", typ, n, inv, sc)
+        with on_stream(device):
+            di, do = torch.from_numpy(x).cuda(), torch.zeros((x.shape[0], oute), dtype=torch.float64, device="cuda")
+            c.batch_device(do, di, st, x.shape[0], do.stride(0) * 8, di.stride(0) * 8)
+            device.sync()
+            assert hashlib.sha256(do.cpu().numpy().tobytes()).hexdigest() == hs[(typ, n, inv, sc)], ("batch", typ, n, inv, sc)
+        c.uninit()
+    rng = np.random.default_rng(47)
+    for (typ, n, inv, sc) in ((2, 1024, 0, 1.0), (3, 2048, 1, 1.0 / 2048), (3, 512, 0, 1.0), (2, 8192, 1, 1.0)):
+        cnt = 500 if n < 8192 else 40
+        x = rng.random((cnt, 2 * n if typ == 2 else (n if inv else 2 * n))) * 2 - 1
+        oute = 2 * n if typ == 2 else n
+        c = tx.av_tx_init(typ, inv, n, scale=sc, device=device)
+        with on_stream(device):
+            di, do = torch.from_numpy(x).cuda(), torch.zeros((cnt, oute), dtype=torch.float64, device="cuda")
+            c.batch_device(do, di, 16 if typ == 2 else 8, cnt, oute * 8, x.shape[1] * 8)
+            device.sync()
+            got = do.cpu().numpy()
+        assert np.array_equal(got.view(np.uint64), _orc_txd(typ, inv, n, sc, x, oute).view(np.uint64)), (typ, n, inv)
+        c.uninit()
+    with pytest.raises(fb.B200Error):
+        tx.av_tx_init(tx.AV_TX_DOUBLE_FFT, 0, 96, device=device)
