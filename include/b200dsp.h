@@ -558,9 +558,8 @@ int  b200_emulated_edge_mc_hbd_batch_device(B200Device *dev, int64_t n, uint8_t 
                                             ptrdiff_t src_linesize, const int32_t *geom, int w, int h);
 
 /* ------------------------------------------------------------------------------------------------ libavutil/tx
- * Replaces av_tx_init / av_tx_uninit / av_tx_fn (libavutil/tx.h:151,202-208) for AV_TX_FLOAT_FFT, AV_TX_FLOAT_MDCT and
- * AV_TX_FLOAT_RDFT,
- * power-of-two lengths, with the float operation order of the reference's C codelets (bit-identical results).
+ * Replaces av_tx_init / av_tx_uninit / av_tx_fn (libavutil/tx.h:151,202-208) for the types below, with the floating-point operation order
+ * of the reference's C codelets (bit-identical results).
  * Inside FFmpeg the plug point is a codelet list with prio FF_TX_PRIO_MAX (libavutil/tx_priv.h:168, tx.c:340-351). */
 #define B200_TX_FLOAT_FFT   0     /* AV_TX_FLOAT_FFT  */
 #define B200_TX_FLOAT_MDCT  1     /* AV_TX_FLOAT_MDCT */

@@ -1,4 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-ncu --set full --clock-control none --import-source on -k regex:"chroma_kernel_p" -s 1 -c 1 -o gpurun_out/r02_chroma_p python scripts/profile_target.py chroma 32 > gpurun_out/pc.log 2>&1
-ls -la gpurun_out/r02_chroma_p.ncu-rep; tail -2 gpurun_out/pc.log
+python -m pytest tests -m gpu -q > gpurun_out/r02_final_tests_gpu.log 2>&1; tail -6 gpurun_out/r02_final_tests_gpu.log
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/r02_final_smoke.log 2>&1; tail -1 gpurun_out/r02_final_smoke.log
