@@ -2381,7 +2381,10 @@ static int sws_scale_planar_host(B200SwsContext *c, const uint8_t *const srcSlic
         // the whole picture is converted again — an output line only depends on source lines that have arrived once ff_swscale's
         // "enough lines" test (swscale.c:463-465) passes for it — and the lines that became complete are copied back: the return
         // value and the lines written per call are the reference's.
-        if (!c->slice_buf) B200_CUDA_OK(cudaMalloc(&c->slice_buf, total));
+        if (!c->slice_buf) {                                // cleared once: the whole-picture passes below read lines that have not arrived yet
+            B200_CUDA_OK(cudaMalloc(&c->slice_buf, total));
+            B200_CUDA_OK(cudaMemsetAsync(c->slice_buf, 0, total, d->stream));
+        }
         uint8_t *sb = (uint8_t *)c->slice_buf;
         if (srcSliceY == 0) { c->next_dst_y = 0; c->slice_open = true; }
         const int chrY = srcSliceY >> 1, chrH = -((-srcSliceH) >> 1);
@@ -2640,9 +2643,12 @@ B200_API int b200_sws_scale(B200SwsContext *c, const uint8_t *const srcSlice[], 
             c->slice_open = srcSliceY + srcSliceH < p.srcH;
             return srcSliceH;
         }
-        if (!c->slice_buf) B200_CUDA_OK(cudaMalloc(&c->slice_buf, sPitch * p.srcH + dPitch * p.dstH));
-        uint8_t *sb = (uint8_t *)c->slice_buf, *db = sb + sPitch * p.srcH;
         cudaStream_t st2 = dv->stream;
+        if (!c->slice_buf) {
+            B200_CUDA_OK(cudaMalloc(&c->slice_buf, sPitch * p.srcH + dPitch * p.dstH));
+            B200_CUDA_OK(cudaMemsetAsync(c->slice_buf, 0, sPitch * p.srcH + dPitch * p.dstH, st2));
+        }
+        uint8_t *sb = (uint8_t *)c->slice_buf, *db = sb + sPitch * p.srcH;
         if (srcSliceY == 0) { c->next_dst_y = 0; c->slice_open = true; }
         B200_CUDA_OK(b200_h2d_rows(sb + (size_t)srcSliceY * sPitch, sPitch, srcSlice[0], srcStride[0], (size_t)p.srcW * p.src_rgb, srcSliceH, st2));
         const int y0 = c->next_dst_y, avail = srcSliceY + srcSliceH;
