@@ -192,6 +192,7 @@ PROTOTYPES = {
     "b200_me_cmp_init": (C.c_int, [C.POINTER(MECmpContext), C.c_int]),
     "b200_mpv_unquant_idct_mb420_device": (C.c_int, [vp, C.c_int, vp, C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, i32p, i64p]),
     "b200_me_cmp_set_nsse_weight": (None, [C.c_int]),
+    "b200_me_cmp_set_dct_algo": (C.c_int, [C.c_int]),
     "b200_sum_abs_dctelem_batch_device": (C.c_int, [vp, vp, C.c_int64, vp]),
     "b200_me_cmp_batch_device": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, C.c_ssize_t, C.c_int, vp, vp, C.c_int64, vp]),
     "b200_me_esa_device": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, vp, vp]),

@@ -14,6 +14,7 @@
 // (cost, not-the-zero-vector, raster index) reduced with warp shuffles: strict '<' in raster order with the zero
 // vector tested first is exactly "smallest key".  This search is integer-ALU bound (about 2100 op/byte), not HBM bound.
 #include "common.h"
+#include "mecmp_dct.h"
 #include <cstring>
 #include <cstdlib>
 
@@ -444,6 +445,7 @@ int decode(int fn, int idx, int *w, int *mode)
     if (fn == B200_MECMP_HADAMARD8) { if (idx != 0 && idx != 1 && idx != 4 && idx != 5) return B200_EINVAL; *w = 16 >> (idx & 1); *mode = idx >= 4; return 0; }
     if (fn == B200_MECMP_VSAD || fn == B200_MECMP_VSSE) { if (idx != 0 && idx != 1 && idx != 4 && idx != 5) return B200_EINVAL; *w = 16 >> (idx & 1); *mode = idx >= 4; return 0; }
     if (fn == B200_MECMP_NSSE || fn == B200_MECMP_MEDIAN_SAD) { if (idx < 0 || idx > 1) return B200_EINVAL; *w = 16 >> idx; return 0; }
+    if (fn == B200_MECMP_DCT_SAD || fn == B200_MECMP_DCT_MAX || fn == B200_MECMP_DCT264_SAD) { if (idx < 0 || idx > 1) return B200_EINVAL; *w = 16 >> idx; return 0; }   // mecmp_dct.cu
     return B200_EINVAL;
 }
 
@@ -460,7 +462,9 @@ B200_API int b200_me_cmp_batch_device(B200Device *dev, int fn, int idx, const ui
     B200_CUDA_OK(cudaSetDevice(dev->ordinal));
     const long long blocks = (n + 7) / 8;
     if (blocks > 0x7fffffffLL) return B200_EINVAL;
-    if (fn == B200_MECMP_HADAMARD8)                               // 8 wide ignores h; 16 wide: two blocks, four when h == 16
+    if (fn >= B200_MECMP_DCT_SAD)                                 // 8x8 blocks like hadamard8_diff: two of them, four when h == 16
+        mecmp_dct_launch(dev->stream, (unsigned)blocks, 256, fn, w, h, frame1, frame2, stride, off1, off2, n, out);
+    else if (fn == B200_MECMP_HADAMARD8)                          // 8 wide ignores h; 16 wide: two blocks, four when h == 16
         me_satd_kernel<<<(unsigned)blocks, 256, 0, dev->stream>>>(w == 8 ? 1 : h == 16 ? 4 : 2, frame1, frame2, stride, off1, off2, n, out, mode);
     else if (fn >= B200_MECMP_VSAD) {
         if (w * h > 256) return B200_EINVAL;
@@ -548,7 +552,7 @@ int host_cmp(int fn, int idx, const uint8_t *blk1, const uint8_t *blk2, ptrdiff_
     if (!dev) fail("no device");
     int w, mode;
     if (decode(fn, idx, &w, &mode) < 0) fail("bad index");
-    if (fn == B200_MECMP_HADAMARD8) h = (w == 16 && h == 16) ? 16 : 8;         // the reference reads 8 rows unless 16 wide with h == 16
+    if (fn == B200_MECMP_HADAMARD8 || fn >= B200_MECMP_DCT_SAD) h = (w == 16 && h == 16) ? 16 : 8;   // the reference reads 8 rows unless 16 wide with h == 16
     if (cudaSetDevice(dev->ordinal) != cudaSuccess) fail("cudaSetDevice");
     const int cw = w + 1, ch = h + 1;                             // x2/y2/xy2 read one extra column / row of blk2
     const size_t pitch = 32;
@@ -563,7 +567,8 @@ int host_cmp(int fn, int idx, const uint8_t *blk1, const uint8_t *blk2, ptrdiff_
     const int bw = fn == B200_MECMP_PIX_ABS && (mode & 1) ? cw : w, bh = fn == B200_MECMP_PIX_ABS && (mode & 2) ? ch : h;
     if (b200_h2d_rows(d2, pitch, blk2, stride, bw, bh, st) != cudaSuccess) fail("h2d");
     if (cudaMemsetAsync(offs, 0, 16, st) != cudaSuccess) fail("memset");
-    if (fn == B200_MECMP_HADAMARD8) me_satd_kernel<<<1, 32, 0, st>>>(w == 8 ? 1 : h == 16 ? 4 : 2, d1, d2, (long long)pitch, offs, offs + 1, 1, dout, mode);
+    if (fn >= B200_MECMP_DCT_SAD) mecmp_dct_launch(st, 1, 32, fn, w, h, d1, d2, (long long)pitch, offs, offs + 1, 1, dout);
+    else if (fn == B200_MECMP_HADAMARD8) me_satd_kernel<<<1, 32, 0, st>>>(w == 8 ? 1 : h == 16 ? 4 : 2, d1, d2, (long long)pitch, offs, offs + 1, 1, dout, mode);
     else if (fn >= B200_MECMP_VSAD) me_cmp2_kernel<<<1, 32, 0, st>>>(fn, w, mode, g_nsse_weight.load(), d1, d2, (long long)pitch, h, offs, offs + 1, 1, dout);
     else me_cmp_kernel<<<1, 32, 0, st>>>(fn, w, mode, d1, d2, (long long)pitch, h, offs, offs + 1, 1, dout);
     B200_LAUNCHED();
@@ -615,6 +620,9 @@ B200_API int b200_me_cmp_init(B200MECmpContext *c, int codec_flags)
     c->vsse[4] = tab_fn<B200_MECMP_VSSE, 4>; c->vsse[5] = tab_fn<B200_MECMP_VSSE, 5>;
     c->nsse[0] = tab_fn<B200_MECMP_NSSE, 0>; c->nsse[1] = tab_fn<B200_MECMP_NSSE, 1>;
     c->median_sad[0] = tab_fn<B200_MECMP_MEDIAN_SAD, 0>; c->median_sad[1] = tab_fn<B200_MECMP_MEDIAN_SAD, 1>;
+    c->dct_sad[0] = tab_fn<B200_MECMP_DCT_SAD, 0>; c->dct_sad[1] = tab_fn<B200_MECMP_DCT_SAD, 1>;
+    c->dct_max[0] = tab_fn<B200_MECMP_DCT_MAX, 0>; c->dct_max[1] = tab_fn<B200_MECMP_DCT_MAX, 1>;
+    c->dct264_sad[0] = tab_fn<B200_MECMP_DCT264_SAD, 0>; c->dct264_sad[1] = tab_fn<B200_MECMP_DCT264_SAD, 1>;   // upstream: GPL builds only (me_cmp.c:986-988)
     c->sum_abs_dctelem = host_sum_abs_dctelem;
     return 0;
 }

@@ -3,7 +3,8 @@ and of the exhaustive search libavfilter drives it with (libavfilter/motion_esti
 import ctypes as C
 from ._lib import lib, check, vp, MECmpContext
 
-SAD, SSE, PIX_ABS, HADAMARD8, VSAD, VSSE, NSSE, MEDIAN_SAD = 0, 1, 2, 3, 4, 5, 6, 7
+SAD, SSE, PIX_ABS, HADAMARD8, VSAD, VSSE, NSSE, MEDIAN_SAD, DCT_SAD, DCT_MAX, DCT264_SAD = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10
+FF_DCT_AUTO, FF_DCT_FASTINT, FF_DCT_INT, FF_DCT_FAAN = 0, 1, 2, 6                  # AVCodecContext.dct_algo (libavcodec/avcodec.h:1531-1537)
 AV_CODEC_FLAG_BITEXACT = 1 << 23
 
 
@@ -15,6 +16,11 @@ def ff_me_cmp_init(codec_flags=AV_CODEC_FLAG_BITEXACT):
     c = MECmpContext()
     check(lib().b200_me_cmp_init(C.byref(c), codec_flags), "ff_me_cmp_init")
     return c
+
+
+def me_cmp_set_dct_algo(dct_algo):
+    """the forward DCT behind dct_sad / dct_max (the reference reads it from the encoder context: s->fdsp.fdct, me_cmp.c:614-622)"""
+    return check(lib().b200_me_cmp_set_dct_algo(dct_algo), "me_cmp_set_dct_algo")
 
 
 def me_cmp_batch_device(device, fn, idx, frame1, frame2, stride, h, off1, off2, n, out):

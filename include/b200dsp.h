@@ -413,7 +413,9 @@ int  b200_h264_weight_hbd_batch_device(B200Device *dev, int bit_depth, int64_t n
 /* ------------------------------------------------------------------------------------------------ me_cmp
  * Replaces MECmpContext (libavcodec/me_cmp.h:53-77) as filled by ff_me_cmp_init (libavcodec/me_cmp.c:961-1027) for the
  * SAD / SSE entries: sad[0..1] = pix_abs16_c / pix_abs8_c, sse[0..2] = sse16_c / sse8_c / sse4_c,
- * pix_abs[0..1][0..3] = full / x2 / y2 / xy2 (me_cmp.c:37-385).  Entries this library does not implement stay NULL.
+ * pix_abs[0..1][0..3] = full / x2 / y2 / xy2 (me_cmp.c:37-385), and hadamard8_diff, vsad, vsse, nsse, median_sad, dct_sad, dct_max,
+ * dct264_sad ([0] 16 wide, [1] 8 wide; [4] / [5] the intra forms where upstream has them).  Entries this library does not implement
+ * (quant_psnr, bit, rd: they run the encoder's quantiser and VLC tables; w53, w97: the snow wavelets) stay NULL.
  * me_cmp_func (me_cmp.h:47-51): the first argument (MPVEncContext *) is unused by these functions and may be NULL. */
 typedef int (*b200_me_cmp_func)(void *c, const uint8_t *blk1, const uint8_t *blk2, ptrdiff_t stride, int h);
 typedef struct B200MECmpContext {
@@ -447,6 +449,13 @@ int  b200_me_cmp_init(B200MECmpContext *c, int codec_flags);
 #define B200_MECMP_VSSE    5   /* vsse[idx] (me_cmp.c:883-931): same indices */
 #define B200_MECMP_NSSE    6   /* nsse[idx] (me_cmp.c:387-437): idx 0: 16, 1: 8; weight as set by b200_me_cmp_set_nsse_weight (default 8) */
 #define B200_MECMP_MEDIAN_SAD 7 /* median_sad[idx] (me_cmp.c:145-183,292-330): idx 0: 16, 1: 8 */
+#define B200_MECMP_DCT_SAD  8   /* dct_sad[idx] (me_cmp.c:614-622,952): sum |fdct(blk1 - blk2)|; idx 0: 16 wide (h = 8 or 16), 1: 8x8 */
+#define B200_MECMP_DCT_MAX  9   /* dct_max[idx] (me_cmp.c:678-693,956): max |fdct(blk1 - blk2)| per 8x8 block, added up over the blocks */
+#define B200_MECMP_DCT264_SAD 10 /* dct264_sad[idx] (me_cmp.c:624-675,954): the H.264 8x8 integer transform; upstream only in GPL builds */
+/* dct_sad / dct_max run FDCTDSPContext.fdct of the encoder context they are handed (s->fdsp.fdct); the table entries cannot read it, so
+ * the DCT is chosen here with AVCodecContext.dct_algo's values the way ff_fdctdsp_init does for 8-bit samples (fdctdsp.c:27-45):
+ * FF_DCT_FASTINT (1) = ff_fdct_ifast, FF_DCT_FAAN (6) = not implemented (ENOSYS, setting unchanged), anything else = ff_jpeg_fdct_islow_8. */
+int  b200_me_cmp_set_dct_algo(int dct_algo);
 /* nsse multiplies its noise term by MPVEncContext.c.avctx->nsse_weight, or by 8 when the context argument is NULL (me_cmp.c:407-410).
  * The table entries cannot read the caller's context (its layout is private to the encoder): the weight is set here instead. */
 void b200_me_cmp_set_nsse_weight(int weight);

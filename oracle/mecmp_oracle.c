@@ -12,6 +12,12 @@
  *   pix_median_abs16_c / 8_c ........ libavcodec/me_cmp.c:145-183, 292-330    residual of the difference after median (left, top, gradient) prediction
  *   hadamard8_intra8x8_c / 16 ....... libavcodec/me_cmp.c:564-612, 944        SATD of the block itself minus |DC|
  *   sum_abs_dctelem_c ............... libavcodec/me_cmp.c:105-112             sum |block[i]|, i < 64
+ *   dct_sad8x8_c / dct_max8x8_c ..... libavcodec/me_cmp.c:614-622, 678-693     forward DCT of blk1 - blk2 (pixblockdsp.c:40-59), then sum / max of |coef|
+ *   ff_jpeg_fdct_islow_8 ............ libavcodec/jfdctint_template.c:173-340   FDCTDSPContext.fdct for FF_DCT_AUTO (fdctdsp.c:27-45): LL&M, 13-bit
+ *                                                                             constants, PASS1_BITS 4, products modulo 2^32, stores truncated to int16
+ *   ff_fdct_ifast ................... libavcodec/jfdctfst.c:140-284            FF_DCT_FASTINT: AA&N, 8-bit constants, (x * c) >> 8 without rounding
+ *   dct264_sad8x8_c ................. libavcodec/me_cmp.c:624-675              H.264 8x8 integer transform, rows stored as int16, columns summed
+ *   16 wide entries ................. libavcodec/me_cmp.c:933-959              WRAPPER8_16_SQ: two blocks, four when h == 16 (the scores add up)
  *   table layout .................... libavcodec/me_cmp.c:961-1027             sad[0]=16 wide, sad[1]=8; sse[0..2]=16,8,4;
  *                                                                             pix_abs[0=16,1=8][0 full,1 x2,2 y2,3 xy2]
  *   ff_me_cmp_sad, ff_me_search_esa . libavfilter/motion_estimation.c:60-97   cost(0 mv) first, return at once if it is 0,
@@ -140,6 +146,90 @@ static int satd8x8_intra(const uint8_t *src, ptrdiff_t stride)
     return sum - abs(t[0]);
 }
 
+/* ---- transform-domain comparisons: dct_sad (fn 8), dct_max (fn 9), dct264_sad (fn 10) ---- */
+static int g_dct_algo = 0;                      /* AVCodecContext.dct_algo: 0 FF_DCT_AUTO (islow), 1 FF_DCT_FASTINT (ifast) */
+void orc_me_cmp_set_dct_algo(int algo) { g_dct_algo = algo; }
+
+static int16_t descale16(uint32_t x, int n) { return (int16_t)(((int32_t)x + (1 << (n - 1))) >> n); }
+
+/* one 1-D pass of the "slow" integer DCT over eight samples at p[0], p[st], ...; second = the column pass */
+static void islow_pass(int16_t *p, int st, int second)
+{
+    const int x0 = p[0], x1 = p[st], x2 = p[2 * st], x3 = p[3 * st], x4 = p[4 * st], x5 = p[5 * st], x6 = p[6 * st], x7 = p[7 * st];
+    const int s0 = x0 + x7, s1 = x1 + x6, s2 = x2 + x5, s3 = x3 + x4;
+    const int d0 = x0 - x7, d1 = x1 - x6, d2 = x2 - x5, d3 = x3 - x4;
+    const int e0 = s0 + s3, e3 = s0 - s3, e1 = s1 + s2, e2 = s1 - s2;
+    const int sh = second ? 13 + 4 : 13 - 4;
+    if (second) { p[0] = (int16_t)((e0 + e1 + 8) >> 4); p[4 * st] = (int16_t)((e0 - e1 + 8) >> 4); }
+    else        { p[0] = (int16_t)((e0 + e1) * 16);     p[4 * st] = (int16_t)((e0 - e1) * 16); }
+    const uint32_t r = (uint32_t)(e2 + e3) * 4433u;
+    p[2 * st] = descale16(r + (uint32_t)e3 * 6270u, sh);
+    p[6 * st] = descale16(r - (uint32_t)e2 * 15137u, sh);
+    uint32_t z1 = (uint32_t)(d3 + d0), z2 = (uint32_t)(d2 + d1), z3 = (uint32_t)(d3 + d1), z4 = (uint32_t)(d2 + d0);
+    const uint32_t z5 = (z3 + z4) * 9633u;
+    const uint32_t t4 = (uint32_t)d3 * 2446u, t5 = (uint32_t)d2 * 16819u, t6 = (uint32_t)d1 * 25172u, t7 = (uint32_t)d0 * 12299u;
+    z1 *= (uint32_t)-7373; z2 *= (uint32_t)-20995; z3 = z3 * (uint32_t)-16069 + z5; z4 = z4 * (uint32_t)-3196 + z5;
+    p[7 * st] = descale16(t4 + z1 + z3, sh);
+    p[5 * st] = descale16(t5 + z2 + z4, sh);
+    p[3 * st] = descale16(t6 + z2 + z3, sh);
+    p[1 * st] = descale16(t7 + z1 + z4, sh);
+}
+
+static int ifast_mul(int v, int c) { return (int16_t)((v * c) >> 8); }
+static void ifast_pass(int16_t *p, int st)
+{
+    const int x0 = p[0], x1 = p[st], x2 = p[2 * st], x3 = p[3 * st], x4 = p[4 * st], x5 = p[5 * st], x6 = p[6 * st], x7 = p[7 * st];
+    const int s0 = x0 + x7, s1 = x1 + x6, s2 = x2 + x5, s3 = x3 + x4;
+    const int d0 = x0 - x7, d1 = x1 - x6, d2 = x2 - x5, d3 = x3 - x4;
+    const int e0 = s0 + s3, e3 = s0 - s3, e1 = s1 + s2, e2 = s1 - s2;
+    p[0] = (int16_t)(e0 + e1); p[4 * st] = (int16_t)(e0 - e1);
+    const int r = ifast_mul(e2 + e3, 181);
+    p[2 * st] = (int16_t)(e3 + r); p[6 * st] = (int16_t)(e3 - r);
+    const int a = d3 + d2, b = d2 + d1, c = d1 + d0;
+    const int z5 = ifast_mul(a - c, 98), z2 = ifast_mul(a, 139) + z5, z4 = ifast_mul(c, 334) + z5, z3 = ifast_mul(b, 181);
+    const int z11 = d0 + z3, z13 = d0 - z3;
+    p[5 * st] = (int16_t)(z13 + z2); p[3 * st] = (int16_t)(z13 - z2); p[1 * st] = (int16_t)(z11 + z4); p[7 * st] = (int16_t)(z11 - z4);
+}
+
+/* the H.264 8x8 forward transform's 1-D step: in[] -> out[] */
+static void dct264_1d(const int *in, int *out)
+{
+    const int s07 = in[0] + in[7], s16 = in[1] + in[6], s25 = in[2] + in[5], s34 = in[3] + in[4];
+    const int d07 = in[0] - in[7], d16 = in[1] - in[6], d25 = in[2] - in[5], d34 = in[3] - in[4];
+    const int a0 = s07 + s34, a1 = s16 + s25, a2 = s07 - s34, a3 = s16 - s25;
+    const int a4 = d16 + d25 + (d07 + (d07 >> 1)), a5 = d07 - d34 - (d25 + (d25 >> 1));
+    const int a6 = d07 + d34 - (d16 + (d16 >> 1)), a7 = d16 - d25 + (d34 + (d34 >> 1));
+    out[0] = a0 + a1; out[1] = a4 + (a7 >> 2); out[2] = a2 + (a3 >> 1); out[3] = a5 + (a6 >> 2);
+    out[4] = a0 - a1; out[5] = a6 - (a5 >> 2); out[6] = (a2 >> 1) - a3; out[7] = (a4 >> 2) - a7;
+}
+
+static int dct_cmp8x8(int fn, const uint8_t *s1, const uint8_t *s2, ptrdiff_t stride)
+{
+    int16_t t[64];
+    for (int i = 0; i < 8; i++)
+        for (int j = 0; j < 8; j++) t[8 * i + j] = (int16_t)(s1[i * stride + j] - s2[i * stride + j]);
+    int sum = 0;
+    if (fn == 10) {
+        for (int i = 0; i < 8; i++) {
+            int in[8], out[8];
+            for (int j = 0; j < 8; j++) in[j] = t[8 * i + j];
+            dct264_1d(in, out);
+            for (int j = 0; j < 8; j++) t[8 * i + j] = (int16_t)out[j];
+        }
+        for (int j = 0; j < 8; j++) {
+            int in[8], out[8];
+            for (int i = 0; i < 8; i++) in[i] = t[8 * i + j];
+            dct264_1d(in, out);
+            for (int i = 0; i < 8; i++) sum += abs(out[i]);
+        }
+        return sum;
+    }
+    for (int i = 0; i < 8; i++) { if (g_dct_algo == 1) ifast_pass(t + 8 * i, 1); else islow_pass(t + 8 * i, 1, 0); }
+    for (int j = 0; j < 8; j++) { if (g_dct_algo == 1) ifast_pass(t + j, 8); else islow_pass(t + j, 8, 1); }
+    for (int i = 0; i < 64; i++) { const int v = abs(t[i]); if (fn == 8) sum += v; else if (v > sum) sum = v; }
+    return sum;
+}
+
 int orc_sum_abs_dctelem(const int16_t *block)
 {
     int sum = 0;
@@ -149,6 +239,14 @@ int orc_sum_abs_dctelem(const int16_t *block)
 
 int orc_me_cmp(int fn, int idx, const uint8_t *blk1, const uint8_t *blk2, ptrdiff_t stride, int h)
 {
+    if (fn >= 8 && fn <= 10) {                                     /* dct_sad / dct_max / dct264_sad: [0] 16 wide, [1] 8x8 */
+        if (idx != 0 && idx != 1) return -1;
+        int s = dct_cmp8x8(fn, blk1, blk2, stride);
+        if (idx == 1) return s;
+        s += dct_cmp8x8(fn, blk1 + 8, blk2 + 8, stride);
+        if (h == 16) s += dct_cmp8x8(fn, blk1 + 8 * stride, blk2 + 8 * stride, stride) + dct_cmp8x8(fn, blk1 + 8 * stride + 8, blk2 + 8 * stride + 8, stride);
+        return s;
+    }
     if (fn == 3 && (idx == 4 || idx == 5)) {                       /* hadamard8_diff[4] = intra16, [5] = intra8x8 */
         if (idx == 5) return satd8x8_intra(blk1, stride);
         int s = satd8x8_intra(blk1, stride) + satd8x8_intra(blk1 + 8, stride);

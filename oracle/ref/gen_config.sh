@@ -20,7 +20,7 @@ HAVE_SYS_RESOURCE_H HAVE_GETRUSAGE HAVE_MMAP HAVE_MPROTECT HAVE_ERRNO_H_PLACEHOL
 HAVE_GETENV HAVE_SECURE_GETENV_DISABLED HAVE_STDBIT_H_DISABLED
 CONFIG_SWSCALE CONFIG_AVUTIL CONFIG_AVCODEC CONFIG_SMALL_DISABLED CONFIG_MEMORY_POISONING_DISABLED
 CONFIG_IDCTDSP CONFIG_ME_CMP CONFIG_H264QPEL CONFIG_HPELDSP CONFIG_FAANIDCT CONFIG_SWSCALE_ALPHA CONFIG_SAFE_BITSTREAM_READER CONFIG_PIXELUTILS
-CONFIG_UNSTABLE_DISABLED"
+CONFIG_GPL CONFIG_UNSTABLE_DISABLED"
 SYMS=$(cd "$REF" && cat "$@" libavutil/*.h libswscale/*.h libavcodec/idctdsp.h libavcodec/me_cmp.h compat/*.h 2>/dev/null \
        | grep -ohE '\b(HAVE|CONFIG|ARCH)_[A-Za-z0-9_]+\b' | sort -u)
 # symbols only reachable through token pasting (HAVE_ ## ext ## suffix in libavutil/cpu_internal.h)

@@ -315,10 +315,33 @@ static void mecmp_init(void)
     g_mecmp_ok = 1;
 }
 
-/* fn: 0 sad[idx], 1 sse[idx], 2 pix_abs[idx>>2][idx&3], 3 hadamard8_diff[idx] */
+/* dct_sad / dct_max / dct264_sad read the encoder context: pdsp.diff_pixels_unaligned, fdsp.fdct, sum_abs_dctelem (me_cmp.c:614-693) */
+#include "libavcodec/mpegvideoenc.h"
+static MPVEncContext *g_mpvenc; static int g_dct_algo;
+static MPVEncContext *mecmp_enc(void)
+{
+    if (!g_mpvenc) {
+        AVCodecContext *avctx = av_mallocz(sizeof(*avctx));
+        g_mpvenc = av_mallocz(sizeof(*g_mpvenc));
+        avctx->dct_algo = g_dct_algo;
+        avctx->bits_per_raw_sample = 8;
+        ff_fdctdsp_init(&g_mpvenc->fdsp, avctx);
+        ff_pixblockdsp_init(&g_mpvenc->pdsp, 8);
+        g_mpvenc->sum_abs_dctelem = g_mecmp.sum_abs_dctelem;
+        av_free(avctx);
+    }
+    return g_mpvenc;
+}
+API void ffref_me_cmp_set_dct_algo(int algo) { g_dct_algo = algo; av_freep(&g_mpvenc); }
+
+/* fn: 0 sad[idx], 1 sse[idx], 2 pix_abs[idx>>2][idx&3], 3 hadamard8_diff[idx], ..., 8 dct_sad, 9 dct_max, 10 dct264_sad */
 API int ffref_me_cmp(int fn, int idx, const uint8_t *blk1, const uint8_t *blk2, ptrdiff_t stride, int h)
 {
     mecmp_init();
+    if (fn >= 8 && fn <= 10) {
+        me_cmp_func g = fn == 8 ? g_mecmp.dct_sad[idx] : fn == 9 ? g_mecmp.dct_max[idx] : g_mecmp.dct264_sad[idx];
+        return g ? g(mecmp_enc(), blk1, blk2, stride, h) : -1;
+    }
     me_cmp_func f = fn == 0 ? g_mecmp.sad[idx] : fn == 1 ? g_mecmp.sse[idx] : fn == 3 ? g_mecmp.hadamard8_diff[idx] :
                     fn == 4 ? g_mecmp.vsad[idx] : fn == 5 ? g_mecmp.vsse[idx] : fn == 6 ? g_mecmp.nsse[idx] :
                     fn == 7 ? g_mecmp.median_sad[idx] : g_mecmp.pix_abs[idx >> 2][idx & 3];

@@ -599,6 +599,32 @@ def gen_satd():
     np.savez_compressed(os.path.join(OUT, "satd.npz"), cases=np.array(rows, np.int32))
 
 
+def gen_mecmp_dct():
+    """dct_sad / dct_max (ff_jpeg_fdct_islow_8 and ff_fdct_ifast) and dct264_sad, [0] 16 wide (h 8 / 16) and [1] 8x8, from the compiled reference
+    (encoder context with fdsp / pdsp / sum_abs_dctelem set up by ffref_me_cmp_set_dct_algo) on the 64x64 images of mecmp.npz and on a
+    saturated pair (255 against 0 in a checkerboard: the largest coefficients the transforms see)"""
+    R = cl.ref()
+    g = np.load(os.path.join(OUT, "mecmp.npz"))
+    chk = ((np.add.outer(np.arange(64), np.arange(64)) & 1) * 255).astype(np.uint8)
+    pairs = [(g["img1"], g["img2"]), (chk, np.ascontiguousarray(255 - chk)), (np.full((64, 64), 255, np.uint8), np.zeros((64, 64), np.uint8))]
+    rng = np.random.default_rng(2310)
+    rows = []
+    for algo in (0, 1):
+        R.ffref_me_cmp_set_dct_algo(algo)
+        for pi, (img1, img2) in enumerate(pairs):
+            for fn in (8, 9, 10):
+                if fn == 10 and algo == 1:
+                    continue
+                for idx in (0, 1):
+                    for _ in range(12 if pi == 0 else 3):
+                        x1, y1, x2, y2 = (int(v) for v in rng.integers(0, 40, 4))
+                        h = int(rng.choice([8, 16]))
+                        v = R.ffref_me_cmp(fn, idx, C.cast(img1.ctypes.data + y1 * 64 + x1, cl.u8p), C.cast(img2.ctypes.data + y2 * 64 + x2, cl.u8p), 64, h)
+                        rows.append((fn, idx, algo, pi, x1, y1, x2, y2, h, v))
+    R.ffref_me_cmp_set_dct_algo(0)
+    np.savez_compressed(os.path.join(OUT, "mecmp_dct.npz"), cases=np.array(rows, np.int32))
+
+
 def gen_pel():
     R = cl.ref()
     rng = np.random.default_rng(22)
@@ -721,6 +747,7 @@ if __name__ == "__main__":
     gen_h264weight()
     gen_mecmp()
     gen_satd()
+    gen_mecmp_dct()
     gen_pel()
     gen_chroma()
     gen_edge()

@@ -41,17 +41,28 @@ for it in range(N):
     cs = None
     if rnd.random() < 0.4:
         cs = (rnd.choice([1,2,4,5,6,7,9]), rnd.choice([0,1]), rnd.choice([1,5,6,7,9]), rnd.choice([0,1]), rnd.choice([0, 1<<12, -(1<<13)]), rnd.choice([1<<16, 70000, 50000]), rnd.choice([1<<16, 80000, 40000]))
-    desc = (w,h,dw,dh,hex(fl),sf,df,ranges,dpad,cs)
+    filt = None
+    if rnd.random() < 0.25:                                     # srcFilter / dstFilter of sws_getContext
+        def vec():
+            r = rnd.random()
+            if r < 0.4: return None
+            n = rnd.choice([1, 2, 3, 5, 7])
+            c = [rnd.uniform(-0.3, 1.0) for _ in range(n)]
+            t = sum(c) or 1.0
+            return [x / t for x in c] if rnd.random() < 0.7 else c
+        filt = (tuple(vec() for _ in range(4)), tuple(rnd.choice([0, 0, 1, 3, 5]) for _ in range(4)))
+    fk = {} if filt is None else {"filters": filt}
+    desc = (w,h,dw,dh,hex(fl),sf,df,ranges,dpad,cs,filt)
     try:
         if rgbdst:
             if ranges != (0,0): ranges=(0,0)
-            exp = cl.orc_sws(w,h,dw,dh,fl,y,u,v,fmt=df,src_fmt=sf,dst_pad=dpad,colorspace=cs)
+            exp = cl.orc_sws(w,h,dw,dh,fl,y,u,v,fmt=df,src_fmt=sf,dst_pad=dpad,colorspace=cs,**fk)
         else:
-            exp = cl.orc_sws_planar(w,h,dw,dh,fl,y,u,v,src_fmt=sf,dst_fmt=df,ranges=ranges,dst_pad=dpad,details=cs)
+            exp = cl.orc_sws_planar(w,h,dw,dh,fl,y,u,v,src_fmt=sf,dst_fmt=df,ranges=ranges,dst_pad=dpad,details=cs,**fk)
     except Exception as e:
         exp = None
     try:
-        got = er(w,h,dw,dh,fl,y,u,v,fmt=df,src_fmt=sf,dst_pad=dpad,colorspace=cs) if rgbdst else ep(w,h,dw,dh,fl,y,u,v,src_fmt=sf,dst_fmt=df,ranges=ranges,dst_pad=dpad,details=cs)
+        got = er(w,h,dw,dh,fl,y,u,v,fmt=df,src_fmt=sf,dst_pad=dpad,colorspace=cs,**fk) if rgbdst else ep(w,h,dw,dh,fl,y,u,v,src_fmt=sf,dst_fmt=df,ranges=ranges,dst_pad=dpad,details=cs,**fk)
     except AssertionError as e:
         got = "ERR:"+str(e)[:80]
         import traceback
@@ -66,8 +77,12 @@ for it in range(N):
     ran += 1
     if isinstance(got,str): print("PRODUCT ERROR", desc, got); bad += 1; continue
     try:
-        rexp = cl.ref_sws(w,h,dw,dh,fl,y,u,v,fmt=df,src_fmt=sf,dst_pad=dpad,colorspace=cs) if rgbdst else cl.ref_sws_planar(w,h,dw,dh,fl,y,u,v,src_fmt=sf,dst_fmt=df,ranges=ranges,dst_pad=dpad,details=cs)
-        rok = np.array_equal(rexp, exp) if rgbdst else all(np.array_equal(a,b) for a,b in zip(rexp,exp))
+        rexp = cl.ref_sws(w,h,dw,dh,fl,y,u,v,fmt=df,src_fmt=sf,dst_pad=dpad,colorspace=cs,**fk) if rgbdst else cl.ref_sws_planar(w,h,dw,dh,fl,y,u,v,src_fmt=sf,dst_fmt=df,ranges=ranges,dst_pad=dpad,details=cs,**fk)
+        if rgbdst:                                              # picture area only: rgbToRgbWrapper 24-bit -> argb / abgr writes one byte past each row (documented quirk)
+            pw = dw * cl.fmt_bpp(df)
+            rok = np.array_equal(np.asarray(rexp).reshape(dh, -1)[:, :pw], np.asarray(exp).reshape(dh, -1)[:, :pw])
+        else:
+            rok = all(np.array_equal(a,b) for a,b in zip(rexp,exp))
         if not rok: print("ORACLE != REFERENCE", desc); bad += 1
     except Exception as e:
         print("ref failed", desc, str(e)[:60])

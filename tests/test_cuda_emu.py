@@ -51,7 +51,7 @@ def vp(a):
 WARP_KERNELS = {"mpv_unquant_kernel"}                   # kernels that use a warp collective: one OS thread per lane
 BLOCK_KERNELS = {"sws_mma_plane_kernel", "sws_mma_rgb_kernel", "tx_fft_kernel", "tx_mdct_inv_kernel", "tx_mdct_fwd_kernel", "tx_rdft_r2c_kernel", "tx_rdft_c2r_kernel",
                  "sws_fused_plane_kernel", "sws_fused_rgb_kernel", "tx_mdct_pfa_inv_kernel", "tx_mdct_pfa_fwd_kernel", "tx_fft_pfa_kernel", "tx_i32_kernel",
-                 "tx_dbl_fft_kernel", "tx_dbl_mdct_inv_kernel", "tx_dbl_mdct_fwd_kernel"}    # __syncthreads + dynamic shared memory
+                 "tx_dbl_fft_kernel", "tx_dbl_mdct_inv_kernel", "tx_dbl_mdct_fwd_kernel", "me_dct_kernel"}    # __syncthreads + dynamic shared memory
 
 
 def rewrite_launches(txt):
@@ -84,7 +84,7 @@ def emuhost():
     os.makedirs(gen, exist_ok=True)
     cs = os.path.join(ROOT, "ffmpeg_b200", "csrc")
     srcs = []
-    for f in ("fdsp.cu", "unquant.cu", "idct_hbd.cu", "tx_pfa.cu", "h264lf.cu", "pixelutils.cu", "pel_hbd.cu", "h264idct_hbd.cu", "h264lf_hbd.cu"):
+    for f in ("fdsp.cu", "unquant.cu", "idct_hbd.cu", "tx_pfa.cu", "h264lf.cu", "pixelutils.cu", "pel_hbd.cu", "h264idct_hbd.cu", "h264lf_hbd.cu", "mecmp_dct.cu"):
         t = rewrite_launches(open(os.path.join(cs, f)).read())
         t = t.replace("extern __shared__ float2 pfa_z[];", "float2 *pfa_z = (float2 *)emu_smem;")
         assert "<<<" not in t
@@ -94,7 +94,7 @@ def emuhost():
     so = os.path.join(gen, "libemuhost.so")
     cxx = "/opt/gcc/bin/g++" if os.path.exists("/opt/gcc/bin/g++") else "g++"
     r = subprocess.run([cxx, "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread", "-ffp-contract=off", "-w", "-I" + os.path.join(EMU, "fake"), "-I" + cs,
-                        "-I" + os.path.join(ROOT, "include"), "-I" + EMU] + srcs + [os.path.join(EMU, "fake_device.cpp"), os.path.join(EMU, "fake_pel_hbd.cpp"), os.path.join(EMU, "fake_h264idct_hbd.cpp"), "-o", so],
+                        "-I" + os.path.join(ROOT, "include"), "-I" + EMU] + srcs + [os.path.join(EMU, "fake_device.cpp"), os.path.join(EMU, "fake_pel_hbd.cpp"), os.path.join(EMU, "fake_h264idct_hbd.cpp"), os.path.join(EMU, "fake_mecmp_dct.cpp"), "-o", so],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
     return C.CDLL(so)
@@ -1595,3 +1595,41 @@ def test_sws_slice_sequences_from_packed_rgb_sources(emusws):
         assert all(np.array_equal(a, b) for a, b in zip(gp[:n], rp[:n])), (it, w, h, dw, dh, hex(fl), sf, df, bands)
         done += 1
     assert done >= 40, done
+
+
+def test_me_cmp_dct_family_on_emulated_device(emuhost):
+    """mecmp_dct.cu (dct_sad / dct_max with both integer DCTs, dct264_sad; 8x8 and 16 wide with h = 8 / 16) as the library launches it,
+    lane for lane on the CPU, against the checker and the compiled reference: random, near-equal, saturated and checkerboard blocks"""
+    L, O, R = emuhost, cl.oracle(), cl.ref()
+    rng = np.random.default_rng(2309)
+    stride, rows = 48, 40
+    pics = []
+    a = rng.integers(0, 256, (rows, stride), dtype=np.uint8); pics.append((a, rng.integers(0, 256, (rows, stride), dtype=np.uint8)))
+    pics.append((a, np.clip(a.astype(int) + rng.integers(-5, 6, a.shape), 0, 255).astype(np.uint8)))
+    pics.append((np.full((rows, stride), 255, np.uint8), np.zeros((rows, stride), np.uint8)))
+    c = ((np.add.outer(np.arange(rows), np.arange(stride)) & 1) * 255).astype(np.uint8); pics.append((c, (255 - c).astype(np.uint8)))
+    pics.append(((rng.integers(0, 2, (rows, stride)) * 255).astype(np.uint8), (rng.integers(0, 2, (rows, stride)) * 255).astype(np.uint8)))
+    n = 19                                                        # not a multiple of the 8 comparisons of a CTA
+    try:
+        for algo in (0, 1, 2):
+            assert L.b200_me_cmp_set_dct_algo(algo) == 0
+            O.orc_me_cmp_set_dct_algo(1 if algo == 1 else 0)
+            if R is not None: R.ffref_me_cmp_set_dct_algo(algo)
+            for f1, f2 in pics:
+                off1 = (rng.integers(0, rows - 16, n) * stride + rng.integers(0, stride - 16, n)).astype(np.int64)
+                off2 = (rng.integers(0, rows - 16, n) * stride + rng.integers(0, stride - 16, n)).astype(np.int64)
+                for fn in (8, 9, 10):
+                    for w, h in ((16, 16), (16, 8), (8, 8)):
+                        out = np.full(n, -7, np.int32)
+                        assert L.emu_host_me_dct(fn, w, h, vp(f1), vp(f2), C.c_longlong(stride), vp(off1), vp(off2), C.c_longlong(n), vp(out)) == 0
+                        idx = 0 if w == 16 else 1
+                        for i in range(n):
+                            p1, p2 = f1.reshape(-1)[off1[i]:], f2.reshape(-1)[off2[i]:]
+                            e = O.orc_me_cmp(fn, idx, cl.ptr(p1, cl.u8p), cl.ptr(p2, cl.u8p), stride, h)
+                            assert out[i] == e, (algo, fn, w, h, i, int(out[i]), e)
+                            if R is not None:
+                                assert e == R.ffref_me_cmp(fn, idx, cl.ptr(p1, cl.u8p), cl.ptr(p2, cl.u8p), stride, h)
+        assert L.b200_me_cmp_set_dct_algo(6) < 0                  # FF_DCT_FAAN
+    finally:
+        L.b200_me_cmp_set_dct_algo(0); O.orc_me_cmp_set_dct_algo(0)
+        if R is not None: R.ffref_me_cmp_set_dct_algo(0)

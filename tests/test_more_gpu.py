@@ -25,7 +25,7 @@ def test_mecmp_pointer_table_golden(device):
     g = np.load(os.path.join(G, "mecmp.npz"))
     c = me_cmp.ff_me_cmp_init()
     img1, img2 = g["img1"], g["img2"]
-    assert not c.dct_sad[0] and not c.sad[2]                   # entries not implemented stay NULL
+    assert not c.quant_psnr[0] and not c.sad[2]                # entries not implemented stay NULL
     for fn, idx, x1, y1, x2, y2, h, v in g["cases"]:
         f = c.sad[idx] if fn == 0 else c.sse[idx] if fn == 1 else c.pix_abs[idx >> 2][idx & 3]
         got = f(None, C.cast(img1.ctypes.data + int(y1) * 64 + int(x1), u8p), C.cast(img2.ctypes.data + int(y2) * 64 + int(x2), u8p), 64, int(h))
@@ -67,7 +67,7 @@ def test_mecmp_round2_families(device):
     g = np.load(os.path.join(G, "mecmp2.npz"))
     c = me_cmp.ff_me_cmp_init()
     img1, img2 = g["img1"], g["img2"]
-    assert not c.dct_sad[0] and not c.quant_psnr[0] and not c.rd[0] and not c.bit[0] and not c.w53[0]      # these need the encoder's context: stay NULL
+    assert not c.quant_psnr[0] and not c.rd[0] and not c.bit[0] and not c.w53[0] and not c.w97[0]         # these run the encoder's quantiser / VLC tables or the snow wavelets: stay NULL
     tabs = {3: c.hadamard8_diff, 4: c.vsad, 5: c.vsse, 6: c.nsse, 7: c.median_sad}
     for fn, idx, x1, y1, x2, y2, h, v in g["cases"]:
         f = tabs[int(fn)][int(idx)]

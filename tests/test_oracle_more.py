@@ -870,3 +870,42 @@ def test_mecmp_round2_families_oracle_vs_fixture_and_reference():
             for idx in idxs:
                 for h in (8, 16):
                     assert R.ffref_me_cmp(fn, idx, p1, p2, 96, h) == O.orc_me_cmp(fn, idx, p1, p2, 96, h), (fn, idx, h)
+
+
+def mecmp_dct_pairs():
+    """the image pairs of tests/golden/mecmp_dct.npz (scripts/gen_golden.py mecmp_dct): mecmp.npz's random images, a checkerboard against its
+    inverse, white against black"""
+    g = np.load(os.path.join(G, "mecmp.npz"))
+    chk = ((np.add.outer(np.arange(64), np.arange(64)) & 1) * 255).astype(np.uint8)
+    return [(g["img1"], g["img2"]), (chk, np.ascontiguousarray(255 - chk)), (np.full((64, 64), 255, np.uint8), np.zeros((64, 64), np.uint8))]
+
+
+def test_mecmp_dct_families_oracle_vs_fixture_and_reference():
+    """dct_sad / dct_max (islow and ifast DCT) and dct264_sad: the checker against the committed reference values and, where the reference is
+    built, against it on fresh inputs (random, near-equal, binary)"""
+    O = cl.oracle()
+    pairs = mecmp_dct_pairs()
+    try:
+        for fn, idx, algo, pi, x1, y1, x2, y2, h, v in np.load(os.path.join(G, "mecmp_dct.npz"))["cases"]:
+            O.orc_me_cmp_set_dct_algo(int(algo))
+            img1, img2 = pairs[int(pi)]
+            got = O.orc_me_cmp(int(fn), int(idx), C.cast(img1.ctypes.data + int(y1) * 64 + int(x1), cl.u8p),
+                               C.cast(img2.ctypes.data + int(y2) * 64 + int(x2), cl.u8p), 64, int(h))
+            assert got == v, (fn, idx, algo, pi, h)
+        if not cl.have_ref():
+            return
+        R = cl.ref()
+        rng = np.random.default_rng(77)
+        for algo in (0, 1):
+            O.orc_me_cmp_set_dct_algo(algo); R.ffref_me_cmp_set_dct_algo(algo)
+            for trial in range(300):
+                a = rng.integers(0, 256, (24, 40), dtype=np.uint8) if trial % 3 else (rng.integers(0, 2, (24, 40)) * 255).astype(np.uint8)
+                b = rng.integers(0, 256, (24, 40), dtype=np.uint8) if trial % 2 else (a.astype(int) + rng.integers(-3, 4, a.shape)).clip(0, 255).astype(np.uint8)
+                p1, p2 = C.cast(a.ctypes.data + 40 * 2 + 3, cl.u8p), C.cast(b.ctypes.data + 40 * 5 + 7, cl.u8p)
+                for fn in (8, 9, 10):
+                    for idx, h in ((0, 16), (0, 8), (1, 8)):
+                        assert R.ffref_me_cmp(fn, idx, p1, p2, 40, h) == O.orc_me_cmp(fn, idx, p1, p2, 40, h), (algo, fn, idx, h)
+    finally:
+        O.orc_me_cmp_set_dct_algo(0)
+        if cl.have_ref():
+            cl.ref().ffref_me_cmp_set_dct_algo(0)

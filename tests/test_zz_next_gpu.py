@@ -1233,3 +1233,50 @@ def test_tx_double(device):
         c.uninit()
     with pytest.raises(fb.B200Error):
         tx.av_tx_init(tx.AV_TX_DOUBLE_FFT, 0, 96, device=device)
+
+
+# ---------------------------------------------------------------------------------------------- me_cmp: transform-domain comparisons
+def test_mecmp_dct_families(device):
+    """dct_sad / dct_max (both integer DCTs, b200_me_cmp_set_dct_algo) and dct264_sad: the drop-in table entries against the committed
+    reference values, the batched entry against the checker"""
+    import ctypes as C
+    import torch
+    from ffmpeg_b200 import me_cmp
+    from ffmpeg_b200._lib import u8p
+    from test_oracle_more import mecmp_dct_pairs
+    pairs = mecmp_dct_pairs()
+    c = me_cmp.ff_me_cmp_init()
+    tabs = {8: c.dct_sad, 9: c.dct_max, 10: c.dct264_sad}
+    O = cl.oracle()
+    try:
+        for fn, idx, algo, pi, x1, y1, x2, y2, h, v in np.load(os.path.join(G, "mecmp_dct.npz"))["cases"][::2]:
+            me_cmp.me_cmp_set_dct_algo(int(algo))
+            img1, img2 = pairs[int(pi)]
+            got = tabs[int(fn)][int(idx)](None, C.cast(img1.ctypes.data + int(y1) * 64 + int(x1), u8p), C.cast(img2.ctypes.data + int(y2) * 64 + int(x2), u8p), 64, int(h))
+            assert got == v, (fn, idx, algo, pi, h)
+        rng = np.random.default_rng(8)
+        W, H, n = 256, 128, 3001
+        f1 = rng.integers(0, 256, (H, W), dtype=np.uint8)
+        f2 = (f1.astype(int) + rng.integers(-40, 41, f1.shape)).clip(0, 255).astype(np.uint8)
+        off1 = (rng.integers(0, H - 16, n) * W + rng.integers(0, W - 16, n)).astype(np.int64)
+        off2 = (rng.integers(0, H - 16, n) * W + rng.integers(0, W - 16, n)).astype(np.int64)
+        with on_stream(device):
+            d1, d2 = torch.from_numpy(f1).cuda(), torch.from_numpy(f2).cuda()
+            o1, o2 = torch.from_numpy(off1).cuda(), torch.from_numpy(off2).cuda()
+            out = torch.zeros(n, dtype=torch.int32, device="cuda")
+            for algo in (0, 1):
+                me_cmp.me_cmp_set_dct_algo(algo)
+                O.orc_me_cmp_set_dct_algo(algo)
+                for fn in (8, 9, 10):
+                    for idx, h in ((0, 16), (0, 8), (1, 8)):
+                        me_cmp.me_cmp_batch_device(device, fn, idx, d1, d2, W, h, o1, o2, n, out)
+                        device.sync()
+                        got = out.cpu().numpy()
+                        sel = list(range(250)) + [n - 1]
+                        exp = np.array([O.orc_me_cmp(fn, idx, C.cast(f1.ctypes.data + int(off1[i]), cl.u8p), C.cast(f2.ctypes.data + int(off2[i]), cl.u8p), W, h) for i in sel])
+                        assert np.array_equal(got[sel], exp), (algo, fn, idx, h)
+        with pytest.raises(Exception):
+            me_cmp.me_cmp_set_dct_algo(me_cmp.FF_DCT_FAAN)
+    finally:
+        me_cmp.me_cmp_set_dct_algo(0)
+        O.orc_me_cmp_set_dct_algo(0)
