@@ -46,6 +46,11 @@ class MECmpContext(C.Structure):
         [("pix_abs", (_CMP * 4) * 2), ("median_sad", _CMP * 6)]
 
 
+class FDCTDSPContext(C.Structure):
+    """Same member order as FDCTDSPContext, libavcodec/fdctdsp.h:28-31."""
+    _fields_ = [("fdct", C.CFUNCTYPE(None, i16p)), ("fdct248", C.CFUNCTYPE(None, i16p))]
+
+
 _QPEL = C.CFUNCTYPE(None, u8p, u8p, C.c_ssize_t)
 _HPEL = C.CFUNCTYPE(None, u8p, u8p, C.c_ssize_t, C.c_int)
 
@@ -194,6 +199,8 @@ PROTOTYPES = {
     "b200_me_cmp_set_nsse_weight": (None, [C.c_int]),
     "b200_me_cmp_set_dct_algo": (C.c_int, [C.c_int]),
     "b200_sum_abs_dctelem_batch_device": (C.c_int, [vp, vp, C.c_int64, vp]),
+    "b200_fdctdsp_init": (C.c_int, [C.POINTER(FDCTDSPContext), C.c_int, C.c_int]),
+    "b200_fdct_batch_device": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, vp, C.c_int64]),
     "b200_me_cmp_batch_device": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, C.c_ssize_t, C.c_int, vp, vp, C.c_int64, vp]),
     "b200_me_esa_device": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, vp, vp]),
     "b200_h264qpel_init": (C.c_int, [C.POINTER(H264QpelContext), C.c_int]),

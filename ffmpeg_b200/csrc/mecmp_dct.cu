@@ -11,68 +11,12 @@
 // the difference block in registers.  Row pass in the lane, 8x8 transpose across the eight lanes with three rounds of xor-shuffles,
 // column pass in the lane (it now holds a column), then the |.| sum or maximum over the eight lanes and the sum over the blocks.
 #include "mecmp_dct.h"
+#include "fdct_dev.cuh"
 #include <atomic>
 
 namespace {
 
 std::atomic<int> g_dct_fast{0};                                  // 1: ff_fdct_ifast
-
-__device__ __forceinline__ int as_s16(int x) { return (int)(short)x; }
-// DESCALE of jfdctint_template.c:70 on a product kept modulo 2^32, stored as int16
-__device__ __forceinline__ int round_s16(unsigned x, int n) { return as_s16(((int)x + (1 << (n - 1))) >> n); }
-
-// lane r and lane k exchange so that afterwards v[k] of lane r is what v[r] of lane k was (lanes = the 8 of one block, row = lane & 7)
-__device__ __forceinline__ void transpose8(int (&v)[8], int row)
-{
-#pragma unroll
-    for (int span = 1; span < 8; span <<= 1) {
-        const bool upper = row & span;
-#pragma unroll
-        for (int k = 0; k < 8; k++)
-            if (!(k & span)) {
-                const int give = upper ? v[k] : v[k + span];
-                const int got = __shfl_xor_sync(0xffffffffu, give, span);
-                if (upper) v[k] = got; else v[k + span] = got;
-            }
-    }
-}
-
-// Loeffler-Ligtenberg-Moschytz 1-D DCT with 13-bit constants (the "slow" integer DCT); COL = second pass (removes the 4 extra bits)
-template <bool COL>
-__device__ __forceinline__ void fdct_slow8(int (&v)[8])
-{
-    const int s0 = v[0] + v[7], s1 = v[1] + v[6], s2 = v[2] + v[5], s3 = v[3] + v[4];
-    const int d0 = v[0] - v[7], d1 = v[1] - v[6], d2 = v[2] - v[5], d3 = v[3] - v[4];
-    const int e0 = s0 + s3, e3 = s0 - s3, e1 = s1 + s2, e2 = s1 - s2;
-    constexpr int SH = COL ? 17 : 9;
-    v[0] = COL ? as_s16((e0 + e1 + 8) >> 4) : as_s16((e0 + e1) * 16);
-    v[4] = COL ? as_s16((e0 - e1 + 8) >> 4) : as_s16((e0 - e1) * 16);
-    const unsigned r = (unsigned)(e2 + e3) * 4433u;
-    v[2] = round_s16(r + (unsigned)e3 * 6270u, SH);
-    v[6] = round_s16(r - (unsigned)e2 * 15137u, SH);
-    const unsigned q = (unsigned)(d3 + d1 + d2 + d0) * 9633u;
-    const unsigned z1 = (unsigned)(d3 + d0) * 7373u, z2 = (unsigned)(d2 + d1) * 20995u;
-    const unsigned z3 = q - (unsigned)(d3 + d1) * 16069u, z4 = q - (unsigned)(d2 + d0) * 3196u;
-    v[7] = round_s16((unsigned)d3 * 2446u - z1 + z3, SH);
-    v[5] = round_s16((unsigned)d2 * 16819u - z2 + z4, SH);
-    v[3] = round_s16((unsigned)d1 * 25172u - z2 + z3, SH);
-    v[1] = round_s16((unsigned)d0 * 12299u - z1 + z4, SH);
-}
-
-// Arai-Agui-Nakajima 1-D DCT with 8-bit constants, products shifted down without rounding and kept as int16 (the "fast" integer DCT)
-__device__ __forceinline__ int mul8(int x, int c) { return as_s16((x * c) >> 8); }
-__device__ __forceinline__ void fdct_fast8(int (&v)[8])
-{
-    const int s0 = v[0] + v[7], s1 = v[1] + v[6], s2 = v[2] + v[5], s3 = v[3] + v[4];
-    const int d0 = v[0] - v[7], d1 = v[1] - v[6], d2 = v[2] - v[5], d3 = v[3] - v[4];
-    const int e0 = s0 + s3, e3 = s0 - s3, e1 = s1 + s2, e2 = s1 - s2;
-    v[0] = as_s16(e0 + e1); v[4] = as_s16(e0 - e1);
-    const int r = mul8(e2 + e3, 181);
-    v[2] = as_s16(e3 + r); v[6] = as_s16(e3 - r);
-    const int a = d3 + d2, b = d2 + d1, c = d1 + d0;
-    const int z5 = mul8(a - c, 98), z2 = mul8(a, 139) + z5, z4 = mul8(c, 334) + z5, z3 = mul8(b, 181);
-    v[5] = as_s16(d0 - z3 + z2); v[3] = as_s16(d0 - z3 - z2); v[1] = as_s16(d0 + z3 + z4); v[7] = as_s16(d0 + z3 - z4);
-}
 
 // 1-D step of the H.264 8x8 forward transform (exact integers, shifts are arithmetic)
 __device__ __forceinline__ void fwd264_8(int (&v)[8])
@@ -111,7 +55,7 @@ me_dct_kernel(int kind, int fast, int nblk, const uint8_t *f1, const uint8_t *f2
     } else if (fast) {
         fdct_fast8(v); transpose8(v, row); fdct_fast8(v);
     } else {
-        fdct_slow8<false>(v); transpose8(v, row); fdct_slow8<true>(v);
+        fdct_slow8<false, 4, 4>(v); transpose8(v, row); fdct_slow8<true, 4, 4>(v);
     }
     int s = 0;
 #pragma unroll

@@ -410,6 +410,19 @@ int  b200_h264_weight_batch_device(B200Device *dev, int64_t n, const int32_t *pa
 int  b200_h264_weight_hbd_batch_device(B200Device *dev, int bit_depth, int64_t n, const int32_t *params, uint8_t *dst, const int64_t *dst_off,
                                        const uint8_t *src, const int64_t *src_off, ptrdiff_t stride);
 
+/* ------------------------------------------------------------------------------------------------ fdctdsp
+ * Replaces FDCTDSPContext (libavcodec/fdctdsp.h:28-31) as filled by ff_fdctdsp_init(c, avctx) (libavcodec/fdctdsp.c:27-45): the forward
+ * 8x8 DCT in place on 64 int16 (16-byte aligned), fdct248 = the 2-4-8 variant for interlaced blocks.  dct_algo / bits_per_raw_sample are
+ * AVCodecContext's: 9 / 10 bit -> ff_jpeg_fdct_islow_10, else FF_DCT_FASTINT (1) -> ff_fdct_ifast, FF_DCT_FAAN (6) -> ENOSYS (keep the C
+ * functions), anything else -> ff_jpeg_fdct_islow_8. */
+typedef struct B200FDCTDSPContext {
+    void (*fdct)(int16_t *block);       /* HOST pointer */
+    void (*fdct248)(int16_t *block);
+} B200FDCTDSPContext;
+int  b200_fdctdsp_init(B200FDCTDSPContext *c, int dct_algo, int bits_per_raw_sample);
+/* batched, DEVICE pointer: n blocks of 64 coefficients transformed in place (blocks 16-byte aligned) */
+int  b200_fdct_batch_device(B200Device *dev, int dct_algo, int bits_per_raw_sample, int is248, int16_t *blocks, int64_t n);
+
 /* ------------------------------------------------------------------------------------------------ me_cmp
  * Replaces MECmpContext (libavcodec/me_cmp.h:53-77) as filled by ff_me_cmp_init (libavcodec/me_cmp.c:961-1027) for the
  * SAD / SSE entries: sad[0..1] = pix_abs16_c / pix_abs8_c, sse[0..2] = sse16_c / sse8_c / sse4_c,

@@ -153,15 +153,18 @@ void orc_me_cmp_set_dct_algo(int algo) { g_dct_algo = algo; }
 static int16_t descale16(uint32_t x, int n) { return (int16_t)(((int32_t)x + (1 << (n - 1))) >> n); }
 
 /* one 1-D pass of the "slow" integer DCT over eight samples at p[0], p[st], ...; second = the column pass */
-static void islow_pass(int16_t *p, int st, int second)
+static void islow_pass_bits(int16_t *p, int st, int second, int p1, int outs);
+static void islow_pass(int16_t *p, int st, int second) { islow_pass_bits(p, st, second, 4, 4); }
+/* p1 = PASS1_BITS, outs = OUT_SHIFT: 4 / 4 for 8-bit samples, 1 / 2 for 10-bit (jfdctint_template.c:84-92) */
+static void islow_pass_bits(int16_t *p, int st, int second, int p1, int outs)
 {
     const int x0 = p[0], x1 = p[st], x2 = p[2 * st], x3 = p[3 * st], x4 = p[4 * st], x5 = p[5 * st], x6 = p[6 * st], x7 = p[7 * st];
     const int s0 = x0 + x7, s1 = x1 + x6, s2 = x2 + x5, s3 = x3 + x4;
     const int d0 = x0 - x7, d1 = x1 - x6, d2 = x2 - x5, d3 = x3 - x4;
     const int e0 = s0 + s3, e3 = s0 - s3, e1 = s1 + s2, e2 = s1 - s2;
-    const int sh = second ? 13 + 4 : 13 - 4;
-    if (second) { p[0] = (int16_t)((e0 + e1 + 8) >> 4); p[4 * st] = (int16_t)((e0 - e1 + 8) >> 4); }
-    else        { p[0] = (int16_t)((e0 + e1) * 16);     p[4 * st] = (int16_t)((e0 - e1) * 16); }
+    const int sh = second ? 13 + outs : 13 - p1, rnd = 1 << (outs - 1);
+    if (second) { p[0] = (int16_t)((e0 + e1 + rnd) >> outs); p[4 * st] = (int16_t)((e0 - e1 + rnd) >> outs); }
+    else        { p[0] = (int16_t)((e0 + e1) * (1 << p1)); p[4 * st] = (int16_t)((e0 - e1) * (1 << p1)); }
     const uint32_t r = (uint32_t)(e2 + e3) * 4433u;
     p[2 * st] = descale16(r + (uint32_t)e3 * 6270u, sh);
     p[6 * st] = descale16(r - (uint32_t)e2 * 15137u, sh);
@@ -189,6 +192,42 @@ static void ifast_pass(int16_t *p, int st)
     const int z5 = ifast_mul(a - c, 98), z2 = ifast_mul(a, 139) + z5, z4 = ifast_mul(c, 334) + z5, z3 = ifast_mul(b, 181);
     const int z11 = d0 + z3, z13 = d0 - z3;
     p[5 * st] = (int16_t)(z13 + z2); p[3 * st] = (int16_t)(z13 - z2); p[1 * st] = (int16_t)(z11 + z4); p[7 * st] = (int16_t)(z11 - z4);
+}
+
+/* column pass of the 2-4-8 DCT (ff_fdct248_islow, jfdctint_template.c:347-412; ff_fdct_ifast248, jfdctfst.c:286-343): the even part of the
+ * 1-D DCT on the sums of line pairs (rows 0 4 2 6) and on their differences (rows 1 5 3 7) */
+static void col248(int16_t *p, int fast, int outs)
+{
+    const int x[8] = { p[0], p[8], p[16], p[24], p[32], p[40], p[48], p[56] };
+    for (int half = 0; half < 2; half++) {
+        int a[4];
+        for (int k = 0; k < 4; k++) a[k] = half ? x[2 * k] - x[2 * k + 1] : x[2 * k] + x[2 * k + 1];
+        const int t10 = a[0] + a[3], t11 = a[1] + a[2], t12 = a[1] - a[2], t13 = a[0] - a[3];
+        int16_t *o = p + 8 * half;
+        if (fast) {
+            o[0] = (int16_t)(t10 + t11); o[32] = (int16_t)(t10 - t11);
+            const int z = ifast_mul(t12 + t13, 181);
+            o[16] = (int16_t)(t13 + z); o[48] = (int16_t)(t13 - z);
+        } else {
+            const int rnd = 1 << (outs - 1);
+            o[0] = (int16_t)((t10 + t11 + rnd) >> outs); o[32] = (int16_t)((t10 - t11 + rnd) >> outs);
+            const uint32_t z = (uint32_t)(t12 + t13) * 4433u;
+            o[16] = descale16(z + (uint32_t)t13 * 6270u, 13 + outs);
+            o[48] = descale16(z - (uint32_t)t12 * 15137u, 13 + outs);
+        }
+    }
+}
+
+/* FDCTDSPContext.fdct / .fdct248 (fdctdsp.c:27-45): kind 0 islow 8-bit, 1 ifast, 2 islow 10-bit */
+void orc_fdct(int kind, int is248, int16_t *block)
+{
+    const int p1 = kind == 2 ? 1 : 4, outs = kind == 2 ? 2 : 4;
+    for (int i = 0; i < 8; i++) { if (kind == 1) ifast_pass(block + 8 * i, 1); else islow_pass_bits(block + 8 * i, 1, 0, p1, outs); }
+    for (int j = 0; j < 8; j++) {
+        if (is248) col248(block + j, kind == 1, outs);
+        else if (kind == 1) ifast_pass(block + j, 8);
+        else islow_pass_bits(block + j, 8, 1, p1, outs);
+    }
 }
 
 /* the H.264 8x8 forward transform's 1-D step: in[] -> out[] */

@@ -148,6 +148,7 @@ void orc_pixels_clamped(int kind, const int16_t *block, uint8_t *pixels, ptrdiff
 /* fn: 0 sad, 1 sse, 2 pix_abs[idx>>2][idx&3]; idx for sad/sse: 0=16 wide,1=8,2=4 (sse only) */
 int  orc_me_cmp(int fn, int idx, const uint8_t *blk1, const uint8_t *blk2, ptrdiff_t stride, int h);
 int  orc_sum_abs_dctelem(const int16_t *block);
+void orc_fdct(int kind, int is248, int16_t *block);   /* FDCTDSPContext.fdct / fdct248: kind 0 islow_8, 1 ifast, 2 islow_10 */
 void orc_me_cmp_set_dct_algo(int algo);   /* fn 8 / 9 (dct_sad, dct_max): 0 = ff_jpeg_fdct_islow_8, 1 = ff_fdct_ifast */
 int  orc_pixelutils_sad(int bits, const uint8_t *src1, ptrdiff_t stride1, const uint8_t *src2, ptrdiff_t stride2);
 void orc_esa_frame(const uint8_t *cur, const uint8_t *ref, int linesize, int width, int height,

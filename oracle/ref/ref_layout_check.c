@@ -36,6 +36,12 @@ SAME(IDCTDSPContext, B200IDCTDSPContext, idct_permutation);
 SAME_OFF(IDCTDSPContext, B200IDCTDSPContext, perm_type);
 SAME_OFF(IDCTDSPContext, B200IDCTDSPContext, mpeg4_studio_profile);
 
+/* FDCTDSPContext, libavcodec/fdctdsp.h */
+#include "libavcodec/fdctdsp.h"
+SAME_SIZE(FDCTDSPContext, B200FDCTDSPContext);
+SAME(FDCTDSPContext, B200FDCTDSPContext, fdct);
+SAME(FDCTDSPContext, B200FDCTDSPContext, fdct248);
+
 /* ProresDSPContext, libavcodec/proresdsp.h */
 SAME_SIZE(ProresDSPContext, B200ProresDSPContext);
 SAME(ProresDSPContext, B200ProresDSPContext, idct_permutation_type);

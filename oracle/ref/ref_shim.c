@@ -332,6 +332,20 @@ static MPVEncContext *mecmp_enc(void)
     }
     return g_mpvenc;
 }
+/* FDCTDSPContext as ff_fdctdsp_init fills it for (dct_algo, bits_per_raw_sample) */
+API void ffref_fdct(int dct_algo, int bits, int is248, int16_t *block)
+{
+    FDCTDSPContext f;
+    AVCodecContext *avctx = av_mallocz(sizeof(*avctx));
+    LOCAL_ALIGNED_16(int16_t, tmp, [64]);
+    avctx->dct_algo = dct_algo;
+    avctx->bits_per_raw_sample = bits;
+    ff_fdctdsp_init(&f, avctx);
+    av_free(avctx);
+    memcpy(tmp, block, 128);
+    (is248 ? f.fdct248 : f.fdct)(tmp);
+    memcpy(block, tmp, 128);
+}
 API void ffref_me_cmp_set_dct_algo(int algo) { g_dct_algo = algo; av_freep(&g_mpvenc); }
 
 /* fn: 0 sad[idx], 1 sse[idx], 2 pix_abs[idx>>2][idx&3], 3 hadamard8_diff[idx], ..., 8 dct_sad, 9 dct_max, 10 dct264_sad */

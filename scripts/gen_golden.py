@@ -625,6 +625,20 @@ def gen_mecmp_dct():
     np.savez_compressed(os.path.join(OUT, "mecmp_dct.npz"), cases=np.array(rows, np.int32))
 
 
+def gen_fdct():
+    """FDCTDSPContext.fdct / fdct248 of the compiled reference (islow 8 / 10 bit, ifast) on the blocks of test_cuda_emu.fdct_blocks: sha256 per set"""
+    from test_cuda_emu import fdct_blocks
+    R = cl.ref()
+    lines = []
+    for algo, bits in ((0, 8), (1, 8), (0, 10), (1, 9)):
+        for is248 in (0, 1):
+            x = fdct_blocks(bits, 200, 7000 + 10 * algo + bits + is248)
+            for i in range(x.shape[0]):
+                R.ffref_fdct(algo, bits, is248, cl.ptr(x[i], cl.i16p))
+            lines.append(f"{algo} {bits} {is248} {sha(x)}")
+    open(os.path.join(OUT, "fdct_hashes.txt"), "w").write("\n".join(lines) + "\n")
+
+
 def gen_pel():
     R = cl.ref()
     rng = np.random.default_rng(22)
@@ -748,6 +762,7 @@ if __name__ == "__main__":
     gen_mecmp()
     gen_satd()
     gen_mecmp_dct()
+    gen_fdct()
     gen_pel()
     gen_chroma()
     gen_edge()

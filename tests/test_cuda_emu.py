@@ -51,7 +51,7 @@ def vp(a):
 WARP_KERNELS = {"mpv_unquant_kernel"}                   # kernels that use a warp collective: one OS thread per lane
 BLOCK_KERNELS = {"sws_mma_plane_kernel", "sws_mma_rgb_kernel", "tx_fft_kernel", "tx_mdct_inv_kernel", "tx_mdct_fwd_kernel", "tx_rdft_r2c_kernel", "tx_rdft_c2r_kernel",
                  "sws_fused_plane_kernel", "sws_fused_rgb_kernel", "tx_mdct_pfa_inv_kernel", "tx_mdct_pfa_fwd_kernel", "tx_fft_pfa_kernel", "tx_i32_kernel",
-                 "tx_dbl_fft_kernel", "tx_dbl_mdct_inv_kernel", "tx_dbl_mdct_fwd_kernel", "me_dct_kernel"}    # __syncthreads + dynamic shared memory
+                 "tx_dbl_fft_kernel", "tx_dbl_mdct_inv_kernel", "tx_dbl_mdct_fwd_kernel", "me_dct_kernel", "fdct_kernel"}    # __syncthreads + dynamic shared memory
 
 
 def rewrite_launches(txt):
@@ -84,7 +84,7 @@ def emuhost():
     os.makedirs(gen, exist_ok=True)
     cs = os.path.join(ROOT, "ffmpeg_b200", "csrc")
     srcs = []
-    for f in ("fdsp.cu", "unquant.cu", "idct_hbd.cu", "tx_pfa.cu", "h264lf.cu", "pixelutils.cu", "pel_hbd.cu", "h264idct_hbd.cu", "h264lf_hbd.cu", "mecmp_dct.cu"):
+    for f in ("fdsp.cu", "unquant.cu", "idct_hbd.cu", "tx_pfa.cu", "h264lf.cu", "pixelutils.cu", "pel_hbd.cu", "h264idct_hbd.cu", "h264lf_hbd.cu", "mecmp_dct.cu", "fdctdsp.cu"):
         t = rewrite_launches(open(os.path.join(cs, f)).read())
         t = t.replace("extern __shared__ float2 pfa_z[];", "float2 *pfa_z = (float2 *)emu_smem;")
         assert "<<<" not in t
@@ -1633,3 +1633,31 @@ def test_me_cmp_dct_family_on_emulated_device(emuhost):
     finally:
         L.b200_me_cmp_set_dct_algo(0); O.orc_me_cmp_set_dct_algo(0)
         if R is not None: R.ffref_me_cmp_set_dct_algo(0)
+
+
+def fdct_blocks(bits, n, seed):
+    """pixel differences / samples of the given depth, saturated +-max blocks, and anything an int16 block can hold (the products wrap like the
+    reference's unsigned multiplies)"""
+    rng = np.random.default_rng(seed)
+    lim = 256 if bits == 8 else 1 << bits
+    b = np.empty((n, 64), np.int16)
+    for i in range(n):
+        m = i % 4
+        b[i] = rng.integers(-lim + 1, lim, 64) if m == 0 else rng.integers(0, lim, 64) if m == 1 else rng.choice([-lim + 1, lim - 1], 64) if m == 2 else rng.integers(-32768, 32768, 64)
+    return b
+
+
+def test_fdctdsp_on_emulated_device(emuhost):
+    """fdctdsp.cu as the library launches it (batched entry, 32 blocks per CTA, a block count that leaves idle lane groups) on the CPU: islow 8 / 10 bit
+    and ifast, plain and 2-4-8, against the checker and the compiled reference"""
+    L, O, R = emuhost, cl.oracle(), cl.ref()
+    for algo, bits, kind in ((0, 8, 0), (1, 8, 1), (0, 10, 2), (1, 9, 2), (2, 8, 0)):
+        for is248 in (0, 1):
+            x = fdct_blocks(bits, 37, 100 * algo + bits + is248)
+            got = x.copy()
+            assert L.b200_fdct_batch_device(None, algo, bits, is248, vp(got), C.c_int64(37)) == 0
+            for i in range(37):
+                e, r = x[i].copy(), x[i].copy()
+                O.orc_fdct(kind, is248, cl.ptr(e, cl.i16p)); R.ffref_fdct(algo, bits, is248, cl.ptr(r, cl.i16p))
+                assert np.array_equal(e, r) and np.array_equal(got[i], e), (algo, bits, is248, i)
+    assert L.b200_fdct_batch_device(None, 6, 8, 0, vp(got), C.c_int64(1)) < 0          # FF_DCT_FAAN

@@ -909,3 +909,31 @@ def test_mecmp_dct_families_oracle_vs_fixture_and_reference():
         O.orc_me_cmp_set_dct_algo(0)
         if cl.have_ref():
             cl.ref().ffref_me_cmp_set_dct_algo(0)
+
+
+def fdct_hashes():
+    return {tuple(int(v) for v in l.split()[:3]): l.split()[3] for l in open(os.path.join(G, "fdct_hashes.txt"))}
+
+
+def test_fdct_oracle_vs_fixture_and_reference():
+    """FDCTDSPContext.fdct / fdct248 (islow 8 / 10 bit, ifast): the checker against the hashes of the compiled reference's outputs
+    (tests/golden/fdct_hashes.txt, scripts/gen_golden.py fdct) and, where the reference is built, block by block on other inputs"""
+    import hashlib
+    from test_cuda_emu import fdct_blocks
+    O = cl.oracle()
+    for (algo, bits, is248), h in fdct_hashes().items():
+        kind = 2 if bits in (9, 10) else 1 if algo == 1 else 0
+        x = fdct_blocks(bits, 200, 7000 + 10 * algo + bits + is248)
+        for i in range(x.shape[0]):
+            O.orc_fdct(kind, is248, cl.ptr(x[i], cl.i16p))
+        assert hashlib.sha256(x.tobytes()).hexdigest() == h, (algo, bits, is248)
+    if not cl.have_ref():
+        return
+    R = cl.ref()
+    for algo, bits, kind in ((0, 8, 0), (2, 8, 0), (1, 8, 1), (0, 10, 2), (1, 9, 2)):
+        for is248 in (0, 1):
+            x = fdct_blocks(bits, 400, 31 + algo + bits + is248)
+            for i in range(x.shape[0]):
+                e, r = x[i].copy(), x[i].copy()
+                O.orc_fdct(kind, is248, cl.ptr(e, cl.i16p)); R.ffref_fdct(algo, bits, is248, cl.ptr(r, cl.i16p))
+                assert np.array_equal(e, r), (algo, bits, is248, i)

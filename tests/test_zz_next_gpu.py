@@ -1280,3 +1280,44 @@ def test_mecmp_dct_families(device):
     finally:
         me_cmp.me_cmp_set_dct_algo(0)
         O.orc_me_cmp_set_dct_algo(0)
+
+
+# ---------------------------------------------------------------------------------------------- fdctdsp
+def test_fdctdsp(device):
+    """FDCTDSPContext (fdct / fdct248; islow 8 / 10 bit and ifast): the batched device entry against the hashes of the compiled reference's
+    outputs, the drop-in table entries (host pointers) against the checker, FF_DCT_FAAN refused"""
+    import hashlib
+    import torch
+    import ffmpeg_b200 as fb
+    from ffmpeg_b200 import fdctdsp
+    from ffmpeg_b200._lib import i16p
+    from test_oracle_more import fdct_hashes
+    from test_cuda_emu import fdct_blocks
+    O = cl.oracle()
+    for (algo, bits, is248), h in fdct_hashes().items():
+        x = fdct_blocks(bits, 200, 7000 + 10 * algo + bits + is248)
+        with on_stream(device):
+            d = torch.from_numpy(x).cuda()
+            fdctdsp.fdct_batch_device(device, d, x.shape[0], algo, bits, is248)
+            device.sync()
+            assert hashlib.sha256(d.cpu().numpy().tobytes()).hexdigest() == h, (algo, bits, is248)
+        c = fdctdsp.ff_fdctdsp_init(algo, bits)
+        kind = 2 if bits in (9, 10) else 1 if algo == 1 else 0
+        for i in range(6):
+            got, exp = x[i].copy(), x[i].copy()
+            (c.fdct248 if is248 else c.fdct)(got.ctypes.data_as(i16p))
+            O.orc_fdct(kind, is248, cl.ptr(exp, cl.i16p))
+            assert np.array_equal(got, exp), (algo, bits, is248, i)
+    rng = np.random.default_rng(12)
+    big = rng.integers(-255, 256, (100003, 64)).astype(np.int16)       # not a multiple of the 32 blocks of a CTA
+    with on_stream(device):
+        d = torch.from_numpy(big).cuda()
+        fdctdsp.fdct_batch_device(device, d, big.shape[0])
+        device.sync()
+        got = d.cpu().numpy()
+    for i in list(range(64)) + [big.shape[0] - 1]:
+        e = big[i].copy()
+        O.orc_fdct(0, 0, cl.ptr(e, cl.i16p))
+        assert np.array_equal(got[i], e), i
+    with pytest.raises(fb.B200Error):
+        fdctdsp.ff_fdctdsp_init(fdctdsp.FF_DCT_FAAN, 8)
