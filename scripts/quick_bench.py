@@ -159,4 +159,22 @@ with torch.cuda.stream(stream):
         nmb = (W // 16) * (H // 16)
         mv = torch.zeros((npairs, nmb, 2), dtype=torch.int32, device="cuda"); cost = torch.zeros((npairs, nmb), dtype=torch.int64, device="cuda")
         timed(lambda: me_cmp.me_esa_device(dev, cur, ref, W, W, H, W * H, npairs, 16, 32, mv, cost), npairs, "pairs")
+    elif what == "fdct":
+        from ffmpeg_b200 import fdctdsp
+        nb = 4 * 1024 * 1024                                    # 512 MB of coefficients: larger than L2
+        blocks = torch.randint(-255, 256, (nb, 64), dtype=torch.int16, device="cuda", generator=g)
+        for algo, bits, is248, name in ((0, 8, 0, "islow_8"), (1, 8, 0, "ifast"), (0, 10, 0, "islow_10"), (0, 8, 1, "islow_8 2-4-8")):
+            what = f"fdct {name} (in place: 128 B read + 128 B written per block)"
+            timed(lambda: fdctdsp.fdct_batch_device(dev, blocks, nb, algo, bits, is248), nb, "blocks", 256)
+    elif what == "dctcmp":
+        W, H = 3840, 2160
+        f1 = torch.randint(0, 256, (H, W), dtype=torch.uint8, device="cuda", generator=g)
+        f2 = torch.randint(0, 256, (H, W), dtype=torch.uint8, device="cuda", generator=g)
+        n = 2 * 1024 * 1024
+        o1 = (torch.randint(0, H - 16, (n,), device="cuda", generator=g) * W + torch.randint(0, W - 16, (n,), device="cuda", generator=g)).to(torch.int64)
+        o2 = (torch.randint(0, H - 16, (n,), device="cuda", generator=g) * W + torch.randint(0, W - 16, (n,), device="cuda", generator=g)).to(torch.int64)
+        out = torch.zeros(n, dtype=torch.int32, device="cuda")
+        for fn, name in ((8, "dct_sad"), (9, "dct_max"), (10, "dct264_sad"), (3, "hadamard8_diff")):
+            what = f"me_cmp {name}16 (h = 16, random offsets in a 4K frame pair)"
+            timed(lambda: me_cmp.me_cmp_batch_device(dev, fn, 0, f1, f2, W, 16, o1, o2, n, out), n, "cmp")
 dev.close()
